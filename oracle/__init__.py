@@ -1,0 +1,187 @@
+"""TEST INFRASTRUCTURE: ctypes front for the CPU oracle (oracle/*.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package.  Parity pinning status: see oracle/oracle_common.h.
+"""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_DIR = Path(__file__).resolve().parent
+_LIB = _DIR / "libplvi_oracle.so"
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")]
+)
+assert KEYPOINT_DTYPE.itemsize == 28
+
+KEYLINE_DTYPE = np.dtype(
+    [("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+     ("response", "<f4"), ("size", "<f4"), ("startPointX", "<f4"), ("startPointY", "<f4"),
+     ("endPointX", "<f4"), ("endPointY", "<f4"), ("sPointInOctaveX", "<f4"),
+     ("sPointInOctaveY", "<f4"), ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+     ("lineLength", "<f4"), ("numOfPixels", "<i4")]
+)
+assert KEYLINE_DTYPE.itemsize == 68
+
+
+def build(force: bool = False) -> Path:
+    srcs = list(_DIR.glob("*.cpp")) + list(_DIR.glob("*.h"))
+    stale = (not _LIB.exists()) or any(s.stat().st_mtime > _LIB.stat().st_mtime for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", str(_DIR), "-B", "libplvi_oracle.so"], check=True,
+                       capture_output=True)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB))
+        _lib.plvio_fast_atan2.restype = C.c_float
+        _lib.plvio_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _lib.plvio_ic_angle.restype = C.c_float
+        _lib.plvio_ic_angle.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
+        _lib.plvio_orb_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,
+                                              C.c_void_p]
+        _lib.plvio_orb_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 5
+        _lib.plvio_orb_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _u8(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 2
+    return img
+
+
+# ---- OpenCV-resident primitives ------------------------------------------------
+def fast_atan2(y, x):
+    return float(lib().plvio_fast_atan2(float(y), float(x)))
+
+
+def resize_linear(img, dw, dh):
+    img = _u8(img)
+    out = np.empty((dh, dw), np.uint8)
+    lib().plvio_resize_linear_u8(_p(img), img.strides[0], img.shape[1], img.shape[0], _p(out), dw, dw, dh)
+    return out
+
+
+def gaussian_blur7(img):
+    img = _u8(img)
+    out = np.empty_like(img)
+    lib().plvio_gaussian_blur7_u8(_p(img), img.strides[0], img.shape[1], img.shape[0], _p(out), img.shape[1])
+    return out
+
+
+def gaussian_blur5(img):
+    img = _u8(img)
+    out = np.empty_like(img)
+    lib().plvio_gaussian_blur5_u8(_p(img), img.strides[0], img.shape[1], img.shape[0], _p(out), img.shape[1])
+    return out
+
+
+def fast_score_map(img):
+    img = _u8(img)
+    out = np.empty(img.shape, np.int32)
+    lib().plvio_fast_score_map(_p(img), img.strides[0], img.shape[1], img.shape[0], _p(out))
+    return out
+
+
+def fast_roi(img, th):
+    """cv::FAST(img, th, nms=True) -> (n,3) float32 [x,y,response] in row-major order."""
+    img = _u8(img)
+    cap = img.size
+    out = np.empty((cap, 3), np.float32)
+    n = lib().plvio_fast_roi(_p(img), img.strides[0], img.shape[1], img.shape[0], int(th), _p(out), cap)
+    return out[:n].copy()
+
+
+def grid_fast(img, ini_th=20, min_th=7):
+    """Candidates of ComputeKeyPointsOctTree for one level, relative to (16,16)."""
+    img = _u8(img)
+    cap = img.size
+    out = np.empty((cap, 3), np.float32)
+    n = lib().plvio_grid_fast(_p(img), img.strides[0], img.shape[1], img.shape[0], ini_th, min_th, _p(out), cap)
+    return out[:n].copy()
+
+
+def distribute_octree(cands, min_x, max_x, min_y, max_y, n_target):
+    cands = np.ascontiguousarray(cands, np.float32)
+    out = np.empty(len(cands) + 8, np.int32)
+    n = lib().plvio_distribute_octree(_p(cands), len(cands), min_x, max_x, min_y, max_y, n_target,
+                                      _p(out), len(out))
+    return out[:n].copy()
+
+
+def ic_angle(img, x, y):
+    img = _u8(img)
+    return float(lib().plvio_ic_angle(_p(img), img.strides[0], float(x), float(y)))
+
+
+def orb_descriptor(img, x, y, angle):
+    img = _u8(img)
+    d = np.empty(32, np.uint8)
+    lib().plvio_orb_descriptor(_p(img), img.strides[0], float(x), float(y), float(angle), _p(d))
+    return d
+
+
+# ---- ORBextractor ---------------------------------------------------------------
+def orb_plan(w, h, nfeatures=1000, scale_factor=1.2, nlevels=8):
+    lw = np.empty(nlevels, np.int32)
+    lh = np.empty(nlevels, np.int32)
+    sc = np.empty(nlevels, np.float32)
+    q = np.empty(nlevels, np.int32)
+    um = np.empty(16, np.int32)
+    lib().plvio_orb_plan(w, h, nfeatures, scale_factor, nlevels, _p(lw), _p(lh), _p(sc), _p(q), _p(um))
+    return {"w": lw, "h": lh, "scale": sc, "quota": q, "umax": um}
+
+
+def orb_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
+                lapping=(0, 0), debug=False):
+    """ORBextractor::operator().  Returns dict(keypoints, descriptors, mono_index[, pyramid, blurred, level_counts])."""
+    img = _u8(img)
+    h, w = img.shape
+    plan = orb_plan(w, h, nfeatures, scale_factor, nlevels)
+    cap = nfeatures + 3 * nlevels + 64
+    kps = np.zeros(cap, KEYPOINT_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    mono = C.c_int(0)
+    npx = int((plan["w"].astype(np.int64) * plan["h"]).sum())
+    pyr = np.empty(npx, np.uint8) if debug else None
+    blur = np.empty(npx, np.uint8) if debug else None
+    lc = np.zeros(nlevels, np.int32)
+    n = lib().plvio_orb_extract(_p(img), w, h, img.strides[0], nfeatures, scale_factor, nlevels,
+                                ini_th, min_th, int(lapping[0]), int(lapping[1]), _p(kps), _p(desc),
+                                cap, C.byref(mono), _p(pyr), _p(blur), _p(lc))
+    if n < 0:
+        raise RuntimeError(f"oracle orb_extract failed: {n}")
+    out = {"keypoints": kps[:n].copy(), "descriptors": desc[:n].copy(), "mono_index": mono.value,
+           "level_counts": lc, "plan": plan}
+    if debug:
+        out["pyramid"] = split_levels(pyr, plan)
+        out["blurred"] = split_levels(blur, plan)
+    return out
+
+
+def split_levels(flat, plan):
+    res, o = [], 0
+    for w, h in zip(plan["w"], plan["h"]):
+        res.append(flat[o:o + int(w) * int(h)].reshape(int(h), int(w)))
+        o += int(w) * int(h)
+    return res
