@@ -1,0 +1,133 @@
+/*
+ * plvi.h -- C ABI of libplvi_cuda.so: the B200 (sm_100a) implementation of the
+ * PL-VI-ORBSLAM3 visual front-end hot path.
+ *
+ * The reference has no FFI/plugin seam; its seam is the C++ class interface
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference interface it
+ * stands behind (paths relative to the reference tree).  The C++ shim in
+ * pl_vi_orbslam3_b200/shim/ re-exposes the reference signatures on top of this ABI;
+ * INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status
+ * (PLVI_OK = 0, < 0 = error) unless stated; nothing throws across the ABI; the caller
+ * allocates outputs at the stated capacity and the callee reports counts.  A handle
+ * owns one CUDA stream and all device scratch; it is NOT re-entrant (like the
+ * reference objects, which mutate mvImagePyramid), but distinct handles may run
+ * concurrently.  There is no CPU fallback: without a CUDA device every call fails
+ * with PLVI_ERR_CUDA.
+ */
+#ifndef PLVI_H_
+#define PLVI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLVI_OK 0
+#define PLVI_ERR_INVALID (-1)  /* bad argument */
+#define PLVI_ERR_CUDA (-2)     /* CUDA runtime error; see plvi_last_error() */
+#define PLVI_ERR_CAPACITY (-3) /* batch / image larger than the handle was created for */
+#define PLVI_ERR_EMPTY (-4)    /* empty image: the reference operator() returns -1 */
+
+#define PLVI_MAX_LEVELS 12
+
+/* cv::KeyPoint as laid out by OpenCV (28 bytes) -- filled exactly as
+ * ORBextractor::operator() fills it (src/ORBextractor.cc:862-872,1131-1144). */
+typedef struct plvi_keypoint {
+  float x, y;     /* pt, in level-0 pixels (level coords * mvScaleFactor[octave]) */
+  float size;     /* (int)(31 * mvScaleFactor[octave]) */
+  float angle;    /* IC_Angle, degrees [0,360) */
+  float response; /* FAST score */
+  int32_t octave;
+  int32_t class_id; /* -1 */
+} plvi_keypoint;
+
+/* cv::line_descriptor::KeyLine (68 bytes),
+ * Thirdparty/line_descriptor/include/line_descriptor/descriptor_custom.hpp:107-146 */
+typedef struct plvi_keyline {
+  float angle;
+  int32_t class_id;
+  int32_t octave;
+  float pt_x, pt_y;
+  float response;
+  float size;
+  float startPointX, startPointY, endPointX, endPointY;
+  float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+  float lineLength;
+  int32_t numOfPixels;
+} plvi_keyline;
+
+const char* plvi_last_error(void);
+/* number of CUDA devices visible, or PLVI_ERR_CUDA */
+int plvi_device_count(void);
+
+/* ------------------------------------------------------------------ ORB ---- */
+typedef struct plvi_orb plvi_orb;
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (include/ORBextractor.h:50-51, src/ORBextractor.cc:408-468).  max_width/max_height/
+ * max_batch size the device scratch; device = CUDA ordinal; stream = an existing
+ * cudaStream_t to run on, or NULL to let the handle create its own. */
+int plvi_orb_create(plvi_orb** out, int nfeatures, float scale_factor, int nlevels,
+                    int ini_th_fast, int min_th_fast, int max_width, int max_height,
+                    int max_batch, int device, void* stream);
+void plvi_orb_destroy(plvi_orb* h);
+
+/* Rows to allocate per frame in kps/desc: sum over levels of max(quota+3, 8)
+ * (DistributeOctTree may exceed a level's quota by up to 3, src/ORBextractor.cc:667-736). */
+int plvi_orb_capacity(const plvi_orb* h);
+/* getters of include/ORBextractor.h:62-82 */
+int plvi_orb_levels(const plvi_orb* h);
+float plvi_orb_scale_factor(const plvi_orb* h);
+int plvi_orb_scale_factors(const plvi_orb* h, float* scale, float* inv_scale, float* sigma2,
+                           float* inv_sigma2);
+int plvi_orb_features_per_level(const plvi_orb* h, int* quota);
+/* level sizes for a w x h input (ComputePyramid, src/ORBextractor.cc:1156-1157) */
+int plvi_orb_level_sizes(const plvi_orb* h, int w, int h_, int* lw, int* lh);
+void* plvi_orb_stream(const plvi_orb* h);
+
+/* int ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea)
+ * (include/ORBextractor.h:58-60, src/ORBextractor.cc:1068-1150) over a batch of n
+ * equally sized CV_8UC1 frames in HOST memory: frame i starts at imgs + i*frame_stride,
+ * rows are `stride` bytes apart.  Outputs (host): kps[n][cap], desc[n][cap][32],
+ * counts[n] = keypoints per frame, mono_idx[n] = the reference operator()'s return
+ * value (monoIndex).  Blocking.  The mask argument of the reference is ignored there
+ * and absent here. */
+int plvi_orb_extract_batch(plvi_orb* h, const uint8_t* imgs, int n, int w, int h_, int stride,
+                           size_t frame_stride, int lap0, int lap1, plvi_keypoint* kps,
+                           uint8_t* desc, int* counts, int* mono_idx);
+
+/* Same, asynchronous on the handle's stream: returns once the work is enqueued; host
+ * buffers must stay valid (and should be pinned) until plvi_orb_sync() returns. */
+int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w, int h_,
+                                 int stride, size_t frame_stride, int lap0, int lap1,
+                                 plvi_keypoint* kps, uint8_t* desc, int* counts,
+                                 int* mono_idx);
+int plvi_orb_sync(plvi_orb* h);
+
+/* Same computation with every buffer already resident in DEVICE memory (inputs and
+ * outputs are device pointers); enqueued on the handle's stream, not synchronised. */
+int plvi_orb_extract_batch_device(plvi_orb* h, const uint8_t* d_imgs, int n, int w, int h_,
+                                  int stride, size_t frame_stride, int lap0, int lap1,
+                                  plvi_keypoint* d_kps, uint8_t* d_desc, int* d_counts,
+                                  int* d_mono_idx);
+
+/* Read-back of the last batch's internals (host pointers; blocking):
+ *  - pyramid level (ORBextractor::mvImagePyramid[level], include/ORBextractor.h:84),
+ *    dense w_l x h_l u8 into out; blurred != 0 selects the GaussianBlur'ed working
+ *    copy used for descriptors (src/ORBextractor.cc:1114-1115);
+ *  - FAST grid candidates of one level (vToDistributeKeys, src/ORBextractor.cc:766-855)
+ *    as packed u32 (x | y << 12 | score << 24, relative to minBorder), unordered. */
+int plvi_orb_read_level(plvi_orb* h, int frame, int level, int blurred, uint8_t* out);
+int plvi_orb_read_candidates(plvi_orb* h, int frame, int level, uint32_t* out, int cap,
+                             int* count);
+/* number of kernel launches enqueued by the last extract call */
+int plvi_orb_last_launches(const plvi_orb* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLVI_H_ */

@@ -1,0 +1,94 @@
+"""ctypes bindings of include/plvi.h.  Fails loudly when libplvi_cuda.so is missing."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libplvi_cuda.so"
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")]
+)
+KEYLINE_DTYPE = np.dtype(
+    [("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+     ("response", "<f4"), ("size", "<f4"), ("startPointX", "<f4"), ("startPointY", "<f4"),
+     ("endPointX", "<f4"), ("endPointY", "<f4"), ("sPointInOctaveX", "<f4"),
+     ("sPointInOctaveY", "<f4"), ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+     ("lineLength", "<f4"), ("numOfPixels", "<i4")]
+)
+assert KEYPOINT_DTYPE.itemsize == 28 and KEYLINE_DTYPE.itemsize == 68
+
+
+class PlviError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"plvi error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+vp, ci, cf, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+_SIGS = {
+    "plvi_last_error": (C.c_char_p, []),
+    "plvi_device_count": (ci, []),
+    "plvi_orb_create": (ci, [C.POINTER(vp), ci, cf, ci, ci, ci, ci, ci, ci, ci, vp]),
+    "plvi_orb_destroy": (None, [vp]),
+    "plvi_orb_capacity": (ci, [vp]),
+    "plvi_orb_levels": (ci, [vp]),
+    "plvi_orb_scale_factor": (cf, [vp]),
+    "plvi_orb_scale_factors": (ci, [vp, vp, vp, vp, vp]),
+    "plvi_orb_features_per_level": (ci, [vp, vp]),
+    "plvi_orb_level_sizes": (ci, [vp, ci, ci, vp, vp]),
+    "plvi_orb_stream": (vp, [vp]),
+    "plvi_orb_extract_batch": (ci, [vp, vp, ci, ci, ci, ci, sz, ci, ci, vp, vp, vp, vp]),
+    "plvi_orb_extract_batch_async": (ci, [vp, vp, ci, ci, ci, ci, sz, ci, ci, vp, vp, vp, vp]),
+    "plvi_orb_sync": (ci, [vp]),
+    "plvi_orb_extract_batch_device": (ci, [vp, vp, ci, ci, ci, ci, sz, ci, ci, vp, vp, vp, vp]),
+    "plvi_orb_read_level": (ci, [vp, ci, ci, ci, vp]),
+    "plvi_orb_read_candidates": (ci, [vp, ci, ci, vp, ci, vp]),
+    "plvi_orb_last_launches": (ci, [vp]),
+}
+
+
+def declared_symbols():
+    """Every function name declared in include/plvi.h (parsed from the header)."""
+    import re
+    hdr = (_PKG.parent / "include" / "plvi.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(plvi_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m pl_vi_orbslam3_b200.build` "
+                "(there is no CPU fallback)")
+        _lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def check(rc):
+    if rc < 0:
+        raise PlviError(rc, lib().plvi_last_error().decode(errors="replace"))
+    return rc
+
+
+def ptr(a):
+    """void* of a numpy array, torch tensor (host or device), int address or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))

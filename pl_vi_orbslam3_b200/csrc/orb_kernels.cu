@@ -1,0 +1,793 @@
+// ORB extraction kernels for sm_100a.
+//
+//   k_resize     ComputePyramid            src/ORBextractor.cc:1152-1177 (cv::resize INTER_LINEAR, u8)
+//   k_fast       grid FAST + per-cell th   src/ORBextractor.cc:763-855   (cv::FAST 9/16 + 3x3 NMS)
+//   k_octree     DistributeOctTree         src/ORBextractor.cc:537-761
+//   k_blur7      GaussianBlur 7x7 s=2      src/ORBextractor.cc:1114-1115
+//   k_layout     output row assignment     src/ORBextractor.cc:1104-1144 (lapping split)
+//   k_orient_desc IC_Angle + rBRIEF        src/ORBextractor.cc:75-145
+//
+// All stages are integer/byte streaming or gather work (no dense contraction): the
+// design rules are coalesced loads, shared-memory tiles and enough CTAs per launch to
+// fill 148 SMs -- every launch covers all frames of the batch (and all levels where the
+// stage allows), so grids are thousands of CTAs.
+#include "orb_pattern_table.h"
+#include "plvi_internal.cuh"
+
+namespace plvi {
+
+__device__ const signed char d_pattern[1024] = PLVI_ORB_PATTERN_VALUES;
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// ---------------------------------------------------------------------------------
+// block-wide helpers
+// ---------------------------------------------------------------------------------
+// In-place exclusive scan of arr[0..n) (shared memory); returns the total.  Must be
+// called by all NT threads; wtmp needs 33 ints.
+template <int NT>
+__device__ int block_excl_scan(int* arr, int n, int* wtmp) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int chunk = (n + NT - 1) / NT;
+  const int beg = min(tid * chunk, n), end = min(beg + chunk, n);
+  int sum = 0;
+  for (int i = beg; i < end; i++) sum += arr[i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wtmp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int v = lane < NT / 32 ? wtmp[lane] : 0;
+    int iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) iv += t;
+    }
+    wtmp[lane] = iv - v;
+    if (lane == 31) wtmp[32] = iv;
+  }
+  __syncthreads();
+  int base = wtmp[wid] + incl - sum;
+  const int total = wtmp[32];
+  for (int i = beg; i < end; i++) {
+    int t = arr[i];
+    arr[i] = base;
+    base += t;
+  }
+  __syncthreads();
+  return total;
+}
+
+// ---------------------------------------------------------------------------------
+// k_resize: one pyramid level from the previous one.  Fixed-point bilinear exactly as
+// OpenCV's 8-bit INTER_LINEAR path: coefficient rows (ofs, a0 | a1 << 16) are computed
+// on the host in float32; H = S[s]*a0 + S[s+1]*a1;
+// dst = (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.
+// Thread = 4 horizontally adjacent dst pixels (one aligned 32-bit store).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const u8* __restrict__ src, int spitch, size_t sfs,
+                                                int sw, int sh, u8* __restrict__ dst, int dpitch,
+                                                size_t dfs, int dw, int dh,
+                                                const int2* __restrict__ xtab,
+                                                const int2* __restrict__ ytab) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x4 >= dw || y >= dh) return;
+  const int2 yt = __ldg(&ytab[y]);
+  const int b0 = (short)(yt.y & 0xffff), b1 = yt.y >> 16;
+  const u8* r0 = src + (size_t)blockIdx.z * sfs + (size_t)yt.x * spitch;
+  const u8* r1 = src + (size_t)blockIdx.z * sfs + (size_t)min(yt.x + 1, sh - 1) * spitch;
+  uint32_t out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int x = x4 + i;
+    if (x < dw) {
+      const int2 xt = __ldg(&xtab[x]);
+      const int a0 = (short)(xt.y & 0xffff), a1 = xt.y >> 16;
+      const int s0 = xt.x, s1 = min(xt.x + 1, sw - 1);
+      const int h0 = __ldg(r0 + s0) * a0 + __ldg(r0 + s1) * a1;
+      const int h1 = __ldg(r1 + s0) * a0 + __ldg(r1 + s1) * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      out |= (uint32_t)v << (8 * i);
+    }
+  }
+  *reinterpret_cast<uint32_t*>(dst + (size_t)blockIdx.z * dfs + (size_t)y * dpitch + x4) = out;
+}
+
+// ---------------------------------------------------------------------------------
+// k_fast.  One CTA = up to 4 horizontally adjacent FAST cells of one cell row of one
+// level of one frame.  The reference runs cv::FAST on each cell's ROI
+// [ini, ini+cell+6) separately: scores exist only >= 3 px inside the ROI, so the
+// detection strips of the cells tile the level without overlap and the 3x3 NMS never
+// sees a score from a neighbouring cell.  A cell keeps its th=iniTh survivors, or, if
+// it has none, its th=minTh survivors (the score is threshold independent).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ int fast_arc_score(const int (&d)[16]) {
+  // max over the 16 arcs of 9 contiguous ring pixels of min(d) and of min(-d)
+  int bp = -256, bn = -256;
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    int mn = min(d[(k + 1) & 15], d[(k + 2) & 15]);
+    int mx = max(d[(k + 1) & 15], d[(k + 2) & 15]);
+#pragma unroll
+    for (int j = 3; j <= 8; j++) {
+      mn = min(mn, d[(k + j) & 15]);
+      mx = max(mx, d[(k + j) & 15]);
+    }
+    bp = max(bp, max(min(mn, d[k]), min(mn, d[(k + 9) & 15])));
+    bn = max(bn, max(-max(mx, d[k]), -max(mx, d[(k + 9) & 15])));
+  }
+  return max(bp, bn) - 1;
+}
+
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
+                                              const __grid_constant__ OrbPtrs p,
+                                              const FastTile* __restrict__ tiles,
+                                              uint32_t* __restrict__ cand,
+                                              int* __restrict__ candCount, int tilePitch,
+                                              int tileRows, int survCap) {
+  extern __shared__ __align__(16) u8 smem[];
+  const FastTile t = tiles[blockIdx.x];
+  const int f = blockIdx.y;
+  const OrbLevel& L = g.lv[t.level];
+  const int maxBX = L.w - kEdge, maxBY = L.h - kEdge;
+  const int iniY = kEdge + t.cellRow * L.hCell;
+  const int iniX = kEdge + t.cellCol0 * L.wCell;
+  const int maxY = min(iniY + L.hCell + 6, maxBY);
+  const int maxX = min(iniX + t.ncells * L.wCell + 6, maxBX);
+  const int rw = maxX - iniX, rh = maxY - iniY;
+  if (rw < 7 || rh < 7) return;
+
+  u8* simg = smem;                                   // [tileRows][tilePitch]
+  u8* ssc = smem + tileRows * tilePitch;             // scores, same shape
+  uint32_t* surv = reinterpret_cast<uint32_t*>(ssc + tileRows * tilePitch);  // [survCap]
+  uint32_t* kept = surv + survCap;                   // [survCap]
+  __shared__ int s_nsurv, s_nkept, s_base;
+  __shared__ int s_cellFlag[8];
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_nsurv = 0; s_nkept = 0; }
+  if (tid < 8) s_cellFlag[tid] = 0;
+
+  const int ipitch = p.ipitch[t.level];
+  const u8* gimg = p.img[t.level] + (size_t)f * p.ifs[t.level] + (size_t)iniY * ipitch + iniX;
+  for (int i = tid; i < rh * tilePitch; i += 256) {
+    const int r = i / tilePitch, c = i - r * tilePitch;
+    simg[i] = c < rw ? __ldg(gimg + (size_t)r * ipitch + c) : 0;
+  }
+  for (int i = tid; i < (tileRows * tilePitch) / 4; i += 256) reinterpret_cast<uint32_t*>(ssc)[i] = 0;
+  __syncthreads();
+
+  const int minTh = g.minTh, iniTh = g.iniTh;
+  const int dw = rw - 6, dh = rh - 6;
+  const int lane = tid & 31, wid = tid >> 5;
+  // ---- score pass: warp per row, lanes stride the columns
+  for (int dy = wid; dy < dh; dy += 8) {
+    const u8* row = simg + (dy + 3) * tilePitch + 3;
+    for (int dx = lane; dx < dw; dx += 32) {
+      const u8* q = row + dx;
+      const int c = q[0];
+      const int hi = c + minTh, lo = c - minTh;
+      // compass pre-test: any 9-arc holds >= 2 of the 4 compass pixels
+      const int v0 = q[3 * tilePitch], v8 = q[-3 * tilePitch], v4 = q[3], v12 = q[-3];
+      const int nb = (v0 > hi) + (v8 > hi) + (v4 > hi) + (v12 > hi);
+      const int nd = (v0 < lo) + (v8 < lo) + (v4 < lo) + (v12 < lo);
+      if (nb < 2 && nd < 2) continue;
+      int d[16];
+      d[0] = c - v0;
+      d[1] = c - q[3 * tilePitch + 1];
+      d[2] = c - q[2 * tilePitch + 2];
+      d[3] = c - q[tilePitch + 3];
+      d[4] = c - v4;
+      d[5] = c - q[-tilePitch + 3];
+      d[6] = c - q[-2 * tilePitch + 2];
+      d[7] = c - q[-3 * tilePitch + 1];
+      d[8] = c - v8;
+      d[9] = c - q[-3 * tilePitch - 1];
+      d[10] = c - q[-2 * tilePitch - 2];
+      d[11] = c - q[-tilePitch - 3];
+      d[12] = c - v12;
+      d[13] = c - q[tilePitch - 3];
+      d[14] = c - q[2 * tilePitch - 2];
+      d[15] = c - q[3 * tilePitch - 1];
+      uint32_t mb = 0, md = 0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        mb |= (uint32_t)(d[k] < -minTh) << k;  // ring brighter than centre + th
+        md |= (uint32_t)(d[k] > minTh) << k;   // ring darker than centre - th
+      }
+      mb |= mb << 16;
+      md |= md << 16;
+      mb &= mb >> 1; mb &= mb >> 2; mb &= mb >> 4; mb &= mb >> 1;
+      md &= md >> 1; md &= md >> 2; md &= md >> 4; md &= md >> 1;
+      if (((mb | md) & 0xffffu) == 0) continue;
+      ssc[(dy + 3) * tilePitch + 3 + dx] = (u8)fast_arc_score(d);
+    }
+  }
+  __syncthreads();
+  // ---- NMS confined to the cell; survivors to shared list
+  const int wCell = L.wCell;
+  for (int dy = wid; dy < dh; dy += 8) {
+    const u8* row = ssc + (dy + 3) * tilePitch + 3;
+    for (int dx = lane; dx < dw; dx += 32) {
+      const int s = row[dx];
+      if (s == 0) continue;
+      const int cell = dx / wCell, xin = dx - cell * wCell;
+      const bool hasL = xin > 0, hasR = (xin < wCell - 1) && (dx + 1 < dw);
+      bool keep = true;
+#pragma unroll
+      for (int oy = -1; oy <= 1; oy++) {
+        if (dy + oy < 0 || dy + oy >= dh) continue;
+        const u8* r2 = row + oy * tilePitch + dx;
+        if (hasL && r2[-1] >= s) keep = false;
+        if (oy != 0 && r2[0] >= s) keep = false;
+        if (hasR && r2[1] >= s) keep = false;
+      }
+      if (!keep) continue;
+      const int idx = atomicAdd(&s_nsurv, 1);
+      if (idx < survCap)
+        surv[idx] = pack_xys(iniX + 3 + dx - kEdge, iniY + 3 + dy - kEdge, s) ;
+      if (s >= iniTh) s_cellFlag[cell] = 1;
+    }
+  }
+  __syncthreads();
+  const int ns = min(s_nsurv, survCap);
+  for (int i = tid; i < ns; i += 256) {
+    const uint32_t v = surv[i];
+    const int cell = (unpack_x(v) + kEdge - iniX - 3) / wCell;
+    const int th = s_cellFlag[cell] ? iniTh : minTh;
+    if (unpack_s(v) >= th) kept[atomicAdd(&s_nkept, 1)] = v;
+  }
+  __syncthreads();
+  const int nk = s_nkept;
+  if (nk == 0) return;
+  if (tid == 0) s_base = atomicAdd(&candCount[f * g.nlevels + t.level], nk);
+  __syncthreads();
+  const int base = s_base;
+  uint32_t* out = cand + (size_t)f * g.candTotal + L.candOff;
+  for (int i = tid; i < nk; i += 256)
+    if (base + i < L.candCap) out[base + i] = kept[i];
+}
+
+// ---------------------------------------------------------------------------------
+// k_octree: one CTA per (level, frame).  The reference's list-of-nodes algorithm is
+// re-expressed as passes over (a) the keys -- each key knows the list position of its
+// node -- and (b) the node list, which is rebuilt per pass as
+//     reversed(children in creation order) ++ (surviving nodes in old order)
+// which is exactly what push_front + erase produce.  Phase 1 splits every multi-key
+// node per pass; phase 2 splits the multi-key nodes largest-first (ties: later created
+// first, see oracle/oracle_orb.cpp) and stops as soon as the list holds N nodes.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ int oct_quadrant(uint32_t key, ushort4 gm) {
+  const int mx = gm.x + ((gm.z - gm.x + 1) >> 1);
+  const int my = gm.y + ((gm.w - gm.y + 1) >> 1);
+  return (unpack_x(key) < mx ? 0 : 1) + (unpack_y(key) < my ? 0 : 2);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ OrbGeom g,
+                                               const uint32_t* __restrict__ cand,
+                                               const int* __restrict__ candCount,
+                                               uint16_t* __restrict__ knodeAll,
+                                               uint32_t* __restrict__ lvlKp,
+                                               int* __restrict__ lvlCount) {
+  extern __shared__ __align__(16) u8 smem[];
+  const int lvl = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  const OrbLevel& L = g.lv[lvl];
+  const int M = g.maxNodes;
+  const int n = min(candCount[f * g.nlevels + lvl], L.candCap);
+  const int N = L.quota;
+  if (n == 0) {
+    if (tid == 0) lvlCount[f * g.nlevels + lvl] = 0;
+    return;
+  }
+  const uint32_t* keys = cand + (size_t)f * g.candTotal + L.candOff;
+  uint16_t* knode = knodeAll + (size_t)f * g.candTotal + L.candOff;
+
+  // shared carve-up
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(smem);  // [M] (8B aligned first)
+  ushort4* geomA = reinterpret_cast<ushort4*>(best + M);
+  ushort4* geomB = geomA + M;
+  int* cntA = reinterpret_cast<int*>(geomB + M);
+  int* cntB = cntA + M;
+  int* seqA = cntB + M;
+  int* seqB = seqA + M;
+  int* cc = seqB + M;          // [4M] child key counts
+  int* order = cc + 4 * M;     // [M] node at processing rank r
+  int* cstart = order + M;     // [M] first child creation index per rank
+  int* keep = cstart + M;      // [M] survivor rank per position
+  int* srank = keep + M;       // [M] processing rank per position or -1
+  int* tmp = srank + M;        // [M] scratch
+  unsigned short* cpos = reinterpret_cast<unsigned short*>(tmp + M);  // [4M] new position of child
+  __shared__ int wtmp[33];
+  __shared__ int s_rstar, s_nexp;
+
+  // ---- root nodes (src/ORBextractor.cc:541-583)
+  const int nIni = L.nIni;
+  const float hX = L.hX;
+  const int H = L.h - 2 * kEdge;
+  for (int i = tid; i < nIni; i += NT) {
+    geomA[i] = make_ushort4((unsigned short)(int)__fmul_rn(hX, (float)i), 0,
+                            (unsigned short)(int)__fmul_rn(hX, (float)(i + 1)), (unsigned short)H);
+    cntA[i] = 0;
+    seqA[i] = i;
+  }
+  __syncthreads();
+  for (int k = tid; k < n; k += NT) {
+    int idx = (int)__fdiv_rn((float)unpack_x(keys[k]), hX);
+    idx = min(idx, nIni - 1);
+    atomicAdd(&cntA[idx], 1);
+    knode[k] = (uint16_t)idx;
+  }
+  __syncthreads();
+  for (int i = tid; i < nIni; i += NT) keep[i] = cntA[i] > 0;
+  __syncthreads();
+  int Lsz = block_excl_scan<NT>(keep, nIni, wtmp);
+  for (int i = tid; i < nIni; i += NT)
+    if (cntA[i] > 0) {
+      geomB[keep[i]] = geomA[i];
+      cntB[keep[i]] = cntA[i];
+      seqB[keep[i]] = seqA[i];
+    }
+  for (int k = tid; k < n; k += NT) knode[k] = (uint16_t)keep[knode[k]];
+  __syncthreads();
+  ushort4 *geom = geomB, *geomN = geomA;
+  int *cnt = cntB, *cntN = cntA, *seq = seqB, *seqN = seqA;
+  int seqBase = nIni;
+  int phase = 1;
+
+  while (true) {
+    const int prevL = Lsz;
+    for (int i = tid; i < 4 * Lsz; i += NT) cc[i] = 0;
+    if (tid == 0) { s_rstar = 0x7fffffff; s_nexp = 0; }
+    __syncthreads();
+    for (int k = tid; k < n; k += NT) {
+      const int nd = knode[k];
+      if (cnt[nd] > 1) atomicAdd(&cc[nd * 4 + oct_quadrant(keys[k], geom[nd])], 1);
+    }
+    __syncthreads();
+    // multi-key nodes in list order -> order[0..Mc)
+    for (int i = tid; i < Lsz; i += NT) tmp[i] = cnt[i] > 1;
+    __syncthreads();
+    const int Mc = block_excl_scan<NT>(tmp, Lsz, wtmp);
+    for (int i = tid; i < Lsz; i += NT) {
+      srank[i] = -1;
+      if (cnt[i] > 1) order[tmp[i]] = i;
+    }
+    __syncthreads();
+    int nSplit = Mc;
+    if (phase == 2 && Mc > 0) {
+      // processing order: (size, creation seq) descending  (src/ORBextractor.cc:679-683)
+      for (int i = tid; i < Mc; i += NT) {
+        const int a = order[i], ca = cnt[a], sa = seq[a];
+        int r = 0;
+        for (int j = 0; j < Mc; j++) {
+          const int b = order[j], cb = cnt[b];
+          r += (cb > ca) || (cb == ca && seq[b] > sa);
+        }
+        cstart[r] = a;  // sorted order, staged
+      }
+      __syncthreads();
+      for (int i = tid; i < Mc; i += NT) {
+        const int a = cstart[i];
+        order[i] = a;
+        const int* c4 = cc + a * 4;
+        tmp[i] = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0) - 1;
+      }
+      __syncthreads();
+      // inclusive growth of the list; stop right after the split that reaches N (:728-729)
+      for (int i = tid; i < Mc; i += NT) keep[i] = tmp[i];
+      __syncthreads();
+      block_excl_scan<NT>(keep, Mc, wtmp);
+      for (int i = tid; i < Mc; i += NT)
+        if (Lsz + keep[i] + tmp[i] >= N) atomicMin(&s_rstar, i);
+      __syncthreads();
+      nSplit = min(Mc, s_rstar == 0x7fffffff ? Mc : s_rstar + 1);
+    }
+    for (int r = tid; r < nSplit; r += NT) {
+      const int a = order[r];
+      srank[a] = r;
+      const int* c4 = cc + a * 4;
+      cstart[r] = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
+    }
+    __syncthreads();
+    const int C = block_excl_scan<NT>(cstart, nSplit, wtmp);
+    for (int i = tid; i < Lsz; i += NT) keep[i] = srank[i] < 0;
+    __syncthreads();
+    const int K = block_excl_scan<NT>(keep, Lsz, wtmp);
+    const int Lnew = C + K;
+    // build the new list (positions double as node ids)
+    int myExp = 0;
+    for (int r = tid; r < nSplit; r += NT) {
+      const int a = order[r];
+      const ushort4 gm = geom[a];
+      const unsigned short mx = gm.x + ((gm.z - gm.x + 1) >> 1);
+      const unsigned short my = gm.y + ((gm.w - gm.y + 1) >> 1);
+      int ci = cstart[r];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int c = cc[a * 4 + q];
+        if (c == 0) continue;
+        const int np = C - 1 - ci;
+        ushort4 ch;
+        ch.x = (q & 1) ? mx : gm.x;
+        ch.z = (q & 1) ? gm.z : mx;
+        ch.y = (q & 2) ? my : gm.y;
+        ch.w = (q & 2) ? gm.w : my;
+        geomN[np] = ch;
+        cntN[np] = c;
+        seqN[np] = seqBase + ci;
+        cpos[a * 4 + q] = (unsigned short)np;
+        myExp += c > 1;
+        ci++;
+      }
+    }
+    for (int i = tid; i < Lsz; i += NT)
+      if (srank[i] < 0) {
+        const int np = C + keep[i];
+        geomN[np] = geom[i];
+        cntN[np] = cnt[i];
+        seqN[np] = seq[i];
+      }
+    if (myExp) atomicAdd(&s_nexp, myExp);
+    __syncthreads();
+    for (int k = tid; k < n; k += NT) {
+      const int nd = knode[k];
+      knode[k] = srank[nd] >= 0 ? cpos[nd * 4 + oct_quadrant(keys[k], geom[nd])]
+                                : (uint16_t)(C + keep[nd]);
+    }
+    __syncthreads();
+    const int nToExpand = s_nexp;
+    { ushort4* t = geom; geom = geomN; geomN = t; }
+    { int* t = cnt; cnt = cntN; cntN = t; }
+    { int* t = seq; seq = seqN; seqN = t; }
+    Lsz = Lnew;
+    seqBase += C;
+    if (Lsz >= N || Lsz == prevL) break;
+    if (phase == 1 && Lsz + 3 * nToExpand > N) phase = 2;
+    __syncthreads();
+  }
+
+  // ---- best key per node: max response, first in the reference's emission order
+  // (cell row, cell col, y, x) wins ties (src/ORBextractor.cc:742-758)
+  for (int i = tid; i < Lsz; i += NT) best[i] = 0ull;
+  __syncthreads();
+  for (int k = tid; k < n; k += NT) {
+    const uint32_t key = keys[k];
+    const int x = unpack_x(key), y = unpack_y(key);
+    const unsigned cr = 255u - (unsigned)((y - 3) / L.hCell), ccol = 255u - (unsigned)((x - 3) / L.wCell);
+    const unsigned long long v = ((unsigned long long)unpack_s(key) << 40) |
+                                 ((unsigned long long)cr << 32) | ((unsigned long long)ccol << 24) |
+                                 ((unsigned long long)(4095 - y) << 12) | (unsigned long long)(4095 - x);
+    atomicMax(&best[knode[k]], v);
+  }
+  __syncthreads();
+  const int nOut = min(Lsz, L.kpCap);
+  uint32_t* out = lvlKp + (size_t)f * g.kpTotal + L.kpOff;
+  for (int i = tid; i < nOut; i += NT) {
+    const unsigned long long v = best[i];
+    const int x = 4095 - (int)(v & 0xFFF), y = 4095 - (int)((v >> 12) & 0xFFF);
+    out[i] = pack_xys(x + kEdge, y + kEdge, (int)(v >> 40));
+  }
+  if (tid == 0) lvlCount[f * g.nlevels + lvl] = nOut;
+}
+
+// ---------------------------------------------------------------------------------
+// k_blur7: GaussianBlur(7x7, sigma 2, REFLECT_101) of every level, fixed point
+// {18,34,48,56,48,34,18}/256 per axis, (v + 32768) >> 16.  Tile 128x32 outputs.
+// ---------------------------------------------------------------------------------
+#define BLUR_TW 128
+#define BLUR_TH 32
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g,
+                                               const __grid_constant__ OrbPtrs p,
+                                               const BlurTile* __restrict__ tiles) {
+  __shared__ __align__(16) u8 sin_[(BLUR_TH + 6) * (BLUR_TW + 8)];
+  __shared__ __align__(16) unsigned short sh_[(BLUR_TH + 6) * BLUR_TW];
+  const BlurTile t = tiles[blockIdx.x];
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const OrbLevel& L = g.lv[t.level];
+  const int x0 = t.tx * BLUR_TW, y0 = t.ty * BLUR_TH;
+  const int ipitch = p.ipitch[t.level];
+  const u8* src = p.img[t.level] + (size_t)f * p.ifs[t.level];
+  const int SP = BLUR_TW + 8;
+  for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+    const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
+    const int gy = reflect101(min(y0 + r - 3, L.h + 2), L.h);
+    const int gx = reflect101(min(x0 + c - 3, L.w + 2), L.w);
+    sin_[r * SP + c] = __ldg(src + (size_t)gy * ipitch + gx);
+  }
+  __syncthreads();
+  // horizontal: items = rows x 32 groups of 4 columns
+  for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW / 4); i += 256) {
+    const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
+    const u8* q = sin_ + r * SP + c4;
+    int v[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) v[k] = q[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int s = 18 * (v[k] + v[k + 6]) + 34 * (v[k + 1] + v[k + 5]) + 48 * (v[k + 2] + v[k + 4]) +
+                    56 * v[k + 3];
+      sh_[r * BLUR_TW + c4 + k] = (unsigned short)s;
+    }
+  }
+  __syncthreads();
+  u8* dst = p.blur[t.level] + (size_t)f * p.bfs[t.level];
+  for (int i = tid; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
+    const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
+    const int gy = y0 + r, gx = x0 + c4;
+    if (gy >= L.h || gx >= L.w) continue;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned short* q = sh_ + r * BLUR_TW + c4 + k;
+      const uint32_t s = 18u * (q[0] + q[6 * BLUR_TW]) + 34u * (q[BLUR_TW] + q[5 * BLUR_TW]) +
+                         48u * (q[2 * BLUR_TW] + q[4 * BLUR_TW]) + 56u * q[3 * BLUR_TW];
+      out |= ((s + 32768u) >> 16) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = out;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_layout: output row of every staged keypoint.  Keypoints are visited level by level
+// in octree list order; those with lap0 <= x_scaled <= lap1 fill the output from the
+// back, the others from the front (src/ORBextractor.cc:1104-1144).
+// ---------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k_layout(const __grid_constant__ OrbGeom g,
+                                               const uint32_t* __restrict__ lvlKp,
+                                               const int* __restrict__ lvlCount, int lap0,
+                                               int lap1, int* __restrict__ slot,
+                                               int* __restrict__ counts, int* __restrict__ mono) {
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  __shared__ int wv[NT / 32], wl[NT / 32], tot[2];
+  const int total = g.kpTotal;
+  const int chunk = (total + NT - 1) / NT;
+  const int beg = min(tid * chunk, total), end = min(beg + chunk, total);
+  const uint32_t* kp = lvlKp + (size_t)f * total;
+  const int* lc = lvlCount + f * g.nlevels;
+  auto classify = [&](int s, bool& valid, bool& lap) {
+    int l = 0;
+    while (l + 1 < g.nlevels && s >= g.lv[l + 1].kpOff) l++;
+    valid = (s - g.lv[l].kpOff) < lc[l];
+    lap = false;
+    if (valid) {
+      float x = (float)unpack_x(kp[s]);
+      if (l) x = __fmul_rn(x, g.lv[l].scale);
+      lap = x >= (float)lap0 && x <= (float)lap1;
+    }
+  };
+  int nv = 0, nl = 0;
+  for (int s = beg; s < end; s++) {
+    bool v, l;
+    classify(s, v, l);
+    nv += v;
+    nl += l;
+  }
+  int iv = nv, il = nl;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int a = __shfl_up_sync(0xffffffffu, iv, o), b = __shfl_up_sync(0xffffffffu, il, o);
+    if (lane >= o) { iv += a; il += b; }
+  }
+  if (lane == 31) { wv[wid] = iv; wl[wid] = il; }
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0, b = 0;
+    for (int w = 0; w < NT / 32; w++) {
+      int ta = wv[w], tb = wl[w];
+      wv[w] = a; wl[w] = b;
+      a += ta; b += tb;
+    }
+    tot[0] = a; tot[1] = b;
+  }
+  __syncthreads();
+  int bv = wv[wid] + iv - nv, bl = wl[wid] + il - nl;
+  const int n = tot[0];
+  for (int s = beg; s < end; s++) {
+    bool v, l;
+    classify(s, v, l);
+    int o = -1;
+    if (v) o = l ? (n - 1 - bl) : (bv - bl);
+    slot[(size_t)f * total + s] = o;
+    bv += v;
+    bl += l;
+  }
+  if (tid == 0) {
+    counts[f] = n;
+    mono[f] = n - tot[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_orient_desc: warp per keypoint.  IC_Angle on the unblurred level (lane = column
+// offset u in [-15,15]), cv::fastAtan2 polynomial, then 256 rotated pair tests on the
+// blurred level (lane = descriptor byte).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float dev_fast_atan2(float y, float x) {
+  const float sc = 57.29577951308232f;
+  const float p1 = __fmul_rn(0.9997878412794807f, sc), p3 = __fmul_rn(-0.3258083974640975f, sc);
+  const float p5 = __fmul_rn(0.1555786518463281f, sc), p7 = __fmul_rn(-0.04432655554792128f, sc);
+  const float eps = 2.220446049250313e-16f;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+#define OD_WARPS 4
+__global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(
+    const __grid_constant__ OrbGeom g, const __grid_constant__ OrbPtrs p,
+    const uint32_t* __restrict__ lvlKp, const int* __restrict__ lvlCount,
+    const int* __restrict__ slot, int kpPerCta, plvi_keypoint* __restrict__ kps,
+    uint8_t* __restrict__ desc, int cap) {
+  const int f = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // this lane's 8 pair tests
+  int px[16], py[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    px[j] = d_pattern[lane * 32 + j * 2];
+    py[j] = d_pattern[lane * 32 + j * 2 + 1];
+  }
+  const int sBeg = blockIdx.x * kpPerCta, sEnd = min(sBeg + kpPerCta, g.kpTotal);
+  for (int s = sBeg + wid; s < sEnd; s += OD_WARPS) {
+    int l = 0;
+    while (l + 1 < g.nlevels && s >= g.lv[l + 1].kpOff) l++;
+    if (s - g.lv[l].kpOff >= lvlCount[f * g.nlevels + l]) continue;
+    const uint32_t pk = lvlKp[(size_t)f * g.kpTotal + s];
+    const int x = unpack_x(pk), y = unpack_y(pk);
+    const int ipitch = p.ipitch[l];
+    const u8* c0 = p.img[l] + (size_t)f * p.ifs[l] + (size_t)y * ipitch + x;
+    const int u = lane - 15;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+      const int au = abs(u);
+#pragma unroll 4
+      for (int v = -15; v <= 15; v++) {
+        if (au <= c_umax[abs(v)]) {
+          const int val = __ldg(c0 + v * ipitch + u);
+          m10 += u * val;
+          m01 += v * val;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = dev_fast_atan2((float)m01, (float)m10);
+    float a = 0.f, b = 0.f;
+    if (lane == 0) {
+      const float rad = __fmul_rn(angle, 0.017453292519943295f);
+      a = (float)cos((double)rad);
+      b = (float)sin((double)rad);
+    }
+    a = __shfl_sync(0xffffffffu, a, 0);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    const int bp = g.lv[l].pitch;
+    const u8* cb = p.blur[l] + (size_t)f * p.bfs[l] + (size_t)y * bp + x;
+    int val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float x0 = (float)px[2 * j], y0 = (float)py[2 * j];
+      const float x1 = (float)px[2 * j + 1], y1 = (float)py[2 * j + 1];
+      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+      const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+      const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+      const int t0 = __ldg(cb + r0 * bp + q0), t1 = __ldg(cb + r1 * bp + q1);
+      val |= (t0 < t1) << j;
+    }
+    const int o = slot[(size_t)f * g.kpTotal + s];
+    desc[((size_t)f * cap + o) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+      plvi_keypoint k;
+      const float sc = g.lv[l].scale;
+      k.x = l ? __fmul_rn((float)x, sc) : (float)x;
+      k.y = l ? __fmul_rn((float)y, sc) : (float)y;
+      k.size = (float)g.lv[l].sizeField;
+      k.angle = angle;
+      k.response = (float)unpack_s(pk);
+      k.octave = l;
+      k.class_id = -1;
+      kps[(size_t)f * cap + o] = k;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// host-side launch sequence
+// ---------------------------------------------------------------------------------
+#define OCT_NT 256
+
+static size_t octree_smem_bytes(int M) {
+  // best 8 | geom 2x8 | cnt 2x4 | seq 2x4 | cc 16 | order,cstart,keep,srank,tmp 5x4 | cpos 8
+  return (size_t)M * (8 + 16 + 8 + 8 + 16 + 20 + 8) + 64;
+}
+
+static void fast_tile_dims(const OrbGeom& g, int* tilePitch, int* tileRows, int* survCap) {
+  int maxW = 0, maxH = 0, maxSurv = 0;
+  for (int l = 0; l < g.nlevels; l++) {
+    const OrbLevel& L = g.lv[l];
+    maxW = max(maxW, 4 * L.wCell + 6);
+    maxH = max(maxH, L.hCell + 6);
+    maxSurv = max(maxSurv, 4 * ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2));
+  }
+  *tilePitch = (maxW + 15) & ~15;
+  *tileRows = maxH;
+  *survCap = maxSurv;
+}
+
+int orb_kernel_attrs(const OrbGeom& g, int* fastSmem, int* octSmem) {
+  int tp, tr, sc;
+  fast_tile_dims(g, &tp, &tr, &sc);
+  *fastSmem = 2 * tp * tr + 2 * sc * (int)sizeof(uint32_t);
+  *octSmem = (int)octree_smem_bytes(g.maxNodes);
+  if (*octSmem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_octree<OCT_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, *octSmem));
+  if (*fastSmem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, *fastSmem));
+  return PLVI_OK;
+}
+
+int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s, int n, int lap0,
+                        int lap1, plvi_keypoint* d_kps, uint8_t* d_desc, int* d_counts,
+                        int* d_mono, int cap, cudaStream_t st, int* launches) {
+  int nl = 0;
+  PLVI_CUDA_TRY(cudaMemsetAsync(s.candCount, 0, sizeof(int) * (size_t)n * g.nlevels, st));
+  // pyramid (chained: level l from level l-1)
+  for (int l = 1; l < g.nlevels; l++) {
+    const OrbLevel& d = g.lv[l];
+    const OrbLevel& sl = g.lv[l - 1];
+    dim3 blk(64, 4), grd((d.w + 255) / 256, (d.h + 3) / 4, n);
+    k_resize<<<grd, blk, 0, st>>>(p.img[l - 1], p.ipitch[l - 1], p.ifs[l - 1], sl.w, sl.h,
+                                  const_cast<u8*>(p.img[l]), p.ipitch[l], p.ifs[l], d.w, d.h,
+                                  s.rsTab + d.rsOff, s.rsTab + d.rsOff + d.w);
+    nl++;
+  }
+  // FAST tile geometry recomputed here must match capi's smem sizing
+  {
+    int tilePitch, maxH, maxSurv;
+    fast_tile_dims(g, &tilePitch, &maxH, &maxSurv);
+    k_fast<<<dim3(s.nFastTiles, n), 256, s.fastSmem, st>>>(g, p, s.fastTiles, s.cand, s.candCount,
+                                                          tilePitch, maxH, maxSurv);
+    nl++;
+  }
+  k_octree<OCT_NT><<<dim3(g.nlevels, n), OCT_NT, s.octSmem, st>>>(g, s.cand, s.candCount, s.knode,
+                                                               s.lvlKp, s.lvlCount);
+  nl++;
+  k_blur7<<<dim3(s.nBlurTiles, n), 256, 0, st>>>(g, p, s.blurTiles);
+  nl++;
+  k_layout<256><<<n, 256, 0, st>>>(g, s.lvlKp, s.lvlCount, lap0, lap1, s.slot, d_counts, d_mono);
+  nl++;
+  const int kpPerCta = 32;
+  k_orient_desc<<<dim3((g.kpTotal + kpPerCta - 1) / kpPerCta, n), OD_WARPS * 32, 0, st>>>(
+      g, p, s.lvlKp, s.lvlCount, s.slot, kpPerCta, d_kps, d_desc, cap);
+  nl++;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  if (launches) *launches = nl;
+  return PLVI_OK;
+}
+
+}  // namespace plvi

@@ -1,0 +1,146 @@
+"""GPU parity: CUDA ORB path (through the C ABI) vs the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): pyramid pixels, FAST candidates/scores and keypoint
+sets bit-exact; orientation within 1e-3 rad; ORB descriptor bits >= 99.9 %.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from pl_vi_orbslam3_b200 import ORBextractor, synth
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_DEG = np.degrees(1e-3)
+DESC_BIT_AGREEMENT = 0.999
+
+
+def _bits_equal(a, b):
+    return 1.0 - np.unpackbits(a ^ b).mean() if a.size else 1.0
+
+
+def _check_frame(kps, desc, mono, ref, exact_desc_required=False):
+    rk, rd = ref["keypoints"], ref["descriptors"]
+    assert len(kps) == len(rk), (len(kps), len(rk))
+    assert mono == ref["mono_index"]
+    for fld in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(kps[fld], rk[fld]), fld
+    da = np.abs(kps["angle"] - rk["angle"])
+    da = np.minimum(da, 360.0 - da)
+    assert da.max(initial=0.0) <= ANGLE_TOL_DEG, da.max()
+    agree = _bits_equal(desc, rd)
+    assert agree >= DESC_BIT_AGREEMENT, agree
+    return float(da.max(initial=0.0)), agree
+
+
+@pytest.fixture(scope="module")
+def ext(gpu):
+    e = ORBextractor(1000, 1.2, 8, 20, 7, max_width=752, max_height=480, max_batch=8)
+    yield e
+    e.close()
+
+
+def test_pyramid_blur_candidates_bit_exact(ext):
+    img = synth.frame_euroc(0)
+    ext(img)
+    ref = oracle.orb_extract(img, debug=True)
+    for l in range(8):
+        got = ext.read_level(0, l, 752, 480)
+        assert np.array_equal(got, ref["pyramid"][l]), f"pyramid level {l}"
+        got = ext.read_level(0, l, 752, 480, blurred=True)
+        assert np.array_equal(got, ref["blurred"][l]), f"blurred level {l}"
+        c = ext.read_candidates(0, l)
+        rc = oracle.grid_fast(ref["pyramid"][l]).astype(np.int32)
+        c = c[np.lexsort((c[:, 0], c[:, 1]))]
+        rc = rc[np.lexsort((rc[:, 0], rc[:, 1]))]
+        assert np.array_equal(c, rc), f"FAST candidates level {l}: {len(c)} vs {len(rc)}"
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 7])
+def test_orb_single_frame_matches_oracle(ext, seed):
+    img = synth.frame_euroc(seed)
+    mono, kps, desc = ext(img)
+    ref = oracle.orb_extract(img)
+    _check_frame(kps, desc, mono, ref)
+
+
+def test_orb_batch_equals_single(ext):
+    frames = np.stack([synth.frame_euroc(s) for s in range(10, 18)])
+    kps, desc, counts, mono = ext.extract_batch(frames)
+    for i in range(len(frames)):
+        ref = oracle.orb_extract(frames[i])
+        n = counts[i]
+        _check_frame(kps[i, :n], desc[i, :n], mono[i], ref)
+
+
+def test_orb_lapping_area_reverse_fill(ext):
+    img = synth.frame_euroc(5)
+    for lap in ((0, 1000), (300, 500)):
+        mono, kps, desc = ext(img, None, lap)
+        ref = oracle.orb_extract(img, lapping=lap)
+        _check_frame(kps, desc, mono, ref)
+
+
+def test_orb_flat_and_noise_images(ext):
+    flat = np.full((480, 752), 128, np.uint8)
+    mono, kps, desc = ext(flat)
+    assert mono == 0 and len(kps) == 0
+    rng = np.random.RandomState(3)
+    noise = rng.randint(0, 256, (480, 752)).astype(np.uint8)
+    mono, kps, desc = ext(noise)
+    _check_frame(kps, desc, mono, oracle.orb_extract(noise))
+
+
+def test_orb_empty_image_returns_minus_one(ext):
+    mono, kps, desc = ext(np.zeros((0, 0), np.uint8))
+    assert mono == -1 and len(kps) == 0
+
+
+def test_orb_strided_input(ext):
+    big = np.zeros((480, 800), np.uint8)
+    img = synth.frame_euroc(21)
+    big[:, :752] = img
+    view = big[:, :752]
+    kps, desc, counts, mono = ext.extract_batch.__func__(ext, np.ascontiguousarray(view)[None])
+    _check_frame(kps[0, :counts[0]], desc[0, :counts[0]], mono[0], oracle.orb_extract(img))
+
+
+def test_orb_device_resident_api(ext):
+    import torch
+    frames = np.stack([synth.frame_euroc(s) for s in (30, 31)])
+    d = torch.from_numpy(frames).cuda()
+    import ctypes
+    st = torch.cuda.ExternalStream(ext.stream)
+    with torch.cuda.stream(st):
+        kps, desc, counts, mono = ext.extract_batch_device(d)
+    st.synchronize()
+    kps = kps.cpu().numpy().view(np.uint8).reshape(2, ext.capacity, 28).copy().view(oracle.KEYPOINT_DTYPE)[..., 0]
+    desc, counts, mono = desc.cpu().numpy(), counts.cpu().numpy(), mono.cpu().numpy()
+    for i in range(2):
+        n = counts[i]
+        _check_frame(kps[i, :n], desc[i, :n], mono[i], oracle.orb_extract(frames[i]))
+
+
+@pytest.mark.parametrize("w,h,nfeat", [(640, 480, 2000), (1280, 720, 2000), (752, 480, 5000)])
+def test_orb_other_configs(gpu, w, h, nfeat):
+    e = ORBextractor(nfeat, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=2)
+    try:
+        frames = np.stack([synth.frame_euroc(40 + i, w, h) for i in range(2)])
+        kps, desc, counts, mono = e.extract_batch(frames)
+        for i in range(2):
+            ref = oracle.orb_extract(frames[i], nfeatures=nfeat)
+            n = counts[i]
+            _check_frame(kps[i, :n], desc[i, :n], mono[i], ref)
+    finally:
+        e.close()
+
+
+def test_orb_smaller_image_on_bigger_handle(gpu):
+    e = ORBextractor(1000, 1.2, 8, 20, 7, max_width=1280, max_height=720, max_batch=2)
+    try:
+        for (w, h) in ((752, 480), (640, 480), (1280, 720)):
+            img = synth.frame_euroc(50, w, h)
+            mono, kps, desc = e(img)
+            _check_frame(kps, desc, mono, oracle.orb_extract(img))
+    finally:
+        e.close()
