@@ -127,6 +127,77 @@ int plvi_orb_read_candidates(plvi_orb* h, int frame, int level, uint32_t* out, i
 /* number of kernel launches enqueued by the last extract call */
 int plvi_orb_last_launches(const plvi_orb* h);
 
+/* ------------------------------------------------------- Hamming searches ---- */
+typedef struct plvi_matcher plvi_matcher;
+
+/* Frame grid parameters: Frame::mnMinX, mnMinY, mfGridElementWidthInv,
+ * mfGridElementHeightInv (src/Frame.cc:163-170; 64 x 48 cells, include/Frame.h:47-48). */
+typedef struct plvi_grid {
+  float min_x, min_y, inv_w, inv_h;
+} plvi_grid;
+
+/* One projected query point of a guided search (28 bytes). */
+typedef struct plvi_query {
+  float u, v;        /* projection (uv) or vbPrevMatched[i1] */
+  float radius;      /* th*mvScaleFactors[octave] | r*th*scale[level] | windowSize */
+  int32_t min_level, max_level; /* GetFeaturesInArea level filter (-1 = open) */
+  float angle;       /* keypoint angle of the query, for the rotation histogram */
+  int32_t flags;     /* bit0: skip (no map point / outlier / octave>0 at init);
+                        bit1: map point without observations (a match does not block) */
+} plvi_query;
+
+#define PLVI_SEARCH_FRAME 0     /* ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) src/ORBmatcher.cc:1962 */
+#define PLVI_SEARCH_MAPPOINTS 1 /* ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, ...) src/ORBmatcher.cc:44 */
+#define PLVI_SEARCH_INIT 2      /* ORBmatcher::SearchForInitialization src/ORBmatcher.cc:706 */
+
+/* max_train <= 65535 keypoints per frame. stream: existing cudaStream_t or NULL. */
+int plvi_matcher_create(plvi_matcher** out, int max_pairs, int max_train, int max_query, int device,
+                        void* stream);
+void plvi_matcher_destroy(plvi_matcher* m);
+void* plvi_matcher_stream(const plvi_matcher* m);
+int plvi_matcher_last_launches(const plvi_matcher* m);
+
+/* static int ORBmatcher::DescriptorDistance(a, b) (include/ORBmatcher.h:43,
+ * src/ORBmatcher.cc:2350-2366) and LineMatcher::distance (src/LineMatcher.cpp:173-189)
+ * over n descriptor pairs (row i of a vs row i of b, 32 bytes each).  shift25 != 0
+ * gives LineMatcher::DescriptorDistance (src/LineMatcher.cpp:487-499), which sums
+ * floor(popcount/2) per 32-bit word.  on_device: pointers are device pointers (16-byte
+ * aligned) and the call only enqueues; otherwise host pointers, blocking. */
+int plvi_hamming256(plvi_matcher* m, const uint8_t* a, const uint8_t* b, int n, int shift25, int* out,
+                    int on_device);
+
+/* Guided (windowed) Hamming search over npairs independent frame pairs.  The geometry
+ * that precedes the search in the reference (projection, frustum tests) stays with the
+ * caller, who passes one plvi_query per candidate map point / keypoint in the
+ * reference's iteration order; the train side is a Frame: undistorted keypoints
+ * (mvKeysUn) + descriptors (+ optional "already has a map point with observations"
+ * flags), from which the 64x48 grid (AssignFeaturesToGrid) is rebuilt on the device.
+ *   train_keys [npairs][train_stride], train_desc [npairs][train_stride][32],
+ *   train_blocked [npairs][train_stride] or NULL, train_counts [npairs];
+ *   queries [npairs][query_stride] (INIT: u,v updated like vbPrevMatched),
+ *   query_desc [npairs][query_stride][32], query_counts [npairs];
+ *   th_dist: TH_HIGH (100) / TH_LOW (50); nnratio: mfNNratio; check_orientation:
+ *   mbCheckOrientation (rotation histogram + ComputeThreeMaxima);
+ *   match_train [npairs][train_stride]: query index assigned to each train keypoint or
+ *   -1 (CurrentFrame.mvpMapPoints / vnMatches21); match_query [npairs][query_stride]:
+ *   train index per query or -1 (vnMatches12); nmatches [npairs]: the return value. */
+int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_keypoint* train_keys,
+                              const uint8_t* train_desc, const uint8_t* train_blocked,
+                              const int* train_counts, int train_stride, const plvi_grid* grid,
+                              plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                              int query_stride, int th_dist, float nnratio, int check_orientation,
+                              int* match_train, int* match_query, int* nmatches, int on_device);
+
+/* static int LineMatcher::match(desc1, desc2, nnr, matches_12) (include/LineMatcher.h:87-107,
+ * src/LineMatcher.cpp:92-111) with mutual != 0, LineMatcher::matchNNR (:41-61) with
+ * mutual == 0, on a fresh matches_12, over npairs descriptor-set pairs:
+ * BFMatcher(NORM_HAMMING).knnMatch(k=2), accept d0 < d1*nnr, both directions, keep
+ * mutual matches.  With fewer than 2 train rows the reference reads out of bounds; here
+ * such a pair yields no matches.  matches12 [npairs][stride1], nmatches [npairs]. */
+int plvi_line_match(plvi_matcher* m, int npairs, const uint8_t* desc1, const int* n1, int stride1,
+                    const uint8_t* desc2, const int* n2, int stride2, float nnr, int mutual,
+                    int* matches12, int* nmatches, int on_device);
+
 #ifdef __cplusplus
 }
 #endif

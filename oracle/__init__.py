@@ -185,3 +185,72 @@ def split_levels(flat, plan):
         res.append(flat[o:o + int(w) * int(h)].reshape(int(h), int(w)))
         o += int(w) * int(h)
     return res
+
+
+# ---- matchers ----------------------------------------------------------------------
+QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("min_level", "<i4"),
+                        ("max_level", "<i4"), ("angle", "<f4"), ("flags", "<i4")])
+
+
+def hamming256(a, b, shift25=False):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    f = lib().plvio_hamming256_shift25 if shift25 else lib().plvio_hamming256
+    return int(f(_p(a), _p(b)))
+
+
+def _grid_args(grid):
+    g = np.asarray(grid).reshape(-1)[0]
+    return [C.c_float(float(g["min_x"])), C.c_float(float(g["min_y"])), C.c_float(float(g["inv_w"])),
+            C.c_float(float(g["inv_h"]))]
+
+
+def search_frame(keys, desc, grid, queries, qdesc, th=100, check_ori=True, blocked=None):
+    keys = np.ascontiguousarray(keys)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    blocked = None if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+    mt = np.empty(max(len(keys), 1), np.int32)
+    n = lib().plvio_search_frame(_p(keys), _p(desc), len(keys), _p(blocked), *_grid_args(grid), _p(queries),
+                                 _p(qdesc), len(queries), int(th), int(check_ori), _p(mt))
+    return n, mt[:len(keys)]
+
+
+def search_mappoints(keys, desc, grid, queries, qdesc, th=100, nnratio=0.8, blocked=None):
+    keys = np.ascontiguousarray(keys)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    blocked = None if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+    mt = np.empty(max(len(keys), 1), np.int32)
+    n = lib().plvio_search_mappoints(_p(keys), _p(desc), len(keys), _p(blocked), *_grid_args(grid),
+                                     _p(queries), _p(qdesc), len(queries), int(th), C.c_float(nnratio), _p(mt))
+    return n, mt[:len(keys)]
+
+
+def search_init(keys2, desc2, grid, queries, desc1, th=50, nnratio=0.9, check_ori=True):
+    keys2 = np.ascontiguousarray(keys2)
+    desc2 = np.ascontiguousarray(desc2, np.uint8)
+    queries = np.ascontiguousarray(queries).copy()
+    desc1 = np.ascontiguousarray(desc1, np.uint8)
+    m12 = np.empty(max(len(queries), 1), np.int32)
+    n = lib().plvio_search_init(_p(keys2), _p(desc2), len(keys2), *_grid_args(grid), _p(queries), _p(desc1),
+                                len(queries), int(th), C.c_float(nnratio), int(check_ori), _p(m12))
+    return n, m12[:len(queries)], queries
+
+
+def match_nnr(d1, d2, nnr):
+    d1 = np.ascontiguousarray(d1, np.uint8)
+    d2 = np.ascontiguousarray(d2, np.uint8)
+    m = np.empty(max(len(d1), 1), np.int32)
+    n = lib().plvio_match_nnr(_p(d1), len(d1), _p(d2), len(d2), C.c_float(nnr), _p(m))
+    return n, m[:len(d1)]
+
+
+def line_match(d1, d2, nnr):
+    d1 = np.ascontiguousarray(d1, np.uint8)
+    d2 = np.ascontiguousarray(d2, np.uint8)
+    m = np.empty(max(len(d1), 1), np.int32)
+    n = lib().plvio_line_match(_p(d1), len(d1), _p(d2), len(d2), C.c_float(nnr), _p(m))
+    return n, m[:len(d1)]

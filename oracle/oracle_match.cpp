@@ -1,0 +1,291 @@
+// TEST INFRASTRUCTURE (see oracle_common.h).  CPU restatement of the Hamming searches:
+//   ORBmatcher::DescriptorDistance            src/ORBmatcher.cc:2350-2366
+//   ORBmatcher::SearchByProjection(F,F)       src/ORBmatcher.cc:1962-2178  (mono path)
+//   ORBmatcher::SearchByProjection(F,MPs)     src/ORBmatcher.cc:44-214     (mono path)
+//   ORBmatcher::SearchForInitialization       src/ORBmatcher.cc:706-820
+//   ORBmatcher::ComputeThreeMaxima            src/ORBmatcher.cc:2304-2345
+//   Frame::AssignFeaturesToGrid/PosInGrid/GetFeaturesInArea  src/Frame.cc:644-675,1006-1087
+//   LineMatcher::matchNNR / match / distance / DescriptorDistance  src/LineMatcher.cpp:41-111,173-189,487-499
+//   cv::BFMatcher(NORM_HAMMING).knnMatch(k=2): two smallest distances, ties -> lowest train index
+#include <algorithm>
+#include <climits>
+
+#include "oracle_common.h"
+
+namespace plvio {
+
+static const int GRID_COLS = 64, GRID_ROWS = 48;  // include/Frame.h:47-48
+static const int HISTO_LENGTH = 30;
+
+struct Kp {
+  float x, y, size, angle, response;
+  int octave, class_id;
+};
+
+int hamming256(const u8* a, const u8* b) {
+  const uint32_t* pa = (const uint32_t*)a;
+  const uint32_t* pb = (const uint32_t*)b;
+  int dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t v = pa[i] ^ pb[i];
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+  }
+  return dist;
+}
+
+// LineMatcher::DescriptorDistance: the >>25 variant (sum of floor(popcount32/2)).
+int hamming256_shift25(const u8* a, const u8* b) {
+  const uint32_t* pa = (const uint32_t*)a;
+  const uint32_t* pb = (const uint32_t*)b;
+  int dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t v = pa[i] ^ pb[i];
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 25;
+  }
+  return dist;
+}
+
+struct Grid {
+  float minX, minY, invW, invH;
+  std::vector<int> cell[GRID_COLS][GRID_ROWS];
+  const Kp* keys;
+  int n;
+};
+
+static void build_grid(Grid& g, const Kp* keys, int n, float minX, float minY, float invW, float invH) {
+  g.minX = minX; g.minY = minY; g.invW = invW; g.invH = invH; g.keys = keys; g.n = n;
+  for (int i = 0; i < n; i++) {
+    int px = (int)std::round((keys[i].x - minX) * invW);
+    int py = (int)std::round((keys[i].y - minY) * invH);
+    if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+    g.cell[px][py].push_back(i);
+  }
+}
+
+static void features_in_area(const Grid& g, float x, float y, float r, int minLevel, int maxLevel,
+                             std::vector<int>& out) {
+  out.clear();
+  const int nMinCellX = std::max(0, (int)std::floor((x - g.minX - r) * g.invW));
+  if (nMinCellX >= GRID_COLS) return;
+  const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - g.minX + r) * g.invW));
+  if (nMaxCellX < 0) return;
+  const int nMinCellY = std::max(0, (int)std::floor((y - g.minY - r) * g.invH));
+  if (nMinCellY >= GRID_ROWS) return;
+  const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - g.minY + r) * g.invH));
+  if (nMaxCellY < 0) return;
+  const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+    for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+      for (int id : g.cell[ix][iy]) {
+        const Kp& k = g.keys[id];
+        if (bCheckLevels) {
+          if (k.octave < minLevel) continue;
+          if (maxLevel >= 0 && k.octave > maxLevel) continue;
+        }
+        const float dx = k.x - x, dy = k.y - y;
+        if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(id);
+      }
+}
+
+static void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = (int)histo[i].size();
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+  else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+static int rot_bin(float a1, float a2) {
+  const float factor = 1.0f / HISTO_LENGTH;  // the reference's quirk: only bins 0..12 are hit
+  float rot = a1 - a2;
+  if (rot < 0.0) rot += 360.0f;
+  int bin = (int)std::round(rot * factor);
+  if (bin == HISTO_LENGTH) bin = 0;
+  return bin;
+}
+
+struct Query {  // one projected point
+  float u, v, radius;
+  int minLevel, maxLevel;
+  float angle;
+  int flags;  // bit0: skip this query; bit1: its map point has no observations (does not block)
+};
+
+}  // namespace plvio
+
+using namespace plvio;
+
+extern "C" {
+
+int plvio_hamming256(const u8* a, const u8* b) { return hamming256(a, b); }
+int plvio_hamming256_shift25(const u8* a, const u8* b) { return hamming256_shift25(a, b); }
+
+// SearchByProjection(CurrentFrame, LastFrame, th, bMono=true): queries are the last
+// frame's tracked points already projected by the host (u, v, radius=th*scale[octave],
+// levels octave-1..octave+1).  match_train[i2] = query index or -1 (mvpMapPoints).
+int plvio_search_frame(const Kp* keys, const u8* desc, int n, const u8* blocked, float minX,
+                       float minY, float invW, float invH, const Query* q, const u8* qdesc, int nq,
+                       int thHigh, int checkOri, int* match_train) {
+  Grid g;
+  build_grid(g, keys, n, minX, minY, invW, invH);
+  std::vector<int> owner(n, -1);
+  std::vector<char> blk(n, 0);
+  if (blocked) for (int i = 0; i < n; i++) blk[i] = blocked[i];
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int nmatches = 0;
+  std::vector<int> idx;
+  for (int i = 0; i < nq; i++) {
+    if (q[i].flags & 1) continue;
+    features_in_area(g, q[i].u, q[i].v, q[i].radius, q[i].minLevel, q[i].maxLevel, idx);
+    if (idx.empty()) continue;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : idx) {
+      if (blk[i2]) continue;
+      const int d = hamming256(qdesc + 32 * (size_t)i, desc + 32 * (size_t)i2);
+      if (d < bestDist) { bestDist = d; bestIdx2 = i2; }
+    }
+    if (bestDist <= thHigh) {
+      owner[bestIdx2] = i;
+      if (!(q[i].flags & 2)) blk[bestIdx2] = 1;
+      nmatches++;
+      if (checkOri) rotHist[rot_bin(q[i].angle, keys[bestIdx2].angle)].push_back(bestIdx2);
+    }
+  }
+  if (checkOri) {
+    int i1 = -1, i2 = -1, i3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+    for (int b = 0; b < HISTO_LENGTH; b++)
+      if (b != i1 && b != i2 && b != i3)
+        for (int id : rotHist[b]) { owner[id] = -1; nmatches--; }
+  }
+  for (int i = 0; i < n; i++) match_train[i] = owner[i];
+  return nmatches;
+}
+
+// SearchByProjection(F, vpMapPoints, th, ...), mono path: best / second best with the
+// level-aware ratio test.  radius = r*th*scale[level]; levels level-1..level.
+int plvio_search_mappoints(const Kp* keys, const u8* desc, int n, const u8* blocked, float minX,
+                           float minY, float invW, float invH, const Query* q, const u8* qdesc,
+                           int nq, int thHigh, float nnratio, int* match_train) {
+  Grid g;
+  build_grid(g, keys, n, minX, minY, invW, invH);
+  std::vector<int> owner(n, -1);
+  std::vector<char> blk(n, 0);
+  if (blocked) for (int i = 0; i < n; i++) blk[i] = blocked[i];
+  int nmatches = 0;
+  std::vector<int> idx;
+  for (int i = 0; i < nq; i++) {
+    if (q[i].flags & 1) continue;
+    features_in_area(g, q[i].u, q[i].v, q[i].radius, q[i].minLevel, q[i].maxLevel, idx);
+    if (idx.empty()) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int i2 : idx) {
+      if (blk[i2]) continue;
+      const int d = hamming256(qdesc + 32 * (size_t)i, desc + 32 * (size_t)i2);
+      if (d < bestDist) {
+        bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = keys[i2].octave; bestIdx = i2;
+      } else if (d < bestDist2) {
+        bestLevel2 = keys[i2].octave; bestDist2 = d;
+      }
+    }
+    if (bestDist <= thHigh) {
+      if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+      if (bestLevel != bestLevel2 || bestDist <= nnratio * bestDist2) {
+        owner[bestIdx] = i;
+        if (!(q[i].flags & 2)) blk[bestIdx] = 1;
+        nmatches++;
+      }
+    }
+  }
+  for (int i = 0; i < n; i++) match_train[i] = owner[i];
+  return nmatches;
+}
+
+// SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize): queries are
+// ALL F1 keypoints (flags bit0 set for octave > 0), (u,v) = vbPrevMatched, radius =
+// windowSize, levels 0..0.  matches12[nq]; prev_matched (u,v pairs) updated in place.
+int plvio_search_init(const Kp* keys2, const u8* desc2, int n2, float minX, float minY, float invW,
+                      float invH, Query* q, const u8* desc1, int n1, int thLow, float nnratio,
+                      int checkOri, int* matches12) {
+  Grid g;
+  build_grid(g, keys2, n2, minX, minY, invW, invH);
+  int nmatches = 0;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  std::vector<int> matchedDist(n2, INT_MAX), m21(n2, -1);
+  std::vector<int> idx;
+  for (int i1 = 0; i1 < n1; i1++) {
+    if (q[i1].flags & 1) continue;
+    features_in_area(g, q[i1].u, q[i1].v, q[i1].radius, q[i1].minLevel, q[i1].maxLevel, idx);
+    if (idx.empty()) continue;
+    int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+    for (int i2 : idx) {
+      const int d = hamming256(desc1 + 32 * (size_t)i1, desc2 + 32 * (size_t)i2);
+      if (matchedDist[i2] <= d) continue;
+      if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx2 = i2; }
+      else if (d < bestDist2) bestDist2 = d;
+    }
+    if (bestDist <= thLow) {
+      if (bestDist < (float)bestDist2 * nnratio) {
+        if (m21[bestIdx2] >= 0) { matches12[m21[bestIdx2]] = -1; nmatches--; }
+        matches12[i1] = bestIdx2;
+        m21[bestIdx2] = i1;
+        matchedDist[bestIdx2] = bestDist;
+        nmatches++;
+        if (checkOri) rotHist[rot_bin(q[i1].angle, keys2[bestIdx2].angle)].push_back(i1);
+      }
+    }
+  }
+  if (checkOri) {
+    int a = -1, b = -1, c = -1;
+    three_maxima(rotHist, HISTO_LENGTH, a, b, c);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == a || i == b || i == c) continue;
+      for (int id : rotHist[i])
+        if (matches12[id] >= 0) { matches12[id] = -1; nmatches--; }
+    }
+  }
+  for (int i1 = 0; i1 < n1; i1++)
+    if (matches12[i1] >= 0) { q[i1].u = keys2[matches12[i1]].x; q[i1].v = keys2[matches12[i1]].y; }
+  return nmatches;
+}
+
+// LineMatcher::matchNNR on fresh output: knn-2 + ratio.  Needs n2 >= 2 (the reference
+// indexes matches_[idx][1] unconditionally: undefined for fewer train rows; here: no match).
+int plvio_match_nnr(const u8* d1, int n1, const u8* d2, int n2, float nnr, int* m12) {
+  int matches = 0;
+  for (int i = 0; i < n1; i++) {
+    m12[i] = -1;
+    if (n2 < 2) continue;
+    int b0 = INT_MAX, b1 = INT_MAX, i0 = -1;
+    for (int j = 0; j < n2; j++) {
+      const int d = hamming256(d1 + 32 * (size_t)i, d2 + 32 * (size_t)j);
+      if (d < b0) { b1 = b0; b0 = d; i0 = j; }
+      else if (d < b1) b1 = d;
+    }
+    if ((float)b0 < (float)b1 * nnr) { m12[i] = i0; matches++; }
+  }
+  return matches;
+}
+
+// LineMatcher::match(desc1, desc2, nnr, matches_12): both directions + mutual check.
+int plvio_line_match(const u8* d1, int n1, const u8* d2, int n2, float nnr, int* m12) {
+  std::vector<int> m21(std::max(n2, 1));
+  int matches = plvio_match_nnr(d1, n1, d2, n2, nnr, m12);
+  plvio_match_nnr(d2, n2, d1, n1, nnr, m21.data());
+  for (int i1 = 0; i1 < n1; i1++) {
+    int& i2 = m12[i1];
+    if (i2 >= 0 && m21[i2] != i1) { i2 = -1; matches--; }
+  }
+  return matches;
+}
+
+}  // extern "C"

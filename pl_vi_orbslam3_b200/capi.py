@@ -49,7 +49,20 @@ _SIGS = {
     "plvi_orb_read_level": (ci, [vp, ci, ci, ci, vp]),
     "plvi_orb_read_candidates": (ci, [vp, ci, ci, vp, ci, vp]),
     "plvi_orb_last_launches": (ci, [vp]),
+    "plvi_matcher_create": (ci, [C.POINTER(vp), ci, ci, ci, ci, vp]),
+    "plvi_matcher_destroy": (None, [vp]),
+    "plvi_matcher_stream": (vp, [vp]),
+    "plvi_matcher_last_launches": (ci, [vp]),
+    "plvi_hamming256": (ci, [vp, vp, vp, ci, ci, vp, ci]),
+    "plvi_search_by_projection": (ci, [vp, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, ci, cf, ci,
+                                       vp, vp, vp, ci]),
+    "plvi_line_match": (ci, [vp, ci, vp, vp, ci, vp, vp, ci, cf, ci, vp, vp, ci]),
 }
+
+QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("min_level", "<i4"),
+                        ("max_level", "<i4"), ("angle", "<f4"), ("flags", "<i4")])
+GRID_DTYPE = np.dtype([("min_x", "<f4"), ("min_y", "<f4"), ("inv_w", "<f4"), ("inv_h", "<f4")])
+assert QUERY_DTYPE.itemsize == 28
 
 
 def declared_symbols():

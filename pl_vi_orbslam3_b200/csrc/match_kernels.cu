@@ -1,0 +1,613 @@
+// Hamming descriptor search kernels for sm_100a + their C ABI.
+//
+//   k_hamming_pairs   ORBmatcher::DescriptorDistance / LineMatcher::distance /
+//                     LineMatcher::DescriptorDistance      src/ORBmatcher.cc:2350-2366,
+//                                                          src/LineMatcher.cpp:173-189,487-499
+//   k_search          ORBmatcher::SearchByProjection(F,F)  src/ORBmatcher.cc:1962-2178
+//                     ORBmatcher::SearchByProjection(F,MP) src/ORBmatcher.cc:44-214
+//                     ORBmatcher::SearchForInitialization  src/ORBmatcher.cc:706-820
+//                     + Frame::AssignFeaturesToGrid / GetFeaturesInArea src/Frame.cc:644-675,1006-1087
+//                     + ComputeThreeMaxima                 src/ORBmatcher.cc:2304-2345
+//   k_line_match      LineMatcher::matchNNR / match        src/LineMatcher.cpp:41-111
+//
+// The reference searches are sequential over the queries: a query skips train features
+// that an earlier query claimed (or, for initialisation, matched at a smaller distance).
+// k_search keeps that order exactly but takes the Hamming work out of the serial chain:
+// one CTA per frame pair; its warps evaluate W consecutive queries in parallel against
+// the state as of the chunk start, then warp 0 commits them in query order and
+// re-evaluates the rare query whose best / second-best candidate was taken by an earlier
+// query of the same chunk.  "best" and "second best" are the two smallest candidates
+// under the key (distance, position in GetFeaturesInArea order), which is what the
+// reference's `<` update chain produces.
+#include <vector>
+
+#include "plvi_internal.cuh"
+
+namespace plvi {
+
+#define GRID_COLS 64
+#define GRID_ROWS 48
+#define GRID_CELLS (GRID_COLS * GRID_ROWS)
+#define HISTO_LENGTH 30
+#define SEARCH_WARPS 16
+
+__device__ __forceinline__ int hamming256_regs(const uint32_t (&q)[8], const uint8_t* __restrict__ d) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(d));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+  return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
+         __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+}
+
+__global__ void k_hamming_pairs(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n,
+                                int shift25, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(a + (size_t)i * 32);
+  const uint32_t* pb = reinterpret_cast<const uint32_t*>(b + (size_t)i * 32);
+  int d = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int c = __popc(__ldg(pa + k) ^ __ldg(pb + k));
+    d += shift25 ? (c >> 1) : c;   // the >>25 variant sums floor(popcount/2) per word
+  }
+  out[i] = d;
+}
+
+// top-2 by (key) with payload
+struct Top2 {
+  uint32_t k0, k1;  // keys: dist << 23 | cell ordinal << 11 | rank in cell
+  int i0, i1;
+};
+__device__ __forceinline__ void top2_insert(Top2& t, uint32_t k, int i) {
+  if (k < t.k0) { t.k1 = t.k0; t.i1 = t.i0; t.k0 = k; t.i0 = i; }
+  else if (k < t.k1) { t.k1 = k; t.i1 = i; }
+}
+__device__ __forceinline__ void top2_warp_merge(Top2& t) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t ok0 = __shfl_xor_sync(0xffffffffu, t.k0, o), ok1 = __shfl_xor_sync(0xffffffffu, t.k1, o);
+    const int oi0 = __shfl_xor_sync(0xffffffffu, t.i0, o), oi1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+    top2_insert(t, ok0, oi0);
+    top2_insert(t, ok1, oi1);
+  }
+}
+
+struct SearchArgs {
+  int mode;  // 0 frame-frame, 1 map points, 2 initialisation
+  const plvi_keypoint* keys; const uint8_t* desc; const uint8_t* blocked; const int* tcount; int tstride;
+  plvi_grid grid;
+  plvi_query* q; const uint8_t* qdesc; const int* qcount; int qstride;
+  int th; float nnratio; int checkOri;
+  int* matchTrain; int* matchQuery; int* nmatches;
+  int* matchedDist;  // scratch [P][tstride] (init mode)
+};
+
+struct QRes {
+  int best, bestDist, second, secondDist;  // indices or -1; dist INT_MAX when absent
+};
+
+__device__ __forceinline__ bool eligible(const SearchArgs& a, int i2, int d, const uint8_t* blk,
+                                         const int* mdist) {
+  if (a.mode == 2) return !(mdist[i2] <= d);
+  return !blk[i2];
+}
+
+// Evaluate one query with a full warp.  cellStart/items describe mGrid in smem.
+__device__ QRes eval_query(const SearchArgs& a, const plvi_keypoint* __restrict__ keys,
+                           const uint8_t* __restrict__ desc, const plvi_query& q,
+                           const uint8_t* __restrict__ qd, const int* cellStart,
+                           const unsigned short* items, const uint8_t* blk, const int* mdist) {
+  const int lane = threadIdx.x & 31;
+  QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
+  const float x = q.u, y = q.v, rad = q.radius;
+  const plvi_grid& g = a.grid;
+  const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, g.min_x), rad), g.inv_w)));
+  const int cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, g.min_x), rad), g.inv_w)));
+  const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, g.min_y), rad), g.inv_h)));
+  const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, g.min_y), rad), g.inv_h)));
+  if (cx0 >= GRID_COLS || cx1 < 0 || cy0 >= GRID_ROWS || cy1 < 0) return r;
+  const bool checkLevels = (q.min_level > 0) || (q.max_level >= 0);
+  uint32_t qw[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) qw[k] = __ldg(reinterpret_cast<const uint32_t*>(qd) + k);
+  const int ny = cy1 - cy0 + 1, nc = (cx1 - cx0 + 1) * ny;
+  Top2 t = {0xffffffffu, 0xffffffffu, -1, -1};
+  for (int c = lane; c < nc; c += 32) {
+    const int ix = cx0 + c / ny, iy = cy0 + c % ny;
+    const int cell = ix * GRID_ROWS + iy;
+    const int s = cellStart[cell], e = cellStart[cell + 1];
+    for (int k = s; k < e; k++) {
+      const int i2 = items[k];
+      const plvi_keypoint kp = keys[i2];
+      if (checkLevels) {
+        if (kp.octave < q.min_level) continue;
+        if (q.max_level >= 0 && kp.octave > q.max_level) continue;
+      }
+      if (!(fabsf(__fsub_rn(kp.x, x)) < rad && fabsf(__fsub_rn(kp.y, y)) < rad)) continue;
+      const int d = hamming256_regs(qw, desc + (size_t)i2 * 32);
+      if (!eligible(a, i2, d, blk, mdist)) continue;
+      top2_insert(t, ((uint32_t)d << 23) | ((uint32_t)c << 11) | (uint32_t)min(k - s, 2047), i2);
+    }
+  }
+  top2_warp_merge(t);
+  if (t.i0 >= 0) { r.best = t.i0; r.bestDist = (int)(t.k0 >> 23); }
+  if (t.i1 >= 0) { r.second = t.i1; r.secondDist = (int)(t.k1 >> 23); }
+  return r;
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2) {
+  float rot = __fsub_rn(a1, a2);
+  if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+  int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+  if (bin == HISTO_LENGTH) bin = 0;
+  return bin;
+}
+
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int NT = SEARCH_WARPS * 32;
+  const int n = a.tcount[pair], nq = a.qcount[pair];
+  const plvi_keypoint* keys = a.keys + (size_t)pair * a.tstride;
+  const uint8_t* desc = a.desc + (size_t)pair * a.tstride * 32;
+  plvi_query* q = a.q + (size_t)pair * a.qstride;
+  const uint8_t* qdesc = a.qdesc + (size_t)pair * a.qstride * 32;
+  int* owner = a.matchTrain + (size_t)pair * a.tstride;   // train -> query (mvpMapPoints / vnMatches21)
+  int* m12 = a.matchQuery + (size_t)pair * a.qstride;     // query -> train
+  int* mdist = a.matchedDist ? a.matchedDist + (size_t)pair * a.tstride : nullptr;
+
+  int* cellStart = reinterpret_cast<int*>(smem);                 // [GRID_CELLS + 1]
+  int* cursor = cellStart + GRID_CELLS + 1;                      // [GRID_CELLS]
+  unsigned short* items = reinterpret_cast<unsigned short*>(cursor + GRID_CELLS);  // [tstride]
+  uint8_t* blk = reinterpret_cast<uint8_t*>(items + a.tstride);  // [tstride]
+  signed char* qbin = reinterpret_cast<signed char*>(blk + a.tstride);  // [qstride] rot bin of a commit
+  __shared__ QRes res[SEARCH_WARPS];
+  __shared__ int hist[HISTO_LENGTH];
+  __shared__ int s_nm, s_keep[3];
+  __shared__ int wtmp[33];
+
+  // ---- AssignFeaturesToGrid: CSR of the 64x48 grid, cell lists in keypoint order
+  for (int i = tid; i < GRID_CELLS; i += NT) cursor[i] = 0;
+  if (tid < HISTO_LENGTH) hist[tid] = 0;
+  if (tid == 0) s_nm = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += NT) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, a.grid.min_x), a.grid.inv_w));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, a.grid.min_y), a.grid.inv_h));
+    if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) atomicAdd(&cursor[px * GRID_ROWS + py], 1);
+    owner[i] = -1;
+    blk[i] = a.blocked ? a.blocked[(size_t)pair * a.tstride + i] : 0;
+    if (mdist) mdist[i] = 0x7fffffff;
+  }
+  for (int i = tid; i < nq; i += NT) { m12[i] = -1; qbin[i] = -1; }
+  __syncthreads();
+  {  // exclusive scan of the cell counts (chunked, NT threads)
+    const int chunk = (GRID_CELLS + NT - 1) / NT;
+    const int beg = min(tid * chunk, GRID_CELLS), end = min(beg + chunk, GRID_CELLS);
+    int sum = 0;
+    for (int i = beg; i < end; i++) sum += cursor[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wtmp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int v = lane < SEARCH_WARPS ? wtmp[lane] : 0;
+      int iv = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, iv, o);
+        if (lane >= o) iv += t;
+      }
+      wtmp[lane] = iv - v;
+    }
+    __syncthreads();
+    int base = wtmp[wid] + incl - sum;
+    for (int i = beg; i < end; i++) {
+      cellStart[i] = base;
+      base += cursor[i];
+      cursor[i] = 0;
+    }
+    if (end == GRID_CELLS && beg < end) cellStart[GRID_CELLS] = base;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += NT) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, a.grid.min_x), a.grid.inv_w));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, a.grid.min_y), a.grid.inv_h));
+    if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) {
+      const int c = px * GRID_ROWS + py;
+      items[cellStart[c] + atomicAdd(&cursor[c], 1)] = (unsigned short)i;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < GRID_CELLS; c += NT) {  // restore insertion (index) order inside each cell
+    const int s = cellStart[c], e = cellStart[c + 1];
+    for (int i = s + 1; i < e; i++) {
+      const unsigned short v = items[i];
+      int j = i - 1;
+      while (j >= s && items[j] > v) { items[j + 1] = items[j]; j--; }
+      items[j + 1] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- queries, W at a time
+  for (int q0 = 0; q0 < nq; q0 += SEARCH_WARPS) {
+    const int qi = q0 + wid;
+    QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
+    if (qi < nq && !(q[qi].flags & 1))
+      r = eval_query(a, keys, desc, q[qi], qdesc + (size_t)qi * 32, cellStart, items, blk, mdist);
+    if (lane == 0) res[wid] = r;
+    __syncthreads();
+    if (wid == 0) {
+      for (int j = 0; j < SEARCH_WARPS && q0 + j < nq; j++) {
+        const int qj = q0 + j;
+        const plvi_query qq = q[qj];
+        if (qq.flags & 1) continue;
+        QRes rr = res[j];
+        // stale if an earlier commit of this chunk removed the best or the second best
+        bool stale = false;
+        if (a.mode == 2) {
+          stale = (rr.best >= 0 && mdist[rr.best] <= rr.bestDist) ||
+                  (rr.second >= 0 && mdist[rr.second] <= rr.secondDist);
+        } else {
+          stale = (rr.best >= 0 && blk[rr.best]) || (a.mode == 1 && rr.second >= 0 && blk[rr.second]);
+        }
+        if (stale) rr = eval_query(a, keys, desc, qq, qdesc + (size_t)qj * 32, cellStart, items, blk, mdist);
+        if (lane == 0 && rr.best >= 0) {
+          if (a.mode == 0) {
+            if (rr.bestDist <= a.th) {
+              owner[rr.best] = qj;
+              m12[qj] = rr.best;
+              if (!(qq.flags & 2)) blk[rr.best] = 1;
+              s_nm++;
+              if (a.checkOri) {
+                const int b = rot_bin(qq.angle, keys[rr.best].angle);
+                qbin[qj] = (signed char)b;
+                hist[b]++;
+              }
+            }
+          } else if (a.mode == 1) {
+            if (rr.bestDist <= a.th) {
+              const int l1 = keys[rr.best].octave, l2 = rr.second >= 0 ? keys[rr.second].octave : -1;
+              const int d2 = rr.second >= 0 ? rr.secondDist : 256;
+              const bool reject = (l1 == l2) && ((float)rr.bestDist > __fmul_rn(a.nnratio, (float)d2));
+              if (!reject && (l1 != l2 || (float)rr.bestDist <= __fmul_rn(a.nnratio, (float)d2))) {
+                owner[rr.best] = qj;
+                m12[qj] = rr.best;
+                if (!(qq.flags & 2)) blk[rr.best] = 1;
+                s_nm++;
+              }
+            }
+          } else {
+            if (rr.bestDist <= a.th &&
+                (float)rr.bestDist < __fmul_rn((float)rr.secondDist, a.nnratio)) {
+              if (owner[rr.best] >= 0) { m12[owner[rr.best]] = -1; s_nm--; }
+              m12[qj] = rr.best;
+              owner[rr.best] = qj;
+              mdist[rr.best] = rr.bestDist;
+              s_nm++;
+              if (a.checkOri) {
+                const int b = rot_bin(qq.angle, keys[rr.best].angle);
+                qbin[qj] = (signed char)b;
+                hist[b]++;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- rotation consistency (ComputeThreeMaxima)
+  if (a.checkOri && a.mode != 1) {
+    if (tid == 0) {
+      int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+      for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int s = hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+        else if (s > max3) { max3 = s; i3 = i; }
+      }
+      if ((float)max2 < 0.1f * (float)max1) { i2 = -1; i3 = -1; }
+      else if ((float)max3 < 0.1f * (float)max1) { i3 = -1; }
+      s_keep[0] = i1; s_keep[1] = i2; s_keep[2] = i3;
+    }
+    __syncthreads();
+    int dec = 0;
+    for (int i = tid; i < nq; i += NT) {
+      const int b = qbin[i];
+      if (b < 0 || b == s_keep[0] || b == s_keep[1] || b == s_keep[2]) continue;
+      if (a.mode == 0) {
+        // the reference nulls mvpMapPoints[bestIdx2] of every culled assignment
+        const int i2 = m12[i];
+        owner[i2] = -1;
+        m12[i] = -1;
+        dec++;
+      } else if (m12[i] >= 0) {
+        owner[m12[i]] = -1;
+        m12[i] = -1;
+        dec++;
+      }
+    }
+    if (dec) atomicSub(&s_nm, dec);
+    __syncthreads();
+  }
+  if (a.mode == 2) {  // "Update prev matched"
+    for (int i = tid; i < nq; i += NT)
+      if (m12[i] >= 0) { q[i].u = keys[m12[i]].x; q[i].v = keys[m12[i]].y; }
+  }
+  if (tid == 0) a.nmatches[pair] = s_nm;
+}
+
+// ---- lines: knn-2 + ratio in both directions + mutual check, one CTA per pair ---------
+__device__ void nnr_rows(const uint8_t* sa, int na, const uint8_t* sb, int nb, float nnr, int* out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = wid; i < na; i += nw) {
+    uint32_t qw[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) qw[k] = reinterpret_cast<const uint32_t*>(sa + i * 32)[k];
+    Top2 t = {0xffffffffu, 0xffffffffu, -1, -1};
+    for (int j = lane; j < nb; j += 32) {
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(sb + j * 32);
+      int d = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) d += __popc(qw[k] ^ pb[k]);
+      top2_insert(t, ((uint32_t)d << 16) | (uint32_t)j, j);
+    }
+    top2_warp_merge(t);
+    if (lane == 0) {
+      int m = -1;
+      if (nb >= 2 && (float)(t.k0 >> 16) < __fmul_rn((float)(t.k1 >> 16), nnr)) m = t.i0;
+      out[i] = m;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_line_match(const uint8_t* __restrict__ d1, const int* __restrict__ n1p,
+                                                    int stride1, const uint8_t* __restrict__ d2,
+                                                    const int* __restrict__ n2p, int stride2, float nnr,
+                                                    int mutual, int* __restrict__ m12out,
+                                                    int* __restrict__ nmatches) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  const int n1 = n1p[pair], n2 = n2p[pair];
+  uint8_t* s1 = smem;
+  uint8_t* s2 = s1 + (size_t)stride1 * 32;
+  int* m12 = reinterpret_cast<int*>(s2 + (size_t)stride2 * 32);
+  int* m21 = m12 + stride1;
+  __shared__ int s_cnt;
+  if (tid == 0) s_cnt = 0;
+  const uint4* g1 = reinterpret_cast<const uint4*>(d1 + (size_t)pair * stride1 * 32);
+  const uint4* g2 = reinterpret_cast<const uint4*>(d2 + (size_t)pair * stride2 * 32);
+  for (int i = tid; i < n1 * 2; i += blockDim.x) reinterpret_cast<uint4*>(s1)[i] = __ldg(g1 + i);
+  for (int i = tid; i < n2 * 2; i += blockDim.x) reinterpret_cast<uint4*>(s2)[i] = __ldg(g2 + i);
+  __syncthreads();
+  nnr_rows(s1, n1, s2, n2, nnr, m12);
+  if (mutual) nnr_rows(s2, n2, s1, n1, nnr, m21);
+  __syncthreads();
+  int cnt = 0;
+  for (int i = tid; i < n1; i += blockDim.x) {
+    int m = m12[i];
+    if (mutual && m >= 0 && m21[m] != i) m = -1;
+    m12out[(size_t)pair * stride1 + i] = m;
+    cnt += m >= 0;
+  }
+  if (cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (tid == 0) nmatches[pair] = s_cnt;
+}
+
+}  // namespace plvi
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+using namespace plvi;
+
+struct plvi_matcher {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  int maxPairs = 0, maxTrain = 0, maxQuery = 0;
+  // device staging for the host-pointer entry points
+  plvi_keypoint* dKeys = nullptr; uint8_t* dDesc = nullptr; uint8_t* dBlocked = nullptr;
+  int* dTCount = nullptr; plvi_query* dQ = nullptr; uint8_t* dQDesc = nullptr; int* dQCount = nullptr;
+  int* dMatchTrain = nullptr; int* dMatchQuery = nullptr; int* dNMatches = nullptr; int* dMatchedDist = nullptr;
+  int lastLaunches = 0;
+};
+
+extern "C" {
+
+int plvi_matcher_create(plvi_matcher** out, int max_pairs, int max_train, int max_query, int device,
+                        void* stream) {
+  if (!out || max_pairs < 1 || max_train < 1 || max_query < 1 || max_train > 65535) {
+    set_error("plvi_matcher_create: invalid argument (max_train <= 65535)");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(device));
+  plvi_matcher* m = new plvi_matcher();
+  m->device = device;
+  m->maxPairs = max_pairs;
+  m->maxTrain = max_train;
+  m->maxQuery = max_query;
+  if (stream) m->stream = (cudaStream_t)stream;
+  else {
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); delete m; return PLVI_ERR_CUDA; }
+    m->ownStream = true;
+  }
+  const size_t P = max_pairs, T = max_train, Q = max_query;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  A((void**)&m->dKeys, P * T * sizeof(plvi_keypoint));
+  A((void**)&m->dDesc, P * (T > Q ? T : Q) * 32);
+  A((void**)&m->dBlocked, P * T);
+  A((void**)&m->dTCount, P * sizeof(int));
+  A((void**)&m->dQ, P * Q * sizeof(plvi_query));
+  A((void**)&m->dQDesc, P * (T > Q ? T : Q) * 32);
+  A((void**)&m->dQCount, P * sizeof(int));
+  A((void**)&m->dMatchTrain, P * T * sizeof(int));
+  A((void**)&m->dMatchQuery, P * (T > Q ? T : Q) * sizeof(int));
+  A((void**)&m->dNMatches, P * sizeof(int));
+  A((void**)&m->dMatchedDist, P * T * sizeof(int));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    plvi_matcher_destroy(m);
+    return PLVI_ERR_CUDA;
+  }
+  *out = m;
+  return PLVI_OK;
+}
+
+void plvi_matcher_destroy(plvi_matcher* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  cudaFree(m->dKeys); cudaFree(m->dDesc); cudaFree(m->dBlocked); cudaFree(m->dTCount);
+  cudaFree(m->dQ); cudaFree(m->dQDesc); cudaFree(m->dQCount); cudaFree(m->dMatchTrain);
+  cudaFree(m->dMatchQuery); cudaFree(m->dNMatches); cudaFree(m->dMatchedDist);
+  if (m->ownStream && m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+void* plvi_matcher_stream(const plvi_matcher* m) { return m ? (void*)m->stream : nullptr; }
+int plvi_matcher_last_launches(const plvi_matcher* m) { return m ? m->lastLaunches : PLVI_ERR_INVALID; }
+
+int plvi_hamming256(plvi_matcher* m, const uint8_t* a, const uint8_t* b, int n, int shift25, int* out,
+                    int on_device) {
+  if (!m || !a || !b || !out || n < 0) { set_error("plvi_hamming256: invalid argument"); return PLVI_ERR_INVALID; }
+  if (n == 0) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  const uint8_t *da = a, *db = b;
+  int* dout = out;
+  if (!on_device) {
+    if ((size_t)n > (size_t)m->maxPairs * (m->maxTrain > m->maxQuery ? m->maxTrain : m->maxQuery)) {
+      set_error("plvi_hamming256: n exceeds matcher capacity");
+      return PLVI_ERR_CAPACITY;
+    }
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dDesc, a, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQDesc, b, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+    da = m->dDesc; db = m->dQDesc; dout = m->dMatchQuery;
+  }
+  k_hamming_pairs<<<(n + 255) / 256, 256, 0, m->stream>>>(da, db, n, shift25, dout);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  if (!on_device) {
+    PLVI_CUDA_TRY(cudaMemcpyAsync(out, dout, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    PLVI_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  }
+  return PLVI_OK;
+}
+
+int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_keypoint* train_keys,
+                              const uint8_t* train_desc, const uint8_t* train_blocked,
+                              const int* train_counts, int train_stride, const plvi_grid* grid,
+                              plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                              int query_stride, int th_dist, float nnratio, int check_orientation,
+                              int* match_train, int* match_query, int* nmatches, int on_device) {
+  if (!m || mode < 0 || mode > 2 || npairs < 1 || !train_keys || !train_desc || !train_counts || !grid ||
+      !queries || !query_desc || !query_counts || !match_train || !match_query || !nmatches) {
+    set_error("plvi_search_by_projection: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  if (npairs > m->maxPairs || train_stride > m->maxTrain || query_stride > m->maxQuery) {
+    set_error("plvi_search_by_projection: exceeds matcher capacity");
+    return PLVI_ERR_CAPACITY;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  SearchArgs a;
+  a.mode = mode;
+  a.grid = *grid;
+  a.tstride = train_stride;
+  a.qstride = query_stride;
+  a.th = th_dist;
+  a.nnratio = nnratio;
+  a.checkOri = check_orientation;
+  a.matchedDist = mode == 2 ? m->dMatchedDist : nullptr;
+  const size_t P = npairs, T = train_stride, Q = query_stride;
+  cudaStream_t st = m->stream;
+  if (on_device) {
+    a.keys = train_keys; a.desc = train_desc; a.blocked = train_blocked; a.tcount = train_counts;
+    a.q = queries; a.qdesc = query_desc; a.qcount = query_counts;
+    a.matchTrain = match_train; a.matchQuery = match_query; a.nmatches = nmatches;
+  } else {
+    for (size_t p = 0; p < P; p++)
+      if (train_counts[p] < 0 || train_counts[p] > train_stride || query_counts[p] < 0 || query_counts[p] > query_stride) {
+        set_error("plvi_search_by_projection: count exceeds stride");
+        return PLVI_ERR_INVALID;
+      }
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dKeys, train_keys, P * T * sizeof(plvi_keypoint), cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dDesc, train_desc, P * T * 32, cudaMemcpyHostToDevice, st));
+    if (train_blocked) PLVI_CUDA_TRY(cudaMemcpyAsync(m->dBlocked, train_blocked, P * T, cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dTCount, train_counts, P * sizeof(int), cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQ, queries, P * Q * sizeof(plvi_query), cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQDesc, query_desc, P * Q * 32, cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQCount, query_counts, P * sizeof(int), cudaMemcpyHostToDevice, st));
+    a.keys = m->dKeys; a.desc = m->dDesc; a.blocked = train_blocked ? m->dBlocked : nullptr;
+    a.tcount = m->dTCount; a.q = m->dQ; a.qdesc = m->dQDesc; a.qcount = m->dQCount;
+    a.matchTrain = m->dMatchTrain; a.matchQuery = m->dMatchQuery; a.nmatches = m->dNMatches;
+  }
+  const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + 16;
+  if (smem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_search<<<npairs, SEARCH_WARPS * 32, smem, st>>>(a);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  if (!on_device) {
+    PLVI_CUDA_TRY(cudaMemcpyAsync(match_train, m->dMatchTrain, P * T * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(match_query, m->dMatchQuery, P * Q * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(nmatches, m->dNMatches, P * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (mode == 2)
+      PLVI_CUDA_TRY(cudaMemcpyAsync(queries, m->dQ, P * Q * sizeof(plvi_query), cudaMemcpyDeviceToHost, st));
+    PLVI_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return PLVI_OK;
+}
+
+int plvi_line_match(plvi_matcher* m, int npairs, const uint8_t* desc1, const int* n1, int stride1,
+                    const uint8_t* desc2, const int* n2, int stride2, float nnr, int mutual,
+                    int* matches12, int* nmatches, int on_device) {
+  if (!m || npairs < 1 || !desc1 || !desc2 || !n1 || !n2 || !matches12 || !nmatches || stride1 < 1 || stride2 < 1) {
+    set_error("plvi_line_match: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  const int cap = m->maxTrain > m->maxQuery ? m->maxTrain : m->maxQuery;
+  if (npairs > m->maxPairs || stride1 > cap || stride2 > cap) {
+    set_error("plvi_line_match: exceeds matcher capacity");
+    return PLVI_ERR_CAPACITY;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = m->stream;
+  const size_t P = npairs;
+  const uint8_t *a = desc1, *b = desc2;
+  const int *c1 = n1, *c2 = n2;
+  int *o = matches12, *nm = nmatches;
+  if (!on_device) {
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dDesc, desc1, P * stride1 * 32, cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQDesc, desc2, P * stride2 * 32, cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dTCount, n1, P * sizeof(int), cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQCount, n2, P * sizeof(int), cudaMemcpyHostToDevice, st));
+    a = m->dDesc; b = m->dQDesc; c1 = m->dTCount; c2 = m->dQCount; o = m->dMatchQuery; nm = m->dNMatches;
+  }
+  const size_t smem = (size_t)(stride1 + stride2) * 32 + (size_t)(stride1 + stride2) * sizeof(int);
+  if (smem > 200 * 1024) { set_error("plvi_line_match: descriptor sets too large for one CTA"); return PLVI_ERR_CAPACITY; }
+  if (smem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_line_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_line_match<<<npairs, 256, smem, st>>>(a, c1, stride1, b, c2, stride2, nnr, mutual, o, nm);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  if (!on_device) {
+    PLVI_CUDA_TRY(cudaMemcpyAsync(matches12, o, P * stride1 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(nmatches, nm, P * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLVI_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return PLVI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+"""Host-side mirrors of ORBmatcher (include/ORBmatcher.h:40-89) and LineMatcher
+(include/LineMatcher.h:87-107) on top of the C ABI.
+
+The reference's searches take Frame / MapPoint objects; the geometry (projection,
+frustum tests) is host code there and stays with the caller here: a search receives the
+train Frame as `FrameView` (mvKeysUn + mDescriptors + grid bounds) and one `QUERY_DTYPE`
+record per candidate point in the reference's iteration order.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from .capi import GRID_DTYPE, KEYPOINT_DTYPE, QUERY_DTYPE, check, lib, ptr
+
+FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48
+
+
+def frame_grid(min_x, max_x, min_y, max_y):
+    """Frame::mfGridElementWidthInv/HeightInv (src/Frame.cc:163-170), float32 like the reference."""
+    g = np.zeros(1, GRID_DTYPE)
+    g["min_x"], g["min_y"] = np.float32(min_x), np.float32(min_y)
+    g["inv_w"] = np.float32(FRAME_GRID_COLS) / (np.float32(max_x) - np.float32(min_x))
+    g["inv_h"] = np.float32(FRAME_GRID_ROWS) / (np.float32(max_y) - np.float32(min_y))
+    return g
+
+
+@dataclass
+class FrameView:
+    keys: np.ndarray            # KEYPOINT_DTYPE [n]  (mvKeysUn)
+    desc: np.ndarray            # u8 [n,32]          (mDescriptors)
+    grid: np.ndarray            # GRID_DTYPE [1]
+    blocked: np.ndarray = None  # u8 [n]: mvpMapPoints[i] && Observations()>0
+
+
+class _Matcher:
+    def __init__(self, max_pairs=1, max_train=8192, max_query=8192, device=0, stream=None):
+        self._h = C.c_void_p()
+        check(lib().plvi_matcher_create(C.byref(self._h), max_pairs, max_train, max_query, device,
+                                        ptr(stream) if stream else None))
+        self.max_pairs = max_pairs
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().plvi_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return lib().plvi_matcher_stream(self._h)
+
+    def _hamming(self, a, b, shift25):
+        a = np.ascontiguousarray(np.atleast_2d(a), np.uint8)
+        b = np.ascontiguousarray(np.atleast_2d(b), np.uint8)
+        out = np.empty(len(a), np.int32)
+        check(lib().plvi_hamming256(self._h, ptr(a), ptr(b), len(a), shift25, ptr(out), 0))
+        return out
+
+
+class ORBmatcher(_Matcher):
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30   # src/ORBmatcher.cc:36-38
+
+    def __init__(self, nnratio=0.6, checkOri=True, **kw):
+        super().__init__(**kw)
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+
+    def DescriptorDistance(self, a, b):
+        """a, b: u8 [n,32] (or [32]) -> int32 [n] (src/ORBmatcher.cc:2350-2366)."""
+        return self._hamming(a, b, 0)
+
+    def search_batch(self, mode, frames, queries, qdescs, th):
+        """Batched guided search: frames = [FrameView], queries = [QUERY_DTYPE array],
+        qdescs = [u8 [nq,32]].  Returns (match_train list, match_query list, nmatches, queries out)."""
+        P = len(frames)
+        T = max(max(len(f.keys) for f in frames), 1)
+        Q = max(max(len(q) for q in queries), 1)
+        keys = np.zeros((P, T), KEYPOINT_DTYPE)
+        desc = np.zeros((P, T, 32), np.uint8)
+        blocked = np.zeros((P, T), np.uint8) if any(f.blocked is not None for f in frames) else None
+        qs = np.zeros((P, Q), QUERY_DTYPE)
+        qd = np.zeros((P, Q, 32), np.uint8)
+        tc = np.array([len(f.keys) for f in frames], np.int32)
+        qc = np.array([len(q) for q in queries], np.int32)
+        for i, f in enumerate(frames):
+            keys[i, :tc[i]] = f.keys
+            desc[i, :tc[i]] = f.desc
+            if blocked is not None and f.blocked is not None:
+                blocked[i, :tc[i]] = f.blocked
+            qs[i, :qc[i]] = queries[i]
+            qd[i, :qc[i]] = qdescs[i]
+        mt = np.empty((P, T), np.int32)
+        mq = np.empty((P, Q), np.int32)
+        nm = np.empty(P, np.int32)
+        grid = np.ascontiguousarray(frames[0].grid)
+        check(lib().plvi_search_by_projection(
+            self._h, mode, P, ptr(keys), ptr(desc), ptr(blocked), ptr(tc), T, ptr(grid), ptr(qs), ptr(qd),
+            ptr(qc), Q, th, self.mfNNratio, int(self.mbCheckOrientation), ptr(mt), ptr(mq), ptr(nm), 0))
+        return ([mt[i, :tc[i]] for i in range(P)], [mq[i, :qc[i]] for i in range(P)], nm,
+                [qs[i, :qc[i]] for i in range(P)])
+
+    def SearchByProjection(self, CurrentFrame, queries, qdesc, mappoints=False):
+        """Frame-to-frame (src/ORBmatcher.cc:1962) or, with mappoints=True, Frame vs local
+        map points (src/ORBmatcher.cc:44).  Returns (nmatches, match_train, match_query)."""
+        mode = 1 if mappoints else 0
+        mt, mq, nm, _ = self.search_batch(mode, [CurrentFrame], [queries], [qdesc], self.TH_HIGH)
+        return int(nm[0]), mt[0], mq[0]
+
+    @staticmethod
+    def init_queries(F1_keys, vbPrevMatched, windowSize):
+        n1 = len(F1_keys)
+        q = np.zeros(n1, QUERY_DTYPE)
+        q["u"], q["v"] = vbPrevMatched[:, 0], vbPrevMatched[:, 1]
+        q["radius"] = windowSize
+        q["min_level"], q["max_level"] = 0, 0
+        q["angle"] = F1_keys["angle"]
+        q["flags"] = (F1_keys["octave"] > 0).astype(np.int32)
+        return q
+
+    def SearchForInitialization(self, F1_keys, F1_desc, F2, vbPrevMatched, windowSize=10):
+        """src/ORBmatcher.cc:706-820.  Returns (nmatches, vnMatches12, updated vbPrevMatched)."""
+        q = self.init_queries(F1_keys, vbPrevMatched, windowSize)
+        mt, mq, nm, qs = self.search_batch(2, [F2], [q], [F1_desc], self.TH_LOW)
+        prev = np.stack([qs[0]["u"], qs[0]["v"]], axis=1)
+        return int(nm[0]), mq[0], prev
+
+
+class LineMatcher(_Matcher):
+    TH_HIGH, TH_LOW = 100, 50   # src/LineMatcher.cpp:37-38
+
+    def match_batch(self, pairs, nnr, mutual=True):
+        P = len(pairs)
+        S1 = max(max(len(a) for a, _ in pairs), 1)
+        S2 = max(max(len(b) for _, b in pairs), 1)
+        d1 = np.zeros((P, S1, 32), np.uint8)
+        d2 = np.zeros((P, S2, 32), np.uint8)
+        n1 = np.array([len(a) for a, _ in pairs], np.int32)
+        n2 = np.array([len(b) for _, b in pairs], np.int32)
+        for i, (a, b) in enumerate(pairs):
+            d1[i, :n1[i]] = a
+            d2[i, :n2[i]] = b
+        m12 = np.empty((P, S1), np.int32)
+        nm = np.empty(P, np.int32)
+        check(lib().plvi_line_match(self._h, P, ptr(d1), ptr(n1), S1, ptr(d2), ptr(n2), S2, float(nnr),
+                                    int(mutual), ptr(m12), ptr(nm), 0))
+        return [m12[i, :n1[i]] for i in range(P)], nm
+
+    def match(self, desc1, desc2, nnr):
+        """LineMatcher::match(desc1, desc2, nnr, matches_12) -> (count, matches_12)."""
+        m, nm = self.match_batch([(desc1, desc2)], nnr, True)
+        return int(nm[0]), m[0]
+
+    def matchNNR(self, desc1, desc2, nnr):
+        m, nm = self.match_batch([(desc1, desc2)], nnr, False)
+        return int(nm[0]), m[0]
+
+    def distance(self, a, b):
+        return self._hamming(a, b, 0)
+
+    def DescriptorDistance(self, a, b):
+        """The reference's >>25 variant (src/LineMatcher.cpp:487-499), kept bit-compatible."""
+        return self._hamming(a, b, 1)

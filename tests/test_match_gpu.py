@@ -1,0 +1,218 @@
+"""GPU parity: CUDA Hamming searches (through the C ABI) vs the CPU oracle.
+
+Bar: bit-exact -- distances, match lists and match counts are integer work.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from pl_vi_orbslam3_b200 import FrameView, LineMatcher, ORBmatcher, frame_grid, synth
+from pl_vi_orbslam3_b200.capi import QUERY_DTYPE
+
+pytestmark = pytest.mark.gpu
+
+GRID = frame_grid(0, 752, 0, 480)
+SCALES = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+
+
+@pytest.fixture(scope="module")
+def pair_features():
+    """C3: ORB features (from the oracle) of a synthetic frame and its affine warp."""
+    f1, f2, A = synth.warp_pair(3)
+    r1, r2 = oracle.orb_extract(f1), oracle.orb_extract(f2)
+    return r1, r2, A
+
+
+def _proj_queries(r1, A, th=15.0, lo=-1, hi=+1):
+    k = r1["keypoints"]
+    q = np.zeros(len(k), QUERY_DTYPE)
+    q["u"] = (A[0, 0] * k["x"] + A[0, 1] * k["y"] + A[0, 2]).astype(np.float32)
+    q["v"] = (A[1, 0] * k["x"] + A[1, 1] * k["y"] + A[1, 2]).astype(np.float32)
+    q["radius"] = np.float32(th) * SCALES[k["octave"]]
+    q["min_level"] = k["octave"] + lo
+    q["max_level"] = k["octave"] + hi
+    q["angle"] = k["angle"]
+    return q
+
+
+@pytest.fixture(scope="module")
+def om(gpu):
+    m = ORBmatcher(0.9, True, max_pairs=8, max_train=6000, max_query=6000)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def lm(gpu):
+    m = LineMatcher(max_pairs=64, max_train=512, max_query=512)
+    yield m
+    m.close()
+
+
+def test_descriptor_distance_bit_exact(om, lm):
+    rng = np.random.RandomState(0)
+    a = rng.randint(0, 256, (4096, 32)).astype(np.uint8)
+    b = rng.randint(0, 256, (4096, 32)).astype(np.uint8)
+    b[:100] = a[:100]
+    b[100:200] = ~a[100:200]
+    ref = np.array([oracle.hamming256(a[i], b[i]) for i in range(len(a))])
+    assert np.array_equal(om.DescriptorDistance(a, b), ref)
+    assert np.array_equal(lm.distance(a, b), ref)
+    ref25 = np.array([oracle.hamming256(a[i], b[i], shift25=True) for i in range(len(a))])
+    assert np.array_equal(lm.DescriptorDistance(a, b), ref25)
+    assert ref[:100].max() == 0 and ref[100:200].min() == 256
+
+
+@pytest.mark.parametrize("th", [15.0, 30.0])
+@pytest.mark.parametrize("ori", [True, False])
+def test_search_by_projection_frame(om, pair_features, th, ori):
+    r1, r2, A = pair_features
+    q = _proj_queries(r1, A, th)
+    om.mbCheckOrientation = ori
+    F = FrameView(r2["keypoints"], r2["descriptors"], GRID)
+    n, mt, mq = om.SearchByProjection(F, q, r1["descriptors"])
+    rn, rmt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, q, r1["descriptors"], 100, ori)
+    om.mbCheckOrientation = True
+    assert n == rn and n > 300
+    assert np.array_equal(mt, rmt)
+
+
+def test_search_frame_blocked_and_flags(om, pair_features):
+    r1, r2, A = pair_features
+    q = _proj_queries(r1, A, 15.0)
+    rng = np.random.RandomState(1)
+    q["flags"] = rng.choice([0, 0, 0, 1, 2], len(q)).astype(np.int32)
+    blocked = (rng.rand(len(r2["keypoints"])) < 0.2).astype(np.uint8)
+    F = FrameView(r2["keypoints"], r2["descriptors"], GRID, blocked)
+    n, mt, mq = om.SearchByProjection(F, q, r1["descriptors"])
+    rn, rmt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, q, r1["descriptors"], 100, True, blocked)
+    assert n == rn
+    assert np.array_equal(mt, rmt)
+
+
+@pytest.mark.parametrize("nnratio", [0.8, 0.6])
+def test_search_by_projection_mappoints(om, pair_features, nnratio):
+    r1, r2, A = pair_features
+    q = _proj_queries(r1, A, 4.0 * 2.5, lo=-1, hi=0)
+    om.mfNNratio = nnratio
+    F = FrameView(r2["keypoints"], r2["descriptors"], GRID)
+    n, mt, mq = om.SearchByProjection(F, q, r1["descriptors"], mappoints=True)
+    om.mfNNratio = 0.9
+    rn, rmt = oracle.search_mappoints(r2["keypoints"], r2["descriptors"], GRID, q, r1["descriptors"], 100, nnratio)
+    assert n == rn and n > 100
+    assert np.array_equal(mt, rmt)
+
+
+@pytest.mark.parametrize("window", [100, 30])
+def test_search_for_initialization(om, pair_features, window):
+    r1, r2, A = pair_features
+    k1 = r1["keypoints"]
+    prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+    F2 = FrameView(r2["keypoints"], r2["descriptors"], GRID)
+    n, m12, prev_out = om.SearchForInitialization(k1, r1["descriptors"], F2, prev, window)
+    q = ORBmatcher.init_queries(k1, prev, window)
+    rn, rm12, rq = oracle.search_init(r2["keypoints"], r2["descriptors"], GRID, q, r1["descriptors"], 50, 0.9, True)
+    assert n == rn and n > 30
+    assert np.array_equal(m12, rm12)
+    assert np.array_equal(prev_out[:, 0], rq["u"]) and np.array_equal(prev_out[:, 1], rq["v"])
+
+
+def _tie_heavy_case(seed, n=1500, nq=1200):
+    """Lattice keypoints with descriptors from a tiny codebook: distance ties and
+    overlapping windows everywhere -> exercises tie-breaks, claims and steals."""
+    rng = np.random.RandomState(seed)
+    keys = np.zeros(n, oracle.KEYPOINT_DTYPE)
+    keys["x"] = rng.randint(20, 732, n).astype(np.float32)
+    keys["y"] = rng.randint(20, 460, n).astype(np.float32)
+    keys["octave"] = rng.randint(0, 3, n)
+    keys["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    book = rng.randint(0, 256, (6, 32)).astype(np.uint8)
+    desc = book[rng.randint(0, 6, n)].copy()
+    flip = rng.rand(n) < 0.5
+    desc[flip, 0] ^= 1
+    q = np.zeros(nq, QUERY_DTYPE)
+    q["u"] = rng.uniform(0, 752, nq).astype(np.float32)
+    q["v"] = rng.uniform(0, 480, nq).astype(np.float32)
+    q["radius"] = rng.choice([12.0, 25.0, 60.0], nq).astype(np.float32)
+    q["min_level"] = rng.choice([-1, 0, 1], nq)
+    q["max_level"] = q["min_level"] + rng.choice([0, 1, 2], nq)
+    q["angle"] = rng.uniform(0, 360, nq).astype(np.float32)
+    qd = book[rng.randint(0, 6, nq)].copy()
+    qd[rng.rand(nq) < 0.3, 1] ^= 3
+    return keys, desc, q, qd
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_search_tie_heavy_all_modes(om, seed):
+    keys, desc, q, qd = _tie_heavy_case(seed)
+    F = FrameView(keys, desc, GRID)
+    n, mt, _ = om.SearchByProjection(F, q, qd)
+    rn, rmt = oracle.search_frame(keys, desc, GRID, q, qd, 100, True)
+    assert n == rn and np.array_equal(mt, rmt)
+    om.mfNNratio = 1.0
+    n, mt, _ = om.SearchByProjection(F, q, qd, mappoints=True)
+    om.mfNNratio = 0.9
+    rn, rmt = oracle.search_mappoints(keys, desc, GRID, q, qd, 100, 1.0)
+    assert n == rn and np.array_equal(mt, rmt)
+    q2 = q.copy()
+    q2["min_level"], q2["max_level"] = 0, 0
+    mt, mq, nm, qs = om.search_batch(2, [F], [q2], [qd], 50)
+    rn, rm12, rq = oracle.search_init(keys, desc, GRID, q2, qd, 50, 0.9, True)
+    assert nm[0] == rn and np.array_equal(mq[0], rm12)
+
+
+def test_search_batch_of_pairs(om):
+    cases = [_tie_heavy_case(10 + i, n=700 + 50 * i, nq=500 + 30 * i) for i in range(6)]
+    frames = [FrameView(c[0], c[1], GRID) for c in cases]
+    mt, mq, nm, _ = om.search_batch(0, frames, [c[2] for c in cases], [c[3] for c in cases], 100)
+    for i, c in enumerate(cases):
+        rn, rmt = oracle.search_frame(c[0], c[1], GRID, c[2], c[3], 100, True)
+        assert nm[i] == rn and np.array_equal(mt[i], rmt)
+
+
+def test_search_empty_sets(om):
+    keys, desc, q, qd = _tie_heavy_case(5, n=50, nq=40)
+    F0 = FrameView(keys[:0], desc[:0], GRID)
+    n, mt, mq = om.SearchByProjection(F0, q, qd)
+    assert n == 0 and len(mt) == 0 and (mq == -1).all()
+    n, mt, mq = om.SearchByProjection(FrameView(keys, desc, GRID), q[:0], qd[:0])
+    assert n == 0 and (mt == -1).all()
+
+
+def _line_descs(rng, n, dup_of=None):
+    d = rng.randint(0, 256, (n, 32)).astype(np.uint8)
+    if dup_of is not None and n and len(dup_of):
+        idx = rng.randint(0, len(dup_of), n)
+        noisy = dup_of[idx].copy()
+        noisy[np.arange(n), rng.randint(0, 32, n)] ^= (1 << rng.randint(0, 8, n)).astype(np.uint8)
+        take = rng.rand(n) < 0.6
+        d[take] = noisy[take]
+    return d
+
+
+@pytest.mark.parametrize("n1,n2", [(200, 200), (200, 137), (1, 5), (5, 1), (0, 7), (7, 0), (2, 2), (400, 380)])
+def test_line_match_bit_exact(lm, n1, n2):
+    rng = np.random.RandomState(n1 * 1000 + n2)
+    d1 = _line_descs(rng, n1)
+    d2 = _line_descs(rng, n2, d1)
+    if n2 > 10:
+        d2[3] = d2[7]  # exact duplicate train rows: tie -> lowest index
+    for nnr in (0.9, 0.75):
+        n, m = lm.match(d1, d2, nnr)
+        rn, rm = oracle.line_match(d1, d2, nnr)
+        assert n == rn and np.array_equal(m, rm)
+        n, m = lm.matchNNR(d1, d2, nnr)
+        rn, rm = oracle.match_nnr(d1, d2, nnr)
+        assert n == rn and np.array_equal(m, rm)
+
+
+def test_line_match_batch(lm):
+    rng = np.random.RandomState(77)
+    pairs = []
+    for i in range(48):
+        d1 = _line_descs(rng, rng.randint(0, 220))
+        pairs.append((d1, _line_descs(rng, rng.randint(0, 220), d1)))
+    ms, nm = lm.match_batch(pairs, 0.9)
+    for i, (a, b) in enumerate(pairs):
+        rn, rm = oracle.line_match(a, b, 0.9)
+        assert nm[i] == rn and np.array_equal(ms[i], rm)
