@@ -254,3 +254,92 @@ def line_match(d1, d2, nnr):
     m = np.empty(max(len(d1), 1), np.int32)
     n = lib().plvio_line_match(_p(d1), len(d1), _p(d2), len(d2), C.c_float(nnr), _p(m))
     return n, m[:len(d1)]
+
+
+# ---- lines -------------------------------------------------------------------------
+def gaussian_kernel_f64(n, sigma):
+    k = np.empty(n, np.float64)
+    lib().plvio_gaussian_kernel_f64(int(n), C.c_double(sigma), _p(k))
+    return k
+
+
+def gaussian_blur_f64(img, k):
+    img = np.ascontiguousarray(img, np.float64)
+    k = np.ascontiguousarray(k, np.float64)
+    out = np.empty_like(img)
+    lib().plvio_gaussian_blur_f64(_p(img), img.shape[1], img.shape[0], _p(out), _p(k), len(k))
+    return out
+
+
+def resize_linear_f64(img, dw, dh, fx, fy):
+    img = np.ascontiguousarray(img, np.float64)
+    out = np.empty((dh, dw), np.float64)
+    lib().plvio_resize_linear_f64(_p(img), img.shape[1], img.shape[0], _p(out), dw, dh, C.c_double(fx), C.c_double(fy))
+    return out
+
+
+def pyr_down(img):
+    img = _u8(img)
+    h, w = img.shape
+    out = np.empty((h // 2, w // 2), np.uint8)
+    lib().plvio_pyr_down_u8(_p(img), w, h, _p(out), w // 2, h // 2)
+    return out
+
+
+def sobel3(img):
+    img = _u8(img)
+    dx = np.empty(img.shape, np.int16)
+    dy = np.empty(img.shape, np.int16)
+    lib().plvio_sobel3_s16(_p(img), img.shape[1], img.shape[0], _p(dx), _p(dy))
+    return dx, dy
+
+
+def lsd(img, lsd_scale=0.8, debug=False):
+    """LineSegmentDetectorImpl::detect (refine 0) on one u8 image -> (segments [n,4] f32[, dict])."""
+    img = _u8(img)
+    h, w = img.shape
+    sw, sh = C.c_int(0), C.c_int(0)
+    cap = 1 << 16
+    segs = np.empty((cap, 4), np.float32)
+    rs = np.empty(cap, np.int32)
+    W, H = int(round(w * float(np.float32(lsd_scale)))), int(round(h * float(np.float32(lsd_scale))))
+    big = (W + 2) * (H + 2)
+    scaled = np.empty(big, np.float64) if debug else None
+    ang = np.empty(big, np.float64) if debug else None
+    mg = np.empty(big, np.float64) if debug else None
+    n = lib().plvio_lsd(_p(img), img.strides[0], w, h, C.c_float(lsd_scale), C.byref(sw), C.byref(sh),
+                        _p(scaled), _p(ang), _p(mg), _p(segs), cap, _p(rs))
+    out = segs[:n].copy()
+    if not debug:
+        return out
+    m = sw.value * sh.value
+    return out, {"w": sw.value, "h": sh.value, "scaled": scaled[:m].reshape(sh.value, sw.value),
+                 "angles": ang[:m].reshape(sh.value, sw.value), "modgrad": mg[:m].reshape(sh.value, sw.value),
+                 "region_sizes": rs[:n].copy()}
+
+
+def lbd(keyline, dx, dy):
+    kl = np.ascontiguousarray(np.asarray(keyline, KEYLINE_DTYPE).reshape(1))
+    dx = np.ascontiguousarray(dx, np.int16)
+    dy = np.ascontiguousarray(dy, np.int16)
+    des = np.empty(72, np.float32)
+    b = np.empty(32, np.uint8)
+    lib().plvio_lbd(_p(kl), _p(dx), _p(dy), dx.shape[1], dx.shape[0], _p(des), _p(b))
+    return des, b
+
+
+def line_extract(img, lsd_nfeatures=200, lsd_refine=0, lsd_scale=0.8, nlevels=2, scale=2.0):
+    """Lineextractor::operator() -> dict(keylines, descriptors, line_eq, raw_counts)."""
+    img = _u8(img)
+    h, w = img.shape
+    cap = 1 << 15
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    eq = np.zeros((cap, 3), np.float64)
+    raw = np.zeros(max(nlevels, 1), np.int32)
+    n = lib().plvio_line_extract(_p(img), w, h, img.strides[0], int(lsd_nfeatures), int(lsd_refine),
+                                 C.c_float(lsd_scale), int(nlevels), C.c_float(scale), _p(kl), _p(desc), _p(eq),
+                                 cap, _p(raw))
+    if n < 0:
+        raise RuntimeError(f"oracle line_extract failed: {n}")
+    return {"keylines": kl[:n].copy(), "descriptors": desc[:n].copy(), "line_eq": eq[:n].copy(), "raw_counts": raw}

@@ -1,0 +1,562 @@
+// TEST INFRASTRUCTURE (see oracle_common.h).  CPU restatement of the line path:
+//   Lineextractor::operator()            src/LineExtractor.cc:45-117
+//   LSDDetectorC::ComputePyramid/detect  Thirdparty/line_descriptor/src/LSDDetector_custom.cpp:76-138,254-362
+//   LineSegmentDetectorImpl (refine=0)   src/LSD/lsd.cpp:412-782,1136-1152
+//   BinaryDescriptor (LBD)               Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:76-118,219-261,351-413,540-688,1027-1373
+// and of the OpenCV primitives they call (f64 GaussianBlur/resize, pyrDown, Sobel,
+// LineIterator count).
+//
+// Floating-point conventions of this restatement (the reference build's exact choice of
+// float vs double libm overloads and FMA contraction is not knowable without building it):
+//   * every product/sum is rounded separately (no FMA contraction);
+//   * cos/sin/atan2 of float arguments are evaluated in double and rounded to float;
+//   * the f64 7x7 Gaussian uses row-sequential / column-symmetric summation, which
+//     reproduces cv2 4.13 to <= 1e-13 (cv2 itself is not reproducible to the bit here).
+#include <algorithm>
+#include <map>
+
+#include "oracle_common.h"
+
+namespace plvio {
+
+void resize_linear_u8(const u8* src, int sstride, int sw, int sh, u8* dst, int dstride, int dw, int dh);
+void gaussian_blur_u8(const u8* src, int sstride, int w, int h, u8* dst, int dstride, const int* k, int ksize);
+
+static const double kPi = 3.14159265358979323846;
+static const double NOTDEF = -1024.0;
+
+struct KeyLine {  // 68 bytes, descriptor_custom.hpp:107-146
+  float angle; int class_id; int octave; float pt_x, pt_y; float response; float size;
+  float startPointX, startPointY, endPointX, endPointY;
+  float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+  float lineLength; int numOfPixels;
+};
+
+// ---- OpenCV primitives ---------------------------------------------------------------
+// cv::getGaussianKernel(n, sigma, CV_64F).  OpenCV >= 4.x builds it with soft-float
+// arithmetic; for the reference's fixed LSD setting (n=7, sigma=0.6/(double)0.8f) the
+// values probed from cv2 4.13 are used verbatim, otherwise the defining formula.
+void gaussian_kernel_f64(int n, double sigma, double* k) {
+  const double s08 = 0.6 / (double)0.8f;
+  if (n == 7 && sigma == s08) {
+    static const uint64_t bits[7] = {0x3f276349157f1ab0ull, 0x3f8f1e22f611221dull, 0x3fcbfd7fa6a94f5aull,
+                                     0x3fe10562abd81f5full, 0x3fcbfd7fa6a94f5aull, 0x3f8f1e22f611221dull,
+                                     0x3f276349157f1ab0ull};
+    memcpy(k, bits, sizeof(bits));
+    return;
+  }
+  const double scale2X = -0.5 / (sigma * sigma);
+  double sum = 0;
+  for (int i = 0; i < n; i++) {
+    const double x = i - (n - 1) * 0.5;
+    k[i] = std::exp(scale2X * x * x);
+    sum += k[i];
+  }
+  sum = 1. / sum;
+  for (int i = 0; i < n; i++) k[i] *= sum;
+}
+
+// cv::GaussianBlur(CV_64F, ksize, sigma), BORDER_REFLECT_101 (src/LSD/lsd.cpp:455)
+void gaussian_blur_f64(const double* src, int w, int h, double* dst, const double* k, int ksize) {
+  const int r = ksize / 2;
+  std::vector<double> tmp((size_t)w * h);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      double s = k[0] * src[(size_t)y * w + reflect101(x - r, w)];
+      for (int i = 1; i < ksize; i++) s = s + k[i] * src[(size_t)y * w + reflect101(x - r + i, w)];
+      tmp[(size_t)y * w + x] = s;
+    }
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      double s = k[r] * tmp[(size_t)y * w + x];
+      for (int i = 1; i <= r; i++)
+        s = s + k[r + i] * (tmp[(size_t)reflect101(y + i, h) * w + x] + tmp[(size_t)reflect101(y - i, h) * w + x]);
+      dst[(size_t)y * w + x] = s;
+    }
+}
+
+// cv::resize(CV_64F, Size(), fx, fy, INTER_LINEAR): float32 weights applied in double,
+// horizontal then vertical (src/LSD/lsd.cpp:457)
+static void linear_coeffs_f(int ssize, int dsize, double inv_scale, std::vector<int>& ofs, std::vector<float>& a0,
+                            std::vector<float>& a1) {
+  ofs.resize(dsize); a0.resize(dsize); a1.resize(dsize);
+  const double scale = 1.0 / inv_scale;
+  for (int d = 0; d < dsize; d++) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = cv_floor(f);
+    f -= s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+    ofs[d] = s; a0[d] = 1.f - f; a1[d] = f;
+  }
+}
+
+void resize_linear_f64(const double* src, int sw, int sh, double* dst, int dw, int dh, double fx, double fy) {
+  std::vector<int> xo, yo;
+  std::vector<float> xa0, xa1, ya0, ya1;
+  linear_coeffs_f(sw, dw, fx, xo, xa0, xa1);
+  linear_coeffs_f(sh, dh, fy, yo, ya0, ya1);
+  for (int y = 0; y < dh; y++) {
+    const double* r0 = src + (size_t)yo[y] * sw;
+    const double* r1 = src + (size_t)std::min(yo[y] + 1, sh - 1) * sw;
+    for (int x = 0; x < dw; x++) {
+      const int s0 = xo[x], s1 = std::min(s0 + 1, sw - 1);
+      const double h0 = r0[s0] * xa0[x] + r0[s1] * xa1[x];
+      const double h1 = r1[s0] * xa0[x] + r1[s1] * xa1[x];
+      dst[(size_t)y * dw + x] = h0 * ya0[y] + h1 * ya1[y];
+    }
+  }
+}
+
+// cv::pyrDown(u8) to (w/2, h/2): [1,4,6,4,1]^2, (v+128)>>8, REFLECT_101
+void pyr_down_u8(const u8* src, int w, int h, u8* dst, int dw, int dh) {
+  static const int k[5] = {1, 4, 6, 4, 1};
+  for (int y = 0; y < dh; y++)
+    for (int x = 0; x < dw; x++) {
+      int s = 0;
+      for (int j = 0; j < 5; j++) {
+        const int sy = reflect101(2 * y + j - 2, h);
+        int rs = 0;
+        for (int i = 0; i < 5; i++) rs += k[i] * src[(size_t)sy * w + reflect101(2 * x + i - 2, w)];
+        s += k[j] * rs;
+      }
+      dst[(size_t)y * dw + x] = (u8)((s + 128) >> 8);
+    }
+}
+
+// cv::Sobel(u8 -> CV_16S, ksize 3), BORDER_REFLECT_101
+void sobel3_s16(const u8* src, int w, int h, short* dx, short* dy) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      int p[3][3];
+      for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) p[j][i] = src[(size_t)reflect101(y + j - 1, h) * w + reflect101(x + i - 1, w)];
+      dx[(size_t)y * w + x] = (short)((p[0][2] - p[0][0]) + 2 * (p[1][2] - p[1][0]) + (p[2][2] - p[2][0]));
+      dy[(size_t)y * w + x] = (short)((p[2][0] - p[0][0]) + 2 * (p[2][1] - p[0][1]) + (p[2][2] - p[0][2]));
+    }
+}
+
+static inline float cosf_d(float a) { return (float)std::cos((double)a); }
+static inline float sinf_d(float a) { return (float)std::sin((double)a); }
+
+// ---- LSD (src/LSD/lsd.cpp, refine = LSD_REFINE_NONE) -----------------------------------
+struct LsdImage {
+  int w, h;
+  std::vector<double> img, angles, modgrad;
+};
+
+// detect(): u8 -> f64, blur, scale (flsd :438-457), then ll_angle (:536-633)
+void lsd_prepare(const u8* src, int stride, int w, int h, double scale, double sigma_scale, double quant,
+                 double ang_th, LsdImage& L) {
+  std::vector<double> image((size_t)w * h);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) image[(size_t)y * w + x] = src[(size_t)y * stride + x];
+  const double prec = kPi * ang_th / 180;
+  const double rho = quant / std::sin(prec);
+  if (scale != 1) {
+    const double sigma = (scale < 1) ? (sigma_scale / scale) : sigma_scale;
+    const unsigned int hk = (unsigned int)(std::ceil(sigma * std::sqrt(2 * 3.0 * std::log(10.0))));
+    const int ksize = 1 + 2 * hk;
+    std::vector<double> k(ksize), g((size_t)w * h);
+    gaussian_kernel_f64(ksize, sigma, k.data());
+    gaussian_blur_f64(image.data(), w, h, g.data(), k.data(), ksize);
+    L.w = cv_round(w * scale);
+    L.h = cv_round(h * scale);
+    L.img.resize((size_t)L.w * L.h);
+    resize_linear_f64(g.data(), w, h, L.img.data(), L.w, L.h, scale, scale);
+  } else {
+    L.w = w; L.h = h; L.img = image;
+  }
+  const int W = L.w, H = L.h;
+  L.angles.assign((size_t)W * H, NOTDEF);
+  L.modgrad.assign((size_t)W * H, 0.0);
+  const double DEG_TO_RADS = kPi / 180;
+  for (int y = 0; y < H - 1; ++y)
+    for (int x = 0; x < W - 1; ++x) {
+      const size_t a = (size_t)y * W + x;
+      const double DA = L.img[a + W + 1] - L.img[a];
+      const double BC = L.img[a + 1] - L.img[a + W];
+      const double gx = DA + BC, gy = DA - BC;
+      const double norm = std::sqrt((gx * gx + gy * gy) / 4);
+      L.modgrad[a] = norm;
+      if (norm <= rho) L.angles[a] = NOTDEF;
+      else L.angles[a] = fast_atan2((float)gx, (float)-gy) * DEG_TO_RADS;
+    }
+}
+
+static inline bool is_aligned(double a, double theta, double prec) {
+  if (a == NOTDEF) return false;
+  double n_theta = theta - a;
+  if (n_theta < 0) n_theta = -n_theta;
+  if (n_theta > (3 * kPi) / 2) {
+    n_theta -= (2 * kPi);
+    if (n_theta < 0) n_theta = -n_theta;
+  }
+  return n_theta <= prec;
+}
+
+static inline double angle_diff(double a, double b) {
+  double diff = a - b;
+  while (diff <= -kPi) diff += 2 * kPi;
+  while (diff > kPi) diff -= 2 * kPi;
+  return std::fabs(diff);
+}
+
+struct RegPt { int x, y; };
+
+// flsd (:438-534): seeds in raster order over the interior (the vendored code walks the
+// coordinate vector, not the gradient-sorted list); returns Vec4f segments.
+void lsd_detect(const LsdImage& L, double scale, double ang_th, std::vector<float>& lines,
+                std::vector<int>* region_sizes) {
+  const int W = L.w, H = L.h;
+  const double prec = kPi * ang_th / 180;
+  const double p = ang_th / 180;
+  const double DEG_TO_RADS = kPi / 180;
+  const double LOG_NT = 5 * (std::log10((double)W) + std::log10((double)H)) / 2 + std::log10(11.0);
+  const int min_reg_size = (int)(-LOG_NT / std::log10(p));
+  std::vector<u8> used((size_t)W * H, 0);
+  std::vector<RegPt> reg((size_t)W * H);
+  lines.clear();
+  for (int sy = 0; sy < H - 1; sy++)
+    for (int sx = 0; sx < W - 1; sx++) {
+      const size_t adx = (size_t)sy * W + sx;
+      if (used[adx] || L.angles[adx] == NOTDEF) continue;
+      // region_grow (:635-686)
+      int reg_size = 1;
+      reg[0] = {sx, sy};
+      double reg_angle = L.angles[adx];
+      float sumdx = (float)std::cos(reg_angle), sumdy = (float)std::sin(reg_angle);
+      used[adx] = 1;
+      for (int i = 0; i < reg_size; ++i) {
+        const RegPt rp = reg[i];
+        const int xx_min = std::max(rp.x - 1, 0), xx_max = std::min(rp.x + 1, W - 1);
+        const int yy_min = std::max(rp.y - 1, 0), yy_max = std::min(rp.y + 1, H - 1);
+        for (int yy = yy_min; yy <= yy_max; ++yy)
+          for (int xx = xx_min; xx <= xx_max; ++xx) {
+            const size_t c = (size_t)yy * W + xx;
+            if (!used[c] && is_aligned(L.angles[c], reg_angle, prec)) {
+              used[c] = 1;
+              reg[reg_size++] = {xx, yy};
+              const double angle = L.angles[c];
+              sumdx += cosf_d((float)angle);
+              sumdy += sinf_d((float)angle);
+              reg_angle = fast_atan2(sumdy, sumdx) * DEG_TO_RADS;
+            }
+          }
+      }
+      if (reg_size < min_reg_size) continue;
+      if (region_sizes) region_sizes->push_back(reg_size);
+      // region2rect (:688-744)
+      double x = 0, y = 0, sum = 0;
+      for (int i = 0; i < reg_size; ++i) {
+        const double wgt = L.modgrad[(size_t)reg[i].y * W + reg[i].x];
+        x += (double)reg[i].x * wgt;
+        y += (double)reg[i].y * wgt;
+        sum += wgt;
+      }
+      x /= sum;
+      y /= sum;
+      // get_theta (:746-782)
+      double Ixx = 0, Iyy = 0, Ixy = 0;
+      for (int i = 0; i < reg_size; ++i) {
+        const double wgt = L.modgrad[(size_t)reg[i].y * W + reg[i].x];
+        const double dx = (double)reg[i].x - x, dy = (double)reg[i].y - y;
+        Ixx += dy * dy * wgt;
+        Iyy += dx * dx * wgt;
+        Ixy -= dx * dy * wgt;
+      }
+      const double lambda = 0.5 * (Ixx + Iyy - std::sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+      double theta = (std::fabs(Ixx) > std::fabs(Iyy)) ? (double)fast_atan2((float)(lambda - Ixx), (float)Ixy)
+                                                        : (double)fast_atan2((float)Ixy, (float)(lambda - Iyy));
+      theta *= DEG_TO_RADS;
+      if (angle_diff(theta, reg_angle) > prec) theta += kPi;
+      const double dx = std::cos(theta), dy = std::sin(theta);
+      double l_min = 0, l_max = 0;
+      for (int i = 0; i < reg_size; ++i) {
+        const double rdx = (double)reg[i].x - x, rdy = (double)reg[i].y - y;
+        const double l = rdx * dx + rdy * dy;
+        if (l > l_max) l_max = l;
+        else if (l < l_min) l_min = l;
+      }
+      double x1 = x + l_min * dx, y1 = y + l_min * dy, x2 = x + l_max * dx, y2 = y + l_max * dy;
+      x1 += 0.5; y1 += 0.5; x2 += 0.5; y2 += 0.5;
+      if (scale != 1) { x1 /= scale; y1 /= scale; x2 /= scale; y2 /= scale; }
+      lines.push_back((float)x1); lines.push_back((float)y1); lines.push_back((float)x2); lines.push_back((float)y2);
+    }
+}
+
+// ---- LSDDetectorC::detectImpl KeyLine assembly (LSDDetector_custom.cpp:304-346) -------
+static void make_keylines(const std::vector<float>& seg, int octave, int ow, int oh, float lineScale,
+                          double min_length, int& class_counter, std::vector<KeyLine>& out) {
+  const float octaveScale = (float)std::pow((double)lineScale, (double)octave);
+  for (size_t k = 0; k + 3 < seg.size(); k += 4) {
+    float e[4] = {seg[k], seg[k + 1], seg[k + 2], seg[k + 3]};
+    if (e[0] < 0) e[0] = 0;
+    if (e[0] >= ow) e[0] = (float)ow - 1.0f;
+    if (e[2] < 0) e[2] = 0;
+    if (e[2] >= ow) e[2] = (float)ow - 1.0f;
+    if (e[1] < 0) e[1] = 0;
+    if (e[1] >= oh) e[1] = (float)oh - 1.0f;
+    if (e[3] < 0) e[3] = 0;
+    if (e[3] >= oh) e[3] = (float)oh - 1.0f;
+    const float ddx = e[0] - e[2], ddy = e[1] - e[3];
+    const double length = (float)std::sqrt((double)ddx * ddx + (double)ddy * ddy);
+    if (!(length > min_length)) continue;
+    KeyLine kl;
+    kl.startPointX = e[0] * octaveScale; kl.startPointY = e[1] * octaveScale;
+    kl.endPointX = e[2] * octaveScale; kl.endPointY = e[3] * octaveScale;
+    kl.sPointInOctaveX = e[0]; kl.sPointInOctaveY = e[1];
+    kl.ePointInOctaveX = e[2]; kl.ePointInOctaveY = e[3];
+    kl.lineLength = (float)length;
+    // cv::LineIterator(img, Point(pt1), Point(pt2)).count, 8-connected, endpoints inside
+    const int ax = cv_roundf(e[0]), ay = cv_roundf(e[1]), bx = cv_roundf(e[2]), by = cv_roundf(e[3]);
+    kl.numOfPixels = std::max(std::abs(bx - ax), std::abs(by - ay)) + 1;
+    kl.angle = (float)std::atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
+    kl.class_id = ++class_counter;
+    kl.octave = octave;
+    kl.size = (kl.endPointX - kl.startPointX) * (kl.endPointY - kl.startPointY);
+    kl.response = kl.lineLength / (float)std::max(ow, oh);
+    kl.pt_x = (kl.endPointX + kl.startPointX) / 2;
+    kl.pt_y = (kl.endPointY + kl.startPointY) / 2;
+    out.push_back(kl);
+  }
+}
+
+// ---- LBD -----------------------------------------------------------------------------
+static const int kComb[32][2] = {{0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6},
+                                 {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7}, {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8},
+                                 {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
+
+struct LbdWeights {
+  double L[21], G[63];
+  LbdWeights() {  // BinaryDescriptor ctor (:219-261); note the integer divisions
+    double u = (7 * 3 - 1) / 2;
+    double sigma = (7 * 2 + 1) / 2;
+    double inv = -1 / (2 * sigma * sigma);
+    for (int i = 0; i < 21; i++) { const double d = i - u; L[i] = std::exp(d * d * inv); }
+    u = (9 * 7 - 1) / 2;
+    sigma = u;
+    inv = -1 / (2 * sigma * sigma);
+    for (int i = 0; i < 63; i++) { const double d = i - u; G[i] = std::exp(d * d * inv); }
+  }
+};
+
+// computeLBD for one line (:1027-1373) + binary packing (:402-413,663-667)
+void lbd_descriptor(const KeyLine& kl, const short* dxImg, const short* dyImg, int realWidth, int realHeight,
+                    float* desVec /*72*/, u8* bin /*32*/) {
+  static const LbdWeights Wt;
+  const short heightOfLSP = 63, halfHeight = 31;
+  const short imageWidth = (short)(realWidth - 1), imageHeight = (short)(realHeight - 1);
+  float band[8][9];
+  memset(band, 0, sizeof(band));
+  const short lengthOfLSP = (short)kl.numOfPixels;
+  const short halfWidth = (short)((lengthOfLSP - 1) / 2);
+  const float midX = (float)(0.5 * (kl.sPointInOctaveX + kl.ePointInOctaveX));
+  const float midY = (float)(0.5 * (kl.sPointInOctaveY + kl.ePointInOctaveY));
+  const float dL0 = cosf_d(kl.angle), dL1 = sinf_d(kl.angle);
+  const float dO0 = -dL1, dO1 = dL0;
+  float t1 = -dL0 * halfWidth, t2 = dL1 * halfHeight;
+  float sCorX0 = (t1 + t2) + midX;
+  t1 = -dL1 * halfWidth; t2 = dL0 * halfHeight;
+  float sCorY0 = (t1 - t2) + midY;
+  for (short hID = 0; hID < heightOfLSP; hID++) {
+    float sCorX = sCorX0, sCorY = sCorY0;
+    float pL = 0, nL = 0, pO = 0, nO = 0;
+    for (short wID = 0; wID < lengthOfLSP; wID++) {
+      short tc = (short)std::round(sCorX);
+      const short xCor = (tc < 0) ? 0 : (tc > imageWidth) ? imageWidth : tc;
+      tc = (short)std::round(sCorY);
+      const short yCor = (tc < 0) ? 0 : (tc > imageHeight) ? imageHeight : tc;
+      const short dx = dxImg[yCor * realWidth + xCor], dy = dyImg[yCor * realWidth + xCor];
+      float a = dx * dL0, b = dy * dL1;
+      const float gDL = a + b;
+      a = dx * dO0; b = dy * dO1;
+      const float gDO = a + b;
+      if (gDL > 0) pL += gDL; else nL -= gDL;
+      if (gDO > 0) pO += gDO; else nO -= gDO;
+      sCorX += dL0;
+      sCorY += dL1;
+    }
+    sCorX0 -= dL1;
+    sCorY0 += dL0;
+    float c = (float)Wt.G[hID];
+    pL = c * pL; nL = c * nL;
+    const float pL2 = pL * pL, nL2 = nL * nL;
+    pO = c * pO; nO = c * nO;
+    const float pO2 = pO * pO, nO2 = nO * nO;
+    const float rs[8] = {pL, nL, pL2, nL2, pO, nO, pO2, nO2};
+    auto add = [&](int b, float cf) {
+      for (int q = 0; q < 8; q++) {
+        const bool sq = (q == 2 || q == 3 || q == 6 || q == 7);
+        const float term = sq ? (cf * cf) * rs[q] : cf * rs[q];
+        band[q][b] += term;
+      }
+    };
+    short bandID = (short)(hID / 7);
+    add(bandID, (float)Wt.L[hID % 7 + 7]);
+    bandID--;
+    if (bandID >= 0) add(bandID, (float)Wt.L[hID % 7 + 14]);
+    bandID = bandID + 2;
+    if (bandID < 9) add(bandID, (float)Wt.L[hID % 7]);
+  }
+  const float invN2 = (float)(1.0 / (7 * 2.0)), invN3 = (float)(1.0 / (7 * 3.0));
+  for (int b = 0; b < 9; b++) {
+    const float invN = (b == 0 || b == 8) ? invN2 : invN3;
+    const int d = b * 8;
+    float temp, m2, tt;
+    temp = band[0][b] * invN; desVec[d] = temp; m2 = band[2][b] * invN; tt = temp * temp; desVec[d + 4] = std::sqrt(m2 - tt);
+    temp = band[1][b] * invN; desVec[d + 1] = temp; m2 = band[3][b] * invN; tt = temp * temp; desVec[d + 5] = std::sqrt(m2 - tt);
+    temp = band[4][b] * invN; desVec[d + 2] = temp; m2 = band[6][b] * invN; tt = temp * temp; desVec[d + 6] = std::sqrt(m2 - tt);
+    temp = band[5][b] * invN; desVec[d + 3] = temp; m2 = band[7][b] * invN; tt = temp * temp; desVec[d + 7] = std::sqrt(m2 - tt);
+  }
+  float tempM = 0, tempS = 0;
+  for (int b = 0; b < 9; b++) {
+    const float* v = desVec + 8 * b;
+    for (int j = 0; j < 4; j++) { const float s = v[j] * v[j]; tempM += s; }
+    for (int j = 4; j < 8; j++) { const float s = v[j] * v[j]; tempS += s; }
+  }
+  tempM = 1 / std::sqrt(tempM);
+  tempS = 1 / std::sqrt(tempS);
+  for (int b = 0; b < 9; b++) {
+    float* v = desVec + 8 * b;
+    for (int j = 0; j < 4; j++) v[j] = v[j] * tempM;
+    for (int j = 4; j < 8; j++) v[j] = v[j] * tempS;
+  }
+  for (int i = 0; i < 72; i++)
+    if ((double)desVec[i] > 0.4) desVec[i] = (float)0.4;
+  float temp = 0;
+  for (int i = 0; i < 72; i++) { const float s = desVec[i] * desVec[i]; temp += s; }
+  temp = 1 / std::sqrt(temp);
+  for (int i = 0; i < 72; i++) desVec[i] = desVec[i] * temp;
+  for (int c = 0; c < 32; c++) {
+    const float* f1 = desVec + 8 * kComb[c][0];
+    const float* f2 = desVec + 8 * kComb[c][1];
+    u8 r = 0;
+    for (int i = 0; i < 8; i++)
+      if (f1[i] > f2[i]) r += (u8)(1 << i);
+    bin[c] = r;
+  }
+}
+
+}  // namespace plvio
+
+using namespace plvio;
+
+extern "C" {
+
+void plvio_gaussian_kernel_f64(int n, double sigma, double* k) { gaussian_kernel_f64(n, sigma, k); }
+void plvio_gaussian_blur_f64(const double* src, int w, int h, double* dst, const double* k, int ksize) {
+  gaussian_blur_f64(src, w, h, dst, k, ksize);
+}
+void plvio_resize_linear_f64(const double* src, int sw, int sh, double* dst, int dw, int dh, double fx, double fy) {
+  resize_linear_f64(src, sw, sh, dst, dw, dh, fx, fy);
+}
+void plvio_pyr_down_u8(const u8* src, int w, int h, u8* dst, int dw, int dh) { pyr_down_u8(src, w, h, dst, dw, dh); }
+void plvio_sobel3_s16(const u8* src, int w, int h, short* dx, short* dy) { sobel3_s16(src, w, h, dx, dy); }
+
+// LSD on one u8 octave image.  Outputs (optional): scaled f64 image, angles, modgrad of
+// size *sw x *sh; segments as x1,y1,x2,y2 floats (cap = max segments).  Returns count.
+int plvio_lsd(const u8* img, int stride, int w, int h, float lsd_scale, int* sw, int* sh, double* scaled,
+              double* angles, double* modgrad, float* segs, int cap, int* region_sizes) {
+  LsdImage L;
+  lsd_prepare(img, stride, w, h, (double)lsd_scale, 0.6, 2.0, 22.5, L);
+  if (sw) *sw = L.w;
+  if (sh) *sh = L.h;
+  const size_t n = (size_t)L.w * L.h;
+  if (scaled) memcpy(scaled, L.img.data(), n * sizeof(double));
+  if (angles) memcpy(angles, L.angles.data(), n * sizeof(double));
+  if (modgrad) memcpy(modgrad, L.modgrad.data(), n * sizeof(double));
+  std::vector<float> lines;
+  std::vector<int> rs;
+  lsd_detect(L, (double)lsd_scale, 22.5, lines, &rs);
+  const int m = (int)(lines.size() / 4);
+  for (int i = 0; i < std::min(m, cap) * 4; i++) segs[i] = lines[i];
+  if (region_sizes) for (int i = 0; i < std::min(m, cap); i++) region_sizes[i] = rs[i];
+  return m;
+}
+
+void plvio_lbd(const plvio::KeyLine* kl, const short* dx, const short* dy, int w, int h, float* des72, u8* bin32) {
+  lbd_descriptor(*kl, dx, dy, w, h, des72, bin32);
+}
+
+// Lineextractor::operator() (LSD branch).  keylines/desc/lineeq caller-allocated with
+// capacity cap (lineeq: 3 doubles per line).  Returns number of lines (0: descriptors
+// untouched, like the reference).  Optional debug: raw per-octave segment counts.
+int plvio_line_extract(const u8* img, int w, int h, int stride, int lsd_nfeatures, int lsd_refine,
+                       float lsd_scale, int nlevels, float scale, plvio::KeyLine* keylines, u8* desc,
+                       double* lineeq, int cap, int* raw_counts) {
+  (void)lsd_refine;  // only LSD_REFINE_NONE is restated (all shipped yaml files use 0)
+  if (nlevels < 1 || nlevels > 2) return -1;
+  // LSDDetectorC::ComputePyramid (:76-109)
+  std::vector<std::vector<u8>> pyr(nlevels);
+  std::vector<int> pw(nlevels), ph(nlevels);
+  std::vector<float> sf(nlevels, 1.0f), isf(nlevels, 1.0f);
+  for (int l = 0; l < nlevels; l++) {
+    if (l > 0) sf[l] = sf[l - 1] * scale;
+    isf[l] = 1.0f / sf[l];
+    pw[l] = cv_roundf((float)w * isf[l]);
+    ph[l] = cv_roundf((float)h * isf[l]);
+    pyr[l].resize((size_t)pw[l] * ph[l]);
+    if (l == 0) for (int y = 0; y < h; y++) memcpy(&pyr[0][(size_t)y * w], img + (size_t)y * stride, w);
+    else resize_linear_u8(pyr[l - 1].data(), pw[l - 1], pw[l - 1], ph[l - 1], pyr[l].data(), pw[l], pw[l], ph[l]);
+  }
+  const double min_length = 0.025 * (std::min(w, h));
+  std::vector<KeyLine> kls;
+  int class_counter = -1;
+  for (int l = 0; l < nlevels; l++) {
+    LsdImage L;
+    lsd_prepare(pyr[l].data(), pw[l], pw[l], ph[l], (double)lsd_scale, 0.6, 2.0, 22.5, L);
+    std::vector<float> lines;
+    lsd_detect(L, (double)lsd_scale, 22.5, lines, nullptr);
+    if (raw_counts) raw_counts[l] = (int)(lines.size() / 4);
+    make_keylines(lines, l, pw[l], ph[l], scale, min_length, class_counter, kls);
+  }
+  // top-N by response (src/LineExtractor.cc:75-84).  std::sort there is unstable; this
+  // oracle DEFINES ties as "earlier detection first" (stable).
+  if ((int)kls.size() > lsd_nfeatures && lsd_nfeatures != 0) {
+    std::stable_sort(kls.begin(), kls.end(), [](const KeyLine& a, const KeyLine& b) { return a.response > b.response; });
+    kls.resize(lsd_nfeatures);
+    for (int i = 0; i < lsd_nfeatures; i++) kls[i].class_id = i;
+  }
+  const int n = (int)kls.size();
+  if (n > cap) return -2;
+  if (n == 0) return 0;
+  // BinaryDescriptor::computeSobel (:374-399) on its own pyramid (:351-371)
+  int maxOct = 0;
+  for (auto& k : kls) maxOct = std::max(maxOct, k.octave);
+  std::vector<std::vector<short>> dxs(maxOct + 1), dys(maxOct + 1);
+  std::vector<int> ow(maxOct + 1), oh(maxOct + 1);
+  std::vector<u8> cur((size_t)w * h), tmp;
+  {
+    std::vector<u8> dense((size_t)w * h);
+    for (int y = 0; y < h; y++) memcpy(&dense[(size_t)y * w], img + (size_t)y * stride, w);
+    static const int k5[5] = {14, 62, 104, 62, 14};
+    gaussian_blur_u8(dense.data(), w, w, h, cur.data(), w, k5, 5);
+  }
+  ow[0] = w; oh[0] = h;
+  for (int o = 0; o <= maxOct; o++) {
+    if (o > 0) {
+      ow[o] = ow[o - 1] / 2; oh[o] = oh[o - 1] / 2;
+      tmp.resize((size_t)ow[o] * oh[o]);
+      pyr_down_u8(cur.data(), ow[o - 1], oh[o - 1], tmp.data(), ow[o], oh[o]);
+      cur.swap(tmp);
+    }
+    dxs[o].resize((size_t)ow[o] * oh[o]);
+    dys[o].resize((size_t)ow[o] * oh[o]);
+    sobel3_s16(cur.data(), ow[o], oh[o], dxs[o].data(), dys[o].data());
+  }
+  for (int i = 0; i < n; i++) {
+    float des[72];
+    const int o = kls[i].octave;
+    lbd_descriptor(kls[i], dxs[o].data(), dys[o].data(), ow[o], oh[o], des, desc + (size_t)i * 32);
+    keylines[i] = kls[i];
+    // line equation (src/LineExtractor.cc:106-116): l = sp x ep, normalised by |(l0,l1)|
+    const double sx = kls[i].startPointX, sy = kls[i].startPointY, ex = kls[i].endPointX, ey = kls[i].endPointY;
+    double l0 = sy * 1.0 - 1.0 * ey, l1 = 1.0 * ex - sx * 1.0, l2 = sx * ey - sy * ex;
+    const double nrm = std::sqrt(l0 * l0 + l1 * l1);
+    lineeq[3 * i] = l0 / nrm; lineeq[3 * i + 1] = l1 / nrm; lineeq[3 * i + 2] = l2 / nrm;
+  }
+  return n;
+}
+
+}  // extern "C"
