@@ -127,6 +127,54 @@ int plvi_orb_read_candidates(plvi_orb* h, int frame, int level, uint32_t* out, i
 /* number of kernel launches enqueued by the last extract call */
 int plvi_orb_last_launches(const plvi_orb* h);
 
+/* ---------------------------------------------------------------- lines ---- */
+typedef struct plvi_line plvi_line;
+
+/* Lineextractor::Lineextractor(lsd_nfeatures, lsd_refine, lsd_scale, nlevels, scale, extractor)
+ * (include/LineExtractor.h:55, src/LineExtractor.cc:39-43).  Implemented: extractor = 0
+ * (LSD), lsd_refine = 0, nlevels 1 or 2, scale = 2.0 -- every configuration the
+ * reference ships; anything else returns PLVI_ERR_INVALID.  lsd_nfeatures = 0 keeps all
+ * lines (capacity 4096 per frame). */
+int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float lsd_scale, int nlevels,
+                     float scale, int extractor, int max_width, int max_height, int max_batch,
+                     int device, void* stream);
+void plvi_line_destroy(plvi_line* h);
+/* rows per frame in keylines / desc / line_eq */
+int plvi_line_capacity(const plvi_line* h);
+int plvi_line_levels(const plvi_line* h);
+void* plvi_line_stream(const plvi_line* h);
+int plvi_line_last_launches(const plvi_line* h);
+/* mvScaleFactor_l / mvInvScaleFactor_l / mvLevelSigma2_l / mvInvLevelSigma2_l
+ * (src/LineExtractor.cc:86-101) */
+int plvi_line_scale_factors(const plvi_line* h, float* scale, float* inv_scale, float* sigma2,
+                            float* inv_sigma2);
+/* octave image sizes (LSDDetectorC::ComputePyramid) and LSD working sizes after lsd_scale */
+int plvi_line_octave_sizes(const plvi_line* h, int w, int h_, int* ow, int* oh, int* sw, int* sh);
+
+/* void Lineextractor::operator()(image, mask, keylines, descriptors_line, keylineFunction)
+ * (include/LineExtractor.h:59-61, src/LineExtractor.cc:45-117) over n equally sized
+ * CV_8UC1 host frames.  Outputs (host): keylines[n][cap], desc[n][cap][32],
+ * line_eq[n][cap][3] (normalised homogeneous line sp x ep, f64), counts[n]
+ * (PLVI_ERR_CAPACITY in counts[i] if frame i overflowed the internal segment table).
+ * A frame with no lines leaves its descriptor rows untouched, like the reference. */
+int plvi_line_extract_batch(plvi_line* h, const uint8_t* imgs, int n, int w, int h_, int stride,
+                            size_t frame_stride, plvi_keyline* keylines, uint8_t* desc,
+                            double* line_eq, int* counts);
+int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int w, int h_, int stride,
+                                  size_t frame_stride, plvi_keyline* keylines, uint8_t* desc,
+                                  double* line_eq, int* counts);
+int plvi_line_sync(plvi_line* h);
+/* all buffers in device memory; enqueued on the handle's stream */
+int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, int w, int h_,
+                                   int stride, size_t frame_stride, plvi_keyline* d_keylines,
+                                   uint8_t* d_desc, double* d_line_eq, int* d_counts);
+/* Read-back of LSD internals of the last batch (parity tests).  what: 0 scaled f64 image
+ * (after plvi_line_set_debug(h,1)), 1 level-line angle in degrees f32 (-1024 = NOTDEF),
+ * 2 gradient magnitude f64, 3 raw segments (x1,y1,x2,y2 f32; *count = number),
+ * 4 pyramid octave image u8 (gaussianPyrs[octave]). */
+int plvi_line_set_debug(plvi_line* h, int on);
+int plvi_line_read_lsd(plvi_line* h, int frame, int octave, int what, void* out, int cap, int* count);
+
 /* ------------------------------------------------------- Hamming searches ---- */
 typedef struct plvi_matcher plvi_matcher;
 

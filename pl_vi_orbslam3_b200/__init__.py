@@ -9,3 +9,4 @@ built library raises.
 from .capi import lib, PlviError, KEYPOINT_DTYPE, KEYLINE_DTYPE  # noqa: F401
 from .orbextractor import ORBextractor  # noqa: F401
 from .matchers import ORBmatcher, LineMatcher, FrameView, frame_grid  # noqa: F401
+from .lineextractor import Lineextractor  # noqa: F401

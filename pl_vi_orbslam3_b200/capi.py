@@ -49,6 +49,20 @@ _SIGS = {
     "plvi_orb_read_level": (ci, [vp, ci, ci, ci, vp]),
     "plvi_orb_read_candidates": (ci, [vp, ci, ci, vp, ci, vp]),
     "plvi_orb_last_launches": (ci, [vp]),
+    "plvi_line_create": (ci, [C.POINTER(vp), ci, ci, cf, ci, cf, ci, ci, ci, ci, ci, vp]),
+    "plvi_line_destroy": (None, [vp]),
+    "plvi_line_capacity": (ci, [vp]),
+    "plvi_line_levels": (ci, [vp]),
+    "plvi_line_stream": (vp, [vp]),
+    "plvi_line_last_launches": (ci, [vp]),
+    "plvi_line_scale_factors": (ci, [vp, vp, vp, vp, vp]),
+    "plvi_line_octave_sizes": (ci, [vp, ci, ci, vp, vp, vp, vp]),
+    "plvi_line_extract_batch": (ci, [vp, vp, ci, ci, ci, ci, sz, vp, vp, vp, vp]),
+    "plvi_line_extract_batch_async": (ci, [vp, vp, ci, ci, ci, ci, sz, vp, vp, vp, vp]),
+    "plvi_line_sync": (ci, [vp]),
+    "plvi_line_extract_batch_device": (ci, [vp, vp, ci, ci, ci, ci, sz, vp, vp, vp, vp]),
+    "plvi_line_set_debug": (ci, [vp, ci]),
+    "plvi_line_read_lsd": (ci, [vp, ci, ci, ci, vp, ci, vp]),
     "plvi_matcher_create": (ci, [C.POINTER(vp), ci, ci, ci, ci, vp]),
     "plvi_matcher_destroy": (None, [vp]),
     "plvi_matcher_stream": (vp, [vp]),

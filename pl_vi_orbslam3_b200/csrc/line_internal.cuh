@@ -1,0 +1,68 @@
+// Geometry / buffer tables of the line pipeline (shared by line_kernels.cu and plvi_line_capi.cu).
+#pragma once
+#include "plvi_internal.cuh"
+
+namespace plvi {
+
+struct LineOct {
+  int w, h, pitch;     // LSD pyramid octave image (u8)
+  int sw, sh;          // LSD working size after lsd_scale (flsd: resize(gaussian_img, scaled_image, Size(), SCALE, SCALE))
+  int wpr;             // "available" bitmap words per row
+  int minRegSize;      // int(-LOG_NT / log10(p)), src/LSD/lsd.cpp:466-467
+  size_t pxOff;        // offset of this octave in per-frame scaled-pixel arrays
+  size_t rawOff;       // offset in the per-frame row-filtered f64 array
+  int bmOff;           // offset (words) in the per-frame bitmap array
+  int segOff, segCap;  // raw segment slots of this octave per frame
+  int xtabOff, ytabOff;
+  int lw, lh, lpitch;  // LBD octave image (w >> o, h >> o)
+  size_t lbdOff;       // offset in the per-frame gradient array
+};
+
+struct LineGeom {
+  int noct;
+  LineOct o[2];
+  size_t pxTotal, rawTotal, lbdTotal;
+  int bmTotal, segTotal;
+  double rho, prec, lsdScale, minLength;
+  double kern[7];
+  float lineScale;
+  int nfeat, keepCap;
+};
+
+struct LineTab { int ofs; float a0, a1; };       // f64 bilinear taps (float32 weights)
+struct LineRegion { int start, size; double angle; };
+
+struct LinePtrs {
+  const u8* img[2];
+  int ipitch[2];
+  size_t ifs[2];
+};
+
+struct LineBufs {
+  double* rowf;          // [B][rawTotal]
+  float* ang;            // [B][pxTotal]   gradient angle, degrees, -1024 = NOTDEF
+  float4* cs;            // [B][pxTotal]   cos/sin of float(angle) | cos/sin of angle (seed)
+  double* mod;           // [B][pxTotal]   gradient magnitude
+  unsigned* bitmap;      // [B][bmTotal]   angle defined & not used
+  unsigned* reg;         // [B][pxTotal]   region pixel lists (x | y << 16)
+  LineRegion* regTab;    // [B][segTotal]
+  int* regCount;         // [B][2]  (-1: segment table overflow)
+  float4* segs;          // [B][segTotal]
+  float* tmpResp;        // [B][segTotal]
+  int* tmpCls;           // [B][segTotal]
+  u8* lbdImg0; u8* lbdImg1;
+  short2* grad;          // [B][lbdTotal] Sobel (dx, dy)
+  const LineTab* tabs;
+  const int2* rsTab;     // u8 bilinear table for pyramid level 1 (x rows then y rows)
+  const double* lbdG;    // [63] gaussCoefG_
+  const double* lbdL;    // [21] gaussCoefL_
+  double* scaledDbg;     // [B][pxTotal] or nullptr
+};
+
+int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b, int n, plvi_keyline* dKl,
+                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, int* launches);
+int line_kernel_attrs(const LineGeom& g);
+void launch_resize_u8(const u8* src, int spitch, size_t sfs, int sw, int sh, u8* dst, int dpitch, size_t dfs, int dw,
+                      int dh, const int2* xtab, const int2* ytab, int n, cudaStream_t st);
+
+}  // namespace plvi

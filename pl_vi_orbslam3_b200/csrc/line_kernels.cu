@@ -1,0 +1,753 @@
+// Line feature kernels for sm_100a: LSD (refine 0) + KeyLine assembly + LBD.
+//
+//   k_lsd_rowfilter   u8 -> f64 horizontal 7-tap Gaussian         src/LSD/lsd.cpp:415-455
+//   k_lsd_scale_grad  vertical Gaussian + 0.8x bilinear (f64) +
+//                     ll_angle gradient/angle/"available" bitmap   src/LSD/lsd.cpp:457,536-585
+//   k_lsd_grow        seed scan (raster order) + region_grow       src/LSD/lsd.cpp:476-487,635-686,1136-1152
+//   k_lsd_rect        region2rect + get_theta                      src/LSD/lsd.cpp:688-782, 506-521
+//   k_line_assemble   LSDDetectorC::detectImpl KeyLine fields,     LSDDetector_custom.cpp:304-346
+//                     top-N by response                            src/LineExtractor.cc:75-84
+//   k_gauss5 / k_pyrdown / k_sobel   LBD pyramid + Sobel           binary_descriptor_custom.cpp:351-399
+//   k_lbd             computeLBD + binary packing + line equation  binary_descriptor_custom.cpp:1027-1373,402-413,663-667;
+//                                                                  src/LineExtractor.cc:106-116
+//
+// Region growing is sequential by construction (raster-order seeds coupled through the
+// `used` marks, a float running mean angle updated after every accepted pixel), so one
+// warp owns one (frame, octave): the "available" bitmap lives in shared memory, the 3x3
+// neighbourhoods of up to three queued pixels are fetched by 27 lanes at once, and only
+// the accept/update chain is serial.  Parallelism comes from frames x octaves.
+// All f64/f32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction)
+// so results follow oracle/oracle_line.cpp operation by operation.
+#include "plvi_internal.cuh"
+#include "line_internal.cuh"
+
+namespace plvi {
+
+__device__ __forceinline__ int reflect101_l(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+  return p;
+}
+
+__device__ __forceinline__ float fast_atan2_dev(float y, float x) {
+  const float sc = 57.29577951308232f;
+  const float p1 = __fmul_rn(0.9997878412794807f, sc), p3 = __fmul_rn(-0.3258083974640975f, sc);
+  const float p5 = __fmul_rn(0.1555786518463281f, sc), p7 = __fmul_rn(-0.04432655554792128f, sc);
+  const float eps = 2.220446049250313e-16f;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+#define D2R 0.017453292519943295  // CV_PI / 180
+#define PI_D 3.14159265358979323846
+
+// ---------------------------------------------------------------------------------------
+// k_lsd_rowfilter: f64 row pass of cv::GaussianBlur (sequential tap order), REFLECT_101.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lsd_rowfilter(const u8* __restrict__ src, int spitch, size_t sfs, int w,
+                                                       int h, double* __restrict__ dst, size_t dfs,
+                                                       const __grid_constant__ LineGeom g) {
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= w || y >= h) return;
+  const u8* row = src + (size_t)blockIdx.z * sfs + (size_t)y * spitch;
+  double s = __dmul_rn(g.kern[0], (double)__ldg(row + reflect101_l(x - 3, w)));
+#pragma unroll
+  for (int i = 1; i < 7; i++)
+    s = __dadd_rn(s, __dmul_rn(g.kern[i], (double)__ldg(row + reflect101_l(x - 3 + i, w))));
+  dst[(size_t)blockIdx.z * dfs + (size_t)y * w + x] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_lsd_scale_grad: CTA = 32x8 tile of the scaled image.  Phase A builds the 33x9 scaled
+// pixels (column pass of the Gaussian at the 2x2 source taps, then bilinear with float32
+// weights applied in double); phase B is ll_angle.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double col_blur(const double* __restrict__ rf, int w, int h, int x, int y,
+                                           const double* k) {
+  double s = __dmul_rn(k[3], rf[(size_t)y * w + x]);
+#pragma unroll
+  for (int i = 1; i <= 3; i++)
+    s = __dadd_rn(s, __dmul_rn(k[3 + i], __dadd_rn(rf[(size_t)reflect101_l(y + i, h) * w + x],
+                                                  rf[(size_t)reflect101_l(y - i, h) * w + x])));
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ LineGeom g, int oct,
+                                                        const double* __restrict__ rowf, size_t rfs,
+                                                        const LineTab* __restrict__ tabs, LineBufs b) {
+  __shared__ double ssc[9][34];
+  const LineOct& O = g.o[oct];
+  const int f = blockIdx.z, tid = threadIdx.x;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  const double* rf = rowf + (size_t)f * rfs + O.rawOff;
+  const LineTab* xt = tabs + O.xtabOff;
+  const LineTab* yt = tabs + O.ytabOff;
+  for (int i = tid; i < 9 * 33; i += 256) {
+    const int ty = i / 33, tx = i - ty * 33;
+    const int sx = x0 + tx, sy = y0 + ty;
+    double v = 0.0;
+    if (sx < O.sw && sy < O.sh) {
+      const LineTab X = xt[sx], Y = yt[sy];
+      const int xa = X.ofs, xb = min(X.ofs + 1, O.w - 1), ya = Y.ofs, yb = min(Y.ofs + 1, O.h - 1);
+      const double g00 = col_blur(rf, O.w, O.h, xa, ya, g.kern), g01 = col_blur(rf, O.w, O.h, xb, ya, g.kern);
+      const double g10 = col_blur(rf, O.w, O.h, xa, yb, g.kern), g11 = col_blur(rf, O.w, O.h, xb, yb, g.kern);
+      const double h0 = __dadd_rn(__dmul_rn(g00, (double)X.a0), __dmul_rn(g01, (double)X.a1));
+      const double h1 = __dadd_rn(__dmul_rn(g10, (double)X.a0), __dmul_rn(g11, (double)X.a1));
+      v = __dadd_rn(__dmul_rn(h0, (double)Y.a0), __dmul_rn(h1, (double)Y.a1));
+      if (b.scaledDbg && tx < 32 && ty < 8) b.scaledDbg[(size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx] = v;
+    }
+    ssc[ty][tx] = v;
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  const int sx = x0 + tx, sy = y0 + ty;
+  bool avail = false;
+  if (sx < O.sw && sy < O.sh) {
+    float angDeg = -1024.f;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    double norm = 0.0;
+    if (sx < O.sw - 1 && sy < O.sh - 1) {
+      const double DA = __dsub_rn(ssc[ty + 1][tx + 1], ssc[ty][tx]);
+      const double BC = __dsub_rn(ssc[ty][tx + 1], ssc[ty + 1][tx]);
+      const double gx = __dadd_rn(DA, BC), gy = __dsub_rn(DA, BC);
+      norm = __dsqrt_rn(__ddiv_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), 4.0));
+      if (!(norm <= g.rho)) {
+        angDeg = fast_atan2_dev((float)gx, (float)(-gy));
+        const double a = __dmul_rn((double)angDeg, D2R);
+        double sd, cd, sf, cf;
+        sincos(a, &sd, &cd);
+        sincos((double)(float)a, &sf, &cf);
+        cs = make_float4((float)cf, (float)sf, (float)cd, (float)sd);
+        avail = true;
+      }
+    }
+    const size_t p = (size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx;
+    b.ang[p] = angDeg;
+    b.cs[p] = cs;
+    b.mod[p] = norm;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, avail);
+  if (tx == 0 && sy < O.sh) b.bitmap[(size_t)f * g.bmTotal + O.bmOff + (size_t)sy * O.wpr + (x0 >> 5)] = m;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_lsd_grow: one warp per (octave, frame).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_aligned_dev(double a, double theta, double prec) {
+  double n = __dsub_rn(theta, a);
+  if (n < 0) n = -n;
+  if (n > (3 * PI_D) / 2) {
+    n = __dsub_rn(n, 2 * PI_D);
+    if (n < 0) n = -n;
+  }
+  return n <= prec;
+}
+
+__global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeom g, LineBufs b) {
+  extern __shared__ unsigned sbm[];
+  const int oct = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
+  if (oct >= g.noct) return;
+  const LineOct& O = g.o[oct];
+  const int W = O.sw, H = O.sh, wpr = O.wpr, nwords = wpr * H;
+  const unsigned* gbm = b.bitmap + (size_t)f * g.bmTotal + O.bmOff;
+  for (int i = lane; i < nwords; i += 32) sbm[i] = gbm[i];
+  __syncwarp();
+  const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
+  const float* __restrict__ ang = b.ang + pbase;
+  const float4* __restrict__ cs = b.cs + pbase;
+  unsigned* reg = b.reg + pbase;
+  LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
+  const double prec = g.prec;
+  int regBase = 0, nreg = 0;
+  bool overflow = false;
+  // lane -> (entry e = lane / 9, neighbour k = lane % 9)
+  const int e = lane / 9, kk = lane - e * 9;
+  const int ndx = kk % 3 - 1, ndy = kk / 3 - 1;
+
+  for (int w0 = 0; w0 < nwords; w0 += 32) {
+    // next seed: first set bit in raster order
+    while (true) {
+      const int wi = w0 + lane;
+      const unsigned word = wi < nwords ? sbm[wi] : 0u;
+      const unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
+      if (!nz) break;
+      const int wl = __ffs(nz) - 1;
+      const unsigned sw_ = __shfl_sync(0xffffffffu, word, wl);
+      const int bit = __ffs(sw_) - 1;
+      const int swi = w0 + wl;
+      const int sy = swi / wpr, sx = (swi - sy * wpr) * 32 + bit;
+      if (lane == 0) sbm[swi] = sw_ & ~(1u << bit);
+      // region_grow
+      const int sp = sy * W + sx;
+      const float4 c0 = cs[sp];
+      double regAngle = __dmul_rn((double)ang[sp], D2R);
+      float sumdx = c0.z, sumdy = c0.w;
+      int regSize = 1;
+      if (lane == 0) reg[regBase] = (unsigned)sx | ((unsigned)sy << 16);
+      __syncwarp();
+      for (int i = 0; i < regSize;) {
+        const int nb = min(3, regSize - i);
+        // fetch: lanes of entry e < nb look at their neighbour
+        bool cand = false;
+        int cx = 0, cy = 0;
+        float ca = 0.f;
+        float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < nb && kk != 4) {
+          const unsigned p = reg[regBase + i + e];
+          cx = (int)(p & 0xffff) + ndx;
+          cy = (int)(p >> 16) + ndy;
+          if (cx >= 0 && cx < W && cy >= 0 && cy < H && ((sbm[cy * wpr + (cx >> 5)] >> (cx & 31)) & 1u)) {
+            cand = true;
+            ca = ang[cy * W + cx];
+            cc = cs[cy * W + cx];
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        // serial accept chain in (entry, yy, xx) order == lane order
+        while (m) {
+          const int l = __ffs(m) - 1;
+          m &= m - 1;
+          const int qx = __shfl_sync(0xffffffffu, cx, l), qy = __shfl_sync(0xffffffffu, cy, l);
+          const float qa = __shfl_sync(0xffffffffu, ca, l);
+          const float qc = __shfl_sync(0xffffffffu, cc.x, l), qs = __shfl_sync(0xffffffffu, cc.y, l);
+          const int wi2 = qy * wpr + (qx >> 5);
+          const unsigned wv = sbm[wi2];
+          if (!((wv >> (qx & 31)) & 1u)) continue;  // taken by an earlier entry of this batch
+          if (!is_aligned_dev(__dmul_rn((double)qa, D2R), regAngle, prec)) continue;
+          __syncwarp();
+          if (lane == 0) {
+            sbm[wi2] = wv & ~(1u << (qx & 31));
+            reg[regBase + regSize] = (unsigned)qx | ((unsigned)qy << 16);
+          }
+          regSize++;
+          sumdx = __fadd_rn(sumdx, qc);
+          sumdy = __fadd_rn(sumdy, qs);
+          regAngle = __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
+          __syncwarp();
+        }
+        i += nb;
+        __syncwarp();
+      }
+      if (regSize >= O.minRegSize) {
+        if (nreg < O.segCap) {
+          if (lane == 0) {
+            LineRegion r;
+            r.start = regBase;
+            r.size = regSize;
+            r.angle = regAngle;
+            rtab[nreg] = r;
+          }
+          nreg++;
+          regBase += regSize;
+        } else {
+          overflow = true;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) b.regCount[f * 2 + oct] = overflow ? -1 : nreg;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_lsd_rect: warp per region.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGeom g, LineBufs b) {
+  const int oct = blockIdx.x, f = blockIdx.y, part = blockIdx.z, nparts = gridDim.z;
+  if (oct >= g.noct) return;
+  const LineOct& O = g.o[oct];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nreg = b.regCount[f * 2 + oct];
+  const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
+  const unsigned* reg = b.reg + pbase;
+  const double* mod = b.mod + pbase;
+  const LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
+  float4* segs = b.segs + (size_t)f * g.segTotal + O.segOff;
+  const int W = O.sw;
+  for (int r = part * nw + wid; r < nreg; r += nparts * nw) {
+    const LineRegion R = rtab[r];
+    const unsigned* rp = reg + R.start;
+    double x = 0, y = 0, sum = 0;
+    for (int i = lane; i < R.size; i += 32) {
+      const unsigned p = rp[i];
+      const int px = p & 0xffff, py = p >> 16;
+      const double wgt = mod[py * W + px];
+      x += (double)px * wgt;
+      y += (double)py * wgt;
+      sum += wgt;
+    }
+    x = warp_sum_d(x); y = warp_sum_d(y); sum = warp_sum_d(sum);
+    x /= sum;
+    y /= sum;
+    double Ixx = 0, Iyy = 0, Ixy = 0;
+    for (int i = lane; i < R.size; i += 32) {
+      const unsigned p = rp[i];
+      const int px = p & 0xffff, py = p >> 16;
+      const double wgt = mod[py * W + px];
+      const double dx = (double)px - x, dy = (double)py - y;
+      Ixx += dy * dy * wgt;
+      Iyy += dx * dx * wgt;
+      Ixy -= dx * dy * wgt;
+    }
+    Ixx = warp_sum_d(Ixx); Iyy = warp_sum_d(Iyy); Ixy = warp_sum_d(Ixy);
+    const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_dev((float)(lambda - Ixx), (float)Ixy)
+                                           : (double)fast_atan2_dev((float)Ixy, (float)(lambda - Iyy));
+    theta *= D2R;
+    {
+      double diff = theta - R.angle;
+      while (diff <= -PI_D) diff += 2 * PI_D;
+      while (diff > PI_D) diff -= 2 * PI_D;
+      if (fabs(diff) > g.prec) theta += PI_D;
+    }
+    double dx, dy;
+    sincos(theta, &dy, &dx);
+    double lmin = 0, lmax = 0;
+    for (int i = lane; i < R.size; i += 32) {
+      const unsigned p = rp[i];
+      const double rdx = (double)(p & 0xffff) - x, rdy = (double)(p >> 16) - y;
+      const double l = __dadd_rn(__dmul_rn(rdx, dx), __dmul_rn(rdy, dy));
+      lmax = fmax(lmax, l);
+      lmin = fmin(lmin, l);
+    }
+    lmin = warp_min_d(lmin);
+    lmax = warp_max_d(lmax);
+    if (lane == 0) {
+      double x1 = x + lmin * dx, y1 = y + lmin * dy, x2 = x + lmax * dx, y2 = y + lmax * dy;
+      x1 += 0.5; y1 += 0.5; x2 += 0.5; y2 += 0.5;
+      if (g.lsdScale != 1.0) { x1 /= g.lsdScale; y1 /= g.lsdScale; x2 /= g.lsdScale; y2 /= g.lsdScale; }
+      segs[r] = make_float4((float)x1, (float)y1, (float)x2, (float)y2);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_line_assemble: one CTA per frame.
+// ---------------------------------------------------------------------------------------
+struct RawLine {
+  float e[4];
+  float length;
+  bool valid;
+};
+__device__ __forceinline__ RawLine raw_line(float4 s, int ow, int oh, double minLength) {
+  RawLine r;
+  r.e[0] = s.x; r.e[1] = s.y; r.e[2] = s.z; r.e[3] = s.w;
+  if (r.e[0] < 0) r.e[0] = 0;
+  if (r.e[0] >= ow) r.e[0] = (float)ow - 1.0f;
+  if (r.e[2] < 0) r.e[2] = 0;
+  if (r.e[2] >= ow) r.e[2] = (float)ow - 1.0f;
+  if (r.e[1] < 0) r.e[1] = 0;
+  if (r.e[1] >= oh) r.e[1] = (float)oh - 1.0f;
+  if (r.e[3] < 0) r.e[3] = 0;
+  if (r.e[3] >= oh) r.e[3] = (float)oh - 1.0f;
+  const float ddx = __fsub_rn(r.e[0], r.e[2]), ddy = __fsub_rn(r.e[1], r.e[3]);
+  const double l = (double)(float)__dsqrt_rn(__dadd_rn(__dmul_rn((double)ddx, (double)ddx), __dmul_rn((double)ddy, (double)ddy)));
+  r.length = (float)l;
+  r.valid = l > minLength;
+  return r;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_line_assemble(const __grid_constant__ LineGeom g, LineBufs b,
+                                                      plvi_keyline* __restrict__ outKl, int* __restrict__ outCount) {
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  __shared__ int wsum[NT / 32], s_total, s_bad;
+  float* resp = b.tmpResp + (size_t)f * g.segTotal;
+  int* cls = b.tmpCls + (size_t)f * g.segTotal;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  // raw lines in detection order: octave 0 then octave 1; index space = [segOff, segOff + count)
+  int total = 0;
+  int cnt[2] = {0, 0};
+  for (int o = 0; o < g.noct; o++) {
+    cnt[o] = b.regCount[f * 2 + o];
+    if (cnt[o] < 0) { if (tid == 0) s_bad = 1; cnt[o] = 0; }
+    total += cnt[o];
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) outCount[f] = PLVI_ERR_CAPACITY;
+    return;
+  }
+  // pass 1: validity + response; class ids = running index of valid lines
+  const int chunk = (total + NT - 1) / NT;
+  const int beg = min(tid * chunk, total), end = min(beg + chunk, total);
+  auto locate = [&](int j, int& o, int& r) { o = (j < cnt[0]) ? 0 : 1; r = o ? j - cnt[0] : j; };
+  int nv = 0;
+  for (int j = beg; j < end; j++) {
+    int o, r;
+    locate(j, o, r);
+    const LineOct& O = g.o[o];
+    const RawLine rl = raw_line(b.segs[(size_t)f * g.segTotal + O.segOff + r], O.w, O.h, g.minLength);
+    nv += rl.valid;
+  }
+  int incl = nv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0;
+    for (int w = 0; w < NT / 32; w++) { const int t = wsum[w]; wsum[w] = a; a += t; }
+    s_total = a;
+  }
+  __syncthreads();
+  int id = wsum[wid] + incl - nv;
+  const int nvalid = s_total;
+  for (int j = beg; j < end; j++) {
+    int o, r;
+    locate(j, o, r);
+    const LineOct& O = g.o[o];
+    const RawLine rl = raw_line(b.segs[(size_t)f * g.segTotal + O.segOff + r], O.w, O.h, g.minLength);
+    if (rl.valid) {
+      resp[id] = __fdiv_rn(rl.length, (float)max(O.w, O.h));
+      cls[id] = j;  // raw index of the id-th valid line
+      id++;
+    }
+  }
+  __syncthreads();
+  const bool select = (nvalid > g.nfeat) && g.nfeat != 0;
+  const int nout = select ? g.nfeat : min(nvalid, g.keepCap);
+  if (!select && nvalid > g.keepCap) {
+    if (tid == 0) outCount[f] = PLVI_ERR_CAPACITY;
+    return;
+  }
+  for (int v = tid; v < nvalid; v += NT) {
+    int pos = v;
+    if (select) {  // rank by (response desc, detection order asc)
+      const float rv = resp[v];
+      int rank = 0;
+      for (int u = 0; u < nvalid; u++) {
+        const float ru = resp[u];
+        rank += (ru > rv) || (ru == rv && u < v);
+      }
+      pos = rank;
+    }
+    if (pos >= nout) continue;
+    const int j = cls[v];
+    int o, r;
+    locate(j, o, r);
+    const LineOct& O = g.o[o];
+    const RawLine rl = raw_line(b.segs[(size_t)f * g.segTotal + O.segOff + r], O.w, O.h, g.minLength);
+    const float octaveScale = o ? g.lineScale : 1.0f;   // pow(scale, octave), octave in {0,1}
+    plvi_keyline k;
+    k.startPointX = __fmul_rn(rl.e[0], octaveScale); k.startPointY = __fmul_rn(rl.e[1], octaveScale);
+    k.endPointX = __fmul_rn(rl.e[2], octaveScale); k.endPointY = __fmul_rn(rl.e[3], octaveScale);
+    k.sPointInOctaveX = rl.e[0]; k.sPointInOctaveY = rl.e[1];
+    k.ePointInOctaveX = rl.e[2]; k.ePointInOctaveY = rl.e[3];
+    k.lineLength = rl.length;
+    const int ax = __float2int_rn(rl.e[0]), ay = __float2int_rn(rl.e[1]);
+    const int bx = __float2int_rn(rl.e[2]), by = __float2int_rn(rl.e[3]);
+    k.numOfPixels = max(abs(bx - ax), abs(by - ay)) + 1;
+    k.angle = (float)atan2((double)__fsub_rn(k.endPointY, k.startPointY), (double)__fsub_rn(k.endPointX, k.startPointX));
+    k.class_id = select ? pos : v;
+    k.octave = o;
+    k.size = __fmul_rn(__fsub_rn(k.endPointX, k.startPointX), __fsub_rn(k.endPointY, k.startPointY));
+    k.response = resp[v];
+    k.pt_x = __fdiv_rn(__fadd_rn(k.endPointX, k.startPointX), 2.f);
+    k.pt_y = __fdiv_rn(__fadd_rn(k.endPointY, k.startPointY), 2.f);
+    outKl[(size_t)f * g.keepCap + pos] = k;
+  }
+  if (tid == 0) outCount[f] = nout;
+}
+
+// ---------------------------------------------------------------------------------------
+// LBD preprocessing
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gauss5(const u8* __restrict__ src, int spitch, size_t sfs, u8* __restrict__ dst,
+                                                int dpitch, size_t dfs, int w, int h) {
+  __shared__ __align__(16) u8 sin_[(32 + 4) * (128 + 8)];
+  __shared__ __align__(16) unsigned short sh_[(32 + 4) * 128];
+  const int tid = threadIdx.x, x0 = blockIdx.x * 128, y0 = blockIdx.y * 32;
+  const u8* s = src + (size_t)blockIdx.z * sfs;
+  const int SP = 136;
+  for (int i = tid; i < 36 * 132; i += 256) {
+    const int r = i / 132, c = i - r * 132;
+    const int gy = reflect101_l(min(y0 + r - 2, h + 1), h), gx = reflect101_l(min(x0 + c - 2, w + 1), w);
+    sin_[r * SP + c] = __ldg(s + (size_t)gy * spitch + gx);
+  }
+  __syncthreads();
+  for (int i = tid; i < 36 * 32; i += 256) {
+    const int r = i >> 5, c4 = (i & 31) * 4;
+    const u8* q = sin_ + r * SP + c4;
+    int v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = q[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      sh_[r * 128 + c4 + k] = (unsigned short)(14 * (v[k] + v[k + 4]) + 62 * (v[k + 1] + v[k + 3]) + 104 * v[k + 2]);
+  }
+  __syncthreads();
+  u8* d = dst + (size_t)blockIdx.z * dfs;
+  for (int i = tid; i < 32 * 32; i += 256) {
+    const int r = i >> 5, c4 = (i & 31) * 4;
+    const int gy = y0 + r, gx = x0 + c4;
+    if (gy >= h || gx >= w) continue;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned short* q = sh_ + r * 128 + c4 + k;
+      const uint32_t sv = 14u * (q[0] + q[4 * 128]) + 62u * (q[128] + q[3 * 128]) + 104u * q[2 * 128];
+      out |= ((sv + 32768u) >> 16) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(d + (size_t)gy * dpitch + gx) = out;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pyrdown(const u8* __restrict__ src, int spitch, size_t sfs, int w, int h,
+                                                 u8* __restrict__ dst, int dpitch, size_t dfs, int dw, int dh) {
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= dw || y >= dh) return;
+  const u8* s = src + (size_t)blockIdx.z * sfs;
+  const int k[5] = {1, 4, 6, 4, 1};
+  int acc = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const u8* row = s + (size_t)reflect101_l(2 * y + j - 2, h) * spitch;
+    int rs = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) rs += k[i] * __ldg(row + reflect101_l(2 * x + i - 2, w));
+    acc += k[j] * rs;
+  }
+  dst[(size_t)blockIdx.z * dfs + (size_t)y * dpitch + x] = (u8)((acc + 128) >> 8);
+}
+
+__global__ void __launch_bounds__(256) k_sobel(const u8* __restrict__ src, int spitch, size_t sfs, int w, int h,
+                                               short2* __restrict__ dst, size_t dfs) {
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= w || y >= h) return;
+  const u8* s = src + (size_t)blockIdx.z * sfs;
+  const int xm = reflect101_l(x - 1, w), xp = reflect101_l(x + 1, w);
+  const u8* r0 = s + (size_t)reflect101_l(y - 1, h) * spitch;
+  const u8* r1 = s + (size_t)y * spitch;
+  const u8* r2 = s + (size_t)reflect101_l(y + 1, h) * spitch;
+  const int p00 = __ldg(r0 + xm), p01 = __ldg(r0 + x), p02 = __ldg(r0 + xp);
+  const int p10 = __ldg(r1 + xm), p12 = __ldg(r1 + xp);
+  const int p20 = __ldg(r2 + xm), p21 = __ldg(r2 + x), p22 = __ldg(r2 + xp);
+  const int dx = (p02 - p00) + 2 * (p12 - p10) + (p22 - p20);
+  const int dy = (p20 - p00) + 2 * (p21 - p01) + (p22 - p02);
+  dst[(size_t)blockIdx.z * dfs + (size_t)y * w + x] = make_short2((short)dx, (short)dy);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_lbd: CTA of 64 threads per line; thread = one of the 63 rows of the support region
+// (the reference accumulates sample coordinates and row sums serially along the line in
+// float, so a row is one sequential chain); then 8 lanes fold rows into bands in row order.
+// ---------------------------------------------------------------------------------------
+__constant__ unsigned char c_comb[32][2] = {
+    {0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7},
+    {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8}, {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
+
+__global__ void __launch_bounds__(64) k_lbd(const __grid_constant__ LineGeom g, LineBufs b,
+                                            const plvi_keyline* __restrict__ kls, const int* __restrict__ counts,
+                                            uint8_t* __restrict__ desc, double* __restrict__ lineEq) {
+  const int li = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  const int n = counts[f];
+  if (li >= n) return;
+  const plvi_keyline kl = kls[(size_t)f * g.keepCap + li];
+  const LineOct& O = g.o[kl.octave];
+  const short2* grad = b.grad + (size_t)f * g.lbdTotal + O.lbdOff;
+  const int realWidth = O.lw, imageWidth = O.lw - 1, imageHeight = O.lh - 1;
+  __shared__ float rows[8][64];
+  __shared__ float des[72];
+  const int L = kl.numOfPixels;
+  const int halfWidth = (L - 1) / 2;
+  const float midX = __fmul_rn(0.5f, __fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
+  const float midY = __fmul_rn(0.5f, __fadd_rn(kl.sPointInOctaveY, kl.ePointInOctaveY));
+  double sd, cd;
+  sincos((double)kl.angle, &sd, &cd);
+  const float dL0 = (float)cd, dL1 = (float)sd;
+  const float dO0 = -dL1, dO1 = dL0;
+  if (tid < 63) {
+    float sX0 = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, 31.f)), midX);
+    float sY0 = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, 31.f)), midY);
+    for (int r = 0; r < tid; r++) {
+      sX0 = __fsub_rn(sX0, dL1);
+      sY0 = __fadd_rn(sY0, dL0);
+    }
+    float sX = sX0, sY = sY0, pL = 0.f, nL = 0.f, pO = 0.f, nO = 0.f;
+    for (int wID = 0; wID < L; wID++) {
+      int tc = (int)(short)(int)roundf(sX);
+      const int xCor = tc < 0 ? 0 : (tc > imageWidth ? imageWidth : tc);
+      tc = (int)(short)(int)roundf(sY);
+      const int yCor = tc < 0 ? 0 : (tc > imageHeight ? imageHeight : tc);
+      const short2 gv = __ldg(grad + yCor * realWidth + xCor);
+      const float gDL = __fadd_rn(__fmul_rn((float)gv.x, dL0), __fmul_rn((float)gv.y, dL1));
+      const float gDO = __fadd_rn(__fmul_rn((float)gv.x, dO0), __fmul_rn((float)gv.y, dO1));
+      if (gDL > 0) pL = __fadd_rn(pL, gDL); else nL = __fsub_rn(nL, gDL);
+      if (gDO > 0) pO = __fadd_rn(pO, gDO); else nO = __fsub_rn(nO, gDO);
+      sX = __fadd_rn(sX, dL0);
+      sY = __fadd_rn(sY, dL1);
+    }
+    const float c = (float)b.lbdG[tid];
+    pL = __fmul_rn(c, pL); nL = __fmul_rn(c, nL);
+    pO = __fmul_rn(c, pO); nO = __fmul_rn(c, nO);
+    rows[0][tid] = pL; rows[1][tid] = nL; rows[2][tid] = __fmul_rn(pL, pL); rows[3][tid] = __fmul_rn(nL, nL);
+    rows[4][tid] = pO; rows[5][tid] = nO; rows[6][tid] = __fmul_rn(pO, pO); rows[7][tid] = __fmul_rn(nO, nO);
+  }
+  __syncthreads();
+  if (tid < 8) {  // one lane per statistic; rows folded in order into the 9 bands
+    const int q = tid;
+    const bool sq = (q == 2 || q == 3 || q == 6 || q == 7);
+    float band[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) band[k] = 0.f;
+    for (int hID = 0; hID < 63; hID++) {
+      const float rs = rows[q][hID];
+      const int bandID = hID / 7, m = hID % 7;
+      float cf = (float)b.lbdL[m + 7];
+      band[bandID] = __fadd_rn(band[bandID], sq ? __fmul_rn(__fmul_rn(cf, cf), rs) : __fmul_rn(cf, rs));
+      if (bandID - 1 >= 0) {
+        cf = (float)b.lbdL[m + 14];
+        band[bandID - 1] = __fadd_rn(band[bandID - 1], sq ? __fmul_rn(__fmul_rn(cf, cf), rs) : __fmul_rn(cf, rs));
+      }
+      if (bandID + 1 < 9) {
+        cf = (float)b.lbdL[m];
+        band[bandID + 1] = __fadd_rn(band[bandID + 1], sq ? __fmul_rn(__fmul_rn(cf, cf), rs) : __fmul_rn(cf, rs));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) rows[q][k] = band[k];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float invN2 = (float)(1.0 / 14.0), invN3 = (float)(1.0 / 21.0);
+    for (int k = 0; k < 9; k++) {
+      const float invN = (k == 0 || k == 8) ? invN2 : invN3;
+      const int d = k * 8;
+      float t;
+      t = __fmul_rn(rows[0][k], invN); des[d] = t;
+      des[d + 4] = __fsqrt_rn(__fsub_rn(__fmul_rn(rows[2][k], invN), __fmul_rn(t, t)));
+      t = __fmul_rn(rows[1][k], invN); des[d + 1] = t;
+      des[d + 5] = __fsqrt_rn(__fsub_rn(__fmul_rn(rows[3][k], invN), __fmul_rn(t, t)));
+      t = __fmul_rn(rows[4][k], invN); des[d + 2] = t;
+      des[d + 6] = __fsqrt_rn(__fsub_rn(__fmul_rn(rows[6][k], invN), __fmul_rn(t, t)));
+      t = __fmul_rn(rows[5][k], invN); des[d + 3] = t;
+      des[d + 7] = __fsqrt_rn(__fsub_rn(__fmul_rn(rows[7][k], invN), __fmul_rn(t, t)));
+    }
+    float tM = 0.f, tS = 0.f;
+    for (int k = 0; k < 9; k++) {
+      for (int j = 0; j < 4; j++) tM = __fadd_rn(tM, __fmul_rn(des[8 * k + j], des[8 * k + j]));
+      for (int j = 4; j < 8; j++) tS = __fadd_rn(tS, __fmul_rn(des[8 * k + j], des[8 * k + j]));
+    }
+    tM = __fdiv_rn(1.f, __fsqrt_rn(tM));
+    tS = __fdiv_rn(1.f, __fsqrt_rn(tS));
+    for (int k = 0; k < 9; k++) {
+      for (int j = 0; j < 4; j++) des[8 * k + j] = __fmul_rn(des[8 * k + j], tM);
+      for (int j = 4; j < 8; j++) des[8 * k + j] = __fmul_rn(des[8 * k + j], tS);
+    }
+    for (int i = 0; i < 72; i++)
+      if ((double)des[i] > 0.4) des[i] = 0.4f;
+    float t = 0.f;
+    for (int i = 0; i < 72; i++) t = __fadd_rn(t, __fmul_rn(des[i], des[i]));
+    t = __fdiv_rn(1.f, __fsqrt_rn(t));
+    for (int i = 0; i < 72; i++) des[i] = __fmul_rn(des[i], t);
+    // line equation (f64)
+    const double sx = kl.startPointX, sy = kl.startPointY, ex = kl.endPointX, ey = kl.endPointY;
+    const double l0 = __dsub_rn(sy, ey), l1 = __dsub_rn(ex, sx), l2 = __dsub_rn(__dmul_rn(sx, ey), __dmul_rn(sy, ex));
+    const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(l0, l0), __dmul_rn(l1, l1)));
+    double* eq = lineEq + ((size_t)f * g.keepCap + li) * 3;
+    eq[0] = __ddiv_rn(l0, nrm); eq[1] = __ddiv_rn(l1, nrm); eq[2] = __ddiv_rn(l2, nrm);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const float* f1 = des + 8 * c_comb[tid][0];
+    const float* f2 = des + 8 * c_comb[tid][1];
+    unsigned r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r |= (unsigned)(f1[i] > f2[i]) << i;
+    desc[((size_t)f * g.keepCap + li) * 32 + tid] = (uint8_t)r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// launch sequence
+// ---------------------------------------------------------------------------------------
+int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b, int n, plvi_keyline* dKl,
+                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, int* launches) {
+  int nl = 0;
+  // LSD pyramid level 1 (2x bilinear; LSDDetectorC::ComputePyramid)
+  if (g.noct > 1) {
+    const LineOct& d = g.o[1];
+    launch_resize_u8(p.img[0], p.ipitch[0], p.ifs[0], g.o[0].w, g.o[0].h, const_cast<u8*>(p.img[1]), p.ipitch[1],
+                     p.ifs[1], d.w, d.h, b.rsTab, b.rsTab + d.w, n, st);
+    nl++;
+  }
+  for (int o = 0; o < g.noct; o++) {
+    const LineOct& O = g.o[o];
+    k_lsd_rowfilter<<<dim3((O.w + 63) / 64, (O.h + 3) / 4, n), 256, 0, st>>>(p.img[o], p.ipitch[o], p.ifs[o], O.w, O.h,
+                                                                             b.rowf + O.rawOff, g.rawTotal, g);
+    k_lsd_scale_grad<<<dim3((O.sw + 31) / 32, (O.sh + 7) / 8, n), 256, 0, st>>>(g, o, b.rowf, g.rawTotal, b.tabs, b);
+    nl += 2;
+  }
+  const size_t growSmem = (size_t)g.o[0].wpr * g.o[0].sh * sizeof(unsigned);
+  k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b);
+  k_lsd_rect<<<dim3(g.noct, n, 2), 256, 0, st>>>(g, b);
+  k_line_assemble<512><<<n, 512, 0, st>>>(g, b, dKl, dCounts);
+  nl += 3;
+  // LBD pyramid + Sobel
+  {
+    const LineOct& O0 = g.o[0];
+    k_gauss5<<<dim3((O0.lw + 127) / 128, (O0.lh + 31) / 32, n), 256, 0, st>>>(p.img[0], p.ipitch[0], p.ifs[0], b.lbdImg0,
+                                                                             O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw, O0.lh);
+    k_sobel<<<dim3((O0.lw + 63) / 64, (O0.lh + 3) / 4, n), 256, 0, st>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw,
+                                                                        O0.lh, b.grad + O0.lbdOff, g.lbdTotal);
+    nl += 2;
+    if (g.noct > 1) {
+      const LineOct& O1 = g.o[1];
+      k_pyrdown<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, st>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh,
+                                                                            O0.lw, O0.lh, b.lbdImg1, O1.lpitch,
+                                                                            (size_t)O1.lpitch * O1.lh, O1.lw, O1.lh);
+      k_sobel<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, st>>>(b.lbdImg1, O1.lpitch, (size_t)O1.lpitch * O1.lh,
+                                                                          O1.lw, O1.lh, b.grad + O1.lbdOff, g.lbdTotal);
+      nl += 2;
+    }
+  }
+  k_lbd<<<dim3(g.keepCap, n), 64, 0, st>>>(g, b, dKl, dCounts, dDesc, dEq);
+  nl++;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  if (launches) *launches = nl;
+  return PLVI_OK;
+}
+
+int line_kernel_attrs(const LineGeom& g) {
+  const size_t growSmem = (size_t)g.o[0].wpr * g.o[0].sh * sizeof(unsigned);
+  if (growSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
+  if (growSmem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)growSmem));
+  return PLVI_OK;
+}
+
+}  // namespace plvi

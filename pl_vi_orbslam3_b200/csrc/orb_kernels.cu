@@ -13,6 +13,7 @@
 // stage allows), so grids are thousands of CTAs.
 #include "orb_pattern_table.h"
 #include "plvi_internal.cuh"
+#include "line_internal.cuh"
 
 namespace plvi {
 
@@ -714,6 +715,12 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(
       kps[(size_t)f * cap + o] = k;
     }
   }
+}
+
+void launch_resize_u8(const u8* src, int spitch, size_t sfs, int sw, int sh, u8* dst, int dpitch, size_t dfs,
+                      int dw, int dh, const int2* xtab, const int2* ytab, int n, cudaStream_t st) {
+  dim3 blk(64, 4), grd((dw + 255) / 256, (dh + 3) / 4, n);
+  k_resize<<<grd, blk, 0, st>>>(src, spitch, sfs, sw, sh, dst, dpitch, dfs, dw, dh, xtab, ytab);
 }
 
 // ---------------------------------------------------------------------------------

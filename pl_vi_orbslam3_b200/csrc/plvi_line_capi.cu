@@ -1,0 +1,431 @@
+// C ABI for the line extractor (include/plvi.h): Lineextractor ctor / operator()
+// (include/LineExtractor.h:55-61, src/LineExtractor.cc:39-117), geometry planning for
+// LSDDetectorC::ComputePyramid + LineSegmentDetectorImpl::flsd + BinaryDescriptor.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "line_internal.cuh"
+
+using namespace plvi;
+
+struct plvi_line {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  int nfeat = 0, nlevels = 0;
+  float lsdScale = 0.8f, scale = 2.f;
+  int maxW = 0, maxH = 0, maxBatch = 0;
+  int curW = -1, curH = -1;
+  LineGeom geom, capGeom;
+  LineBufs buf = {};
+  u8* dImg[2] = {nullptr, nullptr};
+  LineTab* dTabs = nullptr;
+  int2* dRsTab = nullptr;
+  double* dLbdG = nullptr;
+  double* dLbdL = nullptr;
+  size_t tabCap = 0, rsCap = 0;
+  plvi_keyline* dKl = nullptr;
+  uint8_t* dDesc = nullptr;
+  double* dEq = nullptr;
+  int* dCounts = nullptr;
+  int lastN = 0, lastLaunches = 0;
+  bool debug = false;
+  LinePtrs lastPtrs = {};
+};
+
+namespace {
+
+inline int round_even_f(float v) { return (int)nearbyintf(v); }
+inline int round_even_d(double v) { return (int)nearbyint(v); }
+
+void linear_rows_u8(int ssize, int dsize, std::vector<int2>& out) {
+  const double scale = 1.0 / ((double)dsize / ssize);
+  for (int d = 0; d < dsize; d++) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+    const int a0 = round_even_f((1.f - f) * 2048.f), a1 = round_even_f(f * 2048.f);
+    out.push_back(make_int2(s, (a0 & 0xffff) | (a1 << 16)));
+  }
+}
+
+void linear_rows_f64(int ssize, int dsize, double inv_scale, std::vector<LineTab>& out) {
+  const double scale = 1.0 / inv_scale;
+  for (int d = 0; d < dsize; d++) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+    out.push_back(LineTab{s, 1.f - f, f});
+  }
+}
+
+void gaussian_kernel7(double sigma, double* k) {
+  // cv::getGaussianKernel(7, sigma, CV_64F); the reference's fixed setting (0.6/(double)0.8f)
+  // uses the values OpenCV 4.x produces (soft-float exp), other sigmas the defining formula.
+  if (sigma == 0.6 / (double)0.8f) {
+    static const unsigned long long bits[7] = {0x3f276349157f1ab0ull, 0x3f8f1e22f611221dull, 0x3fcbfd7fa6a94f5aull,
+                                               0x3fe10562abd81f5full, 0x3fcbfd7fa6a94f5aull, 0x3f8f1e22f611221dull,
+                                               0x3f276349157f1ab0ull};
+    memcpy(k, bits, sizeof(bits));
+    return;
+  }
+  const double s2 = -0.5 / (sigma * sigma);
+  double sum = 0;
+  for (int i = 0; i < 7; i++) { const double x = i - 3.0; k[i] = exp(s2 * x * x); sum += k[i]; }
+  sum = 1. / sum;
+  for (int i = 0; i < 7; i++) k[i] *= sum;
+}
+
+int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTab>* tabs, std::vector<int2>* rs) {
+  memset(&g, 0, sizeof(g));
+  g.noct = h->nlevels;
+  g.nfeat = h->nfeat;
+  g.keepCap = h->nfeat > 0 ? h->nfeat : 4096;
+  g.lineScale = h->scale;
+  g.lsdScale = (double)h->lsdScale;
+  g.prec = M_PI * 22.5 / 180;
+  g.rho = 2.0 / sin(g.prec);
+  g.minLength = 0.025 * std::min(w, hh);
+  const double sigma = (g.lsdScale < 1) ? (0.6 / g.lsdScale) : 0.6;
+  const unsigned hk = (unsigned)ceil(sigma * sqrt(2 * 3.0 * log(10.0)));
+  if (g.lsdScale == 1.0 || hk != 3) {
+    set_error("lsd_scale outside the supported range (7-tap Gaussian, scale != 1)");
+    return PLVI_ERR_INVALID;
+  }
+  gaussian_kernel7(sigma, g.kern);
+  float sf = 1.f;
+  size_t px = 0, raw = 0, lbd = 0;
+  int bm = 0, seg = 0, tabOff = 0;
+  for (int o = 0; o < g.noct; o++) {
+    LineOct& O = g.o[o];
+    if (o > 0) sf = sf * h->scale;
+    const float isf = 1.0f / sf;
+    O.w = round_even_f((float)w * isf);
+    O.h = round_even_f((float)hh * isf);
+    O.pitch = (O.w + 63) & ~63;
+    O.sw = round_even_d(O.w * g.lsdScale);
+    O.sh = round_even_d(O.h * g.lsdScale);
+    if (O.sw < 8 || O.sh < 8 || O.sw > 65535 || O.sh > 65535) { set_error("image size unsupported for LSD"); return PLVI_ERR_INVALID; }
+    O.wpr = (O.sw + 31) / 32;
+    const double LOG_NT = 5 * (log10((double)O.sw) + log10((double)O.sh)) / 2 + log10(11.0);
+    O.minRegSize = (int)(-LOG_NT / log10(22.5 / 180));
+    O.pxOff = px; px += ((size_t)O.sw * O.sh + 3) & ~(size_t)3;
+    O.rawOff = raw; raw += (size_t)O.w * O.h;
+    O.bmOff = bm; bm += O.wpr * O.sh;
+    O.segOff = seg;
+    O.segCap = std::min((O.sw * O.sh) / std::max(O.minRegSize, 1), std::max(1024, 8192 >> (2 * o)));
+    seg += O.segCap;
+    O.xtabOff = tabOff; tabOff += O.sw;
+    O.ytabOff = tabOff; tabOff += O.sh;
+    if (tabs) {
+      linear_rows_f64(O.w, O.sw, g.lsdScale, *tabs);
+      linear_rows_f64(O.h, O.sh, g.lsdScale, *tabs);
+    }
+    O.lw = o == 0 ? w : g.o[o - 1].lw / 2;
+    O.lh = o == 0 ? hh : g.o[o - 1].lh / 2;
+    O.lpitch = (O.lw + 63) & ~63;
+    O.lbdOff = lbd; lbd += (size_t)O.lw * O.lh;
+    if (o > 0 && (O.lw != O.w || O.lh != O.h)) {
+      // LSD octave coordinates index the LBD octave image; the reference relies on both
+      // pyramids having equal sizes (true for scale 2.0)
+      set_error("line pyramid scale must be 2.0 (LBD octaves are pyrDown halves)");
+      return PLVI_ERR_INVALID;
+    }
+  }
+  if (rs && g.noct > 1) {
+    linear_rows_u8(g.o[0].w, g.o[1].w, *rs);
+    linear_rows_u8(g.o[0].h, g.o[1].h, *rs);
+  }
+  g.pxTotal = px; g.rawTotal = raw; g.lbdTotal = lbd; g.bmTotal = bm; g.segTotal = seg;
+  return PLVI_OK;
+}
+
+int ensure_geom(plvi_line* h, int w, int hh) {
+  if (w == h->curW && hh == h->curH) return PLVI_OK;
+  if (w > h->maxW || hh > h->maxH) { set_error("image larger than the handle's max_width/max_height"); return PLVI_ERR_CAPACITY; }
+  std::vector<LineTab> tabs;
+  std::vector<int2> rs;
+  LineGeom g;
+  int rc = make_geom(h, w, hh, g, &tabs, &rs);
+  if (rc) return rc;
+  const LineGeom& c = h->capGeom;
+  if (tabs.size() > h->tabCap || rs.size() > h->rsCap || g.pxTotal > c.pxTotal || g.rawTotal > c.rawTotal ||
+      g.lbdTotal > c.lbdTotal || g.bmTotal > c.bmTotal || g.segTotal > c.segTotal) {
+    set_error("internal: line geometry exceeds allocated capacity");
+    return PLVI_ERR_CAPACITY;
+  }
+  PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  PLVI_CUDA_TRY(cudaMemcpy(h->dTabs, tabs.data(), tabs.size() * sizeof(LineTab), cudaMemcpyHostToDevice));
+  if (!rs.empty()) PLVI_CUDA_TRY(cudaMemcpy(h->dRsTab, rs.data(), rs.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  // keep the allocated per-frame strides
+  g.pxTotal = c.pxTotal; g.rawTotal = c.rawTotal; g.lbdTotal = c.lbdTotal; g.bmTotal = c.bmTotal; g.segTotal = c.segTotal;
+  for (int o = 0; o < g.noct; o++) {
+    g.o[o].pxOff = c.o[o].pxOff; g.o[o].rawOff = c.o[o].rawOff; g.o[o].bmOff = c.o[o].bmOff;
+    g.o[o].segOff = c.o[o].segOff; g.o[o].segCap = std::min(g.o[o].segCap, c.o[o].segCap);
+    g.o[o].lbdOff = c.o[o].lbdOff;
+  }
+  h->geom = g;
+  rc = line_kernel_attrs(h->geom);
+  if (rc) return rc;
+  h->curW = w;
+  h->curH = hh;
+  return PLVI_OK;
+}
+
+void fill_ptrs(plvi_line* h, const u8* l0, int l0pitch, size_t l0fs, LinePtrs& p) {
+  for (int o = 0; o < 2; o++) {
+    p.img[o] = h->dImg[o];
+    p.ipitch[o] = h->geom.o[o].pitch;
+    p.ifs[o] = (size_t)h->geom.o[o].pitch * h->geom.o[o].h;
+  }
+  if (l0) { p.img[0] = l0; p.ipitch[0] = l0pitch; p.ifs[0] = l0fs; }
+}
+
+int check_batch(plvi_line* h, const void* imgs, int n, int w, int hh, int stride) {
+  if (!h) { set_error("null handle"); return PLVI_ERR_INVALID; }
+  if (!imgs || w <= 0 || hh <= 0 || n <= 0) { set_error("empty image batch"); return PLVI_ERR_EMPTY; }
+  if (stride < w) { set_error("stride < width"); return PLVI_ERR_INVALID; }
+  if (n > h->maxBatch) { set_error("batch larger than max_batch"); return PLVI_ERR_CAPACITY; }
+  return PLVI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float lsd_scale, int nlevels, float scale,
+                     int extractor, int max_width, int max_height, int max_batch, int device, void* stream) {
+  if (!out || lsd_nfeatures < 0 || max_batch < 1 || max_width < 1 || max_height < 1 || !(lsd_scale > 0.f)) {
+    set_error("plvi_line_create: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  if (extractor != 0) { set_error("extractor=1 (EDLines) is outside the hot path: only the LSD branch is implemented"); return PLVI_ERR_INVALID; }
+  if (lsd_refine != 0) { set_error("lsd_refine > 0 is not implemented (no shipped configuration uses it)"); return PLVI_ERR_INVALID; }
+  if (nlevels < 1 || nlevels > 2) { set_error("levels must be 1 or 2 (as in the reference's yaml contract)"); return PLVI_ERR_INVALID; }
+  PLVI_CUDA_TRY(cudaSetDevice(device));
+  plvi_line* h = new plvi_line();
+  h->device = device;
+  h->nfeat = lsd_nfeatures;
+  h->lsdScale = lsd_scale;
+  h->nlevels = nlevels;
+  h->scale = scale;
+  h->maxW = max_width;
+  h->maxH = max_height;
+  h->maxBatch = max_batch;
+  std::vector<LineTab> tabs;
+  std::vector<int2> rs;
+  int rc = make_geom(h, max_width, max_height, h->capGeom, &tabs, &rs);
+  if (rc) { delete h; return rc; }
+  if (stream) h->stream = (cudaStream_t)stream;
+  else {
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); delete h; return PLVI_ERR_CUDA; }
+    h->ownStream = true;
+  }
+  const LineGeom& c = h->capGeom;
+  const size_t B = max_batch;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes + 256); };
+  for (int o = 0; o < nlevels; o++) A((void**)&h->dImg[o], B * c.o[o].pitch * c.o[o].h);
+  A((void**)&h->buf.rowf, B * c.rawTotal * sizeof(double));
+  A((void**)&h->buf.ang, B * c.pxTotal * sizeof(float));
+  A((void**)&h->buf.cs, B * c.pxTotal * sizeof(float4));
+  A((void**)&h->buf.mod, B * c.pxTotal * sizeof(double));
+  A((void**)&h->buf.bitmap, B * c.bmTotal * sizeof(unsigned));
+  A((void**)&h->buf.reg, B * c.pxTotal * sizeof(unsigned));
+  A((void**)&h->buf.regTab, B * c.segTotal * sizeof(LineRegion));
+  A((void**)&h->buf.regCount, B * 2 * sizeof(int));
+  A((void**)&h->buf.segs, B * c.segTotal * sizeof(float4));
+  A((void**)&h->buf.tmpResp, B * c.segTotal * sizeof(float));
+  A((void**)&h->buf.tmpCls, B * c.segTotal * sizeof(int));
+  A((void**)&h->buf.lbdImg0, B * c.o[0].lpitch * c.o[0].lh);
+  if (nlevels > 1) A((void**)&h->buf.lbdImg1, B * c.o[1].lpitch * c.o[1].lh);
+  A((void**)&h->buf.grad, B * c.lbdTotal * sizeof(short2));
+  h->tabCap = tabs.size() + 64;
+  h->rsCap = rs.size() + 64;
+  A((void**)&h->dTabs, h->tabCap * sizeof(LineTab));
+  A((void**)&h->dRsTab, h->rsCap * sizeof(int2));
+  A((void**)&h->dLbdG, 63 * sizeof(double));
+  A((void**)&h->dLbdL, 21 * sizeof(double));
+  A((void**)&h->dKl, B * c.keepCap * sizeof(plvi_keyline));
+  A((void**)&h->dDesc, B * c.keepCap * 32);
+  A((void**)&h->dEq, B * c.keepCap * 3 * sizeof(double));
+  A((void**)&h->dCounts, B * sizeof(int));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    plvi_line_destroy(h);
+    return PLVI_ERR_CUDA;
+  }
+  {  // BinaryDescriptor ctor weights (binary_descriptor_custom.cpp:219-261; integer divisions kept)
+    double L[21], G[63];
+    double u = (7 * 3 - 1) / 2, sigma = (7 * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
+    for (int i = 0; i < 21; i++) { const double d = i - u; L[i] = exp(d * d * inv); }
+    u = (9 * 7 - 1) / 2; sigma = u; inv = -1 / (2 * sigma * sigma);
+    for (int i = 0; i < 63; i++) { const double d = i - u; G[i] = exp(d * d * inv); }
+    cudaMemcpy(h->dLbdG, G, sizeof(G), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->dLbdL, L, sizeof(L), cudaMemcpyHostToDevice);
+  }
+  h->buf.tabs = h->dTabs;
+  h->buf.rsTab = h->dRsTab;
+  h->buf.lbdG = h->dLbdG;
+  h->buf.lbdL = h->dLbdL;
+  *out = h;
+  return PLVI_OK;
+}
+
+void plvi_line_destroy(plvi_line* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
+  cudaFree(h->buf.rowf); cudaFree(h->buf.ang); cudaFree(h->buf.cs); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
+  cudaFree(h->buf.reg); cudaFree(h->buf.regTab); cudaFree(h->buf.regCount); cudaFree(h->buf.segs);
+  cudaFree(h->buf.tmpResp); cudaFree(h->buf.tmpCls); cudaFree(h->buf.lbdImg0); cudaFree(h->buf.lbdImg1);
+  cudaFree(h->buf.grad); cudaFree(h->buf.scaledDbg);
+  cudaFree(h->dTabs); cudaFree(h->dRsTab); cudaFree(h->dLbdG); cudaFree(h->dLbdL);
+  cudaFree(h->dKl); cudaFree(h->dDesc); cudaFree(h->dEq); cudaFree(h->dCounts);
+  if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int plvi_line_capacity(const plvi_line* h) { return h ? h->capGeom.keepCap : PLVI_ERR_INVALID; }
+void* plvi_line_stream(const plvi_line* h) { return h ? (void*)h->stream : nullptr; }
+int plvi_line_last_launches(const plvi_line* h) { return h ? h->lastLaunches : PLVI_ERR_INVALID; }
+int plvi_line_levels(const plvi_line* h) { return h ? h->nlevels : PLVI_ERR_INVALID; }
+
+int plvi_line_scale_factors(const plvi_line* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2) {
+  if (!h) return PLVI_ERR_INVALID;
+  float sf = 1.f;
+  for (int i = 0; i < h->nlevels; i++) {
+    if (i > 0) sf = sf * h->scale;
+    if (scale) scale[i] = sf;
+    if (inv_scale) inv_scale[i] = 1.0f / sf;
+    const float s2 = i > 0 ? sf * sf : 1.0f;
+    if (sigma2) sigma2[i] = s2;
+    if (inv_sigma2) inv_sigma2[i] = 1.0f / s2;
+  }
+  return PLVI_OK;
+}
+
+int plvi_line_octave_sizes(const plvi_line* h, int w, int hh, int* ow, int* oh, int* sw, int* sh) {
+  if (!h) return PLVI_ERR_INVALID;
+  LineGeom g;
+  int rc = make_geom(h, w, hh, g, nullptr, nullptr);
+  if (rc) return rc;
+  for (int o = 0; o < g.noct; o++) {
+    if (ow) ow[o] = g.o[o].w;
+    if (oh) oh[o] = g.o[o].h;
+    if (sw) sw[o] = g.o[o].sw;
+    if (sh) sh[o] = g.o[o].sh;
+  }
+  return PLVI_OK;
+}
+
+int plvi_line_set_debug(plvi_line* h, int on) {
+  if (!h) return PLVI_ERR_INVALID;
+  PLVI_CUDA_TRY(cudaSetDevice(h->device));
+  PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (on && !h->buf.scaledDbg)
+    PLVI_CUDA_TRY(cudaMalloc((void**)&h->buf.scaledDbg, (size_t)h->maxBatch * h->capGeom.pxTotal * sizeof(double)));
+  if (!on && h->buf.scaledDbg) { cudaFree(h->buf.scaledDbg); h->buf.scaledDbg = nullptr; }
+  h->debug = on != 0;
+  return PLVI_OK;
+}
+
+int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, int w, int hh, int stride,
+                                   size_t frame_stride, plvi_keyline* d_kl, uint8_t* d_desc, double* d_eq,
+                                   int* d_counts) {
+  int rc = check_batch(h, d_imgs, n, w, hh, stride);
+  if (rc) return rc;
+  if (!d_kl || !d_desc || !d_eq || !d_counts) { set_error("null output"); return PLVI_ERR_INVALID; }
+  PLVI_CUDA_TRY(cudaSetDevice(h->device));
+  if ((rc = ensure_geom(h, w, hh))) return rc;
+  LinePtrs p;
+  fill_ptrs(h, d_imgs, stride, frame_stride, p);
+  h->lastPtrs = p;
+  h->lastN = n;
+  return launch_line_pipeline(h->geom, p, h->buf, n, d_kl, d_desc, d_eq, d_counts, h->stream, &h->lastLaunches);
+}
+
+int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int w, int hh, int stride,
+                                  size_t frame_stride, plvi_keyline* kl, uint8_t* desc, double* line_eq,
+                                  int* counts) {
+  int rc = check_batch(h, imgs, n, w, hh, stride);
+  if (rc) return rc;
+  if (!kl || !desc || !line_eq || !counts) { set_error("null output"); return PLVI_ERR_INVALID; }
+  PLVI_CUDA_TRY(cudaSetDevice(h->device));
+  if ((rc = ensure_geom(h, w, hh))) return rc;
+  const LineOct& O0 = h->geom.o[0];
+  if (frame_stride == (size_t)stride * hh) {
+    PLVI_CUDA_TRY(cudaMemcpy2DAsync(h->dImg[0], O0.pitch, imgs, stride, w, (size_t)hh * n, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    for (int i = 0; i < n; i++)
+      PLVI_CUDA_TRY(cudaMemcpy2DAsync(h->dImg[0] + (size_t)i * O0.pitch * O0.h, O0.pitch, imgs + (size_t)i * frame_stride,
+                                      stride, w, hh, cudaMemcpyHostToDevice, h->stream));
+  }
+  LinePtrs p;
+  fill_ptrs(h, nullptr, 0, 0, p);
+  h->lastPtrs = p;
+  h->lastN = n;
+  rc = launch_line_pipeline(h->geom, p, h->buf, n, h->dKl, h->dDesc, h->dEq, h->dCounts, h->stream, &h->lastLaunches);
+  if (rc) return rc;
+  const size_t rows = (size_t)n * h->geom.keepCap;
+  PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(kl, h->dKl, rows * sizeof(plvi_keyline), cudaMemcpyDeviceToHost, h->stream));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(desc, h->dDesc, rows * 32, cudaMemcpyDeviceToHost, h->stream));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(line_eq, h->dEq, rows * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return PLVI_OK;
+}
+
+int plvi_line_sync(plvi_line* h) {
+  if (!h) return PLVI_ERR_INVALID;
+  PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PLVI_OK;
+}
+
+int plvi_line_extract_batch(plvi_line* h, const uint8_t* imgs, int n, int w, int hh, int stride, size_t frame_stride,
+                            plvi_keyline* kl, uint8_t* desc, double* line_eq, int* counts) {
+  int rc = plvi_line_extract_batch_async(h, imgs, n, w, hh, stride, frame_stride, kl, desc, line_eq, counts);
+  if (rc) return rc;
+  return plvi_line_sync(h);
+}
+
+// what: 0 scaled f64 image (needs set_debug), 1 angle degrees f32 (-1024 = NOTDEF), 2 gradient magnitude f64,
+// 3 raw segments float4 (out holds cap entries; *count receives the number), 4 pyramid octave u8 (dense w x h)
+int plvi_line_read_lsd(plvi_line* h, int frame, int octave, int what, void* out, int cap, int* count) {
+  if (!h || !out || frame < 0 || frame >= h->lastN || octave < 0 || octave >= h->nlevels || h->curW < 0) return PLVI_ERR_INVALID;
+  PLVI_CUDA_TRY(cudaSetDevice(h->device));
+  PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  const LineGeom& g = h->geom;
+  const LineOct& O = g.o[octave];
+  const size_t npx = (size_t)O.sw * O.sh, pb = (size_t)frame * g.pxTotal + O.pxOff;
+  switch (what) {
+    case 0:
+      if (!h->buf.scaledDbg) { set_error("debug not enabled"); return PLVI_ERR_INVALID; }
+      PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.scaledDbg + pb, npx * sizeof(double), cudaMemcpyDeviceToHost));
+      break;
+    case 1: PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.ang + pb, npx * sizeof(float), cudaMemcpyDeviceToHost)); break;
+    case 2: PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.mod + pb, npx * sizeof(double), cudaMemcpyDeviceToHost)); break;
+    case 3: {
+      int n = 0;
+      PLVI_CUDA_TRY(cudaMemcpy(&n, h->buf.regCount + frame * 2 + octave, sizeof(int), cudaMemcpyDeviceToHost));
+      if (count) *count = n;
+      const int m = std::max(0, std::min(n, cap));
+      PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.segs + (size_t)frame * g.segTotal + O.segOff, m * sizeof(float4), cudaMemcpyDeviceToHost));
+      break;
+    }
+    case 4:
+      PLVI_CUDA_TRY(cudaMemcpy2D(out, O.w, h->lastPtrs.img[octave] + (size_t)frame * h->lastPtrs.ifs[octave],
+                                 h->lastPtrs.ipitch[octave], O.w, O.h, cudaMemcpyDeviceToHost));
+      break;
+    default: return PLVI_ERR_INVALID;
+  }
+  return PLVI_OK;
+}
+
+}  // extern "C"

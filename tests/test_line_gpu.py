@@ -1,0 +1,131 @@
+"""GPU parity: CUDA line path (LSD + KeyLine assembly + LBD, through the C ABI) vs the
+CPU oracle.  Bars (BASELINE.json north_star): segment counts equal, endpoints within
+0.5 px, LBD bits >= 99.5 %.  The integer / bit-reproducible parts (octave images, scaled
+f64 image, level-line angles, gradient magnitudes, region growing => raw segment list)
+are additionally required to be exact."""
+import numpy as np
+import pytest
+
+import oracle
+from pl_vi_orbslam3_b200 import Lineextractor, synth
+
+pytestmark = pytest.mark.gpu
+
+ENDPOINT_TOL_PX = 0.5
+LBD_BIT_AGREEMENT = 0.995
+
+
+@pytest.fixture(scope="module")
+def ext(gpu):
+    e = Lineextractor(200, 0, 0.8, 2, 2.0, 0, max_width=752, max_height=480, max_batch=4)
+    yield e
+    e.close()
+
+
+def _check_lines(kl, desc, eq, ref):
+    rk, rd, re_ = ref["keylines"], ref["descriptors"], ref["line_eq"]
+    assert len(kl) == len(rk), (len(kl), len(rk))
+    if len(kl) == 0:
+        return 1.0
+    for f in ("class_id", "octave", "numOfPixels"):
+        assert np.array_equal(kl[f], rk[f]), f
+    for f in ("startPointX", "startPointY", "endPointX", "endPointY", "sPointInOctaveX", "sPointInOctaveY",
+              "ePointInOctaveX", "ePointInOctaveY", "pt_x", "pt_y"):
+        assert np.abs(kl[f] - rk[f]).max() <= ENDPOINT_TOL_PX, f
+    assert np.abs(kl["lineLength"] - rk["lineLength"]).max() <= 2 * ENDPOINT_TOL_PX
+    assert np.allclose(kl["angle"], rk["angle"], atol=1e-3)
+    assert np.allclose(kl["response"], rk["response"], atol=2e-3)
+    agree = 1.0 - np.unpackbits(desc ^ rd).mean()
+    assert agree >= LBD_BIT_AGREEMENT, agree
+    assert np.allclose(eq, re_, rtol=1e-6, atol=1e-3)
+    return agree
+
+
+def test_lsd_internals_exact(ext):
+    img = synth.frame_euroc(0)
+    ext.set_debug(True)
+    ext(img)
+    ow, oh, sw, sh = ext.octave_sizes(752, 480)
+    oct1 = oracle.resize_linear(img, int(ow[1]), int(oh[1]))
+    assert np.array_equal(ext.read_lsd(0, 1, "octave", 752, 480), oct1)
+    for o, im in enumerate((img, oct1)):
+        segs, dbg = oracle.lsd(im, 0.8, debug=True)
+        assert (dbg["w"], dbg["h"]) == (int(sw[o]), int(sh[o]))
+        assert np.array_equal(ext.read_lsd(0, o, "scaled", 752, 480), dbg["scaled"]), f"scaled octave {o}"
+        assert np.array_equal(ext.read_lsd(0, o, "modgrad", 752, 480), dbg["modgrad"]), f"modgrad octave {o}"
+        ang = ext.read_lsd(0, o, "angle_deg", 752, 480)
+        ang_rad = np.where(ang == -1024.0, -1024.0, ang.astype(np.float64) * (np.pi / 180))
+        assert np.array_equal(ang_rad, dbg["angles"]), f"angles octave {o}"
+        got = ext.read_lsd(0, o, "segments", 752, 480)
+        assert len(got) == len(segs), (o, len(got), len(segs))
+        assert np.abs(got - segs).max() <= ENDPOINT_TOL_PX
+    ext.set_debug(False)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 5])
+def test_line_extract_matches_oracle(ext, seed):
+    img = synth.frame_euroc(seed)
+    kl, desc, eq = ext(img)
+    ref = oracle.line_extract(img)
+    assert len(kl) == 200
+    _check_lines(kl, desc, eq, ref)
+
+
+def test_line_batch(ext):
+    frames = np.stack([synth.frame_euroc(20 + s) for s in range(4)])
+    kl, desc, eq, counts = ext.extract_batch(frames)
+    for i in range(4):
+        n = counts[i]
+        _check_lines(kl[i, :n], desc[i, :n], eq[i, :n], oracle.line_extract(frames[i]))
+
+
+def test_line_flat_image_no_lines(ext):
+    flat = np.full((480, 752), 90, np.uint8)
+    kl, desc, eq = ext(flat)
+    assert len(kl) == 0
+
+
+def test_line_noise_image(ext):
+    rng = np.random.RandomState(4)
+    img = rng.randint(0, 256, (480, 752)).astype(np.uint8)
+    kl, desc, eq = ext(img)
+    _check_lines(kl, desc, eq, oracle.line_extract(img))
+
+
+def test_line_rejects_unsupported_configs(gpu):
+    from pl_vi_orbslam3_b200.capi import PlviError
+    for args in ((200, 1, 0.8, 2, 2.0, 0), (200, 0, 0.8, 2, 2.0, 1), (200, 0, 0.8, 3, 2.0, 0)):
+        with pytest.raises(PlviError):
+            Lineextractor(*args)
+    e = Lineextractor(200, 0, 0.8, 2, 2.0, 0)
+    with pytest.raises(RuntimeError):
+        e(np.zeros((480, 752), np.uint16))
+    with pytest.raises(RuntimeError):
+        e(np.zeros((480, 752), np.uint8), mask=np.zeros((10, 10), np.uint8))
+    e.close()
+
+
+@pytest.mark.parametrize("w,h,nfeat,levels", [(640, 480, 200, 2), (1280, 720, 200, 2), (752, 480, 0, 2), (752, 480, 200, 1)])
+def test_line_other_configs(gpu, w, h, nfeat, levels):
+    e = Lineextractor(nfeat, 0, 0.8, levels, 2.0, 0, max_width=w, max_height=h, max_batch=1)
+    try:
+        img = synth.frame_euroc(60, w, h)
+        kl, desc, eq = e(img)
+        _check_lines(kl, desc, eq, oracle.line_extract(img, lsd_nfeatures=nfeat, nlevels=levels))
+    finally:
+        e.close()
+
+
+def test_line_device_resident_api(ext):
+    import torch
+    frames = np.stack([synth.frame_euroc(s) for s in (70, 71)])
+    d = torch.from_numpy(frames).cuda()
+    st = torch.cuda.ExternalStream(ext.stream)
+    with torch.cuda.stream(st):
+        kl, desc, eq, counts = ext.extract_batch_device(d)
+    st.synchronize()
+    kl = kl.cpu().numpy().view(np.uint8).reshape(2, ext.capacity, 68).copy().view(oracle.KEYLINE_DTYPE)[..., 0]
+    desc, eq, counts = desc.cpu().numpy(), eq.cpu().numpy(), counts.cpu().numpy()
+    for i in range(2):
+        n = counts[i]
+        _check_lines(kl[i, :n], desc[i, :n], eq[i, :n], oracle.line_extract(frames[i]))
