@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""Benchmark of the front-end hot path (BASELINE.json): frames/s on synthetic 752x480
+EuRoC-shaped frames through ORB (1000 feats, 8 levels, 1.2, FAST 20/7) + LSD/LBD lines
+(200 lines, refine 0, lsd_scale 0.8, 2 levels) + frame-to-frame Hamming matching
+(SearchByProjection semantics for points, LineMatcher::match for lines).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path, one JSON line
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port) on host cores
+
+One "step" = one batch of B frames per GPU through the whole path.  `value` is measured
+with the frames already resident in HBM; `e2e` includes the pinned-host -> device copy of
+every frame and the device -> host read of every result.  Frames shard across ranks by
+contiguous range with no collective (weak scaling: B frames per GPU per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H = 752, 480
+WORKLOAD = "C2+C3: 752x480, ORB 1000f/8lvl/1.2 FAST20/7 + LSD/LBD 200 lines (refine0, 0.8, 2 lvl) + frame-to-frame Hamming match"
+
+# Algorithmic (compulsory) bytes per frame of each kernel at 752x480 -- DESIGN.md section 4.
+P_ORB = 1117367                       # pyramid pixels, 8 levels
+P_LSD = 602 * 384 + 301 * 192         # LSD working pixels, 2 octaves
+P_RAW = 752 * 480 + 376 * 240         # line pyramid pixels
+ALGO_BYTES = {
+    "k_resize": 1089227 + 756407 + 360960 + 90240,
+    "k_fast": P_ORB + 8 * 13000,
+    "k_octree": 13000 * 6 + 1021 * 4,
+    "k_blur7": 2 * P_ORB,
+    "k_layout": 1021 * 8,
+    "k_orient_desc": 1021 * (709 + 512 + 60),
+    "k_lsd_rowfilter": P_RAW * (1 + 8),
+    "k_lsd_scale_grad": P_RAW * 8 + P_LSD * (4 + 16 + 8) + P_LSD // 8,
+    "k_lsd_grow": P_LSD * 4 + (P_LSD // 2) * (16 + 4) + P_LSD // 8,
+    "k_lsd_rect": (P_LSD // 2) * (4 + 8) + 2600 * 32,
+    "k_line_assemble": 2600 * 16 + 200 * 68,
+    "k_gauss5": 2 * 752 * 480,
+    "k_pyrdown": 752 * 480 + 376 * 240,
+    "k_sobel": P_RAW * (1 + 4),
+    "k_lbd": 200 * 63 * 60 * 4 + 200 * (68 + 32 + 24),
+}
+
+
+def _cpu_pair_job(idx_frames):
+    """CPU arm over a contiguous shard: every frame is extracted once (ORB + lines) and matched
+    against the previous frame of the shard, like a sequential tracker."""
+    import oracle
+    from pl_vi_orbslam3_b200.capi import QUERY_DTYPE
+    from pl_vi_orbslam3_b200.matchers import frame_grid
+    frames = idx_frames
+    prev_r = prev_l = None
+    grid = frame_grid(0, W, 0, H)
+    for f in frames:
+        r = oracle.orb_extract(f)
+        l = oracle.line_extract(f)
+        if prev_r is not None:
+            k = prev_r["keypoints"]
+            q = np.zeros(len(k), QUERY_DTYPE)
+            q["u"], q["v"] = k["x"], k["y"]
+            q["radius"] = np.float32(15.0) * (np.float32(1.2) ** k["octave"].astype(np.float32))
+            q["min_level"], q["max_level"], q["angle"] = k["octave"] - 1, k["octave"] + 1, k["angle"]
+            oracle.search_frame(r["keypoints"], r["descriptors"], grid, q, prev_r["descriptors"], 100, True)
+            oracle.line_match(prev_l["descriptors"], l["descriptors"], 0.9)
+        prev_r, prev_l = r, l
+    return len(frames)
+
+
+def cpu_arm(frames, cores):
+    """Times the oracle port over `frames` with `cores` worker processes (contiguous shards).
+    Returns frames/s.  Must run before CUDA is initialised in this process (fork)."""
+    import multiprocessing as mp
+    import oracle
+    oracle.build()
+    shards = [s for s in np.array_split(frames, cores) if len(s)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(shards)) as pool:
+        pool.map(_cpu_pair_job, [s[:1] for s in shards])  # warm-up: library load, page-in
+        t0 = time.perf_counter()
+        done = sum(pool.map(_cpu_pair_job, shards))
+        dt = time.perf_counter() - t0
+    return done / dt, dt
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLVI_BENCH_BATCH", 1024)))
+    ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU baseline sample (0 = 4 per core)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--orb-only", action="store_true", help="diagnostic: time ORB extraction alone (not the bench metric)")
+    ap.add_argument("--profile-out", default="")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    cores = os.cpu_count() or 1
+
+    from pl_vi_orbslam3_b200 import synth
+
+    # ------------------------------------------------------------------ CPU arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        per_step = args.cpu_sample or min(4 * cores, 256)
+        frames = synth.frame_batch(per_step, W, H, base_seed=0, distinct=16)
+        for _ in range(max(args.warmup, 0)):
+            cpu_arm(frames[: max(cores, 2)], cores)
+        t = 0.0
+        done = 0
+        for _ in range(args.steps):
+            fps, dt = cpu_arm(frames, cores)
+            t += dt
+            done += len(frames)
+        v = done / t
+        print(json.dumps({
+            "impl": "reference", "metric": "frames/s", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": per_step},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} synthetic frames per step, contiguous shards over {cores} worker processes "
+                                       "(oracle/ C++ port of the reference path; the reference itself needs OpenCV C++/Eigen and cannot be built here)"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    # ------------------------------------------------------------------ CUDA arm
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nsamp = args.cpu_sample or min(4 * cores, 128)
+        fps, dt = cpu_arm(synth.frame_batch(nsamp, W, H, base_seed=0, distinct=16), cores)
+        cpu_base = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                    "sample": f"{nsamp} synthetic 752x480 frames (same generator), contiguous shards over {cores} worker "
+                              f"processes, {dt:.1f} s wall; oracle/ C++ port (reference needs OpenCV C++/Eigen: not buildable here)"}
+
+    import torch
+    import torch.distributed as dist
+    from pl_vi_orbslam3_b200.frontend import FrontEnd
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    frames = synth.frame_batch(B, W, H, base_seed=1000 * rank, distinct=16)
+    h_frames = torch.from_numpy(frames).pin_memory()
+    fe = FrontEnd(B, W, H, device=local_rank, with_lines=not args.orb_only, with_match=not args.orb_only)
+    st = fe.stream
+    with torch.cuda.stream(st):
+        d_frames = h_frames.to(dev, non_blocking=True)
+    st.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    with torch.cuda.stream(st):
+        for _ in range(args.warmup):
+            fe.step(d_frames)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with torch.cuda.stream(st):
+        e0.record(st)
+        for _ in range(args.steps):
+            launches += fe.step(d_frames)
+        e1.record(st)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+
+    # ---- end to end: pinned host frames in, every result back on the host
+    outs = fe.outputs()
+    h_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
+    d_in = torch.empty_like(d_frames)
+
+    def e2e_step():
+        d_in.copy_(h_frames, non_blocking=True)
+        fe.step(d_in)
+        for k, v in fe.outputs().items():
+            h_out[k].copy_(v, non_blocking=True)
+
+    with torch.cuda.stream(st):
+        for _ in range(2):
+            e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        f0.record(st)
+        for _ in range(args.steps):
+            e2e_step()
+        f1.record(st)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    h2d = int(h_frames.numel())
+    d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()))
+
+    # ---- per-kernel profile of one extra step (events after every launch; not part of the timed numbers)
+    fe.set_profile(True)
+    with torch.cuda.stream(st):
+        fe.step(d_frames)
+    st.synchronize()
+    prof = fe.profile()
+    fe.set_profile(False)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    counts = outs["counts"].float().mean().item()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        top = max(prof, key=prof.get) if prof else None
+        roof = None
+        if top:
+            ach = ALGO_BYTES.get(top, 0) * B / (prof[top] * 1e-3) / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                    "kernel_ms_per_launch": prof[top], "frames_per_launch": B,
+                    "note": "latency-bound serial region growing; see DESIGN.md section 4" if top == "k_lsd_grow" else ""}
+        total_prof = sum(prof.values()) or 1.0
+        line = {
+            "metric": "frames/s", "value": world * B * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD if not args.orb_only else "DIAGNOSTIC orb-only", "frames_per_step_per_gpu": B,
+                       "width": W, "height": H, "l2_policy": "inputs larger than L2 (%.0f MB of frames per step)" % (B * W * H / 1e6),
+                       "parallelism": f"frame-sharded x{world}, no collective", "mean_keypoints": counts},
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu_base,
+            "kernel_ms": {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
+            "kernel_share": {k: round(v / total_prof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
+        }
+        print(json.dumps(line))
+        if args.profile_out:
+            Path(args.profile_out).write_text(json.dumps(line, indent=1))
+    fe.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

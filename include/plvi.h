@@ -126,6 +126,11 @@ int plvi_orb_read_candidates(plvi_orb* h, int frame, int level, uint32_t* out, i
                              int* count);
 /* number of kernel launches enqueued by the last extract call */
 int plvi_orb_last_launches(const plvi_orb* h);
+/* Per-kernel device time of the last batch: with profiling on, a CUDA event is recorded
+ * on the handle's stream after every launch; plvi_orb_profile() synchronises and returns
+ * "kernel=ms;kernel=ms;..." (valid until the next call). */
+int plvi_orb_set_profile(plvi_orb* h, int on);
+const char* plvi_orb_profile(plvi_orb* h);
 
 /* ---------------------------------------------------------------- lines ---- */
 typedef struct plvi_line plvi_line;
@@ -173,6 +178,8 @@ int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, i
  * 2 gradient magnitude f64, 3 raw segments (x1,y1,x2,y2 f32; *count = number),
  * 4 pyramid octave image u8 (gaussianPyrs[octave]). */
 int plvi_line_set_debug(plvi_line* h, int on);
+int plvi_line_set_profile(plvi_line* h, int on);
+const char* plvi_line_profile(plvi_line* h);
 int plvi_line_read_lsd(plvi_line* h, int frame, int octave, int what, void* out, int cap, int* count);
 
 /* ------------------------------------------------------- Hamming searches ---- */
@@ -235,6 +242,14 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
                               plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
                               int query_stride, int th_dist, float nnratio, int check_orientation,
                               int* match_train, int* match_query, int* nmatches, int on_device);
+
+/* Test / benchmark utility (device pointers only): builds the plvi_query records of
+ * SearchByProjection(Frame,Frame) for an identity pose -- every keypoint of the query
+ * frame projects onto its own position (u,v = pt), radius = th * scale_factor^octave,
+ * levels octave-1..octave+1 (src/ORBmatcher.cc:2014-2023).  With a real pose the caller
+ * fills plvi_query from its own projection code instead. */
+int plvi_queries_from_keypoints(plvi_matcher* m, const plvi_keypoint* d_kps, const int* d_counts, int npairs,
+                                int stride, float th, float scale_factor, plvi_query* d_queries);
 
 /* static int LineMatcher::match(desc1, desc2, nnr, matches_12) (include/LineMatcher.h:87-107,
  * src/LineMatcher.cpp:92-111) with mutual != 0, LineMatcher::matchNNR (:41-61) with

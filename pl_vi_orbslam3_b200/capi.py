@@ -49,6 +49,10 @@ _SIGS = {
     "plvi_orb_read_level": (ci, [vp, ci, ci, ci, vp]),
     "plvi_orb_read_candidates": (ci, [vp, ci, ci, vp, ci, vp]),
     "plvi_orb_last_launches": (ci, [vp]),
+    "plvi_orb_set_profile": (ci, [vp, ci]),
+    "plvi_orb_profile": (C.c_char_p, [vp]),
+    "plvi_line_set_profile": (ci, [vp, ci]),
+    "plvi_line_profile": (C.c_char_p, [vp]),
     "plvi_line_create": (ci, [C.POINTER(vp), ci, ci, cf, ci, cf, ci, ci, ci, ci, ci, vp]),
     "plvi_line_destroy": (None, [vp]),
     "plvi_line_capacity": (ci, [vp]),
@@ -70,6 +74,7 @@ _SIGS = {
     "plvi_hamming256": (ci, [vp, vp, vp, ci, ci, vp, ci]),
     "plvi_search_by_projection": (ci, [vp, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, ci, cf, ci,
                                        vp, vp, vp, ci]),
+    "plvi_queries_from_keypoints": (ci, [vp, vp, vp, ci, ci, cf, cf, vp]),
     "plvi_line_match": (ci, [vp, ci, vp, vp, ci, vp, vp, ci, cf, ci, vp, vp, ci]),
 }
 

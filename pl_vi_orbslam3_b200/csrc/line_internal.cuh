@@ -60,7 +60,7 @@ struct LineBufs {
 };
 
 int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b, int n, plvi_keyline* dKl,
-                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, int* launches);
+                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, int* launches, StageProf* prof);
 int line_kernel_attrs(const LineGeom& g);
 void launch_resize_u8(const u8* src, int spitch, size_t sfs, int sw, int sh, u8* dst, int dpitch, size_t dfs, int dw,
                       int dh, const int2* xtab, const int2* ytab, int n, cudaStream_t st);

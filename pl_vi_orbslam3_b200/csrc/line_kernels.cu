@@ -696,47 +696,61 @@ __global__ void __launch_bounds__(64) k_lbd(const __grid_constant__ LineGeom g, 
 // launch sequence
 // ---------------------------------------------------------------------------------------
 int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b, int n, plvi_keyline* dKl,
-                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, int* launches) {
+                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, int* launches, StageProf* prof) {
   int nl = 0;
+  StageProf nop;
+  if (!prof) prof = &nop;
+  prof->begin(st);
   // LSD pyramid level 1 (2x bilinear; LSDDetectorC::ComputePyramid)
   if (g.noct > 1) {
     const LineOct& d = g.o[1];
     launch_resize_u8(p.img[0], p.ipitch[0], p.ifs[0], g.o[0].w, g.o[0].h, const_cast<u8*>(p.img[1]), p.ipitch[1],
                      p.ifs[1], d.w, d.h, b.rsTab, b.rsTab + d.w, n, st);
     nl++;
+    prof->mark("k_resize", st);
   }
   for (int o = 0; o < g.noct; o++) {
     const LineOct& O = g.o[o];
     k_lsd_rowfilter<<<dim3((O.w + 63) / 64, (O.h + 3) / 4, n), 256, 0, st>>>(p.img[o], p.ipitch[o], p.ifs[o], O.w, O.h,
                                                                              b.rowf + O.rawOff, g.rawTotal, g);
+    prof->mark("k_lsd_rowfilter", st);
     k_lsd_scale_grad<<<dim3((O.sw + 31) / 32, (O.sh + 7) / 8, n), 256, 0, st>>>(g, o, b.rowf, g.rawTotal, b.tabs, b);
+    prof->mark("k_lsd_scale_grad", st);
     nl += 2;
   }
   const size_t growSmem = (size_t)g.o[0].wpr * g.o[0].sh * sizeof(unsigned);
   k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b);
+  prof->mark("k_lsd_grow", st);
   k_lsd_rect<<<dim3(g.noct, n, 2), 256, 0, st>>>(g, b);
+  prof->mark("k_lsd_rect", st);
   k_line_assemble<512><<<n, 512, 0, st>>>(g, b, dKl, dCounts);
+  prof->mark("k_line_assemble", st);
   nl += 3;
   // LBD pyramid + Sobel
   {
     const LineOct& O0 = g.o[0];
     k_gauss5<<<dim3((O0.lw + 127) / 128, (O0.lh + 31) / 32, n), 256, 0, st>>>(p.img[0], p.ipitch[0], p.ifs[0], b.lbdImg0,
                                                                              O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw, O0.lh);
+    prof->mark("k_gauss5", st);
     k_sobel<<<dim3((O0.lw + 63) / 64, (O0.lh + 3) / 4, n), 256, 0, st>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw,
                                                                         O0.lh, b.grad + O0.lbdOff, g.lbdTotal);
+    prof->mark("k_sobel", st);
     nl += 2;
     if (g.noct > 1) {
       const LineOct& O1 = g.o[1];
       k_pyrdown<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, st>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh,
                                                                             O0.lw, O0.lh, b.lbdImg1, O1.lpitch,
                                                                             (size_t)O1.lpitch * O1.lh, O1.lw, O1.lh);
+      prof->mark("k_pyrdown", st);
       k_sobel<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, st>>>(b.lbdImg1, O1.lpitch, (size_t)O1.lpitch * O1.lh,
                                                                           O1.lw, O1.lh, b.grad + O1.lbdOff, g.lbdTotal);
+      prof->mark("k_sobel", st);
       nl += 2;
     }
   }
   k_lbd<<<dim3(g.keepCap, n), 64, 0, st>>>(g, b, dKl, dCounts, dDesc, dEq);
   nl++;
+  prof->mark("k_lbd", st);
   PLVI_CUDA_TRY(cudaGetLastError());
   if (launches) *launches = nl;
   return PLVI_OK;

@@ -345,6 +345,26 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
   if (tid == 0) a.nmatches[pair] = s_nm;
 }
 
+// Identity-pose stand-in for the host-side projection of SearchByProjection(Frame,Frame)
+// (src/ORBmatcher.cc:1992-2023): every keypoint of the query frame "projects" onto its own
+// position; radius = th * mvScaleFactors[octave]; levels octave-1 .. octave+1.
+__global__ void k_queries_from_keypoints(const plvi_keypoint* __restrict__ kps, const int* __restrict__ counts,
+                                         int stride, float th, float scaleFactor, plvi_query* __restrict__ q) {
+  const int pair = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= counts[pair]) return;
+  const plvi_keypoint k = kps[(size_t)pair * stride + i];
+  float sf = 1.f;
+  for (int l = 0; l < k.octave; l++) sf = __fmul_rn(sf, scaleFactor);
+  plvi_query o;
+  o.u = k.x; o.v = k.y;
+  o.radius = __fmul_rn(th, sf);
+  o.min_level = k.octave - 1;
+  o.max_level = k.octave + 1;
+  o.angle = k.angle;
+  o.flags = 0;
+  q[(size_t)pair * stride + i] = o;
+}
+
 // ---- lines: knn-2 + ratio in both directions + mutual check, one CTA per pair ---------
 __device__ void nnr_rows(const uint8_t* sa, int na, const uint8_t* sb, int nb, float nnr, int* out) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -567,6 +587,20 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
       PLVI_CUDA_TRY(cudaMemcpyAsync(queries, m->dQ, P * Q * sizeof(plvi_query), cudaMemcpyDeviceToHost, st));
     PLVI_CUDA_TRY(cudaStreamSynchronize(st));
   }
+  return PLVI_OK;
+}
+
+int plvi_queries_from_keypoints(plvi_matcher* m, const plvi_keypoint* d_kps, const int* d_counts, int npairs,
+                                int stride, float th, float scale_factor, plvi_query* d_queries) {
+  if (!m || !d_kps || !d_counts || !d_queries || npairs < 1 || stride < 1) {
+    set_error("plvi_queries_from_keypoints: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  k_queries_from_keypoints<<<dim3((stride + 255) / 256, npairs), 256, 0, m->stream>>>(d_kps, d_counts, stride, th,
+                                                                                     scale_factor, d_queries);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
   return PLVI_OK;
 }
 

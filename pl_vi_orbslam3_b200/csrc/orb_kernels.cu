@@ -760,8 +760,11 @@ int orb_kernel_attrs(const OrbGeom& g, int* fastSmem, int* octSmem) {
 
 int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s, int n, int lap0,
                         int lap1, plvi_keypoint* d_kps, uint8_t* d_desc, int* d_counts,
-                        int* d_mono, int cap, cudaStream_t st, int* launches) {
+                        int* d_mono, int cap, cudaStream_t st, int* launches, StageProf* prof) {
   int nl = 0;
+  StageProf nop;
+  if (!prof) prof = &nop;
+  prof->begin(st);
   PLVI_CUDA_TRY(cudaMemsetAsync(s.candCount, 0, sizeof(int) * (size_t)n * g.nlevels, st));
   // pyramid (chained: level l from level l-1)
   for (int l = 1; l < g.nlevels; l++) {
@@ -773,6 +776,7 @@ int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s,
                                   s.rsTab + d.rsOff, s.rsTab + d.rsOff + d.w);
     nl++;
   }
+  prof->mark("k_resize", st);
   // FAST tile geometry recomputed here must match capi's smem sizing
   {
     int tilePitch, maxH, maxSurv;
@@ -781,17 +785,22 @@ int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s,
                                                           tilePitch, maxH, maxSurv);
     nl++;
   }
+  prof->mark("k_fast", st);
   k_octree<OCT_NT><<<dim3(g.nlevels, n), OCT_NT, s.octSmem, st>>>(g, s.cand, s.candCount, s.knode,
                                                                s.lvlKp, s.lvlCount);
   nl++;
+  prof->mark("k_octree", st);
   k_blur7<<<dim3(s.nBlurTiles, n), 256, 0, st>>>(g, p, s.blurTiles);
   nl++;
+  prof->mark("k_blur7", st);
   k_layout<256><<<n, 256, 0, st>>>(g, s.lvlKp, s.lvlCount, lap0, lap1, s.slot, d_counts, d_mono);
   nl++;
+  prof->mark("k_layout", st);
   const int kpPerCta = 32;
   k_orient_desc<<<dim3((g.kpTotal + kpPerCta - 1) / kpPerCta, n), OD_WARPS * 32, 0, st>>>(
       g, p, s.lvlKp, s.lvlCount, s.slot, kpPerCta, d_kps, d_desc, cap);
   nl++;
+  prof->mark("k_orient_desc", st);
   PLVI_CUDA_TRY(cudaGetLastError());
   if (launches) *launches = nl;
   return PLVI_OK;

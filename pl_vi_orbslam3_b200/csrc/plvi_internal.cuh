@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/plvi.h"
 
@@ -21,6 +23,37 @@ void set_error(const std::string& msg);
       return PLVI_ERR_CUDA;                                                              \
     }                                                                                    \
   } while (0)
+
+// ---- optional per-kernel timing (CUDA events on the launching stream) ----------------
+struct StageProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> names;
+  int n = 0;
+  void begin(cudaStream_t st) { n = 0; names.clear(); if (on) mark(nullptr, st); }
+  void mark(const char* name, cudaStream_t st) {
+    if (!on) return;
+    if ((int)ev.size() <= n) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+    cudaEventRecord(ev[n], st);
+    if (name) names.push_back(name);
+    n++;
+  }
+  // after the stream has been synchronised: "name=ms;name=ms;..." (same-named stages summed)
+  std::string report() {
+    std::string out;
+    std::vector<std::pair<std::string, float>> acc;
+    for (int i = 1; i < n; i++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[i - 1], ev[i]) != cudaSuccess) continue;
+      bool found = false;
+      for (auto& a : acc) if (a.first == names[i - 1]) { a.second += ms; found = true; }
+      if (!found) acc.push_back({names[i - 1], ms});
+    }
+    for (auto& a : acc) out += a.first + "=" + std::to_string(a.second) + ";";
+    return out;
+  }
+  ~StageProf() { for (auto e : ev) cudaEventDestroy(e); }
+};
 
 // ---- ORB geometry (ORBextractor ctor + ComputeKeyPointsOctTree grid) ----------------
 static const int kEdge = 16;      // minBorder = EDGE_THRESHOLD - 3, src/ORBextractor.cc:771
@@ -87,7 +120,7 @@ struct OrbScratch {
 
 int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s, int n, int lap0,
                         int lap1, plvi_keypoint* d_kps, uint8_t* d_desc, int* d_counts,
-                        int* d_mono, int cap, cudaStream_t st, int* launches);
+                        int* d_mono, int cap, cudaStream_t st, int* launches, StageProf* prof);
 int orb_kernel_attrs(const OrbGeom& g, int* fastSmem, int* octSmem);
 
 }  // namespace plvi

@@ -30,6 +30,8 @@ struct plvi_line {
   double* dEq = nullptr;
   int* dCounts = nullptr;
   int lastN = 0, lastLaunches = 0;
+  StageProf prof;
+  std::string profText;
   bool debug = false;
   LinePtrs lastPtrs = {};
 };
@@ -349,7 +351,7 @@ int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, i
   fill_ptrs(h, d_imgs, stride, frame_stride, p);
   h->lastPtrs = p;
   h->lastN = n;
-  return launch_line_pipeline(h->geom, p, h->buf, n, d_kl, d_desc, d_eq, d_counts, h->stream, &h->lastLaunches);
+  return launch_line_pipeline(h->geom, p, h->buf, n, d_kl, d_desc, d_eq, d_counts, h->stream, &h->lastLaunches, &h->prof);
 }
 
 int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int w, int hh, int stride,
@@ -372,7 +374,7 @@ int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int 
   fill_ptrs(h, nullptr, 0, 0, p);
   h->lastPtrs = p;
   h->lastN = n;
-  rc = launch_line_pipeline(h->geom, p, h->buf, n, h->dKl, h->dDesc, h->dEq, h->dCounts, h->stream, &h->lastLaunches);
+  rc = launch_line_pipeline(h->geom, p, h->buf, n, h->dKl, h->dDesc, h->dEq, h->dCounts, h->stream, &h->lastLaunches, &h->prof);
   if (rc) return rc;
   const size_t rows = (size_t)n * h->geom.keepCap;
   PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -386,6 +388,20 @@ int plvi_line_sync(plvi_line* h) {
   if (!h) return PLVI_ERR_INVALID;
   PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PLVI_OK;
+}
+
+int plvi_line_set_profile(plvi_line* h, int on) {
+  if (!h) return PLVI_ERR_INVALID;
+  h->prof.on = on != 0;
+  return PLVI_OK;
+}
+
+const char* plvi_line_profile(plvi_line* h) {
+  if (!h) return "";
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->profText = h->prof.report();
+  return h->profText.c_str();
 }
 
 int plvi_line_extract_batch(plvi_line* h, const uint8_t* imgs, int n, int w, int hh, int stride, size_t frame_stride,

@@ -45,6 +45,8 @@ struct plvi_orb {
   int* dMono = nullptr;
   int cap = 0;
   int lastN = 0, lastLaunches = 0;
+  StageProf prof;
+  std::string profText;
   OrbPtrs lastPtrs = {};
 };
 
@@ -386,7 +388,7 @@ int plvi_orb_extract_batch_device(plvi_orb* h, const uint8_t* d_imgs, int n, int
   h->lastPtrs = p;
   h->lastN = n;
   return launch_orb_pipeline(h->geom, p, h->scr, n, lap0, lap1, d_kps, d_desc, d_counts, d_mono,
-                             h->cap, h->stream, &h->lastLaunches);
+                             h->cap, h->stream, &h->lastLaunches, &h->prof);
 }
 
 int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w, int hh, int stride,
@@ -412,7 +414,7 @@ int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w,
   h->lastPtrs = p;
   h->lastN = n;
   rc = launch_orb_pipeline(h->geom, p, h->scr, n, lap0, lap1, h->dKps, h->dDesc, h->dCounts,
-                           h->dMono, h->cap, h->stream, &h->lastLaunches);
+                           h->dMono, h->cap, h->stream, &h->lastLaunches, &h->prof);
   if (rc) return rc;
   const size_t rows = (size_t)n * h->cap;
   PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -426,6 +428,20 @@ int plvi_orb_sync(plvi_orb* h) {
   if (!h) return PLVI_ERR_INVALID;
   PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PLVI_OK;
+}
+
+int plvi_orb_set_profile(plvi_orb* h, int on) {
+  if (!h) return PLVI_ERR_INVALID;
+  h->prof.on = on != 0;
+  return PLVI_OK;
+}
+
+const char* plvi_orb_profile(plvi_orb* h) {
+  if (!h) return "";
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->profText = h->prof.report();
+  return h->profText.c_str();
 }
 
 int plvi_orb_extract_batch(plvi_orb* h, const uint8_t* imgs, int n, int w, int hh, int stride,

@@ -1,0 +1,119 @@
+"""Batched front-end step on one GPU: ORB + LSD/LBD extraction of a batch of frames and
+frame-to-frame Hamming matching of consecutive frames, all on one CUDA stream with every
+buffer resident in HBM.  This is the unit bench.py times and the multi-GPU runs shard:
+frames are independent, so each rank owns a contiguous range of frames and there is no
+collective.
+
+torch is used for device memory and streams only; every kernel is in libplvi_cuda.so.
+"""
+import numpy as np
+
+from .capi import QUERY_DTYPE, check, lib, ptr
+from .lineextractor import Lineextractor
+from .matchers import LineMatcher, ORBmatcher, frame_grid
+from .orbextractor import ORBextractor
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous frame range [lo, hi) of `rank` (4096/G frames per GPU for config 5)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class FrontEnd:
+    def __init__(self, batch, w=752, h=480, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
+                 lsd_nfeatures=200, lsd_scale=0.8, line_levels=2, line_scale=2.0, device=0, stream=None,
+                 with_lines=True, with_match=True, match_th=15.0, nnratio=0.9):
+        import torch
+        self.torch = torch
+        self.B, self.w, self.h = batch, w, h
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
+        sp = self.stream.cuda_stream
+        self.scale_factor = float(scale_factor)
+        self.match_th = float(match_th)
+        self.orb = ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th, max_width=w, max_height=h,
+                                max_batch=batch, device=device, stream=sp)
+        self.orb_out = self.orb.alloc_device_outputs(batch, self.device)
+        self.line = None
+        self.om = self.lm = None
+        if with_lines:
+            self.line = Lineextractor(lsd_nfeatures, 0, lsd_scale, line_levels, line_scale, 0, max_width=w,
+                                      max_height=h, max_batch=batch, device=device, stream=sp)
+            self.line_out = self.line.alloc_device_outputs(batch, self.device)
+        if with_match and batch > 1:
+            cap = self.orb.capacity
+            self.om = ORBmatcher(nnratio, True, max_pairs=batch, max_train=cap, max_query=cap, device=device, stream=sp)
+            self.grid = frame_grid(0, w, 0, h)
+            P = batch - 1
+            self.queries = torch.zeros((batch, cap, 7), dtype=torch.float32, device=self.device)
+            self.match_train = torch.zeros((P, cap), dtype=torch.int32, device=self.device)
+            self.match_query = torch.zeros((P, cap), dtype=torch.int32, device=self.device)
+            self.nmatches = torch.zeros(P, dtype=torch.int32, device=self.device)
+            if with_lines:
+                lc = self.line.capacity
+                self.lm = LineMatcher(max_pairs=batch, max_train=lc, max_query=lc, device=device, stream=sp)
+                self.line_m12 = torch.zeros((P, lc), dtype=torch.int32, device=self.device)
+                self.line_nm = torch.zeros(P, dtype=torch.int32, device=self.device)
+        self.launches = 0
+
+    def close(self):
+        for o in (self.orb, self.line, self.om, self.lm):
+            if o is not None:
+                o.close()
+
+    def step(self, d_frames):
+        """d_frames: uint8 CUDA tensor [n<=B, h, w].  Enqueues everything on self.stream."""
+        n = d_frames.shape[0]
+        kps, desc, counts, mono = self.orb.extract_batch_device(d_frames, out=self.orb_out)
+        nl = self.orb.last_launches
+        if self.line is not None:
+            kl, ldesc, leq, lcounts = self.line.extract_batch_device(d_frames, out=self.line_out)
+            nl += self.line.last_launches
+        if self.om is not None and n > 1:
+            P, cap = n - 1, self.orb.capacity
+            # frame p's keypoints are the "last frame" points searched in frame p+1
+            check(lib().plvi_queries_from_keypoints(self.om._h, ptr(kps), ptr(counts), P, cap, self.match_th,
+                                                    self.scale_factor, ptr(self.queries)))
+            check(lib().plvi_search_by_projection(
+                self.om._h, 0, P, ptr(kps[1:]), ptr(desc[1:]), None, ptr(counts[1:]), cap, ptr(self.grid),
+                ptr(self.queries), ptr(desc), ptr(counts), cap, ORBmatcher.TH_HIGH, self.om.mfNNratio, 1,
+                ptr(self.match_train), ptr(self.match_query), ptr(self.nmatches), 1))
+            nl += 2
+            if self.lm is not None:
+                lc = self.line.capacity
+                check(lib().plvi_line_match(self.lm._h, P, ptr(ldesc), ptr(lcounts), lc, ptr(ldesc[1:]), ptr(lcounts[1:]),
+                                            lc, 0.9, 1, ptr(self.line_m12), ptr(self.line_nm), 1))
+                nl += 1
+        self.launches = nl
+        return nl
+
+    def outputs(self):
+        out = {"kps": self.orb_out[0], "desc": self.orb_out[1], "counts": self.orb_out[2], "mono": self.orb_out[3]}
+        if self.line is not None:
+            out.update(keylines=self.line_out[0], line_desc=self.line_out[1], line_eq=self.line_out[2],
+                       line_counts=self.line_out[3])
+        if self.om is not None:
+            out.update(match_train=self.match_train, nmatches=self.nmatches)
+        if self.lm is not None:
+            out.update(line_matches=self.line_m12, line_nmatches=self.line_nm)
+        return out
+
+    def set_profile(self, on=True):
+        check(lib().plvi_orb_set_profile(self.orb._h, int(on)))
+        if self.line is not None:
+            check(lib().plvi_line_set_profile(self.line._h, int(on)))
+
+    def profile(self):
+        """{kernel: ms} of the last step (extractor kernels; needs set_profile(True) before the step)."""
+        txt = lib().plvi_orb_profile(self.orb._h).decode()
+        if self.line is not None:
+            txt += lib().plvi_line_profile(self.line._h).decode()
+        prof = {}
+        for item in txt.split(";"):
+            if "=" in item:
+                k, v = item.split("=")
+                prof[k] = prof.get(k, 0.0) + float(v)
+        return prof
