@@ -24,6 +24,7 @@ struct LineGeom {
   size_t pxTotal, rawTotal, lbdTotal;
   int bmTotal, segTotal;
   double rho, prec, lsdScale, minLength;
+  float alignHi2, alignLo2;   // cos^2(prec -/+ margin): bounds of the cheap alignment test in k_lsd_grow
   double kern[7];
   float lineScale;
   int nfeat, keepCap;
@@ -40,8 +41,8 @@ struct LinePtrs {
 
 struct LineBufs {
   double* rowf;          // [B][rawTotal]
-  float* ang;            // [B][pxTotal]   gradient angle, degrees, -1024 = NOTDEF
-  float4* cs;            // [B][pxTotal]   cos/sin of float(angle) | cos/sin of angle (seed)
+  float4* rec;           // [B][pxTotal]   {level-line angle in degrees (-1024 = NOTDEF), cos, sin of float(angle), -}
+  float2* seed;          // [B][pxTotal]   cos, sin of the f64 angle (region seed: float(std::cos(reg_angle)))
   double* mod;           // [B][pxTotal]   gradient magnitude
   unsigned* bitmap;      // [B][bmTotal]   angle defined & not used
   unsigned* reg;         // [B][pxTotal]   region pixel lists (x | y << 16)

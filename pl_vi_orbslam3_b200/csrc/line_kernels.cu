@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ 
       }
     }
     const size_t p = (size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx;
-    b.ang[p] = angDeg;
-    b.cs[p] = cs;
+    b.rec[p] = make_float4(angDeg, cs.x, cs.y, 0.f);
+    b.seed[p] = make_float2(cs.z, cs.w);
     b.mod[p] = norm;
   }
   const unsigned m = __ballot_sync(0xffffffffu, avail);
@@ -156,107 +156,196 @@ __device__ __forceinline__ bool is_aligned_dev(double a, double theta, double pr
   return n <= prec;
 }
 
+#define GROW_RQ 512   // shared ring holding the most recent region pixels (BFS frontier)
+#define GROW_K 64     // bitmap rows kept in shared memory (sliding window below the seed row)
+
+// "Available" (gradient defined & not used) bitmap of one (frame, octave).  Rows above the
+// current seed row hold no available pixel any more (every earlier pixel in raster order
+// has been a seed or was absorbed), so only rows [top, top + GROW_K) are cached in shared
+// memory; the rare region that reaches further down works on the global copy directly.
+struct GrowBitmap {
+  unsigned* sm;    // [GROW_K][wpr]
+  unsigned* gm;    // [H][wpr]
+  int wpr, top;
+  __device__ __forceinline__ unsigned word(int y, int wi) const {
+    return (y - top < GROW_K) ? sm[(y & (GROW_K - 1)) * wpr + wi] : __ldcg(gm + y * wpr + wi);
+  }
+  __device__ __forceinline__ bool test(int x, int y) const { return (word(y, x >> 5) >> (x & 31)) & 1u; }
+  __device__ __forceinline__ void clear(int x, int y) {   // one lane only
+    const unsigned m = ~(1u << (x & 31));
+    if (y - top < GROW_K) sm[(y & (GROW_K - 1)) * wpr + (x >> 5)] &= m;
+    else { unsigned* p = gm + y * wpr + (x >> 5); __stcg(p, __ldcg(p) & m); }
+  }
+};
+
+struct GrowBatch {   // up to 4 queue entries x 8 neighbours, one neighbour per lane
+  bool cand;
+  int cx, cy;
+  float4 rec;        // {angle deg, cos(float angle), sin(float angle), -}
+};
+
+// Neighbourhood fetch for queue entries [i, i+nb): lane (e, k) tests the availability bit of
+// its neighbour and, if set, issues the 16-byte record load (consumed later => the load
+// latency overlaps the accept chain of the previous batch).
+__device__ __forceinline__ GrowBatch grow_fetch(const GrowBitmap& bm, const unsigned* ring, const unsigned* reg,
+                                                int regBase, int regSize, int i, int nb, int e, int ndx, int ndy,
+                                                int W, int H, const float4* __restrict__ rec) {
+  GrowBatch g;
+  g.cand = false; g.cx = 0; g.cy = 0; g.rec = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e < nb) {
+    const int idx = i + e;
+    const unsigned p = (regSize - idx <= GROW_RQ) ? ring[idx & (GROW_RQ - 1)] : __ldcg(reg + regBase + idx);
+    g.cx = (int)(p & 0xffff) + ndx;
+    g.cy = (int)(p >> 16) + ndy;
+    if (g.cx >= 0 && g.cx < W && g.cy >= bm.top && g.cy < H && bm.test(g.cx, g.cy)) {
+      g.cand = true;
+      g.rec = __ldg(rec + g.cy * W + g.cx);
+    }
+    // radial look-ahead: the breadth-first front moves about one pixel per batch, so the
+    // records three pixels further out in this lane's direction are pulled towards L1 now
+    const int fx = g.cx + 3 * ndx, fy = g.cy + 3 * ndy;
+    if (fx >= 0 && fx < W && fy >= bm.top && fy < H)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + fy * W + fx));
+  }
+  return g;
+}
+
 __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeom g, LineBufs b) {
-  extern __shared__ unsigned sbm[];
+  extern __shared__ unsigned smem_u[];
   const int oct = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
   if (oct >= g.noct) return;
   const LineOct& O = g.o[oct];
-  const int W = O.sw, H = O.sh, wpr = O.wpr, nwords = wpr * H;
-  const unsigned* gbm = b.bitmap + (size_t)f * g.bmTotal + O.bmOff;
-  for (int i = lane; i < nwords; i += 32) sbm[i] = gbm[i];
+  const int W = O.sw, H = O.sh, wpr = O.wpr;
+  unsigned* ring = smem_u;
+  GrowBitmap bm;
+  bm.sm = smem_u + GROW_RQ;
+  bm.gm = b.bitmap + (size_t)f * g.bmTotal + O.bmOff;
+  bm.wpr = wpr;
+  bm.top = 0;
+  for (int i = lane; i < min(GROW_K, H) * wpr; i += 32) bm.sm[i] = __ldcg(bm.gm + i);
   __syncwarp();
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
-  const float* __restrict__ ang = b.ang + pbase;
-  const float4* __restrict__ cs = b.cs + pbase;
+  const float4* __restrict__ rec = b.rec + pbase;
+  const float2* __restrict__ seedcs = b.seed + pbase;
   unsigned* reg = b.reg + pbase;
   LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
   const double prec = g.prec;
+  const float kHi = g.alignHi2, kLo = g.alignLo2;
   int regBase = 0, nreg = 0;
   bool overflow = false;
-  // lane -> (entry e = lane / 9, neighbour k = lane % 9)
-  const int e = lane / 9, kk = lane - e * 9;
-  const int ndx = kk % 3 - 1, ndy = kk / 3 - 1;
+  const int e = lane >> 3, k8 = lane & 7;        // lane -> (queue entry of the batch, neighbour)
+  const int nidx = k8 < 4 ? k8 : k8 + 1;         // 3x3 raster index without the centre
+  const int ndx = nidx % 3 - 1, ndy = nidx / 3 - 1;
 
-  for (int w0 = 0; w0 < nwords; w0 += 32) {
-    // next seed: first set bit in raster order
-    while (true) {
-      const int wi = w0 + lane;
-      const unsigned word = wi < nwords ? sbm[wi] : 0u;
-      const unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
-      if (!nz) break;
-      const int wl = __ffs(nz) - 1;
-      const unsigned sw_ = __shfl_sync(0xffffffffu, word, wl);
-      const int bit = __ffs(sw_) - 1;
-      const int swi = w0 + wl;
-      const int sy = swi / wpr, sx = (swi - sy * wpr) * 32 + bit;
-      if (lane == 0) sbm[swi] = sw_ & ~(1u << bit);
-      // region_grow
-      const int sp = sy * W + sx;
-      const float4 c0 = cs[sp];
-      double regAngle = __dmul_rn((double)ang[sp], D2R);
-      float sumdx = c0.z, sumdy = c0.w;
-      int regSize = 1;
-      if (lane == 0) reg[regBase] = (unsigned)sx | ((unsigned)sy << 16);
+  for (int row = 0; row < H - 1; row++) {
+    // slide the shared window: rows [top, row) are exhausted, rows up to row + GROW_K enter
+    if (row > bm.top) {
+      const int r0 = bm.top + GROW_K, r1 = min(row + GROW_K, H);
+      for (int r = r0; r < r1; r++)
+        for (int wv = lane; wv < wpr; wv += 32) bm.sm[(r & (GROW_K - 1)) * wpr + wv] = __ldcg(bm.gm + r * wpr + wv);
+      bm.top = row;
       __syncwarp();
-      for (int i = 0; i < regSize;) {
-        const int nb = min(3, regSize - i);
-        // fetch: lanes of entry e < nb look at their neighbour
-        bool cand = false;
-        int cx = 0, cy = 0;
-        float ca = 0.f;
-        float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < nb && kk != 4) {
-          const unsigned p = reg[regBase + i + e];
-          cx = (int)(p & 0xffff) + ndx;
-          cy = (int)(p >> 16) + ndy;
-          if (cx >= 0 && cx < W && cy >= 0 && cy < H && ((sbm[cy * wpr + (cx >> 5)] >> (cx & 31)) & 1u)) {
-            cand = true;
-            ca = ang[cy * W + cx];
-            cc = cs[cy * W + cx];
+    }
+    {  // pull the records of the row after next towards L2 (seed and neighbour loads then miss at most to L2)
+      const int pr = min(row + 2, H - 1);
+      for (int x = lane * 8; x < W; x += 256) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + pr * W + x));
+        if ((x & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(seedcs + pr * W + x));
+      }
+    }
+    for (int c0 = 0; c0 < wpr; c0 += 32) {
+      while (true) {
+        // next seed: first available pixel in raster order (src/LSD/lsd.cpp:476-479)
+        const int wi = c0 + lane;
+        const unsigned word = wi < wpr ? bm.sm[(row & (GROW_K - 1)) * wpr + wi] : 0u;
+        const unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
+        if (!nz) break;
+        const int wl = __ffs(nz) - 1;
+        const unsigned sw_ = __shfl_sync(0xffffffffu, word, wl);
+        const int bit = __ffs(sw_) - 1;
+        const int sx = (c0 + wl) * 32 + bit, sy = row;
+        const int sp = sy * W + sx;
+        const float sang = __ldg(&rec[sp].x);
+        const float2 scs = __ldg(seedcs + sp);
+        if (lane == 0) {
+          bm.clear(sx, sy);
+          ring[0] = (unsigned)sx | ((unsigned)sy << 16);
+          __stcg(reg + regBase, (unsigned)sx | ((unsigned)sy << 16));
+        }
+        __syncwarp();
+        // region_grow (src/LSD/lsd.cpp:635-686).  The region angle is a pure function of the
+        // float sums (fastAtan2(sumdy, sumdx)), so it is only evaluated when a candidate falls
+        // inside the band where the cheap dot-product test cannot decide.
+        const double seedAngle = __dmul_rn((double)sang, D2R);
+        float sumdx = scs.x, sumdy = scs.y;
+        bool fresh = true;   // no pixel accepted yet: reg_angle is the seed's own angle
+        int regSize = 1;
+        int i = 0, nb = 1;
+        GrowBatch cur = grow_fetch(bm, ring, reg, regBase, regSize, 0, 1, e, ndx, ndy, W, H, rec);
+        while (nb > 0) {
+          const int ni = i + nb, nnb = min(4, regSize - ni);
+          GrowBatch nxt = grow_fetch(bm, ring, reg, regBase, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
+          bool pend = cur.cand && bm.test(cur.cx, cur.cy);
+          float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+          while (true) {
+            // all pending candidates against the current region direction at once; the first
+            // aligned one in (entry, yy, xx) order is accepted, those before it are rejected
+            bool yes = false, maybe = false;
+            if (pend) {
+              const float dot = __fmaf_rn(sumdx, cur.rec.y, sumdy * cur.rec.z);
+              const float d2 = dot * dot;
+              if (dot > 0.f && d2 >= kHi * n2) yes = true;
+              else if (!(dot <= 0.f || d2 <= kLo * n2)) maybe = true;
+            }
+            if (__ballot_sync(0xffffffffu, maybe)) {
+              const double regAngle = fresh ? seedAngle : __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
+              if (maybe) yes = is_aligned_dev(__dmul_rn((double)cur.rec.x, D2R), regAngle, prec);
+            }
+            const unsigned am = __ballot_sync(0xffffffffu, yes);
+            if (!am) break;
+            const int l = __ffs(am) - 1;
+            const int qx = __shfl_sync(0xffffffffu, cur.cx, l), qy = __shfl_sync(0xffffffffu, cur.cy, l);
+            const float qc = __shfl_sync(0xffffffffu, cur.rec.y, l), qs = __shfl_sync(0xffffffffu, cur.rec.z, l);
+            if (lane <= l || (cur.cx == qx && cur.cy == qy)) pend = false;
+            if (lane == 0) {
+              bm.clear(qx, qy);
+              const unsigned pk = (unsigned)qx | ((unsigned)qy << 16);
+              ring[regSize & (GROW_RQ - 1)] = pk;
+              __stcg(reg + regBase + regSize, pk);
+            }
+            regSize++;
+            fresh = false;
+            sumdx = __fadd_rn(sumdx, qc);
+            sumdy = __fadd_rn(sumdy, qs);
+            n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+          }
+          __syncwarp();
+          i = ni;
+          if (nnb > 0) {
+            cur = nxt;
+            nb = nnb;
+          } else {
+            nb = min(4, regSize - i);
+            if (nb > 0) cur = grow_fetch(bm, ring, reg, regBase, regSize, i, nb, e, ndx, ndy, W, H, rec);
           }
         }
-        unsigned m = __ballot_sync(0xffffffffu, cand);
-        // serial accept chain in (entry, yy, xx) order == lane order
-        while (m) {
-          const int l = __ffs(m) - 1;
-          m &= m - 1;
-          const int qx = __shfl_sync(0xffffffffu, cx, l), qy = __shfl_sync(0xffffffffu, cy, l);
-          const float qa = __shfl_sync(0xffffffffu, ca, l);
-          const float qc = __shfl_sync(0xffffffffu, cc.x, l), qs = __shfl_sync(0xffffffffu, cc.y, l);
-          const int wi2 = qy * wpr + (qx >> 5);
-          const unsigned wv = sbm[wi2];
-          if (!((wv >> (qx & 31)) & 1u)) continue;  // taken by an earlier entry of this batch
-          if (!is_aligned_dev(__dmul_rn((double)qa, D2R), regAngle, prec)) continue;
-          __syncwarp();
-          if (lane == 0) {
-            sbm[wi2] = wv & ~(1u << (qx & 31));
-            reg[regBase + regSize] = (unsigned)qx | ((unsigned)qy << 16);
+        if (regSize >= O.minRegSize) {
+          if (nreg < O.segCap) {
+            if (lane == 0) {
+              LineRegion r;
+              r.start = regBase;
+              r.size = regSize;
+              r.angle = fresh ? seedAngle : __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
+              rtab[nreg] = r;
+            }
+            nreg++;
+            regBase += regSize;
+          } else {
+            overflow = true;
           }
-          regSize++;
-          sumdx = __fadd_rn(sumdx, qc);
-          sumdy = __fadd_rn(sumdy, qs);
-          regAngle = __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
-          __syncwarp();
         }
-        i += nb;
         __syncwarp();
       }
-      if (regSize >= O.minRegSize) {
-        if (nreg < O.segCap) {
-          if (lane == 0) {
-            LineRegion r;
-            r.start = regBase;
-            r.size = regSize;
-            r.angle = regAngle;
-            rtab[nreg] = r;
-          }
-          nreg++;
-          regBase += regSize;
-        } else {
-          overflow = true;
-        }
-      }
-      __syncwarp();
     }
   }
   if (lane == 0) b.regCount[f * 2 + oct] = overflow ? -1 : nreg;
@@ -718,7 +807,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     prof->mark("k_lsd_scale_grad", st);
     nl += 2;
   }
-  const size_t growSmem = (size_t)g.o[0].wpr * g.o[0].sh * sizeof(unsigned);
+  const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
   k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b);
   prof->mark("k_lsd_grow", st);
   k_lsd_rect<<<dim3(g.noct, n, 2), 256, 0, st>>>(g, b);
@@ -757,7 +846,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
 }
 
 int line_kernel_attrs(const LineGeom& g) {
-  const size_t growSmem = (size_t)g.o[0].wpr * g.o[0].sh * sizeof(unsigned);
+  const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
   if (growSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
   if (growSmem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)growSmem));

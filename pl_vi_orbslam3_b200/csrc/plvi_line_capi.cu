@@ -92,6 +92,9 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
   g.lsdScale = (double)h->lsdScale;
   g.prec = M_PI * 22.5 / 180;
   g.rho = 2.0 / sin(g.prec);
+  // fastAtan2 deviates from atan2 by <= 0.0092 deg (1.6e-4 rad); 2e-3 rad leaves a 10x margin
+  g.alignHi2 = (float)(cos(g.prec - 2e-3) * cos(g.prec - 2e-3));
+  g.alignLo2 = (float)(cos(g.prec + 2e-3) * cos(g.prec + 2e-3));
   g.minLength = 0.025 * std::min(w, hh);
   const double sigma = (g.lsdScale < 1) ? (0.6 / g.lsdScale) : 0.6;
   const unsigned hk = (unsigned)ceil(sigma * sqrt(2 * 3.0 * log(10.0)));
@@ -235,8 +238,8 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes + 256); };
   for (int o = 0; o < nlevels; o++) A((void**)&h->dImg[o], B * c.o[o].pitch * c.o[o].h);
   A((void**)&h->buf.rowf, B * c.rawTotal * sizeof(double));
-  A((void**)&h->buf.ang, B * c.pxTotal * sizeof(float));
-  A((void**)&h->buf.cs, B * c.pxTotal * sizeof(float4));
+  A((void**)&h->buf.rec, B * c.pxTotal * sizeof(float4));
+  A((void**)&h->buf.seed, B * c.pxTotal * sizeof(float2));
   A((void**)&h->buf.mod, B * c.pxTotal * sizeof(double));
   A((void**)&h->buf.bitmap, B * c.bmTotal * sizeof(unsigned));
   A((void**)&h->buf.reg, B * c.pxTotal * sizeof(unsigned));
@@ -285,7 +288,7 @@ void plvi_line_destroy(plvi_line* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
-  cudaFree(h->buf.rowf); cudaFree(h->buf.ang); cudaFree(h->buf.cs); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
+  cudaFree(h->buf.rowf); cudaFree(h->buf.rec); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
   cudaFree(h->buf.reg); cudaFree(h->buf.regTab); cudaFree(h->buf.regCount); cudaFree(h->buf.segs);
   cudaFree(h->buf.tmpResp); cudaFree(h->buf.tmpCls); cudaFree(h->buf.lbdImg0); cudaFree(h->buf.lbdImg1);
   cudaFree(h->buf.grad); cudaFree(h->buf.scaledDbg);
@@ -425,7 +428,9 @@ int plvi_line_read_lsd(plvi_line* h, int frame, int octave, int what, void* out,
       if (!h->buf.scaledDbg) { set_error("debug not enabled"); return PLVI_ERR_INVALID; }
       PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.scaledDbg + pb, npx * sizeof(double), cudaMemcpyDeviceToHost));
       break;
-    case 1: PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.ang + pb, npx * sizeof(float), cudaMemcpyDeviceToHost)); break;
+    case 1:
+      PLVI_CUDA_TRY(cudaMemcpy2D(out, sizeof(float), h->buf.rec + pb, sizeof(float4), sizeof(float), npx, cudaMemcpyDeviceToHost));
+      break;
     case 2: PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.mod + pb, npx * sizeof(double), cudaMemcpyDeviceToHost)); break;
     case 3: {
       int n = 0;
