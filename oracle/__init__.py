@@ -78,7 +78,7 @@ def fast_atan2(y, x):
 def resize_linear(img, dw, dh):
     img = _u8(img)
     out = np.empty((dh, dw), np.uint8)
-    lib().plvio_resize_linear_u8(_p(img), img.strides[0], img.shape[1], img.shape[0], _p(out), dw, dw, dh)
+    lib().plvio_resize_linear_u8(_p(img), img.strides[0], img.shape[1], img.shape[0], _p(out), int(dw), int(dw), int(dh))
     return out
 
 
@@ -274,7 +274,7 @@ def gaussian_blur_f64(img, k):
 def resize_linear_f64(img, dw, dh, fx, fy):
     img = np.ascontiguousarray(img, np.float64)
     out = np.empty((dh, dw), np.float64)
-    lib().plvio_resize_linear_f64(_p(img), img.shape[1], img.shape[0], _p(out), dw, dh, C.c_double(fx), C.c_double(fy))
+    lib().plvio_resize_linear_f64(_p(img), img.shape[1], img.shape[0], _p(out), int(dw), int(dh), C.c_double(fx), C.c_double(fy))
     return out
 
 

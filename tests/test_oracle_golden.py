@@ -1,0 +1,156 @@
+"""CPU: the oracle against the committed golden vectors (tests/golden/, made by
+tools/gen_golden.py).  cv2_* vectors are OpenCV 4.13 outputs on the reference's own
+frames and on synthetic frames: they pin the oracle's restatement of the OpenCV primitives
+the reference calls.  oracle_* vectors pin the reference-owned logic against regressions
+(the reference has no tests and cannot be built here: "parity unpinned" for those)."""
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from pl_vi_orbslam3_b200 import synth
+
+GOLD = Path(__file__).resolve().parent / "golden"
+G = np.load(GOLD / "golden.npz")
+S = float(np.float32(0.8))
+SIGMA = 0.6 / S
+
+
+def crc(a):
+    return np.uint32(zlib.crc32(np.ascontiguousarray(a).tobytes()))
+
+
+def _frame(name):
+    if name == "synth_0":
+        return synth.frame_euroc(0)
+    if name == "synth_7_640":
+        return synth.frame_euroc(7, 640, 480)
+    return np.load(GOLD / f"frame_{name}.npz")["img"]
+
+
+NAMES = ["data2_1", "data2_3", "data_1_gray", "synth_0", "synth_7_640"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_pyramid_blur_fast_match_opencv(name):
+    img = _frame(name)
+    h, w = img.shape
+    plan = oracle.orb_plan(w, h)
+    cur = img
+    for l in range(1, 8):
+        cur = oracle.resize_linear(cur, int(plan["w"][l]), int(plan["h"][l]))
+        assert crc(cur) == G[f"cv2_pyr_{name}_{l}"], f"resize level {l}"
+        if l in (1, 4, 7):
+            assert crc(oracle.gaussian_blur7(cur)) == G[f"cv2_blur7_{name}_{l}"]
+            c = oracle.grid_fast(cur)
+            ref = G[f"cv2_gridfast_{name}_{l}"]
+            if ref.ndim == 2:
+                assert np.array_equal(c, ref), f"grid FAST level {l}"
+            else:
+                assert (len(c), crc(c)) == (ref[0], np.uint32(ref[1]))
+    assert crc(oracle.gaussian_blur7(img)) == G[f"cv2_blur7_{name}_0"]
+    c0 = oracle.grid_fast(img)
+    assert (len(c0), crc(c0)) == (G[f"cv2_gridfast_{name}_0"][0], np.uint32(G[f"cv2_gridfast_{name}_0"][1]))
+    assert crc(oracle.resize_linear(img, w // 2, h // 2)) == G[f"cv2_half_{name}"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_lbd_and_lsd_preprocessing_match_opencv(name):
+    img = _frame(name)
+    b5 = oracle.gaussian_blur5(img)
+    assert crc(b5) == G[f"cv2_blur5_{name}"]
+    pd = oracle.pyr_down(b5)
+    assert crc(pd) == G[f"cv2_pyrdown_{name}"]
+    assert crc(oracle.sobel3(b5)[0]) == G[f"cv2_sobelx_{name}"]
+    assert crc(oracle.sobel3(pd)[1]) == G[f"cv2_sobely_{name}"]
+    k = oracle.gaussian_kernel_f64(7, SIGMA)
+    assert np.array_equal(k, G["cv2_gauss_kernel7"])
+    gb = oracle.gaussian_blur_f64(img.astype(np.float64), k)
+    # OpenCV's own f64 blur is only reproducible to ~1e-13 (SIMD/FMA inside the library)
+    assert np.abs(gb[::37, ::41] - G[f"cv2_blurf64_sample_{name}"]).max() <= 1e-12
+    sh = tuple(G[f"cv2_scaled_shape_{name}"])
+    sc = oracle.resize_linear_f64(gb, sh[1], sh[0], S, S)
+    assert crc(sc) == G[f"cv2_resizef64_of_oracleblur_{name}"]
+
+
+def test_fast_atan2_matches_opencv():
+    yx = G["cv2_atan2_in"]
+    got = np.array([oracle.fast_atan2(a, b) for a, b in yx], np.float32)
+    assert np.array_equal(got, G["cv2_atan2_out"])
+
+
+def test_knn2_tie_rule_matches_bfmatcher():
+    d1, d2, ref = G["cv2_knn_d1"], G["cv2_knn_d2"], G["cv2_knn"]
+    for i in range(len(d1)):
+        dist = np.array([oracle.hamming256(d1[i], d2[j]) for j in range(len(d2))])
+        order = np.lexsort((np.arange(len(d2)), dist))
+        assert order[0] == int(ref[i, 0]) and dist[order[0]] == ref[i, 1]
+        assert dist[order[1]] == ref[i, 3]
+    n, m = oracle.match_nnr(d1, d2, 0.9)
+    exp = np.where(ref[:, 1] < ref[:, 3] * np.float32(0.9), ref[:, 0], -1).astype(np.int32)
+    assert np.array_equal(m, exp)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_orb_and_line_regression(name):
+    img = _frame(name)
+    r = oracle.orb_extract(img)
+    ref = G[f"oracle_orb_{name}"]
+    assert (len(r["keypoints"]), r["mono_index"]) == (ref[0], ref[1])
+    assert crc(r["keypoints"]) == np.uint32(ref[2]) and crc(r["descriptors"]) == np.uint32(ref[3])
+    assert np.array_equal(r["keypoints"][:16], G[f"oracle_orb_head_{name}"])
+    lr = oracle.line_extract(img)
+    ref = G[f"oracle_line_{name}"]
+    assert (len(lr["keylines"]), lr["raw_counts"][0], lr["raw_counts"][1]) == (ref[0], ref[1], ref[2])
+    assert crc(lr["keylines"]) == np.uint32(ref[3]) and crc(lr["descriptors"]) == np.uint32(ref[4])
+
+
+def test_oracle_structural_properties():
+    img = synth.frame_euroc(4)
+    r = oracle.orb_extract(img, debug=True)
+    k = r["keypoints"]
+    quota = r["plan"]["quota"]
+    assert (np.diff(k["octave"]) >= 0).all()                      # mono fill: level by level
+    for l in range(8):
+        n = (k["octave"] == l).sum()
+        assert n <= max(quota[l] + 3, 8)
+    lv = k["octave"]
+    x = k["x"] / r["plan"]["scale"][lv]
+    y = k["y"] / r["plan"]["scale"][lv]
+    assert (x >= 18.99).all() and (y >= 18.99).all()              # EDGE_THRESHOLD
+    assert (x <= r["plan"]["w"][lv] - 19.99 + 1e-3).all() and (y <= r["plan"]["h"][lv] - 19.99 + 1e-3).all()
+    assert len({(a, b, c) for a, b, c in zip(k["x"], k["y"], k["octave"])}) == len(k)
+    # lapping area: {0,1000} reverses the output (all keys are "stereo" candidates)
+    r2 = oracle.orb_extract(img, lapping=(0, 1000))
+    assert r2["mono_index"] == 0
+    assert np.array_equal(r2["keypoints"][::-1], k) and np.array_equal(r2["descriptors"][::-1], r["descriptors"])
+    # Hamming distance properties
+    d = r["descriptors"]
+    assert oracle.hamming256(d[0], d[0]) == 0
+    assert oracle.hamming256(d[0], ~d[0]) == 256
+    assert oracle.hamming256(d[0], d[1]) == int(np.unpackbits(d[0] ^ d[1]).sum())
+    assert oracle.hamming256(d[0], d[1], shift25=True) == sum(
+        int(np.unpackbits((d[0] ^ d[1])[4 * i:4 * i + 4]).sum()) // 2 for i in range(8))
+    # line match is symmetric under swapping the sets (mutual check)
+    la, lb = oracle.line_extract(img), oracle.line_extract(synth.frame_euroc(5))
+    n12, m12 = oracle.line_match(la["descriptors"], lb["descriptors"], 0.9)
+    n21, m21 = oracle.line_match(lb["descriptors"], la["descriptors"], 0.9)
+    assert n12 == n21
+    assert all(m21[j] == i for i, j in enumerate(m12) if j >= 0)
+
+
+def test_oracle_edge_cases():
+    flat = np.full((480, 752), 77, np.uint8)
+    r = oracle.orb_extract(flat)
+    assert len(r["keypoints"]) == 0 and r["mono_index"] == 0
+    assert len(oracle.line_extract(flat)["keylines"]) == 0
+    n, m = oracle.line_match(np.zeros((0, 32), np.uint8), np.zeros((5, 32), np.uint8), 0.9)
+    assert n == 0 and len(m) == 0
+    n, m = oracle.line_match(np.zeros((3, 32), np.uint8), np.zeros((1, 32), np.uint8), 0.9)
+    assert n == 0 and (m == -1).all()
+    # octree on a handful of candidates: every isolated candidate survives
+    c = np.array([[10, 10, 30], [300, 40, 25], [600, 400, 21]], np.float32)
+    sel = oracle.distribute_octree(c, 16, 736, 16, 464, 217)
+    assert sorted(sel.tolist()) == [0, 1, 2]
