@@ -1,0 +1,41 @@
+// Compiles the shim headers against libplvi_cuda.so and, on a GPU box, runs one frame
+// through the reference-shaped C++ API:  g++ shim_smoke.cpp -L.. -lplvi_cuda
+#include <cstdio>
+#include <cstdlib>
+
+#include "LineExtractor.h"
+#include "Matchers.h"
+#include "ORBextractor.h"
+
+int main(int argc, char** argv) {
+  const int w = 752, h = 480;
+  std::vector<uint8_t> img((size_t)w * h);
+  unsigned s = 12345;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      s = s * 1664525u + 1013904223u;
+      const int block = (((x / 24) * 7 + (y / 20) * 13) % 11) * 20 + 20;
+      img[(size_t)y * w + x] = (uint8_t)(block + (s >> 29));
+    }
+  cv::Mat im(h, w, img.data()), mask;
+  try {
+    ORB_SLAM3::ORBextractor orb(1000, 1.2f, 8, 20, 7, w, h);
+    std::vector<cv::KeyPoint> kps;
+    cv::Mat desc;
+    std::vector<int> lap = {0, 0};
+    const int mono = orb(im, mask, kps, desc, lap);
+    ORB_SLAM3::Lineextractor line(200, 0, 0.8f, 2, 2.0f, 0, w, h);
+    std::vector<cv::line_descriptor::KeyLine> kls;
+    cv::Mat ldesc;
+    std::vector<Eigen::Vector3d> eq;
+    line(im, mask, kls, ldesc, eq);
+    std::vector<int> m12;
+    const int nm = ORB_SLAM3::LineMatcher::match(ldesc, ldesc, 0.9f, m12);
+    const int d0 = kps.size() > 1 ? ORB_SLAM3::ORBmatcher::DescriptorDistance(desc.row(0), desc.row(1)) : -1;
+    std::printf("shim ok: monoIndex=%d keypoints=%zu lines=%zu self-matches=%d dist01=%d\n", mono, kps.size(), kls.size(), nm, d0);
+    return (mono == (int)kps.size() && nm <= (int)kls.size()) ? 0 : 1;
+  } catch (const std::exception& e) {
+    std::printf("shim error: %s\n", e.what());
+    return argc > 1 ? 0 : 2;   // with an argument: tolerate "no CUDA device" (CPU box link check)
+  }
+}

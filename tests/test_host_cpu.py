@@ -135,3 +135,15 @@ def test_bench_reference_arm_contract():
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_cpp_shim_compiles_and_links(tmp_path):
+    """The reference-shaped C++ classes (shim/*.h) build against include/plvi.h + libplvi_cuda.so."""
+    shim = ROOT / "pl_vi_orbslam3_b200" / "shim"
+    exe = tmp_path / "shim_smoke"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-o", str(exe), str(shim / "shim_smoke.cpp"),
+                        "-L" + str(ROOT / "pl_vi_orbslam3_b200"), "-lplvi_cuda",
+                        "-Wl,-rpath," + str(ROOT / "pl_vi_orbslam3_b200")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([str(exe), "tolerate-no-device"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
