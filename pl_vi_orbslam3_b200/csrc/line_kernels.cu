@@ -178,9 +178,11 @@ struct GrowBitmap {
   }
 };
 
-struct GrowBatch {   // up to 4 queue entries x 8 neighbours, one neighbour per lane
-  bool cand;
-  int cx, cy;
+// One neighbour per lane: lane = 8 * e + k, e = queue entry of the batch (0..3), k = 3x3
+// neighbour index without the centre, in the reference's (yy, xx) scan order.
+struct GrowBatch {
+  unsigned mask;     // lanes holding an available neighbour (warp-uniform)
+  int cpk;           // neighbour coordinates x | y << 16
   float4 rec;        // {angle deg, cos(float angle), sin(float angle), -}
 };
 
@@ -191,22 +193,22 @@ __device__ __forceinline__ GrowBatch grow_fetch(const GrowBitmap& bm, const unsi
                                                 int regBase, int regSize, int i, int nb, int e, int ndx, int ndy,
                                                 int W, int H, const float4* __restrict__ rec) {
   GrowBatch g;
-  g.cand = false; g.cx = 0; g.cy = 0; g.rec = make_float4(0.f, 0.f, 0.f, 0.f);
+  g.cpk = 0;
+  g.rec = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool cand = false;
   if (e < nb) {
     const int idx = i + e;
     const unsigned p = (regSize - idx <= GROW_RQ) ? ring[idx & (GROW_RQ - 1)] : __ldcg(reg + regBase + idx);
-    g.cx = (int)(p & 0xffff) + ndx;
-    g.cy = (int)(p >> 16) + ndy;
-    if (g.cx >= 0 && g.cx < W && g.cy >= bm.top && g.cy < H && bm.test(g.cx, g.cy)) {
-      g.cand = true;
-      g.rec = __ldg(rec + g.cy * W + g.cx);
+    const int cx = (int)(p & 0xffff) + ndx, cy = (int)(p >> 16) + ndy;
+    // x = -1 and x = W land on padding bits of the bitmap rows (always 0); rows above the
+    // window top hold no available pixel
+    if (cy >= bm.top && cy < H && cx >= 0 && bm.test(cx, cy)) {
+      cand = true;
+      g.cpk = cx | (cy << 16);
+      g.rec = __ldg(rec + cy * W + cx);
     }
-    // radial look-ahead: the breadth-first front moves about one pixel per batch, so the
-    // records three pixels further out in this lane's direction are pulled towards L1 now
-    const int fx = g.cx + 3 * ndx, fy = g.cy + 3 * ndy;
-    if (fx >= 0 && fx < W && fy >= bm.top && fy < H)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + fy * W + fx));
   }
+  g.mask = __ballot_sync(0xffffffffu, cand);
   return g;
 }
 
@@ -233,9 +235,10 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
   const float kHi = g.alignHi2, kLo = g.alignLo2;
   int regBase = 0, nreg = 0;
   bool overflow = false;
-  const int e = lane >> 3, k8 = lane & 7;        // lane -> (queue entry of the batch, neighbour)
-  const int nidx = k8 < 4 ? k8 : k8 + 1;         // 3x3 raster index without the centre
+  const int e = lane >> 3, k8 = lane & 7;
+  const int nidx = k8 < 4 ? k8 : k8 + 1;
   const int ndx = nidx % 3 - 1, ndy = nidx / 3 - 1;
+  const unsigned laneBit = 1u << lane;
 
   for (int row = 0; row < H - 1; row++) {
     // slide the shared window: rows [top, row) are exhausted, rows up to row + GROW_K enter
@@ -246,13 +249,12 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
       bm.top = row;
       __syncwarp();
     }
-    {  // pull the records of the row after next towards L2 (seed and neighbour loads then miss at most to L2)
-      const int pr = min(row + 2, H - 1);
-      for (int x = lane * 8; x < W; x += 256) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + pr * W + x));
-        if ((x & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(seedcs + pr * W + x));
-      }
+#ifdef PLVI_GROW_PREFETCH_ROWS
+    {
+      const int pr = min(row + PLVI_GROW_PREFETCH_ROWS, H - 1);
+      for (int x = lane * 8; x < W; x += 256) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + pr * W + x));
     }
+#endif
     for (int c0 = 0; c0 < wpr; c0 += 32) {
       while (true) {
         // next seed: first available pixel in raster order (src/LSD/lsd.cpp:476-479)
@@ -274,8 +276,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
         }
         __syncwarp();
         // region_grow (src/LSD/lsd.cpp:635-686).  The region angle is a pure function of the
-        // float sums (fastAtan2(sumdy, sumdx)), so it is only evaluated when a candidate falls
-        // inside the band where the cheap dot-product test cannot decide.
+        // float sums (fastAtan2(sumdy, sumdx)), so it is only evaluated when the candidate that
+        // is next in scan order falls inside the band where the dot-product test cannot decide.
         const double seedAngle = __dmul_rn((double)sang, D2R);
         float sumdx = scs.x, sumdy = scs.y;
         bool fresh = true;   // no pixel accepted yet: reg_angle is the seed's own angle
@@ -285,33 +287,33 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
         while (nb > 0) {
           const int ni = i + nb, nnb = min(4, regSize - ni);
           GrowBatch nxt = grow_fetch(bm, ring, reg, regBase, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
-          bool pend = cur.cand && bm.test(cur.cx, cur.cy);
+          // candidates fetched ahead may have been absorbed by the previous batch in the meantime
+          unsigned pm = cur.mask;
+          if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && bm.test(cur.cpk & 0xffff, cur.cpk >> 16));
           float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
-          while (true) {
-            // all pending candidates against the current region direction at once; the first
-            // aligned one in (entry, yy, xx) order is accepted, those before it are rejected
-            bool yes = false, maybe = false;
-            if (pend) {
-              const float dot = __fmaf_rn(sumdx, cur.rec.y, sumdy * cur.rec.z);
-              const float d2 = dot * dot;
-              if (dot > 0.f && d2 >= kHi * n2) yes = true;
-              else if (!(dot <= 0.f || d2 <= kLo * n2)) maybe = true;
-            }
-            if (__ballot_sync(0xffffffffu, maybe)) {
+          while (pm) {
+            // every pending candidate against the current region direction at once
+            const float dot = __fmaf_rn(sumdx, cur.rec.y, sumdy * cur.rec.z);
+            const float d2 = dot * dot;
+            const bool poss = (pm & laneBit) && dot > 0.f && d2 > kLo * n2;
+            const unsigned possm = __ballot_sync(0xffffffffu, poss);
+            if (!possm) break;                       // nobody can be aligned: batch done
+            const int l = __ffs(possm) - 1;          // first in (entry, yy, xx) order
+            const unsigned surem = __ballot_sync(0xffffffffu, poss && d2 >= kHi * n2);
+            pm &= ~((2u << l) - 1u);                 // l and everything before it is decided now
+            if (!((surem >> l) & 1u)) {              // undecided band: the exact test of the reference
               const double regAngle = fresh ? seedAngle : __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
-              if (maybe) yes = is_aligned_dev(__dmul_rn((double)cur.rec.x, D2R), regAngle, prec);
+              const float la = __shfl_sync(0xffffffffu, cur.rec.x, l);
+              if (!is_aligned_dev(__dmul_rn((double)la, D2R), regAngle, prec)) continue;
             }
-            const unsigned am = __ballot_sync(0xffffffffu, yes);
-            if (!am) break;
-            const int l = __ffs(am) - 1;
-            const int qx = __shfl_sync(0xffffffffu, cur.cx, l), qy = __shfl_sync(0xffffffffu, cur.cy, l);
+            // accept lane l's pixel
             const float qc = __shfl_sync(0xffffffffu, cur.rec.y, l), qs = __shfl_sync(0xffffffffu, cur.rec.z, l);
-            if (lane <= l || (cur.cx == qx && cur.cy == qy)) pend = false;
-            if (lane == 0) {
-              bm.clear(qx, qy);
-              const unsigned pk = (unsigned)qx | ((unsigned)qy << 16);
-              ring[regSize & (GROW_RQ - 1)] = pk;
-              __stcg(reg + regBase + regSize, pk);
+            const int qpk = __shfl_sync(0xffffffffu, cur.cpk, l);
+            pm &= ~__ballot_sync(0xffffffffu, cur.cpk == qpk);   // the same pixel seen from another entry
+            if (lane == l) {
+              bm.clear(qpk & 0xffff, qpk >> 16);
+              ring[regSize & (GROW_RQ - 1)] = (unsigned)qpk;
+              __stcg(reg + regBase + regSize, (unsigned)qpk);
             }
             regSize++;
             fresh = false;
@@ -803,7 +805,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     k_lsd_rowfilter<<<dim3((O.w + 63) / 64, (O.h + 3) / 4, n), 256, 0, st>>>(p.img[o], p.ipitch[o], p.ifs[o], O.w, O.h,
                                                                              b.rowf + O.rawOff, g.rawTotal, g);
     prof->mark("k_lsd_rowfilter", st);
-    k_lsd_scale_grad<<<dim3((O.sw + 31) / 32, (O.sh + 7) / 8, n), 256, 0, st>>>(g, o, b.rowf, g.rawTotal, b.tabs, b);
+    k_lsd_scale_grad<<<dim3(O.wpr, (O.sh + 7) / 8, n), 256, 0, st>>>(g, o, b.rowf, g.rawTotal, b.tabs, b);
     prof->mark("k_lsd_scale_grad", st);
     nl += 2;
   }

@@ -116,7 +116,7 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
     O.sw = round_even_d(O.w * g.lsdScale);
     O.sh = round_even_d(O.h * g.lsdScale);
     if (O.sw < 8 || O.sh < 8 || O.sw > 65535 || O.sh > 65535) { set_error("image size unsupported for LSD"); return PLVI_ERR_INVALID; }
-    O.wpr = (O.sw + 31) / 32;
+    O.wpr = O.sw / 32 + 1;   // at least one padding bit per row: x = -1 and x = W read as "not available"
     const double LOG_NT = 5 * (log10((double)O.sw) + log10((double)O.sh)) / 2 + log10(11.0);
     O.minRegSize = (int)(-LOG_NT / log10(22.5 / 180));
     O.pxOff = px; px += ((size_t)O.sw * O.sh + 3) & ~(size_t)3;
