@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--orb-only", action="store_true", help="diagnostic: time ORB extraction alone (not the bench metric)")
     ap.add_argument("--profile-out", default="")
+    ap.add_argument("--no-overlap", action="store_true", help="run the line pipeline on the same stream as ORB")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -207,7 +208,8 @@ def main():
     B = args.batch
     frames = synth.frame_batch(B, W, H, base_seed=1000 * rank, distinct=16)
     h_frames = torch.from_numpy(frames).pin_memory()
-    fe = FrontEnd(B, W, H, device=local_rank, with_lines=not args.orb_only, with_match=not args.orb_only)
+    fe = FrontEnd(B, W, H, device=local_rank, with_lines=not args.orb_only, with_match=not args.orb_only,
+                  overlap_lines=not args.no_overlap)
     st = fe.stream
     with torch.cuda.stream(st):
         d_frames = h_frames.to(dev, non_blocking=True)
@@ -267,7 +269,7 @@ def main():
     # ---- per-kernel profile of one extra step (events after every launch; not part of the timed numbers)
     fe.set_profile(True)
     with torch.cuda.stream(st):
-        fe.step(d_frames)
+        fe.step(d_frames, serialize=True)   # points and lines back to back: per-kernel times without co-scheduling
     st.synchronize()
     prof = fe.profile()
     fe.set_profile(False)

@@ -125,12 +125,16 @@ __device__ __forceinline__ int fast_arc_score(const int (&d)[16]) {
   return max(bp, bn) - 1;
 }
 
+// Shared-memory tile layout: ROI column c is stored at byte column c + 1, so that the first
+// detection column (c = 3) is word aligned and groups of 4 detection pixels are one 32-bit word.
+#define FAST_PAD 1
+
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
                                               const __grid_constant__ OrbPtrs p,
                                               const FastTile* __restrict__ tiles,
                                               uint32_t* __restrict__ cand,
                                               int* __restrict__ candCount, int tilePitch,
-                                              int tileRows, int survCap) {
+                                              int tileRows, int listCap, int survCap) {
   extern __shared__ __align__(16) u8 smem[];
   const FastTile t = tiles[blockIdx.x];
   const int f = blockIdx.y;
@@ -145,94 +149,134 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
 
   u8* simg = smem;                                   // [tileRows][tilePitch]
   u8* ssc = smem + tileRows * tilePitch;             // scores, same shape
-  uint32_t* surv = reinterpret_cast<uint32_t*>(ssc + tileRows * tilePitch);  // [survCap]
-  uint32_t* kept = surv + survCap;                   // [survCap]
-  __shared__ int s_nsurv, s_nkept, s_base;
+  unsigned short* list1 = reinterpret_cast<unsigned short*>(ssc + tileRows * tilePitch);  // [listCap] dy << 8 | dx
+  unsigned short* list2 = list1 + listCap;                                               // [listCap] corners
+  uint32_t* surv = reinterpret_cast<uint32_t*>(list2 + listCap);                         // [survCap]
+  uint32_t* kept = surv + survCap;                                                       // [survCap]
+  __shared__ int s_n1, s_n2, s_nsurv, s_nkept, s_base;
   __shared__ int s_cellFlag[8];
   const int tid = threadIdx.x;
-  if (tid == 0) { s_nsurv = 0; s_nkept = 0; }
+  if (tid == 0) { s_n1 = 0; s_n2 = 0; s_nsurv = 0; s_nkept = 0; }
   if (tid < 8) s_cellFlag[tid] = 0;
 
+  // ---- tile load: smem word k of a row holds ROI bytes 4k-1 .. 4k+2
   const int ipitch = p.ipitch[t.level];
-  const u8* gimg = p.img[t.level] + (size_t)f * p.ifs[t.level] + (size_t)iniY * ipitch + iniX;
-  for (int i = tid; i < rh * tilePitch; i += 256) {
-    const int r = i / tilePitch, c = i - r * tilePitch;
-    simg[i] = c < rw ? __ldg(gimg + (size_t)r * ipitch + c) : 0;
+  const u8* gbase = p.img[t.level] + (size_t)f * p.ifs[t.level];
+  const int nwords = (rw + FAST_PAD + 3) >> 2;
+  const bool aligned4 = ((ipitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(gbase) & 3) == 0);
+  const int tx = tid & 63, ty = tid >> 6;
+  if (tx < nwords) {
+    const int gx = iniX + 4 * tx - FAST_PAD;          // global x of the word's first byte (>= 15)
+    for (int r = ty; r < rh; r += 4) {
+      const u8* grow = gbase + (size_t)(iniY + r) * ipitch;
+      uint32_t w;
+      if (aligned4) {
+        const int ax = gx & ~3, sh = (gx & 3) * 8;
+        const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(grow + ax));
+        const uint32_t hi = __ldg(reinterpret_cast<const uint32_t*>(grow + min(ax + 4, (L.w - 1) & ~3)));
+        w = __funnelshift_r(lo, hi, sh);
+      } else {
+        w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) w |= (uint32_t)__ldg(grow + min(gx + k, L.w - 1)) << (8 * k);
+      }
+      reinterpret_cast<uint32_t*>(simg + r * tilePitch)[tx] = w;
+    }
   }
-  for (int i = tid; i < (tileRows * tilePitch) / 4; i += 256) reinterpret_cast<uint32_t*>(ssc)[i] = 0;
+  for (int i = tid; i < (tileRows * tilePitch) >> 2; i += 256) reinterpret_cast<uint32_t*>(ssc)[i] = 0;
   __syncthreads();
 
   const int minTh = g.minTh, iniTh = g.iniTh;
   const int dw = rw - 6, dh = rh - 6;
-  const int lane = tid & 31, wid = tid >> 5;
-  // ---- score pass: warp per row, lanes stride the columns
-  for (int dy = wid; dy < dh; dy += 8) {
-    const u8* row = simg + (dy + 3) * tilePitch + 3;
-    for (int dx = lane; dx < dw; dx += 32) {
-      const u8* q = row + dx;
-      const int c = q[0];
-      const int hi = c + minTh, lo = c - minTh;
-      // compass pre-test: any 9-arc holds >= 2 of the 4 compass pixels
-      const int v0 = q[3 * tilePitch], v8 = q[-3 * tilePitch], v4 = q[3], v12 = q[-3];
-      const int nb = (v0 > hi) + (v8 > hi) + (v4 > hi) + (v12 > hi);
-      const int nd = (v0 < lo) + (v8 < lo) + (v4 < lo) + (v12 < lo);
-      if (nb < 2 && nd < 2) continue;
-      int d[16];
-      d[0] = c - v0;
-      d[1] = c - q[3 * tilePitch + 1];
-      d[2] = c - q[2 * tilePitch + 2];
-      d[3] = c - q[tilePitch + 3];
-      d[4] = c - v4;
-      d[5] = c - q[-tilePitch + 3];
-      d[6] = c - q[-2 * tilePitch + 2];
-      d[7] = c - q[-3 * tilePitch + 1];
-      d[8] = c - v8;
-      d[9] = c - q[-3 * tilePitch - 1];
-      d[10] = c - q[-2 * tilePitch - 2];
-      d[11] = c - q[-tilePitch - 3];
-      d[12] = c - v12;
-      d[13] = c - q[tilePitch - 3];
-      d[14] = c - q[2 * tilePitch - 2];
-      d[15] = c - q[3 * tilePitch - 1];
-      uint32_t mb = 0, md = 0;
+  // ---- pass A: 4 pixels per thread.  Any 9-arc holds >= 2 of the 4 compass ring pixels, so a
+  // corner needs >= 2 compass pixels that differ from the centre by more than minTh.
+  {
+    const int dwords = (dw + 3) >> 2;
+    const uint32_t th4 = (uint32_t)minTh * 0x01010101u;
+    for (int dy = ty; dy < dh; dy += 4) {
+      if (tx >= dwords) continue;
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(simg + (dy + 3) * tilePitch) + 1 + tx;
+      const uint32_t c = row[0], lft = row[-1], rgt = row[1];
+      const uint32_t up = row[-3 * (tilePitch >> 2)], dn = row[3 * (tilePitch >> 2)];
+      const uint32_t l3 = __funnelshift_r(lft, c, 8), r3 = __funnelshift_r(c, rgt, 24);   // columns -3 / +3
+      uint32_t cnt = __vsetgtu4(__vabsdiffu4(up, c), th4) + __vsetgtu4(__vabsdiffu4(dn, c), th4) +
+                     __vsetgtu4(__vabsdiffu4(l3, c), th4) + __vsetgtu4(__vabsdiffu4(r3, c), th4);
+      cnt = (cnt + 0x7e7e7e7eu) & 0x80808080u;          // bit 7 of a byte set <=> its count >= 2
+      if (!cnt) continue;
+      const int dx0 = tx * 4;
+      int npass = 0;
+      unsigned short loc[4];
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        mb |= (uint32_t)(d[k] < -minTh) << k;  // ring brighter than centre + th
-        md |= (uint32_t)(d[k] > minTh) << k;   // ring darker than centre - th
+      for (int k = 0; k < 4; k++)
+        if ((cnt >> (8 * k + 7)) & 1u && dx0 + k < dw) loc[npass++] = (unsigned short)((dy << 8) | (dx0 + k));
+      if (npass) {
+        const int o = atomicAdd(&s_n1, npass);
+        for (int k = 0; k < npass; k++) list1[o + k] = loc[k];
       }
-      mb |= mb << 16;
-      md |= md << 16;
-      mb &= mb >> 1; mb &= mb >> 2; mb &= mb >> 4; mb &= mb >> 1;
-      md &= md >> 1; md &= md >> 2; md &= md >> 4; md &= md >> 1;
-      if (((mb | md) & 0xffffu) == 0) continue;
-      ssc[(dy + 3) * tilePitch + 3 + dx] = (u8)fast_arc_score(d);
     }
   }
   __syncthreads();
-  // ---- NMS confined to the cell; survivors to shared list
-  const int wCell = L.wCell;
-  for (int dy = wid; dy < dh; dy += 8) {
-    const u8* row = ssc + (dy + 3) * tilePitch + 3;
-    for (int dx = lane; dx < dw; dx += 32) {
-      const int s = row[dx];
-      if (s == 0) continue;
-      const int cell = dx / wCell, xin = dx - cell * wCell;
-      const bool hasL = xin > 0, hasR = (xin < wCell - 1) && (dx + 1 < dw);
-      bool keep = true;
-#pragma unroll
-      for (int oy = -1; oy <= 1; oy++) {
-        if (dy + oy < 0 || dy + oy >= dh) continue;
-        const u8* r2 = row + oy * tilePitch + dx;
-        if (hasL && r2[-1] >= s) keep = false;
-        if (oy != 0 && r2[0] >= s) keep = false;
-        if (hasR && r2[1] >= s) keep = false;
-      }
-      if (!keep) continue;
-      const int idx = atomicAdd(&s_nsurv, 1);
-      if (idx < survCap)
-        surv[idx] = pack_xys(iniX + 3 + dx - kEdge, iniY + 3 + dy - kEdge, s) ;
-      if (s >= iniTh) s_cellFlag[cell] = 1;
+  // ---- pass B: exact segment test for the listed pixels; corners go to a second list
+  const int n1 = s_n1;
+  for (int i = tid; i < n1; i += 256) {
+    const unsigned short pos = list1[i];
+    const int dy = pos >> 8, dx = pos & 0xff;
+    const u8* q = simg + (dy + 3) * tilePitch + 3 + FAST_PAD + dx;
+    const int c = q[0];
+    const int hi = c + minTh, lo = c - minTh;
+    uint32_t mb = 0, md = 0;       // one bit per ring pixel: brighter than c+th / darker than c-th
+#define FAST_RING(OFF)                                              \
+    {                                                               \
+      const int v = q[OFF];                                         \
+      mb = __funnelshift_l((uint32_t)(hi - v), mb, 1);              \
+      md = __funnelshift_l((uint32_t)(v - lo), md, 1);              \
     }
+    FAST_RING(3 * tilePitch) FAST_RING(3 * tilePitch + 1) FAST_RING(2 * tilePitch + 2) FAST_RING(tilePitch + 3)
+    FAST_RING(3) FAST_RING(-tilePitch + 3) FAST_RING(-2 * tilePitch + 2) FAST_RING(-3 * tilePitch + 1)
+    FAST_RING(-3 * tilePitch) FAST_RING(-3 * tilePitch - 1) FAST_RING(-2 * tilePitch - 2) FAST_RING(-tilePitch - 3)
+    FAST_RING(-3) FAST_RING(tilePitch - 3) FAST_RING(2 * tilePitch - 2) FAST_RING(3 * tilePitch - 1)
+#undef FAST_RING
+    mb |= mb << 16;
+    md |= md << 16;
+    mb &= mb >> 1; mb &= mb >> 2; mb &= mb >> 4; mb &= mb >> 1;
+    md &= md >> 1; md &= md >> 2; md &= md >> 4; md &= md >> 1;
+    if (((mb | md) & 0xffffu) == 0) continue;
+    list2[atomicAdd(&s_n2, 1)] = pos;
+  }
+  __syncthreads();
+  // ---- pass C: score of every corner (all lanes busy)
+  const int n2 = s_n2;
+  for (int i = tid; i < n2; i += 256) {
+    const int dy = list2[i] >> 8, dx = list2[i] & 0xff;
+    const u8* q = simg + (dy + 3) * tilePitch + 3 + FAST_PAD + dx;
+    const int c = q[0];
+    int d[16];
+    d[0] = c - q[3 * tilePitch];        d[1] = c - q[3 * tilePitch + 1];   d[2] = c - q[2 * tilePitch + 2];
+    d[3] = c - q[tilePitch + 3];        d[4] = c - q[3];                   d[5] = c - q[-tilePitch + 3];
+    d[6] = c - q[-2 * tilePitch + 2];   d[7] = c - q[-3 * tilePitch + 1];  d[8] = c - q[-3 * tilePitch];
+    d[9] = c - q[-3 * tilePitch - 1];   d[10] = c - q[-2 * tilePitch - 2]; d[11] = c - q[-tilePitch - 3];
+    d[12] = c - q[-3];                  d[13] = c - q[tilePitch - 3];      d[14] = c - q[2 * tilePitch - 2];
+    d[15] = c - q[3 * tilePitch - 1];
+    ssc[(dy + 3) * tilePitch + 3 + FAST_PAD + dx] = (u8)fast_arc_score(d);
+  }
+  __syncthreads();
+  // ---- pass D: 3x3 non-maximum suppression confined to the cell
+  const int wCell = L.wCell;
+  for (int i = tid; i < n2; i += 256) {
+    const int dy = list2[i] >> 8, dx = list2[i] & 0xff;
+    const u8* r1 = ssc + (dy + 3) * tilePitch + 3 + FAST_PAD + dx;
+    const int s = r1[0];
+    const int cell = dx / wCell, xin = dx - cell * wCell;
+    // scores outside the detection area are 0 in the tile; only the cell's vertical borders need masking
+    const int mL = xin > 0 ? 0xff : 0, mR = (xin < wCell - 1) ? 0xff : 0;
+    const u8* r0 = r1 - tilePitch;
+    const u8* r2 = r1 + tilePitch;
+    const int m = max(max(max(r0[-1] & mL, r1[-1] & mL), max(r2[-1] & mL, r0[0])),
+                      max(max(r2[0], r0[1] & mR), max(r1[1] & mR, r2[1] & mR)));
+    if (m >= s) continue;
+    const int idx = atomicAdd(&s_nsurv, 1);
+    if (idx < survCap) surv[idx] = pack_xys(iniX + 3 + dx - kEdge, iniY + 3 + dy - kEdge, s);
+    if (s >= iniTh) s_cellFlag[cell] = 1;
   }
   __syncthreads();
   const int ns = min(s_nsurv, survCap);
@@ -733,23 +777,25 @@ static size_t octree_smem_bytes(int M) {
   return (size_t)M * (8 + 16 + 8 + 8 + 16 + 20 + 8) + 64;
 }
 
-static void fast_tile_dims(const OrbGeom& g, int* tilePitch, int* tileRows, int* survCap) {
-  int maxW = 0, maxH = 0, maxSurv = 0;
+static void fast_tile_dims(const OrbGeom& g, int* tilePitch, int* tileRows, int* listCap, int* survCap) {
+  int maxW = 0, maxH = 0, maxSurv = 0, maxList = 0;
   for (int l = 0; l < g.nlevels; l++) {
     const OrbLevel& L = g.lv[l];
     maxW = max(maxW, 4 * L.wCell + 6);
     maxH = max(maxH, L.hCell + 6);
     maxSurv = max(maxSurv, 4 * ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2));
+    maxList = max(maxList, 4 * L.wCell * L.hCell);
   }
-  *tilePitch = (maxW + 15) & ~15;
+  *tilePitch = (maxW + 1 + 4 + 15) & ~15;   // +1 pad column, +4: word reads one word past the last detection word
   *tileRows = maxH;
+  *listCap = (maxList + 7) & ~7;
   *survCap = maxSurv;
 }
 
 int orb_kernel_attrs(const OrbGeom& g, int* fastSmem, int* octSmem) {
-  int tp, tr, sc;
-  fast_tile_dims(g, &tp, &tr, &sc);
-  *fastSmem = 2 * tp * tr + 2 * sc * (int)sizeof(uint32_t);
+  int tp, tr, lc, sc;
+  fast_tile_dims(g, &tp, &tr, &lc, &sc);
+  *fastSmem = 2 * tp * tr + 2 * lc * (int)sizeof(unsigned short) + 2 * sc * (int)sizeof(uint32_t);
   *octSmem = (int)octree_smem_bytes(g.maxNodes);
   if (*octSmem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_octree<OCT_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, *octSmem));
@@ -779,10 +825,10 @@ int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s,
   prof->mark("k_resize", st);
   // FAST tile geometry recomputed here must match capi's smem sizing
   {
-    int tilePitch, maxH, maxSurv;
-    fast_tile_dims(g, &tilePitch, &maxH, &maxSurv);
+    int tilePitch, maxH, listCap, maxSurv;
+    fast_tile_dims(g, &tilePitch, &maxH, &listCap, &maxSurv);
     k_fast<<<dim3(s.nFastTiles, n), 256, s.fastSmem, st>>>(g, p, s.fastTiles, s.cand, s.candCount,
-                                                          tilePitch, maxH, maxSurv);
+                                                          tilePitch, maxH, listCap, maxSurv);
     nl++;
   }
   prof->mark("k_fast", st);

@@ -24,7 +24,7 @@ def shard_range(n_items, rank, world):
 class FrontEnd:
     def __init__(self, batch, w=752, h=480, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
                  lsd_nfeatures=200, lsd_scale=0.8, line_levels=2, line_scale=2.0, device=0, stream=None,
-                 with_lines=True, with_match=True, match_th=15.0, nnratio=0.9):
+                 with_lines=True, with_match=True, match_th=15.0, nnratio=0.9, overlap_lines=True):
         import torch
         self.torch = torch
         self.B, self.w, self.h = batch, w, h
@@ -32,6 +32,12 @@ class FrontEnd:
         torch.cuda.set_device(self.device)
         self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
         sp = self.stream.cuda_stream
+        # points and lines are independent (the reference runs them on two threads, src/Frame.cc:558-561):
+        # the line pipeline gets its own stream, forked from / joined into self.stream every step, so the
+        # latency-bound LSD region growing overlaps the throughput-bound ORB kernels
+        self.line_stream = torch.cuda.Stream(device=self.device) if overlap_lines else self.stream
+        self._ev_fork = torch.cuda.Event()
+        self._ev_join = torch.cuda.Event()
         self.scale_factor = float(scale_factor)
         self.match_th = float(match_th)
         self.orb = ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th, max_width=w, max_height=h,
@@ -41,7 +47,8 @@ class FrontEnd:
         self.om = self.lm = None
         if with_lines:
             self.line = Lineextractor(lsd_nfeatures, 0, lsd_scale, line_levels, line_scale, 0, max_width=w,
-                                      max_height=h, max_batch=batch, device=device, stream=sp)
+                                      max_height=h, max_batch=batch, device=device,
+                                      stream=self.line_stream.cuda_stream)
             self.line_out = self.line.alloc_device_outputs(batch, self.device)
         if with_match and batch > 1:
             cap = self.orb.capacity
@@ -64,14 +71,27 @@ class FrontEnd:
             if o is not None:
                 o.close()
 
-    def step(self, d_frames):
-        """d_frames: uint8 CUDA tensor [n<=B, h, w].  Enqueues everything on self.stream."""
+    def step(self, d_frames, serialize=False):
+        """d_frames: uint8 CUDA tensor [n<=B, h, w].  Enqueues everything on self.stream (the line
+        pipeline on self.line_stream, joined before matching).  serialize=True makes the ORB kernels
+        wait for the line pipeline (clean per-kernel timings for the profile pass)."""
         n = d_frames.shape[0]
-        kps, desc, counts, mono = self.orb.extract_batch_device(d_frames, out=self.orb_out)
-        nl = self.orb.last_launches
+        nl = 0
+        forked = self.line is not None and self.line_stream is not self.stream
+        if forked:
+            self._ev_fork.record(self.stream)
+            self.line_stream.wait_event(self._ev_fork)
         if self.line is not None:
             kl, ldesc, leq, lcounts = self.line.extract_batch_device(d_frames, out=self.line_out)
             nl += self.line.last_launches
+        if forked and serialize:
+            self._ev_join.record(self.line_stream)
+            self.stream.wait_event(self._ev_join)
+        kps, desc, counts, mono = self.orb.extract_batch_device(d_frames, out=self.orb_out)
+        nl += self.orb.last_launches
+        if forked and not serialize:
+            self._ev_join.record(self.line_stream)
+            self.stream.wait_event(self._ev_join)
         if self.om is not None and n > 1:
             P, cap = n - 1, self.orb.capacity
             # frame p's keypoints are the "last frame" points searched in frame p+1
