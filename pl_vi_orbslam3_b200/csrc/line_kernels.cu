@@ -183,29 +183,43 @@ struct GrowBitmap {
 struct GrowBatch {
   unsigned mask;     // lanes holding an available neighbour (warp-uniform)
   int cpk;           // neighbour coordinates x | y << 16
+  int bw;            // bitmap word of the neighbour: >= 0 index into the shared window, < 0: ~index into the global copy
+  unsigned bbit;     // its bit
   float4 rec;        // {angle deg, cos(float angle), sin(float angle), -}
 };
+
+__device__ __forceinline__ bool grow_bit(const GrowBitmap& bm, int bw, unsigned bbit) {
+  return ((bw >= 0 ? bm.sm[bw] : __ldcg(bm.gm + ~bw)) & bbit) != 0u;
+}
+__device__ __forceinline__ void grow_clear(GrowBitmap& bm, int bw, unsigned bbit) {   // one lane only
+  if (bw >= 0) bm.sm[bw] &= ~bbit;
+  else { unsigned* p = bm.gm + ~bw; __stcg(p, __ldcg(p) & ~bbit); }
+}
 
 // Neighbourhood fetch for queue entries [i, i+nb): lane (e, k) tests the availability bit of
 // its neighbour and, if set, issues the 16-byte record load (consumed later => the load
 // latency overlaps the accept chain of the previous batch).
 __device__ __forceinline__ GrowBatch grow_fetch(const GrowBitmap& bm, const unsigned* ring, const unsigned* reg,
-                                                int regBase, int regSize, int i, int nb, int e, int ndx, int ndy,
-                                                int W, int H, const float4* __restrict__ rec) {
+                                                int regSize, int i, int nb, int e, int ndx, int ndy, int W, int H,
+                                                const float4* __restrict__ rec) {
   GrowBatch g;
-  g.cpk = 0;
+  g.cpk = 0; g.bw = 0; g.bbit = 0u;
   g.rec = make_float4(0.f, 0.f, 0.f, 0.f);
   bool cand = false;
   if (e < nb) {
     const int idx = i + e;
-    const unsigned p = (regSize - idx <= GROW_RQ) ? ring[idx & (GROW_RQ - 1)] : __ldcg(reg + regBase + idx);
+    const unsigned p = (regSize - idx <= GROW_RQ) ? ring[idx & (GROW_RQ - 1)] : __ldcg(reg + idx);
     const int cx = (int)(p & 0xffff) + ndx, cy = (int)(p >> 16) + ndy;
-    // x = -1 and x = W land on padding bits of the bitmap rows (always 0); rows above the
-    // window top hold no available pixel
-    if (cy >= bm.top && cy < H && cx >= 0 && bm.test(cx, cy)) {
-      cand = true;
-      g.cpk = cx | (cy << 16);
-      g.rec = __ldg(rec + cy * W + cx);
+    // x = -1 is rejected; x = W lands on a padding bit of the bitmap row (always 0); rows above
+    // the window top hold no available pixel
+    if (cy >= bm.top && cy < H && cx >= 0) {
+      g.bw = (cy - bm.top < GROW_K) ? (cy & (GROW_K - 1)) * bm.wpr + (cx >> 5) : ~(cy * bm.wpr + (cx >> 5));
+      g.bbit = 1u << (cx & 31);
+      if (grow_bit(bm, g.bw, g.bbit)) {
+        cand = true;
+        g.cpk = cx | (cy << 16);
+        g.rec = __ldg(rec + cy * W + cx);
+      }
     }
   }
   g.mask = __ballot_sync(0xffffffffu, cand);
@@ -229,7 +243,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
   const float4* __restrict__ rec = b.rec + pbase;
   const float2* __restrict__ seedcs = b.seed + pbase;
-  unsigned* reg = b.reg + pbase;
+  unsigned* regAll = b.reg + pbase;
   LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
   const double prec = g.prec;
   const float kHi = g.alignHi2, kLo = g.alignLo2;
@@ -249,17 +263,12 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
       bm.top = row;
       __syncwarp();
     }
-#ifdef PLVI_GROW_PREFETCH_ROWS
-    {
-      const int pr = min(row + PLVI_GROW_PREFETCH_ROWS, H - 1);
-      for (int x = lane * 8; x < W; x += 256) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + pr * W + x));
-    }
-#endif
     for (int c0 = 0; c0 < wpr; c0 += 32) {
       while (true) {
         // next seed: first available pixel in raster order (src/LSD/lsd.cpp:476-479)
         const int wi = c0 + lane;
-        const unsigned word = wi < wpr ? bm.sm[(row & (GROW_K - 1)) * wpr + wi] : 0u;
+        const int rowBase = (row & (GROW_K - 1)) * wpr;
+        const unsigned word = wi < wpr ? bm.sm[rowBase + wi] : 0u;
         const unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
         if (!nz) break;
         const int wl = __ffs(nz) - 1;
@@ -269,10 +278,10 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
         const int sp = sy * W + sx;
         const float sang = __ldg(&rec[sp].x);
         const float2 scs = __ldg(seedcs + sp);
+        unsigned* reg = regAll + regBase;          // pixel list of the region being grown
         if (lane == 0) {
-          bm.clear(sx, sy);
+          bm.sm[rowBase + c0 + wl] = sw_ & ~(1u << bit);
           ring[0] = (unsigned)sx | ((unsigned)sy << 16);
-          __stcg(reg + regBase, (unsigned)sx | ((unsigned)sy << 16));
         }
         __syncwarp();
         // region_grow (src/LSD/lsd.cpp:635-686).  The region angle is a pure function of the
@@ -282,14 +291,15 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
         float sumdx = scs.x, sumdy = scs.y;
         bool fresh = true;   // no pixel accepted yet: reg_angle is the seed's own angle
         int regSize = 1;
+        int flushed = 0;     // ring entries [flushed, regSize) are not in global memory yet
         int i = 0, nb = 1;
-        GrowBatch cur = grow_fetch(bm, ring, reg, regBase, regSize, 0, 1, e, ndx, ndy, W, H, rec);
+        GrowBatch cur = grow_fetch(bm, ring, reg, regSize, 0, 1, e, ndx, ndy, W, H, rec);
         while (nb > 0) {
           const int ni = i + nb, nnb = min(4, regSize - ni);
-          GrowBatch nxt = grow_fetch(bm, ring, reg, regBase, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
+          GrowBatch nxt = grow_fetch(bm, ring, reg, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
           // candidates fetched ahead may have been absorbed by the previous batch in the meantime
           unsigned pm = cur.mask;
-          if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && bm.test(cur.cpk & 0xffff, cur.cpk >> 16));
+          if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cur.bw, cur.bbit));
           float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
           while (pm) {
             // every pending candidate against the current region direction at once
@@ -311,9 +321,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
             const int qpk = __shfl_sync(0xffffffffu, cur.cpk, l);
             pm &= ~__ballot_sync(0xffffffffu, cur.cpk == qpk);   // the same pixel seen from another entry
             if (lane == l) {
-              bm.clear(qpk & 0xffff, qpk >> 16);
+              grow_clear(bm, cur.bw, cur.bbit);
               ring[regSize & (GROW_RQ - 1)] = (unsigned)qpk;
-              __stcg(reg + regBase + regSize, (unsigned)qpk);
             }
             regSize++;
             fresh = false;
@@ -322,17 +331,24 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
             n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
           }
           __syncwarp();
+          // spill the ring to the region's global pixel list in coalesced chunks (needed by
+          // k_lsd_rect, and by grow_fetch when the frontier outgrows the ring)
+          while (regSize - flushed >= 32) {
+            __stcg(reg + flushed + lane, ring[(flushed + lane) & (GROW_RQ - 1)]);
+            flushed += 32;
+          }
           i = ni;
           if (nnb > 0) {
             cur = nxt;
             nb = nnb;
           } else {
             nb = min(4, regSize - i);
-            if (nb > 0) cur = grow_fetch(bm, ring, reg, regBase, regSize, i, nb, e, ndx, ndy, W, H, rec);
+            if (nb > 0) cur = grow_fetch(bm, ring, reg, regSize, i, nb, e, ndx, ndy, W, H, rec);
           }
         }
         if (regSize >= O.minRegSize) {
           if (nreg < O.segCap) {
+            if (flushed + lane < regSize) __stcg(reg + flushed + lane, ring[(flushed + lane) & (GROW_RQ - 1)]);
             if (lane == 0) {
               LineRegion r;
               r.start = regBase;

@@ -65,6 +65,8 @@ class FrontEnd:
                 self.line_m12 = torch.zeros((P, lc), dtype=torch.int32, device=self.device)
                 self.line_nm = torch.zeros(P, dtype=torch.int32, device=self.device)
         self.launches = 0
+        self._profiling = False
+        self._mev = None
 
     def close(self):
         for o in (self.orb, self.line, self.om, self.lm):
@@ -92,6 +94,9 @@ class FrontEnd:
         if forked and not serialize:
             self._ev_join.record(self.line_stream)
             self.stream.wait_event(self._ev_join)
+        if self._profiling:
+            self._mev = [self.torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            self._mev[0].record(self.stream)
         if self.om is not None and n > 1:
             P, cap = n - 1, self.orb.capacity
             # frame p's keypoints are the "last frame" points searched in frame p+1
@@ -102,11 +107,15 @@ class FrontEnd:
                 ptr(self.queries), ptr(desc), ptr(counts), cap, ORBmatcher.TH_HIGH, self.om.mfNNratio, 1,
                 ptr(self.match_train), ptr(self.match_query), ptr(self.nmatches), 1))
             nl += 2
+            if self._profiling:
+                self._mev[1].record(self.stream)
             if self.lm is not None:
                 lc = self.line.capacity
                 check(lib().plvi_line_match(self.lm._h, P, ptr(ldesc), ptr(lcounts), lc, ptr(ldesc[1:]), ptr(lcounts[1:]),
                                             lc, 0.9, 1, ptr(self.line_m12), ptr(self.line_nm), 1))
                 nl += 1
+                if self._profiling:
+                    self._mev[2].record(self.stream)
         self.launches = nl
         return nl
 
@@ -122,6 +131,7 @@ class FrontEnd:
         return out
 
     def set_profile(self, on=True):
+        self._profiling = bool(on)
         check(lib().plvi_orb_set_profile(self.orb._h, int(on)))
         if self.line is not None:
             check(lib().plvi_line_set_profile(self.line._h, int(on)))
@@ -132,6 +142,11 @@ class FrontEnd:
         if self.line is not None:
             txt += lib().plvi_line_profile(self.line._h).decode()
         prof = {}
+        if self.om is not None and getattr(self, "_mev", None):
+            self.stream.synchronize()
+            prof["k_search(+queries)"] = self._mev[0].elapsed_time(self._mev[1])
+            if self.lm is not None:
+                prof["k_line_match"] = self._mev[1].elapsed_time(self._mev[2])
         for item in txt.split(";"):
             if "=" in item:
                 k, v = item.split("=")
