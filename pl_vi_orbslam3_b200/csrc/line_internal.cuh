@@ -57,11 +57,15 @@ struct LineBufs {
   const int2* rsTab;     // u8 bilinear table for pyramid level 1 (x rows then y rows)
   const double* lbdG;    // [63] gaussCoefG_
   const double* lbdL;    // [21] gaussCoefL_
+  const double2* trig;   // [1024] {cos, sin}(k * 2 pi / 1024), host libm values
   double* scaledDbg;     // [B][pxTotal] or nullptr
 };
 
+struct LineAux { cudaStream_t stream; cudaEvent_t fork, join; };   // side stream for the LBD pre-processing
+
 int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b, int n, plvi_keyline* dKl,
-                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, int* launches, StageProf* prof);
+                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, LineAux aux, int* launches,
+                         StageProf* prof);
 int line_kernel_attrs(const LineGeom& g);
 void launch_resize_u8(const u8* src, int spitch, size_t sfs, int sw, int sh, u8* dst, int dpitch, size_t dfs, int dw,
                       int dh, const int2* xtab, const int2* ytab, int n, cudaStream_t st);

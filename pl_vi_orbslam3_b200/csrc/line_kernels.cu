@@ -85,31 +85,63 @@ __device__ __forceinline__ double col_blur(const double* __restrict__ rf, int w,
   return s;
 }
 
+// cos/sin of a level-line angle a in [0, 2 pi): a = k * (2 pi / 1024) + r, table values for the
+// grid point (correctly rounded doubles from the host libm) and short Taylor series for |r| <=
+// pi/1024.  Accurate to a few ulp of double, i.e. far below the float rounding that follows.
+#define TRIG_N 1024
+__device__ __forceinline__ void sincos_tab(double a, const double2* __restrict__ tab, double& s, double& c) {
+  const double step = 2.0 * PI_D / TRIG_N;
+  int k = __double2int_rn(a * (TRIG_N / (2.0 * PI_D)));
+  const double r = a - (double)k * step;
+  const double2 t = __ldg(tab + (k & (TRIG_N - 1)));   // {cos, sin} of k * step
+  const double r2 = r * r;
+  const double cr = 1.0 + r2 * (-0.5 + r2 * (1.0 / 24 + r2 * (-1.0 / 720 + r2 * (1.0 / 40320))));
+  const double sr = r * (1.0 + r2 * (-1.0 / 6 + r2 * (1.0 / 120 + r2 * (-1.0 / 5040))));
+  c = t.x * cr - t.y * sr;
+  s = t.y * cr + t.x * sr;
+}
+
+#define SG_TW 32
+#define SG_TH 8
+#define SG_SRC_W 48   // source columns needed by 33 scaled columns at scale >= 0.75: <= 33/0.75 + 3
+#define SG_SRC_H 16   // source rows needed by 9 scaled rows
+
 __global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ LineGeom g, int oct,
                                                         const double* __restrict__ rowf, size_t rfs,
                                                         const LineTab* __restrict__ tabs, LineBufs b) {
-  __shared__ double ssc[9][34];
+  __shared__ double sblur[SG_SRC_H][SG_SRC_W];   // column-blurred source pixels of this tile
+  __shared__ double ssc[SG_TH + 1][SG_TW + 2];   // scaled image tile (+1 halo)
   const LineOct& O = g.o[oct];
   const int f = blockIdx.z, tid = threadIdx.x;
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  const int x0 = blockIdx.x * SG_TW, y0 = blockIdx.y * SG_TH;
   const double* rf = rowf + (size_t)f * rfs + O.rawOff;
   const LineTab* xt = tabs + O.xtabOff;
   const LineTab* yt = tabs + O.ytabOff;
-  for (int i = tid; i < 9 * 33; i += 256) {
-    const int ty = i / 33, tx = i - ty * 33;
-    const int sx = x0 + tx, sy = y0 + ty;
-    double v = 0.0;
-    if (sx < O.sw && sy < O.sh) {
-      const LineTab X = xt[sx], Y = yt[sy];
-      const int xa = X.ofs, xb = min(X.ofs + 1, O.w - 1), ya = Y.ofs, yb = min(Y.ofs + 1, O.h - 1);
-      const double g00 = col_blur(rf, O.w, O.h, xa, ya, g.kern), g01 = col_blur(rf, O.w, O.h, xb, ya, g.kern);
-      const double g10 = col_blur(rf, O.w, O.h, xa, yb, g.kern), g11 = col_blur(rf, O.w, O.h, xb, yb, g.kern);
-      const double h0 = __dadd_rn(__dmul_rn(g00, (double)X.a0), __dmul_rn(g01, (double)X.a1));
-      const double h1 = __dadd_rn(__dmul_rn(g10, (double)X.a0), __dmul_rn(g11, (double)X.a1));
-      v = __dadd_rn(__dmul_rn(h0, (double)Y.a0), __dmul_rn(h1, (double)Y.a1));
-      if (b.scaledDbg && tx < 32 && ty < 8) b.scaledDbg[(size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx] = v;
+  if (x0 < O.sw) {
+    // source window of the tile
+    const int sx0 = xt[x0].ofs, sx1 = min(xt[min(x0 + SG_TW, O.sw - 1)].ofs + 1, O.w - 1);
+    const int sy0 = yt[y0].ofs, sy1 = min(yt[min(y0 + SG_TH, O.sh - 1)].ofs + 1, O.h - 1);
+    const int nsx = sx1 - sx0 + 1, nsy = sy1 - sy0 + 1;   // <= SG_SRC_W, SG_SRC_H (checked on the host)
+    for (int i = tid; i < nsx * nsy; i += 256) {
+      const int r = i / nsx, c = i - r * nsx;
+      sblur[r][c] = col_blur(rf, O.w, O.h, sx0 + c, sy0 + r, g.kern);
     }
-    ssc[ty][tx] = v;
+    __syncthreads();
+    for (int i = tid; i < (SG_TH + 1) * (SG_TW + 1); i += 256) {
+      const int ty = i / (SG_TW + 1), tx = i - ty * (SG_TW + 1);
+      const int sx = x0 + tx, sy = y0 + ty;
+      double v = 0.0;
+      if (sx < O.sw && sy < O.sh) {
+        const LineTab X = xt[sx], Y = yt[sy];
+        const int xa = X.ofs - sx0, xb = min(X.ofs + 1, O.w - 1) - sx0;
+        const int ya = Y.ofs - sy0, yb = min(Y.ofs + 1, O.h - 1) - sy0;
+        const double h0 = __dadd_rn(__dmul_rn(sblur[ya][xa], (double)X.a0), __dmul_rn(sblur[ya][xb], (double)X.a1));
+        const double h1 = __dadd_rn(__dmul_rn(sblur[yb][xa], (double)X.a0), __dmul_rn(sblur[yb][xb], (double)X.a1));
+        v = __dadd_rn(__dmul_rn(h0, (double)Y.a0), __dmul_rn(h1, (double)Y.a1));
+        if (b.scaledDbg && tx < SG_TW && ty < SG_TH) b.scaledDbg[(size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx] = v;
+      }
+      ssc[ty][tx] = v;
+    }
   }
   __syncthreads();
   const int tx = tid & 31, ty = tid >> 5;
@@ -127,9 +159,12 @@ __global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ 
       if (!(norm <= g.rho)) {
         angDeg = fast_atan2_dev((float)gx, (float)(-gy));
         const double a = __dmul_rn((double)angDeg, D2R);
-        double sd, cd, sf, cf;
-        sincos(a, &sd, &cd);
-        sincos((double)(float)a, &sf, &cf);
+        double sd, cd;
+        sincos_tab(a, b.trig, sd, cd);
+        // cos/sin of float(a) = a + dl, |dl| < 2.4e-7: rotate by dl (series exact to < 1e-20)
+        const double dl = (double)(float)a - a;
+        const double cdl = 1.0 - 0.5 * dl * dl, sdl = dl - dl * dl * dl * (1.0 / 6);
+        const double cf = cd * cdl - sd * sdl, sf = sd * cdl + cd * sdl;
         cs = make_float4((float)cf, (float)sf, (float)cd, (float)sd);
         avail = true;
       }
@@ -803,7 +838,8 @@ __global__ void __launch_bounds__(64) k_lbd(const __grid_constant__ LineGeom g, 
 // launch sequence
 // ---------------------------------------------------------------------------------------
 int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b, int n, plvi_keyline* dKl,
-                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, int* launches, StageProf* prof) {
+                         uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, LineAux aux, int* launches,
+                         StageProf* prof) {
   int nl = 0;
   StageProf nop;
   if (!prof) prof = &nop;
@@ -825,6 +861,36 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     prof->mark("k_lsd_scale_grad", st);
     nl += 2;
   }
+  // The LBD pyramid + Sobel only depend on the input frame: they run on the auxiliary stream while
+  // the latency-bound region growing occupies the main one (serially when profiling, for clean times).
+  const bool fork = aux.stream != nullptr && !prof->on;
+  cudaStream_t ls = fork ? aux.stream : st;
+  if (fork) {
+    PLVI_CUDA_TRY(cudaEventRecord(aux.fork, st));
+    PLVI_CUDA_TRY(cudaStreamWaitEvent(aux.stream, aux.fork, 0));
+  }
+  {
+    const LineOct& O0 = g.o[0];
+    k_gauss5<<<dim3((O0.lw + 127) / 128, (O0.lh + 31) / 32, n), 256, 0, ls>>>(p.img[0], p.ipitch[0], p.ifs[0], b.lbdImg0,
+                                                                             O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw, O0.lh);
+    prof->mark("k_gauss5", st);
+    k_sobel<<<dim3((O0.lw + 63) / 64, (O0.lh + 3) / 4, n), 256, 0, ls>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw,
+                                                                        O0.lh, b.grad + O0.lbdOff, g.lbdTotal);
+    prof->mark("k_sobel", st);
+    nl += 2;
+    if (g.noct > 1) {
+      const LineOct& O1 = g.o[1];
+      k_pyrdown<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, ls>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh,
+                                                                            O0.lw, O0.lh, b.lbdImg1, O1.lpitch,
+                                                                            (size_t)O1.lpitch * O1.lh, O1.lw, O1.lh);
+      prof->mark("k_pyrdown", st);
+      k_sobel<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, ls>>>(b.lbdImg1, O1.lpitch, (size_t)O1.lpitch * O1.lh,
+                                                                          O1.lw, O1.lh, b.grad + O1.lbdOff, g.lbdTotal);
+      prof->mark("k_sobel", st);
+      nl += 2;
+    }
+  }
+  if (fork) PLVI_CUDA_TRY(cudaEventRecord(aux.join, aux.stream));
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
   k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b);
   prof->mark("k_lsd_grow", st);
@@ -833,28 +899,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   k_line_assemble<512><<<n, 512, 0, st>>>(g, b, dKl, dCounts);
   prof->mark("k_line_assemble", st);
   nl += 3;
-  // LBD pyramid + Sobel
-  {
-    const LineOct& O0 = g.o[0];
-    k_gauss5<<<dim3((O0.lw + 127) / 128, (O0.lh + 31) / 32, n), 256, 0, st>>>(p.img[0], p.ipitch[0], p.ifs[0], b.lbdImg0,
-                                                                             O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw, O0.lh);
-    prof->mark("k_gauss5", st);
-    k_sobel<<<dim3((O0.lw + 63) / 64, (O0.lh + 3) / 4, n), 256, 0, st>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw,
-                                                                        O0.lh, b.grad + O0.lbdOff, g.lbdTotal);
-    prof->mark("k_sobel", st);
-    nl += 2;
-    if (g.noct > 1) {
-      const LineOct& O1 = g.o[1];
-      k_pyrdown<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, st>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh,
-                                                                            O0.lw, O0.lh, b.lbdImg1, O1.lpitch,
-                                                                            (size_t)O1.lpitch * O1.lh, O1.lw, O1.lh);
-      prof->mark("k_pyrdown", st);
-      k_sobel<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, st>>>(b.lbdImg1, O1.lpitch, (size_t)O1.lpitch * O1.lh,
-                                                                          O1.lw, O1.lh, b.grad + O1.lbdOff, g.lbdTotal);
-      prof->mark("k_sobel", st);
-      nl += 2;
-    }
-  }
+  if (fork) PLVI_CUDA_TRY(cudaStreamWaitEvent(st, aux.join, 0));
   k_lbd<<<dim3(g.keepCap, n), 64, 0, st>>>(g, b, dKl, dCounts, dDesc, dEq);
   nl++;
   prof->mark("k_lbd", st);

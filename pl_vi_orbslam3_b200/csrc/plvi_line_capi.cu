@@ -24,6 +24,7 @@ struct plvi_line {
   int2* dRsTab = nullptr;
   double* dLbdG = nullptr;
   double* dLbdL = nullptr;
+  double2* dTrig = nullptr;
   size_t tabCap = 0, rsCap = 0;
   plvi_keyline* dKl = nullptr;
   uint8_t* dDesc = nullptr;
@@ -33,6 +34,7 @@ struct plvi_line {
   StageProf prof;
   std::string profText;
   bool debug = false;
+  LineAux aux = {nullptr, nullptr, nullptr};
   LinePtrs lastPtrs = {};
 };
 
@@ -98,8 +100,8 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
   g.minLength = 0.025 * std::min(w, hh);
   const double sigma = (g.lsdScale < 1) ? (0.6 / g.lsdScale) : 0.6;
   const unsigned hk = (unsigned)ceil(sigma * sqrt(2 * 3.0 * log(10.0)));
-  if (g.lsdScale == 1.0 || hk != 3) {
-    set_error("lsd_scale outside the supported range (7-tap Gaussian, scale != 1)");
+  if (g.lsdScale == 1.0 || hk != 3 || g.lsdScale < 0.75) {
+    set_error("lsd_scale outside the supported range (7-tap Gaussian, 0.75 <= scale < 1)");
     return PLVI_ERR_INVALID;
   }
   gaussian_kernel7(sigma, g.kern);
@@ -232,6 +234,13 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); delete h; return PLVI_ERR_CUDA; }
     h->ownStream = true;
   }
+  if (cudaStreamCreateWithFlags(&h->aux.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->aux.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->aux.join, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("cannot create the auxiliary stream");
+    plvi_line_destroy(h);
+    return PLVI_ERR_CUDA;
+  }
   const LineGeom& c = h->capGeom;
   const size_t B = max_batch;
   cudaError_t e = cudaSuccess;
@@ -257,6 +266,7 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   A((void**)&h->dRsTab, h->rsCap * sizeof(int2));
   A((void**)&h->dLbdG, 63 * sizeof(double));
   A((void**)&h->dLbdL, 21 * sizeof(double));
+  A((void**)&h->dTrig, 1024 * sizeof(double2));
   A((void**)&h->dKl, B * c.keepCap * sizeof(plvi_keyline));
   A((void**)&h->dDesc, B * c.keepCap * 32);
   A((void**)&h->dEq, B * c.keepCap * 3 * sizeof(double));
@@ -274,11 +284,15 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
     for (int i = 0; i < 63; i++) { const double d = i - u; G[i] = exp(d * d * inv); }
     cudaMemcpy(h->dLbdG, G, sizeof(G), cudaMemcpyHostToDevice);
     cudaMemcpy(h->dLbdL, L, sizeof(L), cudaMemcpyHostToDevice);
+    std::vector<double2> trig(1024);
+    for (int k = 0; k < 1024; k++) trig[k] = make_double2(cos(k * (2.0 * M_PI / 1024)), sin(k * (2.0 * M_PI / 1024)));
+    cudaMemcpy(h->dTrig, trig.data(), trig.size() * sizeof(double2), cudaMemcpyHostToDevice);
   }
   h->buf.tabs = h->dTabs;
   h->buf.rsTab = h->dRsTab;
   h->buf.lbdG = h->dLbdG;
   h->buf.lbdL = h->dLbdL;
+  h->buf.trig = h->dTrig;
   *out = h;
   return PLVI_OK;
 }
@@ -287,12 +301,15 @@ void plvi_line_destroy(plvi_line* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->aux.stream) { cudaStreamSynchronize(h->aux.stream); cudaStreamDestroy(h->aux.stream); }
+  if (h->aux.fork) cudaEventDestroy(h->aux.fork);
+  if (h->aux.join) cudaEventDestroy(h->aux.join);
   cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
   cudaFree(h->buf.rowf); cudaFree(h->buf.rec); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
   cudaFree(h->buf.reg); cudaFree(h->buf.regTab); cudaFree(h->buf.regCount); cudaFree(h->buf.segs);
   cudaFree(h->buf.tmpResp); cudaFree(h->buf.tmpCls); cudaFree(h->buf.lbdImg0); cudaFree(h->buf.lbdImg1);
   cudaFree(h->buf.grad); cudaFree(h->buf.scaledDbg);
-  cudaFree(h->dTabs); cudaFree(h->dRsTab); cudaFree(h->dLbdG); cudaFree(h->dLbdL);
+  cudaFree(h->dTabs); cudaFree(h->dRsTab); cudaFree(h->dLbdG); cudaFree(h->dLbdL); cudaFree(h->dTrig);
   cudaFree(h->dKl); cudaFree(h->dDesc); cudaFree(h->dEq); cudaFree(h->dCounts);
   if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -354,7 +371,7 @@ int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, i
   fill_ptrs(h, d_imgs, stride, frame_stride, p);
   h->lastPtrs = p;
   h->lastN = n;
-  return launch_line_pipeline(h->geom, p, h->buf, n, d_kl, d_desc, d_eq, d_counts, h->stream, &h->lastLaunches, &h->prof);
+  return launch_line_pipeline(h->geom, p, h->buf, n, d_kl, d_desc, d_eq, d_counts, h->stream, h->aux, &h->lastLaunches, &h->prof);
 }
 
 int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int w, int hh, int stride,
@@ -377,7 +394,7 @@ int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int 
   fill_ptrs(h, nullptr, 0, 0, p);
   h->lastPtrs = p;
   h->lastN = n;
-  rc = launch_line_pipeline(h->geom, p, h->buf, n, h->dKl, h->dDesc, h->dEq, h->dCounts, h->stream, &h->lastLaunches, &h->prof);
+  rc = launch_line_pipeline(h->geom, p, h->buf, n, h->dKl, h->dDesc, h->dEq, h->dCounts, h->stream, h->aux, &h->lastLaunches, &h->prof);
   if (rc) return rc;
   const size_t rows = (size_t)n * h->geom.keepCap;
   PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
