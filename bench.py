@@ -147,12 +147,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLVI_BENCH_BATCH", 1024)))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLVI_BENCH_BATCH", 2048)))
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU baseline sample (0 = 4 per core)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--orb-only", action="store_true", help="diagnostic: time ORB extraction alone (not the bench metric)")
     ap.add_argument("--profile-out", default="")
     ap.add_argument("--no-overlap", action="store_true", help="run the line pipeline on the same stream as ORB")
+    ap.add_argument("--pipes", type=int, default=int(os.environ.get("PLVI_BENCH_PIPES", 1)),
+                    help="independent pipelines the batch is split over (overlap across slices)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -201,7 +203,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pl_vi_orbslam3_b200.frontend import FrontEnd
+    from pl_vi_orbslam3_b200.frontend import PipelinedFrontEnd
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -210,8 +212,8 @@ def main():
     B = args.batch
     frames = synth.frame_batch(B, W, H, base_seed=1000 * rank, distinct=16)
     h_frames = torch.from_numpy(frames).pin_memory()
-    fe = FrontEnd(B, W, H, device=local_rank, with_lines=not args.orb_only, with_match=not args.orb_only,
-                  overlap_lines=not args.no_overlap)
+    fe = PipelinedFrontEnd(B, pipes=args.pipes, device=local_rank, w=W, h=H, with_lines=not args.orb_only,
+                           with_match=not args.orb_only, overlap_lines=not args.no_overlap)
     st = fe.stream
     with torch.cuda.stream(st):
         d_frames = h_frames.to(dev, non_blocking=True)
@@ -244,14 +246,15 @@ def main():
 
     # ---- end to end: pinned host frames in, every result back on the host
     outs = fe.outputs()
-    h_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
+    h_out = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()} for o in outs]
     d_in = torch.empty_like(d_frames)
 
     def e2e_step():
         d_in.copy_(h_frames, non_blocking=True)
         fe.step(d_in)
-        for k, v in fe.outputs().items():
-            h_out[k].copy_(v, non_blocking=True)
+        for o, ho in zip(fe.outputs(), h_out):
+            for k, v in o.items():
+                ho[k].copy_(v, non_blocking=True)
 
     with torch.cuda.stream(st):
         for _ in range(2):
@@ -266,7 +269,7 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     h2d = int(h_frames.numel())
-    d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()))
+    d2h = int(sum(v.numel() * v.element_size() for ho in h_out for v in ho.values()))
 
     # ---- per-kernel profile of one extra step (events after every launch; not part of the timed numbers)
     fe.set_profile(True)
@@ -280,7 +283,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    counts = outs["counts"].float().mean().item()
+    counts = float(np.mean([o["counts"].float().mean().item() for o in outs]))
     if rank == 0:
         peaks = {}
         try:
@@ -303,7 +306,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD if not args.orb_only else "DIAGNOSTIC orb-only", "frames_per_step_per_gpu": B,
                        "width": W, "height": H, "l2_policy": "inputs larger than L2 (%.0f MB of frames per step)" % (B * W * H / 1e6),
-                       "parallelism": f"frame-sharded x{world}, no collective", "mean_keypoints": counts},
+                       "parallelism": f"frame-sharded x{world}, no collective", "mean_keypoints": counts,
+                       "pipelines_per_gpu": args.pipes},
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

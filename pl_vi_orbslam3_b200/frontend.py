@@ -152,3 +152,56 @@ class FrontEnd:
                 k, v = item.split("=")
                 prof[k] = prof.get(k, 0.0) + float(v)
         return prof
+
+
+class PipelinedFrontEnd:
+    """`pipes` independent FrontEnd pipelines (own handles, streams and scratch), each taking a
+    contiguous slice of the batch.  Their work is enqueued back to back on different streams, so the
+    latency-bound LSD region growing of one slice overlaps the throughput-bound kernels of the other
+    (frames are independent; frame-to-frame matching stays inside a slice)."""
+
+    def __init__(self, batch, pipes=2, device=0, **kw):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.Stream(device=self.device)      # master stream: fork / join point
+        self.sizes = [shard_range(batch, i, pipes)[1] - shard_range(batch, i, pipes)[0] for i in range(pipes)]
+        self.offsets = [shard_range(batch, i, pipes)[0] for i in range(pipes)]
+        self.fes = [FrontEnd(sz, device=device, **kw) for sz in self.sizes]
+        self._fork = torch.cuda.Event()
+        self._joins = [torch.cuda.Event() for _ in self.fes]
+        self.B = batch
+
+    def close(self):
+        for fe in self.fes:
+            fe.close()
+
+    def step(self, d_frames, serialize=False):
+        nl = 0
+        self._fork.record(self.stream)
+        for fe, off, sz, ev in zip(self.fes, self.offsets, self.sizes, self._joins):
+            fe.stream.wait_event(self._fork)
+            with self.torch.cuda.stream(fe.stream):
+                nl += fe.step(d_frames[off:off + sz], serialize=serialize)
+            ev.record(fe.stream)
+            if serialize:
+                self.stream.wait_event(ev)
+                self._fork.record(self.stream)
+        for ev in self._joins:
+            self.stream.wait_event(ev)
+        return nl
+
+    def outputs(self):
+        return [fe.outputs() for fe in self.fes]
+
+    def set_profile(self, on=True):
+        for fe in self.fes:
+            fe.set_profile(on)
+
+    def profile(self):
+        prof = {}
+        for fe in self.fes:
+            for k, v in fe.profile().items():
+                prof[k] = prof.get(k, 0.0) + v
+        return prof
