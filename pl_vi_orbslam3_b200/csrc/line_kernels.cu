@@ -59,15 +59,28 @@ __device__ __forceinline__ float fast_atan2_dev(float y, float x) {
 __global__ void __launch_bounds__(256) k_lsd_rowfilter(const u8* __restrict__ src, int spitch, size_t sfs, int w,
                                                        int h, double* __restrict__ dst, size_t dfs,
                                                        const __grid_constant__ LineGeom g) {
-  const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+  // thread = 4 horizontally adjacent pixels: the 10 input bytes are converted to f64 once
+  const int x4 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
   const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (x >= w || y >= h) return;
+  if (x4 >= w || y >= h) return;
   const u8* row = src + (size_t)blockIdx.z * sfs + (size_t)y * spitch;
-  double s = __dmul_rn(g.kern[0], (double)__ldg(row + reflect101_l(x - 3, w)));
+  double v[10];
+  if (x4 >= 3 && x4 + 6 < w) {
 #pragma unroll
-  for (int i = 1; i < 7; i++)
-    s = __dadd_rn(s, __dmul_rn(g.kern[i], (double)__ldg(row + reflect101_l(x - 3 + i, w))));
-  dst[(size_t)blockIdx.z * dfs + (size_t)y * w + x] = s;
+    for (int i = 0; i < 10; i++) v[i] = (double)__ldg(row + x4 - 3 + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 10; i++) v[i] = (double)__ldg(row + reflect101_l(min(x4 - 3 + i, w + 2), w));
+  }
+  double* out = dst + (size_t)blockIdx.z * dfs + (size_t)y * w + x4;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (x4 + k >= w) break;
+    double s = __dmul_rn(g.kern[0], v[k]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) s = __dadd_rn(s, __dmul_rn(g.kern[i], v[k + i]));
+    out[k] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -688,19 +701,36 @@ __global__ void __launch_bounds__(256) k_pyrdown(const u8* __restrict__ src, int
 
 __global__ void __launch_bounds__(256) k_sobel(const u8* __restrict__ src, int spitch, size_t sfs, int w, int h,
                                                short2* __restrict__ dst, size_t dfs) {
-  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (x >= w || y >= h) return;
+  // thread = 4 horizontally adjacent pixels; three rows x 6 bytes (x4-1 .. x4+4)
+  const int x4 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x4 >= w || y >= h) return;
   const u8* s = src + (size_t)blockIdx.z * sfs;
-  const int xm = reflect101_l(x - 1, w), xp = reflect101_l(x + 1, w);
-  const u8* r0 = s + (size_t)reflect101_l(y - 1, h) * spitch;
-  const u8* r1 = s + (size_t)y * spitch;
-  const u8* r2 = s + (size_t)reflect101_l(y + 1, h) * spitch;
-  const int p00 = __ldg(r0 + xm), p01 = __ldg(r0 + x), p02 = __ldg(r0 + xp);
-  const int p10 = __ldg(r1 + xm), p12 = __ldg(r1 + xp);
-  const int p20 = __ldg(r2 + xm), p21 = __ldg(r2 + x), p22 = __ldg(r2 + xp);
-  const int dx = (p02 - p00) + 2 * (p12 - p10) + (p22 - p20);
-  const int dy = (p20 - p00) + 2 * (p21 - p01) + (p22 - p02);
-  dst[(size_t)blockIdx.z * dfs + (size_t)y * w + x] = make_short2((short)dx, (short)dy);
+  const u8* rows[3] = {s + (size_t)reflect101_l(y - 1, h) * spitch, s + (size_t)y * spitch,
+                       s + (size_t)reflect101_l(y + 1, h) * spitch};
+  int p[3][6];
+  const bool inner = x4 >= 4 && x4 + 7 < w && ((spitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(s) & 3) == 0);
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    if (inner) {
+      const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(rows[r] + x4 - 4));
+      const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(rows[r] + x4));
+      const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(rows[r] + x4 + 4));
+      p[r][0] = a >> 24;
+      p[r][1] = b & 0xff; p[r][2] = (b >> 8) & 0xff; p[r][3] = (b >> 16) & 0xff; p[r][4] = b >> 24;
+      p[r][5] = c & 0xff;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; i++) p[r][i] = __ldg(rows[r] + reflect101_l(min(x4 - 1 + i, w + 1), w));
+    }
+  }
+  short2* out = dst + (size_t)blockIdx.z * dfs + (size_t)y * w + x4;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (x4 + k >= w) break;
+    const int dx = (p[0][k + 2] - p[0][k]) + 2 * (p[1][k + 2] - p[1][k]) + (p[2][k + 2] - p[2][k]);
+    const int dy = (p[2][k] - p[0][k]) + 2 * (p[2][k + 1] - p[0][k + 1]) + (p[2][k + 2] - p[0][k + 2]);
+    out[k] = make_short2((short)dx, (short)dy);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -854,7 +884,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   }
   for (int o = 0; o < g.noct; o++) {
     const LineOct& O = g.o[o];
-    k_lsd_rowfilter<<<dim3((O.w + 63) / 64, (O.h + 3) / 4, n), 256, 0, st>>>(p.img[o], p.ipitch[o], p.ifs[o], O.w, O.h,
+    k_lsd_rowfilter<<<dim3((O.w + 255) / 256, (O.h + 3) / 4, n), 256, 0, st>>>(p.img[o], p.ipitch[o], p.ifs[o], O.w, O.h,
                                                                              b.rowf + O.rawOff, g.rawTotal, g);
     prof->mark("k_lsd_rowfilter", st);
     k_lsd_scale_grad<<<dim3(O.wpr, (O.sh + 7) / 8, n), 256, 0, st>>>(g, o, b.rowf, g.rawTotal, b.tabs, b);
@@ -874,7 +904,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     k_gauss5<<<dim3((O0.lw + 127) / 128, (O0.lh + 31) / 32, n), 256, 0, ls>>>(p.img[0], p.ipitch[0], p.ifs[0], b.lbdImg0,
                                                                              O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw, O0.lh);
     prof->mark("k_gauss5", st);
-    k_sobel<<<dim3((O0.lw + 63) / 64, (O0.lh + 3) / 4, n), 256, 0, ls>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw,
+    k_sobel<<<dim3((O0.lw + 255) / 256, (O0.lh + 3) / 4, n), 256, 0, ls>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh, O0.lw,
                                                                         O0.lh, b.grad + O0.lbdOff, g.lbdTotal);
     prof->mark("k_sobel", st);
     nl += 2;
@@ -884,7 +914,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
                                                                             O0.lw, O0.lh, b.lbdImg1, O1.lpitch,
                                                                             (size_t)O1.lpitch * O1.lh, O1.lw, O1.lh);
       prof->mark("k_pyrdown", st);
-      k_sobel<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, ls>>>(b.lbdImg1, O1.lpitch, (size_t)O1.lpitch * O1.lh,
+      k_sobel<<<dim3((O1.lw + 255) / 256, (O1.lh + 3) / 4, n), 256, 0, ls>>>(b.lbdImg1, O1.lpitch, (size_t)O1.lpitch * O1.lh,
                                                                           O1.lw, O1.lh, b.grad + O1.lbdOff, g.lbdTotal);
       prof->mark("k_sobel", st);
       nl += 2;

@@ -532,54 +532,73 @@ __device__ __forceinline__ int reflect101(int p, int len) {
   return p;
 }
 
+// Tile = 128 x 32 outputs.  The input tile (38 rows x 136 bytes, starting 4 bytes left of the
+// tile so that words stay aligned) is loaded as 32-bit words; the horizontal pass builds the
+// two 4-byte tap windows of each pixel with funnel shifts and uses two u8 dot products
+// (IDP.4A); the vertical pass works on 32-bit row sums.
 __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g,
                                                const __grid_constant__ OrbPtrs p,
                                                const BlurTile* __restrict__ tiles) {
-  __shared__ __align__(16) u8 sin_[(BLUR_TH + 6) * (BLUR_TW + 8)];
-  __shared__ __align__(16) unsigned short sh_[(BLUR_TH + 6) * BLUR_TW];
+  __shared__ __align__(16) uint32_t sin_[(BLUR_TH + 6) * 36];          // 34 words used per row
+  __shared__ __align__(16) uint32_t sh_[(BLUR_TH + 6) * BLUR_TW];      // horizontal sums (<= 65280)
   const BlurTile t = tiles[blockIdx.x];
   const int f = blockIdx.y, tid = threadIdx.x;
   const OrbLevel& L = g.lv[t.level];
   const int x0 = t.tx * BLUR_TW, y0 = t.ty * BLUR_TH;
   const int ipitch = p.ipitch[t.level];
   const u8* src = p.img[t.level] + (size_t)f * p.ifs[t.level];
-  const int SP = BLUR_TW + 8;
-  for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-    const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
+  const bool aligned4 = ((ipitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+  for (int i = tid; i < (BLUR_TH + 6) * 34; i += 256) {
+    const int r = i / 34, wq = i - r * 34;
     const int gy = reflect101(min(y0 + r - 3, L.h + 2), L.h);
-    const int gx = reflect101(min(x0 + c - 3, L.w + 2), L.w);
-    sin_[r * SP + c] = __ldg(src + (size_t)gy * ipitch + gx);
+    const int gx = x0 - 4 + 4 * wq;
+    const u8* row = src + (size_t)gy * ipitch;
+    uint32_t w;
+    if (aligned4 && gx >= 0 && gx + 3 < L.w) {
+      w = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+    } else {
+      w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) w |= (uint32_t)__ldg(row + reflect101(min(gx + k, L.w + 2), L.w)) << (8 * k);
+    }
+    sin_[r * 36 + wq] = w;
   }
   __syncthreads();
-  // horizontal: items = rows x 32 groups of 4 columns
+  const uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
   for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW / 4); i += 256) {
-    const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
-    const u8* q = sin_ + r * SP + c4;
-    int v[10];
-#pragma unroll
-    for (int k = 0; k < 10; k++) v[k] = q[k];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int s = 18 * (v[k] + v[k + 6]) + 34 * (v[k + 1] + v[k + 5]) + 48 * (v[k + 2] + v[k + 4]) +
-                    56 * v[k + 3];
-      sh_[r * BLUR_TW + c4 + k] = (unsigned short)s;
-    }
+    const int r = i >> 5, j = i & 31;               // output pixels 4j .. 4j+3 of row r
+    const uint32_t* q = sin_ + r * 36 + j;          // words holding tile bytes 4j-4 .. 4j+7
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+    uint4 o;
+    o.x = __dp4a(__funnelshift_r(w0, w1, 8), K0, __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
+    o.y = __dp4a(__funnelshift_r(w0, w1, 16), K0, __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
+    o.z = __dp4a(__funnelshift_r(w0, w1, 24), K0, __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
+    o.w = __dp4a(w1, K0, __dp4a(w2, K1, 0u));
+    *reinterpret_cast<uint4*>(sh_ + r * BLUR_TW + 4 * j) = o;
   }
   __syncthreads();
   u8* dst = p.blur[t.level] + (size_t)f * p.bfs[t.level];
-  for (int i = tid; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
-    const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
-    const int gy = y0 + r, gx = x0 + c4;
-    if (gy >= L.h || gx >= L.w) continue;
-    uint32_t out = 0;
+  for (int i = tid; i < (BLUR_TH / 2) * (BLUR_TW / 4); i += 256) {
+    const int r = (i >> 5) * 2, c4 = (i & 31) * 4;  // output rows r, r+1; columns c4 .. c4+3
+    const int gx = x0 + c4;
+    if (gx >= L.w) continue;
+    uint4 v[8];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const unsigned short* q = sh_ + r * BLUR_TW + c4 + k;
-      const uint32_t s = 18u * (q[0] + q[6 * BLUR_TW]) + 34u * (q[BLUR_TW] + q[5 * BLUR_TW]) +
-                         48u * (q[2 * BLUR_TW] + q[4 * BLUR_TW]) + 56u * q[3 * BLUR_TW];
-      out |= ((s + 32768u) >> 16) << (8 * k);
+    for (int k = 0; k < 8; k++) v[k] = *reinterpret_cast<const uint4*>(sh_ + (r + k) * BLUR_TW + c4);
+    uint32_t out0 = 0, out1 = 0;
+#define BLUR_COL(FIELD, SHIFT)                                                                             \
+    {                                                                                                      \
+      const uint32_t a = 18u * (v[0].FIELD + v[6].FIELD) + 34u * (v[1].FIELD + v[5].FIELD) +               \
+                         48u * (v[2].FIELD + v[4].FIELD) + 56u * v[3].FIELD;                               \
+      const uint32_t bq = 18u * (v[1].FIELD + v[7].FIELD) + 34u * (v[2].FIELD + v[6].FIELD) +              \
+                          48u * (v[3].FIELD + v[5].FIELD) + 56u * v[4].FIELD;                              \
+      out0 |= ((a + 32768u) >> 16) << SHIFT;                                                               \
+      out1 |= ((bq + 32768u) >> 16) << SHIFT;                                                              \
     }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = out;
+    BLUR_COL(x, 0) BLUR_COL(y, 8) BLUR_COL(z, 16) BLUR_COL(w, 24)
+#undef BLUR_COL
+    if (y0 + r < L.h) *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * L.pitch + gx) = out0;
+    if (y0 + r + 1 < L.h) *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r + 1) * L.pitch + gx) = out1;
   }
 }
 
