@@ -244,28 +244,48 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
 
-    # ---- end to end: pinned host frames in, every result back on the host
+    # ---- end to end: pinned host frames in, every result back on the host.  Copies run on their own
+    # streams: the H2D of step i+1 overlaps the compute of step i (two input buffers); the D2H of step
+    # i must finish before step i+1 overwrites the output buffers.
     outs = fe.outputs()
     h_out = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()} for o in outs]
-    d_in = torch.empty_like(d_frames)
+    d_in = [torch.empty_like(d_frames), torch.empty_like(d_frames)]
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
-    def e2e_step():
-        d_in.copy_(h_frames, non_blocking=True)
-        fe.step(d_in)
-        for o, ho in zip(fe.outputs(), h_out):
-            for k, v in o.items():
-                ho[k].copy_(v, non_blocking=True)
+    def e2e_run(nsteps):
+        ev_h2d = [torch.cuda.Event() for _ in range(nsteps)]
+        ev_cmp = [torch.cuda.Event() for _ in range(nsteps)]
+        ev_d2h = [torch.cuda.Event() for _ in range(nsteps)]
+        start = torch.cuda.Event(enable_timing=True)
+        stop = torch.cuda.Event(enable_timing=True)
+        start.record(st)
+        s_in.wait_event(start)
+        s_out.wait_event(start)
+        for i in range(nsteps):
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_cmp[i - 2])          # input buffer i%2 was read by step i-2
+                d_in[i % 2].copy_(h_frames, non_blocking=True)
+                ev_h2d[i].record(s_in)
+            with torch.cuda.stream(st):
+                st.wait_event(ev_h2d[i])
+                if i >= 1:
+                    st.wait_event(ev_d2h[i - 1])            # outputs of step i-1 are on the host
+                fe.step(d_in[i % 2])
+                ev_cmp[i].record(st)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[i])
+                for o, ho in zip(fe.outputs(), h_out):
+                    for k, v in o.items():
+                        ho[k].copy_(v, non_blocking=True)
+                ev_d2h[i].record(s_out)
+        st.wait_event(ev_d2h[nsteps - 1])
+        stop.record(st)
+        return start, stop
 
-    with torch.cuda.stream(st):
-        for _ in range(2):
-            e2e_step()
+    e2e_run(2)
     barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(st):
-        f0.record(st)
-        for _ in range(args.steps):
-            e2e_step()
-        f1.record(st)
+    f0, f1 = e2e_run(args.steps)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     h2d = int(h_frames.numel())
