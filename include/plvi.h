@@ -204,6 +204,7 @@ typedef struct plvi_query {
 #define PLVI_SEARCH_FRAME 0     /* ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) src/ORBmatcher.cc:1962 */
 #define PLVI_SEARCH_MAPPOINTS 1 /* ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, ...) src/ORBmatcher.cc:44 */
 #define PLVI_SEARCH_INIT 2      /* ORBmatcher::SearchForInitialization src/ORBmatcher.cc:706 */
+#define PLVI_SEARCH_BOW 3       /* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) src/ORBmatcher.cc:269 (plvi_search_by_bow) */
 
 /* max_train <= 65535 keypoints per frame. stream: existing cudaStream_t or NULL. */
 int plvi_matcher_create(plvi_matcher** out, int max_pairs, int max_train, int max_query, int device,
@@ -242,6 +243,21 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
                               plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
                               int query_stride, int th_dist, float nnratio, int check_orientation,
                               int* match_train, int* match_query, int* nmatches, int on_device);
+
+/* Descriptor part of int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>&)
+ * (include/ORBmatcher.h:56, src/ORBmatcher.cc:269-471, mono path).  The walk over the two
+ * DBoW2::FeatureVectors stays with the caller, who passes (a) group_items
+ * [npairs][items_stride]: the frame's feature indices grouped by vocabulary node, each
+ * group in vIndicesF order, and (b) one plvi_query per keyframe feature of a common node,
+ * in the reference's iteration order, with min_level/max_level = [start, end) of the node's
+ * group inside group_items, angle = keyframe keypoint angle, flags bit0 = no / bad map
+ * point.  TH_LOW, mfNNratio, rotation histogram as in the reference.  items_stride <=
+ * max_train.  match_train = vpMapPointMatches as query indices. */
+int plvi_search_by_bow(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                       const int* train_counts, int train_stride, const int* group_items, int items_stride,
+                       const plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                       int query_stride, int th_dist, float nnratio, int check_orientation, int* match_train,
+                       int* match_query, int* nmatches, int on_device);
 
 /* Test / benchmark utility (device pointers only): builds the plvi_query records of
  * SearchByProjection(Frame,Frame) for an identity pose -- every keypoint of the query

@@ -240,6 +240,18 @@ def search_init(keys2, desc2, grid, queries, desc1, th=50, nnratio=0.9, check_or
     return n, m12[:len(queries)], queries
 
 
+def search_bow(keys, desc, items, queries, qdesc, th=50, nnratio=0.7, check_ori=True):
+    keys = np.ascontiguousarray(keys)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    items = np.ascontiguousarray(items, np.int32)
+    queries = np.ascontiguousarray(queries)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    mt = np.empty(max(len(keys), 1), np.int32)
+    n = lib().plvio_search_bow(_p(keys), _p(desc), len(keys), _p(items), _p(queries), _p(qdesc), len(queries),
+                               int(th), C.c_float(nnratio), int(check_ori), _p(mt))
+    return n, mt[:len(keys)]
+
+
 def match_nnr(d1, d2, nnr):
     d1 = np.ascontiguousarray(d1, np.uint8)
     d2 = np.ascontiguousarray(d2, np.uint8)

@@ -258,6 +258,46 @@ int plvio_search_init(const Kp* keys2, const u8* desc2, int n2, float minX, floa
   return nmatches;
 }
 
+// SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), mono path (src/ORBmatcher.cc:269-471).
+// The caller walks the two DBoW2 feature vectors (host code) and passes, in that order, one
+// query per keyframe feature of a common vocabulary node: q.min_level/max_level = [start,end)
+// range of the node's frame features inside `items` (the frame's vIndicesF order), flags bit0 =
+// no map point / bad.  match_train[i2] = query index or -1 (vpMapPointMatches).
+int plvio_search_bow(const Kp* keys, const u8* desc, int n, const int* items, const Query* q, const u8* qdesc,
+                     int nq, int thLow, float nnratio, int checkOri, int* match_train) {
+  std::vector<int> owner(n, -1);
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int nmatches = 0;
+  for (int i = 0; i < nq; i++) {
+    if (q[i].flags & 1) continue;
+    int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+    for (int k = q[i].minLevel; k < q[i].maxLevel; k++) {
+      const int idx = items[k];
+      if (owner[idx] >= 0) continue;
+      const int d = hamming256(qdesc + 32 * (size_t)i, desc + 32 * (size_t)idx);
+      if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdxF = idx; }
+      else if (d < bestDist2) bestDist2 = d;
+    }
+    if (bestDist1 <= thLow) {
+      if ((float)bestDist1 < nnratio * (float)bestDist2) {
+        owner[bestIdxF] = i;
+        if (checkOri) rotHist[rot_bin(q[i].angle, keys[bestIdxF].angle)].push_back(bestIdxF);
+        nmatches++;
+      }
+    }
+  }
+  if (checkOri) {
+    int a = -1, b = -1, c = -1;
+    three_maxima(rotHist, HISTO_LENGTH, a, b, c);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == a || i == b || i == c) continue;
+      for (int id : rotHist[i]) { owner[id] = -1; nmatches--; }
+    }
+  }
+  for (int i = 0; i < n; i++) match_train[i] = owner[i];
+  return nmatches;
+}
+
 // LineMatcher::matchNNR on fresh output: knn-2 + ratio.  Needs n2 >= 2 (the reference
 // indexes matches_[idx][1] unconditionally: undefined for fewer train rows; here: no match).
 int plvio_match_nnr(const u8* d1, int n1, const u8* d2, int n2, float nnr, int* m12) {

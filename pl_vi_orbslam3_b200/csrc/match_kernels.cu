@@ -19,6 +19,7 @@
 // query of the same chunk.  "best" and "second best" are the two smallest candidates
 // under the key (distance, position in GetFeaturesInArea order), which is what the
 // reference's `<` update chain produces.
+#include <cstring>
 #include <vector>
 
 #include "plvi_internal.cuh"
@@ -73,7 +74,8 @@ __device__ __forceinline__ void top2_warp_merge(Top2& t) {
 }
 
 struct SearchArgs {
-  int mode;  // 0 frame-frame, 1 map points, 2 initialisation
+  int mode;  // 0 frame-frame, 1 map points, 2 initialisation, 3 bag-of-words groups
+  const int* items; int istride;   // mode 3: frame features grouped by vocabulary node
   const plvi_keypoint* keys; const uint8_t* desc; const uint8_t* blocked; const int* tcount; int tstride;
   plvi_grid grid;
   plvi_query* q; const uint8_t* qdesc; const int* qcount; int qstride;
@@ -128,6 +130,28 @@ __device__ QRes eval_query(const SearchArgs& a, const plvi_keypoint* __restrict_
       if (!eligible(a, i2, d, blk, mdist)) continue;
       top2_insert(t, ((uint32_t)d << 23) | ((uint32_t)c << 11) | (uint32_t)min(k - s, 2047), i2);
     }
+  }
+  top2_warp_merge(t);
+  if (t.i0 >= 0) { r.best = t.i0; r.bestDist = (int)(t.k0 >> 23); }
+  if (t.i1 >= 0) { r.second = t.i1; r.secondDist = (int)(t.k1 >> 23); }
+  return r;
+}
+
+// Mode 3 (SearchByBoW): candidates are the frame features of the query's vocabulary node,
+// items[min_level .. max_level), in vIndicesF order.
+__device__ QRes eval_query_bow(const uint8_t* __restrict__ desc, const plvi_query& q, const uint8_t* __restrict__ qd,
+                               const int* __restrict__ items, const uint8_t* blk) {
+  const int lane = threadIdx.x & 31;
+  QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
+  uint32_t qw[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) qw[k] = __ldg(reinterpret_cast<const uint32_t*>(qd) + k);
+  Top2 t = {0xffffffffu, 0xffffffffu, -1, -1};
+  for (int k = q.min_level + lane; k < q.max_level; k += 32) {
+    const int i2 = __ldg(items + k);
+    if (blk[i2]) continue;
+    const int d = hamming256_regs(qw, desc + (size_t)i2 * 32);
+    top2_insert(t, ((uint32_t)d << 23) | (uint32_t)min(k - q.min_level, (1 << 23) - 1), i2);
   }
   top2_warp_merge(t);
   if (t.i0 >= 0) { r.best = t.i0; r.bestDist = (int)(t.k0 >> 23); }
@@ -239,7 +263,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
     const int qi = q0 + wid;
     QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
     if (qi < nq && !(q[qi].flags & 1))
-      r = eval_query(a, keys, desc, q[qi], qdesc + (size_t)qi * 32, cellStart, items, blk, mdist);
+      r = a.mode == 3 ? eval_query_bow(desc, q[qi], qdesc + (size_t)qi * 32, a.items + (size_t)pair * a.istride, blk)
+                      : eval_query(a, keys, desc, q[qi], qdesc + (size_t)qi * 32, cellStart, items, blk, mdist);
     if (lane == 0) res[wid] = r;
     __syncthreads();
     if (wid == 0) {
@@ -254,9 +279,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
           stale = (rr.best >= 0 && mdist[rr.best] <= rr.bestDist) ||
                   (rr.second >= 0 && mdist[rr.second] <= rr.secondDist);
         } else {
-          stale = (rr.best >= 0 && blk[rr.best]) || (a.mode == 1 && rr.second >= 0 && blk[rr.second]);
+          stale = (rr.best >= 0 && blk[rr.best]) || (a.mode != 0 && rr.second >= 0 && blk[rr.second]);
         }
-        if (stale) rr = eval_query(a, keys, desc, qq, qdesc + (size_t)qj * 32, cellStart, items, blk, mdist);
+        if (stale)
+          rr = a.mode == 3 ? eval_query_bow(desc, qq, qdesc + (size_t)qj * 32, a.items + (size_t)pair * a.istride, blk)
+                           : eval_query(a, keys, desc, qq, qdesc + (size_t)qj * 32, cellStart, items, blk, mdist);
         if (lane == 0 && rr.best >= 0) {
           if (a.mode == 0) {
             if (rr.bestDist <= a.th) {
@@ -280,6 +307,19 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
                 m12[qj] = rr.best;
                 if (!(qq.flags & 2)) blk[rr.best] = 1;
                 s_nm++;
+              }
+            }
+          } else if (a.mode == 3) {
+            const int d2 = rr.second >= 0 ? rr.secondDist : 256;
+            if (rr.bestDist <= a.th && (float)rr.bestDist < __fmul_rn(a.nnratio, (float)d2)) {
+              owner[rr.best] = qj;
+              m12[qj] = rr.best;
+              blk[rr.best] = 1;       // vpMapPointMatches[realIdxF] != NULL blocks, whatever the observations
+              s_nm++;
+              if (a.checkOri) {
+                const int b = rot_bin(qq.angle, keys[rr.best].angle);
+                qbin[qj] = (signed char)b;
+                hist[b]++;
               }
             }
           } else {
@@ -323,7 +363,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
     for (int i = tid; i < nq; i += NT) {
       const int b = qbin[i];
       if (b < 0 || b == s_keep[0] || b == s_keep[1] || b == s_keep[2]) continue;
-      if (a.mode == 0) {
+      if (a.mode == 0 || a.mode == 3) {
         // the reference nulls mvpMapPoints[bestIdx2] of every culled assignment
         const int i2 = m12[i];
         owner[i2] = -1;
@@ -550,6 +590,8 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
   a.nnratio = nnratio;
   a.checkOri = check_orientation;
   a.matchedDist = mode == 2 ? m->dMatchedDist : nullptr;
+  a.items = nullptr;
+  a.istride = 0;
   const size_t P = npairs, T = train_stride, Q = query_stride;
   cudaStream_t st = m->stream;
   if (on_device) {
@@ -585,6 +627,64 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
     PLVI_CUDA_TRY(cudaMemcpyAsync(nmatches, m->dNMatches, P * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (mode == 2)
       PLVI_CUDA_TRY(cudaMemcpyAsync(queries, m->dQ, P * Q * sizeof(plvi_query), cudaMemcpyDeviceToHost, st));
+    PLVI_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return PLVI_OK;
+}
+
+int plvi_search_by_bow(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                       const int* train_counts, int train_stride, const int* group_items, int items_stride,
+                       const plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                       int query_stride, int th_dist, float nnratio, int check_orientation, int* match_train,
+                       int* match_query, int* nmatches, int on_device) {
+  if (!m || npairs < 1 || !train_keys || !train_desc || !train_counts || !group_items || !queries || !query_desc ||
+      !query_counts || !match_train || !match_query || !nmatches || items_stride < 1) {
+    set_error("plvi_search_by_bow: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  if (npairs > m->maxPairs || train_stride > m->maxTrain || query_stride > m->maxQuery || items_stride > m->maxTrain) {
+    set_error("plvi_search_by_bow: exceeds matcher capacity");
+    return PLVI_ERR_CAPACITY;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  SearchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 3;
+  a.grid = plvi_grid{0.f, 0.f, 1.f, 1.f};
+  a.tstride = train_stride;
+  a.qstride = query_stride;
+  a.istride = items_stride;
+  a.th = th_dist;
+  a.nnratio = nnratio;
+  a.checkOri = check_orientation;
+  const size_t P = npairs, T = train_stride, Q = query_stride;
+  cudaStream_t st = m->stream;
+  if (on_device) {
+    a.keys = train_keys; a.desc = train_desc; a.tcount = train_counts; a.items = group_items;
+    a.q = const_cast<plvi_query*>(queries); a.qdesc = query_desc; a.qcount = query_counts;
+    a.matchTrain = match_train; a.matchQuery = match_query; a.nmatches = nmatches;
+  } else {
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dKeys, train_keys, P * T * sizeof(plvi_keypoint), cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dDesc, train_desc, P * T * 32, cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dTCount, train_counts, P * sizeof(int), cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dMatchedDist, group_items, P * items_stride * sizeof(int), cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQ, queries, P * Q * sizeof(plvi_query), cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQDesc, query_desc, P * Q * 32, cudaMemcpyHostToDevice, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQCount, query_counts, P * sizeof(int), cudaMemcpyHostToDevice, st));
+    a.keys = m->dKeys; a.desc = m->dDesc; a.tcount = m->dTCount; a.items = m->dMatchedDist; a.istride = items_stride;
+    a.q = m->dQ; a.qdesc = m->dQDesc; a.qcount = m->dQCount;
+    a.matchTrain = m->dMatchTrain; a.matchQuery = m->dMatchQuery; a.nmatches = m->dNMatches;
+  }
+  const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + 16;
+  if (smem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_search<<<npairs, SEARCH_WARPS * 32, smem, st>>>(a);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  if (!on_device) {
+    PLVI_CUDA_TRY(cudaMemcpyAsync(match_train, m->dMatchTrain, P * T * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(match_query, m->dMatchQuery, P * Q * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLVI_CUDA_TRY(cudaMemcpyAsync(nmatches, m->dNMatches, P * sizeof(int), cudaMemcpyDeviceToHost, st));
     PLVI_CUDA_TRY(cudaStreamSynchronize(st));
   }
   return PLVI_OK;

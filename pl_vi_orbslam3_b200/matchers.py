@@ -111,6 +111,24 @@ class ORBmatcher(_Matcher):
         mt, mq, nm, _ = self.search_batch(mode, [CurrentFrame], [queries], [qdesc], self.TH_HIGH)
         return int(nm[0]), mt[0], mq[0]
 
+    def SearchByBoW(self, F, group_items, queries, qdesc):
+        """Descriptor part of SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:269-471).
+        group_items: int32 frame feature indices grouped by vocabulary node; queries: QUERY_DTYPE with
+        min_level/max_level = [start, end) of the node group.  Returns (nmatches, match_train, match_query)."""
+        n, nq = len(F.keys), len(queries)
+        T, Q, I = max(n, 1), max(nq, 1), max(len(group_items), 1)
+        keys = np.zeros(T, KEYPOINT_DTYPE); keys[:n] = F.keys
+        desc = np.zeros((T, 32), np.uint8); desc[:n] = F.desc
+        items = np.zeros(I, np.int32); items[:len(group_items)] = group_items
+        qs = np.zeros(Q, QUERY_DTYPE); qs[:nq] = queries
+        qd = np.zeros((Q, 32), np.uint8); qd[:nq] = qdesc
+        tc, qc = np.array([n], np.int32), np.array([nq], np.int32)
+        mt, mq, nm = np.empty(T, np.int32), np.empty(Q, np.int32), np.empty(1, np.int32)
+        check(lib().plvi_search_by_bow(self._h, 1, ptr(keys), ptr(desc), ptr(tc), T, ptr(items), I, ptr(qs), ptr(qd),
+                                       ptr(qc), Q, self.TH_LOW, self.mfNNratio, int(self.mbCheckOrientation),
+                                       ptr(mt), ptr(mq), ptr(nm), 0))
+        return int(nm[0]), mt[:n], mq[:nq]
+
     @staticmethod
     def init_queries(F1_keys, vbPrevMatched, windowSize):
         n1 = len(F1_keys)

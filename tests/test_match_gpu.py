@@ -216,3 +216,38 @@ def test_line_match_batch(lm):
     for i, (a, b) in enumerate(pairs):
         rn, rm = oracle.line_match(a, b, 0.9)
         assert nm[i] == rn and np.array_equal(ms[i], rm)
+
+
+def _bow_case(r1, r2, seed, nodes=40):
+    """Synthetic DBoW2-like feature vectors: a 'vocabulary node' per feature (from two descriptor
+    bytes, so that similar descriptors tend to share a node), frame features grouped by node."""
+    rng = np.random.RandomState(seed)
+    node1 = (r1["descriptors"][:, 0].astype(np.int32) * 3 + r1["descriptors"][:, 5]) % nodes
+    node2 = (r2["descriptors"][:, 0].astype(np.int32) * 3 + r2["descriptors"][:, 5]) % nodes
+    items, start, end = [], {}, {}
+    for nd in range(nodes):
+        idx = np.nonzero(node2 == nd)[0]
+        start[nd], end[nd] = len(items), len(items) + len(idx)
+        items.extend(idx.tolist())
+    order = [i for nd in range(nodes) for i in np.nonzero(node1 == nd)[0] if end[nd] > start[nd]]
+    q = np.zeros(len(order), QUERY_DTYPE)
+    k1 = r1["keypoints"]
+    for j, i in enumerate(order):
+        q[j]["min_level"], q[j]["max_level"] = start[node1[i]], end[node1[i]]
+        q[j]["angle"] = k1["angle"][i]
+        q[j]["flags"] = int(rng.rand() < 0.1)
+    return np.array(items, np.int32), q, r1["descriptors"][order]
+
+
+@pytest.mark.parametrize("nodes,nnratio", [(40, 0.7), (6, 0.9), (300, 0.7)])
+def test_search_by_bow(om, pair_features, nodes, nnratio):
+    r1, r2, _ = pair_features
+    items, q, qd = _bow_case(r1, r2, nodes, nodes)
+    om.mfNNratio = nnratio
+    F = FrameView(r2["keypoints"], r2["descriptors"], GRID)
+    n, mt, mq = om.SearchByBoW(F, items, q, qd)
+    om.mfNNratio = 0.9
+    rn, rmt = oracle.search_bow(r2["keypoints"], r2["descriptors"], items, q, qd, 50, nnratio, True)
+    assert n == rn and np.array_equal(mt, rmt)
+    if nodes == 6:
+        assert n > 20
