@@ -48,7 +48,8 @@ ALGO_BYTES = {
     "k_gauss5": 2 * 752 * 480,
     "k_pyrdown": 752 * 480 + 376 * 240,
     "k_sobel": P_RAW * (1 + 4),
-    "k_lbd": 200 * 63 * 60 * 4 + 200 * (68 + 32 + 24),
+    "k_lbd_rows": 200 * 63 * 60 * 4 + 200 * (68 + 2048),
+    "k_lbd_fold": 200 * (2048 + 32 + 24),
     "k_search(+queries)": 2 * 1021 * (28 + 32) + 1021 * 28 + 1021 * 8,
     "k_line_match": 2 * 200 * 32 + 200 * 4,
 }

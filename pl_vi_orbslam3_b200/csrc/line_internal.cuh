@@ -53,6 +53,7 @@ struct LineBufs {
   int* tmpCls;           // [B][segTotal]
   u8* lbdImg0; u8* lbdImg1;
   short2* grad;          // [B][lbdTotal] Sobel (dx, dy)
+  float* lbdRows;        // [B][keepCap][8][64] weighted row sums of the LBD support region
   const LineTab* tabs;
   const int2* rsTab;     // u8 bilinear table for pyramid level 1 (x rows then y rows)
   const double* lbdG;    // [63] gaussCoefG_

@@ -8,7 +8,7 @@
 //   k_line_assemble   LSDDetectorC::detectImpl KeyLine fields,     LSDDetector_custom.cpp:304-346
 //                     top-N by response                            src/LineExtractor.cc:75-84
 //   k_gauss5 / k_pyrdown / k_sobel   LBD pyramid + Sobel           binary_descriptor_custom.cpp:351-399
-//   k_lbd             computeLBD + binary packing + line equation  binary_descriptor_custom.cpp:1027-1373,402-413,663-667;
+//   k_lbd_rows/_fold  computeLBD + binary packing + line equation  binary_descriptor_custom.cpp:1027-1373,402-413,663-667;
 //                                                                  src/LineExtractor.cc:106-116
 //
 // Region growing is sequential by construction (raster-order seeds coupled through the
@@ -742,18 +742,17 @@ __constant__ unsigned char c_comb[32][2] = {
     {0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7},
     {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8}, {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
 
-__global__ void __launch_bounds__(64) k_lbd(const __grid_constant__ LineGeom g, LineBufs b,
-                                            const plvi_keyline* __restrict__ kls, const int* __restrict__ counts,
-                                            uint8_t* __restrict__ desc, double* __restrict__ lineEq) {
+// k_lbd_rows: the 63 support-region rows of every line (thread = row; serial float chains kept).
+__global__ void __launch_bounds__(64, 16) k_lbd_rows(const __grid_constant__ LineGeom g, LineBufs b,
+                                                     const plvi_keyline* __restrict__ kls,
+                                                     const int* __restrict__ counts) {
   const int li = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
   const int n = counts[f];
-  if (li >= n) return;
+  if (li >= n || tid >= 63) return;
   const plvi_keyline kl = kls[(size_t)f * g.keepCap + li];
   const LineOct& O = g.o[kl.octave];
   const short2* grad = b.grad + (size_t)f * g.lbdTotal + O.lbdOff;
   const int realWidth = O.lw, imageWidth = O.lw - 1, imageHeight = O.lh - 1;
-  __shared__ float rows[8][64];
-  __shared__ float des[72];
   const int L = kl.numOfPixels;
   const int halfWidth = (L - 1) / 2;
   const float midX = __fmul_rn(0.5f, __fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
@@ -762,72 +761,89 @@ __global__ void __launch_bounds__(64) k_lbd(const __grid_constant__ LineGeom g, 
   sincos((double)kl.angle, &sd, &cd);
   const float dL0 = (float)cd, dL1 = (float)sd;
   const float dO0 = -dL1, dO1 = dL0;
-  if (tid < 63) {
-    float sX0 = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, 31.f)), midX);
-    float sY0 = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, 31.f)), midY);
-    for (int r = 0; r < tid; r++) {
-      sX0 = __fsub_rn(sX0, dL1);
-      sY0 = __fadd_rn(sY0, dL0);
-    }
-    float sX = sX0, sY = sY0, pL = 0.f, nL = 0.f, pO = 0.f, nO = 0.f;
-    for (int wID = 0; wID < L; wID++) {
-      int tc = (int)(short)(int)roundf(sX);
-      const int xCor = tc < 0 ? 0 : (tc > imageWidth ? imageWidth : tc);
-      tc = (int)(short)(int)roundf(sY);
-      const int yCor = tc < 0 ? 0 : (tc > imageHeight ? imageHeight : tc);
-      const short2 gv = __ldg(grad + yCor * realWidth + xCor);
-      const float gDL = __fadd_rn(__fmul_rn((float)gv.x, dL0), __fmul_rn((float)gv.y, dL1));
-      const float gDO = __fadd_rn(__fmul_rn((float)gv.x, dO0), __fmul_rn((float)gv.y, dO1));
-      if (gDL > 0) pL = __fadd_rn(pL, gDL); else nL = __fsub_rn(nL, gDL);
-      if (gDO > 0) pO = __fadd_rn(pO, gDO); else nO = __fsub_rn(nO, gDO);
-      sX = __fadd_rn(sX, dL0);
-      sY = __fadd_rn(sY, dL1);
-    }
-    const float c = (float)b.lbdG[tid];
-    pL = __fmul_rn(c, pL); nL = __fmul_rn(c, nL);
-    pO = __fmul_rn(c, pO); nO = __fmul_rn(c, nO);
-    rows[0][tid] = pL; rows[1][tid] = nL; rows[2][tid] = __fmul_rn(pL, pL); rows[3][tid] = __fmul_rn(nL, nL);
-    rows[4][tid] = pO; rows[5][tid] = nO; rows[6][tid] = __fmul_rn(pO, pO); rows[7][tid] = __fmul_rn(nO, nO);
+  float sX = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, 31.f)), midX);
+  float sY = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, 31.f)), midY);
+  for (int r = 0; r < tid; r++) {
+    sX = __fsub_rn(sX, dL1);
+    sY = __fadd_rn(sY, dL0);
   }
-  __syncthreads();
-  if (tid < 8) {  // one lane per statistic; rows folded in order into the 9 bands
-    const int q = tid;
+  float pL = 0.f, nL = 0.f, pO = 0.f, nO = 0.f;
+  for (int wID = 0; wID < L; wID++) {
+    int tc = (int)(short)(int)roundf(sX);
+    const int xCor = tc < 0 ? 0 : (tc > imageWidth ? imageWidth : tc);
+    tc = (int)(short)(int)roundf(sY);
+    const int yCor = tc < 0 ? 0 : (tc > imageHeight ? imageHeight : tc);
+    const short2 gv = __ldg(grad + yCor * realWidth + xCor);
+    const float gDL = __fadd_rn(__fmul_rn((float)gv.x, dL0), __fmul_rn((float)gv.y, dL1));
+    const float gDO = __fadd_rn(__fmul_rn((float)gv.x, dO0), __fmul_rn((float)gv.y, dO1));
+    if (gDL > 0) pL = __fadd_rn(pL, gDL); else nL = __fsub_rn(nL, gDL);
+    if (gDO > 0) pO = __fadd_rn(pO, gDO); else nO = __fsub_rn(nO, gDO);
+    sX = __fadd_rn(sX, dL0);
+    sY = __fadd_rn(sY, dL1);
+  }
+  const float c = (float)b.lbdG[tid];
+  pL = __fmul_rn(c, pL); nL = __fmul_rn(c, nL);
+  pO = __fmul_rn(c, pO); nO = __fmul_rn(c, nO);
+  float* rows = b.lbdRows + ((size_t)f * g.keepCap + li) * 512;   // [8][64]
+  rows[0 * 64 + tid] = pL; rows[1 * 64 + tid] = nL; rows[2 * 64 + tid] = __fmul_rn(pL, pL); rows[3 * 64 + tid] = __fmul_rn(nL, nL);
+  rows[4 * 64 + tid] = pO; rows[5 * 64 + tid] = nO; rows[6 * 64 + tid] = __fmul_rn(pO, pO); rows[7 * 64 + tid] = __fmul_rn(nO, nO);
+}
+
+// k_lbd_fold: one warp per line.  Lanes 0-7 fold the 63 rows of one statistic into the 9 bands
+// in row order, lane 0 forms / normalises the 72 floats, all lanes pack the 32 bytes.
+__global__ void __launch_bounds__(128) k_lbd_fold(const __grid_constant__ LineGeom g, LineBufs b,
+                                                  const plvi_keyline* __restrict__ kls,
+                                                  const int* __restrict__ counts, uint8_t* __restrict__ desc,
+                                                  double* __restrict__ lineEq) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int li = blockIdx.x * 4 + wid, f = blockIdx.y;
+  if (li >= counts[f]) return;
+  __shared__ float sband[4][8][9];
+  __shared__ float sdes[4][72];
+  const float* rows = b.lbdRows + ((size_t)f * g.keepCap + li) * 512;
+  float* des = sdes[wid];
+  if (lane < 8) {
+    const int q = lane;
     const bool sq = (q == 2 || q == 3 || q == 6 || q == 7);
     float band[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) band[k] = 0.f;
-    for (int hID = 0; hID < 63; hID++) {
-      const float rs = rows[q][hID];
-      const int bandID = hID / 7, m = hID % 7;
-      float cf = (float)b.lbdL[m + 7];
-      band[bandID] = __fadd_rn(band[bandID], sq ? __fmul_rn(__fmul_rn(cf, cf), rs) : __fmul_rn(cf, rs));
-      if (bandID - 1 >= 0) {
-        cf = (float)b.lbdL[m + 14];
-        band[bandID - 1] = __fadd_rn(band[bandID - 1], sq ? __fmul_rn(__fmul_rn(cf, cf), rs) : __fmul_rn(cf, rs));
-      }
-      if (bandID + 1 < 9) {
-        cf = (float)b.lbdL[m];
-        band[bandID + 1] = __fadd_rn(band[bandID + 1], sq ? __fmul_rn(__fmul_rn(cf, cf), rs) : __fmul_rn(cf, rs));
+#pragma unroll
+    for (int bandID = 0; bandID < 9; bandID++) {
+#pragma unroll
+      for (int m = 0; m < 7; m++) {
+        const float rs = rows[q * 64 + bandID * 7 + m];
+        float cf = (float)b.lbdL[m + 7];
+        band[bandID] = __fadd_rn(band[bandID], sq ? __fmul_rn(__fmul_rn(cf, cf), rs) : __fmul_rn(cf, rs));
+        if (bandID - 1 >= 0) {
+          cf = (float)b.lbdL[m + 14];
+          band[bandID - 1] = __fadd_rn(band[bandID - 1], sq ? __fmul_rn(__fmul_rn(cf, cf), rs) : __fmul_rn(cf, rs));
+        }
+        if (bandID + 1 < 9) {
+          cf = (float)b.lbdL[m];
+          band[bandID + 1] = __fadd_rn(band[bandID + 1], sq ? __fmul_rn(__fmul_rn(cf, cf), rs) : __fmul_rn(cf, rs));
+        }
       }
     }
 #pragma unroll
-    for (int k = 0; k < 9; k++) rows[q][k] = band[k];
+    for (int k = 0; k < 9; k++) sband[wid][q][k] = band[k];
   }
-  __syncthreads();
-  if (tid == 0) {
+  __syncwarp();
+  if (lane == 0) {
+    const plvi_keyline kl = kls[(size_t)f * g.keepCap + li];
     const float invN2 = (float)(1.0 / 14.0), invN3 = (float)(1.0 / 21.0);
     for (int k = 0; k < 9; k++) {
       const float invN = (k == 0 || k == 8) ? invN2 : invN3;
       const int d = k * 8;
       float t;
-      t = __fmul_rn(rows[0][k], invN); des[d] = t;
-      des[d + 4] = __fsqrt_rn(__fsub_rn(__fmul_rn(rows[2][k], invN), __fmul_rn(t, t)));
-      t = __fmul_rn(rows[1][k], invN); des[d + 1] = t;
-      des[d + 5] = __fsqrt_rn(__fsub_rn(__fmul_rn(rows[3][k], invN), __fmul_rn(t, t)));
-      t = __fmul_rn(rows[4][k], invN); des[d + 2] = t;
-      des[d + 6] = __fsqrt_rn(__fsub_rn(__fmul_rn(rows[6][k], invN), __fmul_rn(t, t)));
-      t = __fmul_rn(rows[5][k], invN); des[d + 3] = t;
-      des[d + 7] = __fsqrt_rn(__fsub_rn(__fmul_rn(rows[7][k], invN), __fmul_rn(t, t)));
+      t = __fmul_rn(sband[wid][0][k], invN); des[d] = t;
+      des[d + 4] = __fsqrt_rn(__fsub_rn(__fmul_rn(sband[wid][2][k], invN), __fmul_rn(t, t)));
+      t = __fmul_rn(sband[wid][1][k], invN); des[d + 1] = t;
+      des[d + 5] = __fsqrt_rn(__fsub_rn(__fmul_rn(sband[wid][3][k], invN), __fmul_rn(t, t)));
+      t = __fmul_rn(sband[wid][4][k], invN); des[d + 2] = t;
+      des[d + 6] = __fsqrt_rn(__fsub_rn(__fmul_rn(sband[wid][6][k], invN), __fmul_rn(t, t)));
+      t = __fmul_rn(sband[wid][5][k], invN); des[d + 3] = t;
+      des[d + 7] = __fsqrt_rn(__fsub_rn(__fmul_rn(sband[wid][7][k], invN), __fmul_rn(t, t)));
     }
     float tM = 0.f, tS = 0.f;
     for (int k = 0; k < 9; k++) {
@@ -846,21 +862,21 @@ __global__ void __launch_bounds__(64) k_lbd(const __grid_constant__ LineGeom g, 
     for (int i = 0; i < 72; i++) t = __fadd_rn(t, __fmul_rn(des[i], des[i]));
     t = __fdiv_rn(1.f, __fsqrt_rn(t));
     for (int i = 0; i < 72; i++) des[i] = __fmul_rn(des[i], t);
-    // line equation (f64)
+    // line equation (f64), src/LineExtractor.cc:106-116
     const double sx = kl.startPointX, sy = kl.startPointY, ex = kl.endPointX, ey = kl.endPointY;
     const double l0 = __dsub_rn(sy, ey), l1 = __dsub_rn(ex, sx), l2 = __dsub_rn(__dmul_rn(sx, ey), __dmul_rn(sy, ex));
     const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(l0, l0), __dmul_rn(l1, l1)));
     double* eq = lineEq + ((size_t)f * g.keepCap + li) * 3;
     eq[0] = __ddiv_rn(l0, nrm); eq[1] = __ddiv_rn(l1, nrm); eq[2] = __ddiv_rn(l2, nrm);
   }
-  __syncthreads();
-  if (tid < 32) {
-    const float* f1 = des + 8 * c_comb[tid][0];
-    const float* f2 = des + 8 * c_comb[tid][1];
+  __syncwarp();
+  {
+    const float* f1 = des + 8 * c_comb[lane][0];
+    const float* f2 = des + 8 * c_comb[lane][1];
     unsigned r = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) r |= (unsigned)(f1[i] > f2[i]) << i;
-    desc[((size_t)f * g.keepCap + li) * 32 + tid] = (uint8_t)r;
+    desc[((size_t)f * g.keepCap + li) * 32 + lane] = (uint8_t)r;
   }
 }
 
@@ -930,9 +946,11 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   prof->mark("k_line_assemble", st);
   nl += 3;
   if (fork) PLVI_CUDA_TRY(cudaStreamWaitEvent(st, aux.join, 0));
-  k_lbd<<<dim3(g.keepCap, n), 64, 0, st>>>(g, b, dKl, dCounts, dDesc, dEq);
-  nl++;
-  prof->mark("k_lbd", st);
+  k_lbd_rows<<<dim3(g.keepCap, n), 64, 0, st>>>(g, b, dKl, dCounts);
+  prof->mark("k_lbd_rows", st);
+  k_lbd_fold<<<dim3((g.keepCap + 3) / 4, n), 128, 0, st>>>(g, b, dKl, dCounts, dDesc, dEq);
+  prof->mark("k_lbd_fold", st);
+  nl += 2;
   PLVI_CUDA_TRY(cudaGetLastError());
   if (launches) *launches = nl;
   return PLVI_OK;

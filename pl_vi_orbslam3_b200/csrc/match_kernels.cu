@@ -30,7 +30,7 @@ namespace plvi {
 #define GRID_ROWS 48
 #define GRID_CELLS (GRID_COLS * GRID_ROWS)
 #define HISTO_LENGTH 30
-#define SEARCH_WARPS 16
+#define SEARCH_WARPS 8
 
 __device__ __forceinline__ int hamming256_regs(const uint32_t (&q)[8], const uint8_t* __restrict__ d) {
   const uint4 a = __ldg(reinterpret_cast<const uint4*>(d));

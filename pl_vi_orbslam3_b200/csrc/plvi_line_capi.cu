@@ -260,6 +260,7 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   A((void**)&h->buf.lbdImg0, B * c.o[0].lpitch * c.o[0].lh);
   if (nlevels > 1) A((void**)&h->buf.lbdImg1, B * c.o[1].lpitch * c.o[1].lh);
   A((void**)&h->buf.grad, B * c.lbdTotal * sizeof(short2));
+  A((void**)&h->buf.lbdRows, B * c.keepCap * 512 * sizeof(float));
   h->tabCap = tabs.size() + 64;
   h->rsCap = rs.size() + 64;
   A((void**)&h->dTabs, h->tabCap * sizeof(LineTab));
@@ -308,7 +309,7 @@ void plvi_line_destroy(plvi_line* h) {
   cudaFree(h->buf.rowf); cudaFree(h->buf.rec); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
   cudaFree(h->buf.reg); cudaFree(h->buf.regTab); cudaFree(h->buf.regCount); cudaFree(h->buf.segs);
   cudaFree(h->buf.tmpResp); cudaFree(h->buf.tmpCls); cudaFree(h->buf.lbdImg0); cudaFree(h->buf.lbdImg1);
-  cudaFree(h->buf.grad); cudaFree(h->buf.scaledDbg);
+  cudaFree(h->buf.grad); cudaFree(h->buf.lbdRows); cudaFree(h->buf.scaledDbg);
   cudaFree(h->dTabs); cudaFree(h->dRsTab); cudaFree(h->dLbdG); cudaFree(h->dLbdL); cudaFree(h->dTrig);
   cudaFree(h->dKl); cudaFree(h->dDesc); cudaFree(h->dEq); cudaFree(h->dCounts);
   if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
