@@ -135,25 +135,48 @@ __global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ 
     const int sx0 = xt[x0].ofs, sx1 = min(xt[min(x0 + SG_TW, O.sw - 1)].ofs + 1, O.w - 1);
     const int sy0 = yt[y0].ofs, sy1 = min(yt[min(y0 + SG_TH, O.sh - 1)].ofs + 1, O.h - 1);
     const int nsx = sx1 - sx0 + 1, nsy = sy1 - sy0 + 1;   // <= SG_SRC_W, SG_SRC_H (checked on the host)
-    for (int i = tid; i < nsx * nsy; i += 256) {
-      const int r = i / nsx, c = i - r * nsx;
-      sblur[r][c] = col_blur(rf, O.w, O.h, sx0 + c, sy0 + r, g.kern);
+    {
+      // column pass of the Gaussian for the source window: 64 lanes across, 4 rows per sweep
+      const int c = tid & 63;
+      const bool interior = sy0 - 3 >= 0 && sy1 + 3 < O.h;
+      if (c < nsx) {
+        for (int r = tid >> 6; r < nsy; r += 4) {
+          double v;
+          if (interior) {
+            const double* q = rf + (size_t)(sy0 + r - 3) * O.w + (sx0 + c);
+            const size_t w = (size_t)O.w;
+            v = __dmul_rn(g.kern[3], q[3 * w]);
+            v = __dadd_rn(v, __dmul_rn(g.kern[4], __dadd_rn(q[4 * w], q[2 * w])));
+            v = __dadd_rn(v, __dmul_rn(g.kern[5], __dadd_rn(q[5 * w], q[w])));
+            v = __dadd_rn(v, __dmul_rn(g.kern[6], __dadd_rn(q[6 * w], q[0])));
+          } else {
+            v = col_blur(rf, O.w, O.h, sx0 + c, sy0 + r, g.kern);
+          }
+          sblur[r][c] = v;
+        }
+      }
     }
     __syncthreads();
-    for (int i = tid; i < (SG_TH + 1) * (SG_TW + 1); i += 256) {
-      const int ty = i / (SG_TW + 1), tx = i - ty * (SG_TW + 1);
-      const int sx = x0 + tx, sy = y0 + ty;
-      double v = 0.0;
-      if (sx < O.sw && sy < O.sh) {
-        const LineTab X = xt[sx], Y = yt[sy];
-        const int xa = X.ofs - sx0, xb = min(X.ofs + 1, O.w - 1) - sx0;
-        const int ya = Y.ofs - sy0, yb = min(Y.ofs + 1, O.h - 1) - sy0;
-        const double h0 = __dadd_rn(__dmul_rn(sblur[ya][xa], (double)X.a0), __dmul_rn(sblur[ya][xb], (double)X.a1));
-        const double h1 = __dadd_rn(__dmul_rn(sblur[yb][xa], (double)X.a0), __dmul_rn(sblur[yb][xb], (double)X.a1));
-        v = __dadd_rn(__dmul_rn(h0, (double)Y.a0), __dmul_rn(h1, (double)Y.a1));
-        if (b.scaledDbg && tx < SG_TW && ty < SG_TH) b.scaledDbg[(size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx] = v;
+    {
+      const int tx = tid & 63;
+      if (tx <= SG_TW) {
+        const int sx = x0 + tx;
+        for (int ty = tid >> 6; ty <= SG_TH; ty += 4) {
+          const int sy = y0 + ty;
+          double v = 0.0;
+          if (sx < O.sw && sy < O.sh) {
+            const LineTab X = xt[sx], Y = yt[sy];
+            const int xa = X.ofs - sx0, xb = min(X.ofs + 1, O.w - 1) - sx0;
+            const int ya = Y.ofs - sy0, yb = min(Y.ofs + 1, O.h - 1) - sy0;
+            const double h0 = __dadd_rn(__dmul_rn(sblur[ya][xa], (double)X.a0), __dmul_rn(sblur[ya][xb], (double)X.a1));
+            const double h1 = __dadd_rn(__dmul_rn(sblur[yb][xa], (double)X.a0), __dmul_rn(sblur[yb][xb], (double)X.a1));
+            v = __dadd_rn(__dmul_rn(h0, (double)Y.a0), __dmul_rn(h1, (double)Y.a1));
+            if (b.scaledDbg && tx < SG_TW && ty < SG_TH)
+              b.scaledDbg[(size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx] = v;
+          }
+          ssc[ty][tx] = v;
+        }
       }
-      ssc[ty][tx] = v;
     }
   }
   __syncthreads();
