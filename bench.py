@@ -164,7 +164,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     cores = os.cpu_count() or 1
 
-    from pl_vi_orbslam3_b200 import synth
+    from pl_vi_orbslam3_b200 import build as _build, synth
+    if not _build.LIB.exists():        # the built library normally travels with the repo snapshot
+        _build.build(force=True)
 
     # ------------------------------------------------------------------ CPU arm
     if args.impl == "reference":

@@ -13,6 +13,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _ensure_built():
+    """The CUDA library travels with the repo snapshot; build it only if it is missing."""
+    from pl_vi_orbslam3_b200 import build
+    if not build.LIB.exists():
+        build.build(force=True)
+
+
+_ensure_built()
+
+
 def _have_gpu():
     try:
         from pl_vi_orbslam3_b200 import capi
