@@ -59,20 +59,30 @@ void gaussian_kernel_f64(int n, double sigma, double* k) {
 // cv::GaussianBlur(CV_64F, ksize, sigma), BORDER_REFLECT_101 (src/LSD/lsd.cpp:455)
 void gaussian_blur_f64(const double* src, int w, int h, double* dst, const double* k, int ksize) {
   const int r = ksize / 2;
-  std::vector<double> tmp((size_t)w * h);
-  for (int y = 0; y < h; y++)
+  std::vector<double> tmp((size_t)w * h), pad(w + 2 * r);
+  for (int y = 0; y < h; y++) {
+    const double* row = src + (size_t)y * w;
+    for (int x = -r; x < w + r; x++) pad[x + r] = row[reflect101(x, w)];
+    double* t = &tmp[(size_t)y * w];
     for (int x = 0; x < w; x++) {
-      double s = k[0] * src[(size_t)y * w + reflect101(x - r, w)];
-      for (int i = 1; i < ksize; i++) s = s + k[i] * src[(size_t)y * w + reflect101(x - r + i, w)];
-      tmp[(size_t)y * w + x] = s;
+      double s = k[0] * pad[x];
+      for (int i = 1; i < ksize; i++) s = s + k[i] * pad[x + i];
+      t[x] = s;
     }
-  for (int y = 0; y < h; y++)
+  }
+  std::vector<const double*> up(r + 1), dn(r + 1);
+  for (int y = 0; y < h; y++) {
+    for (int i = 0; i <= r; i++) {
+      dn[i] = &tmp[(size_t)reflect101(y + i, h) * w];
+      up[i] = &tmp[(size_t)reflect101(y - i, h) * w];
+    }
+    double* d = dst + (size_t)y * w;
     for (int x = 0; x < w; x++) {
-      double s = k[r] * tmp[(size_t)y * w + x];
-      for (int i = 1; i <= r; i++)
-        s = s + k[r + i] * (tmp[(size_t)reflect101(y + i, h) * w + x] + tmp[(size_t)reflect101(y - i, h) * w + x]);
-      dst[(size_t)y * w + x] = s;
+      double s = k[r] * dn[0][x];
+      for (int i = 1; i <= r; i++) s = s + k[r + i] * (dn[i][x] + up[i][x]);
+      d[x] = s;
     }
+  }
 }
 
 // cv::resize(CV_64F, Size(), fx, fy, INTER_LINEAR): float32 weights applied in double,
@@ -110,30 +120,41 @@ void resize_linear_f64(const double* src, int sw, int sh, double* dst, int dw, i
 
 // cv::pyrDown(u8) to (w/2, h/2): [1,4,6,4,1]^2, (v+128)>>8, REFLECT_101
 void pyr_down_u8(const u8* src, int w, int h, u8* dst, int dw, int dh) {
-  static const int k[5] = {1, 4, 6, 4, 1};
-  for (int y = 0; y < dh; y++)
+  // horizontal [1,4,6,4,1] at even columns for every source row, then vertical at even rows
+  std::vector<int> hrow((size_t)h * dw);
+  for (int y = 0; y < h; y++) {
+    const u8* row = src + (size_t)y * w;
+    int* o = &hrow[(size_t)y * dw];
     for (int x = 0; x < dw; x++) {
-      int s = 0;
-      for (int j = 0; j < 5; j++) {
-        const int sy = reflect101(2 * y + j - 2, h);
-        int rs = 0;
-        for (int i = 0; i < 5; i++) rs += k[i] * src[(size_t)sy * w + reflect101(2 * x + i - 2, w)];
-        s += k[j] * rs;
-      }
-      dst[(size_t)y * dw + x] = (u8)((s + 128) >> 8);
+      const int c = 2 * x;
+      if (c >= 2 && c + 2 < w) o[x] = row[c - 2] + 4 * row[c - 1] + 6 * row[c] + 4 * row[c + 1] + row[c + 2];
+      else o[x] = row[reflect101(c - 2, w)] + 4 * row[reflect101(c - 1, w)] + 6 * row[c] + 4 * row[reflect101(c + 1, w)] +
+                  row[reflect101(c + 2, w)];
     }
+  }
+  for (int y = 0; y < dh; y++) {
+    const int* r0 = &hrow[(size_t)reflect101(2 * y - 2, h) * dw];
+    const int* r1 = &hrow[(size_t)reflect101(2 * y - 1, h) * dw];
+    const int* r2 = &hrow[(size_t)(2 * y) * dw];
+    const int* r3 = &hrow[(size_t)reflect101(2 * y + 1, h) * dw];
+    const int* r4 = &hrow[(size_t)reflect101(2 * y + 2, h) * dw];
+    for (int x = 0; x < dw; x++)
+      dst[(size_t)y * dw + x] = (u8)((r0[x] + 4 * r1[x] + 6 * r2[x] + 4 * r3[x] + r4[x] + 128) >> 8);
+  }
 }
 
 // cv::Sobel(u8 -> CV_16S, ksize 3), BORDER_REFLECT_101
 void sobel3_s16(const u8* src, int w, int h, short* dx, short* dy) {
-  for (int y = 0; y < h; y++)
+  for (int y = 0; y < h; y++) {
+    const u8* r0 = src + (size_t)reflect101(y - 1, h) * w;
+    const u8* r1 = src + (size_t)y * w;
+    const u8* r2 = src + (size_t)reflect101(y + 1, h) * w;
     for (int x = 0; x < w; x++) {
-      int p[3][3];
-      for (int j = 0; j < 3; j++)
-        for (int i = 0; i < 3; i++) p[j][i] = src[(size_t)reflect101(y + j - 1, h) * w + reflect101(x + i - 1, w)];
-      dx[(size_t)y * w + x] = (short)((p[0][2] - p[0][0]) + 2 * (p[1][2] - p[1][0]) + (p[2][2] - p[2][0]));
-      dy[(size_t)y * w + x] = (short)((p[2][0] - p[0][0]) + 2 * (p[2][1] - p[0][1]) + (p[2][2] - p[0][2]));
+      const int xm = x > 0 ? x - 1 : reflect101(-1, w), xp = x + 1 < w ? x + 1 : reflect101(w, w);
+      dx[(size_t)y * w + x] = (short)((r0[xp] - r0[xm]) + 2 * (r1[xp] - r1[xm]) + (r2[xp] - r2[xm]));
+      dy[(size_t)y * w + x] = (short)((r2[xm] - r0[xm]) + 2 * (r2[x] - r0[x]) + (r2[xp] - r0[xp]));
     }
+  }
 }
 
 static inline float cosf_d(float a) { return (float)std::cos((double)a); }

@@ -88,20 +88,29 @@ void resize_linear_u8(const u8* src, int sstride, int sw, int sh, u8* dst, int d
 // 5x5 sigma=1 -> {14,62,104,62,14} (binary_descriptor_custom.cpp:359).
 void gaussian_blur_u8(const u8* src, int sstride, int w, int h, u8* dst, int dstride,
                       const int* k, int ksize) {
-  int r = ksize / 2;
+  const int r = ksize / 2;
   std::vector<uint32_t> tmp((size_t)w * h);
-  for (int y = 0; y < h; y++)
+  std::vector<int> pad(w + 2 * r);               // one row with its REFLECT_101 border
+  for (int y = 0; y < h; y++) {
+    const u8* row = src + (size_t)y * sstride;
+    for (int x = -r; x < w + r; x++) pad[x + r] = row[reflect101(x, w)];
+    uint32_t* t = &tmp[(size_t)y * w];
     for (int x = 0; x < w; x++) {
       uint32_t s = 0;
-      for (int i = 0; i < ksize; i++) s += k[i] * src[(size_t)y * sstride + reflect101(x + i - r, w)];
-      tmp[(size_t)y * w + x] = s;
+      for (int i = 0; i < ksize; i++) s += k[i] * pad[x + i];
+      t[x] = s;
     }
-  for (int y = 0; y < h; y++)
+  }
+  std::vector<const uint32_t*> rows(ksize);
+  for (int y = 0; y < h; y++) {
+    for (int i = 0; i < ksize; i++) rows[i] = &tmp[(size_t)reflect101(y + i - r, h) * w];
+    u8* d = dst + (size_t)y * dstride;
     for (int x = 0; x < w; x++) {
       uint32_t s = 0;
-      for (int i = 0; i < ksize; i++) s += k[i] * tmp[(size_t)reflect101(y + i - r, h) * w + x];
-      dst[(size_t)y * dstride + x] = (u8)((s + 32768u) >> 16);
+      for (int i = 0; i < ksize; i++) s += k[i] * rows[i][x];
+      d[x] = (u8)((s + 32768u) >> 16);
     }
+  }
 }
 
 // FAST-9/16 corner score of one pixel: the largest threshold t for which the pixel
@@ -141,7 +150,14 @@ void fast_roi(const u8* roi, int stride, int w, int h, int th, std::vector<RawKp
   std::vector<int> sc((size_t)w * h, 0);
   for (int y = 3; y < h - 3; y++)
     for (int x = 3; x < w - 3; x++) {
-      int s = fast_score(roi + (size_t)y * stride + x, stride);
+      const u8* p = roi + (size_t)y * stride + x;
+      // any arc of 9 ring pixels holds at least 2 of the 4 compass pixels: cheap necessary test
+      const int c = p[0], hi = c + th, lo = c - th;
+      const int v0 = p[3 * stride], v8 = p[-3 * stride], v4 = p[3], v12 = p[-3];
+      const int nb = (v0 > hi) + (v8 > hi) + (v4 > hi) + (v12 > hi);
+      const int nd = (v0 < lo) + (v8 < lo) + (v4 < lo) + (v12 < lo);
+      if (nb < 2 && nd < 2) continue;
+      int s = fast_score(p, stride);
       if (s >= th) sc[(size_t)y * w + x] = s;
     }
   for (int y = 3; y < h - 3; y++)
