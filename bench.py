@@ -316,12 +316,17 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         top = max(prof, key=prof.get) if prof else None
         roof = None
+        traffic = None
         if top:
+            tj = ROOT / "profiles" / f"r01_{top}_traffic.json"   # dram bytes from the committed ncu --set full capture
+            if tj.exists():
+                traffic = json.loads(tj.read_text())["dram_bytes_per_frame"] * B
             ach = ALGO_BYTES.get(top, 0) * B / (prof[top] * 1e-3) / 1e9
             roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                    "traffic": traffic, "algorithmic_bytes_per_launch": ALGO_BYTES.get(top, 0) * B, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                     "kernel_ms_per_launch": prof[top], "frames_per_launch": B,
-                    "note": "latency-bound serial region growing; see DESIGN.md section 4" if top == "k_lsd_grow" else ""}
+                    "note": ("serial region growing: issue/latency bound (ncu: 68% issue-active, 2.2% DRAM throughput), "
+                             "see DESIGN.md section 4 and profiles/r01_k_lsd_grow.md") if top == "k_lsd_grow" else ""}
         total_prof = sum(prof.values()) or 1.0
         line = {
             "metric": "frames/s", "value": world * B * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
