@@ -137,7 +137,7 @@ typedef struct plvi_line plvi_line;
 
 /* Lineextractor::Lineextractor(lsd_nfeatures, lsd_refine, lsd_scale, nlevels, scale, extractor)
  * (include/LineExtractor.h:55, src/LineExtractor.cc:39-43).  Implemented: extractor = 0
- * (LSD), lsd_refine = 0, nlevels 1 or 2, scale = 2.0 -- every configuration the
+ * (LSD), lsd_refine = 0, nlevels 1 or 2, 0.75 <= lsd_scale < 1 -- every configuration the
  * reference ships; anything else returns PLVI_ERR_INVALID.  lsd_nfeatures = 0 keeps all
  * lines (capacity 4096 per frame). */
 int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float lsd_scale, int nlevels,

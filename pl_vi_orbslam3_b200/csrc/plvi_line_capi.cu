@@ -137,12 +137,8 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
     O.lh = o == 0 ? hh : g.o[o - 1].lh / 2;
     O.lpitch = (O.lw + 63) & ~63;
     O.lbdOff = lbd; lbd += (size_t)O.lw * O.lh;
-    if (o > 0 && (O.lw != O.w || O.lh != O.h)) {
-      // LSD octave coordinates index the LBD octave image; the reference relies on both
-      // pyramids having equal sizes (true for scale 2.0)
-      set_error("line pyramid scale must be 2.0 (LBD octaves are pyrDown halves)");
-      return PLVI_ERR_INVALID;
-    }
+    // (for odd sizes the LBD octave (w/2, h/2) can be one pixel smaller than the LSD octave
+    //  cvRound(w/2): computeLBD clamps its sample coordinates, exactly like the reference)
   }
   if (rs && g.noct > 1) {
     linear_rows_u8(g.o[0].w, g.o[1].w, *rs);

@@ -129,3 +129,35 @@ def test_line_device_resident_api(ext):
     for i in range(2):
         n = counts[i]
         _check_lines(kl[i, :n], desc[i, :n], eq[i, :n], oracle.line_extract(frames[i]))
+
+
+@pytest.mark.parametrize("w,h", [(750, 481), (641, 479)])
+def test_line_odd_sizes_and_unaligned_device_input(gpu, w, h):
+    import torch
+    e = Lineextractor(200, 0, 0.8, 2, 2.0, 0, max_width=w, max_height=h, max_batch=1)
+    try:
+        img = synth.frame_euroc(85, w, h)
+        ref = oracle.line_extract(img)
+        kl, desc, eq = e(img)
+        _check_lines(kl, desc, eq, ref)
+        flat = torch.zeros(img.size + 8, dtype=torch.uint8, device="cuda")
+        flat[3:3 + img.size] = torch.from_numpy(img.reshape(-1)).cuda()
+        st = torch.cuda.ExternalStream(e.stream)
+        with torch.cuda.stream(st):
+            dk, dd, de, dc = e.extract_batch_device(flat[3:3 + img.size].view(1, h, w))
+        st.synchronize()
+        n = int(dc.cpu()[0])
+        dk = dk.cpu().numpy().view(np.uint8).reshape(1, e.capacity, 68).copy().view(oracle.KEYLINE_DTYPE)[..., 0]
+        _check_lines(dk[0, :n], dd.cpu().numpy()[0, :n], de.cpu().numpy()[0, :n], ref)
+    finally:
+        e.close()
+
+
+def test_line_scale_075(gpu):
+    e = Lineextractor(150, 0, 0.75, 2, 2.0, 0, max_batch=1)
+    try:
+        img = synth.frame_euroc(86)
+        kl, desc, eq = e(img)
+        _check_lines(kl, desc, eq, oracle.line_extract(img, lsd_nfeatures=150, lsd_scale=0.75))
+    finally:
+        e.close()

@@ -144,3 +144,45 @@ def test_orb_smaller_image_on_bigger_handle(gpu):
             _check_frame(kps, desc, mono, oracle.orb_extract(img))
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("w,h", [(750, 481), (641, 479), (333, 250)])
+def test_orb_odd_sizes_and_unaligned_device_input(gpu, w, h):
+    """Widths that are not multiples of 4 exercise the unaligned tile-load paths; the device API
+    reads the caller's buffer in place (row stride = width, odd base offset)."""
+    import torch
+    e = ORBextractor(1000, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=2)
+    try:
+        frames = np.stack([synth.frame_euroc(80 + i, w, h) for i in range(2)])
+        kps, desc, counts, mono = e.extract_batch(frames)
+        refs = [oracle.orb_extract(f) for f in frames]
+        for i in range(2):
+            _check_frame(kps[i, :counts[i]], desc[i, :counts[i]], mono[i], refs[i])
+        # device-resident, deliberately misaligned by one byte
+        flat = torch.zeros(frames.size + 8, dtype=torch.uint8, device="cuda")
+        flat[1:1 + frames.size] = torch.from_numpy(frames.reshape(-1)).cuda()
+        view = flat[1:1 + frames.size].view(2, h, w)
+        st = torch.cuda.ExternalStream(e.stream)
+        with torch.cuda.stream(st):
+            dk, dd, dc, dm = e.extract_batch_device(view)
+        st.synchronize()
+        dk = dk.cpu().numpy().view(np.uint8).reshape(2, e.capacity, 28).copy().view(oracle.KEYPOINT_DTYPE)[..., 0]
+        dd, dc, dm = dd.cpu().numpy(), dc.cpu().numpy(), dm.cpu().numpy()
+        for i in range(2):
+            _check_frame(dk[i, :dc[i]], dd[i, :dc[i]], dm[i], refs[i])
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("nfeat,sf,nlev,ini,mn", [(500, 1.5, 4, 30, 10), (1500, 1.1, 10, 15, 5), (300, 2.0, 3, 20, 7)])
+def test_orb_other_extractor_parameters(gpu, nfeat, sf, nlev, ini, mn):
+    e = ORBextractor(nfeat, sf, nlev, ini, mn, max_batch=1)
+    try:
+        img = synth.frame_euroc(90)
+        mono, kps, desc = e(img)
+        ref = oracle.orb_extract(img, nfeatures=nfeat, scale_factor=sf, nlevels=nlev, ini_th=ini, min_th=mn)
+        _check_frame(kps, desc, mono, ref)
+        assert np.array_equal(e.features_per_level(), ref["plan"]["quota"])
+        assert np.array_equal(e.GetScaleFactors(), ref["plan"]["scale"])
+    finally:
+        e.close()
