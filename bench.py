@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--orb-only", action="store_true", help="diagnostic: time ORB extraction alone (not the bench metric)")
     ap.add_argument("--profile-out", default="")
     ap.add_argument("--no-overlap", action="store_true", help="run the line pipeline on the same stream as ORB")
+    ap.add_argument("--line-priority", type=int, default=0)
     ap.add_argument("--pipes", type=int, default=int(os.environ.get("PLVI_BENCH_PIPES", 1)),
                     help="independent pipelines the batch is split over (overlap across slices)")
     args = ap.parse_args()
@@ -216,7 +217,8 @@ def main():
     frames = synth.frame_batch(B, W, H, base_seed=1000 * rank, distinct=16)
     h_frames = torch.from_numpy(frames).pin_memory()
     fe = PipelinedFrontEnd(B, pipes=args.pipes, device=local_rank, w=W, h=H, with_lines=not args.orb_only,
-                           with_match=not args.orb_only, overlap_lines=not args.no_overlap)
+                           with_match=not args.orb_only, overlap_lines=not args.no_overlap,
+                           line_priority=args.line_priority)
     st = fe.stream
     with torch.cuda.stream(st):
         d_frames = h_frames.to(dev, non_blocking=True)

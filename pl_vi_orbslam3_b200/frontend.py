@@ -24,7 +24,7 @@ def shard_range(n_items, rank, world):
 class FrontEnd:
     def __init__(self, batch, w=752, h=480, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
                  lsd_nfeatures=200, lsd_scale=0.8, line_levels=2, line_scale=2.0, device=0, stream=None,
-                 with_lines=True, with_match=True, match_th=15.0, nnratio=0.9, overlap_lines=True):
+                 with_lines=True, with_match=True, match_th=15.0, nnratio=0.9, overlap_lines=True, line_priority=0):
         import torch
         self.torch = torch
         self.B, self.w, self.h = batch, w, h
@@ -35,7 +35,7 @@ class FrontEnd:
         # points and lines are independent (the reference runs them on two threads, src/Frame.cc:558-561):
         # the line pipeline gets its own stream, forked from / joined into self.stream every step, so the
         # latency-bound LSD region growing overlaps the throughput-bound ORB kernels
-        self.line_stream = torch.cuda.Stream(device=self.device) if overlap_lines else self.stream
+        self.line_stream = torch.cuda.Stream(device=self.device, priority=line_priority) if overlap_lines else self.stream
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
         self.scale_factor = float(scale_factor)
