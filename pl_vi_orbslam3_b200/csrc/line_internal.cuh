@@ -16,12 +16,21 @@ struct LineOct {
   int xtabOff, ytabOff;
   int lw, lh, lpitch;  // LBD octave image (w >> o, h >> o)
   size_t lbdOff;       // offset in the per-frame gradient array
+  // band speculation of the region growing (k_lsd_spec / k_lsd_commit)
+  int nbands, bandRows;       // bands of bandRows working rows; band j covers rows [j * bandRows, ...)
+  int bandPxCap, bandRecCap;  // pixel-list / record slots of one band
+  size_t regOff;              // offset in the per-frame region pixel array: serial area (sw * sh) then the band areas
+  size_t specBmOff;           // offset (words) in the per-frame private-bitmap array; band j holds rows [j * bandRows, sh)
+  size_t specRecOff;          // offset in the per-frame speculative record array
+  int taskOff;                // first speculation task of this octave within a frame
 };
 
 struct LineGeom {
   int noct;
   LineOct o[2];
   size_t pxTotal, rawTotal, lbdTotal;
+  size_t regTotal, specBmTotal, specRecTotal;
+  int tasksPerFrame;
   int bmTotal, segTotal;
   double rho, prec, lsdScale, minLength;
   float alignHi2, alignLo2;   // cos^2(prec -/+ margin): bounds of the cheap alignment test in k_lsd_grow
@@ -32,6 +41,7 @@ struct LineGeom {
 
 struct LineTab { int ofs; float a0, a1; };       // f64 bilinear taps (float32 weights)
 struct LineRegion { int start, size; double angle; };
+struct SpecRec { unsigned seed, start, size; float angDeg; };   // speculative region: seed x | y << 16, pixel list slice, region angle
 
 struct LinePtrs {
   const u8* img[2];
@@ -45,7 +55,12 @@ struct LineBufs {
   float2* seed;          // [B][pxTotal]   cos, sin of the f64 angle (region seed: float(std::cos(reg_angle)))
   double* mod;           // [B][pxTotal]   gradient magnitude
   unsigned* bitmap;      // [B][bmTotal]   angle defined & not used
-  unsigned* reg;         // [B][pxTotal]   region pixel lists (x | y << 16)
+  unsigned* reg;         // [B][regTotal]  region pixel lists (x | y << 16)
+  unsigned* specBm;      // [B][specBmTotal] private availability bitmaps of the speculation bands
+  SpecRec* specRec;      // [B][specRecTotal]
+  int* specCnt;          // [B][tasksPerFrame] speculative regions per band
+  unsigned* phantom;     // [B][bmTotal]   pixels a discarded speculative region had consumed
+  int useSpec;           // 0: serial k_lsd_grow only
   LineRegion* regTab;    // [B][segTotal]
   int* regCount;         // [B][2]  (-1: segment table overflow)
   float4* segs;          // [B][segTotal]

@@ -228,7 +228,7 @@ __device__ __forceinline__ bool is_aligned_dev(double a, double theta, double pr
 }
 
 #define GROW_RQ 512   // shared ring holding the most recent region pixels (BFS frontier)
-#define GROW_K 64     // bitmap rows kept in shared memory (sliding window below the seed row)
+#define GROW_K 32     // bitmap rows kept in shared memory (sliding window below the seed row)
 
 // "Available" (gradient defined & not used) bitmap of one (frame, octave).  Rows above the
 // current seed row hold no available pixel any more (every earlier pixel in raster order
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
   const float4* __restrict__ rec = b.rec + pbase;
   const float2* __restrict__ seedcs = b.seed + pbase;
-  unsigned* regAll = b.reg + pbase;
+  unsigned* regAll = b.reg + (size_t)f * g.regTotal + O.regOff;
   LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
   const double prec = g.prec;
   const float kHi = g.alignHi2, kLo = g.alignLo2;
@@ -441,6 +441,461 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
 }
 
 // ---------------------------------------------------------------------------------------
+// Band-speculative region growing.  The reference grows regions one after another in raster
+// order of their seeds (src/LSD/lsd.cpp:476-487) - a serial chain over the whole image.  Here
+//   k_lsd_spec_init  gives every band (O.bandRows working rows) a private copy of the initial
+//                    availability bitmap (rows above the band are exhausted by definition),
+//   k_lsd_spec       grows, one thread per band, the regions seeded in that band as if the
+//                    band were the first one: 32 independent serial chains per warp,
+//   k_lsd_commit     walks the true seeds in raster order (one warp per frame and octave).  A
+//                    speculative region is adopted when it starts at the true next seed, all
+//                    of its pixels are still available and no pixel it saw as "used" is in
+//                    fact available ("phantom": consumed only by a discarded speculation of
+//                    the same band); its growth then saw the same availability and the same
+//                    angles as the serial algorithm, so it is the region the reference grows.
+//                    Everything else is grown serially as in k_lsd_grow.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lsd_spec_init(const __grid_constant__ LineGeom g, LineBufs b) {
+  const int t = blockIdx.y, f = blockIdx.z;
+  const int oct = (g.noct > 1 && t >= g.o[1].taskOff) ? 1 : 0;
+  const LineOct& O = g.o[oct];
+  const int j = t - O.taskOff;
+  if (j >= O.nbands) return;
+  const int r0 = j * O.bandRows;
+  const int nw = (O.sh - r0) * O.wpr;
+  const unsigned* __restrict__ src = b.bitmap + (size_t)f * g.bmTotal + O.bmOff + r0 * O.wpr;
+  unsigned* __restrict__ dst = b.specBm + (size_t)f * g.specBmTotal + O.specBmOff + (size_t)j * O.wpr * O.sh + r0 * O.wpr;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < nw; i += gridDim.x * 256) dst[i] = src[i];
+  if (j == 0) {   // the commit pass starts without phantom pixels
+    unsigned* ph = b.phantom + (size_t)f * g.bmTotal + O.bmOff;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nw; i += gridDim.x * 256) ph[i] = 0u;
+  }
+}
+
+#define SPEC_SCAN_WORDS 8
+#define SPEC_RING 16
+
+// One thread per (band, frame); the 32 lanes of a warp hold the same band of 32 consecutive
+// frames (similar content => similar amount of work).  Single flat loop: every iteration
+// expands one queue entry of the lane's current region, so lanes with regions of different
+// sizes stay converged.  Same tests, in the same order, as k_lsd_grow.
+__global__ void __launch_bounds__(32) k_lsd_spec(const __grid_constant__ LineGeom g, LineBufs b, int n) {
+  const int t = blockIdx.x;
+  const int f = blockIdx.y * 32 + threadIdx.x;
+  const int oct = (g.noct > 1 && t >= g.o[1].taskOff) ? 1 : 0;
+  const LineOct& O = g.o[oct];
+  const int j = t - O.taskOff;
+  if (f >= n || j >= O.nbands) return;
+  const int W = O.sw, H = O.sh, wpr = O.wpr;
+  const int r0 = j * O.bandRows, r1 = min(r0 + O.bandRows, H - 1);
+  unsigned* P = b.specBm + (size_t)f * g.specBmTotal + O.specBmOff + (size_t)j * wpr * H;
+  unsigned* list = b.reg + (size_t)f * g.regTotal + O.regOff + (size_t)W * H + (size_t)j * O.bandPxCap;
+  uint4* recs = reinterpret_cast<uint4*>(b.specRec + (size_t)f * g.specRecTotal + O.specRecOff + (size_t)j * O.bandRecCap);
+  const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
+  const float4* __restrict__ rec = b.rec + pbase;
+  const float2* __restrict__ seedcs = b.seed + pbase;
+  const int pxCap = O.bandPxCap, recCap = O.bandRecCap, minReg = O.minRegSize;
+  const double prec = g.prec;
+  const float kHi = g.alignHi2, kLo = g.alignLo2;
+
+  __shared__ unsigned sring[SPEC_RING * 32];   // the last SPEC_RING pixels of each lane's region (BFS frontier)
+  const int lane = threadIdx.x;
+  int row = r0, wi = 0;
+  unsigned word = (r0 < r1) ? P[r0 * wpr] : 0u;
+  int nrec = 0, npx = 0, base = 0, size = 0, i = 0;
+  unsigned seedpk = 0u;
+  float sang = 0.f, sumdx = 0.f, sumdy = 0.f, n2 = 0.f;
+  bool fresh = true;
+  bool done = r0 >= r1;
+  while (!done) {
+    bool isNew = false;
+    float sangNew = 0.f;
+    float2 scsNew = make_float2(0.f, 0.f);
+    if (i == size) {
+      if (size > 0) {   // close the finished region
+        const float ang = fresh ? sang : (size >= minReg ? fast_atan2_dev(sumdy, sumdx) : 0.f);
+        recs[nrec++] = make_uint4(seedpk, (unsigned)base, (unsigned)size, __float_as_uint(ang));
+        npx += size;
+        size = 0; i = 0;
+        word = P[row * wpr + wi];   // the region may have taken pixels of the seed's own word
+      }
+      int guard = 0;
+      while (word == 0u && guard < SPEC_SCAN_WORDS) {
+        if (++wi == wpr) { wi = 0; ++row; }
+        if (row >= r1) break;
+        word = P[row * wpr + wi];
+        ++guard;
+      }
+      if (row >= r1 || nrec >= recCap) { done = true; continue; }
+      if (word == 0u) continue;
+      const int bit = __ffs(word) - 1;
+      const int sx = wi * 32 + bit;
+      seedpk = (unsigned)sx | ((unsigned)row << 16);
+      word &= ~(1u << bit);
+      P[row * wpr + wi] = word;
+      base = npx;
+      list[base] = seedpk;
+      size = 1;
+      const int sp = row * W + sx;
+      // consumed after the neighbourhood loads below have been issued
+      sangNew = __ldg(&rec[sp].x);
+      scsNew = __ldg(seedcs + sp);
+      isNew = true;
+    }
+    if (base + size + 8 > pxCap) { done = true; continue; }   // list full: the unfinished region is dropped
+    // expand queue entry i
+    const unsigned p = (i == 0) ? seedpk
+                                : ((size - i <= SPEC_RING) ? sring[(i & (SPEC_RING - 1)) * 32 + lane] : list[base + i]);
+    const int ex = (int)(p & 0xffff), ey = (int)(p >> 16);
+    const int xm = ex - 1;
+    const int wa = max(xm, 0) >> 5;
+    const int sh = xm - (wa << 5);   // -1 .. 31: bit of column ex - 1 in word wa
+    const bool needHi = sh >= 30 && wa + 1 < wpr;
+    unsigned lo[3], hi[3];
+    unsigned m9 = 0u;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int y = ey - 1 + r;
+      const bool ok = y >= r0 && y < H;
+      lo[r] = ok ? P[y * wpr + wa] : 0u;
+      hi[r] = (ok && needHi) ? P[y * wpr + wa + 1] : 0u;
+      const unsigned long long comb = ((unsigned long long)hi[r] << 32) | lo[r];
+      const unsigned three = sh >= 0 ? ((unsigned)(comb >> sh) & 7u) : ((lo[r] << 1) & 7u);
+      m9 |= three << (3 * r);
+    }
+    float4 rk[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      rk[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k != 4 && ((m9 >> k) & 1u)) rk[k] = __ldg(rec + (ey + k / 3 - 1) * W + (ex + k % 3 - 1));
+    }
+    if (isNew) {
+      sang = sangNew;
+      sumdx = scsNew.x; sumdy = scsNew.y;
+      n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+      fresh = true;
+    }
+    unsigned acc = 0u;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      if (k == 4 || !((m9 >> k) & 1u)) continue;
+      const float dot = __fmaf_rn(sumdx, rk[k].y, sumdy * rk[k].z);
+      const float d2 = dot * dot;
+      if (!(dot > 0.f && d2 > kLo * n2)) continue;
+      if (!(d2 >= kHi * n2)) {
+        const double regAngle = __dmul_rn((double)(fresh ? sang : fast_atan2_dev(sumdy, sumdx)), D2R);
+        if (!is_aligned_dev(__dmul_rn((double)rk[k].x, D2R), regAngle, prec)) continue;
+      }
+      acc |= 1u << k;
+      const unsigned q = (unsigned)(ex + k % 3 - 1) | ((unsigned)(ey + k / 3 - 1) << 16);
+      list[base + size] = q;
+      sring[(size & (SPEC_RING - 1)) * 32 + lane] = q;
+      size++;
+      fresh = false;
+      sumdx = __fadd_rn(sumdx, rk[k].y);
+      sumdy = __fadd_rn(sumdy, rk[k].z);
+      n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+    }
+    if (acc) {
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const unsigned a3 = (acc >> (3 * r)) & 7u;
+        if (a3) {
+          const unsigned long long mk = sh >= 0 ? ((unsigned long long)a3 << sh) : (unsigned long long)(a3 >> 1);
+          const int y = ey - 1 + r;
+          P[y * wpr + wa] = lo[r] & ~(unsigned)mk;
+          if ((unsigned)(mk >> 32)) P[y * wpr + wa + 1] = hi[r] & ~(unsigned)(mk >> 32);
+        }
+      }
+    }
+    i++;
+  }
+  b.specCnt[(size_t)f * g.tasksPerFrame + t] = nrec;
+}
+
+// Pixels that a discarded speculative region had consumed in its band's private bitmap but
+// that are still available in the true state.  A later speculative region of that band saw
+// them as "used"; it can only be adopted if none of them touches it.
+struct PhantomMap {
+  unsigned* sm;      // [GROW_K][wpr] shared window, slides with the availability window
+  unsigned* gm;      // [H][wpr] global copy (rows below the window)
+  bool any;          // warp-uniform: some phantom pixel exists
+  __device__ __forceinline__ unsigned word(const GrowBitmap& bm, int y, int wi) const {
+    return (y - bm.top < GROW_K) ? sm[(y & (GROW_K - 1)) * bm.wpr + wi] : __ldcg(gm + y * bm.wpr + wi);
+  }
+  __device__ __forceinline__ void mark(const GrowBitmap& bm, int x, int y) {
+    const unsigned bit = 1u << (x & 31);
+    if (y - bm.top < GROW_K) atomicOr(&sm[(y & (GROW_K - 1)) * bm.wpr + (x >> 5)], bit);
+    else atomicOr(gm + y * bm.wpr + (x >> 5), bit);
+  }
+  // any available phantom pixel in the 3x3 neighbourhood of (x, y)?  (rows >= bm.top only:
+  // the rows above hold no available pixel)
+  __device__ __forceinline__ bool near(const GrowBitmap& bm, int x, int y, int H) const {
+    const int xm = x - 1;
+    const int wa = max(xm, 0) >> 5;
+    const int sh = xm - (wa << 5);   // -1 .. 31
+    const bool two = sh >= 30 && wa + 1 < bm.wpr;
+    for (int yy = max(y - 1, bm.top); yy <= min(y + 1, H - 1); yy++) {
+      const unsigned plo = word(bm, yy, wa), phi = two ? word(bm, yy, wa + 1) : 0u;
+      const unsigned long long pc = ((unsigned long long)phi << 32) | plo;
+      const unsigned p3 = sh >= 0 ? ((unsigned)(pc >> sh) & 7u) : ((plo << 1) & 7u);
+      if (p3) {
+        const unsigned alo = bm.word(yy, wa), ahi = two ? bm.word(yy, wa + 1) : 0u;
+        const unsigned long long ac = ((unsigned long long)ahi << 32) | alo;
+        const unsigned a3 = sh >= 0 ? ((unsigned)(ac >> sh) & 7u) : ((alo << 1) & 7u);
+        if (p3 & a3) return true;
+      }
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ void grow_clear_atomic(GrowBitmap& bm, int x, int y) {
+  const unsigned m = ~(1u << (x & 31));
+  if (y - bm.top < GROW_K) atomicAnd(&bm.sm[(y & (GROW_K - 1)) * bm.wpr + (x >> 5)], m);
+  else atomicAnd(bm.gm + y * bm.wpr + (x >> 5), m);
+}
+
+__global__ void __launch_bounds__(32) k_lsd_commit(const __grid_constant__ LineGeom g, LineBufs b) {
+  extern __shared__ unsigned smem_u[];
+  const int oct = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
+  if (oct >= g.noct) return;
+  const LineOct& O = g.o[oct];
+  const int W = O.sw, H = O.sh, wpr = O.wpr;
+  unsigned* ring = smem_u;
+  GrowBitmap bm;
+  bm.sm = smem_u + GROW_RQ;
+  bm.gm = b.bitmap + (size_t)f * g.bmTotal + O.bmOff;
+  bm.wpr = wpr;
+  bm.top = 0;
+  PhantomMap ph;
+  ph.gm = b.phantom + (size_t)f * g.bmTotal + O.bmOff;
+  ph.sm = bm.sm + GROW_K * wpr;
+  ph.any = false;
+  for (int i = lane; i < min(GROW_K, H) * wpr; i += 32) { bm.sm[i] = __ldcg(bm.gm + i); ph.sm[i] = 0u; }
+  __syncwarp();
+  const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
+  const float4* __restrict__ rec = b.rec + pbase;
+  const float2* __restrict__ seedcs = b.seed + pbase;
+  unsigned* regAll = b.reg + (size_t)f * g.regTotal + O.regOff;
+  LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
+  const double prec = g.prec;
+  const float kHi = g.alignHi2, kLo = g.alignLo2;
+  int regBase = 0, nreg = 0;
+  bool overflow = false;
+  const int e = lane >> 3, k8 = lane & 7;
+  const int nidx = k8 < 4 ? k8 : k8 + 1;
+  const int ndx = nidx % 3 - 1, ndy = nidx / 3 - 1;
+  const unsigned laneBit = 1u << lane;
+
+  // speculative records of the band the seed scan is in; `cur` / `curPix` are fetched one
+  // region ahead (record and the first 32 pixels of its list)
+  int band = -1, bandEnd = 0, bp = 0, bcnt = 0, runStart = 0, bandList = 0;
+  const uint4* brecs = nullptr;
+  const unsigned* blist = nullptr;
+  uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+  unsigned curPix = 0u;
+
+  for (int row = 0; row < H - 1; row++) {
+    if (row == bandEnd) {
+      band++;
+      bandEnd = min((band + 1) * O.bandRows, H);
+      bp = 0; runStart = 0;
+      bcnt = b.specCnt[(size_t)f * g.tasksPerFrame + O.taskOff + band];
+      brecs = reinterpret_cast<const uint4*>(b.specRec + (size_t)f * g.specRecTotal + O.specRecOff + (size_t)band * O.bandRecCap);
+      bandList = W * H + band * O.bandPxCap;
+      blist = regAll + bandList;
+      if (bcnt > 0) { cur = __ldcg(brecs); curPix = __ldcg(blist + lane); }
+    }
+    // slide the shared windows: rows [top, row) are exhausted, rows up to row + GROW_K enter
+    if (row > bm.top) {
+      const int r0 = bm.top + GROW_K, r1 = min(row + GROW_K, H);
+      for (int r = r0; r < r1; r++)
+        for (int wv = lane; wv < wpr; wv += 32) {
+          bm.sm[(r & (GROW_K - 1)) * wpr + wv] = __ldcg(bm.gm + r * wpr + wv);
+          ph.sm[(r & (GROW_K - 1)) * wpr + wv] = ph.any ? __ldcg(ph.gm + r * wpr + wv) : 0u;
+        }
+      bm.top = row;
+      __syncwarp();
+    }
+    for (int c0 = 0; c0 < wpr; c0 += 32) {
+      while (true) {
+        // next seed: first available pixel in raster order (src/LSD/lsd.cpp:476-479)
+        const int wi = c0 + lane;
+        const int rowBase = (row & (GROW_K - 1)) * wpr;
+        const unsigned word = wi < wpr ? bm.sm[rowBase + wi] : 0u;
+        const unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
+        if (!nz) break;
+        const int wl = __ffs(nz) - 1;
+        const unsigned sw_ = __shfl_sync(0xffffffffu, word, wl);
+        const int bit = __ffs(sw_) - 1;
+        const int sx = (c0 + wl) * 32 + bit, sy = row;
+        const unsigned spk = (unsigned)sx | ((unsigned)sy << 16);
+
+        // speculative regions seeded before this pixel never happened: their pixels that are
+        // still available become phantoms
+        while (bp < bcnt && cur.x < spk) {
+          bool marked = false;
+          for (int i0 = 0; i0 < (int)cur.z; i0 += 32) {
+            const int idx = i0 + lane;
+            if (idx < (int)cur.z) {
+              const unsigned q = i0 == 0 ? curPix : __ldcg(blist + cur.y + idx);
+              const int qx = q & 0xffff, qy = q >> 16;
+              if (qy >= bm.top && bm.test(qx, qy)) { ph.mark(bm, qx, qy); marked = true; }
+            }
+          }
+          if (__any_sync(0xffffffffu, marked)) ph.any = true;
+          runStart += (int)cur.z;
+          bp++;
+          if (bp < bcnt) { cur = __ldcg(brecs + bp); curPix = __ldcg(blist + runStart + lane); }
+          __syncwarp();
+        }
+        bool haveSpec = bp < bcnt && cur.x == spk;
+        uint4 sr = cur;
+        unsigned srPix = curPix;
+        if (haveSpec) {
+          runStart += (int)cur.z;
+          bp++;
+          if (bp < bcnt) { cur = __ldcg(brecs + bp); curPix = __ldcg(blist + runStart + lane); }
+          bool ok = true;
+          for (int i0 = 0; i0 < (int)sr.z && ok; i0 += 32) {
+            const int idx = i0 + lane;
+            bool good = true;
+            if (idx < (int)sr.z) {
+              const unsigned q = i0 == 0 ? srPix : __ldcg(blist + sr.y + idx);
+              const int qx = q & 0xffff, qy = q >> 16;
+              good = bm.test(qx, qy) && !(ph.any && ph.near(bm, qx, qy, H));
+            }
+            ok = __all_sync(0xffffffffu, good);
+          }
+          if (ok) {   // adopt: this is the region the serial algorithm grows from this seed
+            for (int i0 = 0; i0 < (int)sr.z; i0 += 32) {
+              const int idx = i0 + lane;
+              if (idx < (int)sr.z) {
+                const unsigned q = i0 == 0 ? srPix : __ldcg(blist + sr.y + idx);
+                grow_clear_atomic(bm, q & 0xffff, q >> 16);
+              }
+            }
+            if ((int)sr.z >= O.minRegSize) {
+              if (nreg < O.segCap) {
+                if (lane == 0) {
+                  LineRegion r;
+                  r.start = bandList + (int)sr.y;
+                  r.size = (int)sr.z;
+                  r.angle = __dmul_rn((double)__uint_as_float(sr.w), D2R);
+                  rtab[nreg] = r;
+                }
+                nreg++;
+              } else {
+                overflow = true;
+              }
+            }
+            __syncwarp();
+            continue;
+          }
+        }
+
+        const int sp = sy * W + sx;
+        const float sang = __ldg(&rec[sp].x);
+        const float2 scs = __ldg(seedcs + sp);
+        unsigned* reg = regAll + regBase;          // pixel list of the region being grown
+        if (lane == 0) {
+          bm.sm[rowBase + c0 + wl] = sw_ & ~(1u << bit);
+          ring[0] = spk;
+        }
+        __syncwarp();
+        // region_grow (src/LSD/lsd.cpp:635-686), see k_lsd_grow
+        const double seedAngle = __dmul_rn((double)sang, D2R);
+        float sumdx = scs.x, sumdy = scs.y;
+        bool fresh = true;
+        int regSize = 1;
+        int flushed = 0;
+        int i = 0, nb = 1;
+        GrowBatch cb = grow_fetch(bm, ring, reg, regSize, 0, 1, e, ndx, ndy, W, H, rec);
+        while (nb > 0) {
+          const int ni = i + nb, nnb = min(4, regSize - ni);
+          GrowBatch nxt = grow_fetch(bm, ring, reg, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
+          unsigned pm = cb.mask;
+          if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cb.bw, cb.bbit));
+          float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+          while (pm) {
+            const float dot = __fmaf_rn(sumdx, cb.rec.y, sumdy * cb.rec.z);
+            const float d2 = dot * dot;
+            const bool poss = (pm & laneBit) && dot > 0.f && d2 > kLo * n2;
+            const unsigned possm = __ballot_sync(0xffffffffu, poss);
+            if (!possm) break;
+            const int l = __ffs(possm) - 1;
+            const unsigned surem = __ballot_sync(0xffffffffu, poss && d2 >= kHi * n2);
+            pm &= ~((2u << l) - 1u);
+            if (!((surem >> l) & 1u)) {
+              const double regAngle = fresh ? seedAngle : __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
+              const float la = __shfl_sync(0xffffffffu, cb.rec.x, l);
+              if (!is_aligned_dev(__dmul_rn((double)la, D2R), regAngle, prec)) continue;
+            }
+            const float qc = __shfl_sync(0xffffffffu, cb.rec.y, l), qs = __shfl_sync(0xffffffffu, cb.rec.z, l);
+            const int qpk = __shfl_sync(0xffffffffu, cb.cpk, l);
+            pm &= ~__ballot_sync(0xffffffffu, cb.cpk == qpk);
+            if (lane == l) {
+              grow_clear(bm, cb.bw, cb.bbit);
+              ring[regSize & (GROW_RQ - 1)] = (unsigned)qpk;
+            }
+            regSize++;
+            fresh = false;
+            sumdx = __fadd_rn(sumdx, qc);
+            sumdy = __fadd_rn(sumdy, qs);
+            n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+          }
+          __syncwarp();
+          while (regSize - flushed >= 32) {
+            __stcg(reg + flushed + lane, ring[(flushed + lane) & (GROW_RQ - 1)]);
+            flushed += 32;
+          }
+          i = ni;
+          if (nnb > 0) {
+            cb = nxt;
+            nb = nnb;
+          } else {
+            nb = min(4, regSize - i);
+            if (nb > 0) cb = grow_fetch(bm, ring, reg, regSize, i, nb, e, ndx, ndy, W, H, rec);
+          }
+        }
+        if (regSize >= O.minRegSize) {
+          if (nreg < O.segCap) {
+            if (flushed + lane < regSize) __stcg(reg + flushed + lane, ring[(flushed + lane) & (GROW_RQ - 1)]);
+            if (lane == 0) {
+              LineRegion r;
+              r.start = regBase;
+              r.size = regSize;
+              r.angle = fresh ? seedAngle : __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
+              rtab[nreg] = r;
+            }
+            nreg++;
+            regBase += regSize;
+          } else {
+            overflow = true;
+          }
+        }
+        __syncwarp();
+        if (haveSpec) {   // the discarded speculation of this seed: what it had taken beyond the true region
+          bool marked = false;
+          for (int i0 = 0; i0 < (int)sr.z; i0 += 32) {
+            const int idx = i0 + lane;
+            if (idx < (int)sr.z) {
+              const unsigned q = i0 == 0 ? srPix : __ldcg(blist + sr.y + idx);
+              const int qx = q & 0xffff, qy = q >> 16;
+              if (qy >= bm.top && bm.test(qx, qy)) { ph.mark(bm, qx, qy); marked = true; }
+            }
+          }
+          if (__any_sync(0xffffffffu, marked)) ph.any = true;
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (lane == 0) b.regCount[f * 2 + oct] = overflow ? -1 : nreg;
+}
+
+// ---------------------------------------------------------------------------------------
 // k_lsd_rect: warp per region.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -466,7 +921,7 @@ __global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGe
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nreg = b.regCount[f * 2 + oct];
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
-  const unsigned* reg = b.reg + pbase;
+  const unsigned* reg = b.reg + (size_t)f * g.regTotal + O.regOff;
   const double* mod = b.mod + pbase;
   const LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
   float4* segs = b.segs + (size_t)f * g.segTotal + O.segOff;
@@ -961,8 +1416,18 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   }
   if (fork) PLVI_CUDA_TRY(cudaEventRecord(aux.join, aux.stream));
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
-  k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b);
-  prof->mark("k_lsd_grow", st);
+  if (b.useSpec) {
+    k_lsd_spec_init<<<dim3(8, g.tasksPerFrame, n), 256, 0, st>>>(g, b);
+    prof->mark("k_lsd_spec_init", st);
+    k_lsd_spec<<<dim3(g.tasksPerFrame, (n + 31) / 32), 32, 0, st>>>(g, b, n);
+    prof->mark("k_lsd_spec", st);
+    k_lsd_commit<<<dim3(g.noct, n), 32, growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned), st>>>(g, b);
+    prof->mark("k_lsd_commit", st);
+    nl += 2;
+  } else {
+    k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b);
+    prof->mark("k_lsd_grow", st);
+  }
   k_lsd_rect<<<dim3(g.noct, n, 2), 256, 0, st>>>(g, b);
   prof->mark("k_lsd_rect", st);
   k_line_assemble<512><<<n, 512, 0, st>>>(g, b, dKl, dCounts);
@@ -982,8 +1447,11 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
 int line_kernel_attrs(const LineGeom& g) {
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
   if (growSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
-  if (growSmem > 48 * 1024)
+  if (growSmem > 24 * 1024) {
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)growSmem));
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned))));
+  }
   return PLVI_OK;
 }
 

@@ -2,6 +2,7 @@
 // (include/LineExtractor.h:55-61, src/LineExtractor.cc:39-117), geometry planning for
 // LSDDetectorC::ComputePyramid + LineSegmentDetectorImpl::flsd + BinaryDescriptor.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -106,8 +107,8 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
   }
   gaussian_kernel7(sigma, g.kern);
   float sf = 1.f;
-  size_t px = 0, raw = 0, lbd = 0;
-  int bm = 0, seg = 0, tabOff = 0;
+  size_t px = 0, raw = 0, lbd = 0, reg = 0, sbm = 0, srec = 0;
+  int bm = 0, seg = 0, tabOff = 0, task = 0;
   for (int o = 0; o < g.noct; o++) {
     LineOct& O = g.o[o];
     if (o > 0) sf = sf * h->scale;
@@ -127,6 +128,17 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
     O.segOff = seg;
     O.segCap = std::min((O.sw * O.sh) / std::max(O.minRegSize, 1), std::max(1024, 8192 >> (2 * o)));
     seg += O.segCap;
+    {  // speculation bands: equal pixel counts per band across octaves (16 bands on octave 0, 4 on octave 1)
+      const int nbT = std::max(1, 16 >> (2 * o));
+      O.bandRows = (O.sh + nbT - 1) / nbT;
+      O.nbands = (O.sh + O.bandRows - 1) / O.bandRows;
+      O.bandPxCap = 2 * O.bandRows * O.sw;
+      O.bandRecCap = std::min(std::max(O.bandRows * O.sw / 2, 64), 4096);
+      O.regOff = reg; reg += ((size_t)O.sw * O.sh + (size_t)nbT * O.bandPxCap + 3) & ~(size_t)3;
+      O.specBmOff = sbm; sbm += (size_t)nbT * O.wpr * O.sh;
+      O.specRecOff = srec; srec += (size_t)nbT * O.bandRecCap;
+      O.taskOff = task; task += nbT;
+    }
     O.xtabOff = tabOff; tabOff += O.sw;
     O.ytabOff = tabOff; tabOff += O.sh;
     if (tabs) {
@@ -145,6 +157,7 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
     linear_rows_u8(g.o[0].h, g.o[1].h, *rs);
   }
   g.pxTotal = px; g.rawTotal = raw; g.lbdTotal = lbd; g.bmTotal = bm; g.segTotal = seg;
+  g.regTotal = reg; g.specBmTotal = sbm; g.specRecTotal = srec; g.tasksPerFrame = task;
   return PLVI_OK;
 }
 
@@ -158,7 +171,8 @@ int ensure_geom(plvi_line* h, int w, int hh) {
   if (rc) return rc;
   const LineGeom& c = h->capGeom;
   if (tabs.size() > h->tabCap || rs.size() > h->rsCap || g.pxTotal > c.pxTotal || g.rawTotal > c.rawTotal ||
-      g.lbdTotal > c.lbdTotal || g.bmTotal > c.bmTotal || g.segTotal > c.segTotal) {
+      g.lbdTotal > c.lbdTotal || g.bmTotal > c.bmTotal || g.segTotal > c.segTotal || g.regTotal > c.regTotal ||
+      g.specBmTotal > c.specBmTotal || g.specRecTotal > c.specRecTotal || g.tasksPerFrame != c.tasksPerFrame) {
     set_error("internal: line geometry exceeds allocated capacity");
     return PLVI_ERR_CAPACITY;
   }
@@ -167,7 +181,9 @@ int ensure_geom(plvi_line* h, int w, int hh) {
   if (!rs.empty()) PLVI_CUDA_TRY(cudaMemcpy(h->dRsTab, rs.data(), rs.size() * sizeof(int2), cudaMemcpyHostToDevice));
   // keep the allocated per-frame strides
   g.pxTotal = c.pxTotal; g.rawTotal = c.rawTotal; g.lbdTotal = c.lbdTotal; g.bmTotal = c.bmTotal; g.segTotal = c.segTotal;
+  g.regTotal = c.regTotal; g.specBmTotal = c.specBmTotal; g.specRecTotal = c.specRecTotal;
   for (int o = 0; o < g.noct; o++) {
+    g.o[o].regOff = c.o[o].regOff; g.o[o].specBmOff = c.o[o].specBmOff; g.o[o].specRecOff = c.o[o].specRecOff;
     g.o[o].pxOff = c.o[o].pxOff; g.o[o].rawOff = c.o[o].rawOff; g.o[o].bmOff = c.o[o].bmOff;
     g.o[o].segOff = c.o[o].segOff; g.o[o].segCap = std::min(g.o[o].segCap, c.o[o].segCap);
     g.o[o].lbdOff = c.o[o].lbdOff;
@@ -247,7 +263,11 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   A((void**)&h->buf.seed, B * c.pxTotal * sizeof(float2));
   A((void**)&h->buf.mod, B * c.pxTotal * sizeof(double));
   A((void**)&h->buf.bitmap, B * c.bmTotal * sizeof(unsigned));
-  A((void**)&h->buf.reg, B * c.pxTotal * sizeof(unsigned));
+  A((void**)&h->buf.reg, B * c.regTotal * sizeof(unsigned));
+  A((void**)&h->buf.specBm, B * c.specBmTotal * sizeof(unsigned));
+  A((void**)&h->buf.specRec, B * c.specRecTotal * sizeof(SpecRec));
+  A((void**)&h->buf.specCnt, B * c.tasksPerFrame * sizeof(int));
+  A((void**)&h->buf.phantom, B * c.bmTotal * sizeof(unsigned));
   A((void**)&h->buf.regTab, B * c.segTotal * sizeof(LineRegion));
   A((void**)&h->buf.regCount, B * 2 * sizeof(int));
   A((void**)&h->buf.segs, B * c.segTotal * sizeof(float4));
@@ -290,6 +310,10 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   h->buf.lbdG = h->dLbdG;
   h->buf.lbdL = h->dLbdL;
   h->buf.trig = h->dTrig;
+  {  // PLVI_LSD_SPEC=0 selects the serial region growing (A/B measurements)
+    const char* ev = getenv("PLVI_LSD_SPEC");
+    h->buf.useSpec = !(ev && ev[0] == '0');
+  }
   *out = h;
   return PLVI_OK;
 }
@@ -303,6 +327,7 @@ void plvi_line_destroy(plvi_line* h) {
   if (h->aux.join) cudaEventDestroy(h->aux.join);
   cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
   cudaFree(h->buf.rowf); cudaFree(h->buf.rec); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
+  cudaFree(h->buf.specBm); cudaFree(h->buf.specRec); cudaFree(h->buf.specCnt); cudaFree(h->buf.phantom);
   cudaFree(h->buf.reg); cudaFree(h->buf.regTab); cudaFree(h->buf.regCount); cudaFree(h->buf.segs);
   cudaFree(h->buf.tmpResp); cudaFree(h->buf.tmpCls); cudaFree(h->buf.lbdImg0); cudaFree(h->buf.lbdImg1);
   cudaFree(h->buf.grad); cudaFree(h->buf.lbdRows); cudaFree(h->buf.scaledDbg);
