@@ -51,7 +51,8 @@ struct LinePtrs {
 
 struct LineBufs {
   double* rowf;          // [B][rawTotal]
-  float4* rec;           // [B][pxTotal]   {level-line angle in degrees (-1024 = NOTDEF), cos, sin of float(angle), -}
+  float* ang;            // [B][pxTotal]   level-line angle in degrees (-1024 = NOTDEF)
+  float2* cs;            // [B][pxTotal]   cos, sin of float(angle): what a region accumulates (lsd.cpp:673-675)
   float2* seed;          // [B][pxTotal]   cos, sin of the f64 angle (region seed: float(std::cos(reg_angle)))
   double* mod;           // [B][pxTotal]   gradient magnitude
   unsigned* bitmap;      // [B][bmTotal]   angle defined & not used

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ 
       }
     }
     const size_t p = (size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx;
-    b.rec[p] = make_float4(angDeg, cs.x, cs.y, 0.f);
+    b.ang[p] = angDeg;
+    b.cs[p] = make_float2(cs.x, cs.y);
     b.seed[p] = make_float2(cs.z, cs.w);
     b.mod[p] = norm;
   }
@@ -256,7 +257,7 @@ struct GrowBatch {
   int cpk;           // neighbour coordinates x | y << 16
   int bw;            // bitmap word of the neighbour: >= 0 index into the shared window, < 0: ~index into the global copy
   unsigned bbit;     // its bit
-  float4 rec;        // {angle deg, cos(float angle), sin(float angle), -}
+  float2 rec;        // cos, sin of the neighbour's float angle
 };
 
 __device__ __forceinline__ bool grow_bit(const GrowBitmap& bm, int bw, unsigned bbit) {
@@ -272,10 +273,10 @@ __device__ __forceinline__ void grow_clear(GrowBitmap& bm, int bw, unsigned bbit
 // latency overlaps the accept chain of the previous batch).
 __device__ __forceinline__ GrowBatch grow_fetch(const GrowBitmap& bm, const unsigned* ring, const unsigned* reg,
                                                 int regSize, int i, int nb, int e, int ndx, int ndy, int W, int H,
-                                                const float4* __restrict__ rec) {
+                                                const float2* __restrict__ rec) {
   GrowBatch g;
   g.cpk = 0; g.bw = 0; g.bbit = 0u;
-  g.rec = make_float4(0.f, 0.f, 0.f, 0.f);
+  g.rec = make_float2(0.f, 0.f);
   bool cand = false;
   if (e < nb) {
     const int idx = i + e;
@@ -312,7 +313,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
   for (int i = lane; i < min(GROW_K, H) * wpr; i += 32) bm.sm[i] = __ldcg(bm.gm + i);
   __syncwarp();
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
-  const float4* __restrict__ rec = b.rec + pbase;
+  const float2* __restrict__ rec = b.cs + pbase;
+  const float* __restrict__ ang = b.ang + pbase;
   const float2* __restrict__ seedcs = b.seed + pbase;
   unsigned* regAll = b.reg + (size_t)f * g.regTotal + O.regOff;
   LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
         const int bit = __ffs(sw_) - 1;
         const int sx = (c0 + wl) * 32 + bit, sy = row;
         const int sp = sy * W + sx;
-        const float sang = __ldg(&rec[sp].x);
+        const float sang = __ldg(ang + sp);
         const float2 scs = __ldg(seedcs + sp);
         unsigned* reg = regAll + regBase;          // pixel list of the region being grown
         if (lane == 0) {
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
           float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
           while (pm) {
             // every pending candidate against the current region direction at once
-            const float dot = __fmaf_rn(sumdx, cur.rec.y, sumdy * cur.rec.z);
+            const float dot = __fmaf_rn(sumdx, cur.rec.x, sumdy * cur.rec.y);
             const float d2 = dot * dot;
             const bool poss = (pm & laneBit) && dot > 0.f && d2 > kLo * n2;
             const unsigned possm = __ballot_sync(0xffffffffu, poss);
@@ -384,11 +386,12 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
             pm &= ~((2u << l) - 1u);                 // l and everything before it is decided now
             if (!((surem >> l) & 1u)) {              // undecided band: the exact test of the reference
               const double regAngle = fresh ? seedAngle : __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
-              const float la = __shfl_sync(0xffffffffu, cur.rec.x, l);
+              const int lpk = __shfl_sync(0xffffffffu, cur.cpk, l);
+              const float la = __ldg(ang + (lpk >> 16) * W + (lpk & 0xffff));
               if (!is_aligned_dev(__dmul_rn((double)la, D2R), regAngle, prec)) continue;
             }
             // accept lane l's pixel
-            const float qc = __shfl_sync(0xffffffffu, cur.rec.y, l), qs = __shfl_sync(0xffffffffu, cur.rec.z, l);
+            const float qc = __shfl_sync(0xffffffffu, cur.rec.x, l), qs = __shfl_sync(0xffffffffu, cur.rec.y, l);
             const int qpk = __shfl_sync(0xffffffffu, cur.cpk, l);
             pm &= ~__ballot_sync(0xffffffffu, cur.cpk == qpk);   // the same pixel seen from another entry
             if (lane == l) {
@@ -492,7 +495,8 @@ __global__ void __launch_bounds__(32) k_lsd_spec(const __grid_constant__ LineGeo
   unsigned* list = b.reg + (size_t)f * g.regTotal + O.regOff + (size_t)W * H + (size_t)j * O.bandPxCap;
   uint4* recs = reinterpret_cast<uint4*>(b.specRec + (size_t)f * g.specRecTotal + O.specRecOff + (size_t)j * O.bandRecCap);
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
-  const float4* __restrict__ rec = b.rec + pbase;
+  const float2* __restrict__ rec = b.cs + pbase;
+  const float* __restrict__ ang = b.ang + pbase;
   const float2* __restrict__ seedcs = b.seed + pbase;
   const int pxCap = O.bandPxCap, recCap = O.bandRecCap, minReg = O.minRegSize;
   const double prec = g.prec;
@@ -538,7 +542,7 @@ __global__ void __launch_bounds__(32) k_lsd_spec(const __grid_constant__ LineGeo
       size = 1;
       const int sp = row * W + sx;
       // consumed after the neighbourhood loads below have been issued
-      sangNew = __ldg(&rec[sp].x);
+      sangNew = __ldg(ang + sp);
       scsNew = __ldg(seedcs + sp);
       isNew = true;
     }
@@ -563,10 +567,10 @@ __global__ void __launch_bounds__(32) k_lsd_spec(const __grid_constant__ LineGeo
       const unsigned three = sh >= 0 ? ((unsigned)(comb >> sh) & 7u) : ((lo[r] << 1) & 7u);
       m9 |= three << (3 * r);
     }
-    float4 rk[9];
+    float2 rk[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) {
-      rk[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rk[k] = make_float2(0.f, 0.f);
       if (k != 4 && ((m9 >> k) & 1u)) rk[k] = __ldg(rec + (ey + k / 3 - 1) * W + (ex + k % 3 - 1));
     }
     if (isNew) {
@@ -579,12 +583,13 @@ __global__ void __launch_bounds__(32) k_lsd_spec(const __grid_constant__ LineGeo
 #pragma unroll
     for (int k = 0; k < 9; k++) {
       if (k == 4 || !((m9 >> k) & 1u)) continue;
-      const float dot = __fmaf_rn(sumdx, rk[k].y, sumdy * rk[k].z);
+      const float dot = __fmaf_rn(sumdx, rk[k].x, sumdy * rk[k].y);
       const float d2 = dot * dot;
       if (!(dot > 0.f && d2 > kLo * n2)) continue;
       if (!(d2 >= kHi * n2)) {
         const double regAngle = __dmul_rn((double)(fresh ? sang : fast_atan2_dev(sumdy, sumdx)), D2R);
-        if (!is_aligned_dev(__dmul_rn((double)rk[k].x, D2R), regAngle, prec)) continue;
+        const float la = __ldg(ang + (ey + k / 3 - 1) * W + (ex + k % 3 - 1));
+        if (!is_aligned_dev(__dmul_rn((double)la, D2R), regAngle, prec)) continue;
       }
       acc |= 1u << k;
       const unsigned q = (unsigned)(ex + k % 3 - 1) | ((unsigned)(ey + k / 3 - 1) << 16);
@@ -592,8 +597,8 @@ __global__ void __launch_bounds__(32) k_lsd_spec(const __grid_constant__ LineGeo
       sring[(size & (SPEC_RING - 1)) * 32 + lane] = q;
       size++;
       fresh = false;
-      sumdx = __fadd_rn(sumdx, rk[k].y);
-      sumdy = __fadd_rn(sumdy, rk[k].z);
+      sumdx = __fadd_rn(sumdx, rk[k].x);
+      sumdy = __fadd_rn(sumdy, rk[k].y);
       n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
     }
     if (acc) {
@@ -675,7 +680,8 @@ __global__ void __launch_bounds__(32) k_lsd_commit(const __grid_constant__ LineG
   for (int i = lane; i < min(GROW_K, H) * wpr; i += 32) { bm.sm[i] = __ldcg(bm.gm + i); ph.sm[i] = 0u; }
   __syncwarp();
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
-  const float4* __restrict__ rec = b.rec + pbase;
+  const float2* __restrict__ rec = b.cs + pbase;
+  const float* __restrict__ ang = b.ang + pbase;
   const float2* __restrict__ seedcs = b.seed + pbase;
   unsigned* regAll = b.reg + (size_t)f * g.regTotal + O.regOff;
   LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
@@ -796,7 +802,7 @@ __global__ void __launch_bounds__(32) k_lsd_commit(const __grid_constant__ LineG
         }
 
         const int sp = sy * W + sx;
-        const float sang = __ldg(&rec[sp].x);
+        const float sang = __ldg(ang + sp);
         const float2 scs = __ldg(seedcs + sp);
         unsigned* reg = regAll + regBase;          // pixel list of the region being grown
         if (lane == 0) {
@@ -819,7 +825,7 @@ __global__ void __launch_bounds__(32) k_lsd_commit(const __grid_constant__ LineG
           if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cb.bw, cb.bbit));
           float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
           while (pm) {
-            const float dot = __fmaf_rn(sumdx, cb.rec.y, sumdy * cb.rec.z);
+            const float dot = __fmaf_rn(sumdx, cb.rec.x, sumdy * cb.rec.y);
             const float d2 = dot * dot;
             const bool poss = (pm & laneBit) && dot > 0.f && d2 > kLo * n2;
             const unsigned possm = __ballot_sync(0xffffffffu, poss);
@@ -829,10 +835,11 @@ __global__ void __launch_bounds__(32) k_lsd_commit(const __grid_constant__ LineG
             pm &= ~((2u << l) - 1u);
             if (!((surem >> l) & 1u)) {
               const double regAngle = fresh ? seedAngle : __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
-              const float la = __shfl_sync(0xffffffffu, cb.rec.x, l);
+              const int lpk = __shfl_sync(0xffffffffu, cb.cpk, l);
+              const float la = __ldg(ang + (lpk >> 16) * W + (lpk & 0xffff));
               if (!is_aligned_dev(__dmul_rn((double)la, D2R), regAngle, prec)) continue;
             }
-            const float qc = __shfl_sync(0xffffffffu, cb.rec.y, l), qs = __shfl_sync(0xffffffffu, cb.rec.z, l);
+            const float qc = __shfl_sync(0xffffffffu, cb.rec.x, l), qs = __shfl_sync(0xffffffffu, cb.rec.y, l);
             const int qpk = __shfl_sync(0xffffffffu, cb.cpk, l);
             pm &= ~__ballot_sync(0xffffffffu, cb.cpk == qpk);
             if (lane == l) {

@@ -259,7 +259,8 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes + 256); };
   for (int o = 0; o < nlevels; o++) A((void**)&h->dImg[o], B * c.o[o].pitch * c.o[o].h);
   A((void**)&h->buf.rowf, B * c.rawTotal * sizeof(double));
-  A((void**)&h->buf.rec, B * c.pxTotal * sizeof(float4));
+  A((void**)&h->buf.ang, B * c.pxTotal * sizeof(float));
+  A((void**)&h->buf.cs, B * c.pxTotal * sizeof(float2));
   A((void**)&h->buf.seed, B * c.pxTotal * sizeof(float2));
   A((void**)&h->buf.mod, B * c.pxTotal * sizeof(double));
   A((void**)&h->buf.bitmap, B * c.bmTotal * sizeof(unsigned));
@@ -326,7 +327,7 @@ void plvi_line_destroy(plvi_line* h) {
   if (h->aux.fork) cudaEventDestroy(h->aux.fork);
   if (h->aux.join) cudaEventDestroy(h->aux.join);
   cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
-  cudaFree(h->buf.rowf); cudaFree(h->buf.rec); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
+  cudaFree(h->buf.rowf); cudaFree(h->buf.ang); cudaFree(h->buf.cs); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
   cudaFree(h->buf.specBm); cudaFree(h->buf.specRec); cudaFree(h->buf.specCnt); cudaFree(h->buf.phantom);
   cudaFree(h->buf.reg); cudaFree(h->buf.regTab); cudaFree(h->buf.regCount); cudaFree(h->buf.segs);
   cudaFree(h->buf.tmpResp); cudaFree(h->buf.tmpCls); cudaFree(h->buf.lbdImg0); cudaFree(h->buf.lbdImg1);
@@ -468,7 +469,7 @@ int plvi_line_read_lsd(plvi_line* h, int frame, int octave, int what, void* out,
       PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.scaledDbg + pb, npx * sizeof(double), cudaMemcpyDeviceToHost));
       break;
     case 1:
-      PLVI_CUDA_TRY(cudaMemcpy2D(out, sizeof(float), h->buf.rec + pb, sizeof(float4), sizeof(float), npx, cudaMemcpyDeviceToHost));
+      PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.ang + pb, npx * sizeof(float), cudaMemcpyDeviceToHost));
       break;
     case 2: PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.mod + pb, npx * sizeof(double), cudaMemcpyDeviceToHost)); break;
     case 3: {
