@@ -155,6 +155,9 @@ def main():
     ap.add_argument("--profile-out", default="")
     ap.add_argument("--no-overlap", action="store_true", help="run the line pipeline on the same stream as ORB")
     ap.add_argument("--line-priority", type=int, default=0)
+    ap.add_argument("--pipe-mode", choices=("slice", "alternate"), default=os.environ.get("PLVI_BENCH_PIPE_MODE", "alternate"),
+                    help="alternate: whole batches go to the pipelines in turn (consecutive batches in flight at "
+                         "different phases); slice: every batch is split across the pipelines")
     ap.add_argument("--pipes", type=int, default=int(os.environ.get("PLVI_BENCH_PIPES", 1)),
                     help="independent pipelines the batch is split over (overlap across slices)")
     args = ap.parse_args()
@@ -216,7 +219,7 @@ def main():
     B = args.batch
     frames = synth.frame_batch(B, W, H, base_seed=1000 * rank, distinct=16)
     h_frames = torch.from_numpy(frames).pin_memory()
-    fe = PipelinedFrontEnd(B, pipes=args.pipes, device=local_rank, w=W, h=H, with_lines=not args.orb_only,
+    fe = PipelinedFrontEnd(B, pipes=args.pipes, mode=args.pipe_mode, device=local_rank, w=W, h=H, with_lines=not args.orb_only,
                            with_match=not args.orb_only, overlap_lines=not args.no_overlap,
                            line_priority=args.line_priority)
     st = fe.stream
@@ -234,6 +237,7 @@ def main():
     with torch.cuda.stream(st):
         for _ in range(args.warmup):
             fe.step(d_frames)
+        fe.drain()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -244,6 +248,7 @@ def main():
         e0.record(st)
         for _ in range(args.steps):
             launches += fe.step(d_frames)
+        fe.drain()
         e1.record(st)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -252,14 +257,17 @@ def main():
     # ---- end to end: pinned host frames in, every result back on the host.  Copies run on their own
     # streams: the H2D of step i+1 overlaps the compute of step i (two input buffers); the D2H of step
     # i must finish before step i+1 overwrites the output buffers.
+    alt = args.pipe_mode == "alternate"
+    npipe = args.pipes if alt else 1           # steps whose outputs are alive at the same time
     outs = fe.outputs()
     h_out = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()} for o in outs]
-    d_in = [torch.empty_like(d_frames), torch.empty_like(d_frames)]
+    nbuf = npipe + 1
+    d_in = [torch.empty_like(d_frames) for _ in range(nbuf)]
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
     def e2e_run(nsteps):
         ev_h2d = [torch.cuda.Event() for _ in range(nsteps)]
-        ev_cmp = [torch.cuda.Event() for _ in range(nsteps)]
+        ev_cmp = [None] * nsteps
         ev_d2h = [torch.cuda.Event() for _ in range(nsteps)]
         start = torch.cuda.Event(enable_timing=True)
         stop = torch.cuda.Event(enable_timing=True)
@@ -268,16 +276,24 @@ def main():
         s_out.wait_event(start)
         for i in range(nsteps):
             with torch.cuda.stream(s_in):
-                if i >= 2:
-                    s_in.wait_event(ev_cmp[i - 2])          # input buffer i%2 was read by step i-2
-                d_in[i % 2].copy_(h_frames, non_blocking=True)
+                if i >= nbuf:
+                    s_in.wait_event(ev_cmp[i - nbuf])       # input buffer i % nbuf was read by step i - nbuf
+                d_in[i % nbuf].copy_(h_frames, non_blocking=True)
                 ev_h2d[i].record(s_in)
             with torch.cuda.stream(st):
-                st.wait_event(ev_h2d[i])
-                if i >= 1:
-                    st.wait_event(ev_d2h[i - 1])            # outputs of step i-1 are on the host
-                fe.step(d_in[i % 2])
-                ev_cmp[i].record(st)
+                # step i overwrites the output buffers of step i - npipe: those must be on the host
+                waits = [ev_h2d[i]] + ([ev_d2h[i - npipe]] if i >= npipe else [])
+                fe.step(d_in[i % nbuf], wait=waits)
+                ev = fe.done_event()
+                if ev is None:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                else:                                       # the event object is reused by step i + npipe
+                    own = torch.cuda.Event()
+                    s_out.wait_event(ev)
+                    own.record(s_out)
+                    ev = own
+                ev_cmp[i] = ev
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp[i])
                 for o, ho in zip(fe.outputs(), h_out):
@@ -285,6 +301,7 @@ def main():
                         ho[k].copy_(v, non_blocking=True)
                 ev_d2h[i].record(s_out)
         st.wait_event(ev_d2h[nsteps - 1])
+        fe.drain()
         stop.record(st)
         return start, stop
 
@@ -337,7 +354,7 @@ def main():
             "config": {"workload": WORKLOAD if not args.orb_only else "DIAGNOSTIC orb-only", "frames_per_step_per_gpu": B,
                        "width": W, "height": H, "l2_policy": "inputs larger than L2 (%.0f MB of frames per step)" % (B * W * H / 1e6),
                        "parallelism": f"frame-sharded x{world}, no collective", "mean_keypoints": counts,
-                       "pipelines_per_gpu": args.pipes},
+                       "pipelines_per_gpu": args.pipes, "pipeline_mode": args.pipe_mode},
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

@@ -228,6 +228,7 @@ __device__ __forceinline__ bool is_aligned_dev(double a, double theta, double pr
   return n <= prec;
 }
 
+#define GROW_WPB 4    // independent warps per block in k_lsd_spec / k_lsd_commit
 #define GROW_RQ 512   // shared ring holding the most recent region pixels (BFS frontier)
 #define GROW_K 32     // bitmap rows kept in shared memory (sliding window below the seed row)
 
@@ -482,9 +483,9 @@ __global__ void __launch_bounds__(256) k_lsd_spec_init(const __grid_constant__ L
 // frames (similar content => similar amount of work).  Single flat loop: every iteration
 // expands one queue entry of the lane's current region, so lanes with regions of different
 // sizes stay converged.  Same tests, in the same order, as k_lsd_grow.
-__global__ void __launch_bounds__(32) k_lsd_spec(const __grid_constant__ LineGeom g, LineBufs b, int n) {
+__global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constant__ LineGeom g, LineBufs b, int n) {
   const int t = blockIdx.x;
-  const int f = blockIdx.y * 32 + threadIdx.x;
+  const int f = blockIdx.y * (32 * GROW_WPB) + threadIdx.x;
   const int oct = (g.noct > 1 && t >= g.o[1].taskOff) ? 1 : 0;
   const LineOct& O = g.o[oct];
   const int j = t - O.taskOff;
@@ -502,8 +503,9 @@ __global__ void __launch_bounds__(32) k_lsd_spec(const __grid_constant__ LineGeo
   const double prec = g.prec;
   const float kHi = g.alignHi2, kLo = g.alignLo2;
 
-  __shared__ unsigned sring[SPEC_RING * 32];   // the last SPEC_RING pixels of each lane's region (BFS frontier)
-  const int lane = threadIdx.x;
+  __shared__ unsigned sring_all[GROW_WPB][SPEC_RING * 32];   // the last SPEC_RING pixels of each lane's region (BFS frontier)
+  unsigned* sring = sring_all[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
   int row = r0, wi = 0;
   unsigned word = (r0 < r1) ? P[r0 * wpr] : 0u;
   int nrec = 0, npx = 0, base = 0, size = 0, i = 0;
@@ -661,10 +663,14 @@ __device__ __forceinline__ void grow_clear_atomic(GrowBitmap& bm, int x, int y) 
   else atomicAnd(bm.gm + y * bm.wpr + (x >> 5), m);
 }
 
-__global__ void __launch_bounds__(32) k_lsd_commit(const __grid_constant__ LineGeom g, LineBufs b) {
-  extern __shared__ unsigned smem_u[];
-  const int oct = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
-  if (oct >= g.noct) return;
+__global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_commit(const __grid_constant__ LineGeom g, LineBufs b, int n,
+                                                              int smemWordsPerWarp) {
+  // GROW_WPB independent warps per block (consecutive frames of one octave): single-warp blocks
+  // would fill the SM's 32 block slots and keep the kernels of the other streams out
+  extern __shared__ unsigned smem_all[];
+  unsigned* smem_u = smem_all + (threadIdx.x >> 5) * smemWordsPerWarp;
+  const int oct = blockIdx.x, f = blockIdx.y * GROW_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (oct >= g.noct || f >= n) return;
   const LineOct& O = g.o[oct];
   const int W = O.sw, H = O.sh, wpr = O.wpr;
   unsigned* ring = smem_u;
@@ -1426,9 +1432,11 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   if (b.useSpec) {
     k_lsd_spec_init<<<dim3(8, g.tasksPerFrame, n), 256, 0, st>>>(g, b);
     prof->mark("k_lsd_spec_init", st);
-    k_lsd_spec<<<dim3(g.tasksPerFrame, (n + 31) / 32), 32, 0, st>>>(g, b, n);
+    k_lsd_spec<<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
     prof->mark("k_lsd_spec", st);
-    k_lsd_commit<<<dim3(g.noct, n), 32, growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned), st>>>(g, b);
+    const size_t commitSmem = growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned);
+    k_lsd_commit<<<dim3(g.noct, (n + GROW_WPB - 1) / GROW_WPB), 32 * GROW_WPB, commitSmem * GROW_WPB, st>>>(
+        g, b, n, (int)(commitSmem / sizeof(unsigned)));
     prof->mark("k_lsd_commit", st);
     nl += 2;
   } else {
@@ -1453,11 +1461,11 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
 
 int line_kernel_attrs(const LineGeom& g) {
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
-  if (growSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
-  if (growSmem > 24 * 1024) {
-    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)growSmem));
-    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned))));
+  const size_t commitSmem = (growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned)) * GROW_WPB;
+  if (commitSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
+  if (commitSmem > 40 * 1024) {
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
   }
   return PLVI_OK;
 }

@@ -129,7 +129,8 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
     O.segCap = std::min((O.sw * O.sh) / std::max(O.minRegSize, 1), std::max(1024, 8192 >> (2 * o)));
     seg += O.segCap;
     {  // speculation bands: equal pixel counts per band across octaves (16 bands on octave 0, 4 on octave 1)
-      const int nbT = std::max(1, 16 >> (2 * o));
+      static const int nb0 = [] { const char* ev = getenv("PLVI_LSD_BANDS"); return ev ? std::max(1, atoi(ev)) : 16; }();
+      const int nbT = std::max(1, nb0 >> (2 * o));
       O.bandRows = (O.sh + nbT - 1) / nbT;
       O.nbands = (O.sh + O.bandRows - 1) / O.bandRows;
       O.bandPxCap = 2 * O.bandRows * O.sw;

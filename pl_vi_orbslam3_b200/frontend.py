@@ -155,31 +155,64 @@ class FrontEnd:
 
 
 class PipelinedFrontEnd:
-    """`pipes` independent FrontEnd pipelines (own handles, streams and scratch), each taking a
-    contiguous slice of the batch.  Their work is enqueued back to back on different streams, so the
-    latency-bound LSD region growing of one slice overlaps the throughput-bound kernels of the other
-    (frames are independent; frame-to-frame matching stays inside a slice)."""
+    """`pipes` independent FrontEnd pipelines (own handles, streams and scratch).
 
-    def __init__(self, batch, pipes=2, device=0, **kw):
+    mode="slice": every step is split into `pipes` contiguous slices of the batch that run side
+    by side (frame-to-frame matching stays inside a slice).
+    mode="alternate": whole batches go to the pipelines in turn (step i -> pipeline i % pipes)
+    with no join in between, so consecutive batches are in flight at different phases: the
+    latency-bound LSD region growing of one batch (two long serial chains per frame, the GPU's
+    issue slots mostly idle) overlaps the throughput-bound kernels of the next.  The outputs of
+    step i stay valid until step i + pipes; `done_event()` is the completion of the last step."""
+
+    def __init__(self, batch, pipes=2, device=0, mode="slice", **kw):
         import torch
         self.torch = torch
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.Stream(device=self.device)      # master stream: fork / join point
-        self.sizes = [shard_range(batch, i, pipes)[1] - shard_range(batch, i, pipes)[0] for i in range(pipes)]
-        self.offsets = [shard_range(batch, i, pipes)[0] for i in range(pipes)]
+        self.mode = mode
+        self.pipes = pipes
+        if mode == "alternate":
+            self.sizes = [batch] * pipes
+            self.offsets = [0] * pipes
+        else:
+            self.sizes = [shard_range(batch, i, pipes)[1] - shard_range(batch, i, pipes)[0] for i in range(pipes)]
+            self.offsets = [shard_range(batch, i, pipes)[0] for i in range(pipes)]
         self.fes = [FrontEnd(sz, device=device, **kw) for sz in self.sizes]
         self._fork = torch.cuda.Event()
         self._joins = [torch.cuda.Event() for _ in self.fes]
+        self._k = 0          # steps issued (alternate mode)
+        self._last = None    # pipeline of the last step
         self.B = batch
 
     def close(self):
         for fe in self.fes:
             fe.close()
 
-    def step(self, d_frames, serialize=False):
+    def step(self, d_frames, serialize=False, wait=()):
+        """Enqueue one step.  slice mode: forked from / joined into self.stream.  alternate mode:
+        runs on the next pipeline's own stream after the events in `wait` and whatever self.stream
+        held when the step was issued; nothing is joined back (see done_event / drain)."""
         nl = 0
+        if self.mode != "alternate":
+            for w in wait:
+                self.stream.wait_event(w)
         self._fork.record(self.stream)
+        if self.mode == "alternate":
+            idx = self._k % self.pipes
+            self._k += 1
+            fe, ev = self.fes[idx], self._joins[idx]
+            fe.stream.wait_event(self._fork)
+            for w in wait:
+                fe.stream.wait_event(w)
+            with self.torch.cuda.stream(fe.stream):
+                nl = fe.step(d_frames, serialize=serialize)
+            ev.record(fe.stream)
+            self._last = idx
+            if serialize:
+                self.stream.wait_event(ev)
+            return nl
         for fe, off, sz, ev in zip(self.fes, self.offsets, self.sizes, self._joins):
             fe.stream.wait_event(self._fork)
             with self.torch.cuda.stream(fe.stream):
@@ -192,7 +225,22 @@ class PipelinedFrontEnd:
             self.stream.wait_event(ev)
         return nl
 
+    def done_event(self):
+        """Completion event of the last issued step (alternate mode); None in slice mode, where
+        the step is already joined into self.stream."""
+        return self._joins[self._last] if self.mode == "alternate" and self._last is not None else None
+
+    def drain(self):
+        """Make self.stream wait for every step issued so far."""
+        if self.mode == "alternate":
+            for i, ev in enumerate(self._joins):
+                if self._k > i:
+                    self.stream.wait_event(ev)
+
     def outputs(self):
+        """slice mode: list of per-slice output dicts.  alternate mode: [outputs of the last issued step]."""
+        if self.mode == "alternate":
+            return [self.fes[self._last or 0].outputs()]
         return [fe.outputs() for fe in self.fes]
 
     def set_profile(self, on=True):
@@ -200,8 +248,9 @@ class PipelinedFrontEnd:
             fe.set_profile(on)
 
     def profile(self):
+        """{kernel: ms} of the last step."""
         prof = {}
-        for fe in self.fes:
+        for fe in ([self.fes[self._last or 0]] if self.mode == "alternate" else self.fes):
             for k, v in fe.profile().items():
                 prof[k] = prof.get(k, 0.0) + v
         return prof
