@@ -42,7 +42,16 @@ ALGO_BYTES = {
     "k_orient_desc": 1021 * (709 + 512 + 60),
     "k_lsd_rowfilter": P_RAW * (1 + 8),
     "k_lsd_scale_grad": P_RAW * 8 + P_LSD * (4 + 16 + 8) + P_LSD // 8,
-    "k_lsd_grow": P_LSD * 4 + (P_LSD // 2) * (16 + 4) + P_LSD // 8,
+    "k_lsd_grow": P_LSD * 4 + (P_LSD // 2) * (8 + 4) + P_LSD // 8,
+    # band speculation: private bitmap copies (rows below each band's first row: 8.5x / 2.5x the octave bitmaps)
+    # + the zeroed phantom bitmap
+    "k_lsd_spec_init": (P_LSD // 8) * 2 + 267000,
+    # every defined pixel's cos/sin once (8 B) + its list entry (4 B), seeds: angle + f64-derived cos/sin (12 B) and a
+    # 16 B record each (~16k regions per frame), the touched part of the private bitmaps read and written once
+    "k_lsd_spec": (P_LSD // 2) * (8 + 4) + 16000 * (12 + 16) + 2 * (P_LSD // 8),
+    # records + pixel lists of the speculative regions, the availability bitmap read and written once, the ~12 % of
+    # the pixels that are re-grown serially (cos/sin + list entry) and the region table
+    "k_lsd_commit": 16000 * 16 + (P_LSD // 2) * 4 + 2 * (P_LSD // 8) + (P_LSD // 16) * (8 + 4) + 2600 * 16,
     "k_lsd_rect": (P_LSD // 2) * (4 + 8) + 2600 * 32,
     "k_line_assemble": 2600 * 16 + 200 * 68,
     "k_gauss5": 2 * 752 * 480,
@@ -53,6 +62,11 @@ ALGO_BYTES = {
     "k_search(+queries)": 2 * 1021 * (28 + 32) + 1021 * 28 + 1021 * 8,
     "k_line_match": 2 * 200 * 32 + 200 * 4,
 }
+
+
+GROW_NOTE = ("LSD region growing is a serial dependency chain per band (k_lsd_spec) / per frame and octave (k_lsd_commit): "
+             "bound by instruction latency along the chain, not by HBM (ncu: IPC 0.6-1.7, DRAM throughput < 10 %); "
+             "see DESIGN.md section 4 and profiles/r01_k_lsd_spec.md")
 
 
 def _cpu_pair_job(idx_frames):
@@ -148,7 +162,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLVI_BENCH_BATCH", 2048)))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLVI_BENCH_BATCH", 4096)))
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU baseline sample (0 = 4 per core)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--orb-only", action="store_true", help="diagnostic: time ORB extraction alone (not the bench metric)")
@@ -344,8 +358,7 @@ def main():
             roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "algorithmic_bytes_per_launch": ALGO_BYTES.get(top, 0) * B, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                     "kernel_ms_per_launch": prof[top], "frames_per_launch": B,
-                    "note": ("serial region growing: issue/latency bound (ncu: 68% issue-active, 2.2% DRAM throughput), "
-                             "see DESIGN.md section 4 and profiles/r01_k_lsd_grow.md") if top == "k_lsd_grow" else ""}
+                    "note": GROW_NOTE if top in ("k_lsd_grow", "k_lsd_spec", "k_lsd_commit") else ""}
         total_prof = sum(prof.values()) or 1.0
         line = {
             "metric": "frames/s", "value": world * B * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
