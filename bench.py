@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("PLVI_BENCH_BATCH", 4096)))
-    ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU baseline sample (0 = 4 per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU baseline sample (0 = 32 per core: 10-30 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--orb-only", action="store_true", help="diagnostic: time ORB extraction alone (not the bench metric)")
     ap.add_argument("--profile-out", default="")
@@ -190,7 +190,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        per_step = args.cpu_sample or min(4 * cores, 256)
+        per_step = args.cpu_sample or min(32 * cores, 1024)
         frames = synth.frame_batch(per_step, W, H, base_seed=0, distinct=16)
         for _ in range(max(args.warmup, 0)):
             cpu_arm(frames[: max(cores, 2)], cores)
@@ -216,7 +216,7 @@ def main():
     # ------------------------------------------------------------------ CUDA arm
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        nsamp = args.cpu_sample or min(4 * cores, 128)
+        nsamp = args.cpu_sample or min(32 * cores, 1024)
         fps, dt = cpu_arm(synth.frame_batch(nsamp, W, H, base_seed=0, distinct=16), cores)
         cpu_base = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                     "sample": f"{nsamp} synthetic 752x480 frames (same generator), contiguous shards over {cores} worker "

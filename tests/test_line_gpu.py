@@ -92,6 +92,46 @@ def test_line_noise_image(ext):
     _check_lines(kl, desc, eq, oracle.line_extract(img))
 
 
+def _stress_images():
+    """Images that push the band speculation of the region growing to its limits."""
+    h, w = 480, 752
+    xx, yy = np.meshgrid(np.arange(w), np.arange(h))
+    rng = np.random.RandomState(11)
+    saw = ((xx * 7 + yy * 3) % 256).astype(np.uint8)                      # one gradient direction everywhere: giant
+    stripes = (((xx // 9) % 2) * 170 + 30).astype(np.uint8)               # regions crossing every band (list overflow)
+    diag = ((((xx + yy) // 11) % 2) * 150 + 40 + rng.randint(0, 8, (h, w))).astype(np.uint8)
+    mixed = synth.frame_euroc(3).copy()
+    mixed[:200] = rng.randint(0, 256, (200, w))                           # > 4096 tiny regions per band (record overflow)
+    blobs = np.zeros((h, w), np.float32)
+    for _ in range(60):
+        cx, cy, r = rng.randint(0, w), rng.randint(0, h), rng.randint(10, 80)
+        blobs += 90.0 * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2.0 * r * r))
+    blobs = np.clip(blobs, 0, 255).astype(np.uint8)                       # curved level lines: regions end by angle drift
+    return {"saw": saw, "stripes": stripes, "diag": diag, "mixed": mixed, "blobs": blobs}
+
+
+def test_lsd_speculation_stress(ext):
+    """Raw LSD segments (the output of seed scan + region growing + rectangle fit) stay exact when
+    speculative regions overflow their lists, collide across bands or are discarded in bulk; the
+    images run as one batch so the lanes of a warp follow very different paths."""
+    imgs = _stress_images()
+    names = sorted(imgs)
+    batch = np.stack([imgs[n] for n in names[:4]])
+    kl, desc, eq, counts = ext.extract_batch(batch)
+    ow, oh, sw, sh = ext.octave_sizes(752, 480)
+    for i, n in enumerate(names[:4]):
+        oct1 = oracle.resize_linear(imgs[n], int(ow[1]), int(oh[1]))
+        for o, im in enumerate((imgs[n], oct1)):
+            segs, _ = oracle.lsd(im, 0.8, debug=True)
+            got = ext.read_lsd(i, o, "segments", 752, 480)
+            assert len(got) == len(segs), (n, o, len(got), len(segs))
+            if len(segs):
+                assert np.array_equal(got, segs.astype(np.float32)) or np.abs(got - segs).max() <= 1e-4, (n, o)
+        _check_lines(kl[i, :counts[i]], desc[i, :counts[i]], eq[i, :counts[i]], oracle.line_extract(imgs[n]))
+    k1, d1, e1 = ext(imgs[names[4]])
+    _check_lines(k1, d1, e1, oracle.line_extract(imgs[names[4]]))
+
+
 def test_line_rejects_unsupported_configs(gpu):
     from pl_vi_orbslam3_b200.capi import PlviError
     for args in ((200, 1, 0.8, 2, 2.0, 0), (200, 0, 0.8, 2, 2.0, 1), (200, 0, 0.8, 3, 2.0, 0)):
