@@ -176,7 +176,8 @@ int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, i
 /* Read-back of LSD internals of the last batch (parity tests).  what: 0 scaled f64 image
  * (after plvi_line_set_debug(h,1)), 1 level-line angle in degrees f32 (-1024 = NOTDEF),
  * 2 gradient magnitude f64, 3 raw segments (x1,y1,x2,y2 f32; *count = number),
- * 4 pyramid octave image u8 (gaussianPyrs[octave]). */
+ * 4 pyramid octave image u8 (gaussianPyrs[octave]), 5 LBD octave image u8 (w>>octave x h>>octave;
+ * binary_descriptor_custom.cpp:351-371), 6 its Sobel gradients s16 {dx, dy} per pixel (:374-399). */
 int plvi_line_set_debug(plvi_line* h, int on);
 int plvi_line_set_profile(plvi_line* h, int on);
 const char* plvi_line_profile(plvi_line* h);

@@ -1132,62 +1132,118 @@ __global__ void __launch_bounds__(NT) k_line_assemble(const __grid_constant__ Li
 // ---------------------------------------------------------------------------------------
 // LBD preprocessing
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gauss5(const u8* __restrict__ src, int spitch, size_t sfs, u8* __restrict__ dst,
-                                                int dpitch, size_t dfs, int w, int h) {
-  __shared__ __align__(16) u8 sin_[(32 + 4) * (128 + 8)];
-  __shared__ __align__(16) unsigned short sh_[(32 + 4) * 128];
-  const int tid = threadIdx.x, x0 = blockIdx.x * 128, y0 = blockIdx.y * 32;
-  const u8* s = src + (size_t)blockIdx.z * sfs;
-  const int SP = 136;
-  for (int i = tid; i < 36 * 132; i += 256) {
-    const int r = i / 132, c = i - r * 132;
-    const int gy = reflect101_l(min(y0 + r - 2, h + 1), h), gx = reflect101_l(min(x0 + c - 2, w + 1), w);
-    sin_[r * SP + c] = __ldg(s + (size_t)gy * spitch + gx);
-  }
-  __syncthreads();
-  for (int i = tid; i < 36 * 32; i += 256) {
-    const int r = i >> 5, c4 = (i & 31) * 4;
-    const u8* q = sin_ + r * SP + c4;
-    int v[8];
+// Loads a (rows x 34 words) u8 tile whose first byte is global column gx0 (a multiple of 4) of
+// rows gy0 .. gy0+rows-1, BORDER_REFLECT_101 outside the image.  sm pitch = 34 words.
+__device__ __forceinline__ void load_tile34(const u8* __restrict__ s, int spitch, int w, int h, int gx0, int gy0,
+                                            int rows, uint32_t* sm, int tid) {
+  const bool aligned4 = ((spitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(s) & 3) == 0);
+  for (int i = tid; i < rows * 34; i += 256) {
+    const int r = i / 34, wq = i - r * 34;
+    const int gy = reflect101_l(min(gy0 + r, h + 1), h);
+    const int gx = gx0 + 4 * wq;
+    const u8* row = s + (size_t)gy * spitch;
+    uint32_t v;
+    if (aligned4 && gx >= 0 && gx + 3 < w) {
+      v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+    } else {
+      v = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = q[k];
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      sh_[r * 128 + c4 + k] = (unsigned short)(14 * (v[k] + v[k + 4]) + 62 * (v[k + 1] + v[k + 3]) + 104 * v[k + 2]);
-  }
-  __syncthreads();
-  u8* d = dst + (size_t)blockIdx.z * dfs;
-  for (int i = tid; i < 32 * 32; i += 256) {
-    const int r = i >> 5, c4 = (i & 31) * 4;
-    const int gy = y0 + r, gx = x0 + c4;
-    if (gy >= h || gx >= w) continue;
-    uint32_t out = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const unsigned short* q = sh_ + r * 128 + c4 + k;
-      const uint32_t sv = 14u * (q[0] + q[4 * 128]) + 62u * (q[128] + q[3 * 128]) + 104u * q[2 * 128];
-      out |= ((sv + 32768u) >> 16) << (8 * k);
+      for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(row + reflect101_l(min(gx + k, w + 1), w)) << (8 * k);
     }
-    *reinterpret_cast<uint32_t*>(d + (size_t)gy * dpitch + gx) = out;
+    sm[i] = v;
   }
 }
 
+// k_gauss5: GaussianBlur(5x5, sigma 1) in OpenCV's 8.8 fixed point: kernel [14,62,104,62,14]/256 in
+// both directions, no intermediate rounding, (v + 32768) >> 16.  All integer, so the passes commute:
+// the vertical pass runs first on two 16-bit lanes per register (a column sum is <= 255 * 256), the
+// horizontal pass combines the lane pairs with dp2a.  Tile = 128 x 32 output pixels.
+__global__ void __launch_bounds__(256) k_gauss5(const u8* __restrict__ src, int spitch, size_t sfs, u8* __restrict__ dst,
+                                                int dpitch, size_t dfs, int w, int h) {
+  __shared__ __align__(16) uint32_t sin_[36 * 34];      // input rows y0-2 .. y0+33, bytes x0-4 .. x0+131
+  __shared__ __align__(16) uint2 sv_[32 * 34];          // column sums: .x = even bytes of the word, .y = odd bytes
+  const int tid = threadIdx.x, x0 = blockIdx.x * 128, y0 = blockIdx.y * 32;
+  load_tile34(src + (size_t)blockIdx.z * sfs, spitch, w, h, x0 - 4, y0 - 2, 36, sin_, tid);
+  __syncthreads();
+  for (int i = tid; i < 32 * 34; i += 256) {
+    const int r = i / 34, wq = i - r * 34;
+    const uint32_t* q = sin_ + r * 34 + wq;
+    const uint32_t w0 = q[0], w1 = q[34], w2 = q[68], w3 = q[102], w4 = q[136];
+    const uint32_t M = 0x00ff00ffu;
+    const uint32_t e = 14u * ((w0 & M) + (w4 & M)) + 62u * ((w1 & M) + (w3 & M)) + 104u * (w2 & M);
+    const uint32_t o = 14u * (((w0 >> 8) & M) + ((w4 >> 8) & M)) + 62u * (((w1 >> 8) & M) + ((w3 >> 8) & M)) +
+                       104u * ((w2 >> 8) & M);
+    sv_[i] = make_uint2(e, o);
+  }
+  __syncthreads();
+  u8* d = dst + (size_t)blockIdx.z * dfs;
+  // weights as dp2a operand bytes (b0 multiplies the low 16-bit lane, b1 the high one)
+  const uint32_t K_0_14 = 14u << 8, K_0_62 = 62u << 8, K_104_14 = 104u | (14u << 8), K_62_0 = 62u, K_62_62 = 62u | (62u << 8),
+                 K_14_104 = 14u | (104u << 8), K_14_0 = 14u;
+  for (int i = tid; i < 32 * 32; i += 256) {
+    const int r = i >> 5, j = (i & 31) + 1;             // tile word j holds output columns x0 + 4(j-1) ..
+    const int gy = y0 + r, gx = x0 + 4 * (j - 1);
+    if (gy >= h || gx >= w) continue;
+    const uint2 A = sv_[r * 34 + j - 1], B = sv_[r * 34 + j], Cn = sv_[r * 34 + j + 1];
+    // V[4j-2] = A.x.hi, V[4j-1] = A.y.hi, V[4j] = B.x.lo, V[4j+1] = B.y.lo, V[4j+2] = B.x.hi, V[4j+3] = B.y.hi,
+    // V[4j+4] = Cn.x.lo, V[4j+5] = Cn.y.lo
+    const uint32_t o0 = __dp2a_lo(A.x, K_0_14, __dp2a_lo(A.y, K_0_62, __dp2a_lo(B.x, K_104_14, __dp2a_lo(B.y, K_62_0, 32768u))));
+    const uint32_t o1 = __dp2a_lo(A.y, K_0_14, __dp2a_lo(B.x, K_62_62, __dp2a_lo(B.y, K_104_14, 32768u)));
+    const uint32_t o2 = __dp2a_lo(B.x, K_14_104, __dp2a_lo(B.y, K_62_62, __dp2a_lo(Cn.x, K_14_0, 32768u)));
+    const uint32_t o3 = __dp2a_lo(B.y, K_14_104, __dp2a_lo(B.x, K_0_62, __dp2a_lo(Cn.x, K_62_0, __dp2a_lo(Cn.y, K_14_0, 32768u))));
+    const uint32_t out = (o0 >> 16) | ((o1 >> 16) << 8) | ((o2 >> 16) << 16) | ((o3 >> 16) << 24);
+    u8* dp = d + (size_t)gy * dpitch + gx;
+    if (gx + 3 < w) {
+      *reinterpret_cast<uint32_t*>(dp) = out;
+    } else {
+      for (int k = 0; gx + k < w; k++) dp[k] = (u8)(out >> (8 * k));
+    }
+  }
+}
+
+// k_pyrdown: cv::pyrDown ([1,4,6,4,1]^2, (v + 128) >> 8, BORDER_REFLECT_101).  Tile = 64 x 16 output
+// pixels; horizontal pass with dp4a into 16-bit sums (<= 4080), vertical pass on two lanes per
+// register (<= 65408, no carry between the lanes).
 __global__ void __launch_bounds__(256) k_pyrdown(const u8* __restrict__ src, int spitch, size_t sfs, int w, int h,
                                                  u8* __restrict__ dst, int dpitch, size_t dfs, int dw, int dh) {
-  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (x >= dw || y >= dh) return;
-  const u8* s = src + (size_t)blockIdx.z * sfs;
-  const int k[5] = {1, 4, 6, 4, 1};
-  int acc = 0;
-#pragma unroll
-  for (int j = 0; j < 5; j++) {
-    const u8* row = s + (size_t)reflect101_l(2 * y + j - 2, h) * spitch;
-    int rs = 0;
-#pragma unroll
-    for (int i = 0; i < 5; i++) rs += k[i] * __ldg(row + reflect101_l(2 * x + i - 2, w));
-    acc += k[j] * rs;
+  __shared__ __align__(16) uint32_t sin_[36 * 34];      // source rows 2*Y0-2 .. 2*Y0+33, bytes 2*X0-4 .. 2*X0+131
+  __shared__ __align__(16) uint32_t sh_[36 * 32];       // horizontal sums, two 16-bit values per word
+  const int tid = threadIdx.x, X0 = blockIdx.x * 64, Y0 = blockIdx.y * 16;
+  load_tile34(src + (size_t)blockIdx.z * sfs, spitch, w, h, 2 * X0 - 4, 2 * Y0 - 2, 36, sin_, tid);
+  __syncthreads();
+  const uint32_t K = 1u | (4u << 8) | (6u << 16) | (4u << 24);
+  for (int i = tid; i < 36 * 16; i += 256) {
+    const int r = i >> 4, q = i & 15;                   // outputs X0 + 4q .. 4q+3 of source row r
+    const uint32_t* p = sin_ + r * 34 + 2 * q;          // tile bytes 8q .. 8q+15; output j uses bytes 8q+2+2j .. +4
+    const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+    const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 16), K, (w1 >> 16) & 0xffu);
+    const uint32_t h1 = __dp4a(w1, K, w2 & 0xffu);
+    const uint32_t h2 = __dp4a(__funnelshift_r(w1, w2, 16), K, (w2 >> 16) & 0xffu);
+    const uint32_t h3 = __dp4a(w2, K, w3 & 0xffu);
+    *reinterpret_cast<uint2*>(sh_ + r * 32 + 2 * q) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
   }
-  dst[(size_t)blockIdx.z * dfs + (size_t)y * dpitch + x] = (u8)((acc + 128) >> 8);
+  __syncthreads();
+  u8* d = dst + (size_t)blockIdx.z * dfs;
+  {
+    const int Y = tid >> 4, q = tid & 15;               // 16 rows x 16 groups of 4 outputs
+    const int gy = Y0 + Y, gx = X0 + 4 * q;
+    if (gy < dh && gx < dw) {
+      const uint32_t* p = sh_ + (2 * Y) * 32 + 2 * q;
+      uint32_t acc[2];
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const uint32_t v0 = p[k], v1 = p[32 + k], v2 = p[64 + k], v3 = p[96 + k], v4 = p[128 + k];
+        acc[k] = ((v0 + v4 + 4u * (v1 + v3) + 6u * v2 + 0x00800080u) >> 8) & 0x00ff00ffu;
+      }
+      const uint32_t out = (acc[0] & 0xffu) | ((acc[0] >> 8) & 0xff00u) | ((acc[1] & 0xffu) << 16) | ((acc[1] >> 16) << 24);
+      u8* dp = d + (size_t)gy * dpitch + gx;
+      if (gx + 3 < dw) {
+        *reinterpret_cast<uint32_t*>(dp) = out;
+      } else {
+        for (int k = 0; gx + k < dw; k++) dp[k] = (u8)(out >> (8 * k));
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) k_sobel(const u8* __restrict__ src, int spitch, size_t sfs, int w, int h,
@@ -1417,7 +1473,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     nl += 2;
     if (g.noct > 1) {
       const LineOct& O1 = g.o[1];
-      k_pyrdown<<<dim3((O1.lw + 63) / 64, (O1.lh + 3) / 4, n), 256, 0, ls>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh,
+      k_pyrdown<<<dim3((O1.lw + 63) / 64, (O1.lh + 15) / 16, n), 256, 0, ls>>>(b.lbdImg0, O0.lpitch, (size_t)O0.lpitch * O0.lh,
                                                                             O0.lw, O0.lh, b.lbdImg1, O1.lpitch,
                                                                             (size_t)O1.lpitch * O1.lh, O1.lw, O1.lh);
       prof->mark("k_pyrdown", st);

@@ -456,7 +456,8 @@ int plvi_line_extract_batch(plvi_line* h, const uint8_t* imgs, int n, int w, int
 }
 
 // what: 0 scaled f64 image (needs set_debug), 1 angle degrees f32 (-1024 = NOTDEF), 2 gradient magnitude f64,
-// 3 raw segments float4 (out holds cap entries; *count receives the number), 4 pyramid octave u8 (dense w x h)
+// 3 raw segments float4 (out holds cap entries; *count receives the number), 4 pyramid octave u8 (dense w x h),
+// 5 LBD octave image u8 (dense lw x lh), 6 LBD Sobel gradients s16 (lw x lh x {dx, dy})
 int plvi_line_read_lsd(plvi_line* h, int frame, int octave, int what, void* out, int cap, int* count) {
   if (!h || !out || frame < 0 || frame >= h->lastN || octave < 0 || octave >= h->nlevels || h->curW < 0) return PLVI_ERR_INVALID;
   PLVI_CUDA_TRY(cudaSetDevice(h->device));
@@ -484,6 +485,15 @@ int plvi_line_read_lsd(plvi_line* h, int frame, int octave, int what, void* out,
     case 4:
       PLVI_CUDA_TRY(cudaMemcpy2D(out, O.w, h->lastPtrs.img[octave] + (size_t)frame * h->lastPtrs.ifs[octave],
                                  h->lastPtrs.ipitch[octave], O.w, O.h, cudaMemcpyDeviceToHost));
+      break;
+    case 5: {  // LBD pyramid octave (Gaussian 5x5 of the frame / its pyrDown), dense lw x lh u8
+      const u8* img = octave == 0 ? h->buf.lbdImg0 : h->buf.lbdImg1;
+      PLVI_CUDA_TRY(cudaMemcpy2D(out, O.lw, img + (size_t)frame * O.lpitch * O.lh, O.lpitch, O.lw, O.lh, cudaMemcpyDeviceToHost));
+      break;
+    }
+    case 6:    // Sobel (dx, dy) of the LBD octave, lw x lh x 2 s16
+      PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.grad + (size_t)frame * g.lbdTotal + O.lbdOff, (size_t)O.lw * O.lh * sizeof(short2),
+                               cudaMemcpyDeviceToHost));
       break;
     default: return PLVI_ERR_INVALID;
   }

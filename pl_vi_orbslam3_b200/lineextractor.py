@@ -130,6 +130,14 @@ class Lineextractor:
         elif what == "octave":
             out = np.empty((int(oh[octave]), int(ow[octave])), np.uint8)
             check(lib().plvi_line_read_lsd(self._h, frame, octave, 4, ptr(out), 0, None))
+        elif what in ("lbd_image", "lbd_grad"):
+            lw, lh = w >> octave, h >> octave
+            if what == "lbd_image":
+                out = np.empty((lh, lw), np.uint8)
+                check(lib().plvi_line_read_lsd(self._h, frame, octave, 5, ptr(out), 0, None))
+            else:
+                out = np.empty((lh, lw, 2), np.int16)
+                check(lib().plvi_line_read_lsd(self._h, frame, octave, 6, ptr(out), 0, None))
         else:
             raise ValueError(what)
         return out

@@ -79,6 +79,27 @@ def test_line_batch(ext):
         _check_lines(kl[i, :n], desc[i, :n], eq[i, :n], oracle.line_extract(frames[i]))
 
 
+@pytest.mark.parametrize("w,h", [(752, 480), (641, 479), (1280, 720)])
+def test_lbd_pyramid_and_sobel_exact(gpu, w, h):
+    """computeGaussianPyramid / computeSobel (binary_descriptor_custom.cpp:351-399): Gaussian 5x5, pyrDown and
+    Sobel are integer arithmetic => bit-exact against the oracle's models (themselves pinned against cv2)."""
+    e = Lineextractor(200, 0, 0.8, 2, 2.0, 0, max_width=w, max_height=h, max_batch=2)
+    try:
+        rng = np.random.RandomState(7)
+        imgs = np.stack([synth.frame_euroc(3, w, h), rng.randint(0, 256, (h, w)).astype(np.uint8)])
+        e.extract_batch(imgs)
+        for i in range(2):
+            g0 = oracle.gaussian_blur5(imgs[i])
+            g1 = oracle.pyr_down(g0)
+            for o, ref in enumerate((g0, g1)):
+                assert np.array_equal(e.read_lsd(i, o, "lbd_image", w, h), ref), (i, o)
+                dx, dy = oracle.sobel3(ref)
+                got = e.read_lsd(i, o, "lbd_grad", w, h)
+                assert np.array_equal(got[..., 0], dx) and np.array_equal(got[..., 1], dy), (i, o)
+    finally:
+        e.close()
+
+
 def test_line_flat_image_no_lines(ext):
     flat = np.full((480, 752), 90, np.uint8)
     kl, desc, eq = ext(flat)
