@@ -23,10 +23,10 @@
 
 namespace plvi {
 
+// BORDER_REFLECT_101 for -len < p < 2 * len - 1 (one reflection: halos are <= 3 pixels, images >= 8)
 __device__ __forceinline__ int reflect101_l(int p, int len) {
-  if (len == 1) return 0;
-  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
-  return p;
+  p = p < 0 ? -p : p;
+  return p >= len ? 2 * (len - 1) - p : p;
 }
 
 __device__ __forceinline__ float fast_atan2_dev(float y, float x) {
@@ -1248,29 +1248,55 @@ __global__ void __launch_bounds__(256) k_pyrdown(const u8* __restrict__ src, int
 
 __global__ void __launch_bounds__(256) k_sobel(const u8* __restrict__ src, int spitch, size_t sfs, int w, int h,
                                                short2* __restrict__ dst, size_t dfs) {
-  // thread = 4 horizontally adjacent pixels; three rows x 6 bytes (x4-1 .. x4+4)
+  // thread = 4 horizontally adjacent pixels: one aligned word per row plus the two bytes next to
+  // it.  dx = S[k+1] - S[k-1] with the column sums S = p0 + 2 p1 + p2, dy = D[k-1] + 2 D[k] + D[k+1]
+  // with D = p2 - p0; the four in-word columns are handled as two 16-bit lanes per register.
   const int x4 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
   if (x4 >= w || y >= h) return;
   const u8* s = src + (size_t)blockIdx.z * sfs;
   const u8* rows[3] = {s + (size_t)reflect101_l(y - 1, h) * spitch, s + (size_t)y * spitch,
                        s + (size_t)reflect101_l(y + 1, h) * spitch};
-  int p[3][6];
-  const bool inner = x4 >= 4 && x4 + 7 < w && ((spitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(s) & 3) == 0);
-#pragma unroll
-  for (int r = 0; r < 3; r++) {
-    if (inner) {
-      const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(rows[r] + x4 - 4));
-      const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(rows[r] + x4));
-      const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(rows[r] + x4 + 4));
-      p[r][0] = a >> 24;
-      p[r][1] = b & 0xff; p[r][2] = (b >> 8) & 0xff; p[r][3] = (b >> 16) & 0xff; p[r][4] = b >> 24;
-      p[r][5] = c & 0xff;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 6; i++) p[r][i] = __ldg(rows[r] + reflect101_l(min(x4 - 1 + i, w + 1), w));
-    }
-  }
   short2* out = dst + (size_t)blockIdx.z * dfs + (size_t)y * w + x4;
+  const bool fast = x4 + 3 < w && ((spitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(s) & 3) == 0);
+  if (fast) {
+    const int xl = x4 > 0 ? x4 - 1 : 1, xr = x4 + 4 < w ? x4 + 4 : 2 * (w - 1) - (x4 + 4);
+    uint32_t b[3];
+    int l[3], r[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      b[i] = __ldg(reinterpret_cast<const uint32_t*>(rows[i] + x4));
+      l[i] = __ldg(rows[i] + xl);
+      r[i] = __ldg(rows[i] + xr);
+    }
+    const uint32_t M = 0x00ff00ffu;
+    const uint32_t e0 = b[0] & M, e1 = b[1] & M, e2 = b[2] & M;
+    const uint32_t o0 = (b[0] >> 8) & M, o1 = (b[1] >> 8) & M, o2 = (b[2] >> 8) & M;
+    const uint32_t SE = e0 + 2u * e1 + e2, SO = o0 + 2u * o1 + o2;   // lanes: S[0] | S[2] << 16, S[1] | S[3] << 16
+    const uint32_t DE = e2 + (M - e0), DO = o2 + (M - o0);           // lanes: D + 255
+    const int S0 = SE & 0xffff, S2 = SE >> 16, S1 = SO & 0xffff, S3 = SO >> 16;
+    const int D0 = (int)(DE & 0xffff) - 255, D2 = (int)(DE >> 16) - 255, D1 = (int)(DO & 0xffff) - 255, D3 = (int)(DO >> 16) - 255;
+    const int SL = l[0] + 2 * l[1] + l[2], SR = r[0] + 2 * r[1] + r[2];
+    const int DL = l[2] - l[0], DR = r[2] - r[0];
+    const int dx0 = S1 - SL, dx1 = S2 - S0, dx2 = S3 - S1, dx3 = SR - S2;
+    const int dy0 = DL + 2 * D0 + D1, dy1 = D0 + 2 * D1 + D2, dy2 = D1 + 2 * D2 + D3, dy3 = D2 + 2 * D3 + DR;
+    uint4 v;
+    v.x = (uint32_t)(dx0 & 0xffff) | ((uint32_t)dy0 << 16);
+    v.y = (uint32_t)(dx1 & 0xffff) | ((uint32_t)dy1 << 16);
+    v.z = (uint32_t)(dx2 & 0xffff) | ((uint32_t)dy2 << 16);
+    v.w = (uint32_t)(dx3 & 0xffff) | ((uint32_t)dy3 << 16);
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      *reinterpret_cast<uint4*>(out) = v;
+    } else {
+      uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+      o32[0] = v.x; o32[1] = v.y; o32[2] = v.z; o32[3] = v.w;
+    }
+    return;
+  }
+  int p[3][6];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int i = 0; i < 6; i++) p[r][i] = __ldg(rows[r] + reflect101_l(min(x4 - 1 + i, w + 1), w));
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     if (x4 + k >= w) break;

@@ -526,10 +526,10 @@ __global__ void __launch_bounds__(NT) k_octree(const __grid_constant__ OrbGeom g
 // ---------------------------------------------------------------------------------
 #define BLUR_TW 128
 #define BLUR_TH 32
+// BORDER_REFLECT_101 for -len < p < 2 * len - 1 (one reflection: the halos are 3 pixels, levels >= 30)
 __device__ __forceinline__ int reflect101(int p, int len) {
-  if (len == 1) return 0;
-  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
-  return p;
+  p = p < 0 ? -p : p;
+  return p >= len ? 2 * (len - 1) - p : p;
 }
 
 // Tile = 128 x 32 outputs.  The input tile (38 rows x 136 bytes, starting 4 bytes left of the
@@ -556,6 +556,8 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g
     uint32_t w;
     if (aligned4 && gx >= 0 && gx + 3 < L.w) {
       w = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+    } else if (gx > L.w + 2 || y0 + r - 3 > L.h + 2) {
+      w = 0;   // beyond the reflected border: read by no output pixel
     } else {
       w = 0;
 #pragma unroll
