@@ -172,6 +172,8 @@ def main():
     ap.add_argument("--pipe-mode", choices=("slice", "alternate"), default=os.environ.get("PLVI_BENCH_PIPE_MODE", "alternate"),
                     help="alternate: whole batches go to the pipelines in turn (consecutive batches in flight at "
                          "different phases); slice: every batch is split across the pipelines")
+    ap.add_argument("--out-sets", type=int, default=2, help="alternating output buffer sets per pipeline (e2e: the D2H of "
+                    "step i overlaps the compute of step i+1)")
     ap.add_argument("--pipes", type=int, default=int(os.environ.get("PLVI_BENCH_PIPES", 1)),
                     help="independent pipelines the batch is split over (overlap across slices)")
     args = ap.parse_args()
@@ -235,7 +237,7 @@ def main():
     h_frames = torch.from_numpy(frames).pin_memory()
     fe = PipelinedFrontEnd(B, pipes=args.pipes, mode=args.pipe_mode, device=local_rank, w=W, h=H, with_lines=not args.orb_only,
                            with_match=not args.orb_only, overlap_lines=not args.no_overlap,
-                           line_priority=args.line_priority)
+                           line_priority=args.line_priority, out_sets=args.out_sets)
     st = fe.stream
     with torch.cuda.stream(st):
         d_frames = h_frames.to(dev, non_blocking=True)
@@ -272,7 +274,7 @@ def main():
     # streams: the H2D of step i+1 overlaps the compute of step i (two input buffers); the D2H of step
     # i must finish before step i+1 overwrites the output buffers.
     alt = args.pipe_mode == "alternate"
-    npipe = args.pipes if alt else 1           # steps whose outputs are alive at the same time
+    npipe = fe.alive_steps                     # steps whose outputs are alive at the same time
     outs = fe.outputs()
     h_out = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()} for o in outs]
     nbuf = npipe + 1

@@ -24,7 +24,8 @@ def shard_range(n_items, rank, world):
 class FrontEnd:
     def __init__(self, batch, w=752, h=480, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
                  lsd_nfeatures=200, lsd_scale=0.8, line_levels=2, line_scale=2.0, device=0, stream=None,
-                 with_lines=True, with_match=True, match_th=15.0, nnratio=0.9, overlap_lines=True, line_priority=0):
+                 with_lines=True, with_match=True, match_th=15.0, nnratio=0.9, overlap_lines=True, line_priority=0,
+                 out_sets=1):
         import torch
         self.torch = torch
         self.B, self.w, self.h = batch, w, h
@@ -42,28 +43,36 @@ class FrontEnd:
         self.match_th = float(match_th)
         self.orb = ORBextractor(nfeatures, scale_factor, nlevels, ini_th, min_th, max_width=w, max_height=h,
                                 max_batch=batch, device=device, stream=sp)
-        self.orb_out = self.orb.alloc_device_outputs(batch, self.device)
+        # out_sets > 1: the results of consecutive steps go to alternating output buffers, so the
+        # device-to-host copy of step i can still run while step i+1 computes
+        self.out_sets = max(1, int(out_sets))
+        self._set = 0
+        self.orb_outs = [self.orb.alloc_device_outputs(batch, self.device) for _ in range(self.out_sets)]
+        self.orb_out = self.orb_outs[0]
         self.line = None
         self.om = self.lm = None
         if with_lines:
             self.line = Lineextractor(lsd_nfeatures, 0, lsd_scale, line_levels, line_scale, 0, max_width=w,
                                       max_height=h, max_batch=batch, device=device,
                                       stream=self.line_stream.cuda_stream)
-            self.line_out = self.line.alloc_device_outputs(batch, self.device)
+            self.line_outs = [self.line.alloc_device_outputs(batch, self.device) for _ in range(self.out_sets)]
+            self.line_out = self.line_outs[0]
         if with_match and batch > 1:
             cap = self.orb.capacity
             self.om = ORBmatcher(nnratio, True, max_pairs=batch, max_train=cap, max_query=cap, device=device, stream=sp)
             self.grid = frame_grid(0, w, 0, h)
             P = batch - 1
             self.queries = torch.zeros((batch, cap, 7), dtype=torch.float32, device=self.device)
-            self.match_train = torch.zeros((P, cap), dtype=torch.int32, device=self.device)
-            self.match_query = torch.zeros((P, cap), dtype=torch.int32, device=self.device)
-            self.nmatches = torch.zeros(P, dtype=torch.int32, device=self.device)
+            self.match_sets = [(torch.zeros((P, cap), dtype=torch.int32, device=self.device),
+                                torch.zeros((P, cap), dtype=torch.int32, device=self.device),
+                                torch.zeros(P, dtype=torch.int32, device=self.device)) for _ in range(self.out_sets)]
+            self.match_train, self.match_query, self.nmatches = self.match_sets[0]
             if with_lines:
                 lc = self.line.capacity
                 self.lm = LineMatcher(max_pairs=batch, max_train=lc, max_query=lc, device=device, stream=sp)
-                self.line_m12 = torch.zeros((P, lc), dtype=torch.int32, device=self.device)
-                self.line_nm = torch.zeros(P, dtype=torch.int32, device=self.device)
+                self.lmatch_sets = [(torch.zeros((P, lc), dtype=torch.int32, device=self.device),
+                                     torch.zeros(P, dtype=torch.int32, device=self.device)) for _ in range(self.out_sets)]
+                self.line_m12, self.line_nm = self.lmatch_sets[0]
         self.launches = 0
         self._profiling = False
         self._mev = None
@@ -79,6 +88,15 @@ class FrontEnd:
         wait for the line pipeline (clean per-kernel timings for the profile pass)."""
         n = d_frames.shape[0]
         nl = 0
+        if self.out_sets > 1:   # next output buffer set
+            self._set = (self._set + 1) % self.out_sets
+            self.orb_out = self.orb_outs[self._set]
+            if self.line is not None:
+                self.line_out = self.line_outs[self._set]
+            if self.om is not None:
+                self.match_train, self.match_query, self.nmatches = self.match_sets[self._set]
+            if self.lm is not None:
+                self.line_m12, self.line_nm = self.lmatch_sets[self._set]
         forked = self.line is not None and self.line_stream is not self.stream
         if forked:
             self._ev_fork.record(self.stream)
@@ -224,6 +242,11 @@ class PipelinedFrontEnd:
         for ev in self._joins:
             self.stream.wait_event(ev)
         return nl
+
+    @property
+    def alive_steps(self):
+        """Number of consecutive steps whose outputs exist at the same time."""
+        return self.fes[0].out_sets * (self.pipes if self.mode == "alternate" else 1)
 
     def done_event(self):
         """Completion event of the last issued step (alternate mode); None in slice mode, where
