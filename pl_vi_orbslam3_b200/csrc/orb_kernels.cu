@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
 
   const int minTh = g.minTh, iniTh = g.iniTh;
   const int dw = rw - 6, dh = rh - 6;
-  // ---- pass A: 4 pixels per thread.  Any 9-arc holds >= 2 of the 4 compass ring pixels, so a
-  // corner needs >= 2 compass pixels that differ from the centre by more than minTh.
+  // ---- pass A: 4 pixels per thread.  Any 9-arc of the 16-pixel ring covers two neighbouring compass
+  // pixels (ring 0/4/8/12), so a corner needs two neighbouring compass pixels that are both brighter
+  // than c + minTh or both darker than c - minTh.
   {
     const int dwords = (dw + 3) >> 2;
     const uint32_t th4 = (uint32_t)minTh * 0x01010101u;
@@ -199,16 +200,17 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
       const uint32_t c = row[0], lft = row[-1], rgt = row[1];
       const uint32_t up = row[-3 * (tilePitch >> 2)], dn = row[3 * (tilePitch >> 2)];
       const uint32_t l3 = __funnelshift_r(lft, c, 8), r3 = __funnelshift_r(c, rgt, 24);   // columns -3 / +3
-      uint32_t cnt = __vsetgtu4(__vabsdiffu4(up, c), th4) + __vsetgtu4(__vabsdiffu4(dn, c), th4) +
-                     __vsetgtu4(__vabsdiffu4(l3, c), th4) + __vsetgtu4(__vabsdiffu4(r3, c), th4);
-      cnt = (cnt + 0x7e7e7e7eu) & 0x80808080u;          // bit 7 of a byte set <=> its count >= 2
+      const uint32_t hi4 = __vaddus4(c, th4), lo4 = __vsubus4(c, th4);                    // saturated: never passed if clipped
+      const uint32_t bU = __vsetgtu4(up, hi4), bD = __vsetgtu4(dn, hi4), bL = __vsetgtu4(l3, hi4), bR = __vsetgtu4(r3, hi4);
+      const uint32_t kU = __vsetltu4(up, lo4), kD = __vsetltu4(dn, lo4), kL = __vsetltu4(l3, lo4), kR = __vsetltu4(r3, lo4);
+      const uint32_t cnt = ((bU | bD) & (bL | bR)) | ((kU | kD) & (kL | kR));             // 0x01 per candidate byte
       if (!cnt) continue;
       const int dx0 = tx * 4;
       int npass = 0;
       unsigned short loc[4];
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        if ((cnt >> (8 * k + 7)) & 1u && dx0 + k < dw) loc[npass++] = (unsigned short)((dy << 8) | (dx0 + k));
+        if ((cnt >> (8 * k)) & 1u && dx0 + k < dw) loc[npass++] = (unsigned short)((dy << 8) | (dx0 + k));
       if (npass) {
         const int o = atomicAdd(&s_n1, npass);
         for (int k = 0; k < npass; k++) list1[o + k] = loc[k];
