@@ -65,7 +65,15 @@ __global__ void __launch_bounds__(256) k_lsd_rowfilter(const u8* __restrict__ sr
   if (x4 >= w || y >= h) return;
   const u8* row = src + (size_t)blockIdx.z * sfs + (size_t)y * spitch;
   double v[10];
-  if (x4 >= 3 && x4 + 6 < w) {
+  const bool aligned4 = ((spitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(src + (size_t)blockIdx.z * sfs) & 3) == 0);
+  if (aligned4 && x4 >= 4 && x4 + 7 < w) {
+    const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(row + x4 - 4));
+    const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(row + x4));
+    const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(row + x4 + 4));
+    v[0] = (double)((a >> 8) & 0xffu); v[1] = (double)((a >> 16) & 0xffu); v[2] = (double)(a >> 24);
+    v[3] = (double)(b & 0xffu); v[4] = (double)((b >> 8) & 0xffu); v[5] = (double)((b >> 16) & 0xffu); v[6] = (double)(b >> 24);
+    v[7] = (double)(c & 0xffu); v[8] = (double)((c >> 8) & 0xffu); v[9] = (double)((c >> 16) & 0xffu);
+  } else if (x4 >= 3 && x4 + 6 < w) {
 #pragma unroll
     for (int i = 0; i < 10; i++) v[i] = (double)__ldg(row + x4 - 3 + i);
   } else {
