@@ -192,6 +192,33 @@ typedef struct plvi_grid {
   float min_x, min_y, inv_w, inv_h;
 } plvi_grid;
 
+/* Pinhole camera + distortion for cv::undistortPoints(src, dst, K, distCoeffs, noArray(), P):
+ * K = (fx, fy, cx, cy), dist = (k1, k2, p1, p2, k3, k4, k5, k6, s1, s2, s3, s4, tx, ty) zero padded
+ * (the tilt terms tx, ty must be 0), P = (new_fx, new_fy, new_cx, new_cy) - the reference passes
+ * P = mK.  iters <= 0 selects OpenCV's default (5 iterations). */
+typedef struct plvi_camera {
+  double fx, fy, cx, cy;
+  double dist[14];
+  double new_fx, new_fy, new_cx, new_cy;
+  int32_t iters;
+} plvi_camera;
+
+/* void Frame::UndistortKeyPoints() (src/Frame.cc:1124-1159): d_out[f][i] = d_in[f][i] with pt
+ * undistorted; a plain copy when dist[0] == 0 (as the reference).  Device pointers, [n_frames][stride]
+ * records, d_counts[f] valid ones; runs on `stream` (cudaStream_t) of the current device.
+ * d_out may alias d_in. */
+int plvi_undistort_keypoints(void* stream, const plvi_keypoint* d_in, const int* d_counts, int n_frames, int stride,
+                             const plvi_camera* cam, plvi_keypoint* d_out);
+/* void Frame::UndistortKeyLines() (src/Frame.cc:1161-1197): startPoint and endPoint undistorted;
+ * the other KeyLine fields are copied (the reference leaves them default-constructed). */
+int plvi_undistort_keylines(void* stream, const plvi_keyline* d_in, const int* d_counts, int n_frames, int stride,
+                            const plvi_camera* cam, plvi_keyline* d_out);
+/* void Frame::AssignFeaturesToGrid() + PosInGrid (src/Frame.cc:644-675,1077-1087), mono path:
+ * mGrid[i][j] = d_cell_items[f][d_cell_start[f][i*48+j] .. d_cell_start[f][i*48+j+1]) in keypoint
+ * order.  d_cell_start: [n_frames][64*48+1] ints, d_cell_items: [n_frames][stride] ints. */
+int plvi_assign_features_to_grid(void* stream, const plvi_keypoint* d_keys, const int* d_counts, int n_frames, int stride,
+                                 const plvi_grid* grid, int* d_cell_start, int* d_cell_items);
+
 /* One projected query point of a guided search (28 bytes). */
 typedef struct plvi_query {
   float u, v;        /* projection (uv) or vbPrevMatched[i1] */

@@ -355,3 +355,38 @@ def line_extract(img, lsd_nfeatures=200, lsd_refine=0, lsd_scale=0.8, nlevels=2,
     if n < 0:
         raise RuntimeError(f"oracle line_extract failed: {n}")
     return {"keylines": kl[:n].copy(), "descriptors": desc[:n].copy(), "line_eq": eq[:n].copy(), "raw_counts": raw}
+
+
+# ---- Frame steps after extraction (oracle_frame.cpp)
+EUROC_CAMERA = dict(fx=458.654, fy=457.296, cx=367.215, cy=248.375,
+                    dist=(-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05))   # Examples/Monocular-Inertial/EuRoC.yaml
+
+
+def camera_arrays(cam):
+    """(K[4], dist[14], P[4]) float64 arrays; K and dist go through float32 like the reference's cv::Mat(CV_32F)."""
+    K = np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32).astype(np.float64)
+    k = np.zeros(14, np.float64)
+    d = np.asarray(cam["dist"], np.float32).astype(np.float64)
+    k[:len(d)] = d
+    P = np.array([cam.get("new_fx", K[0]), cam.get("new_fy", K[1]), cam.get("new_cx", K[2]), cam.get("new_cy", K[3])], np.float64)
+    return K, k, P
+
+
+def undistort_points(xy, cam=EUROC_CAMERA, iters=5):
+    """cv::undistortPoints(xy, K, dist, P=K) as Frame::UndistortKeyPoints calls it: [n,2] f32 -> [n,2] f32."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    K, k, P = camera_arrays(cam)
+    out = np.empty_like(xy)
+    lib().plvio_undistort_points(_p(xy), C.c_int(len(xy)), _p(K), _p(k), _p(P), C.c_int(iters), _p(out))
+    return out
+
+
+def assign_grid(xy, grid):
+    """Frame::AssignFeaturesToGrid: (cell_start[3073], items[n_in_grid]) of the 64x48 grid, cell = ix*48+iy."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    start = np.zeros(64 * 48 + 1, np.int32)
+    items = np.zeros(max(len(xy), 1), np.int32)
+    g = np.asarray(grid).reshape(-1)[0]
+    lib().plvio_assign_grid(_p(xy), C.c_int(len(xy)), C.c_float(g["min_x"]), C.c_float(g["min_y"]), C.c_float(g["inv_w"]),
+                            C.c_float(g["inv_h"]), _p(start), _p(items))
+    return start, items[:start[-1]]

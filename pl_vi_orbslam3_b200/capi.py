@@ -77,8 +77,15 @@ _SIGS = {
     "plvi_search_by_bow": (ci, [vp, ci, vp, vp, vp, ci, vp, ci, vp, vp, vp, ci, ci, cf, ci, vp, vp, vp, ci]),
     "plvi_queries_from_keypoints": (ci, [vp, vp, vp, ci, ci, cf, cf, vp]),
     "plvi_line_match": (ci, [vp, ci, vp, vp, ci, vp, vp, ci, cf, ci, vp, vp, ci]),
+    "plvi_undistort_keypoints": (ci, [vp, vp, vp, ci, ci, vp, vp]),
+    "plvi_undistort_keylines": (ci, [vp, vp, vp, ci, ci, vp, vp]),
+    "plvi_assign_features_to_grid": (ci, [vp, vp, vp, ci, ci, vp, vp, vp]),
 }
 
+CAMERA_DTYPE = np.dtype([("fx", "<f8"), ("fy", "<f8"), ("cx", "<f8"), ("cy", "<f8"), ("dist", "<f8", (14,)),
+                         ("new_fx", "<f8"), ("new_fy", "<f8"), ("new_cx", "<f8"), ("new_cy", "<f8"),
+                         ("iters", "<i4"), ("_pad", "<i4")])
+assert CAMERA_DTYPE.itemsize == 184
 QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("min_level", "<i4"),
                         ("max_level", "<i4"), ("angle", "<f4"), ("flags", "<i4")])
 GRID_DTYPE = np.dtype([("min_x", "<f4"), ("min_y", "<f4"), ("inv_w", "<f4"), ("inv_h", "<f4")])
