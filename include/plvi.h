@@ -219,6 +219,32 @@ int plvi_undistort_keylines(void* stream, const plvi_keyline* d_in, const int* d
 int plvi_assign_features_to_grid(void* stream, const plvi_keypoint* d_keys, const int* d_counts, int n_frames, int stride,
                                  const plvi_grid* grid, int* d_cell_start, int* d_cell_items);
 
+/* ------------------------------------------------------------- vocabulary ---- */
+/* DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (ORBVocabulary, include/ORBVocabulary.h;
+ * Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h).  Nodes in id order as loadFromTextFile (:1338-1424)
+ * creates them: node 0 = root, parent[i] < n_nodes, the children of a node are the nodes naming it as
+ * parent in id order, word ids are given to the leaves in id order.  desc: 32 bytes per node,
+ * weight: WordValue (double) per node, scoring / weighting: DBoW2::ScoringType / WeightingType as in
+ * the first line of ORBvoc.txt ("k L scoring weighting"). */
+typedef struct plvi_vocab plvi_vocab;
+int plvi_vocab_create(plvi_vocab** out, int k, int L, int scoring, int weighting, int n_nodes, const int* parent,
+                      const uint8_t* is_leaf, const uint8_t* desc, const double* weight, int device);
+void plvi_vocab_destroy(plvi_vocab* v);
+int plvi_vocab_words(const plvi_vocab* v);
+/* void TemplatedVocabulary::transform(features, BowVector& v, FeatureVector& fv, int levelsup)
+ * (TemplatedVocabulary.h:1126-1194) as called by Frame::ComputeBoW (src/Frame.cc:1115-1122, levelsup 4)
+ * for n_frames frames of d_counts[f] descriptors ([n_frames][stride][32] bytes).  Device pointers.
+ *   per feature [n_frames][stride]: d_word_id, d_word_weight (0 = stopped word), d_node_id
+ *   BowVector (std::map<WordId, WordValue>): d_bow_count[f] entries, ascending word id, in
+ *     d_bow_words / d_bow_values [n_frames][stride], normalised as ScoringObject::mustNormalize says
+ *   FeatureVector (std::map<NodeId, vector<unsigned>>): d_fv_count[f] nodes, ascending, in d_fv_nodes
+ *     [n_frames][stride]; node r owns d_fv_features[f][d_fv_start[f][r] .. d_fv_start[f][r+1])
+ *     (d_fv_start: [n_frames][stride + 1]), feature indices ascending. */
+int plvi_bow_transform(plvi_vocab* v, void* stream, const uint8_t* d_desc, const int* d_counts, int n_frames, int stride,
+                       int levelsup, int* d_word_id, double* d_word_weight, int* d_node_id, int* d_bow_count,
+                       int* d_bow_words, double* d_bow_values, int* d_fv_count, int* d_fv_nodes, int* d_fv_start,
+                       int* d_fv_features);
+
 /* One projected query point of a guided search (28 bytes). */
 typedef struct plvi_query {
   float u, v;        /* projection (uv) or vbPrevMatched[i1] */

@@ -390,3 +390,23 @@ def assign_grid(xy, grid):
     lib().plvio_assign_grid(_p(xy), C.c_int(len(xy)), C.c_float(g["min_x"]), C.c_float(g["min_y"]), C.c_float(g["inv_w"]),
                             C.c_float(g["inv_h"]), _p(start), _p(items))
     return start, items[:start[-1]]
+
+
+# ---- DBoW2 transform (oracle_bow.cpp)
+def bow_transform(vocab, desc, levelsup=4):
+    """vocab: dict(k, L, scoring, weighting, parent[int32 n], desc[u8 n,32], weight[f64 n]); desc u8 [m,32].
+    Returns dict(word_id, word_weight, node_id, bow=(words, values), fv=(nodes, start, features))."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    m = len(desc)
+    parent = np.ascontiguousarray(vocab["parent"], np.int32)
+    nd = np.ascontiguousarray(vocab["desc"], np.uint8)
+    nw = np.ascontiguousarray(vocab["weight"], np.float64)
+    wid, ww, nid = np.zeros(m, np.int32), np.zeros(m, np.float64), np.zeros(m, np.int32)
+    bc, fc = C.c_int(0), C.c_int(0)
+    bw, bv = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.float64)
+    fn, fs, ff = np.zeros(max(m, 1), np.int32), np.zeros(m + 1, np.int32), np.zeros(max(m, 1), np.int32)
+    lib().plvio_bow_transform(C.c_int(vocab["L"]), C.c_int(vocab["scoring"]), C.c_int(vocab["weighting"]), C.c_int(len(parent)),
+                              _p(parent), _p(nd), _p(nw), _p(desc), C.c_int(m), C.c_int(levelsup), _p(wid), _p(ww), _p(nid),
+                              C.byref(bc), _p(bw), _p(bv), C.byref(fc), _p(fn), _p(fs), _p(ff))
+    return {"word_id": wid, "word_weight": ww, "node_id": nid, "bow": (bw[:bc.value].copy(), bv[:bc.value].copy()),
+            "fv": (fn[:fc.value].copy(), fs[:fc.value + 1].copy(), ff[:fs[fc.value]].copy())}

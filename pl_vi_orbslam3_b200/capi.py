@@ -80,6 +80,10 @@ _SIGS = {
     "plvi_undistort_keypoints": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "plvi_undistort_keylines": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "plvi_assign_features_to_grid": (ci, [vp, vp, vp, ci, ci, vp, vp, vp]),
+    "plvi_vocab_create": (ci, [C.POINTER(vp), ci, ci, ci, ci, ci, vp, vp, vp, vp, ci]),
+    "plvi_vocab_destroy": (None, [vp]),
+    "plvi_vocab_words": (ci, [vp]),
+    "plvi_bow_transform": (ci, [vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
 }
 
 CAMERA_DTYPE = np.dtype([("fx", "<f8"), ("fy", "<f8"), ("cx", "<f8"), ("cy", "<f8"), ("dist", "<f8", (14,)),
