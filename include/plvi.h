@@ -219,6 +219,23 @@ int plvi_undistort_keylines(void* stream, const plvi_keyline* d_in, const int* d
 int plvi_assign_features_to_grid(void* stream, const plvi_keypoint* d_keys, const int* d_counts, int n_frames, int stride,
                                  const plvi_grid* grid, int* d_cell_start, int* d_cell_items);
 
+/* int LineMatcher::SerachForInitialize(Frame&, Frame&, vector<pair<int,int>>&) (src/LineMatcher.cpp:113-141,
+ * factor 0.5) and int LineMatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, vector<pair<size_t,size_t>>&)
+ * (:143-171, factor 0.1, has_line1/has_line2 = "GetMapLine(idx) != NULL" flags, may be NULL), with the threshold
+ * of Frame/KeyFrame::lineDescriptorMAD (src/Frame.cc:1089-1113).  Device pointers only, runs on the matcher's
+ * stream.  matches12[pair][i] = matched row of desc2 or -1 (the reference's pair list is (i, matches12[i]) in
+ * ascending i), mad[pair] = {nn_mad, nn12_mad}.  Pairs with fewer than two rows in desc2 give no match
+ * (the reference's knnMatch(k=2) result would be read out of bounds). */
+int plvi_line_match_mad(plvi_matcher* m, int npairs, const uint8_t* desc1, const int* n1, int stride1, const uint8_t* desc2,
+                        const int* n2, int stride2, const uint8_t* has_line1, const uint8_t* has_line2, double factor,
+                        int* matches12, int* nmatches, double* mad);
+/* void MapPoint::ComputeDistinctiveDescriptors() (src/MapPoint.cc:330-402) for n_points map points:
+ * d_desc [n_points][stride][32] observed descriptors (d_counts[p] valid), d_best_idx[p] = index of the
+ * descriptor with the least median Hamming distance to the others (-1 if none), d_best_desc (optional)
+ * [n_points][32] = that descriptor (mDescriptor).  Device pointers, `stream` = cudaStream_t. */
+int plvi_distinctive_descriptors(void* stream, const uint8_t* d_desc, const int* d_counts, int n_points, int stride,
+                                 int* d_best_idx, uint8_t* d_best_desc);
+
 /* ------------------------------------------------------------- vocabulary ---- */
 /* DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (ORBVocabulary, include/ORBVocabulary.h;
  * Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h).  Nodes in id order as loadFromTextFile (:1338-1424)

@@ -410,3 +410,21 @@ def bow_transform(vocab, desc, levelsup=4):
                               C.byref(bc), _p(bw), _p(bv), C.byref(fc), _p(fn), _p(fs), _p(ff))
     return {"word_id": wid, "word_weight": ww, "node_id": nid, "bow": (bw[:bc.value].copy(), bv[:bc.value].copy()),
             "fv": (fn[:fc.value].copy(), fs[:fc.value + 1].copy(), ff[:fs[fc.value]].copy())}
+
+
+def line_match_mad(d1, d2, factor, has1=None, has2=None):
+    """LineMatcher::SerachForInitialize (factor 0.5) / SearchForTriangulation (factor 0.1): (n, matches12, (nn_mad, nn12_mad))."""
+    d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32)
+    d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+    m = np.full(max(len(d1), 1), -1, np.int32)
+    mad = np.zeros(2, np.float64)
+    h1 = None if has1 is None else np.ascontiguousarray(has1, np.uint8)
+    h2 = None if has2 is None else np.ascontiguousarray(has2, np.uint8)
+    n = lib().plvio_line_match_mad(_p(d1), C.c_int(len(d1)), _p(d2), C.c_int(len(d2)), _p(h1), _p(h2), C.c_double(factor), _p(m), _p(mad))
+    return n, m[:len(d1)], mad
+
+
+def distinctive_descriptor(desc):
+    """MapPoint::ComputeDistinctiveDescriptors: index of the descriptor with the least median distance."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    return int(lib().plvio_distinctive_descriptor(_p(desc), C.c_int(len(desc))))

@@ -329,3 +329,67 @@ int plvio_line_match(const u8* d1, int n1, const u8* d2, int n2, float nnr, int*
 }
 
 }  // extern "C"
+
+// ---- LineMatcher::SerachForInitialize / SearchForTriangulation(KF, KF) (src/LineMatcher.cpp:113-171) with
+// Frame/KeyFrame::lineDescriptorMAD (src/Frame.cc:1089-1113, src/KeyFrame.cc:411-435); comparators
+// include/LineMatcher.h:56-76 (NN distance ascending, NN12 difference DESCENDING).
+extern "C" int plvio_line_match_mad(const uint8_t* d1, int n1, const uint8_t* d2, int n2, const uint8_t* has1,
+                                    const uint8_t* has2, double factor, int* matches12, double* mad) {
+  using namespace plvio;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  mad[0] = mad[1] = 0.0;
+  if (n1 < 1 || n2 < 2) return 0;
+  struct M { float d0, d1; int q, t; };
+  std::vector<M> lm(n1);
+  for (int i = 0; i < n1; i++) {   // knnMatch(k = 2): two smallest distances, ties -> lowest train index
+    int b0 = -1, b1 = -1, e0 = 1 << 30, e1 = 1 << 30;
+    for (int j = 0; j < n2; j++) {
+      const int d = hamming256(d1 + 32 * (size_t)i, d2 + 32 * (size_t)j);
+      if (d < e0) { e1 = e0; b1 = b0; e0 = d; b0 = j; }
+      else if (d < e1) { e1 = d; b1 = j; }
+    }
+    (void)b1;
+    lm[i] = M{(float)e0, (float)e1, i, b0};
+  }
+  std::vector<M> nn = lm, m12 = lm;
+  std::stable_sort(nn.begin(), nn.end(), [](const M& a, const M& b) { return a.d0 < b.d0; });
+  const double nn_median = nn[int(nn.size() / 2)].d0;
+  for (auto& m : nn) m.d0 = fabsf(m.d0 - nn_median);
+  std::stable_sort(nn.begin(), nn.end(), [](const M& a, const M& b) { return a.d0 < b.d0; });
+  mad[0] = 1.4826 * nn[int(nn.size() / 2)].d0;
+  std::stable_sort(m12.begin(), m12.end(), [](const M& a, const M& b) { return (a.d1 - a.d0) > (b.d1 - b.d0); });
+  const double nn12_median = m12[int(m12.size() / 2)].d1 - m12[int(m12.size() / 2)].d0;
+  for (auto& m : m12) m.d0 = fabsf(m.d1 - m.d0 - nn12_median);
+  std::stable_sort(m12.begin(), m12.end(), [](const M& a, const M& b) { return a.d0 < b.d0; });
+  mad[1] = 1.4826 * m12[int(m12.size() / 2)].d0;
+  const double th = mad[1] * factor;
+  int nmatches = 0;
+  for (int i = 0; i < n1; i++) {   // lmatches sorted by queryIdx
+    const int qdx = lm[i].q, tdx = lm[i].t;
+    if ((has1 && has1[qdx]) || (has2 && has2[tdx])) continue;
+    const double dist_12 = lm[i].d1 - lm[i].d0;
+    if (dist_12 > th) { matches12[qdx] = tdx; nmatches++; }
+  }
+  return nmatches;
+}
+
+// ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:330-402)
+extern "C" int plvio_distinctive_descriptor(const uint8_t* desc, int n) {
+  using namespace plvio;
+  if (n <= 0) return -1;
+  std::vector<std::vector<float>> D(n, std::vector<float>(n, 0.f));
+  for (int i = 0; i < n; i++)
+    for (int j = i + 1; j < n; j++) {
+      const int d = hamming256(desc + 32 * (size_t)i, desc + 32 * (size_t)j);
+      D[i][j] = (float)d;
+      D[j][i] = (float)d;
+    }
+  int BestMedian = INT_MAX, BestIdx = 0;
+  for (int i = 0; i < n; i++) {
+    std::vector<int> v(D[i].begin(), D[i].end());
+    std::sort(v.begin(), v.end());
+    const int median = v[(size_t)(0.5 * (n - 1))];
+    if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+  }
+  return BestIdx;
+}

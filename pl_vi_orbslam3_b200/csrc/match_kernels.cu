@@ -470,6 +470,147 @@ __global__ void __launch_bounds__(256) k_line_match(const uint8_t* __restrict__ 
 // ---------------------------------------------------------------------------------------
 using namespace plvi;
 
+// ---------------------------------------------------------------------------------
+// k_line_match_mad: LineMatcher::SerachForInitialize / SearchForTriangulation(KF, KF)
+// (src/LineMatcher.cpp:113-171): kNN-2 of every row of desc1 in desc2, then the robust
+// threshold of Frame/KeyFrame::lineDescriptorMAD (src/Frame.cc:1089-1113):
+//   nn_mad   = 1.4826 * median(|d0 - median(d0)|)
+//   nn12_mad = 1.4826 * median(|(d1 - d0) - median(d1 - d0)|),  "median" = element n/2 of the sorted list
+// a query is matched to its nearest neighbour iff d1 - d0 > factor * nn12_mad.  All distances
+// are integers in [0, 256], so the medians come from 257-bin histograms.
+// ---------------------------------------------------------------------------------
+__device__ int hist_select(const int* hist, int rank) {   // smallest v with #{x <= v} > rank
+  int cum = 0;
+  for (int v = 0; v <= 256; v++) {
+    cum += hist[v];
+    if (cum > rank) return v;
+  }
+  return 256;
+}
+
+__global__ void __launch_bounds__(256) k_line_match_mad(const uint8_t* __restrict__ d1, const int* __restrict__ n1p, int stride1,
+                                                        const uint8_t* __restrict__ d2, const int* __restrict__ n2p, int stride2,
+                                                        const uint8_t* __restrict__ mask1, const uint8_t* __restrict__ mask2,
+                                                        double factor, int* __restrict__ m12out, int* __restrict__ nmatches,
+                                                        double* __restrict__ madOut) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int n1 = n1p[pair], n2 = n2p[pair];
+  uint8_t* s1 = smem;
+  uint8_t* s2 = s1 + (size_t)stride1 * 32;
+  int* dist0 = reinterpret_cast<int*>(s2 + (size_t)stride2 * 32);   // [stride1]
+  int* dist1 = dist0 + stride1;
+  int* train = dist1 + stride1;
+  __shared__ int hist[257];
+  __shared__ int s_med, s_cnt;
+  __shared__ double s_mad[2];
+  int* out = m12out + (size_t)pair * stride1;
+  if (n1 < 1 || n2 < 2) {   // knnMatch(k = 2) needs two train rows (the reference reads lmatches[i][1] unconditionally)
+    for (int i = tid; i < n1; i += blockDim.x) out[i] = -1;
+    if (tid == 0) { nmatches[pair] = 0; madOut[2 * pair] = 0.0; madOut[2 * pair + 1] = 0.0; }
+    return;
+  }
+  const uint4* g1 = reinterpret_cast<const uint4*>(d1 + (size_t)pair * stride1 * 32);
+  const uint4* g2 = reinterpret_cast<const uint4*>(d2 + (size_t)pair * stride2 * 32);
+  for (int i = tid; i < n1 * 2; i += blockDim.x) reinterpret_cast<uint4*>(s1)[i] = __ldg(g1 + i);
+  for (int i = tid; i < n2 * 2; i += blockDim.x) reinterpret_cast<uint4*>(s2)[i] = __ldg(g2 + i);
+  __syncthreads();
+  for (int i = wid; i < n1; i += nw) {
+    uint32_t qw[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) qw[k] = reinterpret_cast<const uint32_t*>(s1 + i * 32)[k];
+    Top2 t = {0xffffffffu, 0xffffffffu, -1, -1};
+    for (int j = lane; j < n2; j += 32) {
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(s2 + j * 32);
+      int d = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) d += __popc(qw[k] ^ pb[k]);
+      top2_insert(t, ((uint32_t)d << 16) | (uint32_t)j, j);
+    }
+    top2_warp_merge(t);
+    if (lane == 0) { dist0[i] = (int)(t.k0 >> 16); dist1[i] = (int)(t.k1 >> 16); train[i] = t.i0; }
+  }
+  __syncthreads();
+  const int mid = n1 / 2;
+  // pass 0: d0, pass 1: d1 - d0
+  for (int pass = 0; pass < 2; pass++) {
+    for (int v = tid; v < 257; v += blockDim.x) hist[v] = 0;
+    __syncthreads();
+    for (int i = tid; i < n1; i += blockDim.x) atomicAdd(&hist[pass == 0 ? dist0[i] : dist1[i] - dist0[i]], 1);
+    __syncthreads();
+    // d0 is sorted ascending, d1 - d0 DESCENDING (conpare_descriptor_by_NN12_dist, include/LineMatcher.h:63-68)
+    if (tid == 0) s_med = hist_select(hist, pass == 0 ? mid : n1 - 1 - mid);
+    __syncthreads();
+    const int med = s_med;
+    for (int v = tid; v < 257; v += blockDim.x) hist[v] = 0;
+    __syncthreads();
+    for (int i = tid; i < n1; i += blockDim.x) atomicAdd(&hist[abs((pass == 0 ? dist0[i] : dist1[i] - dist0[i]) - med)], 1);
+    __syncthreads();
+    if (tid == 0) s_mad[pass] = __dmul_rn(1.4826, (double)(float)hist_select(hist, mid));
+    __syncthreads();
+  }
+  const double th = __dmul_rn(s_mad[1], factor);
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int i = tid; i < n1; i += blockDim.x) {
+    int m = train[i];
+    if ((mask1 && mask1[(size_t)pair * stride1 + i]) || (mask2 && mask2[(size_t)pair * stride2 + m])) m = -1;
+    else if (!((double)(dist1[i] - dist0[i]) > th)) m = -1;
+    out[i] = m;
+    cnt += m >= 0;
+  }
+  if (cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (tid == 0) { nmatches[pair] = s_cnt; madOut[2 * pair] = s_mad[0]; madOut[2 * pair + 1] = s_mad[1]; }
+}
+
+// ---------------------------------------------------------------------------------
+// k_distinctive: MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:330-402): of the N observed
+// descriptors of a map point keep the one with the least median distance to the others; median =
+// element int(0.5 * (N - 1)) of the sorted row (self distance 0 included), first index wins ties.
+// One warp per map point: lane = row, 257-bin u16 histogram per lane in shared memory.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_distinctive(const uint8_t* __restrict__ desc, const int* __restrict__ counts, int stride,
+                                                    int* __restrict__ bestIdx, uint8_t* __restrict__ bestDesc) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int mp = blockIdx.x, lane = threadIdx.x;
+  const int n = min(counts[mp], stride);
+  uint8_t* sd = smem;                                                   // [stride][32]
+  unsigned short* hist = reinterpret_cast<unsigned short*>(sd + (size_t)stride * 32) + lane * 258;   // [32][258]
+  if (n <= 0) {
+    if (lane == 0) bestIdx[mp] = -1;
+    return;
+  }
+  const uint4* g = reinterpret_cast<const uint4*>(desc + (size_t)mp * stride * 32);
+  for (int i = lane; i < n * 2; i += 32) reinterpret_cast<uint4*>(sd)[i] = __ldg(g + i);
+  __syncwarp();
+  const int mid = (int)(0.5 * (n - 1));
+  unsigned bestKey = 0xffffffffu;    // median << 16 | row
+  for (int i = lane; i < n; i += 32) {
+    for (int v = 0; v < 257; v++) hist[v] = 0;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(sd + i * 32);
+    for (int j = 0; j < n; j++) {
+      const uint32_t* bq = reinterpret_cast<const uint32_t*>(sd + j * 32);
+      int d = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) d += __popc(a[k] ^ bq[k]);
+      hist[d]++;
+    }
+    int cum = 0, med = 256;
+    for (int v = 0; v <= 256; v++) {
+      cum += hist[v];
+      if (cum > mid) { med = v; break; }
+    }
+    bestKey = min(bestKey, ((unsigned)med << 16) | (unsigned)i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bestKey = min(bestKey, __shfl_xor_sync(0xffffffffu, bestKey, o));
+  const int b = (int)(bestKey & 0xffffu);
+  if (lane == 0) bestIdx[mp] = b;
+  if (bestDesc && lane < 8) reinterpret_cast<uint32_t*>(bestDesc + (size_t)mp * 32)[lane] = reinterpret_cast<const uint32_t*>(sd + b * 32)[lane];
+}
+
 struct plvi_matcher {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -741,6 +882,40 @@ int plvi_line_match(plvi_matcher* m, int npairs, const uint8_t* desc1, const int
     PLVI_CUDA_TRY(cudaMemcpyAsync(nmatches, nm, P * sizeof(int), cudaMemcpyDeviceToHost, st));
     PLVI_CUDA_TRY(cudaStreamSynchronize(st));
   }
+  return PLVI_OK;
+}
+
+int plvi_line_match_mad(plvi_matcher* m, int npairs, const uint8_t* desc1, const int* n1, int stride1, const uint8_t* desc2,
+                        const int* n2, int stride2, const uint8_t* has_line1, const uint8_t* has_line2, double factor,
+                        int* matches12, int* nmatches, double* mad) {
+  if (!m || npairs < 1 || !desc1 || !desc2 || !n1 || !n2 || !matches12 || !nmatches || !mad || stride1 < 1 || stride2 < 1) {
+    set_error("plvi_line_match_mad: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  const size_t smem = (size_t)(stride1 + stride2) * 32 + (size_t)stride1 * 3 * sizeof(int);
+  if (smem > 200 * 1024) { set_error("plvi_line_match_mad: descriptor sets too large for one CTA"); return PLVI_ERR_CAPACITY; }
+  if (smem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_line_match_mad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_line_match_mad<<<npairs, 256, smem, m->stream>>>(desc1, n1, stride1, desc2, n2, stride2, has_line1, has_line2, factor,
+                                                     matches12, nmatches, mad);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  return PLVI_OK;
+}
+
+int plvi_distinctive_descriptors(void* stream, const uint8_t* d_desc, const int* d_counts, int n_points, int stride,
+                                 int* d_best_idx, uint8_t* d_best_desc) {
+  if (!d_desc || !d_counts || !d_best_idx || n_points < 1 || stride < 1) {
+    set_error("plvi_distinctive_descriptors: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  if (stride > 4096) { set_error("plvi_distinctive_descriptors: more than 4096 observations per map point"); return PLVI_ERR_CAPACITY; }
+  const size_t smem = (size_t)stride * 32 + 32 * 258 * sizeof(unsigned short);
+  if (smem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_distinctive<<<n_points, 32, smem, (cudaStream_t)stream>>>(d_desc, d_counts, stride, d_best_idx, d_best_desc);
+  PLVI_CUDA_TRY(cudaGetLastError());
   return PLVI_OK;
 }
 

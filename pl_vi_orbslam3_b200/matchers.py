@@ -39,6 +39,11 @@ class _Matcher:
         check(lib().plvi_matcher_create(C.byref(self._h), max_pairs, max_train, max_query, device,
                                         ptr(stream) if stream else None))
         self.max_pairs = max_pairs
+        self.device = device
+
+    def sync(self):
+        import torch
+        torch.cuda.synchronize(self.device)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -183,3 +188,56 @@ class LineMatcher(_Matcher):
     def DescriptorDistance(self, a, b):
         """The reference's >>25 variant (src/LineMatcher.cpp:487-499), kept bit-compatible."""
         return self._hamming(a, b, 1)
+
+    def _match_mad_batch(self, pairs, factor, masks=None):
+        import torch
+        P = len(pairs)
+        S1 = max(max(len(a) for a, _ in pairs), 1)
+        S2 = max(max(len(b) for _, b in pairs), 1)
+        d1 = np.zeros((P, S1, 32), np.uint8)
+        d2 = np.zeros((P, S2, 32), np.uint8)
+        h1 = np.zeros((P, S1), np.uint8)
+        h2 = np.zeros((P, S2), np.uint8)
+        n1 = np.array([len(a) for a, _ in pairs], np.int32)
+        n2 = np.array([len(b) for _, b in pairs], np.int32)
+        for i, (a, b) in enumerate(pairs):
+            d1[i, :n1[i]] = a
+            d2[i, :n2[i]] = b
+            if masks is not None:
+                h1[i, :n1[i]], h2[i, :n2[i]] = masks[i]
+        dev = torch.device("cuda", self.device)
+        t = [torch.from_numpy(x).to(dev) for x in (d1, n1, d2, n2, h1, h2)]
+        m12 = torch.empty((P, S1), dtype=torch.int32, device=dev)
+        nm = torch.empty(P, dtype=torch.int32, device=dev)
+        mad = torch.empty((P, 2), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        check(lib().plvi_line_match_mad(self._h, P, ptr(t[0]), ptr(t[1]), S1, ptr(t[2]), ptr(t[3]), S2,
+                                        ptr(t[4]) if masks is not None else None, ptr(t[5]) if masks is not None else None,
+                                        float(factor), ptr(m12), ptr(nm), ptr(mad)))
+        self.sync()
+        m12, nm, mad = m12.cpu().numpy(), nm.cpu().numpy(), mad.cpu().numpy()
+        return [m12[i, :n1[i]] for i in range(P)], nm, mad
+
+    def SerachForInitialize(self, desc_initial, desc_current):
+        """int LineMatcher::SerachForInitialize(Frame&, Frame&, vector<pair<int,int>>&) (src/LineMatcher.cpp:113-141)
+        on the two frames' line descriptors -> (count, [(qdx, tdx), ...])."""
+        m, nm, _ = self._match_mad_batch([(desc_initial, desc_current)], 0.5)
+        return int(nm[0]), [(i, int(t)) for i, t in enumerate(m[0]) if t >= 0]
+
+    def SearchForTriangulation(self, desc_kf1, desc_kf2, has_line1, has_line2):
+        """int LineMatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, vector<pair<size_t,size_t>>&) (:143-171);
+        has_lineN[i] = pKFN->GetMapLine(i) != NULL."""
+        m, nm, _ = self._match_mad_batch([(desc_kf1, desc_kf2)], 0.1, [(has_line1, has_line2)])
+        return int(nm[0]), [(i, int(t)) for i, t in enumerate(m[0]) if t >= 0]
+
+
+def compute_distinctive_descriptors(d_desc, d_counts, stream=None):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:330-402) for a batch of map points.
+    d_desc: CUDA uint8 [n_points, max_obs, 32], d_counts int32 [n_points] -> (best_idx int32 [n], mDescriptor uint8 [n, 32])."""
+    import torch
+    n, cap = d_desc.shape[0], d_desc.shape[1]
+    idx = torch.empty(n, dtype=torch.int32, device=d_desc.device)
+    best = torch.zeros((n, 32), dtype=torch.uint8, device=d_desc.device)
+    sp = int(stream.cuda_stream) if stream is not None else 0
+    check(lib().plvi_distinctive_descriptors(sp, ptr(d_desc), ptr(d_counts), n, cap, ptr(idx), ptr(best)))
+    return idx, best

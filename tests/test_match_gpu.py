@@ -251,3 +251,82 @@ def test_search_by_bow(om, pair_features, nodes, nnratio):
     assert n == rn and np.array_equal(mt, rmt)
     if nodes == 6:
         assert n > 20
+
+
+# ---- LineMatcher::SerachForInitialize / SearchForTriangulation (kNN-2 + MAD threshold) and
+# MapPoint::ComputeDistinctiveDescriptors
+def _line_sets(seed, n1, n2):
+    rng = np.random.RandomState(seed)
+    a = rng.randint(0, 256, (n1, 32)).astype(np.uint8)
+    b = rng.randint(0, 256, (n2, 32)).astype(np.uint8)
+    k = min(n1, n2) * 2 // 3
+    sel = rng.permutation(n2)[:k]
+    b[sel] = a[:k]
+    flips = rng.randint(0, 40, k)                       # noisy copies: 0..40 flipped bits
+    for j, f in zip(sel, flips):
+        bits = rng.permutation(256)[:f]
+        for bit in bits:
+            b[j, bit // 8] ^= 1 << (bit % 8)
+    return a, b
+
+
+@pytest.mark.parametrize("n1,n2,seed", [(200, 200, 0), (199, 150, 1), (64, 201, 2), (2, 2, 3), (7, 1, 4)])
+def test_line_search_for_initialize_and_triangulation(gpu, n1, n2, seed):
+    from pl_vi_orbslam3_b200 import LineMatcher
+    a, b = _line_sets(seed, n1, n2)
+    lm = LineMatcher(max_pairs=2, max_train=256, max_query=256)
+    try:
+        rn, rm, rmad = oracle.line_match_mad(a, b, 0.5)
+        n, pairs = lm.SerachForInitialize(a, b)
+        assert n == rn and pairs == [(i, int(t)) for i, t in enumerate(rm) if t >= 0]
+        rng = np.random.RandomState(seed + 50)
+        h1, h2 = (rng.rand(n1) < 0.2).astype(np.uint8), (rng.rand(n2) < 0.2).astype(np.uint8)
+        rn, rm, _ = oracle.line_match_mad(a, b, 0.1, h1, h2)
+        n, pairs = lm.SearchForTriangulation(a, b, h1, h2)
+        assert n == rn and pairs == [(i, int(t)) for i, t in enumerate(rm) if t >= 0]
+        m, nm, mad = lm._match_mad_batch([(a, b), (b, a)], 0.5)
+        assert np.array_equal(mad[0], rmad) and np.array_equal(mad[1], oracle.line_match_mad(b, a, 0.5)[2])
+        assert np.array_equal(m[1], oracle.line_match_mad(b, a, 0.5)[1])
+    finally:
+        lm.close()
+
+
+def test_line_mad_on_extracted_lines(gpu):
+    from pl_vi_orbslam3_b200 import LineMatcher, Lineextractor
+    f1, f2, _ = synth.warp_pair(5)
+    l = Lineextractor(200, 0, 0.8, 2, 2.0, 0)
+    lm = LineMatcher(max_pairs=1, max_train=256, max_query=256)
+    try:
+        _, d1, _ = l(f1)
+        _, d2, _ = l(f2)
+        n, pairs = lm.SerachForInitialize(d1, d2)
+        rn, rm, _ = oracle.line_match_mad(d1, d2, 0.5)
+        assert n == rn > 20 and pairs == [(i, int(t)) for i, t in enumerate(rm) if t >= 0]
+    finally:
+        l.close()
+        lm.close()
+
+
+def test_compute_distinctive_descriptors(gpu):
+    import torch
+    from pl_vi_orbslam3_b200.matchers import compute_distinctive_descriptors
+    rng = np.random.RandomState(8)
+    M, cap = 300, 70
+    counts = rng.randint(0, cap + 1, M).astype(np.int32)
+    counts[:4] = (0, 1, 2, cap)
+    desc = np.zeros((M, cap, 32), np.uint8)
+    for p in range(M):
+        base = rng.randint(0, 256, 32).astype(np.uint8)
+        for i in range(counts[p]):
+            d = base.copy()
+            for bit in rng.permutation(256)[:rng.randint(0, 60)]:
+                d[bit // 8] ^= 1 << (bit % 8)
+            desc[p, i] = d
+    desc[5, :counts[5]] = desc[5, 0]                      # all identical: index 0 wins
+    idx, best = compute_distinctive_descriptors(torch.from_numpy(desc).cuda(), torch.from_numpy(counts).cuda())
+    idx, best = idx.cpu().numpy(), best.cpu().numpy()
+    for p in range(M):
+        r = oracle.distinctive_descriptor(desc[p, :counts[p]])
+        assert idx[p] == r, p
+        if r >= 0:
+            assert np.array_equal(best[p], desc[p, r])
