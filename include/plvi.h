@@ -330,6 +330,18 @@ int plvi_search_by_bow(plvi_matcher* m, int npairs, const plvi_keypoint* train_k
                        int query_stride, int th_dist, float nnratio, int check_orientation, int* match_train,
                        int* match_query, int* nmatches, int on_device);
 
+/* Descriptor part of int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)
+ * (include/ORBmatcher.h:57, src/ORBmatcher.cc:823-963, mono path).  Same calling scheme as plvi_search_by_bow
+ * with pKF2 as the "train" side: group_items = pKF2's feature indices grouped by vocabulary node, one query per
+ * pKF1 feature of a common node (flags bit0 = no / bad map point), train_blocked[i2] != 0 for pKF2 features
+ * without a (good) map point (may be NULL).  th_low = TH_LOW: this variant accepts bestDist1 < TH_LOW.
+ * match_query[q] = pKF2 feature matched to query q (vpMatches12[idx1] = vpMapPoints2[match_query]) or -1. */
+int plvi_search_by_bow_kf(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                          const uint8_t* train_blocked, const int* train_counts, int train_stride, const int* group_items,
+                          int items_stride, const plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                          int query_stride, int th_low, float nnratio, int check_orientation, int* match_train,
+                          int* match_query, int* nmatches, int on_device);
+
 /* Test / benchmark utility (device pointers only): builds the plvi_query records of
  * SearchByProjection(Frame,Frame) for an identity pose -- every keypoint of the query
  * frame projects onto its own position (u,v = pt), radius = th * scale_factor^octave,

@@ -428,3 +428,18 @@ def distinctive_descriptor(desc):
     """MapPoint::ComputeDistinctiveDescriptors: index of the descriptor with the least median distance."""
     desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
     return int(lib().plvio_distinctive_descriptor(_p(desc), C.c_int(len(desc))))
+
+
+def search_bow_kfkf(keys1, desc1, mp1, fv1, keys2, desc2, mp2, fv2, nnratio=0.8, check_ori=True):
+    """ORBmatcher::SearchByBoW(KF1, KF2, vpMatches12): fvN = (nodes, start, features) FeatureVector CSR; mpN = has-map-point
+    flags.  Returns (nmatches, matches12[n1]) with matches12[idx1] = idx2 or -1."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    mp1, mp2 = np.ascontiguousarray(mp1, np.uint8), np.ascontiguousarray(mp2, np.uint8)
+    a = [np.ascontiguousarray(x, np.int32) for x in fv1]
+    b = [np.ascontiguousarray(x, np.int32) for x in fv2]
+    m = np.full(max(len(keys1), 1), -1, np.int32)
+    n = lib().plvio_search_bow_kfkf(_p(keys1), _p(desc1), _p(mp1), C.c_int(len(keys1)), _p(a[0]), _p(a[1]), _p(a[2]), C.c_int(len(a[0])),
+                                    _p(keys2), _p(desc2), _p(mp2), C.c_int(len(keys2)), _p(b[0]), _p(b[1]), _p(b[2]), C.c_int(len(b[0])),
+                                    C.c_float(nnratio), C.c_int(int(check_ori)), _p(m))
+    return n, m[:len(keys1)]

@@ -393,3 +393,57 @@ extern "C" int plvio_distinctive_descriptor(const uint8_t* desc, int n) {
   }
   return BestIdx;
 }
+
+// ---- ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (src/ORBmatcher.cc:823-963), mono path,
+// restated on the raw FeatureVectors: fvN_nodes ascending node ids, fvN_start CSR into fvN_feat (feature indices).
+// mpN[i] != 0: vpMapPointsN[i] exists and is not bad.  matches12[idx1] = idx2 (the reference stores vpMapPoints2[idx2]).
+extern "C" int plvio_search_bow_kfkf(const plvio::Kp* keys1, const uint8_t* desc1, const uint8_t* mp1, int n1, const int* fv1_nodes,
+                                     const int* fv1_start, const int* fv1_feat, int nfv1, const plvio::Kp* keys2,
+                                     const uint8_t* desc2, const uint8_t* mp2, int n2, const int* fv2_nodes, const int* fv2_start,
+                                     const int* fv2_feat, int nfv2, float nnratio, int checkOri, int* matches12) {
+  using namespace plvio;
+  const int TH_LOW = 50;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  std::vector<char> matched2(n2, 0);
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int nmatches = 0;
+  int a = 0, b = 0;
+  while (a < nfv1 && b < nfv2) {
+    if (fv1_nodes[a] == fv2_nodes[b]) {
+      for (int p1 = fv1_start[a]; p1 < fv1_start[a + 1]; p1++) {
+        const int idx1 = fv1_feat[p1];
+        if (!mp1[idx1]) continue;
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int p2 = fv2_start[b]; p2 < fv2_start[b + 1]; p2++) {
+          const int idx2 = fv2_feat[p2];
+          if (matched2[idx2] || !mp2[idx2]) continue;
+          const int dist = hamming256(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 < TH_LOW) {
+          if ((float)bestDist1 < nnratio * (float)bestDist2) {
+            matches12[idx1] = bestIdx2;
+            matched2[bestIdx2] = 1;
+            if (checkOri) rotHist[rot_bin(keys1[idx1].angle, keys2[bestIdx2].angle)].push_back(idx1);
+            nmatches++;
+          }
+        }
+      }
+      a++; b++;
+    } else if (fv1_nodes[a] < fv2_nodes[b]) {
+      while (a < nfv1 && fv1_nodes[a] < fv2_nodes[b]) a++;     // lower_bound
+    } else {
+      while (b < nfv2 && fv2_nodes[b] < fv1_nodes[a]) b++;
+    }
+  }
+  if (checkOri) {
+    int i1 = -1, i2 = -1, i3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == i1 || i == i2 || i == i3) continue;
+      for (int id : rotHist[i]) { matches12[id] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}

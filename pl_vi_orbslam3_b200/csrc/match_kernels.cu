@@ -773,11 +773,11 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
   return PLVI_OK;
 }
 
-int plvi_search_by_bow(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
-                       const int* train_counts, int train_stride, const int* group_items, int items_stride,
-                       const plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
-                       int query_stride, int th_dist, float nnratio, int check_orientation, int* match_train,
-                       int* match_query, int* nmatches, int on_device) {
+static int search_by_bow_impl(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                              const uint8_t* train_blocked, const int* train_counts, int train_stride, const int* group_items,
+                              int items_stride, const plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                              int query_stride, int th_dist, float nnratio, int check_orientation, int* match_train,
+                              int* match_query, int* nmatches, int on_device) {
   if (!m || npairs < 1 || !train_keys || !train_desc || !train_counts || !group_items || !queries || !query_desc ||
       !query_counts || !match_train || !match_query || !nmatches || items_stride < 1) {
     set_error("plvi_search_by_bow: invalid argument");
@@ -802,11 +802,16 @@ int plvi_search_by_bow(plvi_matcher* m, int npairs, const plvi_keypoint* train_k
   cudaStream_t st = m->stream;
   if (on_device) {
     a.keys = train_keys; a.desc = train_desc; a.tcount = train_counts; a.items = group_items;
+    a.blocked = train_blocked;
     a.q = const_cast<plvi_query*>(queries); a.qdesc = query_desc; a.qcount = query_counts;
     a.matchTrain = match_train; a.matchQuery = match_query; a.nmatches = nmatches;
   } else {
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dKeys, train_keys, P * T * sizeof(plvi_keypoint), cudaMemcpyHostToDevice, st));
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dDesc, train_desc, P * T * 32, cudaMemcpyHostToDevice, st));
+    if (train_blocked) {
+      PLVI_CUDA_TRY(cudaMemcpyAsync(m->dBlocked, train_blocked, P * T, cudaMemcpyHostToDevice, st));
+      a.blocked = m->dBlocked;
+    }
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dTCount, train_counts, P * sizeof(int), cudaMemcpyHostToDevice, st));
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dMatchedDist, group_items, P * items_stride * sizeof(int), cudaMemcpyHostToDevice, st));
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQ, queries, P * Q * sizeof(plvi_query), cudaMemcpyHostToDevice, st));
@@ -829,6 +834,27 @@ int plvi_search_by_bow(plvi_matcher* m, int npairs, const plvi_keypoint* train_k
     PLVI_CUDA_TRY(cudaStreamSynchronize(st));
   }
   return PLVI_OK;
+}
+
+int plvi_search_by_bow(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                       const int* train_counts, int train_stride, const int* group_items, int items_stride,
+                       const plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                       int query_stride, int th_dist, float nnratio, int check_orientation, int* match_train,
+                       int* match_query, int* nmatches, int on_device) {
+  return search_by_bow_impl(m, npairs, train_keys, train_desc, nullptr, train_counts, train_stride, group_items, items_stride,
+                            queries, query_desc, query_counts, query_stride, th_dist, nnratio, check_orientation, match_train,
+                            match_query, nmatches, on_device);
+}
+
+int plvi_search_by_bow_kf(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                          const uint8_t* train_blocked, const int* train_counts, int train_stride, const int* group_items,
+                          int items_stride, const plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                          int query_stride, int th_low, float nnratio, int check_orientation, int* match_train,
+                          int* match_query, int* nmatches, int on_device) {
+  // the keyframe-keyframe variant accepts bestDist1 < TH_LOW (strict, src/ORBmatcher.cc:911); distances are integers
+  return search_by_bow_impl(m, npairs, train_keys, train_desc, train_blocked, train_counts, train_stride, group_items,
+                            items_stride, queries, query_desc, query_counts, query_stride, th_low - 1, nnratio,
+                            check_orientation, match_train, match_query, nmatches, on_device);
 }
 
 int plvi_queries_from_keypoints(plvi_matcher* m, const plvi_keypoint* d_kps, const int* d_counts, int npairs,

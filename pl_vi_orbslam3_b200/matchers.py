@@ -134,6 +134,25 @@ class ORBmatcher(_Matcher):
                                        ptr(mt), ptr(mq), ptr(nm), 0))
         return int(nm[0]), mt[:n], mq[:nq]
 
+    def SearchByBoW_KF(self, KF2, has_mappoint2, group_items, queries, qdesc):
+        """Descriptor part of SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:823-963): KF2 is the
+        searched side, has_mappoint2[i] = vpMapPoints2[i] is a good map point.  Returns (nmatches, match_query) with
+        match_query[q] = KF2 feature matched to query q or -1."""
+        n, nq = len(KF2.keys), len(queries)
+        T, Q, I = max(n, 1), max(nq, 1), max(len(group_items), 1)
+        keys = np.zeros(T, KEYPOINT_DTYPE); keys[:n] = KF2.keys
+        desc = np.zeros((T, 32), np.uint8); desc[:n] = KF2.desc
+        blk = np.ones(T, np.uint8); blk[:n] = ~np.asarray(has_mappoint2, bool)
+        items = np.zeros(I, np.int32); items[:len(group_items)] = group_items
+        qs = np.zeros(Q, QUERY_DTYPE); qs[:nq] = queries
+        qd = np.zeros((Q, 32), np.uint8); qd[:nq] = qdesc
+        tc, qc = np.array([n], np.int32), np.array([nq], np.int32)
+        mt, mq, nm = np.empty(T, np.int32), np.empty(Q, np.int32), np.empty(1, np.int32)
+        check(lib().plvi_search_by_bow_kf(self._h, 1, ptr(keys), ptr(desc), ptr(blk), ptr(tc), T, ptr(items), I, ptr(qs),
+                                          ptr(qd), ptr(qc), Q, self.TH_LOW, self.mfNNratio, int(self.mbCheckOrientation),
+                                          ptr(mt), ptr(mq), ptr(nm), 0))
+        return int(nm[0]), mq[:nq]
+
     @staticmethod
     def init_queries(F1_keys, vbPrevMatched, windowSize):
         n1 = len(F1_keys)

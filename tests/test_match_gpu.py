@@ -330,3 +330,42 @@ def test_compute_distinctive_descriptors(gpu):
         assert idx[p] == r, p
         if r >= 0:
             assert np.array_equal(best[p], desc[p, r])
+
+
+# ---- ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) through plvi_search_by_bow_kf, with real
+# FeatureVectors from the DBoW2 transform oracle on a synthetic vocabulary
+@pytest.mark.parametrize("k,L,levelsup,nnratio", [(6, 3, 2, 0.8), (10, 4, 2, 0.9), (4, 2, 1, 0.6)])
+def test_search_by_bow_keyframes(om, pair_features, k, L, levelsup, nnratio):
+    from pl_vi_orbslam3_b200.vocabulary import ORBVocabulary
+    r1, r2, _ = pair_features
+    v = ORBVocabulary.random_tree(k=k, L=L, seed=k)
+    rng = np.random.RandomState(L)
+    fv1 = oracle.bow_transform(v.as_oracle_dict(), r1["descriptors"], levelsup)["fv"]
+    fv2 = oracle.bow_transform(v.as_oracle_dict(), r2["descriptors"], levelsup)["fv"]
+    mp1 = (rng.rand(len(r1["keypoints"])) < 0.8).astype(np.uint8)
+    mp2 = (rng.rand(len(r2["keypoints"])) < 0.8).astype(np.uint8)
+    # caller side of the reference's walk over the two FeatureVectors: KF2 groups + one query per KF1 feature of a common node
+    items, start2 = fv2[2], {int(nd): (int(fv2[1][i]), int(fv2[1][i + 1])) for i, nd in enumerate(fv2[0])}
+    order, q = [], []
+    for i, nd in enumerate(fv1[0]):
+        if int(nd) not in start2:
+            continue
+        for idx1 in fv1[2][fv1[1][i]:fv1[1][i + 1]]:
+            order.append(int(idx1))
+            q.append((start2[int(nd)][0], start2[int(nd)][1], r1["keypoints"]["angle"][idx1], 0 if mp1[idx1] else 1))
+    qs = np.zeros(len(q), QUERY_DTYPE)
+    for j, (s, e, ang, fl) in enumerate(q):
+        qs[j]["min_level"], qs[j]["max_level"], qs[j]["angle"], qs[j]["flags"] = s, e, ang, fl
+    om.mfNNratio = nnratio
+    KF2 = FrameView(r2["keypoints"], r2["descriptors"], GRID)
+    n, mq = om.SearchByBoW_KF(KF2, mp2, items, qs, r1["descriptors"][order])
+    om.mfNNratio = 0.9
+    got = np.full(len(r1["keypoints"]), -1, np.int32)
+    for j, idx1 in enumerate(order):
+        if mq[j] >= 0:
+            got[idx1] = mq[j]
+    rn, rm = oracle.search_bow_kfkf(r1["keypoints"], r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2,
+                                    nnratio, True)
+    assert n == rn and np.array_equal(got, rm)
+    if L <= 3:
+        assert n > 10
