@@ -671,7 +671,7 @@ __device__ __forceinline__ void grow_clear_atomic(GrowBitmap& bm, int x, int y) 
   else atomicAnd(bm.gm + y * bm.wpr + (x >> 5), m);
 }
 
-__global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_commit(const __grid_constant__ LineGeom g, LineBufs b, int n,
+__global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_constant__ LineGeom g, LineBufs b, int n,
                                                               int smemWordsPerWarp) {
   // GROW_WPB independent warps per block (consecutive frames of one octave): single-warp blocks
   // would fill the SM's 32 block slots and keep the kernels of the other streams out
@@ -1553,6 +1553,8 @@ int line_kernel_attrs(const LineGeom& g) {
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
   const size_t commitSmem = (growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned)) * GROW_WPB;
   if (commitSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
+  // the growth kernels want as many resident warps as registers allow: give shared memory the large carve-out
+  PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (commitSmem > 40 * 1024) {
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
