@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ 
       const double DA = __dsub_rn(ssc[ty + 1][tx + 1], ssc[ty][tx]);
       const double BC = __dsub_rn(ssc[ty][tx + 1], ssc[ty + 1][tx]);
       const double gx = __dadd_rn(DA, BC), gy = __dsub_rn(DA, BC);
-      norm = __dsqrt_rn(__ddiv_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), 4.0));
+      // (gx^2 + gy^2) / 4: the division by a power of two is exact, so the multiplication is identical
+      norm = __dsqrt_rn(__dmul_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), 0.25));
       if (!(norm <= g.rho)) {
         angDeg = fast_atan2_dev((float)gx, (float)(-gy));
         const double a = __dmul_rn((double)angDeg, D2R);
@@ -960,8 +961,11 @@ __global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGe
       sum += wgt;
     }
     x = warp_sum_d(x); y = warp_sum_d(y); sum = warp_sum_d(sum);
-    x /= sum;
-    y /= sum;
+    {   // x / sum and y / sum in one division sequence (odd lanes take y)
+      const double q = ((lane & 1) ? y : x) / sum;
+      x = __shfl_sync(0xffffffffu, q, 0);
+      y = __shfl_sync(0xffffffffu, q, 1);
+    }
     double Ixx = 0, Iyy = 0, Ixy = 0;
     for (int i = lane; i < R.size; i += 32) {
       const unsigned p = rp[i];
@@ -995,11 +999,13 @@ __global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGe
     }
     lmin = warp_min_d(lmin);
     lmax = warp_max_d(lmax);
-    if (lane == 0) {
-      double x1 = x + lmin * dx, y1 = y + lmin * dy, x2 = x + lmax * dx, y2 = y + lmax * dy;
-      x1 += 0.5; y1 += 0.5; x2 += 0.5; y2 += 0.5;
-      if (g.lsdScale != 1.0) { x1 /= g.lsdScale; y1 /= g.lsdScale; x2 /= g.lsdScale; y2 /= g.lsdScale; }
-      segs[r] = make_float4((float)x1, (float)y1, (float)x2, (float)y2);
+    if (lane < 4) {   // lanes 0..3 finish x1, y1, x2, y2 (all inputs are warp-uniform): one division sequence instead of four
+      const double l = (lane & 2) ? lmax : lmin;
+      const double c = (lane & 1) ? y : x, d = (lane & 1) ? dy : dx;
+      double v = c + l * d;
+      v += 0.5;
+      if (g.lsdScale != 1.0) v /= g.lsdScale;
+      reinterpret_cast<float*>(segs + r)[lane] = (float)v;
     }
   }
 }
