@@ -512,11 +512,13 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
   const double prec = g.prec;
   const float kHi = g.alignHi2, kLo = g.alignLo2;
 
+  // the private bitmap is read and written through L2 only (__ldcg / __stcg): its words are re-read right after
+  // they were stored, and L1 (write-through, shared with 500+ other chains) never keeps them anyway
   __shared__ unsigned sring_all[GROW_WPB][SPEC_RING * 32];   // the last SPEC_RING pixels of each lane's region (BFS frontier)
   unsigned* sring = sring_all[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   int row = r0, wi = 0;
-  unsigned word = (r0 < r1) ? P[r0 * wpr] : 0u;
+  unsigned word = (r0 < r1) ? __ldcg(P + r0 * wpr) : 0u;
   int nrec = 0, npx = 0, base = 0, size = 0, i = 0;
   unsigned seedpk = 0u;
   float sang = 0.f, sumdx = 0.f, sumdy = 0.f, n2 = 0.f;
@@ -532,13 +534,13 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
         recs[nrec++] = make_uint4(seedpk, (unsigned)base, (unsigned)size, __float_as_uint(ang));
         npx += size;
         size = 0; i = 0;
-        word = P[row * wpr + wi];   // the region may have taken pixels of the seed's own word
+        word = __ldcg(P + row * wpr + wi);   // the region may have taken pixels of the seed's own word
       }
       int guard = 0;
       while (word == 0u && guard < SPEC_SCAN_WORDS) {
         if (++wi == wpr) { wi = 0; ++row; }
         if (row >= r1) break;
-        word = P[row * wpr + wi];
+        word = __ldcg(P + row * wpr + wi);
         ++guard;
       }
       if (row >= r1 || nrec >= recCap) { done = true; continue; }
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
       const int sx = wi * 32 + bit;
       seedpk = (unsigned)sx | ((unsigned)row << 16);
       word &= ~(1u << bit);
-      P[row * wpr + wi] = word;
+      __stcg(P + row * wpr + wi, word);
       base = npx;
       list[base] = seedpk;
       size = 1;
@@ -572,8 +574,8 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
     for (int r = 0; r < 3; r++) {
       const int y = ey - 1 + r;
       const bool ok = y >= r0 && y < H;
-      lo[r] = ok ? P[y * wpr + wa] : 0u;
-      hi[r] = (ok && needHi) ? P[y * wpr + wa + 1] : 0u;
+      lo[r] = ok ? __ldcg(P + y * wpr + wa) : 0u;
+      hi[r] = (ok && needHi) ? __ldcg(P + y * wpr + wa + 1) : 0u;
       const unsigned long long comb = ((unsigned long long)hi[r] << 32) | lo[r];
       const unsigned three = sh >= 0 ? ((unsigned)(comb >> sh) & 7u) : ((lo[r] << 1) & 7u);
       m9 |= three << (3 * r);
@@ -619,8 +621,8 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
         if (a3) {
           const unsigned long long mk = sh >= 0 ? ((unsigned long long)a3 << sh) : (unsigned long long)(a3 >> 1);
           const int y = ey - 1 + r;
-          P[y * wpr + wa] = lo[r] & ~(unsigned)mk;
-          if ((unsigned)(mk >> 32)) P[y * wpr + wa + 1] = hi[r] & ~(unsigned)(mk >> 32);
+          __stcg(P + y * wpr + wa, lo[r] & ~(unsigned)mk);
+          if ((unsigned)(mk >> 32)) __stcg(P + y * wpr + wa + 1, hi[r] & ~(unsigned)(mk >> 32));
         }
       }
     }
