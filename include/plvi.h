@@ -342,6 +342,30 @@ int plvi_search_by_bow_kf(plvi_matcher* m, int npairs, const plvi_keypoint* trai
                           int query_stride, int th_low, float nnratio, int check_orientation, int* match_train,
                           int* match_query, int* nmatches, int on_device);
 
+/* Geometry of one keyframe pair for ORBmatcher::SearchForTriangulation (monocular pinhole path): F12 row-major
+ * as Pinhole::epipolarConstrain builds it (K1^-T [t12]x R12 K2^-1, src/CameraModels/Pinhole.cpp:137-140), ep =
+ * projection of pKF1's camera centre into pKF2 (src/ORBmatcher.cc:971-976), pKF2->mvScaleFactors /
+ * mvLevelSigma2, coarse = bCoarse, check_epipole = 1 for the mono case (!bStereo1 && !bStereo2). */
+typedef struct plvi_epipolar {
+  float F12[9];
+  float ep_x, ep_y;
+  float scale_factors[16];
+  float level_sigma2[16];
+  int32_t coarse, check_epipole;
+} plvi_epipolar;
+
+/* Descriptor + epipolar part of int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
+ * vector<pair<size_t,size_t>>& vMatchedPairs, bool bOnlyStereo = false, bool bCoarse) (include/ORBmatcher.h:64-65,
+ * src/ORBmatcher.cc:965-1206).  Calling scheme of plvi_search_by_bow_kf: pKF2 is the searched side (train_blocked
+ * = has a map point), one query per pKF1 feature WITHOUT map point of a common vocabulary node (u, v = kp1.pt,
+ * min_level/max_level = the node's group range, angle, flags bit0 = skip).  Device pointers only, runs on the
+ * matcher's stream.  match_query[q] = pKF2 feature or -1; vMatchedPairs = {(idx1(q), match_query[q])}. */
+int plvi_search_for_triangulation(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                                  const uint8_t* train_blocked, const int* train_counts, int train_stride, const int* group_items,
+                                  int items_stride, const plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                                  int query_stride, const plvi_epipolar* geometry, int th_low, int check_orientation,
+                                  int* match_query, int* nmatches);
+
 /* Test / benchmark utility (device pointers only): builds the plvi_query records of
  * SearchByProjection(Frame,Frame) for an identity pose -- every keypoint of the query
  * frame projects onto its own position (u,v = pt), radius = th * scale_factor^octave,

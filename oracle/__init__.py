@@ -443,3 +443,21 @@ def search_bow_kfkf(keys1, desc1, mp1, fv1, keys2, desc2, mp2, fv2, nnratio=0.8,
                                     _p(keys2), _p(desc2), _p(mp2), C.c_int(len(keys2)), _p(b[0]), _p(b[1]), _p(b[2]), C.c_int(len(b[0])),
                                     C.c_float(nnratio), C.c_int(int(check_ori)), _p(m))
     return n, m[:len(keys1)]
+
+
+def search_triangulation(keys1, desc1, mp1, fv1, keys2, desc2, mp2, fv2, F12, ep, sf2, sigma2_2, coarse=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation (mono pinhole): (nmatches, matches12[n1]); vMatchedPairs = [(i, m[i]) for m[i] >= 0]."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    mp1, mp2 = np.ascontiguousarray(mp1, np.uint8), np.ascontiguousarray(mp2, np.uint8)
+    a = [np.ascontiguousarray(x, np.int32) for x in fv1]
+    b = [np.ascontiguousarray(x, np.int32) for x in fv2]
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    sf = np.ascontiguousarray(sf2, np.float32)
+    sg = np.ascontiguousarray(sigma2_2, np.float32)
+    m = np.full(max(len(keys1), 1), -1, np.int32)
+    n = lib().plvio_search_triangulation(_p(keys1), _p(desc1), _p(mp1), C.c_int(len(keys1)), _p(a[0]), _p(a[1]), _p(a[2]), C.c_int(len(a[0])),
+                                         _p(keys2), _p(desc2), _p(mp2), C.c_int(len(keys2)), _p(b[0]), _p(b[1]), _p(b[2]), C.c_int(len(b[0])),
+                                         _p(F), C.c_float(ep[0]), C.c_float(ep[1]), _p(sf), _p(sg), C.c_int(int(coarse)),
+                                         C.c_int(int(check_ori)), _p(m))
+    return n, m[:len(keys1)]

@@ -447,3 +447,75 @@ extern "C" int plvio_search_bow_kfkf(const plvio::Kp* keys1, const uint8_t* desc
   }
   return nmatches;
 }
+
+// ---- ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo=false, bCoarse)
+// (src/ORBmatcher.cc:965-1206), monocular pinhole path, with Pinhole::epipolarConstrain
+// (src/CameraModels/Pinhole.cpp:135-157).  mpN[i] != 0: feature i has a map point.  F12 row-major 3x3 float,
+// ep = epipole in image 2, sf2 / sigma2_2 = pKF2->mvScaleFactors / mvLevelSigma2.  matches12[idx1] = idx2 or -1.
+extern "C" int plvio_search_triangulation(const plvio::Kp* keys1, const uint8_t* desc1, const uint8_t* mp1, int n1,
+                                          const int* fv1_nodes, const int* fv1_start, const int* fv1_feat, int nfv1,
+                                          const plvio::Kp* keys2, const uint8_t* desc2, const uint8_t* mp2, int n2,
+                                          const int* fv2_nodes, const int* fv2_start, const int* fv2_feat, int nfv2,
+                                          const float* F12, float epx, float epy, const float* sf2, const float* sigma2_2,
+                                          int coarse, int checkOri, int* matches12) {
+  using namespace plvio;
+  const int TH_LOW = 50;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  std::vector<char> vbMatched2(n2, 0);   // never set by the reference
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int nmatches = 0, a = 0, b = 0;
+  while (a < nfv1 && b < nfv2) {
+    if (fv1_nodes[a] == fv2_nodes[b]) {
+      for (int p1 = fv1_start[a]; p1 < fv1_start[a + 1]; p1++) {
+        const int idx1 = fv1_feat[p1];
+        if (mp1[idx1]) continue;
+        const Kp& kp1 = keys1[idx1];
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (int p2 = fv2_start[b]; p2 < fv2_start[b + 1]; p2++) {
+          const int idx2 = fv2_feat[p2];
+          if (vbMatched2[idx2] || mp2[idx2]) continue;
+          const int dist = hamming256(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+          if (dist > TH_LOW || dist > bestDist) continue;
+          const Kp& kp2 = keys2[idx2];
+          {   // !bStereo1 && !bStereo2 && !pKF1->mpCamera2
+            const float distex = epx - kp2.x;
+            const float distey = epy - kp2.y;
+            if (distex * distex + distey * distey < 100 * sf2[kp2.octave]) continue;
+          }
+          bool ok = coarse != 0;
+          if (!ok) {   // Pinhole::epipolarConstrain
+            const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+            const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+            const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+            const float num = la * kp2.x + lb * kp2.y + lc;
+            const float den = la * la + lb * lb;
+            if (den != 0) {
+              const float dsqr = num * num / den;
+              ok = dsqr < 3.84 * sigma2_2[kp2.octave];
+            }
+          }
+          if (ok) { bestIdx2 = idx2; bestDist = dist; }
+        }
+        if (bestIdx2 >= 0) {
+          matches12[idx1] = bestIdx2;
+          nmatches++;
+          if (checkOri) rotHist[rot_bin(kp1.angle, keys2[bestIdx2].angle)].push_back(idx1);
+        }
+      }
+      a++; b++;
+    } else if (fv1_nodes[a] < fv2_nodes[b]) {
+      while (a < nfv1 && fv1_nodes[a] < fv2_nodes[b]) a++;
+    } else {
+      while (b < nfv2 && fv2_nodes[b] < fv1_nodes[a]) b++;
+    }
+  }
+  if (checkOri) {
+    int i1 = -1, i2 = -1, i3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == i1 || i == i2 || i == i3) continue;
+      for (int id : rotHist[i]) { matches12[id] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}

@@ -76,6 +76,7 @@ _SIGS = {
                                        vp, vp, vp, ci]),
     "plvi_search_by_bow": (ci, [vp, ci, vp, vp, vp, ci, vp, ci, vp, vp, vp, ci, ci, cf, ci, vp, vp, vp, ci]),
     "plvi_search_by_bow_kf": (ci, [vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, vp, ci, ci, cf, ci, vp, vp, vp, ci]),
+    "plvi_search_for_triangulation": (ci, [vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, vp, ci, vp, ci, ci, vp, vp]),
     "plvi_queries_from_keypoints": (ci, [vp, vp, vp, ci, ci, cf, cf, vp]),
     "plvi_line_match": (ci, [vp, ci, vp, vp, ci, vp, vp, ci, cf, ci, vp, vp, ci]),
     "plvi_undistort_keypoints": (ci, [vp, vp, vp, ci, ci, vp, vp]),
@@ -89,6 +90,9 @@ _SIGS = {
     "plvi_bow_transform": (ci, [vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
 }
 
+EPIPOLAR_DTYPE = np.dtype([("F12", "<f4", (9,)), ("ep_x", "<f4"), ("ep_y", "<f4"), ("scale_factors", "<f4", (16,)),
+                           ("level_sigma2", "<f4", (16,)), ("coarse", "<i4"), ("check_epipole", "<i4")])
+assert EPIPOLAR_DTYPE.itemsize == 180
 CAMERA_DTYPE = np.dtype([("fx", "<f8"), ("fy", "<f8"), ("cx", "<f8"), ("cy", "<f8"), ("dist", "<f8", (14,)),
                          ("new_fx", "<f8"), ("new_fy", "<f8"), ("new_cx", "<f8"), ("new_cy", "<f8"),
                          ("iters", "<i4"), ("_pad", "<i4")])

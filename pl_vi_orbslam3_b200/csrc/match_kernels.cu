@@ -611,6 +611,112 @@ __global__ void __launch_bounds__(32) k_distinctive(const uint8_t* __restrict__ 
   if (bestDesc && lane < 8) reinterpret_cast<uint32_t*>(bestDesc + (size_t)mp * 32)[lane] = reinterpret_cast<const uint32_t*>(sd + b * 32)[lane];
 }
 
+// ---------------------------------------------------------------------------------
+// k_search_triangulation: descriptor + epipolar part of ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12,
+// vMatchedPairs, bOnlyStereo = false, bCoarse) (src/ORBmatcher.cc:965-1206), monocular pinhole path with
+// Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:135-157).  Nothing is claimed in this function
+// (vbMatched2 is never set), so the queries are independent: one warp per query, lanes over the
+// candidates of the vocabulary node.  The reference's scan keeps the candidate with the smallest
+// distance among those passing the geometric tests, the LAST one on ties (dist > bestDist is skipped,
+// equality replaces).  float arithmetic without contraction.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_search_triangulation(const plvi_keypoint* __restrict__ keysAll, const uint8_t* __restrict__ descAll,
+                                                              const uint8_t* __restrict__ blockedAll, const int* __restrict__ tcount,
+                                                              int tstride, const int* __restrict__ itemsAll, int istride,
+                                                              const plvi_query* __restrict__ qAll, const uint8_t* __restrict__ qdescAll,
+                                                              const int* __restrict__ qcount, int qstride,
+                                                              const plvi_epipolar* __restrict__ geomAll, int thLow, int checkOri,
+                                                              int* __restrict__ m12All, int* __restrict__ nmatches) {
+  __shared__ int hist[HISTO_LENGTH];
+  __shared__ int s_keep[3], s_nm;
+  __shared__ plvi_epipolar G;
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nq = min(qcount[pair], qstride);
+  const plvi_keypoint* keys = keysAll + (size_t)pair * tstride;
+  const uint8_t* desc = descAll + (size_t)pair * tstride * 32;
+  const uint8_t* blk = blockedAll ? blockedAll + (size_t)pair * tstride : nullptr;
+  const int* items = itemsAll + (size_t)pair * istride;
+  const plvi_query* q = qAll + (size_t)pair * qstride;
+  const uint8_t* qdesc = qdescAll + (size_t)pair * qstride * 32;
+  int* m12 = m12All + (size_t)pair * qstride;
+  (void)tcount;
+  if (tid < HISTO_LENGTH) hist[tid] = 0;
+  if (tid == 0) { s_nm = 0; G = geomAll[pair]; }
+  __syncthreads();
+  for (int qi = wid; qi < nq; qi += 8) {
+    const plvi_query Q = q[qi];
+    unsigned best = 0xffffffffu;
+    if (!(Q.flags & 1)) {
+      uint32_t qw[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) qw[k] = __ldg(reinterpret_cast<const uint32_t*>(qdesc + (size_t)qi * 32) + k);
+      // epipolar line of kp1 in image 2: l = x1' F12 = [a b c]
+      const float a = __fadd_rn(__fadd_rn(__fmul_rn(Q.u, G.F12[0]), __fmul_rn(Q.v, G.F12[3])), G.F12[6]);
+      const float b = __fadd_rn(__fadd_rn(__fmul_rn(Q.u, G.F12[1]), __fmul_rn(Q.v, G.F12[4])), G.F12[7]);
+      const float c = __fadd_rn(__fadd_rn(__fmul_rn(Q.u, G.F12[2]), __fmul_rn(Q.v, G.F12[5])), G.F12[8]);
+      const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+      for (int k = Q.min_level + lane; k < Q.max_level; k += 32) {
+        const int i2 = __ldg(items + k);
+        if (blk && blk[i2]) continue;
+        const int d = hamming256_regs(qw, desc + (size_t)i2 * 32);
+        if (d > thLow) continue;
+        const plvi_keypoint kp2 = keys[i2];
+        if (G.check_epipole) {
+          const float ex = __fsub_rn(G.ep_x, kp2.x), ey = __fsub_rn(G.ep_y, kp2.y);
+          if (__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < __fmul_rn(100.f, G.scale_factors[kp2.octave])) continue;
+        }
+        if (!G.coarse) {
+          if (den == 0.f) continue;
+          const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, kp2.x), __fmul_rn(b, kp2.y)), c);
+          const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+          if (!((double)dsqr < __dmul_rn(3.84, (double)G.level_sigma2[kp2.octave]))) continue;
+        }
+        // smallest distance, last candidate on ties
+        best = min(best, ((unsigned)d << 20) | (unsigned)(0xfffff - min(k - Q.min_level, 0xfffff)));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) {
+      int m = -1;
+      if (best != 0xffffffffu) {
+        m = items[Q.min_level + (0xfffff - (int)(best & 0xfffffu))];
+        atomicAdd(&s_nm, 1);
+        if (checkOri) atomicAdd(&hist[rot_bin(Q.angle, keys[m].angle)], 1);
+      }
+      m12[qi] = m;
+    }
+  }
+  __syncthreads();
+  if (checkOri) {
+    if (tid == 0) {
+      int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+      for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int sN = hist[i];
+        if (sN > max1) { max3 = max2; max2 = max1; max1 = sN; i3 = i2; i2 = i1; i1 = i; }
+        else if (sN > max2) { max3 = max2; max2 = sN; i3 = i2; i2 = i; }
+        else if (sN > max3) { max3 = sN; i3 = i; }
+      }
+      if ((float)max2 < 0.1f * (float)max1) { i2 = -1; i3 = -1; }
+      else if ((float)max3 < 0.1f * (float)max1) { i3 = -1; }
+      s_keep[0] = i1; s_keep[1] = i2; s_keep[2] = i3;
+    }
+    __syncthreads();
+    int dec = 0;
+    for (int i = tid; i < nq; i += 256) {
+      const int m = m12[i];
+      if (m < 0) continue;
+      const int bb = rot_bin(q[i].angle, keys[m].angle);
+      if (bb == s_keep[0] || bb == s_keep[1] || bb == s_keep[2]) continue;
+      m12[i] = -1;
+      dec++;
+    }
+    if (dec) atomicSub(&s_nm, dec);
+    __syncthreads();
+  }
+  if (tid == 0) nmatches[pair] = s_nm;
+}
+
 struct plvi_matcher {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -941,6 +1047,25 @@ int plvi_distinctive_descriptors(void* stream, const uint8_t* d_desc, const int*
   if (smem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_distinctive<<<n_points, 32, smem, (cudaStream_t)stream>>>(d_desc, d_counts, stride, d_best_idx, d_best_desc);
+  PLVI_CUDA_TRY(cudaGetLastError());
+  return PLVI_OK;
+}
+
+int plvi_search_for_triangulation(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                                  const uint8_t* train_blocked, const int* train_counts, int train_stride, const int* group_items,
+                                  int items_stride, const plvi_query* queries, const uint8_t* query_desc, const int* query_counts,
+                                  int query_stride, const plvi_epipolar* geometry, int th_low, int check_orientation,
+                                  int* match_query, int* nmatches) {
+  if (!m || npairs < 1 || !train_keys || !train_desc || !train_counts || !group_items || !queries || !query_desc || !query_counts ||
+      !geometry || !match_query || !nmatches || train_stride < 1 || items_stride < 1 || query_stride < 1) {
+    set_error("plvi_search_for_triangulation: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  k_search_triangulation<<<npairs, 256, 0, m->stream>>>(train_keys, train_desc, train_blocked, train_counts, train_stride, group_items,
+                                                        items_stride, queries, query_desc, query_counts, query_stride, geometry, th_low,
+                                                        check_orientation, match_query, nmatches);
+  m->lastLaunches = 1;
   PLVI_CUDA_TRY(cudaGetLastError());
   return PLVI_OK;
 }

@@ -153,6 +153,40 @@ class ORBmatcher(_Matcher):
                                           ptr(mt), ptr(mq), ptr(nm), 0))
         return int(nm[0]), mq[:nq]
 
+    def SearchForTriangulation(self, KF2, has_mappoint2, group_items, queries, qdesc, F12, ep, scale_factors2, level_sigma2_2,
+                               coarse=False):
+        """Descriptor + epipolar part of SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, false, bCoarse)
+        (src/ORBmatcher.cc:965-1206, mono pinhole).  queries: one per KF1 feature without map point of a common node
+        (u, v = kp1.pt).  Returns (nmatches, match_query)."""
+        import torch
+        from .capi import EPIPOLAR_DTYPE
+        n, nq = len(KF2.keys), len(queries)
+        T, Q, I = max(n, 1), max(nq, 1), max(len(group_items), 1)
+        keys = np.zeros(T, KEYPOINT_DTYPE); keys[:n] = KF2.keys
+        desc = np.zeros((T, 32), np.uint8); desc[:n] = KF2.desc
+        blk = np.ones(T, np.uint8); blk[:n] = np.asarray(has_mappoint2, bool)
+        items = np.zeros(I, np.int32); items[:len(group_items)] = group_items
+        qs = np.zeros(Q, QUERY_DTYPE); qs[:nq] = queries
+        qd = np.zeros((Q, 32), np.uint8); qd[:nq] = qdesc
+        g = np.zeros(1, EPIPOLAR_DTYPE)
+        g["F12"][0] = np.asarray(F12, np.float32).reshape(9)
+        g["ep_x"], g["ep_y"] = np.float32(ep[0]), np.float32(ep[1])
+        g["scale_factors"][0, :len(scale_factors2)] = scale_factors2
+        g["level_sigma2"][0, :len(level_sigma2_2)] = level_sigma2_2
+        g["coarse"], g["check_epipole"] = int(coarse), 1
+        dev = torch.device("cuda", self.device)
+        def up(a):
+            return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+        t = [up(x) for x in (keys, desc, blk, np.array([n], np.int32), items, qs, qd, np.array([nq], np.int32), g)]
+        mq = torch.empty(Q, dtype=torch.int32, device=dev)
+        nm = torch.empty(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        check(lib().plvi_search_for_triangulation(self._h, 1, ptr(t[0]), ptr(t[1]), ptr(t[2]), ptr(t[3]), T, ptr(t[4]), I, ptr(t[5]),
+                                                  ptr(t[6]), ptr(t[7]), Q, ptr(t[8]), self.TH_LOW, int(self.mbCheckOrientation),
+                                                  ptr(mq), ptr(nm)))
+        self.sync()
+        return int(nm.cpu().numpy()[0]), mq.cpu().numpy()[:nq]
+
     @staticmethod
     def init_queries(F1_keys, vbPrevMatched, windowSize):
         n1 = len(F1_keys)

@@ -369,3 +369,45 @@ def test_search_by_bow_keyframes(om, pair_features, k, L, levelsup, nnratio):
     assert n == rn and np.array_equal(got, rm)
     if L <= 3:
         assert n > 10
+
+
+# ---- ORBmatcher::SearchForTriangulation (mono pinhole path: Hamming + epipole + epipolar-line tests)
+@pytest.mark.parametrize("k,L,levelsup,coarse,seed", [(6, 3, 2, False, 0), (10, 4, 2, False, 1), (4, 2, 1, True, 2), (6, 3, 2, False, 3)])
+def test_search_for_triangulation(om, pair_features, k, L, levelsup, coarse, seed):
+    from pl_vi_orbslam3_b200.vocabulary import ORBVocabulary
+    r1, r2, _ = pair_features
+    v = ORBVocabulary.random_tree(k=k, L=L, seed=k + 3)
+    rng = np.random.RandomState(seed)
+    fv1 = oracle.bow_transform(v.as_oracle_dict(), r1["descriptors"], levelsup)["fv"]
+    fv2 = oracle.bow_transform(v.as_oracle_dict(), r2["descriptors"], levelsup)["fv"]
+    mp1 = (rng.rand(len(r1["keypoints"])) < 0.4).astype(np.uint8)
+    mp2 = (rng.rand(len(r2["keypoints"])) < 0.4).astype(np.uint8)
+    # a fundamental matrix of a (noisy) sideways motion: epipolar lines roughly horizontal; random scale
+    F12 = (np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32) + rng.normal(0, 2e-4, (3, 3)).astype(np.float32)) * np.float32(rng.uniform(0.5, 3))
+    ep = (np.float32(rng.uniform(100, 600)), np.float32(rng.uniform(100, 400)))
+    sf2 = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    sg2 = (sf2 * sf2 * np.float32(4.0 if seed == 3 else 1.0)).astype(np.float32)
+    items, start2 = fv2[2], {int(nd): (int(fv2[1][i]), int(fv2[1][i + 1])) for i, nd in enumerate(fv2[0])}
+    order, q = [], []
+    k1 = r1["keypoints"]
+    for i, nd in enumerate(fv1[0]):
+        if int(nd) not in start2:
+            continue
+        for idx1 in fv1[2][fv1[1][i]:fv1[1][i + 1]]:
+            if mp1[idx1]:
+                continue                                   # only features without a map point are queried
+            order.append(int(idx1))
+            q.append((k1["x"][idx1], k1["y"][idx1], start2[int(nd)][0], start2[int(nd)][1], k1["angle"][idx1]))
+    qs = np.zeros(len(q), QUERY_DTYPE)
+    for j, (u, vv, s, e, ang) in enumerate(q):
+        qs[j]["u"], qs[j]["v"], qs[j]["min_level"], qs[j]["max_level"], qs[j]["angle"] = u, vv, s, e, ang
+    KF2 = FrameView(r2["keypoints"], r2["descriptors"], GRID)
+    n, mq = om.SearchForTriangulation(KF2, mp2, items, qs, r1["descriptors"][order], F12, ep, sf2, sg2, coarse)
+    got = np.full(len(k1), -1, np.int32)
+    for j, idx1 in enumerate(order):
+        got[idx1] = mq[j]
+    rn, rm = oracle.search_triangulation(k1, r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2, F12, ep,
+                                         sf2, sg2, coarse, True)
+    assert n == rn and np.array_equal(got, rm)
+    if coarse:
+        assert n > 20
