@@ -30,7 +30,7 @@ assert KEYLINE_DTYPE.itemsize == 68
 
 
 def build(force: bool = False) -> Path:
-    srcs = list(_DIR.glob("*.cpp")) + list(_DIR.glob("*.h"))
+    srcs = list(_DIR.glob("oracle_*.cpp")) + list(_DIR.glob("*.h"))
     stale = (not _LIB.exists()) or any(s.stat().st_mtime > _LIB.stat().st_mtime for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", str(_DIR), "-B", "libplvi_oracle.so"], check=True,
@@ -461,3 +461,93 @@ def search_triangulation(keys1, desc1, mp1, fv1, keys2, desc2, mp2, fv2, F12, ep
                                          _p(F), C.c_float(ep[0]), C.c_float(ep[1]), _p(sf), _p(sg), C.c_int(int(coarse)),
                                          C.c_int(int(check_ori)), _p(m))
     return n, m[:len(keys1)]
+
+
+# ---- oracle/_ref: the reference's own sources compiled against the cvmini stand-in ----------------
+# (oracle/Makefile.ref; built where /root/reference exists, shipped prebuilt to the GPU box)
+_REF_LIB = _DIR / "_ref" / "libplvi_ref.so"
+REFERENCE_ROOT = Path(os.environ.get("PLVI_REFERENCE_ROOT", "/root/reference"))
+_ref = None
+
+
+def ref_build(force: bool = False):
+    """Build oracle/_ref/libplvi_ref.so if the reference tree is present.  Returns the path or None."""
+    if not (REFERENCE_ROOT / "src" / "ORBextractor.cc").exists():
+        return _REF_LIB if _REF_LIB.exists() else None
+    build()
+    srcs = [_DIR / "ref_glue.cpp", _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _LIB]
+    stale = (not _REF_LIB.exists()) or any(s.stat().st_mtime > _REF_LIB.stat().st_mtime for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", str(_DIR), "-f", "Makefile.ref", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []),
+                       check=True, capture_output=True)
+    return _REF_LIB
+
+
+def ref_available() -> bool:
+    return ref_build() is not None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        p = ref_build()
+        if p is None:
+            raise RuntimeError("oracle/_ref/libplvi_ref.so is not built and /root/reference is absent")
+        lib()   # libplvi_oracle.so first (the stand-in's primitives resolve into it)
+        _ref = C.CDLL(str(p))
+        _ref.plviref_orb_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_void_p]
+        _ref.plviref_lsd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int]
+        _ref.plviref_line_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                              C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    return _ref
+
+
+def ref_orb_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, lapping=(0, 0),
+                    debug=False):
+    """The reference's ORBextractor::operator() itself (src/ORBextractor.cc), same outputs as orb_extract."""
+    img = _u8(img)
+    h, w = img.shape
+    plan = orb_plan(w, h, nfeatures, scale_factor, nlevels)
+    cap = 4 * nfeatures + 64
+    kps = np.zeros(cap, KEYPOINT_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    mono = C.c_int(0)
+    npx = int((plan["w"].astype(np.int64) * plan["h"]).sum())
+    pyr = np.empty(npx, np.uint8) if debug else None
+    n = ref_lib().plviref_orb_extract(_p(img), w, h, img.strides[0], nfeatures, scale_factor, nlevels, ini_th,
+                                      min_th, int(lapping[0]), int(lapping[1]), _p(kps), _p(desc), cap,
+                                      C.byref(mono), _p(pyr))
+    if n < 0:
+        raise RuntimeError(f"reference orb_extract failed: {n}")
+    out = {"keypoints": kps[:n].copy(), "descriptors": desc[:n].copy(), "mono_index": mono.value}
+    if debug:
+        out["pyramid"] = split_levels(pyr, plan)
+    return out
+
+
+def ref_lsd(img, lsd_scale=0.8, refine=0):
+    """The reference's LineSegmentDetectorImpl::detect itself (src/LSD/lsd.cpp) on one u8 image."""
+    img = _u8(img)
+    h, w = img.shape
+    cap = 1 << 16
+    segs = np.empty((cap, 4), np.float32)
+    n = ref_lib().plviref_lsd(_p(img), img.strides[0], w, h, int(refine), C.c_float(lsd_scale), _p(segs), cap)
+    return segs[:n].copy()
+
+
+def ref_line_extract(img, lsd_nfeatures=200, lsd_refine=0, lsd_scale=0.8, nlevels=2, scale=2.0):
+    """The reference's Lineextractor::operator() itself (LSD + LBD), same outputs as line_extract."""
+    img = _u8(img)
+    h, w = img.shape
+    cap = 1 << 15
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    eq = np.zeros((cap, 3), np.float64)
+    n = ref_lib().plviref_line_extract(_p(img), w, h, img.strides[0], int(lsd_nfeatures), int(lsd_refine),
+                                       C.c_float(lsd_scale), int(nlevels), C.c_float(scale), _p(kl), _p(desc),
+                                       _p(eq), cap)
+    if n < 0:
+        raise RuntimeError(f"reference line_extract failed: {n}")
+    return {"keylines": kl[:n].copy(), "descriptors": desc[:n].copy(), "line_eq": eq[:n].copy()}

@@ -1,0 +1,25 @@
+// TEST INFRASTRUCTURE -- stand-in for the three Eigen operations src/LineExtractor.cc:106-116 uses on
+// Eigen::Vector3d (comma initialiser, cross product, division by a scalar); Eigen is absent in this image.
+// See cvmini.hpp for the purpose (compiling the reference's sources unmodified into oracle/_ref).
+#pragma once
+namespace Eigen {
+struct Vector3d {
+  double v[3];
+  Vector3d() { v[0] = v[1] = v[2] = 0; }
+  Vector3d(double a, double b, double c) { v[0] = a; v[1] = b; v[2] = c; }
+  double& operator()(int i) { return v[i]; }
+  const double& operator()(int i) const { return v[i]; }
+  double& operator[](int i) { return v[i]; }
+  const double& operator[](int i) const { return v[i]; }
+  struct CommaInit {
+    Vector3d& t; int n;
+    CommaInit& operator,(double x) { t.v[n++] = x; return *this; }
+  };
+  CommaInit operator<<(double x) { v[0] = x; return CommaInit{*this, 1}; }
+  CommaInit operator<<(const Vector3d& o) { *this = o; return CommaInit{*this, 3}; }
+  Vector3d cross(const Vector3d& o) const {   // same expression order as Eigen's cross3 (a1*b2 - a2*b1, ...)
+    return Vector3d(v[1] * o.v[2] - v[2] * o.v[1], v[2] * o.v[0] - v[0] * o.v[2], v[0] * o.v[1] - v[1] * o.v[0]);
+  }
+  Vector3d operator/(double s) const { return Vector3d(v[0] / s, v[1] / s, v[2] / s); }
+};
+}  // namespace Eigen

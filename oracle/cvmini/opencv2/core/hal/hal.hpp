@@ -1,0 +1,3 @@
+// forwards to the stand-in (see cvmini.hpp)
+#pragma once
+#include "../../../cvmini.hpp"

@@ -306,6 +306,56 @@ void lsd_detect(const LsdImage& L, double scale, double ang_th, std::vector<floa
     }
 }
 
+// cv::clipLine(Size2l, Point2l&, Point2l&) (OpenCV imgproc/src/drawing.cpp), the clip cv::LineIterator applies
+// when an endpoint lies outside the image (an LSD endpoint in (w-1.5, w) rounds to w).  Returns 0 when the line
+// misses the image.  Pinned against cv2.clipLine (tests/test_oracle_vs_cv2.py).
+int clip_line(int w, int h, long long& x1, long long& y1, long long& x2, long long& y2) {
+  const long long right = w - 1, bottom = h - 1;
+  if (w <= 0 || h <= 0) return 0;
+  int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+  int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+  if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+    long long a;
+    if (c1 & 12) {
+      a = c1 < 8 ? 0 : bottom;
+      x1 += (long long)((double)(a - y1) * (x2 - x1) / (y2 - y1));
+      y1 = a;
+      c1 = (x1 < 0) + (x1 > right) * 2;
+    }
+    if (c2 & 12) {
+      a = c2 < 8 ? 0 : bottom;
+      x2 += (long long)((double)(a - y2) * (x2 - x1) / (y2 - y1));
+      y2 = a;
+      c2 = (x2 < 0) + (x2 > right) * 2;
+    }
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+      if (c1) {
+        a = c1 == 1 ? 0 : right;
+        y1 += (long long)((double)(a - x1) * (y2 - y1) / (x2 - x1));
+        x1 = a;
+        c1 = 0;
+      }
+      if (c2) {
+        a = c2 == 1 ? 0 : right;
+        y2 += (long long)((double)(a - x2) * (y2 - y1) / (x2 - x1));
+        x2 = a;
+        c2 = 0;
+      }
+    }
+  }
+  return (c1 | c2) == 0;
+}
+
+// cv::LineIterator(img, pt1, pt2, 8).count for integer endpoints
+int line_iterator_count(int w, int h, int ax, int ay, int bx, int by) {
+  if ((unsigned)ax >= (unsigned)w || (unsigned)bx >= (unsigned)w || (unsigned)ay >= (unsigned)h || (unsigned)by >= (unsigned)h) {
+    long long x1 = ax, y1 = ay, x2 = bx, y2 = by;
+    if (!clip_line(w, h, x1, y1, x2, y2)) return 0;
+    ax = (int)x1; ay = (int)y1; bx = (int)x2; by = (int)y2;
+  }
+  return std::max(std::abs(bx - ax), std::abs(by - ay)) + 1;
+}
+
 // ---- LSDDetectorC::detectImpl KeyLine assembly (LSDDetector_custom.cpp:304-346) -------
 static void make_keylines(const std::vector<float>& seg, int octave, int ow, int oh, float lineScale,
                           double min_length, int& class_counter, std::vector<KeyLine>& out) {
@@ -329,9 +379,9 @@ static void make_keylines(const std::vector<float>& seg, int octave, int ow, int
     kl.sPointInOctaveX = e[0]; kl.sPointInOctaveY = e[1];
     kl.ePointInOctaveX = e[2]; kl.ePointInOctaveY = e[3];
     kl.lineLength = (float)length;
-    // cv::LineIterator(img, Point(pt1), Point(pt2)).count, 8-connected, endpoints inside
+    // cv::LineIterator(img, Point(pt1), Point(pt2)).count, 8-connected (clipped when a rounded endpoint is outside)
     const int ax = cv_roundf(e[0]), ay = cv_roundf(e[1]), bx = cv_roundf(e[2]), by = cv_roundf(e[3]);
-    kl.numOfPixels = std::max(std::abs(bx - ax), std::abs(by - ay)) + 1;
+    kl.numOfPixels = line_iterator_count(ow, oh, ax, ay, bx, by);
     kl.angle = (float)std::atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
     kl.class_id = ++class_counter;
     kl.octave = octave;
@@ -474,6 +524,13 @@ void plvio_resize_linear_f64(const double* src, int sw, int sh, double* dst, int
 }
 void plvio_pyr_down_u8(const u8* src, int w, int h, u8* dst, int dw, int dh) { pyr_down_u8(src, w, h, dst, dw, dh); }
 void plvio_sobel3_s16(const u8* src, int w, int h, short* dx, short* dy) { sobel3_s16(src, w, h, dx, dy); }
+int plvio_clip_line(int w, int h, int* x1, int* y1, int* x2, int* y2) {
+  long long a = *x1, b = *y1, c = *x2, d = *y2;
+  const int r = clip_line(w, h, a, b, c, d);
+  *x1 = (int)a; *y1 = (int)b; *x2 = (int)c; *y2 = (int)d;
+  return r;
+}
+int plvio_line_iterator_count(int w, int h, int ax, int ay, int bx, int by) { return line_iterator_count(w, h, ax, ay, bx, by); }
 
 // LSD on one u8 octave image.  Outputs (optional): scaled f64 image, angles, modgrad of
 // size *sw x *sh; segments as x1,y1,x2,y2 floats (cap = max segments).  Returns count.

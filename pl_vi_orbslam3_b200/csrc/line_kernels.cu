@@ -1038,6 +1038,54 @@ __device__ __forceinline__ RawLine raw_line(float4 s, int ow, int oh, double min
   return r;
 }
 
+// cv::LineIterator(img, pt1, pt2, 8).count (LSDDetector_custom.cpp:333-334).  An LSD endpoint in (w - 1.5, w)
+// rounds to w, i.e. outside the image: OpenCV then clips the segment with cv::clipLine (integer
+// Cohen-Sutherland on [0, w-1] x [0, h-1], int64 coordinates, double quotient truncated toward zero) before
+// counting; a segment that misses the image counts 0.  Same steps as oracle_line.cpp:clip_line.
+__device__ __forceinline__ long long clip_step(long long num, long long mul, long long den) {
+  return (long long)__ddiv_rn(__dmul_rn((double)num, (double)mul), (double)den);
+}
+__device__ __forceinline__ int line_iterator_count(int w, int h, int ax, int ay, int bx, int by) {
+  if ((unsigned)ax >= (unsigned)w || (unsigned)bx >= (unsigned)w || (unsigned)ay >= (unsigned)h || (unsigned)by >= (unsigned)h) {
+    long long x1 = ax, y1 = ay, x2 = bx, y2 = by;
+    const long long right = w - 1, bottom = h - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+      long long a;
+      if (c1 & 12) {
+        a = c1 < 8 ? 0 : bottom;
+        x1 += clip_step(a - y1, x2 - x1, y2 - y1);
+        y1 = a;
+        c1 = (x1 < 0) + (x1 > right) * 2;
+      }
+      if (c2 & 12) {
+        a = c2 < 8 ? 0 : bottom;
+        x2 += clip_step(a - y2, x2 - x1, y2 - y1);
+        y2 = a;
+        c2 = (x2 < 0) + (x2 > right) * 2;
+      }
+      if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        if (c1) {
+          a = c1 == 1 ? 0 : right;
+          y1 += clip_step(a - x1, y2 - y1, x2 - x1);
+          x1 = a;
+          c1 = 0;
+        }
+        if (c2) {
+          a = c2 == 1 ? 0 : right;
+          y2 += clip_step(a - x2, y2 - y1, x2 - x1);
+          x2 = a;
+          c2 = 0;
+        }
+      }
+    }
+    if ((c1 | c2) != 0) return 0;
+    ax = (int)x1; ay = (int)y1; bx = (int)x2; by = (int)y2;
+  }
+  return max(abs(bx - ax), abs(by - ay)) + 1;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) k_line_assemble(const __grid_constant__ LineGeom g, LineBufs b,
                                                       plvi_keyline* __restrict__ outKl, int* __restrict__ outCount) {
@@ -1132,7 +1180,7 @@ __global__ void __launch_bounds__(NT) k_line_assemble(const __grid_constant__ Li
     k.lineLength = rl.length;
     const int ax = __float2int_rn(rl.e[0]), ay = __float2int_rn(rl.e[1]);
     const int bx = __float2int_rn(rl.e[2]), by = __float2int_rn(rl.e[3]);
-    k.numOfPixels = max(abs(bx - ax), abs(by - ay)) + 1;
+    k.numOfPixels = line_iterator_count(O.w, O.h, ax, ay, bx, by);
     k.angle = (float)atan2((double)__fsub_rn(k.endPointY, k.startPointY), (double)__fsub_rn(k.endPointX, k.startPointX));
     k.class_id = select ? pos : v;
     k.octave = o;

@@ -1,0 +1,136 @@
+"""CPU: the oracle restatement against THE REFERENCE'S OWN CODE.
+
+oracle/_ref/libplvi_ref.so = the unmodified reference sources (ORBextractor.cc, LSD/lsd.cpp, LineExtractor.cc,
+LSDDetector_custom.cpp, binary_descriptor_custom.cpp) compiled where they lie, against the OpenCV/Eigen stand-in of
+oracle/cvmini (OpenCV primitives = the scalar models pinned against cv2).  tests/golden/ref_outputs.npz holds its
+outputs (tools/gen_golden_ref.py), so the first test runs everywhere; the live tests run where the library exists
+(build container: built from /root/reference; GPU box: the prebuilt .so travels with the snapshot).
+
+Bar: everything bit-exact, except KeyLine.angle = atan2f(float, float) of the host libm (not correctly rounded and
+build specific; the oracle uses the correctly rounded value): <= 1 ulp.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from pl_vi_orbslam3_b200 import synth
+
+GOLD = Path(__file__).resolve().parent / "golden"
+R = np.load(GOLD / "ref_outputs.npz")
+CASES = [c.split("|") for c in R["cases"]]
+
+
+def frame(name):
+    if name.startswith("synth_"):
+        p = name.split("_")
+        return synth.frame_euroc(int(p[1]), *(int(v) for v in p[2:4])) if len(p) > 2 else synth.frame_euroc(int(p[1]))
+    return np.load(GOLD / f"frame_{name}.npz")["img"]
+
+
+def ulp_diff(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b).max(initial=0)
+
+
+def check_orb(got, kp, desc, mono):
+    assert len(got["keypoints"]) == len(kp)
+    assert got["mono_index"] == int(mono)
+    for f in kp.dtype.names:
+        assert np.array_equal(got["keypoints"][f], kp[f]), f
+    assert np.array_equal(got["descriptors"], desc)
+
+
+def check_lines(got, kl, desc, eq):
+    assert len(got["keylines"]) == len(kl)
+    for f in kl.dtype.names:
+        if f == "angle":
+            assert ulp_diff(got["keylines"][f], kl[f]) <= 1
+        else:
+            assert np.array_equal(got["keylines"][f], kl[f]), f
+    assert np.array_equal(got["descriptors"], desc)
+    assert np.array_equal(got["line_eq"], eq)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_oracle_equals_reference_outputs(case):
+    name, nf, lap0, lap1, lnf = case[0], int(case[1]), int(case[2]), int(case[3]), int(case[4])
+    img = frame(name)
+    check_orb(oracle.orb_extract(img, nfeatures=nf, lapping=(lap0, lap1)), R[f"{name}/orb_kp"], R[f"{name}/orb_desc"],
+              R[f"{name}/orb_mono"])
+    assert np.array_equal(oracle.lsd(img), R[f"{name}/lsd_raw"])
+    check_lines(oracle.line_extract(img, lsd_nfeatures=lnf), R[f"{name}/line_kl"], R[f"{name}/line_desc"],
+                R[f"{name}/line_eq"])
+
+
+def test_clipped_line_iterator_count_is_covered():
+    """synth_0 / synth_10 with all lines kept contain a segment whose rounded endpoint falls outside the octave
+    image: cv::LineIterator clips it (numOfPixels is one less than max(|dx|, |dy|) + 1)."""
+    hit = 0
+    for name in ("synth_0", "synth_10"):
+        k = R[f"{name}/line_kl"]
+        ax, ay = np.rint(k["sPointInOctaveX"]).astype(int), np.rint(k["sPointInOctaveY"]).astype(int)
+        bx, by = np.rint(k["ePointInOctaveX"]).astype(int), np.rint(k["ePointInOctaveY"]).astype(int)
+        hit += int((np.maximum(abs(bx - ax), abs(by - ay)) + 1 != k["numOfPixels"]).sum())
+    assert hit >= 2
+
+
+def test_clip_line_matches_cv2():
+    cv2 = pytest.importorskip("cv2")
+    import ctypes as C
+    rng = np.random.RandomState(1)
+    L = oracle.lib()
+    for _ in range(20000):
+        w, h = int(rng.randint(1, 60)), int(rng.randint(1, 60))
+        p = [int(v) for v in rng.randint(-40, 100, size=4)]
+        r, a, b = cv2.clipLine((0, 0, w, h), (p[0], p[1]), (p[2], p[3]))
+        c = [C.c_int(v) for v in p]
+        r2 = L.plvio_clip_line(w, h, *[C.byref(v) for v in c])
+        assert bool(r) == bool(r2)
+        if r:
+            assert (a, b) == ((c[0].value, c[1].value), (c[2].value, c[3].value))
+
+
+needs_ref = pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref/libplvi_ref.so not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,w,h,nf", [(1, 752, 480, 1000), (2, 752, 480, 2000), (4, 640, 480, 2000),
+                                         (5, 701, 413, 1000), (6, 1280, 720, 1000)])
+def test_live_reference_orb(seed, w, h, nf):
+    img = synth.frame_euroc(seed, w, h)
+    r = oracle.ref_orb_extract(img, nfeatures=nf, debug=True)
+    o = oracle.orb_extract(img, nfeatures=nf, debug=True)
+    check_orb(o, r["keypoints"], r["descriptors"], r["mono_index"])
+    for a, b in zip(o["pyramid"], r["pyramid"]):
+        assert np.array_equal(a, b)
+
+
+@needs_ref
+def test_live_reference_orb_edge_images():
+    rng = np.random.RandomState(5)
+    for img in (rng.randint(0, 256, (480, 752)).astype(np.uint8), np.full((480, 752), 128, np.uint8)):
+        r = oracle.ref_orb_extract(img)
+        check_orb(oracle.orb_extract(img), r["keypoints"], r["descriptors"], r["mono_index"])
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,w,h,lnf,levels", [(1, 752, 480, 200, 2), (2, 752, 480, 0, 2), (7, 752, 480, 0, 2),
+                                                 (4, 640, 480, 100, 2), (5, 701, 413, 200, 1), (6, 1280, 720, 200, 2)])
+def test_live_reference_lines(seed, w, h, lnf, levels):
+    img = synth.frame_euroc(seed, w, h)
+    r = oracle.ref_line_extract(img, lsd_nfeatures=lnf, nlevels=levels)
+    check_lines(oracle.line_extract(img, lsd_nfeatures=lnf, nlevels=levels), r["keylines"], r["descriptors"], r["line_eq"])
+    assert np.array_equal(oracle.lsd(img), oracle.ref_lsd(img))
+
+
+@needs_ref
+def test_live_reference_lines_edge_images():
+    rng = np.random.RandomState(5)
+    noise = rng.randint(0, 256, (480, 752)).astype(np.uint8)
+    r = oracle.ref_line_extract(noise)
+    check_lines(oracle.line_extract(noise), r["keylines"], r["descriptors"], r["line_eq"])
+    flat = np.full((480, 752), 128, np.uint8)
+    assert len(oracle.ref_line_extract(flat)["keylines"]) == 0 and len(oracle.line_extract(flat)["keylines"]) == 0

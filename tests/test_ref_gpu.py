@@ -1,0 +1,74 @@
+"""GPU parity against THE REFERENCE'S OWN CODE: the CUDA path (through the C ABI) vs the outputs of
+oracle/_ref/libplvi_ref.so (reference sources compiled unmodified, see tests/test_oracle_vs_ref.py) -- the committed
+vectors of tests/golden/ref_outputs.npz and, where the prebuilt library travelled with the snapshot, live runs.
+
+Bar: keypoints (all fields incl. angle), ORB descriptors, KeyLine fields, LBD bytes and line equations bit-exact;
+KeyLine.angle (atan2f of the host libm) <= 1 ulp.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from pl_vi_orbslam3_b200 import Lineextractor, ORBextractor, synth
+from test_oracle_vs_ref import CASES, R, frame, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+def check_orb(kps, desc, mono, rk, rd, rmono):
+    assert len(kps) == len(rk) and mono == int(rmono)
+    for f in rk.dtype.names:
+        assert np.array_equal(kps[f], rk[f]), f
+    assert np.array_equal(desc, rd)
+
+
+def check_lines(kl, desc, eq, rk, rd, req):
+    assert len(kl) == len(rk)
+    for f in rk.dtype.names:
+        if f == "angle":
+            assert ulp_diff(kl[f], rk[f]) <= 1
+        else:
+            assert np.array_equal(kl[f], rk[f]), f
+    assert np.array_equal(desc, rd)
+    assert np.array_equal(eq, req)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_cuda_equals_reference_outputs(gpu, case):
+    name, nf, lap0, lap1, lnf = case[0], int(case[1]), int(case[2]), int(case[3]), int(case[4])
+    img = frame(name)
+    h, w = img.shape
+    e = ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=1)
+    try:
+        mono, kps, desc = e(img, vLappingArea=(lap0, lap1))
+        check_orb(kps, desc, mono, R[f"{name}/orb_kp"], R[f"{name}/orb_desc"], R[f"{name}/orb_mono"])
+    finally:
+        e.close()
+    le = Lineextractor(lnf, 0, 0.8, 2, 2.0, 0, max_width=w, max_height=h, max_batch=1)
+    try:
+        kl, ld, eq = le(img)
+        check_lines(kl, ld, eq, R[f"{name}/line_kl"], R[f"{name}/line_desc"], R[f"{name}/line_eq"])
+    finally:
+        le.close()
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref/libplvi_ref.so did not travel")
+def test_cuda_equals_live_reference_batch(gpu):
+    frames = np.stack([synth.frame_euroc(100 + s) for s in range(8)])
+    e = ORBextractor(1000, 1.2, 8, 20, 7, max_width=752, max_height=480, max_batch=8)
+    le = Lineextractor(200, 0, 0.8, 2, 2.0, 0, max_width=752, max_height=480, max_batch=8)
+    try:
+        kps, desc, counts, mono = e.extract_batch(frames)
+        kl, ld, eq, lc = le.extract_batch(frames)
+        for i in range(len(frames)):
+            r = oracle.ref_orb_extract(frames[i])
+            n = counts[i]
+            check_orb(kps[i, :n], desc[i, :n], mono[i], r["keypoints"], r["descriptors"], r["mono_index"])
+            rl = oracle.ref_line_extract(frames[i])
+            m = lc[i]
+            check_lines(kl[i, :m], ld[i, :m], eq[i, :m], rl["keylines"], rl["descriptors"], rl["line_eq"])
+    finally:
+        e.close()
+        le.close()

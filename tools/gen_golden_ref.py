@@ -1,0 +1,58 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/ref_outputs.npz: outputs of THE REFERENCE'S OWN CODE, run in the build container.
+
+oracle/_ref/libplvi_ref.so is built by oracle/Makefile.ref from the unmodified sources under /root/reference
+(src/ORBextractor.cc, src/LSD/lsd.cpp, src/LineExtractor.cc, Thirdparty/line_descriptor/src/LSDDetector_custom.cpp,
+binary_descriptor_custom.cpp) against the OpenCV/Eigen stand-in of oracle/cvmini/ (OpenCV primitives = the
+scalar models pinned against cv2; heap addresses monotone, see oracle/ref_glue.cpp).  These vectors pin the oracle
+restatement -- and through it the CUDA path -- to what the reference's authors wrote, on boxes where
+/root/reference does not exist.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import oracle  # noqa: E402
+from pl_vi_orbslam3_b200 import synth  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+
+
+def frame(name):
+    if name.startswith("synth_"):
+        p = name.split("_")
+        return synth.frame_euroc(int(p[1]), *(int(v) for v in p[2:4])) if len(p) > 2 else synth.frame_euroc(int(p[1]))
+    return np.load(GOLD / f"frame_{name}.npz")["img"]
+
+
+# (frame, ORB nfeatures, lapping, line nfeatures)
+CASES = [("data2_1", 1000, (0, 0), 200), ("data2_3", 2000, (0, 1000), 200), ("data_1_gray", 1000, (0, 0), 200),
+         ("synth_0", 1000, (0, 0), 0), ("synth_7_640_480", 2000, (100, 300), 200), ("synth_10", 1000, (0, 0), 0),
+         ("synth_3_1280_720", 2000, (0, 0), 200)]
+
+
+def main():
+    assert oracle.ref_available(), "needs /root/reference"
+    out = {}
+    for name, nf, lap, lnf in CASES:
+        img = frame(name)
+        o = oracle.ref_orb_extract(img, nfeatures=nf, lapping=lap)
+        out[f"{name}/orb_kp"] = o["keypoints"]
+        out[f"{name}/orb_desc"] = o["descriptors"]
+        out[f"{name}/orb_mono"] = np.int32(o["mono_index"])
+        li = oracle.ref_line_extract(img, lsd_nfeatures=lnf)
+        out[f"{name}/line_kl"] = li["keylines"]
+        out[f"{name}/line_desc"] = li["descriptors"]
+        out[f"{name}/line_eq"] = li["line_eq"]
+        out[f"{name}/lsd_raw"] = oracle.ref_lsd(img)
+        print(name, len(o["keypoints"]), len(li["keylines"]), len(out[f"{name}/lsd_raw"]))
+    out["cases"] = np.array([f"{n}|{nf}|{lap[0]}|{lap[1]}|{lnf}" for n, nf, lap, lnf in CASES])
+    np.savez_compressed(GOLD / "ref_outputs.npz", **out)
+    print((GOLD / "ref_outputs.npz").stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()
