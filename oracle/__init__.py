@@ -504,6 +504,12 @@ def ref_lib():
     return _ref
 
 
+def ref_set_monotone(on: bool):
+    """Heap addresses monotone inside the compiled reference (default, makes DistributeOctTree's pointer-ordered
+    ties deterministic = the oracle's definition) or plain malloc (timing runs)."""
+    ref_lib().plviref_set_monotone(int(bool(on)))
+
+
 def ref_orb_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, lapping=(0, 0),
                     debug=False):
     """The reference's ORBextractor::operator() itself (src/ORBextractor.cc), same outputs as orb_extract."""

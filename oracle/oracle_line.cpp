@@ -157,8 +157,8 @@ void sobel3_s16(const u8* src, int w, int h, short* dx, short* dy) {
   }
 }
 
-static inline float cosf_d(float a) { return (float)std::cos((double)a); }
-static inline float sinf_d(float a) { return (float)std::sin((double)a); }
+static inline float cosf_d(float a) { return glibcm::cosf(a); }   // the reference's cos(float) / sin(float)
+static inline float sinf_d(float a) { return glibcm::sinf(a); }
 
 // ---- LSD (src/LSD/lsd.cpp, refine = LSD_REFINE_NONE) -----------------------------------
 struct LsdImage {
@@ -382,7 +382,7 @@ static void make_keylines(const std::vector<float>& seg, int octave, int ow, int
     // cv::LineIterator(img, Point(pt1), Point(pt2)).count, 8-connected (clipped when a rounded endpoint is outside)
     const int ax = cv_roundf(e[0]), ay = cv_roundf(e[1]), bx = cv_roundf(e[2]), by = cv_roundf(e[3]);
     kl.numOfPixels = line_iterator_count(ow, oh, ax, ay, bx, by);
-    kl.angle = (float)std::atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
+    kl.angle = glibcm::atan2f(kl.endPointY - kl.startPointY, kl.endPointX - kl.startPointX);   // the reference's atan2(float, float)
     kl.class_id = ++class_counter;
     kl.octave = octave;
     kl.size = (kl.endPointX - kl.startPointX) * (kl.endPointY - kl.startPointY);

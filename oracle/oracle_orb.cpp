@@ -392,7 +392,7 @@ static const signed char kPattern[1024] = PLVI_ORB_PATTERN_VALUES;
 void orb_descriptor(const u8* img, int stride, float px, float py, float angle_deg, u8* desc) {
   const float factorPI = (float)(3.14159265358979323846 / 180.f);
   float angle = angle_deg * factorPI;
-  float a = std::cos(angle), b = std::sin(angle);
+  float a = glibcm::cosf(angle), b = glibcm::sinf(angle);
   const u8* center = img + (size_t)cv_roundf(py) * stride + cv_roundf(px);
   for (int i = 0; i < 32; i++) {
     int val = 0;
@@ -423,6 +423,21 @@ struct plvio_keypoint {  // cv::KeyPoint POD layout, 28 bytes
 };
 
 float plvio_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+
+// restated host-libm float functions (oracle_common.h, namespace glibcm), vectorised for the tests
+void plvio_glibc_sincosf(const float* x, int n, float* s, float* c) {
+  for (int i = 0; i < n; i++) { s[i] = glibcm::sinf(x[i]); c[i] = glibcm::cosf(x[i]); }
+}
+void plvio_glibc_atan2f(const float* y, const float* x, int n, float* r) {
+  for (int i = 0; i < n; i++) r[i] = glibcm::atan2f(y[i], x[i]);
+}
+// the same functions of the libm this library is linked against
+void plvio_host_sincosf(const float* x, int n, float* s, float* c) {
+  for (int i = 0; i < n; i++) { s[i] = ::sinf(x[i]); c[i] = ::cosf(x[i]); }
+}
+void plvio_host_atan2f(const float* y, const float* x, int n, float* r) {
+  for (int i = 0; i < n; i++) r[i] = ::atan2f(y[i], x[i]);
+}
 
 int plvio_orb_plan(int w, int h, int nfeatures, float sf, int nlevels, int* lw, int* lh,
                    float* scale, int* quota, int* umax) {

@@ -37,14 +37,17 @@ void* arena_alloc(size_t n) {
   return p;
 }
 inline bool arena_owns(void* p) { return g_base && (char*)p >= g_base && (char*)p < g_base + kArenaBytes; }
+bool g_monotone = true;   // plviref_set_monotone(0): plain malloc (timing runs; ties then follow malloc's addresses)
 struct ArenaScope {   // one per plviref_* call: everything allocated inside is released at the end
   ArenaScope() {
+    if (!g_monotone) return;
     void* m = mmap(nullptr, kArenaBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (m == MAP_FAILED) { fprintf(stderr, "libplvi_ref: cannot reserve the arena\n"); abort(); }
     g_base = g_cur = (char*)m;
     g_arena_on = true;
   }
   ~ArenaScope() {
+    if (!g_base) return;
     g_arena_on = false;
     munmap(g_base, kArenaBytes);
     g_base = g_cur = nullptr;
@@ -68,6 +71,8 @@ static_assert(sizeof(cv::KeyPoint) == 28, "cv::KeyPoint POD layout");
 static_assert(sizeof(KeyLine) == 68, "KeyLine POD layout");
 
 extern "C" {
+
+void plviref_set_monotone(int on) { g_monotone = on != 0; }
 
 // ORB_SLAM3::ORBextractor::operator() (src/ORBextractor.cc:1068-1150).  Returns the number of keypoints
 // (-1: empty image, -2: capacity); *mono_index = the operator's return value.  Optional: pyr_out receives

@@ -206,11 +206,10 @@ __global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ 
         const double a = __dmul_rn((double)angDeg, D2R);
         double sd, cd;
         sincos_tab(a, b.trig, sd, cd);
-        // cos/sin of float(a) = a + dl, |dl| < 2.4e-7: rotate by dl (series exact to < 1e-20)
-        const double dl = (double)(float)a - a;
-        const double cdl = 1.0 - 0.5 * dl * dl, sdl = dl - dl * dl * dl * (1.0 / 6);
-        const double cf = cd * cdl - sd * sdl, sf = sd * cdl + cd * sdl;
-        cs = make_float4((float)cf, (float)sf, (float)cd, (float)sd);
+        // what a region accumulates is cos(float(angle)), sin(float(angle)) evaluated by the host libm's cosf / sinf
+        float cf, sf;
+        glibc_sincosf((float)a, sf, cf);
+        cs = make_float4(cf, sf, (float)cd, (float)sd);
         avail = true;
       }
     }
@@ -1181,7 +1180,7 @@ __global__ void __launch_bounds__(NT) k_line_assemble(const __grid_constant__ Li
     const int ax = __float2int_rn(rl.e[0]), ay = __float2int_rn(rl.e[1]);
     const int bx = __float2int_rn(rl.e[2]), by = __float2int_rn(rl.e[3]);
     k.numOfPixels = line_iterator_count(O.w, O.h, ax, ay, bx, by);
-    k.angle = (float)atan2((double)__fsub_rn(k.endPointY, k.startPointY), (double)__fsub_rn(k.endPointX, k.startPointX));
+    k.angle = glibc_atan2f(__fsub_rn(k.endPointY, k.startPointY), __fsub_rn(k.endPointX, k.startPointX));   // atan2(float, float)
     k.class_id = select ? pos : v;
     k.octave = o;
     k.size = __fmul_rn(__fsub_rn(k.endPointX, k.startPointX), __fsub_rn(k.endPointY, k.startPointY));
@@ -1394,9 +1393,8 @@ __global__ void __launch_bounds__(64, 16) k_lbd_rows(const __grid_constant__ Lin
   const int halfWidth = (L - 1) / 2;
   const float midX = __fmul_rn(0.5f, __fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
   const float midY = __fmul_rn(0.5f, __fadd_rn(kl.sPointInOctaveY, kl.ePointInOctaveY));
-  double sd, cd;
-  sincos((double)kl.angle, &sd, &cd);
-  const float dL0 = (float)cd, dL1 = (float)sd;
+  float dL0, dL1;
+  glibc_sincosf(kl.angle, dL1, dL0);   // cos(direction), sin(direction) on a float: host libm cosf / sinf
   const float dO0 = -dL1, dO1 = dL0;
   float sX = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, 31.f)), midX);
   float sY = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, 31.f)), midY);

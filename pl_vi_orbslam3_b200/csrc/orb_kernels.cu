@@ -748,8 +748,7 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(
     float a = 0.f, b = 0.f;
     if (lane == 0) {
       const float rad = __fmul_rn(angle, 0.017453292519943295f);
-      a = (float)cos((double)rad);
-      b = (float)sin((double)rad);
+      glibc_sincosf(rad, b, a);   // the reference's cos(float) / sin(float): host libm cosf / sinf
     }
     a = __shfl_sync(0xffffffffu, a, 0);
     b = __shfl_sync(0xffffffffu, b, 0);

@@ -25,6 +25,107 @@ void set_error(const std::string& msg);
   } while (0)
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) ----------------
+// ---------------------------------------------------------------------------------------------------
+// The host libm functions the reference calls on float arguments (cos / sin / atan2 with <cmath>'s overloads in
+// scope: src/ORBextractor.cc:110-111, src/LSD/lsd.cpp:678-679, binary_descriptor_custom.cpp:1131-1132,
+// LSDDetector_custom.cpp:336), restated operation by operation so that the results are the ones of glibc
+// 2.28 .. 2.40 on an x86-64 CPU with FMA3 (see oracle/oracle_common.h, namespace glibcm, for the provenance and the
+// exhaustive checks against the build image's libm).  Valid for |x| < 120.
+// ---------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float glibc_sincos_poly(double x, double x2, bool negc, int n) {
+  if ((n & 1) == 0) {
+    const double x3 = __dmul_rn(x, x2), s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+    const double x7 = __dmul_rn(x3, x2), s = __fma_rn(x3, -0x1.555545995a603p-3, x);
+    return (float)__fma_rn(x7, s1, s);
+  }
+  const double sg = negc ? -1.0 : 1.0;   // the second coefficient table is the negated first one
+  const double x4 = __dmul_rn(x2, x2);
+  const double c2 = __fma_rn(x2, sg * 0x1.99343027bf8c3p-16, sg * -0x1.6c087e89a359dp-10);
+  const double c1 = __fma_rn(x2, sg * -0x1.ffffffd0c621cp-2, sg * 0x1p0);
+  const double x6 = __dmul_rn(x4, x2);
+  return (float)__fma_rn(x6, c2, __fma_rn(x4, sg * 0x1.55553e1068f19p-5, c1));
+}
+__device__ __forceinline__ void glibc_sincosf(float y, float& s, float& c) {
+  const double x = (double)y;
+  const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu;
+  if (top < 0x3f4u) {                 // |y| < pi/4 (abstop12(0x1.921FB6p-1f))
+    if (top < 0x398u) { s = y; c = 1.0f; return; }   // |y| < 2^-12
+    const double x2 = __dmul_rn(x, x);
+    s = glibc_sincos_poly(x, x2, false, 0);
+    c = glibc_sincos_poly(x, x2, false, 1);
+    return;
+  }
+  const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+  const int n = (__double2int_rz(r) + 0x800000) >> 24;
+  const double xr = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
+  const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+  const double xs = __dmul_rn(xr, sgn), x2 = __dmul_rn(xr, xr);
+  s = glibc_sincos_poly(xs, x2, (n & 2) != 0, n);
+  c = glibc_sincos_poly(xs, x2, (n & 2) != 0, n ^ 1);
+}
+__device__ __forceinline__ float glibc_atanf(float x) {
+  const int hx = __float_as_int(x), ix = hx & 0x7fffffff;
+  int id;
+  if (ix >= 0x4c000000) {
+    if (ix > 0x7f800000) return __fadd_rn(x, x);
+    return hx > 0 ? __fadd_rn(1.5707962513e+00f, 7.5497894159e-08f) : __fsub_rn(-1.5707962513e+00f, 7.5497894159e-08f);
+  }
+  if (ix < 0x3ee00000) {
+    if (ix < 0x31000000) return x;
+    id = -1;
+  } else {
+    x = fabsf(x);
+    if (ix < 0x3f980000) {
+      if (ix < 0x3f300000) { id = 0; x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x)); }
+      else { id = 1; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
+    } else {
+      if (ix < 0x401c0000) { id = 2; x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x))); }
+      else { id = 3; x = __fdiv_rn(-1.0f, x); }
+    }
+  }
+  const float z = __fmul_rn(x, x), w = __fmul_rn(z, z);
+  float s1 = __fadd_rn(4.9768779427e-02f, __fmul_rn(w, 1.6285819933e-02f));
+  s1 = __fadd_rn(6.6610731184e-02f, __fmul_rn(w, s1));
+  s1 = __fadd_rn(9.0908870101e-02f, __fmul_rn(w, s1));
+  s1 = __fadd_rn(1.4285714924e-01f, __fmul_rn(w, s1));
+  s1 = __fadd_rn(3.3333334327e-01f, __fmul_rn(w, s1));
+  s1 = __fmul_rn(z, s1);
+  float s2 = __fadd_rn(-5.8335702866e-02f, __fmul_rn(w, -3.6531571299e-02f));
+  s2 = __fadd_rn(-7.6918758452e-02f, __fmul_rn(w, s2));
+  s2 = __fadd_rn(-1.1111110449e-01f, __fmul_rn(w, s2));
+  s2 = __fadd_rn(-2.0000000298e-01f, __fmul_rn(w, s2));
+  s2 = __fmul_rn(w, s2);
+  const float xs = __fmul_rn(x, __fadd_rn(s1, s2));
+  if (id < 0) return __fsub_rn(x, xs);
+  const float hi = id == 0 ? 4.6364760399e-01f : id == 1 ? 7.8539812565e-01f : id == 2 ? 9.8279368877e-01f : 1.5707962513e+00f;
+  const float lo = id == 0 ? 5.0121582440e-09f : id == 1 ? 3.7748947079e-08f : id == 2 ? 3.4473217170e-08f : 7.5497894159e-08f;
+  const float r = __fsub_rn(hi, __fsub_rn(__fsub_rn(xs, lo), x));
+  return hx < 0 ? -r : r;
+}
+__device__ __forceinline__ float glibc_atan2f(float y, float x) {
+  const float tiny = 1.0e-30f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+  const int hx = __float_as_int(x), hy = __float_as_int(y);
+  const int ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return __fadd_rn(x, y);
+  if (hx == 0x3f800000) return glibc_atanf(y);
+  const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+  if (iy == 0) return m < 2 ? y : (m == 2 ? __fadd_rn(pi, tiny) : __fsub_rn(-pi, tiny));
+  if (ix == 0) return hy < 0 ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+  const int k = (iy - ix) >> 23;
+  float z;
+  if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+  else if (hx < 0 && k < -60) z = 0.0f;
+  else z = glibc_atanf(fabsf(__fdiv_rn(y, x)));
+  switch (m) {
+    case 0: return z;
+    case 1: return -z;
+    case 2: return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+    default: return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+  }
+}
+#endif
+
 struct StageProf {
   bool on = false;
   std::vector<cudaEvent_t> ev;

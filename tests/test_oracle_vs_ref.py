@@ -6,8 +6,10 @@ oracle/cvmini (OpenCV primitives = the scalar models pinned against cv2).  tests
 outputs (tools/gen_golden_ref.py), so the first test runs everywhere; the live tests run where the library exists
 (build container: built from /root/reference; GPU box: the prebuilt .so travels with the snapshot).
 
-Bar: everything bit-exact, except KeyLine.angle = atan2f(float, float) of the host libm (not correctly rounded and
-build specific; the oracle uses the correctly rounded value): <= 1 ulp.
+Bar: everything bit-exact.  That includes the results of the host libm functions the reference calls on float
+arguments (cosf / sinf in rBRIEF, in LSD's region sums and in LBD; atan2f in KeyLine::angle): the oracle restates
+glibc's algorithms operation by operation (oracle/oracle_common.h, namespace glibcm; exhaustively equal to this
+image's libm, tools/scan_libm.c).
 """
 from pathlib import Path
 
@@ -46,10 +48,7 @@ def check_orb(got, kp, desc, mono):
 def check_lines(got, kl, desc, eq):
     assert len(got["keylines"]) == len(kl)
     for f in kl.dtype.names:
-        if f == "angle":
-            assert ulp_diff(got["keylines"][f], kl[f]) <= 1
-        else:
-            assert np.array_equal(got["keylines"][f], kl[f]), f
+        assert np.array_equal(got["keylines"][f], kl[f]), f
     assert np.array_equal(got["descriptors"], desc)
     assert np.array_equal(got["line_eq"], eq)
 
@@ -134,3 +133,32 @@ def test_live_reference_lines_edge_images():
     check_lines(oracle.line_extract(noise), r["keylines"], r["descriptors"], r["line_eq"])
     flat = np.full((480, 752), 128, np.uint8)
     assert len(oracle.ref_line_extract(flat)["keylines"]) == 0 and len(oracle.line_extract(flat)["keylines"]) == 0
+
+
+def test_restated_libm_equals_host_libm():
+    """glibcm::sinf / cosf / atan2f (oracle_common.h) against the libm the oracle library is linked with, on 4M
+    sampled arguments (tools/scan_libm.cpp does the exhaustive scan).  Only meaningful on glibc 2.28 .. 2.40,
+    x86-64 with FMA3 -- the build image and the GPU box; skipped elsewhere."""
+    import platform
+    ver = tuple(int(v) for v in platform.libc_ver()[1].split(".")[:2]) if platform.libc_ver()[0] == "glibc" else (0, 0)
+    flags = open("/proc/cpuinfo").read() if Path("/proc/cpuinfo").exists() else ""
+    if not ((2, 28) <= ver <= (2, 40)) or " fma " not in flags or platform.machine() != "x86_64":
+        pytest.skip(f"host libm {ver} / CPU is not the reference platform model")
+    L = oracle.lib()
+    rng = np.random.RandomState(3)
+    n = 1 << 21
+    x = np.concatenate([rng.uniform(-7, 7, n), rng.uniform(-119, 119, n // 2),
+                        rng.standard_normal(n // 2) * 1e-3]).astype(np.float32)
+    s1, c1, s2, c2 = (np.empty_like(x) for _ in range(4))
+    L.plvio_glibc_sincosf(oracle._p(x), len(x), oracle._p(s1), oracle._p(c1))
+    L.plvio_host_sincosf(oracle._p(x), len(x), oracle._p(s2), oracle._p(c2))
+    assert np.array_equal(s1.view(np.uint32), s2.view(np.uint32)) and np.array_equal(c1.view(np.uint32), c2.view(np.uint32))
+    y = (rng.uniform(-800, 800, n) * rng.choice([1.0, 0.125, 1e-3], n)).astype(np.float32)
+    xx = (rng.uniform(-800, 800, n) * rng.choice([1.0, 0.125, 1e-3], n)).astype(np.float32)
+    y[:64] = 0.0
+    xx[64:128] = 0.0
+    xx[128:192] = 1.0
+    r1, r2 = np.empty_like(y), np.empty_like(y)
+    L.plvio_glibc_atan2f(oracle._p(y), oracle._p(xx), n, oracle._p(r1))
+    L.plvio_host_atan2f(oracle._p(y), oracle._p(xx), n, oracle._p(r2))
+    assert np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
