@@ -134,7 +134,8 @@ def test_bench_reference_arm_contract():
     import json
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == ("reference" if __import__("oracle").ref_available() else "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0
 
 
 def test_cpp_shim_compiles_and_links(tmp_path):
