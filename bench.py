@@ -392,6 +392,12 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu_base,
+            # every kernel against the HBM roofline: algorithmic GB/s = ALGO_BYTES x frames / its time in the serialised
+            # profile pass, as a fraction of the measured copy peak (streaming kernels should be judged on this one;
+            # k_lsd_spec / k_lsd_commit / k_octree / k_search are latency or issue bound)
+            "kernel_hbm": {k: {"gbs": round(ALGO_BYTES[k] * B / (v * 1e-3) / 1e9, 1),
+                               "frac": round(ALGO_BYTES[k] * B / (v * 1e-3) / 1e9 / peak, 4)}
+                           for k, v in sorted(prof.items(), key=lambda kv: -kv[1]) if k in ALGO_BYTES and v > 0},
             "kernel_ms": {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
             "kernel_share": {k: round(v / total_prof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
         }

@@ -126,6 +126,10 @@ int plvi_orb_read_candidates(plvi_orb* h, int frame, int level, uint32_t* out, i
                              int* count);
 /* number of kernel launches enqueued by the last extract call */
 int plvi_orb_last_launches(const plvi_orb* h);
+/* The per-batch launch sequence is captured once per (batch size, geometry, buffer set) into a CUDA graph and
+ * replayed with a single graph launch afterwards (off while profiling or with PLVI_GRAPHS=0).  Returns the number
+ * of graph replays so far; *captures (may be NULL) receives the number of captured graphs. */
+int plvi_orb_graph_stats(const plvi_orb* h, int* captures);
 /* Per-kernel device time of the last batch: with profiling on, a CUDA event is recorded
  * on the handle's stream after every launch; plvi_orb_profile() synchronises and returns
  * "kernel=ms;kernel=ms;..." (valid until the next call). */
@@ -149,6 +153,7 @@ int plvi_line_capacity(const plvi_line* h);
 int plvi_line_levels(const plvi_line* h);
 void* plvi_line_stream(const plvi_line* h);
 int plvi_line_last_launches(const plvi_line* h);
+int plvi_line_graph_stats(const plvi_line* h, int* captures);   /* see plvi_orb_graph_stats */
 /* mvScaleFactor_l / mvInvScaleFactor_l / mvLevelSigma2_l / mvInvLevelSigma2_l
  * (src/LineExtractor.cc:86-101) */
 int plvi_line_scale_factors(const plvi_line* h, float* scale, float* inv_scale, float* sigma2,

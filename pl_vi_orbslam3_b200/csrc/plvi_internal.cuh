@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 
 #include <string>
 #include <utility>
@@ -154,6 +155,62 @@ struct StageProf {
     return out;
   }
   ~StageProf() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// CUDA-graph cache of a handle's per-batch launch sequence.  The sequence is static for a given (batch size,
+// geometry, pointer set): it is captured once from the launching stream (the side stream of the line pipeline
+// joins the capture through its fork / join events) and replayed with one cudaGraphLaunch afterwards.  Keys are
+// the values baked into the kernel parameters; a handle that alternates between a few buffer sets (the batched
+// front-end does) keeps one executable graph per set.  Disabled while profiling (events between the launches),
+// by PLVI_GRAPHS=0, and cleared whenever the handle's device tables change.
+// ---------------------------------------------------------------------------------------------------
+struct GraphCache {
+  struct Entry { std::vector<uint64_t> key; cudaGraph_t graph; cudaGraphExec_t exec; int launches; };
+  std::vector<Entry> entries;
+  int enabled = -1;
+  long replays = 0, captures = 0;
+  static const size_t kMaxEntries = 8;
+  bool on() {
+    if (enabled < 0) { const char* e = getenv("PLVI_GRAPHS"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    return enabled == 1;
+  }
+  void clear() {
+    for (auto& e : entries) { cudaGraphExecDestroy(e.exec); cudaGraphDestroy(e.graph); }
+    entries.clear();
+  }
+  ~GraphCache() { clear(); }
+  // record(launches*) issues the launch sequence on `st`; returns a PLVI status
+  template <class F> int run(cudaStream_t st, const std::vector<uint64_t>& key, int* launches, F&& record) {
+    for (auto& e : entries)
+      if (e.key == key) {
+        PLVI_CUDA_TRY(cudaGraphLaunch(e.exec, st));
+        if (launches) *launches = e.launches;
+        replays++;
+        return PLVI_OK;
+      }
+    Entry e;
+    e.key = key;
+    e.launches = 0;
+    PLVI_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = record(&e.launches);
+    cudaGraph_t gph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &gph);
+    if (rc != PLVI_OK) { if (gph) cudaGraphDestroy(gph); return rc; }
+    PLVI_CUDA_TRY(ce);
+    e.graph = gph;
+    PLVI_CUDA_TRY(cudaGraphInstantiate(&e.exec, e.graph, 0));
+    if (entries.size() >= kMaxEntries) {
+      cudaGraphExecDestroy(entries.front().exec);
+      cudaGraphDestroy(entries.front().graph);
+      entries.erase(entries.begin());
+    }
+    entries.push_back(e);
+    captures++;
+    PLVI_CUDA_TRY(cudaGraphLaunch(e.exec, st));
+    if (launches) *launches = e.launches;
+    return PLVI_OK;
+  }
 };
 
 // ---- ORB geometry (ORBextractor ctor + ComputeKeyPointsOctTree grid) ----------------

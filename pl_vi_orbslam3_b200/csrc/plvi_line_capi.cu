@@ -33,6 +33,7 @@ struct plvi_line {
   int* dCounts = nullptr;
   int lastN = 0, lastLaunches = 0;
   StageProf prof;
+  GraphCache graphs;
   std::string profText;
   bool debug = false;
   LineAux aux = {nullptr, nullptr, nullptr};
@@ -178,6 +179,7 @@ int ensure_geom(plvi_line* h, int w, int hh) {
     return PLVI_ERR_CAPACITY;
   }
   PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->graphs.clear();   // captured graphs hold the old geometry
   PLVI_CUDA_TRY(cudaMemcpy(h->dTabs, tabs.data(), tabs.size() * sizeof(LineTab), cudaMemcpyHostToDevice));
   if (!rs.empty()) PLVI_CUDA_TRY(cudaMemcpy(h->dRsTab, rs.data(), rs.size() * sizeof(int2), cudaMemcpyHostToDevice));
   // keep the allocated per-frame strides
@@ -342,6 +344,11 @@ void plvi_line_destroy(plvi_line* h) {
 int plvi_line_capacity(const plvi_line* h) { return h ? h->capGeom.keepCap : PLVI_ERR_INVALID; }
 void* plvi_line_stream(const plvi_line* h) { return h ? (void*)h->stream : nullptr; }
 int plvi_line_last_launches(const plvi_line* h) { return h ? h->lastLaunches : PLVI_ERR_INVALID; }
+int plvi_line_graph_stats(const plvi_line* h, int* captures) {
+  if (!h) return PLVI_ERR_INVALID;
+  if (captures) *captures = (int)h->graphs.captures;
+  return (int)h->graphs.replays;
+}
 int plvi_line_levels(const plvi_line* h) { return h ? h->nlevels : PLVI_ERR_INVALID; }
 
 int plvi_line_scale_factors(const plvi_line* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2) {
@@ -376,11 +383,25 @@ int plvi_line_set_debug(plvi_line* h, int on) {
   if (!h) return PLVI_ERR_INVALID;
   PLVI_CUDA_TRY(cudaSetDevice(h->device));
   PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->graphs.clear();   // the debug buffer pointer is baked into captured graphs
   if (on && !h->buf.scaledDbg)
     PLVI_CUDA_TRY(cudaMalloc((void**)&h->buf.scaledDbg, (size_t)h->maxBatch * h->capGeom.pxTotal * sizeof(double)));
   if (!on && h->buf.scaledDbg) { cudaFree(h->buf.scaledDbg); h->buf.scaledDbg = nullptr; }
   h->debug = on != 0;
   return PLVI_OK;
+}
+
+// The per-batch launch sequence, replayed from a captured CUDA graph when possible (GraphCache).
+static int run_line_pipeline(plvi_line* h, const LinePtrs& p, int n, plvi_keyline* d_kl, uint8_t* d_desc, double* d_eq,
+                             int* d_counts) {
+  auto record = [&](int* launches) {
+    return launch_line_pipeline(h->geom, p, h->buf, n, d_kl, d_desc, d_eq, d_counts, h->stream, h->aux, launches, &h->prof);
+  };
+  if (h->prof.on || !h->graphs.on()) return record(&h->lastLaunches);
+  std::vector<uint64_t> key = {(uint64_t)n, (uint64_t)h->curW, (uint64_t)h->curH, (uint64_t)(uintptr_t)p.img[0],
+                               (uint64_t)p.ipitch[0], (uint64_t)p.ifs[0], (uint64_t)(uintptr_t)d_kl,
+                               (uint64_t)(uintptr_t)d_desc, (uint64_t)(uintptr_t)d_eq, (uint64_t)(uintptr_t)d_counts};
+  return h->graphs.run(h->stream, key, &h->lastLaunches, record);
 }
 
 int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, int w, int hh, int stride,
@@ -395,7 +416,7 @@ int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, i
   fill_ptrs(h, d_imgs, stride, frame_stride, p);
   h->lastPtrs = p;
   h->lastN = n;
-  return launch_line_pipeline(h->geom, p, h->buf, n, d_kl, d_desc, d_eq, d_counts, h->stream, h->aux, &h->lastLaunches, &h->prof);
+  return run_line_pipeline(h, p, n, d_kl, d_desc, d_eq, d_counts);
 }
 
 int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int w, int hh, int stride,
@@ -418,7 +439,7 @@ int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int 
   fill_ptrs(h, nullptr, 0, 0, p);
   h->lastPtrs = p;
   h->lastN = n;
-  rc = launch_line_pipeline(h->geom, p, h->buf, n, h->dKl, h->dDesc, h->dEq, h->dCounts, h->stream, h->aux, &h->lastLaunches, &h->prof);
+  rc = run_line_pipeline(h, p, n, h->dKl, h->dDesc, h->dEq, h->dCounts);
   if (rc) return rc;
   const size_t rows = (size_t)n * h->geom.keepCap;
   PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));

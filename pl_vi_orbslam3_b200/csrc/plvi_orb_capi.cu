@@ -46,6 +46,7 @@ struct plvi_orb {
   int cap = 0;
   int lastN = 0, lastLaunches = 0;
   StageProf prof;
+  GraphCache graphs;
   std::string profText;
   OrbPtrs lastPtrs = {};
 };
@@ -157,6 +158,7 @@ int ensure_geom(plvi_orb* h, int w, int hh) {
   }
   // tables are read by kernels of earlier batches: drain the stream first
   PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->graphs.clear();   // captured graphs hold the old geometry
   PLVI_CUDA_TRY(cudaMemcpy(h->dRsTab, tab.rs.data(), tab.rs.size() * sizeof(int2), cudaMemcpyHostToDevice));
   PLVI_CUDA_TRY(cudaMemcpy(h->dFastTiles, tab.fast.data(), tab.fast.size() * sizeof(FastTile), cudaMemcpyHostToDevice));
   PLVI_CUDA_TRY(cudaMemcpy(h->dBlurTiles, tab.blur.data(), tab.blur.size() * sizeof(BlurTile), cudaMemcpyHostToDevice));
@@ -346,6 +348,11 @@ int plvi_orb_levels(const plvi_orb* h) { return h ? h->nlevels : PLVI_ERR_INVALI
 float plvi_orb_scale_factor(const plvi_orb* h) { return h ? h->scaleFactor : 0.f; }
 void* plvi_orb_stream(const plvi_orb* h) { return h ? (void*)h->stream : nullptr; }
 int plvi_orb_last_launches(const plvi_orb* h) { return h ? h->lastLaunches : PLVI_ERR_INVALID; }
+int plvi_orb_graph_stats(const plvi_orb* h, int* captures) {
+  if (!h) return PLVI_ERR_INVALID;
+  if (captures) *captures = (int)h->graphs.captures;
+  return (int)h->graphs.replays;
+}
 
 int plvi_orb_scale_factors(const plvi_orb* h, float* scale, float* inv_scale, float* sigma2,
                            float* inv_sigma2) {
@@ -374,6 +381,21 @@ int plvi_orb_level_sizes(const plvi_orb* h, int w, int hh, int* lw, int* lh) {
   return PLVI_OK;
 }
 
+// The per-batch launch sequence, replayed from a captured CUDA graph when possible (GraphCache).
+static int run_orb_pipeline(plvi_orb* h, const OrbPtrs& p, int n, int lap0, int lap1, plvi_keypoint* d_kps,
+                            uint8_t* d_desc, int* d_counts, int* d_mono) {
+  auto record = [&](int* launches) {
+    return launch_orb_pipeline(h->geom, p, h->scr, n, lap0, lap1, d_kps, d_desc, d_counts, d_mono, h->cap, h->stream,
+                               launches, &h->prof);
+  };
+  if (h->prof.on || !h->graphs.on()) return record(&h->lastLaunches);
+  std::vector<uint64_t> key = {(uint64_t)n, (uint64_t)h->curW, (uint64_t)h->curH, (uint64_t)(uintptr_t)p.img[0],
+                               (uint64_t)p.ipitch[0], (uint64_t)p.ifs[0], (uint64_t)(uint32_t)lap0, (uint64_t)(uint32_t)lap1,
+                               (uint64_t)(uintptr_t)d_kps, (uint64_t)(uintptr_t)d_desc, (uint64_t)(uintptr_t)d_counts,
+                               (uint64_t)(uintptr_t)d_mono};
+  return h->graphs.run(h->stream, key, &h->lastLaunches, record);
+}
+
 int plvi_orb_extract_batch_device(plvi_orb* h, const uint8_t* d_imgs, int n, int w, int hh,
                                   int stride, size_t frame_stride, int lap0, int lap1,
                                   plvi_keypoint* d_kps, uint8_t* d_desc, int* d_counts,
@@ -387,8 +409,7 @@ int plvi_orb_extract_batch_device(plvi_orb* h, const uint8_t* d_imgs, int n, int
   fill_ptrs(h, d_imgs, stride, frame_stride, p);
   h->lastPtrs = p;
   h->lastN = n;
-  return launch_orb_pipeline(h->geom, p, h->scr, n, lap0, lap1, d_kps, d_desc, d_counts, d_mono,
-                             h->cap, h->stream, &h->lastLaunches, &h->prof);
+  return run_orb_pipeline(h, p, n, lap0, lap1, d_kps, d_desc, d_counts, d_mono);
 }
 
 int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w, int hh, int stride,
@@ -413,8 +434,7 @@ int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w,
   fill_ptrs(h, nullptr, 0, 0, p);
   h->lastPtrs = p;
   h->lastN = n;
-  rc = launch_orb_pipeline(h->geom, p, h->scr, n, lap0, lap1, h->dKps, h->dDesc, h->dCounts,
-                           h->dMono, h->cap, h->stream, &h->lastLaunches, &h->prof);
+  rc = run_orb_pipeline(h, p, n, lap0, lap1, h->dKps, h->dDesc, h->dCounts, h->dMono);
   if (rc) return rc;
   const size_t rows = (size_t)n * h->cap;
   PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));

@@ -45,6 +45,13 @@ class Lineextractor:
     def last_launches(self):
         return lib().plvi_line_last_launches(self._h)
 
+    def graph_stats(self):
+        """(captured CUDA graphs, graph replays) of this handle's per-batch launch sequence."""
+        import ctypes
+        c = ctypes.c_int(0)
+        r = lib().plvi_line_graph_stats(self._h, ctypes.byref(c))
+        return c.value, r
+
     def octave_sizes(self, w, h):
         a = [np.empty(self.nlevels_l, np.int32) for _ in range(4)]
         check(lib().plvi_line_octave_sizes(self._h, w, h, *[ptr(x) for x in a]))

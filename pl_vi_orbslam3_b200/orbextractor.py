@@ -79,6 +79,13 @@ class ORBextractor:
     def last_launches(self):
         return lib().plvi_orb_last_launches(self._h)
 
+    def graph_stats(self):
+        """(captured CUDA graphs, graph replays) of this handle's per-batch launch sequence."""
+        import ctypes
+        c = ctypes.c_int(0)
+        r = lib().plvi_orb_graph_stats(self._h, ctypes.byref(c))
+        return c.value, r
+
     # ---- operator() (include/ORBextractor.h:58-60)
     def __call__(self, image, mask=None, vLappingArea=(0, 0)):
         """Returns (monoIndex, keypoints[KEYPOINT_DTYPE], descriptors[N,32] u8).
