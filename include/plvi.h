@@ -130,6 +130,8 @@ int plvi_orb_last_launches(const plvi_orb* h);
  * replayed with a single graph launch afterwards (off while profiling or with PLVI_GRAPHS=0).  Returns the number
  * of graph replays so far; *captures (may be NULL) receives the number of captured graphs. */
 int plvi_orb_graph_stats(const plvi_orb* h, int* captures);
+/* Makes the handle's stream wait for a cudaEvent_t (e.g. plvi_line_stage_event) before the next batch. */
+int plvi_orb_wait_event(plvi_orb* h, void* cuda_event);
 /* Per-kernel device time of the last batch: with profiling on, a CUDA event is recorded
  * on the handle's stream after every launch; plvi_orb_profile() synchronises and returns
  * "kernel=ms;kernel=ms;..." (valid until the next call). */
@@ -154,6 +156,12 @@ int plvi_line_levels(const plvi_line* h);
 void* plvi_line_stream(const plvi_line* h);
 int plvi_line_last_launches(const plvi_line* h);
 int plvi_line_graph_stats(const plvi_line* h, int* captures);   /* see plvi_orb_graph_stats */
+/* A cudaEvent_t (owned by the handle) that every batch records on the handle's stream once its streaming kernels
+ * (pyramid, Gaussian, gradient) are done and only the latency-bound region growing is left, which uses a fraction of
+ * the issue slots.  A caller running the ORB pipeline of the same frames on another stream can hold it back until then
+ * (plvi_orb_wait_event): the two issue-bound phases no longer share the SMs and the ORB kernels fill the slots region
+ * growing leaves idle.  The reference runs both extractors as two host threads per frame (src/Frame.cc:558-561). */
+void* plvi_line_stage_event(plvi_line* h);
 /* mvScaleFactor_l / mvInvScaleFactor_l / mvLevelSigma2_l / mvInvLevelSigma2_l
  * (src/LineExtractor.cc:86-101) */
 int plvi_line_scale_factors(const plvi_line* h, float* scale, float* inv_scale, float* sigma2,

@@ -50,6 +50,7 @@ _SIGS = {
     "plvi_orb_read_candidates": (ci, [vp, ci, ci, vp, ci, vp]),
     "plvi_orb_last_launches": (ci, [vp]),
     "plvi_orb_graph_stats": (ci, [vp, vp]),
+    "plvi_orb_wait_event": (ci, [vp, vp]),
     "plvi_orb_set_profile": (ci, [vp, ci]),
     "plvi_orb_profile": (C.c_char_p, [vp]),
     "plvi_line_set_profile": (ci, [vp, ci]),
@@ -61,6 +62,7 @@ _SIGS = {
     "plvi_line_stream": (vp, [vp]),
     "plvi_line_last_launches": (ci, [vp]),
     "plvi_line_graph_stats": (ci, [vp, vp]),
+    "plvi_line_stage_event": (vp, [vp]),
     "plvi_line_scale_factors": (ci, [vp, vp, vp, vp, vp]),
     "plvi_line_octave_sizes": (ci, [vp, ci, ci, vp, vp, vp, vp]),
     "plvi_line_extract_batch": (ci, [vp, vp, ci, ci, ci, ci, sz, vp, vp, vp, vp]),

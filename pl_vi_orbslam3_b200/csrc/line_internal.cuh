@@ -78,7 +78,7 @@ struct LineBufs {
   double* scaledDbg;     // [B][pxTotal] or nullptr
 };
 
-struct LineAux { cudaStream_t stream; cudaEvent_t fork, join; };   // side stream for the LBD pre-processing
+struct LineAux { cudaStream_t stream; cudaEvent_t fork, join; cudaEvent_t stage; };   // stage: recorded when the streaming kernels are done and region growing starts   // side stream for the LBD pre-processing
 
 int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b, int n, plvi_keyline* dKl,
                          uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, LineAux aux, int* launches,

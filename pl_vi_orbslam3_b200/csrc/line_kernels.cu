@@ -1542,6 +1542,13 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     prof->mark("k_lsd_scale_grad", st);
     nl += 2;
   }
+  // From here on the main stream holds the latency-bound region growing (low issue-slot use): a caller may hold
+  // other issue-bound work (the ORB pipeline) back until this point (plvi_line_stage_event).
+  if (aux.stage && !prof->on) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    PLVI_CUDA_TRY(cudaEventRecordWithFlags(aux.stage, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+  }
   // The LBD pyramid + Sobel only depend on the input frame: they run on the auxiliary stream while
   // the latency-bound region growing occupies the main one (serially when profiling, for clean times).
   const bool fork = aux.stream != nullptr && !prof->on;

@@ -251,7 +251,8 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   }
   if (cudaStreamCreateWithFlags(&h->aux.stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->aux.fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->aux.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->aux.join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->aux.stage, cudaEventDisableTiming) != cudaSuccess) {
     set_error("cannot create the auxiliary stream");
     plvi_line_destroy(h);
     return PLVI_ERR_CUDA;
@@ -329,6 +330,7 @@ void plvi_line_destroy(plvi_line* h) {
   if (h->aux.stream) { cudaStreamSynchronize(h->aux.stream); cudaStreamDestroy(h->aux.stream); }
   if (h->aux.fork) cudaEventDestroy(h->aux.fork);
   if (h->aux.join) cudaEventDestroy(h->aux.join);
+  if (h->aux.stage) cudaEventDestroy(h->aux.stage);
   cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
   cudaFree(h->buf.rowf); cudaFree(h->buf.ang); cudaFree(h->buf.cs); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
   cudaFree(h->buf.specBm); cudaFree(h->buf.specRec); cudaFree(h->buf.specCnt); cudaFree(h->buf.phantom);
@@ -344,6 +346,7 @@ void plvi_line_destroy(plvi_line* h) {
 int plvi_line_capacity(const plvi_line* h) { return h ? h->capGeom.keepCap : PLVI_ERR_INVALID; }
 void* plvi_line_stream(const plvi_line* h) { return h ? (void*)h->stream : nullptr; }
 int plvi_line_last_launches(const plvi_line* h) { return h ? h->lastLaunches : PLVI_ERR_INVALID; }
+void* plvi_line_stage_event(plvi_line* h) { return h ? (void*)h->aux.stage : nullptr; }
 int plvi_line_graph_stats(const plvi_line* h, int* captures) {
   if (!h) return PLVI_ERR_INVALID;
   if (captures) *captures = (int)h->graphs.captures;

@@ -348,6 +348,12 @@ int plvi_orb_levels(const plvi_orb* h) { return h ? h->nlevels : PLVI_ERR_INVALI
 float plvi_orb_scale_factor(const plvi_orb* h) { return h ? h->scaleFactor : 0.f; }
 void* plvi_orb_stream(const plvi_orb* h) { return h ? (void*)h->stream : nullptr; }
 int plvi_orb_last_launches(const plvi_orb* h) { return h ? h->lastLaunches : PLVI_ERR_INVALID; }
+int plvi_orb_wait_event(plvi_orb* h, void* cuda_event) {
+  if (!h || !cuda_event) return PLVI_ERR_INVALID;
+  PLVI_CUDA_TRY(cudaSetDevice(h->device));
+  PLVI_CUDA_TRY(cudaStreamWaitEvent(h->stream, (cudaEvent_t)cuda_event, 0));
+  return PLVI_OK;
+}
 int plvi_orb_graph_stats(const plvi_orb* h, int* captures) {
   if (!h) return PLVI_ERR_INVALID;
   if (captures) *captures = (int)h->graphs.captures;

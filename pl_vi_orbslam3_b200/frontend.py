@@ -6,6 +6,8 @@ collective.
 
 torch is used for device memory and streams only; every kernel is in libplvi_cuda.so.
 """
+import os
+
 import numpy as np
 
 from .capi import QUERY_DTYPE, check, lib, ptr
@@ -46,6 +48,7 @@ class FrontEnd:
         # out_sets > 1: the results of consecutive steps go to alternating output buffers, so the
         # device-to-host copy of step i can still run while step i+1 computes
         self.out_sets = max(1, int(out_sets))
+        self.skew = os.environ.get("PLVI_SKEW", "1") != "0"   # ORB kernels start when the line pipeline reaches region growing
         self._set = 0
         self.orb_outs = [self.orb.alloc_device_outputs(batch, self.device) for _ in range(self.out_sets)]
         self.orb_out = self.orb_outs[0]
@@ -107,6 +110,9 @@ class FrontEnd:
         if forked and serialize:
             self._ev_join.record(self.line_stream)
             self.stream.wait_event(self._ev_join)
+        elif forked and self.skew:
+            # hold the (issue-bound) ORB kernels back until the line pipeline has reached region growing
+            check(lib().plvi_orb_wait_event(self.orb._h, lib().plvi_line_stage_event(self.line._h)))
         kps, desc, counts, mono = self.orb.extract_batch_device(d_frames, out=self.orb_out)
         nl += self.orb.last_launches
         if forked and not serialize:
