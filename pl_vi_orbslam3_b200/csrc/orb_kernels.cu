@@ -99,6 +99,86 @@ __global__ void __launch_bounds__(256) k_resize(const u8* __restrict__ src, int 
   *reinterpret_cast<uint32_t*>(dst + (size_t)blockIdx.z * dfs + (size_t)y * dpitch + x4) = out;
 }
 
+// k_resize_tma: the same arithmetic on a source window staged in shared memory by the TMA engine.  One CTA
+// produces a RS_TW x RS_TH tile of the destination level; its source rows (<= RS_SRC_H rows of <= RS_SRC_W bytes,
+// 16-byte aligned) are fetched with one bulk asynchronous copy per row (cp.async.bulk, completion counted on an
+// mbarrier), so no thread issues byte-granular global loads and the two dependent global round trips per pixel of
+// k_resize (table entry -> source bytes) become one bulk wait plus shared-memory reads.
+#define RS_TW 256
+#define RS_TH 8
+#define RS_SRC_W 576
+#define RS_SRC_H 20
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) k_resize_tma(const u8* __restrict__ src, int spitch, size_t sfs, int sw, int sh,
+                                                    u8* __restrict__ dst, int dpitch, size_t dfs, int dw, int dh,
+                                                    const int2* __restrict__ xtab, const int2* __restrict__ ytab) {
+  __shared__ __align__(128) u8 tile[RS_SRC_H * RS_SRC_W];
+  __shared__ __align__(8) unsigned long long bar;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * RS_TW, y0 = blockIdx.y * RS_TH;
+  const int ys0 = __ldg(&ytab[y0]).x;
+  const int ys1 = min(__ldg(&ytab[min(y0 + RS_TH - 1, dh - 1)]).x + 1, sh - 1);
+  const int xs0 = __ldg(&xtab[x0]).x & ~15;
+  const int xe = min(__ldg(&xtab[min(x0 + RS_TW - 1, dw - 1)]).x + 1, sw - 1);
+  const int nrows = ys1 - ys0 + 1;
+  const int nbytes = (xe + 1 - xs0 + 15) & ~15;
+  const uint32_t barAddr = smem_addr_u32(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barAddr), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(nrows * nbytes) : "memory");
+    const u8* g = src + (size_t)blockIdx.z * sfs + (size_t)ys0 * spitch + xs0;
+    for (int r = 0; r < nrows; r++)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_addr_u32(tile + r * RS_SRC_W)),
+                   "l"(g + (size_t)r * spitch), "r"(nbytes), "r"(barAddr)
+                   : "memory");
+  }
+  // everybody waits for the transaction count of phase 0
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "RS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra RS_DONE;\n"
+      "bra RS_WAIT;\n"
+      "RS_DONE:\n"
+      "}" ::"r"(barAddr),
+      "r"(0)
+      : "memory");
+  const int x4 = x0 + (tid & 63) * 4;
+  if (x4 >= dw) return;
+  int s0[4], s1[4], a0[4], a1[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int2 xt = __ldg(&xtab[min(x4 + i, dw - 1)]);
+    a0[i] = (short)(xt.y & 0xffff); a1[i] = xt.y >> 16;
+    s0[i] = xt.x - xs0; s1[i] = min(xt.x + 1, sw - 1) - xs0;
+  }
+#pragma unroll
+  for (int k = 0; k < RS_TH / 4; k++) {
+    const int y = y0 + (tid >> 6) + 4 * k;
+    if (y >= dh) break;
+    const int2 yt = __ldg(&ytab[y]);
+    const int b0 = (short)(yt.y & 0xffff), b1 = yt.y >> 16;
+    const u8* r0 = tile + (yt.x - ys0) * RS_SRC_W;
+    const u8* r1 = tile + (min(yt.x + 1, sh - 1) - ys0) * RS_SRC_W;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int h0 = r0[s0[i]] * a0[i] + r0[s1[i]] * a1[i];
+      const int h1 = r1[s0[i]] * a0[i] + r1[s1[i]] * a1[i];
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      if (x4 + i < dw) out |= (uint32_t)v << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)blockIdx.z * dfs + (size_t)y * dpitch + x4) = out;
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // k_fast.  One CTA = up to 4 horizontally adjacent FAST cells of one cell row of one
 // level of one frame.  The reference runs cv::FAST on each cell's ROI
@@ -785,6 +865,14 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(
 
 void launch_resize_u8(const u8* src, int spitch, size_t sfs, int sw, int sh, u8* dst, int dpitch, size_t dfs,
                       int dw, int dh, const int2* xtab, const int2* ytab, int n, cudaStream_t st) {
+  // staged variant: 16-byte aligned rows and a source window that fits the shared tile (scale factors up to 2)
+  const bool aligned = ((uintptr_t)src & 15) == 0 && (spitch & 15) == 0 && (sfs & 15) == 0 && spitch >= ((sw + 15) & ~15);
+  const long spanW = ((long)RS_TW * sw + dw - 1) / dw + 3 + 32, spanH = ((long)RS_TH * sh + dh - 1) / dh + 3;
+  if (aligned && spanW <= RS_SRC_W && spanH <= RS_SRC_H) {
+    dim3 grd((dw + RS_TW - 1) / RS_TW, (dh + RS_TH - 1) / RS_TH, n);
+    k_resize_tma<<<grd, 256, 0, st>>>(src, spitch, sfs, sw, sh, dst, dpitch, dfs, dw, dh, xtab, ytab);
+    return;
+  }
   dim3 blk(64, 4), grd((dw + 255) / 256, (dh + 3) / 4, n);
   k_resize<<<grd, blk, 0, st>>>(src, spitch, sfs, sw, sh, dst, dpitch, dfs, dw, dh, xtab, ytab);
 }
@@ -838,10 +926,8 @@ int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s,
   for (int l = 1; l < g.nlevels; l++) {
     const OrbLevel& d = g.lv[l];
     const OrbLevel& sl = g.lv[l - 1];
-    dim3 blk(64, 4), grd((d.w + 255) / 256, (d.h + 3) / 4, n);
-    k_resize<<<grd, blk, 0, st>>>(p.img[l - 1], p.ipitch[l - 1], p.ifs[l - 1], sl.w, sl.h,
-                                  const_cast<u8*>(p.img[l]), p.ipitch[l], p.ifs[l], d.w, d.h,
-                                  s.rsTab + d.rsOff, s.rsTab + d.rsOff + d.w);
+    launch_resize_u8(p.img[l - 1], p.ipitch[l - 1], p.ifs[l - 1], sl.w, sl.h, const_cast<u8*>(p.img[l]), p.ipitch[l],
+                     p.ifs[l], d.w, d.h, s.rsTab + d.rsOff, s.rsTab + d.rsOff + d.w, n, st);
     nl++;
   }
   prof->mark("k_resize", st);
