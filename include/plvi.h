@@ -379,6 +379,30 @@ int plvi_search_for_triangulation(plvi_matcher* m, int npairs, const plvi_keypoi
                                   int query_stride, const plvi_epipolar* geometry, int th_low, int check_orientation,
                                   int* match_query, int* nmatches);
 
+/* The per-map-point search shared by
+ *   int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th, const bool bRight)
+ *       (include/ORBmatcher.h:76, src/ORBmatcher.cc:1399-1610, mono: chi2 = 5.99, th_dist = TH_LOW),
+ *   int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>&
+ *       vpReplacePoint) (include/ORBmatcher.h:79, src/ORBmatcher.cc:1612-1734: chi2 = 0, TH_LOW),
+ *   int ORBmatcher::SearchBySim3(KeyFrame*, KeyFrame*, vector<MapPoint*>&, s12, R12, t12, th)
+ *       (include/ORBmatcher.h:71, src/ORBmatcher.cc:1736-1960: once per direction, chi2 = 0, TH_HIGH; the mutual
+ *       agreement test of :1944-1957 compares the two best_idx arrays),
+ *   int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints,
+ *       vector<MapPoint*>& vpMatched, int th, float ratioHamming) (include/ORBmatcher.h:53, src/ORBmatcher.cc:473-596:
+ *       chi2 = 0, th_dist = TH_LOW * ratioHamming).
+ * The caller projects every candidate map point (u, v, radius = th * mvScaleFactors[nPredictedLevel], min_level =
+ * nPredictedLevel - 1, max_level = nPredictedLevel, flags bit0 = skipped by the checks before the search); the
+ * kernel enumerates KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:1200-1244), applies the level test, the optional
+ * mono reprojection gate e2 * inv_level_sigma2[level] > chi2 (chi2 <= 0: none) and keeps the first smallest Hamming
+ * distance.  Queries are independent.  best_idx[q] = keyframe feature when bestDist <= th_dist, else -1;
+ * best_dist[q] = the smallest distance seen (256: no candidate); nfound[pair] = number of accepted queries.  What
+ * is done with a hit (Replace / AddObservation / AddMapPoint) is map bookkeeping and stays with the caller.
+ * Device pointers only; inv_level_sigma2 is a host array of 16 floats; runs on the matcher's stream. */
+int plvi_search_in_radius(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                          const int* train_counts, int train_stride, const plvi_grid* grid, const plvi_query* queries,
+                          const uint8_t* query_desc, const int* query_counts, int query_stride, const float* inv_level_sigma2,
+                          double chi2, int th_dist, int* best_idx, int* best_dist, int* nfound);
+
 /* Test / benchmark utility (device pointers only): builds the plvi_query records of
  * SearchByProjection(Frame,Frame) for an identity pose -- every keypoint of the query
  * frame projects onto its own position (u,v = pt), radius = th * scale_factor^octave,

@@ -217,6 +217,24 @@ def search_frame(keys, desc, grid, queries, qdesc, th=100, check_ori=True, block
     return n, mt[:len(keys)]
 
 
+def search_in_radius(keys, desc, grid, queries, qdesc, inv_level_sigma2, chi2=5.99, th=50):
+    """Per-map-point search of Fuse / SearchBySim3 / SearchByProjection(KF, Scw): (found, best_idx, best_dist)."""
+    keys = np.ascontiguousarray(keys)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    s2 = np.zeros(16, np.float32)
+    s2[:len(inv_level_sigma2)] = inv_level_sigma2
+    bi = np.empty(max(len(queries), 1), np.int32)
+    bd = np.empty(max(len(queries), 1), np.int32)
+    f = lib().plvio_search_in_radius
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                  C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    n = f(_p(keys), _p(desc), len(keys), *_grid_args(grid), _p(queries), _p(qdesc), len(queries), _p(s2),
+          float(chi2), int(th), _p(bi), _p(bd))
+    return n, bi[:len(queries)], bd[:len(queries)]
+
+
 def search_mappoints(keys, desc, grid, queries, qdesc, th=100, nnratio=0.8, blocked=None):
     keys = np.ascontiguousarray(keys)
     desc = np.ascontiguousarray(desc, np.uint8)

@@ -519,3 +519,44 @@ extern "C" int plvio_search_triangulation(const plvio::Kp* keys1, const uint8_t*
   }
   return nmatches;
 }
+
+
+// The per-map-point search shared by ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:1399-1610),
+// Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (:1612-1734), SearchBySim3 (:1736-1960, both directions) and
+// SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th, ratioHamming) (:473-596): the point is projected by the
+// host (u, v, radius = th * mvScaleFactors[nPredictedLevel], levels nPredictedLevel-1 .. nPredictedLevel);
+// candidates = KeyFrame::GetFeaturesInArea(u, v, radius) (src/KeyFrame.cc:1200-1244) with the level test applied in
+// the loop; optional mono reprojection gate  e2 * mvInvLevelSigma2[kpLevel] > chi2  (Fuse: 5.99, :1546-1552;
+// chi2 <= 0: no gate); best = first smallest Hamming distance; accepted when bestDist <= th.  Queries are
+// independent (nothing is claimed while iterating); what the caller does with bestIdx (Replace / AddObservation /
+// mutual check) is map bookkeeping.  best_idx[q] = feature or -1, best_dist[q] = its distance (256 when no candidate).
+extern "C" int plvio_search_in_radius(const plvio::Kp* keys, const uint8_t* desc, int n, float minX, float minY, float invW,
+                                      float invH, const plvio::Query* q, const uint8_t* qdesc, int nq,
+                                      const float* inv_level_sigma2, double chi2, int th, int* best_idx, int* best_dist) {
+  using namespace plvio;
+  Grid g;
+  build_grid(g, keys, n, minX, minY, invW, invH);
+  std::vector<int> idx;
+  int found = 0;
+  for (int i = 0; i < nq; i++) {
+    best_idx[i] = -1;
+    best_dist[i] = 256;
+    if (q[i].flags & 1) continue;
+    features_in_area(g, q[i].u, q[i].v, q[i].radius, -1, -1, idx);
+    int bestDist = 256, bestIdx = -1;
+    for (int i2 : idx) {
+      const Kp& kp = keys[i2];
+      if (kp.octave < q[i].minLevel || kp.octave > q[i].maxLevel) continue;
+      if (chi2 > 0) {
+        const float ex = q[i].u - kp.x, ey = q[i].v - kp.y;
+        const float e2 = ex * ex + ey * ey;
+        if (e2 * inv_level_sigma2[kp.octave] > chi2) continue;
+      }
+      const int d = hamming256(qdesc + 32 * (size_t)i, desc + 32 * (size_t)i2);
+      if (d < bestDist) { bestDist = d; bestIdx = i2; }
+    }
+    best_dist[i] = bestDist;
+    if (bestIdx >= 0 && bestDist <= th) { best_idx[i] = bestIdx; found++; }
+  }
+  return found;
+}

@@ -717,6 +717,159 @@ __global__ void __launch_bounds__(256) k_search_triangulation(const plvi_keypoin
   if (tid == 0) nmatches[pair] = s_nm;
 }
 
+// ---------------------------------------------------------------------------------------
+// k_search_in_radius: the per-map-point search of ORBmatcher::Fuse (both overloads), SearchBySim3 (both directions)
+// and SearchByProjection(KeyFrame*, Scw, ...) (src/ORBmatcher.cc:1399-1610, 1612-1734, 1736-1960, 473-596).
+// Queries never claim anything, so they are independent: CTA per keyframe, the 64x48 grid as CSR in shared memory
+// (KeyFrame::AssignFeaturesToGrid order), one warp per query, lanes over the cells of GetFeaturesInArea.  The best
+// candidate is the minimum of (distance, cell position, position inside the cell) = the first smallest distance in
+// the reference's iteration order.
+// ---------------------------------------------------------------------------------------
+struct RadiusArgs {
+  const plvi_keypoint* keys; const uint8_t* desc; const int* tcount; int tstride;
+  plvi_grid grid;
+  const plvi_query* q; const uint8_t* qdesc; const int* qcount; int qstride;
+  float invSigma2[16];
+  double chi2;
+  int th;
+  int* bestIdx; int* bestDist; int* nfound;
+};
+
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search_in_radius(const RadiusArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int NT = SEARCH_WARPS * 32;
+  const int n = a.tcount[pair], nq = a.qcount[pair];
+  const plvi_keypoint* keys = a.keys + (size_t)pair * a.tstride;
+  const uint8_t* desc = a.desc + (size_t)pair * a.tstride * 32;
+  const plvi_query* q = a.q + (size_t)pair * a.qstride;
+  const uint8_t* qdesc = a.qdesc + (size_t)pair * a.qstride * 32;
+  int* cellStart = reinterpret_cast<int*>(smem);                 // [GRID_CELLS + 1]
+  int* cursor = cellStart + GRID_CELLS + 1;                      // [GRID_CELLS]
+  unsigned short* items = reinterpret_cast<unsigned short*>(cursor + GRID_CELLS);  // [tstride]
+  __shared__ int wtmp[33];
+  __shared__ int s_found;
+
+  // ---- AssignFeaturesToGrid: CSR of the grid, cell lists in keypoint order
+  for (int i = tid; i < GRID_CELLS; i += NT) cursor[i] = 0;
+  if (tid == 0) s_found = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += NT) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, a.grid.min_x), a.grid.inv_w));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, a.grid.min_y), a.grid.inv_h));
+    if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) atomicAdd(&cursor[px * GRID_ROWS + py], 1);
+  }
+  __syncthreads();
+  {
+    const int chunk = (GRID_CELLS + NT - 1) / NT;
+    const int beg = min(tid * chunk, GRID_CELLS), end = min(beg + chunk, GRID_CELLS);
+    int sum = 0;
+    for (int i = beg; i < end; i++) sum += cursor[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wtmp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int v = lane < SEARCH_WARPS ? wtmp[lane] : 0;
+      int iv = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, iv, o);
+        if (lane >= o) iv += t;
+      }
+      wtmp[lane] = iv - v;
+    }
+    __syncthreads();
+    int base = wtmp[wid] + incl - sum;
+    for (int i = beg; i < end; i++) {
+      cellStart[i] = base;
+      base += cursor[i];
+      cursor[i] = 0;
+    }
+    if (end == GRID_CELLS && beg < end) cellStart[GRID_CELLS] = base;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += NT) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, a.grid.min_x), a.grid.inv_w));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, a.grid.min_y), a.grid.inv_h));
+    if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) {
+      const int c = px * GRID_ROWS + py;
+      items[cellStart[c] + atomicAdd(&cursor[c], 1)] = (unsigned short)i;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < GRID_CELLS; c += NT) {  // insertion (index) order inside each cell
+    const int s = cellStart[c], e = cellStart[c + 1];
+    for (int i = s + 1; i < e; i++) {
+      const unsigned short v = items[i];
+      int j = i - 1;
+      while (j >= s && items[j] > v) { items[j + 1] = items[j]; j--; }
+      items[j + 1] = v;
+    }
+  }
+  __syncthreads();
+
+  const plvi_grid& g = a.grid;
+  int found = 0;
+  for (int qi = wid; qi < nq; qi += SEARCH_WARPS) {
+    const plvi_query qq = q[qi];
+    int best = -1, bestDist = 256;
+    if (!(qq.flags & 1)) {
+      const float x = qq.u, y = qq.v, rad = qq.radius;
+      const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, g.min_x), rad), g.inv_w)));
+      const int cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, g.min_x), rad), g.inv_w)));
+      const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, g.min_y), rad), g.inv_h)));
+      const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, g.min_y), rad), g.inv_h)));
+      if (!(cx0 >= GRID_COLS || cx1 < 0 || cy0 >= GRID_ROWS || cy1 < 0)) {
+        uint32_t qw[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) qw[k] = __ldg(reinterpret_cast<const uint32_t*>(qdesc + (size_t)qi * 32) + k);
+        const int ny = cy1 - cy0 + 1, nc = (cx1 - cx0 + 1) * ny;
+        uint32_t bk = 0xffffffffu;
+        int bi = -1;
+        for (int c = lane; c < nc; c += 32) {
+          const int cell = (cx0 + c / ny) * GRID_ROWS + cy0 + c % ny;
+          const int s = cellStart[cell], e = cellStart[cell + 1];
+          for (int k = s; k < e; k++) {
+            const int i2 = items[k];
+            const plvi_keypoint kp = keys[i2];
+            if (!(fabsf(__fsub_rn(kp.x, x)) < rad && fabsf(__fsub_rn(kp.y, y)) < rad)) continue;
+            if (kp.octave < qq.min_level || kp.octave > qq.max_level) continue;
+            if (a.chi2 > 0) {   // mono reprojection gate of Fuse: float product compared with the double constant
+              const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+              const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+              if ((double)__fmul_rn(e2, a.invSigma2[kp.octave & 15]) > a.chi2) continue;
+            }
+            const int d = hamming256_regs(qw, desc + (size_t)i2 * 32);
+            const uint32_t key = ((uint32_t)d << 23) | ((uint32_t)min(c, 4095) << 11) | (uint32_t)min(k - s, 2047);
+            if (key < bk) { bk = key; bi = i2; }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ok < bk) { bk = ok; bi = oi; }
+        }
+        if (bi >= 0) { best = bi; bestDist = (int)(bk >> 23); }
+      }
+    }
+    if (lane == 0) {
+      const bool ok = best >= 0 && bestDist <= a.th;
+      a.bestIdx[(size_t)pair * a.qstride + qi] = ok ? best : -1;
+      a.bestDist[(size_t)pair * a.qstride + qi] = bestDist;
+      found += ok;
+    }
+  }
+  if (lane == 0 && found) atomicAdd(&s_found, found);
+  __syncthreads();
+  if (tid == 0) a.nfound[pair] = s_found;
+}
+
 struct plvi_matcher {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -1065,6 +1218,32 @@ int plvi_search_for_triangulation(plvi_matcher* m, int npairs, const plvi_keypoi
   k_search_triangulation<<<npairs, 256, 0, m->stream>>>(train_keys, train_desc, train_blocked, train_counts, train_stride, group_items,
                                                         items_stride, queries, query_desc, query_counts, query_stride, geometry, th_low,
                                                         check_orientation, match_query, nmatches);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  return PLVI_OK;
+}
+
+int plvi_search_in_radius(plvi_matcher* m, int npairs, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                          const int* train_counts, int train_stride, const plvi_grid* grid, const plvi_query* queries,
+                          const uint8_t* query_desc, const int* query_counts, int query_stride, const float* inv_level_sigma2,
+                          double chi2, int th_dist, int* best_idx, int* best_dist, int* nfound) {
+  if (!m || npairs < 1 || !train_keys || !train_desc || !train_counts || !grid || !queries || !query_desc || !query_counts ||
+      !inv_level_sigma2 || !best_idx || !best_dist || !nfound || train_stride < 1 || query_stride < 1 || train_stride > 65535) {
+    set_error("plvi_search_in_radius: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  RadiusArgs a;
+  a.keys = train_keys; a.desc = train_desc; a.tcount = train_counts; a.tstride = train_stride;
+  a.grid = *grid;
+  a.q = queries; a.qdesc = query_desc; a.qcount = query_counts; a.qstride = query_stride;
+  for (int i = 0; i < 16; i++) a.invSigma2[i] = inv_level_sigma2[i];
+  a.chi2 = chi2; a.th = th_dist;
+  a.bestIdx = best_idx; a.bestDist = best_dist; a.nfound = nfound;
+  const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + (size_t)train_stride * 2 + 16;
+  if (smem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search_in_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_search_in_radius<<<npairs, SEARCH_WARPS * 32, smem, m->stream>>>(a);
   m->lastLaunches = 1;
   PLVI_CUDA_TRY(cudaGetLastError());
   return PLVI_OK;

@@ -187,6 +187,35 @@ class ORBmatcher(_Matcher):
         self.sync()
         return int(nm.cpu().numpy()[0]), mq.cpu().numpy()[:nq]
 
+    def SearchInRadius(self, KF, queries, qdesc, inv_level_sigma2, chi2=5.99, th_dist=None):
+        """The per-map-point search of Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:1399-1610; chi2 = 5.99, TH_LOW),
+        Fuse(pKF, Scw, ...) (:1612; chi2 = 0), SearchBySim3 (:1736; chi2 = 0, TH_HIGH, once per direction) and
+        SearchByProjection(pKF, Scw, ...) (:473; chi2 = 0, TH_LOW * ratioHamming).  queries: one per projected map point
+        (u, v, radius, min_level = nPredictedLevel - 1, max_level = nPredictedLevel, flags bit0 = skipped).
+        Returns (nfound, best_idx, best_dist)."""
+        import torch
+        th_dist = self.TH_LOW if th_dist is None else int(th_dist)
+        n, nq = len(KF.keys), len(queries)
+        T, Q = max(n, 1), max(nq, 1)
+        keys = np.zeros(T, KEYPOINT_DTYPE); keys[:n] = KF.keys
+        desc = np.zeros((T, 32), np.uint8); desc[:n] = KF.desc
+        qs = np.zeros(Q, QUERY_DTYPE); qs[:nq] = queries
+        qd = np.zeros((Q, 32), np.uint8); qd[:nq] = qdesc
+        s2 = np.zeros(16, np.float32); s2[:len(inv_level_sigma2)] = inv_level_sigma2
+        grid = np.ascontiguousarray(KF.grid)
+        dev = torch.device("cuda", self.device)
+        def up(a):
+            return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+        t = [up(x) for x in (keys, desc, np.array([n], np.int32), qs, qd, np.array([nq], np.int32))]
+        bi = torch.empty(Q, dtype=torch.int32, device=dev)
+        bd = torch.empty(Q, dtype=torch.int32, device=dev)
+        nf = torch.empty(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        check(lib().plvi_search_in_radius(self._h, 1, ptr(t[0]), ptr(t[1]), ptr(t[2]), T, ptr(grid), ptr(t[3]), ptr(t[4]),
+                                          ptr(t[5]), Q, ptr(s2), float(chi2), th_dist, ptr(bi), ptr(bd), ptr(nf)))
+        self.sync()
+        return int(nf.cpu().numpy()[0]), bi.cpu().numpy()[:nq], bd.cpu().numpy()[:nq]
+
     @staticmethod
     def init_queries(F1_keys, vbPrevMatched, windowSize):
         n1 = len(F1_keys)

@@ -411,3 +411,42 @@ def test_search_for_triangulation(om, pair_features, k, L, levelsup, coarse, see
     assert n == rn and np.array_equal(got, rm)
     if coarse:
         assert n > 20
+
+
+INV_SIGMA2 = (np.float32(1.0) / (SCALES * SCALES)).astype(np.float32)
+
+
+@pytest.mark.parametrize("chi2,th_dist", [(5.99, 50), (0.0, 50), (0.0, 100)])
+def test_search_in_radius_fuse_and_sim3_patterns(om, pair_features, chi2, th_dist):
+    """Fuse (chi2 gate, TH_LOW), Fuse(Scw) / SearchByProjection(KF, Scw) (no gate, TH_LOW) and one direction of
+    SearchBySim3 (no gate, TH_HIGH) on the warped pair: projected points of frame 1 searched in frame 2."""
+    r1, r2, A = pair_features
+    q = _proj_queries(r1, A, th=3.0, lo=-1, hi=0)
+    q["flags"][::7] = 1          # points rejected before the search (bad / already in the keyframe / out of image)
+    F = FrameView(r2["keypoints"], r2["descriptors"], GRID)
+    n, bi, bd = om.SearchInRadius(F, q, r1["descriptors"], INV_SIGMA2, chi2, th_dist)
+    rn, rbi, rbd = oracle.search_in_radius(r2["keypoints"], r2["descriptors"], GRID, q, r1["descriptors"], INV_SIGMA2, chi2, th_dist)
+    assert n == rn and n > 100
+    assert np.array_equal(bi, rbi) and np.array_equal(bd, rbd)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_search_in_radius_tie_heavy(om, seed):
+    keys, desc, q, qd = _tie_heavy_case(seed)
+    q["max_level"] = q["min_level"] + 1
+    F = FrameView(keys, desc, GRID)
+    for chi2, th in ((5.99, 50), (0.0, 100), (50.0, 256)):
+        n, bi, bd = om.SearchInRadius(F, q, qd, INV_SIGMA2, chi2, th)
+        rn, rbi, rbd = oracle.search_in_radius(keys, desc, GRID, q, qd, INV_SIGMA2, chi2, th)
+        assert n == rn and np.array_equal(bi, rbi) and np.array_equal(bd, rbd)
+    # SearchBySim3's mutual agreement (src/ORBmatcher.cc:1944-1957) from the two directions
+    n12, m12, _ = om.SearchInRadius(F, q, qd, INV_SIGMA2, 0.0, 100)
+    assert n12 == int((m12 >= 0).sum())
+
+
+def test_search_in_radius_empty(om):
+    keys, desc, q, qd = _tie_heavy_case(3, n=50, nq=40)
+    n, bi, bd = om.SearchInRadius(FrameView(keys[:0], desc[:0], GRID), q, qd, INV_SIGMA2)
+    assert n == 0 and (bi == -1).all() and (bd == 256).all()
+    n, bi, bd = om.SearchInRadius(FrameView(keys, desc, GRID), q[:0], qd[:0], INV_SIGMA2)
+    assert n == 0 and len(bi) == 0

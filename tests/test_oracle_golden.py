@@ -154,3 +154,43 @@ def test_oracle_edge_cases():
     c = np.array([[10, 10, 30], [300, 40, 25], [600, 400, 21]], np.float32)
     sel = oracle.distribute_octree(c, 16, 736, 16, 464, 217)
     assert sorted(sel.tolist()) == [0, 1, 2]
+
+
+def test_search_in_radius_oracle_matches_brute_force():
+    """Independent model of the Fuse / SearchBySim3 per-point search: brute force over all keypoints in index order
+    restricted to the reference's cell range equals the grid walk whenever distances are unique."""
+    rng = np.random.RandomState(11)
+    n, nq = 800, 300
+    keys = np.zeros(n, oracle.KEYPOINT_DTYPE)
+    keys["x"] = rng.uniform(20, 730, n).astype(np.float32)
+    keys["y"] = rng.uniform(20, 460, n).astype(np.float32)
+    keys["octave"] = rng.randint(0, 4, n)
+    desc = rng.randint(0, 256, (n, 32)).astype(np.uint8)
+    from pl_vi_orbslam3_b200 import frame_grid
+    from pl_vi_orbslam3_b200.capi import QUERY_DTYPE
+    grid = frame_grid(0, 752, 0, 480)
+    q = np.zeros(nq, QUERY_DTYPE)
+    q["u"] = rng.uniform(0, 752, nq).astype(np.float32)
+    q["v"] = rng.uniform(0, 480, nq).astype(np.float32)
+    q["radius"] = rng.choice([20.0, 45.0], nq).astype(np.float32)
+    q["min_level"] = rng.randint(0, 3, nq)
+    q["max_level"] = q["min_level"] + 1
+    qd = rng.randint(0, 256, (nq, 32)).astype(np.uint8)
+    s2 = (1.0 / (1.2 ** np.arange(8)) ** 2).astype(np.float32)
+    for chi2, th in ((5.99, 256), (0.0, 256), (400.0, 120)):
+        found, bi, bd = oracle.search_in_radius(keys, desc, grid, q, qd, s2, chi2, th)
+        for i in range(nq):
+            dx, dy = np.abs(keys["x"] - q["u"][i]), np.abs(keys["y"] - q["v"][i])
+            ok = (dx < q["radius"][i]) & (dy < q["radius"][i]) & (keys["octave"] >= q["min_level"][i]) & (keys["octave"] <= q["max_level"][i])
+            if chi2 > 0:
+                ex, ey = (q["u"][i] - keys["x"]).astype(np.float32), (q["v"][i] - keys["y"]).astype(np.float32)
+                e2 = (ex * ex + ey * ey).astype(np.float32)
+                ok &= ~((e2 * s2[keys["octave"]]).astype(np.float32).astype(np.float64) > chi2)
+            d = np.unpackbits(desc ^ qd[i], axis=1).sum(axis=1)
+            d = np.where(ok, d, 999)
+            best = int(d.min()) if ok.any() else 256
+            assert bd[i] == best
+            if best <= th and (d == best).sum() == 1:
+                assert bi[i] == int(d.argmin())
+            if best > th:
+                assert bi[i] == -1
