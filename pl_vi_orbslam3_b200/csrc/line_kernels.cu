@@ -35,16 +35,12 @@ __device__ __forceinline__ float fast_atan2_dev(float y, float x) {
   const float p5 = __fmul_rn(0.1555786518463281f, sc), p7 = __fmul_rn(-0.04432655554792128f, sc);
   const float eps = 2.220446049250313e-16f;
   const float ax = fabsf(x), ay = fabsf(y);
-  float a, c, c2;
-  if (ax >= ay) {
-    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-    c2 = __fmul_rn(c, c);
-    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-  } else {
-    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-    c2 = __fmul_rn(c, c);
-    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-  }
+  // one division and one polynomial for both octants (same operations as the two branches of cv::fastAtan2)
+  const bool steep = !(ax >= ay);
+  const float c = __fdiv_rn(steep ? ax : ay, __fadd_rn(steep ? ay : ax, eps));
+  const float c2 = __fmul_rn(c, c);
+  float a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  if (steep) a = __fsub_rn(90.f, a);
   if (x < 0) a = __fsub_rn(180.f, a);
   if (y < 0) a = __fsub_rn(360.f, a);
   return a;
@@ -138,53 +134,53 @@ __global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ 
   const double* rf = rowf + (size_t)f * rfs + O.rawOff;
   const LineTab* xt = tabs + O.xtabOff;
   const LineTab* yt = tabs + O.ytabOff;
-  if (x0 < O.sw) {
-    // source window of the tile
+  __shared__ int s_win[4];
+  if (tid == 0) {   // source window of the tile
     const int sx0 = xt[x0].ofs, sx1 = min(xt[min(x0 + SG_TW, O.sw - 1)].ofs + 1, O.w - 1);
     const int sy0 = yt[y0].ofs, sy1 = min(yt[min(y0 + SG_TH, O.sh - 1)].ofs + 1, O.h - 1);
-    const int nsx = sx1 - sx0 + 1, nsy = sy1 - sy0 + 1;   // <= SG_SRC_W, SG_SRC_H (checked on the host)
+    s_win[0] = sx0; s_win[1] = sx1 - sx0 + 1; s_win[2] = sy0; s_win[3] = sy1 - sy0 + 1;   // <= SG_SRC_W, SG_SRC_H (checked on the host)
+  }
+  __syncthreads();
+  {
+    const int sx0 = s_win[0], nsx = s_win[1], sy0 = s_win[2], nsy = s_win[3];
     {
-      // column pass of the Gaussian for the source window: 64 lanes across, 4 rows per sweep
-      const int c = tid & 63;
-      const bool interior = sy0 - 3 >= 0 && sy1 + 3 < O.h;
-      if (c < nsx) {
-        for (int r = tid >> 6; r < nsy; r += 4) {
-          double v;
-          if (interior) {
-            const double* q = rf + (size_t)(sy0 + r - 3) * O.w + (sx0 + c);
-            const size_t w = (size_t)O.w;
-            v = __dmul_rn(g.kern[3], q[3 * w]);
-            v = __dadd_rn(v, __dmul_rn(g.kern[4], __dadd_rn(q[4 * w], q[2 * w])));
-            v = __dadd_rn(v, __dmul_rn(g.kern[5], __dadd_rn(q[5 * w], q[w])));
-            v = __dadd_rn(v, __dmul_rn(g.kern[6], __dadd_rn(q[6 * w], q[0])));
-          } else {
-            v = col_blur(rf, O.w, O.h, sx0 + c, sy0 + r, g.kern);
-          }
-          sblur[r][c] = v;
+      // column pass of the Gaussian for the source window: SG_SRC_W lanes across (dense lane use: the window is
+      // 41-42 of 48 columns wide), 256 / SG_SRC_W rows per sweep
+      const bool interior = sy0 - 3 >= 0 && sy0 + nsy - 1 + 3 < O.h;
+      for (int e = tid; e < nsy * SG_SRC_W; e += 256) {
+        const int r = e / SG_SRC_W, c = e - r * SG_SRC_W;
+        if (c >= nsx) continue;
+        double v;
+        if (interior) {
+          const double* q = rf + (size_t)(sy0 + r - 3) * O.w + (sx0 + c);
+          const size_t w = (size_t)O.w;
+          v = __dmul_rn(g.kern[3], q[3 * w]);
+          v = __dadd_rn(v, __dmul_rn(g.kern[4], __dadd_rn(q[4 * w], q[2 * w])));
+          v = __dadd_rn(v, __dmul_rn(g.kern[5], __dadd_rn(q[5 * w], q[w])));
+          v = __dadd_rn(v, __dmul_rn(g.kern[6], __dadd_rn(q[6 * w], q[0])));
+        } else {
+          v = col_blur(rf, O.w, O.h, sx0 + c, sy0 + r, g.kern);
         }
+        sblur[r][c] = v;
       }
     }
     __syncthreads();
-    {
-      const int tx = tid & 63;
-      if (tx <= SG_TW) {
-        const int sx = x0 + tx;
-        for (int ty = tid >> 6; ty <= SG_TH; ty += 4) {
-          const int sy = y0 + ty;
-          double v = 0.0;
-          if (sx < O.sw && sy < O.sh) {
-            const LineTab X = xt[sx], Y = yt[sy];
-            const int xa = X.ofs - sx0, xb = min(X.ofs + 1, O.w - 1) - sx0;
-            const int ya = Y.ofs - sy0, yb = min(Y.ofs + 1, O.h - 1) - sy0;
-            const double h0 = __dadd_rn(__dmul_rn(sblur[ya][xa], (double)X.a0), __dmul_rn(sblur[ya][xb], (double)X.a1));
-            const double h1 = __dadd_rn(__dmul_rn(sblur[yb][xa], (double)X.a0), __dmul_rn(sblur[yb][xb], (double)X.a1));
-            v = __dadd_rn(__dmul_rn(h0, (double)Y.a0), __dmul_rn(h1, (double)Y.a1));
-            if (b.scaledDbg && tx < SG_TW && ty < SG_TH)
-              b.scaledDbg[(size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx] = v;
-          }
-          ssc[ty][tx] = v;
-        }
+    // bilinear resize: the (SG_TW + 1) x (SG_TH + 1) scaled pixels of the tile and its halo, one per thread
+    for (int e = tid; e < (SG_TW + 1) * (SG_TH + 1); e += 256) {
+      const int ty = e / (SG_TW + 1), tx = e - ty * (SG_TW + 1);
+      const int sx = x0 + tx, sy = y0 + ty;
+      double v = 0.0;
+      if (sx < O.sw && sy < O.sh) {
+        const LineTab X = xt[sx], Y = yt[sy];
+        const int xa = X.ofs - sx0, xb = min(X.ofs + 1, O.w - 1) - sx0;
+        const int ya = Y.ofs - sy0, yb = min(Y.ofs + 1, O.h - 1) - sy0;
+        const double h0 = __dadd_rn(__dmul_rn(sblur[ya][xa], (double)X.a0), __dmul_rn(sblur[ya][xb], (double)X.a1));
+        const double h1 = __dadd_rn(__dmul_rn(sblur[yb][xa], (double)X.a0), __dmul_rn(sblur[yb][xb], (double)X.a1));
+        v = __dadd_rn(__dmul_rn(h0, (double)Y.a0), __dmul_rn(h1, (double)Y.a1));
+        if (b.scaledDbg && tx < SG_TW && ty < SG_TH)
+          b.scaledDbg[(size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx] = v;
       }
+      ssc[ty][tx] = v;
     }
   }
   __syncthreads();

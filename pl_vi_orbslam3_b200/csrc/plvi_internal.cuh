@@ -34,36 +34,31 @@ void set_error(const std::string& msg);
 // exhaustive checks against the build image's libm).  Valid for |x| < 120.
 // ---------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
-__device__ __forceinline__ float glibc_sincos_poly(double x, double x2, bool negc, int n) {
-  if ((n & 1) == 0) {
-    const double x3 = __dmul_rn(x, x2), s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
-    const double x7 = __dmul_rn(x3, x2), s = __fma_rn(x3, -0x1.555545995a603p-3, x);
-    return (float)__fma_rn(x7, s1, s);
-  }
-  const double sg = negc ? -1.0 : 1.0;   // the second coefficient table is the negated first one
-  const double x4 = __dmul_rn(x2, x2);
-  const double c2 = __fma_rn(x2, sg * 0x1.99343027bf8c3p-16, sg * -0x1.6c087e89a359dp-10);
-  const double c1 = __fma_rn(x2, sg * -0x1.ffffffd0c621cp-2, sg * 0x1p0);
-  const double x6 = __dmul_rn(x4, x2);
-  return (float)__fma_rn(x6, c2, __fma_rn(x4, sg * 0x1.55553e1068f19p-5, c1));
-}
+// sinf and cosf of the same argument share the reduction; each needs one of the two polynomials (which one is
+// decided by the quadrant n), so both are evaluated once for all lanes and swapped by n & 1: no divergence.
 __device__ __forceinline__ void glibc_sincosf(float y, float& s, float& c) {
   const double x = (double)y;
   const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu;
-  if (top < 0x3f4u) {                 // |y| < pi/4 (abstop12(0x1.921FB6p-1f))
-    if (top < 0x398u) { s = y; c = 1.0f; return; }   // |y| < 2^-12
-    const double x2 = __dmul_rn(x, x);
-    s = glibc_sincos_poly(x, x2, false, 0);
-    c = glibc_sincos_poly(x, x2, false, 1);
-    return;
-  }
+  // quadrant reduction (for |y| < pi/4 it yields n = 0 and xr = x, i.e. glibc's short path)
   const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
   const int n = (__double2int_rz(r) + 0x800000) >> 24;
   const double xr = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
-  const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+  const double sgn = ((n + 1) & 2) ? -1.0 : 1.0;          // sign table {1, -1, -1, 1}[n & 3]
+  const double sg = (n & 2) ? -1.0 : 1.0;                 // second coefficient table = negated cosine coefficients
   const double xs = __dmul_rn(xr, sgn), x2 = __dmul_rn(xr, xr);
-  s = glibc_sincos_poly(xs, x2, (n & 2) != 0, n);
-  c = glibc_sincos_poly(xs, x2, (n & 2) != 0, n ^ 1);
+  // sine polynomial of xs
+  const double x3 = __dmul_rn(xs, x2), s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+  const double x7 = __dmul_rn(x3, x2), sp = __fma_rn(x3, -0x1.555545995a603p-3, xs);
+  const float fs = (float)__fma_rn(x7, s1, sp);
+  // cosine polynomial
+  const double x4 = __dmul_rn(x2, x2);
+  const double c2 = __fma_rn(x2, sg * 0x1.99343027bf8c3p-16, sg * -0x1.6c087e89a359dp-10);
+  const double c1 = __fma_rn(x2, sg * -0x1.ffffffd0c621cp-2, sg);
+  const double x6 = __dmul_rn(x4, x2);
+  const float fc = (float)__fma_rn(x6, c2, __fma_rn(x4, sg * 0x1.55553e1068f19p-5, c1));
+  s = (n & 1) ? fc : fs;
+  c = (n & 1) ? fs : fc;
+  if (top < 0x398u) { s = y; c = 1.0f; }   // |y| < 2^-12
 }
 __device__ __forceinline__ float glibc_atanf(float x) {
   const int hx = __float_as_int(x), ix = hx & 0x7fffffff;
