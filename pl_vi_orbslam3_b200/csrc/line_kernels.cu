@@ -641,25 +641,26 @@ struct PhantomMap {
     if (y - bm.top < GROW_K) atomicOr(&sm[(y & (GROW_K - 1)) * bm.wpr + (x >> 5)], bit);
     else atomicOr(gm + y * bm.wpr + (x >> 5), bit);
   }
-  // any available phantom pixel in the 3x3 neighbourhood of (x, y)?  (rows >= bm.top only:
-  // the rows above hold no available pixel)
+  // any available phantom pixel in the 3x3 neighbourhood of (x, y)?  (y >= bm.top; rows above the window top hold
+  // no available pixel).  Same instruction path for every lane: the three rows are read unconditionally (a row
+  // outside [top, H) is replaced by row y and masked out) and phantom & available is formed before the 3-bit extract.
   __device__ __forceinline__ bool near(const GrowBitmap& bm, int x, int y, int H) const {
     const int xm = x - 1;
     const int wa = max(xm, 0) >> 5;
     const int sh = xm - (wa << 5);   // -1 .. 31
     const bool two = sh >= 30 && wa + 1 < bm.wpr;
-    for (int yy = max(y - 1, bm.top); yy <= min(y + 1, H - 1); yy++) {
-      const unsigned plo = word(bm, yy, wa), phi = two ? word(bm, yy, wa + 1) : 0u;
-      const unsigned long long pc = ((unsigned long long)phi << 32) | plo;
-      const unsigned p3 = sh >= 0 ? ((unsigned)(pc >> sh) & 7u) : ((plo << 1) & 7u);
-      if (p3) {
-        const unsigned alo = bm.word(yy, wa), ahi = two ? bm.word(yy, wa + 1) : 0u;
-        const unsigned long long ac = ((unsigned long long)ahi << 32) | alo;
-        const unsigned a3 = sh >= 0 ? ((unsigned)(ac >> sh) & 7u) : ((alo << 1) & 7u);
-        if (p3 & a3) return true;
-      }
+    unsigned hit = 0u;
+#pragma unroll
+    for (int r = -1; r <= 1; r++) {
+      const int yy = y + r;
+      const bool ok = yy >= bm.top && yy < H;
+      const int yc = ok ? yy : y;
+      unsigned long long pa = (unsigned long long)(word(bm, yc, wa) & bm.word(yc, wa));
+      if (two) pa |= (unsigned long long)(word(bm, yc, wa + 1) & bm.word(yc, wa + 1)) << 32;
+      const unsigned m3 = sh >= 0 ? ((unsigned)(pa >> sh) & 7u) : (((unsigned)pa << 1) & 7u);
+      hit |= ok ? m3 : 0u;
     }
-    return false;
+    return hit != 0u;
   }
 };
 
