@@ -676,7 +676,9 @@ __global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_co
   // would fill the SM's 32 block slots and keep the kernels of the other streams out
   extern __shared__ unsigned smem_all[];
   unsigned* smem_u = smem_all + (threadIdx.x >> 5) * smemWordsPerWarp;
-  const int oct = blockIdx.x, f = blockIdx.y * GROW_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  // longest jobs first: all octave-0 blocks (four times the pixels) precede the octave-1 blocks in launch order
+  const int nblk = (n + GROW_WPB - 1) / GROW_WPB;
+  const int oct = (int)blockIdx.x / nblk, f = ((int)blockIdx.x - oct * nblk) * GROW_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (oct >= g.noct || f >= n) return;
   const LineOct& O = g.o[oct];
   const int W = O.sw, H = O.sh, wpr = O.wpr;
@@ -1583,7 +1585,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     k_lsd_spec<<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
     prof->mark("k_lsd_spec", st);
     const size_t commitSmem = growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned);
-    k_lsd_commit<<<dim3(g.noct, (n + GROW_WPB - 1) / GROW_WPB), 32 * GROW_WPB, commitSmem * GROW_WPB, st>>>(
+    k_lsd_commit<<<dim3(g.noct * ((n + GROW_WPB - 1) / GROW_WPB)), 32 * GROW_WPB, commitSmem * GROW_WPB, st>>>(
         g, b, n, (int)(commitSmem / sizeof(unsigned)));
     prof->mark("k_lsd_commit", st);
     nl += 2;
