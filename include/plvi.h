@@ -130,6 +130,16 @@ int plvi_orb_last_launches(const plvi_orb* h);
  * replayed with a single graph launch afterwards (off while profiling or with PLVI_GRAPHS=0).  Returns the number
  * of graph replays so far; *captures (may be NULL) receives the number of captured graphs. */
 int plvi_orb_graph_stats(const plvi_orb* h, int* captures);
+/* void Frame::ComputeStereoMatches() (include/Frame.h, src/Frame.cc:1228-1406) for the last batch of two extractors
+ * (mpORBextractorLeft / mpORBextractorRight): reads their device-resident pyramids (mvImagePyramid), so nothing is
+ * copied.  Per left keypoint: candidates = right keypoints whose row band [floor(y - 2 s), ceil(y + 2 s)] contains the
+ * left row, levels +-1, uR in [uL - bf / b, uL]; best Hamming distance < (TH_HIGH + TH_LOW) / 2; 11x11 SAD over +-5 px
+ * on the left keypoint's level, parabola fit; mvDepth = bf / disparity; finally matches with SAD >= 1.5 * 1.4 * median
+ * are dropped.  d_u_right / d_depth: [n][stride] floats (-1 = no stereo match), d_nstereo[n] = matches kept.  Device
+ * pointers; runs on the left handle's stream after the right handle's pending work. */
+int plvi_orb_stereo_matches(plvi_orb* left, plvi_orb* right, int n, const plvi_keypoint* d_kps_l, const uint8_t* d_desc_l,
+                            const int* d_counts_l, const plvi_keypoint* d_kps_r, const uint8_t* d_desc_r, const int* d_counts_r,
+                            int stride, float mb, float mbf, float* d_u_right, float* d_depth, int* d_nstereo);
 /* Makes the handle's stream wait for a cudaEvent_t (e.g. plvi_line_stage_event) before the next batch. */
 int plvi_orb_wait_event(plvi_orb* h, void* cuda_event);
 /* Per-kernel device time of the last batch: with profiling on, a CUDA event is recorded

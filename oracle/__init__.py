@@ -380,6 +380,27 @@ EUROC_CAMERA = dict(fx=458.654, fy=457.296, cx=367.215, cy=248.375,
                     dist=(-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05))   # Examples/Monocular-Inertial/EuRoC.yaml
 
 
+def stereo_matches(kps_l, desc_l, kps_r, desc_r, pyr_l, pyr_r, scale_factors, mb, mbf):
+    """Frame::ComputeStereoMatches (src/Frame.cc:1228-1406).  pyr_l / pyr_r: lists of level images (orb_extract(...,
+    debug=True)["pyramid"]).  Returns (mvuRight, mvDepth, number of stereo points kept)."""
+    kl, kr = np.ascontiguousarray(kps_l), np.ascontiguousarray(kps_r)
+    dl, dr = np.ascontiguousarray(desc_l, np.uint8), np.ascontiguousarray(desc_r, np.uint8)
+    lw = np.array([p.shape[1] for p in pyr_l], np.int32)
+    lh = np.array([p.shape[0] for p in pyr_l], np.int32)
+    pl = np.concatenate([np.ascontiguousarray(p, np.uint8).reshape(-1) for p in pyr_l])
+    pr = np.concatenate([np.ascontiguousarray(p, np.uint8).reshape(-1) for p in pyr_r])
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    isf = (np.float32(1.0) / sf).astype(np.float32)
+    ur = np.empty(max(len(kl), 1), np.float32)
+    dp = np.empty(max(len(kl), 1), np.float32)
+    f = lib().plvio_stereo_matches
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    n = f(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(pl), _p(pr), _p(lw), _p(lh), len(lw), _p(sf), _p(isf),
+          float(mb), float(mbf), _p(ur), _p(dp))
+    return ur[:len(kl)], dp[:len(kl)], n
+
+
 def camera_arrays(cam):
     """(K[4], dist[14], P[4]) float64 arrays; K and dist go through float32 like the reference's cv::Mat(CV_32F)."""
     K = np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32).astype(np.float64)

@@ -6,7 +6,10 @@
 //        double, project with P).  Pinned against cv2.undistortPoints in tests/test_frame_cpu.py
 //        (bit-exact on 5000 points) and against tests/golden/undistort_euroc.npz.
 //   Frame::AssignFeaturesToGrid + PosInGrid         src/Frame.cc:644-675,1077-1087
+#include <algorithm>
+#include <climits>
 #include <cmath>
+#include <utility>
 #include <vector>
 
 #include "oracle_common.h"
@@ -72,3 +75,118 @@ void plvio_assign_grid(const float* xy, int n, float minX, float minY, float inv
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Frame::ComputeStereoMatches (src/Frame.cc:1228-1406): for every left keypoint the best right keypoint of its row
+// band by Hamming distance (levels +-1, disparity range), 11x11 SAD refinement over +-5 px on the pyramid level of
+// the left keypoint (patches minus their centre pixel, CV_16S, cv::norm NORM_L1), parabola fit, depth = bf /
+// disparity, then removal of matches whose SAD is >= 1.5 * 1.4 * median.  pyrL / pyrR: dense level images
+// concatenated (level 0 first), lw / lh: level sizes.  An empty match list leaves everything at -1 (the reference
+// indexes vDistIdx[0] of an empty vector there: undefined).
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int plvio_stereo_matches(const float* kL /* x,y,size,angle,response,octave(int),class_id(int) */, const uint8_t* dL,
+                                    int nL, const float* kR, const uint8_t* dR, int nR, const uint8_t* pyrL,
+                                    const uint8_t* pyrR, const int* lw, const int* lh, int nlevels, const float* scaleFactors,
+                                    const float* invScaleFactors, float mb, float mbf, float* uRight, float* depth) {
+  struct KP { float x, y, size, angle, response; int octave, class_id; };
+  const KP* L = reinterpret_cast<const KP*>(kL);
+  const KP* R = reinterpret_cast<const KP*>(kR);
+  std::vector<size_t> off(nlevels + 1, 0);
+  for (int l = 0; l < nlevels; l++) off[l + 1] = off[l] + (size_t)lw[l] * lh[l];
+  for (int i = 0; i < nL; i++) { uRight[i] = -1.0f; depth[i] = -1.0f; }
+  const int TH_HIGH = 100, TH_LOW = 50;
+  const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+  const int nRows = lh[0];
+  std::vector<std::vector<int>> rows(nRows);
+  for (int iR = 0; iR < nR; iR++) {
+    const float kpY = R[iR].y;
+    const float r = 2.0f * scaleFactors[R[iR].octave];
+    const int maxr = (int)std::ceil(kpY + r), minr = (int)std::floor(kpY - r);
+    for (int yi = minr; yi <= maxr; yi++)
+      if (yi >= 0 && yi < nRows) rows[yi].push_back(iR);
+  }
+  const float minZ = mb, minD = 0, maxD = mbf / minZ;
+  std::vector<std::pair<int, int>> vDistIdx;
+  auto hamming = [](const uint8_t* a, const uint8_t* b) {
+    int d = 0;
+    for (int i = 0; i < 32; i++) d += __builtin_popcount((unsigned)(a[i] ^ b[i]));
+    return d;
+  };
+  for (int iL = 0; iL < nL; iL++) {
+    const KP& kpL = L[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;
+    if (row < 0 || row >= nRows) continue;
+    const std::vector<int>& cand = rows[row];
+    if (cand.empty()) continue;
+    const float minU = uL - maxD, maxU = uL - minD;
+    if (maxU < 0) continue;
+    int bestDist = TH_HIGH;
+    int bestIdxR = 0;
+    for (int iR : cand) {
+      const KP& kpR = R[iR];
+      if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+      const float uR = kpR.x;
+      if (uR >= minU && uR <= maxU) {
+        const int dist = hamming(dL + 32 * (size_t)iL, dR + 32 * (size_t)iR);
+        if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+      }
+    }
+    if (!(bestDist < thOrbDist)) continue;
+    const float uR0 = R[bestIdxR].x;
+    const float scaleFactor = invScaleFactors[kpL.octave];
+    const float scaleduL = std::round(kpL.x * scaleFactor);
+    const float scaledvL = std::round(kpL.y * scaleFactor);
+    const float scaleduR0 = std::round(uR0 * scaleFactor);
+    const int w = 5, Ls = 5;
+    const int W = lw[kpL.octave], H = lh[kpL.octave];
+    const uint8_t* IL = pyrL + off[kpL.octave];
+    const uint8_t* IR = pyrR + off[kpL.octave];
+    const int cuL = (int)scaleduL, cvL = (int)scaledvL, cuR = (int)scaleduR0;
+    if (cvL - w < 0 || cvL + w >= H || cuL - w < 0 || cuL + w >= W) continue;   // cv::Mat::rowRange / colRange would throw
+    const float iniu = scaleduR0 + Ls - w, endu = scaleduR0 + Ls + w + 1;
+    if (iniu < 0 || endu >= W) continue;
+    if (cuR - Ls - w < 0) continue;                                             // colRange with a negative start would throw
+    int bestSad = INT32_MAX, bestincR = 0;
+    float vDists[11];
+    const int cL = IL[(size_t)cvL * W + cuL];
+    for (int incR = -Ls; incR <= Ls; incR++) {
+      const int cR = IR[(size_t)cvL * W + cuR + incR];
+      int sad = 0;
+      for (int dy = -w; dy <= w; dy++)
+        for (int dx = -w; dx <= w; dx++) {
+          const int a = (int)IL[(size_t)(cvL + dy) * W + cuL + dx] - cL;
+          const int b = (int)IR[(size_t)(cvL + dy) * W + cuR + incR + dx] - cR;
+          sad += std::abs(a - b);
+        }
+      const float dist = (float)sad;
+      if (dist < bestSad) { bestSad = (int)dist; bestincR = incR; }
+      vDists[Ls + incR] = dist;
+    }
+    if (bestincR == -Ls || bestincR == Ls) continue;
+    const float dist1 = vDists[Ls + bestincR - 1], dist2 = vDists[Ls + bestincR], dist3 = vDists[Ls + bestincR + 1];
+    const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+    if (deltaR < -1 || deltaR > 1) continue;
+    float bestuR = scaleFactors[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+    float disparity = uL - bestuR;
+    if (disparity >= minD && disparity < maxD) {
+      if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+      depth[iL] = mbf / disparity;
+      uRight[iL] = bestuR;
+      vDistIdx.push_back(std::pair<int, int>(bestSad, iL));
+    }
+  }
+  if (vDistIdx.empty()) return 0;
+  std::sort(vDistIdx.begin(), vDistIdx.end());
+  const float median = vDistIdx[vDistIdx.size() / 2].first;
+  const float thDist = 1.5f * 1.4f * median;
+  int kept = (int)vDistIdx.size();
+  for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {
+    if (vDistIdx[i].first < thDist) break;
+    uRight[vDistIdx[i].second] = -1;
+    depth[vDistIdx[i].second] = -1;
+    kept--;
+  }
+  return kept;
+}

@@ -271,6 +271,10 @@ struct OrbScratch {
   int fastSmem, octSmem;
 };
 
+int launch_stereo(const OrbGeom& g, const OrbPtrs& L, const OrbPtrs& R, const float* scale, const float* invScale, int n,
+                  const plvi_keypoint* kl, const uint8_t* dl, const int* nl, const plvi_keypoint* kr, const uint8_t* dr,
+                  const int* nr, int stride, float mb, float mbf, float* uRight, float* depth, int* sad, int* nstereo,
+                  cudaStream_t st);
 int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s, int n, int lap0,
                         int lap1, plvi_keypoint* d_kps, uint8_t* d_desc, int* d_counts,
                         int* d_mono, int cap, cudaStream_t st, int* launches, StageProf* prof);

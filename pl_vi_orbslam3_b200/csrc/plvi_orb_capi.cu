@@ -47,6 +47,9 @@ struct plvi_orb {
   int lastN = 0, lastLaunches = 0;
   StageProf prof;
   GraphCache graphs;
+  int* dStereoSad = nullptr;      // scratch of plvi_orb_stereo_matches
+  size_t stereoSadCap = 0;
+  cudaEvent_t stereoEv = nullptr;
   std::string profText;
   OrbPtrs lastPtrs = {};
 };
@@ -327,6 +330,8 @@ void plvi_orb_destroy(plvi_orb* h) {
     cudaFree(h->dBlur[l]);
   }
   cudaFree(h->dRsTab);
+  if (h->dStereoSad) cudaFree(h->dStereoSad);
+  if (h->stereoEv) cudaEventDestroy(h->stereoEv);
   cudaFree(h->dFastTiles);
   cudaFree(h->dBlurTiles);
   cudaFree(h->scr.cand);
@@ -348,6 +353,37 @@ int plvi_orb_levels(const plvi_orb* h) { return h ? h->nlevels : PLVI_ERR_INVALI
 float plvi_orb_scale_factor(const plvi_orb* h) { return h ? h->scaleFactor : 0.f; }
 void* plvi_orb_stream(const plvi_orb* h) { return h ? (void*)h->stream : nullptr; }
 int plvi_orb_last_launches(const plvi_orb* h) { return h ? h->lastLaunches : PLVI_ERR_INVALID; }
+int plvi_orb_stereo_matches(plvi_orb* left, plvi_orb* right, int n, const plvi_keypoint* d_kps_l, const uint8_t* d_desc_l,
+                            const int* d_counts_l, const plvi_keypoint* d_kps_r, const uint8_t* d_desc_r, const int* d_counts_r,
+                            int stride, float mb, float mbf, float* d_u_right, float* d_depth, int* d_nstereo) {
+  if (!left || !right || n < 1 || !d_kps_l || !d_desc_l || !d_counts_l || !d_kps_r || !d_desc_r || !d_counts_r || stride < 1 ||
+      stride > 65535 || !(mb > 0) || !d_u_right || !d_depth || !d_nstereo) {
+    set_error("plvi_orb_stereo_matches: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  if (left->device != right->device || left->nlevels != right->nlevels || left->curW != right->curW || left->curH != right->curH ||
+      left->curW < 0 || n > left->lastN || n > right->lastN || left->scaleFactor != right->scaleFactor) {
+    set_error("plvi_orb_stereo_matches: the two extractors must hold the pyramids of the same batch geometry");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(left->device));
+  const size_t need = (size_t)n * stride;
+  if (need > left->stereoSadCap) {
+    PLVI_CUDA_TRY(cudaStreamSynchronize(left->stream));
+    if (left->dStereoSad) cudaFree(left->dStereoSad);
+    left->dStereoSad = nullptr; left->stereoSadCap = 0;
+    PLVI_CUDA_TRY(cudaMalloc((void**)&left->dStereoSad, need * sizeof(int)));
+    left->stereoSadCap = need;
+  }
+  if (!left->stereoEv) PLVI_CUDA_TRY(cudaEventCreateWithFlags(&left->stereoEv, cudaEventDisableTiming));
+  // the right pyramid is produced on the right handle's stream
+  PLVI_CUDA_TRY(cudaEventRecord(left->stereoEv, right->stream));
+  PLVI_CUDA_TRY(cudaStreamWaitEvent(left->stream, left->stereoEv, 0));
+  return launch_stereo(left->geom, left->lastPtrs, right->lastPtrs, left->scale.data(), left->invScale.data(), n, d_kps_l, d_desc_l,
+                       d_counts_l, d_kps_r, d_desc_r, d_counts_r, stride, mb, mbf, d_u_right, d_depth, left->dStereoSad, d_nstereo,
+                       left->stream);
+}
+
 int plvi_orb_wait_event(plvi_orb* h, void* cuda_event) {
   if (!h || !cuda_event) return PLVI_ERR_INVALID;
   PLVI_CUDA_TRY(cudaSetDevice(h->device));

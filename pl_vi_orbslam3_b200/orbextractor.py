@@ -79,6 +79,21 @@ class ORBextractor:
     def last_launches(self):
         return lib().plvi_orb_last_launches(self._h)
 
+    def stereo_matches(self, right, left_out, right_out, mb, mbf):
+        """Frame::ComputeStereoMatches (src/Frame.cc:1228-1406) for the last device batch of this (left) extractor and
+        `right`: left_out / right_out = the (kps, desc, counts, mono) CUDA tensors extract_batch_device returned.
+        Returns CUDA tensors (mvuRight [n, cap] f32, mvDepth [n, cap] f32, nstereo [n] i32); -1 = no stereo match."""
+        import torch
+        kl, dl, cl, _ = left_out
+        kr, dr, cr, _ = right_out
+        n, cap = cl.shape[0], kl.shape[1]
+        ur = torch.empty((n, cap), dtype=torch.float32, device=kl.device)
+        dp = torch.empty((n, cap), dtype=torch.float32, device=kl.device)
+        ns = torch.empty(n, dtype=torch.int32, device=kl.device)
+        check(lib().plvi_orb_stereo_matches(self._h, right._h, n, ptr(kl), ptr(dl), ptr(cl), ptr(kr), ptr(dr), ptr(cr), cap,
+                                            float(mb), float(mbf), ptr(ur), ptr(dp), ptr(ns)))
+        return ur, dp, ns
+
     def graph_stats(self):
         """(captured CUDA graphs, graph replays) of this handle's per-batch launch sequence."""
         import ctypes

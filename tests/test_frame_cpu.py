@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import oracle
+from pl_vi_orbslam3_b200 import synth
 from pl_vi_orbslam3_b200.matchers import frame_grid
 
 GOLD = np.load(__import__("pathlib").Path(__file__).parent / "golden" / "undistort_euroc.npz")
@@ -51,3 +52,23 @@ def test_assign_grid_orders_and_bounds():
         cell = items[start[c]:start[c + 1]]
         assert (np.diff(cell) > 0).all()                                  # insertion = index order
         assert all(int(px[i]) * 48 + int(py[i]) == c for i in cell)
+
+
+def test_stereo_oracle_recovers_known_disparity():
+    """Frame::ComputeStereoMatches restatement on a synthetic pair with a constant 12 px disparity: most keypoints get
+    a stereo match, the sub-pixel disparities sit at 12 px, depth = bf / disparity, SAD outliers are removed."""
+    left = synth.frame_euroc(5)
+    d = 12
+    right = np.empty_like(left)
+    right[:, :-d] = left[:, d:]
+    right[:, -d:] = left[:, -1:]
+    a, b = oracle.orb_extract(left, debug=True), oracle.orb_extract(right, debug=True)
+    mbf, mb = 47.906, np.float32(47.906) / np.float32(435.2)
+    ur, dp, n = oracle.stereo_matches(a["keypoints"], a["descriptors"], b["keypoints"], b["descriptors"], a["pyramid"],
+                                      b["pyramid"], a["plan"]["scale"], mb, mbf)
+    ok = ur >= 0
+    assert n == ok.sum() and n > 0.4 * len(ur)
+    disp = a["keypoints"]["x"][ok] - ur[ok]
+    assert abs(np.median(disp) - d) < 0.05 and np.percentile(np.abs(disp - d), 75) < 0.5
+    assert np.allclose(dp[ok], np.float32(mbf) / disp, rtol=1e-6)
+    assert (dp[~ok] == -1).all()
