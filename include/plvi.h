@@ -413,6 +413,19 @@ int plvi_search_in_radius(plvi_matcher* m, int npairs, const plvi_keypoint* trai
                           const uint8_t* query_desc, const int* query_counts, int query_stride, const float* inv_level_sigma2,
                           double chi2, int th_dist, int* best_idx, int* best_dist, int* nfound);
 
+/* The per-map-line search of int LineMatcher::Fuse(KeyFrame* pKF, const vector<MapLine*>& vpMapLines, const float th)
+ * (include/LineMatcher.h, src/LineMatcher.cpp:373-485): the caller projects the two endpoints of every candidate map
+ * line and predicts its level; queries = 6 floats each (u1, v1, u2, v2, radius = th * mvScaleFactors[level], level),
+ * query_flags[q] != 0 = skipped by the checks before the search (may be NULL).  Candidates =
+ * KeyFrame::GetLinesInArea(u1, v1, u2, v2, radius) (src/KeyFrame.cc:1170-1198, tests exactly as written there), level
+ * in [level - 1, level]; distance = LineMatcher::DescriptorDistance, i.e. the ">> 25" variant (src/LineMatcher.cpp:
+ * 487-499); first smallest distance; best_idx[q] = keyline index when <= th_low (TH_LOW), else -1; best_dist[q] = the
+ * smallest distance (INT_MAX: no candidate).  Replace / AddObservation / AddMapLine stay with the caller.  Device
+ * pointers; runs on the matcher's stream. */
+int plvi_line_fuse_search(plvi_matcher* m, int npairs, const plvi_keyline* keylines, const uint8_t* desc, const int* counts,
+                          int stride, const float* queries, const uint8_t* query_flags, const uint8_t* query_desc,
+                          const int* query_counts, int query_stride, int th_low, int* best_idx, int* best_dist, int* nfound);
+
 /* Test / benchmark utility (device pointers only): builds the plvi_query records of
  * SearchByProjection(Frame,Frame) for an identity pose -- every keypoint of the query
  * frame projects onto its own position (u,v = pt), radius = th * scale_factor^octave,

@@ -235,6 +235,21 @@ def search_in_radius(keys, desc, grid, queries, qdesc, inv_level_sigma2, chi2=5.
     return n, bi[:len(queries)], bd[:len(queries)]
 
 
+def line_fuse_search(keylines, desc, queries, qdesc, flags=None, th_low=50):
+    """Per-map-line search of LineMatcher::Fuse: queries [nq, 6] f32 = u1, v1, u2, v2, radius, predicted level."""
+    kl = np.ascontiguousarray(keylines)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    q = np.ascontiguousarray(queries, np.float32).reshape(-1, 6)
+    qd = np.ascontiguousarray(qdesc, np.uint8)
+    fl = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+    bi = np.empty(max(len(q), 1), np.int32)
+    bd = np.empty(max(len(q), 1), np.int32)
+    f = lib().plvio_line_fuse_search
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    n = f(_p(kl), _p(desc), len(kl), _p(q), _p(fl), _p(qd), len(q), int(th_low), _p(bi), _p(bd))
+    return n, bi[:len(q)], bd[:len(q)]
+
+
 def search_mappoints(keys, desc, grid, queries, qdesc, th=100, nnratio=0.8, blocked=None):
     keys = np.ascontiguousarray(keys)
     desc = np.ascontiguousarray(desc, np.uint8)

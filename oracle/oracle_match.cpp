@@ -560,3 +560,42 @@ extern "C" int plvio_search_in_radius(const plvio::Kp* keys, const uint8_t* desc
   }
   return found;
 }
+
+
+// The per-map-line search of LineMatcher::Fuse(KeyFrame*, vpMapLines, th) (src/LineMatcher.cpp:373-485): the host
+// projects the two endpoints (u1, v1, u2, v2), predicts the level and radius = th * mvScaleFactors[level];
+// candidates = KeyFrame::GetLinesInArea(u1, v1, u2, v2, radius) (src/KeyFrame.cc:1170-1198: midpoint distance,
+// then the "slope - angle" test as written there), level in [nPredictedLevel - 1, nPredictedLevel], distance =
+// LineMatcher::DescriptorDistance (the >> 25 variant, :487-499), first smallest; accepted when <= th_low.
+// q: 6 floats per query = u1, v1, u2, v2, radius, nPredictedLevel (as float); flags[q] != 0 = skipped.
+// keylines: 68-byte KeyLine records (angle at offset 0, octave at 8, pt at 12/16).
+extern "C" int plvio_line_fuse_search(const uint8_t* keylines, const uint8_t* desc, int n, const float* q, const uint8_t* flags,
+                                      const uint8_t* qdesc, int nq, int th_low, int* best_idx, int* best_dist) {
+  using namespace plvio;
+  struct KL { float angle; int class_id; int octave; float pt_x, pt_y; float rest[12]; };
+  static_assert(sizeof(KL) == 68, "KeyLine layout");
+  const KL* kl = reinterpret_cast<const KL*>(keylines);
+  int found = 0;
+  for (int i = 0; i < nq; i++) {
+    best_idx[i] = -1;
+    best_dist[i] = INT32_MAX;
+    if (flags && flags[i]) continue;
+    const float x1 = q[6 * i], y1 = q[6 * i + 1], x2 = q[6 * i + 2], y2 = q[6 * i + 3], r = q[6 * i + 4];
+    const int level = (int)q[6 * i + 5];
+    int bestDist = INT32_MAX, bestIdx = -1;
+    for (int k = 0; k < n; k++) {
+      const KL& keyLine = kl[k];
+      const float distance = (0.5 * (x1 + x2) - keyLine.pt_x) * (0.5 * (x1 + x2) - keyLine.pt_x) +
+                             (0.5 * (y1 + y2) - keyLine.pt_y) * (0.5 * (y1 + y2) - keyLine.pt_y);
+      if (distance > r * r) continue;
+      const float slope = (y1 - y2) / (x1 - x2) - keyLine.angle;
+      if (slope > r * 0.01) continue;
+      if (keyLine.octave < level - 1 || keyLine.octave > level) continue;
+      const int dist = hamming256_shift25(qdesc + 32 * (size_t)i, desc + 32 * (size_t)k);
+      if (dist < bestDist) { bestDist = dist; bestIdx = k; }
+    }
+    best_dist[i] = bestDist;
+    if (bestIdx >= 0 && bestDist <= th_low) { best_idx[i] = bestIdx; found++; }
+  }
+  return found;
+}

@@ -83,6 +83,7 @@ _SIGS = {
     "plvi_search_by_bow_kf": (ci, [vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, vp, ci, ci, cf, ci, vp, vp, vp, ci]),
     "plvi_search_for_triangulation": (ci, [vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, vp, ci, vp, ci, ci, vp, vp]),
     "plvi_search_in_radius": (ci, [vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp, C.c_double, ci, vp, vp, vp]),
+    "plvi_line_fuse_search": (ci, [vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, ci, ci, vp, vp, vp]),
     "plvi_queries_from_keypoints": (ci, [vp, vp, vp, ci, ci, cf, cf, vp]),
     "plvi_line_match": (ci, [vp, ci, vp, vp, ci, vp, vp, ci, cf, ci, vp, vp, ci]),
     "plvi_undistort_keypoints": (ci, [vp, vp, vp, ci, ci, vp, vp]),

@@ -870,6 +870,66 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search_in_radius(const Ra
   if (tid == 0) a.nfound[pair] = s_found;
 }
 
+// ---------------------------------------------------------------------------------------
+// k_line_fuse_search: the per-map-line search of LineMatcher::Fuse (src/LineMatcher.cpp:373-485) over
+// KeyFrame::GetLinesInArea (src/KeyFrame.cc:1170-1198).  Warp per query, lanes over the keyframe's keylines; the
+// mixed float / double expressions of the reference are evaluated operation by operation; distance = the >> 25
+// variant of LineMatcher::DescriptorDistance; min over (distance, index) = first smallest distance.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_line_fuse_search(const plvi_keyline* __restrict__ klAll, const uint8_t* __restrict__ descAll,
+                                                          const int* __restrict__ ncount, int stride, const float* __restrict__ qAll,
+                                                          const uint8_t* __restrict__ flagsAll, const uint8_t* __restrict__ qdescAll,
+                                                          const int* __restrict__ qcount, int qstride, int thLow,
+                                                          int* __restrict__ bestIdx, int* __restrict__ bestDist, int* __restrict__ nfound) {
+  const int pair = blockIdx.y, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n = ncount[pair], nq = qcount[pair];
+  if (qi >= qstride) return;
+  const size_t qo = (size_t)pair * qstride + qi;
+  int outIdx = -1, outDist = 0x7fffffff;
+  if (qi < nq && !(flagsAll && flagsAll[qo])) {
+    const float* q = qAll + qo * 6;
+    const float x1 = q[0], y1 = q[1], x2 = q[2], y2 = q[3], r = q[4];
+    const int level = (int)q[5];
+    const double mx = __dmul_rn(0.5, (double)__fadd_rn(x1, x2)), my = __dmul_rn(0.5, (double)__fadd_rn(y1, y2));
+    const float r2 = __fmul_rn(r, r);
+    const float slope0 = __fdiv_rn(__fsub_rn(y1, y2), __fsub_rn(x1, x2));
+    const double slopeTh = __dmul_rn((double)r, 0.01);
+    uint32_t qw[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) qw[k] = __ldg(reinterpret_cast<const uint32_t*>(qdescAll + qo * 32) + k);
+    const plvi_keyline* kl = klAll + (size_t)pair * stride;
+    const uint8_t* desc = descAll + (size_t)pair * stride * 32;
+    unsigned long long best = ~0ull;
+    for (int k = lane; k < n; k += 32) {
+      const plvi_keyline L = kl[k];
+      const double dx = __dsub_rn(mx, (double)L.pt_x), dy = __dsub_rn(my, (double)L.pt_y);
+      const float distance = (float)__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      if (distance > r2) continue;
+      const float slope = __fsub_rn(slope0, L.angle);
+      if ((double)slope > slopeTh) continue;
+      if (L.octave < level - 1 || L.octave > level) continue;
+      const uint32_t* d = reinterpret_cast<const uint32_t*>(desc + (size_t)k * 32);
+      int dist = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) dist += __popc(qw[w] ^ __ldg(d + w)) >> 1;   // (popcount * 0x1010101 >> 24) >> 1
+      const unsigned long long key = ((unsigned long long)(unsigned)dist << 32) | (unsigned)k;
+      best = best < key ? best : key;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, s);
+      best = best < o ? best : o;
+    }
+    if (best != ~0ull) { outDist = (int)(best >> 32); if (outDist <= thLow) outIdx = (int)(best & 0xffffffffu); }
+  }
+  if (lane == 0) {
+    bestIdx[qo] = outIdx;
+    bestDist[qo] = outDist;
+    if (outIdx >= 0) atomicAdd(&nfound[pair], 1);
+  }
+}
+
 struct plvi_matcher {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -1244,6 +1304,24 @@ int plvi_search_in_radius(plvi_matcher* m, int npairs, const plvi_keypoint* trai
   if (smem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search_in_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_search_in_radius<<<npairs, SEARCH_WARPS * 32, smem, m->stream>>>(a);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  return PLVI_OK;
+}
+
+int plvi_line_fuse_search(plvi_matcher* m, int npairs, const plvi_keyline* keylines, const uint8_t* desc, const int* counts,
+                          int stride, const float* queries, const uint8_t* query_flags, const uint8_t* query_desc,
+                          const int* query_counts, int query_stride, int th_low, int* best_idx, int* best_dist, int* nfound) {
+  if (!m || npairs < 1 || !keylines || !desc || !counts || !queries || !query_desc || !query_counts || !best_idx || !best_dist ||
+      !nfound || stride < 1 || query_stride < 1) {
+    set_error("plvi_line_fuse_search: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  PLVI_CUDA_TRY(cudaMemsetAsync(nfound, 0, sizeof(int) * npairs, m->stream));
+  k_line_fuse_search<<<dim3((query_stride + 7) / 8, npairs), 256, 0, m->stream>>>(keylines, desc, counts, stride, queries, query_flags,
+                                                                                 query_desc, query_counts, query_stride, th_low,
+                                                                                 best_idx, best_dist, nfound);
   m->lastLaunches = 1;
   PLVI_CUDA_TRY(cudaGetLastError());
   return PLVI_OK;

@@ -238,6 +238,34 @@ class ORBmatcher(_Matcher):
 class LineMatcher(_Matcher):
     TH_HIGH, TH_LOW = 100, 50   # src/LineMatcher.cpp:37-38
 
+    def FuseSearch(self, keylines, desc, queries, qdesc, flags=None):
+        """The per-map-line search of LineMatcher::Fuse (src/LineMatcher.cpp:373-485): keylines / desc = the keyframe's
+        mvKeys_Line / mDescriptors_l, queries [nq, 6] f32 = projected endpoints u1, v1, u2, v2, radius, predicted level.
+        Returns (nfound, best_idx, best_dist)."""
+        import torch
+        from .capi import KEYLINE_DTYPE
+        n, nq = len(keylines), len(queries)
+        T, Q = max(n, 1), max(nq, 1)
+        kl = np.zeros(T, KEYLINE_DTYPE); kl[:n] = keylines
+        d = np.zeros((T, 32), np.uint8); d[:n] = desc
+        q = np.zeros((Q, 6), np.float32); q[:nq] = np.asarray(queries, np.float32).reshape(-1, 6)
+        qd = np.zeros((Q, 32), np.uint8); qd[:nq] = qdesc
+        fl = np.zeros(Q, np.uint8)
+        if flags is not None:
+            fl[:nq] = flags
+        dev = torch.device("cuda", self.device)
+        def up(a):
+            return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+        t = [up(x) for x in (kl, d, np.array([n], np.int32), q, fl, qd, np.array([nq], np.int32))]
+        bi = torch.empty(Q, dtype=torch.int32, device=dev)
+        bd = torch.empty(Q, dtype=torch.int32, device=dev)
+        nf = torch.empty(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        check(lib().plvi_line_fuse_search(self._h, 1, ptr(t[0]), ptr(t[1]), ptr(t[2]), T, ptr(t[3]), ptr(t[4]), ptr(t[5]),
+                                          ptr(t[6]), Q, self.TH_LOW, ptr(bi), ptr(bd), ptr(nf)))
+        self.sync()
+        return int(nf.cpu().numpy()[0]), bi.cpu().numpy()[:nq], bd.cpu().numpy()[:nq]
+
     def match_batch(self, pairs, nnr, mutual=True):
         P = len(pairs)
         S1 = max(max(len(a) for a, _ in pairs), 1)

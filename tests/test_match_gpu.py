@@ -450,3 +450,37 @@ def test_search_in_radius_empty(om):
     assert n == 0 and (bi == -1).all() and (bd == 256).all()
     n, bi, bd = om.SearchInRadius(FrameView(keys, desc, GRID), q[:0], qd[:0], INV_SIGMA2)
     assert n == 0 and len(bi) == 0
+
+
+def _line_fuse_case(seed):
+    """Keylines + LBD descriptors of a synthetic frame (oracle) and map lines = perturbed copies of them."""
+    rng = np.random.RandomState(seed)
+    r = oracle.line_extract(synth.frame_euroc(40 + seed))
+    kl, desc = r["keylines"], r["descriptors"]
+    nq = 300
+    src = rng.randint(0, len(kl), nq)
+    q = np.zeros((nq, 6), np.float32)
+    jit = rng.uniform(-6, 6, (nq, 4)).astype(np.float32)
+    q[:, 0] = kl["startPointX"][src] + jit[:, 0]
+    q[:, 1] = kl["startPointY"][src] + jit[:, 1]
+    q[:, 2] = kl["endPointX"][src] + jit[:, 2]
+    q[:, 3] = kl["endPointY"][src] + jit[:, 3]
+    q[:, 4] = rng.choice([3.0, 8.0, 20.0, 60.0], nq).astype(np.float32) * np.float32(1.2)
+    q[:, 5] = kl["octave"][src] + rng.randint(0, 2, nq)
+    q[::17, 2] = q[::17, 0]                      # vertical projections: x1 == x2 -> division by zero in the slope
+    qd = desc[src].copy()
+    flip = rng.rand(nq, 32) < 0.08
+    qd ^= (flip * rng.randint(0, 256, (nq, 32))).astype(np.uint8)
+    flags = (rng.rand(nq) < 0.1).astype(np.uint8)
+    return kl, desc, q, qd, flags
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_line_fuse_search(lm, seed):
+    kl, desc, q, qd, flags = _line_fuse_case(seed)
+    n, bi, bd = lm.FuseSearch(kl, desc, q, qd, flags)
+    rn, rbi, rbd = oracle.line_fuse_search(kl, desc, q, qd, flags, 50)
+    assert n == rn and n > 20
+    assert np.array_equal(bi, rbi) and np.array_equal(bd, rbd)
+    n0, bi0, bd0 = lm.FuseSearch(kl[:0], desc[:0], q, qd)
+    assert n0 == 0 and (bi0 == -1).all()

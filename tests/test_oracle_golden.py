@@ -194,3 +194,37 @@ def test_search_in_radius_oracle_matches_brute_force():
                 assert bi[i] == int(d.argmin())
             if best > th:
                 assert bi[i] == -1
+
+
+def test_line_fuse_search_oracle_uses_the_shift25_distance_and_first_minimum():
+    """LineMatcher::Fuse measures with LineMatcher::DescriptorDistance (sum of floor(popcount32 / 2), the >> 25 bug of
+    src/LineMatcher.cpp:487-499), not with the Hamming distance: a numpy model of GetLinesInArea + that distance."""
+    rng = np.random.RandomState(4)
+    r = oracle.line_extract(synth.frame_euroc(41))
+    kl, desc = r["keylines"], r["descriptors"]
+    nq = 120
+    src = rng.randint(0, len(kl), nq)
+    q = np.zeros((nq, 6), np.float32)
+    q[:, 0], q[:, 1] = kl["startPointX"][src] + 1, kl["startPointY"][src] - 1
+    q[:, 2], q[:, 3] = kl["endPointX"][src] - 1, kl["endPointY"][src] + 1
+    q[:, 4] = 30.0
+    q[:, 5] = kl["octave"][src]
+    qd = desc[src] ^ (rng.rand(nq, 32) < 0.1).astype(np.uint8)
+    found, bi, bd = oracle.line_fuse_search(kl, desc, q, qd, None, 50)
+    w = lambda a: np.ascontiguousarray(a).view(np.uint32)
+    for i in range(nq):
+        mx, my = 0.5 * np.float64(q[i, 0] + q[i, 2]), 0.5 * np.float64(q[i, 1] + q[i, 3])
+        dist = ((mx - kl["pt_x"]) ** 2 + (my - kl["pt_y"]) ** 2).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            slope = np.float32(q[i, 1] - q[i, 3]) / np.float32(q[i, 0] - q[i, 2]) - kl["angle"]
+        ok = ~(dist > q[i, 4] * q[i, 4]) & ~(slope.astype(np.float64) > np.float64(q[i, 4]) * 0.01)
+        ok &= (kl["octave"] >= int(q[i, 5]) - 1) & (kl["octave"] <= int(q[i, 5]))
+        x = w(desc) ^ w(qd[i])
+        d = np.array([[bin(int(v)).count("1") >> 1 for v in row] for row in x]).sum(axis=1)
+        d = np.where(ok, d, 1 << 30)
+        if ok.any():
+            assert bd[i] == d.min()
+            assert bi[i] == (int(d.argmin()) if d.min() <= 50 else -1)
+        else:
+            assert bi[i] == -1
+    assert found > 50
