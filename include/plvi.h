@@ -140,6 +140,12 @@ int plvi_orb_graph_stats(const plvi_orb* h, int* captures);
 int plvi_orb_stereo_matches(plvi_orb* left, plvi_orb* right, int n, const plvi_keypoint* d_kps_l, const uint8_t* d_desc_l,
                             const int* d_counts_l, const plvi_keypoint* d_kps_r, const uint8_t* d_desc_r, const int* d_counts_r,
                             int stride, float mb, float mbf, float* d_u_right, float* d_depth, int* d_nstereo);
+/* Host-pointer form of plvi_orb_stereo_matches for one stereo frame: mvKeys / mDescriptors / mvKeysRight /
+ * mDescriptorsRight in, mvuRight / mvDepth (n_l floats each) out; synchronous.  Both handles must have just
+ * extracted the two images of the frame (their pyramids are read on the device). */
+int plvi_orb_stereo_matches_host(plvi_orb* left, plvi_orb* right, const plvi_keypoint* kps_l, const uint8_t* desc_l, int n_l,
+                                 const plvi_keypoint* kps_r, const uint8_t* desc_r, int n_r, float mb, float mbf, float* u_right,
+                                 float* depth, int* nstereo);
 /* Makes the handle's stream wait for a cudaEvent_t (e.g. plvi_line_stage_event) before the next batch. */
 int plvi_orb_wait_event(plvi_orb* h, void* cuda_event);
 /* Per-kernel device time of the last batch: with profiling on, a CUDA event is recorded

@@ -6,6 +6,8 @@
 #include <mutex>
 #include <vector>
 
+#include <algorithm>
+
 #include "plvi_internal.cuh"
 
 namespace plvi {
@@ -382,6 +384,52 @@ int plvi_orb_stereo_matches(plvi_orb* left, plvi_orb* right, int n, const plvi_k
   return launch_stereo(left->geom, left->lastPtrs, right->lastPtrs, left->scale.data(), left->invScale.data(), n, d_kps_l, d_desc_l,
                        d_counts_l, d_kps_r, d_desc_r, d_counts_r, stride, mb, mbf, d_u_right, d_depth, left->dStereoSad, d_nstereo,
                        left->stream);
+}
+
+// Host-pointer form for one stereo frame (the reference's Frame::ComputeStereoMatches works on the host vectors
+// mvKeys / mvKeysRight / mDescriptors / mDescriptorsRight and fills mvuRight / mvDepth): staged through device
+// scratch owned by the left handle, synchronous.
+int plvi_orb_stereo_matches_host(plvi_orb* left, plvi_orb* right, const plvi_keypoint* kps_l, const uint8_t* desc_l, int n_l,
+                                 const plvi_keypoint* kps_r, const uint8_t* desc_r, int n_r, float mb, float mbf, float* u_right,
+                                 float* depth, int* nstereo) {
+  if (!left || !right || n_l < 0 || n_r < 0 || (n_l && (!kps_l || !desc_l || !u_right || !depth)) || (n_r && (!kps_r || !desc_r))) {
+    set_error("plvi_orb_stereo_matches_host: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  if (nstereo) *nstereo = 0;
+  if (n_l == 0) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaSetDevice(left->device));
+  const int stride = std::max(std::max(n_l, n_r), 1);
+  const size_t kb = (size_t)stride * sizeof(plvi_keypoint), db = (size_t)stride * 32;
+  const size_t total = 2 * kb + 2 * db + 2 * (size_t)stride * sizeof(float) + 4 * sizeof(int) + 256;
+  char* buf = nullptr;
+  PLVI_CUDA_TRY(cudaMalloc((void**)&buf, total));
+  char* p = buf;
+  auto take = [&](size_t n) { char* r = p; p += (n + 15) & ~(size_t)15; return r; };
+  plvi_keypoint* dkl = (plvi_keypoint*)take(kb); plvi_keypoint* dkr = (plvi_keypoint*)take(kb);
+  uint8_t* ddl = (uint8_t*)take(db); uint8_t* ddr = (uint8_t*)take(db);
+  float* dur = (float*)take((size_t)stride * sizeof(float)); float* ddp = (float*)take((size_t)stride * sizeof(float));
+  int* dcnt = (int*)take(4 * sizeof(int));
+  const int cnt[3] = {n_l, n_r, 0};
+  cudaStream_t st = left->stream;
+  int rc = PLVI_OK;
+  cudaError_t e = cudaMemcpyAsync(dkl, kps_l, (size_t)n_l * sizeof(plvi_keypoint), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ddl, desc_l, (size_t)n_l * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_r) e = cudaMemcpyAsync(dkr, kps_r, (size_t)n_r * sizeof(plvi_keypoint), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n_r) e = cudaMemcpyAsync(ddr, desc_r, (size_t)n_r * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dcnt, cnt, sizeof(cnt), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    rc = plvi_orb_stereo_matches(left, right, 1, dkl, ddl, dcnt, dkr, ddr, dcnt + 1, stride, mb, mbf, dur, ddp, dcnt + 2);
+  int ns = 0;
+  if (e == cudaSuccess && rc == PLVI_OK) e = cudaMemcpyAsync(u_right, dur, (size_t)n_l * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == PLVI_OK) e = cudaMemcpyAsync(depth, ddp, (size_t)n_l * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == PLVI_OK) e = cudaMemcpyAsync(&ns, dcnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  if (rc != PLVI_OK) return rc;
+  PLVI_CUDA_TRY(e);
+  if (nstereo) *nstereo = ns;
+  return PLVI_OK;
 }
 
 int plvi_orb_wait_event(plvi_orb* h, void* cuda_event) {

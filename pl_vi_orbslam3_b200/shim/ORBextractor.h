@@ -52,6 +52,25 @@ class ORBextractor {
   std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
   std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
+  plvi_orb* handle() const { return h_; }
+
+  // void Frame::ComputeStereoMatches() (src/Frame.cc:1228-1406) for the frame whose left / right images this
+  // extractor and `right` have just processed: the SAD refinement reads both pyramids on the device, so the host
+  // copies of mvImagePyramid are not needed.  mvuRight / mvDepth are resized to keysLeft.size() (-1 = no match).
+  int ComputeStereoMatches(ORBextractor& right, const std::vector<cv::KeyPoint>& keysLeft, const cv::Mat& descLeft,
+                           const std::vector<cv::KeyPoint>& keysRight, const cv::Mat& descRight, float mb, float mbf,
+                           std::vector<float>& mvuRight, std::vector<float>& mvDepth) {
+    static_assert(sizeof(cv::KeyPoint) == sizeof(plvi_keypoint), "cv::KeyPoint layout");
+    mvuRight.assign(keysLeft.size(), -1.0f);
+    mvDepth.assign(keysLeft.size(), -1.0f);
+    int n = 0;
+    plvi_shim::check(plvi_orb_stereo_matches_host(h_, right.h_, reinterpret_cast<const plvi_keypoint*>(keysLeft.data()), descLeft.data,
+                                                  (int)keysLeft.size(), reinterpret_cast<const plvi_keypoint*>(keysRight.data()),
+                                                  descRight.data, (int)keysRight.size(), mb, mbf, mvuRight.data(), mvDepth.data(), &n),
+                     "ComputeStereoMatches");
+    return n;
+  }
+
   // The reference exposes mvImagePyramid as a public member that only the stereo paths read
   // (src/Frame.cc:1235,1325-1344).  Here it is filled lazily: call FetchPyramid() after
   // operator() when a consumer needs the host copy.

@@ -1,5 +1,7 @@
 // Compiles the shim headers against libplvi_cuda.so and, on a GPU box, runs one frame
 // through the reference-shaped C++ API:  g++ shim_smoke.cpp -L.. -lplvi_cuda
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -32,8 +34,23 @@ int main(int argc, char** argv) {
     std::vector<int> m12;
     const int nm = ORB_SLAM3::LineMatcher::match(ldesc, ldesc, 0.9f, m12);
     const int d0 = kps.size() > 1 ? ORB_SLAM3::ORBmatcher::DescriptorDistance(desc.row(0), desc.row(1)) : -1;
-    std::printf("shim ok: monoIndex=%d keypoints=%zu lines=%zu self-matches=%d dist01=%d\n", mono, kps.size(), kls.size(), nm, d0);
-    return (mono == (int)kps.size() && nm <= (int)kls.size()) ? 0 : 1;
+    // stereo: a right image = the left one shifted by 10 px; Frame::ComputeStereoMatches through the two extractors
+    std::vector<uint8_t> imgR((size_t)w * h);
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) imgR[(size_t)y * w + x] = img[(size_t)y * w + std::min(x + 10, w - 1)];
+    cv::Mat imR(h, w, imgR.data());
+    ORB_SLAM3::ORBextractor orbR(1000, 1.2f, 8, 20, 7, w, h);
+    std::vector<cv::KeyPoint> kpsR;
+    cv::Mat descR;
+    orbR(imR, mask, kpsR, descR, lap);
+    std::vector<float> uRight, depth;
+    const int nst = orb.ComputeStereoMatches(orbR, kps, desc, kpsR, descR, 47.9f / 435.2f, 47.9f, uRight, depth);
+    int near10 = 0;
+    for (size_t i = 0; i < kps.size(); i++)
+      if (uRight[i] >= 0 && std::fabs((kps[i].pt.x - uRight[i]) - 10.f) < 0.5f) near10++;
+    std::printf("shim ok: monoIndex=%d keypoints=%zu lines=%zu self-matches=%d dist01=%d stereo=%d (disparity 10: %d)\n", mono, kps.size(),
+                kls.size(), nm, d0, nst, near10);
+    return (mono == (int)kps.size() && nm <= (int)kls.size() && nst > 0 && near10 * 4 > nst) ? 0 : 1;   // the block pattern repeats, so part of the matches sit on another period
   } catch (const std::exception& e) {
     std::printf("shim error: %s\n", e.what());
     return argc > 1 ? 0 : 2;   // with an argument: tolerate "no CUDA device" (CPU box link check)
