@@ -177,6 +177,10 @@ struct GraphCache {
   ~GraphCache() { clear(); }
   // record(launches*) issues the launch sequence on `st`; returns a PLVI status
   template <class F> int run(cudaStream_t st, const std::vector<uint64_t>& key, int* launches, F&& record) {
+    // a caller that is itself capturing this stream (e.g. into a larger graph) gets plain launches: they become
+    // nodes of the caller's graph
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return record(launches);
     for (auto& e : entries)
       if (e.key == key) {
         PLVI_CUDA_TRY(cudaGraphLaunch(e.exec, st));
