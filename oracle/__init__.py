@@ -529,7 +529,7 @@ def ref_build(force: bool = False):
     if not (REFERENCE_ROOT / "src" / "ORBextractor.cc").exists():
         return _REF_LIB if _REF_LIB.exists() else None
     build()
-    srcs = [_DIR / "ref_glue.cpp", _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _LIB]
+    srcs = [_DIR / "ref_glue.cpp", _DIR / "Makefile.ref", _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _LIB]
     stale = (not _REF_LIB.exists()) or any(s.stat().st_mtime > _REF_LIB.stat().st_mtime for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", str(_DIR), "-f", "Makefile.ref", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []),
@@ -585,6 +585,23 @@ def ref_orb_extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20,
     if debug:
         out["pyramid"] = split_levels(pyr, plan)
     return out
+
+
+def ref_bow_transform(voc_text_path, desc, levelsup=4):
+    """The reference's own DBoW2 (TemplatedVocabulary::loadFromTextFile + transform) on a vocabulary text file.
+    Returns dict(words=vocabulary size, bow=(words, values), fv=(nodes, start, features))."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    m = len(desc)
+    bc, fc = C.c_int(0), C.c_int(0)
+    bw, bv = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.float64)
+    fn, fs, ff = np.zeros(max(m, 1), np.int32), np.zeros(m + 1, np.int32), np.zeros(max(m, 1), np.int32)
+    f = ref_lib().plviref_bow_transform
+    f.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+    n = f(str(voc_text_path).encode(), _p(desc), m, int(levelsup), C.byref(bc), _p(bw), _p(bv), C.byref(fc), _p(fn), _p(fs), _p(ff))
+    if n < 0:
+        raise RuntimeError("reference DBoW2 could not load the vocabulary text file")
+    return {"words": n, "bow": (bw[:bc.value].copy(), bv[:bc.value].copy()),
+            "fv": (fn[:fc.value].copy(), fs[:fc.value + 1].copy(), ff[:fs[fc.value]].copy())}
 
 
 def ref_lsd(img, lsd_scale=0.8, refine=0):

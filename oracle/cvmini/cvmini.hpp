@@ -23,7 +23,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <fstream>
+#include <iomanip>
+#include <list>
+#include <map>
 #include <memory>
+#include <numeric>
+#include <set>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -235,16 +242,29 @@ template <typename T> struct Ptr : public std::shared_ptr<T> {
 };
 template <typename T, typename... A> static inline Ptr<T> makePtr(A&&... a) { return Ptr<T>(new T(std::forward<A>(a)...)); }
 
-class FileNode {
+class FileNode {   // yml (de)serialisation is outside the path: every accessor throws
  public:
   template <typename T> void operator>>(T&) const { cvmini_unreachable("FileNode"); }
-  FileNode operator[](const char*) const { return FileNode(); }
-  FileNode operator[](const String&) const { return FileNode(); }
+  FileNode operator[](const char*) const { cvmini_unreachable("FileNode"); }
+  FileNode operator[](const String&) const { cvmini_unreachable("FileNode"); }
+  FileNode operator[](int) const { cvmini_unreachable("FileNode"); }
+  FileNode operator[](unsigned) const { cvmini_unreachable("FileNode"); }
   operator int() const { cvmini_unreachable("FileNode"); }
+  operator float() const { cvmini_unreachable("FileNode"); }
+  operator double() const { cvmini_unreachable("FileNode"); }
+  operator String() const { cvmini_unreachable("FileNode"); }
+  size_t size() const { cvmini_unreachable("FileNode"); }
   bool empty() const { return true; }
 };
 class FileStorage {
  public:
+  enum { READ = 0, WRITE = 1 };
+  FileStorage() {}
+  FileStorage(const String&, int) {}
+  bool isOpened() const { return false; }
+  void release() {}
+  FileNode operator[](const char*) const { cvmini_unreachable("FileStorage"); }
+  FileNode operator[](const String&) const { cvmini_unreachable("FileStorage"); }
   template <typename T> FileStorage& operator<<(const T&) { cvmini_unreachable("FileStorage"); }
 };
 class Algorithm {

@@ -11,14 +11,14 @@
 //     pinned against python cv2 4.13 (tests/test_oracle_vs_cv2.py in the build container, committed vectors
 //     under tests/golden/).
 //  2. Reference-owned logic (grid FAST loop, DistributeOctTree, IC_Angle, rBRIEF, LSD, KeyLine assembly, LBD,
-//     Lineextractor): pinned against the reference's OWN SOURCES, compiled unmodified from /root/reference by
+//     Lineextractor, DBoW2 vocabulary loading + transform): pinned against the reference's OWN SOURCES, compiled unmodified from /root/reference by
 //     oracle/Makefile.ref into oracle/_ref/libplvi_ref.so over the OpenCV/Eigen stand-in of oracle/cvmini/
 //     (containers re-implemented; primitives = layer 1).  tests/test_oracle_vs_ref.py (live + the committed
 //     outputs tests/golden/ref_outputs.npz): keypoints, descriptors, KeyLines, LBD bytes and line equations are
 //     byte-identical.  Host-libm float functions the reference calls (cosf, sinf, atan2f) are restated from
 //     glibc (namespace glibcm below) and equal the image's libm exhaustively.
-//  The searches (ORBmatcher.cc / LineMatcher.cpp include the whole SLAM object graph: Frame, KeyFrame, MapPoint,
-//  DBoW2, g2o, Eigen, Sophus) cannot be compiled that way: they stay "parity unpinned" (line-by-line
+//  The searches (ORBmatcher.cc / LineMatcher.cpp / Frame.cc include the whole SLAM object graph: Frame, KeyFrame,
+//  MapPoint, g2o, Eigen, Sophus) cannot be compiled that way: they stay "parity unpinned" (line-by-line
 //  restatement, regression vectors only); see DESIGN.md section 2.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl

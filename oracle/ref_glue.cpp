@@ -6,6 +6,8 @@
 #include <vector>
 
 #include <Eigen/Core>          // cvmini/ stand-in
+#include "DBoW2/FORB.h"                  // /root/reference/Thirdparty/DBoW2
+#include "DBoW2/TemplatedVocabulary.h"
 #include "ORBextractor.h"      // /root/reference/include
 #include "LineExtractor.h"     // /root/reference/include
 
@@ -135,6 +137,39 @@ int plviref_line_extract(const uchar* img, int w, int h, int stride, int lsd_nfe
 }
 
 }  // extern "C"
+
+// Frame::ComputeBoW (src/Frame.cc:1115-1122): ORBVocabulary (include/ORBVocabulary.h) = DBoW2's
+// TemplatedVocabulary<FORB::TDescriptor, FORB>, loaded with the reference's own loadFromTextFile (the ORBvoc.txt
+// format) and applied with transform(features, BowVector, FeatureVector, levelsup).  The two maps are returned in key
+// order: BowVector as (word, value) pairs, FeatureVector as CSR (node, start, feature indices).
+extern "C" int plviref_bow_transform(const char* voc_text_path, const uchar* desc, int n, int levelsup, int* bow_count, int* bow_words,
+                                     double* bow_values, int* fv_count, int* fv_nodes, int* fv_start, int* fv_features) {
+  typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> ORBVocabulary;
+  ORBVocabulary voc;
+  if (!voc.loadFromTextFile(voc_text_path)) return -1;
+  std::vector<cv::Mat> vDesc;   // Converter::toDescriptorVector: one 1 x 32 row per feature
+  vDesc.reserve(n);
+  for (int i = 0; i < n; i++) {
+    cv::Mat row(1, 32, CV_8UC1);
+    memcpy(row.data, desc + 32 * (size_t)i, 32);
+    vDesc.push_back(row);
+  }
+  DBoW2::BowVector bv;
+  DBoW2::FeatureVector fv;
+  voc.transform(vDesc, bv, fv, levelsup);
+  int k = 0;
+  for (auto it = bv.begin(); it != bv.end(); ++it, ++k) { bow_words[k] = (int)it->first; bow_values[k] = it->second; }
+  *bow_count = k;
+  int f = 0, pos = 0;
+  for (auto it = fv.begin(); it != fv.end(); ++it, ++f) {
+    fv_nodes[f] = (int)it->first;
+    fv_start[f] = pos;
+    for (unsigned int idx : it->second) fv_features[pos++] = (int)idx;
+  }
+  fv_start[f] = pos;
+  *fv_count = f;
+  return (int)voc.size();
+}
 
 // The EDLines detector (extractor: 1, not the shipped configuration) lives in ED_Lib, which is not compiled
 // here; LSDDetector_custom.cpp only references these three entry points.  They abort if ever reached.

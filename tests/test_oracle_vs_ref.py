@@ -162,3 +162,50 @@ def test_restated_libm_equals_host_libm():
     L.plvio_glibc_atan2f(oracle._p(y), oracle._p(xx), n, oracle._p(r1))
     L.plvio_host_atan2f(oracle._p(y), oracle._p(xx), n, oracle._p(r2))
     assert np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
+
+
+def _write_voc(v, path, trailing_newline=False):
+    v.save_text(path)
+    if not trailing_newline:
+        txt = Path(path).read_text().rstrip("\n")
+        Path(path).write_text(txt)
+
+
+@needs_ref
+@pytest.mark.parametrize("k,L,stop,early,scoring,weighting,levelsup", [(10, 4, 0.0, 0.0, 0, 0, 4), (8, 3, 0.1, 0.0, 0, 0, 2),
+                                                                       (10, 4, 0.05, 0.1, 0, 0, 3), (6, 5, 0.0, 0.3, 1, 1, 4),
+                                                                       (9, 4, 0.02, 0.05, 5, 0, 2), (10, 3, 0.0, 0.0, 0, 3, 1)])
+def test_live_reference_dbow2_transform(tmp_path, k, L, stop, early, scoring, weighting, levelsup):
+    """Frame::ComputeBoW: the oracle against the reference's own DBoW2 sources (TemplatedVocabulary::loadFromTextFile
+    reads the ORBvoc text format written by vocabulary.save_text, then transform): BowVector ids and values (doubles,
+    bit for bit) and FeatureVector.  The file is written without a trailing newline: the reference's loader turns a
+    final empty line into an extra child of the root with an uninitialised descriptor (TemplatedVocabulary.h:1378-1392),
+    and for a full tree that extra node outgrows the reserve() and leaves m_words dangling."""
+    from pl_vi_orbslam3_b200.vocabulary import ORBVocabulary
+    v = ORBVocabulary.random_tree(k=k, L=L, seed=k + L, stop_fraction=stop, early_leaf_fraction=early, scoring=scoring,
+                                  weighting=weighting)
+    path = tmp_path / "voc.txt"
+    _write_voc(v, path)
+    rng = np.random.RandomState(L)
+    desc = rng.randint(0, 256, (1500, 32)).astype(np.uint8)
+    desc[:200] = v.desc[rng.randint(1, len(v.desc), 200)]          # exact hits on node descriptors: distance ties at 0
+    a = oracle.bow_transform(v.as_oracle_dict(), desc, levelsup)
+    b = oracle.ref_bow_transform(path, desc, levelsup)
+    assert b["words"] == v.words
+    assert np.array_equal(a["bow"][0], b["bow"][0]) and np.array_equal(a["bow"][1], b["bow"][1])
+    for x, y in zip(a["fv"], b["fv"]):
+        assert np.array_equal(x, y)
+    # the round trip of the text format through load_text is the same tree
+    w = ORBVocabulary.load_text(path)
+    assert np.array_equal(w.parent, v.parent) and np.array_equal(w.desc[1:], v.desc[1:]) and np.array_equal(w.weight[1:], v.weight[1:])
+
+
+def test_oracle_equals_reference_dbow2_outputs():
+    """Committed outputs of the reference's DBoW2 (tools/gen_golden_ref.py) for a seeded synthetic vocabulary."""
+    from pl_vi_orbslam3_b200.vocabulary import ORBVocabulary
+    v = ORBVocabulary.random_tree(k=8, L=4, seed=21, stop_fraction=0.03, early_leaf_fraction=0.1)
+    desc = oracle.orb_extract(frame("synth_0"))["descriptors"]
+    a = oracle.bow_transform(v.as_oracle_dict(), desc, 4)
+    assert np.array_equal(a["bow"][0], R["bow/words"]) and np.array_equal(a["bow"][1], R["bow/values"])
+    assert np.array_equal(a["fv"][0], R["bow/fv_nodes"]) and np.array_equal(a["fv"][1], R["bow/fv_start"])
+    assert np.array_equal(a["fv"][2], R["bow/fv_features"])

@@ -68,3 +68,32 @@ def test_cuda_equals_live_reference_batch(gpu):
     finally:
         e.close()
         le.close()
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref/libplvi_ref.so did not travel")
+def test_cuda_bow_equals_reference_dbow2(gpu, tmp_path):
+    """Frame::ComputeBoW on the GPU against the reference's own DBoW2 (loadFromTextFile + transform)."""
+    import torch
+    from pl_vi_orbslam3_b200.vocabulary import ORBVocabulary
+    v = ORBVocabulary.random_tree(k=10, L=5, seed=4, stop_fraction=0.03, early_leaf_fraction=0.05)
+    path = tmp_path / "voc.txt"
+    v.save_text(path)
+    path.write_text(path.read_text().rstrip("\n"))
+    frames = np.stack([synth.frame_euroc(s) for s in (3, 9)])
+    e = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=2)
+    try:
+        kps, desc, counts, _ = e.extract_batch_device(torch.from_numpy(frames).cuda())
+        out = {k: t.cpu().numpy() for k, t in v.transform(desc, counts, 4).items()}
+        d, c = desc.cpu().numpy(), counts.cpu().numpy()
+        for f in range(2):
+            r = oracle.ref_bow_transform(path, d[f, :c[f]], 4)
+            bw, bv = r["bow"]
+            assert out["bow_count"][f] == len(bw)
+            assert np.array_equal(out["bow_words"][f, :len(bw)], bw) and np.array_equal(out["bow_values"][f, :len(bw)], bv)
+            fn, fs, ff = r["fv"]
+            assert out["fv_count"][f] == len(fn)
+            assert np.array_equal(out["fv_nodes"][f, :len(fn)], fn) and np.array_equal(out["fv_start"][f, :len(fn) + 1], fs)
+            assert np.array_equal(out["fv_features"][f, :fs[-1]], ff)
+    finally:
+        e.close()
+        v.close()

@@ -49,6 +49,17 @@ def main():
         out[f"{name}/line_eq"] = li["line_eq"]
         out[f"{name}/lsd_raw"] = oracle.ref_lsd(img)
         print(name, len(o["keypoints"]), len(li["keylines"]), len(out[f"{name}/lsd_raw"]))
+    # Frame::ComputeBoW through the reference's own DBoW2 (loadFromTextFile + transform) on a seeded synthetic vocabulary
+    import tempfile
+    from pl_vi_orbslam3_b200.vocabulary import ORBVocabulary
+    v = ORBVocabulary.random_tree(k=8, L=4, seed=21, stop_fraction=0.03, early_leaf_fraction=0.1)
+    with tempfile.TemporaryDirectory() as td:
+        path = Path(td) / "voc.txt"
+        v.save_text(path)
+        path.write_text(path.read_text().rstrip("\n"))      # see tests/test_oracle_vs_ref.py on the trailing newline
+        b = oracle.ref_bow_transform(path, oracle.orb_extract(frame("synth_0"))["descriptors"], 4)
+    out["bow/words"], out["bow/values"] = b["bow"]
+    out["bow/fv_nodes"], out["bow/fv_start"], out["bow/fv_features"] = b["fv"]
     out["cases"] = np.array([f"{n}|{nf}|{lap[0]}|{lap[1]}|{lnf}" for n, nf, lap, lnf in CASES])
     np.savez_compressed(GOLD / "ref_outputs.npz", **out)
     print((GOLD / "ref_outputs.npz").stat().st_size, "bytes")
