@@ -628,3 +628,60 @@ def ref_line_extract(img, lsd_nfeatures=200, lsd_refine=0, lsd_scale=0.8, nlevel
     if n < 0:
         raise RuntimeError(f"reference line_extract failed: {n}")
     return {"keylines": kl[:n].copy(), "descriptors": desc[:n].copy(), "line_eq": eq[:n].copy()}
+
+
+def _ref_descs(d1, d2):
+    d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32)
+    d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+    return d1, d2
+
+
+def ref_line_match(d1, d2, nnr, variant="match"):
+    """The reference's LineMatcher::matchNNR ("nnr"), match(desc1, desc2) ("match") or match(vpLocalMapLines, Frame)
+    ("maplines") itself (src/LineMatcher.cpp:40-111).  Needs >= 2 rows on both sides (the reference reads
+    matches_[idx][1] unconditionally).  Returns (nmatches, matches12)."""
+    d1, d2 = _ref_descs(d1, d2)
+    if len(d1) < 2 or len(d2) < 2:
+        raise ValueError("the reference's matchNNR is undefined for fewer than 2 descriptors on a side")
+    f = getattr(ref_lib(), {"nnr": "plviref_line_match_nnr", "match": "plviref_line_match",
+                            "maplines": "plviref_line_match_maplines"}[variant])
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+    m = np.full(len(d1), -1, np.int32)
+    n = f(_p(d1), len(d1), _p(d2), len(d2), C.c_float(nnr), _p(m))
+    return n, m
+
+
+def ref_line_match_mad(d1, d2, factor, has1=None, has2=None):
+    """The reference's LineMatcher::SerachForInitialize (factor 0.5, no has-flags) or SearchForTriangulation(KF, KF)
+    (factor 0.1) itself (src/LineMatcher.cpp:113-171); lineDescriptorMAD is the oracle's restatement of
+    src/Frame.cc:1089-1113 (Frame.cc itself needs the whole SLAM object graph).  Returns (nmatches, matches12) in the
+    layout of line_match_mad."""
+    d1, d2 = _ref_descs(d1, d2)
+    if len(d1) < 1 or len(d2) < 2:
+        raise ValueError("the reference's knn-2 needs >= 2 train descriptors")
+    pairs = np.zeros((len(d1), 2), np.int32)
+    if factor == 0.5:
+        assert has1 is None and has2 is None
+        f = ref_lib().plviref_line_search_for_initialize
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        n = f(_p(d1), len(d1), _p(d2), len(d2), _p(pairs))
+    elif factor == 0.1:
+        h1 = None if has1 is None else np.ascontiguousarray(has1, np.uint8)
+        h2 = None if has2 is None else np.ascontiguousarray(has2, np.uint8)
+        f = ref_lib().plviref_line_search_for_triangulation
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        n = f(_p(d1), len(d1), _p(d2), len(d2), _p(h1), _p(h2), _p(pairs))
+    else:
+        raise ValueError("the reference hard-codes the factors 0.5 (initialize) and 0.1 (triangulation)")
+    m = np.full(len(d1), -1, np.int32)
+    m[pairs[:n, 0]] = pairs[:n, 1]
+    assert np.all(np.diff(pairs[:n, 0]) > 0)   # query order
+    return n, m
+
+
+def ref_line_distance(a, b, which=0):
+    """LineMatcher::distance (which=0) / DescriptorDistance (which=1) of the reference on two 32-byte descriptors."""
+    a, b = np.ascontiguousarray(a, np.uint8).reshape(32), np.ascontiguousarray(b, np.uint8).reshape(32)
+    f = ref_lib().plviref_line_distance
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    return int(f(_p(a), _p(b), int(which)))

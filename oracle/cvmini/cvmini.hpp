@@ -393,7 +393,18 @@ class Mat {
   static Mat zeros(int r, int c, int type) { Mat m(r, c, type); for (int y = 0; y < r; y++) memset(m.ptr(y), 0, (size_t)c * m.elemSize()); return m; }
   static Mat zeros(Size sz, int type) { return zeros(sz.height, sz.width, type); }
   static Mat ones(int r, int c, int type) { Mat m(r, c, type); m.setTo(Scalar::all(1)); return m; }
-  void push_back(const Mat&) { cvmini_unreachable("Mat::push_back"); }
+  void reserve(size_t) {}
+  void push_back(const Mat& m) {   // appends the rows of m (same type and width)
+    if (m.empty()) return;
+    if (empty()) { m.copyTo(*this); return; }
+    CV_Assert(m.type() == type() && m.cols == cols);
+    Mat out(rows + m.rows, cols, type());
+    const size_t rb = (size_t)cols * elemSize();
+    for (int r = 0; r < rows; r++) memcpy(out.ptr(r), ptr(r), rb);
+    for (int r = 0; r < m.rows; r++) memcpy(out.ptr(rows + r), m.ptr(r), rb);
+    *this = out;
+  }
+  double dot(const Mat&) const { cvmini_unreachable("Mat::dot"); }
   Mat t() const { cvmini_unreachable("Mat::t"); }
   Mat reshape(int, int = 0) const { cvmini_unreachable("Mat::reshape"); }
   int checkVector(int, int = -1, bool = true) const { cvmini_unreachable("Mat::checkVector"); }
@@ -704,6 +715,44 @@ enum { THRESH_BINARY = 0, THRESH_TOZERO = 3 };
 enum { CMP_EQ = 0, CMP_GT = 1, CMP_GE = 2, CMP_LT = 3, CMP_LE = 4, CMP_NE = 5 };
 static inline Mat abs(const Mat&) { cvmini_unreachable("abs(Mat)"); }
 static inline Mat operator/(const Mat&, double) { cvmini_unreachable("Mat / scalar"); }
+static inline Mat operator*(double, const Mat&) { cvmini_unreachable("scalar * Mat"); }
+static inline double norm(const Mat&, int = NORM_L2) { cvmini_unreachable("norm(Mat)"); }
+static inline double norm(const Mat&, const Mat&, int = NORM_L2) { cvmini_unreachable("norm(Mat, Mat)"); }
+template <typename T> struct MatCommaInitializer_ {   // (Mat_<T>(r, c) << a, b, ...)
+  Mat_<T> m;
+  int i;
+  MatCommaInitializer_(const Mat_<T>& m_, T first) : m(m_), i(0) { *this, first; }
+  MatCommaInitializer_& operator,(T v) { if (i < (int)m.total()) m(i / m.cols, i % m.cols) = v; i++; return *this; }
+  operator Mat_<T>() const { return m; }
+  operator Mat() const { return m; }
+};
+template <typename T, typename U> static inline MatCommaInitializer_<T> operator<<(const Mat_<T>& m, U v) { return MatCommaInitializer_<T>(m, (T)v); }
+
+// cv::BFMatcher(NORM_HAMMING).knnMatch: the k nearest train rows of every query row, ordered by (distance, train
+// index) -- the tie rule probed on cv2.BFMatcher (tests/test_oracle_vs_cv2.py); fewer than k entries when the train
+// set is smaller.
+class BFMatcher : public Algorithm {
+ public:
+  BFMatcher(int normType = NORM_L2, bool crossCheck = false) {
+    if (normType != NORM_HAMMING || crossCheck) cvmini_unreachable("BFMatcher other than NORM_HAMMING without cross-check");
+  }
+  static Ptr<BFMatcher> create(int normType = NORM_L2, bool crossCheck = false) { return Ptr<BFMatcher>(new BFMatcher(normType, crossCheck)); }
+  void knnMatch(const Mat& q, const Mat& t, std::vector<std::vector<DMatch>>& matches, int k) const {
+    CV_Assert(q.type() == CV_8UC1 && (t.empty() || (t.type() == CV_8UC1 && t.cols == q.cols)));
+    matches.assign(q.rows, std::vector<DMatch>());
+    for (int i = 0; i < q.rows; i++) {
+      std::vector<std::pair<int, int>> d(t.rows);
+      for (int j = 0; j < t.rows; j++) {
+        int c = 0;
+        for (int b = 0; b < q.cols; b++) c += __builtin_popcount((unsigned)(q.ptr(i)[b] ^ t.ptr(j)[b]));
+        d[j] = std::make_pair(c, j);
+      }
+      const int kk = std::min(k, t.rows);
+      std::partial_sort(d.begin(), d.begin() + kk, d.end());
+      for (int r = 0; r < kk; r++) matches[i].push_back(DMatch(i, d[r].second, (float)d[r].first));
+    }
+  }
+};
 static inline Mat operator*(const Mat&, const Mat&) { cvmini_unreachable("Mat * Mat"); }
 static inline Mat operator*(const Mat&, double) { cvmini_unreachable("Mat * scalar"); }
 static inline Mat operator+(const Mat&, const Mat&) { cvmini_unreachable("Mat + Mat"); }

@@ -22,4 +22,12 @@ struct Vector3d {
   }
   Vector3d operator/(double s) const { return Vector3d(v[0] / s, v[1] / s, v[2] / s); }
 };
+struct Vector6d {   // Eigen::Matrix<double, 6, 1>: only head(3) / tail(3) / operator() are used (never reached)
+  double v[6];
+  Vector6d() { for (double& x : v) x = 0; }
+  Vector3d head(int) const { return Vector3d(v[0], v[1], v[2]); }
+  Vector3d tail(int) const { return Vector3d(v[3], v[4], v[5]); }
+  double& operator()(int i) { return v[i]; }
+  const double& operator()(int i) const { return v[i]; }
+};
 }  // namespace Eigen

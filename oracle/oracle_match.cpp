@@ -333,6 +333,25 @@ int plvio_line_match(const u8* d1, int n1, const u8* d2, int n2, float nnr, int*
 // ---- LineMatcher::SerachForInitialize / SearchForTriangulation(KF, KF) (src/LineMatcher.cpp:113-171) with
 // Frame/KeyFrame::lineDescriptorMAD (src/Frame.cc:1089-1113, src/KeyFrame.cc:411-435); comparators
 // include/LineMatcher.h:56-76 (NN distance ascending, NN12 difference DESCENDING).
+// Frame::lineDescriptorMAD / KeyFrame::lineDescriptorMAD on the kNN-2 distances (d0 = nearest, d1 = second nearest of
+// every query): 1.4826 x median absolute deviation of d0 and of d1 - d0 (src/Frame.cc:1089-1113).
+extern "C" void plvio_line_descriptor_mad(const int* d0, const int* d1, int n, double* nn_mad, double* nn12_mad) {
+  struct M { float d0, d1; };
+  std::vector<M> lm(n);
+  for (int i = 0; i < n; i++) lm[i] = M{(float)d0[i], (float)d1[i]};
+  std::vector<M> nn = lm, m12 = lm;
+  std::stable_sort(nn.begin(), nn.end(), [](const M& a, const M& b) { return a.d0 < b.d0; });
+  const double nn_median = nn[int(nn.size() / 2)].d0;
+  for (auto& m : nn) m.d0 = fabsf(m.d0 - nn_median);
+  std::stable_sort(nn.begin(), nn.end(), [](const M& a, const M& b) { return a.d0 < b.d0; });
+  *nn_mad = 1.4826 * nn[int(nn.size() / 2)].d0;
+  std::stable_sort(m12.begin(), m12.end(), [](const M& a, const M& b) { return (a.d1 - a.d0) > (b.d1 - b.d0); });
+  const double nn12_median = m12[int(m12.size() / 2)].d1 - m12[int(m12.size() / 2)].d0;
+  for (auto& m : m12) m.d0 = fabsf(m.d1 - m.d0 - nn12_median);
+  std::stable_sort(m12.begin(), m12.end(), [](const M& a, const M& b) { return a.d0 < b.d0; });
+  *nn12_mad = 1.4826 * m12[int(m12.size() / 2)].d0;
+}
+
 extern "C" int plvio_line_match_mad(const uint8_t* d1, int n1, const uint8_t* d2, int n2, const uint8_t* has1,
                                     const uint8_t* has2, double factor, int* matches12, double* mad) {
   using namespace plvio;
@@ -351,17 +370,11 @@ extern "C" int plvio_line_match_mad(const uint8_t* d1, int n1, const uint8_t* d2
     (void)b1;
     lm[i] = M{(float)e0, (float)e1, i, b0};
   }
-  std::vector<M> nn = lm, m12 = lm;
-  std::stable_sort(nn.begin(), nn.end(), [](const M& a, const M& b) { return a.d0 < b.d0; });
-  const double nn_median = nn[int(nn.size() / 2)].d0;
-  for (auto& m : nn) m.d0 = fabsf(m.d0 - nn_median);
-  std::stable_sort(nn.begin(), nn.end(), [](const M& a, const M& b) { return a.d0 < b.d0; });
-  mad[0] = 1.4826 * nn[int(nn.size() / 2)].d0;
-  std::stable_sort(m12.begin(), m12.end(), [](const M& a, const M& b) { return (a.d1 - a.d0) > (b.d1 - b.d0); });
-  const double nn12_median = m12[int(m12.size() / 2)].d1 - m12[int(m12.size() / 2)].d0;
-  for (auto& m : m12) m.d0 = fabsf(m.d1 - m.d0 - nn12_median);
-  std::stable_sort(m12.begin(), m12.end(), [](const M& a, const M& b) { return a.d0 < b.d0; });
-  mad[1] = 1.4826 * m12[int(m12.size() / 2)].d0;
+  {
+    std::vector<int> e0(n1), e1(n1);
+    for (int i = 0; i < n1; i++) { e0[i] = (int)lm[i].d0; e1[i] = (int)lm[i].d1; }
+    plvio_line_descriptor_mad(e0.data(), e1.data(), n1, &mad[0], &mad[1]);
+  }
   const double th = mad[1] * factor;
   int nmatches = 0;
   for (int i = 0; i < n1; i++) {   // lmatches sorted by queryIdx

@@ -171,6 +171,9 @@ extern "C" int plviref_bow_transform(const char* voc_text_path, const uchar* des
   return (int)voc.size();
 }
 
+// LineMatcher (src/LineMatcher.cpp, compiled unmodified with cvmini/slam_mock.h force-included in place of the
+// Frame / KeyFrame / MapLine headers): the descriptor matchers.  plviref_line_mock.cpp holds the calls (it needs the
+// stand-in classes, which cannot share a translation unit with the real ORBextractor.h / LineExtractor.h).
 // The EDLines detector (extractor: 1, not the shipped configuration) lives in ED_Lib, which is not compiled
 // here; LSDDetector_custom.cpp only references these three entry points.  They abort if ever reached.
 #define PLVIREF_STUB(fn, sym)                                                         \

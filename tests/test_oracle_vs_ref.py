@@ -209,3 +209,57 @@ def test_oracle_equals_reference_dbow2_outputs():
     assert np.array_equal(a["bow"][0], R["bow/words"]) and np.array_equal(a["bow"][1], R["bow/values"])
     assert np.array_equal(a["fv"][0], R["bow/fv_nodes"]) and np.array_equal(a["fv"][1], R["bow/fv_start"])
     assert np.array_equal(a["fv"][2], R["bow/fv_features"])
+
+
+# ---- LineMatcher.cpp of the reference, compiled unmodified against the stand-in SLAM classes (cvmini/slam_mock.h) ----
+def _line_desc_pair(rng, n1, n2, p):
+    """n2 noisy copies (bit-flip probability p) of random rows of n1 random 256-bit descriptors."""
+    d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    noise = (rng.random((n2, 32, 8)) < p).astype(np.uint8)
+    d2 = d1[rng.integers(0, n1, n2)] ^ np.packbits(noise, axis=2).reshape(n2, 32)
+    return d1, d2
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(12))
+def test_live_reference_line_matcher(seed):
+    """matchNNR, both match() overloads, SerachForInitialize, SearchForTriangulation(KF, KF), distance and
+    DescriptorDistance of the reference itself against the oracle restatement (ties included: p = 0 gives
+    duplicate descriptors, i.e. equal distances and equal NN12 differences)."""
+    rng = np.random.default_rng(seed)
+    n1, n2 = (int(x) for x in rng.integers(2, 300, 2))
+    p = [0.0, 0.02, 0.1, 0.3][seed % 4]
+    d1, d2 = _line_desc_pair(rng, n1, n2, p)
+    for nnr in (0.75, 0.9, 1.0):
+        n, m = oracle.ref_line_match(d1, d2, nnr, "nnr")
+        on, om = oracle.match_nnr(d1, d2, nnr)
+        assert n == on and np.array_equal(m, om)
+        for variant in ("match", "maplines"):
+            n, m = oracle.ref_line_match(d1, d2, nnr, variant)
+            on, om = oracle.line_match(d1, d2, nnr)
+            assert n == on and np.array_equal(m, om)
+    n, m = oracle.ref_line_match_mad(d1, d2, 0.5)
+    on, om, _ = oracle.line_match_mad(d1, d2, 0.5)
+    assert n == on and np.array_equal(m, om)
+    h1, h2 = (rng.random(n1) < 0.3).astype(np.uint8), (rng.random(n2) < 0.3).astype(np.uint8)
+    for a, b in ((None, None), (h1, h2)):
+        n, m = oracle.ref_line_match_mad(d1, d2, 0.1, a, b)
+        on, om, _ = oracle.line_match_mad(d1, d2, 0.1, a, b)
+        assert n == on and np.array_equal(m, om)
+    for i in range(min(n1, n2, 16)):
+        assert oracle.ref_line_distance(d1[i], d2[i], 0) == oracle.hamming256(d1[i], d2[i])
+        assert oracle.ref_line_distance(d1[i], d2[i], 1) == oracle.hamming256(d1[i], d2[i], shift25=True)
+
+
+def test_oracle_equals_reference_line_matcher_outputs():
+    """Committed outputs of the reference's LineMatcher (tools/gen_golden_ref.py) on the LBD descriptors of two
+    synthetic frames."""
+    d1 = oracle.line_extract(frame("synth_0"))["descriptors"]
+    d2 = oracle.line_extract(frame("synth_1"))["descriptors"]
+    n, m = oracle.line_match(d1, d2, 0.75)
+    assert n == int(R["linematch/match_n"]) and np.array_equal(m, R["linematch/match"])
+    n, m, _ = oracle.line_match_mad(d1, d2, 0.5)
+    assert n == int(R["linematch/init_n"]) and np.array_equal(m, R["linematch/init"])
+    h1, h2 = R["linematch/has1"], R["linematch/has2"]
+    n, m, _ = oracle.line_match_mad(d1, d2, 0.1, h1, h2)
+    assert n == int(R["linematch/tri_n"]) and np.array_equal(m, R["linematch/tri"])

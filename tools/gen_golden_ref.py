@@ -60,6 +60,19 @@ def main():
         b = oracle.ref_bow_transform(path, oracle.orb_extract(frame("synth_0"))["descriptors"], 4)
     out["bow/words"], out["bow/values"] = b["bow"]
     out["bow/fv_nodes"], out["bow/fv_start"], out["bow/fv_features"] = b["fv"]
+    # LineMatcher.cpp of the reference (compiled with the stand-in SLAM classes) on the reference's own LBD descriptors
+    d1 = oracle.ref_line_extract(frame("synth_0"))["descriptors"]
+    d2 = oracle.ref_line_extract(frame("synth_1"))["descriptors"]
+    n, m = oracle.ref_line_match(d1, d2, 0.75, "match")
+    out["linematch/match_n"], out["linematch/match"] = np.int32(n), m
+    n, m = oracle.ref_line_match_mad(d1, d2, 0.5)
+    out["linematch/init_n"], out["linematch/init"] = np.int32(n), m
+    rng = np.random.default_rng(5)
+    h1, h2 = (rng.random(len(d1)) < 0.3).astype(np.uint8), (rng.random(len(d2)) < 0.3).astype(np.uint8)
+    n, m = oracle.ref_line_match_mad(d1, d2, 0.1, h1, h2)
+    out["linematch/has1"], out["linematch/has2"] = h1, h2
+    out["linematch/tri_n"], out["linematch/tri"] = np.int32(n), m
+    print("linematch", len(d1), len(d2), out["linematch/match_n"], out["linematch/init_n"], out["linematch/tri_n"])
     out["cases"] = np.array([f"{n}|{nf}|{lap[0]}|{lap[1]}|{lnf}" for n, nf, lap, lnf in CASES])
     np.savez_compressed(GOLD / "ref_outputs.npz", **out)
     print((GOLD / "ref_outputs.npz").stat().st_size, "bytes")
