@@ -205,6 +205,11 @@ def _grid_args(grid):
             C.c_float(float(g["inv_h"]))]
 
 
+def _grid_floats(grid):
+    g = np.asarray(grid).reshape(-1)[0]
+    return [float(g["min_x"]), float(g["min_y"]), float(g["inv_w"]), float(g["inv_h"])]
+
+
 def search_frame(keys, desc, grid, queries, qdesc, th=100, check_ori=True, blocked=None):
     keys = np.ascontiguousarray(keys)
     desc = np.ascontiguousarray(desc, np.uint8)
@@ -520,6 +525,8 @@ def search_triangulation(keys1, desc1, mp1, fv1, keys2, desc2, mp2, fv2, F12, ep
 # ---- oracle/_ref: the reference's own sources compiled against the cvmini stand-in ----------------
 # (oracle/Makefile.ref; built where /root/reference exists, shipped prebuilt to the GPU box)
 _REF_LIB = _DIR / "_ref" / "libplvi_ref.so"
+_REF_ORB_LIB = _DIR / "_ref" / "libplvi_ref_orbmatcher.so"   # ORBmatcher.cc (stand-in classes of its own, see Makefile.ref)
+_ref_orb = None
 REFERENCE_ROOT = Path(os.environ.get("PLVI_REFERENCE_ROOT", "/root/reference"))
 _ref = None
 
@@ -529,8 +536,10 @@ def ref_build(force: bool = False):
     if not (REFERENCE_ROOT / "src" / "ORBextractor.cc").exists():
         return _REF_LIB if _REF_LIB.exists() else None
     build()
-    srcs = [_DIR / "ref_glue.cpp", _DIR / "Makefile.ref", _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _LIB]
-    stale = (not _REF_LIB.exists()) or any(s.stat().st_mtime > _REF_LIB.stat().st_mtime for s in srcs)
+    srcs = [_DIR / "ref_glue.cpp", _DIR / "ref_glue_linematcher.cpp", _DIR / "ref_glue_orbmatcher.cpp", _DIR / "Makefile.ref",
+            _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _DIR / "cvmini" / "slam_mock.h",
+            _DIR / "cvmini" / "slam_mock_orb.h", _LIB]
+    stale = any((not t.exists()) or any(s.stat().st_mtime > t.stat().st_mtime for s in srcs) for t in (_REF_LIB, _REF_ORB_LIB))
     if force or stale:
         subprocess.run(["make", "-C", str(_DIR), "-f", "Makefile.ref", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []),
                        check=True, capture_output=True)
@@ -685,3 +694,98 @@ def ref_line_distance(a, b, which=0):
     f = ref_lib().plviref_line_distance
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     return int(f(_p(a), _p(b), int(which)))
+
+
+def ref_orbmatcher_lib():
+    """oracle/_ref/libplvi_ref_orbmatcher.so: the reference's src/ORBmatcher.cc compiled unmodified against the stand-in
+    Frame / KeyFrame / MapPoint of cvmini/slam_mock_orb.h."""
+    global _ref_orb
+    if _ref_orb is None:
+        if ref_build() is None or not _REF_ORB_LIB.exists():
+            raise RuntimeError("oracle/_ref/libplvi_ref_orbmatcher.so is not built and /root/reference is absent")
+        lib()
+        _ref_orb = C.CDLL(str(_REF_ORB_LIB))
+    return _ref_orb
+
+
+def _fv_args(fv):
+    a = [np.ascontiguousarray(x, np.int32) for x in fv]
+    return a, [_p(a[0]), _p(a[1]), _p(a[2]), C.c_int(len(a[0]))]
+
+
+def ref_search_mappoints(keys, desc, grid, scale_factors, proj, viewcos, level, flags, qdesc, th=1.0, nnratio=0.8, blocked=None):
+    """The reference's ORBmatcher::SearchByProjection(F, vpMapPoints, th) itself (src/ORBmatcher.cc:44-214, monocular
+    frame).  flags: bit0 not in view, bit1 Observations() == 0, bit2 isBad().  Returns (nmatches, match_train)."""
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    g = np.array(_grid_floats(grid), np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    proj = np.ascontiguousarray(proj, np.float32).reshape(-1, 2)
+    vc, lv, fl = np.ascontiguousarray(viewcos, np.float32), np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.int32)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    blk = None if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+    mt = np.full(max(len(keys), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_search_by_projection_mappoints
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    n = f(_p(keys), _p(desc), len(keys), _p(blk), _p(g), _p(sf), len(sf), _p(proj), _p(vc), _p(lv), _p(fl), _p(qdesc), len(proj),
+          C.c_float(th), C.c_float(nnratio), _p(mt))
+    return n, mt[:len(keys)]
+
+
+def ref_search_init(keys1, desc1, keys2, desc2, grid2, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    """The reference's ORBmatcher::SearchForInitialization itself (src/ORBmatcher.cc:706-821).
+    Returns (nmatches, matches12, prev_matched updated)."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    g = np.array(_grid_floats(grid2), np.float32)
+    pm = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    m12 = np.full(max(len(keys1), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_search_for_initialization
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                  C.c_int, C.c_void_p]
+    n = f(_p(keys1), _p(desc1), len(keys1), _p(keys2), _p(desc2), len(keys2), _p(g), _p(pm), int(window), C.c_float(nnratio),
+          int(check_ori), _p(m12))
+    return n, m12[:len(keys1)], pm
+
+
+def ref_search_bow_kf_f(keys1, desc1, mp1, fv1, keys2, desc2, fv2, nnratio=0.7, check_ori=True):
+    """The reference's ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) itself (src/ORBmatcher.cc:269-471, monocular).
+    mp1: 0 none / 1 good / 2 bad map point.  Returns (nmatches, match_train[n2] = keyframe feature or -1)."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    mp1 = np.ascontiguousarray(mp1, np.uint8)
+    a, fa = _fv_args(fv1)
+    b, fb = _fv_args(fv2)
+    mt = np.full(max(len(keys2), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_search_by_bow_kf_f
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = f(_p(keys1), _p(desc1), _p(mp1), len(keys1), *fa, _p(keys2), _p(desc2), len(keys2), *fb, C.c_float(nnratio), int(check_ori),
+          _p(mt))
+    return n, mt[:len(keys2)]
+
+
+def ref_search_bow_kfkf(keys1, desc1, mp1, fv1, keys2, desc2, mp2, fv2, nnratio=0.8, check_ori=True):
+    """The reference's ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) itself (src/ORBmatcher.cc:823-963); arguments and
+    result as search_bow_kfkf."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    mp1, mp2 = np.ascontiguousarray(mp1, np.uint8), np.ascontiguousarray(mp2, np.uint8)
+    a, fa = _fv_args(fv1)
+    b, fb = _fv_args(fv2)
+    m = np.full(max(len(keys1), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_search_by_bow_kf_kf
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int,
+                  C.c_void_p]
+    n = f(_p(keys1), _p(desc1), _p(mp1), len(keys1), *fa, _p(keys2), _p(desc2), _p(mp2), len(keys2), *fb, C.c_float(nnratio),
+          int(check_ori), _p(m))
+    return n, m[:len(keys1)]
+
+
+def ref_orb_descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8).reshape(32), np.ascontiguousarray(b, np.uint8).reshape(32)
+    f = ref_orbmatcher_lib().plviref_orb_descriptor_distance
+    f.argtypes = [C.c_void_p, C.c_void_p]
+    return int(f(_p(a), _p(b)))

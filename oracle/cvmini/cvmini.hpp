@@ -150,6 +150,8 @@ template <typename T> static inline std::ostream& operator<<(std::ostream& os, c
 typedef Point_<int> Point2i;
 typedef Point_<int> Point;
 typedef Point_<float> Point2f;
+template <typename T> struct Point3_ { T x, y, z; Point3_() : x(0), y(0), z(0) {} Point3_(T a, T b, T c) : x(a), y(b), z(c) {} };
+typedef Point3_<float> Point3f;
 typedef Point_<double> Point2d;
 
 template <typename T> struct Size_ {
@@ -757,5 +759,6 @@ static inline Mat operator*(const Mat&, const Mat&) { cvmini_unreachable("Mat * 
 static inline Mat operator*(const Mat&, double) { cvmini_unreachable("Mat * scalar"); }
 static inline Mat operator+(const Mat&, const Mat&) { cvmini_unreachable("Mat + Mat"); }
 static inline Mat operator-(const Mat&, const Mat&) { cvmini_unreachable("Mat - Mat"); }
+static inline Mat operator-(const Mat&) { cvmini_unreachable("-Mat"); }
 
 }  // namespace cv

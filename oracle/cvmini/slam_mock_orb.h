@@ -1,0 +1,137 @@
+// TEST INFRASTRUCTURE -- lets src/ORBmatcher.cc of the reference compile unmodified without the SLAM object graph.
+// Force-included (-include) ahead of the translation unit: it defines the include guards of Frame.h, KeyFrame.h and
+// MapPoint.h (the real headers pull in DBoW2's vocabulary, g2o, Sophus, boost serialization, the IMU types, the Atlas)
+// and declares stand-ins carrying exactly the members ORBmatcher.cc touches.  State the matchers read (keys,
+// descriptors, map points, feature vectors, scale tables, image bounds, projections cached on the map points) is
+// plain data filled by oracle/ref_glue_orbmatcher.cpp; Frame::GetFeaturesInArea
+// (src/Frame.cc:677-763; not compiled -- it belongs to Frame.cc) forwards to the oracle's restatement.  Pose / camera arithmetic (cv::Mat products) compiles against the stand-ins and aborts if reached:
+// only the functions listed in ref_glue_orbmatcher.cpp are called.
+#pragma once
+#define FRAME_H
+#define KEYFRAME_H
+#define MAPPOINT_H
+#include <cmath>
+#include <map>
+#include <set>
+#include <list>
+#include <vector>
+#include "cvmini.hpp"
+#include "Thirdparty/DBoW2/DBoW2/BowVector.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+
+using namespace std;
+
+namespace ORB_SLAM3 {
+using cv::cvmini_unreachable;
+
+class KeyFrame;
+class Frame;
+class MapPoint;
+
+class GeometricCamera {
+ public:
+  virtual ~GeometricCamera() {}
+  virtual cv::Point2f project(const cv::Point3f&) { cvmini_unreachable("GeometricCamera::project"); }
+  virtual cv::Point2f project(const cv::Mat&) { cvmini_unreachable("GeometricCamera::project"); }
+  virtual float uncertainty2(const cv::Mat&) { cvmini_unreachable("GeometricCamera::uncertainty2"); }
+  virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint&, const cv::KeyPoint&, const cv::Mat&, const cv::Mat&,
+                                 const float, const float) { cvmini_unreachable("GeometricCamera::epipolarConstrain"); }
+  virtual bool matchAndtriangulate(const cv::KeyPoint&, const cv::KeyPoint&, GeometricCamera*, cv::Mat&, cv::Mat&, const float,
+                                   const float, cv::Mat&) { cvmini_unreachable("GeometricCamera::matchAndtriangulate"); }
+};
+
+// Frame::GetFeaturesInArea forwards to the oracle's restatement (oracle_match.cpp: plvio_grid_*)
+extern "C" int plvio_grid_features_in_area(const void* g, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap);
+
+class MapPoint {
+ public:
+  // SearchByProjection(F, vpMapPoints) reads the projection cached by Frame::isInFrustum (src/Frame.cc:765-...)
+  bool mbTrackInView = false, mbTrackInViewR = false;
+  float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackProjYR = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackViewCos = 0,
+        mTrackViewCosR = 0;
+  int mnTrackScaleLevel = 0, mnTrackScaleLevelR = 0;
+  long unsigned int mnLastFrameSeen = 0, mnFuseCandidateForKF = 0, mnId = 0;
+  cv::Mat mDesc;
+  bool mBad = false;
+  int mObs = 1;
+  cv::Mat GetDescriptor() { return mDesc; }
+  bool isBad() { return mBad; }
+  int Observations() { return mObs; }
+  cv::Mat GetWorldPos() { cvmini_unreachable("MapPoint::GetWorldPos"); }
+  cv::Mat GetNormal() { cvmini_unreachable("MapPoint::GetNormal"); }
+  float GetMaxDistanceInvariance() { cvmini_unreachable("MapPoint"); }
+  float GetMinDistanceInvariance() { cvmini_unreachable("MapPoint"); }
+  int PredictScale(const float&, KeyFrame*) { cvmini_unreachable("MapPoint"); }
+  int PredictScale(const float&, Frame*) { cvmini_unreachable("MapPoint"); }
+  bool IsInKeyFrame(KeyFrame*) { cvmini_unreachable("MapPoint"); }
+  void Replace(MapPoint*) { cvmini_unreachable("MapPoint"); }
+  void AddObservation(KeyFrame*, int) { cvmini_unreachable("MapPoint"); }
+  std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { cvmini_unreachable("MapPoint"); }
+};
+
+class Frame {
+ public:
+  int N = 0, Nleft = -1, Nright = -1;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+  std::vector<float> mvuRight, mvDepth;
+  cv::Mat mDescriptors, mDescriptorsRight, mTcw, mTlr, mTrl;
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<bool> mvbOutlier;
+  std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+  DBoW2::BowVector mBowVec;
+  DBoW2::FeatureVector mFeatVec;
+  GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
+  float mbf = 0, mb = 0, fx = 0, fy = 0, cx = 0, cy = 0, invfx = 0, invfy = 0;
+  float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;
+  std::vector<float> mvScaleFactors, mvInvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+  long unsigned int mnId = 0;
+  const void* grid = nullptr;   // plvio_grid_create over mvKeysUn
+  std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1,
+                                        const bool bRight = false) const {
+    if (bRight) cvmini_unreachable("Frame::GetFeaturesInArea(bRight)");
+    std::vector<int> tmp(N > 0 ? N : 1);
+    const int k = plvio_grid_features_in_area(grid, x, y, r, minLevel, maxLevel, tmp.data(), (int)tmp.size());
+    return std::vector<size_t>(tmp.begin(), tmp.begin() + k);
+  }
+  cv::Mat GetRelativePoseTrl() { cvmini_unreachable("Frame"); }
+  cv::Mat GetRelativePoseTlr() { cvmini_unreachable("Frame"); }
+};
+
+class KeyFrame {
+ public:
+  int N = 0, NLeft = -1, NRight = -1;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+  std::vector<float> mvuRight, mvDepth;
+  cv::Mat mDescriptors;
+  std::vector<MapPoint*> mvpMapPoints;
+  DBoW2::BowVector mBowVec;
+  DBoW2::FeatureVector mFeatVec;
+  GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
+  float fx = 0, fy = 0, cx = 0, cy = 0, invfx = 0, invfy = 0, mbf = 0, mb = 0, mThDepth = 0;
+  float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0, mfLogScaleFactor = 0;
+  int mnScaleLevels = 0;
+  std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+  long unsigned int mnId = 0;
+  std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+  MapPoint* GetMapPoint(const size_t& i) { return mvpMapPoints[i]; }
+  std::set<MapPoint*> GetMapPoints() { cvmini_unreachable("KeyFrame::GetMapPoints"); }
+  std::vector<size_t> GetFeaturesInArea(const float&, const float&, const float&, const bool = false) const {
+    cvmini_unreachable("KeyFrame::GetFeaturesInArea");
+  }
+  bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
+  cv::Mat GetRotation() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetTranslation() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetCameraCenter() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetPose() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetPoseInverse() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetRightPose() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetRightPoseInverse() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetRightCameraCenter() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetRightRotation() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetRightTranslation() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetRelativePoseTrl() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat GetRelativePoseTlr() { cvmini_unreachable("KeyFrame"); }
+  void AddMapPoint(MapPoint*, const size_t&) { cvmini_unreachable("KeyFrame"); }
+};
+
+}  // namespace ORB_SLAM3

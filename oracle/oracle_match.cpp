@@ -128,6 +128,22 @@ extern "C" {
 int plvio_hamming256(const u8* a, const u8* b) { return hamming256(a, b); }
 int plvio_hamming256_shift25(const u8* a, const u8* b) { return hamming256_shift25(a, b); }
 
+// Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea (src/Frame.cc:644-675, 677-763) as a stand-alone query object:
+// used by the stand-in Frame of oracle/cvmini/slam_mock_orb.h (the reference's ORBmatcher.cc compiled unmodified; Frame.cc
+// itself needs the whole SLAM object graph) and by tests.
+void* plvio_grid_create(const Kp* keys, int n, float minX, float minY, float invW, float invH) {
+  Grid* g = new Grid();
+  build_grid(*g, keys, n, minX, minY, invW, invH);
+  return g;
+}
+void plvio_grid_destroy(void* g) { delete (Grid*)g; }
+int plvio_grid_features_in_area(const void* g, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap) {
+  std::vector<int> idx;
+  features_in_area(*(const Grid*)g, x, y, r, minLevel, maxLevel, idx);
+  for (int i = 0; i < (int)idx.size() && i < cap; i++) out[i] = idx[i];
+  return (int)idx.size();
+}
+
 // SearchByProjection(CurrentFrame, LastFrame, th, bMono=true): queries are the last
 // frame's tracked points already projected by the host (u, v, radius=th*scale[octave],
 // levels octave-1..octave+1).  match_train[i2] = query index or -1 (mvpMapPoints).

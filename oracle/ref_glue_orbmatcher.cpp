@@ -1,0 +1,164 @@
+// TEST INFRASTRUCTURE -- C entry points over the reference's ORBmatcher (src/ORBmatcher.cc compiled unmodified with
+// cvmini/slam_mock_orb.h force-included in place of Frame.h / KeyFrame.h / MapPoint.h; oracle/Makefile.ref).
+// Called: SearchByProjection(F, vpMapPoints, th), SearchForInitialization, SearchByBoW(KF, F), SearchByBoW(KF, KF)
+// (and through them DescriptorDistance, RadiusByViewingCos, ComputeThreeMaxima).  The other overloads need pose /
+// camera arithmetic on cv::Mat, which the stand-in does not implement; they compile and are never reached.
+// Compiled with the same -include so that it sees the same stand-in classes as ORBmatcher.cc.
+#include <cstring>
+#include <vector>
+#include "ORBmatcher.h"   // /root/reference/include (its includes of Frame.h etc. are guarded out by slam_mock_orb.h)
+
+using namespace ORB_SLAM3;
+
+extern "C" void* plvio_grid_create(const void* keys, int n, float minX, float minY, float invW, float invH);
+extern "C" void plvio_grid_destroy(void* g);
+
+static_assert(sizeof(cv::KeyPoint) == 28, "cv::KeyPoint POD layout");
+
+namespace {
+cv::Mat desc_mat(const unsigned char* d, int n) {
+  cv::Mat m(n > 0 ? n : 1, 32, CV_8UC1);
+  for (int r = 0; r < n; r++) memcpy(m.ptr(r), d + 32 * (size_t)r, 32);
+  return m;
+}
+std::vector<cv::KeyPoint> key_vec(const cv::KeyPoint* k, int n) { return std::vector<cv::KeyPoint>(k, k + n); }
+void fill_fv(DBoW2::FeatureVector& fv, const int* nodes, const int* start, const int* feats, int nn) {
+  for (int i = 0; i < nn; i++)
+    for (int j = start[i]; j < start[i + 1]; j++) fv.addFeature((DBoW2::NodeId)nodes[i], (unsigned int)feats[j]);
+}
+struct GridOwner {
+  void* g;
+  GridOwner(const cv::KeyPoint* k, int n, const float* grid) : g(plvio_grid_create(k, n, grid[0], grid[1], grid[2], grid[3])) {}
+  ~GridOwner() { plvio_grid_destroy(g); }
+};
+}  // namespace
+
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints=false) (src/ORBmatcher.cc:44-214), monocular frame
+// (Nleft == -1, mvuRight < 0, no right-camera projections).  grid = {mnMinX, mnMinY, mfGridElementWidthInv,
+// mfGridElementHeightInv}; blocked[i] = F.mvpMapPoints[i] already holds a point with Observations() > 0; per map point:
+// proj (x, y), viewCos, predicted level, flags bit0 = !mbTrackInView, bit1 = Observations() == 0, bit2 = isBad().
+// match_train[i] = index of the map point assigned to feature i by this call, or -1.
+extern "C" int plviref_orb_search_by_projection_mappoints(const cv::KeyPoint* keys, const unsigned char* desc, int n,
+                                                           const unsigned char* blocked, const float* grid, const float* scale_factors,
+                                                           int nlevels, const float* proj, const float* viewcos, const int* level,
+                                                           const int* flags, const unsigned char* qdesc, int nq, float th,
+                                                           float nnratio, int* match_train) {
+  Frame F;
+  F.N = n;
+  F.mvKeysUn = F.mvKeys = key_vec(keys, n);
+  F.mDescriptors = desc_mat(desc, n);
+  F.mvuRight.assign(n, -1.0f);
+  F.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+  GridOwner go(keys, n, grid);
+  F.grid = go.g;
+  MapPoint old;   // stands for every map point the frame held before the call
+  old.mObs = 1;
+  F.mvpMapPoints.assign(n, nullptr);
+  for (int i = 0; i < n; i++) if (blocked && blocked[i]) F.mvpMapPoints[i] = &old;
+  std::vector<MapPoint> mps(nq);
+  std::vector<MapPoint*> ptrs(nq);
+  for (int i = 0; i < nq; i++) {
+    MapPoint& m = mps[i];
+    m.mnId = i;
+    m.mbTrackInView = !(flags[i] & 1);
+    m.mObs = (flags[i] & 2) ? 0 : 1;
+    m.mBad = (flags[i] & 4) != 0;
+    m.mTrackProjX = proj[2 * i];
+    m.mTrackProjY = proj[2 * i + 1];
+    m.mTrackViewCos = viewcos[i];
+    m.mnTrackScaleLevel = level[i];
+    m.mDesc = desc_mat(qdesc + 32 * (size_t)i, 1);
+    ptrs[i] = &m;
+  }
+  ORBmatcher matcher(nnratio, true);
+  const int k = matcher.SearchByProjection(F, ptrs, th, false, 50.0f);
+  for (int i = 0; i < n; i++) match_train[i] = (F.mvpMapPoints[i] && F.mvpMapPoints[i] != &old) ? (int)F.mvpMapPoints[i]->mnId : -1;
+  return k;
+}
+
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:706-821): prev_matched (x, y per F1 key) is updated in place.
+extern "C" int plviref_orb_search_for_initialization(const cv::KeyPoint* keys1, const unsigned char* desc1, int n1,
+                                                      const cv::KeyPoint* keys2, const unsigned char* desc2, int n2, const float* grid2,
+                                                      float* prev_matched, int window, float nnratio, int check_ori, int* matches12) {
+  Frame F1, F2;
+  F1.N = n1;
+  F1.mvKeysUn = F1.mvKeys = key_vec(keys1, n1);
+  F1.mDescriptors = desc_mat(desc1, n1);
+  F2.N = n2;
+  F2.mvKeysUn = F2.mvKeys = key_vec(keys2, n2);
+  F2.mDescriptors = desc_mat(desc2, n2);
+  GridOwner go(keys2, n2, grid2);
+  F2.grid = go.g;
+  std::vector<cv::Point2f> prev(n1);
+  for (int i = 0; i < n1; i++) prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
+  std::vector<int> m12;
+  ORBmatcher matcher(nnratio, check_ori != 0);
+  const int k = matcher.SearchForInitialization(F1, F2, prev, m12, window);
+  for (int i = 0; i < n1; i++) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
+  return k;
+}
+
+// ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:269-471), monocular (Nleft == -1, no second
+// camera).  mp1[i]: 0 = no map point, 1 = good map point, 2 = bad map point.  Feature vectors as CSR (nodes ascending).
+// match_train[i2] = keyframe feature whose map point was assigned to frame feature i2, or -1.
+extern "C" int plviref_orb_search_by_bow_kf_f(const cv::KeyPoint* keys1, const unsigned char* desc1, const unsigned char* mp1, int n1,
+                                               const int* fv1_nodes, const int* fv1_start, const int* fv1_feats, int nn1,
+                                               const cv::KeyPoint* keys2, const unsigned char* desc2, int n2, const int* fv2_nodes,
+                                               const int* fv2_start, const int* fv2_feats, int nn2, float nnratio, int check_ori,
+                                               int* match_train) {
+  KeyFrame KF;
+  KF.N = n1;
+  KF.mvKeysUn = KF.mvKeys = key_vec(keys1, n1);
+  KF.mDescriptors = desc_mat(desc1, n1);
+  std::vector<MapPoint> mps(n1);
+  KF.mvpMapPoints.assign(n1, nullptr);
+  for (int i = 0; i < n1; i++) {
+    mps[i].mnId = i;
+    mps[i].mBad = mp1[i] == 2;
+    if (mp1[i]) KF.mvpMapPoints[i] = &mps[i];
+  }
+  fill_fv(KF.mFeatVec, fv1_nodes, fv1_start, fv1_feats, nn1);
+  Frame F;
+  F.N = n2;
+  F.mvKeysUn = F.mvKeys = key_vec(keys2, n2);
+  F.mDescriptors = desc_mat(desc2, n2);
+  fill_fv(F.mFeatVec, fv2_nodes, fv2_start, fv2_feats, nn2);
+  std::vector<MapPoint*> out;
+  ORBmatcher matcher(nnratio, check_ori != 0);
+  const int k = matcher.SearchByBoW(&KF, F, out);
+  for (int i = 0; i < n2; i++) match_train[i] = out[i] ? (int)out[i]->mnId : -1;
+  return k;
+}
+
+// ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (src/ORBmatcher.cc:823-963).  matches12[i1] = KF2 feature whose map
+// point was matched to KF1 feature i1, or -1.
+extern "C" int plviref_orb_search_by_bow_kf_kf(const cv::KeyPoint* keys1, const unsigned char* desc1, const unsigned char* mp1, int n1,
+                                                const int* fv1_nodes, const int* fv1_start, const int* fv1_feats, int nn1,
+                                                const cv::KeyPoint* keys2, const unsigned char* desc2, const unsigned char* mp2, int n2,
+                                                const int* fv2_nodes, const int* fv2_start, const int* fv2_feats, int nn2,
+                                                float nnratio, int check_ori, int* matches12) {
+  KeyFrame K1, K2;
+  std::vector<MapPoint> m1(n1), m2(n2);
+  K1.N = n1;
+  K1.mvKeysUn = K1.mvKeys = key_vec(keys1, n1);
+  K1.mDescriptors = desc_mat(desc1, n1);
+  K1.mvpMapPoints.assign(n1, nullptr);
+  for (int i = 0; i < n1; i++) { m1[i].mnId = i; m1[i].mBad = mp1[i] == 2; if (mp1[i]) K1.mvpMapPoints[i] = &m1[i]; }
+  fill_fv(K1.mFeatVec, fv1_nodes, fv1_start, fv1_feats, nn1);
+  K2.N = n2;
+  K2.mvKeysUn = K2.mvKeys = key_vec(keys2, n2);
+  K2.mDescriptors = desc_mat(desc2, n2);
+  K2.mvpMapPoints.assign(n2, nullptr);
+  for (int i = 0; i < n2; i++) { m2[i].mnId = i; m2[i].mBad = mp2[i] == 2; if (mp2[i]) K2.mvpMapPoints[i] = &m2[i]; }
+  fill_fv(K2.mFeatVec, fv2_nodes, fv2_start, fv2_feats, nn2);
+  std::vector<MapPoint*> out;
+  ORBmatcher matcher(nnratio, check_ori != 0);
+  const int k = matcher.SearchByBoW(&K1, &K2, out);
+  for (int i = 0; i < n1; i++) matches12[i] = out[i] ? (int)out[i]->mnId : -1;
+  return k;
+}
+
+// ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2350-2366)
+extern "C" int plviref_orb_descriptor_distance(const unsigned char* a, const unsigned char* b) {
+  return ORBmatcher::DescriptorDistance(desc_mat(a, 1), desc_mat(b, 1));
+}

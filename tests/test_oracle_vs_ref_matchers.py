@@ -1,0 +1,182 @@
+"""CPU: the oracle's ORB searches against THE REFERENCE'S OWN src/ORBmatcher.cc.
+
+oracle/_ref/libplvi_ref_orbmatcher.so = ORBmatcher.cc compiled unmodified, where it lies, with the stand-in Frame /
+KeyFrame / MapPoint of oracle/cvmini/slam_mock_orb.h force-included in place of the reference's headers (which need
+DBoW2's vocabulary, g2o, Sophus, boost, the Atlas).  The stand-ins carry plain data; Frame::GetFeaturesInArea
+(Frame.cc, not compilable for the same reason) is the oracle's restatement.  Called: SearchByProjection(F,
+vpMapPoints, th), SearchForInitialization, SearchByBoW(KF, F), SearchByBoW(KF, KF), DescriptorDistance.
+
+Bar: bit-exact (match tables and counts).  The committed outputs (tests/golden/ref_outputs.npz, tools/gen_golden_ref.py)
+run everywhere; the live tests run where the library exists.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import QUERY_DTYPE
+from pl_vi_orbslam3_b200 import synth
+from pl_vi_orbslam3_b200.matchers import frame_grid, ORBmatcher
+from pl_vi_orbslam3_b200.vocabulary import ORBVocabulary
+
+GOLD = Path(__file__).resolve().parent / "golden"
+R = np.load(GOLD / "ref_outputs.npz")
+GRID = frame_grid(0, 752, 0, 480)
+SCALES = np.cumprod(np.concatenate([[np.float32(1.0)], np.full(7, np.float32(1.2))]).astype(np.float32), dtype=np.float32)
+needs_ref = pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def pair_features():
+    f1, f2, A = synth.warp_pair(3)
+    return oracle.orb_extract(f1), oracle.orb_extract(f2), A
+
+
+# ---- case builders shared by the live tests and tools/gen_golden_ref.py ----------------------------------------------
+def mappoint_case(r1, r2, A, seed, th):
+    """Map points = the features of frame 1 projected into frame 2 by the warp; random view cosines / flags."""
+    rng = np.random.RandomState(seed)
+    k = r1["keypoints"]
+    n = len(k)
+    proj = np.stack([A[0, 0] * k["x"] + A[0, 1] * k["y"] + A[0, 2], A[1, 0] * k["x"] + A[1, 1] * k["y"] + A[1, 2]], 1).astype(np.float32)
+    viewcos = np.where(rng.rand(n) < 0.5, 0.9995, 0.9).astype(np.float32)
+    level = k["octave"].astype(np.int32)
+    flags = ((rng.rand(n) < 0.1) * 1 + (rng.rand(n) < 0.15) * 2 + (rng.rand(n) < 0.05) * 4).astype(np.int32)
+    blocked = (rng.rand(len(r2["keypoints"])) < 0.1).astype(np.uint8)
+    return dict(proj=proj, viewcos=viewcos, level=level, flags=flags, blocked=blocked, th=np.float32(th))
+
+
+def mappoint_queries(c):
+    """Caller side of SearchByProjection(F, vpMapPoints, th) in front of the oracle / plvi_search_by_projection:
+    r = RadiusByViewingCos (2.5 above 0.998, else 4.0), x th unless th == 1, x scale factor of the predicted level;
+    levels level-1 .. level (src/ORBmatcher.cc:66-74)."""
+    n = len(c["proj"])
+    q = np.zeros(n, QUERY_DTYPE)
+    q["u"], q["v"] = c["proj"][:, 0], c["proj"][:, 1]
+    r = np.where(c["viewcos"] > np.float32(0.998), np.float32(2.5), np.float32(4.0)).astype(np.float32)
+    if c["th"] != 1.0:
+        r = (r * np.float32(c["th"])).astype(np.float32)
+    q["radius"] = (r * SCALES[c["level"]]).astype(np.float32)
+    q["min_level"], q["max_level"] = c["level"] - 1, c["level"]
+    q["flags"] = ((c["flags"] & 1) | ((c["flags"] & 4) >> 2)) | (c["flags"] & 2)
+    return q
+
+
+def bow_case(r1, r2, k, L, levelsup, seed):
+    v = ORBVocabulary.random_tree(k=k, L=L, seed=seed)
+    rng = np.random.RandomState(seed)
+    fv1 = oracle.bow_transform(v.as_oracle_dict(), r1["descriptors"], levelsup)["fv"]
+    fv2 = oracle.bow_transform(v.as_oracle_dict(), r2["descriptors"], levelsup)["fv"]
+    u1, u2 = rng.rand(len(r1["keypoints"])), rng.rand(len(r2["keypoints"]))
+    mp1 = np.where(u1 < 0.75, 1, np.where(u1 < 0.85, 2, 0)).astype(np.uint8)   # 1 good, 2 bad, 0 none
+    mp2 = np.where(u2 < 0.75, 1, np.where(u2 < 0.85, 2, 0)).astype(np.uint8)
+    return fv1, fv2, mp1, mp2
+
+
+def bow_queries(r1, fv1, fv2, mp1):
+    """Caller side of the walk over the two FeatureVectors (src/ORBmatcher.cc:286-300): one query per keyframe feature
+    of a common node, in the reference's order."""
+    start2 = {int(nd): (int(fv2[1][i]), int(fv2[1][i + 1])) for i, nd in enumerate(fv2[0])}
+    order, rows = [], []
+    for i, nd in enumerate(fv1[0]):
+        if int(nd) not in start2:
+            continue
+        for idx1 in fv1[2][fv1[1][i]:fv1[1][i + 1]]:
+            order.append(int(idx1))
+            rows.append((start2[int(nd)][0], start2[int(nd)][1], r1["keypoints"]["angle"][idx1], 0 if mp1[idx1] == 1 else 1))
+    q = np.zeros(len(rows), QUERY_DTYPE)
+    for j, (s, e, ang, fl) in enumerate(rows):
+        q[j]["min_level"], q[j]["max_level"], q[j]["angle"], q[j]["flags"] = s, e, ang, fl
+    return np.asarray(fv2[2], np.int32), q, np.array(order, np.int64)
+
+
+def oracle_mappoints(r2, c, nnratio):
+    return oracle.search_mappoints(r2["keypoints"], r2["descriptors"], GRID, mappoint_queries(c), c["qdesc"], 100, nnratio, c["blocked"])
+
+
+def oracle_bow_kf_f(r1, r2, fv1, fv2, mp1, nnratio, check_ori):
+    items, q, order = bow_queries(r1, fv1, fv2, mp1)
+    n, mt = oracle.search_bow(r2["keypoints"], r2["descriptors"], items, q, r1["descriptors"][order], 50, nnratio, check_ori)
+    return n, np.where(mt >= 0, order[np.maximum(mt, 0)], -1).astype(np.int32)
+
+
+# ---- live ------------------------------------------------------------------------------------------------------------
+@needs_ref
+@pytest.mark.parametrize("seed,th,nnratio", [(0, 1.0, 0.8), (1, 3.0, 0.8), (2, 5.0, 0.9), (3, 15.0, 0.6)])
+def test_live_reference_search_by_projection_mappoints(pair_features, seed, th, nnratio):
+    r1, r2, A = pair_features
+    c = mappoint_case(r1, r2, A, seed, th)
+    c["qdesc"] = r1["descriptors"]
+    n, mt = oracle.ref_search_mappoints(r2["keypoints"], r2["descriptors"], GRID, SCALES, c["proj"], c["viewcos"], c["level"],
+                                        c["flags"], c["qdesc"], th, nnratio, c["blocked"])
+    on, omt = oracle_mappoints(r2, c, nnratio)
+    assert n == on and np.array_equal(mt, omt)
+    assert n > 50
+
+
+@needs_ref
+@pytest.mark.parametrize("window,nnratio,check_ori", [(100, 0.9, True), (30, 0.9, True), (100, 0.7, False), (10, 0.9, True)])
+def test_live_reference_search_for_initialization(pair_features, window, nnratio, check_ori):
+    r1, r2, _ = pair_features
+    k1 = r1["keypoints"]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m12, pm = oracle.ref_search_init(k1, r1["descriptors"], r2["keypoints"], r2["descriptors"], GRID, prev, window, nnratio, check_ori)
+    q = ORBmatcher.init_queries(k1, prev, window)
+    on, om12, oq = oracle.search_init(r2["keypoints"], r2["descriptors"], GRID, q, r1["descriptors"], 50, nnratio, check_ori)
+    assert n == on and np.array_equal(m12, om12)
+    assert np.array_equal(pm[:, 0], oq["u"]) and np.array_equal(pm[:, 1], oq["v"])
+    if window == 100:
+        assert n > 50
+        # second round, as Tracking::MonocularInitialization does with the updated mvbPrevMatched
+        n2, m12b, _ = oracle.ref_search_init(k1, r1["descriptors"], r2["keypoints"], r2["descriptors"], GRID, pm, window, nnratio, check_ori)
+        on2, om12b, _ = oracle.search_init(r2["keypoints"], r2["descriptors"], GRID, ORBmatcher.init_queries(k1, pm, window),
+                                           r1["descriptors"], 50, nnratio, check_ori)
+        assert n2 == on2 and np.array_equal(m12b, om12b)
+
+
+@needs_ref
+@pytest.mark.parametrize("k,L,levelsup,nnratio,check_ori", [(6, 3, 2, 0.7, True), (10, 4, 2, 0.9, True), (4, 2, 1, 0.6, True),
+                                                            (5, 3, 3, 0.75, False), (3, 2, 2, 0.95, True)])
+def test_live_reference_search_by_bow(pair_features, k, L, levelsup, nnratio, check_ori):
+    r1, r2, _ = pair_features
+    fv1, fv2, mp1, mp2 = bow_case(r1, r2, k, L, levelsup, k + L)
+    n, mt = oracle.ref_search_bow_kf_f(r1["keypoints"], r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], fv2, nnratio,
+                                       check_ori)
+    on, omt = oracle_bow_kf_f(r1, r2, fv1, fv2, mp1, nnratio, check_ori)
+    assert n == on and np.array_equal(mt, omt)
+    n, m = oracle.ref_search_bow_kfkf(r1["keypoints"], r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2, nnratio,
+                                      check_ori)
+    on, om = oracle.search_bow_kfkf(r1["keypoints"], r1["descriptors"], mp1 == 1, fv1, r2["keypoints"], r2["descriptors"], mp2 == 1, fv2,
+                                    nnratio, check_ori)
+    assert n == on and np.array_equal(m, om)
+    if L == 2:
+        assert n > 10
+
+
+@needs_ref
+def test_live_reference_orb_descriptor_distance(pair_features):
+    r1, r2, _ = pair_features
+    for i in range(64):
+        assert oracle.ref_orb_descriptor_distance(r1["descriptors"][i], r2["descriptors"][i]) == \
+            oracle.hamming256(r1["descriptors"][i], r2["descriptors"][i])
+
+
+# ---- committed outputs of the reference (run everywhere) -------------------------------------------------------------
+def test_oracle_equals_reference_orbmatcher_outputs(pair_features):
+    r1, r2, A = pair_features
+    c = mappoint_case(r1, r2, A, 1, 3.0)
+    c["qdesc"] = r1["descriptors"]
+    n, mt = oracle_mappoints(r2, c, 0.8)
+    assert n == int(R["orbmatch/mappoints_n"]) and np.array_equal(mt, R["orbmatch/mappoints"])
+    k1 = r1["keypoints"]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m12, q = oracle.search_init(r2["keypoints"], r2["descriptors"], GRID, ORBmatcher.init_queries(k1, prev, 100), r1["descriptors"],
+                                   50, 0.9, True)
+    assert n == int(R["orbmatch/init_n"]) and np.array_equal(m12, R["orbmatch/init"])
+    assert np.array_equal(np.stack([q["u"], q["v"]], 1), R["orbmatch/init_prev"])
+    fv1, fv2, mp1, mp2 = bow_case(r1, r2, 6, 3, 2, 9)
+    n, mt = oracle_bow_kf_f(r1, r2, fv1, fv2, mp1, 0.7, True)
+    assert n == int(R["orbmatch/bow_n"]) and np.array_equal(mt, R["orbmatch/bow"])
+    n, m = oracle.search_bow_kfkf(k1, r1["descriptors"], mp1 == 1, fv1, r2["keypoints"], r2["descriptors"], mp2 == 1, fv2, 0.8, True)
+    assert n == int(R["orbmatch/bowkf_n"]) and np.array_equal(m, R["orbmatch/bowkf"])

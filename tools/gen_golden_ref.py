@@ -73,6 +73,25 @@ def main():
     out["linematch/has1"], out["linematch/has2"] = h1, h2
     out["linematch/tri_n"], out["linematch/tri"] = np.int32(n), m
     print("linematch", len(d1), len(d2), out["linematch/match_n"], out["linematch/init_n"], out["linematch/tri_n"])
+    # ORBmatcher.cc of the reference (compiled with the stand-in SLAM classes): the four searches on a warped frame pair
+    sys.path.insert(0, str(ROOT / "tests"))
+    import test_oracle_vs_ref_matchers as T
+    f1, f2, A = synth.warp_pair(3)
+    r1, r2 = oracle.ref_orb_extract(f1), oracle.ref_orb_extract(f2)
+    c = T.mappoint_case(r1, r2, A, 1, 3.0)
+    n, mt = oracle.ref_search_mappoints(r2["keypoints"], r2["descriptors"], T.GRID, T.SCALES, c["proj"], c["viewcos"], c["level"],
+                                        c["flags"], r1["descriptors"], 3.0, 0.8, c["blocked"])
+    out["orbmatch/mappoints_n"], out["orbmatch/mappoints"] = np.int32(n), mt
+    k1 = r1["keypoints"]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m12, pm = oracle.ref_search_init(k1, r1["descriptors"], r2["keypoints"], r2["descriptors"], T.GRID, prev, 100, 0.9, True)
+    out["orbmatch/init_n"], out["orbmatch/init"], out["orbmatch/init_prev"] = np.int32(n), m12, pm
+    fv1, fv2, mp1, mp2 = T.bow_case(r1, r2, 6, 3, 2, 9)
+    n, mt = oracle.ref_search_bow_kf_f(k1, r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], fv2, 0.7, True)
+    out["orbmatch/bow_n"], out["orbmatch/bow"] = np.int32(n), mt
+    n, m = oracle.ref_search_bow_kfkf(k1, r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2, 0.8, True)
+    out["orbmatch/bowkf_n"], out["orbmatch/bowkf"] = np.int32(n), m
+    print("orbmatch", out["orbmatch/mappoints_n"], out["orbmatch/init_n"], out["orbmatch/bow_n"], out["orbmatch/bowkf_n"])
     out["cases"] = np.array([f"{n}|{nf}|{lap[0]}|{lap[1]}|{lnf}" for n, nf, lap, lnf in CASES])
     np.savez_compressed(GOLD / "ref_outputs.npz", **out)
     print((GOLD / "ref_outputs.npz").stat().st_size, "bytes")
