@@ -406,8 +406,18 @@ class Mat {
     for (int r = 0; r < m.rows; r++) memcpy(out.ptr(rows + r), m.ptr(r), rb);
     *this = out;
   }
-  double dot(const Mat&) const { cvmini_unreachable("Mat::dot"); }
-  Mat t() const { cvmini_unreachable("Mat::t"); }
+  double dot(const Mat& o) const {   // CV_32F only (pose arithmetic); accumulates in double like cv::Mat::dot
+    if (type() != CV_32FC1 || o.type() != CV_32FC1 || rows != o.rows || cols != o.cols) cvmini_unreachable("Mat::dot other than CV_32F");
+    double acc = 0;
+    for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) acc += (double)at<float>(r, c) * (double)o.at<float>(r, c);
+    return acc;
+  }
+  Mat t() const {   // CV_32F only (pose arithmetic)
+    if (type() != CV_32FC1) cvmini_unreachable("Mat::t other than CV_32F");
+    Mat m(cols, rows, CV_32FC1);
+    for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.at<float>(c, r) = at<float>(r, c);
+    return m;
+  }
   Mat reshape(int, int = 0) const { cvmini_unreachable("Mat::reshape"); }
   int checkVector(int, int = -1, bool = true) const { cvmini_unreachable("Mat::checkVector"); }
 };
@@ -755,10 +765,33 @@ class BFMatcher : public Algorithm {
     }
   }
 };
-static inline Mat operator*(const Mat&, const Mat&) { cvmini_unreachable("Mat * Mat"); }
+// Small CV_32F matrix algebra (pose arithmetic of the matchers: 3x3 / 3x1 / 4x4).  Products accumulate in double and
+// round once per element.  cv::gemm's rounding for such sizes is NOT modelled: the tests that reach these operators use
+// poses whose products are exact in any order (identity rotations, integer-valued terms), see slam_mock_orb.h.
+static inline Mat operator*(const Mat& a, const Mat& b) {
+  if (a.type() != CV_32FC1 || b.type() != CV_32FC1 || a.cols != b.rows) cvmini_unreachable("Mat * Mat other than CV_32F with matching sizes");
+  Mat c(a.rows, b.cols, CV_32FC1);
+  for (int i = 0; i < a.rows; i++)
+    for (int j = 0; j < b.cols; j++) {
+      double acc = 0;
+      for (int k = 0; k < a.cols; k++) acc += (double)a.at<float>(i, k) * (double)b.at<float>(k, j);
+      c.at<float>(i, j) = (float)acc;
+    }
+  return c;
+}
+static inline Mat cvmini_f32_elementwise(const Mat& a, const Mat* b, int op, const char* what) {
+  if (a.type() != CV_32FC1 || (b && (b->type() != CV_32FC1 || b->rows != a.rows || b->cols != a.cols))) cvmini_unreachable(what);
+  Mat c(a.rows, a.cols, CV_32FC1);
+  for (int i = 0; i < a.rows; i++)
+    for (int j = 0; j < a.cols; j++) {
+      const float x = a.at<float>(i, j), y = b ? b->at<float>(i, j) : 0.f;
+      c.at<float>(i, j) = op == 0 ? x + y : (op == 1 ? x - y : -x);
+    }
+  return c;
+}
 static inline Mat operator*(const Mat&, double) { cvmini_unreachable("Mat * scalar"); }
-static inline Mat operator+(const Mat&, const Mat&) { cvmini_unreachable("Mat + Mat"); }
-static inline Mat operator-(const Mat&, const Mat&) { cvmini_unreachable("Mat - Mat"); }
-static inline Mat operator-(const Mat&) { cvmini_unreachable("-Mat"); }
+static inline Mat operator+(const Mat& a, const Mat& b) { return cvmini_f32_elementwise(a, &b, 0, "Mat + Mat other than CV_32F"); }
+static inline Mat operator-(const Mat& a, const Mat& b) { return cvmini_f32_elementwise(a, &b, 1, "Mat - Mat other than CV_32F"); }
+static inline Mat operator-(const Mat& a) { return cvmini_f32_elementwise(a, nullptr, 2, "-Mat other than CV_32F"); }
 
 }  // namespace cv

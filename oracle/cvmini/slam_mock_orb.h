@@ -28,14 +28,32 @@ class KeyFrame;
 class Frame;
 class MapPoint;
 
+// Stand-in pinhole camera.  project = Pinhole::project (src/CameraModels/Pinhole.cpp:27-39: fx * x / z + cx in float).
+// epipolarConstrain: Pinhole.cpp:135-157 builds F12 = K1^-T [t12]x R12 K2^-1 with cv::Mat products and a matrix inverse
+// (not modelled by the stand-in) and then applies the point-to-epipolar-line test; here F12 is GIVEN (mF12, what the
+// oracle and the CUDA path take as input) and only the test itself (Pinhole.cpp:142-156) is restated.
 class GeometricCamera {
  public:
+  float fx = 1, fy = 1, cx = 0, cy = 0;
+  float mF12[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   virtual ~GeometricCamera() {}
-  virtual cv::Point2f project(const cv::Point3f&) { cvmini_unreachable("GeometricCamera::project"); }
-  virtual cv::Point2f project(const cv::Mat&) { cvmini_unreachable("GeometricCamera::project"); }
+  virtual cv::Point2f project(const cv::Point3f& p) { return cv::Point2f(fx * p.x / p.z + cx, fy * p.y / p.z + cy); }
+  virtual cv::Point2f project(const cv::Mat& m) {
+    const float* p = m.ptr<float>();
+    return project(cv::Point3f(m.at<float>(0), m.at<float>(1), m.at<float>(2)));
+  }
   virtual float uncertainty2(const cv::Mat&) { cvmini_unreachable("GeometricCamera::uncertainty2"); }
-  virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint&, const cv::KeyPoint&, const cv::Mat&, const cv::Mat&,
-                                 const float, const float) { cvmini_unreachable("GeometricCamera::epipolarConstrain"); }
+  virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat&, const cv::Mat&,
+                                 const float, const float unc) {
+    const float a = kp1.pt.x * mF12[0] + kp1.pt.y * mF12[3] + mF12[6];
+    const float b = kp1.pt.x * mF12[1] + kp1.pt.y * mF12[4] + mF12[7];
+    const float c = kp1.pt.x * mF12[2] + kp1.pt.y * mF12[5] + mF12[8];
+    const float num = a * kp2.pt.x + b * kp2.pt.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * unc;
+  }
   virtual bool matchAndtriangulate(const cv::KeyPoint&, const cv::KeyPoint&, GeometricCamera*, cv::Mat&, cv::Mat&, const float,
                                    const float, cv::Mat&) { cvmini_unreachable("GeometricCamera::matchAndtriangulate"); }
 };
@@ -51,13 +69,13 @@ class MapPoint {
         mTrackViewCosR = 0;
   int mnTrackScaleLevel = 0, mnTrackScaleLevelR = 0;
   long unsigned int mnLastFrameSeen = 0, mnFuseCandidateForKF = 0, mnId = 0;
-  cv::Mat mDesc;
+  cv::Mat mDesc, mWorldPos;
   bool mBad = false;
   int mObs = 1;
   cv::Mat GetDescriptor() { return mDesc; }
   bool isBad() { return mBad; }
   int Observations() { return mObs; }
-  cv::Mat GetWorldPos() { cvmini_unreachable("MapPoint::GetWorldPos"); }
+  cv::Mat GetWorldPos() { return mWorldPos; }
   cv::Mat GetNormal() { cvmini_unreachable("MapPoint::GetNormal"); }
   float GetMaxDistanceInvariance() { cvmini_unreachable("MapPoint"); }
   float GetMinDistanceInvariance() { cvmini_unreachable("MapPoint"); }
@@ -119,9 +137,10 @@ class KeyFrame {
     cvmini_unreachable("KeyFrame::GetFeaturesInArea");
   }
   bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
-  cv::Mat GetRotation() { cvmini_unreachable("KeyFrame"); }
-  cv::Mat GetTranslation() { cvmini_unreachable("KeyFrame"); }
-  cv::Mat GetCameraCenter() { cvmini_unreachable("KeyFrame"); }
+  cv::Mat mRcw, mtcw, mOw;   // 3x3, 3x1, 3x1 CV_32F
+  cv::Mat GetRotation() { return mRcw.clone(); }
+  cv::Mat GetTranslation() { return mtcw.clone(); }
+  cv::Mat GetCameraCenter() { return mOw.clone(); }
   cv::Mat GetPose() { cvmini_unreachable("KeyFrame"); }
   cv::Mat GetPoseInverse() { cvmini_unreachable("KeyFrame"); }
   cv::Mat GetRightPose() { cvmini_unreachable("KeyFrame"); }

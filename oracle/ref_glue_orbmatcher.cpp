@@ -158,6 +158,113 @@ extern "C" int plviref_orb_search_by_bow_kf_kf(const cv::KeyPoint* keys1, const 
   return k;
 }
 
+namespace {
+cv::Mat eye_f32(int n) {
+  cv::Mat m = cv::Mat::zeros(n, n, CV_32F);
+  for (int i = 0; i < n; i++) m.at<float>(i, i) = 1.0f;
+  return m;
+}
+cv::Mat vec3_f32(float x, float y, float z) {
+  cv::Mat m(3, 1, CV_32F);
+  m.at<float>(0) = x; m.at<float>(1) = y; m.at<float>(2) = z;
+  return m;
+}
+}  // namespace
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono = true) (src/ORBmatcher.cc:1962-2178), monocular
+// frames.  The oracle / CUDA boundary starts at the PROJECTED point, so the poses are the identity and map point i sits
+// at (uv[i], 1) in front of a unit pinhole camera: Rcw * x + tcw and fx * x / z + cx are then exact and the
+// reference's own projection code yields uv[i] bit for bit.  bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}.
+// flags bit0: LastFrame holds no map point there (or it is an outlier), bit1: Observations() == 0.
+extern "C" int plviref_orb_search_by_projection_frame(const cv::KeyPoint* keys2, const unsigned char* desc2, int n2,
+                                                       const unsigned char* blocked, const float* grid, const float* bounds,
+                                                       const float* scale_factors, int nlevels, const cv::KeyPoint* keys1, int n1,
+                                                       const float* uv, const int* flags, const unsigned char* qdesc, float th,
+                                                       int check_ori, int* match_train) {
+  GeometricCamera cam;
+  Frame C, L;
+  C.N = n2;
+  C.mvKeysUn = C.mvKeys = key_vec(keys2, n2);
+  C.mDescriptors = desc_mat(desc2, n2);
+  C.mvuRight.assign(n2, -1.0f);
+  C.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+  C.mnMinX = bounds[0]; C.mnMaxX = bounds[1]; C.mnMinY = bounds[2]; C.mnMaxY = bounds[3];
+  C.mpCamera = &cam;
+  C.mTcw = eye_f32(4);
+  GridOwner go(keys2, n2, grid);
+  C.grid = go.g;
+  MapPoint old;
+  C.mvpMapPoints.assign(n2, nullptr);
+  for (int i = 0; i < n2; i++) if (blocked && blocked[i]) C.mvpMapPoints[i] = &old;
+  L.N = n1;
+  L.mvKeysUn = L.mvKeys = key_vec(keys1, n1);
+  L.mTcw = eye_f32(4);
+  L.mvbOutlier.assign(n1, false);
+  std::vector<MapPoint> mps(n1);
+  L.mvpMapPoints.assign(n1, nullptr);
+  for (int i = 0; i < n1; i++) {
+    MapPoint& m = mps[i];
+    m.mnId = i;
+    m.mObs = (flags[i] & 2) ? 0 : 1;
+    m.mWorldPos = vec3_f32(uv[2 * i], uv[2 * i + 1], 1.0f);
+    m.mDesc = desc_mat(qdesc + 32 * (size_t)i, 1);
+    if (!(flags[i] & 1)) L.mvpMapPoints[i] = &m;
+  }
+  ORBmatcher matcher(0.9f, check_ori != 0);
+  const int k = matcher.SearchByProjection(C, L, th, true);
+  for (int i = 0; i < n2; i++) match_train[i] = (C.mvpMapPoints[i] && C.mvpMapPoints[i] != &old) ? (int)C.mvpMapPoints[i]->mnId : -1;
+  return k;
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo = false, bCoarse) (src/ORBmatcher.cc:
+// 965-1206), monocular pinhole keyframes.  Identity rotations, zero translations and camera centre (ep, 1) make the
+// reference's own epipole computation (:972-978) yield ep exactly; F12 is handed to the stand-in camera (see
+// slam_mock_orb.h on epipolarConstrain).  mpN[i] != 0: the feature already has a map point.
+extern "C" int plviref_orb_search_for_triangulation(const cv::KeyPoint* keys1, const unsigned char* desc1, const unsigned char* mp1, int n1,
+                                                     const int* fv1_nodes, const int* fv1_start, const int* fv1_feats, int nn1,
+                                                     const cv::KeyPoint* keys2, const unsigned char* desc2, const unsigned char* mp2, int n2,
+                                                     const int* fv2_nodes, const int* fv2_start, const int* fv2_feats, int nn2,
+                                                     const float* F12, float epx, float epy, const float* sf2, const float* sigma2_1,
+                                                     const float* sigma2_2, int nlevels, int coarse, int check_ori, int* matches12) {
+  GeometricCamera cam1, cam2;
+  memcpy(cam1.mF12, F12, sizeof(cam1.mF12));
+  KeyFrame K1, K2;
+  MapPoint some;
+  KeyFrame* ks[2] = {&K1, &K2};
+  const cv::KeyPoint* keys[2] = {keys1, keys2};
+  const unsigned char* descs[2] = {desc1, desc2};
+  const unsigned char* mps[2] = {mp1, mp2};
+  const int ns[2] = {n1, n2};
+  for (int s = 0; s < 2; s++) {
+    KeyFrame& K = *ks[s];
+    K.N = ns[s];
+    K.mvKeysUn = K.mvKeys = key_vec(keys[s], ns[s]);
+    K.mDescriptors = desc_mat(descs[s], ns[s]);
+    K.mvuRight.assign(ns[s], -1.0f);
+    K.mvpMapPoints.assign(ns[s], nullptr);
+    for (int i = 0; i < ns[s]; i++) if (mps[s][i]) K.mvpMapPoints[i] = &some;
+    K.mRcw = eye_f32(3);
+    K.mtcw = vec3_f32(0, 0, 0);
+    K.mOw = vec3_f32(0, 0, 0);
+  }
+  K1.mOw = vec3_f32(epx, epy, 1.0f);
+  K1.mpCamera = &cam1;
+  K2.mpCamera = &cam2;
+  K1.mvLevelSigma2.assign(sigma2_1, sigma2_1 + nlevels);
+  K2.mvLevelSigma2.assign(sigma2_2, sigma2_2 + nlevels);
+  K2.mvScaleFactors.assign(sf2, sf2 + nlevels);
+  fill_fv(K1.mFeatVec, fv1_nodes, fv1_start, fv1_feats, nn1);
+  fill_fv(K2.mFeatVec, fv2_nodes, fv2_start, fv2_feats, nn2);
+  cv::Mat F(3, 3, CV_32F);
+  for (int i = 0; i < 9; i++) F.at<float>(i / 3, i % 3) = F12[i];
+  std::vector<std::pair<size_t, size_t>> pairs;
+  ORBmatcher matcher(0.6f, check_ori != 0);
+  const int k = matcher.SearchForTriangulation(&K1, &K2, F, pairs, false, coarse != 0);
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  for (auto& p : pairs) matches12[p.first] = (int)p.second;
+  return k;
+}
+
 // ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2350-2366)
 extern "C" int plviref_orb_descriptor_distance(const unsigned char* a, const unsigned char* b) {
   return ORBmatcher::DescriptorDistance(desc_mat(a, 1), desc_mat(b, 1));

@@ -1,0 +1,148 @@
+"""GPU parity of the matchers against THE REFERENCE'S OWN src/ORBmatcher.cc and src/LineMatcher.cpp (compiled unmodified
+against stand-in SLAM classes, see tests/test_oracle_vs_ref_matchers.py / test_oracle_vs_ref.py): the CUDA path through
+the C ABI vs the committed reference outputs (tests/golden/ref_outputs.npz) and, where the prebuilt libraries
+travelled with the snapshot, live runs of the reference.  Bar: bit-exact match tables and counts.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from pl_vi_orbslam3_b200.matchers import FrameView, LineMatcher, ORBmatcher
+from test_oracle_vs_ref import frame
+import test_oracle_vs_ref_matchers as T
+from test_oracle_vs_ref_matchers import GRID, R, SCALES, pair_features  # noqa: F401  (fixture)
+
+pytestmark = pytest.mark.gpu
+live = pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref did not travel")
+
+
+@pytest.fixture(scope="module")
+def om(gpu):
+    m = ORBmatcher(0.9, True, max_pairs=2, max_train=6000, max_query=6000)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def lm(gpu):
+    m = LineMatcher(max_pairs=4, max_train=512, max_query=512)
+    yield m
+    m.close()
+
+
+def cuda_mappoints(om, r2, c, qdesc, nnratio):
+    om.mfNNratio = nnratio
+    F = FrameView(r2["keypoints"], r2["descriptors"], GRID, c["blocked"])
+    n, mt, _ = om.SearchByProjection(F, T.mappoint_queries(c), qdesc, mappoints=True)
+    return n, mt
+
+
+def cuda_init(om, r1, r2, prev, window, nnratio, ori):
+    om.mfNNratio, om.mbCheckOrientation = nnratio, ori
+    F2 = FrameView(r2["keypoints"], r2["descriptors"], GRID)
+    out = om.SearchForInitialization(r1["keypoints"], r1["descriptors"], F2, prev, window)
+    om.mbCheckOrientation = True
+    return out
+
+
+def cuda_bow_kf_f(om, r1, r2, fv1, fv2, mp1, nnratio, ori):
+    om.mfNNratio, om.mbCheckOrientation = nnratio, ori
+    items, q, order = T.bow_queries(r1, fv1, fv2, mp1)
+    n, mt, _ = om.SearchByBoW(FrameView(r2["keypoints"], r2["descriptors"], GRID), items, q, r1["descriptors"][order])
+    om.mbCheckOrientation = True
+    return n, np.where(mt >= 0, order[np.maximum(mt, 0)], -1).astype(np.int32)
+
+
+def cuda_bow_kfkf(om, r1, r2, fv1, fv2, mp1, mp2, nnratio, ori):
+    om.mfNNratio, om.mbCheckOrientation = nnratio, ori
+    items, q, order = T.bow_queries(r1, fv1, fv2, mp1)
+    n, mq = om.SearchByBoW_KF(FrameView(r2["keypoints"], r2["descriptors"], GRID), mp2 == 1, items, q, r1["descriptors"][order])
+    om.mbCheckOrientation = True
+    got = np.full(len(r1["keypoints"]), -1, np.int32)
+    got[order[mq >= 0]] = mq[mq >= 0]
+    return n, got
+
+
+def test_cuda_equals_reference_orbmatcher_outputs(om, pair_features):
+    r1, r2, A = pair_features
+    c = T.mappoint_case(r1, r2, A, 1, 3.0)
+    n, mt = cuda_mappoints(om, r2, c, r1["descriptors"], 0.8)
+    assert n == int(R["orbmatch/mappoints_n"]) and np.array_equal(mt, R["orbmatch/mappoints"])
+    k1 = r1["keypoints"]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m12, pm = cuda_init(om, r1, r2, prev, 100, 0.9, True)
+    assert n == int(R["orbmatch/init_n"]) and np.array_equal(m12, R["orbmatch/init"]) and np.array_equal(pm, R["orbmatch/init_prev"])
+    fv1, fv2, mp1, mp2 = T.bow_case(r1, r2, 6, 3, 2, 9)
+    n, mt = cuda_bow_kf_f(om, r1, r2, fv1, fv2, mp1, 0.7, True)
+    assert n == int(R["orbmatch/bow_n"]) and np.array_equal(mt, R["orbmatch/bow"])
+    n, m = cuda_bow_kfkf(om, r1, r2, fv1, fv2, mp1, mp2, 0.8, True)
+    assert n == int(R["orbmatch/bowkf_n"]) and np.array_equal(m, R["orbmatch/bowkf"])
+
+
+def test_cuda_equals_reference_linematcher_outputs(lm):
+    d1 = oracle.line_extract(frame("synth_0"))["descriptors"]
+    d2 = oracle.line_extract(frame("synth_1"))["descriptors"]
+    n, m = lm.match(d1, d2, 0.75)
+    assert n == int(R["linematch/match_n"]) and np.array_equal(m, R["linematch/match"])
+    ms, nm, _ = lm._match_mad_batch([(d1, d2)], 0.5)
+    assert nm[0] == int(R["linematch/init_n"]) and np.array_equal(ms[0], R["linematch/init"])
+    ms, nm, _ = lm._match_mad_batch([(d1, d2)], 0.1, [(R["linematch/has1"], R["linematch/has2"])])
+    assert nm[0] == int(R["linematch/tri_n"]) and np.array_equal(ms[0], R["linematch/tri"])
+
+
+@live
+@pytest.mark.parametrize("seed,th,nnratio", [(0, 1.0, 0.8), (2, 5.0, 0.9), (3, 15.0, 0.6)])
+def test_cuda_equals_live_reference_search_by_projection(om, pair_features, seed, th, nnratio):
+    r1, r2, A = pair_features
+    c = T.mappoint_case(r1, r2, A, seed, th)
+    n, mt = cuda_mappoints(om, r2, c, r1["descriptors"], nnratio)
+    rn, rmt = oracle.ref_search_mappoints(r2["keypoints"], r2["descriptors"], GRID, SCALES, c["proj"], c["viewcos"], c["level"],
+                                          c["flags"], r1["descriptors"], th, nnratio, c["blocked"])
+    assert n == rn and np.array_equal(mt, rmt)
+
+
+@live
+@pytest.mark.parametrize("window,nnratio,ori", [(100, 0.9, True), (30, 0.9, True), (100, 0.7, False)])
+def test_cuda_equals_live_reference_search_for_initialization(om, pair_features, window, nnratio, ori):
+    r1, r2, _ = pair_features
+    k1 = r1["keypoints"]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m12, pm = cuda_init(om, r1, r2, prev, window, nnratio, ori)
+    rn, rm12, rpm = oracle.ref_search_init(k1, r1["descriptors"], r2["keypoints"], r2["descriptors"], GRID, prev, window, nnratio, ori)
+    assert n == rn and np.array_equal(m12, rm12) and np.array_equal(pm, rpm)
+
+
+@live
+@pytest.mark.parametrize("k,L,levelsup,nnratio,ori", [(10, 4, 2, 0.9, True), (4, 2, 1, 0.6, True), (5, 3, 3, 0.75, False)])
+def test_cuda_equals_live_reference_search_by_bow(om, pair_features, k, L, levelsup, nnratio, ori):
+    r1, r2, _ = pair_features
+    fv1, fv2, mp1, mp2 = T.bow_case(r1, r2, k, L, levelsup, k + L)
+    n, mt = cuda_bow_kf_f(om, r1, r2, fv1, fv2, mp1, nnratio, ori)
+    rn, rmt = oracle.ref_search_bow_kf_f(r1["keypoints"], r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], fv2, nnratio, ori)
+    assert n == rn and np.array_equal(mt, rmt)
+    n, m = cuda_bow_kfkf(om, r1, r2, fv1, fv2, mp1, mp2, nnratio, ori)
+    rn, rm = oracle.ref_search_bow_kfkf(r1["keypoints"], r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2,
+                                        nnratio, ori)
+    assert n == rn and np.array_equal(m, rm)
+
+
+@live
+@pytest.mark.parametrize("seed", range(4))
+def test_cuda_equals_live_reference_line_matcher(lm, seed):
+    rng = np.random.default_rng(seed)
+    n1, n2 = (int(x) for x in rng.integers(2, 300, 2))
+    d1, d2 = __import__("test_oracle_vs_ref")._line_desc_pair(rng, n1, n2, [0.0, 0.02, 0.1, 0.3][seed])
+    for nnr in (0.75, 1.0):
+        n, m = lm.matchNNR(d1, d2, nnr)
+        rn, rm = oracle.ref_line_match(d1, d2, nnr, "nnr")
+        assert n == rn and np.array_equal(m, rm)
+        n, m = lm.match(d1, d2, nnr)
+        rn, rm = oracle.ref_line_match(d1, d2, nnr, "maplines")
+        assert n == rn and np.array_equal(m, rm)
+    ms, nm, _ = lm._match_mad_batch([(d1, d2)], 0.5)
+    rn, rm = oracle.ref_line_match_mad(d1, d2, 0.5)
+    assert nm[0] == rn and np.array_equal(ms[0], rm)
+    h1, h2 = (rng.random(n1) < 0.3).astype(np.uint8), (rng.random(n2) < 0.3).astype(np.uint8)
+    ms, nm, _ = lm._match_mad_batch([(d1, d2)], 0.1, [(h1, h2)])
+    rn, rm = oracle.ref_line_match_mad(d1, d2, 0.1, h1, h2)
+    assert nm[0] == rn and np.array_equal(ms[0], rm)
