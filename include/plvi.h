@@ -336,7 +336,15 @@ int plvi_hamming256(plvi_matcher* m, const uint8_t* a, const uint8_t* b, int n, 
  *   mbCheckOrientation (rotation histogram + ComputeThreeMaxima);
  *   match_train [npairs][train_stride]: query index assigned to each train keypoint or
  *   -1 (CurrentFrame.mvpMapPoints / vnMatches21); match_query [npairs][query_stride]:
- *   train index per query or -1 (vnMatches12); nmatches [npairs]: the return value. */
+ *   train index per query or -1 (vnMatches12); nmatches [npairs]: the return value.
+ * PLVI_SEARCH_FRAME with check_orientation = 0 is also the search of
+ *   int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints,
+ *       vector<MapPoint*>& vpMatched, int th, float ratioHamming) and its vpPointsKFs overload
+ *       (include/ORBmatcher.h:53-57, src/ORBmatcher.cc:473-704),
+ * which CLAIMS features while it iterates (vpMatched[idx] != NULL is skipped, :554-555; vpMatched[bestIdx] = pMP, :575):
+ * train_blocked = vpMatched[i] != NULL on entry, one query per surviving map point (u, v, radius = th *
+ * mvScaleFactors[nPredictedLevel], levels nPredictedLevel-1 .. nPredictedLevel, flags 0), th_dist = floor(TH_LOW *
+ * ratioHamming).  Pinned against the reference's compiled ORBmatcher.cc (tests/test_oracle_vs_ref_matchers.py). */
 int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_keypoint* train_keys,
                               const uint8_t* train_desc, const uint8_t* train_blocked,
                               const int* train_counts, int train_stride, const plvi_grid* grid,
@@ -402,10 +410,9 @@ int plvi_search_for_triangulation(plvi_matcher* m, int npairs, const plvi_keypoi
  *       vpReplacePoint) (include/ORBmatcher.h:79, src/ORBmatcher.cc:1612-1734: chi2 = 0, TH_LOW),
  *   int ORBmatcher::SearchBySim3(KeyFrame*, KeyFrame*, vector<MapPoint*>&, s12, R12, t12, th)
  *       (include/ORBmatcher.h:71, src/ORBmatcher.cc:1736-1960: once per direction, chi2 = 0, TH_HIGH; the mutual
- *       agreement test of :1944-1957 compares the two best_idx arrays),
- *   int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints,
- *       vector<MapPoint*>& vpMatched, int th, float ratioHamming) (include/ORBmatcher.h:53, src/ORBmatcher.cc:473-596:
- *       chi2 = 0, th_dist = TH_LOW * ratioHamming).
+ *       agreement test of :1944-1957 compares the two best_idx arrays).
+ * (SearchByProjection(KeyFrame*, Scw, ...) is NOT one of them: it claims features while iterating, see
+ * plvi_search_by_projection.)
  * The caller projects every candidate map point (u, v, radius = th * mvScaleFactors[nPredictedLevel], min_level =
  * nPredictedLevel - 1, max_level = nPredictedLevel, flags bit0 = skipped by the checks before the search); the
  * kernel enumerates KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:1200-1244), applies the level test, the optional

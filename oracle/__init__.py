@@ -789,3 +789,86 @@ def ref_orb_descriptor_distance(a, b):
     f = ref_orbmatcher_lib().plviref_orb_descriptor_distance
     f.argtypes = [C.c_void_p, C.c_void_p]
     return int(f(_p(a), _p(b)))
+
+
+def ref_search_frame(keys2, desc2, grid, bounds, scale_factors, keys1, uv, flags, qdesc, th, check_ori=True, blocked=None):
+    """The reference's ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=true) itself (src/ORBmatcher.cc:
+    1962-2178) with identity poses and map point i at (uv[i], 1) before a unit pinhole camera (its projection code then
+    yields uv[i] exactly).  bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY); flags bit0: no map point / outlier, bit1:
+    Observations() == 0.  Returns (nmatches, match_train)."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc2, qdesc = np.ascontiguousarray(desc2, np.uint8), np.ascontiguousarray(qdesc, np.uint8)
+    g, b = np.array(_grid_floats(grid), np.float32), np.array(bounds, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+    fl = np.ascontiguousarray(flags, np.int32)
+    blk = None if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+    mt = np.full(max(len(keys2), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_search_by_projection_frame
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+    n = f(_p(keys2), _p(desc2), len(keys2), _p(blk), _p(g), _p(b), _p(sf), len(sf), _p(keys1), len(keys1), _p(uv), _p(fl), _p(qdesc),
+          C.c_float(th), int(check_ori), _p(mt))
+    return n, mt[:len(keys2)]
+
+
+def ref_search_triangulation(keys1, desc1, mp1, fv1, keys2, desc2, mp2, fv2, F12, ep, sf2, sigma2_1, sigma2_2, coarse=False,
+                             check_ori=True):
+    """The reference's ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, false, bCoarse) itself
+    (src/ORBmatcher.cc:965-1206), monocular; epipole through its own pose arithmetic (identity rotations), F12 handed to
+    the stand-in camera's epipolar-line test.  Arguments / result as search_triangulation."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    mp1, mp2 = np.ascontiguousarray(mp1, np.uint8), np.ascontiguousarray(mp2, np.uint8)
+    a, fa = _fv_args(fv1)
+    b, fb = _fv_args(fv2)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    sf, s1, s2 = (np.ascontiguousarray(x, np.float32) for x in (sf2, sigma2_1, sigma2_2))
+    m = np.full(max(len(keys1), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_search_for_triangulation
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    n = f(_p(keys1), _p(desc1), _p(mp1), len(keys1), *fa, _p(keys2), _p(desc2), _p(mp2), len(keys2), *fb, _p(F), C.c_float(ep[0]),
+          C.c_float(ep[1]), _p(sf), _p(s1), _p(s2), len(sf), int(coarse), int(check_ori), _p(m))
+    return n, m[:len(keys1)]
+
+
+def _ref_projection_args(keys, desc, grid, bounds, scale_factors, uv, level, flags, qdesc):
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    desc, qdesc = np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(qdesc, np.uint8)
+    g, b = np.array(_grid_floats(grid), np.float32), np.array(bounds, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+    lv, fl = np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.int32)
+    return keys, desc, g, b, sf, uv, lv, fl, qdesc
+
+
+def ref_fuse(keys, desc, grid, bounds, scale_factors, inv_level_sigma2, uv, level, flags, qdesc, th=3.0, sim3=False):
+    """The reference's ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:1399-1610) or, sim3=True,
+    Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (:1612-1734) itself: identity pose, map point i at (uv[i], 1), predicted
+    level[i]; flags bit0 = isBad().  Returns (nFused, best_idx[nq])."""
+    keys, desc, g, b, sf, uv, lv, fl, qdesc = _ref_projection_args(keys, desc, grid, bounds, scale_factors, uv, level, flags, qdesc)
+    inv = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    bi = np.full(max(len(uv), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_fuse_sim3 if sim3 else ref_orbmatcher_lib().plviref_orb_fuse
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+    n = f(_p(keys), _p(desc), len(keys), _p(g), _p(b), _p(sf), _p(inv), len(sf), _p(uv), _p(lv), _p(fl), _p(qdesc), len(uv),
+          C.c_float(th), _p(bi))
+    return n, bi[:len(uv)]
+
+
+def ref_search_by_projection_kf(keys, desc, grid, bounds, scale_factors, uv, level, flags, qdesc, th, ratio_hamming=1.0,
+                                matched_in=None):
+    """The reference's ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) itself
+    (src/ORBmatcher.cc:473-586), Scw = identity.  Returns (nmatches, match_train[n])."""
+    keys, desc, g, b, sf, uv, lv, fl, qdesc = _ref_projection_args(keys, desc, grid, bounds, scale_factors, uv, level, flags, qdesc)
+    mi = None if matched_in is None else np.ascontiguousarray(matched_in, np.uint8)
+    mt = np.full(max(len(keys), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_search_by_projection_kf
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    n = f(_p(keys), _p(desc), len(keys), _p(mi), _p(g), _p(b), _p(sf), len(sf), _p(uv), _p(lv), _p(fl), _p(qdesc), len(uv), int(th),
+          C.c_float(ratio_hamming), _p(mt))
+    return n, mt[:len(keys)]

@@ -726,9 +726,17 @@ template <typename... A> static inline void compare(A&&...) { cvmini_unreachable
 enum { THRESH_BINARY = 0, THRESH_TOZERO = 3 };
 enum { CMP_EQ = 0, CMP_GT = 1, CMP_GE = 2, CMP_LT = 3, CMP_LE = 4, CMP_NE = 5 };
 static inline Mat abs(const Mat&) { cvmini_unreachable("abs(Mat)"); }
-static inline Mat operator/(const Mat&, double) { cvmini_unreachable("Mat / scalar"); }
+static inline Mat operator/(const Mat& a, double d) {   // CV_32F only (pose arithmetic): element / d, rounded to float once
+  if (a.type() != CV_32FC1) cvmini_unreachable("Mat / scalar other than CV_32F");
+  Mat c(a.rows, a.cols, CV_32FC1);
+  for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) c.at<float>(i, j) = (float)((double)a.at<float>(i, j) / d);
+  return c;
+}
 static inline Mat operator*(double, const Mat&) { cvmini_unreachable("scalar * Mat"); }
-static inline double norm(const Mat&, int = NORM_L2) { cvmini_unreachable("norm(Mat)"); }
+static inline double norm(const Mat& a, int t = NORM_L2) {   // CV_32F L2 only (pose arithmetic), double accumulation
+  if (a.type() != CV_32FC1 || t != NORM_L2) cvmini_unreachable("norm(Mat) other than CV_32F L2");
+  return std::sqrt(a.dot(a));
+}
 static inline double norm(const Mat&, const Mat&, int = NORM_L2) { cvmini_unreachable("norm(Mat, Mat)"); }
 template <typename T> struct MatCommaInitializer_ {   // (Mat_<T>(r, c) << a, b, ...)
   Mat_<T> m;

@@ -76,14 +76,19 @@ class MapPoint {
   bool isBad() { return mBad; }
   int Observations() { return mObs; }
   cv::Mat GetWorldPos() { return mWorldPos; }
-  cv::Mat GetNormal() { cvmini_unreachable("MapPoint::GetNormal"); }
-  float GetMaxDistanceInvariance() { cvmini_unreachable("MapPoint"); }
-  float GetMinDistanceInvariance() { cvmini_unreachable("MapPoint"); }
-  int PredictScale(const float&, KeyFrame*) { cvmini_unreachable("MapPoint"); }
-  int PredictScale(const float&, Frame*) { cvmini_unreachable("MapPoint"); }
-  bool IsInKeyFrame(KeyFrame*) { cvmini_unreachable("MapPoint"); }
-  void Replace(MapPoint*) { cvmini_unreachable("MapPoint"); }
-  void AddObservation(KeyFrame*, int) { cvmini_unreachable("MapPoint"); }
+  // Fuse / SearchByProjection(KF, Scw): the checks before the search read these; the glue sets them so that every
+  // point passes (the oracle / CUDA boundary starts after those checks); the bookkeeping after a hit is recorded, not applied
+  cv::Mat mNormal;
+  float mMaxDist = 1e30f, mMinDist = 0.0f;
+  int mnPredLevel = 0, mFusedIdx = -1;
+  cv::Mat GetNormal() { return mNormal; }
+  float GetMaxDistanceInvariance() { return mMaxDist; }
+  float GetMinDistanceInvariance() { return mMinDist; }
+  int PredictScale(const float&, KeyFrame*) { return mnPredLevel; }
+  int PredictScale(const float&, Frame*) { return mnPredLevel; }
+  bool IsInKeyFrame(KeyFrame*) { return false; }
+  void Replace(MapPoint*) { cvmini_unreachable("MapPoint::Replace"); }
+  void AddObservation(KeyFrame*, int idx) { mFusedIdx = idx; }
   std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { cvmini_unreachable("MapPoint"); }
 };
 
@@ -132,9 +137,15 @@ class KeyFrame {
   long unsigned int mnId = 0;
   std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
   MapPoint* GetMapPoint(const size_t& i) { return mvpMapPoints[i]; }
-  std::set<MapPoint*> GetMapPoints() { cvmini_unreachable("KeyFrame::GetMapPoints"); }
-  std::vector<size_t> GetFeaturesInArea(const float&, const float&, const float&, const bool = false) const {
-    cvmini_unreachable("KeyFrame::GetFeaturesInArea");
+  std::set<MapPoint*> GetMapPoints() { return std::set<MapPoint*>(); }
+  const void* grid = nullptr;   // plvio_grid_create over mvKeysUn
+  // KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:1200-1244) = the cell walk and radius test of the Frame version without
+  // a level test: the oracle's restatement with minLevel = maxLevel = -1
+  std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const {
+    if (bRight) cvmini_unreachable("KeyFrame::GetFeaturesInArea(bRight)");
+    std::vector<int> tmp(N > 0 ? N : 1);
+    const int k = plvio_grid_features_in_area(grid, x, y, r, -1, -1, tmp.data(), (int)tmp.size());
+    return std::vector<size_t>(tmp.begin(), tmp.begin() + k);
   }
   bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
   cv::Mat mRcw, mtcw, mOw;   // 3x3, 3x1, 3x1 CV_32F
@@ -150,7 +161,7 @@ class KeyFrame {
   cv::Mat GetRightTranslation() { cvmini_unreachable("KeyFrame"); }
   cv::Mat GetRelativePoseTrl() { cvmini_unreachable("KeyFrame"); }
   cv::Mat GetRelativePoseTlr() { cvmini_unreachable("KeyFrame"); }
-  void AddMapPoint(MapPoint*, const size_t&) { cvmini_unreachable("KeyFrame"); }
+  void AddMapPoint(MapPoint*, const size_t&) {}   // recorded on the map point (AddObservation), not applied
 };
 
 }  // namespace ORB_SLAM3

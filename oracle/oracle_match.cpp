@@ -551,8 +551,9 @@ extern "C" int plvio_search_triangulation(const plvio::Kp* keys1, const uint8_t*
 
 
 // The per-map-point search shared by ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:1399-1610),
-// Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (:1612-1734), SearchBySim3 (:1736-1960, both directions) and
-// SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th, ratioHamming) (:473-596): the point is projected by the
+// Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (:1612-1734) and SearchBySim3 (:1736-1960, both directions)
+// [NOT SearchByProjection(KeyFrame*, Scw, ...) (:473-704): that one skips vpMatched[idx] != NULL and claims
+// vpMatched[bestIdx] while iterating = plvio_search_frame without the rotation check]: the point is projected by the
 // host (u, v, radius = th * mvScaleFactors[nPredictedLevel], levels nPredictedLevel-1 .. nPredictedLevel);
 // candidates = KeyFrame::GetFeaturesInArea(u, v, radius) (src/KeyFrame.cc:1200-1244) with the level test applied in
 // the loop; optional mono reprojection gate  e2 * mvInvLevelSigma2[kpLevel] > chi2  (Fuse: 5.99, :1546-1552;

@@ -1,8 +1,11 @@
 // TEST INFRASTRUCTURE -- C entry points over the reference's ORBmatcher (src/ORBmatcher.cc compiled unmodified with
 // cvmini/slam_mock_orb.h force-included in place of Frame.h / KeyFrame.h / MapPoint.h; oracle/Makefile.ref).
-// Called: SearchByProjection(F, vpMapPoints, th), SearchForInitialization, SearchByBoW(KF, F), SearchByBoW(KF, KF)
-// (and through them DescriptorDistance, RadiusByViewingCos, ComputeThreeMaxima).  The other overloads need pose /
-// camera arithmetic on cv::Mat, which the stand-in does not implement; they compile and are never reached.
+// Called: SearchByProjection(F, vpMapPoints, th), SearchByProjection(CurrentFrame, LastFrame, th, bMono),
+// SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming), SearchForInitialization, SearchByBoW(KF, F),
+// SearchByBoW(KF, KF), SearchForTriangulation, Fuse (both overloads) -- and through them DescriptorDistance,
+// RadiusByViewingCos, ComputeThreeMaxima.  Pose arithmetic runs on the stand-in's small CV_32F algebra with identity
+// poses (every product exact; the oracle / CUDA boundary starts at the projected point).  Not called: SearchBySim3, the
+// relocalisation overload SearchByProjection(F, pKF, sAlreadyFound, ...), the stereo / two-camera branches.
 // Compiled with the same -include so that it sees the same stand-in classes as ORBmatcher.cc.
 #include <cstring>
 #include <vector>
@@ -262,6 +265,99 @@ extern "C" int plviref_orb_search_for_triangulation(const cv::KeyPoint* keys1, c
   const int k = matcher.SearchForTriangulation(&K1, &K2, F, pairs, false, coarse != 0);
   for (int i = 0; i < n1; i++) matches12[i] = -1;
   for (auto& p : pairs) matches12[p.first] = (int)p.second;
+  return k;
+}
+
+namespace {
+// keyframe + map points of the projection searches: identity pose, unit pinhole, map point i at (uv[i], 1) with its
+// normal along PO (PO . Pn = |PO|^2 >= 0.5 |PO|), unbounded distance invariance, PredictScale = level[i]: every point
+// passes the checks before the search, and the reference's own projection yields uv[i] exactly
+void fill_projection_case(KeyFrame& K, GeometricCamera& cam, const cv::KeyPoint* keys, const unsigned char* desc, int n,
+                          const float* bounds, const float* scale_factors, const float* inv_sigma2, int nlevels,
+                          std::vector<MapPoint>& mps, const float* uv, const int* level, const int* flags, const unsigned char* qdesc) {
+  K.N = n;
+  K.mvKeysUn = K.mvKeys = key_vec(keys, n);
+  K.mDescriptors = desc_mat(desc, n);
+  K.mvuRight.assign(n, -1.0f);
+  K.mvpMapPoints.assign(n, nullptr);
+  K.mnMinX = bounds[0]; K.mnMaxX = bounds[1]; K.mnMinY = bounds[2]; K.mnMaxY = bounds[3];
+  K.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+  K.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + nlevels);
+  K.mpCamera = &cam;
+  K.mRcw = eye_f32(3);
+  K.mtcw = vec3_f32(0, 0, 0);
+  K.mOw = vec3_f32(0, 0, 0);
+  K.fx = K.fy = 1; K.cx = K.cy = 0; K.mbf = 0;
+  for (size_t i = 0; i < mps.size(); i++) {
+    MapPoint& m = mps[i];
+    m.mnId = i;
+    m.mBad = (flags[i] & 1) != 0;
+    m.mWorldPos = vec3_f32(uv[2 * i], uv[2 * i + 1], 1.0f);
+    m.mNormal = m.mWorldPos.clone();   // PO . Pn = |PO|^2 >= 0.5 |PO| (|PO| >= 1)
+    m.mnPredLevel = level[i];
+    m.mDesc = desc_mat(qdesc + 32 * i, 1);
+  }
+}
+}  // namespace
+
+// ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = false) (src/ORBmatcher.cc:1399-1610), monocular keyframe.
+// flags bit0: isBad().  best_idx[i] = keyframe feature the reference fused map point i with (AddObservation), or -1.
+extern "C" int plviref_orb_fuse(const cv::KeyPoint* keys, const unsigned char* desc, int n, const float* grid, const float* bounds,
+                                const float* scale_factors, const float* inv_sigma2, int nlevels, const float* uv, const int* level,
+                                const int* flags, const unsigned char* qdesc, int nq, float th, int* best_idx) {
+  GeometricCamera cam;
+  KeyFrame K;
+  std::vector<MapPoint> mps(nq);
+  fill_projection_case(K, cam, keys, desc, n, bounds, scale_factors, inv_sigma2, nlevels, mps, uv, level, flags, qdesc);
+  GridOwner go(keys, n, grid);
+  K.grid = go.g;
+  std::vector<MapPoint*> ptrs(nq);
+  for (int i = 0; i < nq; i++) ptrs[i] = &mps[i];
+  ORBmatcher matcher(0.6f, true);
+  const int k = matcher.Fuse(&K, ptrs, th, false);
+  for (int i = 0; i < nq; i++) best_idx[i] = mps[i].mFusedIdx;
+  return k;
+}
+
+// ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:1612-1734), Scw = identity.
+extern "C" int plviref_orb_fuse_sim3(const cv::KeyPoint* keys, const unsigned char* desc, int n, const float* grid, const float* bounds,
+                                     const float* scale_factors, const float* inv_sigma2, int nlevels, const float* uv,
+                                     const int* level, const int* flags, const unsigned char* qdesc, int nq, float th, int* best_idx) {
+  GeometricCamera cam;
+  KeyFrame K;
+  std::vector<MapPoint> mps(nq);
+  fill_projection_case(K, cam, keys, desc, n, bounds, scale_factors, inv_sigma2, nlevels, mps, uv, level, flags, qdesc);
+  GridOwner go(keys, n, grid);
+  K.grid = go.g;
+  std::vector<MapPoint*> ptrs(nq), repl(nq, nullptr);
+  for (int i = 0; i < nq; i++) ptrs[i] = &mps[i];
+  ORBmatcher matcher(0.6f, true);
+  const int k = matcher.Fuse(&K, eye_f32(4), ptrs, th, repl);
+  for (int i = 0; i < nq; i++) best_idx[i] = mps[i].mFusedIdx;
+  return k;
+}
+
+// ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (src/ORBmatcher.cc:473-586), Scw =
+// identity.  matched_in[i] != 0: vpMatched[i] already holds a point on entry (a point not among vpPoints).
+// match_train[i] = index of the point of vpPoints assigned to feature i by this call, or -1.
+extern "C" int plviref_orb_search_by_projection_kf(const cv::KeyPoint* keys, const unsigned char* desc, int n, const unsigned char* matched_in,
+                                                    const float* grid, const float* bounds, const float* scale_factors, int nlevels,
+                                                    const float* uv, const int* level, const int* flags, const unsigned char* qdesc,
+                                                    int nq, int th, float ratio_hamming, int* match_train) {
+  GeometricCamera cam;
+  KeyFrame K;
+  std::vector<MapPoint> mps(nq);
+  std::vector<float> inv(nlevels, 1.0f);
+  fill_projection_case(K, cam, keys, desc, n, bounds, scale_factors, inv.data(), nlevels, mps, uv, level, flags, qdesc);
+  GridOwner go(keys, n, grid);
+  K.grid = go.g;
+  MapPoint old;
+  std::vector<MapPoint*> ptrs(nq), matched(n, nullptr);
+  for (int i = 0; i < nq; i++) ptrs[i] = &mps[i];
+  for (int i = 0; i < n; i++) if (matched_in && matched_in[i]) matched[i] = &old;
+  ORBmatcher matcher(0.75f, true);
+  const int k = matcher.SearchByProjection(&K, eye_f32(4), ptrs, matched, th, ratio_hamming);
+  for (int i = 0; i < n; i++) match_train[i] = (matched[i] && matched[i] != &old) ? (int)matched[i]->mnId : -1;
   return k;
 }
 

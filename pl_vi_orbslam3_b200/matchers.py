@@ -116,6 +116,19 @@ class ORBmatcher(_Matcher):
         mt, mq, nm, _ = self.search_batch(mode, [CurrentFrame], [queries], [qdesc], self.TH_HIGH)
         return int(nm[0]), mt[0], mq[0]
 
+    def SearchByProjection_KF(self, KF, queries, qdesc, ratioHamming=1.0):
+        """Search of SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th, ratioHamming) and its
+        vpPointsKFs overload (src/ORBmatcher.cc:473-704): the reference skips vpMatched[idx] != NULL and claims
+        vpMatched[bestIdx] while it iterates, i.e. the sequential frame search without the rotation check.
+        KF.blocked = vpMatched[i] != NULL on entry; queries: u, v, radius = th * mvScaleFactors[nPredictedLevel],
+        levels nPredictedLevel-1 .. nPredictedLevel.  Returns (nmatches, match_train, match_query)."""
+        ori, self.mbCheckOrientation = self.mbCheckOrientation, False
+        try:
+            mt, mq, nm, _ = self.search_batch(0, [KF], [queries], [qdesc], int(np.floor(self.TH_LOW * ratioHamming)))
+        finally:
+            self.mbCheckOrientation = ori
+        return int(nm[0]), mt[0], mq[0]
+
     def SearchByBoW(self, F, group_items, queries, qdesc):
         """Descriptor part of SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:269-471).
         group_items: int32 frame feature indices grouped by vocabulary node; queries: QUERY_DTYPE with
@@ -189,8 +202,8 @@ class ORBmatcher(_Matcher):
 
     def SearchInRadius(self, KF, queries, qdesc, inv_level_sigma2, chi2=5.99, th_dist=None):
         """The per-map-point search of Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:1399-1610; chi2 = 5.99, TH_LOW),
-        Fuse(pKF, Scw, ...) (:1612; chi2 = 0), SearchBySim3 (:1736; chi2 = 0, TH_HIGH, once per direction) and
-        SearchByProjection(pKF, Scw, ...) (:473; chi2 = 0, TH_LOW * ratioHamming).  queries: one per projected map point
+        Fuse(pKF, Scw, ...) (:1612; chi2 = 0), SearchBySim3 (:1736; chi2 = 0, TH_HIGH, once per direction)
+        [SearchByProjection(pKF, Scw, ...) claims features while iterating: SearchByProjection_KF].  queries: one per projected map point
         (u, v, radius, min_level = nPredictedLevel - 1, max_level = nPredictedLevel, flags bit0 = skipped).
         Returns (nfound, best_idx, best_dist)."""
         import torch

@@ -4,7 +4,10 @@ oracle/_ref/libplvi_ref_orbmatcher.so = ORBmatcher.cc compiled unmodified, where
 KeyFrame / MapPoint of oracle/cvmini/slam_mock_orb.h force-included in place of the reference's headers (which need
 DBoW2's vocabulary, g2o, Sophus, boost, the Atlas).  The stand-ins carry plain data; Frame::GetFeaturesInArea
 (Frame.cc, not compilable for the same reason) is the oracle's restatement.  Called: SearchByProjection(F,
-vpMapPoints, th), SearchForInitialization, SearchByBoW(KF, F), SearchByBoW(KF, KF), DescriptorDistance.
+vpMapPoints, th), SearchByProjection(CurrentFrame, LastFrame), SearchByProjection(pKF, Scw, ...), SearchForInitialization,
+SearchByBoW(KF, F), SearchByBoW(KF, KF), SearchForTriangulation, Fuse (both overloads), DescriptorDistance.  The oracle /
+CUDA boundary starts at the projected point: poses are the identity and map points sit at (u, v, 1) before a unit
+pinhole camera, so that the reference's own pose and projection arithmetic is exact.
 
 Bar: bit-exact (match tables and counts).  The committed outputs (tests/golden/ref_outputs.npz, tools/gen_golden_ref.py)
 run everywhere; the live tests run where the library exists.
@@ -162,6 +165,131 @@ def test_live_reference_orb_descriptor_distance(pair_features):
             oracle.hamming256(r1["descriptors"][i], r2["descriptors"][i])
 
 
+def frame_case(r1, r2, A, seed, th):
+    """SearchByProjection(CurrentFrame, LastFrame): last-frame points projected into the current frame by the warp."""
+    rng = np.random.RandomState(seed)
+    k = r1["keypoints"]
+    uv = np.stack([A[0, 0] * k["x"] + A[0, 1] * k["y"] + A[0, 2], A[1, 0] * k["x"] + A[1, 1] * k["y"] + A[1, 2]], 1).astype(np.float32)
+    flags = rng.choice([0, 0, 0, 0, 1, 2], len(k)).astype(np.int32)
+    blocked = (rng.rand(len(r2["keypoints"])) < 0.15).astype(np.uint8)
+    return dict(uv=uv, flags=flags, blocked=blocked, th=np.float32(th))
+
+
+BOUNDS = (0.0, 752.0, 0.0, 480.0)
+
+
+def frame_queries(r1, c):
+    """Caller side of SearchByProjection(CurrentFrame, LastFrame, th, true) (src/ORBmatcher.cc:1999-2023): points outside
+    the image bounds are dropped, radius = th * scale factor of the last octave, levels octave-1 .. octave+1."""
+    k = r1["keypoints"]
+    q = np.zeros(len(k), QUERY_DTYPE)
+    q["u"], q["v"] = c["uv"][:, 0], c["uv"][:, 1]
+    q["radius"] = (np.float32(c["th"]) * SCALES[k["octave"]]).astype(np.float32)
+    q["min_level"], q["max_level"] = k["octave"] - 1, k["octave"] + 1
+    q["angle"] = k["angle"]
+    outside = (q["u"] < BOUNDS[0]) | (q["u"] > BOUNDS[1]) | (q["v"] < BOUNDS[2]) | (q["v"] > BOUNDS[3])
+    q["flags"] = (c["flags"] & 2) | ((c["flags"] & 1) | outside)
+    return q
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,th,check_ori", [(0, 15.0, True), (1, 7.0, True), (2, 30.0, False), (3, 15.0, True)])
+def test_live_reference_search_by_projection_frame(pair_features, seed, th, check_ori):
+    r1, r2, A = pair_features
+    c = frame_case(r1, r2, A, seed, th)
+    n, mt = oracle.ref_search_frame(r2["keypoints"], r2["descriptors"], GRID, BOUNDS, SCALES, r1["keypoints"], c["uv"], c["flags"],
+                                    r1["descriptors"], th, check_ori, c["blocked"])
+    on, omt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, frame_queries(r1, c), r1["descriptors"], 100, check_ori,
+                                  c["blocked"])
+    assert n == on and np.array_equal(mt, omt)
+    assert n > 100
+
+
+def triangulation_case(r1, r2, k, L, levelsup, seed):
+    v = ORBVocabulary.random_tree(k=k, L=L, seed=k + 3)
+    rng = np.random.RandomState(seed)
+    fv1 = oracle.bow_transform(v.as_oracle_dict(), r1["descriptors"], levelsup)["fv"]
+    fv2 = oracle.bow_transform(v.as_oracle_dict(), r2["descriptors"], levelsup)["fv"]
+    mp1 = (rng.rand(len(r1["keypoints"])) < 0.4).astype(np.uint8)
+    mp2 = (rng.rand(len(r2["keypoints"])) < 0.4).astype(np.uint8)
+    F12 = (np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32) + rng.normal(0, 2e-4, (3, 3)).astype(np.float32)) * np.float32(rng.uniform(0.5, 3))
+    ep = (np.float32(rng.uniform(100, 600)), np.float32(rng.uniform(100, 400)))
+    sg2 = (SCALES * SCALES * np.float32(4.0 if seed == 3 else 1.0)).astype(np.float32)
+    return fv1, fv2, mp1, mp2, F12, ep, sg2
+
+
+@needs_ref
+@pytest.mark.parametrize("k,L,levelsup,coarse,seed", [(6, 3, 2, False, 0), (10, 4, 2, False, 1), (4, 2, 1, True, 2), (6, 3, 2, False, 3),
+                                                      (3, 2, 2, False, 4)])
+def test_live_reference_search_for_triangulation(pair_features, k, L, levelsup, coarse, seed):
+    r1, r2, _ = pair_features
+    fv1, fv2, mp1, mp2, F12, ep, sg2 = triangulation_case(r1, r2, k, L, levelsup, seed)
+    n, m = oracle.ref_search_triangulation(r1["keypoints"], r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2,
+                                           F12, ep, SCALES, sg2, sg2, coarse, True)
+    on, om = oracle.search_triangulation(r1["keypoints"], r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2,
+                                         F12, ep, SCALES, sg2, coarse, True)
+    assert n == on and np.array_equal(m, om)
+    if coarse:
+        assert n > 20
+
+
+INV_SIGMA2 = (np.float32(1.0) / (SCALES * SCALES)).astype(np.float32)
+
+
+def kf_case(r1, r2, A, seed, th):
+    """Fuse / SearchByProjection(KF, Scw): map points = frame-1 features projected into keyframe 2 by the warp (+ a
+    little noise so that the chi2 gate of Fuse bites), predicted level = their octave (+1 sometimes)."""
+    rng = np.random.RandomState(seed)
+    k = r1["keypoints"]
+    uv = np.stack([A[0, 0] * k["x"] + A[0, 1] * k["y"] + A[0, 2], A[1, 0] * k["x"] + A[1, 1] * k["y"] + A[1, 2]], 1)
+    uv = (uv + rng.normal(0, 1.0, uv.shape)).astype(np.float32)
+    level = np.minimum(k["octave"] + (rng.rand(len(k)) < 0.3), 7).astype(np.int32)
+    flags = (rng.rand(len(k)) < 0.1).astype(np.int32)
+    matched_in = (rng.rand(len(r2["keypoints"])) < 0.15).astype(np.uint8)
+    return dict(uv=uv, level=level, flags=flags, matched_in=matched_in, th=th)
+
+
+def kf_queries(c):
+    """Caller side of the keyframe projection searches (src/ORBmatcher.cc:1473-1505, 520-548): IsInImage (x >= min, x < max),
+    radius = th * scale factor of the predicted level, levels level-1 .. level."""
+    q = np.zeros(len(c["uv"]), QUERY_DTYPE)
+    q["u"], q["v"] = c["uv"][:, 0], c["uv"][:, 1]
+    q["radius"] = (np.float32(c["th"]) * SCALES[c["level"]]).astype(np.float32)
+    q["min_level"], q["max_level"] = c["level"] - 1, c["level"]
+    inside = (q["u"] >= BOUNDS[0]) & (q["u"] < BOUNDS[1]) & (q["v"] >= BOUNDS[2]) & (q["v"] < BOUNDS[3])
+    q["flags"] = (c["flags"] & 1) | ~inside
+    return q
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,th,sim3", [(0, 3.0, False), (1, 4.0, False), (2, 3.0, True), (3, 7.5, True)])
+def test_live_reference_fuse(pair_features, seed, th, sim3):
+    r1, r2, A = pair_features
+    c = kf_case(r1, r2, A, seed, th)
+    n, bi = oracle.ref_fuse(r2["keypoints"], r2["descriptors"], GRID, BOUNDS, SCALES, INV_SIGMA2, c["uv"], c["level"], c["flags"],
+                            r1["descriptors"], th, sim3)
+    on, obi, _ = oracle.search_in_radius(r2["keypoints"], r2["descriptors"], GRID, kf_queries(c), r1["descriptors"], INV_SIGMA2,
+                                         0.0 if sim3 else 5.99, 50)
+    assert n == on and np.array_equal(bi, obi)
+    assert n > 50
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,th,ratio", [(0, 8, 1.0), (1, 15, 1.5), (2, 30, 1.0), (3, 15, 0.8)])
+def test_live_reference_search_by_projection_keyframe(pair_features, seed, th, ratio):
+    """SearchByProjection(pKF, Scw, ...) CLAIMS features while it iterates (vpMatched[idx] != NULL is skipped,
+    src/ORBmatcher.cc:554-555, 575): it is the sequential search of search_frame without the rotation check, not the
+    independent per-point search of Fuse."""
+    r1, r2, A = pair_features
+    c = kf_case(r1, r2, A, seed, float(th))
+    n, mt = oracle.ref_search_by_projection_kf(r2["keypoints"], r2["descriptors"], GRID, BOUNDS, SCALES, c["uv"], c["level"], c["flags"],
+                                               r1["descriptors"], th, ratio, c["matched_in"])
+    on, omt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, kf_queries(c), r1["descriptors"], int(np.floor(50 * ratio)),
+                                  False, c["matched_in"])
+    assert n == on and np.array_equal(mt, omt)
+    assert n > 100
+
+
 # ---- committed outputs of the reference (run everywhere) -------------------------------------------------------------
 def test_oracle_equals_reference_orbmatcher_outputs(pair_features):
     r1, r2, A = pair_features
@@ -180,3 +308,17 @@ def test_oracle_equals_reference_orbmatcher_outputs(pair_features):
     assert n == int(R["orbmatch/bow_n"]) and np.array_equal(mt, R["orbmatch/bow"])
     n, m = oracle.search_bow_kfkf(k1, r1["descriptors"], mp1 == 1, fv1, r2["keypoints"], r2["descriptors"], mp2 == 1, fv2, 0.8, True)
     assert n == int(R["orbmatch/bowkf_n"]) and np.array_equal(m, R["orbmatch/bowkf"])
+    c = frame_case(r1, r2, A, 1, 7.0)
+    n, mt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, frame_queries(r1, c), r1["descriptors"], 100, True, c["blocked"])
+    assert n == int(R["orbmatch/frame_n"]) and np.array_equal(mt, R["orbmatch/frame"])
+    fv1, fv2, mp1, mp2, F12, ep, sg2 = triangulation_case(r1, r2, 6, 3, 2, 3)
+    n, m = oracle.search_triangulation(k1, r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2, F12, ep, SCALES, sg2,
+                                       False, True)
+    assert n == int(R["orbmatch/tri_n"]) and np.array_equal(m, R["orbmatch/tri"])
+    c = kf_case(r1, r2, A, 1, 4.0)
+    for key, chi2 in (("fuse", 5.99), ("fuse_sim3", 0.0)):
+        n, bi, _ = oracle.search_in_radius(r2["keypoints"], r2["descriptors"], GRID, kf_queries(c), r1["descriptors"], INV_SIGMA2, chi2, 50)
+        assert n == int(R[f"orbmatch/{key}_n"]) and np.array_equal(bi, R[f"orbmatch/{key}"])
+    c = kf_case(r1, r2, A, 1, 15.0)
+    n, mt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, kf_queries(c), r1["descriptors"], 75, False, c["matched_in"])
+    assert n == int(R["orbmatch/kf_n"]) and np.array_equal(mt, R["orbmatch/kf"])

@@ -146,3 +146,105 @@ def test_cuda_equals_live_reference_line_matcher(lm, seed):
     ms, nm, _ = lm._match_mad_batch([(d1, d2)], 0.1, [(h1, h2)])
     rn, rm = oracle.ref_line_match_mad(d1, d2, 0.1, h1, h2)
     assert nm[0] == rn and np.array_equal(ms[0], rm)
+
+
+# ---- the searches behind pose arithmetic (identity poses in the reference run, see test_oracle_vs_ref_matchers.py) ----
+def cuda_frame(om, r1, r2, c, ori):
+    om.mbCheckOrientation = ori
+    F = FrameView(r2["keypoints"], r2["descriptors"], GRID, c["blocked"])
+    n, mt, _ = om.SearchByProjection(F, T.frame_queries(r1, c), r1["descriptors"])
+    om.mbCheckOrientation = True
+    return n, mt
+
+
+def cuda_triangulation(om, r1, r2, fv1, fv2, mp1, mp2, F12, ep, sg2, coarse):
+    k1 = r1["keypoints"]
+    start2 = {int(nd): (int(fv2[1][i]), int(fv2[1][i + 1])) for i, nd in enumerate(fv2[0])}
+    order, rows = [], []
+    for i, nd in enumerate(fv1[0]):
+        if int(nd) not in start2:
+            continue
+        for idx1 in fv1[2][fv1[1][i]:fv1[1][i + 1]]:
+            if mp1[idx1]:
+                continue
+            order.append(int(idx1))
+            rows.append((k1["x"][idx1], k1["y"][idx1], start2[int(nd)][0], start2[int(nd)][1], k1["angle"][idx1]))
+    qs = np.zeros(len(rows), T.QUERY_DTYPE)
+    for j, (u, v, s, e, ang) in enumerate(rows):
+        qs[j]["u"], qs[j]["v"], qs[j]["min_level"], qs[j]["max_level"], qs[j]["angle"] = u, v, s, e, ang
+    n, mq = om.SearchForTriangulation(FrameView(r2["keypoints"], r2["descriptors"], GRID), mp2, np.asarray(fv2[2], np.int32), qs,
+                                      r1["descriptors"][order], F12, ep, SCALES, sg2, coarse)
+    got = np.full(len(k1), -1, np.int32)
+    got[np.array(order, np.int64)] = mq
+    return n, got
+
+
+def cuda_fuse(om, r2, c, qdesc, chi2):
+    n, bi, _ = om.SearchInRadius(FrameView(r2["keypoints"], r2["descriptors"], GRID), T.kf_queries(c), qdesc, T.INV_SIGMA2, chi2, 50)
+    return n, bi
+
+
+def cuda_kf(om, r2, c, qdesc, ratio):
+    KF = FrameView(r2["keypoints"], r2["descriptors"], GRID, c["matched_in"])
+    n, mt, _ = om.SearchByProjection_KF(KF, T.kf_queries(c), qdesc, ratio)
+    return n, mt
+
+
+def test_cuda_equals_reference_orbmatcher_outputs_projection(om, pair_features):
+    r1, r2, A = pair_features
+    k1 = r1["keypoints"]
+    n, mt = cuda_frame(om, r1, r2, T.frame_case(r1, r2, A, 1, 7.0), True)
+    assert n == int(R["orbmatch/frame_n"]) and np.array_equal(mt, R["orbmatch/frame"])
+    fv1, fv2, mp1, mp2, F12, ep, sg2 = T.triangulation_case(r1, r2, 6, 3, 2, 3)
+    n, m = cuda_triangulation(om, r1, r2, fv1, fv2, mp1, mp2, F12, ep, sg2, False)
+    assert n == int(R["orbmatch/tri_n"]) and np.array_equal(m, R["orbmatch/tri"])
+    c = T.kf_case(r1, r2, A, 1, 4.0)
+    for key, chi2 in (("fuse", 5.99), ("fuse_sim3", 0.0)):
+        n, bi = cuda_fuse(om, r2, c, r1["descriptors"], chi2)
+        assert n == int(R[f"orbmatch/{key}_n"]) and np.array_equal(bi, R[f"orbmatch/{key}"])
+    n, mt = cuda_kf(om, r2, T.kf_case(r1, r2, A, 1, 15.0), r1["descriptors"], 1.5)
+    assert n == int(R["orbmatch/kf_n"]) and np.array_equal(mt, R["orbmatch/kf"])
+
+
+@live
+@pytest.mark.parametrize("seed,th,ori", [(0, 15.0, True), (2, 30.0, False)])
+def test_cuda_equals_live_reference_search_by_projection_frame(om, pair_features, seed, th, ori):
+    r1, r2, A = pair_features
+    c = T.frame_case(r1, r2, A, seed, th)
+    n, mt = cuda_frame(om, r1, r2, c, ori)
+    rn, rmt = oracle.ref_search_frame(r2["keypoints"], r2["descriptors"], GRID, T.BOUNDS, SCALES, r1["keypoints"], c["uv"], c["flags"],
+                                      r1["descriptors"], th, ori, c["blocked"])
+    assert n == rn and np.array_equal(mt, rmt)
+
+
+@live
+@pytest.mark.parametrize("k,L,levelsup,coarse,seed", [(6, 3, 2, False, 0), (4, 2, 1, True, 2), (3, 2, 2, False, 4)])
+def test_cuda_equals_live_reference_search_for_triangulation(om, pair_features, k, L, levelsup, coarse, seed):
+    r1, r2, _ = pair_features
+    fv1, fv2, mp1, mp2, F12, ep, sg2 = T.triangulation_case(r1, r2, k, L, levelsup, seed)
+    n, m = cuda_triangulation(om, r1, r2, fv1, fv2, mp1, mp2, F12, ep, sg2, coarse)
+    rn, rm = oracle.ref_search_triangulation(r1["keypoints"], r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2,
+                                             F12, ep, SCALES, sg2, sg2, coarse, True)
+    assert n == rn and np.array_equal(m, rm)
+
+
+@live
+@pytest.mark.parametrize("seed,th,sim3", [(0, 3.0, False), (3, 7.5, True)])
+def test_cuda_equals_live_reference_fuse(om, pair_features, seed, th, sim3):
+    r1, r2, A = pair_features
+    c = T.kf_case(r1, r2, A, seed, th)
+    n, bi = cuda_fuse(om, r2, c, r1["descriptors"], 0.0 if sim3 else 5.99)
+    rn, rbi = oracle.ref_fuse(r2["keypoints"], r2["descriptors"], GRID, T.BOUNDS, SCALES, T.INV_SIGMA2, c["uv"], c["level"], c["flags"],
+                              r1["descriptors"], th, sim3)
+    assert n == rn and np.array_equal(bi, rbi)
+
+
+@live
+@pytest.mark.parametrize("seed,th,ratio", [(0, 8, 1.0), (1, 15, 1.5), (3, 15, 0.8)])
+def test_cuda_equals_live_reference_search_by_projection_keyframe(om, pair_features, seed, th, ratio):
+    r1, r2, A = pair_features
+    c = T.kf_case(r1, r2, A, seed, float(th))
+    n, mt = cuda_kf(om, r2, c, r1["descriptors"], ratio)
+    rn, rmt = oracle.ref_search_by_projection_kf(r2["keypoints"], r2["descriptors"], GRID, T.BOUNDS, SCALES, c["uv"], c["level"],
+                                                 c["flags"], r1["descriptors"], th, ratio, c["matched_in"])
+    assert n == rn and np.array_equal(mt, rmt)

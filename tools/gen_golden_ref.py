@@ -91,6 +91,26 @@ def main():
     out["orbmatch/bow_n"], out["orbmatch/bow"] = np.int32(n), mt
     n, m = oracle.ref_search_bow_kfkf(k1, r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2, 0.8, True)
     out["orbmatch/bowkf_n"], out["orbmatch/bowkf"] = np.int32(n), m
+    c = T.frame_case(r1, r2, A, 1, 7.0)
+    n, mt = oracle.ref_search_frame(r2["keypoints"], r2["descriptors"], T.GRID, T.BOUNDS, T.SCALES, k1, c["uv"], c["flags"], r1["descriptors"],
+                                    7.0, True, c["blocked"])
+    out["orbmatch/frame_n"], out["orbmatch/frame"] = np.int32(n), mt
+    fv1, fv2, mp1, mp2, F12, ep, sg2 = T.triangulation_case(r1, r2, 6, 3, 2, 3)
+    n, m = oracle.ref_search_triangulation(k1, r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], mp2, fv2, F12, ep, T.SCALES,
+                                           sg2, sg2, False, True)
+    out["orbmatch/tri_n"], out["orbmatch/tri"] = np.int32(n), m
+    c = T.kf_case(r1, r2, A, 1, 4.0)
+    n, bi = oracle.ref_fuse(r2["keypoints"], r2["descriptors"], T.GRID, T.BOUNDS, T.SCALES, T.INV_SIGMA2, c["uv"], c["level"], c["flags"],
+                            r1["descriptors"], 4.0, False)
+    out["orbmatch/fuse_n"], out["orbmatch/fuse"] = np.int32(n), bi
+    n, bi = oracle.ref_fuse(r2["keypoints"], r2["descriptors"], T.GRID, T.BOUNDS, T.SCALES, T.INV_SIGMA2, c["uv"], c["level"], c["flags"],
+                            r1["descriptors"], 4.0, True)
+    out["orbmatch/fuse_sim3_n"], out["orbmatch/fuse_sim3"] = np.int32(n), bi
+    c = T.kf_case(r1, r2, A, 1, 15.0)
+    n, mt = oracle.ref_search_by_projection_kf(r2["keypoints"], r2["descriptors"], T.GRID, T.BOUNDS, T.SCALES, c["uv"], c["level"],
+                                               c["flags"], r1["descriptors"], 15, 1.5, c["matched_in"])
+    out["orbmatch/kf_n"], out["orbmatch/kf"] = np.int32(n), mt
+    print("orbmatch2", out["orbmatch/frame_n"], out["orbmatch/tri_n"], out["orbmatch/fuse_n"], out["orbmatch/fuse_sim3_n"], out["orbmatch/kf_n"])
     print("orbmatch", out["orbmatch/mappoints_n"], out["orbmatch/init_n"], out["orbmatch/bow_n"], out["orbmatch/bowkf_n"])
     out["cases"] = np.array([f"{n}|{nf}|{lap[0]}|{lap[1]}|{lnf}" for n, nf, lap, lnf in CASES])
     np.savez_compressed(GOLD / "ref_outputs.npz", **out)
