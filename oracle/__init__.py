@@ -872,3 +872,21 @@ def ref_search_by_projection_kf(keys, desc, grid, bounds, scale_factors, uv, lev
     n = f(_p(keys), _p(desc), len(keys), _p(mi), _p(g), _p(b), _p(sf), len(sf), _p(uv), _p(lv), _p(fl), _p(qdesc), len(uv), int(th),
           C.c_float(ratio_hamming), _p(mt))
     return n, mt[:len(keys)]
+
+
+def ref_line_fuse(keylines, desc, bounds, scale_factors, queries, qdesc, flags=None, th=3.0):
+    """The reference's LineMatcher::Fuse(pKF, vpMapLines, th) itself (src/LineMatcher.cpp:373-485): identity pose, unit
+    pinhole, map line i with endpoints (u1, v1, 1) / (u2, v2, 1) and predicted level queries[i, 5] (queries[i, 4] is not
+    read: the reference computes radius = th * mvScaleFactors[level]); flags[i] != 0 = isBad().
+    Returns (nFused, best_idx[nq])."""
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    desc, qd = np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(qdesc, np.uint8)
+    q = np.ascontiguousarray(queries, np.float32).reshape(-1, 6)
+    b, sf = np.array(bounds, np.float32), np.ascontiguousarray(scale_factors, np.float32)
+    fl = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+    bi = np.full(max(len(q), 1), -1, np.int32)
+    f = ref_lib().plviref_line_fuse
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_float, C.c_void_p]
+    n = f(_p(kl), _p(desc), len(kl), _p(b), _p(sf), len(sf), _p(q), _p(fl), _p(qd), len(q), C.c_float(th), _p(bi))
+    return n, bi[:len(q)]

@@ -732,7 +732,12 @@ static inline Mat operator/(const Mat& a, double d) {   // CV_32F only (pose ari
   for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) c.at<float>(i, j) = (float)((double)a.at<float>(i, j) / d);
   return c;
 }
-static inline Mat operator*(double, const Mat&) { cvmini_unreachable("scalar * Mat"); }
+static inline Mat operator*(double d, const Mat& a) {   // CV_32F only (pose arithmetic): d * element, rounded to float once
+  if (a.type() != CV_32FC1) cvmini_unreachable("scalar * Mat other than CV_32F");
+  Mat c(a.rows, a.cols, CV_32FC1);
+  for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) c.at<float>(i, j) = (float)(d * (double)a.at<float>(i, j));
+  return c;
+}
 static inline double norm(const Mat& a, int t = NORM_L2) {   // CV_32F L2 only (pose arithmetic), double accumulation
   if (a.type() != CV_32FC1 || t != NORM_L2) cvmini_unreachable("norm(Mat) other than CV_32F L2");
   return std::sqrt(a.dot(a));

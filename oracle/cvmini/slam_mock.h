@@ -2,9 +2,10 @@
 // It is force-included (-include) ahead of the translation unit: it defines the include guards of Frame.h, KeyFrame.h,
 // MapPoint.h, MapLine.h and Converter.h (so the real headers, which pull in DBoW2 / g2o / Sophus / boost, are skipped)
 // and declares stand-ins carrying exactly the members LineMatcher.cpp touches.  Only the descriptor matchers
-// (matchNNR, match, SerachForInitialize, SearchForTriangulation, distance, DescriptorDistance) are called; the
-// projection-based functions compile against the stand-ins and are never reached.  lineDescriptorMAD (Frame.cc /
-// KeyFrame.cc, not compiled) forwards to the oracle's restatement.
+// (matchNNR, match, SerachForInitialize, SearchForTriangulation, distance, DescriptorDistance) and Fuse are called
+// (Fuse with an identity pose and a unit pinhole: its own projection arithmetic is then exact); SearchByProjection and
+// matchGrid compile against the stand-ins and are never reached.  lineDescriptorMAD and GetLinesInArea (Frame.cc /
+// KeyFrame.cc, not compiled) forward to the oracle's restatement.
 #pragma once
 #define FRAME_H
 #define KEYFRAME_H
@@ -22,6 +23,7 @@ using namespace std;
 using namespace cv;
 using namespace cv::line_descriptor;
 
+extern "C" int plvio_lines_in_area(const unsigned char* keylines, int n, float x1, float y1, float x2, float y2, float r, int* out);
 extern "C" void plvio_line_descriptor_mad(const int* d0, const int* d1, int n, double* nn_mad, double* nn12_mad);
 
 namespace ORB_SLAM3 {
@@ -40,18 +42,21 @@ class MapPoint {};
 
 class MapLine {
  public:
-  cv::Mat mDesc;
+  cv::Mat mDesc, mNormal;
+  Vector6d mWorldPos;
+  bool mBad = false;
+  int mnPredLevel = 0, mFusedIdx = -1;
   cv::Mat GetDescriptor() { return mDesc; }
-  Vector6d GetWorldPos() { cvmini_unreachable("MapLine::GetWorldPos"); }
-  bool isBad() { return false; }
+  Vector6d GetWorldPos() { return mWorldPos; }
+  bool isBad() { return mBad; }
   int Observations() { return 0; }
   void Replace(MapLine*) { cvmini_unreachable("MapLine::Replace"); }
-  void AddObservation(KeyFrame*, size_t) { cvmini_unreachable("MapLine::AddObservation"); }
-  float GetMaxDistanceInvariance() { cvmini_unreachable("MapLine"); }
-  float GetMinDistanceInvariance() { cvmini_unreachable("MapLine"); }
-  cv::Mat GetNormal() { cvmini_unreachable("MapLine"); }
-  int PredictScale(const float&, const float&) { cvmini_unreachable("MapLine"); }
-  int PredictScale(const float&, KeyFrame*) { cvmini_unreachable("MapLine"); }
+  void AddObservation(KeyFrame*, size_t idx) { mFusedIdx = (int)idx; }   // bookkeeping recorded, not applied
+  float GetMaxDistanceInvariance() { return 1e30f; }
+  float GetMinDistanceInvariance() { return 0.0f; }
+  cv::Mat GetNormal() { return mNormal; }
+  int PredictScale(const float&, const float&) { return mnPredLevel; }
+  int PredictScale(const float&, KeyFrame*) { return mnPredLevel; }
 };
 
 // Frame::lineDescriptorMAD / KeyFrame::lineDescriptorMAD (src/Frame.cc:1089-1113, src/KeyFrame.cc:411-435)
@@ -88,12 +93,19 @@ class KeyFrame {
     slam_mock_mad(matches, nn_mad, nn12_mad);
   }
   MapLine* GetMapLine(const size_t& i) { return i < mvpMapLines.size() ? mvpMapLines[i] : nullptr; }
-  cv::Mat GetRotation() { cvmini_unreachable("KeyFrame"); }
-  cv::Mat GetTranslation() { cvmini_unreachable("KeyFrame"); }
-  cv::Mat GetCameraCenter() { cvmini_unreachable("KeyFrame"); }
-  std::vector<size_t> GetLinesInArea(const float&, const float&, const float&, const float&, const float&, const int = -1,
-                                     const int = -1) const { cvmini_unreachable("KeyFrame::GetLinesInArea"); }
-  void AddMapLine(MapLine*, const size_t&) { cvmini_unreachable("KeyFrame"); }
+  cv::Mat mRcw, mtcw, mOw;   // 3x3, 3x1, 3x1 CV_32F
+  cv::Mat GetRotation() { return mRcw.clone(); }
+  cv::Mat GetTranslation() { return mtcw.clone(); }
+  cv::Mat GetCameraCenter() { return mOw.clone(); }
+  std::vector<size_t> GetLinesInArea(const float& x1, const float& y1, const float& x2, const float& y2, const float& r,
+                                     const int minLevel = -1, const int maxLevel = -1) const {
+    if (minLevel > 0 || maxLevel > 0) cvmini_unreachable("KeyFrame::GetLinesInArea with levels");
+    static_assert(sizeof(KeyLine) == 68, "KeyLine POD layout");
+    std::vector<int> tmp(mvKeys_Line.size() + 1);
+    const int k = plvio_lines_in_area((const unsigned char*)mvKeys_Line.data(), (int)mvKeys_Line.size(), x1, y1, x2, y2, r, tmp.data());
+    return std::vector<size_t>(tmp.begin(), tmp.begin() + k);
+  }
+  void AddMapLine(MapLine*, const size_t&) {}   // recorded on the map line (AddObservation), not applied
 };
 
 class Converter {

@@ -17,9 +17,16 @@
 //     outputs tests/golden/ref_outputs.npz): keypoints, descriptors, KeyLines, LBD bytes and line equations are
 //     byte-identical.  Host-libm float functions the reference calls (cosf, sinf, atan2f) are restated from
 //     glibc (namespace glibcm below) and equal the image's libm exhaustively.
-//  The searches (ORBmatcher.cc / LineMatcher.cpp / Frame.cc include the whole SLAM object graph: Frame, KeyFrame,
-//  MapPoint, g2o, Eigen, Sophus) cannot be compiled that way: they stay "parity unpinned" (line-by-line
-//  restatement, regression vectors only); see DESIGN.md section 2.
+//  3. The searches: src/ORBmatcher.cc and src/LineMatcher.cpp include the whole SLAM object graph (Frame, KeyFrame,
+//     MapPoint, g2o, Sophus, boost).  They are compiled unmodified with a force-included header that defines those
+//     headers' include guards and declares plain-data stand-ins (oracle/cvmini/slam_mock_orb.h, slam_mock.h), into
+//     oracle/_ref/libplvi_ref_orbmatcher.so and libplvi_ref.so; tests/test_oracle_vs_ref_matchers.py and
+//     test_oracle_vs_ref.py pin every search restated in oracle_match.cpp against them bit-exactly (identity poses:
+//     the oracle boundary starts at the projected point).  Frame.cc / KeyFrame.cc / MapPoint.cc cannot be compiled
+//     that way (their class definitions are the thing being replaced): GetFeaturesInArea, GetLinesInArea,
+//     lineDescriptorMAD are supplied to the compiled matchers by this restatement, and
+//     MapPoint::ComputeDistinctiveDescriptors / Frame::ComputeStereoMatches stay "parity unpinned" (line-by-line
+//     restatement, regression vectors only); see DESIGN.md section 2.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library.  The product (libplvi_cuda.so) never does.

@@ -597,6 +597,24 @@ extern "C" int plvio_search_in_radius(const plvio::Kp* keys, const uint8_t* desc
 // candidates = KeyFrame::GetLinesInArea(u1, v1, u2, v2, radius) (src/KeyFrame.cc:1170-1198: midpoint distance,
 // then the "slope - angle" test as written there), level in [nPredictedLevel - 1, nPredictedLevel], distance =
 // LineMatcher::DescriptorDistance (the >> 25 variant, :487-499), first smallest; accepted when <= th_low.
+// KeyFrame::GetLinesInArea(x1, y1, x2, y2, r) without level arguments (src/KeyFrame.cc:1170-1198) on 68-byte KeyLine
+// records, for the stand-in KeyFrame of oracle/cvmini/slam_mock.h (KeyFrame.cc needs the whole SLAM object graph).
+extern "C" int plvio_lines_in_area(const uint8_t* keylines, int n, float x1, float y1, float x2, float y2, float r, int* out) {
+  struct KL { float angle; int class_id; int octave; float pt_x, pt_y; float rest[12]; };
+  const KL* kl = reinterpret_cast<const KL*>(keylines);
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    const KL& keyLine = kl[i];
+    const float distance = (0.5 * (x1 + x2) - keyLine.pt_x) * (0.5 * (x1 + x2) - keyLine.pt_x) +
+                           (0.5 * (y1 + y2) - keyLine.pt_y) * (0.5 * (y1 + y2) - keyLine.pt_y);
+    if (distance > r * r) continue;
+    const float slope = (y1 - y2) / (x1 - x2) - keyLine.angle;
+    if (slope > r * 0.01) continue;
+    out[k++] = i;
+  }
+  return k;
+}
+
 // q: 6 floats per query = u1, v1, u2, v2, radius, nPredictedLevel (as float); flags[q] != 0 = skipped.
 // keylines: 68-byte KeyLine records (angle at offset 0, octave at 8, pt at 12/16).
 extern "C" int plvio_line_fuse_search(const uint8_t* keylines, const uint8_t* desc, int n, const float* q, const uint8_t* flags,

@@ -80,3 +80,43 @@ extern "C" int plviref_line_search_for_triangulation(const unsigned char* d1, in
 extern "C" int plviref_line_distance(const unsigned char* a, const unsigned char* b, int which) {
   return which ? LineMatcher::DescriptorDistance(desc_mat(a, 1), desc_mat(b, 1)) : LineMatcher::distance(desc_mat(a, 1), desc_mat(b, 1));
 }
+
+// LineMatcher::Fuse(pKF, vpMapLines, th) (src/LineMatcher.cpp:373-485): identity pose, fx = fy = 1, cx = cy = 0, map line i
+// with endpoints (u1, v1, 1) / (u2, v2, 1), its normal along OM, unbounded distance invariance, PredictScale = level:
+// every line passes the checks before the search and the reference's own projection yields the given endpoints
+// exactly.  q: 6 floats per line = u1, v1, u2, v2, (unused), level; flags[i] != 0: isBad().  bounds = {mnMinX, mnMaxX,
+// mnMinY, mnMaxY}.  best_idx[i] = keyline the reference fused map line i with (AddObservation), or -1.
+extern "C" int plviref_line_fuse(const unsigned char* keylines, const unsigned char* desc, int n, const float* bounds,
+                                 const float* scale_factors, int nlevels, const float* q, const unsigned char* flags,
+                                 const unsigned char* qdesc, int nq, float th, int* best_idx) {
+  ORB_SLAM3::KeyFrame K;
+  K.mvKeys_Line.resize(n);
+  memcpy((void*)K.mvKeys_Line.data(), keylines, (size_t)n * sizeof(KeyLine));
+  K.mDescriptors_l = desc_mat(desc, n);
+  K.mvpMapLines.assign(n, nullptr);
+  K.fx = K.fy = 1; K.cx = K.cy = 0; K.mbf = 0;
+  K.mnMinX = bounds[0]; K.mnMaxX = bounds[1]; K.mnMinY = bounds[2]; K.mnMaxY = bounds[3];
+  K.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+  K.mRcw = cv::Mat::zeros(3, 3, CV_32F);
+  for (int i = 0; i < 3; i++) K.mRcw.at<float>(i, i) = 1.0f;
+  K.mtcw = cv::Mat::zeros(3, 1, CV_32F);
+  K.mOw = cv::Mat::zeros(3, 1, CV_32F);
+  std::vector<ORB_SLAM3::MapLine> lines(nq);
+  std::vector<ORB_SLAM3::MapLine*> ptrs(nq);
+  for (int i = 0; i < nq; i++) {
+    ORB_SLAM3::MapLine& m = lines[i];
+    m.mBad = flags && flags[i];
+    const float* p = q + 6 * (size_t)i;
+    m.mWorldPos(0) = p[0]; m.mWorldPos(1) = p[1]; m.mWorldPos(2) = 1.0;
+    m.mWorldPos(3) = p[2]; m.mWorldPos(4) = p[3]; m.mWorldPos(5) = 1.0;
+    m.mNormal = cv::Mat(3, 1, CV_32F);   // along OM = midpoint - Ow:  OM . pn = |OM|^2 >= 0.5 |OM|  (|OM| >= 1)
+    m.mNormal.at<float>(0) = 0.5f * (p[0] + p[2]); m.mNormal.at<float>(1) = 0.5f * (p[1] + p[3]); m.mNormal.at<float>(2) = 1.0f;
+    m.mnPredLevel = (int)p[5];
+    m.mDesc = desc_mat(qdesc + 32 * (size_t)i, 1);
+    ptrs[i] = &m;
+  }
+  LineMatcher lm;
+  const int k = lm.Fuse(&K, ptrs, th);
+  for (int i = 0; i < nq; i++) best_idx[i] = lines[i].mFusedIdx;
+  return k;
+}

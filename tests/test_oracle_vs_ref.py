@@ -263,3 +263,53 @@ def test_oracle_equals_reference_line_matcher_outputs():
     h1, h2 = R["linematch/has1"], R["linematch/has2"]
     n, m, _ = oracle.line_match_mad(d1, d2, 0.1, h1, h2)
     assert n == int(R["linematch/tri_n"]) and np.array_equal(m, R["linematch/tri"])
+    kl, desc, sf, q, qd, bad = line_fuse_case(1, 8.0)
+    n, bi, _ = oracle.line_fuse_search(kl, desc, q, qd, line_fuse_flags(q, bad), 50)
+    assert n == int(R["linematch/fuse_n"]) and np.array_equal(bi, R["linematch/fuse"])
+
+
+def line_fuse_case(seed, th):
+    """Keylines + LBD descriptors of a synthetic frame and map lines = perturbed copies of them, projected endpoints
+    given directly (the reference runs with an identity pose and a unit pinhole, see oracle.ref_line_fuse)."""
+    rng = np.random.RandomState(seed)
+    r = oracle.line_extract(synth.frame_euroc(40 + seed))
+    kl, desc = r["keylines"], r["descriptors"]
+    nq = 300
+    src = rng.randint(0, len(kl), nq)
+    sf = np.array([1, 2, 4, 8], np.float32)
+    q = np.zeros((nq, 6), np.float32)
+    jit = rng.uniform(-6, 6, (nq, 4)).astype(np.float32)
+    q[:, 0] = kl["startPointX"][src] + jit[:, 0]
+    q[:, 1] = kl["startPointY"][src] + jit[:, 1]
+    q[:, 2] = kl["endPointX"][src] + jit[:, 2]
+    q[:, 3] = kl["endPointY"][src] + jit[:, 3]
+    q[::17, 2] = q[::17, 0]                      # vertical projections: x1 == x2 -> division by zero in the slope
+    q[:, 5] = kl["octave"][src] + rng.randint(0, 2, nq)
+    q[:, 4] = np.float32(th) * sf[q[:, 5].astype(np.int32)]   # radius = th * mvScaleFactors[nPredictedLevel]
+    qd = desc[src].copy()
+    qd ^= ((rng.rand(nq, 32) < 0.08) * rng.randint(0, 256, (nq, 32))).astype(np.uint8)
+    bad = (rng.rand(nq) < 0.1).astype(np.uint8)
+    return kl, desc, sf, q, qd, bad
+
+
+LINE_BOUNDS = (0.0, 752.0, 0.0, 480.0)
+
+
+def line_fuse_flags(q, bad):
+    """Caller side of LineMatcher::Fuse in front of the search (src/LineMatcher.cpp:414-429): both projected endpoints
+    must lie inside [mnMinX, mnMaxX] x [mnMinY, mnMaxY]."""
+    b = LINE_BOUNDS
+    out = (q[:, 0] < b[0]) | (q[:, 0] > b[1]) | (q[:, 1] < b[2]) | (q[:, 1] > b[3]) | \
+          (q[:, 2] < b[0]) | (q[:, 2] > b[1]) | (q[:, 3] < b[2]) | (q[:, 3] > b[3])
+    return (bad.astype(bool) | out).astype(np.uint8)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,th", [(0, 3.0), (1, 8.0), (2, 20.0), (3, 60.0)])
+def test_live_reference_line_fuse(seed, th):
+    kl, desc, sf, q, qd, bad = line_fuse_case(seed, th)
+    n, bi = oracle.ref_line_fuse(kl, desc, LINE_BOUNDS, sf, q, qd, bad, th)
+    on, obi, _ = oracle.line_fuse_search(kl, desc, q, qd, line_fuse_flags(q, bad), 50)
+    assert n == on and np.array_equal(bi, obi)
+    if th >= 8.0:
+        assert n > 20

@@ -9,6 +9,7 @@ import pytest
 import oracle
 from pl_vi_orbslam3_b200.matchers import FrameView, LineMatcher, ORBmatcher
 from test_oracle_vs_ref import frame
+import test_oracle_vs_ref as TL
 import test_oracle_vs_ref_matchers as T
 from test_oracle_vs_ref_matchers import GRID, R, SCALES, pair_features  # noqa: F401  (fixture)
 
@@ -88,6 +89,9 @@ def test_cuda_equals_reference_linematcher_outputs(lm):
     assert nm[0] == int(R["linematch/init_n"]) and np.array_equal(ms[0], R["linematch/init"])
     ms, nm, _ = lm._match_mad_batch([(d1, d2)], 0.1, [(R["linematch/has1"], R["linematch/has2"])])
     assert nm[0] == int(R["linematch/tri_n"]) and np.array_equal(ms[0], R["linematch/tri"])
+    kl, desc, sf, q, qd, bad = TL.line_fuse_case(1, 8.0)
+    n, bi, _ = lm.FuseSearch(kl, desc, q, qd, TL.line_fuse_flags(q, bad))
+    assert n == int(R["linematch/fuse_n"]) and np.array_equal(bi, R["linematch/fuse"])
 
 
 @live
@@ -248,3 +252,12 @@ def test_cuda_equals_live_reference_search_by_projection_keyframe(om, pair_featu
     rn, rmt = oracle.ref_search_by_projection_kf(r2["keypoints"], r2["descriptors"], GRID, T.BOUNDS, SCALES, c["uv"], c["level"],
                                                  c["flags"], r1["descriptors"], th, ratio, c["matched_in"])
     assert n == rn and np.array_equal(mt, rmt)
+
+
+@live
+@pytest.mark.parametrize("seed,th", [(0, 3.0), (2, 20.0), (3, 60.0)])
+def test_cuda_equals_live_reference_line_fuse(lm, seed, th):
+    kl, desc, sf, q, qd, bad = TL.line_fuse_case(seed, th)
+    n, bi, _ = lm.FuseSearch(kl, desc, q, qd, TL.line_fuse_flags(q, bad))
+    rn, rbi = oracle.ref_line_fuse(kl, desc, TL.LINE_BOUNDS, sf, q, qd, bad, th)
+    assert n == rn and np.array_equal(bi, rbi)

@@ -61,6 +61,7 @@ def main():
     out["bow/words"], out["bow/values"] = b["bow"]
     out["bow/fv_nodes"], out["bow/fv_start"], out["bow/fv_features"] = b["fv"]
     # LineMatcher.cpp of the reference (compiled with the stand-in SLAM classes) on the reference's own LBD descriptors
+    sys.path.insert(0, str(ROOT / "tests"))
     d1 = oracle.ref_line_extract(frame("synth_0"))["descriptors"]
     d2 = oracle.ref_line_extract(frame("synth_1"))["descriptors"]
     n, m = oracle.ref_line_match(d1, d2, 0.75, "match")
@@ -72,6 +73,11 @@ def main():
     n, m = oracle.ref_line_match_mad(d1, d2, 0.1, h1, h2)
     out["linematch/has1"], out["linematch/has2"] = h1, h2
     out["linematch/tri_n"], out["linematch/tri"] = np.int32(n), m
+    import test_oracle_vs_ref as TL
+    kl, desc, sf, q, qd, bad = TL.line_fuse_case(1, 8.0)
+    n, bi = oracle.ref_line_fuse(kl, desc, TL.LINE_BOUNDS, sf, q, qd, bad, 8.0)
+    out["linematch/fuse_n"], out["linematch/fuse"] = np.int32(n), bi
+    print("linefuse", n)
     print("linematch", len(d1), len(d2), out["linematch/match_n"], out["linematch/init_n"], out["linematch/tri_n"])
     # ORBmatcher.cc of the reference (compiled with the stand-in SLAM classes): the four searches on a warped frame pair
     sys.path.insert(0, str(ROOT / "tests"))
