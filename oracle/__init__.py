@@ -526,7 +526,9 @@ def search_triangulation(keys1, desc1, mp1, fv1, keys2, desc2, mp2, fv2, F12, ep
 # (oracle/Makefile.ref; built where /root/reference exists, shipped prebuilt to the GPU box)
 _REF_LIB = _DIR / "_ref" / "libplvi_ref.so"
 _REF_ORB_LIB = _DIR / "_ref" / "libplvi_ref_orbmatcher.so"   # ORBmatcher.cc (stand-in classes of its own, see Makefile.ref)
+_REF_MP_LIB = _DIR / "_ref" / "libplvi_ref_mappoint.so"     # MapPoint.cc + MapPoint.h over stand-in KeyFrame / Frame / Map
 _ref_orb = None
+_ref_mp = None
 REFERENCE_ROOT = Path(os.environ.get("PLVI_REFERENCE_ROOT", "/root/reference"))
 _ref = None
 
@@ -536,10 +538,11 @@ def ref_build(force: bool = False):
     if not (REFERENCE_ROOT / "src" / "ORBextractor.cc").exists():
         return _REF_LIB if _REF_LIB.exists() else None
     build()
-    srcs = [_DIR / "ref_glue.cpp", _DIR / "ref_glue_linematcher.cpp", _DIR / "ref_glue_orbmatcher.cpp", _DIR / "Makefile.ref",
+    srcs = [_DIR / "ref_glue.cpp", _DIR / "ref_glue_linematcher.cpp", _DIR / "ref_glue_orbmatcher.cpp", _DIR / "ref_glue_mappoint.cpp",
+            _DIR / "Makefile.ref",
             _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _DIR / "cvmini" / "slam_mock.h",
             _DIR / "cvmini" / "slam_mock_orb.h", _LIB]
-    stale = any((not t.exists()) or any(s.stat().st_mtime > t.stat().st_mtime for s in srcs) for t in (_REF_LIB, _REF_ORB_LIB))
+    stale = any((not t.exists()) or any(s.stat().st_mtime > t.stat().st_mtime for s in srcs) for t in (_REF_LIB, _REF_ORB_LIB, _REF_MP_LIB))
     if force or stale:
         subprocess.run(["make", "-C", str(_DIR), "-f", "Makefile.ref", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []),
                        check=True, capture_output=True)
@@ -890,3 +893,21 @@ def ref_line_fuse(keylines, desc, bounds, scale_factors, queries, qdesc, flags=N
                   C.c_float, C.c_void_p]
     n = f(_p(kl), _p(desc), len(kl), _p(b), _p(sf), len(sf), _p(q), _p(fl), _p(qd), len(q), C.c_float(th), _p(bi))
     return n, bi[:len(q)]
+
+
+def ref_distinctive_descriptor(desc, bad=None):
+    """The reference's MapPoint::ComputeDistinctiveDescriptors itself (src/MapPoint.cc:330-402; MapPoint.cc and MapPoint.h
+    compiled unmodified over stand-in KeyFrame / Frame / Map): observation i = feature 0 of keyframe i with descriptor
+    desc[i]; bad[i] = pKF->isBad().  Returns the chosen 32-byte descriptor, or None when the reference returns early."""
+    global _ref_mp
+    if _ref_mp is None:
+        if ref_build() is None or not _REF_MP_LIB.exists():
+            raise RuntimeError("oracle/_ref/libplvi_ref_mappoint.so is not built and /root/reference is absent")
+        lib()
+        _ref_mp = C.CDLL(str(_REF_MP_LIB))
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    b = None if bad is None else np.ascontiguousarray(bad, np.uint8)
+    out = np.zeros(32, np.uint8)
+    f = _ref_mp.plviref_distinctive_descriptor
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    return out if f(_p(desc), _p(b), len(desc), _p(out)) else None

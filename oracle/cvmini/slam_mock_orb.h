@@ -9,7 +9,12 @@
 #pragma once
 #define FRAME_H
 #define KEYFRAME_H
+#ifdef SLAM_MOCK_REAL_MAPPOINT   // libplvi_ref_mappoint.so: the reference's own MapPoint.h / MapPoint.cc over stand-in KeyFrame / Frame / Map
+#define MAP_H
+#include <mutex>
+#else
 #define MAPPOINT_H
+#endif
 #include <cmath>
 #include <map>
 #include <set>
@@ -27,6 +32,7 @@ using cv::cvmini_unreachable;
 class KeyFrame;
 class Frame;
 class MapPoint;
+class Map;
 
 // Stand-in pinhole camera.  project = Pinhole::project (src/CameraModels/Pinhole.cpp:27-39: fx * x / z + cx in float).
 // epipolarConstrain: Pinhole.cpp:135-157 builds F12 = K1^-T [t12]x R12 K2^-1 with cv::Mat products and a matrix inverse
@@ -61,6 +67,7 @@ class GeometricCamera {
 // Frame::GetFeaturesInArea forwards to the oracle's restatement (oracle_match.cpp: plvio_grid_*)
 extern "C" int plvio_grid_features_in_area(const void* g, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap);
 
+#ifndef SLAM_MOCK_REAL_MAPPOINT
 class MapPoint {
  public:
   // SearchByProjection(F, vpMapPoints) reads the projection cached by Frame::isInFrustum (src/Frame.cc:765-...)
@@ -92,6 +99,16 @@ class MapPoint {
   std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { cvmini_unreachable("MapPoint"); }
 };
 
+#else
+class Map {
+ public:
+  long unsigned int mnId = 0;
+  std::mutex mMutexPointCreation;
+  void EraseMapPoint(MapPoint*) {}
+  long unsigned int GetId() { return mnId; }
+};
+#endif
+
 class Frame {
  public:
   int N = 0, Nleft = -1, Nright = -1;
@@ -118,6 +135,11 @@ class Frame {
   }
   cv::Mat GetRelativePoseTrl() { cvmini_unreachable("Frame"); }
   cv::Mat GetRelativePoseTlr() { cvmini_unreachable("Frame"); }
+  // MapPoint.cc (only compiled into libplvi_ref_mappoint.so; never reached)
+  cv::Mat mRwc, mOw;
+  int mnScaleLevels = 0;
+  float mfLogScaleFactor = 0;
+  cv::Mat GetCameraCenter() { cvmini_unreachable("Frame::GetCameraCenter"); }
 };
 
 class KeyFrame {
@@ -162,6 +184,14 @@ class KeyFrame {
   cv::Mat GetRelativePoseTrl() { cvmini_unreachable("KeyFrame"); }
   cv::Mat GetRelativePoseTlr() { cvmini_unreachable("KeyFrame"); }
   void AddMapPoint(MapPoint*, const size_t&) {}   // recorded on the map point (AddObservation), not applied
+  // MapPoint.cc (only compiled into libplvi_ref_mappoint.so)
+  bool mBad = false;
+  long unsigned int mnFrameId = 0;
+  bool isBad() { return mBad; }
+  void EraseMapPointMatch(const int&) {}
+  void EraseMapPointMatch(MapPoint*) {}
+  void ReplaceMapPointMatch(const int&, MapPoint*) {}
+  Map* GetMap() { return nullptr; }
 };
 
 }  // namespace ORB_SLAM3

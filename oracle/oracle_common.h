@@ -24,9 +24,10 @@
 //     test_oracle_vs_ref.py pin every search restated in oracle_match.cpp against them bit-exactly (identity poses:
 //     the oracle boundary starts at the projected point).  Frame.cc / KeyFrame.cc / MapPoint.cc cannot be compiled
 //     that way (their class definitions are the thing being replaced): GetFeaturesInArea, GetLinesInArea,
-//     lineDescriptorMAD are supplied to the compiled matchers by this restatement, and
-//     MapPoint::ComputeDistinctiveDescriptors / Frame::ComputeStereoMatches stay "parity unpinned" (line-by-line
-//     restatement, regression vectors only); see DESIGN.md section 2.
+//     lineDescriptorMAD are supplied to the compiled matchers by this restatement.  MapPoint.cc + MapPoint.h compile
+//     unmodified over stand-in KeyFrame / Frame / Map (libplvi_ref_mappoint.so): ComputeDistinctiveDescriptors is
+//     pinned.  Frame::ComputeStereoMatches / UndistortKeyPoints / AssignFeaturesToGrid (Frame.cc) stay "parity
+//     unpinned" (line-by-line restatement, regression vectors only); see DESIGN.md section 2.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library.  The product (libplvi_cuda.so) never does.

@@ -322,3 +322,44 @@ def test_oracle_equals_reference_orbmatcher_outputs(pair_features):
     c = kf_case(r1, r2, A, 1, 15.0)
     n, mt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, kf_queries(c), r1["descriptors"], 75, False, c["matched_in"])
     assert n == int(R["orbmatch/kf_n"]) and np.array_equal(mt, R["orbmatch/kf"])
+
+
+# ---- MapPoint::ComputeDistinctiveDescriptors: the reference's own MapPoint.cc + MapPoint.h over stand-in KeyFrame / Map --
+def distinctive_case(seed, M=48, max_obs=40):
+    """M map points with 1..max_obs observed descriptors each: noisy copies of a base descriptor (ties are frequent: the
+    medians are small integers); every fifth point has identical observations."""
+    rng = np.random.RandomState(seed)
+    counts = rng.randint(1, max_obs + 1, M).astype(np.int32)
+    desc = np.zeros((M, max_obs, 32), np.uint8)
+    for p in range(M):
+        base = rng.randint(0, 256, 32).astype(np.uint8)
+        for i in range(counts[p]):
+            d = base.copy()
+            for bit in rng.permutation(256)[:rng.randint(0, 60)]:
+                d[bit // 8] ^= 1 << (bit % 8)
+            desc[p, i] = d
+        if p % 5 == 0:
+            desc[p, :counts[p]] = desc[p, 0]
+    return desc, counts
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_live_reference_distinctive_descriptors(seed):
+    desc, counts = distinctive_case(seed)
+    rng = np.random.RandomState(seed + 100)
+    for p in range(len(counts)):
+        d = desc[p, :counts[p]]
+        r = oracle.ref_distinctive_descriptor(d)
+        assert np.array_equal(r, d[oracle.distinctive_descriptor(d)])
+        bad = (rng.rand(len(d)) < 0.3).astype(np.uint8)       # observations from bad keyframes are left out
+        r = oracle.ref_distinctive_descriptor(d, bad)
+        good = d[bad == 0]
+        assert (r is None and len(good) == 0) or np.array_equal(r, good[oracle.distinctive_descriptor(good)])
+
+
+def test_oracle_equals_reference_distinctive_outputs():
+    desc, counts = distinctive_case(7)
+    for p in range(len(counts)):
+        d = desc[p, :counts[p]]
+        assert np.array_equal(d[oracle.distinctive_descriptor(d)], R["mappoint/distinctive"][p])

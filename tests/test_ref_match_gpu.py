@@ -261,3 +261,19 @@ def test_cuda_equals_live_reference_line_fuse(lm, seed, th):
     n, bi, _ = lm.FuseSearch(kl, desc, q, qd, TL.line_fuse_flags(q, bad))
     rn, rbi = oracle.ref_line_fuse(kl, desc, TL.LINE_BOUNDS, sf, q, qd, bad, th)
     assert n == rn and np.array_equal(bi, rbi)
+
+
+def test_cuda_equals_reference_distinctive_descriptors(gpu):
+    """plvi_distinctive_descriptors vs the reference's own MapPoint::ComputeDistinctiveDescriptors (committed outputs and,
+    where the library travelled, live)."""
+    import torch
+    from pl_vi_orbslam3_b200.matchers import compute_distinctive_descriptors
+    for seed, golden in ((7, True), (0, False), (2, False)):
+        desc, counts = T.distinctive_case(seed)
+        idx, best = compute_distinctive_descriptors(torch.from_numpy(desc).cuda(), torch.from_numpy(counts).cuda())
+        best = best.cpu().numpy()
+        if golden:
+            assert np.array_equal(best, R["mappoint/distinctive"])
+        elif oracle.ref_available():
+            for p in range(len(counts)):
+                assert np.array_equal(best[p], oracle.ref_distinctive_descriptor(desc[p, :counts[p]])), p

@@ -116,6 +116,8 @@ def main():
     n, mt = oracle.ref_search_by_projection_kf(r2["keypoints"], r2["descriptors"], T.GRID, T.BOUNDS, T.SCALES, c["uv"], c["level"],
                                                c["flags"], r1["descriptors"], 15, 1.5, c["matched_in"])
     out["orbmatch/kf_n"], out["orbmatch/kf"] = np.int32(n), mt
+    dd, dc = T.distinctive_case(7)
+    out["mappoint/distinctive"] = np.stack([oracle.ref_distinctive_descriptor(dd[p, :dc[p]]) for p in range(len(dc))])
     print("orbmatch2", out["orbmatch/frame_n"], out["orbmatch/tri_n"], out["orbmatch/fuse_n"], out["orbmatch/fuse_sim3_n"], out["orbmatch/kf_n"])
     print("orbmatch", out["orbmatch/mappoints_n"], out["orbmatch/init_n"], out["orbmatch/bow_n"], out["orbmatch/bowkf_n"])
     out["cases"] = np.array([f"{n}|{nf}|{lap[0]}|{lap[1]}|{lnf}" for n, nf, lap, lnf in CASES])
