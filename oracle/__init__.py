@@ -911,3 +911,23 @@ def ref_distinctive_descriptor(desc, bad=None):
     f = _ref_mp.plviref_distinctive_descriptor
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     return out if f(_p(desc), _p(b), len(desc), _p(out)) else None
+
+
+def ref_search_by_sim3(keys1, desc1, uv1, level1, flags1, keys2, desc2, uv2, level2, flags2, grid, bounds, scale_factors, th):
+    """The reference's ORBmatcher::SearchBySim3 itself (src/ORBmatcher.cc:1736-1960) with s12 = 1, R12 = I, t12 = 0 and
+    identity keyframe poses: the map point of feature i of keyframe A sits at (uvA[i], 1) and projects to uvA[i] in the
+    other keyframe, predicted level levelA[i].  flags bit0: no map point, bit1: isBad(), bit2 (keyframe 1): already in
+    vpMatches12.  Returns (nFound, matches12[n1])."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    uv1, uv2 = (np.ascontiguousarray(x, np.float32).reshape(-1, 2) for x in (uv1, uv2))
+    l1, l2, f1, f2 = (np.ascontiguousarray(x, np.int32) for x in (level1, level2, flags1, flags2))
+    g, b = np.array(_grid_floats(grid), np.float32), np.array(bounds, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    m = np.full(max(len(keys1), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_search_by_sim3
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+    n = f(_p(keys1), _p(desc1), len(keys1), _p(uv1), _p(l1), _p(f1), _p(keys2), _p(desc2), len(keys2), _p(uv2), _p(l2), _p(f2), _p(g),
+          _p(b), _p(sf), len(sf), C.c_float(th), _p(m))
+    return n, m[:len(keys1)]

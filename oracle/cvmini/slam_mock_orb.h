@@ -96,7 +96,7 @@ class MapPoint {
   bool IsInKeyFrame(KeyFrame*) { return false; }
   void Replace(MapPoint*) { cvmini_unreachable("MapPoint::Replace"); }
   void AddObservation(KeyFrame*, int idx) { mFusedIdx = idx; }
-  std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { cvmini_unreachable("MapPoint"); }
+  std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { return std::tuple<int, int>(-1, -1); }
 };
 
 #else

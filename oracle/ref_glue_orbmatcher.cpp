@@ -2,9 +2,9 @@
 // cvmini/slam_mock_orb.h force-included in place of Frame.h / KeyFrame.h / MapPoint.h; oracle/Makefile.ref).
 // Called: SearchByProjection(F, vpMapPoints, th), SearchByProjection(CurrentFrame, LastFrame, th, bMono),
 // SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming), SearchForInitialization, SearchByBoW(KF, F),
-// SearchByBoW(KF, KF), SearchForTriangulation, Fuse (both overloads) -- and through them DescriptorDistance,
+// SearchByBoW(KF, KF), SearchForTriangulation, Fuse (both overloads), SearchBySim3 -- and through them DescriptorDistance,
 // RadiusByViewingCos, ComputeThreeMaxima.  Pose arithmetic runs on the stand-in's small CV_32F algebra with identity
-// poses (every product exact; the oracle / CUDA boundary starts at the projected point).  Not called: SearchBySim3, the
+// poses (every product exact; the oracle / CUDA boundary starts at the projected point).  Not called: the
 // relocalisation overload SearchByProjection(F, pKF, sAlreadyFound, ...), the stereo / two-camera branches.
 // Compiled with the same -include so that it sees the same stand-in classes as ORBmatcher.cc.
 #include <cstring>
@@ -358,6 +358,42 @@ extern "C" int plviref_orb_search_by_projection_kf(const cv::KeyPoint* keys, con
   ORBmatcher matcher(0.75f, true);
   const int k = matcher.SearchByProjection(&K, eye_f32(4), ptrs, matched, th, ratio_hamming);
   for (int i = 0; i < n; i++) match_train[i] = (matched[i] && matched[i] != &old) ? (int)matched[i]->mnId : -1;
+  return k;
+}
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12 = 1, R12 = I, t12 = 0, th) (src/ORBmatcher.cc:1736-1960): both
+// keyframes at the identity pose with a unit pinhole; feature i of keyframe A owns a map point at (uvA[i], 1), which
+// the reference's own arithmetic projects to uvA[i] in the other keyframe; levelA[i] = its predicted level there;
+// flagsA bit0: no map point, bit1: isBad(), bit2 (keyframe 1 only): vpMatches12[i] already set on entry.
+// matches12[i1] = keyframe-2 feature whose map point the call stored in vpMatches12[i1], or -1.
+extern "C" int plviref_orb_search_by_sim3(const cv::KeyPoint* keys1, const unsigned char* desc1, int n1, const float* uv1, const int* level1,
+                                          const int* flags1, const cv::KeyPoint* keys2, const unsigned char* desc2, int n2,
+                                          const float* uv2, const int* level2, const int* flags2, const float* grid, const float* bounds,
+                                          const float* scale_factors, int nlevels, float th, int* matches12) {
+  GeometricCamera cam;
+  KeyFrame K1, K2;
+  std::vector<MapPoint> m1(n1), m2(n2);
+  std::vector<float> inv(nlevels, 1.0f);
+  fill_projection_case(K1, cam, keys1, desc1, n1, bounds, scale_factors, inv.data(), nlevels, m1, uv1, level1, flags1, desc1);
+  fill_projection_case(K2, cam, keys2, desc2, n2, bounds, scale_factors, inv.data(), nlevels, m2, uv2, level2, flags2, desc2);
+  GridOwner g1(keys1, n1, grid), g2(keys2, n2, grid);
+  K1.grid = g1.g;
+  K2.grid = g2.g;
+  MapPoint old;
+  std::vector<MapPoint*> out(n1, nullptr);
+  for (int i = 0; i < n1; i++) {
+    m1[i].mBad = (flags1[i] & 2) != 0;
+    if (!(flags1[i] & 1)) K1.mvpMapPoints[i] = &m1[i];
+    if (flags1[i] & 4) out[i] = &old;
+  }
+  for (int i = 0; i < n2; i++) {
+    m2[i].mBad = (flags2[i] & 2) != 0;
+    if (!(flags2[i] & 1)) K2.mvpMapPoints[i] = &m2[i];
+  }
+  ORBmatcher matcher(0.75f, true);
+  const float s12 = 1.0f;
+  const int k = matcher.SearchBySim3(&K1, &K2, out, s12, eye_f32(3), vec3_f32(0, 0, 0), th);
+  for (int i = 0; i < n1; i++) matches12[i] = (out[i] && out[i] != &old) ? (int)out[i]->mnId : -1;
   return k;
 }
 

@@ -5,7 +5,7 @@ KeyFrame / MapPoint of oracle/cvmini/slam_mock_orb.h force-included in place of 
 DBoW2's vocabulary, g2o, Sophus, boost, the Atlas).  The stand-ins carry plain data; Frame::GetFeaturesInArea
 (Frame.cc, not compilable for the same reason) is the oracle's restatement.  Called: SearchByProjection(F,
 vpMapPoints, th), SearchByProjection(CurrentFrame, LastFrame), SearchByProjection(pKF, Scw, ...), SearchForInitialization,
-SearchByBoW(KF, F), SearchByBoW(KF, KF), SearchForTriangulation, Fuse (both overloads), DescriptorDistance.  The oracle /
+SearchByBoW(KF, F), SearchByBoW(KF, KF), SearchForTriangulation, Fuse (both overloads), SearchBySim3, DescriptorDistance.  The oracle /
 CUDA boundary starts at the projected point: poses are the identity and map points sit at (u, v, 1) before a unit
 pinhole camera, so that the reference's own pose and projection arithmetic is exact.
 
@@ -290,6 +290,55 @@ def test_live_reference_search_by_projection_keyframe(pair_features, seed, th, r
     assert n > 100
 
 
+def sim3_case(r1, r2, A, seed):
+    """SearchBySim3: the map points of keyframe 1 projected into keyframe 2 by the warp, those of keyframe 2 into
+    keyframe 1 by its inverse (+ noise); some features without / with bad map points, some already matched."""
+    rng = np.random.RandomState(seed)
+    Ai = np.linalg.inv(np.vstack([A, [0, 0, 1]]))[:2]
+    out = []
+    for r, M in ((r1, A), (r2, Ai)):
+        k = r["keypoints"]
+        uv = np.stack([M[0, 0] * k["x"] + M[0, 1] * k["y"] + M[0, 2], M[1, 0] * k["x"] + M[1, 1] * k["y"] + M[1, 2]], 1)
+        uv = (uv + rng.normal(0, 0.7, uv.shape)).astype(np.float32)
+        level = np.minimum(k["octave"] + (rng.rand(len(k)) < 0.3), 7).astype(np.int32)
+        flags = ((rng.rand(len(k)) < 0.15) * 1 + (rng.rand(len(k)) < 0.05) * 2).astype(np.int32)
+        out.append((uv, level, flags))
+    out[0][2][:] |= ((rng.rand(len(r1["keypoints"])) < 0.05) * 4).astype(np.int32)
+    return out
+
+
+def sim3_queries(uv, level, flags, th):
+    """Caller side of one direction of SearchBySim3 (src/ORBmatcher.cc:1783-1825)."""
+    q = kf_queries(dict(uv=uv, level=level, flags=np.zeros(len(uv), np.int32), th=th))
+    q["flags"] |= (flags != 0)
+    return q
+
+
+def sim3_mutual(bi12, bi21):
+    """The agreement test of src/ORBmatcher.cc:1944-1957 on the two best-index arrays."""
+    m = np.full(len(bi12), -1, np.int32)
+    ok = bi12 >= 0
+    ok[ok] = bi21[bi12[ok]] == np.nonzero(ok)[0]
+    m[ok] = bi12[ok]
+    return int(ok.sum()), m
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,th", [(0, 7.5), (1, 3.0), (2, 15.0)])
+def test_live_reference_search_by_sim3(pair_features, seed, th):
+    r1, r2, A = pair_features
+    (uv1, l1, f1), (uv2, l2, f2) = sim3_case(r1, r2, A, seed)
+    n, m = oracle.ref_search_by_sim3(r1["keypoints"], r1["descriptors"], uv1, l1, f1, r2["keypoints"], r2["descriptors"], uv2, l2, f2,
+                                     GRID, BOUNDS, SCALES, th)
+    _, bi12, _ = oracle.search_in_radius(r2["keypoints"], r2["descriptors"], GRID, sim3_queries(uv1, l1, f1, th), r1["descriptors"],
+                                         INV_SIGMA2, 0.0, 100)
+    _, bi21, _ = oracle.search_in_radius(r1["keypoints"], r1["descriptors"], GRID, sim3_queries(uv2, l2, f2, th), r2["descriptors"],
+                                         INV_SIGMA2, 0.0, 100)
+    on, om = sim3_mutual(bi12, bi21)
+    assert n == on and np.array_equal(m, om)
+    assert n > 100
+
+
 # ---- committed outputs of the reference (run everywhere) -------------------------------------------------------------
 def test_oracle_equals_reference_orbmatcher_outputs(pair_features):
     r1, r2, A = pair_features
@@ -322,6 +371,12 @@ def test_oracle_equals_reference_orbmatcher_outputs(pair_features):
     c = kf_case(r1, r2, A, 1, 15.0)
     n, mt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, kf_queries(c), r1["descriptors"], 75, False, c["matched_in"])
     assert n == int(R["orbmatch/kf_n"]) and np.array_equal(mt, R["orbmatch/kf"])
+    (uv1, l1, f1), (uv2, l2, f2) = sim3_case(r1, r2, A, 1)
+    _, bi12, _ = oracle.search_in_radius(r2["keypoints"], r2["descriptors"], GRID, sim3_queries(uv1, l1, f1, 7.5), r1["descriptors"],
+                                         INV_SIGMA2, 0.0, 100)
+    _, bi21, _ = oracle.search_in_radius(k1, r1["descriptors"], GRID, sim3_queries(uv2, l2, f2, 7.5), r2["descriptors"], INV_SIGMA2, 0.0, 100)
+    n, m = sim3_mutual(bi12, bi21)
+    assert n == int(R["orbmatch/sim3_n"]) and np.array_equal(m, R["orbmatch/sim3"])
 
 
 # ---- MapPoint::ComputeDistinctiveDescriptors: the reference's own MapPoint.cc + MapPoint.h over stand-in KeyFrame / Map --

@@ -277,3 +277,27 @@ def test_cuda_equals_reference_distinctive_descriptors(gpu):
         elif oracle.ref_available():
             for p in range(len(counts)):
                 assert np.array_equal(best[p], oracle.ref_distinctive_descriptor(desc[p, :counts[p]])), p
+
+
+def cuda_sim3(om, r1, r2, case, th):
+    (uv1, l1, f1), (uv2, l2, f2) = case
+    _, bi12, _ = om.SearchInRadius(FrameView(r2["keypoints"], r2["descriptors"], GRID), T.sim3_queries(uv1, l1, f1, th), r1["descriptors"],
+                                   T.INV_SIGMA2, 0.0, 100)
+    _, bi21, _ = om.SearchInRadius(FrameView(r1["keypoints"], r1["descriptors"], GRID), T.sim3_queries(uv2, l2, f2, th), r2["descriptors"],
+                                   T.INV_SIGMA2, 0.0, 100)
+    return T.sim3_mutual(bi12, bi21)
+
+
+def test_cuda_equals_reference_search_by_sim3(om, pair_features):
+    """SearchBySim3 = plvi_search_in_radius once per direction (TH_HIGH, no chi2 gate) + the caller's agreement test."""
+    r1, r2, A = pair_features
+    n, m = cuda_sim3(om, r1, r2, T.sim3_case(r1, r2, A, 1), 7.5)
+    assert n == int(R["orbmatch/sim3_n"]) and np.array_equal(m, R["orbmatch/sim3"])
+    if oracle.ref_available():
+        for seed, th in ((0, 7.5), (2, 15.0)):
+            case = T.sim3_case(r1, r2, A, seed)
+            n, m = cuda_sim3(om, r1, r2, case, th)
+            (uv1, l1, f1), (uv2, l2, f2) = case
+            rn, rm = oracle.ref_search_by_sim3(r1["keypoints"], r1["descriptors"], uv1, l1, f1, r2["keypoints"], r2["descriptors"], uv2,
+                                               l2, f2, GRID, T.BOUNDS, SCALES, th)
+            assert n == rn and np.array_equal(m, rm)

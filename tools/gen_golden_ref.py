@@ -116,6 +116,11 @@ def main():
     n, mt = oracle.ref_search_by_projection_kf(r2["keypoints"], r2["descriptors"], T.GRID, T.BOUNDS, T.SCALES, c["uv"], c["level"],
                                                c["flags"], r1["descriptors"], 15, 1.5, c["matched_in"])
     out["orbmatch/kf_n"], out["orbmatch/kf"] = np.int32(n), mt
+    (uv1, l1, f1), (uv2, l2, f2) = T.sim3_case(r1, r2, A, 1)
+    n, m = oracle.ref_search_by_sim3(k1, r1["descriptors"], uv1, l1, f1, r2["keypoints"], r2["descriptors"], uv2, l2, f2, T.GRID, T.BOUNDS,
+                                     T.SCALES, 7.5)
+    out["orbmatch/sim3_n"], out["orbmatch/sim3"] = np.int32(n), m
+    print("sim3", n)
     dd, dc = T.distinctive_case(7)
     out["mappoint/distinctive"] = np.stack([oracle.ref_distinctive_descriptor(dd[p, :dc[p]]) for p in range(len(dc))])
     print("orbmatch2", out["orbmatch/frame_n"], out["orbmatch/tri_n"], out["orbmatch/fuse_n"], out["orbmatch/fuse_sim3_n"], out["orbmatch/kf_n"])
