@@ -931,3 +931,24 @@ def ref_search_by_sim3(keys1, desc1, uv1, level1, flags1, keys2, desc2, uv2, lev
     n = f(_p(keys1), _p(desc1), len(keys1), _p(uv1), _p(l1), _p(f1), _p(keys2), _p(desc2), len(keys2), _p(uv2), _p(l2), _p(f2), _p(g),
           _p(b), _p(sf), len(sf), C.c_float(th), _p(m))
     return n, m[:len(keys1)]
+
+
+def ref_search_reloc(keys2, desc2, grid, bounds, scale_factors, keys1, uv, level, flags, qdesc, th, orb_dist, check_ori=True, blocked=None):
+    """The reference's ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) itself
+    (src/ORBmatcher.cc:2180-2302): identity pose, keyframe map point i at (uv[i], 1), predicted level[i]; flags bit0: no map
+    point, bit1: isBad(), bit2: in sAlreadyFound; blocked: frame features that already hold a map point.
+    Returns (nmatches, match_train[n2])."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc2, qdesc = np.ascontiguousarray(desc2, np.uint8), np.ascontiguousarray(qdesc, np.uint8)
+    g, b = np.array(_grid_floats(grid), np.float32), np.array(bounds, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+    lv, fl = np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.int32)
+    blk = None if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+    mt = np.full(max(len(keys2), 1), -1, np.int32)
+    f = ref_orbmatcher_lib().plviref_orb_search_by_projection_reloc
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    n = f(_p(keys2), _p(desc2), len(keys2), _p(blk), _p(g), _p(b), _p(sf), len(sf), _p(keys1), len(keys1), _p(uv), _p(lv), _p(fl),
+          _p(qdesc), C.c_float(th), int(orb_dist), int(check_ori), _p(mt))
+    return n, mt[:len(keys2)]

@@ -4,8 +4,8 @@
 // SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming), SearchForInitialization, SearchByBoW(KF, F),
 // SearchByBoW(KF, KF), SearchForTriangulation, Fuse (both overloads), SearchBySim3 -- and through them DescriptorDistance,
 // RadiusByViewingCos, ComputeThreeMaxima.  Pose arithmetic runs on the stand-in's small CV_32F algebra with identity
-// poses (every product exact; the oracle / CUDA boundary starts at the projected point).  Not called: the
-// relocalisation overload SearchByProjection(F, pKF, sAlreadyFound, ...), the stereo / two-camera branches.
+// poses (every product exact; the oracle / CUDA boundary starts at the projected point).  Also the relocalisation
+// overload SearchByProjection(F, pKF, sAlreadyFound, th, ORBdist).  Not called: the stereo / two-camera branches.
 // Compiled with the same -include so that it sees the same stand-in classes as ORBmatcher.cc.
 #include <cstring>
 #include <vector>
@@ -394,6 +394,52 @@ extern "C" int plviref_orb_search_by_sim3(const cv::KeyPoint* keys1, const unsig
   const float s12 = 1.0f;
   const int k = matcher.SearchBySim3(&K1, &K2, out, s12, eye_f32(3), vec3_f32(0, 0, 0), th);
   for (int i = 0; i < n1; i++) matches12[i] = (out[i] && out[i] != &old) ? (int)out[i]->mnId : -1;
+  return k;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:2180-2302, the
+// relocalisation overload): identity frame pose, unit pinhole, the map point of keyframe feature i at (uv[i], 1) with
+// predicted level[i].  flags bit0: no map point, bit1: isBad(), bit2: in sAlreadyFound.  blocked[i2] != 0: the
+// frame feature already holds a map point.  match_train[i2] = keyframe feature assigned by this call, or -1.
+extern "C" int plviref_orb_search_by_projection_reloc(const cv::KeyPoint* keys2, const unsigned char* desc2, int n2,
+                                                       const unsigned char* blocked, const float* grid, const float* bounds,
+                                                       const float* scale_factors, int nlevels, const cv::KeyPoint* keys1, int n1,
+                                                       const float* uv, const int* level, const int* flags, const unsigned char* qdesc,
+                                                       float th, int orb_dist, int check_ori, int* match_train) {
+  GeometricCamera cam;
+  Frame C;
+  C.N = n2;
+  C.mvKeysUn = C.mvKeys = key_vec(keys2, n2);
+  C.mDescriptors = desc_mat(desc2, n2);
+  C.mvuRight.assign(n2, -1.0f);
+  C.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+  C.mnMinX = bounds[0]; C.mnMaxX = bounds[1]; C.mnMinY = bounds[2]; C.mnMaxY = bounds[3];
+  C.mpCamera = &cam;
+  C.mTcw = eye_f32(4);
+  GridOwner go(keys2, n2, grid);
+  C.grid = go.g;
+  MapPoint old;
+  C.mvpMapPoints.assign(n2, nullptr);
+  for (int i = 0; i < n2; i++) if (blocked && blocked[i]) C.mvpMapPoints[i] = &old;
+  KeyFrame K;
+  K.N = n1;
+  K.mvKeysUn = K.mvKeys = key_vec(keys1, n1);
+  K.mvpMapPoints.assign(n1, nullptr);
+  std::vector<MapPoint> mps(n1);
+  std::set<MapPoint*> found;
+  for (int i = 0; i < n1; i++) {
+    MapPoint& m = mps[i];
+    m.mnId = i;
+    m.mBad = (flags[i] & 2) != 0;
+    m.mWorldPos = vec3_f32(uv[2 * i], uv[2 * i + 1], 1.0f);
+    m.mnPredLevel = level[i];
+    m.mDesc = desc_mat(qdesc + 32 * (size_t)i, 1);
+    if (!(flags[i] & 1)) K.mvpMapPoints[i] = &m;
+    if (flags[i] & 4) found.insert(&m);
+  }
+  ORBmatcher matcher(0.9f, check_ori != 0);
+  const int k = matcher.SearchByProjection(C, &K, found, th, orb_dist);
+  for (int i = 0; i < n2; i++) match_train[i] = (C.mvpMapPoints[i] && C.mvpMapPoints[i] != &old) ? (int)C.mvpMapPoints[i]->mnId : -1;
   return k;
 }
 

@@ -339,6 +339,40 @@ def test_live_reference_search_by_sim3(pair_features, seed, th):
     assert n > 100
 
 
+def reloc_queries(r1, c):
+    """Caller side of the relocalisation overload (src/ORBmatcher.cc:2205-2232): bounds test as in the frame-to-frame
+    search, radius = th * scale factor of the predicted level, levels pred-1 .. pred+1; every claim blocks."""
+    k = r1["keypoints"]
+    q = np.zeros(len(k), QUERY_DTYPE)
+    q["u"], q["v"] = c["uv"][:, 0], c["uv"][:, 1]
+    q["radius"] = (np.float32(c["th"]) * SCALES[c["level"]]).astype(np.float32)
+    q["min_level"], q["max_level"] = c["level"] - 1, c["level"] + 1
+    q["angle"] = k["angle"]
+    outside = (q["u"] < BOUNDS[0]) | (q["u"] > BOUNDS[1]) | (q["v"] < BOUNDS[2]) | (q["v"] > BOUNDS[3])
+    q["flags"] = (c["flags"] != 0) | outside
+    return q
+
+
+def reloc_case(r1, r2, A, seed, th):
+    c = kf_case(r1, r2, A, seed, th)
+    rng = np.random.RandomState(seed + 50)
+    c["flags"] = ((rng.rand(len(c["uv"])) < 0.1) * 1 + (rng.rand(len(c["uv"])) < 0.05) * 2 + (rng.rand(len(c["uv"])) < 0.1) * 4).astype(np.int32)
+    return c
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,th,orb_dist,check_ori", [(0, 10.0, 100, True), (1, 3.0, 64, True), (2, 10.0, 100, False)])
+def test_live_reference_search_by_projection_relocalisation(pair_features, seed, th, orb_dist, check_ori):
+    r1, r2, A = pair_features
+    c = reloc_case(r1, r2, A, seed, th)
+    n, mt = oracle.ref_search_reloc(r2["keypoints"], r2["descriptors"], GRID, BOUNDS, SCALES, r1["keypoints"], c["uv"], c["level"],
+                                    c["flags"], r1["descriptors"], th, orb_dist, check_ori, c["matched_in"])
+    on, omt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, reloc_queries(r1, c), r1["descriptors"], orb_dist, check_ori,
+                                  c["matched_in"])
+    assert n == on and np.array_equal(mt, omt)
+    assert n > 100
+
+
 # ---- committed outputs of the reference (run everywhere) -------------------------------------------------------------
 def test_oracle_equals_reference_orbmatcher_outputs(pair_features):
     r1, r2, A = pair_features

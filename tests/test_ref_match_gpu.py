@@ -301,3 +301,18 @@ def test_cuda_equals_reference_search_by_sim3(om, pair_features):
             rn, rm = oracle.ref_search_by_sim3(r1["keypoints"], r1["descriptors"], uv1, l1, f1, r2["keypoints"], r2["descriptors"], uv2,
                                                l2, f2, GRID, T.BOUNDS, SCALES, th)
             assert n == rn and np.array_equal(m, rm)
+
+
+@live
+@pytest.mark.parametrize("seed,th,orb_dist,ori", [(0, 10.0, 100, True), (1, 3.0, 64, True), (2, 10.0, 100, False)])
+def test_cuda_equals_live_reference_search_by_projection_relocalisation(om, pair_features, seed, th, orb_dist, ori):
+    """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) = mode FRAME with th_dist = ORBdist."""
+    r1, r2, A = pair_features
+    c = T.reloc_case(r1, r2, A, seed, th)
+    om.mbCheckOrientation = ori
+    F = FrameView(r2["keypoints"], r2["descriptors"], GRID, c["matched_in"])
+    mt, _, nm, _ = om.search_batch(0, [F], [T.reloc_queries(r1, c)], [r1["descriptors"]], orb_dist)
+    om.mbCheckOrientation = True
+    rn, rmt = oracle.ref_search_reloc(r2["keypoints"], r2["descriptors"], GRID, T.BOUNDS, SCALES, r1["keypoints"], c["uv"], c["level"],
+                                      c["flags"], r1["descriptors"], th, orb_dist, ori, c["matched_in"])
+    assert int(nm[0]) == rn and np.array_equal(mt[0], rmt)
