@@ -452,3 +452,35 @@ def test_oracle_equals_reference_distinctive_outputs():
     for p in range(len(counts)):
         d = desc[p, :counts[p]]
         assert np.array_equal(d[oracle.distinctive_descriptor(d)], R["mappoint/distinctive"][p])
+
+
+# ---- the reference's real frames (tests/golden/frame_data2_{1,3}.npz = /root/reference/data2/color/{1,3}.png, gray) ----
+def real_pair():
+    a = np.load(GOLD / "frame_data2_1.npz")["img"]
+    b = np.load(GOLD / "frame_data2_3.npz")["img"]
+    return a, b
+
+
+@needs_ref
+def test_live_reference_matchers_on_real_frames():
+    """Initialisation matching (points and lines) between two frames of the reference's own sequence: features from the
+    reference's extractors, matches from the reference's matchers, against the oracle end to end."""
+    a, b = real_pair()
+    h, w = a.shape
+    grid = frame_grid(0, w, 0, h)
+    ra, rb = oracle.ref_orb_extract(a, nfeatures=1000), oracle.ref_orb_extract(b, nfeatures=1000)
+    oa, ob = oracle.orb_extract(a, nfeatures=1000), oracle.orb_extract(b, nfeatures=1000)
+    ka = ra["keypoints"]
+    prev = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+    n, m12, pm = oracle.ref_search_init(ka, ra["descriptors"], rb["keypoints"], rb["descriptors"], grid, prev, 100, 0.9, True)
+    on, om12, oq = oracle.search_init(ob["keypoints"], ob["descriptors"], grid, ORBmatcher.init_queries(oa["keypoints"], prev, 100),
+                                      oa["descriptors"], 50, 0.9, True)
+    assert n == on and np.array_equal(m12, om12) and n > 30
+    la, lb = oracle.ref_line_extract(a), oracle.ref_line_extract(b)
+    pa, pb = oracle.line_extract(a), oracle.line_extract(b)
+    n, m = oracle.ref_line_match(la["descriptors"], lb["descriptors"], 0.75, "match")
+    on, om = oracle.line_match(pa["descriptors"], pb["descriptors"], 0.75)
+    assert n == on and np.array_equal(m, om)
+    n, m = oracle.ref_line_match_mad(la["descriptors"], lb["descriptors"], 0.5)
+    on, om, _ = oracle.line_match_mad(pa["descriptors"], pb["descriptors"], 0.5)
+    assert n == on and np.array_equal(m, om) and n > 20
