@@ -69,6 +69,9 @@ GROW_NOTE = ("LSD region growing is a serial dependency chain per band (k_lsd_sp
              "see DESIGN.md section 4 and profiles/r01_k_lsd_spec.md")
 
 
+SCALE_FACTORS = np.cumprod(np.concatenate([[np.float32(1.0)], np.full(7, np.float32(1.2))]).astype(np.float32), dtype=np.float32)
+
+
 def _cpu_pair_job(idx_frames):
     """CPU arm over a contiguous shard: every frame is extracted once (ORB + lines) and matched
     against the previous frame of the shard, like a sequential tracker."""
@@ -82,8 +85,8 @@ def _cpu_pair_job(idx_frames):
     if use_ref:
         oracle.ref_set_monotone(False)   # plain malloc while timing
     for f in frames:
-        # extraction: the reference's own ORBextractor / Lineextractor code (oracle/_ref) when it was built,
-        # else the oracle port; the searches are always the oracle port (ORBmatcher.cc needs the whole SLAM graph)
+        # the reference's own ORBextractor / Lineextractor / ORBmatcher / LineMatcher code (oracle/_ref: sources compiled
+        # unmodified, the matchers against stand-in Frame / MapPoint classes) when it was built, else the oracle port
         r = oracle.ref_orb_extract(f) if use_ref else oracle.orb_extract(f)
         l = oracle.ref_line_extract(f) if use_ref else oracle.line_extract(f)
         if prev_r is not None:
@@ -92,8 +95,16 @@ def _cpu_pair_job(idx_frames):
             q["u"], q["v"] = k["x"], k["y"]
             q["radius"] = np.float32(15.0) * (np.float32(1.2) ** k["octave"].astype(np.float32))
             q["min_level"], q["max_level"], q["angle"] = k["octave"] - 1, k["octave"] + 1, k["angle"]
-            oracle.search_frame(r["keypoints"], r["descriptors"], grid, q, prev_r["descriptors"], 100, True)
-            oracle.line_match(prev_l["descriptors"], l["descriptors"], 0.9)
+            if use_ref:
+                # SearchByProjection(CurrentFrame, LastFrame, 15, true) with the identity pose: every tracked point of the
+                # last frame projects onto its own position
+                oracle.ref_search_frame(r["keypoints"], r["descriptors"], grid, (0.0, float(W), 0.0, float(H)), SCALE_FACTORS,
+                                        k, np.stack([k["x"], k["y"]], 1), np.zeros(len(k), np.int32), prev_r["descriptors"], 15.0, True)
+                if len(prev_l["descriptors"]) >= 2 and len(l["descriptors"]) >= 2:
+                    oracle.ref_line_match(prev_l["descriptors"], l["descriptors"], 0.9, "match")
+            else:
+                oracle.search_frame(r["keypoints"], r["descriptors"], grid, q, prev_r["descriptors"], 100, True)
+                oracle.line_match(prev_l["descriptors"], l["descriptors"], 0.9)
         prev_r, prev_l = r, l
     return len(frames)
 
@@ -105,7 +116,8 @@ def cpu_kind():
                              "binary_descriptor_custom.cpp / LineExtractor.cc compiled unmodified with g++ -O2; the OpenCV "
                              "primitives underneath (resize, GaussianBlur, FAST, pyrDown, Sobel) are the oracle's scalar "
                              "models, not OpenCV's SIMD code, so this understates a real OpenCV build; the two searches "
-                             "are the oracle port")
+                             "are the reference's own ORBmatcher::SearchByProjection(Frame, Frame) and LineMatcher::match "
+                             "(ORBmatcher.cc / LineMatcher.cpp compiled unmodified against stand-in Frame / MapPoint classes)")
     return "port", "oracle/ C++ port of the reference path (oracle/_ref not built)"
 
 
