@@ -527,8 +527,10 @@ def search_triangulation(keys1, desc1, mp1, fv1, keys2, desc2, mp2, fv2, F12, ep
 _REF_LIB = _DIR / "_ref" / "libplvi_ref.so"
 _REF_ORB_LIB = _DIR / "_ref" / "libplvi_ref_orbmatcher.so"   # ORBmatcher.cc (stand-in classes of its own, see Makefile.ref)
 _REF_MP_LIB = _DIR / "_ref" / "libplvi_ref_mappoint.so"     # MapPoint.cc + MapPoint.h over stand-in KeyFrame / Frame / Map
+_REF_FR_LIB = _DIR / "_ref" / "libplvi_ref_frame.so"        # Frame.cc + Frame.h over stand-in MapPoint / KeyFrame / cameras / IMU types
 _ref_orb = None
 _ref_mp = None
+_ref_fr = None
 REFERENCE_ROOT = Path(os.environ.get("PLVI_REFERENCE_ROOT", "/root/reference"))
 _ref = None
 
@@ -538,11 +540,12 @@ def ref_build(force: bool = False):
     if not (REFERENCE_ROOT / "src" / "ORBextractor.cc").exists():
         return _REF_LIB if _REF_LIB.exists() else None
     build()
-    srcs = [_DIR / "ref_glue.cpp", _DIR / "ref_glue_linematcher.cpp", _DIR / "ref_glue_orbmatcher.cpp", _DIR / "ref_glue_mappoint.cpp",
+    srcs = [_DIR / "ref_glue.cpp", _DIR / "ref_glue_linematcher.cpp", _DIR / "ref_glue_orbmatcher.cpp", _DIR / "ref_glue_mappoint.cpp", _DIR / "ref_glue_frame.cpp",
+            _DIR / "cvmini" / "slam_mock_frame.h",
             _DIR / "Makefile.ref",
             _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _DIR / "cvmini" / "slam_mock.h",
             _DIR / "cvmini" / "slam_mock_orb.h", _LIB]
-    stale = any((not t.exists()) or any(s.stat().st_mtime > t.stat().st_mtime for s in srcs) for t in (_REF_LIB, _REF_ORB_LIB, _REF_MP_LIB))
+    stale = any((not t.exists()) or any(s.stat().st_mtime > t.stat().st_mtime for s in srcs) for t in (_REF_LIB, _REF_ORB_LIB, _REF_MP_LIB, _REF_FR_LIB))
     if force or stale:
         subprocess.run(["make", "-C", str(_DIR), "-f", "Makefile.ref", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []),
                        check=True, capture_output=True)
@@ -952,3 +955,129 @@ def ref_search_reloc(keys2, desc2, grid, bounds, scale_factors, keys1, uv, level
     n = f(_p(keys2), _p(desc2), len(keys2), _p(blk), _p(g), _p(b), _p(sf), len(sf), _p(keys1), len(keys1), _p(uv), _p(lv), _p(fl),
           _p(qdesc), C.c_float(th), int(orb_dist), int(check_ori), _p(mt))
     return n, mt[:len(keys2)]
+
+
+def ref_frame_lib():
+    """oracle/_ref/libplvi_ref_frame.so: the reference's src/Frame.cc + include/Frame.h compiled unmodified over the stand-ins
+    of cvmini/slam_mock_frame.h."""
+    global _ref_fr
+    if _ref_fr is None:
+        if ref_build() is None or not _REF_FR_LIB.exists():
+            raise RuntimeError("oracle/_ref/libplvi_ref_frame.so is not built and /root/reference is absent")
+        lib()
+        _ref_fr = C.CDLL(str(_REF_FR_LIB))
+    return _ref_fr
+
+
+def ref_assign_grid(keys, bounds):
+    """The reference's Frame::AssignFeaturesToGrid / PosInGrid itself: (cell_start[3073], items) like assign_grid."""
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    b = np.array(bounds, np.float32)
+    start = np.zeros(64 * 48 + 1, np.int32)
+    items = np.zeros(max(len(keys), 1), np.int32)
+    f = ref_frame_lib().plviref_frame_assign_grid
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(_p(keys), len(keys), _p(b), _p(start), _p(items))
+    return start, items[:start[-1]]
+
+
+def ref_features_in_area(keys, bounds, xyr, levels):
+    """The reference's Frame::GetFeaturesInArea itself for queries xyr [nq,3] (x, y, r), levels [nq,2] (min, max):
+    list of index arrays in the reference's output order."""
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    b = np.array(bounds, np.float32)
+    xyr = np.ascontiguousarray(xyr, np.float32).reshape(-1, 3)
+    lv = np.ascontiguousarray(levels, np.int32).reshape(-1, 2)
+    cap = max(len(keys), 1) * len(xyr)
+    start, out = np.zeros(len(xyr) + 1, np.int32), np.zeros(max(cap, 1), np.int32)
+    f = ref_frame_lib().plviref_frame_features_in_area
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    f(_p(keys), len(keys), _p(b), _p(xyr), _p(lv), len(xyr), _p(start), _p(out), cap)
+    return [out[start[i]:start[i + 1]].copy() for i in range(len(xyr))]
+
+
+def features_in_area(keys, grid, xyr, levels):
+    """The oracle's restatement of Frame::GetFeaturesInArea (plvio_grid_*), same arguments / result as ref_features_in_area."""
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    g = _grid_floats(grid)
+    L = lib()
+    L.plvio_grid_create.restype = C.c_void_p
+    L.plvio_grid_create.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.plvio_grid_destroy.argtypes = [C.c_void_p]
+    L.plvio_grid_features_in_area.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    h = L.plvio_grid_create(_p(keys), len(keys), *g)
+    out = []
+    tmp = np.zeros(max(len(keys), 1), np.int32)
+    xyr = np.ascontiguousarray(xyr, np.float32).reshape(-1, 3)
+    lv = np.ascontiguousarray(levels, np.int32).reshape(-1, 2)
+    for (x, y, r), (a, b) in zip(xyr, lv):
+        k = L.plvio_grid_features_in_area(h, C.c_float(x), C.c_float(y), C.c_float(r), int(a), int(b), _p(tmp), len(tmp))
+        out.append(tmp[:k].copy())
+    L.plvio_grid_destroy(h)
+    return out
+
+
+def ref_line_descriptor_mad(d0, d1):
+    """The reference's Frame::lineDescriptorMAD itself on kNN-2 distances: (nn_mad, nn12_mad)."""
+    d0, d1 = np.ascontiguousarray(d0, np.int32), np.ascontiguousarray(d1, np.int32)
+    a, b = C.c_double(0), C.c_double(0)
+    f = ref_frame_lib().plviref_frame_line_descriptor_mad
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    f(_p(d0), _p(d1), len(d0), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def line_descriptor_mad(d0, d1):
+    d0, d1 = np.ascontiguousarray(d0, np.int32), np.ascontiguousarray(d1, np.int32)
+    a, b = C.c_double(0), C.c_double(0)
+    f = lib().plvio_line_descriptor_mad
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    f(_p(d0), _p(d1), len(d0), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def _cam_f32(cam):
+    K = np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32)
+    return K, np.asarray(cam["dist"], np.float32)
+
+
+def ref_undistort_keypoints(keys, cam=None):
+    """The reference's Frame::UndistortKeyPoints itself (cv::undistortPoints = the oracle's cv2-pinned restatement)."""
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    K, d = _cam_f32(cam or EUROC_CAMERA)
+    out = np.zeros(max(len(keys), 1), KEYPOINT_DTYPE)
+    f = ref_frame_lib().plviref_frame_undistort_keypoints
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    f(_p(keys), len(keys), _p(K), _p(d), len(d), _p(out))
+    return out[:len(keys)]
+
+
+def ref_undistort_keylines(keylines, cam=None):
+    """The reference's Frame::UndistortKeyLines itself."""
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    K, d = _cam_f32(cam or EUROC_CAMERA)
+    out = np.zeros(max(len(kl), 1), KEYLINE_DTYPE)
+    f = ref_frame_lib().plviref_frame_undistort_keylines
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    f(_p(kl), len(kl), _p(K), _p(d), len(d), _p(out))
+    return out[:len(kl)]
+
+
+def ref_stereo_matches(kps_l, desc_l, kps_r, desc_r, pyr_l, pyr_r, scale_factors, mb, mbf):
+    """The reference's Frame::ComputeStereoMatches itself; arguments / result as stereo_matches."""
+    kl, kr = np.ascontiguousarray(kps_l, KEYPOINT_DTYPE), np.ascontiguousarray(kps_r, KEYPOINT_DTYPE)
+    dl, dr = np.ascontiguousarray(desc_l, np.uint8), np.ascontiguousarray(desc_r, np.uint8)
+    lw = np.array([p.shape[1] for p in pyr_l], np.int32)
+    lh = np.array([p.shape[0] for p in pyr_l], np.int32)
+    pl = [np.ascontiguousarray(p, np.uint8) for p in pyr_l]
+    pr = [np.ascontiguousarray(p, np.uint8) for p in pyr_r]
+    ptr_l = (C.c_void_p * len(pl))(*[p.ctypes.data for p in pl])
+    ptr_r = (C.c_void_p * len(pr))(*[p.ctypes.data for p in pr])
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    ur, dp = np.empty(max(len(kl), 1), np.float32), np.empty(max(len(kl), 1), np.float32)
+    f = ref_frame_lib().plviref_frame_compute_stereo_matches
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    n = f(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), ptr_l, ptr_r, _p(lw), _p(lh), len(lw), _p(sf), C.c_float(mb), C.c_float(mbf),
+          _p(ur), _p(dp))
+    return ur[:len(kl)], dp[:len(kl)], n

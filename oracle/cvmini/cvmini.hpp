@@ -418,7 +418,15 @@ class Mat {
     for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.at<float>(c, r) = at<float>(r, c);
     return m;
   }
-  Mat reshape(int, int = 0) const { cvmini_unreachable("Mat::reshape"); }
+  Mat reshape(int cn, int = 0) const {   // continuous matrices only: same memory, another channel count (rows kept)
+    if (!isContinuous() || (cols * channels()) % cn) cvmini_unreachable("Mat::reshape of a non-continuous matrix");
+    Mat m = *this;
+    m.flags = CV_MAKETYPE(depth(), cn);
+    m.cols = cols * channels() / cn;
+    m.step = (size_t)m.cols * m.elemSize();
+    return m;
+  }
+  static Mat eye(int r, int c, int type) { Mat m = zeros(r, c, type); if (CV_MAT_DEPTH(type) != CV_32F) cvmini_unreachable("Mat::eye other than CV_32F"); for (int i = 0; i < (r < c ? r : c); i++) m.at<float>(i, i) = 1.0f; return m; }
   int checkVector(int, int = -1, bool = true) const { cvmini_unreachable("Mat::checkVector"); }
 };
 
@@ -742,7 +750,40 @@ static inline double norm(const Mat& a, int t = NORM_L2) {   // CV_32F L2 only (
   if (a.type() != CV_32FC1 || t != NORM_L2) cvmini_unreachable("norm(Mat) other than CV_32F L2");
   return std::sqrt(a.dot(a));
 }
-static inline double norm(const Mat&, const Mat&, int = NORM_L2) { cvmini_unreachable("norm(Mat, Mat)"); }
+static inline double norm(const Mat& a, const Mat& b, int t = NORM_L2) {   // CV_16S NORM_L1 only (Frame::ComputeStereoMatches' SAD)
+  if (a.type() != CV_16SC1 || b.type() != CV_16SC1 || t != NORM_L1 || a.rows != b.rows || a.cols != b.cols)
+    cvmini_unreachable("norm(Mat, Mat) other than CV_16S NORM_L1");
+  double s = 0;   // cv::norm accumulates the L1 norm of 16-bit data in int and returns it as double: exact either way here
+  for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) s += std::abs((int)a.at<short>(r, c) - (int)b.at<short>(r, c));
+  return s;
+}
+static inline Mat operator-(const Mat& a, short v) {   // MatExpr a - Scalar on CV_16S: saturate_cast<short>(a - v)
+  if (a.type() != CV_16SC1) cvmini_unreachable("Mat - scalar other than CV_16S");
+  Mat c(a.rows, a.cols, CV_16SC1);
+  for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) c.at<short>(i, j) = saturate_cast<short>((int)a.at<short>(i, j) - (int)v);
+  return c;
+}
+// cv::undistortPoints(src, dst, K, dist, noArray(), P): N x 1 CV_32FC2 points, CV_32F 3x3 K / P, 4..14 CV_32F distortion
+// coefficients -> the oracle's restatement of OpenCV 4.x (pinned against cv2.undistortPoints, tests/test_frame_cpu.py)
+extern "C" void plvio_cv_undistort_points(const float* xy, int n, const double* K, const double* k, const double* P, float* out);
+static inline void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& dist, const Mat& R = Mat(), const Mat& P = Mat()) {
+  if (src.type() != CV_MAKETYPE(CV_32F, 2) || !src.isContinuous() || K.type() != CV_32FC1 || dist.type() != CV_32FC1 || !R.empty() ||
+      P.type() != CV_32FC1)
+    cvmini_unreachable("undistortPoints other than CV_32FC2 points with CV_32F K / dist / P and no R");
+  const double k4[4] = {K.at<float>(0, 0), K.at<float>(1, 1), K.at<float>(0, 2), K.at<float>(1, 2)};
+  const double p4[4] = {P.at<float>(0, 0), P.at<float>(1, 1), P.at<float>(0, 2), P.at<float>(1, 2)};
+  double k[14] = {0};
+  const int nk = (int)dist.total();
+  for (int i = 0; i < nk && i < 14; i++) k[i] = dist.at<float>(i);
+  const int n = (int)src.total();
+  std::vector<float> out(2 * (size_t)n + 2);
+  plvio_cv_undistort_points(src.ptr<float>(), n, k4, k, p4, out.data());
+  Mat d(src.rows, src.cols, src.type());
+  memcpy(d.data, out.data(), sizeof(float) * 2 * (size_t)n);
+  dst = d;
+}
+static inline void hconcat(const Mat&, const Mat&, Mat&) { cvmini_unreachable("hconcat"); }
+static inline void vconcat(const Mat&, const Mat&, Mat&) { cvmini_unreachable("vconcat"); }
 template <typename T> struct MatCommaInitializer_ {   // (Mat_<T>(r, c) << a, b, ...)
   Mat_<T> m;
   int i;

@@ -3,6 +3,12 @@
 // See cvmini.hpp for the purpose (compiling the reference's sources unmodified into oracle/_ref).
 #pragma once
 namespace Eigen {
+struct Vector2d {   // named by Frame.h / Frame.cc (stereo-line helpers, never reached)
+  double v[2];
+  Vector2d() { v[0] = v[1] = 0; }
+  double& operator()(int i) { return v[i]; }
+  const double& operator()(int i) const { return v[i]; }
+};
 struct Vector3d {
   double v[3];
   Vector3d() { v[0] = v[1] = v[2] = 0; }
@@ -21,6 +27,7 @@ struct Vector3d {
     return Vector3d(v[1] * o.v[2] - v[2] * o.v[1], v[2] * o.v[0] - v[0] * o.v[2], v[0] * o.v[1] - v[1] * o.v[0]);
   }
   Vector3d operator/(double s) const { return Vector3d(v[0] / s, v[1] / s, v[2] / s); }
+  Vector2d head(int) const { Vector2d r; r.v[0] = v[0]; r.v[1] = v[1]; return r; }
 };
 struct Vector6d {   // Eigen::Matrix<double, 6, 1>: only head(3) / tail(3) / operator() are used (never reached)
   double v[6];

@@ -7,7 +7,9 @@
 // (src/Frame.cc:677-763; not compiled -- it belongs to Frame.cc) forwards to the oracle's restatement.  Pose / camera arithmetic (cv::Mat products) compiles against the stand-ins and aborts if reached:
 // only the functions listed in ref_glue_orbmatcher.cpp are called.
 #pragma once
+#ifndef SLAM_MOCK_REAL_FRAME   // libplvi_ref_frame.so: the reference's own Frame.h / Frame.cc (see slam_mock_frame.h)
 #define FRAME_H
+#endif
 #define KEYFRAME_H
 #ifdef SLAM_MOCK_REAL_MAPPOINT   // libplvi_ref_mappoint.so: the reference's own MapPoint.h / MapPoint.cc over stand-in KeyFrame / Frame / Map
 #define MAP_H
@@ -48,6 +50,12 @@ class GeometricCamera {
     const float* p = m.ptr<float>();
     return project(cv::Point3f(m.at<float>(0), m.at<float>(1), m.at<float>(2)));
   }
+  virtual cv::Mat toK() {   // Pinhole::toK (src/CameraModels/Pinhole.cpp:124-128)
+    cv::Mat K = cv::Mat::zeros(3, 3, CV_32F);
+    K.at<float>(0, 0) = fx; K.at<float>(0, 2) = cx; K.at<float>(1, 1) = fy; K.at<float>(1, 2) = cy; K.at<float>(2, 2) = 1.0f;
+    return K;
+  }
+  virtual float getParameter(const int i) { return i == 0 ? fx : (i == 1 ? fy : (i == 2 ? cx : cy)); }
   virtual float uncertainty2(const cv::Mat&) { cvmini_unreachable("GeometricCamera::uncertainty2"); }
   virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat&, const cv::Mat&,
                                  const float, const float unc) {
@@ -109,6 +117,7 @@ class Map {
 };
 #endif
 
+#ifndef SLAM_MOCK_REAL_FRAME
 class Frame {
  public:
   int N = 0, Nleft = -1, Nright = -1;
@@ -141,6 +150,8 @@ class Frame {
   float mfLogScaleFactor = 0;
   cv::Mat GetCameraCenter() { cvmini_unreachable("Frame::GetCameraCenter"); }
 };
+
+#endif
 
 class KeyFrame {
  public:

@@ -56,6 +56,12 @@ void plvio_undistort_points(const float* xy, int n, const double* K, const doubl
   for (int i = 0; i < n; i++) undistort_point(xy[2 * i], xy[2 * i + 1], K, k, P, iters > 0 ? iters : 5, out + 2 * i);
 }
 
+// cv::undistortPoints(src, dst, K, distCoeffs, noArray(), P) itself (no Frame-level shortcut), for the OpenCV stand-in of
+// oracle/cvmini (the reference's Frame.cc compiled unmodified calls it): same arithmetic as above.
+void plvio_cv_undistort_points(const float* xy, int n, const double* K, const double* k, const double* P, float* out) {
+  for (int i = 0; i < n; i++) undistort_point(xy[2 * i], xy[2 * i + 1], K, k, P, 5, out + 2 * i);
+}
+
 // mGrid as a CSR: cell (i, j) = items[cell_start[i*48+j] .. cell_start[i*48+j+1])
 void plvio_assign_grid(const float* xy, int n, float minX, float minY, float invW, float invH, int* cell_start, int* items) {
   const int COLS = 64, ROWS = 48;

@@ -1,0 +1,154 @@
+// TEST INFRASTRUCTURE -- C entry points over the reference's Frame (src/Frame.cc + include/Frame.h compiled unmodified;
+// MapPoint / KeyFrame / MapLine / cameras / IMU types / vocabulary are the stand-ins of cvmini/slam_mock_frame.h;
+// ORBextractor.cc, ORBmatcher.cc, gridStructure.cpp, LineIterator.cpp are the reference's own).  oracle/Makefile.ref
+// builds it into a library of its own (oracle/_ref/libplvi_ref_frame.so).  Frames are default-constructed and their
+// public data members filled in; private member functions are reached through explicit template instantiation (the
+// standard's access exemption), so that Frame.cc and Frame.h stay untouched.
+#include <cstring>
+#include <vector>
+#include "Frame.h"          // /root/reference/include
+#include "ORBextractor.h"   // /root/reference/include
+
+using namespace ORB_SLAM3;
+
+namespace {
+template <typename Tag, typename Tag::type M> struct Rob { friend typename Tag::type get(Tag) { return M; } };
+struct TagUndistortKP { typedef void (Frame::*type)(); friend type get(TagUndistortKP); };
+struct TagUndistortKL { typedef void (Frame::*type)(); friend type get(TagUndistortKL); };
+struct TagAssignGrid { typedef void (Frame::*type)(); friend type get(TagAssignGrid); };
+}  // namespace
+template struct Rob<TagUndistortKP, &Frame::UndistortKeyPoints>;
+template struct Rob<TagUndistortKL, &Frame::UndistortKeyLines>;
+template struct Rob<TagAssignGrid, &Frame::AssignFeaturesToGrid>;
+
+namespace {
+cv::Mat desc_mat(const unsigned char* d, int n) {
+  cv::Mat m(n > 0 ? n : 1, 32, CV_8UC1);
+  for (int r = 0; r < n; r++) memcpy(m.ptr(r), d + 32 * (size_t)r, 32);
+  return m;
+}
+void set_bounds_and_grid(const float* bounds) {   // what Frame's constructors compute once (src/Frame.cc:150-170)
+  Frame::mnMinX = bounds[0]; Frame::mnMaxX = bounds[1]; Frame::mnMinY = bounds[2]; Frame::mnMaxY = bounds[3];
+  Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+  Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+}
+}  // namespace
+
+// Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:644-675, 1077-1087): mGrid as a CSR (cell = i * 48 + j).
+extern "C" void plviref_frame_assign_grid(const cv::KeyPoint* keys, int n, const float* bounds, int* cell_start, int* items) {
+  set_bounds_and_grid(bounds);
+  Frame F;
+  F.N = n;
+  F.Nleft = -1;
+  F.mvKeysUn.assign(keys, keys + n);
+  (F.*get(TagAssignGrid()))();
+  int pos = 0;
+  for (int i = 0; i < FRAME_GRID_COLS; i++)
+    for (int j = 0; j < FRAME_GRID_ROWS; j++) {
+      cell_start[i * FRAME_GRID_ROWS + j] = pos;
+      for (size_t v : F.mGrid[i][j]) items[pos++] = (int)v;
+    }
+  cell_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = pos;
+}
+
+// Frame::GetFeaturesInArea (src/Frame.cc:1006-1075) for nq queries (x, y, r, minLevel, maxLevel): CSR of index lists.
+extern "C" void plviref_frame_features_in_area(const cv::KeyPoint* keys, int n, const float* bounds, const float* xyr, const int* levels,
+                                               int nq, int* start, int* out, int cap) {
+  set_bounds_and_grid(bounds);
+  Frame F;
+  F.N = n;
+  F.Nleft = -1;
+  F.mvKeysUn.assign(keys, keys + n);
+  (F.*get(TagAssignGrid()))();
+  int pos = 0;
+  for (int q = 0; q < nq; q++) {
+    start[q] = pos;
+    const std::vector<size_t> v = F.GetFeaturesInArea(xyr[3 * q], xyr[3 * q + 1], xyr[3 * q + 2], levels[2 * q], levels[2 * q + 1]);
+    for (size_t i : v) if (pos < cap) out[pos++] = (int)i;
+  }
+  start[nq] = pos;
+}
+
+// Frame::lineDescriptorMAD (src/Frame.cc:1089-1113) on the kNN-2 distances.
+extern "C" void plviref_frame_line_descriptor_mad(const int* d0, const int* d1, int n, double* nn_mad, double* nn12_mad) {
+  std::vector<std::vector<cv::DMatch>> m(n, std::vector<cv::DMatch>(2));
+  for (int i = 0; i < n; i++) { m[i][0] = cv::DMatch(i, 0, (float)d0[i]); m[i][1] = cv::DMatch(i, 1, (float)d1[i]); }
+  Frame F;
+  F.lineDescriptorMAD(m, *nn_mad, *nn12_mad);
+}
+
+// Frame::UndistortKeyPoints (src/Frame.cc:1124-1157): K = (fx, fy, cx, cy); dist = nd CV_32F coefficients.
+extern "C" void plviref_frame_undistort_keypoints(const cv::KeyPoint* keys, int n, const float* K, const float* dist, int nd,
+                                                  cv::KeyPoint* out) {
+  GeometricCamera cam;
+  cam.fx = K[0]; cam.fy = K[1]; cam.cx = K[2]; cam.cy = K[3];
+  Frame F;
+  F.N = n;
+  F.mvKeys.assign(keys, keys + n);
+  F.mpCamera = &cam;
+  F.mK = cam.toK();
+  F.mDistCoef = cv::Mat(nd, 1, CV_32F);
+  for (int i = 0; i < nd; i++) F.mDistCoef.at<float>(i) = dist[i];
+  (F.*get(TagUndistortKP()))();
+  for (int i = 0; i < n; i++) out[i] = F.mvKeysUn[i];
+}
+
+// Frame::UndistortKeyLines (src/Frame.cc:1159-1197): the four endpoint coordinates of every KeyLine.
+extern "C" void plviref_frame_undistort_keylines(const cv::line_descriptor::KeyLine* kl, int n, const float* K, const float* dist, int nd,
+                                                 cv::line_descriptor::KeyLine* out) {
+  GeometricCamera cam;
+  cam.fx = K[0]; cam.fy = K[1]; cam.cx = K[2]; cam.cy = K[3];
+  Frame F;
+  F.mvKeys_Line.assign(kl, kl + n);
+  F.N_l = n;
+  F.mK = cam.toK();
+  F.mDistCoef = cv::Mat(nd, 1, CV_32F);
+  for (int i = 0; i < nd; i++) F.mDistCoef.at<float>(i) = dist[i];
+  (F.*get(TagUndistortKL()))();
+  for (int i = 0; i < n; i++) out[i] = F.mvKeysUn_Line[i];
+}
+
+// Frame::ComputeStereoMatches (src/Frame.cc:1228-1406) on given left / right keypoints, descriptors and the two image
+// pyramids (level images WITHOUT the extractor's border; the function only reads inside them).
+extern "C" int plviref_frame_compute_stereo_matches(const cv::KeyPoint* kl, const unsigned char* dl, int nl, const cv::KeyPoint* kr,
+                                                    const unsigned char* dr, int nr, const unsigned char* const* pyr_l,
+                                                    const unsigned char* const* pyr_r, const int* widths, const int* heights,
+                                                    int nlevels, const float* scale_factors, float mb, float mbf, float* u_right,
+                                                    float* depth) {
+  ORBextractor L(1000, 1.2f, nlevels, 20, 7), R(1000, 1.2f, nlevels, 20, 7);
+  for (int l = 0; l < nlevels; l++) {
+    cv::Mat a(heights[l], widths[l], CV_8UC1), b(heights[l], widths[l], CV_8UC1);
+    for (int y = 0; y < heights[l]; y++) {
+      memcpy(a.ptr(y), pyr_l[l] + (size_t)y * widths[l], widths[l]);
+      memcpy(b.ptr(y), pyr_r[l] + (size_t)y * widths[l], widths[l]);
+    }
+    L.mvImagePyramid[l] = a;
+    R.mvImagePyramid[l] = b;
+  }
+  Frame F;
+  F.N = nl;
+  F.mvKeys.assign(kl, kl + nl);
+  F.mvKeysRight.assign(kr, kr + nr);
+  F.mDescriptors = desc_mat(dl, nl);
+  F.mDescriptorsRight = desc_mat(dr, nr);
+  F.mpORBextractorLeft = &L;
+  F.mpORBextractorRight = &R;
+  F.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+  F.mvInvScaleFactors.resize(nlevels);
+  for (int l = 0; l < nlevels; l++) F.mvInvScaleFactors[l] = 1.0f / scale_factors[l];
+  F.mb = mb;
+  F.mbf = mbf;
+  F.ComputeStereoMatches();
+  int k = 0;
+  for (int i = 0; i < nl; i++) { u_right[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; k += F.mvuRight[i] >= 0; }
+  return k;
+}
+
+// Frame::ComputeStereoMatches_Lines (stereo lines, never reached here) names LineMatcher::matchGrid; LineMatcher.cpp is
+// part of libplvi_ref.so (it needs stand-in classes of its own), so this library only carries an aborting stub.
+#include "LineMatcher.h"
+int LineMatcher::matchGrid(const std::vector<line_2d>&, const cv::Mat&, const GridStructure&, const cv::Mat&,
+                           const std::vector<std::pair<double, double>>&, const GridWindow&, std::vector<int>&) {
+  fprintf(stderr, "libplvi_ref_frame: LineMatcher::matchGrid is not part of this build\n");
+  abort();
+}
