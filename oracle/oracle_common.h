@@ -23,11 +23,13 @@
 //     oracle/_ref/libplvi_ref_orbmatcher.so and libplvi_ref.so; tests/test_oracle_vs_ref_matchers.py and
 //     test_oracle_vs_ref.py pin every search restated in oracle_match.cpp against them bit-exactly (identity poses:
 //     the oracle boundary starts at the projected point).  Frame.cc / KeyFrame.cc / MapPoint.cc cannot be compiled
-//     that way (their class definitions are the thing being replaced): GetFeaturesInArea, GetLinesInArea,
-//     lineDescriptorMAD are supplied to the compiled matchers by this restatement.  MapPoint.cc + MapPoint.h compile
+//     in the same library (their class definitions are the thing being replaced there): GetFeaturesInArea,
+//     GetLinesInArea, lineDescriptorMAD are supplied to the compiled matchers by this restatement.  MapPoint.cc + MapPoint.h compile
 //     unmodified over stand-in KeyFrame / Frame / Map (libplvi_ref_mappoint.so): ComputeDistinctiveDescriptors is
-//     pinned.  Frame::ComputeStereoMatches / UndistortKeyPoints / AssignFeaturesToGrid (Frame.cc) stay "parity
-//     unpinned" (line-by-line restatement, regression vectors only); see DESIGN.md section 2.
+//     pinned.  Frame.cc + Frame.h compile unmodified over stand-in collaborators (slam_mock_frame.h,
+//     libplvi_ref_frame.so): AssignFeaturesToGrid, GetFeaturesInArea, lineDescriptorMAD, UndistortKeyPoints/KeyLines
+//     and ComputeStereoMatches are pinned (tests/test_oracle_vs_ref_frame.py).  Only KeyFrame.cc's GetLinesInArea and
+//     the tail of Pinhole::epipolarConstrain remain restated without a pin; see DESIGN.md section 2.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library.  The product (libplvi_cuda.so) never does.

@@ -43,6 +43,15 @@ def test_undistort_keypoints_and_grid_after_extraction(gpu):
             assert np.abs(ref - k_in[f, :n, :2]).max() > 1.0                                           # the model does move points
             rs, ri = oracle.assign_grid(ref, grid)
             assert np.array_equal(start[f], rs) and np.array_equal(items[f, :rs[-1]], ri)
+            if oracle.ref_available():   # the reference's own Frame::UndistortKeyPoints / AssignFeaturesToGrid (Frame.cc compiled unmodified)
+                keys = np.zeros(n, oracle.KEYPOINT_DTYPE)
+                keys.view(np.float32).reshape(n, 7)[:] = k_in[f, :n].view(np.float32).reshape(n, 7)
+                ru = oracle.ref_undistort_keypoints(keys)
+                assert np.array_equal(k_un[f, :n, 0], ru["x"]) and np.array_equal(k_un[f, :n, 1], ru["y"])
+                g = np.asarray(grid).reshape(-1)[0]
+                bounds = (float(g["min_x"]), float(max(corners[1, 0], corners[3, 0])), float(g["min_y"]), float(max(corners[2, 1], corners[3, 1])))
+                fs, fi = oracle.ref_assign_grid(ru, bounds)
+                assert np.array_equal(start[f], fs) and np.array_equal(items[f, :fs[-1]], fi)
     finally:
         e.close()
 

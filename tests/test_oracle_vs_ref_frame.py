@@ -113,3 +113,20 @@ def test_live_reference_compute_stereo_matches(seed, d):
     our, odp, on = oracle.stereo_matches(*args)
     assert rn == on and np.array_equal(rur, our) and np.array_equal(rdp, odp)
     assert rn > 0.3 * len(rur)
+
+
+def test_oracle_equals_reference_frame_outputs():
+    """Committed outputs of the reference's Frame.cc (tools/gen_golden_ref.py)."""
+    a, b = stereo_pair(5, 12)
+    ur, dp, n = oracle.stereo_matches(a["keypoints"], a["descriptors"], b["keypoints"], b["descriptors"], a["pyramid"], b["pyramid"],
+                                      a["plan"]["scale"], MB, MBF)
+    assert n == int(R["frame/stereo_n"]) and np.array_equal(ur, R["frame/stereo_ur"]) and np.array_equal(dp, R["frame/stereo_depth"])
+    keys = oracle.orb_extract(synth.frame_euroc(0))["keypoints"]
+    grid = frame_grid(0, 752, 0, 480)
+    xyr, lv = area_queries(keys, 0)
+    lists = oracle.features_in_area(keys, grid, xyr, lv)
+    assert np.array_equal(np.cumsum([0] + [len(x) for x in lists]), R["frame/area_start"])
+    assert np.array_equal(np.concatenate(lists), R["frame/area_items"])
+    gs, gi = oracle.assign_grid(np.stack([keys["x"], keys["y"]], 1), grid)
+    assert np.array_equal(gs, R["frame/grid_start"]) and np.array_equal(gi, R["frame/grid_items"])
+    assert np.array_equal(oracle.undistort_points(np.stack([keys["x"], keys["y"]], 1)), R["frame/undistorted_xy"])

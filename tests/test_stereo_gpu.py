@@ -48,6 +48,11 @@ def test_stereo_matches_bit_exact(gpu, w, h, nfeat):
             assert np.array_equal(ur[i, :n].view(np.uint32), rur.view(np.uint32)), i
             assert np.array_equal(dp[i, :n].view(np.uint32), rdp.view(np.uint32)), i
             assert ns[i] == rn == int((rur >= 0).sum())
+            if oracle.ref_available():   # the reference's own Frame::ComputeStereoMatches (Frame.cc compiled unmodified)
+                fur, fdp, fn = oracle.ref_stereo_matches(a["keypoints"], a["descriptors"], b["keypoints"], b["descriptors"],
+                                                         a["pyramid"], b["pyramid"], a["plan"]["scale"], MB, MBF)
+                assert fn == ns[i] and np.array_equal(ur[i, :n].view(np.uint32), fur.view(np.uint32))
+                assert np.array_equal(dp[i, :n].view(np.uint32), fdp.view(np.uint32))
             assert (ur[i, n:] == -1).all()
             total += rn
         assert total > 800          # the pairs really produce stereo points

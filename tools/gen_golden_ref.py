@@ -121,6 +121,22 @@ def main():
                                      T.SCALES, 7.5)
     out["orbmatch/sim3_n"], out["orbmatch/sim3"] = np.int32(n), m
     print("sim3", n)
+    # Frame.cc of the reference (its own Frame.h over stand-in collaborators)
+    import test_oracle_vs_ref_frame as TF
+    fa, fb = TF.stereo_pair(5, 12)
+    ur, dp, n = oracle.ref_stereo_matches(fa["keypoints"], fa["descriptors"], fb["keypoints"], fb["descriptors"], fa["pyramid"],
+                                          fb["pyramid"], fa["plan"]["scale"], TF.MB, TF.MBF)
+    out["frame/stereo_ur"], out["frame/stereo_depth"], out["frame/stereo_n"] = ur, dp, np.int32(n)
+    keys = oracle.ref_orb_extract(frame("synth_0"))["keypoints"]
+    bounds = (0.0, 752.0, 0.0, 480.0)
+    xyr, lv = TF.area_queries(keys, 0)
+    lists = oracle.ref_features_in_area(keys, bounds, xyr, lv)
+    out["frame/area_start"] = np.cumsum([0] + [len(x) for x in lists]).astype(np.int32)
+    out["frame/area_items"] = np.concatenate(lists).astype(np.int32)
+    out["frame/grid_start"], out["frame/grid_items"] = oracle.ref_assign_grid(keys, bounds)
+    uk = oracle.ref_undistort_keypoints(keys)
+    out["frame/undistorted_xy"] = np.stack([uk["x"], uk["y"]], 1)
+    print("frame", n, len(out["frame/area_items"]))
     dd, dc = T.distinctive_case(7)
     out["mappoint/distinctive"] = np.stack([oracle.ref_distinctive_descriptor(dd[p, :dc[p]]) for p in range(len(dc))])
     print("orbmatch2", out["orbmatch/frame_n"], out["orbmatch/tri_n"], out["orbmatch/fuse_n"], out["orbmatch/fuse_sim3_n"], out["orbmatch/kf_n"])
