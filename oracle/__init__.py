@@ -541,7 +541,7 @@ def ref_build(force: bool = False):
         return _REF_LIB if _REF_LIB.exists() else None
     build()
     srcs = [_DIR / "ref_glue.cpp", _DIR / "ref_glue_linematcher.cpp", _DIR / "ref_glue_orbmatcher.cpp", _DIR / "ref_glue_mappoint.cpp", _DIR / "ref_glue_frame.cpp",
-            _DIR / "cvmini" / "slam_mock_frame.h",
+            _DIR / "cvmini" / "slam_mock_frame.h", _DIR / "cvmini" / "slam_mock_keyframe.h",
             _DIR / "Makefile.ref",
             _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _DIR / "cvmini" / "slam_mock.h",
             _DIR / "cvmini" / "slam_mock_orb.h", _LIB]
@@ -1081,3 +1081,58 @@ def ref_stereo_matches(kps_l, desc_l, kps_r, desc_r, pyr_l, pyr_r, scale_factors
     n = f(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), ptr_l, ptr_r, _p(lw), _p(lh), len(lw), _p(sf), C.c_float(mb), C.c_float(mbf),
           _p(ur), _p(dp))
     return ur[:len(kl)], dp[:len(kl)], n
+
+
+def _csr_lists(start, out):
+    return [out[start[i]:start[i + 1]].copy() for i in range(len(start) - 1)]
+
+
+def ref_keyframe_features_in_area(keys, bounds, xyr):
+    """The reference's KeyFrame::GetFeaturesInArea itself (src/KeyFrame.cc:1200-1244; the keyframe is built by the reference's
+    own KeyFrame(Frame&, Map*, KeyFrameDatabase*) from a frame holding `keys`): list of index arrays."""
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    b = np.array(bounds, np.float32)
+    xyr = np.ascontiguousarray(xyr, np.float32).reshape(-1, 3)
+    cap = max(len(keys), 1) * len(xyr)
+    start, out = np.zeros(len(xyr) + 1, np.int32), np.zeros(max(cap, 1), np.int32)
+    f = ref_frame_lib().plviref_keyframe_features_in_area
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    f(_p(keys), len(keys), _p(b), _p(xyr), len(xyr), _p(start), _p(out), cap)
+    return _csr_lists(start, out)
+
+
+def ref_keyframe_lines_in_area(keylines, bounds, q5):
+    """The reference's KeyFrame::GetLinesInArea(x1, y1, x2, y2, r) itself (src/KeyFrame.cc:1170-1198): list of index arrays."""
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    b = np.array(bounds, np.float32)
+    q5 = np.ascontiguousarray(q5, np.float32).reshape(-1, 5)
+    cap = max(len(kl), 1) * len(q5)
+    start, out = np.zeros(len(q5) + 1, np.int32), np.zeros(max(cap, 1), np.int32)
+    f = ref_frame_lib().plviref_keyframe_lines_in_area
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    f(_p(kl), len(kl), _p(b), _p(q5), len(q5), _p(start), _p(out), cap)
+    return _csr_lists(start, out)
+
+
+def lines_in_area(keylines, q5):
+    """The oracle's restatement of KeyFrame::GetLinesInArea (plvio_lines_in_area)."""
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    q5 = np.ascontiguousarray(q5, np.float32).reshape(-1, 5)
+    f = lib().plvio_lines_in_area
+    f.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    tmp = np.zeros(max(len(kl), 1), np.int32)
+    out = []
+    for q in q5:
+        k = f(_p(kl), len(kl), *[C.c_float(v) for v in q], _p(tmp))
+        out.append(tmp[:k].copy())
+    return out
+
+
+def ref_keyframe_line_descriptor_mad(d0, d1):
+    """The reference's KeyFrame::lineDescriptorMAD itself (src/KeyFrame.cc:411-435)."""
+    d0, d1 = np.ascontiguousarray(d0, np.int32), np.ascontiguousarray(d1, np.int32)
+    a, b = C.c_double(0), C.c_double(0)
+    f = ref_frame_lib().plviref_keyframe_line_descriptor_mad
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    f(_p(d0), _p(d1), len(d0), C.byref(a), C.byref(b))
+    return a.value, b.value

@@ -25,6 +25,7 @@
 #include <unordered_set>
 #include "cvmini.hpp"
 #include "eigenmini.hpp"
+#include <boost/serialization/array.hpp>
 #define SLAM_MOCK_REAL_FRAME
 #include "slam_mock_orb.h"   // stand-in MapPoint / KeyFrame / GeometricCamera (the set ORBmatcher.cc compiles against)
 
@@ -47,12 +48,20 @@ class MapLine {
   cv::Mat GetNormal() { cvmini_unreachable("MapLine"); }
   float GetMaxDistanceInvariance() { cvmini_unreachable("MapLine"); }
   float GetMinDistanceInvariance() { cvmini_unreachable("MapLine"); }
+  // KeyFrame.cc
+  int GetIndexInKeyFrame(KeyFrame*) { return -1; }
+  std::map<KeyFrame*, size_t> GetObservations() { return std::map<KeyFrame*, size_t>(); }
+  void EraseObservation(KeyFrame*) {}
 };
 class ConstraintPoseImu {};
 namespace IMU {
 class Bias { public: float bax = 0, bay = 0, baz = 0, bwx = 0, bwy = 0, bwz = 0; };
 class Calib { public: cv::Mat Tcb, Tbc; };
-class Preintegrated { public: void SetNewBias(const Bias&) { cvmini_unreachable("IMU::Preintegrated"); } };
+class Preintegrated {
+ public:
+  void SetNewBias(const Bias&) { cvmini_unreachable("IMU::Preintegrated"); }
+  void CopyFrom(Preintegrated*) { cvmini_unreachable("IMU::Preintegrated"); }
+};
 }  // namespace IMU
 // ORBVocabulary / LineVocabulary = DBoW2::TemplatedVocabulary: only transform() is named (Frame::ComputeBoW; pinned
 // separately through the reference's own DBoW2, libplvi_ref.so)

@@ -10,7 +10,9 @@
 #ifndef SLAM_MOCK_REAL_FRAME   // libplvi_ref_frame.so: the reference's own Frame.h / Frame.cc (see slam_mock_frame.h)
 #define FRAME_H
 #endif
+#ifndef SLAM_MOCK_REAL_KEYFRAME   // libplvi_ref_keyframe.so: the reference's own KeyFrame.h / KeyFrame.cc (see slam_mock_keyframe.h)
 #define KEYFRAME_H
+#endif
 #ifdef SLAM_MOCK_REAL_MAPPOINT   // libplvi_ref_mappoint.so: the reference's own MapPoint.h / MapPoint.cc over stand-in KeyFrame / Frame / Map
 #define MAP_H
 #include <mutex>
@@ -55,6 +57,7 @@ class GeometricCamera {
     K.at<float>(0, 0) = fx; K.at<float>(0, 2) = cx; K.at<float>(1, 1) = fy; K.at<float>(1, 2) = cy; K.at<float>(2, 2) = 1.0f;
     return K;
   }
+  unsigned int GetId() { return 0; }
   virtual float getParameter(const int i) { return i == 0 ? fx : (i == 1 ? fy : (i == 2 ? cx : cy)); }
   virtual float uncertainty2(const cv::Mat&) { cvmini_unreachable("GeometricCamera::uncertainty2"); }
   virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat&, const cv::Mat&,
@@ -105,6 +108,8 @@ class MapPoint {
   void Replace(MapPoint*) { cvmini_unreachable("MapPoint::Replace"); }
   void AddObservation(KeyFrame*, int idx) { mFusedIdx = idx; }
   std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { return std::tuple<int, int>(-1, -1); }
+  std::map<KeyFrame*, std::tuple<int, int>> GetObservations() { return std::map<KeyFrame*, std::tuple<int, int>>(); }   // KeyFrame.cc
+  void EraseObservation(KeyFrame*) {}
 };
 
 #else
@@ -153,6 +158,7 @@ class Frame {
 
 #endif
 
+#ifndef SLAM_MOCK_REAL_KEYFRAME
 class KeyFrame {
  public:
   int N = 0, NLeft = -1, NRight = -1;
@@ -204,5 +210,7 @@ class KeyFrame {
   void ReplaceMapPointMatch(const int&, MapPoint*) {}
   Map* GetMap() { return nullptr; }
 };
+
+#endif
 
 }  // namespace ORB_SLAM3

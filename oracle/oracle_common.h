@@ -28,8 +28,9 @@
 //     unmodified over stand-in KeyFrame / Frame / Map (libplvi_ref_mappoint.so): ComputeDistinctiveDescriptors is
 //     pinned.  Frame.cc + Frame.h compile unmodified over stand-in collaborators (slam_mock_frame.h,
 //     libplvi_ref_frame.so): AssignFeaturesToGrid, GetFeaturesInArea, lineDescriptorMAD, UndistortKeyPoints/KeyLines
-//     and ComputeStereoMatches are pinned (tests/test_oracle_vs_ref_frame.py).  Only KeyFrame.cc's GetLinesInArea and
-//     the tail of Pinhole::epipolarConstrain remain restated without a pin; see DESIGN.md section 2.
+//     and ComputeStereoMatches are pinned (tests/test_oracle_vs_ref_frame.py); KeyFrame.cc + KeyFrame.h live in the
+//     same library: KeyFrame::GetFeaturesInArea / GetLinesInArea / lineDescriptorMAD are pinned too.  Only the tail of
+//     Pinhole::epipolarConstrain remains restated without a pin; see DESIGN.md section 2.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library.  The product (libplvi_cuda.so) never does.

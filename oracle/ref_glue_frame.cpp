@@ -152,3 +152,71 @@ int LineMatcher::matchGrid(const std::vector<line_2d>&, const cv::Mat&, const Gr
   fprintf(stderr, "libplvi_ref_frame: LineMatcher::matchGrid is not part of this build\n");
   abort();
 }
+
+// ---- KeyFrame (src/KeyFrame.cc + include/KeyFrame.h compiled unmodified in the same class set) ----------------------
+#include "KeyFrame.h"   // /root/reference/include
+#include "Map.h"        // guarded out: the stand-in Map / KeyFrameDatabase of slam_mock_keyframe.h
+
+namespace {
+// A keyframe is built the way the reference builds it: KeyFrame(Frame&, Map*, KeyFrameDatabase*) copies the frame's
+// keys, grid and bounds (src/KeyFrame.cc:51-106).
+struct KeyFrameCase {
+  Map map;
+  KeyFrameDatabase db;
+  Frame F;
+  KeyFrame* K = nullptr;
+  KeyFrameCase(const cv::KeyPoint* keys, int n, const cv::line_descriptor::KeyLine* kl, int nl, const float* bounds) {
+    set_bounds_and_grid(bounds);
+    F.N = n;
+    F.Nleft = -1;
+    F.Nright = -1;
+    if (n) { F.mvKeysUn.assign(keys, keys + n); F.mvKeys = F.mvKeysUn; }
+    F.mvuRight.assign(n, -1.0f);
+    F.mvDepth.assign(n, -1.0f);
+    F.mvpMapPoints.assign(n, nullptr);
+    if (nl) { F.mvKeys_Line.assign(kl, kl + nl); F.mvKeysUn_Line = F.mvKeys_Line; }
+    F.N_l = nl;
+    F.mvpMapLines.assign(nl, nullptr);
+    F.mTcw = cv::Mat::eye(4, 4, CV_32F);
+    (F.*get(TagAssignGrid()))();
+    K = new KeyFrame(F, &map, &db);
+  }
+  ~KeyFrameCase() { delete K; }
+};
+}  // namespace
+
+// KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:1200-1244) for nq queries (x, y, r): CSR of index lists.
+extern "C" void plviref_keyframe_features_in_area(const cv::KeyPoint* keys, int n, const float* bounds, const float* xyr, int nq,
+                                                  int* start, int* out, int cap) {
+  KeyFrameCase c(keys, n, nullptr, 0, bounds);
+  int pos = 0;
+  for (int q = 0; q < nq; q++) {
+    start[q] = pos;
+    const std::vector<size_t> v = c.K->GetFeaturesInArea(xyr[3 * q], xyr[3 * q + 1], xyr[3 * q + 2]);
+    for (size_t i : v) if (pos < cap) out[pos++] = (int)i;
+  }
+  start[nq] = pos;
+}
+
+// KeyFrame::GetLinesInArea(x1, y1, x2, y2, r) (src/KeyFrame.cc:1170-1198) for nq queries of 5 floats: CSR of index lists.
+extern "C" void plviref_keyframe_lines_in_area(const cv::line_descriptor::KeyLine* kl, int nl, const float* bounds, const float* q5,
+                                               int nq, int* start, int* out, int cap) {
+  KeyFrameCase c(nullptr, 0, kl, nl, bounds);
+  int pos = 0;
+  for (int q = 0; q < nq; q++) {
+    start[q] = pos;
+    const float* p = q5 + 5 * (size_t)q;
+    const std::vector<size_t> v = c.K->GetLinesInArea(p[0], p[1], p[2], p[3], p[4]);
+    for (size_t i : v) if (pos < cap) out[pos++] = (int)i;
+  }
+  start[nq] = pos;
+}
+
+// KeyFrame::lineDescriptorMAD (src/KeyFrame.cc:411-435) and KeyFrame::IsInImage (:1246-1249).
+extern "C" void plviref_keyframe_line_descriptor_mad(const int* d0, const int* d1, int n, double* nn_mad, double* nn12_mad) {
+  const float bounds[4] = {0, 752, 0, 480};
+  KeyFrameCase c(nullptr, 0, nullptr, 0, bounds);
+  std::vector<std::vector<cv::DMatch>> m(n, std::vector<cv::DMatch>(2));
+  for (int i = 0; i < n; i++) { m[i][0] = cv::DMatch(i, 0, (float)d0[i]); m[i][1] = cv::DMatch(i, 1, (float)d1[i]); }
+  c.K->lineDescriptorMAD(m, *nn_mad, *nn12_mad);
+}

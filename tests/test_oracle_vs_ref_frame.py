@@ -4,7 +4,8 @@ oracle/_ref/libplvi_ref_frame.so = Frame.cc compiled unmodified, with its own cl
 KeyFrame / MapLine / camera / IMU / vocabulary types (oracle/cvmini/slam_mock_frame.h) and the reference's own
 ORBextractor.cc / ORBmatcher.cc / gridStructure.cpp.  Frames are default-constructed and their public members filled in.
 Called: AssignFeaturesToGrid (+ PosInGrid), GetFeaturesInArea, lineDescriptorMAD, UndistortKeyPoints, UndistortKeyLines,
-ComputeStereoMatches.  cv::undistortPoints underneath is the oracle's restatement of OpenCV's (pinned against cv2).
+ComputeStereoMatches; from KeyFrame.cc + KeyFrame.h (same library): GetFeaturesInArea, GetLinesInArea, lineDescriptorMAD on a
+keyframe built by the reference's own KeyFrame(Frame&, ...) constructor.  cv::undistortPoints underneath is the oracle's restatement of OpenCV's (pinned against cv2).
 
 Bar: bit-exact.  Committed outputs (tests/golden/ref_outputs.npz: frame/*) run everywhere, the live tests where the
 library exists.
@@ -113,6 +114,45 @@ def test_live_reference_compute_stereo_matches(seed, d):
     our, odp, on = oracle.stereo_matches(*args)
     assert rn == on and np.array_equal(rur, our) and np.array_equal(rdp, odp)
     assert rn > 0.3 * len(rur)
+
+
+# ---- KeyFrame.cc + KeyFrame.h of the reference, same library: the keyframe is built by the reference's own
+# KeyFrame(Frame&, Map*, KeyFrameDatabase*) from a frame filled as above
+@needs_ref
+@pytest.mark.parametrize("seed", [0, 1])
+def test_live_reference_keyframe_features_in_area(seed):
+    keys = oracle.orb_extract(synth.frame_euroc(seed))["keypoints"]
+    bounds = (0.0, 752.0, 0.0, 480.0)
+    xyr, _ = area_queries(keys, seed + 10)
+    a = oracle.ref_keyframe_features_in_area(keys, bounds, xyr)
+    b = oracle.features_in_area(keys, frame_grid(*bounds), xyr, np.full((len(xyr), 2), -1, np.int32))
+    assert sum(len(x) for x in a) > 5000
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_live_reference_keyframe_lines_in_area(seed):
+    """GetLinesInArea as written in the reference: midpoint distance in mixed float / double, then `slope - angle` with
+    its division by zero for vertical projections."""
+    from test_oracle_vs_ref import line_fuse_case
+    kl, _, _, q, _, _ = line_fuse_case(seed, [3.0, 20.0, 60.0][seed])
+    q5 = q[:, :5]
+    a = oracle.ref_keyframe_lines_in_area(kl, (0.0, 752.0, 0.0, 480.0), q5)
+    b = oracle.lines_in_area(kl, q5)
+    assert sum(len(x) for x in a) > 100
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+@needs_ref
+def test_live_reference_keyframe_line_descriptor_mad():
+    rng = np.random.RandomState(1)
+    for n in (1, 2, 9, 64, 200):
+        d0 = rng.randint(0, 30, n).astype(np.int32)
+        d1 = d0 + rng.randint(0, 30, n).astype(np.int32)
+        assert oracle.ref_keyframe_line_descriptor_mad(d0, d1) == oracle.line_descriptor_mad(d0, d1) == oracle.ref_line_descriptor_mad(d0, d1)
 
 
 def test_oracle_equals_reference_frame_outputs():
