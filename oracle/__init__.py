@@ -719,9 +719,12 @@ def _fv_args(fv):
     return a, [_p(a[0]), _p(a[1]), _p(a[2]), C.c_int(len(a[0]))]
 
 
-def ref_search_mappoints(keys, desc, grid, scale_factors, proj, viewcos, level, flags, qdesc, th=1.0, nnratio=0.8, blocked=None):
+def ref_search_mappoints(keys, desc, grid, scale_factors, proj, viewcos, level, flags, qdesc, th=1.0, nnratio=0.8, blocked=None,
+                         real_frame_bounds=None):
     """The reference's ORBmatcher::SearchByProjection(F, vpMapPoints, th) itself (src/ORBmatcher.cc:44-214, monocular
-    frame).  flags: bit0 not in view, bit1 Observations() == 0, bit2 isBad().  Returns (nmatches, match_train)."""
+    frame).  flags: bit0 not in view, bit1 Observations() == 0, bit2 isBad().  Returns (nmatches, match_train).
+    real_frame_bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY): run it on the reference's own Frame class (libplvi_ref_frame.so:
+    its AssignFeaturesToGrid / GetFeaturesInArea underneath) instead of the stand-in Frame."""
     keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
     desc = np.ascontiguousarray(desc, np.uint8)
     g = np.array(_grid_floats(grid), np.float32)
@@ -731,7 +734,11 @@ def ref_search_mappoints(keys, desc, grid, scale_factors, proj, viewcos, level, 
     qdesc = np.ascontiguousarray(qdesc, np.uint8)
     blk = None if blocked is None else np.ascontiguousarray(blocked, np.uint8)
     mt = np.full(max(len(keys), 1), -1, np.int32)
-    f = ref_orbmatcher_lib().plviref_orb_search_by_projection_mappoints
+    if real_frame_bounds is not None:
+        g = np.array(real_frame_bounds, np.float32)
+        f = ref_frame_lib().plviref_orb_search_by_projection_mappoints_realframe
+    else:
+        f = ref_orbmatcher_lib().plviref_orb_search_by_projection_mappoints
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                   C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
     n = f(_p(keys), _p(desc), len(keys), _p(blk), _p(g), _p(sf), len(sf), _p(proj), _p(vc), _p(lv), _p(fl), _p(qdesc), len(proj),
@@ -739,7 +746,7 @@ def ref_search_mappoints(keys, desc, grid, scale_factors, proj, viewcos, level, 
     return n, mt[:len(keys)]
 
 
-def ref_search_init(keys1, desc1, keys2, desc2, grid2, prev_matched, window=100, nnratio=0.9, check_ori=True):
+def ref_search_init(keys1, desc1, keys2, desc2, grid2, prev_matched, window=100, nnratio=0.9, check_ori=True, real_frame_bounds=None):
     """The reference's ORBmatcher::SearchForInitialization itself (src/ORBmatcher.cc:706-821).
     Returns (nmatches, matches12, prev_matched updated)."""
     keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
@@ -747,7 +754,11 @@ def ref_search_init(keys1, desc1, keys2, desc2, grid2, prev_matched, window=100,
     g = np.array(_grid_floats(grid2), np.float32)
     pm = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
     m12 = np.full(max(len(keys1), 1), -1, np.int32)
-    f = ref_orbmatcher_lib().plviref_orb_search_for_initialization
+    if real_frame_bounds is not None:   # the reference's own Frame class underneath (see ref_search_mappoints)
+        g = np.array(real_frame_bounds, np.float32)
+        f = ref_frame_lib().plviref_orb_search_for_initialization_realframe
+    else:
+        f = ref_orbmatcher_lib().plviref_orb_search_for_initialization
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
                   C.c_int, C.c_void_p]
     n = f(_p(keys1), _p(desc1), len(keys1), _p(keys2), _p(desc2), len(keys2), _p(g), _p(pm), int(window), C.c_float(nnratio),
@@ -797,7 +808,8 @@ def ref_orb_descriptor_distance(a, b):
     return int(f(_p(a), _p(b)))
 
 
-def ref_search_frame(keys2, desc2, grid, bounds, scale_factors, keys1, uv, flags, qdesc, th, check_ori=True, blocked=None):
+def ref_search_frame(keys2, desc2, grid, bounds, scale_factors, keys1, uv, flags, qdesc, th, check_ori=True, blocked=None,
+                     real_frame=False):
     """The reference's ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=true) itself (src/ORBmatcher.cc:
     1962-2178) with identity poses and map point i at (uv[i], 1) before a unit pinhole camera (its projection code then
     yields uv[i] exactly).  bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY); flags bit0: no map point / outlier, bit1:
@@ -810,6 +822,13 @@ def ref_search_frame(keys2, desc2, grid, bounds, scale_factors, keys1, uv, flags
     fl = np.ascontiguousarray(flags, np.int32)
     blk = None if blocked is None else np.ascontiguousarray(blocked, np.uint8)
     mt = np.full(max(len(keys2), 1), -1, np.int32)
+    if real_frame:   # the reference's own Frame class underneath (see ref_search_mappoints); the grid follows from the bounds
+        f = ref_frame_lib().plviref_orb_search_by_projection_frame_realframe
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+        n = f(_p(keys2), _p(desc2), len(keys2), _p(blk), _p(b), _p(sf), len(sf), _p(keys1), len(keys1), _p(uv), _p(fl), _p(qdesc),
+              C.c_float(th), int(check_ori), _p(mt))
+        return n, mt[:len(keys2)]
     f = ref_orbmatcher_lib().plviref_orb_search_by_projection_frame
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]

@@ -220,3 +220,116 @@ extern "C" void plviref_keyframe_line_descriptor_mad(const int* d0, const int* d
   for (int i = 0; i < n; i++) { m[i][0] = cv::DMatch(i, 0, (float)d0[i]); m[i][1] = cv::DMatch(i, 1, (float)d1[i]); }
   c.K->lineDescriptorMAD(m, *nn_mad, *nn12_mad);
 }
+
+// ---- ORBmatcher.cc compiled against THIS class set (the reference's own Frame / KeyFrame, stand-in MapPoint): the three
+// tracking searches end to end, i.e. with the reference's own AssignFeaturesToGrid + GetFeaturesInArea underneath
+// (in libplvi_ref_orbmatcher.so the stand-in Frame borrows those two from the oracle).  Same arguments as the entry
+// points of the same name without "_realframe" in ref_glue_orbmatcher.cpp, bounds instead of the grid record.
+#include "ORBmatcher.h"
+
+namespace {
+cv::Mat vec3(float x, float y, float z) {
+  cv::Mat m(3, 1, CV_32F);
+  m.at<float>(0) = x; m.at<float>(1) = y; m.at<float>(2) = z;
+  return m;
+}
+void fill_frame(Frame& F, const cv::KeyPoint* keys, const unsigned char* desc, int n, const float* scale_factors, int nlevels) {
+  F.N = n;
+  F.Nleft = -1;
+  F.Nright = -1;
+  F.mvKeysUn.assign(keys, keys + n);
+  F.mvKeys = F.mvKeysUn;
+  F.mDescriptors = desc_mat(desc, n);
+  F.mvuRight.assign(n, -1.0f);
+  F.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+  F.mvpMapPoints.assign(n, nullptr);
+  F.mvbOutlier.assign(n, false);
+  F.mTcw = cv::Mat::eye(4, 4, CV_32F);
+  (F.*get(TagAssignGrid()))();
+}
+}  // namespace
+
+extern "C" int plviref_orb_search_by_projection_mappoints_realframe(const cv::KeyPoint* keys, const unsigned char* desc, int n,
+                                                                     const unsigned char* blocked, const float* bounds,
+                                                                     const float* scale_factors, int nlevels, const float* proj,
+                                                                     const float* viewcos, const int* level, const int* flags,
+                                                                     const unsigned char* qdesc, int nq, float th, float nnratio,
+                                                                     int* match_train) {
+  set_bounds_and_grid(bounds);
+  Frame F;
+  fill_frame(F, keys, desc, n, scale_factors, nlevels);
+  MapPoint old;
+  old.mObs = 1;
+  for (int i = 0; i < n; i++) if (blocked && blocked[i]) F.mvpMapPoints[i] = &old;
+  std::vector<MapPoint> mps(nq);
+  std::vector<MapPoint*> ptrs(nq);
+  for (int i = 0; i < nq; i++) {
+    MapPoint& m = mps[i];
+    m.mnId = i;
+    m.mbTrackInView = !(flags[i] & 1);
+    m.mObs = (flags[i] & 2) ? 0 : 1;
+    m.mBad = (flags[i] & 4) != 0;
+    m.mTrackProjX = proj[2 * i];
+    m.mTrackProjY = proj[2 * i + 1];
+    m.mTrackViewCos = viewcos[i];
+    m.mnTrackScaleLevel = level[i];
+    m.mDesc = desc_mat(qdesc + 32 * (size_t)i, 1);
+    ptrs[i] = &m;
+  }
+  ORBmatcher matcher(nnratio, true);
+  const int k = matcher.SearchByProjection(F, ptrs, th, false, 50.0f);
+  for (int i = 0; i < n; i++) match_train[i] = (F.mvpMapPoints[i] && F.mvpMapPoints[i] != &old) ? (int)F.mvpMapPoints[i]->mnId : -1;
+  return k;
+}
+
+extern "C" int plviref_orb_search_by_projection_frame_realframe(const cv::KeyPoint* keys2, const unsigned char* desc2, int n2,
+                                                                 const unsigned char* blocked, const float* bounds,
+                                                                 const float* scale_factors, int nlevels, const cv::KeyPoint* keys1,
+                                                                 int n1, const float* uv, const int* flags, const unsigned char* qdesc,
+                                                                 float th, int check_ori, int* match_train) {
+  set_bounds_and_grid(bounds);
+  GeometricCamera cam;
+  Frame C, L;
+  fill_frame(C, keys2, desc2, n2, scale_factors, nlevels);
+  C.mpCamera = &cam;
+  MapPoint old;
+  for (int i = 0; i < n2; i++) if (blocked && blocked[i]) C.mvpMapPoints[i] = &old;
+  L.N = n1;
+  L.Nleft = -1;
+  L.mvKeysUn.assign(keys1, keys1 + n1);
+  L.mvKeys = L.mvKeysUn;
+  L.mTcw = cv::Mat::eye(4, 4, CV_32F);
+  L.mvbOutlier.assign(n1, false);
+  std::vector<MapPoint> mps(n1);
+  L.mvpMapPoints.assign(n1, nullptr);
+  for (int i = 0; i < n1; i++) {
+    MapPoint& m = mps[i];
+    m.mnId = i;
+    m.mObs = (flags[i] & 2) ? 0 : 1;
+    m.mWorldPos = vec3(uv[2 * i], uv[2 * i + 1], 1.0f);
+    m.mDesc = desc_mat(qdesc + 32 * (size_t)i, 1);
+    if (!(flags[i] & 1)) L.mvpMapPoints[i] = &m;
+  }
+  ORBmatcher matcher(0.9f, check_ori != 0);
+  const int k = matcher.SearchByProjection(C, L, th, true);
+  for (int i = 0; i < n2; i++) match_train[i] = (C.mvpMapPoints[i] && C.mvpMapPoints[i] != &old) ? (int)C.mvpMapPoints[i]->mnId : -1;
+  return k;
+}
+
+extern "C" int plviref_orb_search_for_initialization_realframe(const cv::KeyPoint* keys1, const unsigned char* desc1, int n1,
+                                                                const cv::KeyPoint* keys2, const unsigned char* desc2, int n2,
+                                                                const float* bounds, float* prev_matched, int window, float nnratio,
+                                                                int check_ori, int* matches12) {
+  set_bounds_and_grid(bounds);
+  const float sf1[1] = {1.0f};
+  Frame F1, F2;
+  fill_frame(F1, keys1, desc1, n1, sf1, 1);
+  fill_frame(F2, keys2, desc2, n2, sf1, 1);
+  std::vector<cv::Point2f> prev(n1);
+  for (int i = 0; i < n1; i++) prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
+  std::vector<int> m12;
+  ORBmatcher matcher(nnratio, check_ori != 0);
+  const int k = matcher.SearchForInitialization(F1, F2, prev, m12, window);
+  for (int i = 0; i < n1; i++) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
+  return k;
+}

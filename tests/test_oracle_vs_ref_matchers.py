@@ -373,6 +373,31 @@ def test_live_reference_search_by_projection_relocalisation(pair_features, seed,
     assert n > 100
 
 
+@needs_ref
+def test_live_reference_tracking_searches_on_the_reference_frame_class(pair_features):
+    """The three tracking searches once more, now with ORBmatcher.cc compiled against the reference's OWN Frame class
+    (libplvi_ref_frame.so): AssignFeaturesToGrid and GetFeaturesInArea underneath are the reference's code as well."""
+    r1, r2, A = pair_features
+    c = mappoint_case(r1, r2, A, 2, 5.0)
+    c["qdesc"] = r1["descriptors"]
+    n, mt = oracle.ref_search_mappoints(r2["keypoints"], r2["descriptors"], GRID, SCALES, c["proj"], c["viewcos"], c["level"], c["flags"],
+                                        c["qdesc"], 5.0, 0.9, c["blocked"], real_frame_bounds=BOUNDS)
+    on, omt = oracle_mappoints(r2, c, 0.9)
+    assert n == on and np.array_equal(mt, omt) and n > 50
+    c = frame_case(r1, r2, A, 0, 15.0)
+    n, mt = oracle.ref_search_frame(r2["keypoints"], r2["descriptors"], GRID, BOUNDS, SCALES, r1["keypoints"], c["uv"], c["flags"],
+                                    r1["descriptors"], 15.0, True, c["blocked"], real_frame=True)
+    on, omt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, frame_queries(r1, c), r1["descriptors"], 100, True, c["blocked"])
+    assert n == on and np.array_equal(mt, omt) and n > 100
+    k1 = r1["keypoints"]
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m12, pm = oracle.ref_search_init(k1, r1["descriptors"], r2["keypoints"], r2["descriptors"], GRID, prev, 100, 0.9, True,
+                                        real_frame_bounds=BOUNDS)
+    on, om12, oq = oracle.search_init(r2["keypoints"], r2["descriptors"], GRID, ORBmatcher.init_queries(k1, prev, 100), r1["descriptors"],
+                                      50, 0.9, True)
+    assert n == on and np.array_equal(m12, om12) and np.array_equal(pm[:, 0], oq["u"]) and n > 50
+
+
 # ---- committed outputs of the reference (run everywhere) -------------------------------------------------------------
 def test_oracle_equals_reference_orbmatcher_outputs(pair_features):
     r1, r2, A = pair_features
