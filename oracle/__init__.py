@@ -1155,3 +1155,50 @@ def ref_keyframe_line_descriptor_mad(d0, d1):
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     f(_p(d0), _p(d1), len(d0), C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+# ---- the keyframe searches on the reference's own KeyFrame / Frame classes (libplvi_ref_frame.so) ----------------------
+def ref_fuse_real(keys, desc, bounds, scale_factors, inv_level_sigma2, uv, level, flags, qdesc, th=3.0, sim3=False):
+    """ref_fuse with ORBmatcher.cc compiled against the reference's own KeyFrame (built by its constructor from a Frame):
+    KeyFrame::GetFeaturesInArea, IsInImage, GetMapPoint, AddMapPoint are the reference's code."""
+    keys, desc, _, b, sf, uv, lv, fl, qdesc = _ref_projection_args(keys, desc, np.zeros(1, [("min_x", "<f4"), ("min_y", "<f4"), ("inv_w", "<f4"), ("inv_h", "<f4")]),
+                                                                    bounds, scale_factors, uv, level, flags, qdesc)
+    inv = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    bi = np.full(max(len(uv), 1), -1, np.int32)
+    f = ref_frame_lib().plviref_orb_fuse_realkeyframe
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = f(_p(keys), _p(desc), len(keys), _p(b), _p(sf), _p(inv), len(sf), _p(uv), _p(lv), _p(fl), _p(qdesc), len(uv), C.c_float(th),
+          int(sim3), _p(bi))
+    return n, bi[:len(uv)]
+
+
+def ref_search_by_projection_kf_real(keys, desc, bounds, scale_factors, uv, level, flags, qdesc, th, ratio_hamming=1.0, matched_in=None):
+    """ref_search_by_projection_kf on the reference's own KeyFrame class."""
+    keys, desc, _, b, sf, uv, lv, fl, qdesc = _ref_projection_args(keys, desc, np.zeros(1, [("min_x", "<f4"), ("min_y", "<f4"), ("inv_w", "<f4"), ("inv_h", "<f4")]),
+                                                                    bounds, scale_factors, uv, level, flags, qdesc)
+    mi = None if matched_in is None else np.ascontiguousarray(matched_in, np.uint8)
+    mt = np.full(max(len(keys), 1), -1, np.int32)
+    f = ref_frame_lib().plviref_orb_search_by_projection_kf_realkeyframe
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    n = f(_p(keys), _p(desc), len(keys), _p(mi), _p(b), _p(sf), len(sf), _p(uv), _p(lv), _p(fl), _p(qdesc), len(uv), int(th),
+          C.c_float(ratio_hamming), _p(mt))
+    return n, mt[:len(keys)]
+
+
+def ref_search_bow_kf_f_real(keys1, desc1, mp1, fv1, keys2, desc2, fv2, bounds, nnratio=0.7, check_ori=True):
+    """ref_search_bow_kf_f on the reference's own KeyFrame and Frame classes."""
+    keys1, keys2 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE), np.ascontiguousarray(keys2, KEYPOINT_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    mp1 = np.ascontiguousarray(mp1, np.uint8)
+    a, fa = _fv_args(fv1)
+    b, fb = _fv_args(fv2)
+    bd = np.array(bounds, np.float32)
+    mt = np.full(max(len(keys2), 1), -1, np.int32)
+    f = ref_frame_lib().plviref_orb_search_by_bow_kf_f_real
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+    n = f(_p(keys1), _p(desc1), _p(mp1), len(keys1), *fa, _p(keys2), _p(desc2), len(keys2), *fb, _p(bd), C.c_float(nnratio),
+          int(check_ori), _p(mt))
+    return n, mt[:len(keys2)]

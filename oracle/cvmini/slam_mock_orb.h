@@ -105,7 +105,8 @@ class MapPoint {
   int PredictScale(const float&, KeyFrame*) { return mnPredLevel; }
   int PredictScale(const float&, Frame*) { return mnPredLevel; }
   bool IsInKeyFrame(KeyFrame*) { return false; }
-  void Replace(MapPoint*) { cvmini_unreachable("MapPoint::Replace"); }
+  // pMPinKF->Replace(pMP) (equal Observations(): always this direction): the query point inherits the feature it hit
+  void Replace(MapPoint* p) { p->mFusedIdx = mFusedIdx; }
   void AddObservation(KeyFrame*, int idx) { mFusedIdx = idx; }
   std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { return std::tuple<int, int>(-1, -1); }
   std::map<KeyFrame*, std::tuple<int, int>> GetObservations() { return std::map<KeyFrame*, std::tuple<int, int>>(); }   // KeyFrame.cc

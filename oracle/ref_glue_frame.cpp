@@ -333,3 +333,114 @@ extern "C" int plviref_orb_search_for_initialization_realframe(const cv::KeyPoin
   for (int i = 0; i < n1; i++) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
   return k;
 }
+
+// ---- keyframe searches of ORBmatcher.cc on the reference's own KeyFrame class (built by its own constructor from a
+// frame; identity pose, unit pinhole: see ref_glue_orbmatcher.cpp for the conventions)
+namespace {
+struct KeyFrameSearchCase {
+  GeometricCamera cam;
+  Map map;
+  KeyFrameDatabase db;
+  Frame F;
+  KeyFrame* K = nullptr;
+  KeyFrameSearchCase(const cv::KeyPoint* keys, const unsigned char* desc, int n, const float* bounds, const float* scale_factors,
+                     const float* inv_sigma2, int nlevels, const std::vector<MapPoint*>* mps = nullptr,
+                     const DBoW2::FeatureVector* fv = nullptr) {
+    set_bounds_and_grid(bounds);
+    Frame::fx = Frame::fy = 1.0f; Frame::cx = Frame::cy = 0.0f; Frame::invfx = Frame::invfy = 1.0f;
+    fill_frame(F, keys, desc, n, scale_factors, nlevels);
+    F.mvDepth.assign(n, -1.0f);
+    F.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + nlevels);
+    F.mvLevelSigma2.resize(nlevels);
+    for (int l = 0; l < nlevels; l++) F.mvLevelSigma2[l] = 1.0f / inv_sigma2[l];
+    F.mnScaleLevels = nlevels;
+    F.mpCamera = &cam;
+    F.mb = 0; F.mbf = 0;
+    if (mps) F.mvpMapPoints = *mps;
+    if (fv) F.mFeatVec = *fv;
+    K = new KeyFrame(F, &map, &db);
+  }
+  ~KeyFrameSearchCase() { delete K; }
+};
+void fill_points(std::vector<MapPoint>& mps, const float* uv, const int* level, const int* flags, const unsigned char* qdesc) {
+  for (size_t i = 0; i < mps.size(); i++) {
+    MapPoint& m = mps[i];
+    m.mnId = i;
+    m.mBad = (flags[i] & 1) != 0;
+    m.mWorldPos = vec3(uv[2 * i], uv[2 * i + 1], 1.0f);
+    m.mNormal = m.mWorldPos.clone();
+    m.mnPredLevel = level[i];
+    m.mDesc = desc_mat(qdesc + 32 * i, 1);
+  }
+}
+void fill_fv2(DBoW2::FeatureVector& fv, const int* nodes, const int* start, const int* feats, int nn) {
+  for (int i = 0; i < nn; i++)
+    for (int j = start[i]; j < start[i + 1]; j++) fv.addFeature((DBoW2::NodeId)nodes[i], (unsigned int)feats[j]);
+}
+}  // namespace
+
+// ORBmatcher::Fuse(pKF, vpMapPoints, th) / Fuse(pKF, Scw = I, vpPoints, th, vpReplacePoint) on the reference's KeyFrame.
+extern "C" int plviref_orb_fuse_realkeyframe(const cv::KeyPoint* keys, const unsigned char* desc, int n, const float* bounds,
+                                             const float* scale_factors, const float* inv_sigma2, int nlevels, const float* uv,
+                                             const int* level, const int* flags, const unsigned char* qdesc, int nq, float th, int sim3,
+                                             int* best_idx) {
+  KeyFrameSearchCase c(keys, desc, n, bounds, scale_factors, inv_sigma2, nlevels);
+  std::vector<MapPoint> mps(nq);
+  fill_points(mps, uv, level, flags, qdesc);
+  std::vector<MapPoint*> ptrs(nq), repl(nq, nullptr);
+  for (int i = 0; i < nq; i++) ptrs[i] = &mps[i];
+  ORBmatcher matcher(0.6f, true);
+  const int k = sim3 ? matcher.Fuse(c.K, cv::Mat::eye(4, 4, CV_32F), ptrs, th, repl) : matcher.Fuse(c.K, ptrs, th, false);
+  for (int i = 0; i < nq; i++) {
+    best_idx[i] = mps[i].mFusedIdx;
+    if (sim3 && repl[i]) best_idx[i] = repl[i]->mFusedIdx;   // vpReplacePoint[iMP] = the point already sitting on that feature
+  }
+  return k;
+}
+
+// ORBmatcher::SearchByProjection(pKF, Scw = I, vpPoints, vpMatched, th, ratioHamming) on the reference's KeyFrame.
+extern "C" int plviref_orb_search_by_projection_kf_realkeyframe(const cv::KeyPoint* keys, const unsigned char* desc, int n,
+                                                                 const unsigned char* matched_in, const float* bounds,
+                                                                 const float* scale_factors, int nlevels, const float* uv,
+                                                                 const int* level, const int* flags, const unsigned char* qdesc, int nq,
+                                                                 int th, float ratio_hamming, int* match_train) {
+  std::vector<float> inv(nlevels, 1.0f);
+  KeyFrameSearchCase c(keys, desc, n, bounds, scale_factors, inv.data(), nlevels);
+  std::vector<MapPoint> mps(nq);
+  fill_points(mps, uv, level, flags, qdesc);
+  MapPoint old;
+  std::vector<MapPoint*> ptrs(nq), matched(n, nullptr);
+  for (int i = 0; i < nq; i++) ptrs[i] = &mps[i];
+  for (int i = 0; i < n; i++) if (matched_in && matched_in[i]) matched[i] = &old;
+  ORBmatcher matcher(0.75f, true);
+  const int k = matcher.SearchByProjection(c.K, cv::Mat::eye(4, 4, CV_32F), ptrs, matched, th, ratio_hamming);
+  for (int i = 0; i < n; i++) match_train[i] = (matched[i] && matched[i] != &old) ? (int)matched[i]->mnId : -1;
+  return k;
+}
+
+// ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) on the reference's KeyFrame and Frame.
+extern "C" int plviref_orb_search_by_bow_kf_f_real(const cv::KeyPoint* keys1, const unsigned char* desc1, const unsigned char* mp1, int n1,
+                                                    const int* fv1_nodes, const int* fv1_start, const int* fv1_feats, int nn1,
+                                                    const cv::KeyPoint* keys2, const unsigned char* desc2, int n2, const int* fv2_nodes,
+                                                    const int* fv2_start, const int* fv2_feats, int nn2, const float* bounds,
+                                                    float nnratio, int check_ori, int* match_train) {
+  const float one[1] = {1.0f};
+  std::vector<MapPoint> mps(n1);
+  std::vector<MapPoint*> ptrs(n1, nullptr);
+  for (int i = 0; i < n1; i++) {
+    mps[i].mnId = i;
+    mps[i].mBad = mp1[i] == 2;
+    if (mp1[i]) ptrs[i] = &mps[i];
+  }
+  DBoW2::FeatureVector fv1;
+  fill_fv2(fv1, fv1_nodes, fv1_start, fv1_feats, nn1);
+  KeyFrameSearchCase c(keys1, desc1, n1, bounds, one, one, 1, &ptrs, &fv1);
+  Frame F;
+  fill_frame(F, keys2, desc2, n2, one, 1);
+  fill_fv2(F.mFeatVec, fv2_nodes, fv2_start, fv2_feats, nn2);
+  std::vector<MapPoint*> out;
+  ORBmatcher matcher(nnratio, check_ori != 0);
+  const int k = matcher.SearchByBoW(c.K, F, out);
+  for (int i = 0; i < n2; i++) match_train[i] = out[i] ? (int)out[i]->mnId : -1;
+  return k;
+}

@@ -398,6 +398,31 @@ def test_live_reference_tracking_searches_on_the_reference_frame_class(pair_feat
     assert n == on and np.array_equal(m12, om12) and np.array_equal(pm[:, 0], oq["u"]) and n > 50
 
 
+@needs_ref
+def test_live_reference_keyframe_searches_on_the_reference_keyframe_class(pair_features):
+    """Fuse (both overloads), SearchByProjection(pKF, Scw, ...) and SearchByBoW(pKF, F) with ORBmatcher.cc compiled
+    against the reference's OWN KeyFrame / Frame classes (libplvi_ref_frame.so; the keyframe is built by its own
+    constructor, AddMapPoint / GetMapPoint / GetFeaturesInArea / IsInImage are the reference's code)."""
+    r1, r2, A = pair_features
+    for seed, th, sim3 in ((0, 3.0, False), (3, 7.5, True)):
+        c = kf_case(r1, r2, A, seed, th)
+        n, bi = oracle.ref_fuse_real(r2["keypoints"], r2["descriptors"], BOUNDS, SCALES, INV_SIGMA2, c["uv"], c["level"], c["flags"],
+                                     r1["descriptors"], th, sim3)
+        on, obi, _ = oracle.search_in_radius(r2["keypoints"], r2["descriptors"], GRID, kf_queries(c), r1["descriptors"], INV_SIGMA2,
+                                             0.0 if sim3 else 5.99, 50)
+        assert n == on and np.array_equal(bi, obi) and n > 50
+    c = kf_case(r1, r2, A, 1, 15.0)
+    n, mt = oracle.ref_search_by_projection_kf_real(r2["keypoints"], r2["descriptors"], BOUNDS, SCALES, c["uv"], c["level"], c["flags"],
+                                                    r1["descriptors"], 15, 1.5, c["matched_in"])
+    on, omt = oracle.search_frame(r2["keypoints"], r2["descriptors"], GRID, kf_queries(c), r1["descriptors"], 75, False, c["matched_in"])
+    assert n == on and np.array_equal(mt, omt) and n > 100
+    fv1, fv2, mp1, _ = bow_case(r1, r2, 6, 3, 2, 9)
+    n, mt = oracle.ref_search_bow_kf_f_real(r1["keypoints"], r1["descriptors"], mp1, fv1, r2["keypoints"], r2["descriptors"], fv2, BOUNDS,
+                                            0.7, True)
+    on, omt = oracle_bow_kf_f(r1, r2, fv1, fv2, mp1, 0.7, True)
+    assert n == on and np.array_equal(mt, omt) and n > 50
+
+
 # ---- committed outputs of the reference (run everywhere) -------------------------------------------------------------
 def test_oracle_equals_reference_orbmatcher_outputs(pair_features):
     r1, r2, A = pair_features
