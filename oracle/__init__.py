@@ -528,9 +528,11 @@ _REF_LIB = _DIR / "_ref" / "libplvi_ref.so"
 _REF_ORB_LIB = _DIR / "_ref" / "libplvi_ref_orbmatcher.so"   # ORBmatcher.cc (stand-in classes of its own, see Makefile.ref)
 _REF_MP_LIB = _DIR / "_ref" / "libplvi_ref_mappoint.so"     # MapPoint.cc + MapPoint.h over stand-in KeyFrame / Frame / Map
 _REF_FR_LIB = _DIR / "_ref" / "libplvi_ref_frame.so"        # Frame.cc + Frame.h over stand-in MapPoint / KeyFrame / cameras / IMU types
+_REF_PH_LIB = _DIR / "_ref" / "libplvi_ref_pinhole.so"      # Pinhole.cpp + Pinhole.h + GeometricCamera.h
 _ref_orb = None
 _ref_mp = None
 _ref_fr = None
+_ref_ph = None
 REFERENCE_ROOT = Path(os.environ.get("PLVI_REFERENCE_ROOT", "/root/reference"))
 _ref = None
 
@@ -540,12 +542,13 @@ def ref_build(force: bool = False):
     if not (REFERENCE_ROOT / "src" / "ORBextractor.cc").exists():
         return _REF_LIB if _REF_LIB.exists() else None
     build()
-    srcs = [_DIR / "ref_glue.cpp", _DIR / "ref_glue_linematcher.cpp", _DIR / "ref_glue_orbmatcher.cpp", _DIR / "ref_glue_mappoint.cpp", _DIR / "ref_glue_frame.cpp",
+    srcs = [_DIR / "ref_glue.cpp", _DIR / "ref_glue_linematcher.cpp", _DIR / "ref_glue_orbmatcher.cpp", _DIR / "ref_glue_mappoint.cpp", _DIR / "ref_glue_frame.cpp", _DIR / "ref_glue_pinhole.cpp",
+            _DIR / "cvmini" / "slam_mock_pinhole.h",
             _DIR / "cvmini" / "slam_mock_frame.h", _DIR / "cvmini" / "slam_mock_keyframe.h",
             _DIR / "Makefile.ref",
             _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _DIR / "cvmini" / "slam_mock.h",
             _DIR / "cvmini" / "slam_mock_orb.h", _LIB]
-    stale = any((not t.exists()) or any(s.stat().st_mtime > t.stat().st_mtime for s in srcs) for t in (_REF_LIB, _REF_ORB_LIB, _REF_MP_LIB, _REF_FR_LIB))
+    stale = any((not t.exists()) or any(s.stat().st_mtime > t.stat().st_mtime for s in srcs) for t in (_REF_LIB, _REF_ORB_LIB, _REF_MP_LIB, _REF_FR_LIB, _REF_PH_LIB))
     if force or stale:
         subprocess.run(["make", "-C", str(_DIR), "-f", "Makefile.ref", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []),
                        check=True, capture_output=True)
@@ -1202,3 +1205,44 @@ def ref_search_bow_kf_f_real(keys1, desc1, mp1, fv1, keys2, desc2, fv2, bounds, 
     n = f(_p(keys1), _p(desc1), _p(mp1), len(keys1), *fa, _p(keys2), _p(desc2), len(keys2), *fb, _p(bd), C.c_float(nnratio),
           int(check_ori), _p(mt))
     return n, mt[:len(keys2)]
+
+
+def _ref_pinhole_lib():
+    global _ref_ph
+    if _ref_ph is None:
+        if ref_build() is None or not _REF_PH_LIB.exists():
+            raise RuntimeError("oracle/_ref/libplvi_ref_pinhole.so is not built and /root/reference is absent")
+        lib()
+        _ref_ph = C.CDLL(str(_REF_PH_LIB))
+    return _ref_ph
+
+
+def ref_epipolar_constrain(kp1, kp2, t12, unc, K=(1.0, 1.0, 0.0, 0.0)):
+    """The reference's Pinhole::epipolarConstrain itself (src/CameraModels/Pinhole.cpp:135-157) for keypoint pairs, R12 = I,
+    translation t12, per-pair unc; both cameras with intrinsics K (unit intrinsics: F12 = [t12]x exactly).  Returns bool[n]."""
+    kp1, kp2 = np.ascontiguousarray(kp1, KEYPOINT_DTYPE), np.ascontiguousarray(kp2, KEYPOINT_DTYPE)
+    Kf, t, u = np.array(K, np.float32), np.array(t12, np.float32), np.ascontiguousarray(unc, np.float32)
+    ok = np.zeros(max(len(kp1), 1), np.uint8)
+    f = _ref_pinhole_lib().plviref_pinhole_epipolar_constrain
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(_p(kp1), _p(kp2), len(kp1), _p(Kf), _p(t), _p(u), _p(ok))
+    return ok[:len(kp1)].astype(bool)
+
+
+def epipolar_constrain(kp1, kp2, F12, unc):
+    """The oracle's restatement of the test at the end of Pinhole::epipolarConstrain for a given F12 (plvio_epipolar_constrain)."""
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    f = lib().plvio_epipolar_constrain
+    f.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float]
+    return np.array([bool(f(float(a["x"]), float(a["y"]), float(b["x"]), float(b["y"]), _p(F), float(s))) for a, b, s in zip(kp1, kp2, unc)])
+
+
+def ref_pinhole_project(K, xyz):
+    """The reference's Pinhole::project(cv::Point3f) and toK: (uv [n,2], K 3x3)."""
+    Kf = np.array(K, np.float32)
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    uv, Ko = np.zeros((len(xyz), 2), np.float32), np.zeros(9, np.float32)
+    f = _ref_pinhole_lib().plviref_pinhole_project
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    f(_p(Kf), _p(xyz), len(xyz), _p(uv), _p(Ko))
+    return uv, Ko.reshape(3, 3)

@@ -426,6 +426,21 @@ class Mat {
     m.step = (size_t)m.cols * m.elemSize();
     return m;
   }
+  Mat inv() const {   // 3x3 CV_32F only (adjugate / determinant in double, rounded once): NOT OpenCV's rounding -- the
+                      // tests that reach it invert the identity (unit pinhole K), for which every method is exact
+    if (type() != CV_32FC1 || rows != 3 || cols != 3) cvmini_unreachable("Mat::inv other than 3x3 CV_32F");
+    double a[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] = at<float>(i, j);
+    const double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                       a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    Mat m(3, 3, CV_32FC1);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        const int r0 = (j + 1) % 3, r1 = (j + 2) % 3, c0 = (i + 1) % 3, c1 = (i + 2) % 3;
+        m.at<float>(i, j) = (float)((a[r0][c0] * a[r1][c1] - a[r0][c1] * a[r1][c0]) / det);
+      }
+    return m;
+  }
   static Mat eye(int r, int c, int type) { Mat m = zeros(r, c, type); if (CV_MAT_DEPTH(type) != CV_32F) cvmini_unreachable("Mat::eye other than CV_32F"); for (int i = 0; i < (r < c ? r : c); i++) m.at<float>(i, i) = 1.0f; return m; }
   int checkVector(int, int = -1, bool = true) const { cvmini_unreachable("Mat::checkVector"); }
 };

@@ -8,6 +8,8 @@ struct Vector2d {   // named by Frame.h / Frame.cc (stereo-line helpers, never r
   Vector2d() { v[0] = v[1] = 0; }
   double& operator()(int i) { return v[i]; }
   const double& operator()(int i) const { return v[i]; }
+  double& operator[](int i) { return v[i]; }
+  const double& operator[](int i) const { return v[i]; }
 };
 struct Vector3d {
   double v[3];

@@ -38,10 +38,13 @@ class Frame;
 class MapPoint;
 class Map;
 
+extern "C" int plvio_epipolar_constrain(float x1, float y1, float x2, float y2, const float* F12, float unc);
+
 // Stand-in pinhole camera.  project = Pinhole::project (src/CameraModels/Pinhole.cpp:27-39: fx * x / z + cx in float).
 // epipolarConstrain: Pinhole.cpp:135-157 builds F12 = K1^-T [t12]x R12 K2^-1 with cv::Mat products and a matrix inverse
 // (not modelled by the stand-in) and then applies the point-to-epipolar-line test; here F12 is GIVEN (mF12, what the
-// oracle and the CUDA path take as input) and only the test itself (Pinhole.cpp:142-156) is restated.
+// oracle and the CUDA path take as input) and the test itself (Pinhole.cpp:142-156) is the oracle's restatement, which is
+// pinned against the reference's own Pinhole.cpp for F12 = [t12]x (libplvi_ref_pinhole.so, tests/test_oracle_vs_ref_frame.py).
 class GeometricCamera {
  public:
   float fx = 1, fy = 1, cx = 0, cy = 0;
@@ -62,14 +65,7 @@ class GeometricCamera {
   virtual float uncertainty2(const cv::Mat&) { cvmini_unreachable("GeometricCamera::uncertainty2"); }
   virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat&, const cv::Mat&,
                                  const float, const float unc) {
-    const float a = kp1.pt.x * mF12[0] + kp1.pt.y * mF12[3] + mF12[6];
-    const float b = kp1.pt.x * mF12[1] + kp1.pt.y * mF12[4] + mF12[7];
-    const float c = kp1.pt.x * mF12[2] + kp1.pt.y * mF12[5] + mF12[8];
-    const float num = a * kp2.pt.x + b * kp2.pt.y + c;
-    const float den = a * a + b * b;
-    if (den == 0) return false;
-    const float dsqr = num * num / den;
-    return dsqr < 3.84 * unc;
+    return plvio_epipolar_constrain(kp1.pt.x, kp1.pt.y, kp2.pt.x, kp2.pt.y, mF12, unc) != 0;
   }
   virtual bool matchAndtriangulate(const cv::KeyPoint&, const cv::KeyPoint&, GeometricCamera*, cv::Mat&, cv::Mat&, const float,
                                    const float, cv::Mat&) { cvmini_unreachable("GeometricCamera::matchAndtriangulate"); }

@@ -29,8 +29,9 @@
 //     pinned.  Frame.cc + Frame.h compile unmodified over stand-in collaborators (slam_mock_frame.h,
 //     libplvi_ref_frame.so): AssignFeaturesToGrid, GetFeaturesInArea, lineDescriptorMAD, UndistortKeyPoints/KeyLines
 //     and ComputeStereoMatches are pinned (tests/test_oracle_vs_ref_frame.py); KeyFrame.cc + KeyFrame.h live in the
-//     same library: KeyFrame::GetFeaturesInArea / GetLinesInArea / lineDescriptorMAD are pinned too.  Only the tail of
-//     Pinhole::epipolarConstrain remains restated without a pin; see DESIGN.md section 2.
+//     same library: KeyFrame::GetFeaturesInArea / GetLinesInArea / lineDescriptorMAD are pinned too.  Pinhole.cpp +
+//     Pinhole.h compile unmodified (libplvi_ref_pinhole.so): the epipolar-line test is pinned for F12 = [t12]x.
+//     See DESIGN.md section 2.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library.  The product (libplvi_cuda.so) never does.

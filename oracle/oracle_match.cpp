@@ -477,6 +477,20 @@ extern "C" int plvio_search_bow_kfkf(const plvio::Kp* keys1, const uint8_t* desc
   return nmatches;
 }
 
+// The point-to-epipolar-line test of Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:142-156) for a GIVEN F12
+// (row-major 3x3 float; the reference builds it as K1^-T [t12]x R12 K2^-1 in front of this test): l = x1' F12,
+// dsqr = (l . x2)^2 / (a^2 + b^2) < 3.84 * unc, all in float except the final double comparison.
+extern "C" int plvio_epipolar_constrain(float x1, float y1, float x2, float y2, const float* F12, float unc) {
+  const float la = x1 * F12[0] + y1 * F12[3] + F12[6];
+  const float lb = x1 * F12[1] + y1 * F12[4] + F12[7];
+  const float lc = x1 * F12[2] + y1 * F12[5] + F12[8];
+  const float num = la * x2 + lb * y2 + lc;
+  const float den = la * la + lb * lb;
+  if (den == 0) return 0;
+  const float dsqr = num * num / den;
+  return dsqr < 3.84 * unc;
+}
+
 // ---- ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo=false, bCoarse)
 // (src/ORBmatcher.cc:965-1206), monocular pinhole path, with Pinhole::epipolarConstrain
 // (src/CameraModels/Pinhole.cpp:135-157).  mpN[i] != 0: feature i has a map point.  F12 row-major 3x3 float,
@@ -511,18 +525,7 @@ extern "C" int plvio_search_triangulation(const plvio::Kp* keys1, const uint8_t*
             const float distey = epy - kp2.y;
             if (distex * distex + distey * distey < 100 * sf2[kp2.octave]) continue;
           }
-          bool ok = coarse != 0;
-          if (!ok) {   // Pinhole::epipolarConstrain
-            const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
-            const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
-            const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
-            const float num = la * kp2.x + lb * kp2.y + lc;
-            const float den = la * la + lb * lb;
-            if (den != 0) {
-              const float dsqr = num * num / den;
-              ok = dsqr < 3.84 * sigma2_2[kp2.octave];
-            }
-          }
+          const bool ok = coarse != 0 || plvio_epipolar_constrain(kp1.x, kp1.y, kp2.x, kp2.y, F12, sigma2_2[kp2.octave]) != 0;
           if (ok) { bestIdx2 = idx2; bestDist = dist; }
         }
         if (bestIdx2 >= 0) {

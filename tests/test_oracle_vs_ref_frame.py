@@ -155,6 +155,42 @@ def test_live_reference_keyframe_line_descriptor_mad():
         assert oracle.ref_keyframe_line_descriptor_mad(d0, d1) == oracle.line_descriptor_mad(d0, d1) == oracle.ref_line_descriptor_mad(d0, d1)
 
 
+# ---- Pinhole.cpp + Pinhole.h + GeometricCamera.h of the reference (library of its own)
+@needs_ref
+@pytest.mark.parametrize("t12", [(1.0, 0.0, 0.0), (0.37, -0.05, 0.02), (-2.5, 0.4, 1.25), (0.0, 0.0, 0.0)])
+def test_live_reference_epipolar_constrain(t12):
+    """Pinhole::epipolarConstrain with unit intrinsics (F12 = [t12]x exactly) against the oracle's point-to-line test
+    for that F12, on keypoint pairs around and off the epipolar lines, with the level sigmas of the pyramid."""
+    rng = np.random.RandomState(3)
+    a = oracle.orb_extract(synth.frame_euroc(9))["keypoints"][:600].copy()
+    b = a.copy()
+    b["x"] += rng.normal(0, 6, len(b)).astype(np.float32)
+    b["y"] += rng.normal(0, 1.5, len(b)).astype(np.float32)
+    unc = (np.float32(1.2) ** (2 * b["octave"])).astype(np.float32)
+    tx, ty, tz = (np.float32(v) for v in t12)
+    F12 = np.array([[0, -tz, ty], [tz, 0, -tx], [-ty, tx, 0]], np.float32)
+    r = oracle.ref_epipolar_constrain(a, b, t12, unc)
+    o = oracle.epipolar_constrain(a, b, F12, unc)
+    assert np.array_equal(r, o)
+    if t12[0] == 1.0:
+        assert 50 < r.sum() < len(r) - 50
+    if not any(t12):
+        assert not r.any()          # den == 0 -> false
+
+
+@needs_ref
+def test_live_reference_pinhole_project_equals_stand_in_camera():
+    """Pinhole::project / toK: the two one-liners the stand-in cameras of the matcher libraries restate."""
+    rng = np.random.RandomState(0)
+    K = (458.654, 457.296, 367.215, 248.375)
+    xyz = rng.uniform(-3, 3, (1000, 3)).astype(np.float32)
+    xyz[:, 2] = np.abs(xyz[:, 2]) + np.float32(0.1)
+    uv, Km = oracle.ref_pinhole_project(K, xyz)
+    Kf = np.array(K, np.float32)
+    assert np.array_equal(uv[:, 0], Kf[0] * xyz[:, 0] / xyz[:, 2] + Kf[2]) and np.array_equal(uv[:, 1], Kf[1] * xyz[:, 1] / xyz[:, 2] + Kf[3])
+    assert np.array_equal(Km, np.array([[Kf[0], 0, Kf[2]], [0, Kf[1], Kf[3]], [0, 0, 1]], np.float32))
+
+
 def test_oracle_equals_reference_frame_outputs():
     """Committed outputs of the reference's Frame.cc (tools/gen_golden_ref.py)."""
     a, b = stereo_pair(5, 12)
