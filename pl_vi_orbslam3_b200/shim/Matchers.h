@@ -33,9 +33,13 @@ class ORBmatcher {
 
   // Descriptor part of SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono):
   // the caller projects LastFrame's map points (src/ORBmatcher.cc:1992-2023) into plvi_query records.
+  // blocked (optional, one byte per current key): the key already holds a map point with Observations() > 0
+  // (src/ORBmatcher.cc:87-89, 2037-2039), or, for SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th, ratioHamming)
+  // (:473-704, which claims features while it iterates: mode FRAME, mbCheckOrientation = false), vpMatched[i] != NULL;
+  // thDist < 0: TH_HIGH (TH_LOW for INIT), else e.g. ORBdist of the relocalisation overload or TH_LOW * ratioHamming.
   int SearchByProjection(const std::vector<cv::KeyPoint>& curKeysUn, const cv::Mat& curDesc, const plvi_grid& grid,
                          std::vector<plvi_query>& queries, const cv::Mat& queryDesc, std::vector<int>& matchOfCurKey,
-                         int mode = PLVI_SEARCH_FRAME) {
+                         int mode = PLVI_SEARCH_FRAME, const std::vector<uint8_t>* blocked = nullptr, int thDist = -1) {
     const int n = (int)curKeysUn.size(), nq = (int)queries.size();
     matchOfCurKey.assign(n, -1);
     std::vector<int> mq(nq > 0 ? nq : 1);
@@ -45,8 +49,10 @@ class ORBmatcher {
     for (int i = 0; i < n; i++) std::memcpy(&d[(size_t)i * 32], curDesc.ptr(i), 32);
     for (int i = 0; i < nq; i++) std::memcpy(&qd[(size_t)i * 32], queryDesc.ptr(i), 32);
     plvi_shim::check(plvi_search_by_projection(PlviMatcherHandle::get(), mode, 1,
-                                               reinterpret_cast<const plvi_keypoint*>(curKeysUn.data()), d.data(), nullptr, &n, n,
-                                               &grid, queries.data(), qd.data(), &nq, nq, mode == PLVI_SEARCH_INIT ? TH_LOW : TH_HIGH,
+                                               reinterpret_cast<const plvi_keypoint*>(curKeysUn.data()), d.data(),
+                                               (blocked && (int)blocked->size() >= n) ? blocked->data() : nullptr, &n, n,
+                                               &grid, queries.data(), qd.data(), &nq, nq,
+                                               thDist >= 0 ? thDist : (mode == PLVI_SEARCH_INIT ? TH_LOW : TH_HIGH),
                                                mfNNratio, mbCheckOrientation ? 1 : 0, matchOfCurKey.data(), mq.data(), &nm, 0),
                      "SearchByProjection");
     return nm;

@@ -48,6 +48,24 @@ int main(int argc, char** argv) {
     int near10 = 0;
     for (size_t i = 0; i < kps.size(); i++)
       if (uRight[i] >= 0 && std::fabs((kps[i].pt.x - uRight[i]) - 10.f) < 0.5f) near10++;
+    // SearchByProjection(Frame, Frame) of the frame onto itself (identity pose: every key projects onto its own position)
+    // with the first 10 keys blocked: every other key finds itself at distance 0, or a twin with the same descriptor
+    ORB_SLAM3::ORBmatcher matcher(0.9f, true);
+    std::vector<plvi_query> qs(kps.size());
+    for (size_t i = 0; i < kps.size(); i++) {
+      qs[i].u = kps[i].pt.x; qs[i].v = kps[i].pt.y;
+      qs[i].radius = 15.0f * std::pow(1.2f, (float)kps[i].octave);
+      qs[i].min_level = kps[i].octave - 1; qs[i].max_level = kps[i].octave + 1;
+      qs[i].angle = kps[i].angle; qs[i].flags = 0;
+    }
+    plvi_grid grid = {0.f, 0.f, 64.0f / (float)w, 48.0f / (float)h};
+    std::vector<uint8_t> blocked(kps.size(), 0);
+    for (size_t i = 0; i < blocked.size() && i < 10; i++) blocked[i] = 1;
+    std::vector<int> ofKey;
+    const int nproj = matcher.SearchByProjection(kps, desc, grid, qs, desc, ofKey, PLVI_SEARCH_FRAME, &blocked);
+    int blockedHit = 0;
+    for (size_t i = 0; i < ofKey.size() && i < 10; i++) blockedHit += ofKey[i] >= 0;
+    if (blockedHit != 0 || nproj < (int)kps.size() / 2) { std::printf("shim error: SearchByProjection %d matches, %d on blocked keys\n", nproj, blockedHit); return 1; }
     std::printf("shim ok: monoIndex=%d keypoints=%zu lines=%zu self-matches=%d dist01=%d stereo=%d (disparity 10: %d)\n", mono, kps.size(),
                 kls.size(), nm, d0, nst, near10);
     return (mono == (int)kps.size() && nm <= (int)kls.size() && nst > 0 && near10 * 4 > nst) ? 0 : 1;   // the block pattern repeats, so part of the matches sit on another period
