@@ -1,8 +1,9 @@
 """CPU: the oracle against the committed golden vectors (tests/golden/, made by
 tools/gen_golden.py).  cv2_* vectors are OpenCV 4.13 outputs on the reference's own
 frames and on synthetic frames: they pin the oracle's restatement of the OpenCV primitives
-the reference calls.  oracle_* vectors pin the reference-owned logic against regressions
-(the reference has no tests and cannot be built here: "parity unpinned" for those)."""
+the reference calls.  oracle_* vectors pin the reference-owned logic against regressions; the pin
+against the reference itself (its sources compiled unmodified into oracle/_ref) lives in
+tests/test_oracle_vs_ref*.py."""
 import zlib
 from pathlib import Path
 
