@@ -1246,3 +1246,37 @@ def ref_pinhole_project(K, xyz):
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     f(_p(Kf), _p(xyz), len(xyz), _p(uv), _p(Ko))
     return uv, Ko.reshape(3, 3)
+
+
+# ---- stereo line search (Frame::ComputeStereoMatches_Lines -> LineMatcher::matchGrid) -------------------------
+_MG_ARGS = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+
+
+def _match_grid_call(f, seg1, d1, seg2, d2, inv_width, inv_height, grid_rows, grid_cols, window):
+    f.argtypes = _MG_ARGS
+    f.restype = C.c_int
+    seg1 = np.ascontiguousarray(seg1, np.float32).reshape(-1, 4)
+    seg2 = np.ascontiguousarray(seg2, np.float32).reshape(-1, 4)
+    d1, d2 = _ref_descs(d1, d2)
+    assert len(seg1) == len(d1) and len(seg2) == len(d2)
+    m = np.full(max(len(d1), 1), -1, np.int32)
+    n = f(_p(seg1), _p(d1), len(d1), _p(seg2), _p(d2), len(d2), inv_width, inv_height, grid_rows, grid_cols,
+          *[int(v) for v in window], _p(m))
+    return n, m[:len(d1)]
+
+
+def line_match_grid(seg1, d1, seg2, d2, inv_width, inv_height, grid_rows=48, grid_cols=64, window=(7, 0, 2, 2)):
+    """Oracle restatement of the line search of Frame::ComputeStereoMatches_Lines (src/Frame.cc:1421-1448: grid fill
+    along LineIterator, window (7, 0) x (2, 2)) + LineMatcher::matchGrid (src/LineMatcher.cpp:191-272).
+    seg = (startPointX, startPointY, endPointX, endPointY) in pixels; window = (left, right, up, down) cells.
+    Returns (nmatches, matches12)."""
+    return _match_grid_call(lib().plvio_line_match_grid, seg1, d1, seg2, d2, inv_width, inv_height, grid_rows,
+                            grid_cols, window)
+
+
+def ref_line_match_grid(seg1, d1, seg2, d2, inv_width, inv_height, grid_rows=48, grid_cols=64, window=(7, 0, 2, 2)):
+    """The same search through the reference's own GridStructure / LineIterator / LineMatcher::matchGrid
+    (oracle/_ref/libplvi_ref.so, oracle/ref_glue_linematcher.cpp)."""
+    return _match_grid_call(ref_lib().plviref_line_match_grid, seg1, d1, seg2, d2, inv_width, inv_height, grid_rows,
+                            grid_cols, window)

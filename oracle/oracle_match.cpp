@@ -650,3 +650,88 @@ extern "C" int plvio_line_fuse_search(const uint8_t* keylines, const uint8_t* de
   }
   return found;
 }
+
+// ---- stereo line search of Frame::ComputeStereoMatches_Lines (src/Frame.cc:1421-1448) = grid fill along
+// LineIterator (src/LineIterator.cpp:9-52, src/gridStructure.cpp:14-23,49-60) + LineMatcher::matchGrid
+// (src/LineMatcher.cpp:191-272).  Restated with one occupancy bitmap per right line (bit x of word y = the line
+// passes grid cell (x, y)) in place of the per-cell index lists and the unordered_set of candidates: a right line is
+// a candidate of a left line iff its bitmap meets the window of the left start cell or of the left end cell.  The
+// candidate order is irrelevant (ties on the best distance fail the ratio test; distances[] / matches_21[] are per
+// candidate).  Quirks kept: line_2d holds INT pairs (include/LineMatcher.h:41-42), so the left end points are
+// truncated to grid cells before the direction is formed (a left line inside one cell has a NaN direction, which
+// passes the |cos| test); cells outside the grid are dropped (GridStructure::at -> out_of_bounds).
+// seg = (startPointX, startPointY, endPointX, endPointY) per line; grid_cols, grid_rows <= 64.
+static void grid_line_bitmap(double x1, double y1, double x2, double y2, int cols, int rows, uint64_t* occ /*[rows]*/) {
+  const bool steep = std::fabs(y2 - y1) > std::fabs(x2 - x1);
+  if (steep) { std::swap(x1, y1); std::swap(x2, y2); }
+  if (x1 > x2) { std::swap(x1, x2); std::swap(y1, y2); }
+  const double dx = x2 - x1, dy = std::fabs(y2 - y1);
+  double error = dx / 2.0;
+  const int ystep = (y1 < y2) ? 1 : -1;
+  int y = (int)y1;
+  const int maxX = (int)x2;
+  for (int x = (int)x1; x <= maxX; x++) {
+    const int cx = steep ? y : x, cy = steep ? x : y;
+    if (cx >= 0 && cx < cols && cy >= 0 && cy < rows) occ[cy] |= 1ull << cx;
+    error -= dy;
+    if (error < 0) { y += ystep; error += dx; }
+  }
+}
+
+static uint64_t window_cols(int x, int cols, int wl, int wr) {
+  const int lo = std::max(0, x - wl), hi = std::min(cols, x + wr + 1);   // [lo, hi)
+  if (hi <= lo) return 0;
+  const uint64_t upto_hi = hi >= 64 ? ~0ull : ((1ull << hi) - 1);
+  return upto_hi & ~((1ull << lo) - 1);
+}
+
+extern "C" int plvio_line_match_grid(const float* seg1, const uint8_t* d1, int n1, const float* seg2, const uint8_t* d2,
+                                     int n2, double inv_width, double inv_height, int grid_rows, int grid_cols,
+                                     int win_left, int win_right, int win_up, int win_down, int* m12) {
+  if (grid_rows < 1 || grid_cols < 1 || grid_rows > 64 || grid_cols > 64) return -1;
+  std::vector<uint64_t> occ((size_t)std::max(n2, 1) * grid_rows, 0);
+  std::vector<double> dir(2 * (size_t)std::max(n2, 1));
+  for (int j = 0; j < n2; j++) {
+    const float* s = seg2 + 4 * (size_t)j;
+    double vx = (s[2] - s[0]) * inv_width, vy = (s[3] - s[1]) * inv_height;
+    const double mag = std::sqrt(vx * vx + vy * vy);
+    dir[2 * j] = vx / mag;
+    dir[2 * j + 1] = vy / mag;
+    grid_line_bitmap(s[0] * inv_width, s[1] * inv_height, s[2] * inv_width, s[3] * inv_height, grid_cols, grid_rows,
+                     occ.data() + (size_t)j * grid_rows);
+  }
+  std::vector<int> m21(std::max(n2, 1), -1), dist(std::max(n2, 1), INT_MAX);
+  int matches = 0;
+  for (int i = 0; i < n1; i++) m12[i] = -1;
+  for (int i1 = 0; i1 < n1; i1++) {
+    const float* s = seg1 + 4 * (size_t)i1;
+    const int sx = (int)(s[0] * inv_width), sy = (int)(s[1] * inv_height);
+    const int ex = (int)(s[2] * inv_width), ey = (int)(s[3] * inv_height);
+    double vx = ex - sx, vy = ey - sy;
+    const double mag = std::sqrt(vx * vx + vy * vy);
+    vx /= mag;
+    vy /= mag;
+    const uint64_t cs = window_cols(sx, grid_cols, win_left, win_right), ce = window_cols(ex, grid_cols, win_left, win_right);
+    const int s0 = std::max(0, sy - win_up), s1 = std::min(grid_rows, sy + win_down + 1);
+    const int e0 = std::max(0, ey - win_up), e1 = std::min(grid_rows, ey + win_down + 1);
+    int best = INT_MAX, best2 = INT_MAX, best_idx = -1;
+    for (int i2 = 0; i2 < n2; i2++) {
+      const uint64_t* o = occ.data() + (size_t)i2 * grid_rows;
+      bool cand = false;
+      for (int y = s0; y < s1 && !cand; y++) cand = (o[y] & cs) != 0;
+      for (int y = e0; y < e1 && !cand; y++) cand = (o[y] & ce) != 0;
+      if (!cand) continue;
+      if (std::fabs(vx * dir[2 * i2] + vy * dir[2 * i2 + 1]) < 0.75) continue;
+      const int d = hamming256(d1 + 32 * (size_t)i1, d2 + 32 * (size_t)i2);
+      if (d < dist[i2]) { dist[i2] = d; m21[i2] = i1; } else continue;
+      if (d < best) { best2 = best; best = d; best_idx = i2; }
+      else if (d < best2) best2 = d;
+    }
+    if (best < best2 * 0.9) { m12[i1] = best_idx; matches++; }
+  }
+  for (int i1 = 0; i1 < n1; i1++) {
+    int& i2 = m12[i1];
+    if (i2 >= 0 && m21[i2] != i1) { i2 = -1; matches--; }
+  }
+  return matches;
+}

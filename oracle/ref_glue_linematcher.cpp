@@ -120,3 +120,38 @@ extern "C" int plviref_line_fuse(const unsigned char* keylines, const unsigned c
   for (int i = 0; i < nq; i++) best_idx[i] = lines[i].mFusedIdx;
   return k;
 }
+
+// The line search of Frame::ComputeStereoMatches_Lines (src/Frame.cc:1421-1448): the grid and the direction table are
+// filled exactly as that function does -- with the reference's own GridStructure / getLineCoords / LineIterator
+// (src/gridStructure.cpp, src/LineIterator.cpp, compiled unmodified into this library) -- and handed to the reference's
+// LineMatcher::matchGrid (src/LineMatcher.cpp:191-272).  seg = (startPointX, startPointY, endPointX, endPointY) per line.
+#include "gridStructure.h"
+extern "C" int plviref_line_match_grid(const float* seg1, const unsigned char* d1, int n1, const float* seg2,
+                                       const unsigned char* d2, int n2, double inv_width, double inv_height, int grid_rows,
+                                       int grid_cols, int win_left, int win_right, int win_up, int win_down, int* m12) {
+  using namespace ORB_SLAM3;
+  std::vector<line_2d> coords;
+  for (int i = 0; i < n1; i++) {
+    const float* s = seg1 + 4 * (size_t)i;
+    coords.push_back(std::make_pair(std::make_pair(s[0] * inv_width, s[1] * inv_height),
+                                    std::make_pair(s[2] * inv_width, s[3] * inv_height)));
+  }
+  std::list<std::pair<int, int>> line_coords;
+  GridStructure grid(grid_rows, grid_cols);
+  std::vector<std::pair<double, double>> directions(n2);
+  for (int idx = 0; idx < n2; idx++) {
+    const float* s = seg2 + 4 * (size_t)idx;
+    std::pair<double, double>& v = directions[idx];
+    v = std::make_pair((s[2] - s[0]) * inv_width, (s[3] - s[1]) * inv_height);
+    normalize(v);
+    getLineCoords(s[0] * inv_width, s[1] * inv_height, s[2] * inv_width, s[3] * inv_height, line_coords);
+    for (const std::pair<int, int>& p : line_coords) grid.at(p.first, p.second).push_back(idx);
+  }
+  GridWindow w;
+  w.width = std::make_pair(win_left, win_right);
+  w.height = std::make_pair(win_up, win_down);
+  std::vector<int> m;
+  const int k = LineMatcher::matchGrid(coords, desc_mat(d1, n1), grid, desc_mat(d2, n2), directions, w, m);
+  for (int i = 0; i < n1; i++) m12[i] = m[i];
+  return k;
+}
