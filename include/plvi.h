@@ -457,6 +457,24 @@ int plvi_line_match(plvi_matcher* m, int npairs, const uint8_t* desc1, const int
                     const uint8_t* desc2, const int* n2, int stride2, float nnr, int mutual,
                     int* matches12, int* nmatches, int on_device);
 
+/* The stereo line search of Frame::ComputeStereoMatches_Lines (src/Frame.cc:1421-1448) over npairs left / right
+ * line sets: GridStructure(grid_rows, grid_cols) filled with every right line along ORB_SLAM3::LineIterator
+ * (src/gridStructure.cpp:14-23,49-60, src/LineIterator.cpp:9-52; the reference uses FRAME_GRID_ROWS x
+ * FRAME_GRID_COLS = 48 x 64 and inv_width = 64 / cols, inv_height = 48 / rows, src/Frame.cc:208-209), then
+ * static int LineMatcher::matchGrid(lines1, desc1, grid, desc2, directions2, w, matches_12)
+ * (include/LineMatcher.h:101, src/LineMatcher.cpp:191-272) on a fresh matches_12: candidates = right lines
+ * passing a cell of the window [x - win_left, x + win_right] x [y - win_up, y + win_down] around the left
+ * line's start or end cell (the reference: 7, 0, 2, 2), |cos| of the directions >= 0.75, pre-emption through
+ * distances[] / matches_21[], best < 0.9 * second best, mutual check.  seg = (startPointX, startPointY,
+ * endPointX, endPointY) per keyline, [npairs][stride][4] floats; desc [npairs][stride][32]; grid at most
+ * 64 x 64 cells.  Device pointers only; runs on the matcher's stream.  matches12 [npairs][stride1] (-1 = none),
+ * nmatches [npairs] = the reference's return value.  The depth / disparity filter that follows in
+ * ComputeStereoMatches_Lines stays host code. */
+int plvi_line_match_grid(plvi_matcher* m, int npairs, const float* d_seg1, const uint8_t* d_desc1, const int* d_n1,
+                         int stride1, const float* d_seg2, const uint8_t* d_desc2, const int* d_n2, int stride2,
+                         double inv_width, double inv_height, int grid_rows, int grid_cols, int win_left, int win_right,
+                         int win_up, int win_down, int* d_matches12, int* d_nmatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -942,6 +942,132 @@ struct plvi_matcher {
   int lastLaunches = 0;
 };
 
+// ---------------------------------------------------------------------------------
+// k_line_match_grid: the line search of Frame::ComputeStereoMatches_Lines (src/Frame.cc:1421-1448) =
+// GridStructure fill along LineIterator (src/LineIterator.cpp:9-52, src/gridStructure.cpp:14-23,49-60) +
+// LineMatcher::matchGrid (src/LineMatcher.cpp:191-272).  One warp per stereo pair.  The per-cell index lists and the
+// unordered_set of candidates become one occupancy bitmap per right line in shared memory (word y, bit x = the line
+// passes cell (x, y); layout [row][line] so that the lanes' reads are conflict free): a right line is a candidate iff
+// its bitmap meets the window of the left line's start cell or end cell.  Left lines are visited in order (the
+// distances[] / matches_21[] pre-emption couples them), their candidates in parallel, lane j owning right lines
+// j, j+32, ...; best / second best are merged by shuffles (the candidate order does not matter: a tie on the best
+// distance fails the ratio test).  All double arithmetic is uncontracted, as in the reference's x86-64 build.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long grid_window_cols(int x, int cols, int wl, int wr) {
+  const int lo = max(0, x - wl), hi = min(cols, x + wr + 1);
+  if (hi <= lo) return 0ull;
+  const unsigned long long upto = hi >= 64 ? ~0ull : ((1ull << hi) - 1ull);
+  return upto & ~((1ull << lo) - 1ull);
+}
+
+__global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict__ seg1, const uint8_t* __restrict__ desc1,
+                                                        const int* __restrict__ n1p, int stride1,
+                                                        const float* __restrict__ seg2, const uint8_t* __restrict__ desc2,
+                                                        const int* __restrict__ n2p, int stride2, double invw, double invh,
+                                                        int rows, int cols, int wl, int wr, int wu, int wd,
+                                                        int* __restrict__ matches12, int* __restrict__ nmatches) {
+  extern __shared__ __align__(16) unsigned char lmg_smem[];
+  unsigned long long* occ = reinterpret_cast<unsigned long long*>(lmg_smem);   // [rows][stride2]
+  double* dirx = reinterpret_cast<double*>(occ + (size_t)rows * stride2);       // [stride2]
+  double* diry = dirx + stride2;
+  uint32_t* sd2 = reinterpret_cast<uint32_t*>(diry + stride2);                  // [8][stride2]
+  int* dist = reinterpret_cast<int*>(sd2 + 8 * (size_t)stride2);                // [stride2]
+  int* m21 = dist + stride2;
+  const int pair = blockIdx.x, lane = threadIdx.x;
+  const int n1 = min(n1p[pair], stride1), n2 = min(n2p[pair], stride2);
+  seg1 += (size_t)pair * stride1 * 4;
+  seg2 += (size_t)pair * stride2 * 4;
+  desc1 += (size_t)pair * stride1 * 32;
+  desc2 += (size_t)pair * stride2 * 32;
+  int* m12 = matches12 + (size_t)pair * stride1;
+  for (int i = lane; i < rows * stride2; i += 32) occ[i] = 0ull;
+  __syncwarp();
+  for (int j = lane; j < n2; j += 32) {
+    const float4 s = *reinterpret_cast<const float4*>(seg2 + 4 * j);
+    const double vx = __dmul_rn((double)__fsub_rn(s.z, s.x), invw), vy = __dmul_rn((double)__fsub_rn(s.w, s.y), invh);
+    const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+    dirx[j] = __ddiv_rn(vx, mag);
+    diry[j] = __ddiv_rn(vy, mag);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(desc2 + 32 * j)), b = __ldg(reinterpret_cast<const uint4*>(desc2 + 32 * j) + 1);
+    sd2[0 * stride2 + j] = a.x; sd2[1 * stride2 + j] = a.y; sd2[2 * stride2 + j] = a.z; sd2[3 * stride2 + j] = a.w;
+    sd2[4 * stride2 + j] = b.x; sd2[5 * stride2 + j] = b.y; sd2[6 * stride2 + j] = b.z; sd2[7 * stride2 + j] = b.w;
+    dist[j] = INT_MAX;
+    m21[j] = -1;
+    // LineIterator over the right line in grid units
+    double x1 = __dmul_rn((double)s.x, invw), y1 = __dmul_rn((double)s.y, invh);
+    double x2 = __dmul_rn((double)s.z, invw), y2 = __dmul_rn((double)s.w, invh);
+    const bool steep = fabs(__dsub_rn(y2, y1)) > fabs(__dsub_rn(x2, x1));
+    if (steep) { double t = x1; x1 = y1; y1 = t; t = x2; x2 = y2; y2 = t; }
+    if (x1 > x2) { double t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    const double dx = __dsub_rn(x2, x1), dy = fabs(__dsub_rn(y2, y1));
+    double error = __ddiv_rn(dx, 2.0);
+    const int ystep = (y1 < y2) ? 1 : -1;
+    int y = (int)y1;
+    const int maxX = (int)x2;
+    for (int x = (int)x1; x <= maxX; x++) {
+      const int cx = steep ? y : x, cy = steep ? x : y;
+      if (cx >= 0 && cx < cols && cy >= 0 && cy < rows) occ[(size_t)cy * stride2 + j] |= 1ull << cx;
+      error = __dsub_rn(error, dy);
+      if (error < 0) { y += ystep; error = __dadd_rn(error, dx); }
+    }
+  }
+  for (int i = lane; i < n1; i += 32) m12[i] = -1;
+  __syncwarp();
+  int matches = 0;
+  for (int i1 = 0; i1 < n1; i1++) {
+    const float4 s = __ldg(reinterpret_cast<const float4*>(seg1 + 4 * i1));
+    // line_2d holds int pairs (include/LineMatcher.h:41-42): the end points are truncated to grid cells
+    const int sx = (int)__dmul_rn((double)s.x, invw), sy = (int)__dmul_rn((double)s.y, invh);
+    const int ex = (int)__dmul_rn((double)s.z, invw), ey = (int)__dmul_rn((double)s.w, invh);
+    double vx = (double)(ex - sx), vy = (double)(ey - sy);
+    const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+    vx = __ddiv_rn(vx, mag);
+    vy = __ddiv_rn(vy, mag);
+    const unsigned long long cs = grid_window_cols(sx, cols, wl, wr), ce = grid_window_cols(ex, cols, wl, wr);
+    const int s0 = max(0, sy - wu), s1 = min(rows, sy + wd + 1);
+    const int e0 = max(0, ey - wu), e1 = min(rows, ey + wd + 1);
+    uint32_t q[8];
+    {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(desc1 + 32 * i1)), b = __ldg(reinterpret_cast<const uint4*>(desc1 + 32 * i1) + 1);
+      q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+    }
+    int best = INT_MAX, best2 = INT_MAX, bidx = -1;
+    for (int i2 = lane; i2 < n2; i2 += 32) {
+      unsigned long long hit = 0ull;
+      for (int y = s0; y < s1; y++) hit |= occ[(size_t)y * stride2 + i2] & cs;
+      for (int y = e0; y < e1; y++) hit |= occ[(size_t)y * stride2 + i2] & ce;
+      if (!hit) continue;
+      if (fabs(__dadd_rn(__dmul_rn(vx, dirx[i2]), __dmul_rn(vy, diry[i2]))) < 0.75) continue;
+      int d = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) d += __popc(q[k] ^ sd2[k * stride2 + i2]);
+      if (d < dist[i2]) { dist[i2] = d; m21[i2] = i1; } else continue;
+      if (d < best) { best2 = best; best = d; bidx = i2; }
+      else if (d < best2) best2 = d;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o), ob2 = __shfl_xor_sync(0xffffffffu, best2, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob < best) { best2 = min(best, ob2); best = ob; bidx = oi; }
+      else best2 = min(best2, ob);
+    }
+    if ((double)best < __dmul_rn((double)best2, 0.9)) {
+      if (lane == 0) m12[i1] = bidx;
+      matches++;
+    }
+  }
+  __syncwarp();
+  int dropped = 0;
+  for (int i1 = lane; i1 < n1; i1 += 32) {
+    const int i2 = m12[i1];
+    if (i2 >= 0 && m21[i2] != i1) { m12[i1] = -1; dropped++; }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
+  if (lane == 0) nmatches[pair] = matches - dropped;
+}
+
 extern "C" {
 
 int plvi_matcher_create(plvi_matcher** out, int max_pairs, int max_train, int max_query, int device,
@@ -1244,6 +1370,29 @@ int plvi_line_match_mad(plvi_matcher* m, int npairs, const uint8_t* desc1, const
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_line_match_mad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_line_match_mad<<<npairs, 256, smem, m->stream>>>(desc1, n1, stride1, desc2, n2, stride2, has_line1, has_line2, factor,
                                                      matches12, nmatches, mad);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  return PLVI_OK;
+}
+
+int plvi_line_match_grid(plvi_matcher* m, int npairs, const float* d_seg1, const uint8_t* d_desc1, const int* d_n1,
+                         int stride1, const float* d_seg2, const uint8_t* d_desc2, const int* d_n2, int stride2,
+                         double inv_width, double inv_height, int grid_rows, int grid_cols, int win_left, int win_right,
+                         int win_up, int win_down, int* d_matches12, int* d_nmatches) {
+  if (!m || npairs < 1 || !d_seg1 || !d_desc1 || !d_n1 || !d_seg2 || !d_desc2 || !d_n2 || !d_matches12 || !d_nmatches ||
+      stride1 < 1 || stride2 < 1 || grid_rows < 1 || grid_cols < 1 || grid_rows > 64 || grid_cols > 64 || win_left < 0 ||
+      win_right < 0 || win_up < 0 || win_down < 0 || !(inv_width > 0.0) || !(inv_height > 0.0)) {
+    set_error("plvi_line_match_grid: invalid argument (grid at most 64 x 64 cells)");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  const size_t smem = (size_t)stride2 * ((size_t)grid_rows * 8 + 2 * sizeof(double) + 32 + 2 * sizeof(int));
+  if (smem > 200 * 1024) { set_error("plvi_line_match_grid: right line set too large for one CTA"); return PLVI_ERR_CAPACITY; }
+  if (smem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_line_match_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_line_match_grid<<<npairs, 32, smem, m->stream>>>(d_seg1, d_desc1, d_n1, stride1, d_seg2, d_desc2, d_n2, stride2, inv_width,
+                                                    inv_height, grid_rows, grid_cols, win_left, win_right, win_up, win_down,
+                                                    d_matches12, d_nmatches);
   m->lastLaunches = 1;
   PLVI_CUDA_TRY(cudaGetLastError());
   return PLVI_OK;

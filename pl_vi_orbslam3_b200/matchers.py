@@ -341,6 +341,48 @@ class LineMatcher(_Matcher):
         m12, nm, mad = m12.cpu().numpy(), nm.cpu().numpy(), mad.cpu().numpy()
         return [m12[i, :n1[i]] for i in range(P)], nm, mad
 
+    def matchGrid_batch(self, pairs, inv_width, inv_height, grid_rows=48, grid_cols=64, window=(7, 0, 2, 2)):
+        """The stereo line search of Frame::ComputeStereoMatches_Lines (src/Frame.cc:1421-1448): grid fill along
+        LineIterator + LineMatcher::matchGrid (src/LineMatcher.cpp:191-272) for a batch of stereo pairs.
+        pairs = [(seg_left [n1,4], desc_left [n1,32], seg_right [n2,4], desc_right [n2,32]), ...] with
+        seg = (startPointX, startPointY, endPointX, endPointY); window = (left, right, up, down) grid cells.
+        Returns ([matches_12 per pair], counts)."""
+        import torch
+        P = len(pairs)
+        S1 = max(max(len(p[1]) for p in pairs), 1)
+        S2 = max(max(len(p[3]) for p in pairs), 1)
+        s1 = np.zeros((P, S1, 4), np.float32)
+        s2 = np.zeros((P, S2, 4), np.float32)
+        d1 = np.zeros((P, S1, 32), np.uint8)
+        d2 = np.zeros((P, S2, 32), np.uint8)
+        n1 = np.array([len(p[1]) for p in pairs], np.int32)
+        n2 = np.array([len(p[3]) for p in pairs], np.int32)
+        for i, (a, da, b, db) in enumerate(pairs):
+            if n1[i]:
+                s1[i, :n1[i]] = np.asarray(a, np.float32).reshape(-1, 4)
+                d1[i, :n1[i]] = da
+            if n2[i]:
+                s2[i, :n2[i]] = np.asarray(b, np.float32).reshape(-1, 4)
+                d2[i, :n2[i]] = db
+        dev = torch.device("cuda", self.device)
+        t = [torch.from_numpy(x).to(dev) for x in (s1, d1, n1, s2, d2, n2)]
+        m12 = torch.empty((P, S1), dtype=torch.int32, device=dev)
+        nm = torch.empty(P, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        wl, wr, wu, wd = (int(v) for v in window)
+        check(lib().plvi_line_match_grid(self._h, P, ptr(t[0]), ptr(t[1]), ptr(t[2]), S1, ptr(t[3]), ptr(t[4]), ptr(t[5]), S2,
+                                         float(inv_width), float(inv_height), int(grid_rows), int(grid_cols), wl, wr, wu, wd,
+                                         ptr(m12), ptr(nm)))
+        self.sync()
+        m12, nm = m12.cpu().numpy(), nm.cpu().numpy()
+        return [m12[i, :n1[i]] for i in range(P)], nm
+
+    def matchGrid(self, seg_left, desc_left, seg_right, desc_right, inv_width, inv_height, **kw):
+        """int LineMatcher::matchGrid(lines1, desc1, grid, desc2, directions2, w, matches_12) with the grid and the
+        directions built from the right keylines as Frame::ComputeStereoMatches_Lines does -> (count, matches_12)."""
+        m, nm = self.matchGrid_batch([(seg_left, desc_left, seg_right, desc_right)], inv_width, inv_height, **kw)
+        return int(nm[0]), m[0]
+
     def SerachForInitialize(self, desc_initial, desc_current):
         """int LineMatcher::SerachForInitialize(Frame&, Frame&, vector<pair<int,int>>&) (src/LineMatcher.cpp:113-141)
         on the two frames' line descriptors -> (count, [(qdx, tdx), ...])."""
