@@ -475,6 +475,15 @@ int plvi_line_match_grid(plvi_matcher* m, int npairs, const float* d_seg1, const
                          double inv_width, double inv_height, int grid_rows, int grid_cols, int win_left, int win_right,
                          int win_up, int win_down, int* d_matches12, int* d_nmatches);
 
+/* The same search for ONE stereo pair with HOST buffers (what Frame::ComputeStereoMatches_Lines holds,
+ * src/Frame.cc:1421-1448): copies in, runs k_line_match_grid on the matcher's stream, copies matches12 [n1] and
+ * *nmatches back, synchronises.  n1 == 0 or n2 == 0 yields no matches (the reference returns early,
+ * src/Frame.cc:1419-1420). */
+int plvi_line_match_grid_host(plvi_matcher* m, const float* seg1, const uint8_t* desc1, int n1, const float* seg2,
+                              const uint8_t* desc2, int n2, double inv_width, double inv_height, int grid_rows,
+                              int grid_cols, int win_left, int win_right, int win_up, int win_down, int* matches12,
+                              int* nmatches);
+
 #ifdef __cplusplus
 }
 #endif

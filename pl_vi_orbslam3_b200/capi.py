@@ -91,6 +91,7 @@ _SIGS = {
     "plvi_undistort_keylines": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "plvi_assign_features_to_grid": (ci, [vp, vp, vp, ci, ci, vp, vp, vp]),
     "plvi_line_match_grid": (ci, [vp, ci, vp, vp, vp, ci, vp, vp, vp, ci, C.c_double, C.c_double, ci, ci, ci, ci, ci, ci, vp, vp]),
+    "plvi_line_match_grid_host": (ci, [vp, vp, vp, ci, vp, vp, ci, C.c_double, C.c_double, ci, ci, ci, ci, ci, ci, vp, vp]),
     "plvi_line_match_mad": (ci, [vp, ci, vp, vp, ci, vp, vp, ci, vp, vp, C.c_double, vp, vp, vp]),
     "plvi_distinctive_descriptors": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "plvi_vocab_create": (ci, [C.POINTER(vp), ci, ci, ci, ci, ci, vp, vp, vp, vp, ci]),

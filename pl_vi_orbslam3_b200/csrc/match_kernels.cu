@@ -1398,6 +1398,49 @@ int plvi_line_match_grid(plvi_matcher* m, int npairs, const float* d_seg1, const
   return PLVI_OK;
 }
 
+int plvi_line_match_grid_host(plvi_matcher* m, const float* seg1, const uint8_t* desc1, int n1, const float* seg2,
+                              const uint8_t* desc2, int n2, double inv_width, double inv_height, int grid_rows,
+                              int grid_cols, int win_left, int win_right, int win_up, int win_down, int* matches12,
+                              int* nmatches) {
+  if (!m || n1 < 0 || n2 < 0 || !matches12 || !nmatches || (n1 && (!seg1 || !desc1)) || (n2 && (!seg2 || !desc2))) {
+    set_error("plvi_line_match_grid_host: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  *nmatches = 0;
+  if (n1 == 0) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = m->stream;
+  const int s1 = n1, s2 = n2 > 0 ? n2 : 1;
+  const size_t bSeg1 = (size_t)s1 * 16, bSeg2 = (size_t)s2 * 16, bD1 = (size_t)s1 * 32, bD2 = (size_t)s2 * 32;
+  const size_t oSeg2 = bSeg1, oD1 = oSeg2 + bSeg2, oD2 = oD1 + bD1, oCnt = oD2 + bD2, oM = oCnt + 16;
+  const size_t total = oM + (size_t)s1 * sizeof(int);
+  unsigned char* buf = nullptr;
+  PLVI_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&buf), total, st));
+  const int cnt[3] = {n1, n2, 0};
+  cudaError_t e = cudaMemcpyAsync(buf, seg1, bSeg1, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + oD1, desc1, bD1, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n2) e = cudaMemcpyAsync(buf + oSeg2, seg2, (size_t)n2 * 16, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n2) e = cudaMemcpyAsync(buf + oD2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + oCnt, cnt, sizeof(cnt), cudaMemcpyHostToDevice, st);
+  int rc = PLVI_OK;
+  if (e == cudaSuccess) {
+    int* dc = reinterpret_cast<int*>(buf + oCnt);
+    rc = plvi_line_match_grid(m, 1, reinterpret_cast<const float*>(buf), buf + oD1, dc, s1,
+                              reinterpret_cast<const float*>(buf + oSeg2), buf + oD2, dc + 1, s2, inv_width, inv_height,
+                              grid_rows, grid_cols, win_left, win_right, win_up, win_down, reinterpret_cast<int*>(buf + oM),
+                              dc + 2);
+    if (rc == PLVI_OK) {
+      e = cudaMemcpyAsync(matches12, buf + oM, (size_t)n1 * sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(nmatches, dc + 2, sizeof(int), cudaMemcpyDeviceToHost, st);
+    }
+  }
+  cudaFreeAsync(buf, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (rc != PLVI_OK) return rc;
+  PLVI_CUDA_TRY(e);
+  return PLVI_OK;
+}
+
 int plvi_distinctive_descriptors(void* stream, const uint8_t* d_desc, const int* d_counts, int n_points, int stride,
                                  int* d_best_idx, uint8_t* d_best_desc) {
   if (!d_desc || !d_counts || !d_best_idx || n_points < 1 || stride < 1) {

@@ -383,6 +383,22 @@ class LineMatcher(_Matcher):
         m, nm = self.matchGrid_batch([(seg_left, desc_left, seg_right, desc_right)], inv_width, inv_height, **kw)
         return int(nm[0]), m[0]
 
+    def matchGrid_host(self, seg_left, desc_left, seg_right, desc_right, inv_width, inv_height, grid_rows=48,
+                       grid_cols=64, window=(7, 0, 2, 2)):
+        """The same search through plvi_line_match_grid_host (numpy buffers in and out, one stereo pair): the call the
+        C++ shim makes from Frame::ComputeStereoMatches_Lines -> (count, matches_12)."""
+        s1 = np.ascontiguousarray(seg_left, np.float32).reshape(-1, 4)
+        s2 = np.ascontiguousarray(seg_right, np.float32).reshape(-1, 4)
+        d1 = np.ascontiguousarray(desc_left, np.uint8).reshape(-1, 32)
+        d2 = np.ascontiguousarray(desc_right, np.uint8).reshape(-1, 32)
+        m12 = np.full(max(len(d1), 1), -1, np.int32)
+        nm = np.zeros(1, np.int32)
+        check(lib().plvi_line_match_grid_host(self._h, ptr(s1) if len(d1) else None, ptr(d1) if len(d1) else None, len(d1),
+                                              ptr(s2) if len(d2) else None, ptr(d2) if len(d2) else None, len(d2),
+                                              float(inv_width), float(inv_height), int(grid_rows), int(grid_cols),
+                                              *[int(v) for v in window], ptr(m12), ptr(nm)))
+        return int(nm[0]), m12[:len(d1)]
+
     def SerachForInitialize(self, desc_initial, desc_current):
         """int LineMatcher::SerachForInitialize(Frame&, Frame&, vector<pair<int,int>>&) (src/LineMatcher.cpp:113-141)
         on the two frames' line descriptors -> (count, [(qdx, tdx), ...])."""

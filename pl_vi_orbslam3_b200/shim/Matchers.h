@@ -3,6 +3,7 @@
 // that walk Frame / MapPoint graphs keep their host-side geometry in the caller (see
 // INTEGRATION.md); what is forwarded here is the descriptor work.
 #pragma once
+#include <stdexcept>
 #include "plvi_cv_compat.h"
 
 namespace ORB_SLAM3 {
@@ -86,6 +87,40 @@ class LineMatcher {
     int d = 0;
     plvi_shim::check(plvi_hamming256(PlviMatcherHandle::get(), a.data, b.data, 1, 1, &d, 0), "LineMatcher::DescriptorDistance");
     return d;
+  }
+
+  // The line search of Frame::ComputeStereoMatches_Lines (src/Frame.cc:1421-1448): takes the place of its grid fill
+  // (GridStructure(FRAME_GRID_ROWS, FRAME_GRID_COLS), getLineCoords per right keyline, the directions table) and of
+  // the call LineMatcher::matchGrid(coords, mDescriptors_Line, grid, mDescriptorsRight_Line, directions, w, matches_12)
+  // (include/LineMatcher.h:101, src/LineMatcher.cpp:191-272) with the window of that call site (7, 0) x (2, 2).
+  // The depth / disparity filter that follows stays in Frame.
+  static int matchGrid(const std::vector<cv::line_descriptor::KeyLine>& linesLeft, const cv::Mat& desc1,
+                       const std::vector<cv::line_descriptor::KeyLine>& linesRight, const cv::Mat& desc2, double inv_width,
+                       double inv_height, std::vector<int>& matches_12, int gridRows = 48, int gridCols = 64) {
+    const int n1 = (int)linesLeft.size(), n2 = (int)linesRight.size();
+    if (n1 != desc1.rows) throw std::runtime_error("[matchGrid] Each line needs a corresponding descriptor!");
+    matches_12.resize(n1, -1);
+    if (n1 == 0) return 0;
+    std::vector<float> s1((size_t)n1 * 4), s2((size_t)(n2 > 0 ? n2 : 1) * 4);
+    std::vector<uint8_t> a((size_t)n1 * 32), b((size_t)(n2 > 0 ? n2 : 1) * 32);
+    for (int i = 0; i < n1; i++) {
+      const cv::line_descriptor::KeyLine& k = linesLeft[i];
+      s1[4 * i] = k.startPointX; s1[4 * i + 1] = k.startPointY; s1[4 * i + 2] = k.endPointX; s1[4 * i + 3] = k.endPointY;
+      std::memcpy(&a[(size_t)i * 32], desc1.ptr(i), 32);
+    }
+    for (int i = 0; i < n2; i++) {
+      const cv::line_descriptor::KeyLine& k = linesRight[i];
+      s2[4 * i] = k.startPointX; s2[4 * i + 1] = k.startPointY; s2[4 * i + 2] = k.endPointX; s2[4 * i + 3] = k.endPointY;
+      std::memcpy(&b[(size_t)i * 32], desc2.ptr(i), 32);
+    }
+    std::vector<int> fresh(n1, -1);
+    int nm = 0;
+    plvi_shim::check(plvi_line_match_grid_host(PlviMatcherHandle::get(), s1.data(), a.data(), n1, s2.data(), b.data(), n2,
+                                               inv_width, inv_height, gridRows, gridCols, 7, 0, 2, 2, fresh.data(), &nm),
+                     "LineMatcher::matchGrid");
+    // like the reference, matches_12 is resize()d, not reset: the mutual check rewrites every entry it visits
+    for (int i = 0; i < n1; i++) matches_12[i] = fresh[i];
+    return nm;
   }
 
  private:

@@ -66,6 +66,18 @@ int main(int argc, char** argv) {
     int blockedHit = 0;
     for (size_t i = 0; i < ofKey.size() && i < 10; i++) blockedHit += ofKey[i] >= 0;
     if (blockedHit != 0 || nproj < (int)kps.size() / 2) { std::printf("shim error: SearchByProjection %d matches, %d on blocked keys\n", nproj, blockedHit); return 1; }
+    // stereo lines: the right image's keylines through LineMatcher::matchGrid (Frame::ComputeStereoMatches_Lines' search)
+    ORB_SLAM3::Lineextractor lineR(200, 0, 0.8f, 2, 2.0f, 0, w, h);
+    std::vector<cv::line_descriptor::KeyLine> klsR;
+    cv::Mat ldescR;
+    std::vector<Eigen::Vector3d> eqR;
+    lineR(imR, mask, klsR, ldescR, eqR);
+    std::vector<int> mgrid;
+    const int ngrid = ORB_SLAM3::LineMatcher::matchGrid(kls, ldesc, klsR, ldescR, 64.0 / w, 48.0 / h, mgrid);
+    int gridCount = 0;
+    for (int v : mgrid) gridCount += v >= 0;
+    if (ngrid != gridCount || (int)mgrid.size() != (int)kls.size()) { std::printf("shim error: matchGrid %d vs %d\n", ngrid, gridCount); return 1; }
+    std::printf("shim: matchGrid %d stereo line matches of %zu / %zu lines\n", ngrid, kls.size(), klsR.size());
     std::printf("shim ok: monoIndex=%d keypoints=%zu lines=%zu self-matches=%d dist01=%d stereo=%d (disparity 10: %d)\n", mono, kps.size(),
                 kls.size(), nm, d0, nst, near10);
     return (mono == (int)kps.size() && nm <= (int)kls.size() && nst > 0 && near10 * 4 > nst) ? 0 : 1;   // the block pattern repeats, so part of the matches sit on another period

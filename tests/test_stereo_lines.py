@@ -111,6 +111,10 @@ def test_match_grid_gpu_against_oracle(gpu):
         assert n == rn and np.array_equal(m, rm)
         with pytest.raises(Exception):
             lm.matchGrid(*c, INV_W, INV_H, grid_rows=65, grid_cols=64)
+        for k in (0, 3, 5, 6, 7):      # host-buffer entry (the shim's call), including the empty sides
+            rn, rm = oracle.line_match_grid(*cases[k], INV_W, INV_H)
+            n, m = lm.matchGrid_host(*cases[k], INV_W, INV_H)
+            assert n == rn and np.array_equal(m, rm), k
     finally:
         lm.close()
 
