@@ -946,19 +946,15 @@ struct plvi_matcher {
 // k_line_match_grid: the line search of Frame::ComputeStereoMatches_Lines (src/Frame.cc:1421-1448) =
 // GridStructure fill along LineIterator (src/LineIterator.cpp:9-52, src/gridStructure.cpp:14-23,49-60) +
 // LineMatcher::matchGrid (src/LineMatcher.cpp:191-272).  One warp per stereo pair.  The per-cell index lists and the
-// unordered_set of candidates become one occupancy bitmap per right line in shared memory (word y, bit x = the line
-// passes cell (x, y); layout [row][line] so that the lanes' reads are conflict free): a right line is a candidate iff
-// its bitmap meets the window of the left line's start cell or end cell.  Left lines are visited in order (the
+// unordered_set of candidates become one occupancy record per right line in shared memory: the cells a digital line
+// passes in one grid row are a contiguous run of columns (the iterator advances one cell along its major axis per step
+// and at most one across), so row y of line j is the byte pair (first, last column), (255, 0) when empty; layout
+// [row][line] so that the lanes' reads are conflict free (96 B per line instead of a 384 B bitmap: 7 pairs per SM
+// instead of 2).  A right line is a candidate iff a run meets the window of the left line's start cell or end cell.  Left lines are visited in order (the
 // distances[] / matches_21[] pre-emption couples them), their candidates in parallel, lane j owning right lines
 // j, j+32, ...; best / second best are merged by shuffles (the candidate order does not matter: a tie on the best
 // distance fails the ratio test).  All double arithmetic is uncontracted, as in the reference's x86-64 build.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long grid_window_cols(int x, int cols, int wl, int wr) {
-  const int lo = max(0, x - wl), hi = min(cols, x + wr + 1);
-  if (hi <= lo) return 0ull;
-  const unsigned long long upto = hi >= 64 ? ~0ull : ((1ull << hi) - 1ull);
-  return upto & ~((1ull << lo) - 1ull);
-}
 
 __global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict__ seg1, const uint8_t* __restrict__ desc1,
                                                         const int* __restrict__ n1p, int stride1,
@@ -967,12 +963,12 @@ __global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict_
                                                         int rows, int cols, int wl, int wr, int wu, int wd,
                                                         int* __restrict__ matches12, int* __restrict__ nmatches) {
   extern __shared__ __align__(16) unsigned char lmg_smem[];
-  unsigned long long* occ = reinterpret_cast<unsigned long long*>(lmg_smem);   // [rows][stride2]
-  double* dirx = reinterpret_cast<double*>(occ + (size_t)rows * stride2);       // [stride2]
+  double* dirx = reinterpret_cast<double*>(lmg_smem);                           // [stride2]
   double* diry = dirx + stride2;
   uint32_t* sd2 = reinterpret_cast<uint32_t*>(diry + stride2);                  // [8][stride2]
   int* dist = reinterpret_cast<int*>(sd2 + 8 * (size_t)stride2);                // [stride2]
   int* m21 = dist + stride2;
+  uchar2* run = reinterpret_cast<uchar2*>(m21 + stride2);                       // [rows][stride2] (first, last) column
   const int pair = blockIdx.x, lane = threadIdx.x;
   const int n1 = min(n1p[pair], stride1), n2 = min(n2p[pair], stride2);
   seg1 += (size_t)pair * stride1 * 4;
@@ -980,7 +976,7 @@ __global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict_
   desc1 += (size_t)pair * stride1 * 32;
   desc2 += (size_t)pair * stride2 * 32;
   int* m12 = matches12 + (size_t)pair * stride1;
-  for (int i = lane; i < rows * stride2; i += 32) occ[i] = 0ull;
+  for (int i = lane; i < rows * stride2; i += 32) run[i] = make_uchar2(255, 0);
   __syncwarp();
   for (int j = lane; j < n2; j += 32) {
     const float4 s = *reinterpret_cast<const float4*>(seg2 + 4 * j);
@@ -1006,7 +1002,12 @@ __global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict_
     const int maxX = (int)x2;
     for (int x = (int)x1; x <= maxX; x++) {
       const int cx = steep ? y : x, cy = steep ? x : y;
-      if (cx >= 0 && cx < cols && cy >= 0 && cy < rows) occ[(size_t)cy * stride2 + j] |= 1ull << cx;
+      if (cx >= 0 && cx < cols && cy >= 0 && cy < rows) {
+        uchar2 r = run[cy * stride2 + j];
+        r.x = min((int)r.x, cx);
+        r.y = max((int)r.y, cx);
+        run[cy * stride2 + j] = r;
+      }
       error = __dsub_rn(error, dy);
       if (error < 0) { y += ystep; error = __dadd_rn(error, dx); }
     }
@@ -1023,7 +1024,7 @@ __global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict_
     const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
     vx = __ddiv_rn(vx, mag);
     vy = __ddiv_rn(vy, mag);
-    const unsigned long long cs = grid_window_cols(sx, cols, wl, wr), ce = grid_window_cols(ex, cols, wl, wr);
+    const int slo = max(0, sx - wl), shi = min(cols, sx + wr + 1), elo = max(0, ex - wl), ehi = min(cols, ex + wr + 1);   // [lo, hi)
     const int s0 = max(0, sy - wu), s1 = min(rows, sy + wd + 1);
     const int e0 = max(0, ey - wu), e1 = min(rows, ey + wd + 1);
     uint32_t q[8];
@@ -1033,9 +1034,9 @@ __global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict_
     }
     int best = INT_MAX, best2 = INT_MAX, bidx = -1;
     for (int i2 = lane; i2 < n2; i2 += 32) {
-      unsigned long long hit = 0ull;
-      for (int y = s0; y < s1; y++) hit |= occ[(size_t)y * stride2 + i2] & cs;
-      for (int y = e0; y < e1; y++) hit |= occ[(size_t)y * stride2 + i2] & ce;
+      bool hit = false;
+      for (int y = s0; y < s1; y++) { const uchar2 r = run[y * stride2 + i2]; hit |= (int)r.x < shi && (int)r.y >= slo; }
+      for (int y = e0; y < e1; y++) { const uchar2 r = run[y * stride2 + i2]; hit |= (int)r.x < ehi && (int)r.y >= elo; }
       if (!hit) continue;
       if (fabs(__dadd_rn(__dmul_rn(vx, dirx[i2]), __dmul_rn(vy, diry[i2]))) < 0.75) continue;
       int d = 0;
@@ -1386,7 +1387,7 @@ int plvi_line_match_grid(plvi_matcher* m, int npairs, const float* d_seg1, const
     return PLVI_ERR_INVALID;
   }
   PLVI_CUDA_TRY(cudaSetDevice(m->device));
-  const size_t smem = (size_t)stride2 * ((size_t)grid_rows * 8 + 2 * sizeof(double) + 32 + 2 * sizeof(int));
+  const size_t smem = (size_t)stride2 * ((size_t)grid_rows * 2 + 2 * sizeof(double) + 32 + 2 * sizeof(int));
   if (smem > 200 * 1024) { set_error("plvi_line_match_grid: right line set too large for one CTA"); return PLVI_ERR_CAPACITY; }
   if (smem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_line_match_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
