@@ -21,6 +21,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -333,7 +334,9 @@ int plvi_hamming256(plvi_matcher* m, const uint8_t* a, const uint8_t* b, int n, 
  *   queries [npairs][query_stride] (INIT: u,v updated like vbPrevMatched),
  *   query_desc [npairs][query_stride][32], query_counts [npairs];
  *   th_dist: TH_HIGH (100) / TH_LOW (50); nnratio: mfNNratio; check_orientation:
- *   mbCheckOrientation (rotation histogram + ComputeThreeMaxima);
+ *   mbCheckOrientation (rotation histogram + ComputeThreeMaxima); the value 2 = checked, and a train keypoint whose
+ *   assignment the histogram removed reads -2 instead of -1 in match_train (the reference sets mvpMapPoints[i] = NULL
+ *   there, whatever it held before: src/ORBmatcher.cc:2166-2172);
  *   match_train [npairs][train_stride]: query index assigned to each train keypoint or
  *   -1 (CurrentFrame.mvpMapPoints / vnMatches21); match_query [npairs][query_stride]:
  *   train index per query or -1 (vnMatches12); nmatches [npairs]: the return value.
@@ -483,6 +486,83 @@ int plvi_line_match_grid_host(plvi_matcher* m, const float* seg1, const uint8_t*
                               const uint8_t* desc2, int n2, double inv_width, double inv_height, int grid_rows,
                               int grid_cols, int win_left, int win_right, int win_up, int win_down, int* matches12,
                               int* nmatches);
+
+/* ---- Host-buffer forms of the device-pointer searches (what the C++ shim's reference-signature adapters call:
+ * shim/src/ORBmatcher.cc, shim/src/LineMatcher.cpp).  One frame / keyframe pair per call, plain host arrays in and out,
+ * blocking; the inputs are staged in one stream-ordered device allocation.  Same semantics as the device forms. ---- */
+
+/* Rectified-stereo side information for the NEXT plvi_search_by_projection (modes FRAME / MAPPOINTS) or
+ * plvi_search_in_radius call on this matcher (it is consumed by that call): train_uright [npairs][train_stride] =
+ * Frame::mvuRight / KeyFrame::mvuRight of the searched frame, query_ur [npairs][query_stride] = right-image
+ * coordinate of every query's projection (uv.x - mbf * invz, MapPoint::mTrackProjXR).
+ *   FRAME / MAPPOINTS: a candidate with mvuRight > 0 is skipped when |ur - mvuRight| > radius
+ *     (src/ORBmatcher.cc:91-96, 2041-2047);
+ *   plvi_search_in_radius with chi2 > 0 (ORBmatcher::Fuse): a candidate with mvuRight >= 0 is gated with
+ *     (ex^2 + ey^2 + er^2) * invSigma2 > 7.8 instead of the monocular 5.99 test (src/ORBmatcher.cc:1530-1556).
+ * NULL pointers clear the side information.  on_device = 0: host arrays (copied now). */
+int plvi_matcher_set_stereo(plvi_matcher* m, const float* train_uright, const float* query_ur, int npairs, int train_stride,
+                            int query_stride, int on_device);
+
+/* plvi_search_in_radius for one keyframe with host arrays (ORBmatcher::Fuse x2, SearchBySim3; src/ORBmatcher.cc:1399-1960).
+ * train_uright / query_ur: optional stereo side information (see plvi_matcher_set_stereo), NULL for monocular. */
+int plvi_search_in_radius_host(plvi_matcher* m, const plvi_keypoint* train_keys, const uint8_t* train_desc, int n_train,
+                               const plvi_grid* grid, const plvi_query* queries, const uint8_t* query_desc, int n_query,
+                               const float* inv_level_sigma2, double chi2, int th_dist, const float* train_uright,
+                               const float* query_ur, int* best_idx, int* best_dist, int* nfound);
+
+/* plvi_search_for_triangulation for one keyframe pair with host arrays (src/ORBmatcher.cc:965-1206).  Rectified stereo:
+ * query flags bit2 = bStereo1 (pKF1->mvuRight[idx1] >= 0), train_blocked bit1 = bStereo2; the epipole-distance test only
+ * runs when neither is set (:1073-1081).  bOnlyStereo is applied by the caller (skip flag / blocked bit0). */
+int plvi_search_for_triangulation_host(plvi_matcher* m, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                                       const uint8_t* train_blocked, int n_train, const int* group_items, int n_items,
+                                       const plvi_query* queries, const uint8_t* query_desc, int n_query,
+                                       const plvi_epipolar* geometry, int th_low, int check_orientation, int* match_query,
+                                       int* nmatches);
+
+/* plvi_line_fuse_search for one keyframe with host arrays (LineMatcher::Fuse, src/LineMatcher.cpp:373-485). */
+int plvi_line_fuse_search_host(plvi_matcher* m, const plvi_keyline* keylines, const uint8_t* desc, int n, const float* queries,
+                               const uint8_t* query_flags, const uint8_t* query_desc, int n_query, int th_low, int* best_idx,
+                               int* best_dist, int* nfound);
+
+/* plvi_line_match_mad for one descriptor-set pair with host arrays (LineMatcher::SerachForInitialize, factor 0.5;
+ * LineMatcher::SearchForTriangulation, factor 0.1 with has_line masks; src/LineMatcher.cpp:113-171). */
+int plvi_line_match_mad_host(plvi_matcher* m, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, const uint8_t* has_line1,
+                             const uint8_t* has_line2, double factor, int* matches12, int* nmatches, double* mad);
+
+/* plvi_distinctive_descriptors with host arrays: MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:330-402) and
+ * MapLine::ComputeDistinctiveDescriptors (src/MapLine.cc:305-358; same median-of-distances rule on LBD descriptors with
+ * LineMatcher::distance = the plain popcount).  desc [n_points][stride][32], counts [n_points]. */
+int plvi_distinctive_descriptors_host(plvi_matcher* m, const uint8_t* desc, const int* counts, int n_points, int stride,
+                                      int* best_idx, uint8_t* best_desc);
+
+/* int LineMatcher::matchGrid(const std::vector<line_2d>& lines1, const cv::Mat& desc1, const GridStructure& grid,
+ *     const cv::Mat& desc2, const std::vector<std::pair<double,double>>& directions2, const GridWindow& w,
+ *     std::vector<int>& matches_12)   (include/LineMatcher.h:101, src/LineMatcher.cpp:191-272)
+ * with exactly the data that signature carries: lines1 [n1][4] = the left lines' integer cells (sp.first, sp.second,
+ * ep.first, ep.second); occ2 [n2][grid_rows][2] = per right line and grid row the first / last column of the cells of
+ * `grid` that list the line ((255, 0) = none; the cells of a digital line in one grid row are contiguous, see
+ * plvi_line_match_grid); directions2 [n2][2].  Host arrays, one stereo pair, blocking. */
+int plvi_line_match_grid_occ_host(plvi_matcher* m, const int* lines1, const uint8_t* desc1, int n1, const uint8_t* occ2,
+                                  const double* directions2, const uint8_t* desc2, int n2, int grid_rows, int grid_cols,
+                                  int win_left, int win_right, int win_up, int win_down, int* matches12, int* nmatches);
+
+/* static int ORBmatcher::DescriptorDistance(a, b) (src/ORBmatcher.cc:2350-2366) / LineMatcher::distance
+ * (src/LineMatcher.cpp:173-189) / LineMatcher::DescriptorDistance (:487-499, shift25 != 0) for ONE pair on the host:
+ * a pure function of two 32-byte rows that the reference calls 10^4-10^5 times per frame from MapPoint.cc:378,
+ * MapLine.cc:305 and Frame.cc:1303 -- it must not cost a kernel launch.  plvi_hamming256 is the batched device form. */
+static inline int plvi_inline_hamming256(const void* a, const void* b, int shift25) {
+  const unsigned char* pa = (const unsigned char*)a;
+  const unsigned char* pb = (const unsigned char*)b;
+  int dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t x, y;
+    memcpy(&x, pa + 4 * i, 4);
+    memcpy(&y, pb + 4 * i, 4);
+    const int c = __builtin_popcount(x ^ y);
+    dist += shift25 ? (c >> 1) : c;
+  }
+  return dist;
+}
 
 #ifdef __cplusplus
 }

@@ -536,6 +536,56 @@ _ref_ph = None
 REFERENCE_ROOT = Path(os.environ.get("PLVI_REFERENCE_ROOT", "/root/reference"))
 _ref = None
 
+# DROP-IN PROOF (Makefile.ref): the same glue and the reference's own Frame.cc / KeyFrame.cc compiled against the
+# PRODUCT's drop-in headers (pl_vi_orbslam3_b200/shim) and linked with libplvi_cuda.so.  Inside `with dropin():` every
+# ref_* wrapper of this module runs on those builds, so a test calls the same function twice and compares.
+_DROPIN_LIBS = {"libplvi_ref.so": "libplvi_dropin.so", "libplvi_ref_orbmatcher.so": "libplvi_dropin_orbmatcher.so",
+                "libplvi_ref_frame.so": "libplvi_dropin_frame.so"}
+_dropin_on = False
+_dropin_cache = {}
+
+
+def dropin_available() -> bool:
+    return all((_DIR / "_ref" / n).exists() for n in _DROPIN_LIBS.values())
+
+
+class dropin:
+    """Context manager: route ref_lib() / ref_orbmatcher_lib() / ref_frame_lib() to the drop-in builds."""
+    def __enter__(self):
+        global _dropin_on
+        if not dropin_available():
+            raise RuntimeError("oracle/_ref/libplvi_dropin*.so are not built")
+        self._prev, _dropin_on = _dropin_on, True
+        return self
+
+    def __exit__(self, *exc):
+        global _dropin_on
+        _dropin_on = self._prev
+        return False
+
+
+def _dropin_lib(ref_path):
+    name = _DROPIN_LIBS[Path(ref_path).name]
+    if name not in _dropin_cache:
+        lib()
+        # the product library first, by absolute path (the drop-in builds name it as a dependency)
+        C.CDLL(str(_DIR.parent / "pl_vi_orbslam3_b200" / "libplvi_cuda.so"), mode=C.RTLD_GLOBAL)
+        l = C.CDLL(str(_DIR / "_ref" / name))
+        if name == "libplvi_dropin.so":
+            _ref_argtypes(l)
+        _dropin_cache[name] = l
+    return _dropin_cache[name]
+
+
+def _ref_argtypes(l):
+    l.plviref_orb_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_void_p]
+    if hasattr(l, "plviref_lsd"):
+        l.plviref_lsd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int]
+    l.plviref_line_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                       C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+
 
 def ref_build(force: bool = False):
     """Build oracle/_ref/libplvi_ref.so if the reference tree is present.  Returns the path or None."""
@@ -548,7 +598,10 @@ def ref_build(force: bool = False):
             _DIR / "Makefile.ref",
             _DIR / "cvmini" / "cvmini.hpp", _DIR / "cvmini" / "eigenmini.hpp", _DIR / "cvmini" / "slam_mock.h",
             _DIR / "cvmini" / "slam_mock_orb.h", _LIB]
-    stale = any((not t.exists()) or any(s.stat().st_mtime > t.stat().st_mtime for s in srcs) for t in (_REF_LIB, _REF_ORB_LIB, _REF_MP_LIB, _REF_FR_LIB, _REF_PH_LIB))
+    shim = _DIR.parent / "pl_vi_orbslam3_b200" / "shim"
+    srcs += sorted(shim.glob("include/*.h")) + sorted(shim.glob("src/*")) + [_DIR.parent / "include" / "plvi.h"]
+    targets = [_REF_LIB, _REF_ORB_LIB, _REF_MP_LIB, _REF_FR_LIB, _REF_PH_LIB] + [_DIR / "_ref" / n for n in _DROPIN_LIBS.values()]
+    stale = any((not t.exists()) or any(s.stat().st_mtime > t.stat().st_mtime for s in srcs) for t in targets)
     if force or stale:
         subprocess.run(["make", "-C", str(_DIR), "-f", "Makefile.ref", f"REF={REFERENCE_ROOT}"] + (["-B"] if force else []),
                        check=True, capture_output=True)
@@ -561,18 +614,15 @@ def ref_available() -> bool:
 
 def ref_lib():
     global _ref
+    if _dropin_on:
+        return _dropin_lib(_REF_LIB)
     if _ref is None:
         p = ref_build()
         if p is None:
             raise RuntimeError("oracle/_ref/libplvi_ref.so is not built and /root/reference is absent")
         lib()   # libplvi_oracle.so first (the stand-in's primitives resolve into it)
         _ref = C.CDLL(str(p))
-        _ref.plviref_orb_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
-                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                             C.c_void_p, C.c_void_p]
-        _ref.plviref_lsd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int]
-        _ref.plviref_line_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                              C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _ref_argtypes(_ref)
     return _ref
 
 
@@ -709,6 +759,8 @@ def ref_orbmatcher_lib():
     """oracle/_ref/libplvi_ref_orbmatcher.so: the reference's src/ORBmatcher.cc compiled unmodified against the stand-in
     Frame / KeyFrame / MapPoint of cvmini/slam_mock_orb.h."""
     global _ref_orb
+    if _dropin_on:
+        return _dropin_lib(_REF_ORB_LIB)
     if _ref_orb is None:
         if ref_build() is None or not _REF_ORB_LIB.exists():
             raise RuntimeError("oracle/_ref/libplvi_ref_orbmatcher.so is not built and /root/reference is absent")
@@ -983,6 +1035,8 @@ def ref_frame_lib():
     """oracle/_ref/libplvi_ref_frame.so: the reference's src/Frame.cc + include/Frame.h compiled unmodified over the stand-ins
     of cvmini/slam_mock_frame.h."""
     global _ref_fr
+    if _dropin_on:
+        return _dropin_lib(_REF_FR_LIB)
     if _ref_fr is None:
         if ref_build() is None or not _REF_FR_LIB.exists():
             raise RuntimeError("oracle/_ref/libplvi_ref_frame.so is not built and /root/reference is absent")
@@ -1280,3 +1334,112 @@ def ref_line_match_grid(seg1, d1, seg2, d2, inv_width, inv_height, grid_rows=48,
     (oracle/_ref/libplvi_ref.so, oracle/ref_glue_linematcher.cpp)."""
     return _match_grid_call(ref_lib().plviref_line_match_grid, seg1, d1, seg2, d2, inv_width, inv_height, grid_rows,
                             grid_cols, window)
+
+
+# ---- the consumer's call pattern on the reference's own Frame class (ref_glue_frame.cpp: plviref_track_*) -------------
+KEYLINE_BYTES, KEYPOINT_BYTES = 68, 28
+
+
+class RefTracker:
+    """Frames built by the reference's own constructor Frame::Frame(imGray, ..., ORBextractor*, Lineextractor*, ...)
+    (src/Frame.cc:537-642) and the two searches of Tracking::TrackWithMotionModelWithLines (src/Tracking.cc:3957,3990).
+    Inside `with dropin():` the extractors / matchers underneath are the product's (libplvi_cuda.so)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, lsd_nfeatures=200, lsd_refine=0,
+                 lsd_scale=0.8, line_levels=2, line_scale=2.0):
+        self._l = ref_frame_lib()
+        f = self._l.plviref_track_create
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float]
+        self._h = f(nfeatures, scale_factor, nlevels, ini_th, min_th, lsd_nfeatures, lsd_refine, lsd_scale, line_levels, line_scale)
+        self._l.plviref_track_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        self._l.plviref_track_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        self._l.plviref_track_search.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
+                                                 C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._l.plviref_track_destroy.argtypes = [C.c_void_p]
+
+    def close(self):
+        if self._h:
+            self._l.plviref_track_destroy(self._h)
+            self._h = None
+
+    def frame(self, img, K=(458.654, 457.296, 367.215, 248.375), dist=(-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)):
+        img = _u8(img)
+        K = np.asarray(K, np.float32)
+        d = np.asarray(dist, np.float32)
+        return self._l.plviref_track_frame(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(K), _p(d), len(d))
+
+    def get(self, field, which=0):
+        buf = np.zeros(4 << 20, np.uint8)
+        n = self._l.plviref_track_get(self._h, which, field, _p(buf), buf.nbytes)
+        if n < 0:
+            raise RuntimeError(f"plviref_track_get({field}) -> {n}")
+        size = {0: KEYPOINT_BYTES, 1: KEYPOINT_BYTES, 2: 32, 3: KEYLINE_BYTES, 4: KEYLINE_BYTES, 5: 32, 6: 24}.get(field)
+        return buf[: n * size].copy() if size else buf[:n].copy()
+
+    def members(self, which=0):
+        """Every extracted member of the frame as raw bytes, keyed by the reference's member name."""
+        names = {0: "mvKeys", 1: "mvKeysUn", 2: "mDescriptors", 3: "mvKeys_Line", 4: "mvKeysUn_Line", 5: "mDescriptors_Line",
+                 6: "mvKeyLineFunctions", 7: "mGrid", 8: "bounds+grid", 9: "scale tables", 10: "line scale tables", 11: "counts"}
+        return {v: self.get(k, which) for k, v in names.items()}
+
+    def search(self, th=15.0, mono=True, depth=None, obs0=None, t=(0.0, 0.0, 0.0), nnratio=0.9, check_ori=True, line_nnr=0.9):
+        n_cur = int(np.frombuffer(self.get(11, 0), np.int32)[0])
+        n_last_l = int(np.frombuffer(self.get(11, 1), np.int32)[1])
+        pts = np.full(max(n_cur, 1), -9, np.int32)
+        m12 = np.full(max(n_last_l, 1), -9, np.int32)
+        nl = C.c_int(0)
+        d = None if depth is None else np.ascontiguousarray(depth, np.float32)
+        o = None if obs0 is None else np.ascontiguousarray(obs0, np.uint8)
+        tt = np.asarray(t, np.float32)
+        k = self._l.plviref_track_search(self._h, th, int(mono), _p(d), _p(o), _p(tt), nnratio, int(check_ori), line_nnr, _p(pts), _p(m12),
+                                         C.byref(nl))
+        return k, pts[:n_cur], nl.value, m12[:n_last_l]
+
+
+def ref_search_frame_stereo(keys2, desc2, uright2, bounds, scale_factors, keys1, depth, flags, qdesc, K, mbf, t, th, check_ori=True,
+                            blocked=None):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=false) on a rectified-stereo frame
+    (plviref_orb_search_by_projection_frame_stereo) -> (nmatches, match_train)."""
+    keys2 = np.ascontiguousarray(keys2, KEYPOINT_DTYPE); keys1 = np.ascontiguousarray(keys1, KEYPOINT_DTYPE)
+    desc2 = np.ascontiguousarray(desc2, np.uint8); qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    ur = np.ascontiguousarray(uright2, np.float32); b = np.asarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    dp = np.ascontiguousarray(depth, np.float32); fl = np.ascontiguousarray(flags, np.int32); Kf = np.asarray(K, np.float32)
+    tt = np.asarray(t, np.float32)
+    blk = None if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+    mt = np.full(max(len(keys2), 1), -9, np.int32)
+    f = ref_frame_lib().plviref_orb_search_by_projection_frame_stereo
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+    k = f(_p(keys2), _p(desc2), _p(ur), len(keys2), _p(blk), _p(b), _p(sf), len(sf), _p(keys1), len(keys1), _p(dp), _p(fl), _p(qdesc), _p(Kf),
+          float(mbf), _p(tt), float(th), int(check_ori), _p(mt))
+    return k, mt[:len(keys2)]
+
+
+def ref_fuse_stereo(keys, desc, uright, bounds, scale_factors, inv_level_sigma2, uv, depth, level, flags, qdesc, K, mbf, th=3.0):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) on a keyframe with mvuRight >= 0 observations -> (nFused, best_idx)."""
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE); desc = np.ascontiguousarray(desc, np.uint8); qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    ur = np.ascontiguousarray(uright, np.float32); b = np.asarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    s2 = np.ascontiguousarray(inv_level_sigma2, np.float32); uvf = np.ascontiguousarray(uv, np.float32); dp = np.ascontiguousarray(depth, np.float32)
+    lv = np.ascontiguousarray(level, np.int32); fl = np.ascontiguousarray(flags, np.int32); Kf = np.asarray(K, np.float32)
+    nq = len(lv)
+    best = np.full(max(nq, 1), -9, np.int32)
+    f = ref_frame_lib().plviref_orb_fuse_stereo
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    k = f(_p(keys), _p(desc), _p(ur), len(keys), _p(b), _p(sf), _p(s2), len(sf), _p(uvf), _p(dp), _p(lv), _p(fl), _p(qdesc), nq, _p(Kf),
+          float(mbf), float(th), _p(best))
+    return k, best[:nq]
+
+
+def ref_frame_stereo_lines(kl_left, desc_left, kl_right, desc_right, inv_width, inv_height, mbf):
+    """Frame::ComputeStereoMatches_Lines (src/Frame.cc:1408-1529), unmodified -> (count, [n_left, 4] = disp_s, disp_e,
+    depth_s, depth_e, mvle_l [n_left, 3])."""
+    kl = np.ascontiguousarray(kl_left); kr = np.ascontiguousarray(kl_right)
+    dl = np.ascontiguousarray(desc_left, np.uint8); dr = np.ascontiguousarray(desc_right, np.uint8)
+    out = np.zeros((max(len(kl), 1), 4), np.float32)
+    le = np.zeros((max(len(kl), 1), 3), np.float64)
+    f = ref_frame_lib().plviref_frame_stereo_lines
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_float, C.c_void_p, C.c_void_p]
+    k = f(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), float(inv_width), float(inv_height), float(mbf), _p(out), _p(le))
+    return k, out[:len(kl)], le[:len(kl)]

@@ -1,3 +1,3 @@
 // forwards to the stand-in (see cvmini.hpp)
 #pragma once
-#include "../../cvmini.hpp"
+#include "cvmini.hpp"

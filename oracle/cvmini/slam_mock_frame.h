@@ -42,12 +42,21 @@ class MapLine {
  public:
   bool mbTrackInView = false;
   float mTrackProjsX = 0, mTrackProjsY = 0, mTrackProjeX = 0, mTrackProjeY = 0, mnTrackangle = 0;
-  bool isBad() { return false; }
-  int Observations() { return 1; }
-  Eigen::Matrix<double, 6, 1> GetWorldPos() { cvmini_unreachable("MapLine"); }
-  cv::Mat GetNormal() { cvmini_unreachable("MapLine"); }
-  float GetMaxDistanceInvariance() { cvmini_unreachable("MapLine"); }
-  float GetMinDistanceInvariance() { cvmini_unreachable("MapLine"); }
+  // plain data filled by the glue (the drop-in build compiles the product's LineMatcher.cpp in this class set)
+  cv::Mat mDesc, mNormal;
+  Eigen::Matrix<double, 6, 1> mWorldPos;
+  bool mBad = false;
+  int mObs = 1, mnPredLevel = 0, mFusedIdx = -1;
+  bool isBad() { return mBad; }
+  int Observations() { return mObs; }
+  Eigen::Matrix<double, 6, 1> GetWorldPos() { return mWorldPos; }
+  cv::Mat GetNormal() { return mNormal; }
+  cv::Mat GetDescriptor() { return mDesc; }
+  float GetMaxDistanceInvariance() { return 1e30f; }
+  float GetMinDistanceInvariance() { return 0.0f; }
+  int PredictScale(const float&, const float&) { return mnPredLevel; }
+  void Replace(MapLine* p) { p->mFusedIdx = mFusedIdx; }
+  void AddObservation(KeyFrame*, size_t idx) { mFusedIdx = (int)idx; }
   // KeyFrame.cc
   int GetIndexInKeyFrame(KeyFrame*) { return -1; }
   std::map<KeyFrame*, size_t> GetObservations() { return std::map<KeyFrame*, size_t>(); }

@@ -133,7 +133,7 @@ class Frame {
   DBoW2::FeatureVector mFeatVec;
   GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
   float mbf = 0, mb = 0, fx = 0, fy = 0, cx = 0, cy = 0, invfx = 0, invfy = 0;
-  float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;
+  float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0, mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
   std::vector<float> mvScaleFactors, mvInvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
   long unsigned int mnId = 0;
   const void* grid = nullptr;   // plvio_grid_create over mvKeysUn
@@ -167,7 +167,7 @@ class KeyFrame {
   DBoW2::FeatureVector mFeatVec;
   GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
   float fx = 0, fy = 0, cx = 0, cy = 0, invfx = 0, invfy = 0, mbf = 0, mb = 0, mThDepth = 0;
-  float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0, mfLogScaleFactor = 0;
+  float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0, mfLogScaleFactor = 0, mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
   int mnScaleLevels = 0;
   std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
   long unsigned int mnId = 0;

@@ -24,6 +24,11 @@ using cv::line_descriptor::KeyLine;
 #include <sys/mman.h>
 #include <cstdlib>
 #include <new>
+#ifdef PLVI_DROPIN
+// drop-in build (Makefile.ref, "DROP-IN PROOF"): ORBextractor.h / LineExtractor.h are the product's headers, the work
+// happens in libplvi_cuda.so; only the two extractor entry points below are compiled
+namespace { struct ArenaScope {}; }
+#else
 namespace {
 // one lazily committed virtual range per call: addresses only ever increase inside it
 const size_t kArenaBytes = (size_t)16 << 30;
@@ -68,13 +73,18 @@ void operator delete(void* p) noexcept { if (p && !arena_owns(p)) free(p); }
 void operator delete[](void* p) noexcept { operator delete(p); }
 void operator delete(void* p, size_t) noexcept { operator delete(p); }
 void operator delete[](void* p, size_t) noexcept { operator delete(p); }
+#endif  // PLVI_DROPIN
 
 static_assert(sizeof(cv::KeyPoint) == 28, "cv::KeyPoint POD layout");
 static_assert(sizeof(KeyLine) == 68, "KeyLine POD layout");
 
 extern "C" {
 
+#ifndef PLVI_DROPIN
 void plviref_set_monotone(int on) { g_monotone = on != 0; }
+#else
+void plviref_set_monotone(int) {}
+#endif
 
 // ORB_SLAM3::ORBextractor::operator() (src/ORBextractor.cc:1068-1150).  Returns the number of keypoints
 // (-1: empty image, -2: capacity); *mono_index = the operator's return value.  Optional: pyr_out receives
@@ -105,6 +115,7 @@ int plviref_orb_extract(const uchar* img, int w, int h, int stride, int nfeature
   return n;
 }
 
+#ifndef PLVI_DROPIN
 // cv::createLineSegmentDetector(...)->detect on one u8 image (src/LSD/lsd.cpp:412-534).  segs: x1,y1,x2,y2.
 int plviref_lsd(const uchar* img, int stride, int w, int h, int refine, float lsd_scale, float* segs, int cap) {
   ArenaScope scope;
@@ -116,6 +127,8 @@ int plviref_lsd(const uchar* img, int stride, int w, int h, int refine, float ls
   for (int i = 0; i < std::min(n, cap); i++) memcpy(segs + 4 * i, lines[i].val, 16);
   return n;
 }
+
+#endif  // PLVI_DROPIN
 
 // ORB_SLAM3::Lineextractor::operator() (src/LineExtractor.cc:45-117), extractor 0 (LSD + LBD).
 int plviref_line_extract(const uchar* img, int w, int h, int stride, int lsd_nfeatures, int lsd_refine, float lsd_scale,
@@ -138,6 +151,7 @@ int plviref_line_extract(const uchar* img, int w, int h, int stride, int lsd_nfe
 
 }  // extern "C"
 
+#ifndef PLVI_DROPIN
 // Frame::ComputeBoW (src/Frame.cc:1115-1122): ORBVocabulary (include/ORBVocabulary.h) = DBoW2's
 // TemplatedVocabulary<FORB::TDescriptor, FORB>, loaded with the reference's own loadFromTextFile (the ORBvoc.txt
 // format) and applied with transform(features, BowVector, FeatureVector, levelsup).  The two maps are returned in key
@@ -182,3 +196,4 @@ extern "C" int plviref_bow_transform(const char* voc_text_path, const uchar* des
 PLVIREF_STUB(plviref_stub_edlines_ctor0, "_ZN7EDLinesC1Ev")
 PLVIREF_STUB(plviref_stub_edlines_ctor1, "_ZN7EDLinesC1EN2cv3MatEdidd")
 PLVIREF_STUB(plviref_stub_edlines_getlines, "_ZN7EDLines8getLinesEv")
+#endif  // PLVI_DROPIN

@@ -31,8 +31,18 @@ void fill_fv(DBoW2::FeatureVector& fv, const int* nodes, const int* start, const
 }
 struct GridOwner {
   void* g;
-  GridOwner(const cv::KeyPoint* k, int n, const float* grid) : g(plvio_grid_create(k, n, grid[0], grid[1], grid[2], grid[3])) {}
+  float par[4];
+  GridOwner(const cv::KeyPoint* k, int n, const float* grid) : g(plvio_grid_create(k, n, grid[0], grid[1], grid[2], grid[3])) {
+    memcpy(par, grid, sizeof(par));
+  }
   ~GridOwner() { plvio_grid_destroy(g); }
+  // the reference's ORBmatcher.cc reaches the grid through GetFeaturesInArea (-> the oracle's grid object); the
+  // drop-in build reads the four parameters Frame / KeyFrame hold (mnMinX, mnMinY, mfGridElementWidthInv / HeightInv)
+  template <class FrameLike> void attach(FrameLike& f) const {
+    f.grid = g;
+    f.mnMinX = par[0]; f.mnMinY = par[1];
+    f.mfGridElementWidthInv = par[2]; f.mfGridElementHeightInv = par[3];
+  }
 };
 }  // namespace
 
@@ -53,7 +63,7 @@ extern "C" int plviref_orb_search_by_projection_mappoints(const cv::KeyPoint* ke
   F.mvuRight.assign(n, -1.0f);
   F.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
   GridOwner go(keys, n, grid);
-  F.grid = go.g;
+  go.attach(F);
   MapPoint old;   // stands for every map point the frame held before the call
   old.mObs = 1;
   F.mvpMapPoints.assign(n, nullptr);
@@ -91,7 +101,7 @@ extern "C" int plviref_orb_search_for_initialization(const cv::KeyPoint* keys1, 
   F2.mvKeysUn = F2.mvKeys = key_vec(keys2, n2);
   F2.mDescriptors = desc_mat(desc2, n2);
   GridOwner go(keys2, n2, grid2);
-  F2.grid = go.g;
+  go.attach(F2);
   std::vector<cv::Point2f> prev(n1);
   for (int i = 0; i < n1; i++) prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
   std::vector<int> m12;
@@ -195,7 +205,7 @@ extern "C" int plviref_orb_search_by_projection_frame(const cv::KeyPoint* keys2,
   C.mpCamera = &cam;
   C.mTcw = eye_f32(4);
   GridOwner go(keys2, n2, grid);
-  C.grid = go.g;
+  go.attach(C);
   MapPoint old;
   C.mvpMapPoints.assign(n2, nullptr);
   for (int i = 0; i < n2; i++) if (blocked && blocked[i]) C.mvpMapPoints[i] = &old;
@@ -310,7 +320,7 @@ extern "C" int plviref_orb_fuse(const cv::KeyPoint* keys, const unsigned char* d
   std::vector<MapPoint> mps(nq);
   fill_projection_case(K, cam, keys, desc, n, bounds, scale_factors, inv_sigma2, nlevels, mps, uv, level, flags, qdesc);
   GridOwner go(keys, n, grid);
-  K.grid = go.g;
+  go.attach(K);
   std::vector<MapPoint*> ptrs(nq);
   for (int i = 0; i < nq; i++) ptrs[i] = &mps[i];
   ORBmatcher matcher(0.6f, true);
@@ -328,7 +338,7 @@ extern "C" int plviref_orb_fuse_sim3(const cv::KeyPoint* keys, const unsigned ch
   std::vector<MapPoint> mps(nq);
   fill_projection_case(K, cam, keys, desc, n, bounds, scale_factors, inv_sigma2, nlevels, mps, uv, level, flags, qdesc);
   GridOwner go(keys, n, grid);
-  K.grid = go.g;
+  go.attach(K);
   std::vector<MapPoint*> ptrs(nq), repl(nq, nullptr);
   for (int i = 0; i < nq; i++) ptrs[i] = &mps[i];
   ORBmatcher matcher(0.6f, true);
@@ -350,7 +360,7 @@ extern "C" int plviref_orb_search_by_projection_kf(const cv::KeyPoint* keys, con
   std::vector<float> inv(nlevels, 1.0f);
   fill_projection_case(K, cam, keys, desc, n, bounds, scale_factors, inv.data(), nlevels, mps, uv, level, flags, qdesc);
   GridOwner go(keys, n, grid);
-  K.grid = go.g;
+  go.attach(K);
   MapPoint old;
   std::vector<MapPoint*> ptrs(nq), matched(n, nullptr);
   for (int i = 0; i < nq; i++) ptrs[i] = &mps[i];
@@ -377,8 +387,8 @@ extern "C" int plviref_orb_search_by_sim3(const cv::KeyPoint* keys1, const unsig
   fill_projection_case(K1, cam, keys1, desc1, n1, bounds, scale_factors, inv.data(), nlevels, m1, uv1, level1, flags1, desc1);
   fill_projection_case(K2, cam, keys2, desc2, n2, bounds, scale_factors, inv.data(), nlevels, m2, uv2, level2, flags2, desc2);
   GridOwner g1(keys1, n1, grid), g2(keys2, n2, grid);
-  K1.grid = g1.g;
-  K2.grid = g2.g;
+  g1.attach(K1);
+  g2.attach(K2);
   MapPoint old;
   std::vector<MapPoint*> out(n1, nullptr);
   for (int i = 0; i < n1; i++) {
@@ -417,7 +427,7 @@ extern "C" int plviref_orb_search_by_projection_reloc(const cv::KeyPoint* keys2,
   C.mpCamera = &cam;
   C.mTcw = eye_f32(4);
   GridOwner go(keys2, n2, grid);
-  C.grid = go.g;
+  go.attach(C);
   MapPoint old;
   C.mvpMapPoints.assign(n2, nullptr);
   for (int i = 0; i < n2; i++) if (blocked && blocked[i]) C.mvpMapPoints[i] = &old;

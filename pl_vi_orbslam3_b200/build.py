@@ -39,16 +39,37 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """One object per .cu (compiled in parallel, rebuilt only when the source or a header is newer), then one link."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     extra = os.environ.get("PLVI_NVCC_EXTRA", "").split()
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", str(LIB)] + [str(s) for s in sources()]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    hdr_t = max(d.stat().st_mtime for d in list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "plvi.h"])
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = objdir / (src.stem + ".o")
+        if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_t):
+            return obj, None
+        r = subprocess.run([nvcc_path()] + flags + ["-c", "-o", str(obj), str(src)], capture_output=True, text=True)
+        return obj, r
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    failed = False
+    for obj, r in results:
+        if r is not None and (verbose or r.returncode):
+            sys.stderr.write(r.stdout + r.stderr)
+        failed |= r is not None and r.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed building libplvi_cuda.so")
+    r = subprocess.run([nvcc_path()] + NVCC_FLAGS + ["-o", str(LIB)] + [str(o) for o, _ in results], capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
-        raise RuntimeError("nvcc failed building libplvi_cuda.so")
+        raise RuntimeError("nvcc failed linking libplvi_cuda.so")
     return LIB
 
 

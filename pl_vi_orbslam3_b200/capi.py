@@ -92,6 +92,13 @@ _SIGS = {
     "plvi_assign_features_to_grid": (ci, [vp, vp, vp, ci, ci, vp, vp, vp]),
     "plvi_line_match_grid": (ci, [vp, ci, vp, vp, vp, ci, vp, vp, vp, ci, C.c_double, C.c_double, ci, ci, ci, ci, ci, ci, vp, vp]),
     "plvi_line_match_grid_host": (ci, [vp, vp, vp, ci, vp, vp, ci, C.c_double, C.c_double, ci, ci, ci, ci, ci, ci, vp, vp]),
+    "plvi_line_match_grid_occ_host": (ci, [vp, vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]),
+    "plvi_matcher_set_stereo": (ci, [vp, vp, vp, ci, ci, ci, ci]),
+    "plvi_search_in_radius_host": (ci, [vp, vp, vp, ci, vp, vp, vp, ci, vp, C.c_double, ci, vp, vp, vp, vp, vp]),
+    "plvi_search_for_triangulation_host": (ci, [vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, vp, vp]),
+    "plvi_line_fuse_search_host": (ci, [vp, vp, vp, ci, vp, vp, vp, ci, ci, vp, vp, vp]),
+    "plvi_line_match_mad_host": (ci, [vp, vp, ci, vp, ci, vp, vp, C.c_double, vp, vp, vp]),
+    "plvi_distinctive_descriptors_host": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "plvi_line_match_mad": (ci, [vp, ci, vp, vp, ci, vp, vp, ci, vp, vp, C.c_double, vp, vp, vp]),
     "plvi_distinctive_descriptors": (ci, [vp, vp, vp, ci, ci, vp, vp]),
     "plvi_vocab_create": (ci, [C.POINTER(vp), ci, ci, ci, ci, ci, vp, vp, vp, vp, ci]),
@@ -118,7 +125,8 @@ def declared_symbols():
     import re
     hdr = (_PKG.parent / "include" / "plvi.h").read_text()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(plvi_[a-z0-9_]+)\s*\(", hdr)))
+    # plvi_inline_*: static inline helpers defined in the header itself (no exported symbol)
+    return sorted(n for n in set(re.findall(r"\b(plvi_[a-z0-9_]+)\s*\(", hdr)) if not n.startswith("plvi_inline_"))
 
 
 def lib():

@@ -82,6 +82,9 @@ struct SearchArgs {
   int th; float nnratio; int checkOri;
   int* matchTrain; int* matchQuery; int* nmatches;
   int* matchedDist;  // scratch [P][tstride] (init mode)
+  // rectified-stereo side information (plvi_matcher_set_stereo), or nullptr: mvuRight of the train frame and the
+  // right-image coordinate of every query's projection
+  const float* uright; const float* qur;
 };
 
 struct QRes {
@@ -98,7 +101,8 @@ __device__ __forceinline__ bool eligible(const SearchArgs& a, int i2, int d, con
 __device__ QRes eval_query(const SearchArgs& a, const plvi_keypoint* __restrict__ keys,
                            const uint8_t* __restrict__ desc, const plvi_query& q,
                            const uint8_t* __restrict__ qd, const int* cellStart,
-                           const unsigned short* items, const uint8_t* blk, const int* mdist) {
+                           const unsigned short* items, const uint8_t* blk, const int* mdist,
+                           const float* __restrict__ uright, float qur) {
   const int lane = threadIdx.x & 31;
   QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
   const float x = q.u, y = q.v, rad = q.radius;
@@ -126,6 +130,10 @@ __device__ QRes eval_query(const SearchArgs& a, const plvi_keypoint* __restrict_
         if (q.max_level >= 0 && kp.octave > q.max_level) continue;
       }
       if (!(fabsf(__fsub_rn(kp.x, x)) < rad && fabsf(__fsub_rn(kp.y, y)) < rad)) continue;
+      if (uright) {   // stereo observation: |ur - mvuRight[i2]| must stay inside the window (src/ORBmatcher.cc:91-96, 2041-2047)
+        const float ur2 = __ldg(uright + i2);
+        if (ur2 > 0.f && fabsf(__fsub_rn(qur, ur2)) > rad) continue;
+      }
       const int d = hamming256_regs(qw, desc + (size_t)i2 * 32);
       if (!eligible(a, i2, d, blk, mdist)) continue;
       top2_insert(t, ((uint32_t)d << 23) | ((uint32_t)c << 11) | (uint32_t)min(k - s, 2047), i2);
@@ -171,9 +179,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
   extern __shared__ __align__(16) uint8_t smem[];
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int NT = SEARCH_WARPS * 32;
-  const int n = a.tcount[pair], nq = a.qcount[pair];
+  const int n = min(a.tcount[pair], a.tstride), nq = min(a.qcount[pair], a.qstride);
   const plvi_keypoint* keys = a.keys + (size_t)pair * a.tstride;
   const uint8_t* desc = a.desc + (size_t)pair * a.tstride * 32;
+  const float* uright = (a.uright && a.qur && a.mode < 2) ? a.uright + (size_t)pair * a.tstride : nullptr;
+  const float* qur = uright ? a.qur + (size_t)pair * a.qstride : nullptr;
   plvi_query* q = a.q + (size_t)pair * a.qstride;
   const uint8_t* qdesc = a.qdesc + (size_t)pair * a.qstride * 32;
   int* owner = a.matchTrain + (size_t)pair * a.tstride;   // train -> query (mvpMapPoints / vnMatches21)
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
     QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
     if (qi < nq && !(q[qi].flags & 1))
       r = a.mode == 3 ? eval_query_bow(desc, q[qi], qdesc + (size_t)qi * 32, a.items + (size_t)pair * a.istride, blk)
-                      : eval_query(a, keys, desc, q[qi], qdesc + (size_t)qi * 32, cellStart, items, blk, mdist);
+                      : eval_query(a, keys, desc, q[qi], qdesc + (size_t)qi * 32, cellStart, items, blk, mdist, uright, qur ? qur[qi] : 0.f);
     if (lane == 0) res[wid] = r;
     __syncthreads();
     if (wid == 0) {
@@ -283,7 +293,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
         }
         if (stale)
           rr = a.mode == 3 ? eval_query_bow(desc, qq, qdesc + (size_t)qj * 32, a.items + (size_t)pair * a.istride, blk)
-                           : eval_query(a, keys, desc, qq, qdesc + (size_t)qj * 32, cellStart, items, blk, mdist);
+                           : eval_query(a, keys, desc, qq, qdesc + (size_t)qj * 32, cellStart, items, blk, mdist, uright, qur ? qur[qj] : 0.f);
         if (lane == 0 && rr.best >= 0) {
           if (a.mode == 0) {
             if (rr.bestDist <= a.th) {
@@ -365,8 +375,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
       if (b < 0 || b == s_keep[0] || b == s_keep[1] || b == s_keep[2]) continue;
       if (a.mode == 0 || a.mode == 3) {
         // the reference nulls mvpMapPoints[bestIdx2] of every culled assignment
+        // (check_orientation == 2 reports such a feature as -2, so that a caller holding pointers can tell "assigned,
+        // then nulled" from "never touched")
         const int i2 = m12[i];
-        owner[i2] = -1;
+        owner[i2] = a.checkOri == 2 ? -2 : -1;
         m12[i] = -1;
         dec++;
       } else if (m12[i] >= 0) {
@@ -436,7 +448,7 @@ __global__ void __launch_bounds__(256) k_line_match(const uint8_t* __restrict__ 
                                                     int* __restrict__ nmatches) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int pair = blockIdx.x, tid = threadIdx.x;
-  const int n1 = n1p[pair], n2 = n2p[pair];
+  const int n1 = min(n1p[pair], stride1), n2 = min(n2p[pair], stride2);
   uint8_t* s1 = smem;
   uint8_t* s2 = s1 + (size_t)stride1 * 32;
   int* m12 = reinterpret_cast<int*>(s2 + (size_t)stride2 * 32);
@@ -495,7 +507,7 @@ __global__ void __launch_bounds__(256) k_line_match_mad(const uint8_t* __restric
                                                         double* __restrict__ madOut) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  const int n1 = n1p[pair], n2 = n2p[pair];
+  const int n1 = min(n1p[pair], stride1), n2 = min(n2p[pair], stride2);
   uint8_t* s1 = smem;
   uint8_t* s2 = s1 + (size_t)stride1 * 32;
   int* dist0 = reinterpret_cast<int*>(s2 + (size_t)stride2 * 32);   // [stride1]
@@ -657,11 +669,12 @@ __global__ void __launch_bounds__(256) k_search_triangulation(const plvi_keypoin
       const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
       for (int k = Q.min_level + lane; k < Q.max_level; k += 32) {
         const int i2 = __ldg(items + k);
-        if (blk && blk[i2]) continue;
+        const unsigned bv = blk ? blk[i2] : 0u;   // bit0: has a map point; bit1: bStereo2 (mvuRight[idx2] >= 0)
+        if (bv & 1u) continue;
         const int d = hamming256_regs(qw, desc + (size_t)i2 * 32);
         if (d > thLow) continue;
         const plvi_keypoint kp2 = keys[i2];
-        if (G.check_epipole) {
+        if (G.check_epipole && !(Q.flags & 4) && !(bv & 2u)) {   // only when neither feature is a stereo observation
           const float ex = __fsub_rn(G.ep_x, kp2.x), ey = __fsub_rn(G.ep_y, kp2.y);
           if (__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < __fmul_rn(100.f, G.scale_factors[kp2.octave])) continue;
         }
@@ -733,13 +746,16 @@ struct RadiusArgs {
   double chi2;
   int th;
   int* bestIdx; int* bestDist; int* nfound;
+  const float* uright; const float* qur;   // plvi_matcher_set_stereo: mvuRight of the keyframe, ur of every query (or nullptr)
 };
 
 __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search_in_radius(const RadiusArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int NT = SEARCH_WARPS * 32;
-  const int n = a.tcount[pair], nq = a.qcount[pair];
+  const int n = min(a.tcount[pair], a.tstride), nq = min(a.qcount[pair], a.qstride);
+  const float* uright = (a.uright && a.qur) ? a.uright + (size_t)pair * a.tstride : nullptr;
+  const float* qurAll = uright ? a.qur + (size_t)pair * a.qstride : nullptr;
   const plvi_keypoint* keys = a.keys + (size_t)pair * a.tstride;
   const uint8_t* desc = a.desc + (size_t)pair * a.tstride * 32;
   const plvi_query* q = a.q + (size_t)pair * a.qstride;
@@ -839,10 +855,17 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search_in_radius(const Ra
             const plvi_keypoint kp = keys[i2];
             if (!(fabsf(__fsub_rn(kp.x, x)) < rad && fabsf(__fsub_rn(kp.y, y)) < rad)) continue;
             if (kp.octave < qq.min_level || kp.octave > qq.max_level) continue;
-            if (a.chi2 > 0) {   // mono reprojection gate of Fuse: float product compared with the double constant
+            if (a.chi2 > 0) {   // reprojection gate of Fuse: float product compared with the double constant
               const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
-              const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
-              if ((double)__fmul_rn(e2, a.invSigma2[kp.octave & 15]) > a.chi2) continue;
+              const float ur2 = uright ? __ldg(uright + i2) : -1.f;
+              if (ur2 >= 0.f) {   // stereo observation: 3 degrees of freedom, chi2 = 7.8 (src/ORBmatcher.cc:1530-1543)
+                const float er = __fsub_rn(qurAll[qi], ur2);
+                const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+                if ((double)__fmul_rn(e2, a.invSigma2[kp.octave & 15]) > 7.8) continue;
+              } else {
+                const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                if ((double)__fmul_rn(e2, a.invSigma2[kp.octave & 15]) > a.chi2) continue;
+              }
             }
             const int d = hamming256_regs(qw, desc + (size_t)i2 * 32);
             const uint32_t key = ((uint32_t)d << 23) | ((uint32_t)min(c, 4095) << 11) | (uint32_t)min(k - s, 2047);
@@ -939,7 +962,69 @@ struct plvi_matcher {
   plvi_keypoint* dKeys = nullptr; uint8_t* dDesc = nullptr; uint8_t* dBlocked = nullptr;
   int* dTCount = nullptr; plvi_query* dQ = nullptr; uint8_t* dQDesc = nullptr; int* dQCount = nullptr;
   int* dMatchTrain = nullptr; int* dMatchQuery = nullptr; int* dNMatches = nullptr; int* dMatchedDist = nullptr;
+  bool staged = false;            // the staging buffers above exist (allocated by the first host-pointer call)
+  // plvi_matcher_set_stereo: side information of the next search (device pointers; host arrays are staged below)
+  const float* stereoTrain = nullptr; const float* stereoQuery = nullptr;
+  float* dStereoTrain = nullptr; float* dStereoQuery = nullptr;
   int lastLaunches = 0;
+};
+
+// Device staging of the host-pointer entry points: ~133 B x max_pairs x max_train, only allocated when such an entry
+// point is first used (a matcher driven through device pointers never touches it); dMatchedDist (search mode 2) is
+// allocated with the handle.
+static int ensure_staging(plvi_matcher* m) {
+  if (m->staged) return PLVI_OK;
+  const size_t P = m->maxPairs, T = m->maxTrain, Q = m->maxQuery;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  A((void**)&m->dKeys, P * T * sizeof(plvi_keypoint));
+  A((void**)&m->dDesc, P * (T > Q ? T : Q) * 32);
+  A((void**)&m->dBlocked, P * T);
+  A((void**)&m->dTCount, P * sizeof(int));
+  A((void**)&m->dQ, P * Q * sizeof(plvi_query));
+  A((void**)&m->dQDesc, P * (T > Q ? T : Q) * 32);
+  A((void**)&m->dQCount, P * sizeof(int));
+  A((void**)&m->dMatchTrain, P * T * sizeof(int));
+  A((void**)&m->dMatchQuery, P * (T > Q ? T : Q) * sizeof(int));
+  A((void**)&m->dNMatches, P * sizeof(int));
+  A((void**)&m->dStereoTrain, P * T * sizeof(float));
+  A((void**)&m->dStereoQuery, P * Q * sizeof(float));
+  if (e != cudaSuccess) { set_error(std::string("cudaMalloc (matcher staging): ") + cudaGetErrorString(e)); return PLVI_ERR_CUDA; }
+  m->staged = true;
+  return PLVI_OK;
+}
+#define PLVI_STAGING(m) do { int rc_ = ensure_staging(m); if (rc_ != PLVI_OK) return rc_; } while (0)
+
+// One stream-ordered allocation holding the inputs and outputs of a *_host entry point: segments are 256-byte aligned,
+// inputs are copied in as they are added.
+struct HostStage {
+  cudaStream_t st; size_t total = 0; unsigned char* buf = nullptr; cudaError_t e = cudaSuccess;
+  struct Seg { size_t off, bytes; const void* src; };
+  std::vector<Seg> segs;
+  explicit HostStage(cudaStream_t s) : st(s) {}
+  int add(const void* src, size_t bytes) {   // src may be nullptr (output / scratch segment)
+    segs.push_back({total, bytes, src});
+    total += (bytes + 255) & ~(size_t)255;
+    return (int)segs.size() - 1;
+  }
+  bool commit() {
+    e = cudaMallocAsync(reinterpret_cast<void**>(&buf), total ? total : 256, st);
+    for (size_t i = 0; i < segs.size() && e == cudaSuccess; i++)
+      if (segs[i].src && segs[i].bytes) e = cudaMemcpyAsync(buf + segs[i].off, segs[i].src, segs[i].bytes, cudaMemcpyHostToDevice, st);
+    return e == cudaSuccess;
+  }
+  template <typename T> T* ptr(int i) const { return reinterpret_cast<T*>(buf + segs[i].off); }
+  void fetch(void* dst, int i, size_t bytes) {
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, buf + segs[i].off, bytes, cudaMemcpyDeviceToHost, st);
+  }
+  int finish(int rc) {
+    if (buf) cudaFreeAsync(buf, st);
+    const cudaError_t s = cudaStreamSynchronize(st);
+    if (rc != PLVI_OK) return rc;
+    if (e == cudaSuccess) e = s;
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return PLVI_ERR_CUDA; }
+    return PLVI_OK;
+  }
 };
 
 // ---------------------------------------------------------------------------------
@@ -961,7 +1046,12 @@ __global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict_
                                                         const float* __restrict__ seg2, const uint8_t* __restrict__ desc2,
                                                         const int* __restrict__ n2p, int stride2, double invw, double invh,
                                                         int rows, int cols, int wl, int wr, int wu, int wd,
-                                                        int* __restrict__ matches12, int* __restrict__ nmatches) {
+                                                        int* __restrict__ matches12, int* __restrict__ nmatches,
+                                                        const uchar2* __restrict__ occ2, const double* __restrict__ dir2,
+                                                        const int* __restrict__ coords1) {
+  // occ2 / dir2 / coords1 != nullptr (one pair): the caller hands over what the reference's matchGrid receives -- the
+  // filled GridStructure as (first, last) column per right line and grid row [n2][rows], directions2 [n2][2] and the
+  // left lines' integer end cells lines1 [n1][4] -- instead of the segments
   extern __shared__ __align__(16) unsigned char lmg_smem[];
   double* dirx = reinterpret_cast<double*>(lmg_smem);                           // [stride2]
   double* diry = dirx + stride2;
@@ -979,16 +1069,22 @@ __global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict_
   for (int i = lane; i < rows * stride2; i += 32) run[i] = make_uchar2(255, 0);
   __syncwarp();
   for (int j = lane; j < n2; j += 32) {
-    const float4 s = *reinterpret_cast<const float4*>(seg2 + 4 * j);
-    const double vx = __dmul_rn((double)__fsub_rn(s.z, s.x), invw), vy = __dmul_rn((double)__fsub_rn(s.w, s.y), invh);
-    const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
-    dirx[j] = __ddiv_rn(vx, mag);
-    diry[j] = __ddiv_rn(vy, mag);
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(desc2 + 32 * j)), b = __ldg(reinterpret_cast<const uint4*>(desc2 + 32 * j) + 1);
     sd2[0 * stride2 + j] = a.x; sd2[1 * stride2 + j] = a.y; sd2[2 * stride2 + j] = a.z; sd2[3 * stride2 + j] = a.w;
     sd2[4 * stride2 + j] = b.x; sd2[5 * stride2 + j] = b.y; sd2[6 * stride2 + j] = b.z; sd2[7 * stride2 + j] = b.w;
     dist[j] = INT_MAX;
     m21[j] = -1;
+    if (occ2) {
+      dirx[j] = dir2[2 * j];
+      diry[j] = dir2[2 * j + 1];
+      for (int y = 0; y < rows; y++) run[y * stride2 + j] = occ2[(size_t)j * rows + y];
+      continue;
+    }
+    const float4 s = *reinterpret_cast<const float4*>(seg2 + 4 * j);
+    const double vx = __dmul_rn((double)__fsub_rn(s.z, s.x), invw), vy = __dmul_rn((double)__fsub_rn(s.w, s.y), invh);
+    const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+    dirx[j] = __ddiv_rn(vx, mag);
+    diry[j] = __ddiv_rn(vy, mag);
     // LineIterator over the right line in grid units
     double x1 = __dmul_rn((double)s.x, invw), y1 = __dmul_rn((double)s.y, invh);
     double x2 = __dmul_rn((double)s.z, invw), y2 = __dmul_rn((double)s.w, invh);
@@ -1016,10 +1112,15 @@ __global__ void __launch_bounds__(32) k_line_match_grid(const float* __restrict_
   __syncwarp();
   int matches = 0;
   for (int i1 = 0; i1 < n1; i1++) {
-    const float4 s = __ldg(reinterpret_cast<const float4*>(seg1 + 4 * i1));
     // line_2d holds int pairs (include/LineMatcher.h:41-42): the end points are truncated to grid cells
-    const int sx = (int)__dmul_rn((double)s.x, invw), sy = (int)__dmul_rn((double)s.y, invh);
-    const int ex = (int)__dmul_rn((double)s.z, invw), ey = (int)__dmul_rn((double)s.w, invh);
+    int sx, sy, ex, ey;
+    if (coords1) {
+      sx = coords1[4 * i1]; sy = coords1[4 * i1 + 1]; ex = coords1[4 * i1 + 2]; ey = coords1[4 * i1 + 3];
+    } else {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(seg1 + 4 * i1));
+      sx = (int)__dmul_rn((double)s.x, invw); sy = (int)__dmul_rn((double)s.y, invh);
+      ex = (int)__dmul_rn((double)s.z, invw); ey = (int)__dmul_rn((double)s.w, invh);
+    }
     double vx = (double)(ex - sx), vy = (double)(ey - sy);
     const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
     vx = __ddiv_rn(vx, mag);
@@ -1089,20 +1190,7 @@ int plvi_matcher_create(plvi_matcher** out, int max_pairs, int max_train, int ma
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); delete m; return PLVI_ERR_CUDA; }
     m->ownStream = true;
   }
-  const size_t P = max_pairs, T = max_train, Q = max_query;
-  cudaError_t e = cudaSuccess;
-  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-  A((void**)&m->dKeys, P * T * sizeof(plvi_keypoint));
-  A((void**)&m->dDesc, P * (T > Q ? T : Q) * 32);
-  A((void**)&m->dBlocked, P * T);
-  A((void**)&m->dTCount, P * sizeof(int));
-  A((void**)&m->dQ, P * Q * sizeof(plvi_query));
-  A((void**)&m->dQDesc, P * (T > Q ? T : Q) * 32);
-  A((void**)&m->dQCount, P * sizeof(int));
-  A((void**)&m->dMatchTrain, P * T * sizeof(int));
-  A((void**)&m->dMatchQuery, P * (T > Q ? T : Q) * sizeof(int));
-  A((void**)&m->dNMatches, P * sizeof(int));
-  A((void**)&m->dMatchedDist, P * T * sizeof(int));
+  const cudaError_t e = cudaMalloc((void**)&m->dMatchedDist, (size_t)max_pairs * max_train * sizeof(int));
   if (e != cudaSuccess) {
     set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
     plvi_matcher_destroy(m);
@@ -1119,6 +1207,7 @@ void plvi_matcher_destroy(plvi_matcher* m) {
   cudaFree(m->dKeys); cudaFree(m->dDesc); cudaFree(m->dBlocked); cudaFree(m->dTCount);
   cudaFree(m->dQ); cudaFree(m->dQDesc); cudaFree(m->dQCount); cudaFree(m->dMatchTrain);
   cudaFree(m->dMatchQuery); cudaFree(m->dNMatches); cudaFree(m->dMatchedDist);
+  cudaFree(m->dStereoTrain); cudaFree(m->dStereoQuery);
   if (m->ownStream && m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -1138,6 +1227,7 @@ int plvi_hamming256(plvi_matcher* m, const uint8_t* a, const uint8_t* b, int n, 
       set_error("plvi_hamming256: n exceeds matcher capacity");
       return PLVI_ERR_CAPACITY;
     }
+    PLVI_STAGING(m);
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dDesc, a, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQDesc, b, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
     da = m->dDesc; db = m->dQDesc; dout = m->dMatchQuery;
@@ -1179,6 +1269,8 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
   a.matchedDist = mode == 2 ? m->dMatchedDist : nullptr;
   a.items = nullptr;
   a.istride = 0;
+  a.uright = m->stereoTrain; a.qur = m->stereoQuery;   // side information of this call only
+  m->stereoTrain = m->stereoQuery = nullptr;
   const size_t P = npairs, T = train_stride, Q = query_stride;
   cudaStream_t st = m->stream;
   if (on_device) {
@@ -1191,6 +1283,7 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
         set_error("plvi_search_by_projection: count exceeds stride");
         return PLVI_ERR_INVALID;
       }
+    PLVI_STAGING(m);
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dKeys, train_keys, P * T * sizeof(plvi_keypoint), cudaMemcpyHostToDevice, st));
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dDesc, train_desc, P * T * 32, cudaMemcpyHostToDevice, st));
     if (train_blocked) PLVI_CUDA_TRY(cudaMemcpyAsync(m->dBlocked, train_blocked, P * T, cudaMemcpyHostToDevice, st));
@@ -1252,6 +1345,7 @@ static int search_by_bow_impl(plvi_matcher* m, int npairs, const plvi_keypoint* 
     a.q = const_cast<plvi_query*>(queries); a.qdesc = query_desc; a.qcount = query_counts;
     a.matchTrain = match_train; a.matchQuery = match_query; a.nmatches = nmatches;
   } else {
+    PLVI_STAGING(m);
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dKeys, train_keys, P * T * sizeof(plvi_keypoint), cudaMemcpyHostToDevice, st));
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dDesc, train_desc, P * T * 32, cudaMemcpyHostToDevice, st));
     if (train_blocked) {
@@ -1336,6 +1430,7 @@ int plvi_line_match(plvi_matcher* m, int npairs, const uint8_t* desc1, const int
   const int *c1 = n1, *c2 = n2;
   int *o = matches12, *nm = nmatches;
   if (!on_device) {
+    PLVI_STAGING(m);
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dDesc, desc1, P * stride1 * 32, cudaMemcpyHostToDevice, st));
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dQDesc, desc2, P * stride2 * 32, cudaMemcpyHostToDevice, st));
     PLVI_CUDA_TRY(cudaMemcpyAsync(m->dTCount, n1, P * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1393,7 +1488,7 @@ int plvi_line_match_grid(plvi_matcher* m, int npairs, const float* d_seg1, const
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_line_match_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_line_match_grid<<<npairs, 32, smem, m->stream>>>(d_seg1, d_desc1, d_n1, stride1, d_seg2, d_desc2, d_n2, stride2, inv_width,
                                                     inv_height, grid_rows, grid_cols, win_left, win_right, win_up, win_down,
-                                                    d_matches12, d_nmatches);
+                                                    d_matches12, d_nmatches, nullptr, nullptr, nullptr);
   m->lastLaunches = 1;
   PLVI_CUDA_TRY(cudaGetLastError());
   return PLVI_OK;
@@ -1493,6 +1588,8 @@ int plvi_search_in_radius(plvi_matcher* m, int npairs, const plvi_keypoint* trai
   for (int i = 0; i < 16; i++) a.invSigma2[i] = inv_level_sigma2[i];
   a.chi2 = chi2; a.th = th_dist;
   a.bestIdx = best_idx; a.bestDist = best_dist; a.nfound = nfound;
+  a.uright = m->stereoTrain; a.qur = m->stereoQuery;   // side information of this call only
+  m->stereoTrain = m->stereoQuery = nullptr;
   const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + (size_t)train_stride * 2 + 16;
   if (smem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search_in_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1518,6 +1615,209 @@ int plvi_line_fuse_search(plvi_matcher* m, int npairs, const plvi_keyline* keyli
   m->lastLaunches = 1;
   PLVI_CUDA_TRY(cudaGetLastError());
   return PLVI_OK;
+}
+
+int plvi_matcher_set_stereo(plvi_matcher* m, const float* train_uright, const float* query_ur, int npairs, int train_stride,
+                            int query_stride, int on_device) {
+  if (!m) { set_error("plvi_matcher_set_stereo: invalid argument"); return PLVI_ERR_INVALID; }
+  m->stereoTrain = m->stereoQuery = nullptr;
+  if (!train_uright || !query_ur) return PLVI_OK;   // clears the side information
+  if (on_device) { m->stereoTrain = train_uright; m->stereoQuery = query_ur; return PLVI_OK; }
+  if (npairs < 1 || npairs > m->maxPairs || train_stride < 1 || train_stride > m->maxTrain || query_stride < 1 ||
+      query_stride > m->maxQuery) {
+    set_error("plvi_matcher_set_stereo: exceeds matcher capacity");
+    return PLVI_ERR_CAPACITY;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  PLVI_STAGING(m);
+  PLVI_CUDA_TRY(cudaMemcpyAsync(m->dStereoTrain, train_uright, (size_t)npairs * train_stride * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(m->dStereoQuery, query_ur, (size_t)npairs * query_stride * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  // pageable host memory: the copies above have been staged by the runtime when the calls return
+  m->stereoTrain = m->dStereoTrain; m->stereoQuery = m->dStereoQuery;
+  return PLVI_OK;
+}
+
+int plvi_search_in_radius_host(plvi_matcher* m, const plvi_keypoint* train_keys, const uint8_t* train_desc, int n_train,
+                               const plvi_grid* grid, const plvi_query* queries, const uint8_t* query_desc, int n_query,
+                               const float* inv_level_sigma2, double chi2, int th_dist, const float* train_uright,
+                               const float* query_ur, int* best_idx, int* best_dist, int* nfound) {
+  if (!m || n_train < 0 || n_query < 0 || !grid || !inv_level_sigma2 || !nfound || (n_train && (!train_keys || !train_desc)) ||
+      (n_query && (!queries || !query_desc || !best_idx || !best_dist))) {
+    set_error("plvi_search_in_radius_host: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  *nfound = 0;
+  for (int i = 0; i < n_query; i++) { best_idx[i] = -1; best_dist[i] = 256; }
+  if (n_query == 0 || n_train == 0) return PLVI_OK;
+  if (n_train > 65535) { set_error("plvi_search_in_radius_host: more than 65535 keypoints"); return PLVI_ERR_CAPACITY; }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  HostStage hs(m->stream);
+  const int cnt[2] = {n_train, n_query};
+  const int sK = hs.add(train_keys, (size_t)n_train * sizeof(plvi_keypoint)), sD = hs.add(train_desc, (size_t)n_train * 32);
+  const int sQ = hs.add(queries, (size_t)n_query * sizeof(plvi_query)), sQD = hs.add(query_desc, (size_t)n_query * 32);
+  const int sC = hs.add(cnt, sizeof(cnt));
+  const bool stereo = train_uright && query_ur;
+  const int sU = hs.add(stereo ? train_uright : nullptr, (size_t)n_train * sizeof(float));
+  const int sQU = hs.add(stereo ? query_ur : nullptr, (size_t)n_query * sizeof(float));
+  const int sBI = hs.add(nullptr, (size_t)n_query * sizeof(int)), sBD = hs.add(nullptr, (size_t)n_query * sizeof(int));
+  const int sNF = hs.add(nullptr, sizeof(int));
+  int rc = PLVI_OK;
+  if (hs.commit()) {
+    if (stereo) { m->stereoTrain = hs.ptr<float>(sU); m->stereoQuery = hs.ptr<float>(sQU); }
+    rc = plvi_search_in_radius(m, 1, hs.ptr<plvi_keypoint>(sK), hs.ptr<uint8_t>(sD), hs.ptr<int>(sC), n_train, grid,
+                               hs.ptr<plvi_query>(sQ), hs.ptr<uint8_t>(sQD), hs.ptr<int>(sC) + 1, n_query, inv_level_sigma2, chi2,
+                               th_dist, hs.ptr<int>(sBI), hs.ptr<int>(sBD), hs.ptr<int>(sNF));
+    if (rc == PLVI_OK) {
+      hs.fetch(best_idx, sBI, (size_t)n_query * sizeof(int));
+      hs.fetch(best_dist, sBD, (size_t)n_query * sizeof(int));
+      hs.fetch(nfound, sNF, sizeof(int));
+    }
+  }
+  return hs.finish(rc);
+}
+
+int plvi_search_for_triangulation_host(plvi_matcher* m, const plvi_keypoint* train_keys, const uint8_t* train_desc,
+                                       const uint8_t* train_blocked, int n_train, const int* group_items, int n_items,
+                                       const plvi_query* queries, const uint8_t* query_desc, int n_query,
+                                       const plvi_epipolar* geometry, int th_low, int check_orientation, int* match_query,
+                                       int* nmatches) {
+  if (!m || n_train < 0 || n_items < 0 || n_query < 0 || !geometry || !nmatches || (n_train && (!train_keys || !train_desc)) ||
+      (n_items && !group_items) || (n_query && (!queries || !query_desc || !match_query))) {
+    set_error("plvi_search_for_triangulation_host: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  *nmatches = 0;
+  for (int i = 0; i < n_query; i++) match_query[i] = -1;
+  if (n_query == 0 || n_train == 0 || n_items == 0) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  HostStage hs(m->stream);
+  const int cnt[2] = {n_train, n_query};
+  const int sK = hs.add(train_keys, (size_t)n_train * sizeof(plvi_keypoint)), sD = hs.add(train_desc, (size_t)n_train * 32);
+  const int sB = hs.add(train_blocked, train_blocked ? (size_t)n_train : 0), sI = hs.add(group_items, (size_t)n_items * sizeof(int));
+  const int sQ = hs.add(queries, (size_t)n_query * sizeof(plvi_query)), sQD = hs.add(query_desc, (size_t)n_query * 32);
+  const int sC = hs.add(cnt, sizeof(cnt)), sG = hs.add(geometry, sizeof(plvi_epipolar));
+  const int sM = hs.add(nullptr, (size_t)n_query * sizeof(int)), sN = hs.add(nullptr, sizeof(int));
+  int rc = PLVI_OK;
+  if (hs.commit()) {
+    rc = plvi_search_for_triangulation(m, 1, hs.ptr<plvi_keypoint>(sK), hs.ptr<uint8_t>(sD), train_blocked ? hs.ptr<uint8_t>(sB) : nullptr,
+                                       hs.ptr<int>(sC), n_train, hs.ptr<int>(sI), n_items, hs.ptr<plvi_query>(sQ), hs.ptr<uint8_t>(sQD),
+                                       hs.ptr<int>(sC) + 1, n_query, hs.ptr<plvi_epipolar>(sG), th_low, check_orientation,
+                                       hs.ptr<int>(sM), hs.ptr<int>(sN));
+    if (rc == PLVI_OK) { hs.fetch(match_query, sM, (size_t)n_query * sizeof(int)); hs.fetch(nmatches, sN, sizeof(int)); }
+  }
+  return hs.finish(rc);
+}
+
+int plvi_line_fuse_search_host(plvi_matcher* m, const plvi_keyline* keylines, const uint8_t* desc, int n, const float* queries,
+                               const uint8_t* query_flags, const uint8_t* query_desc, int n_query, int th_low, int* best_idx,
+                               int* best_dist, int* nfound) {
+  if (!m || n < 0 || n_query < 0 || !nfound || (n && (!keylines || !desc)) ||
+      (n_query && (!queries || !query_desc || !best_idx || !best_dist))) {
+    set_error("plvi_line_fuse_search_host: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  *nfound = 0;
+  for (int i = 0; i < n_query; i++) { best_idx[i] = -1; best_dist[i] = 0x7fffffff; }
+  if (n_query == 0 || n == 0) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  HostStage hs(m->stream);
+  const int cnt[2] = {n, n_query};
+  const int sK = hs.add(keylines, (size_t)n * sizeof(plvi_keyline)), sD = hs.add(desc, (size_t)n * 32);
+  const int sQ = hs.add(queries, (size_t)n_query * 6 * sizeof(float)), sF = hs.add(query_flags, query_flags ? (size_t)n_query : 0);
+  const int sQD = hs.add(query_desc, (size_t)n_query * 32), sC = hs.add(cnt, sizeof(cnt));
+  const int sBI = hs.add(nullptr, (size_t)n_query * sizeof(int)), sBD = hs.add(nullptr, (size_t)n_query * sizeof(int));
+  const int sNF = hs.add(nullptr, sizeof(int));
+  int rc = PLVI_OK;
+  if (hs.commit()) {
+    rc = plvi_line_fuse_search(m, 1, hs.ptr<plvi_keyline>(sK), hs.ptr<uint8_t>(sD), hs.ptr<int>(sC), n, hs.ptr<float>(sQ),
+                               query_flags ? hs.ptr<uint8_t>(sF) : nullptr, hs.ptr<uint8_t>(sQD), hs.ptr<int>(sC) + 1, n_query, th_low,
+                               hs.ptr<int>(sBI), hs.ptr<int>(sBD), hs.ptr<int>(sNF));
+    if (rc == PLVI_OK) {
+      hs.fetch(best_idx, sBI, (size_t)n_query * sizeof(int));
+      hs.fetch(best_dist, sBD, (size_t)n_query * sizeof(int));
+      hs.fetch(nfound, sNF, sizeof(int));
+    }
+  }
+  return hs.finish(rc);
+}
+
+int plvi_line_match_mad_host(plvi_matcher* m, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, const uint8_t* has_line1,
+                             const uint8_t* has_line2, double factor, int* matches12, int* nmatches, double* mad) {
+  if (!m || n1 < 0 || n2 < 0 || !nmatches || !mad || (n1 && (!desc1 || !matches12)) || (n2 && !desc2)) {
+    set_error("plvi_line_match_mad_host: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  *nmatches = 0; mad[0] = mad[1] = 0.0;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  if (n1 == 0 || n2 < 2) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  HostStage hs(m->stream);
+  const int cnt[2] = {n1, n2};
+  const bool masks = has_line1 && has_line2;
+  const int sA = hs.add(desc1, (size_t)n1 * 32), sB = hs.add(desc2, (size_t)n2 * 32), sC = hs.add(cnt, sizeof(cnt));
+  const int sH1 = hs.add(masks ? has_line1 : nullptr, (size_t)n1), sH2 = hs.add(masks ? has_line2 : nullptr, (size_t)n2);
+  const int sM = hs.add(nullptr, (size_t)n1 * sizeof(int)), sN = hs.add(nullptr, sizeof(int)), sMad = hs.add(nullptr, 2 * sizeof(double));
+  int rc = PLVI_OK;
+  if (hs.commit()) {
+    rc = plvi_line_match_mad(m, 1, hs.ptr<uint8_t>(sA), hs.ptr<int>(sC), n1, hs.ptr<uint8_t>(sB), hs.ptr<int>(sC) + 1, n2,
+                             masks ? hs.ptr<uint8_t>(sH1) : nullptr, masks ? hs.ptr<uint8_t>(sH2) : nullptr, factor, hs.ptr<int>(sM),
+                             hs.ptr<int>(sN), hs.ptr<double>(sMad));
+    if (rc == PLVI_OK) { hs.fetch(matches12, sM, (size_t)n1 * sizeof(int)); hs.fetch(nmatches, sN, sizeof(int)); hs.fetch(mad, sMad, 2 * sizeof(double)); }
+  }
+  return hs.finish(rc);
+}
+
+int plvi_distinctive_descriptors_host(plvi_matcher* m, const uint8_t* desc, const int* counts, int n_points, int stride,
+                                      int* best_idx, uint8_t* best_desc) {
+  if (!m || !desc || !counts || n_points < 1 || stride < 1 || !best_idx) {
+    set_error("plvi_distinctive_descriptors_host: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  HostStage hs(m->stream);
+  const int sD = hs.add(desc, (size_t)n_points * stride * 32), sC = hs.add(counts, (size_t)n_points * sizeof(int));
+  const int sI = hs.add(nullptr, (size_t)n_points * sizeof(int)), sO = hs.add(nullptr, (size_t)n_points * 32);
+  int rc = PLVI_OK;
+  if (hs.commit()) {
+    rc = plvi_distinctive_descriptors(m->stream, hs.ptr<uint8_t>(sD), hs.ptr<int>(sC), n_points, stride, hs.ptr<int>(sI), hs.ptr<uint8_t>(sO));
+    if (rc == PLVI_OK) { hs.fetch(best_idx, sI, (size_t)n_points * sizeof(int)); if (best_desc) hs.fetch(best_desc, sO, (size_t)n_points * 32); }
+  }
+  return hs.finish(rc);
+}
+
+int plvi_line_match_grid_occ_host(plvi_matcher* m, const int* lines1, const uint8_t* desc1, int n1, const uint8_t* occ2,
+                                  const double* directions2, const uint8_t* desc2, int n2, int grid_rows, int grid_cols,
+                                  int win_left, int win_right, int win_up, int win_down, int* matches12, int* nmatches) {
+  if (!m || n1 < 0 || n2 < 0 || !matches12 || !nmatches || (n1 && (!lines1 || !desc1)) || (n2 && (!occ2 || !directions2 || !desc2)) ||
+      grid_rows < 1 || grid_cols < 1 || grid_rows > 64 || grid_cols > 64 || win_left < 0 || win_right < 0 || win_up < 0 || win_down < 0) {
+    set_error("plvi_line_match_grid_occ_host: invalid argument (grid at most 64 x 64 cells)");
+    return PLVI_ERR_INVALID;
+  }
+  *nmatches = 0;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  if (n1 == 0 || n2 == 0) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  const size_t smem = (size_t)n2 * ((size_t)grid_rows * 2 + 2 * sizeof(double) + 32 + 2 * sizeof(int));
+  if (smem > 200 * 1024) { set_error("plvi_line_match_grid_occ_host: right line set too large for one CTA"); return PLVI_ERR_CAPACITY; }
+  if (smem > 48 * 1024)
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_line_match_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HostStage hs(m->stream);
+  const int cnt[2] = {n1, n2};
+  const int sL = hs.add(lines1, (size_t)n1 * 4 * sizeof(int)), sD1 = hs.add(desc1, (size_t)n1 * 32);
+  const int sO = hs.add(occ2, (size_t)n2 * grid_rows * 2), sDir = hs.add(directions2, (size_t)n2 * 2 * sizeof(double));
+  const int sD2 = hs.add(desc2, (size_t)n2 * 32), sC = hs.add(cnt, sizeof(cnt));
+  const int sM = hs.add(nullptr, (size_t)n1 * sizeof(int)), sN = hs.add(nullptr, sizeof(int));
+  if (hs.commit()) {
+    k_line_match_grid<<<1, 32, smem, m->stream>>>(nullptr, hs.ptr<uint8_t>(sD1), hs.ptr<int>(sC), n1, nullptr, hs.ptr<uint8_t>(sD2),
+                                                  hs.ptr<int>(sC) + 1, n2, 1.0, 1.0, grid_rows, grid_cols, win_left, win_right, win_up,
+                                                  win_down, hs.ptr<int>(sM), hs.ptr<int>(sN), hs.ptr<uchar2>(sO), hs.ptr<double>(sDir),
+                                                  hs.ptr<int>(sL));
+    m->lastLaunches = 1;
+    hs.e = cudaGetLastError();
+    hs.fetch(matches12, sM, (size_t)n1 * sizeof(int));
+    hs.fetch(nmatches, sN, sizeof(int));
+  }
+  return hs.finish(PLVI_OK);
 }
 
 }  // extern "C"

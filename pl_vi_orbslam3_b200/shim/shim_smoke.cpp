@@ -6,8 +6,9 @@
 #include <cstdlib>
 
 #include "LineExtractor.h"
-#include "Matchers.h"
+#include "LineMatcher.h"
 #include "ORBextractor.h"
+#include "ORBmatcher.h"
 
 int main(int argc, char** argv) {
   const int w = 752, h = 480;
@@ -62,7 +63,7 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> blocked(kps.size(), 0);
     for (size_t i = 0; i < blocked.size() && i < 10; i++) blocked[i] = 1;
     std::vector<int> ofKey;
-    const int nproj = matcher.SearchByProjection(kps, desc, grid, qs, desc, ofKey, PLVI_SEARCH_FRAME, &blocked);
+    const int nproj = matcher.SearchByProjectionRaw(kps, desc, grid, qs, desc, ofKey, PLVI_SEARCH_FRAME, &blocked);
     int blockedHit = 0;
     for (size_t i = 0; i < ofKey.size() && i < 10; i++) blockedHit += ofKey[i] >= 0;
     if (blockedHit != 0 || nproj < (int)kps.size() / 2) { std::printf("shim error: SearchByProjection %d matches, %d on blocked keys\n", nproj, blockedHit); return 1; }
@@ -73,7 +74,7 @@ int main(int argc, char** argv) {
     std::vector<Eigen::Vector3d> eqR;
     lineR(imR, mask, klsR, ldescR, eqR);
     std::vector<int> mgrid;
-    const int ngrid = ORB_SLAM3::LineMatcher::matchGrid(kls, ldesc, klsR, ldescR, 64.0 / w, 48.0 / h, mgrid);
+    const int ngrid = ORB_SLAM3::LineMatcher::matchStereoLines(kls, ldesc, klsR, ldescR, 64.0 / w, 48.0 / h, mgrid);
     int gridCount = 0;
     for (int v : mgrid) gridCount += v >= 0;
     if (ngrid != gridCount || (int)mgrid.size() != (int)kls.size()) { std::printf("shim error: matchGrid %d vs %d\n", ngrid, gridCount); return 1; }

@@ -142,7 +142,7 @@ def test_cpp_shim_compiles_and_links(tmp_path):
     """The reference-shaped C++ classes (shim/*.h) build against include/plvi.h + libplvi_cuda.so."""
     shim = ROOT / "pl_vi_orbslam3_b200" / "shim"
     exe = tmp_path / "shim_smoke"
-    r = subprocess.run(["g++", "-std=c++17", "-O1", "-o", str(exe), str(shim / "shim_smoke.cpp"),
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-o", str(exe), str(shim / "shim_smoke.cpp"), "-I" + str(shim / "include"),
                         "-L" + str(ROOT / "pl_vi_orbslam3_b200"), "-lplvi_cuda",
                         "-Wl,-rpath," + str(ROOT / "pl_vi_orbslam3_b200")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 def test_cpp_shim_runs(gpu, tmp_path):
     shim = ROOT / "pl_vi_orbslam3_b200" / "shim"
     exe = tmp_path / "shim_smoke"
-    r = subprocess.run(["g++", "-std=c++17", "-O1", "-o", str(exe), str(shim / "shim_smoke.cpp"),
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-o", str(exe), str(shim / "shim_smoke.cpp"), "-I" + str(shim / "include"),
                         "-L" + str(ROOT / "pl_vi_orbslam3_b200"), "-lplvi_cuda",
                         "-Wl,-rpath," + str(ROOT / "pl_vi_orbslam3_b200")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
