@@ -207,7 +207,9 @@ int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, i
  * (after plvi_line_set_debug(h,1)), 1 level-line angle in degrees f32 (-1024 = NOTDEF),
  * 2 gradient magnitude f64, 3 raw segments (x1,y1,x2,y2 f32; *count = number),
  * 4 pyramid octave image u8 (gaussianPyrs[octave]), 5 LBD octave image u8 (w>>octave x h>>octave;
- * binary_descriptor_custom.cpp:351-371), 6 its Sobel gradients s16 {dx, dy} per pixel (:374-399). */
+ * binary_descriptor_custom.cpp:351-371), 6 its Sobel gradients s16 {dx, dy} per pixel (:374-399),
+ * 7 diagnostics of the small-batch (band-run) region growing: 40 ints = {serial fallback taken, fixed point reached,
+ * -, bands re-run in round 1, 2, ...}; *count = rounds launched. */
 int plvi_line_set_debug(plvi_line* h, int on);
 int plvi_line_set_profile(plvi_line* h, int on);
 const char* plvi_line_profile(plvi_line* h);

@@ -23,6 +23,12 @@ struct LineOct {
   size_t specBmOff;           // offset (words) in the per-frame private-bitmap array; band j holds rows [j * bandRows, sh)
   size_t specRecOff;          // offset in the per-frame speculative record array
   int taskOff;                // first speculation task of this octave within a frame
+  // band-run region growing for small batches (k_lsd_band_*): brBands bands of brRows rows, one warp each
+  int brBands, brRows, brPxCap, brRecCap;
+  int brBandOff;              // first band of this octave among the frame's bands
+  size_t brBmOff;             // words: bitmap of band j at brBmOff + j * wpr * sh
+  size_t brRecOff;            // records (per buffer): band j at brRecOff + j * brRecCap
+  size_t brListOff;           // pixels (per buffer): band j at brListOff + j * brPxCap
 };
 
 struct LineGeom {
@@ -31,6 +37,8 @@ struct LineGeom {
   size_t pxTotal, rawTotal, lbdTotal;
   size_t regTotal, specBmTotal, specRecTotal;
   int tasksPerFrame;
+  int brBandsPerFrame;                       // band-run: bands of both octaves
+  size_t brBmTotal, brRecTotal, brListTotal; // per frame (and per buffer)
   int bmTotal, segTotal;
   double rho, prec, lsdScale, minLength;
   float alignHi2, alignLo2;   // cos^2(prec -/+ margin): bounds of the cheap alignment test in k_lsd_grow
@@ -62,6 +70,15 @@ struct LineBufs {
   int* specCnt;          // [B][tasksPerFrame] speculative regions per band
   unsigned* phantom;     // [B][bmTotal]   pixels a discarded speculative region had consumed
   int useSpec;           // 0: serial k_lsd_grow only
+  // band-run (small batches): per band the last input bitmap, the working / output bitmap, the initial phantom
+  // bitmap of the next run; two generations of region records + pixel lists; per-band state; per-octave flags
+  unsigned* brIn; unsigned* brWk; unsigned* brPh;   // [brMax][brBmTotal]
+  uint4* brRec;          // [brMax][2][brRecTotal]  {seed x | y << 16, list start, size, angle (float bits)}
+  unsigned* brList;      // [brMax][2][brListTotal]
+  int* brState;          // [brMax][brBandsPerFrame][8]  nrec[0], nrec[1], cur, dirty, hasPrev
+  int* brFlags;          // [brMax][2][BR_FLAGS]  [0] fallback to the serial kernel, [1] converged, [2 + r] bands dirty in round r
+  int brMax;             // frames the band-run buffers hold (0: off)
+  int brRounds;          // rounds launched per batch
   LineRegion* regTab;    // [B][segTotal]
   int* regCount;         // [B][2]  (-1: segment table overflow)
   float4* segs;          // [B][segTotal]
@@ -77,6 +94,8 @@ struct LineBufs {
   const double2* trig;   // [1024] {cos, sin}(k * 2 pi / 1024), host libm values
   double* scaledDbg;     // [B][pxTotal] or nullptr
 };
+
+#define BR_FLAGS 40
 
 struct LineAux { cudaStream_t stream; cudaEvent_t fork, join; cudaEvent_t stage; };   // stage: recorded when the streaming kernels are done and region growing starts   // side stream for the LBD pre-processing
 

@@ -240,20 +240,21 @@ __device__ __forceinline__ bool is_aligned_dev(double a, double theta, double pr
 // current seed row hold no available pixel any more (every earlier pixel in raster order
 // has been a seed or was absorbed), so only rows [top, top + GROW_K) are cached in shared
 // memory; the rare region that reaches further down works on the global copy directly.
-struct GrowBitmap {
-  unsigned* sm;    // [GROW_K][wpr]
+template <int K> struct GrowBitmapT {
+  unsigned* sm;    // [K][wpr]
   unsigned* gm;    // [H][wpr]
   int wpr, top;
   __device__ __forceinline__ unsigned word(int y, int wi) const {
-    return (y - top < GROW_K) ? sm[(y & (GROW_K - 1)) * wpr + wi] : __ldcg(gm + y * wpr + wi);
+    return (y - top < K) ? sm[(y & (K - 1)) * wpr + wi] : __ldcg(gm + y * wpr + wi);
   }
   __device__ __forceinline__ bool test(int x, int y) const { return (word(y, x >> 5) >> (x & 31)) & 1u; }
   __device__ __forceinline__ void clear(int x, int y) {   // one lane only
     const unsigned m = ~(1u << (x & 31));
-    if (y - top < GROW_K) sm[(y & (GROW_K - 1)) * wpr + (x >> 5)] &= m;
+    if (y - top < K) sm[(y & (K - 1)) * wpr + (x >> 5)] &= m;
     else { unsigned* p = gm + y * wpr + (x >> 5); __stcg(p, __ldcg(p) & m); }
   }
 };
+typedef GrowBitmapT<GROW_K> GrowBitmap;
 
 // One neighbour per lane: lane = 8 * e + k, e = queue entry of the batch (0..3), k = 3x3
 // neighbour index without the centre, in the reference's (yy, xx) scan order.
@@ -265,10 +266,10 @@ struct GrowBatch {
   float2 rec;        // cos, sin of the neighbour's float angle
 };
 
-__device__ __forceinline__ bool grow_bit(const GrowBitmap& bm, int bw, unsigned bbit) {
+template <int K> __device__ __forceinline__ bool grow_bit(const GrowBitmapT<K>& bm, int bw, unsigned bbit) {
   return ((bw >= 0 ? bm.sm[bw] : __ldcg(bm.gm + ~bw)) & bbit) != 0u;
 }
-__device__ __forceinline__ void grow_clear(GrowBitmap& bm, int bw, unsigned bbit) {   // one lane only
+template <int K> __device__ __forceinline__ void grow_clear(GrowBitmapT<K>& bm, int bw, unsigned bbit) {   // one lane only
   if (bw >= 0) bm.sm[bw] &= ~bbit;
   else { unsigned* p = bm.gm + ~bw; __stcg(p, __ldcg(p) & ~bbit); }
 }
@@ -276,7 +277,7 @@ __device__ __forceinline__ void grow_clear(GrowBitmap& bm, int bw, unsigned bbit
 // Neighbourhood fetch for queue entries [i, i+nb): lane (e, k) tests the availability bit of
 // its neighbour and, if set, issues the 16-byte record load (consumed later => the load
 // latency overlaps the accept chain of the previous batch).
-__device__ __forceinline__ GrowBatch grow_fetch(const GrowBitmap& bm, const unsigned* ring, const unsigned* reg,
+template <int K> __device__ __forceinline__ GrowBatch grow_fetch(const GrowBitmapT<K>& bm, const unsigned* ring, const unsigned* reg,
                                                 int regSize, int i, int nb, int e, int ndx, int ndy, int W, int H,
                                                 const float2* __restrict__ rec) {
   GrowBatch g;
@@ -290,7 +291,7 @@ __device__ __forceinline__ GrowBatch grow_fetch(const GrowBitmap& bm, const unsi
     // x = -1 is rejected; x = W lands on a padding bit of the bitmap row (always 0); rows above
     // the window top hold no available pixel
     if (cy >= bm.top && cy < H && cx >= 0) {
-      g.bw = (cy - bm.top < GROW_K) ? (cy & (GROW_K - 1)) * bm.wpr + (cx >> 5) : ~(cy * bm.wpr + (cx >> 5));
+      g.bw = (cy - bm.top < K) ? (cy & (K - 1)) * bm.wpr + (cx >> 5) : ~(cy * bm.wpr + (cx >> 5));
       g.bbit = 1u << (cx & 31);
       if (grow_bit(bm, g.bw, g.bbit)) {
         cand = true;
@@ -303,10 +304,12 @@ __device__ __forceinline__ GrowBatch grow_fetch(const GrowBitmap& bm, const unsi
   return g;
 }
 
-__global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeom g, LineBufs b) {
+__global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeom g, LineBufs b, int onlyFlagged) {
   extern __shared__ unsigned smem_u[];
   const int oct = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
   if (oct >= g.noct) return;
+  // band-run path: only the (frame, octave) problems that asked for the serial fallback
+  if (onlyFlagged && !b.brFlags[((size_t)f * 2 + oct) * BR_FLAGS]) return;
   const LineOct& O = g.o[oct];
   const int W = O.sw, H = O.sh, wpr = O.wpr;
   unsigned* ring = smem_u;
@@ -629,22 +632,22 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
 // Pixels that a discarded speculative region had consumed in its band's private bitmap but
 // that are still available in the true state.  A later speculative region of that band saw
 // them as "used"; it can only be adopted if none of them touches it.
-struct PhantomMap {
-  unsigned* sm;      // [GROW_K][wpr] shared window, slides with the availability window
+template <int K> struct PhantomMapT {
+  unsigned* sm;      // [K][wpr] shared window, slides with the availability window
   unsigned* gm;      // [H][wpr] global copy (rows below the window)
   bool any;          // warp-uniform: some phantom pixel exists
-  __device__ __forceinline__ unsigned word(const GrowBitmap& bm, int y, int wi) const {
-    return (y - bm.top < GROW_K) ? sm[(y & (GROW_K - 1)) * bm.wpr + wi] : __ldcg(gm + y * bm.wpr + wi);
+  __device__ __forceinline__ unsigned word(const GrowBitmapT<K>& bm, int y, int wi) const {
+    return (y - bm.top < K) ? sm[(y & (K - 1)) * bm.wpr + wi] : __ldcg(gm + y * bm.wpr + wi);
   }
-  __device__ __forceinline__ void mark(const GrowBitmap& bm, int x, int y) {
+  __device__ __forceinline__ void mark(const GrowBitmapT<K>& bm, int x, int y) {
     const unsigned bit = 1u << (x & 31);
-    if (y - bm.top < GROW_K) atomicOr(&sm[(y & (GROW_K - 1)) * bm.wpr + (x >> 5)], bit);
+    if (y - bm.top < K) atomicOr(&sm[(y & (K - 1)) * bm.wpr + (x >> 5)], bit);
     else atomicOr(gm + y * bm.wpr + (x >> 5), bit);
   }
   // any available phantom pixel in the 3x3 neighbourhood of (x, y)?  (y >= bm.top; rows above the window top hold
   // no available pixel).  Same instruction path for every lane: the three rows are read unconditionally (a row
   // outside [top, H) is replaced by row y and masked out) and phantom & available is formed before the 3-bit extract.
-  __device__ __forceinline__ bool near(const GrowBitmap& bm, int x, int y, int H) const {
+  __device__ __forceinline__ bool near(const GrowBitmapT<K>& bm, int x, int y, int H) const {
     const int xm = x - 1;
     const int wa = max(xm, 0) >> 5;
     const int sh = xm - (wa << 5);   // -1 .. 31
@@ -663,10 +666,11 @@ struct PhantomMap {
     return hit != 0u;
   }
 };
+typedef PhantomMapT<GROW_K> PhantomMap;
 
-__device__ __forceinline__ void grow_clear_atomic(GrowBitmap& bm, int x, int y) {
+template <int K> __device__ __forceinline__ void grow_clear_atomic(GrowBitmapT<K>& bm, int x, int y) {
   const unsigned m = ~(1u << (x & 31));
-  if (y - bm.top < GROW_K) atomicAnd(&bm.sm[(y & (GROW_K - 1)) * bm.wpr + (x >> 5)], m);
+  if (y - bm.top < K) atomicAnd(&bm.sm[(y & (K - 1)) * bm.wpr + (x >> 5)], m);
   else atomicAnd(bm.gm + y * bm.wpr + (x >> 5), m);
 }
 
@@ -918,6 +922,390 @@ __global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------
+// Band-run region growing: the exact region sequence of the serial algorithm for SMALL batches, where the
+// serial chains above leave the GPU idle (one frame = 20 chains).  The working image is cut into many bands
+// (O.brBands); one warp owns one band and grows, with the serial building block of k_lsd_grow, every region
+// seeded in its rows -- from an INPUT availability bitmap In_b that is a guess of the true state at the moment
+// the raster scan reaches the band:   In_b = I_0 & ~(M_0 | ... | M_{b-1}),   M_j = pixels band j's latest run consumed
+// (k_lsd_band_compose).  A band whose input changed runs again (k_lsd_band_run); its previous regions serve as
+// speculation records and are adopted under the three conditions of k_lsd_commit (true next seed, all pixels
+// still available, no phantom pixel in the 3x3 neighbourhood; the phantom map starts as In_new & ~In_old), so a
+// re-run only re-grows what the changed input touches.  Rounds repeat until no input changes.  Exactness: band 0
+// always runs on I_0, so its first result is the true one; by induction band b's input is the true state once
+// bands 0..b-1 are final, and a round without any change is a fixed point in which every band ran on the true
+// state.  At most brBands + 1 rounds are needed; if the rounds launched did not reach the fixed point (or a
+// band overflowed its record / pixel capacity) the octave falls back to the serial kernel.
+// ---------------------------------------------------------------------------------------
+#define BR_ST 8   // ints of per-band state: nrec[0], nrec[1], cur, dirty, hasPrev
+#define BR_K 256  // bitmap rows of a band's shared-memory window: the warp has the SM's shared memory to itself, and a
+                  // window that holds (nearly) every region keeps the availability tests off the L2 round trip
+
+// thread = one bitmap word (row, w) of one (frame, octave); walks the bands that contain the row in band order
+__global__ void __launch_bounds__(256) k_lsd_band_compose(const __grid_constant__ LineGeom g, LineBufs b, int round, int check) {
+  const int oct = blockIdx.y, f = blockIdx.z;
+  if (oct >= g.noct) return;
+  const LineOct& O = g.o[oct];
+  int* flags = b.brFlags + ((size_t)f * 2 + oct) * BR_FLAGS;
+  if (flags[0] || flags[1]) return;                       // serial fallback requested / fixed point reached
+  if (round > 1 && flags[2 + round - 1] == 0) {           // nothing ran in the previous round: fixed point
+    __syncthreads();                                      // (every thread has read the flags before one sets converged)
+    if (threadIdx.x == 0 && blockIdx.x == 0) flags[1] = 1;
+    return;
+  }
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int nwords = O.sh * O.wpr;
+  if (i >= nwords) return;
+  const int row = i / O.wpr;
+  const unsigned I0 = __ldg(b.bitmap + (size_t)f * g.bmTotal + O.bmOff + i);
+  const size_t base = (size_t)f * g.brBmTotal + O.brBmOff + i;
+  int* st = b.brState + ((size_t)f * g.brBandsPerFrame + O.brBandOff) * BR_ST;
+  unsigned acc = 0u;
+  bool anyChange = false;
+  for (int j = 0; j < O.brBands; j++) {
+    if (row < j * O.brRows) break;
+    const size_t idx = base + (size_t)j * nwords;
+    const unsigned nin = I0 & ~acc;
+    if (round == 1) {
+      b.brIn[idx] = nin;
+      b.brPh[idx] = 0u;
+      if (i == 0 || row == j * O.brRows) {   // one thread per band is enough; several writing the same values is harmless
+        st[j * BR_ST + 0] = 0; st[j * BR_ST + 1] = 0; st[j * BR_ST + 2] = 0; st[j * BR_ST + 3] = 1; st[j * BR_ST + 4] = 0; st[j * BR_ST + 6] = 0;
+      }
+      anyChange = true;
+      continue;   // nothing is known about what the bands consume yet
+    }
+    const unsigned old = b.brIn[idx];
+    if (nin != old) {
+      if (check) { flags[0] = 1; return; }
+      b.brPh[idx] = nin & ~old;      // available now, was not when the band last ran
+      b.brIn[idx] = nin;
+      st[j * BR_ST + 3] = 1;
+      anyChange = true;
+    } else if (!check) {
+      b.brPh[idx] = 0u;
+    }
+    acc |= old & ~b.brWk[idx];       // what band j's latest run took (from the input that run saw)
+  }
+  if (anyChange && !check) flags[2 + round] = 1;
+}
+
+__global__ void __launch_bounds__(32) k_lsd_band_run(const __grid_constant__ LineGeom g, LineBufs b) {
+  extern __shared__ unsigned smem_u[];
+  const int t = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
+  const int oct = (g.noct > 1 && t >= g.o[1].brBandOff) ? 1 : 0;
+  const LineOct& O = g.o[oct];
+  const int j = t - O.brBandOff;
+  if (j >= O.brBands) return;
+  int* flags = b.brFlags + ((size_t)f * 2 + oct) * BR_FLAGS;
+  int* st = b.brState + ((size_t)f * g.brBandsPerFrame + t) * BR_ST;
+  if (flags[0] || flags[1] || !st[3]) return;
+  const long long tStart = clock64();
+  const int W = O.sw, H = O.sh, wpr = O.wpr;
+  const int r0 = j * O.brRows, r1 = min(r0 + O.brRows, H - 1);
+  const int nwords = H * wpr;
+  const size_t bmBase = (size_t)f * g.brBmTotal + O.brBmOff + (size_t)j * nwords;
+  const unsigned* In = b.brIn + bmBase;
+  unsigned* Wk = b.brWk + bmBase;
+  unsigned* Ph = b.brPh + bmBase;
+  const int cur = st[2], nxt = cur ^ 1;
+  const int bcnt = st[4] ? st[cur] : 0;
+  const uint4* brecs = b.brRec + ((size_t)f * 2 + cur) * g.brRecTotal + O.brRecOff + (size_t)j * O.brRecCap;
+  uint4* nrecs = b.brRec + ((size_t)f * 2 + nxt) * g.brRecTotal + O.brRecOff + (size_t)j * O.brRecCap;
+  const unsigned* blist = b.brList + ((size_t)f * 2 + cur) * g.brListTotal + O.brListOff + (size_t)j * O.brPxCap;
+  unsigned* nlist = b.brList + ((size_t)f * 2 + nxt) * g.brListTotal + O.brListOff + (size_t)j * O.brPxCap;
+  const int pxCap = O.brPxCap, recCap = O.brRecCap;
+
+  const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
+  const float2* __restrict__ rec = b.cs + pbase;
+  const float* __restrict__ ang = b.ang + pbase;
+  const float2* __restrict__ seedcs = b.seed + pbase;
+  {
+    // The warp has an SM sub-partition (and most of its L1) to itself: pull the per-pixel records of the band's own
+    // rows and of the rows right below into L1 while the bitmaps are copied, so that the dependent loads of the
+    // growth (seed angle -> neighbour records -> ...) hit L1 instead of paying an L2 round trip each.
+    const int pr1 = min(r1 + 8, H);
+    const char* c0 = reinterpret_cast<const char*>(rec + (size_t)r0 * W);
+    const char* c1 = reinterpret_cast<const char*>(rec + (size_t)pr1 * W);
+    for (const char* q = c0 + lane * 128; q < c1; q += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+    const char* a0 = reinterpret_cast<const char*>(ang + (size_t)r0 * W);
+    const char* a1 = reinterpret_cast<const char*>(ang + (size_t)min(r1 + 2, H) * W);
+    for (const char* q = a0 + lane * 128; q < a1; q += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+    const char* s0 = reinterpret_cast<const char*>(seedcs + (size_t)r0 * W);
+    const char* s1 = reinterpret_cast<const char*>(seedcs + (size_t)r1 * W);
+    for (const char* q = s0 + lane * 128; q < s1; q += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+  }
+  // working copy of the input (rows above the band hold nothing by definition) + is there any initial phantom?
+  bool anyPh = false;
+  for (int i = r0 * wpr + lane; i < nwords; i += 32) {
+    Wk[i] = In[i];
+    anyPh |= Ph[i] != 0u;
+  }
+  __syncwarp();
+  unsigned* ring = smem_u;
+  GrowBitmapT<BR_K> bm;
+  bm.sm = smem_u + GROW_RQ;
+  bm.gm = Wk;
+  bm.wpr = wpr;
+  bm.top = r0;
+  PhantomMapT<BR_K> ph;
+  ph.gm = Ph;
+  ph.sm = bm.sm + BR_K * wpr;
+  ph.any = bcnt > 0 && __any_sync(0xffffffffu, anyPh);
+  for (int i = lane; i < (min(r0 + BR_K, H) - r0) * wpr; i += 32) {
+    const int r = r0 + i / wpr, wv = i - (r - r0) * wpr;
+    bm.sm[(r & (BR_K - 1)) * wpr + wv] = In[r * wpr + wv];
+    ph.sm[(r & (BR_K - 1)) * wpr + wv] = ph.any ? Ph[r * wpr + wv] : 0u;
+  }
+  __syncwarp();
+  const double prec = g.prec;
+  const float kHi = g.alignHi2, kLo = g.alignLo2;
+  const int e = lane >> 3, k8 = lane & 7;
+  const int nidx = k8 < 4 ? k8 : k8 + 1;
+  const int ndx = nidx % 3 - 1, ndy = nidx / 3 - 1;
+  const unsigned laneBit = 1u << lane;
+  int bp = 0, runStart = 0;           // previous-run records: next record, start of its pixel list
+  int nnew = 0, npx = 0;              // this run's records / pixels
+  bool overflow = false;
+  uint4 curRec = make_uint4(0u, 0u, 0u, 0u);
+  unsigned curPix = 0u;
+  if (bcnt > 0) { curRec = __ldcg(brecs); curPix = __ldcg(blist + lane); }
+
+  for (int row = r0; row < r1 && !overflow; row++) {
+    if (row > bm.top) {   // slide the shared windows
+      const int ra = bm.top + BR_K, rb = min(row + BR_K, H);
+      for (int r = ra; r < rb; r++)
+        for (int wv = lane; wv < wpr; wv += 32) {
+          bm.sm[(r & (BR_K - 1)) * wpr + wv] = __ldcg(bm.gm + r * wpr + wv);
+          ph.sm[(r & (BR_K - 1)) * wpr + wv] = ph.any ? __ldcg(ph.gm + r * wpr + wv) : 0u;
+        }
+      bm.top = row;
+      __syncwarp();
+    }
+    for (int c0 = 0; c0 < wpr && !overflow; c0 += 32) {
+      while (true) {
+        const int wi = c0 + lane;
+        const int rowBase = (row & (BR_K - 1)) * wpr;
+        const unsigned word = wi < wpr ? bm.sm[rowBase + wi] : 0u;
+        const unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
+        if (!nz) break;
+        const int wl = __ffs(nz) - 1;
+        const unsigned sw_ = __shfl_sync(0xffffffffu, word, wl);
+        const int bit = __ffs(sw_) - 1;
+        const int sx = (c0 + wl) * 32 + bit, sy = row;
+        const unsigned spk = (unsigned)sx | ((unsigned)sy << 16);
+        if (nnew >= recCap || npx + 64 > pxCap) { overflow = true; break; }
+
+        // records of the previous run seeded before this pixel never happen now: what they took and is still
+        // available becomes phantom
+        while (bp < bcnt && curRec.x < spk) {
+          bool marked = false;
+          for (int i0 = 0; i0 < (int)curRec.z; i0 += 32) {
+            const int idx = i0 + lane;
+            if (idx < (int)curRec.z) {
+              const unsigned q = i0 == 0 ? curPix : __ldcg(blist + curRec.y + idx);
+              const int qx = q & 0xffff, qy = q >> 16;
+              if (qy >= bm.top && bm.test(qx, qy)) { ph.mark(bm, qx, qy); marked = true; }
+            }
+          }
+          if (__any_sync(0xffffffffu, marked)) ph.any = true;
+          runStart += (int)curRec.z;
+          bp++;
+          if (bp < bcnt) { curRec = __ldcg(brecs + bp); curPix = __ldcg(blist + runStart + lane); }
+          __syncwarp();
+        }
+        const bool haveRec = bp < bcnt && curRec.x == spk;
+        const uint4 sr = curRec;
+        const unsigned srPix = curPix;
+        if (haveRec) {
+          runStart += (int)curRec.z;
+          bp++;
+          if (bp < bcnt) { curRec = __ldcg(brecs + bp); curPix = __ldcg(blist + runStart + lane); }
+          bool ok = npx + (int)sr.z + 64 <= pxCap;
+          for (int i0 = 0; i0 < (int)sr.z && ok; i0 += 32) {
+            const int idx = i0 + lane;
+            bool good = true;
+            if (idx < (int)sr.z) {
+              const unsigned q = i0 == 0 ? srPix : __ldcg(blist + sr.y + idx);
+              const int qx = q & 0xffff, qy = q >> 16;
+              good = bm.test(qx, qy) && !(ph.any && ph.near(bm, qx, qy, H));
+            }
+            ok = __all_sync(0xffffffffu, good);
+          }
+          if (ok) {   // adopt: the region the serial algorithm grows from this seed; carried into this run's lists
+            for (int i0 = 0; i0 < (int)sr.z; i0 += 32) {
+              const int idx = i0 + lane;
+              if (idx < (int)sr.z) {
+                const unsigned q = i0 == 0 ? srPix : __ldcg(blist + sr.y + idx);
+                grow_clear_atomic(bm, q & 0xffff, q >> 16);
+                __stcg(nlist + npx + idx, q);
+              }
+            }
+            if (lane == 0) nrecs[nnew] = make_uint4(sr.x, (unsigned)npx, sr.z, sr.w);
+            nnew++;
+            npx += (int)sr.z;
+            __syncwarp();
+            continue;
+          }
+        }
+
+        const int sp = sy * W + sx;
+        const float sang = __ldg(ang + sp);
+        const float2 scs = __ldg(seedcs + sp);
+        unsigned* reg = nlist + npx;
+        if (lane == 0) {
+          bm.sm[rowBase + c0 + wl] = sw_ & ~(1u << bit);
+          ring[0] = spk;
+        }
+        __syncwarp();
+        // region_grow (src/LSD/lsd.cpp:635-686), see k_lsd_grow
+        float sumdx = scs.x, sumdy = scs.y;
+        bool fresh = true;
+        int regSize = 1;
+        int flushed = 0;
+        int i = 0, nb = 1;
+        GrowBatch cb = grow_fetch(bm, ring, reg, regSize, 0, 1, e, ndx, ndy, W, H, rec);
+        while (nb > 0) {
+          if (npx + regSize + 64 > pxCap) { overflow = true; break; }
+          const int ni = i + nb, nnb = min(4, regSize - ni);
+          GrowBatch nxtb = grow_fetch(bm, ring, reg, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
+          unsigned pm = cb.mask;
+          if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cb.bw, cb.bbit));
+          float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+          while (pm) {
+            const float dot = __fmaf_rn(sumdx, cb.rec.x, sumdy * cb.rec.y);
+            const float d2 = dot * dot;
+            const bool poss = (pm & laneBit) && dot > 0.f && d2 > kLo * n2;
+            const unsigned possm = __ballot_sync(0xffffffffu, poss);
+            if (!possm) break;
+            const int l = __ffs(possm) - 1;
+            const unsigned surem = __ballot_sync(0xffffffffu, poss && d2 >= kHi * n2);
+            pm &= ~((2u << l) - 1u);
+            if (!((surem >> l) & 1u)) {
+              const double regAngle = __dmul_rn((double)(fresh ? sang : fast_atan2_dev(sumdy, sumdx)), D2R);
+              const int lpk = __shfl_sync(0xffffffffu, cb.cpk, l);
+              const float la = __ldg(ang + (lpk >> 16) * W + (lpk & 0xffff));
+              if (!is_aligned_dev(__dmul_rn((double)la, D2R), regAngle, prec)) continue;
+            }
+            const float qc = __shfl_sync(0xffffffffu, cb.rec.x, l), qs = __shfl_sync(0xffffffffu, cb.rec.y, l);
+            const int qpk = __shfl_sync(0xffffffffu, cb.cpk, l);
+            pm &= ~__ballot_sync(0xffffffffu, cb.cpk == qpk);
+            if (lane == l) {
+              grow_clear(bm, cb.bw, cb.bbit);
+              ring[regSize & (GROW_RQ - 1)] = (unsigned)qpk;
+              // this pixel is expanded a few queue entries from now: its lower neighbours' records are what that
+              // expansion waits for (rows up to its own are in L1 already when it was reached from above)
+              const int py = (qpk >> 16) + 1, px = qpk & 0xffff;
+              if (py < H) {
+                const float2* pr = rec + py * W + px;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr - 1));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 1));
+              }
+            }
+            regSize++;
+            fresh = false;
+            sumdx = __fadd_rn(sumdx, qc);
+            sumdy = __fadd_rn(sumdy, qs);
+            n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+          }
+          __syncwarp();
+          while (regSize - flushed >= 32) {
+            __stcg(reg + flushed + lane, ring[(flushed + lane) & (GROW_RQ - 1)]);
+            flushed += 32;
+          }
+          i = ni;
+          if (nnb > 0) {
+            cb = nxtb;
+            nb = nnb;
+          } else {
+            nb = min(4, regSize - i);
+            if (nb > 0) cb = grow_fetch(bm, ring, reg, regSize, i, nb, e, ndx, ndy, W, H, rec);
+          }
+        }
+        if (overflow) break;
+        if (flushed + lane < regSize) __stcg(reg + flushed + lane, ring[(flushed + lane) & (GROW_RQ - 1)]);
+        if (lane == 0) {
+          const float a = fresh ? sang : (regSize >= O.minRegSize ? fast_atan2_dev(sumdy, sumdx) : 0.f);
+          nrecs[nnew] = make_uint4(spk, (unsigned)npx, (unsigned)regSize, __float_as_uint(a));
+        }
+        nnew++;
+        npx += regSize;
+        __syncwarp();
+        if (haveRec) {   // the record that failed: what it had taken beyond the region grown now
+          bool marked = false;
+          for (int i0 = 0; i0 < (int)sr.z; i0 += 32) {
+            const int idx = i0 + lane;
+            if (idx < (int)sr.z) {
+              const unsigned q = i0 == 0 ? srPix : __ldcg(blist + sr.y + idx);
+              const int qx = q & 0xffff, qy = q >> 16;
+              if (qy >= bm.top && bm.test(qx, qy)) { ph.mark(bm, qx, qy); marked = true; }
+            }
+          }
+          if (__any_sync(0xffffffffu, marked)) ph.any = true;
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (overflow) {
+    if (lane == 0) { flags[0] = 1; st[3] = 0; }
+    return;
+  }
+  // output bitmap: the band's own rows are exhausted; rows of the shared window go back to global memory
+  for (int i = r0 * wpr + lane; i < r1 * wpr; i += 32) Wk[i] = 0u;
+  for (int r = max(r1, bm.top); r < min(bm.top + BR_K, H); r++)
+    for (int wv = lane; wv < wpr; wv += 32) Wk[r * wpr + wv] = bm.sm[(r & (BR_K - 1)) * wpr + wv];
+  if (lane == 0) { st[nxt] = nnew; st[2] = nxt; st[3] = 0; st[4] = 1; st[5] = npx; st[6] += 1; st[7] = (int)(clock64() - tStart); }
+}
+
+// one CTA per (frame, octave): the regions of all bands, in band order, into the octave's region table
+__global__ void __launch_bounds__(256) k_lsd_band_gather(const __grid_constant__ LineGeom g, LineBufs b) {
+  const int oct = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  if (oct >= g.noct) return;
+  const LineOct& O = g.o[oct];
+  const int* flags = b.brFlags + ((size_t)f * 2 + oct) * BR_FLAGS;
+  if (flags[0]) return;   // the serial kernel produces this octave
+  __shared__ int s_base, s_wsum[8], s_over;
+  if (tid == 0) { s_base = 0; s_over = 0; }
+  __syncthreads();
+  LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
+  const int* st = b.brState + ((size_t)f * g.brBandsPerFrame + O.brBandOff) * BR_ST;
+  for (int j = 0; j < O.brBands; j++) {
+    const int cur = st[j * BR_ST + 2], n = st[j * BR_ST + cur];
+    const uint4* recs = b.brRec + ((size_t)f * 2 + cur) * g.brRecTotal + O.brRecOff + (size_t)j * O.brRecCap;
+    const size_t listOff = (size_t)cur * g.brListTotal + O.brListOff + (size_t)j * O.brPxCap;   // relative to the frame's lists
+    for (int i0 = 0; i0 < n; i0 += 256) {
+      const int i = i0 + tid;
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      bool keep = false;
+      if (i < n) { r = recs[i]; keep = (int)r.z >= O.minRegSize; }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      const int lane = tid & 31, wid = tid >> 5;
+      if (lane == 0) s_wsum[wid] = __popc(m);
+      __syncthreads();
+      int before = s_base;
+      for (int w = 0; w < wid; w++) before += s_wsum[w];
+      const int slot = before + __popc(m & ((1u << lane) - 1u));
+      if (keep) {
+        if (slot < O.segCap) {
+          LineRegion R;
+          R.start = (int)(listOff + r.y);
+          R.size = (int)r.z;
+          R.angle = __dmul_rn((double)__uint_as_float(r.w), D2R);
+          rtab[slot] = R;
+        } else {
+          s_over = 1;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) { int tot = 0; for (int w = 0; w < 8; w++) tot += s_wsum[w]; s_base += tot; }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) b.regCount[f * 2 + oct] = s_over ? -1 : s_base;
+}
+
+// ---------------------------------------------------------------------------------------
 // k_lsd_rect: warp per region.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -936,14 +1324,17 @@ __device__ __forceinline__ double warp_max_d(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGeom g, LineBufs b) {
+__global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGeom g, LineBufs b, int bandRun) {
   const int oct = blockIdx.x, f = blockIdx.y, part = blockIdx.z, nparts = gridDim.z;
   if (oct >= g.noct) return;
   const LineOct& O = g.o[oct];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nreg = b.regCount[f * 2 + oct];
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
-  const unsigned* reg = b.reg + (size_t)f * g.regTotal + O.regOff;
+  // band-run path: the region table indexes the frame's band lists, unless the octave fell back to the serial kernel
+  const unsigned* reg = (bandRun && !b.brFlags[((size_t)f * 2 + oct) * BR_FLAGS])
+                            ? b.brList + (size_t)f * 2 * g.brListTotal
+                            : b.reg + (size_t)f * g.regTotal + O.regOff;
   const double* mod = b.mod + pbase;
   const LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
   float4* segs = b.segs + (size_t)f * g.segTotal + O.segOff;
@@ -1579,7 +1970,25 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   }
   if (fork) PLVI_CUDA_TRY(cudaEventRecord(aux.join, aux.stream));
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
-  if (b.useSpec) {
+  const bool bandRun = b.brMax > 0 && n <= b.brMax;
+  if (bandRun) {
+    // small batch: many bands per frame, rounds of (compose inputs, run the bands whose input changed)
+    PLVI_CUDA_TRY(cudaMemsetAsync(b.brFlags, 0, (size_t)n * 2 * BR_FLAGS * sizeof(int), st));
+    const int maxWords = g.o[0].sh * g.o[0].wpr;
+    const size_t runSmem = ((size_t)g.o[0].wpr * BR_K * 2 + GROW_RQ) * sizeof(unsigned);
+    const dim3 cgrid((maxWords + 255) / 256, g.noct, n);
+    for (int r = 1; r <= b.brRounds; r++) {
+      k_lsd_band_compose<<<cgrid, 256, 0, st>>>(g, b, r, 0);
+      k_lsd_band_run<<<dim3(g.brBandsPerFrame, n), 32, runSmem, st>>>(g, b);
+      nl += 2;
+    }
+    prof->mark("k_lsd_band_rounds", st);
+    k_lsd_band_compose<<<cgrid, 256, 0, st>>>(g, b, b.brRounds + 1, 1);
+    k_lsd_band_gather<<<dim3(g.noct, n), 256, 0, st>>>(g, b);
+    k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b, 1);
+    prof->mark("k_lsd_band_finish", st);
+    nl += 3;
+  } else if (b.useSpec) {
     k_lsd_spec_init<<<dim3(8, g.tasksPerFrame, n), 256, 0, st>>>(g, b);
     prof->mark("k_lsd_spec_init", st);
     k_lsd_spec<<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
@@ -1590,10 +1999,10 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     prof->mark("k_lsd_commit", st);
     nl += 2;
   } else {
-    k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b);
+    k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b, 0);
     prof->mark("k_lsd_grow", st);
   }
-  k_lsd_rect<<<dim3(g.noct, n, 2), 256, 0, st>>>(g, b);
+  k_lsd_rect<<<dim3(g.noct, n, bandRun ? 8 : 2), 256, 0, st>>>(g, b, bandRun ? 1 : 0);
   prof->mark("k_lsd_rect", st);
   k_line_assemble<512><<<n, 512, 0, st>>>(g, b, dKl, dCounts);
   prof->mark("k_line_assemble", st);
@@ -1615,9 +2024,15 @@ int line_kernel_attrs(const LineGeom& g) {
   if (commitSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
   // the growth kernels want as many resident warps as registers allow: give shared memory the large carve-out
   PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  {
+    const size_t runSmem = ((size_t)g.o[0].wpr * BR_K * 2 + GROW_RQ) * sizeof(unsigned);
+    if (runSmem > 220 * 1024) { set_error("image too wide for the band-run shared-memory window"); return PLVI_ERR_CAPACITY; }
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_band_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)runSmem));
+  }
   if (commitSmem > 40 * 1024) {
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
+
   }
   return PLVI_OK;
 }

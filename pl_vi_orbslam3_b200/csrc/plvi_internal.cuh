@@ -161,7 +161,7 @@ struct StageProf {
 // by PLVI_GRAPHS=0, and cleared whenever the handle's device tables change.
 // ---------------------------------------------------------------------------------------------------
 struct GraphCache {
-  struct Entry { std::vector<uint64_t> key; cudaGraph_t graph; cudaGraphExec_t exec; int launches; };
+  struct Entry { std::vector<uint64_t> key; cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int launches = 0; };
   std::vector<Entry> entries;
   int enabled = -1;
   long replays = 0, captures = 0;
@@ -198,7 +198,12 @@ struct GraphCache {
     if (rc != PLVI_OK) { if (gph) cudaGraphDestroy(gph); return rc; }
     PLVI_CUDA_TRY(ce);
     e.graph = gph;
-    PLVI_CUDA_TRY(cudaGraphInstantiate(&e.exec, e.graph, 0));
+    if (cudaGraphInstantiate(&e.exec, e.graph, 0) != cudaSuccess) {
+      // no executable graph: give the captured one back and run the sequence as plain launches
+      cudaGetLastError();
+      cudaGraphDestroy(gph);
+      return record(launches);
+    }
     if (entries.size() >= kMaxEntries) {
       cudaGraphExecDestroy(entries.front().exec);
       cudaGraphDestroy(entries.front().graph);

@@ -108,8 +108,8 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
   }
   gaussian_kernel7(sigma, g.kern);
   float sf = 1.f;
-  size_t px = 0, raw = 0, lbd = 0, reg = 0, sbm = 0, srec = 0;
-  int bm = 0, seg = 0, tabOff = 0, task = 0;
+  size_t px = 0, raw = 0, lbd = 0, reg = 0, sbm = 0, srec = 0, brBm = 0, brRec = 0, brList = 0;
+  int bm = 0, seg = 0, tabOff = 0, task = 0, brBand = 0;
   for (int o = 0; o < g.noct; o++) {
     LineOct& O = g.o[o];
     if (o > 0) sf = sf * h->scale;
@@ -141,6 +141,17 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
       O.specRecOff = srec; srec += (size_t)nbT * O.bandRecCap;
       O.taskOff = task; task += nbT;
     }
+    {  // band-run (small batches): bands of equal pixel counts across octaves, one warp each
+      static const int rows0 = [] { const char* ev = getenv("PLVI_LSD_BR_ROWS"); return ev ? std::max(2, atoi(ev)) : 6; }();
+      O.brRows = std::min(rows0 << o, std::max(O.sh, 2));
+      O.brBands = (O.sh + O.brRows - 1) / O.brRows;
+      O.brPxCap = 4 * O.brRows * O.sw + 64;
+      O.brRecCap = std::min(std::max(O.brRows * O.sw / 2, 64), 4096);
+      O.brBandOff = brBand; brBand += O.brBands;
+      O.brBmOff = brBm; brBm += (size_t)O.brBands * O.wpr * O.sh;
+      O.brRecOff = brRec; brRec += (size_t)O.brBands * O.brRecCap;
+      O.brListOff = brList; brList += (size_t)O.brBands * O.brPxCap;
+    }
     O.xtabOff = tabOff; tabOff += O.sw;
     O.ytabOff = tabOff; tabOff += O.sh;
     if (tabs) {
@@ -160,6 +171,7 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
   }
   g.pxTotal = px; g.rawTotal = raw; g.lbdTotal = lbd; g.bmTotal = bm; g.segTotal = seg;
   g.regTotal = reg; g.specBmTotal = sbm; g.specRecTotal = srec; g.tasksPerFrame = task;
+  g.brBandsPerFrame = brBand; g.brBmTotal = brBm; g.brRecTotal = brRec; g.brListTotal = brList;
   return PLVI_OK;
 }
 
@@ -174,7 +186,9 @@ int ensure_geom(plvi_line* h, int w, int hh) {
   const LineGeom& c = h->capGeom;
   if (tabs.size() > h->tabCap || rs.size() > h->rsCap || g.pxTotal > c.pxTotal || g.rawTotal > c.rawTotal ||
       g.lbdTotal > c.lbdTotal || g.bmTotal > c.bmTotal || g.segTotal > c.segTotal || g.regTotal > c.regTotal ||
-      g.specBmTotal > c.specBmTotal || g.specRecTotal > c.specRecTotal || g.tasksPerFrame != c.tasksPerFrame) {
+      g.specBmTotal > c.specBmTotal || g.specRecTotal > c.specRecTotal || g.tasksPerFrame != c.tasksPerFrame ||
+      g.brBmTotal > c.brBmTotal || g.brRecTotal > c.brRecTotal || g.brListTotal > c.brListTotal ||
+      g.brBandsPerFrame > c.brBandsPerFrame) {
     set_error("internal: line geometry exceeds allocated capacity");
     return PLVI_ERR_CAPACITY;
   }
@@ -185,6 +199,12 @@ int ensure_geom(plvi_line* h, int w, int hh) {
   // keep the allocated per-frame strides
   g.pxTotal = c.pxTotal; g.rawTotal = c.rawTotal; g.lbdTotal = c.lbdTotal; g.bmTotal = c.bmTotal; g.segTotal = c.segTotal;
   g.regTotal = c.regTotal; g.specBmTotal = c.specBmTotal; g.specRecTotal = c.specRecTotal;
+  // band-run: strides of the allocation; the band offsets inside a frame are those of the current geometry (they
+  // fit: every per-frame total is bounded by the capacity geometry's)
+  g.brBmTotal = c.brBmTotal; g.brRecTotal = c.brRecTotal; g.brListTotal = c.brListTotal;
+  const int curBands = g.brBandsPerFrame;
+  g.brBandsPerFrame = c.brBandsPerFrame;
+  (void)curBands;
   for (int o = 0; o < g.noct; o++) {
     g.o[o].regOff = c.o[o].regOff; g.o[o].specBmOff = c.o[o].specBmOff; g.o[o].specRecOff = c.o[o].specRecOff;
     g.o[o].pxOff = c.o[o].pxOff; g.o[o].rawOff = c.o[o].rawOff; g.o[o].bmOff = c.o[o].bmOff;
@@ -273,6 +293,23 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   A((void**)&h->buf.specRec, B * c.specRecTotal * sizeof(SpecRec));
   A((void**)&h->buf.specCnt, B * c.tasksPerFrame * sizeof(int));
   A((void**)&h->buf.phantom, B * c.bmTotal * sizeof(unsigned));
+  {  // band-run buffers for batches of up to PLVI_LSD_BR_MAX frames (default 16; 0 switches the path off)
+    const char* ev = getenv("PLVI_LSD_BR_MAX");
+    const int brMax = std::min(ev ? std::max(0, atoi(ev)) : 16, max_batch);
+    const char* er = getenv("PLVI_LSD_BR_ROUNDS");
+    h->buf.brRounds = std::min(std::max(er ? atoi(er) : 12, 1), BR_FLAGS - 4);
+    h->buf.brMax = brMax;
+    if (brMax > 0) {
+      const size_t S = brMax;
+      A((void**)&h->buf.brIn, S * c.brBmTotal * sizeof(unsigned));
+      A((void**)&h->buf.brWk, S * c.brBmTotal * sizeof(unsigned));
+      A((void**)&h->buf.brPh, S * c.brBmTotal * sizeof(unsigned));
+      A((void**)&h->buf.brRec, S * 2 * c.brRecTotal * sizeof(uint4));
+      A((void**)&h->buf.brList, S * 2 * c.brListTotal * sizeof(unsigned));
+      A((void**)&h->buf.brState, S * c.brBandsPerFrame * 8 * sizeof(int));
+    }
+    A((void**)&h->buf.brFlags, (size_t)std::max(brMax, 1) * 2 * BR_FLAGS * sizeof(int));
+  }
   A((void**)&h->buf.regTab, B * c.segTotal * sizeof(LineRegion));
   A((void**)&h->buf.regCount, B * 2 * sizeof(int));
   A((void**)&h->buf.segs, B * c.segTotal * sizeof(float4));
@@ -334,6 +371,8 @@ void plvi_line_destroy(plvi_line* h) {
   cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
   cudaFree(h->buf.rowf); cudaFree(h->buf.ang); cudaFree(h->buf.cs); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
   cudaFree(h->buf.specBm); cudaFree(h->buf.specRec); cudaFree(h->buf.specCnt); cudaFree(h->buf.phantom);
+  cudaFree(h->buf.brIn); cudaFree(h->buf.brWk); cudaFree(h->buf.brPh); cudaFree(h->buf.brRec); cudaFree(h->buf.brList);
+  cudaFree(h->buf.brState); cudaFree(h->buf.brFlags);
   cudaFree(h->buf.reg); cudaFree(h->buf.regTab); cudaFree(h->buf.regCount); cudaFree(h->buf.segs);
   cudaFree(h->buf.tmpResp); cudaFree(h->buf.tmpCls); cudaFree(h->buf.lbdImg0); cudaFree(h->buf.lbdImg1);
   cudaFree(h->buf.grad); cudaFree(h->buf.lbdRows); cudaFree(h->buf.scaledDbg);
@@ -519,6 +558,17 @@ int plvi_line_read_lsd(plvi_line* h, int frame, int octave, int what, void* out,
       PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.grad + (size_t)frame * g.lbdTotal + O.lbdOff, (size_t)O.lw * O.lh * sizeof(short2),
                                cudaMemcpyDeviceToHost));
       break;
+    case 7:    // band-run diagnostics of (frame, octave): BR_FLAGS ints = fallback, converged, bands dirty in round r at [2 + r]
+      if (!h->buf.brMax || frame >= h->buf.brMax || cap < BR_FLAGS) { set_error("band-run path not active for this frame"); return PLVI_ERR_INVALID; }
+      PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.brFlags + ((size_t)frame * 2 + octave) * BR_FLAGS, BR_FLAGS * sizeof(int), cudaMemcpyDeviceToHost));
+      if (count) *count = h->buf.brRounds;
+      break;
+    case 8: {  // band-run per-band state of (frame, octave): 8 ints per band (nrec[2], cur, dirty, hasPrev, pixels, runs, cycles of the last run)
+      if (!h->buf.brMax || frame >= h->buf.brMax || cap < O.brBands * 8) { set_error("band-run path not active for this frame"); return PLVI_ERR_INVALID; }
+      PLVI_CUDA_TRY(cudaMemcpy(out, h->buf.brState + ((size_t)frame * g.brBandsPerFrame + O.brBandOff) * 8, (size_t)O.brBands * 8 * sizeof(int), cudaMemcpyDeviceToHost));
+      if (count) *count = O.brBands;
+      break;
+    }
     default: return PLVI_ERR_INVALID;
   }
   return PLVI_OK;

@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(256) k_stereo_match(const StereoArgs a) {
   const size_t o = (size_t)f * a.stride + iL;
   float outU = -1.0f, outD = -1.0f;
   int outSad = -1;
-  const int nL = a.nl[f], nR = a.nr[f];
-  if (iL < nL) {
+  const int nL = min(a.nl[f], a.stride), nR = min(a.nr[f], a.stride);
+  // octaves come straight from the caller's keypoint records: a record outside [0, nlevels) is skipped
+  if (iL < nL && (unsigned)a.kl[o].octave < (unsigned)a.nlevels) {
     const plvi_keypoint kpL = a.kl[o];
     const int levelL = kpL.octave;
     const float vL = kpL.y, uL = kpL.x;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(256) k_stereo_match(const StereoArgs a) {
       unsigned best = 0xffffffffu;
       for (int iR = lane; iR < nR; iR += 32) {
         const plvi_keypoint kpR = kr[iR];
+        if ((unsigned)kpR.octave >= (unsigned)a.nlevels) continue;
         const float r = __fmul_rn(2.0f, a.scale[kpR.octave]);
         const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
         if (row < minr || row > maxr) continue;                       // vRowIndices[row] holds iR
