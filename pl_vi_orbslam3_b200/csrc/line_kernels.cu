@@ -937,8 +937,11 @@ __global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_co
 // band overflowed its record / pixel capacity) the octave falls back to the serial kernel.
 // ---------------------------------------------------------------------------------------
 #define BR_ST 8   // ints of per-band state: nrec[0], nrec[1], cur, dirty, hasPrev
-#define BR_K 256  // bitmap rows of a band's shared-memory window: the warp has the SM's shared memory to itself, and a
-                  // window that holds (nearly) every region keeps the availability tests off the L2 round trip
+// bitmap rows of a band's shared-memory window (template parameter of k_lsd_band_run): 256 while the batch leaves
+// the warp an SM's shared memory to itself (a window that holds nearly every region keeps the availability tests off
+// the L2 round trip), 32 when many frames are in flight and resident warps per SM count more
+#define BR_K_BIG 256
+#define BR_K_SMALL 32
 
 // thread = one bitmap word (row, w) of one (frame, octave); walks the bands that contain the row in band order
 __global__ void __launch_bounds__(256) k_lsd_band_compose(const __grid_constant__ LineGeom g, LineBufs b, int round, int check) {
@@ -989,7 +992,7 @@ __global__ void __launch_bounds__(256) k_lsd_band_compose(const __grid_constant_
   if (anyChange && !check) flags[2 + round] = 1;
 }
 
-__global__ void __launch_bounds__(32) k_lsd_band_run(const __grid_constant__ LineGeom g, LineBufs b) {
+template <int BR_K> __global__ void __launch_bounds__(32) k_lsd_band_run(const __grid_constant__ LineGeom g, LineBufs b) {
   extern __shared__ unsigned smem_u[];
   const int t = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
   const int oct = (g.noct > 1 && t >= g.o[1].brBandOff) ? 1 : 0;
@@ -1975,11 +1978,13 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     // small batch: many bands per frame, rounds of (compose inputs, run the bands whose input changed)
     PLVI_CUDA_TRY(cudaMemsetAsync(b.brFlags, 0, (size_t)n * 2 * BR_FLAGS * sizeof(int), st));
     const int maxWords = g.o[0].sh * g.o[0].wpr;
-    const size_t runSmem = ((size_t)g.o[0].wpr * BR_K * 2 + GROW_RQ) * sizeof(unsigned);
+    const bool bigWindow = (long long)n * g.brBandsPerFrame <= 148 * 5;
+    const size_t runSmem = ((size_t)g.o[0].wpr * (bigWindow ? BR_K_BIG : BR_K_SMALL) * 2 + GROW_RQ) * sizeof(unsigned);
     const dim3 cgrid((maxWords + 255) / 256, g.noct, n);
     for (int r = 1; r <= b.brRounds; r++) {
       k_lsd_band_compose<<<cgrid, 256, 0, st>>>(g, b, r, 0);
-      k_lsd_band_run<<<dim3(g.brBandsPerFrame, n), 32, runSmem, st>>>(g, b);
+      if (bigWindow) k_lsd_band_run<BR_K_BIG><<<dim3(g.brBandsPerFrame, n), 32, runSmem, st>>>(g, b);
+      else k_lsd_band_run<BR_K_SMALL><<<dim3(g.brBandsPerFrame, n), 32, runSmem, st>>>(g, b);
       nl += 2;
     }
     prof->mark("k_lsd_band_rounds", st);
@@ -2025,9 +2030,11 @@ int line_kernel_attrs(const LineGeom& g) {
   // the growth kernels want as many resident warps as registers allow: give shared memory the large carve-out
   PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   {
-    const size_t runSmem = ((size_t)g.o[0].wpr * BR_K * 2 + GROW_RQ) * sizeof(unsigned);
+    const size_t runSmem = ((size_t)g.o[0].wpr * BR_K_BIG * 2 + GROW_RQ) * sizeof(unsigned);
     if (runSmem > 220 * 1024) { set_error("image too wide for the band-run shared-memory window"); return PLVI_ERR_CAPACITY; }
-    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_band_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)runSmem));
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_band_run<BR_K_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)runSmem));
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_band_run<BR_K_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_band_run<BR_K_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
   if (commitSmem > 40 * 1024) {
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));

@@ -293,9 +293,11 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   A((void**)&h->buf.specRec, B * c.specRecTotal * sizeof(SpecRec));
   A((void**)&h->buf.specCnt, B * c.tasksPerFrame * sizeof(int));
   A((void**)&h->buf.phantom, B * c.bmTotal * sizeof(unsigned));
-  {  // band-run buffers for batches of up to PLVI_LSD_BR_MAX frames (default 16; 0 switches the path off)
+  {  // band-run buffers for batches of up to PLVI_LSD_BR_MAX frames (0 switches the path off).  Default 384: measured on
+    // B200 the band-run rounds beat band speculation + serial commit up to ~512 frames per batch (32 frames: 5.1x, 128:
+    // 2.8x, 256: 1.7x, 512: 1.0x, profiles/r02_notes.md); about 10 MB of scratch per frame of that capacity.
     const char* ev = getenv("PLVI_LSD_BR_MAX");
-    const int brMax = std::min(ev ? std::max(0, atoi(ev)) : 16, max_batch);
+    const int brMax = std::min(ev ? std::max(0, atoi(ev)) : 384, max_batch);
     const char* er = getenv("PLVI_LSD_BR_ROUNDS");
     h->buf.brRounds = std::min(std::max(er ? atoi(er) : 12, 1), BR_FLAGS - 4);
     h->buf.brMax = brMax;
