@@ -108,6 +108,9 @@ int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w,
                                  plvi_keypoint* kps, uint8_t* desc, int* counts,
                                  int* mono_idx);
 int plvi_orb_sync(plvi_orb* h);
+/* Device copies of the results of the last plvi_orb_extract_batch[_async] call ([n][capacity] keypoints and
+ * descriptors, [n] counts / mono indices): valid until the next call on the handle, in stream order. */
+int plvi_orb_device_results(plvi_orb* h, plvi_keypoint** d_kps, uint8_t** d_desc, int** d_counts, int** d_mono_idx);
 
 /* Same computation with every buffer already resident in DEVICE memory (inputs and
  * outputs are device pointers); enqueued on the handle's stream, not synchronised. */
@@ -199,6 +202,10 @@ int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int 
                                   size_t frame_stride, plvi_keyline* keylines, uint8_t* desc,
                                   double* line_eq, int* counts);
 int plvi_line_sync(plvi_line* h);
+/* Device copies of the results of the last plvi_line_extract_batch[_async] call ([n][capacity] keylines, descriptors,
+ * line equations, [n] counts): valid until the next call on the handle, in stream order on plvi_line_stream().  Lets a
+ * caller that received the results in host buffers run the batched searches on the device copies. */
+int plvi_line_device_results(plvi_line* h, plvi_keyline** d_keylines, uint8_t** d_desc, double** d_line_eq, int** d_counts);
 /* all buffers in device memory; enqueued on the handle's stream */
 int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, int w, int h_,
                                    int stride, size_t frame_stride, plvi_keyline* d_keylines,
@@ -451,6 +458,21 @@ int plvi_line_fuse_search(plvi_matcher* m, int npairs, const plvi_keyline* keyli
  * fills plvi_query from its own projection code instead. */
 int plvi_queries_from_keypoints(plvi_matcher* m, const plvi_keypoint* d_kps, const int* d_counts, int npairs,
                                 int stride, float th, float scale_factor, plvi_query* d_queries);
+
+/* Test / benchmark utilities for frame PAIRS stored as consecutive frames (query frame 2p, searched frame 2p + 1;
+ * SURVEY.md section 8(d), input C3), device pointers only.  plvi_pair_queries builds, per pair, (a) the plvi_query records of
+ * SearchByProjection(CurrentFrame, LastFrame) for a known image-to-image affine map in the place of the pose:
+ * u = a0 x + a1 y + a2, v = a3 x + a4 y + a5, flags bit0 for points that land outside bounds4 = {min_x, max_x, min_y,
+ * max_y} (dropped by the reference, src/ORBmatcher.cc:2007-2010), radius = th * scale_factor^octave, levels octave-1 ..
+ * octave+1; (b) optionally (d_queries_init != NULL) the query set of SearchForInitialization (src/ORBmatcher.cc:717-727:
+ * level-0 keypoints, window init_window around their own position); and the per-pair counts q_count[p] =
+ * counts[2p], t_count[p] = counts[2p + 1].  d_kps is [2 * npairs][stride]; both query arrays are [npairs][out_stride]
+ * (out_stride = 2 * stride lets the search address the frames of a pair in place).  plvi_gather_i32:
+ * dst[i] = src[first + i * step] (per-pair count arrays of other per-frame counts). */
+int plvi_pair_queries(plvi_matcher* m, const plvi_keypoint* d_kps, const int* d_counts, int npairs, int stride,
+                      int out_stride, float th, float scale_factor, const float* affine6, const float* bounds4, float init_window,
+                      plvi_query* d_queries_proj, plvi_query* d_queries_init, int* d_qcount, int* d_tcount);
+int plvi_gather_i32(void* stream, const int* d_src, int n, int first, int step, int* d_dst);
 
 /* static int LineMatcher::match(desc1, desc2, nnr, matches_12) (include/LineMatcher.h:87-107,
  * src/LineMatcher.cpp:92-111) with mutual != 0, LineMatcher::matchNNR (:41-61) with

@@ -94,6 +94,10 @@ _SIGS = {
     "plvi_line_match_grid_host": (ci, [vp, vp, vp, ci, vp, vp, ci, C.c_double, C.c_double, ci, ci, ci, ci, ci, ci, vp, vp]),
     "plvi_line_match_grid_occ_host": (ci, [vp, vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]),
     "plvi_matcher_set_stereo": (ci, [vp, vp, vp, ci, ci, ci, ci]),
+    "plvi_pair_queries": (ci, [vp, vp, vp, ci, ci, ci, cf, cf, vp, vp, cf, vp, vp, vp, vp]),
+    "plvi_orb_device_results": (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "plvi_line_device_results": (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "plvi_gather_i32": (ci, [vp, vp, ci, ci, ci, vp]),
     "plvi_search_in_radius_host": (ci, [vp, vp, vp, ci, vp, vp, vp, ci, vp, C.c_double, ci, vp, vp, vp, vp, vp]),
     "plvi_search_for_triangulation_host": (ci, [vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, vp, vp]),
     "plvi_line_fuse_search_host": (ci, [vp, vp, vp, ci, vp, vp, vp, ci, ci, vp, vp, vp]),

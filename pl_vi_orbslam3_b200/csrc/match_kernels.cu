@@ -417,6 +417,46 @@ __global__ void k_queries_from_keypoints(const plvi_keypoint* __restrict__ kps, 
   q[(size_t)pair * stride + i] = o;
 }
 
+// C3 pairs stored as consecutive frames (query frame 2p, searched frame 2p + 1) under a known image-to-image affine
+// map: the host-side projection of SearchByProjection(CurrentFrame, LastFrame) (src/ORBmatcher.cc:1992-2023) with the
+// warp in the place of the pose -- u = a0 x + a1 y + a2, v = a3 x + a4 y + a5, points that land outside the image
+// bounds are dropped (:2007-2010), radius = th * mvScaleFactors[octave], levels octave-1 .. octave+1 -- and the
+// query set of SearchForInitialization (src/ORBmatcher.cc:717-727: level-0 keypoints, window around their own
+// position).  Also compacts the per-frame counts into per-pair arrays.
+__global__ void k_pair_queries(const plvi_keypoint* __restrict__ kps, const int* __restrict__ counts, int stride, int ostride, float th,
+                               float scaleFactor, float a0, float a1, float a2, float a3, float a4, float a5, float minX,
+                               float maxX, float minY, float maxY, float initWindow, plvi_query* __restrict__ qProj,
+                               plvi_query* __restrict__ qInit, int* __restrict__ qcount, int* __restrict__ tcount) {
+  const int pair = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(counts[2 * pair], stride);
+  if (i == 0) { qcount[pair] = n; tcount[pair] = min(counts[2 * pair + 1], stride); }
+  if (i >= n) return;
+  const plvi_keypoint k = kps[(size_t)(2 * pair) * stride + i];
+  float sf = 1.f;
+  for (int l = 0; l < k.octave; l++) sf = __fmul_rn(sf, scaleFactor);
+  plvi_query o;
+  o.u = __fadd_rn(__fadd_rn(__fmul_rn(a0, k.x), __fmul_rn(a1, k.y)), a2);
+  o.v = __fadd_rn(__fadd_rn(__fmul_rn(a3, k.x), __fmul_rn(a4, k.y)), a5);
+  o.radius = __fmul_rn(th, sf);
+  o.min_level = k.octave - 1;
+  o.max_level = k.octave + 1;
+  o.angle = k.angle;
+  o.flags = (o.u < minX || o.u > maxX || o.v < minY || o.v > maxY) ? 1 : 0;
+  qProj[(size_t)pair * ostride + i] = o;
+  if (qInit) {
+    o.u = k.x; o.v = k.y;
+    o.radius = initWindow;
+    o.min_level = o.max_level = k.octave;
+    o.flags = k.octave > 0 ? 1 : 0;
+    qInit[(size_t)pair * ostride + i] = o;
+  }
+}
+
+__global__ void k_gather_i32(const int* __restrict__ src, int n, int first, int step, int* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[first + i * step];
+}
+
 // ---- lines: knn-2 + ratio in both directions + mutual check, one CTA per pair ---------
 __device__ void nnr_rows(const uint8_t* sa, int na, const uint8_t* sb, int nb, float nnr, int* out) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -1818,6 +1858,32 @@ int plvi_line_match_grid_occ_host(plvi_matcher* m, const int* lines1, const uint
     hs.fetch(nmatches, sN, sizeof(int));
   }
   return hs.finish(PLVI_OK);
+}
+
+int plvi_pair_queries(plvi_matcher* m, const plvi_keypoint* d_kps, const int* d_counts, int npairs, int stride,
+                      int out_stride, float th, float scale_factor, const float* affine6, const float* bounds4, float init_window,
+                      plvi_query* d_queries_proj, plvi_query* d_queries_init, int* d_qcount, int* d_tcount) {
+  if (!m || !d_kps || !d_counts || !affine6 || !bounds4 || !d_queries_proj || !d_qcount || !d_tcount || npairs < 1 || stride < 1 ||
+      out_stride < stride) {
+    set_error("plvi_pair_queries: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  k_pair_queries<<<dim3((stride + 255) / 256, npairs), 256, 0, m->stream>>>(d_kps, d_counts, stride, out_stride, th, scale_factor, affine6[0],
+                                                                            affine6[1], affine6[2], affine6[3], affine6[4], affine6[5],
+                                                                            bounds4[0], bounds4[1], bounds4[2], bounds4[3], init_window,
+                                                                            d_queries_proj, d_queries_init, d_qcount, d_tcount);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  return PLVI_OK;
+}
+
+int plvi_gather_i32(void* stream, const int* d_src, int n, int first, int step, int* d_dst) {
+  if (!d_src || !d_dst || n < 0 || step < 1 || first < 0) { set_error("plvi_gather_i32: invalid argument"); return PLVI_ERR_INVALID; }
+  if (n == 0) return PLVI_OK;
+  k_gather_i32<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_src, n, first, step, d_dst);
+  PLVI_CUDA_TRY(cudaGetLastError());
+  return PLVI_OK;
 }
 
 }  // extern "C"

@@ -21,6 +21,7 @@ struct plvi_line {
   LineGeom geom, capGeom;
   LineBufs buf = {};
   u8* dImg[2] = {nullptr, nullptr};
+  AsyncInput ain;   // input staging of the host-buffer entry points
   LineTab* dTabs = nullptr;
   int2* dRsTab = nullptr;
   double* dLbdG = nullptr;
@@ -366,6 +367,7 @@ void plvi_line_destroy(plvi_line* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  h->ain.destroy();
   if (h->aux.stream) { cudaStreamSynchronize(h->aux.stream); cudaStreamDestroy(h->aux.stream); }
   if (h->aux.fork) cudaEventDestroy(h->aux.fork);
   if (h->aux.join) cudaEventDestroy(h->aux.join);
@@ -472,24 +474,33 @@ int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int 
   PLVI_CUDA_TRY(cudaSetDevice(h->device));
   if ((rc = ensure_geom(h, w, hh))) return rc;
   const LineOct& O0 = h->geom.o[0];
-  if (frame_stride == (size_t)stride * hh) {
-    PLVI_CUDA_TRY(cudaMemcpy2DAsync(h->dImg[0], O0.pitch, imgs, stride, w, (size_t)hh * n, cudaMemcpyHostToDevice, h->stream));
-  } else {
-    for (int i = 0; i < n; i++)
-      PLVI_CUDA_TRY(cudaMemcpy2DAsync(h->dImg[0] + (size_t)i * O0.pitch * O0.h, O0.pitch, imgs + (size_t)i * frame_stride,
-                                      stride, w, hh, cudaMemcpyHostToDevice, h->stream));
-  }
+  u8* dIn = nullptr;
+  if ((rc = h->ain.begin(h->dImg[0], (size_t)h->maxBatch * h->capGeom.o[0].pitch * h->capGeom.o[0].h, &dIn))) return rc;
+  int inPitch = 0;
+  size_t inFs = 0;
+  if ((rc = h->ain.upload(dIn, O0.pitch, O0.h, imgs, n, w, hh, stride, frame_stride, &inPitch, &inFs))) return rc;
+  if ((rc = h->ain.uploaded(h->stream))) return rc;
   LinePtrs p;
-  fill_ptrs(h, nullptr, 0, 0, p);
+  fill_ptrs(h, dIn, inPitch, inFs, p);
   h->lastPtrs = p;
   h->lastN = n;
   rc = run_line_pipeline(h, p, n, h->dKl, h->dDesc, h->dEq, h->dCounts);
   if (rc) return rc;
+  if ((rc = h->ain.finish(h->stream))) return rc;
   const size_t rows = (size_t)n * h->geom.keepCap;
   PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   PLVI_CUDA_TRY(cudaMemcpyAsync(kl, h->dKl, rows * sizeof(plvi_keyline), cudaMemcpyDeviceToHost, h->stream));
   PLVI_CUDA_TRY(cudaMemcpyAsync(desc, h->dDesc, rows * 32, cudaMemcpyDeviceToHost, h->stream));
   PLVI_CUDA_TRY(cudaMemcpyAsync(line_eq, h->dEq, rows * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return PLVI_OK;
+}
+
+int plvi_line_device_results(plvi_line* h, plvi_keyline** d_keylines, uint8_t** d_desc, double** d_line_eq, int** d_counts) {
+  if (!h) return PLVI_ERR_INVALID;
+  if (d_keylines) *d_keylines = h->dKl;
+  if (d_desc) *d_desc = h->dDesc;
+  if (d_line_eq) *d_line_eq = h->dEq;
+  if (d_counts) *d_counts = h->dCounts;
   return PLVI_OK;
 }
 

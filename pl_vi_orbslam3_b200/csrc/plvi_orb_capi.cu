@@ -35,6 +35,7 @@ struct plvi_orb {
   OrbGeom capGeom;     // geometry of (maxW,maxH): allocation capacities
   size_t lvlCapBytes[PLVI_MAX_LEVELS] = {0};  // per-frame bytes per level at capacity
   u8* dImg[PLVI_MAX_LEVELS] = {nullptr};
+  AsyncInput ain;   // input staging of the host-buffer entry points
   u8* dBlur[PLVI_MAX_LEVELS] = {nullptr};
   OrbScratch scr = {};
   int2* dRsTab = nullptr;
@@ -327,6 +328,7 @@ void plvi_orb_destroy(plvi_orb* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  h->ain.destroy();
   for (int l = 0; l < PLVI_MAX_LEVELS; l++) {
     cudaFree(h->dImg[l]);
     cudaFree(h->dBlur[l]);
@@ -511,26 +513,33 @@ int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w,
   PLVI_CUDA_TRY(cudaSetDevice(h->device));
   if ((rc = ensure_geom(h, w, hh))) return rc;
   const OrbLevel& L0 = h->geom.lv[0];
-  if (frame_stride == (size_t)stride * hh) {
-    PLVI_CUDA_TRY(cudaMemcpy2DAsync(h->dImg[0], L0.pitch, imgs, stride, w, (size_t)hh * n,
-                                    cudaMemcpyHostToDevice, h->stream));
-  } else {
-    for (int i = 0; i < n; i++)
-      PLVI_CUDA_TRY(cudaMemcpy2DAsync(h->dImg[0] + (size_t)i * L0.pitch * L0.h, L0.pitch,
-                                      imgs + (size_t)i * frame_stride, stride, w, hh,
-                                      cudaMemcpyHostToDevice, h->stream));
-  }
+  u8* dIn = nullptr;
+  if ((rc = h->ain.begin(h->dImg[0], (size_t)h->maxBatch * h->lvlCapBytes[0], &dIn))) return rc;
+  int inPitch = 0;
+  size_t inFs = 0;
+  if ((rc = h->ain.upload(dIn, L0.pitch, L0.h, imgs, n, w, hh, stride, frame_stride, &inPitch, &inFs))) return rc;
+  if ((rc = h->ain.uploaded(h->stream))) return rc;
   OrbPtrs p;
-  fill_ptrs(h, nullptr, 0, 0, p);
+  fill_ptrs(h, dIn, inPitch, inFs, p);
   h->lastPtrs = p;
   h->lastN = n;
   rc = run_orb_pipeline(h, p, n, lap0, lap1, h->dKps, h->dDesc, h->dCounts, h->dMono);
   if (rc) return rc;
+  if ((rc = h->ain.finish(h->stream))) return rc;
   const size_t rows = (size_t)n * h->cap;
   PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   PLVI_CUDA_TRY(cudaMemcpyAsync(mono_idx, h->dMono, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   PLVI_CUDA_TRY(cudaMemcpyAsync(kps, h->dKps, rows * sizeof(plvi_keypoint), cudaMemcpyDeviceToHost, h->stream));
   PLVI_CUDA_TRY(cudaMemcpyAsync(desc, h->dDesc, rows * 32, cudaMemcpyDeviceToHost, h->stream));
+  return PLVI_OK;
+}
+
+int plvi_orb_device_results(plvi_orb* h, plvi_keypoint** d_kps, uint8_t** d_desc, int** d_counts, int** d_mono_idx) {
+  if (!h) return PLVI_ERR_INVALID;
+  if (d_kps) *d_kps = h->dKps;
+  if (d_desc) *d_desc = h->dDesc;
+  if (d_counts) *d_counts = h->dCounts;
+  if (d_mono_idx) *d_mono_idx = h->dMono;
   return PLVI_OK;
 }
 

@@ -27,7 +27,7 @@ class FrontEnd:
     def __init__(self, batch, w=752, h=480, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
                  lsd_nfeatures=200, lsd_scale=0.8, line_levels=2, line_scale=2.0, device=0, stream=None,
                  with_lines=True, with_match=True, match_th=15.0, nnratio=0.9, overlap_lines=True, line_priority=0,
-                 out_sets=1):
+                 out_sets=1, pairs=False, affine=None, init_window=100.0):
         import torch
         self.torch = torch
         self.B, self.w, self.h = batch, w, h
@@ -60,7 +60,36 @@ class FrontEnd:
                                       stream=self.line_stream.cuda_stream)
             self.line_outs = [self.line.alloc_device_outputs(batch, self.device) for _ in range(self.out_sets)]
             self.line_out = self.line_outs[0]
-        if with_match and batch > 1:
+        # pairs=True: the batch holds C3 pairs (frame 2p, its warp 2p + 1) and every pair is matched in the
+        # two point modes of C3 -- SearchByProjection(Frame, Frame) semantics with the warp as the "pose" and
+        # SearchForInitialization semantics -- plus LineMatcher::match; else consecutive frames under the identity pose
+        self.pairs = bool(pairs)
+        self.affine = np.asarray(affine if affine is not None else [1, 0, 0, 0, 1, 0], np.float32).reshape(6)
+        self.bounds = np.asarray([0, w, 0, h], np.float32)
+        self.init_window = float(init_window)
+        if with_match and batch > 1 and self.pairs:
+            cap = self.orb.capacity
+            P, S = batch // 2, 2 * cap
+            self.om = ORBmatcher(nnratio, True, max_pairs=P, max_train=S, max_query=S, device=device, stream=sp)
+            self.grid = frame_grid(0, w, 0, h)
+            self.q_proj = torch.zeros((P, S, 7), dtype=torch.float32, device=self.device)
+            self.q_init = torch.zeros((P, S, 7), dtype=torch.float32, device=self.device)
+            self.qcount = torch.zeros(P, dtype=torch.int32, device=self.device)
+            self.tcount = torch.zeros(P, dtype=torch.int32, device=self.device)
+            self.scratch_mq = torch.zeros((P, S), dtype=torch.int32, device=self.device)
+            self.match_sets = [tuple(torch.zeros((P, S), dtype=torch.int32, device=self.device) for _ in range(2)) +
+                               tuple(torch.zeros(P, dtype=torch.int32, device=self.device) for _ in range(2))
+                               for _ in range(self.out_sets)]
+            self.match_train, self.init_m12, self.nmatches, self.init_nm = self.match_sets[0]
+            if with_lines:
+                lc = self.line.capacity
+                self.lm = LineMatcher(max_pairs=P, max_train=2 * lc, max_query=2 * lc, device=device, stream=sp)
+                self.lq = torch.zeros(P, dtype=torch.int32, device=self.device)
+                self.lt = torch.zeros(P, dtype=torch.int32, device=self.device)
+                self.lmatch_sets = [(torch.zeros((P, 2 * lc), dtype=torch.int32, device=self.device),
+                                     torch.zeros(P, dtype=torch.int32, device=self.device)) for _ in range(self.out_sets)]
+                self.line_m12, self.line_nm = self.lmatch_sets[0]
+        elif with_match and batch > 1:
             cap = self.orb.capacity
             self.om = ORBmatcher(nnratio, True, max_pairs=batch, max_train=cap, max_query=cap, device=device, stream=sp)
             self.grid = frame_grid(0, w, 0, h)
@@ -91,15 +120,7 @@ class FrontEnd:
         wait for the line pipeline (clean per-kernel timings for the profile pass)."""
         n = d_frames.shape[0]
         nl = 0
-        if self.out_sets > 1:   # next output buffer set
-            self._set = (self._set + 1) % self.out_sets
-            self.orb_out = self.orb_outs[self._set]
-            if self.line is not None:
-                self.line_out = self.line_outs[self._set]
-            if self.om is not None:
-                self.match_train, self.match_query, self.nmatches = self.match_sets[self._set]
-            if self.lm is not None:
-                self.line_m12, self.line_nm = self.lmatch_sets[self._set]
+        self._next_set()
         forked = self.line is not None and self.line_stream is not self.stream
         if forked:
             self._ev_fork.record(self.stream)
@@ -118,40 +139,181 @@ class FrontEnd:
         if forked and not serialize:
             self._ev_join.record(self.line_stream)
             self.stream.wait_event(self._ev_join)
+        nl += self._match(kps, desc, counts, ldesc if self.line is not None else None,
+                          lcounts if self.line is not None else None, n)
+        self.launches = nl
+        return nl
+
+
+    def _next_set(self):
+        if self.out_sets > 1:   # next output buffer set
+            self._set = (self._set + 1) % self.out_sets
+            self.orb_out = self.orb_outs[self._set]
+            if self.line is not None:
+                self.line_out = self.line_outs[self._set]
+            if self.om is not None and self.pairs:
+                self.match_train, self.init_m12, self.nmatches, self.init_nm = self.match_sets[self._set]
+            elif self.om is not None:
+                self.match_train, self.match_query, self.nmatches = self.match_sets[self._set]
+            if self.lm is not None:
+                self.line_m12, self.line_nm = self.lmatch_sets[self._set]
+
+    def _match(self, kps, desc, counts, ldesc, lcounts, n):
+        """The searches of one step on device-resident extraction results (tensors or raw device addresses), enqueued on
+        self.stream.  Returns the number of kernel launches."""
+        nl = 0
+        if self.om is None or n < 2:
+            return 0
         if self._profiling:
             self._mev = [self.torch.cuda.Event(enable_timing=True) for _ in range(4)]
             self._mev[0].record(self.stream)
-        if self.om is not None and n > 1:
-            P, cap = n - 1, self.orb.capacity
-            # frame p's keypoints are the "last frame" points searched in frame p+1
-            check(lib().plvi_queries_from_keypoints(self.om._h, ptr(kps), ptr(counts), P, cap, self.match_th,
-                                                    self.scale_factor, ptr(self.queries)))
+        cap = self.orb.capacity
+        a = (lambda t: t.data_ptr()) if hasattr(kps, "data_ptr") else (lambda t: t)
+        if self.pairs:
+            P, S = n // 2, 2 * cap
+            check(lib().plvi_pair_queries(self.om._h, ptr(kps), ptr(counts), P, cap, S, self.match_th, self.scale_factor,
+                                          ptr(self.affine), ptr(self.bounds), self.init_window, ptr(self.q_proj), ptr(self.q_init),
+                                          ptr(self.qcount), ptr(self.tcount)))
+            # frame 2p + 1 is the searched ("current") frame, frame 2p the query ("last") frame of pair p
+            k1, d1 = a(kps) + cap * 28, a(desc) + cap * 32
             check(lib().plvi_search_by_projection(
-                self.om._h, 0, P, ptr(kps[1:]), ptr(desc[1:]), None, ptr(counts[1:]), cap, ptr(self.grid),
-                ptr(self.queries), ptr(desc), ptr(counts), cap, ORBmatcher.TH_HIGH, self.om.mfNNratio, 1,
-                ptr(self.match_train), ptr(self.match_query), ptr(self.nmatches), 1))
-            nl += 2
+                self.om._h, 0, P, ptr(k1), ptr(d1), None, ptr(self.tcount), S, ptr(self.grid), ptr(self.q_proj), ptr(desc),
+                ptr(self.qcount), S, ORBmatcher.TH_HIGH, self.om.mfNNratio, 1, ptr(self.match_train), ptr(self.scratch_mq),
+                ptr(self.nmatches), 1))
+            check(lib().plvi_search_by_projection(
+                self.om._h, 2, P, ptr(k1), ptr(d1), None, ptr(self.tcount), S, ptr(self.grid), ptr(self.q_init), ptr(desc),
+                ptr(self.qcount), S, ORBmatcher.TH_LOW, self.om.mfNNratio, 1, ptr(self.scratch_mq), ptr(self.init_m12),
+                ptr(self.init_nm), 1))
+            nl += 3
             if self._profiling:
                 self._mev[1].record(self.stream)
             if self.lm is not None:
                 lc = self.line.capacity
-                check(lib().plvi_line_match(self.lm._h, P, ptr(ldesc), ptr(lcounts), lc, ptr(ldesc[1:]), ptr(lcounts[1:]),
-                                            lc, 0.9, 1, ptr(self.line_m12), ptr(self.line_nm), 1))
-                nl += 1
+                sp = self.stream.cuda_stream
+                check(lib().plvi_gather_i32(ptr(sp), ptr(lcounts), P, 0, 2, ptr(self.lq)))
+                check(lib().plvi_gather_i32(ptr(sp), ptr(lcounts), P, 1, 2, ptr(self.lt)))
+                check(lib().plvi_line_match(self.lm._h, P, ptr(ldesc), ptr(self.lq), 2 * lc, ptr(a(ldesc) + lc * 32), ptr(self.lt),
+                                            2 * lc, 0.9, 1, ptr(self.line_m12), ptr(self.line_nm), 1))
+                nl += 3
                 if self._profiling:
                     self._mev[2].record(self.stream)
+            return nl
+        P = n - 1
+        # frame p's keypoints are the "last frame" points searched in frame p+1
+        check(lib().plvi_queries_from_keypoints(self.om._h, ptr(kps), ptr(counts), P, cap, self.match_th,
+                                                self.scale_factor, ptr(self.queries)))
+        check(lib().plvi_search_by_projection(
+            self.om._h, 0, P, ptr(a(kps) + cap * 28), ptr(a(desc) + cap * 32), None, ptr(a(counts) + 4), cap, ptr(self.grid),
+            ptr(self.queries), ptr(desc), ptr(counts), cap, ORBmatcher.TH_HIGH, self.om.mfNNratio, 1,
+            ptr(self.match_train), ptr(self.match_query), ptr(self.nmatches), 1))
+        nl += 2
+        if self._profiling:
+            self._mev[1].record(self.stream)
+        if self.lm is not None:
+            lc = self.line.capacity
+            check(lib().plvi_line_match(self.lm._h, P, ptr(ldesc), ptr(lcounts), lc, ptr(a(ldesc) + lc * 32), ptr(a(lcounts) + 4),
+                                        lc, 0.9, 1, ptr(self.line_m12), ptr(self.line_nm), 1))
+            nl += 1
+            if self._profiling:
+                self._mev[2].record(self.stream)
+        return nl
+
+    # ---- the same step through the reference-facing C ABI with HOST buffers (what the C++ shim calls) -------------------
+    def alloc_host_io(self):
+        """Pinned host result buffers of one step (the caller-owned vectors / cv::Mat of the reference's operator())."""
+        t = self.torch
+        cap, B = self.orb.capacity, self.B
+        io = {"kps": t.zeros((B, cap, 7), dtype=t.float32).pin_memory(), "desc": t.zeros((B, cap, 32), dtype=t.uint8).pin_memory(),
+              "counts": t.zeros(B, dtype=t.int32).pin_memory(), "mono": t.zeros(B, dtype=t.int32).pin_memory()}
+        if self.line is not None:
+            lc = self.line.capacity
+            io.update(keylines=t.zeros((B, lc, 17), dtype=t.float32).pin_memory(), line_desc=t.zeros((B, lc, 32), dtype=t.uint8).pin_memory(),
+                      line_eq=t.zeros((B, lc, 3), dtype=t.float64).pin_memory(), line_counts=t.zeros(B, dtype=t.int32).pin_memory())
+        for k, v in self.match_outputs().items():
+            io[k] = t.zeros(v.shape, dtype=v.dtype).pin_memory()
+        return io
+
+    def match_outputs(self):
+        out = {}
+        if self.om is not None and self.pairs:
+            out.update(match_train=self.match_train, nmatches=self.nmatches, init_matches=self.init_m12, init_nmatches=self.init_nm)
+        elif self.om is not None:
+            out.update(match_train=self.match_train, nmatches=self.nmatches)
+        if self.lm is not None:
+            out.update(line_matches=self.line_m12, line_nmatches=self.line_nm)
+        return out
+
+    def step_host(self, h_frames, io):
+        """h_frames: pinned uint8 host tensor [n, h, w]; io: alloc_host_io().  plvi_orb_extract_batch_async +
+        plvi_line_extract_batch_async (host image in, host results out; uploads on the handles' copy streams overlap
+        the previous call's kernels), then the searches on the handles' device copies of the results and the match
+        tables back to the host.  Nothing blocks: sync_host() waits for everything issued."""
+        n, h, w = h_frames.shape
+        nl = 0
+        self._next_set()
+        if self.line is not None:
+            if self.line_stream is not self.stream and getattr(self, "_ev_match", None) is not None:
+                self.line_stream.wait_event(self._ev_match)   # the searches of the previous step read the line results
+            check(lib().plvi_line_extract_batch_async(self.line._h, ptr(h_frames), n, w, h, h_frames.stride(1), h_frames.stride(0),
+                                                      ptr(io["keylines"]), ptr(io["line_desc"]), ptr(io["line_eq"]),
+                                                      ptr(io["line_counts"])))
+            nl += self.line.last_launches
+            if self.line_stream is not self.stream:
+                self._ev_join.record(self.line_stream)
+                if self.skew:   # as in step(): the ORB kernels start when the line pipeline has reached region growing
+                    check(lib().plvi_orb_wait_event(self.orb._h, lib().plvi_line_stage_event(self.line._h)))
+        check(lib().plvi_orb_extract_batch_async(self.orb._h, ptr(h_frames), n, w, h, h_frames.stride(1), h_frames.stride(0), 0, 0,
+                                                 ptr(io["kps"]), ptr(io["desc"]), ptr(io["counts"]), ptr(io["mono"])))
+        nl += self.orb.last_launches
+        if self.om is not None and n > 1:
+            import ctypes as C
+            dk, dd, dc, dm = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            check(lib().plvi_orb_device_results(self.orb._h, C.byref(dk), C.byref(dd), C.byref(dc), C.byref(dm)))
+            ld = lcn = None
+            if self.line is not None:
+                lk, ldp, le, lcp = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+                check(lib().plvi_line_device_results(self.line._h, C.byref(lk), C.byref(ldp), C.byref(le), C.byref(lcp)))
+                ld, lcn = ldp.value, lcp.value
+                if self.line_stream is not self.stream:
+                    self.stream.wait_event(self._ev_join)
+            nl += self._match(dk.value, dd.value, dc.value, ld, lcn, n)
+            with self.torch.cuda.stream(self.stream):
+                for k, v in self.match_outputs().items():
+                    io[k].copy_(v, non_blocking=True)
+            if self.line is not None and self.line_stream is not self.stream:
+                self._ev_match = self.torch.cuda.Event()
+                self._ev_match.record(self.stream)
         self.launches = nl
         return nl
+
+    def sync_host(self):
+        if self.line is not None:
+            self.line.sync()
+        self.orb.sync()
+        self.stream.synchronize()
+
+    def wait_event_all(self, ev):
+        """Every stream of this front end waits for `ev` before the work issued next."""
+        self.stream.wait_event(ev)
+        if self.line is not None and self.line_stream is not self.stream:
+            self.line_stream.wait_event(ev)
+
+    def host_done_events(self):
+        """New events that complete when everything the last step_host() issued -- kernels and the result copies to the
+        host -- has finished."""
+        evs = [self.torch.cuda.Event()]
+        evs[0].record(self.stream)
+        if self.line is not None and self.line_stream is not self.stream:
+            evs.append(self.torch.cuda.Event())
+            evs[1].record(self.line_stream)
+        return evs
 
     def outputs(self):
         out = {"kps": self.orb_out[0], "desc": self.orb_out[1], "counts": self.orb_out[2], "mono": self.orb_out[3]}
         if self.line is not None:
             out.update(keylines=self.line_out[0], line_desc=self.line_out[1], line_eq=self.line_out[2],
                        line_counts=self.line_out[3])
-        if self.om is not None:
-            out.update(match_train=self.match_train, nmatches=self.nmatches)
-        if self.lm is not None:
-            out.update(line_matches=self.line_m12, line_nmatches=self.line_nm)
+        out.update(self.match_outputs())
         return out
 
     def set_profile(self, on=True):

@@ -104,3 +104,72 @@ def frame_batch(n, w=752, h=480, base_seed=0, distinct=16):
         k = i // len(base)
         out[i] = np.roll(b, (3 * k, 5 * k), axis=(0, 1)) if k else b
     return out
+
+
+# ---- whole benchmark batches: every frame generated from its own seed (seeds 0...4095), in
+# ---- parallel worker processes, cached on local disk so that back-to-back bench runs on one box generate once ----------
+def _gen_frame(a):
+    return frame_euroc(*a)
+
+
+def _gen_pair(a):
+    f1, f2, _ = warp_pair(*a)
+    return np.stack([f1, f2])
+
+
+def warp_affine(w=752, h=480, angle_deg=1.5, tx=6.0, ty=-4.0, scale=1.01):
+    """The 2x3 forward map of warp_pair (p2 = A @ [p1, 1]) without generating frames."""
+    a = np.deg2rad(angle_deg)
+    cx, cy = (w - 1) / 2.0, (h - 1) / 2.0
+    R = scale * np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+    t = np.array([cx, cy]) - R @ np.array([cx, cy]) + np.array([tx, ty])
+    return np.hstack([R, t[:, None]])
+
+
+def _batch(kind, n, w, h, base_seed, workers, cache):
+    import os
+    import tempfile
+    from pathlib import Path
+    path = None
+    if cache:
+        d = Path(os.environ.get("PLVI_SYNTH_CACHE", Path(tempfile.gettempdir()) / "plvi_synth_cache"))
+        path = d / f"{kind}_{w}x{h}_s{base_seed}_n{n}.npy"
+        try:
+            if path.exists():
+                a = np.load(path)
+                if a.shape == (n, h, w) and a.dtype == np.uint8:
+                    return a
+        except Exception:
+            pass
+    if kind == "pairs":
+        jobs, fn = [(base_seed + p, w, h) for p in range((n + 1) // 2)], _gen_pair
+    else:
+        jobs, fn = [(base_seed + i, w, h) for i in range(n)], _gen_frame
+    workers = max(1, min(workers or (os.cpu_count() or 1), len(jobs)))
+    if workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:     # call before CUDA is initialised in this process
+            parts = pool.map(fn, jobs, chunksize=max(1, len(jobs) // (8 * workers)))
+    else:
+        parts = [fn(j) for j in jobs]
+    out = (np.concatenate(parts) if kind == "pairs" else np.stack(parts))[:n]
+    if path is not None:
+        try:
+            path.parent.mkdir(parents=True, exist_ok=True)
+            tmp = path.with_suffix(f".{os.getpid()}.tmp.npy")
+            np.save(tmp, out)
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return out
+
+
+def seq_batch(n, w=752, h=480, base_seed=0, workers=0, cache=True):
+    """C1 / C4 / C5: frames frame_euroc(base_seed) ... frame_euroc(base_seed + n - 1), [n, h, w] u8."""
+    return _batch("seq", n, w, h, base_seed, workers, cache)
+
+
+def pair_batch(n, w=752, h=480, base_seed=0, workers=0, cache=True):
+    """C3: n frames = n / 2 pairs; frame 2p = frame_euroc(base_seed + p), frame 2p + 1 = its warp (warp_pair, map
+    warp_affine()), [n, h, w] u8."""
+    return _batch("pairs", n, w, h, base_seed, workers, cache)

@@ -196,18 +196,19 @@ def test_cuda_graph_replay_is_used_and_identical(gpu):
     e = ORBextractor(1000, 1.2, 8, 20, 7, max_width=752, max_height=480, max_batch=4)
     le = Lineextractor(200, 0, 0.8, 2, 2.0, 0, max_width=752, max_height=480, max_batch=4)
     try:
-        a = [e.extract_batch(frames) for _ in range(3)]
-        la = [le.extract_batch(frames) for _ in range(3)]
+        # the host-buffer entry points upload into two alternating staging buffers: one graph per buffer
+        a = [e.extract_batch(frames) for _ in range(4)]
+        la = [le.extract_batch(frames) for _ in range(4)]
         cap, rep = e.graph_stats()
-        assert cap == 1 and rep == 2, (cap, rep)
+        assert cap == 2 and rep == 2, (cap, rep)
         lcap, lrep = le.graph_stats()
-        assert lcap == 1 and lrep == 2, (lcap, lrep)
+        assert lcap == 2 and lrep == 2, (lcap, lrep)
         from pl_vi_orbslam3_b200.capi import lib
         lib().plvi_orb_set_profile(e._h, 1)
         lib().plvi_line_set_profile(le._h, 1)
         b = e.extract_batch(frames)          # plain launches
         lb = le.extract_batch(frames)
-        assert e.graph_stats() == (1, 2) and le.graph_stats() == (1, 2)
+        assert e.graph_stats() == (2, 2) and le.graph_stats() == (2, 2)
         for x in a:
             for u, v in zip(x, b):
                 assert np.array_equal(u, v)
@@ -217,7 +218,7 @@ def test_cuda_graph_replay_is_used_and_identical(gpu):
         # another batch size is another graph
         lib().plvi_orb_set_profile(e._h, 0)
         e.extract_batch(frames[:2])
-        assert e.graph_stats()[0] == 2
+        assert e.graph_stats()[0] == 3
     finally:
         e.close()
         le.close()
