@@ -16,6 +16,7 @@
 #include <map>
 
 #include "oracle_common.h"
+#include "lsd_gauss_table.h"
 
 namespace plvio {
 
@@ -35,15 +36,15 @@ struct KeyLine {  // 68 bytes, descriptor_custom.hpp:107-146
 // ---- OpenCV primitives ---------------------------------------------------------------
 // cv::getGaussianKernel(n, sigma, CV_64F).  OpenCV >= 4.x builds it with soft-float
 // arithmetic; for the reference's fixed LSD setting (n=7, sigma=0.6/(double)0.8f) the
-// values probed from cv2 4.13 are used verbatim, otherwise the defining formula.
+// values probed from cv2 4.13 are used verbatim (and for the other common lsd_scale settings, see
+// lsd_gauss_table.h), otherwise the defining formula.
 void gaussian_kernel_f64(int n, double sigma, double* k) {
-  const double s08 = 0.6 / (double)0.8f;
-  if (n == 7 && sigma == s08) {
-    static const uint64_t bits[7] = {0x3f276349157f1ab0ull, 0x3f8f1e22f611221dull, 0x3fcbfd7fa6a94f5aull,
-                                     0x3fe10562abd81f5full, 0x3fcbfd7fa6a94f5aull, 0x3f8f1e22f611221dull,
-                                     0x3f276349157f1ab0ull};
-    memcpy(k, bits, sizeof(bits));
-    return;
+  // values probed from cv2 4.13 for LSD's sigma = 0.6 / (double)lsd_scale at the common lsd_scale settings
+  // (oracle/lsd_gauss_table.h, tools/gen_lsd_gauss.py)
+  for (const LsdGaussEntry& e : kLsdGaussTable) {
+    float sc;
+    memcpy(&sc, &e.scale_bits, 4);
+    if (e.n == n && sigma == 0.6 / (double)sc) { memcpy(k, e.k, sizeof(double) * n); return; }
   }
   const double scale2X = -0.5 / (sigma * sigma);
   double sum = 0;
@@ -102,6 +103,18 @@ static void linear_coeffs_f(int ssize, int dsize, double inv_scale, std::vector<
 }
 
 void resize_linear_f64(const double* src, int sw, int sh, double* dst, int dw, int dh, double fx, double fy) {
+  // cv::resize turns INTER_LINEAR into INTER_AREA when both inverse scales are exactly 2 ("INTER_AREA (fast) also is
+  // equal to INTER_LINEAR"): the 2x2 block is summed in raster order and multiplied by 0.25 -- the same value as the
+  // bilinear form up to the order of the additions, i.e. not to the last bit.  Probed on cv2 4.13
+  // (tests/test_oracle_vs_cv2.py); sizes whose last block would leave the source are not modelled.
+  if (fx == 0.5 && fy == 0.5 && 2 * dw <= sw && 2 * dh <= sh) {
+    for (int y = 0; y < dh; y++) {
+      const double* r0 = src + (size_t)(2 * y) * sw;
+      const double* r1 = r0 + sw;
+      for (int x = 0; x < dw; x++) dst[(size_t)y * dw + x] = (((r0[2 * x] + r0[2 * x + 1]) + r1[2 * x]) + r1[2 * x + 1]) * 0.25;
+    }
+    return;
+  }
   std::vector<int> xo, yo;
   std::vector<float> xa0, xa1, ya0, ya1;
   linear_coeffs_f(sw, dw, fx, xo, xa0, xa1);

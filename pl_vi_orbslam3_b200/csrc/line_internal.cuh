@@ -8,6 +8,7 @@ struct LineOct {
   int w, h, pitch;     // LSD pyramid octave image (u8)
   int sw, sh;          // LSD working size after lsd_scale (flsd: resize(gaussian_img, scaled_image, Size(), SCALE, SCALE))
   int wpr;             // "available" bitmap words per row
+  int preSW, preRH;    // k_lsd_pre: f64 row stride / max source rows of a tile's source window in shared memory
   int minRegSize;      // int(-LOG_NT / log10(p)), src/LSD/lsd.cpp:466-467
   size_t pxOff;        // offset of this octave in per-frame scaled-pixel arrays
   size_t rawOff;       // offset in the per-frame row-filtered f64 array
@@ -42,7 +43,9 @@ struct LineGeom {
   int bmTotal, segTotal;
   double rho, prec, lsdScale, minLength;
   float alignHi2, alignLo2;   // cos^2(prec -/+ margin): bounds of the cheap alignment test in k_lsd_grow
-  double kern[7];
+  int hk;                     // half width of the LSD Gaussian: h = ceil(sigma * sqrt(2 * 3 * ln 10)), src/LSD/lsd.cpp:452; 0: lsd_scale == 1
+  int preTH;                  // k_lsd_pre: scaled rows per tile (tiles are 32 scaled columns wide = one bitmap word)
+  double kern[17];            // cv::getGaussianKernel(1 + 2 hk, sigma, CV_64F)
   float lineScale;
   int nfeat, keepCap;
 };
@@ -58,7 +61,6 @@ struct LinePtrs {
 };
 
 struct LineBufs {
-  double* rowf;          // [B][rawTotal]
   float* ang;            // [B][pxTotal]   level-line angle in degrees (-1024 = NOTDEF)
   float2* cs;            // [B][pxTotal]   cos, sin of float(angle): what a region accumulates (lsd.cpp:673-675)
   float2* seed;          // [B][pxTotal]   cos, sin of the f64 angle (region seed: float(std::cos(reg_angle)))

@@ -1,8 +1,7 @@
 // Line feature kernels for sm_100a: LSD (refine 0) + KeyLine assembly + LBD.
 //
-//   k_lsd_rowfilter   u8 -> f64 horizontal 7-tap Gaussian         src/LSD/lsd.cpp:415-455
-//   k_lsd_scale_grad  vertical Gaussian + 0.8x bilinear (f64) +
-//                     ll_angle gradient/angle/"available" bitmap   src/LSD/lsd.cpp:457,536-585
+//   k_lsd_pre         u8 -> f64 Gaussian blur + lsd_scale bilinear resize +
+//                     ll_angle gradient/angle/"available" bitmap   src/LSD/lsd.cpp:415-457,536-585
 //   k_lsd_grow        seed scan (raster order) + region_grow       src/LSD/lsd.cpp:476-487,635-686,1136-1152
 //   k_lsd_rect        region2rect + get_theta                      src/LSD/lsd.cpp:688-782, 506-521
 //   k_line_assemble   LSDDetectorC::detectImpl KeyLine fields,     LSDDetector_custom.cpp:304-346
@@ -23,7 +22,7 @@
 
 namespace plvi {
 
-// BORDER_REFLECT_101 for -len < p < 2 * len - 1 (one reflection: halos are <= 3 pixels, images >= 8)
+// BORDER_REFLECT_101 for -len < p < 2 * len - 1 (one reflection: halos are <= 8 pixels, images >= 2 * halo + 2)
 __device__ __forceinline__ int reflect101_l(int p, int len) {
   p = p < 0 ? -p : p;
   return p >= len ? 2 * (len - 1) - p : p;
@@ -50,58 +49,14 @@ __device__ __forceinline__ float fast_atan2_dev(float y, float x) {
 #define PI_D 3.14159265358979323846
 
 // ---------------------------------------------------------------------------------------
-// k_lsd_rowfilter: f64 row pass of cv::GaussianBlur (sequential tap order), REFLECT_101.
+// k_lsd_pre: everything flsd does before the seed loop (src/LSD/lsd.cpp:415-457, 536-585) for one tile of the scaled
+// image, with no intermediate in global memory: u8 -> f64 cv::GaussianBlur (row pass in sequential tap order, column
+// pass with the symmetric pairs added first, BORDER_REFLECT_101), cv::resize INTER_LINEAR with float32 weights applied
+// in double (horizontal, then vertical), then ll_angle: 2x2 gradient, level-line angle, cos / sin records of a pixel
+// and the "available" bitmap.  CTA = 32 x preTH scaled pixels (32 columns = one bitmap word); the tile's source window
+// (+ hk halo) lives in shared memory: u8 window -> row-filtered f64 -> column-filtered f64 -> scaled tile (+1 halo).
+// HK = half width of the Gaussian (3 for lsd_scale 0.8; 0: lsd_scale == 1, the image itself is the working image).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_lsd_rowfilter(const u8* __restrict__ src, int spitch, size_t sfs, int w,
-                                                       int h, double* __restrict__ dst, size_t dfs,
-                                                       const __grid_constant__ LineGeom g) {
-  // thread = 4 horizontally adjacent pixels: the 10 input bytes are converted to f64 once
-  const int x4 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
-  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (x4 >= w || y >= h) return;
-  const u8* row = src + (size_t)blockIdx.z * sfs + (size_t)y * spitch;
-  double v[10];
-  const bool aligned4 = ((spitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(src + (size_t)blockIdx.z * sfs) & 3) == 0);
-  if (aligned4 && x4 >= 4 && x4 + 7 < w) {
-    const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(row + x4 - 4));
-    const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(row + x4));
-    const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(row + x4 + 4));
-    v[0] = (double)((a >> 8) & 0xffu); v[1] = (double)((a >> 16) & 0xffu); v[2] = (double)(a >> 24);
-    v[3] = (double)(b & 0xffu); v[4] = (double)((b >> 8) & 0xffu); v[5] = (double)((b >> 16) & 0xffu); v[6] = (double)(b >> 24);
-    v[7] = (double)(c & 0xffu); v[8] = (double)((c >> 8) & 0xffu); v[9] = (double)((c >> 16) & 0xffu);
-  } else if (x4 >= 3 && x4 + 6 < w) {
-#pragma unroll
-    for (int i = 0; i < 10; i++) v[i] = (double)__ldg(row + x4 - 3 + i);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 10; i++) v[i] = (double)__ldg(row + reflect101_l(min(x4 - 3 + i, w + 2), w));
-  }
-  double* out = dst + (size_t)blockIdx.z * dfs + (size_t)y * w + x4;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (x4 + k >= w) break;
-    double s = __dmul_rn(g.kern[0], v[k]);
-#pragma unroll
-    for (int i = 1; i < 7; i++) s = __dadd_rn(s, __dmul_rn(g.kern[i], v[k + i]));
-    out[k] = s;
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// k_lsd_scale_grad: CTA = 32x8 tile of the scaled image.  Phase A builds the 33x9 scaled
-// pixels (column pass of the Gaussian at the 2x2 source taps, then bilinear with float32
-// weights applied in double); phase B is ll_angle.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double col_blur(const double* __restrict__ rf, int w, int h, int x, int y,
-                                           const double* k) {
-  double s = __dmul_rn(k[3], rf[(size_t)y * w + x]);
-#pragma unroll
-  for (int i = 1; i <= 3; i++)
-    s = __dadd_rn(s, __dmul_rn(k[3 + i], __dadd_rn(rf[(size_t)reflect101_l(y + i, h) * w + x],
-                                                  rf[(size_t)reflect101_l(y - i, h) * w + x])));
-  return s;
-}
-
 // cos/sin of a level-line angle a in [0, 2 pi): a = k * (2 pi / 1024) + r, table values for the
 // grid point (correctly rounded doubles from the host libm) and short Taylor series for |r| <=
 // pi/1024.  Accurate to a few ulp of double, i.e. far below the float rounding that follows.
@@ -118,105 +73,179 @@ __device__ __forceinline__ void sincos_tab(double a, const double2* __restrict__
   s = t.y * cr + t.x * sr;
 }
 
-#define SG_TW 32
-#define SG_TH 8
-#define SG_SRC_W 48   // source columns needed by 33 scaled columns at scale >= 0.75: <= 33/0.75 + 3
-#define SG_SRC_H 16   // source rows needed by 9 scaled rows
+#define PRE_TW 32
 
-__global__ void __launch_bounds__(256) k_lsd_scale_grad(const __grid_constant__ LineGeom g, int oct,
-                                                        const double* __restrict__ rowf, size_t rfs,
-                                                        const LineTab* __restrict__ tabs, LineBufs b) {
-  __shared__ double sblur[SG_SRC_H][SG_SRC_W];   // column-blurred source pixels of this tile
-  __shared__ double ssc[SG_TH + 1][SG_TW + 2];   // scaled image tile (+1 halo)
+template <int HK>
+__global__ void __launch_bounds__(256) k_lsd_pre(const __grid_constant__ LineGeom g, int oct, const u8* __restrict__ src,
+                                                 int spitch, size_t sfs, const LineTab* __restrict__ tabs, LineBufs b) {
+  extern __shared__ __align__(16) double smem_d[];
   const LineOct& O = g.o[oct];
+  const int TH = g.preTH, SW = O.preSW, RH = O.preRH;
   const int f = blockIdx.z, tid = threadIdx.x;
-  const int x0 = blockIdx.x * SG_TW, y0 = blockIdx.y * SG_TH;
-  const double* rf = rowf + (size_t)f * rfs + O.rawOff;
-  const LineTab* xt = tabs + O.xtabOff;
-  const LineTab* yt = tabs + O.ytabOff;
-  __shared__ int s_win[4];
-  if (tid == 0) {   // source window of the tile
-    const int sx0 = xt[x0].ofs, sx1 = min(xt[min(x0 + SG_TW, O.sw - 1)].ofs + 1, O.w - 1);
-    const int sy0 = yt[y0].ofs, sy1 = min(yt[min(y0 + SG_TH, O.sh - 1)].ofs + 1, O.h - 1);
-    s_win[0] = sx0; s_win[1] = sx1 - sx0 + 1; s_win[2] = sy0; s_win[3] = sy1 - sy0 + 1;   // <= SG_SRC_W, SG_SRC_H (checked on the host)
+  const int x0 = blockIdx.x * PRE_TW, y0 = blockIdx.y * TH;
+  double* rowf = smem_d;                                      // [RH + 2 HK + 1][SW]  row-filtered source window (+ 1 spare row)
+  double* sblur = rowf + (RH + 2 * HK + 1) * SW;              // [RH][SW]             + column pass
+  double* ssc = smem_d;                                       // [TH + 1][PRE_TW + 2] scaled tile; reuses rowf after the column pass
+  const int UW = (SW + 2 * HK + 11) & ~3;                     // u8 row stride (multiple of 4: 32-bit stores)
+  u8* su8 = reinterpret_cast<u8*>(sblur + RH * SW);           // [RH + 2 HK][UW]
+  const u8* img = src + (size_t)f * sfs;
+  const int SSW = PRE_TW + 2;
+  if (x0 >= O.sw) {   // sw is a multiple of 32: the last word of every bitmap row is padding only
+    for (int ty = tid; ty < TH; ty += 256)
+      if (y0 + ty < O.sh) b.bitmap[(size_t)f * g.bmTotal + O.bmOff + (size_t)(y0 + ty) * O.wpr + (x0 >> 5)] = 0u;
+    return;
   }
-  __syncthreads();
-  {
-    const int sx0 = s_win[0], nsx = s_win[1], sy0 = s_win[2], nsy = s_win[3];
-    {
-      // column pass of the Gaussian for the source window: SG_SRC_W lanes across (dense lane use: the window is
-      // 41-42 of 48 columns wide), 256 / SG_SRC_W rows per sweep
-      const bool interior = sy0 - 3 >= 0 && sy0 + nsy - 1 + 3 < O.h;
-      for (int e = tid; e < nsy * SG_SRC_W; e += 256) {
-        const int r = e / SG_SRC_W, c = e - r * SG_SRC_W;
-        if (c >= nsx) continue;
-        double v;
-        if (interior) {
-          const double* q = rf + (size_t)(sy0 + r - 3) * O.w + (sx0 + c);
-          const size_t w = (size_t)O.w;
-          v = __dmul_rn(g.kern[3], q[3 * w]);
-          v = __dadd_rn(v, __dmul_rn(g.kern[4], __dadd_rn(q[4 * w], q[2 * w])));
-          v = __dadd_rn(v, __dmul_rn(g.kern[5], __dadd_rn(q[5 * w], q[w])));
-          v = __dadd_rn(v, __dmul_rn(g.kern[6], __dadd_rn(q[6 * w], q[0])));
-        } else {
-          v = col_blur(rf, O.w, O.h, sx0 + c, sy0 + r, g.kern);
-        }
-        sblur[r][c] = v;
+
+  if (HK == 0) {
+    // lsd_scale == 1: scaled_image = image (src/LSD/lsd.cpp:461)
+    for (int e = tid; e < (TH + 1) * (PRE_TW + 1); e += 256) {
+      const int ty = e / (PRE_TW + 1), tx = e - ty * (PRE_TW + 1);
+      const int sx = x0 + tx, sy = y0 + ty;
+      double v = 0.0;
+      if (sx < O.sw && sy < O.sh) {
+        v = (double)__ldg(img + (size_t)sy * spitch + sx);
+        if (b.scaledDbg && tx < PRE_TW && ty < TH) b.scaledDbg[(size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx] = v;
+      }
+      ssc[ty * SSW + tx] = v;
+    }
+  } else {
+    const LineTab* xt = tabs + O.xtabOff;
+    const LineTab* yt = tabs + O.ytabOff;
+    // source window of the tile: columns sx0 .. sx0 + nsx - 1, rows sy0 .. sy0 + nsy - 1 (<= SW, RH: checked on the host)
+    const int sx0 = __ldg(&xt[x0].ofs), sx1 = min(__ldg(&xt[min(x0 + PRE_TW, O.sw - 1)].ofs) + 1, O.w - 1);
+    const int sy0 = __ldg(&yt[y0].ofs), sy1 = min(__ldg(&yt[min(y0 + TH, O.sh - 1)].ofs) + 1, O.h - 1);
+    const int nsx = sx1 - sx0 + 1, nsy = sy1 - sy0 + 1;
+    const int G = (nsx + 3) >> 2;                 // groups of 4 row-filter outputs per window row
+    const int ncol = 4 * G + 2 * HK;              // u8 columns the row pass reads
+    const int nrow = nsy + 2 * HK;
+    // ---- u8 window (+ HK halo, reflected at the image border)
+    const int wx0 = sx0 - HK, wy0 = sy0 - HK;
+    int xoff = wx0 & 3;
+    const int ax0 = wx0 - xoff, nw = (ncol + xoff + 3) >> 2;
+    const bool wordsOk = ((spitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0) && wx0 >= 0 && ax0 + 4 * nw <= O.w;
+    if (wordsOk) {   // 32-bit loads from the 4-aligned column below the window
+      const float inw = 1.f / (float)nw;
+      for (int e = tid; e < nrow * nw; e += 256) {
+        const int r = (int)(((float)e + 0.5f) * inw), wv = e - r * nw;   // e / nw (e < 2^16, nw < 2^8: the float quotient cannot cross an integer)
+        const int yy = reflect101_l(wy0 + r, O.h);
+        *reinterpret_cast<uint32_t*>(su8 + r * UW + 4 * wv) = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)yy * spitch + ax0) + wv);
+      }
+    } else {
+      xoff = 0;
+      for (int e = tid; e < nrow * ncol; e += 256) {
+        const int r = e / ncol, c = e - r * ncol;
+        const int yy = reflect101_l(wy0 + r, O.h);
+        const int xx = reflect101_l(min(wx0 + c, O.w + HK), O.w);
+        su8[r * UW + c] = __ldg(img + (size_t)yy * spitch + xx);
       }
     }
     __syncthreads();
-    // bilinear resize: the (SG_TW + 1) x (SG_TH + 1) scaled pixels of the tile and its halo, one per thread
-    for (int e = tid; e < (SG_TW + 1) * (SG_TH + 1); e += 256) {
-      const int ty = e / (SG_TW + 1), tx = e - ty * (SG_TW + 1);
+    // ---- row pass: thread = 4 adjacent outputs of one window row (4 + 2 HK inputs converted once)
+    const float iG = 1.f / (float)G;
+    for (int e = tid; e < nrow * G; e += 256) {
+      const int r = (int)(((float)e + 0.5f) * iG), c4 = (e - r * G) * 4;
+      const u8* q = su8 + r * UW + xoff + c4;
+      double v[4 + 2 * HK];
+#pragma unroll
+      for (int i = 0; i < 4 + 2 * HK; i++) v[i] = (double)q[i];
+      double o[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        double sacc = __dmul_rn(g.kern[0], v[k]);
+#pragma unroll
+        for (int i = 1; i <= 2 * HK; i++) sacc = __dadd_rn(sacc, __dmul_rn(g.kern[i], v[k + i]));
+        o[k] = sacc;
+      }
+      double2* out = reinterpret_cast<double2*>(rowf + r * SW + c4);
+      out[0] = make_double2(o[0], o[1]);
+      out[1] = make_double2(o[2], o[3]);
+    }
+    __syncthreads();
+    // ---- column pass: thread = 2 vertically adjacent outputs of one column
+    {
+      const int npair = (nsy + 1) >> 1;
+      const float insx = 1.f / (float)nsx;
+      for (int e = tid; e < npair * nsx; e += 256) {
+        const int rp = (int)(((float)e + 0.5f) * insx), c = e - rp * nsx;
+        const int r = 2 * rp;
+        const double* q = rowf + r * SW + c;    // window row r + i  <->  image row sy0 + r - HK + i
+        double v[2 * HK + 2];
+#pragma unroll
+        for (int i = 0; i < 2 * HK + 2; i++) v[i] = q[i * SW];   // the last row may be the spare one (its output is dropped)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (r + k >= nsy) break;
+          double sacc = __dmul_rn(g.kern[HK], v[HK + k]);
+#pragma unroll
+          for (int i = 1; i <= HK; i++) sacc = __dadd_rn(sacc, __dmul_rn(g.kern[HK + i], __dadd_rn(v[HK + k + i], v[HK + k - i])));
+          sblur[(r + k) * SW + c] = sacc;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- bilinear resize: the (PRE_TW + 1) x (TH + 1) scaled pixels of the tile and its halo
+    for (int e = tid; e < (PRE_TW + 1) * (TH + 1); e += 256) {
+      const int ty = e / (PRE_TW + 1), tx = e - ty * (PRE_TW + 1);
       const int sx = x0 + tx, sy = y0 + ty;
       double v = 0.0;
       if (sx < O.sw && sy < O.sh) {
         const LineTab X = xt[sx], Y = yt[sy];
         const int xa = X.ofs - sx0, xb = min(X.ofs + 1, O.w - 1) - sx0;
         const int ya = Y.ofs - sy0, yb = min(Y.ofs + 1, O.h - 1) - sy0;
-        const double h0 = __dadd_rn(__dmul_rn(sblur[ya][xa], (double)X.a0), __dmul_rn(sblur[ya][xb], (double)X.a1));
-        const double h1 = __dadd_rn(__dmul_rn(sblur[yb][xa], (double)X.a0), __dmul_rn(sblur[yb][xb], (double)X.a1));
-        v = __dadd_rn(__dmul_rn(h0, (double)Y.a0), __dmul_rn(h1, (double)Y.a1));
-        if (b.scaledDbg && tx < SG_TW && ty < SG_TH)
+        if (g.lsdScale == 0.5) {
+          // cv::resize switches INTER_LINEAR to the 2x2 INTER_AREA sum when both inverse scales are exactly 2
+          v = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(sblur[ya * SW + xa], sblur[ya * SW + xb]), sblur[yb * SW + xa]),
+                                  sblur[yb * SW + xb]), 0.25);
+        } else {
+          const double h0 = __dadd_rn(__dmul_rn(sblur[ya * SW + xa], (double)X.a0), __dmul_rn(sblur[ya * SW + xb], (double)X.a1));
+          const double h1 = __dadd_rn(__dmul_rn(sblur[yb * SW + xa], (double)X.a0), __dmul_rn(sblur[yb * SW + xb], (double)X.a1));
+          v = __dadd_rn(__dmul_rn(h0, (double)Y.a0), __dmul_rn(h1, (double)Y.a1));
+        }
+        if (b.scaledDbg && tx < PRE_TW && ty < TH)
           b.scaledDbg[(size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx] = v;
       }
-      ssc[ty][tx] = v;
+      ssc[ty * SSW + tx] = v;      // rowf is dead: every thread passed the barrier after the column pass
     }
   }
   __syncthreads();
-  const int tx = tid & 31, ty = tid >> 5;
-  const int sx = x0 + tx, sy = y0 + ty;
-  bool avail = false;
-  if (sx < O.sw && sy < O.sh) {
-    float angDeg = -1024.f;
-    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-    double norm = 0.0;
-    if (sx < O.sw - 1 && sy < O.sh - 1) {
-      const double DA = __dsub_rn(ssc[ty + 1][tx + 1], ssc[ty][tx]);
-      const double BC = __dsub_rn(ssc[ty][tx + 1], ssc[ty + 1][tx]);
-      const double gx = __dadd_rn(DA, BC), gy = __dsub_rn(DA, BC);
-      // (gx^2 + gy^2) / 4: the division by a power of two is exact, so the multiplication is identical
-      norm = __dsqrt_rn(__dmul_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), 0.25));
-      if (!(norm <= g.rho)) {
-        angDeg = fast_atan2_dev((float)gx, (float)(-gy));
-        const double a = __dmul_rn((double)angDeg, D2R);
-        double sd, cd;
-        sincos_tab(a, b.trig, sd, cd);
-        // what a region accumulates is cos(float(angle)), sin(float(angle)) evaluated by the host libm's cosf / sinf
-        float cf, sf;
-        glibc_sincosf((float)a, sf, cf);
-        cs = make_float4(cf, sf, (float)cd, (float)sd);
-        avail = true;
+  // ---- ll_angle: warp = one row of the tile at a time, lane = column (the ballot is the row's bitmap word)
+  const int tx = tid & 31;
+  const int sx = x0 + tx;
+  for (int ty = tid >> 5; ty < TH; ty += 8) {
+    const int sy = y0 + ty;
+    if (sy >= O.sh) break;          // warp-uniform
+    bool avail = false;
+    if (sx < O.sw) {
+      float angDeg = -1024.f;
+      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+      double norm = 0.0;
+      if (sx < O.sw - 1 && sy < O.sh - 1) {
+        const double DA = __dsub_rn(ssc[(ty + 1) * SSW + tx + 1], ssc[ty * SSW + tx]);
+        const double BC = __dsub_rn(ssc[ty * SSW + tx + 1], ssc[(ty + 1) * SSW + tx]);
+        const double gx = __dadd_rn(DA, BC), gy = __dsub_rn(DA, BC);
+        // (gx^2 + gy^2) / 4: the division by a power of two is exact, so the multiplication is identical
+        norm = __dsqrt_rn(__dmul_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), 0.25));
+        if (!(norm <= g.rho)) {
+          angDeg = fast_atan2_dev((float)gx, (float)(-gy));
+          const double a = __dmul_rn((double)angDeg, D2R);
+          double sd, cd;
+          sincos_tab(a, b.trig, sd, cd);
+          // what a region accumulates is cos(float(angle)), sin(float(angle)) evaluated by the host libm's cosf / sinf
+          float cf, sf;
+          glibc_sincosf((float)a, sf, cf);
+          cs = make_float4(cf, sf, (float)cd, (float)sd);
+          avail = true;
+        }
       }
+      const size_t p = (size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx;
+      b.ang[p] = angDeg;
+      b.cs[p] = make_float2(cs.x, cs.y);
+      b.seed[p] = make_float2(cs.z, cs.w);
+      b.mod[p] = norm;
     }
-    const size_t p = (size_t)f * g.pxTotal + O.pxOff + (size_t)sy * O.sw + sx;
-    b.ang[p] = angDeg;
-    b.cs[p] = make_float2(cs.x, cs.y);
-    b.seed[p] = make_float2(cs.z, cs.w);
-    b.mod[p] = norm;
+    const unsigned m = __ballot_sync(0xffffffffu, avail);
+    if (tx == 0) b.bitmap[(size_t)f * g.bmTotal + O.bmOff + (size_t)sy * O.wpr + (x0 >> 5)] = m;
   }
-  const unsigned m = __ballot_sync(0xffffffffu, avail);
-  if (tx == 0 && sy < O.sh) b.bitmap[(size_t)f * g.bmTotal + O.bmOff + (size_t)sy * O.wpr + (x0 >> 5)] = m;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1911,6 +1940,13 @@ __global__ void __launch_bounds__(128) k_lbd_fold(const __grid_constant__ LineGe
 // ---------------------------------------------------------------------------------------
 // launch sequence
 // ---------------------------------------------------------------------------------------
+// shared memory of k_lsd_pre for octave O: row-filtered window + column-filtered window (f64) + u8 window
+size_t lsd_pre_smem(const LineGeom& g, const LineOct& O) {
+  if (g.hk == 0) return (size_t)(g.preTH + 1) * (PRE_TW + 2) * sizeof(double);
+  const size_t rows = (size_t)O.preRH + 2 * g.hk;
+  return ((rows + 1) * O.preSW + (size_t)O.preRH * O.preSW) * sizeof(double) + rows * ((O.preSW + 2 * g.hk + 11) & ~3);
+}
+
 int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b, int n, plvi_keyline* dKl,
                          uint8_t* dDesc, double* dEq, int* dCounts, cudaStream_t st, LineAux aux, int* launches,
                          StageProf* prof) {
@@ -1928,12 +1964,19 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   }
   for (int o = 0; o < g.noct; o++) {
     const LineOct& O = g.o[o];
-    k_lsd_rowfilter<<<dim3((O.w + 255) / 256, (O.h + 3) / 4, n), 256, 0, st>>>(p.img[o], p.ipitch[o], p.ifs[o], O.w, O.h,
-                                                                             b.rowf + O.rawOff, g.rawTotal, g);
-    prof->mark("k_lsd_rowfilter", st);
-    k_lsd_scale_grad<<<dim3(O.wpr, (O.sh + 7) / 8, n), 256, 0, st>>>(g, o, b.rowf, g.rawTotal, b.tabs, b);
-    prof->mark("k_lsd_scale_grad", st);
-    nl += 2;
+    const dim3 pgrid(O.wpr, (O.sh + g.preTH - 1) / g.preTH, n);
+    const size_t psm = lsd_pre_smem(g, O);
+    switch (g.hk) {
+      case 0: k_lsd_pre<0><<<pgrid, 256, psm, st>>>(g, o, p.img[o], p.ipitch[o], p.ifs[o], b.tabs, b); break;
+      case 3: k_lsd_pre<3><<<pgrid, 256, psm, st>>>(g, o, p.img[o], p.ipitch[o], p.ifs[o], b.tabs, b); break;
+      case 4: k_lsd_pre<4><<<pgrid, 256, psm, st>>>(g, o, p.img[o], p.ipitch[o], p.ifs[o], b.tabs, b); break;
+      case 5: k_lsd_pre<5><<<pgrid, 256, psm, st>>>(g, o, p.img[o], p.ipitch[o], p.ifs[o], b.tabs, b); break;
+      case 6: k_lsd_pre<6><<<pgrid, 256, psm, st>>>(g, o, p.img[o], p.ipitch[o], p.ifs[o], b.tabs, b); break;
+      case 7: k_lsd_pre<7><<<pgrid, 256, psm, st>>>(g, o, p.img[o], p.ipitch[o], p.ifs[o], b.tabs, b); break;
+      default: k_lsd_pre<8><<<pgrid, 256, psm, st>>>(g, o, p.img[o], p.ipitch[o], p.ifs[o], b.tabs, b); break;
+    }
+    prof->mark("k_lsd_pre", st);
+    nl += 1;
   }
   // From here on the main stream holds the latency-bound region growing (low issue-slot use): a caller may hold
   // other issue-bound work (the ORB pipeline) back until this point (plvi_line_stage_event).
@@ -2027,6 +2070,21 @@ int line_kernel_attrs(const LineGeom& g) {
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
   const size_t commitSmem = (growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned)) * GROW_WPB;
   if (commitSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
+  {
+    size_t psm = 0;
+    for (int o = 0; o < g.noct; o++) psm = std::max(psm, lsd_pre_smem(g, g.o[o]));
+    if (psm > 200 * 1024) { set_error("lsd_scale too small for the shared-memory tile of k_lsd_pre"); return PLVI_ERR_CAPACITY; }
+    if (psm > 40 * 1024) {
+      const int v = (int)psm;
+      PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_pre<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+      PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_pre<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+      PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_pre<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+      PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_pre<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+      PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_pre<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+      PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_pre<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+      PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_pre<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+    }
+  }
   // the growth kernels want as many resident warps as registers allow: give shared memory the large carve-out
   PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   {

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "line_internal.cuh"
+#include "lsd_gauss_table.h"
 
 using namespace plvi;
 
@@ -71,21 +72,42 @@ void linear_rows_f64(int ssize, int dsize, double inv_scale, std::vector<LineTab
   }
 }
 
-void gaussian_kernel7(double sigma, double* k) {
-  // cv::getGaussianKernel(7, sigma, CV_64F); the reference's fixed setting (0.6/(double)0.8f)
-  // uses the values OpenCV 4.x produces (soft-float exp), other sigmas the defining formula.
-  if (sigma == 0.6 / (double)0.8f) {
-    static const unsigned long long bits[7] = {0x3f276349157f1ab0ull, 0x3f8f1e22f611221dull, 0x3fcbfd7fa6a94f5aull,
-                                               0x3fe10562abd81f5full, 0x3fcbfd7fa6a94f5aull, 0x3f8f1e22f611221dull,
-                                               0x3f276349157f1ab0ull};
-    memcpy(k, bits, sizeof(bits));
-    return;
+// first source index of scaled pixel d (the `ofs` of linear_rows_f64)
+static int lsd_src_ofs(int d, int ssize, double inv_scale) {
+  const double scale = 1.0 / inv_scale;
+  const float f = (float)((d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  if (s < 0) s = 0;
+  if (s >= ssize - 1) s = ssize - 1;
+  return s;
+}
+
+// largest source window (columns or rows) of a k_lsd_pre tile of `tile` scaled pixels (+1 halo pixel)
+static int lsd_pre_window(int ssize, int dsize, double inv_scale, int tile) {
+  int m = 0;
+  for (int d0 = 0; d0 < dsize; d0 += tile) {
+    const int a = lsd_src_ofs(d0, ssize, inv_scale);
+    const int b = std::min(lsd_src_ofs(std::min(d0 + tile, dsize - 1), ssize, inv_scale) + 1, ssize - 1);
+    m = std::max(m, b - a + 1);
   }
+  return m;
+}
+
+// cv::getGaussianKernel(n, sigma, CV_64F) for LSD's sigma = 0.6 / (double)lsd_scale.  OpenCV 4.x builds the kernel with
+// its own soft-float exp, whose last bits differ from libm's: for the common lsd_scale settings (0.3 ... 0.95 in steps
+// of 0.05, incl. the shipped 0.8 and the 0.5 / 0.6 the reference's yaml comments recommend) the values probed from
+// OpenCV are used verbatim (lsd_gauss_table.h, tools/gen_lsd_gauss.py); any other scale gets the defining formula
+// evaluated with libm (taps within a few ulp of OpenCV's: documented in DESIGN.md).
+void lsd_gaussian_kernel(float lsdScale, int n, double sigma, double* k) {
+  uint32_t bits;
+  memcpy(&bits, &lsdScale, 4);
+  for (const LsdGaussEntry& e : kLsdGaussTable)
+    if (e.scale_bits == bits && e.n == n) { memcpy(k, e.k, sizeof(double) * n); return; }
   const double s2 = -0.5 / (sigma * sigma);
   double sum = 0;
-  for (int i = 0; i < 7; i++) { const double x = i - 3.0; k[i] = exp(s2 * x * x); sum += k[i]; }
+  for (int i = 0; i < n; i++) { const double x = i - (n - 1) * 0.5; k[i] = exp(s2 * x * x); sum += k[i]; }
   sum = 1. / sum;
-  for (int i = 0; i < 7; i++) k[i] *= sum;
+  for (int i = 0; i < n; i++) k[i] *= sum;
 }
 
 int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTab>* tabs, std::vector<int2>* rs) {
@@ -101,13 +123,22 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
   g.alignHi2 = (float)(cos(g.prec - 2e-3) * cos(g.prec - 2e-3));
   g.alignLo2 = (float)(cos(g.prec + 2e-3) * cos(g.prec + 2e-3));
   g.minLength = 0.025 * std::min(w, hh);
-  const double sigma = (g.lsdScale < 1) ? (0.6 / g.lsdScale) : 0.6;
-  const unsigned hk = (unsigned)ceil(sigma * sqrt(2 * 3.0 * log(10.0)));
-  if (g.lsdScale == 1.0 || hk != 3 || g.lsdScale < 0.75) {
-    set_error("lsd_scale outside the supported range (7-tap Gaussian, 0.75 <= scale < 1)");
-    return PLVI_ERR_INVALID;
+  // flsd (src/LSD/lsd.cpp:446-462): SCALE == 1 works on the image itself; else GaussianBlur(sigma = 0.6 / SCALE, ksize
+  // 1 + 2 h) and resize by SCALE.  The range is (0, 1] by the reference's own yaml comment; h <= 8 <=> scale >= 0.279.
+  g.hk = 0;
+  if (g.lsdScale != 1.0) {
+    const double sigma = 0.6 / g.lsdScale;
+    const unsigned hk = (unsigned)ceil(sigma * sqrt(2 * 3.0 * log(10.0)));
+    if (!(g.lsdScale > 0) || g.lsdScale > 1.0 || hk < 3 || hk > 8) {
+      set_error("lsd_scale outside the supported range [0.28, 1]");
+      return PLVI_ERR_INVALID;
+    }
+    g.hk = (int)hk;
+    lsd_gaussian_kernel(h->lsdScale, 1 + 2 * g.hk, sigma, g.kern);
   }
-  gaussian_kernel7(sigma, g.kern);
+  // k_lsd_pre tiles: 32 x preTH scaled pixels; the taller the tile the less of the Gaussian's row halo is recomputed,
+  // the smaller lsd_scale the larger its source window in shared memory
+  g.preTH = g.lsdScale >= 0.7 ? 32 : (g.lsdScale >= 0.45 ? 16 : 8);
   float sf = 1.f;
   size_t px = 0, raw = 0, lbd = 0, reg = 0, sbm = 0, srec = 0, brBm = 0, brRec = 0, brList = 0;
   int bm = 0, seg = 0, tabOff = 0, task = 0, brBand = 0;
@@ -122,6 +153,17 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
     O.sh = round_even_d(O.h * g.lsdScale);
     if (O.sw < 8 || O.sh < 8 || O.sw > 65535 || O.sh > 65535) { set_error("image size unsupported for LSD"); return PLVI_ERR_INVALID; }
     O.wpr = O.sw / 32 + 1;   // at least one padding bit per row: x = -1 and x = W read as "not available"
+    if (g.hk > 0 && (O.w < 2 * g.hk + 2 || O.h < 2 * g.hk + 2)) { set_error("image smaller than the LSD Gaussian"); return PLVI_ERR_INVALID; }
+    if (g.lsdScale == 0.5 && (2 * O.sw > O.w || 2 * O.sh > O.h)) {
+      // cv::resize runs its 2x2 area path here; the border handling of blocks that leave the image is not modelled
+      set_error("lsd_scale 0.5 needs octave sizes whose halves round down (w, h not 3 mod 4)");
+      return PLVI_ERR_INVALID;
+    }
+    O.preSW = O.preRH = 0;
+    if (g.hk > 0) {
+      O.preSW = (lsd_pre_window(O.w, O.sw, g.lsdScale, 32) + 3) & ~3;
+      O.preRH = lsd_pre_window(O.h, O.sh, g.lsdScale, g.preTH);
+    }
     const double LOG_NT = 5 * (log10((double)O.sw) + log10((double)O.sh)) / 2 + log10(11.0);
     O.minRegSize = (int)(-LOG_NT / log10(22.5 / 180));
     O.pxOff = px; px += ((size_t)O.sw * O.sh + 3) & ~(size_t)3;
@@ -283,7 +325,6 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes + 256); };
   for (int o = 0; o < nlevels; o++) A((void**)&h->dImg[o], B * c.o[o].pitch * c.o[o].h);
-  A((void**)&h->buf.rowf, B * c.rawTotal * sizeof(double));
   A((void**)&h->buf.ang, B * c.pxTotal * sizeof(float));
   A((void**)&h->buf.cs, B * c.pxTotal * sizeof(float2));
   A((void**)&h->buf.seed, B * c.pxTotal * sizeof(float2));
@@ -300,7 +341,9 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
     const char* ev = getenv("PLVI_LSD_BR_MAX");
     const int brMax = std::min(ev ? std::max(0, atoi(ev)) : 384, max_batch);
     const char* er = getenv("PLVI_LSD_BR_ROUNDS");
-    h->buf.brRounds = std::min(std::max(er ? atoi(er) : 12, 1), BR_FLAGS - 4);
+    // 28 rounds: of 3 x 512 (frame, octave) problems measured (640x480, 752x480, 1280x720) the slowest needed 16; rounds
+    // after the fixed point only cost their launches, a problem that has not converged costs a full serial chain
+    h->buf.brRounds = std::min(std::max(er ? atoi(er) : 28, 1), BR_FLAGS - 4);
     h->buf.brMax = brMax;
     if (brMax > 0) {
       const size_t S = brMax;
@@ -373,7 +416,7 @@ void plvi_line_destroy(plvi_line* h) {
   if (h->aux.join) cudaEventDestroy(h->aux.join);
   if (h->aux.stage) cudaEventDestroy(h->aux.stage);
   cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
-  cudaFree(h->buf.rowf); cudaFree(h->buf.ang); cudaFree(h->buf.cs); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
+  cudaFree(h->buf.ang); cudaFree(h->buf.cs); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
   cudaFree(h->buf.specBm); cudaFree(h->buf.specRec); cudaFree(h->buf.specCnt); cudaFree(h->buf.phantom);
   cudaFree(h->buf.brIn); cudaFree(h->buf.brWk); cudaFree(h->buf.brPh); cudaFree(h->buf.brRec); cudaFree(h->buf.brList);
   cudaFree(h->buf.brState); cudaFree(h->buf.brFlags);

@@ -214,11 +214,36 @@ def test_line_odd_sizes_and_unaligned_device_input(gpu, w, h):
         e.close()
 
 
-def test_line_scale_075(gpu):
-    e = Lineextractor(150, 0, 0.75, 2, 2.0, 0, max_batch=1)
+@pytest.mark.parametrize("lsd_scale,w,h", [(0.75, 752, 480), (1.0, 752, 480), (0.6, 752, 480), (0.5, 752, 480), (0.9, 640, 480),
+                                           (0.33, 752, 480), (1.0, 641, 479), (0.5, 1280, 720)])
+def test_line_lsd_scales(gpu, lsd_scale, w, h):
+    """lsd_scale over its documented range (0, 1] (Examples/Stereo-Line/UMA_ueye.yaml ships 1.0, the yaml comments
+    recommend 0.5 / 0.6): Gaussian taps from sigma = 0.6 / scale (src/LSD/lsd.cpp:449-455), no blur / resize at 1.0.
+    Scaled image, gradient magnitudes, angles and raw segments are exact."""
+    e = Lineextractor(150, 0, lsd_scale, 2, 2.0, 0, max_width=w, max_height=h, max_batch=1)
     try:
-        img = synth.frame_euroc(86)
+        img = synth.frame_euroc(86, w, h)
+        e.set_debug(True)
         kl, desc, eq = e(img)
-        _check_lines(kl, desc, eq, oracle.line_extract(img, lsd_nfeatures=150, lsd_scale=0.75))
+        ow, oh, sw, sh = e.octave_sizes(w, h)
+        oct1 = oracle.resize_linear(img, int(ow[1]), int(oh[1]))
+        for o, im in enumerate((img, oct1)):
+            segs, dbg = oracle.lsd(im, lsd_scale, debug=True)
+            assert (dbg["w"], dbg["h"]) == (int(sw[o]), int(sh[o]))
+            assert np.array_equal(e.read_lsd(0, o, "scaled", w, h), dbg["scaled"]), f"scaled octave {o}"
+            assert np.array_equal(e.read_lsd(0, o, "modgrad", w, h), dbg["modgrad"]), f"modgrad octave {o}"
+            got = e.read_lsd(0, o, "segments", w, h)
+            assert len(got) == len(segs) and len(segs) > 20, (o, len(got), len(segs))
+            assert np.array_equal(got, segs.astype(np.float32))
+        e.set_debug(False)
+        _check_lines(kl, desc, eq, oracle.line_extract(img, lsd_nfeatures=150, lsd_scale=lsd_scale))
     finally:
         e.close()
+
+
+def test_line_rejects_lsd_scale_outside_range(gpu):
+    from pl_vi_orbslam3_b200.capi import PlviError
+    for sc in (0.2, 1.5):
+        with pytest.raises((PlviError, RuntimeError)):
+            e = Lineextractor(150, 0, sc, 2, 2.0, 0, max_batch=1)
+            e(synth.frame_euroc(1))

@@ -65,6 +65,23 @@ def test_f64_primitives(idx):
     assert np.array_equal(oracle.resize_linear_f64(mine, ref.shape[1], ref.shape[0], S, S), ref)
 
 
+@pytest.mark.parametrize("scale", [0.3, 0.35, 0.4, 0.45, 0.5, 0.55, 0.6, 0.65, 0.7, 0.75, 0.8, 0.85, 0.9, 0.95])
+def test_lsd_gaussian_kernels_of_common_scales(scale):
+    """The Gaussian of flsd for the tabulated lsd_scale settings (oracle/lsd_gauss_table.h): kernel bit-exact against
+    cv2.getGaussianKernel (soft-float exp), blur within 1e-12, f64 resize bit-exact."""
+    import math
+    S = float(np.float32(scale))
+    sigma = 0.6 / S
+    n = 1 + 2 * int(math.ceil(sigma * math.sqrt(2 * 3.0 * math.log(10.0))))
+    k = oracle.gaussian_kernel_f64(n, sigma)
+    assert np.array_equal(k, cv2.getGaussianKernel(n, sigma, cv2.CV_64F).ravel())
+    img = _imgs()[3].astype(np.float64)
+    mine = oracle.gaussian_blur_f64(img, k)
+    assert np.abs(mine - cv2.GaussianBlur(img, (n, n), sigma)).max() <= 1e-12
+    ref = cv2.resize(mine, None, fx=S, fy=S, interpolation=cv2.INTER_LINEAR)
+    assert np.array_equal(oracle.resize_linear_f64(mine, ref.shape[1], ref.shape[0], S, S), ref)
+
+
 def test_lsd_segment_count_close_to_opencv_lsd():
     """cv2's LSD (4.13) seeds regions by gradient-sorted order, the vendored one in raster
     order, so only the population is comparable."""

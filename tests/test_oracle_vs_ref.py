@@ -126,6 +126,18 @@ def test_live_reference_lines(seed, w, h, lnf, levels):
 
 
 @needs_ref
+@pytest.mark.parametrize("lsd_scale", [1.0, 0.6, 0.5, 0.9, 0.33])
+def test_live_reference_lines_lsd_scales(lsd_scale):
+    """lsd_scale 1.0 (Examples/Stereo-Line/UMA_ueye.yaml; no blur, no resize) and the smaller settings the reference's
+    yaml comments recommend: other Gaussian sizes (9 / 11 / 15 taps) through the reference's own flsd."""
+    img = synth.frame_euroc(9)
+    r = oracle.ref_line_extract(img, lsd_nfeatures=150, lsd_scale=lsd_scale)
+    check_lines(oracle.line_extract(img, lsd_nfeatures=150, lsd_scale=lsd_scale), r["keylines"], r["descriptors"], r["line_eq"])
+    assert np.array_equal(oracle.lsd(img, lsd_scale), oracle.ref_lsd(img, lsd_scale))
+    assert len(r["keylines"]) > 50
+
+
+@needs_ref
 def test_live_reference_lines_edge_images():
     rng = np.random.RandomState(5)
     noise = rng.randint(0, 256, (480, 752)).astype(np.uint8)
