@@ -496,11 +496,27 @@ int plvi_line_match(plvi_matcher* m, int npairs, const uint8_t* desc1, const int
  * endPointX, endPointY) per keyline, [npairs][stride][4] floats; desc [npairs][stride][32]; grid at most
  * 64 x 64 cells.  Device pointers only; runs on the matcher's stream.  matches12 [npairs][stride1] (-1 = none),
  * nmatches [npairs] = the reference's return value.  The depth / disparity filter that follows in
- * ComputeStereoMatches_Lines stays host code. */
+ * ComputeStereoMatches_Lines is plvi_line_stereo_depth. */
 int plvi_line_match_grid(plvi_matcher* m, int npairs, const float* d_seg1, const uint8_t* d_desc1, const int* d_n1,
                          int stride1, const float* d_seg2, const uint8_t* d_desc2, const int* d_n2, int stride2,
                          double inv_width, double inv_height, int grid_rows, int grid_cols, int win_left, int win_right,
                          int win_up, int win_down, int* d_matches12, int* d_nmatches);
+
+/* What follows the search in Frame::ComputeStereoMatches_Lines (src/Frame.cc:1453-1500) for npairs stereo pairs, on the
+ * matcher's stream with device pointers: for every matched left line the end-point disparities on the right line
+ * carried to the left end points' rows (:1466-1470, incl. the order in which the reference overwrites sp_r / ep_r),
+ * Frame::filterLineSegmentDisparity (:1535-1546, ratio 0.7), Frame::lineSegmentOverlapStereo (:1502-1533) and the
+ * acceptance test (disparities >= 1, |dy| > 0.1, overlap > 0.75): disparity [npairs][stride1][2] = mvDisparity_l,
+ * depth [npairs][stride1][2] = mvDepth_l = mbf / disparity, both (-1, -1) when rejected or unmatched; ndepth [npairs] =
+ * lines with depth.  le (optional) [npairs][stride1][3] = mvle_l: the normalised image line through the UNDISTORTED end
+ * points seg1_un (:1495-1500; zeros for a pair without right lines, where the reference returns early).  seg as in
+ * plvi_line_match_grid; matches12 = its result. */
+int plvi_line_stereo_depth(plvi_matcher* m, int npairs, const float* d_seg1, const int* d_n1, int stride1, const float* d_seg2,
+                           const int* d_n2, int stride2, const int* d_matches12, const float* d_seg1_un, float mbf, float* d_disparity,
+                           float* d_depth, double* d_le, int* d_ndepth);
+/* the same for ONE stereo pair with host arrays */
+int plvi_line_stereo_depth_host(plvi_matcher* m, const float* seg1, int n1, const float* seg2, int n2, const int* matches12,
+                                const float* seg1_un, float mbf, float* disparity, float* depth, double* le, int* ndepth);
 
 /* The same search for ONE stereo pair with HOST buffers (what Frame::ComputeStereoMatches_Lines holds,
  * src/Frame.cc:1421-1448): copies in, runs k_line_match_grid on the matcher's stream, copies matches12 [n1] and

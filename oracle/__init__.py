@@ -990,6 +990,19 @@ def ref_distinctive_descriptor(desc, bad=None):
     return out if f(_p(desc), _p(b), len(desc), _p(out)) else None
 
 
+def ref_mapline_distinctive_descriptor(desc, bad=None):
+    """The reference's MapLine::ComputeDistinctiveDescriptors itself (src/MapLine.cc:264-329; MapLine.cc and MapLine.h
+    compiled unmodified over stand-in KeyFrame / Frame / Map): observation i = line 0 of keyframe i with LBD descriptor
+    desc[i]; bad[i] = pKF->isBad().  Returns the chosen 32-byte descriptor, or None when the reference returns early."""
+    ref_distinctive_descriptor(np.zeros((1, 32), np.uint8))   # loads the library
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    b = None if bad is None else np.ascontiguousarray(bad, np.uint8)
+    out = np.zeros(32, np.uint8)
+    f = _ref_mp.plviref_mapline_distinctive_descriptor
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    return out if f(_p(desc), _p(b), len(desc), _p(out)) else None
+
+
 def ref_search_by_sim3(keys1, desc1, uv1, level1, flags1, keys2, desc2, uv2, level2, flags2, grid, bounds, scale_factors, th):
     """The reference's ORBmatcher::SearchBySim3 itself (src/ORBmatcher.cc:1736-1960) with s12 = 1, R12 = I, t12 = 0 and
     identity keyframe poses: the map point of feature i of keyframe A sits at (uvA[i], 1) and projects to uvA[i] in the
@@ -1338,6 +1351,21 @@ def ref_line_match_grid(seg1, d1, seg2, d2, inv_width, inv_height, grid_rows=48,
 
 # ---- the consumer's call pattern on the reference's own Frame class (ref_glue_frame.cpp: plviref_track_*) -------------
 KEYLINE_BYTES, KEYPOINT_BYTES = 68, 28
+
+
+def line_stereo_depth(seg1, seg2, matches12, mbf, seg1_un=None):
+    """The disparity / overlap / depth filter after the search in Frame::ComputeStereoMatches_Lines (src/Frame.cc:1453-1500):
+    (count, disparity [n1, 2] f32, depth [n1, 2] f32, mvle_l [n1, 3] f64)."""
+    s1 = np.ascontiguousarray(seg1, np.float32).reshape(-1, 4)
+    s2 = np.ascontiguousarray(seg2, np.float32).reshape(-1, 4)
+    su = s1 if seg1_un is None else np.ascontiguousarray(seg1_un, np.float32).reshape(-1, 4)
+    m = np.ascontiguousarray(matches12, np.int32)
+    n1 = len(s1)
+    disp = np.zeros((max(n1, 1), 2), np.float32); dep = np.zeros((max(n1, 1), 2), np.float32); le = np.zeros((max(n1, 1), 3), np.float64)
+    f = lib().plvio_line_stereo_depth
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    k = f(_p(s1), n1, _p(s2), len(s2), _p(m), _p(su), C.c_float(mbf), _p(disp), _p(dep), _p(le))
+    return k, disp[:n1], dep[:n1], le[:n1]
 
 
 class RefTracker:

@@ -13,6 +13,10 @@
 #ifndef SLAM_MOCK_REAL_KEYFRAME   // libplvi_ref_keyframe.so: the reference's own KeyFrame.h / KeyFrame.cc (see slam_mock_keyframe.h)
 #define KEYFRAME_H
 #endif
+#ifdef SLAM_MOCK_REAL_MAPLINE   // MapLine.cc + the reference's own MapLine.h (into libplvi_ref_mappoint.so): also needs Map, no Converter.h / g2o
+#define CONVERTER_H
+#include "eigenmini.hpp"
+#endif
 #ifdef SLAM_MOCK_REAL_MAPPOINT   // libplvi_ref_mappoint.so: the reference's own MapPoint.h / MapPoint.cc over stand-in KeyFrame / Frame / Map
 #define MAP_H
 #include <mutex>
@@ -36,6 +40,7 @@ using cv::cvmini_unreachable;
 class KeyFrame;
 class Frame;
 class MapPoint;
+class MapLine;
 class Map;
 
 extern "C" int plvio_epipolar_constrain(float x1, float y1, float x2, float y2, const float* F12, float unc);
@@ -110,12 +115,25 @@ class MapPoint {
 };
 
 #else
+class MapLine;
 class Map {
  public:
   long unsigned int mnId = 0;
-  std::mutex mMutexPointCreation;
+  std::mutex mMutexPointCreation, mMutexLineCreation;
   void EraseMapPoint(MapPoint*) {}
+  void EraseMapLine(MapLine*) {}
   long unsigned int GetId() { return mnId; }
+};
+#endif
+#ifdef SLAM_MOCK_REAL_MAPLINE
+class Converter {
+ public:
+  // Converter::toCvMat(Eigen::Matrix<double,3,1>) (src/Converter.cc): 3x1 CV_32F
+  static cv::Mat toCvMat(const Eigen::Vector3d& m) {
+    cv::Mat r(3, 1, CV_32F);
+    for (int i = 0; i < 3; i++) r.at<float>(i) = (float)m(i);
+    return r.clone();
+  }
 };
 #endif
 
@@ -146,7 +164,12 @@ class Frame {
   }
   cv::Mat GetRelativePoseTrl() { cvmini_unreachable("Frame"); }
   cv::Mat GetRelativePoseTlr() { cvmini_unreachable("Frame"); }
-  // MapPoint.cc (only compiled into libplvi_ref_mappoint.so; never reached)
+  // MapPoint.cc / MapLine.cc (only compiled into libplvi_ref_mappoint.so; never reached)
+  struct KeyLineStub { int octave = 0; };
+  std::vector<KeyLineStub> mvKeysUn_Line;
+  std::vector<float> mvScaleFactors_l;
+  int mnScaleLevels_l = 0;
+  cv::Mat mDescriptors_Line;
   cv::Mat mRwc, mOw;
   int mnScaleLevels = 0;
   float mfLogScaleFactor = 0;
@@ -198,7 +221,14 @@ class KeyFrame {
   cv::Mat GetRelativePoseTrl() { cvmini_unreachable("KeyFrame"); }
   cv::Mat GetRelativePoseTlr() { cvmini_unreachable("KeyFrame"); }
   void AddMapPoint(MapPoint*, const size_t&) {}   // recorded on the map point (AddObservation), not applied
-  // MapPoint.cc (only compiled into libplvi_ref_mappoint.so)
+  // MapPoint.cc / MapLine.cc (only compiled into libplvi_ref_mappoint.so)
+  cv::Mat mDescriptors_l;
+  std::vector<std::pair<float, float>> mvDepth_l;
+  std::vector<float> mvScaleFactors_l;
+  int mnScaleLevels_l = 0;
+  void EraseMapLineMatch(const size_t&) {}
+  void EraseMapLineMatch(MapLine*) {}
+  void ReplaceMapLineMatch(const size_t&, MapLine*) {}
   bool mBad = false;
   long unsigned int mnFrameId = 0;
   bool isBad() { return mBad; }

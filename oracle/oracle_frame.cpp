@@ -196,3 +196,63 @@ extern "C" int plvio_stereo_matches(const float* kL /* x,y,size,angle,response,o
   }
   return kept;
 }
+
+// ---- the disparity / overlap / depth filter that follows the search in Frame::ComputeStereoMatches_Lines
+// (src/Frame.cc:1453-1494), Frame::lineSegmentOverlapStereo (:1502-1533), Frame::filterLineSegmentDisparity (:1535-1546)
+// and mvle_l (:1495-1500), for one stereo pair.  seg = (startPointX, startPointY, endPointX, endPointY) floats.
+namespace plvio {
+static double overlap_stereo(double spl_obs, double epl_obs, double spl_proj, double epl_proj) {
+  double overlap = 1.f;
+  const float lineHorizTh = 0.1;
+  if (std::fabs(epl_obs - spl_obs) > lineHorizTh) {
+    const double sln = std::min(spl_obs, epl_obs), eln = std::max(spl_obs, epl_obs);
+    const double spn = std::min(spl_proj, epl_proj), epn = std::max(spl_proj, epl_proj);
+    const double length = eln - spn;
+    if ((epn < sln) || (spn > eln)) overlap = 0.f;
+    else if ((epn > eln) && (spn < sln)) overlap = eln - sln;
+    else overlap = std::min(eln, epn) - std::max(sln, spn);
+    if (length > 0.01f) overlap = overlap / length;
+    else overlap = 0.f;
+    if (overlap > 1.f) overlap = 1.f;
+  }
+  return overlap;
+}
+}  // namespace plvio
+
+extern "C" int plvio_line_stereo_depth(const float* seg1, int n1, const float* seg2, int n2, const int* matches12, const float* seg1_un,
+                                       float mbf, float* disparity, float* depth, double* le) {
+  int k = 0;
+  for (int i1 = 0; i1 < n1; i1++) {
+    disparity[2 * i1] = disparity[2 * i1 + 1] = -1;
+    depth[2 * i1] = depth[2 * i1 + 1] = -1.0f;
+    if (le && n2 == 0) le[3 * i1] = le[3 * i1 + 1] = le[3 * i1 + 2] = 0;   // the reference returns before mvle_l is filled (:1419-1420)
+    else if (le) {
+      const double a0 = seg1_un[4 * i1], a1 = seg1_un[4 * i1 + 1], b0 = seg1_un[4 * i1 + 2], b1 = seg1_un[4 * i1 + 3];
+      const double c0 = a1 * 1.0 - 1.0 * b1, c1 = 1.0 * b0 - a0 * 1.0, c2 = a0 * b1 - a1 * b0;   // sp.cross(ep)
+      const double nrm = std::sqrt(c0 * c0 + c1 * c1);
+      le[3 * i1] = c0 / nrm; le[3 * i1 + 1] = c1 / nrm; le[3 * i1 + 2] = c2 / nrm;
+    }
+    const int i2 = matches12[i1];
+    if (i2 < 0 || i2 >= n2) continue;
+    const double xl1 = seg1[4 * i1], yl1 = seg1[4 * i1 + 1], xl2 = seg1[4 * i1 + 2], yl2 = seg1[4 * i1 + 3];
+    double xr1 = seg2[4 * i2], yr1 = seg2[4 * i2 + 1], xr2 = seg2[4 * i2 + 2], yr2 = seg2[4 * i2 + 3];
+    const double overlap = plvio::overlap_stereo(yl1, yl2, yr1, yr2);
+    // the comma initialisers overwrite sp_r first: the second expression already reads the new sp_r (:1468-1469)
+    xr1 = (xr1 * (yl1 - yr2) + xr2 * (yr1 - yl1)) / (yr1 - yr2);
+    yr1 = yl1;
+    xr2 = (xr1 * (yl2 - yr2) + xr2 * (yr1 - yl2)) / (yr1 - yr2);
+    yr2 = yl2;
+    double disp_s = xl1 - xr1, disp_e = xl2 - xr2;
+    const float lsMinDispRatio = 0.7;
+    if (std::min(disp_s, disp_e) / std::max(disp_s, disp_e) < lsMinDispRatio) { disp_s = -1.0; disp_e = -1.0; }
+    const int minDisp = 1;
+    const float lineHorizTh = 0.1, stereoOverlapTh = 0.75;
+    if (disp_s >= minDisp && disp_e >= minDisp && std::abs(yl1 - yl2) > lineHorizTh && std::abs(yr1 - yr2) > lineHorizTh &&
+        overlap > stereoOverlapTh) {
+      disparity[2 * i1] = (float)disp_s; disparity[2 * i1 + 1] = (float)disp_e;
+      depth[2 * i1] = mbf / float(disp_s); depth[2 * i1 + 1] = mbf / float(disp_e);
+      k++;
+    }
+  }
+  return k;
+}

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 #include "MapPoint.h"   // /root/reference/include
+#include "MapLine.h"    // /root/reference/include
 
 using namespace ORB_SLAM3;
 
@@ -28,6 +29,28 @@ extern "C" int plviref_distinctive_descriptor(const unsigned char* desc, const u
   for (int i = 0; i < n; i++) mp.AddObservation(&kfs[i], 0);
   mp.ComputeDistinctiveDescriptors();
   cv::Mat d = mp.GetDescriptor();
+  if (d.empty()) return 0;
+  memcpy(out, d.data, 32);
+  return 1;
+}
+
+// MapLine::ComputeDistinctiveDescriptors (src/MapLine.cc:264-329), same construction: observation i = keyframe i holding
+// the LBD descriptor desc[i] as row 0 of mDescriptors_l (a monocular line: mvDepth_l = (-1, -1)).  The distance it uses
+// is ORBmatcher::DescriptorDistance (src/MapLine.cc:305).
+extern "C" int plviref_mapline_distinctive_descriptor(const unsigned char* desc, const unsigned char* bad, int n, unsigned char* out) {
+  Map map;
+  std::vector<KeyFrame> kfs(n > 0 ? n : 1);
+  for (int i = 0; i < n; i++) {
+    kfs[i].mnId = i;
+    kfs[i].mDescriptors_l = cv::Mat(1, 32, CV_8UC1);
+    memcpy(kfs[i].mDescriptors_l.data, desc + 32 * (size_t)i, 32);
+    kfs[i].mvDepth_l.assign(1, std::make_pair(-1.0f, -1.0f));
+    kfs[i].mBad = bad && bad[i];
+  }
+  MapLine ml(Eigen::Vector3d(0, 0, 1), Eigen::Vector3d(1, 0, 1), &kfs[0], &map);
+  for (int i = 0; i < n; i++) ml.AddObservation(&kfs[i], 0);
+  ml.ComputeDistinctiveDescriptors();
+  cv::Mat d = ml.GetDescriptor();
   if (d.empty()) return 0;
   memcpy(out, d.data, 32);
   return 1;

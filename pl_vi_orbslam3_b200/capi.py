@@ -93,6 +93,8 @@ _SIGS = {
     "plvi_line_match_grid": (ci, [vp, ci, vp, vp, vp, ci, vp, vp, vp, ci, C.c_double, C.c_double, ci, ci, ci, ci, ci, ci, vp, vp]),
     "plvi_line_match_grid_host": (ci, [vp, vp, vp, ci, vp, vp, ci, C.c_double, C.c_double, ci, ci, ci, ci, ci, ci, vp, vp]),
     "plvi_line_match_grid_occ_host": (ci, [vp, vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]),
+    "plvi_line_stereo_depth": (ci, [vp, ci, vp, vp, ci, vp, vp, ci, vp, vp, cf, vp, vp, vp, vp]),
+    "plvi_line_stereo_depth_host": (ci, [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp, vp]),
     "plvi_matcher_set_stereo": (ci, [vp, vp, vp, ci, ci, ci, ci]),
     "plvi_pair_queries": (ci, [vp, vp, vp, ci, ci, ci, cf, cf, vp, vp, cf, vp, vp, vp, vp]),
     "plvi_orb_device_results": (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),

@@ -457,6 +457,83 @@ __global__ void k_gather_i32(const int* __restrict__ src, int n, int first, int 
   if (i < n) dst[i] = src[first + i * step];
 }
 
+// ---- the disparity / overlap / depth filter after the stereo line search: Frame::ComputeStereoMatches_Lines
+// (src/Frame.cc:1453-1500), lineSegmentOverlapStereo (:1502-1533), filterLineSegmentDisparity (:1535-1546).  Thread per left
+// line, CTA per stereo pair; doubles with explicit round-to-nearest operations (the reference's Eigen expressions
+// without contraction); std::min / std::max as the reference's comparisons (NaN behaviour included).
+__device__ __forceinline__ double std_min_d(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double std_max_d(double a, double b) { return (a < b) ? b : a; }
+
+__device__ double line_overlap_stereo(double spl_obs, double epl_obs, double spl_proj, double epl_proj) {
+  double overlap = 1.0;
+  const double lineHorizTh = (double)0.1f;
+  if (fabs(__dsub_rn(epl_obs, spl_obs)) > lineHorizTh) {
+    const double sln = std_min_d(spl_obs, epl_obs), eln = std_max_d(spl_obs, epl_obs);
+    const double spn = std_min_d(spl_proj, epl_proj), epn = std_max_d(spl_proj, epl_proj);
+    const double length = __dsub_rn(eln, spn);
+    if ((epn < sln) || (spn > eln)) overlap = 0.0;
+    else if ((epn > eln) && (spn < sln)) overlap = __dsub_rn(eln, sln);
+    else overlap = __dsub_rn(std_min_d(eln, epn), std_max_d(sln, spn));
+    if (length > (double)0.01f) overlap = __ddiv_rn(overlap, length);
+    else overlap = 0.0;
+    if (overlap > 1.0) overlap = 1.0;
+  }
+  return overlap;
+}
+
+__global__ void __launch_bounds__(128) k_line_stereo_depth(const float4* __restrict__ seg1, const int* __restrict__ n1, int stride1,
+                                                           const float4* __restrict__ seg2, const int* __restrict__ n2, int stride2,
+                                                           const int* __restrict__ matches12,
+                                                           const float4* __restrict__ seg1un, float mbf, float2* __restrict__ disparity,
+                                                           float2* __restrict__ depth, double* __restrict__ le, int* __restrict__ ndepth) {
+  const int pair = blockIdx.x;
+  const int n = min(n1[pair], stride1), nr = min(n2[pair], stride2);
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i1 = threadIdx.x; i1 < n; i1 += blockDim.x) {
+    const size_t o = (size_t)pair * stride1 + i1;
+    float2 dsp = make_float2(-1.f, -1.f), dep = make_float2(-1.f, -1.f);
+    if (le && nr == 0) {   // the reference returns before mvle_l is filled (src/Frame.cc:1419-1420)
+      le[3 * o] = 0.0; le[3 * o + 1] = 0.0; le[3 * o + 2] = 0.0;
+    } else if (le) {   // mvle_l: the normalised image line through the undistorted end points
+      const float4 u = seg1un[o];
+      const double a0 = u.x, a1 = u.y, b0 = u.z, b1 = u.w;
+      const double c0 = __dsub_rn(__dmul_rn(a1, 1.0), __dmul_rn(1.0, b1)), c1 = __dsub_rn(__dmul_rn(1.0, b0), __dmul_rn(a0, 1.0));
+      const double c2 = __dsub_rn(__dmul_rn(a0, b1), __dmul_rn(a1, b0));
+      const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(c0, c0), __dmul_rn(c1, c1)));
+      le[3 * o] = __ddiv_rn(c0, nrm); le[3 * o + 1] = __ddiv_rn(c1, nrm); le[3 * o + 2] = __ddiv_rn(c2, nrm);
+    }
+    const int i2 = matches12[o];
+    if (i2 >= 0 && i2 < nr) {
+      const float4 L = seg1[o], R = seg2[(size_t)pair * stride2 + i2];
+      const double xl1 = L.x, yl1 = L.y, xl2 = L.z, yl2 = L.w;
+      double xr1 = R.x, yr1 = R.y, xr2 = R.z, yr2 = R.w;
+      const double overlap = line_overlap_stereo(yl1, yl2, yr1, yr2);
+      // the comma initialisers overwrite sp_r first: the second expression already reads the new sp_r (:1468-1469)
+      xr1 = __ddiv_rn(__dadd_rn(__dmul_rn(xr1, __dsub_rn(yl1, yr2)), __dmul_rn(xr2, __dsub_rn(yr1, yl1))), __dsub_rn(yr1, yr2));
+      yr1 = yl1;
+      xr2 = __ddiv_rn(__dadd_rn(__dmul_rn(xr1, __dsub_rn(yl2, yr2)), __dmul_rn(xr2, __dsub_rn(yr1, yl2))), __dsub_rn(yr1, yr2));
+      yr2 = yl2;
+      double ds = __dsub_rn(xl1, xr1), de = __dsub_rn(xl2, xr2);
+      if (__ddiv_rn(std_min_d(ds, de), std_max_d(ds, de)) < (double)0.7f) { ds = -1.0; de = -1.0; }
+      if (ds >= 1.0 && de >= 1.0 && fabs(__dsub_rn(yl1, yl2)) > (double)0.1f && fabs(__dsub_rn(yr1, yr2)) > (double)0.1f &&
+          overlap > (double)0.75f) {
+        dsp = make_float2((float)ds, (float)de);
+        dep = make_float2(__fdiv_rn(mbf, (float)ds), __fdiv_rn(mbf, (float)de));
+        mine++;
+      }
+    }
+    disparity[o] = dsp;
+    depth[o] = dep;
+  }
+  if (mine) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) ndepth[pair] = s_cnt;
+}
+
+
 // ---- lines: knn-2 + ratio in both directions + mutual check, one CTA per pair ---------
 __device__ void nnr_rows(const uint8_t* sa, int na, const uint8_t* sb, int nb, float nnr, int* out) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -1884,6 +1961,68 @@ int plvi_gather_i32(void* stream, const int* d_src, int n, int first, int step, 
   k_gather_i32<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_src, n, first, step, d_dst);
   PLVI_CUDA_TRY(cudaGetLastError());
   return PLVI_OK;
+}
+
+int plvi_line_stereo_depth(plvi_matcher* m, int npairs, const float* d_seg1, const int* d_n1, int stride1, const float* d_seg2,
+                           const int* d_n2, int stride2, const int* d_matches12, const float* d_seg1_un, float mbf, float* d_disparity,
+                           float* d_depth, double* d_le, int* d_ndepth) {
+  if (!m || npairs < 1 || !d_seg1 || !d_n1 || !d_seg2 || !d_n2 || !d_matches12 || !d_disparity || !d_depth || !d_ndepth || stride1 < 1 ||
+      stride2 < 1 || (d_le && !d_seg1_un)) {
+    set_error("plvi_line_stereo_depth: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  k_line_stereo_depth<<<npairs, 128, 0, m->stream>>>(reinterpret_cast<const float4*>(d_seg1), d_n1, stride1,
+                                                     reinterpret_cast<const float4*>(d_seg2), d_n2, stride2, d_matches12,
+                                                     reinterpret_cast<const float4*>(d_seg1_un), mbf,
+                                                     reinterpret_cast<float2*>(d_disparity), reinterpret_cast<float2*>(d_depth), d_le,
+                                                     d_ndepth);
+  m->lastLaunches = 1;
+  PLVI_CUDA_TRY(cudaGetLastError());
+  return PLVI_OK;
+}
+
+int plvi_line_stereo_depth_host(plvi_matcher* m, const float* seg1, int n1, const float* seg2, int n2, const int* matches12,
+                                const float* seg1_un, float mbf, float* disparity, float* depth, double* le, int* ndepth) {
+  if (!m || n1 < 0 || n2 < 0 || !ndepth || (n1 && (!seg1 || !matches12 || !disparity || !depth)) || (n2 && !seg2) || (n1 && le && !seg1_un)) {
+    set_error("plvi_line_stereo_depth_host: invalid argument");
+    return PLVI_ERR_INVALID;
+  }
+  *ndepth = 0;
+  if (n1 == 0) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = m->stream;
+  const int s2 = n2 > 0 ? n2 : 1;
+  const auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };   // float4 / float2 / double accesses
+  const size_t bS1 = (size_t)n1 * 16, bS2 = (size_t)s2 * 16, bM = (size_t)n1 * 4, bO = (size_t)n1 * 8, bLe = (size_t)n1 * 24;
+  const size_t oLe = 0, oS1 = up16(oLe + bLe), oSu = oS1 + bS1, oS2 = oSu + bS1, oM = oS2 + bS2, oDs = up16(oM + bM), oDp = up16(oDs + bO),
+               oC = up16(oDp + bO);
+  unsigned char* buf = nullptr;
+  PLVI_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&buf), oC + 16, st));
+  const int cnt[3] = {n1, 0, n2};
+  cudaError_t e = cudaMemcpyAsync(buf + oS1, seg1, bS1, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + oSu, le ? seg1_un : seg1, bS1, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && n2) e = cudaMemcpyAsync(buf + oS2, seg2, (size_t)n2 * 16, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + oM, matches12, bM, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf + oC, cnt, sizeof(cnt), cudaMemcpyHostToDevice, st);
+  int rc = PLVI_OK;
+  if (e == cudaSuccess) {
+    int* dc = reinterpret_cast<int*>(buf + oC);
+    rc = plvi_line_stereo_depth(m, 1, reinterpret_cast<const float*>(buf + oS1), dc, n1, reinterpret_cast<const float*>(buf + oS2), dc + 2, s2,
+                                reinterpret_cast<const int*>(buf + oM), reinterpret_cast<const float*>(buf + oSu), mbf,
+                                reinterpret_cast<float*>(buf + oDs), reinterpret_cast<float*>(buf + oDp),
+                                le ? reinterpret_cast<double*>(buf + oLe) : nullptr, dc + 1);
+    if (rc == PLVI_OK) {
+      e = cudaMemcpyAsync(disparity, buf + oDs, bO, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(depth, buf + oDp, bO, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && le) e = cudaMemcpyAsync(le, buf + oLe, bLe, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ndepth, dc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+    }
+  }
+  cudaFreeAsync(buf, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return PLVI_ERR_CUDA; }
+  return rc;
 }
 
 }  // extern "C"

@@ -399,6 +399,22 @@ class LineMatcher(_Matcher):
                                               *[int(v) for v in window], ptr(m12), ptr(nm)))
         return int(nm[0]), m12[:len(d1)]
 
+    def stereo_depth_host(self, seg_left, seg_right, matches12, mbf, seg_left_un=None):
+        """What follows the search in Frame::ComputeStereoMatches_Lines (src/Frame.cc:1453-1500) through
+        plvi_line_stereo_depth_host -> (count, mvDisparity_l [n, 2], mvDepth_l [n, 2], mvle_l [n, 3])."""
+        s1 = np.ascontiguousarray(seg_left, np.float32).reshape(-1, 4)
+        s2 = np.ascontiguousarray(seg_right, np.float32).reshape(-1, 4)
+        su = s1 if seg_left_un is None else np.ascontiguousarray(seg_left_un, np.float32).reshape(-1, 4)
+        m12 = np.ascontiguousarray(matches12, np.int32)
+        n1 = len(s1)
+        disp, dep = np.zeros((max(n1, 1), 2), np.float32), np.zeros((max(n1, 1), 2), np.float32)
+        le = np.zeros((max(n1, 1), 3), np.float64)
+        nd = np.zeros(1, np.int32)
+        check(lib().plvi_line_stereo_depth_host(self._h, ptr(s1) if n1 else None, n1, ptr(s2) if len(s2) else None, len(s2),
+                                                ptr(m12) if n1 else None, ptr(su) if n1 else None, float(mbf), ptr(disp), ptr(dep),
+                                                ptr(le), ptr(nd)))
+        return int(nd[0]), disp[:n1], dep[:n1], le[:n1]
+
     def SerachForInitialize(self, desc_initial, desc_current):
         """int LineMatcher::SerachForInitialize(Frame&, Frame&, vector<pair<int,int>>&) (src/LineMatcher.cpp:113-141)
         on the two frames' line descriptors -> (count, [(qdx, tdx), ...])."""

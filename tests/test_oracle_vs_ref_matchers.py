@@ -497,6 +497,24 @@ def test_live_reference_distinctive_descriptors(seed):
         assert (r is None and len(good) == 0) or np.array_equal(r, good[oracle.distinctive_descriptor(good)])
 
 
+@needs_ref
+@pytest.mark.parametrize("seed", [3, 4])
+def test_live_reference_mapline_distinctive_descriptors(seed):
+    """MapLine::ComputeDistinctiveDescriptors (src/MapLine.cc:264-329, MapLine.cc + MapLine.h compiled unmodified): the same
+    least-median rule over LBD descriptors with ORBmatcher::DescriptorDistance (:305)."""
+    desc, counts = distinctive_case(seed)
+    rng = np.random.RandomState(seed + 100)
+    for p in range(len(counts)):
+        d = desc[p, :counts[p]]
+        r = oracle.ref_mapline_distinctive_descriptor(d)
+        assert np.array_equal(r, d[oracle.distinctive_descriptor(d)])
+        assert np.array_equal(r, oracle.ref_distinctive_descriptor(d))
+        bad = (rng.rand(len(d)) < 0.3).astype(np.uint8)
+        r = oracle.ref_mapline_distinctive_descriptor(d, bad)
+        good = d[bad == 0]
+        assert (r is None and len(good) == 0) or np.array_equal(r, good[oracle.distinctive_descriptor(good)])
+
+
 def test_oracle_equals_reference_distinctive_outputs():
     desc, counts = distinctive_case(7)
     for p in range(len(counts)):

@@ -277,6 +277,8 @@ def test_cuda_equals_reference_distinctive_descriptors(gpu):
         elif oracle.ref_available():
             for p in range(len(counts)):
                 assert np.array_equal(best[p], oracle.ref_distinctive_descriptor(desc[p, :counts[p]])), p
+                # MapLine::ComputeDistinctiveDescriptors (src/MapLine.cc:264-329) is the same rule on LBD descriptors
+                assert np.array_equal(best[p], oracle.ref_mapline_distinctive_descriptor(desc[p, :counts[p]])), p
 
 
 def cuda_sim3(om, r1, r2, case, th):

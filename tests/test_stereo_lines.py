@@ -91,6 +91,95 @@ def test_oracle_match_grid_other_grid_shape():
         assert rn == n and np.array_equal(rm, m)
 
 
+def _keylines(seg):
+    kl = np.zeros(len(seg), oracle.KEYLINE_DTYPE)
+    for j, f in enumerate(("startPointX", "startPointY", "endPointX", "endPointY")):
+        kl[f] = seg[:, j]
+    return kl
+
+
+def _depth_case(seed):
+    n1, n2 = SIZES[seed % len(SIZES)]
+    s1, d1, s2, d2 = stereo_line_case(seed, n1, n2)
+    if seed % 3 == 1 and n1:      # some left lines shifted vertically: partial / no overlap with their right line
+        s1 = s1.copy()
+        s1[::2, 1] += np.float32(9.0)
+        s1[::2, 3] += np.float32(9.0)
+    if seed % 4 == 2 and n2 > 4:  # horizontal right lines: the division by sp_r(1) - ep_r(1) = 0
+        s2 = s2.copy()
+        s2[4:8, 3] = s2[4:8, 1]
+    return s1, d1, s2, d2
+
+
+@needs_ref
+def test_oracle_stereo_line_depth_against_live_reference():
+    """Grid fill + matchGrid + the disparity / overlap / depth filter + mvle_l: the oracle's restatement against the
+    reference's own Frame::ComputeStereoMatches_Lines (src/Frame.cc:1408-1500, Frame.cc compiled unmodified)."""
+    total = 0
+    for seed in range(32):
+        s1, d1, s2, d2 = _depth_case(seed)
+        k, out, le = oracle.ref_frame_stereo_lines(_keylines(s1), d1, _keylines(s2), d2, INV_W, INV_H, 47.9)
+        n, m12 = oracle.line_match_grid(s1, d1, s2, d2, INV_W, INV_H)
+        k2, disp, dep, le2 = oracle.line_stereo_depth(s1, s2, m12, 47.9)
+        assert k == k2, seed
+        assert np.array_equal(out[:, :2].view(np.uint32), disp.view(np.uint32)) and np.array_equal(out[:, 2:].view(np.uint32), dep.view(np.uint32)), seed
+        assert np.array_equal(le.view(np.uint64), le2.view(np.uint64)), seed
+        total += k
+    assert total > 300
+
+
+@pytest.mark.gpu
+def test_stereo_line_depth_gpu(gpu):
+    """plvi_line_stereo_depth (device batch) and plvi_line_stereo_depth_host against the oracle and the live reference."""
+    import torch
+    from pl_vi_orbslam3_b200 import LineMatcher
+    from pl_vi_orbslam3_b200.capi import check, lib, ptr
+    lm = LineMatcher(max_pairs=64, max_train=512, max_query=512)
+    try:
+        cases = [_depth_case(seed) for seed in range(32)]
+        P, S = len(cases), 320
+        seg1 = np.zeros((P, S, 4), np.float32); seg2 = np.zeros((P, S, 4), np.float32); segu = np.zeros((P, S, 4), np.float32)
+        m12 = np.full((P, S), -1, np.int32); n1 = np.zeros(P, np.int32); n2 = np.zeros(P, np.int32)
+        rng = np.random.RandomState(3)
+        want = []
+        for k, (s1, d1, s2, d2) in enumerate(cases):
+            n1[k], n2[k] = len(s1), len(s2)
+            seg1[k, :len(s1)] = s1; seg2[k, :len(s2)] = s2
+            segu[k, :len(s1)] = s1 + rng.normal(0, 0.7, s1.shape).astype(np.float32)      # "undistorted" end points
+            _, m = oracle.line_match_grid(s1, d1, s2, d2, INV_W, INV_H)
+            m12[k, :len(s1)] = m
+            want.append(oracle.line_stereo_depth(s1, s2, m, 47.9, segu[k, :len(s1)]))
+        dev = lambda a: torch.from_numpy(a).cuda()
+        t = [dev(a) for a in (seg1, n1, seg2, n2, m12, segu)]
+        disp = torch.zeros((P, S, 2), dtype=torch.float32, device="cuda"); dep = torch.zeros_like(disp)
+        le = torch.zeros((P, S, 3), dtype=torch.float64, device="cuda"); nd = torch.zeros(P, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        check(lib().plvi_line_stereo_depth(lm._h, P, ptr(t[0]), ptr(t[1]), S, ptr(t[2]), ptr(t[3]), S, ptr(t[4]), ptr(t[5]), 47.9,
+                                           ptr(disp), ptr(dep), ptr(le), ptr(nd)))
+        lm.sync()
+        disp, dep, le, nd = disp.cpu().numpy(), dep.cpu().numpy(), le.cpu().numpy(), nd.cpu().numpy()
+        total = 0
+        for k, (kk, wd, wp, wl) in enumerate(want):
+            n = n1[k]
+            assert nd[k] == kk, k
+            assert np.array_equal(disp[k, :n].view(np.uint32), wd.view(np.uint32)) and np.array_equal(dep[k, :n].view(np.uint32), wp.view(np.uint32)), k
+            assert np.array_equal(le[k, :n].view(np.uint64), wl.view(np.uint64)), k
+            total += kk
+        assert total > 300
+        for k in (0, 1, 2, 5, 6, 9):     # host-buffer entry, incl. the empty sides; the live reference where it travelled
+            s1, d1, s2, d2 = cases[k]
+            n, m = lm.matchGrid_host(s1, d1, s2, d2, INV_W, INV_H)
+            kk, gd, gp, gl = lm.stereo_depth_host(s1, s2, m, 47.9)
+            wk, wd, wp, wl = oracle.line_stereo_depth(s1, s2, m, 47.9)
+            assert kk == wk and np.array_equal(gd.view(np.uint32), wd.view(np.uint32)) and np.array_equal(gp.view(np.uint32), wp.view(np.uint32))
+            assert np.array_equal(gl.view(np.uint64), wl.view(np.uint64))
+            if oracle.ref_available():
+                rk, rout, rle = oracle.ref_frame_stereo_lines(_keylines(s1), d1, _keylines(s2), d2, INV_W, INV_H, 47.9)
+                assert rk == kk and np.array_equal(rout[:, :2].view(np.uint32), gd.view(np.uint32)) and np.array_equal(rle.view(np.uint64), gl.view(np.uint64))
+    finally:
+        lm.close()
+
+
 @pytest.mark.gpu
 def test_match_grid_gpu_against_oracle(gpu):
     from pl_vi_orbslam3_b200 import LineMatcher
