@@ -163,9 +163,11 @@ typedef struct plvi_line plvi_line;
 
 /* Lineextractor::Lineextractor(lsd_nfeatures, lsd_refine, lsd_scale, nlevels, scale, extractor)
  * (include/LineExtractor.h:55, src/LineExtractor.cc:39-43).  Implemented: extractor = 0
- * (LSD), lsd_refine = 0, nlevels 1 or 2, 0.75 <= lsd_scale < 1 -- every configuration the
- * reference ships; anything else returns PLVI_ERR_INVALID.  lsd_nfeatures = 0 keeps all
- * lines (capacity 4096 per frame). */
+ * (LSD); lsd_refine 0 (LSD_REFINE_NONE: what every shipped yaml uses; the batched speculative region growing), 1
+ * (LSD_REFINE_STD) and 2 (LSD_REFINE_ADV): refine / rect_improve / NFA of src/LSD/lsd.cpp:784-1134 in one serial warp
+ * per frame and octave; nlevels 1 or 2; 0.28 <= lsd_scale <= 1 (1.0 = no blur / resize, Examples/Stereo-Line/
+ * UMA_ueye.yaml); anything else returns PLVI_ERR_INVALID.  lsd_nfeatures = 0 keeps all lines (capacity 4096 per
+ * frame). */
 int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float lsd_scale, int nlevels,
                      float scale, int extractor, int max_width, int max_height, int max_batch,
                      int device, void* stream);

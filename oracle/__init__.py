@@ -344,8 +344,8 @@ def sobel3(img):
     return dx, dy
 
 
-def lsd(img, lsd_scale=0.8, debug=False):
-    """LineSegmentDetectorImpl::detect (refine 0) on one u8 image -> (segments [n,4] f32[, dict])."""
+def lsd(img, lsd_scale=0.8, debug=False, refine=0):
+    """LineSegmentDetectorImpl::detect (refine 0 / 1 / 2) on one u8 image -> (segments [n,4] f32[, dict])."""
     img = _u8(img)
     h, w = img.shape
     sw, sh = C.c_int(0), C.c_int(0)
@@ -358,7 +358,7 @@ def lsd(img, lsd_scale=0.8, debug=False):
     ang = np.empty(big, np.float64) if debug else None
     mg = np.empty(big, np.float64) if debug else None
     n = lib().plvio_lsd(_p(img), img.strides[0], w, h, C.c_float(lsd_scale), C.byref(sw), C.byref(sh),
-                        _p(scaled), _p(ang), _p(mg), _p(segs), cap, _p(rs))
+                        _p(scaled), _p(ang), _p(mg), _p(segs), cap, _p(rs), int(refine))
     out = segs[:n].copy()
     if not debug:
         return out

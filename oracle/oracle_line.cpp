@@ -238,82 +238,339 @@ static inline double angle_diff(double a, double b) {
 
 struct RegPt { int x, y; };
 
+// rect of src/LSD/lsd.cpp (struct rect, :166-176)
+struct LsdRect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
+
+struct LsdState {
+  const LsdImage& L;
+  std::vector<u8> used;
+  std::vector<RegPt> reg;
+  double LOG_NT;
+  explicit LsdState(const LsdImage& l) : L(l), used((size_t)l.w * l.h, 0), reg((size_t)l.w * l.h), LOG_NT(0) {}
+};
+
+// region_grow (:635-686): breadth-first over the 8-neighbourhood in (yy, xx) scan order; the region angle is
+// re-derived from the float sums after every accepted pixel
+static void region_grow(LsdState& S, int sx, int sy, int& reg_size, double& reg_angle, double prec) {
+  const LsdImage& L = S.L;
+  const int W = L.w, H = L.h;
+  const double DEG_TO_RADS = kPi / 180;
+  const size_t adx = (size_t)sy * W + sx;
+  reg_size = 1;
+  S.reg[0] = {sx, sy};
+  reg_angle = L.angles[adx];
+  float sumdx = (float)std::cos(reg_angle), sumdy = (float)std::sin(reg_angle);
+  S.used[adx] = 1;
+  for (int i = 0; i < reg_size; ++i) {
+    const RegPt rp = S.reg[i];
+    const int xx_min = std::max(rp.x - 1, 0), xx_max = std::min(rp.x + 1, W - 1);
+    const int yy_min = std::max(rp.y - 1, 0), yy_max = std::min(rp.y + 1, H - 1);
+    for (int yy = yy_min; yy <= yy_max; ++yy)
+      for (int xx = xx_min; xx <= xx_max; ++xx) {
+        const size_t c = (size_t)yy * W + xx;
+        if (!S.used[c] && is_aligned(L.angles[c], reg_angle, prec)) {
+          S.used[c] = 1;
+          S.reg[reg_size++] = {xx, yy};
+          const double angle = L.angles[c];
+          sumdx += cosf_d((float)angle);
+          sumdy += sinf_d((float)angle);
+          reg_angle = fast_atan2(sumdy, sumdx) * DEG_TO_RADS;
+        }
+      }
+  }
+}
+
+// region2rect (:688-744) + get_theta (:746-782)
+static void region2rect(const LsdState& S, int reg_size, double reg_angle, double prec, double p, LsdRect& rec) {
+  const LsdImage& L = S.L;
+  const int W = L.w;
+  const double DEG_TO_RADS = kPi / 180;
+  double x = 0, y = 0, sum = 0;
+  for (int i = 0; i < reg_size; ++i) {
+    const double wgt = L.modgrad[(size_t)S.reg[i].y * W + S.reg[i].x];
+    x += (double)S.reg[i].x * wgt;
+    y += (double)S.reg[i].y * wgt;
+    sum += wgt;
+  }
+  x /= sum;
+  y /= sum;
+  double Ixx = 0, Iyy = 0, Ixy = 0;
+  for (int i = 0; i < reg_size; ++i) {
+    const double wgt = L.modgrad[(size_t)S.reg[i].y * W + S.reg[i].x];
+    const double dx = (double)S.reg[i].x - x, dy = (double)S.reg[i].y - y;
+    Ixx += dy * dy * wgt;
+    Iyy += dx * dx * wgt;
+    Ixy -= dx * dy * wgt;
+  }
+  const double lambda = 0.5 * (Ixx + Iyy - std::sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+  double theta = (std::fabs(Ixx) > std::fabs(Iyy)) ? (double)fast_atan2((float)(lambda - Ixx), (float)Ixy)
+                                                    : (double)fast_atan2((float)Ixy, (float)(lambda - Iyy));
+  theta *= DEG_TO_RADS;
+  if (angle_diff(theta, reg_angle) > prec) theta += kPi;
+  const double dx = std::cos(theta), dy = std::sin(theta);
+  double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+  for (int i = 0; i < reg_size; ++i) {
+    const double rdx = (double)S.reg[i].x - x, rdy = (double)S.reg[i].y - y;
+    const double l = rdx * dx + rdy * dy;
+    const double w = -rdx * dy + rdy * dx;
+    if (l > l_max) l_max = l;
+    else if (l < l_min) l_min = l;
+    if (w > w_max) w_max = w;
+    else if (w < w_min) w_min = w;
+  }
+  rec.x1 = x + l_min * dx; rec.y1 = y + l_min * dy;
+  rec.x2 = x + l_max * dx; rec.y2 = y + l_max * dy;
+  rec.width = w_max - w_min;
+  rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy; rec.prec = prec; rec.p = p;
+  if (rec.width < 1.0) rec.width = 1.0;
+}
+
+static inline double dist_sq(double x1, double y1, double x2, double y2) { return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1); }
+static inline double dist_pts(double x1, double y1, double x2, double y2) { return std::sqrt(dist_sq(x1, y1, x2, y2)); }
+static inline double angle_diff_signed(double a, double b) {
+  double diff = a - b;
+  while (diff <= -kPi) diff += 2 * kPi;
+  while (diff > kPi) diff -= 2 * kPi;
+  return diff;
+}
+static inline double rect_density(const LsdRect& r, int reg_size) {
+  return (double)reg_size / (dist_pts(r.x1, r.y1, r.x2, r.y2) * r.width);
+}
+
+// reduce_region_radius (:831-869): shrink the region around its seed until the rectangle is dense enough; removed
+// pixels become available again; the removal swaps the last point in (the order of the list changes)
+static bool reduce_region_radius(LsdState& S, int& reg_size, double reg_angle, double prec, double p, LsdRect& rec, double density,
+                                 double density_th) {
+  const int W = S.L.w;
+  const double xc = (double)S.reg[0].x, yc = (double)S.reg[0].y;
+  const double r1 = dist_sq(xc, yc, rec.x1, rec.y1), r2 = dist_sq(xc, yc, rec.x2, rec.y2);
+  double radSq = r1 > r2 ? r1 : r2;
+  while (density < density_th) {
+    radSq *= 0.75 * 0.75;
+    for (int i = 0; i < reg_size; ++i) {
+      if (dist_sq(xc, yc, (double)S.reg[i].x, (double)S.reg[i].y) > radSq) {
+        S.used[(size_t)S.reg[i].y * W + S.reg[i].x] = 0;
+        std::swap(S.reg[i], S.reg[reg_size - 1]);
+        --reg_size;
+        --i;
+      }
+    }
+    if (reg_size < 2) return false;
+    region2rect(S, reg_size, reg_angle, prec, p, rec);
+    density = rect_density(rec, reg_size);
+  }
+  return true;
+}
+
+// refine (:784-829): a sparse rectangle is re-grown from the same seed with the tolerance 2 * (standard deviation of the
+// angles near the seed), then shrunk
+static bool refine_region(LsdState& S, int& reg_size, double reg_angle, double prec, double p, LsdRect& rec, double density_th) {
+  const LsdImage& L = S.L;
+  const int W = L.w;
+  double density = rect_density(rec, reg_size);
+  if (density >= density_th) return true;
+  const double xc = (double)S.reg[0].x, yc = (double)S.reg[0].y;
+  const double ang_c = L.angles[(size_t)S.reg[0].y * W + S.reg[0].x];
+  double sum = 0, s_sum = 0;
+  int n = 0;
+  for (int i = 0; i < reg_size; ++i) {
+    const size_t a = (size_t)S.reg[i].y * W + S.reg[i].x;
+    S.used[a] = 0;
+    if (dist_pts(xc, yc, S.reg[i].x, S.reg[i].y) < rec.width) {
+      const double ang_d = angle_diff_signed(L.angles[a], ang_c);
+      sum += ang_d;
+      s_sum += ang_d * ang_d;
+      ++n;
+    }
+  }
+  const double mean_angle = sum / (double)n;
+  const double tau = 2.0 * std::sqrt((s_sum - 2.0 * mean_angle * sum) / (double)n + mean_angle * mean_angle);
+  region_grow(S, S.reg[0].x, S.reg[0].y, reg_size, reg_angle, tau);
+  if (reg_size < 2) return false;
+  region2rect(S, reg_size, reg_angle, prec, p, rec);
+  density = rect_density(rec, reg_size);
+  if (density < density_th) return reduce_region_radius(S, reg_size, reg_angle, prec, p, rec, density, density_th);
+  return true;
+}
+
+// log_gamma (:70,134-158) and nfa (:1094-1133), incl. the term "(double(n) + 1)" the vendored code has in the place of
+// log_gamma(n + 1)
+static double log_gamma_f(double x) {
+  if (x > 15.0) return 0.918938533204673 + (x - 0.5) * std::log(x) - x + 0.5 * x * std::log(x * std::sinh(1 / x) + 1 / (810.0 * std::pow(x, 6.0)));
+  static const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+  double a = (x + 0.5) * std::log(x + 5.5) - (x + 5.5);
+  double b = 0;
+  for (int n = 0; n < 7; ++n) {
+    a -= std::log(x + (double)n);
+    b += q[n] * std::pow(x, (double)n);
+  }
+  return a + std::log(b);
+}
+
+static bool double_equal_rel(double a, double b) {
+  if (a == b) return true;
+  const double abs_diff = std::fabs(a - b), aa = std::fabs(a), bb = std::fabs(b);
+  double abs_max = (aa > bb) ? aa : bb;
+  if (abs_max < 2.2250738585072014e-308) abs_max = 2.2250738585072014e-308;
+  return (abs_diff / abs_max) <= (100.0 * 2.220446049250313e-16);
+}
+
+static double nfa_value(int n, int k, double p, double LOG_NT) {
+  if (n == 0 || k == 0) return -LOG_NT;
+  if (n == k) return -LOG_NT - (double)n * std::log10(p);
+  const double p_term = p / (1 - p);
+  const double log1term = ((double)n + 1) - log_gamma_f((double)k + 1) - log_gamma_f((double)(n - k) + 1) + (double)k * std::log(p) +
+                          (double)(n - k) * std::log(1.0 - p);
+  double term = std::exp(log1term);
+  if (double_equal_rel(term, 0)) {
+    if (k > n * p) return -log1term / 2.30258509299404568402 - LOG_NT;
+    return -LOG_NT;
+  }
+  double bin_tail = term;
+  const double tolerance = 0.1;
+  for (int i = k + 1; i <= n; ++i) {
+    const double bin_term = (double)(n - i + 1) / (double)i;
+    const double mult_term = bin_term * p_term;
+    term *= mult_term;
+    bin_tail += term;
+    if (bin_term < 1) {
+      const double err = term * ((1 - std::pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
+      if (err < tolerance * std::fabs(-std::log10(bin_tail) - LOG_NT) * bin_tail) break;
+    }
+  }
+  return -std::log10(bin_tail) - LOG_NT;
+}
+
+// rect_nfa (:975-1092): scan conversion of the rectangle with the vendored code's integer steps (the quotients of the
+// corner differences are INTEGER divisions; two of the tests compare a y with tailp's x), rows outside the image skip
+// the step update as well
+static double rect_nfa(const LsdState& S, const LsdRect& rec) {
+  const LsdImage& L = S.L;
+  const int W = L.w, H = L.h;
+  int total_pts = 0, alg_pts = 0;
+  const double half_width = rec.width / 2.0;
+  const double dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
+  struct Edge { int x, y; bool taken; };
+  Edge e[4] = {{(int)(rec.x1 - dyhw), (int)(rec.y1 + dxhw), false}, {(int)(rec.x2 - dyhw), (int)(rec.y2 + dxhw), false},
+               {(int)(rec.x2 + dyhw), (int)(rec.y2 - dxhw), false}, {(int)(rec.x1 + dyhw), (int)(rec.y1 - dxhw), false}};
+  std::sort(e, e + 4, [](const Edge& a, const Edge& b) { return a.x == b.x ? a.y < b.y : a.x < b.x; });
+  Edge *min_y = &e[0], *max_y = &e[0];
+  for (int i = 1; i < 4; ++i) {
+    if (min_y->y > e[i].y) min_y = &e[i];
+    if (max_y->y < e[i].y) max_y = &e[i];
+  }
+  min_y->taken = true;
+  Edge* leftmost = nullptr;
+  for (int i = 0; i < 4; ++i)
+    if (!e[i].taken && (!leftmost || leftmost->x > e[i].x)) leftmost = &e[i];
+  leftmost->taken = true;
+  Edge* rightmost = nullptr;
+  for (int i = 0; i < 4; ++i)
+    if (!e[i].taken && (!rightmost || rightmost->x < e[i].x)) rightmost = &e[i];
+  rightmost->taken = true;
+  Edge* tailp = nullptr;
+  for (int i = 0; i < 4; ++i)
+    if (!e[i].taken && (!tailp || tailp->x > e[i].x)) tailp = &e[i];
+  tailp->taken = true;
+  const double flstep = (min_y->y != leftmost->y) ? (min_y->x - leftmost->x) / (min_y->y - leftmost->y) : 0;
+  const double slstep = (leftmost->y != tailp->x) ? (leftmost->x - tailp->x) / (leftmost->y - tailp->x) : 0;
+  const double frstep = (min_y->y != rightmost->y) ? (min_y->x - rightmost->x) / (min_y->y - rightmost->y) : 0;
+  const double srstep = (rightmost->y != tailp->x) ? (rightmost->x - tailp->x) / (rightmost->y - tailp->x) : 0;
+  double lstep = flstep, rstep = frstep;
+  double left_x = min_y->x, right_x = min_y->x;
+  for (int y = min_y->y; y <= max_y->y; ++y) {
+    if (y < 0 || y >= H) continue;
+    for (int x = (int)left_x; x <= (int)right_x; ++x) {
+      if (x < 0 || x >= W) continue;
+      ++total_pts;
+      if (is_aligned(L.angles[(size_t)y * W + x], rec.theta, rec.prec)) ++alg_pts;
+    }
+    if (y >= leftmost->y) lstep = slstep;
+    if (y >= rightmost->y) rstep = srstep;
+    left_x += lstep;
+    right_x += rstep;
+  }
+  return nfa_value(total_pts, alg_pts, rec.p, S.LOG_NT);
+}
+
+// rect_improve (:871-973)
+static double rect_improve(const LsdState& S, LsdRect& rec, double log_eps) {
+  const double delta = 0.5, delta_2 = delta / 2.0;
+  double log_nfa = rect_nfa(S, rec);
+  if (log_nfa > log_eps) return log_nfa;
+  LsdRect r = rec;
+  for (int n = 0; n < 5; ++n) {
+    r.p /= 2;
+    r.prec = r.p * kPi;
+    const double v = rect_nfa(S, r);
+    if (v > log_nfa) { log_nfa = v; rec = r; }
+  }
+  if (log_nfa > log_eps) return log_nfa;
+  r = rec;
+  for (int n = 0; n < 5; ++n) {
+    if ((r.width - delta) >= 0.5) {
+      r.width -= delta;
+      const double v = rect_nfa(S, r);
+      if (v > log_nfa) { rec = r; log_nfa = v; }
+    }
+  }
+  if (log_nfa > log_eps) return log_nfa;
+  for (int side = 0; side < 2; ++side) {
+    r = rec;
+    for (int n = 0; n < 5; ++n) {
+      if ((r.width - delta) >= 0.5) {
+        if (side == 0) { r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2; }
+        else { r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2; }
+        r.width -= delta;
+        const double v = rect_nfa(S, r);
+        if (v > log_nfa) { rec = r; log_nfa = v; }
+      }
+    }
+    if (log_nfa > log_eps) return log_nfa;
+  }
+  r = rec;
+  for (int n = 0; n < 5; ++n) {
+    if ((r.width - delta) >= 0.5) {
+      r.p /= 2;
+      r.prec = r.p * kPi;
+      const double v = rect_nfa(S, r);
+      if (v > log_nfa) { rec = r; log_nfa = v; }
+    }
+  }
+  return log_nfa;
+}
+
 // flsd (:438-534): seeds in raster order over the interior (the vendored code walks the
-// coordinate vector, not the gradient-sorted list); returns Vec4f segments.
+// coordinate vector, not the gradient-sorted list); returns Vec4f segments.  refine: LSD_REFINE_NONE 0 / STD 1 / ADV 2
+// with the thresholds Lineextractor passes (log_eps 1.0, density_th 0.6, src/LineExtractor.cc:60-63).
 void lsd_detect(const LsdImage& L, double scale, double ang_th, std::vector<float>& lines,
-                std::vector<int>* region_sizes) {
+                std::vector<int>* region_sizes, int refine, double log_eps, double density_th) {
   const int W = L.w, H = L.h;
   const double prec = kPi * ang_th / 180;
   const double p = ang_th / 180;
-  const double DEG_TO_RADS = kPi / 180;
-  const double LOG_NT = 5 * (std::log10((double)W) + std::log10((double)H)) / 2 + std::log10(11.0);
-  const int min_reg_size = (int)(-LOG_NT / std::log10(p));
-  std::vector<u8> used((size_t)W * H, 0);
-  std::vector<RegPt> reg((size_t)W * H);
+  LsdState S(L);
+  S.LOG_NT = 5 * (std::log10((double)W) + std::log10((double)H)) / 2 + std::log10(11.0);
+  const int min_reg_size = (int)(-S.LOG_NT / std::log10(p));
   lines.clear();
   for (int sy = 0; sy < H - 1; sy++)
     for (int sx = 0; sx < W - 1; sx++) {
       const size_t adx = (size_t)sy * W + sx;
-      if (used[adx] || L.angles[adx] == NOTDEF) continue;
-      // region_grow (:635-686)
-      int reg_size = 1;
-      reg[0] = {sx, sy};
-      double reg_angle = L.angles[adx];
-      float sumdx = (float)std::cos(reg_angle), sumdy = (float)std::sin(reg_angle);
-      used[adx] = 1;
-      for (int i = 0; i < reg_size; ++i) {
-        const RegPt rp = reg[i];
-        const int xx_min = std::max(rp.x - 1, 0), xx_max = std::min(rp.x + 1, W - 1);
-        const int yy_min = std::max(rp.y - 1, 0), yy_max = std::min(rp.y + 1, H - 1);
-        for (int yy = yy_min; yy <= yy_max; ++yy)
-          for (int xx = xx_min; xx <= xx_max; ++xx) {
-            const size_t c = (size_t)yy * W + xx;
-            if (!used[c] && is_aligned(L.angles[c], reg_angle, prec)) {
-              used[c] = 1;
-              reg[reg_size++] = {xx, yy};
-              const double angle = L.angles[c];
-              sumdx += cosf_d((float)angle);
-              sumdy += sinf_d((float)angle);
-              reg_angle = fast_atan2(sumdy, sumdx) * DEG_TO_RADS;
-            }
-          }
-      }
+      if (S.used[adx] || L.angles[adx] == NOTDEF) continue;
+      int reg_size;
+      double reg_angle;
+      region_grow(S, sx, sy, reg_size, reg_angle, prec);
       if (reg_size < min_reg_size) continue;
+      LsdRect rec;
+      region2rect(S, reg_size, reg_angle, prec, p, rec);
+      if (refine > 0) {
+        if (!refine_region(S, reg_size, reg_angle, prec, p, rec, density_th)) continue;
+        if (refine >= 2) {
+          const double log_nfa = rect_improve(S, rec, log_eps);
+          if (log_nfa <= log_eps) continue;
+        }
+      }
       if (region_sizes) region_sizes->push_back(reg_size);
-      // region2rect (:688-744)
-      double x = 0, y = 0, sum = 0;
-      for (int i = 0; i < reg_size; ++i) {
-        const double wgt = L.modgrad[(size_t)reg[i].y * W + reg[i].x];
-        x += (double)reg[i].x * wgt;
-        y += (double)reg[i].y * wgt;
-        sum += wgt;
-      }
-      x /= sum;
-      y /= sum;
-      // get_theta (:746-782)
-      double Ixx = 0, Iyy = 0, Ixy = 0;
-      for (int i = 0; i < reg_size; ++i) {
-        const double wgt = L.modgrad[(size_t)reg[i].y * W + reg[i].x];
-        const double dx = (double)reg[i].x - x, dy = (double)reg[i].y - y;
-        Ixx += dy * dy * wgt;
-        Iyy += dx * dx * wgt;
-        Ixy -= dx * dy * wgt;
-      }
-      const double lambda = 0.5 * (Ixx + Iyy - std::sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
-      double theta = (std::fabs(Ixx) > std::fabs(Iyy)) ? (double)fast_atan2((float)(lambda - Ixx), (float)Ixy)
-                                                        : (double)fast_atan2((float)Ixy, (float)(lambda - Iyy));
-      theta *= DEG_TO_RADS;
-      if (angle_diff(theta, reg_angle) > prec) theta += kPi;
-      const double dx = std::cos(theta), dy = std::sin(theta);
-      double l_min = 0, l_max = 0;
-      for (int i = 0; i < reg_size; ++i) {
-        const double rdx = (double)reg[i].x - x, rdy = (double)reg[i].y - y;
-        const double l = rdx * dx + rdy * dy;
-        if (l > l_max) l_max = l;
-        else if (l < l_min) l_min = l;
-      }
-      double x1 = x + l_min * dx, y1 = y + l_min * dy, x2 = x + l_max * dx, y2 = y + l_max * dy;
-      x1 += 0.5; y1 += 0.5; x2 += 0.5; y2 += 0.5;
+      double x1 = rec.x1 + 0.5, y1 = rec.y1 + 0.5, x2 = rec.x2 + 0.5, y2 = rec.y2 + 0.5;
       if (scale != 1) { x1 /= scale; y1 /= scale; x2 /= scale; y2 /= scale; }
       lines.push_back((float)x1); lines.push_back((float)y1); lines.push_back((float)x2); lines.push_back((float)y2);
     }
@@ -548,7 +805,7 @@ int plvio_line_iterator_count(int w, int h, int ax, int ay, int bx, int by) { re
 // LSD on one u8 octave image.  Outputs (optional): scaled f64 image, angles, modgrad of
 // size *sw x *sh; segments as x1,y1,x2,y2 floats (cap = max segments).  Returns count.
 int plvio_lsd(const u8* img, int stride, int w, int h, float lsd_scale, int* sw, int* sh, double* scaled,
-              double* angles, double* modgrad, float* segs, int cap, int* region_sizes) {
+              double* angles, double* modgrad, float* segs, int cap, int* region_sizes, int refine) {
   LsdImage L;
   lsd_prepare(img, stride, w, h, (double)lsd_scale, 0.6, 2.0, 22.5, L);
   if (sw) *sw = L.w;
@@ -559,7 +816,7 @@ int plvio_lsd(const u8* img, int stride, int w, int h, float lsd_scale, int* sw,
   if (modgrad) memcpy(modgrad, L.modgrad.data(), n * sizeof(double));
   std::vector<float> lines;
   std::vector<int> rs;
-  lsd_detect(L, (double)lsd_scale, 22.5, lines, &rs);
+  lsd_detect(L, (double)lsd_scale, 22.5, lines, &rs, refine, 1.0, 0.6);
   const int m = (int)(lines.size() / 4);
   for (int i = 0; i < std::min(m, cap) * 4; i++) segs[i] = lines[i];
   if (region_sizes) for (int i = 0; i < std::min(m, cap); i++) region_sizes[i] = rs[i];
@@ -576,8 +833,7 @@ void plvio_lbd(const plvio::KeyLine* kl, const short* dx, const short* dy, int w
 int plvio_line_extract(const u8* img, int w, int h, int stride, int lsd_nfeatures, int lsd_refine,
                        float lsd_scale, int nlevels, float scale, plvio::KeyLine* keylines, u8* desc,
                        double* lineeq, int cap, int* raw_counts) {
-  (void)lsd_refine;  // only LSD_REFINE_NONE is restated (all shipped yaml files use 0)
-  if (nlevels < 1 || nlevels > 2) return -1;
+  if (nlevels < 1 || nlevels > 2 || lsd_refine < 0 || lsd_refine > 2) return -1;
   // LSDDetectorC::ComputePyramid (:76-109)
   std::vector<std::vector<u8>> pyr(nlevels);
   std::vector<int> pw(nlevels), ph(nlevels);
@@ -598,7 +854,7 @@ int plvio_line_extract(const u8* img, int w, int h, int stride, int lsd_nfeature
     LsdImage L;
     lsd_prepare(pyr[l].data(), pw[l], pw[l], ph[l], (double)lsd_scale, 0.6, 2.0, 22.5, L);
     std::vector<float> lines;
-    lsd_detect(L, (double)lsd_scale, 22.5, lines, nullptr);
+    lsd_detect(L, (double)lsd_scale, 22.5, lines, nullptr, lsd_refine, 1.0, 0.6);
     if (raw_counts) raw_counts[l] = (int)(lines.size() / 4);
     make_keylines(lines, l, pw[l], ph[l], scale, min_length, class_counter, kls);
   }

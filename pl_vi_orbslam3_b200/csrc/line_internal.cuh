@@ -48,6 +48,7 @@ struct LineGeom {
   double kern[17];            // cv::getGaussianKernel(1 + 2 hk, sigma, CV_64F)
   float lineScale;
   int nfeat, keepCap;
+  int refine;                 // lsd_refine: 0 none, 1 standard (refine), 2 advanced (+ NFA), src/LSD/lsd.cpp:493-504
 };
 
 struct LineTab { int ofs; float a0, a1; };       // f64 bilinear taps (float32 weights)

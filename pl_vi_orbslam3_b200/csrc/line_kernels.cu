@@ -1434,6 +1434,454 @@ __global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGe
 }
 
 // ---------------------------------------------------------------------------------------
+// k_lsd_grow_refine: lsd_refine > 0 (LSD_REFINE_STD = 1, LSD_REFINE_ADV = 2), src/LSD/lsd.cpp:493-504,784-1134.  refine()
+// gives pixels back to the "not used" state and re-grows regions with another tolerance, so the outcome of one seed
+// feeds the next: the whole seed loop -- region_grow, region2rect, refine, reduce_region_radius, rect_improve / rect_nfa /
+// nfa -- runs in one warp per (frame, octave), in the reference's order; the segments come straight out of this kernel
+// (k_lsd_rect is skipped).  Lanes share the per-pixel work of a region (sums, extents, scan lines of the NFA rectangle).
+// The f64 sums of a region are tree sums over lanes, i.e. not in the reference's left-to-right order: decisions and the
+// float end points agree with the reference except where a comparison or a float rounding falls within ~1e-13 of a tie
+// (same as k_lsd_rect).  The NFA uses CUDA's log / exp / pow / sinh / log10 (<= 2 ulp) where the reference uses libm.
+// ---------------------------------------------------------------------------------------
+struct LsdRectD { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
+
+__device__ __forceinline__ double angle_diff_signed_dev(double a, double b) {
+  double diff = a - b;
+  while (diff <= -PI_D) diff += 2 * PI_D;
+  while (diff > PI_D) diff -= 2 * PI_D;
+  return diff;
+}
+
+// region2rect + get_theta for the pixel list rp[0 .. size) (all lanes return the same rectangle)
+__device__ void warp_region2rect(const unsigned* rp, int size, const double* __restrict__ mod, int W, double regAngle, double prec, double p,
+                                 LsdRectD& rec, int lane) {
+  double x = 0, y = 0, sum = 0;
+  for (int i = lane; i < size; i += 32) {
+    const unsigned q = __ldcg(rp + i);
+    const int px = q & 0xffff, py = q >> 16;
+    const double wgt = mod[py * W + px];
+    x += (double)px * wgt;
+    y += (double)py * wgt;
+    sum += wgt;
+  }
+  x = warp_sum_d(x); y = warp_sum_d(y); sum = warp_sum_d(sum);
+  x /= sum;
+  y /= sum;
+  double Ixx = 0, Iyy = 0, Ixy = 0;
+  for (int i = lane; i < size; i += 32) {
+    const unsigned q = __ldcg(rp + i);
+    const int px = q & 0xffff, py = q >> 16;
+    const double wgt = mod[py * W + px];
+    const double dx = (double)px - x, dy = (double)py - y;
+    Ixx += dy * dy * wgt;
+    Iyy += dx * dx * wgt;
+    Ixy -= dx * dy * wgt;
+  }
+  Ixx = warp_sum_d(Ixx); Iyy = warp_sum_d(Iyy); Ixy = warp_sum_d(Ixy);
+  const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_dev((float)(lambda - Ixx), (float)Ixy)
+                                         : (double)fast_atan2_dev((float)Ixy, (float)(lambda - Iyy));
+  theta *= D2R;
+  if (fabs(angle_diff_signed_dev(theta, regAngle)) > prec) theta += PI_D;
+  double dx, dy;
+  sincos(theta, &dy, &dx);
+  double lmin = 0, lmax = 0, wmin = 0, wmax = 0;
+  for (int i = lane; i < size; i += 32) {
+    const unsigned q = __ldcg(rp + i);
+    const double rdx = (double)(q & 0xffff) - x, rdy = (double)(q >> 16) - y;
+    const double l = __dadd_rn(__dmul_rn(rdx, dx), __dmul_rn(rdy, dy));
+    const double w = __dadd_rn(__dmul_rn(-rdx, dy), __dmul_rn(rdy, dx));
+    lmax = fmax(lmax, l); lmin = fmin(lmin, l);
+    wmax = fmax(wmax, w); wmin = fmin(wmin, w);
+  }
+  lmin = warp_min_d(lmin); lmax = warp_max_d(lmax);
+  wmin = warp_min_d(wmin); wmax = warp_max_d(wmax);
+  rec.x1 = x + lmin * dx; rec.y1 = y + lmin * dy;
+  rec.x2 = x + lmax * dx; rec.y2 = y + lmax * dy;
+  rec.width = wmax - wmin;
+  rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy; rec.prec = prec; rec.p = p;
+  if (rec.width < 1.0) rec.width = 1.0;
+}
+
+__device__ __forceinline__ double rect_density_dev(const LsdRectD& r, int size) {
+  const double ddx = r.x2 - r.x1, ddy = r.y2 - r.y1;
+  return (double)size / (sqrt(ddx * ddx + ddy * ddy) * r.width);
+}
+
+__device__ double log_gamma_dev(double x) {
+  if (x > 15.0) return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+  const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+  double a = (x + 0.5) * log(x + 5.5) - (x + 5.5);
+  double bsum = 0;
+  for (int n = 0; n < 7; ++n) {
+    a -= log(x + (double)n);
+    bsum += q[n] * pow(x, (double)n);
+  }
+  return a + log(bsum);
+}
+
+__device__ double nfa_dev(int n, int k, double p, double LOG_NT) {
+  if (n == 0 || k == 0) return -LOG_NT;
+  if (n == k) return -LOG_NT - (double)n * log10(p);
+  const double p_term = p / (1 - p);
+  const double log1term = ((double)n + 1) - log_gamma_dev((double)k + 1) - log_gamma_dev((double)(n - k) + 1) + (double)k * log(p) +
+                          (double)(n - k) * log(1.0 - p);
+  double term = exp(log1term);
+  {
+    const double aa = fabs(term);
+    const double abs_max = aa < 2.2250738585072014e-308 ? 2.2250738585072014e-308 : aa;
+    if (term == 0.0 || (aa / abs_max) <= (100.0 * 2.220446049250313e-16)) {   // double_equal(term, 0)
+      if (k > n * p) return -log1term / 2.30258509299404568402 - LOG_NT;
+      return -LOG_NT;
+    }
+  }
+  double bin_tail = term;
+  for (int i = k + 1; i <= n; ++i) {
+    const double bin_term = (double)(n - i + 1) / (double)i;
+    const double mult_term = bin_term * p_term;
+    term *= mult_term;
+    bin_tail += term;
+    if (bin_term < 1) {
+      const double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
+      if (err < 0.1 * fabs(-log10(bin_tail) - LOG_NT) * bin_tail) break;
+    }
+  }
+  return -log10(bin_tail) - LOG_NT;
+}
+
+// rect_nfa: the scan conversion runs redundantly in every lane (a handful of scalar steps per row); the pixels of a row
+// are shared among the lanes
+__device__ double warp_rect_nfa(const LsdRectD& rec, const float* __restrict__ ang, int W, int H, double LOG_NT, int lane) {
+  const double half_width = rec.width / 2.0;
+  const double dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
+  int ex[4] = {(int)(rec.x1 - dyhw), (int)(rec.x2 - dyhw), (int)(rec.x2 + dyhw), (int)(rec.x1 + dyhw)};
+  int ey[4] = {(int)(rec.y1 + dxhw), (int)(rec.y2 + dxhw), (int)(rec.y2 - dxhw), (int)(rec.y1 - dxhw)};
+  // sort by (x, y): 4 elements, insertion sort
+#pragma unroll
+  for (int i = 1; i < 4; i++)
+#pragma unroll
+    for (int j = i; j > 0; j--) {
+      const bool lt = ex[j] == ex[j - 1] ? ey[j] < ey[j - 1] : ex[j] < ex[j - 1];
+      if (lt) { int t = ex[j]; ex[j] = ex[j - 1]; ex[j - 1] = t; t = ey[j]; ey[j] = ey[j - 1]; ey[j - 1] = t; }
+    }
+  int iMin = 0, iMax = 0;
+#pragma unroll
+  for (int i = 1; i < 4; i++) {
+    if (ey[iMin] > ey[i]) iMin = i;
+    if (ey[iMax] < ey[i]) iMax = i;
+  }
+  unsigned taken = 1u << iMin;
+  int iL = -1, iR = -1, iT = -1;
+#pragma unroll
+  for (int i = 0; i < 4; i++) if (!((taken >> i) & 1u) && (iL < 0 || ex[iL] > ex[i])) iL = i;
+  taken |= 1u << iL;
+#pragma unroll
+  for (int i = 0; i < 4; i++) if (!((taken >> i) & 1u) && (iR < 0 || ex[iR] < ex[i])) iR = i;
+  taken |= 1u << iR;
+#pragma unroll
+  for (int i = 0; i < 4; i++) if (!((taken >> i) & 1u) && (iT < 0 || ex[iT] > ex[i])) iT = i;
+  const int mx = ex[iMin], my = ey[iMin], lx = ex[iL], ly = ey[iL], rx = ex[iR], ry = ey[iR], tx = ex[iT];
+  // INTEGER quotients, and the tests against tailp's x, as in the vendored code (:1055-1063)
+  const double flstep = (my != ly) ? (double)((mx - lx) / (my - ly)) : 0.0;
+  const double slstep = (ly != tx) ? (double)((lx - tx) / (ly - tx)) : 0.0;
+  const double frstep = (my != ry) ? (double)((mx - rx) / (my - ry)) : 0.0;
+  const double srstep = (ry != tx) ? (double)((rx - tx) / (ry - tx)) : 0.0;
+  double lstep = flstep, rstep = frstep;
+  double left_x = mx, right_x = mx;
+  int total = 0, alg = 0;
+  const int yEnd = ey[iMax];
+  for (int y = my; y <= yEnd; ++y) {
+    if (y < 0 || y >= H) continue;
+    const int xa = max((int)left_x, 0), xb = min((int)right_x, W - 1);
+    for (int x = xa + lane; x <= xb; x += 32) {
+      ++total;
+      const float a = __ldg(ang + y * W + x);
+      if (a != -1024.f && is_aligned_dev(__dmul_rn((double)a, D2R), rec.theta, rec.prec)) ++alg;
+    }
+    if (y >= ly) lstep = slstep;
+    if (y >= ry) rstep = srstep;
+    left_x += lstep;
+    right_x += rstep;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+    alg += __shfl_xor_sync(0xffffffffu, alg, o);
+  }
+  return nfa_dev(total, alg, rec.p, LOG_NT);
+}
+
+__device__ double warp_rect_improve(LsdRectD& rec, const float* __restrict__ ang, int W, int H, double LOG_NT, double logEps, int lane) {
+  const double delta = 0.5, delta_2 = delta / 2.0;
+  double log_nfa = warp_rect_nfa(rec, ang, W, H, LOG_NT, lane);
+  if (log_nfa > logEps) return log_nfa;
+  LsdRectD r = rec;
+  for (int n = 0; n < 5; ++n) {
+    r.p /= 2;
+    r.prec = r.p * PI_D;
+    const double v = warp_rect_nfa(r, ang, W, H, LOG_NT, lane);
+    if (v > log_nfa) { log_nfa = v; rec = r; }
+  }
+  if (log_nfa > logEps) return log_nfa;
+  r = rec;
+  for (int n = 0; n < 5; ++n) {
+    if ((r.width - delta) >= 0.5) {
+      r.width -= delta;
+      const double v = warp_rect_nfa(r, ang, W, H, LOG_NT, lane);
+      if (v > log_nfa) { rec = r; log_nfa = v; }
+    }
+  }
+  if (log_nfa > logEps) return log_nfa;
+  for (int side = 0; side < 2; ++side) {
+    r = rec;
+    for (int n = 0; n < 5; ++n) {
+      if ((r.width - delta) >= 0.5) {
+        if (side == 0) { r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2; }
+        else { r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2; }
+        r.width -= delta;
+        const double v = warp_rect_nfa(r, ang, W, H, LOG_NT, lane);
+        if (v > log_nfa) { rec = r; log_nfa = v; }
+      }
+    }
+    if (log_nfa > logEps) return log_nfa;
+  }
+  r = rec;
+  for (int n = 0; n < 5; ++n) {
+    if ((r.width - delta) >= 0.5) {
+      r.p /= 2;
+      r.prec = r.p * PI_D;
+      const double v = warp_rect_nfa(r, ang, W, H, LOG_NT, lane);
+      if (v > log_nfa) { rec = r; log_nfa = v; }
+    }
+  }
+  return log_nfa;
+}
+
+// region_grow from (sx, sy) with tolerance prec into reg[0 ..): the building block of k_lsd_grow with the tolerance as
+// a parameter.  exactOnly: the dot-product pre-test is skipped (tolerances near or beyond 90 degrees, NaN) and every
+// available neighbour takes the reference's f64 test.  The seed's bit must be available on entry.  Returns the size;
+// regAngleDeg = the float region angle in degrees (fresh: the seed's own angle).
+__device__ int warp_region_grow(GrowBitmap& bm, unsigned* ring, unsigned* reg, int sx, int sy, int W, int H, const float2* __restrict__ rec,
+                                const float* __restrict__ ang, const float2* __restrict__ seedcs, double prec, float kHi, float kLo,
+                                bool exactOnly, int lane, double& regAngle) {
+  const int e = lane >> 3, k8 = lane & 7;
+  const int nidx = k8 < 4 ? k8 : k8 + 1;
+  const int ndx = nidx % 3 - 1, ndy = nidx / 3 - 1;
+  const unsigned laneBit = 1u << lane;
+  const int sp = sy * W + sx;
+  const float sang = __ldg(ang + sp);
+  const float2 scs = __ldg(seedcs + sp);
+  if (lane == 0) {
+    bm.clear(sx, sy);
+    ring[0] = (unsigned)sx | ((unsigned)sy << 16);
+  }
+  __syncwarp();
+  const double seedAngle = __dmul_rn((double)sang, D2R);
+  float sumdx = scs.x, sumdy = scs.y;
+  bool fresh = true;
+  int regSize = 1, flushed = 0;
+  int i = 0, nb = 1;
+  GrowBatch cur = grow_fetch(bm, ring, reg, regSize, 0, 1, e, ndx, ndy, W, H, rec);
+  while (nb > 0) {
+    const int ni = i + nb, nnb = min(4, regSize - ni);
+    GrowBatch nxt = grow_fetch(bm, ring, reg, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
+    unsigned pm = cur.mask;
+    if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cur.bw, cur.bbit));
+    float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+    while (pm) {
+      const float dot = __fmaf_rn(sumdx, cur.rec.x, sumdy * cur.rec.y);
+      const float d2 = dot * dot;
+      const bool poss = (pm & laneBit) && (exactOnly || (dot > 0.f && d2 > kLo * n2));
+      const unsigned possm = __ballot_sync(0xffffffffu, poss);
+      if (!possm) break;
+      const int l = __ffs(possm) - 1;
+      const unsigned surem = __ballot_sync(0xffffffffu, poss && !exactOnly && d2 >= kHi * n2);
+      pm &= ~((2u << l) - 1u);
+      if (!((surem >> l) & 1u)) {
+        const double ra = fresh ? seedAngle : __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
+        const int lpk = __shfl_sync(0xffffffffu, cur.cpk, l);
+        const float la = __ldg(ang + (lpk >> 16) * W + (lpk & 0xffff));
+        if (!is_aligned_dev(__dmul_rn((double)la, D2R), ra, prec)) continue;
+      }
+      const float qc = __shfl_sync(0xffffffffu, cur.rec.x, l), qs = __shfl_sync(0xffffffffu, cur.rec.y, l);
+      const int qpk = __shfl_sync(0xffffffffu, cur.cpk, l);
+      pm &= ~__ballot_sync(0xffffffffu, cur.cpk == qpk);
+      if (lane == l) {
+        grow_clear(bm, cur.bw, cur.bbit);
+        ring[regSize & (GROW_RQ - 1)] = (unsigned)qpk;
+      }
+      regSize++;
+      fresh = false;
+      sumdx = __fadd_rn(sumdx, qc);
+      sumdy = __fadd_rn(sumdy, qs);
+      n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+    }
+    __syncwarp();
+    while (regSize - flushed >= 32) {
+      __stcg(reg + flushed + lane, ring[(flushed + lane) & (GROW_RQ - 1)]);
+      flushed += 32;
+    }
+    i = ni;
+    if (nnb > 0) {
+      cur = nxt;
+      nb = nnb;
+    } else {
+      nb = min(4, regSize - i);
+      if (nb > 0) cur = grow_fetch(bm, ring, reg, regSize, i, nb, e, ndx, ndy, W, H, rec);
+    }
+  }
+  if (flushed + lane < regSize) __stcg(reg + flushed + lane, ring[(flushed + lane) & (GROW_RQ - 1)]);
+  __syncwarp();
+  regAngle = fresh ? seedAngle : __dmul_rn((double)fast_atan2_dev(sumdy, sumdx), D2R);
+  return regSize;
+}
+
+// a pixel back to "not used" (src/LSD/lsd.cpp:799,851): several lanes may hit one word
+__device__ __forceinline__ void grow_release(GrowBitmap& bm, int x, int y) {
+  const unsigned bit = 1u << (x & 31);
+  if (y - bm.top < GROW_K) atomicOr(&bm.sm[(y & (GROW_K - 1)) * bm.wpr + (x >> 5)], bit);
+  else atomicOr(bm.gm + y * bm.wpr + (x >> 5), bit);
+}
+
+__global__ void __launch_bounds__(32) k_lsd_grow_refine(const __grid_constant__ LineGeom g, LineBufs b, int refine, double logEps,
+                                                        double densityTh) {
+  extern __shared__ unsigned smem_u[];
+  const int oct = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
+  if (oct >= g.noct) return;
+  const LineOct& O = g.o[oct];
+  const int W = O.sw, H = O.sh, wpr = O.wpr;
+  unsigned* ring = smem_u;
+  GrowBitmap bm;
+  bm.sm = smem_u + GROW_RQ;
+  bm.gm = b.bitmap + (size_t)f * g.bmTotal + O.bmOff;
+  bm.wpr = wpr;
+  bm.top = 0;
+  for (int i = lane; i < min(GROW_K, H) * wpr; i += 32) bm.sm[i] = __ldcg(bm.gm + i);
+  __syncwarp();
+  const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
+  const float2* __restrict__ rec = b.cs + pbase;
+  const float* __restrict__ ang = b.ang + pbase;
+  const float2* __restrict__ seedcs = b.seed + pbase;
+  const double* __restrict__ mod = b.mod + pbase;
+  unsigned* reg = b.reg + (size_t)f * g.regTotal + O.regOff;      // one region at a time
+  float4* segs = b.segs + (size_t)f * g.segTotal + O.segOff;
+  const double prec = g.prec, p = 22.5 / 180;
+  const double LOG_NT = 5 * (log10((double)W) + log10((double)H)) / 2 + log10(11.0);
+  int nseg = 0;
+  bool overflow = false;
+
+  for (int row = 0; row < H - 1; row++) {
+    if (row > bm.top) {   // slide the shared window: rows [top, row) are exhausted
+      // rows that leave the window go back to global memory first (refine may have released pixels in them -- they are
+      // above `row`, hence exhausted: nothing to write), rows entering it are read
+      const int r0 = bm.top + GROW_K, r1 = min(row + GROW_K, H);
+      for (int r = r0; r < r1; r++)
+        for (int wv = lane; wv < wpr; wv += 32) bm.sm[(r & (GROW_K - 1)) * wpr + wv] = __ldcg(bm.gm + r * wpr + wv);
+      bm.top = row;
+      __syncwarp();
+    }
+    for (int c0 = 0; c0 < wpr; c0 += 32) {
+      while (true) {
+        const int wi = c0 + lane;
+        const int rowBase = (row & (GROW_K - 1)) * wpr;
+        const unsigned word = wi < wpr ? bm.sm[rowBase + wi] : 0u;
+        const unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
+        if (!nz) break;
+        const int wl = __ffs(nz) - 1;
+        const unsigned sw_ = __shfl_sync(0xffffffffu, word, wl);
+        const int sx = (c0 + wl) * 32 + (__ffs(sw_) - 1), sy = row;
+        double regAngle;
+        int regSize = warp_region_grow(bm, ring, reg, sx, sy, W, H, rec, ang, seedcs, prec, g.alignHi2, g.alignLo2, false, lane, regAngle);
+        if (regSize < O.minRegSize) continue;
+        LsdRectD R;
+        warp_region2rect(reg, regSize, mod, W, regAngle, prec, p, R, lane);
+        // ---- refine (:784-829)
+        bool keep = true;
+        double density = rect_density_dev(R, regSize);
+        if (density < densityTh) {
+          const double xc = (double)sx, yc = (double)sy;
+          const double angC = __dmul_rn((double)__ldg(ang + sy * W + sx), D2R);
+          double sum = 0, ssum = 0;
+          int n = 0;
+          for (int i = lane; i < regSize; i += 32) {
+            const unsigned q = __ldcg(reg + i);
+            const int qx = q & 0xffff, qy = q >> 16;
+            grow_release(bm, qx, qy);
+            const double ddx = (double)qx - xc, ddy = (double)qy - yc;
+            if (sqrt(ddx * ddx + ddy * ddy) < R.width) {
+              const double d = angle_diff_signed_dev(__dmul_rn((double)__ldg(ang + qy * W + qx), D2R), angC);
+              sum += d;
+              ssum += d * d;
+              ++n;
+            }
+          }
+          sum = warp_sum_d(sum); ssum = warp_sum_d(ssum);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+          __syncwarp();
+          const double mean = sum / (double)n;
+          const double tau = 2.0 * sqrt((ssum - 2.0 * mean * sum) / (double)n + mean * mean);
+          const bool exactOnly = !(tau + 2e-3 < 1.5);
+          const double cH = cos(fmax(tau - 2e-3, 0.0)), cL = cos(tau + 2e-3);
+          regSize = warp_region_grow(bm, ring, reg, sx, sy, W, H, rec, ang, seedcs, tau, (float)(cH * cH), (float)(cL * cL), exactOnly, lane,
+                                     regAngle);
+          if (regSize < 2) continue;
+          warp_region2rect(reg, regSize, mod, W, regAngle, prec, p, R, lane);
+          density = rect_density_dev(R, regSize);
+          if (density < densityTh) {   // reduce_region_radius (:831-869)
+            const double a1 = (R.x1 - xc) * (R.x1 - xc) + (R.y1 - yc) * (R.y1 - yc);
+            const double a2 = (R.x2 - xc) * (R.x2 - xc) + (R.y2 - yc) * (R.y2 - yc);
+            double radSq = a1 > a2 ? a1 : a2;
+            while (density < densityTh) {
+              radSq *= 0.75 * 0.75;
+              int kept = 0;     // order-preserving compaction of the list (the reference swaps the last point in: only the
+                                // order of the sums differs)
+              for (int i0 = 0; i0 < regSize; i0 += 32) {
+                const int i = i0 + lane;
+                unsigned q = 0u;
+                bool in = false;
+                if (i < regSize) {
+                  q = __ldcg(reg + i);
+                  const double ddx = (double)(q & 0xffff) - xc, ddy = (double)(q >> 16) - yc;
+                  in = !(ddx * ddx + ddy * ddy > radSq);
+                  if (!in) grow_release(bm, q & 0xffff, q >> 16);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                __syncwarp();
+                if (in) __stcg(reg + kept + __popc(m & ((1u << lane) - 1u)), q);
+                kept += __popc(m);
+                __syncwarp();
+              }
+              regSize = kept;
+              if (regSize < 2) { keep = false; break; }
+              warp_region2rect(reg, regSize, mod, W, regAngle, prec, p, R, lane);
+              density = rect_density_dev(R, regSize);
+            }
+          }
+        }
+        if (!keep) continue;
+        if (refine >= 2) {
+          const double logNfa = warp_rect_improve(R, ang, W, H, LOG_NT, logEps, lane);
+          if (logNfa <= logEps) continue;
+        }
+        if (nseg < O.segCap) {
+          if (lane < 4) {
+            double v = (lane & 2) ? ((lane & 1) ? R.y2 : R.x2) : ((lane & 1) ? R.y1 : R.x1);
+            v += 0.5;
+            if (g.lsdScale != 1.0) v /= g.lsdScale;
+            reinterpret_cast<float*>(segs + nseg)[lane] = (float)v;
+          }
+          nseg++;
+        } else {
+          overflow = true;
+        }
+      }
+    }
+  }
+  if (lane == 0) b.regCount[f * 2 + oct] = overflow ? -1 : nseg;
+}
+
+// ---------------------------------------------------------------------------------------
 // k_line_assemble: one CTA per frame.
 // ---------------------------------------------------------------------------------------
 struct RawLine {
@@ -2016,8 +2464,13 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   }
   if (fork) PLVI_CUDA_TRY(cudaEventRecord(aux.join, aux.stream));
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
-  const bool bandRun = b.brMax > 0 && n <= b.brMax;
-  if (bandRun) {
+  const bool bandRun = b.brMax > 0 && n <= b.brMax && g.refine == 0;
+  if (g.refine > 0) {
+    // lsd_refine 1 / 2: refine() couples consecutive seeds through released pixels -- one serial warp per (frame, octave)
+    k_lsd_grow_refine<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b, g.refine, 1.0, 0.6);   // log_eps, density_th: src/LineExtractor.cc:62-63
+    prof->mark("k_lsd_grow_refine", st);
+    nl += 1;
+  } else if (bandRun) {
     // small batch: many bands per frame, rounds of (compose inputs, run the bands whose input changed)
     PLVI_CUDA_TRY(cudaMemsetAsync(b.brFlags, 0, (size_t)n * 2 * BR_FLAGS * sizeof(int), st));
     const int maxWords = g.o[0].sh * g.o[0].wpr;
@@ -2050,8 +2503,10 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     k_lsd_grow<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b, 0);
     prof->mark("k_lsd_grow", st);
   }
-  k_lsd_rect<<<dim3(g.noct, n, bandRun ? 8 : 2), 256, 0, st>>>(g, b, bandRun ? 1 : 0);
-  prof->mark("k_lsd_rect", st);
+  if (g.refine == 0) {
+    k_lsd_rect<<<dim3(g.noct, n, bandRun ? 8 : 2), 256, 0, st>>>(g, b, bandRun ? 1 : 0);
+    prof->mark("k_lsd_rect", st);
+  }
   k_line_assemble<512><<<n, 512, 0, st>>>(g, b, dKl, dCounts);
   prof->mark("k_line_assemble", st);
   nl += 3;
@@ -2096,6 +2551,7 @@ int line_kernel_attrs(const LineGeom& g) {
   }
   if (commitSmem > 40 * 1024) {
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
+    PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_grow_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_lsd_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commitSmem));
 
   }

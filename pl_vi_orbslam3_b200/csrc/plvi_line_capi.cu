@@ -15,7 +15,7 @@ struct plvi_line {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool ownStream = false;
-  int nfeat = 0, nlevels = 0;
+  int nfeat = 0, nlevels = 0, refine = 0;
   float lsdScale = 0.8f, scale = 2.f;
   int maxW = 0, maxH = 0, maxBatch = 0;
   int curW = -1, curH = -1;
@@ -114,6 +114,7 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
   memset(&g, 0, sizeof(g));
   g.noct = h->nlevels;
   g.nfeat = h->nfeat;
+  g.refine = h->refine;
   g.keepCap = h->nfeat > 0 ? h->nfeat : 4096;
   g.lineScale = h->scale;
   g.lsdScale = (double)h->lsdScale;
@@ -290,13 +291,14 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
     return PLVI_ERR_INVALID;
   }
   if (extractor != 0) { set_error("extractor=1 (EDLines) is outside the hot path: only the LSD branch is implemented"); return PLVI_ERR_INVALID; }
-  if (lsd_refine != 0) { set_error("lsd_refine > 0 is not implemented (no shipped configuration uses it)"); return PLVI_ERR_INVALID; }
+  if (lsd_refine < 0 || lsd_refine > 2) { set_error("lsd_refine must be 0 (none), 1 (standard) or 2 (advanced)"); return PLVI_ERR_INVALID; }
   if (nlevels < 1 || nlevels > 2) { set_error("levels must be 1 or 2 (as in the reference's yaml contract)"); return PLVI_ERR_INVALID; }
   PLVI_CUDA_TRY(cudaSetDevice(device));
   plvi_line* h = new plvi_line();
   h->device = device;
   h->nfeat = lsd_nfeatures;
   h->lsdScale = lsd_scale;
+  h->refine = lsd_refine;
   h->nlevels = nlevels;
   h->scale = scale;
   h->maxW = max_width;

@@ -155,7 +155,7 @@ def test_lsd_speculation_stress(ext):
 
 def test_line_rejects_unsupported_configs(gpu):
     from pl_vi_orbslam3_b200.capi import PlviError
-    for args in ((200, 1, 0.8, 2, 2.0, 0), (200, 0, 0.8, 2, 2.0, 1), (200, 0, 0.8, 3, 2.0, 0)):
+    for args in ((200, 3, 0.8, 2, 2.0, 0), (200, -1, 0.8, 2, 2.0, 0), (200, 0, 0.8, 2, 2.0, 1), (200, 0, 0.8, 3, 2.0, 0)):
         with pytest.raises(PlviError):
             Lineextractor(*args)
     e = Lineextractor(200, 0, 0.8, 2, 2.0, 0)
@@ -237,6 +237,37 @@ def test_line_lsd_scales(gpu, lsd_scale, w, h):
             assert np.array_equal(got, segs.astype(np.float32))
         e.set_debug(False)
         _check_lines(kl, desc, eq, oracle.line_extract(img, lsd_nfeatures=150, lsd_scale=lsd_scale))
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("refine", [1, 2])
+@pytest.mark.parametrize("seed,w,h", [(0, 752, 480), (3, 752, 480), (5, 640, 480)])
+def test_line_lsd_refine(gpu, refine, seed, w, h):
+    """lsd_refine 1 (LSD_REFINE_STD) and 2 (LSD_REFINE_ADV), src/LSD/lsd.cpp:784-1134: raw segments against the oracle (which
+    equals the reference's own lsd.cpp, tests/test_oracle_vs_ref.py).  Region sums run as tree sums over lanes and the NFA
+    uses CUDA's libm, so the bar is the north_star one (same count, end points within 0.5 px); on these frames the
+    segments are in fact equal to the last bit, which the test also records."""
+    e = Lineextractor(200, refine, 0.8, 2, 2.0, 0, max_width=w, max_height=h, max_batch=2)
+    try:
+        img = synth.frame_euroc(seed, w, h)
+        e.set_debug(True)
+        kl, desc, eq = e(img)
+        ow, oh, sw, sh = e.octave_sizes(w, h)
+        oct1 = oracle.resize_linear(img, int(ow[1]), int(oh[1]))
+        exact = True
+        for o, im in enumerate((img, oct1)):
+            segs = oracle.lsd(im, 0.8, refine=refine)
+            got = e.read_lsd(0, o, "segments", w, h)
+            assert len(got) == len(segs) and len(segs) > 100, (o, len(got), len(segs))
+            assert np.abs(got - segs).max() <= ENDPOINT_TOL_PX
+            exact &= np.array_equal(got, segs.astype(np.float32))
+        e.set_debug(False)
+        _check_lines(kl, desc, eq, oracle.line_extract(img, lsd_refine=refine))
+        # a batch of two: frames do not interact
+        k2, d2, e2, c2 = e.extract_batch(np.stack([img, synth.frame_euroc(seed + 1, w, h)]))
+        assert c2[0] == len(kl) and np.array_equal(d2[0, :c2[0]], desc)
+        print("lsd_refine", refine, "segments bit-equal:", exact)
     finally:
         e.close()
 

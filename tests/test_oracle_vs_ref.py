@@ -138,6 +138,21 @@ def test_live_reference_lines_lsd_scales(lsd_scale):
 
 
 @needs_ref
+@pytest.mark.parametrize("refine", [1, 2])
+@pytest.mark.parametrize("seed,w,h,lsd_scale", [(1, 752, 480, 0.8), (4, 640, 480, 0.8), (6, 752, 480, 0.6), (8, 752, 480, 1.0)])
+def test_live_reference_lines_lsd_refine(refine, seed, w, h, lsd_scale):
+    """lsd_refine 1 / 2 (refine, reduce_region_radius, rect_improve, rect_nfa, nfa: src/LSD/lsd.cpp:784-1134, with the
+    vendored code's integer steps and its "(double(n) + 1)" term): the oracle's restatement against the reference's own
+    lsd.cpp, raw segments and the whole extractor."""
+    img = synth.frame_euroc(seed, w, h)
+    a, b = oracle.lsd(img, lsd_scale, refine=refine), oracle.ref_lsd(img, lsd_scale, refine)
+    assert len(a) > 200 and np.array_equal(a, b)
+    assert len(a) != len(oracle.lsd(img, lsd_scale))          # refine changes the segment set
+    r = oracle.ref_line_extract(img, lsd_refine=refine, lsd_scale=lsd_scale)
+    check_lines(oracle.line_extract(img, lsd_refine=refine, lsd_scale=lsd_scale), r["keylines"], r["descriptors"], r["line_eq"])
+
+
+@needs_ref
 def test_live_reference_lines_edge_images():
     rng = np.random.RandomState(5)
     noise = rng.randint(0, 256, (480, 752)).astype(np.uint8)

@@ -209,12 +209,14 @@ def test_cuda_graph_replay_is_used_and_identical(gpu):
         b = e.extract_batch(frames)          # plain launches
         lb = le.extract_batch(frames)
         assert e.graph_stats() == (2, 2) and le.graph_stats() == (2, 2)
+        # byte comparison: the rows beyond a frame's count are never written (stale device memory, possibly NaN patterns)
+        same = lambda u, v: np.array_equal(np.ascontiguousarray(u).view(np.uint8), np.ascontiguousarray(v).view(np.uint8))
         for x in a:
             for u, v in zip(x, b):
-                assert np.array_equal(u, v)
+                assert same(u, v)
         for x in la:
             for u, v in zip(x, lb):
-                assert np.array_equal(u, v)
+                assert same(u, v)
         # another batch size is another graph
         lib().plvi_orb_set_profile(e._h, 0)
         e.extract_batch(frames[:2])
