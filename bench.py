@@ -454,7 +454,7 @@ def main():
             done[i] = f.host_done_events()
         for evs in done[-nset * len(fes):]:
             for ev in evs or ():
-                st.wait_event(ev)
+                ev.wait_on(st)
         stop.record(st)
         stop.synchronize()
         return start, stop
@@ -464,7 +464,9 @@ def main():
     f0, f1 = e2e_run(args.steps)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
-    h2d = int(h_frames.numel()) * (2 if fes[0].line is not None else 1)   # each extractor call takes the image
+    # plvi_orb_extract_batch_async_from_line: the ORB handle reads the line handle's upload (one upload per batch); without
+    # it each extractor call takes the image
+    h2d = int(h_frames.numel()) * (2 if (fes[0].line is not None and not fes[0].share_upload) else 1)
     d2h = int(sum(v.numel() * v.element_size() for v in ios[0][0].values()))
 
     # ---- per-kernel profile of one extra step (events after every launch; not part of the timed numbers)
@@ -545,7 +547,7 @@ def main():
                        "pipelines_per_gpu": args.pipes, "pipeline_mode": args.pipe_mode},
             "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "api": "plvi_line_extract_batch_async + plvi_orb_extract_batch_async (host image in, host results out) + "
+                    "api": "plvi_line_extract_batch_async + plvi_orb_extract_batch_async[_from_line] (host image in, host results out) + "
                            "plvi_search_by_projection / plvi_line_match on the handles' device results, match tables to host"},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -108,6 +108,12 @@ int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w,
                                  plvi_keypoint* kps, uint8_t* desc, int* counts,
                                  int* mono_idx);
 int plvi_orb_sync(plvi_orb* h);
+/* The host-buffer calls copy their results back on a device-to-host stream of the handle (two device result sets: the
+ * copy of call i overlaps the kernels of call i + 1).  plvi_*_results_event: the cudaEvent_t that completes when the
+ * results of the LAST call are in the caller's buffers (NULL before the first call); plvi_*_sync waits for everything. */
+void* plvi_orb_results_event(plvi_orb* h);
+int plvi_event_synchronize(void* cuda_event);                  /* host wait */
+int plvi_stream_wait_event(void* stream, void* cuda_event);    /* device-side wait of a cudaStream_t */
 /* Device copies of the results of the last plvi_orb_extract_batch[_async] call ([n][capacity] keypoints and
  * descriptors, [n] counts / mono indices): valid until the next call on the handle, in stream order. */
 int plvi_orb_device_results(plvi_orb* h, plvi_keypoint** d_kps, uint8_t** d_desc, int** d_counts, int** d_mono_idx);
@@ -204,10 +210,20 @@ int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int 
                                   size_t frame_stride, plvi_keyline* keylines, uint8_t* desc,
                                   double* line_eq, int* counts);
 int plvi_line_sync(plvi_line* h);
+void* plvi_line_results_event(plvi_line* h);
 /* Device copies of the results of the last plvi_line_extract_batch[_async] call ([n][capacity] keylines, descriptors,
  * line equations, [n] counts): valid until the next call on the handle, in stream order on plvi_line_stream().  Lets a
  * caller that received the results in host buffers run the batched searches on the device copies. */
 int plvi_line_device_results(plvi_line* h, plvi_keyline** d_keylines, uint8_t** d_desc, double** d_line_eq, int** d_counts);
+/* The reference's Frame constructor hands the SAME image to both extractors (src/Frame.cc:558-561).  A caller that
+ * batches frames can upload them once: after plvi_line_extract_batch_async(line, imgs, ...) this call runs the ORB
+ * extraction on the device copy the line handle holds of those frames (same n / w / h), results to the host buffers as
+ * plvi_orb_extract_batch_async; the line handle keeps that staging buffer alive until the ORB kernels have read it. */
+int plvi_orb_extract_batch_async_from_line(plvi_orb* h, plvi_line* src, int lap0, int lap1, plvi_keypoint* kps, uint8_t* desc,
+                                           int* counts, int* mono_idx);
+int plvi_line_share_input(plvi_line* h, void* reader_stream, const uint8_t** d_img, int* pitch, size_t* frame_stride, int* n, int* w,
+                          int* hh);
+int plvi_line_share_done(plvi_line* h, void* reader_stream);
 /* all buffers in device memory; enqueued on the handle's stream */
 int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, int w, int h_,
                                    int stride, size_t frame_stride, plvi_keyline* d_keylines,

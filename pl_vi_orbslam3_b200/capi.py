@@ -97,6 +97,13 @@ _SIGS = {
     "plvi_line_stereo_depth_host": (ci, [vp, vp, ci, vp, ci, vp, vp, cf, vp, vp, vp, vp]),
     "plvi_matcher_set_stereo": (ci, [vp, vp, vp, ci, ci, ci, ci]),
     "plvi_pair_queries": (ci, [vp, vp, vp, ci, ci, ci, cf, cf, vp, vp, cf, vp, vp, vp, vp]),
+    "plvi_orb_extract_batch_async_from_line": (ci, [vp, vp, ci, ci, vp, vp, vp, vp]),
+    "plvi_line_share_input": (ci, [vp, vp, vp, vp, vp, vp, vp, vp]),
+    "plvi_line_share_done": (ci, [vp, vp]),
+    "plvi_orb_results_event": (vp, [vp]),
+    "plvi_line_results_event": (vp, [vp]),
+    "plvi_event_synchronize": (ci, [vp]),
+    "plvi_stream_wait_event": (ci, [vp, vp]),
     "plvi_orb_device_results": (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "plvi_line_device_results": (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "plvi_gather_i32": (ci, [vp, vp, ci, ci, ci, vp]),

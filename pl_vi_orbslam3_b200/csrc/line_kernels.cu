@@ -665,6 +665,18 @@ template <int K> struct PhantomMapT {
   unsigned* sm;      // [K][wpr] shared window, slides with the availability window
   unsigned* gm;      // [H][wpr] global copy (rows below the window)
   bool any;          // warp-uniform: some phantom pixel exists
+  // warp-uniform bounding box (grown by one pixel) of the phantom pixels marked for the CURRENT band: only a
+  // discarded speculation of the same band can have hidden a pixel from a speculative region, and most regions lie
+  // outside the box -- their pixels skip the neighbourhood test
+  int bx0, bx1, by0, by1;
+  __device__ __forceinline__ void box_reset() { bx0 = 1 << 20; bx1 = -(1 << 20); by0 = 1 << 20; by1 = -(1 << 20); }
+  __device__ __forceinline__ void box_add(int x0, int x1, int y0, int y1) {   // lane-local extents of newly marked pixels
+    bx0 = min(bx0, __reduce_min_sync(0xffffffffu, x0) - 1);
+    bx1 = max(bx1, __reduce_max_sync(0xffffffffu, x1) + 1);
+    by0 = min(by0, __reduce_min_sync(0xffffffffu, y0) - 1);
+    by1 = max(by1, __reduce_max_sync(0xffffffffu, y1) + 1);
+  }
+  __device__ __forceinline__ bool in_box(int x, int y) const { return x >= bx0 && x <= bx1 && y >= by0 && y <= by1; }
   __device__ __forceinline__ unsigned word(const GrowBitmapT<K>& bm, int y, int wi) const {
     return (y - bm.top < K) ? sm[(y & (K - 1)) * bm.wpr + wi] : __ldcg(gm + y * bm.wpr + wi);
   }
@@ -725,6 +737,7 @@ __global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_co
   ph.gm = b.phantom + (size_t)f * g.bmTotal + O.bmOff;
   ph.sm = bm.sm + GROW_K * wpr;
   ph.any = false;
+  ph.box_reset();
   for (int i = lane; i < min(GROW_K, H) * wpr; i += 32) { bm.sm[i] = __ldcg(bm.gm + i); ph.sm[i] = 0u; }
   __syncwarp();
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
@@ -760,6 +773,7 @@ __global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_co
       bandList = W * H + band * O.bandPxCap;
       blist = regAll + bandList;
       if (bcnt > 0) { cur = __ldcg(brecs); curPix = __ldcg(blist + lane); }
+      ph.box_reset();   // phantoms of the previous band cannot have influenced this band's speculation
     }
     // slide the shared windows: rows [top, row) are exhausted, rows up to row + GROW_K enter
     if (row > bm.top) {
@@ -790,15 +804,19 @@ __global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_co
         // still available become phantoms
         while (bp < bcnt && cur.x < spk) {
           bool marked = false;
+          int mx0 = 1 << 20, mx1 = -(1 << 20), my0 = 1 << 20, my1 = -(1 << 20);
           for (int i0 = 0; i0 < (int)cur.z; i0 += 32) {
             const int idx = i0 + lane;
             if (idx < (int)cur.z) {
               const unsigned q = i0 == 0 ? curPix : __ldcg(blist + cur.y + idx);
               const int qx = q & 0xffff, qy = q >> 16;
-              if (qy >= bm.top && bm.test(qx, qy)) { ph.mark(bm, qx, qy); marked = true; }
+              if (qy >= bm.top && bm.test(qx, qy)) {
+                ph.mark(bm, qx, qy); marked = true;
+                mx0 = min(mx0, qx); mx1 = max(mx1, qx); my0 = min(my0, qy); my1 = max(my1, qy);
+              }
             }
           }
-          if (__any_sync(0xffffffffu, marked)) ph.any = true;
+          if (__any_sync(0xffffffffu, marked)) { ph.any = true; ph.box_add(mx0, mx1, my0, my1); }
           runStart += (int)cur.z;
           bp++;
           if (bp < bcnt) { cur = __ldcg(brecs + bp); curPix = __ldcg(blist + runStart + lane); }
@@ -818,7 +836,7 @@ __global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_co
             if (idx < (int)sr.z) {
               const unsigned q = i0 == 0 ? srPix : __ldcg(blist + sr.y + idx);
               const int qx = q & 0xffff, qy = q >> 16;
-              good = bm.test(qx, qy) && !(ph.any && ph.near(bm, qx, qy, H));
+              good = bm.test(qx, qy) && !(ph.in_box(qx, qy) && ph.near(bm, qx, qy, H));
             }
             ok = __all_sync(0xffffffffu, good);
           }
@@ -933,15 +951,19 @@ __global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_co
         __syncwarp();
         if (haveSpec) {   // the discarded speculation of this seed: what it had taken beyond the true region
           bool marked = false;
+          int mx0 = 1 << 20, mx1 = -(1 << 20), my0 = 1 << 20, my1 = -(1 << 20);
           for (int i0 = 0; i0 < (int)sr.z; i0 += 32) {
             const int idx = i0 + lane;
             if (idx < (int)sr.z) {
               const unsigned q = i0 == 0 ? srPix : __ldcg(blist + sr.y + idx);
               const int qx = q & 0xffff, qy = q >> 16;
-              if (qy >= bm.top && bm.test(qx, qy)) { ph.mark(bm, qx, qy); marked = true; }
+              if (qy >= bm.top && bm.test(qx, qy)) {
+                ph.mark(bm, qx, qy); marked = true;
+                mx0 = min(mx0, qx); mx1 = max(mx1, qx); my0 = min(my0, qy); my1 = max(my1, qy);
+              }
             }
           }
-          if (__any_sync(0xffffffffu, marked)) ph.any = true;
+          if (__any_sync(0xffffffffu, marked)) { ph.any = true; ph.box_add(mx0, mx1, my0, my1); }
           __syncwarp();
         }
       }

@@ -226,8 +226,11 @@ struct AsyncInput {
   u8* buf[2] = {nullptr, nullptr};
   int sel = 0;
   cudaStream_t copy = nullptr;
-  cudaEvent_t h2d[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
-  bool doneValid[2] = {false, false};
+  cudaEvent_t h2d[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, shared[2] = {nullptr, nullptr};
+  bool doneValid[2] = {false, false}, sharedValid[2] = {false, false};
+  // the last upload (what another handle may read instead of uploading the same frames again, see share_last)
+  int lastSel = -1, lastPitch = 0;
+  size_t lastFs = 0;
   // the buffer to upload into (on `copy`), after the call that last read it has finished
   int begin(u8* first, size_t bytes, u8** dst) {
     if (!copy) {
@@ -235,11 +238,13 @@ struct AsyncInput {
       for (int k = 0; k < 2; k++) {
         PLVI_CUDA_TRY(cudaEventCreateWithFlags(&h2d[k], cudaEventDisableTiming));
         PLVI_CUDA_TRY(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+        PLVI_CUDA_TRY(cudaEventCreateWithFlags(&shared[k], cudaEventDisableTiming));
       }
       buf[0] = first;
     }
     if (sel == 1 && !buf[1]) PLVI_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&buf[1]), bytes + 256));
     if (doneValid[sel]) PLVI_CUDA_TRY(cudaStreamWaitEvent(copy, done[sel], 0));
+    if (sharedValid[sel]) PLVI_CUDA_TRY(cudaStreamWaitEvent(copy, shared[sel], 0));   // a second reader of that buffer
     *dst = buf[sel];
     return PLVI_OK;
   }
@@ -251,7 +256,21 @@ struct AsyncInput {
   int finish(cudaStream_t compute) {     // everything that reads the buffer has been enqueued
     PLVI_CUDA_TRY(cudaEventRecord(done[sel], compute));
     doneValid[sel] = true;
+    lastSel = sel;
     sel ^= 1;
+    return PLVI_OK;
+  }
+  // Another handle reads the frames of the last upload on its own stream `reader`: it waits for the upload, and the
+  // buffer is not overwritten before share_done() has been recorded on that stream.
+  int share_last(cudaStream_t reader, const u8** img, int* pitch, size_t* fs) {
+    if (lastSel < 0) return PLVI_ERR_INVALID;
+    PLVI_CUDA_TRY(cudaStreamWaitEvent(reader, h2d[lastSel], 0));
+    *img = buf[lastSel]; *pitch = lastPitch; *fs = lastFs;
+    return PLVI_OK;
+  }
+  int share_done(cudaStream_t reader) {
+    PLVI_CUDA_TRY(cudaEventRecord(shared[lastSel], reader));
+    sharedValid[lastSel] = true;
     return PLVI_OK;
   }
   // Uploads n host frames (w x hh, row stride `stride`, frame stride `frame_stride`) into dst on the copy stream and
@@ -264,6 +283,7 @@ struct AsyncInput {
       const size_t fbytes = (size_t)stride * hh;
       *pitch = stride;
       *fs = fbytes;
+      lastPitch = stride; lastFs = fbytes;
       if (frame_stride == fbytes) {
         PLVI_CUDA_TRY(cudaMemcpyAsync(dst, imgs, fbytes * n, cudaMemcpyHostToDevice, copy));
       } else {
@@ -274,6 +294,7 @@ struct AsyncInput {
     }
     *pitch = devPitch;
     *fs = (size_t)devPitch * devRows;
+    lastPitch = devPitch; lastFs = *fs;
     for (int i = 0; i < n; i++)
       PLVI_CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)i * *fs, devPitch, imgs + (size_t)i * frame_stride, stride, w, hh,
                                       cudaMemcpyHostToDevice, copy));
@@ -284,10 +305,55 @@ struct AsyncInput {
     for (int k = 0; k < 2; k++) {
       if (h2d[k]) cudaEventDestroy(h2d[k]);
       if (done[k]) cudaEventDestroy(done[k]);
-      h2d[k] = done[k] = nullptr;
+      if (shared[k]) cudaEventDestroy(shared[k]);
+      h2d[k] = done[k] = shared[k] = nullptr;
     }
     cudaFree(buf[1]);
     buf[1] = nullptr;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Result copies of the host-buffer ("async") entry points: two device result sets and a device-to-host stream, so that
+// the copy of call i's results to the caller's buffers overlaps the kernels of call i + 1 (which write the other set)
+// instead of sitting between them on the compute stream.  Call i + 2 reuses set i after its copy has finished.
+// ---------------------------------------------------------------------------------------------------
+struct AsyncOutput {
+  cudaStream_t d2h = nullptr;
+  cudaEvent_t ready = nullptr, done[2] = {nullptr, nullptr};
+  bool valid[2] = {false, false};
+  int sel = 0, last = 0;
+  int begin(cudaStream_t compute) {      // the result set this call writes is free again
+    if (!d2h) {
+      PLVI_CUDA_TRY(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+      PLVI_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+      for (int k = 0; k < 2; k++) PLVI_CUDA_TRY(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    }
+    if (valid[sel]) PLVI_CUDA_TRY(cudaStreamWaitEvent(compute, done[sel], 0));
+    return PLVI_OK;
+  }
+  int start_copy(cudaStream_t compute) {   // the copies (issued on d2h by the caller) wait for the kernels
+    PLVI_CUDA_TRY(cudaEventRecord(ready, compute));
+    PLVI_CUDA_TRY(cudaStreamWaitEvent(d2h, ready, 0));
+    return PLVI_OK;
+  }
+  int end_copy() {
+    PLVI_CUDA_TRY(cudaEventRecord(done[sel], d2h));
+    valid[sel] = true;
+    last = sel;
+    sel ^= 1;
+    return PLVI_OK;
+  }
+  cudaEvent_t last_done() const { return valid[last] ? done[last] : nullptr; }
+  int sync() {
+    if (d2h) PLVI_CUDA_TRY(cudaStreamSynchronize(d2h));
+    return PLVI_OK;
+  }
+  void destroy() {
+    if (d2h) { cudaStreamSynchronize(d2h); cudaStreamDestroy(d2h); d2h = nullptr; }
+    if (ready) cudaEventDestroy(ready);
+    for (int k = 0; k < 2; k++) if (done[k]) cudaEventDestroy(done[k]);
+    ready = done[0] = done[1] = nullptr;
   }
 };
 

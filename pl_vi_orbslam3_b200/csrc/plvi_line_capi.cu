@@ -29,10 +29,15 @@ struct plvi_line {
   double* dLbdL = nullptr;
   double2* dTrig = nullptr;
   size_t tabCap = 0, rsCap = 0;
-  plvi_keyline* dKl = nullptr;
+  plvi_keyline* dKl = nullptr;      // result set 0 (device copies of the host-buffer entry points' results)
   uint8_t* dDesc = nullptr;
   double* dEq = nullptr;
   int* dCounts = nullptr;
+  plvi_keyline* dKlB = nullptr;     // result set 1, allocated by the second host-buffer call
+  uint8_t* dDescB = nullptr;
+  double* dEqB = nullptr;
+  int* dCountsB = nullptr;
+  AsyncOutput aout;
   int lastN = 0, lastLaunches = 0;
   StageProf prof;
   GraphCache graphs;
@@ -426,7 +431,9 @@ void plvi_line_destroy(plvi_line* h) {
   cudaFree(h->buf.tmpResp); cudaFree(h->buf.tmpCls); cudaFree(h->buf.lbdImg0); cudaFree(h->buf.lbdImg1);
   cudaFree(h->buf.grad); cudaFree(h->buf.lbdRows); cudaFree(h->buf.scaledDbg);
   cudaFree(h->dTabs); cudaFree(h->dRsTab); cudaFree(h->dLbdG); cudaFree(h->dLbdL); cudaFree(h->dTrig);
+  h->aout.destroy();
   cudaFree(h->dKl); cudaFree(h->dDesc); cudaFree(h->dEq); cudaFree(h->dCounts);
+  cudaFree(h->dKlB); cudaFree(h->dDescB); cudaFree(h->dEqB); cudaFree(h->dCountsB);
   if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -529,31 +536,66 @@ int plvi_line_extract_batch_async(plvi_line* h, const uint8_t* imgs, int n, int 
   fill_ptrs(h, dIn, inPitch, inFs, p);
   h->lastPtrs = p;
   h->lastN = n;
-  rc = run_line_pipeline(h, p, n, h->dKl, h->dDesc, h->dEq, h->dCounts);
+  // two device result sets: the copy of this call's results (device-to-host stream) overlaps the next call's kernels
+  if ((rc = h->aout.begin(h->stream))) return rc;
+  if (h->aout.sel == 1 && !h->dKlB) {
+    const size_t B = h->maxBatch, kc = h->capGeom.keepCap;
+    PLVI_CUDA_TRY(cudaMalloc(&h->dKlB, B * kc * sizeof(plvi_keyline)));
+    PLVI_CUDA_TRY(cudaMalloc(&h->dDescB, B * kc * 32));
+    PLVI_CUDA_TRY(cudaMalloc(&h->dEqB, B * kc * 3 * sizeof(double)));
+    PLVI_CUDA_TRY(cudaMalloc(&h->dCountsB, B * sizeof(int)));
+  }
+  const bool sb = h->aout.sel == 1;
+  plvi_keyline* dk = sb ? h->dKlB : h->dKl;
+  uint8_t* dd = sb ? h->dDescB : h->dDesc;
+  double* de = sb ? h->dEqB : h->dEq;
+  int* dc = sb ? h->dCountsB : h->dCounts;
+  rc = run_line_pipeline(h, p, n, dk, dd, de, dc);
   if (rc) return rc;
   if ((rc = h->ain.finish(h->stream))) return rc;
+  if ((rc = h->aout.start_copy(h->stream))) return rc;
   const size_t rows = (size_t)n * h->geom.keepCap;
-  PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
-  PLVI_CUDA_TRY(cudaMemcpyAsync(kl, h->dKl, rows * sizeof(plvi_keyline), cudaMemcpyDeviceToHost, h->stream));
-  PLVI_CUDA_TRY(cudaMemcpyAsync(desc, h->dDesc, rows * 32, cudaMemcpyDeviceToHost, h->stream));
-  PLVI_CUDA_TRY(cudaMemcpyAsync(line_eq, h->dEq, rows * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  cudaStream_t s = h->aout.d2h;
+  PLVI_CUDA_TRY(cudaMemcpyAsync(counts, dc, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(kl, dk, rows * sizeof(plvi_keyline), cudaMemcpyDeviceToHost, s));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(desc, dd, rows * 32, cudaMemcpyDeviceToHost, s));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(line_eq, de, rows * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  return h->aout.end_copy();
+}
+
+// the frames of the last plvi_line_extract_batch_async call, for a second reader (plvi_orb_extract_batch_async_from_line)
+int plvi_line_share_input(plvi_line* h, void* reader_stream, const uint8_t** d_img, int* pitch, size_t* frame_stride, int* n, int* w,
+                          int* hh) {
+  if (!h || !d_img || !pitch || !frame_stride) return PLVI_ERR_INVALID;
+  PLVI_CUDA_TRY(cudaSetDevice(h->device));
+  if (h->ain.share_last((cudaStream_t)reader_stream, d_img, pitch, frame_stride)) { set_error("no host-buffer call has been made on the line handle"); return PLVI_ERR_INVALID; }
+  if (n) *n = h->lastN;
+  if (w) *w = h->curW;
+  if (hh) *hh = h->curH;
   return PLVI_OK;
+}
+int plvi_line_share_done(plvi_line* h, void* reader_stream) {
+  if (!h) return PLVI_ERR_INVALID;
+  return h->ain.share_done((cudaStream_t)reader_stream);
 }
 
 int plvi_line_device_results(plvi_line* h, plvi_keyline** d_keylines, uint8_t** d_desc, double** d_line_eq, int** d_counts) {
   if (!h) return PLVI_ERR_INVALID;
-  if (d_keylines) *d_keylines = h->dKl;
-  if (d_desc) *d_desc = h->dDesc;
-  if (d_line_eq) *d_line_eq = h->dEq;
-  if (d_counts) *d_counts = h->dCounts;
+  const bool sb = h->aout.last == 1;
+  if (d_keylines) *d_keylines = sb ? h->dKlB : h->dKl;
+  if (d_desc) *d_desc = sb ? h->dDescB : h->dDesc;
+  if (d_line_eq) *d_line_eq = sb ? h->dEqB : h->dEq;
+  if (d_counts) *d_counts = sb ? h->dCountsB : h->dCounts;
   return PLVI_OK;
 }
 
 int plvi_line_sync(plvi_line* h) {
   if (!h) return PLVI_ERR_INVALID;
   PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  return PLVI_OK;
+  return h->aout.sync();
 }
+
+void* plvi_line_results_event(plvi_line* h) { return h ? (void*)h->aout.last_done() : nullptr; }
 
 int plvi_line_set_profile(plvi_line* h, int on) {
   if (!h) return PLVI_ERR_INVALID;

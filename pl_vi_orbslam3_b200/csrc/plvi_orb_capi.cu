@@ -42,10 +42,15 @@ struct plvi_orb {
   FastTile* dFastTiles = nullptr;
   BlurTile* dBlurTiles = nullptr;
   size_t rsCap = 0, fastTileCap = 0, blurTileCap = 0;
-  plvi_keypoint* dKps = nullptr;
+  plvi_keypoint* dKps = nullptr;     // result set 0 (device copies of the host-buffer entry points' results)
   uint8_t* dDesc = nullptr;
   int* dCounts = nullptr;
   int* dMono = nullptr;
+  plvi_keypoint* dKpsB = nullptr;    // result set 1, allocated by the second host-buffer call
+  uint8_t* dDescB = nullptr;
+  int* dCountsB = nullptr;
+  int* dMonoB = nullptr;
+  AsyncOutput aout;
   int cap = 0;
   int lastN = 0, lastLaunches = 0;
   StageProf prof;
@@ -344,10 +349,15 @@ void plvi_orb_destroy(plvi_orb* h) {
   cudaFree(h->scr.lvlKp);
   cudaFree(h->scr.lvlCount);
   cudaFree(h->scr.slot);
+  h->aout.destroy();
   cudaFree(h->dKps);
   cudaFree(h->dDesc);
   cudaFree(h->dCounts);
   cudaFree(h->dMono);
+  cudaFree(h->dKpsB);
+  cudaFree(h->dDescB);
+  cudaFree(h->dCountsB);
+  cudaFree(h->dMonoB);
   if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -504,6 +514,35 @@ int plvi_orb_extract_batch_device(plvi_orb* h, const uint8_t* d_imgs, int n, int
   return run_orb_pipeline(h, p, n, lap0, lap1, d_kps, d_desc, d_counts, d_mono);
 }
 
+// result set of the current host-buffer call (second set allocated on first use) + its copy to the caller's buffers on
+// the device-to-host stream
+static int orb_result_set(plvi_orb* h, plvi_keypoint** k, uint8_t** d, int** c, int** m) {
+  int rc = h->aout.begin(h->stream);
+  if (rc) return rc;
+  if (h->aout.sel == 1 && !h->dKpsB) {
+    const size_t B = h->maxBatch, kt = h->cap;
+    PLVI_CUDA_TRY(cudaMalloc(&h->dKpsB, B * kt * sizeof(plvi_keypoint)));
+    PLVI_CUDA_TRY(cudaMalloc(&h->dDescB, B * kt * 32));
+    PLVI_CUDA_TRY(cudaMalloc(&h->dCountsB, B * sizeof(int)));
+    PLVI_CUDA_TRY(cudaMalloc(&h->dMonoB, B * sizeof(int)));
+  }
+  const bool b = h->aout.sel == 1;
+  *k = b ? h->dKpsB : h->dKps; *d = b ? h->dDescB : h->dDesc; *c = b ? h->dCountsB : h->dCounts; *m = b ? h->dMonoB : h->dMono;
+  return PLVI_OK;
+}
+static int orb_copy_back(plvi_orb* h, int n, const plvi_keypoint* dk, const uint8_t* dd, const int* dc, const int* dm, plvi_keypoint* kps,
+                         uint8_t* desc, int* counts, int* mono_idx) {
+  int rc = h->aout.start_copy(h->stream);
+  if (rc) return rc;
+  const size_t rows = (size_t)n * h->cap;
+  cudaStream_t s = h->aout.d2h;
+  PLVI_CUDA_TRY(cudaMemcpyAsync(counts, dc, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(mono_idx, dm, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(kps, dk, rows * sizeof(plvi_keypoint), cudaMemcpyDeviceToHost, s));
+  PLVI_CUDA_TRY(cudaMemcpyAsync(desc, dd, rows * 32, cudaMemcpyDeviceToHost, s));
+  return h->aout.end_copy();
+}
+
 int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w, int hh, int stride,
                                  size_t frame_stride, int lap0, int lap1, plvi_keypoint* kps,
                                  uint8_t* desc, int* counts, int* mono_idx) {
@@ -523,29 +562,67 @@ int plvi_orb_extract_batch_async(plvi_orb* h, const uint8_t* imgs, int n, int w,
   fill_ptrs(h, dIn, inPitch, inFs, p);
   h->lastPtrs = p;
   h->lastN = n;
-  rc = run_orb_pipeline(h, p, n, lap0, lap1, h->dKps, h->dDesc, h->dCounts, h->dMono);
+  plvi_keypoint* dk; uint8_t* dd; int* dc; int* dm;
+  if ((rc = orb_result_set(h, &dk, &dd, &dc, &dm))) return rc;
+  rc = run_orb_pipeline(h, p, n, lap0, lap1, dk, dd, dc, dm);
   if (rc) return rc;
   if ((rc = h->ain.finish(h->stream))) return rc;
-  const size_t rows = (size_t)n * h->cap;
-  PLVI_CUDA_TRY(cudaMemcpyAsync(counts, h->dCounts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
-  PLVI_CUDA_TRY(cudaMemcpyAsync(mono_idx, h->dMono, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
-  PLVI_CUDA_TRY(cudaMemcpyAsync(kps, h->dKps, rows * sizeof(plvi_keypoint), cudaMemcpyDeviceToHost, h->stream));
-  PLVI_CUDA_TRY(cudaMemcpyAsync(desc, h->dDesc, rows * 32, cudaMemcpyDeviceToHost, h->stream));
-  return PLVI_OK;
+  return orb_copy_back(h, n, dk, dd, dc, dm, kps, desc, counts, mono_idx);
+}
+
+int plvi_line_share_input(plvi_line* h, void* reader_stream, const uint8_t** d_img, int* pitch, size_t* frame_stride, int* n, int* w,
+                          int* hh);
+int plvi_line_share_done(plvi_line* h, void* reader_stream);
+
+int plvi_orb_extract_batch_async_from_line(plvi_orb* h, plvi_line* src, int lap0, int lap1, plvi_keypoint* kps, uint8_t* desc,
+                                           int* counts, int* mono_idx) {
+  if (!h || !src || !kps || !desc || !counts || !mono_idx) { set_error("null argument"); return PLVI_ERR_INVALID; }
+  PLVI_CUDA_TRY(cudaSetDevice(h->device));
+  const uint8_t* dIn = nullptr;
+  int pitch = 0, n = 0, w = 0, hh = 0;
+  size_t fs = 0;
+  int rc = plvi_line_share_input(src, h->stream, &dIn, &pitch, &fs, &n, &w, &hh);
+  if (rc) return rc;
+  if ((rc = check_batch(h, dIn, n, w, hh, pitch))) return rc;
+  if ((rc = ensure_geom(h, w, hh))) return rc;
+  OrbPtrs p;
+  fill_ptrs(h, dIn, pitch, fs, p);
+  h->lastPtrs = p;
+  h->lastN = n;
+  plvi_keypoint* dk; uint8_t* dd; int* dc; int* dm;
+  if ((rc = orb_result_set(h, &dk, &dd, &dc, &dm))) return rc;
+  rc = run_orb_pipeline(h, p, n, lap0, lap1, dk, dd, dc, dm);
+  if (rc) return rc;
+  if ((rc = plvi_line_share_done(src, h->stream))) return rc;
+  return orb_copy_back(h, n, dk, dd, dc, dm, kps, desc, counts, mono_idx);
 }
 
 int plvi_orb_device_results(plvi_orb* h, plvi_keypoint** d_kps, uint8_t** d_desc, int** d_counts, int** d_mono_idx) {
   if (!h) return PLVI_ERR_INVALID;
-  if (d_kps) *d_kps = h->dKps;
-  if (d_desc) *d_desc = h->dDesc;
-  if (d_counts) *d_counts = h->dCounts;
-  if (d_mono_idx) *d_mono_idx = h->dMono;
+  const bool b = h->aout.last == 1;
+  if (d_kps) *d_kps = b ? h->dKpsB : h->dKps;
+  if (d_desc) *d_desc = b ? h->dDescB : h->dDesc;
+  if (d_counts) *d_counts = b ? h->dCountsB : h->dCounts;
+  if (d_mono_idx) *d_mono_idx = b ? h->dMonoB : h->dMono;
   return PLVI_OK;
 }
 
 int plvi_orb_sync(plvi_orb* h) {
   if (!h) return PLVI_ERR_INVALID;
   PLVI_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return h->aout.sync();
+}
+
+void* plvi_orb_results_event(plvi_orb* h) { return h ? (void*)h->aout.last_done() : nullptr; }
+
+int plvi_event_synchronize(void* cuda_event) {
+  if (!cuda_event) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaEventSynchronize((cudaEvent_t)cuda_event));
+  return PLVI_OK;
+}
+int plvi_stream_wait_event(void* stream, void* cuda_event) {
+  if (!cuda_event) return PLVI_OK;
+  PLVI_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)cuda_event, 0));
   return PLVI_OK;
 }
 

@@ -23,6 +23,31 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class _Event:
+    """A torch event or a raw cudaEvent_t of a handle behind one interface."""
+
+    def __init__(self, torch_event=None, raw=None):
+        self.ev, self.raw = torch_event, raw
+
+    def synchronize(self):
+        if self.ev is not None:
+            self.ev.synchronize()
+        elif self.raw:
+            check(lib().plvi_event_synchronize(ptr(self.raw)))
+
+    def query(self):
+        if self.ev is not None:
+            return self.ev.query()
+        self.synchronize()
+        return True
+
+    def wait_on(self, stream):
+        if self.ev is not None:
+            stream.wait_event(self.ev)
+        elif self.raw:
+            check(lib().plvi_stream_wait_event(ptr(stream.cuda_stream), ptr(self.raw)))
+
+
 class FrontEnd:
     def __init__(self, batch, w=752, h=480, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
                  lsd_nfeatures=200, lsd_scale=0.8, line_levels=2, line_scale=2.0, device=0, stream=None,
@@ -49,6 +74,7 @@ class FrontEnd:
         # device-to-host copy of step i can still run while step i+1 computes
         self.out_sets = max(1, int(out_sets))
         self.skew = os.environ.get("PLVI_SKEW", "1") != "0"   # ORB kernels start when the line pipeline reaches region growing
+        self.share_upload = os.environ.get("PLVI_SHARE_UPLOAD", "1") != "0"   # step_host: the frames are uploaded once for both extractors
         self._set = 0
         self.orb_outs = [self.orb.alloc_device_outputs(batch, self.device) for _ in range(self.out_sets)]
         self.orb_out = self.orb_outs[0]
@@ -262,8 +288,13 @@ class FrontEnd:
                 self._ev_join.record(self.line_stream)
                 if self.skew:   # as in step(): the ORB kernels start when the line pipeline has reached region growing
                     check(lib().plvi_orb_wait_event(self.orb._h, lib().plvi_line_stage_event(self.line._h)))
-        check(lib().plvi_orb_extract_batch_async(self.orb._h, ptr(h_frames), n, w, h, h_frames.stride(1), h_frames.stride(0), 0, 0,
-                                                 ptr(io["kps"]), ptr(io["desc"]), ptr(io["counts"]), ptr(io["mono"])))
+        if self.line is not None and self.share_upload:
+            # one upload per batch: the ORB handle reads the device copy the line handle just made
+            check(lib().plvi_orb_extract_batch_async_from_line(self.orb._h, self.line._h, 0, 0, ptr(io["kps"]), ptr(io["desc"]),
+                                                               ptr(io["counts"]), ptr(io["mono"])))
+        else:
+            check(lib().plvi_orb_extract_batch_async(self.orb._h, ptr(h_frames), n, w, h, h_frames.stride(1), h_frames.stride(0), 0, 0,
+                                                     ptr(io["kps"]), ptr(io["desc"]), ptr(io["counts"]), ptr(io["mono"])))
         nl += self.orb.last_launches
         if self.om is not None and n > 1:
             import ctypes as C
@@ -299,13 +330,14 @@ class FrontEnd:
             self.line_stream.wait_event(ev)
 
     def host_done_events(self):
-        """New events that complete when everything the last step_host() issued -- kernels and the result copies to the
-        host -- has finished."""
-        evs = [self.torch.cuda.Event()]
-        evs[0].record(self.stream)
-        if self.line is not None and self.line_stream is not self.stream:
-            evs.append(self.torch.cuda.Event())
-            evs[1].record(self.line_stream)
+        """Events (objects with .synchronize(), .query() and .wait_on(stream)) that complete when everything the last
+        step_host() issued -- kernels, the handles' result copies on their device-to-host streams and the match tables --
+        has reached the host buffers."""
+        evs = [_Event(torch_event=self.torch.cuda.Event())]
+        evs[0].ev.record(self.stream)
+        evs.append(_Event(raw=lib().plvi_orb_results_event(self.orb._h)))
+        if self.line is not None:
+            evs.append(_Event(raw=lib().plvi_line_results_event(self.line._h)))
         return evs
 
     def outputs(self):

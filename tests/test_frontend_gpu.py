@@ -60,8 +60,12 @@ def _check_pairs_against_oracle(out, A, B):
             assert rnl == nl and np.array_equal(rlm, lm12)
 
 
-def test_c3_pairs_device_path_and_host_buffer_path(gpu):
+@pytest.mark.parametrize("share", ["1", "0"])
+def test_c3_pairs_device_path_and_host_buffer_path(gpu, share, monkeypatch):
+    """share = 1: the frames are uploaded once (plvi_orb_extract_batch_async_from_line reads the line handle's copy);
+    0: each extractor call uploads them."""
     import torch
+    monkeypatch.setenv("PLVI_SHARE_UPLOAD", share)
     B = 6
     frames = synth.pair_batch(B, W, H, base_seed=40, workers=1, cache=False)
     A = synth.warp_affine(W, H).astype(np.float32).reshape(6)
