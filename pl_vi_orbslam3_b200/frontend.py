@@ -162,11 +162,16 @@ class FrontEnd:
             check(lib().plvi_orb_wait_event(self.orb._h, lib().plvi_line_stage_event(self.line._h)))
         kps, desc, counts, mono = self.orb.extract_batch_device(d_frames, out=self.orb_out)
         nl += self.orb.last_launches
+        # the point searches only need the ORB results: they run while the line pipeline (the longer one) is still busy;
+        # the line matches follow the join
+        join = None
         if forked and not serialize:
             self._ev_join.record(self.line_stream)
-            self.stream.wait_event(self._ev_join)
+            join = self._ev_join
         nl += self._match(kps, desc, counts, ldesc if self.line is not None else None,
-                          lcounts if self.line is not None else None, n)
+                          lcounts if self.line is not None else None, n, join)
+        if join is not None and (self.lm is None or n < 2):
+            self.stream.wait_event(join)
         self.launches = nl
         return nl
 
@@ -184,9 +189,9 @@ class FrontEnd:
             if self.lm is not None:
                 self.line_m12, self.line_nm = self.lmatch_sets[self._set]
 
-    def _match(self, kps, desc, counts, ldesc, lcounts, n):
+    def _match(self, kps, desc, counts, ldesc, lcounts, n, join=None):
         """The searches of one step on device-resident extraction results (tensors or raw device addresses), enqueued on
-        self.stream.  Returns the number of kernel launches."""
+        self.stream; `join`: event of the line pipeline the line matches wait for.  Returns the number of kernel launches."""
         nl = 0
         if self.om is None or n < 2:
             return 0
@@ -214,6 +219,8 @@ class FrontEnd:
             if self._profiling:
                 self._mev[1].record(self.stream)
             if self.lm is not None:
+                if join is not None:
+                    self.stream.wait_event(join)
                 lc = self.line.capacity
                 sp = self.stream.cuda_stream
                 check(lib().plvi_gather_i32(ptr(sp), ptr(lcounts), P, 0, 2, ptr(self.lq)))
@@ -236,6 +243,8 @@ class FrontEnd:
         if self._profiling:
             self._mev[1].record(self.stream)
         if self.lm is not None:
+            if join is not None:
+                self.stream.wait_event(join)
             lc = self.line.capacity
             check(lib().plvi_line_match(self.lm._h, P, ptr(ldesc), ptr(lcounts), lc, ptr(a(ldesc) + lc * 32), ptr(a(lcounts) + 4),
                                         lc, 0.9, 1, ptr(self.line_m12), ptr(self.line_nm), 1))
@@ -305,9 +314,10 @@ class FrontEnd:
                 lk, ldp, le, lcp = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
                 check(lib().plvi_line_device_results(self.line._h, C.byref(lk), C.byref(ldp), C.byref(le), C.byref(lcp)))
                 ld, lcn = ldp.value, lcp.value
-                if self.line_stream is not self.stream:
-                    self.stream.wait_event(self._ev_join)
-            nl += self._match(dk.value, dd.value, dc.value, ld, lcn, n)
+            join = self._ev_join if (self.line is not None and self.line_stream is not self.stream) else None
+            nl += self._match(dk.value, dd.value, dc.value, ld, lcn, n, join)
+            if join is not None and self.lm is None:
+                self.stream.wait_event(join)
             with self.torch.cuda.stream(self.stream):
                 for k, v in self.match_outputs().items():
                     io[k].copy_(v, non_blocking=True)

@@ -229,3 +229,45 @@ def test_line_fuse_search_oracle_uses_the_shift25_distance_and_first_minimum():
         else:
             assert bi[i] == -1
     assert found > 50
+
+
+# ---- round-2 additions of the line path (tests/golden/lsd_extra.npz, tools/gen_golden_lsd.py) ---------------------------
+X = np.load(GOLD / "lsd_extra.npz")
+
+
+@pytest.mark.parametrize("scale", [0.5, 0.6, 0.9])
+def test_lsd_other_scales_match_opencv(scale):
+    """Gaussian kernel of flsd at other lsd_scale settings (OpenCV's soft-float exp, bit-exact) and cv::resize(f64) incl.
+    the 2x2 area path at exactly 0.5 (CRC of the whole image)."""
+    import math
+    S = float(np.float32(scale))
+    sigma = 0.6 / S
+    n = 1 + 2 * int(math.ceil(sigma * math.sqrt(2 * 3.0 * math.log(10.0))))
+    k = oracle.gaussian_kernel_f64(n, sigma)
+    assert np.array_equal(k, X[f"cv2_kernel_{scale}"])
+    img = synth.frame_euroc(9).astype(np.float64)
+    mine = oracle.gaussian_blur_f64(img, k)
+    h, w = (int(v) for v in X[f"cv2_resize_shape_{scale}"])
+    assert crc(oracle.resize_linear_f64(mine, w, h, S, S)) == X[f"cv2_resize_crc_{scale}"]
+
+
+@pytest.mark.parametrize("seed,scale,refine", [(0, 0.8, 1), (0, 0.8, 2), (3, 0.6, 1), (3, 1.0, 2), (5, 1.0, 0), (5, 0.5, 0)])
+def test_lsd_refine_and_scales_equal_committed_reference_outputs(seed, scale, refine):
+    """Raw segments of the reference's own lsd.cpp (compiled unmodified, oracle/_ref) for lsd_refine 1 / 2 and lsd_scale
+    1.0 / 0.6 / 0.5, committed: the oracle's restatement equals them to the last bit."""
+    ref = X[f"ref_lsd_{seed}_{scale}_{refine}"]
+    got = oracle.lsd(synth.frame_euroc(seed), scale, refine=refine)
+    assert len(ref) > 100 and np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 9])
+def test_stereo_line_depth_equals_committed_reference_outputs(seed):
+    """Frame::ComputeStereoMatches_Lines of the reference's own Frame.cc (committed): disparities, depths, mvle_l."""
+    import test_stereo_lines as SL
+    s1, d1, s2, d2 = SL._depth_case(seed)
+    n, m12 = oracle.line_match_grid(s1, d1, s2, d2, SL.INV_W, SL.INV_H)
+    k, disp, dep, le = oracle.line_stereo_depth(s1, s2, m12, 47.9)
+    out = X[f"ref_stereo_lines_{seed}_out"]
+    assert k == int(X[f"ref_stereo_lines_{seed}_k"])
+    assert np.array_equal(out[:, :2].view(np.uint32), disp.view(np.uint32)) and np.array_equal(out[:, 2:].view(np.uint32), dep.view(np.uint32))
+    assert np.array_equal(X[f"ref_stereo_lines_{seed}_le"].view(np.uint64), le.view(np.uint64))

@@ -97,3 +97,26 @@ def test_cuda_bow_equals_reference_dbow2(gpu, tmp_path):
     finally:
         e.close()
         v.close()
+
+
+@pytest.mark.parametrize("seed,scale,refine", [(0, 0.8, 1), (0, 0.8, 2), (3, 0.6, 1), (3, 1.0, 2), (5, 1.0, 0), (5, 0.5, 0)])
+def test_cuda_lsd_equals_committed_reference_refine_and_scale_outputs(gpu, seed, scale, refine):
+    """Raw LSD segments of the CUDA path against the reference's own lsd.cpp outputs for lsd_refine 1 / 2 and lsd_scale
+    1.0 / 0.6 / 0.5 (tests/golden/lsd_extra.npz, tools/gen_golden_lsd.py).  refine 0: equal; refine > 0: same count and end
+    points within 0.5 px (tree sums over lanes, CUDA libm in the NFA: DESIGN.md section 4)."""
+    from pathlib import Path
+    from pl_vi_orbslam3_b200 import Lineextractor, synth
+    X = np.load(Path(__file__).resolve().parent / "golden" / "lsd_extra.npz")
+    ref = X[f"ref_lsd_{seed}_{scale}_{refine}"]
+    e = Lineextractor(0, refine, scale, 1, 2.0, 0, max_batch=1)
+    try:
+        e.set_debug(True)
+        e(synth.frame_euroc(seed))
+        got = e.read_lsd(0, 0, "segments", 752, 480)
+        assert len(got) == len(ref)
+        if refine == 0:
+            assert np.array_equal(got, ref)
+        else:
+            assert np.abs(got - ref).max() <= 0.5
+    finally:
+        e.close()
