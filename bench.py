@@ -313,8 +313,9 @@ def main():
                     help="alternate: whole batches go to the pipelines in turn (consecutive batches in flight at "
                          "different phases); slice: every batch is split across the pipelines")
     ap.add_argument("--out-sets", type=int, default=2, help="alternating output buffer sets per pipeline")
-    ap.add_argument("--pipes", type=int, default=int(os.environ.get("PLVI_BENCH_PIPES", 1)),
-                    help="independent pipelines the batch is split over (overlap across slices)")
+    ap.add_argument("--pipes", type=int, default=int(os.environ.get("PLVI_BENCH_PIPES", 0)),
+                    help="independent pipelines = consecutive steps in flight (0 = by batch size: 1 at 4096 frames per step, "
+                         "8 at <= 512: region growing has a latency floor per batch, mid-size batches overlap)")
     ap.add_argument("--synth-workers", type=int, default=0, help="processes generating the synthetic frames (0 = cores / ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -374,6 +375,8 @@ def main():
         seed0 = rank * (B // 2 if pairs else B)
     if B < 2:
         pairs, affine = False, None
+    if args.pipes <= 0:   # frames in flight ~ 4096 frames of 752x480 (device memory: ~25 MB per frame of capacity at that size)
+        args.pipes = 1 if B < 32 else max(1, min(8, int(4096 * 752 * 480 / (B * W * H))))
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu:
         nsamp = args.cpu_sample or min(32 * cores, 1024)
@@ -438,28 +441,40 @@ def main():
     nset = 2
     ios = [[f.alloc_host_io() for _ in range(nset)] for f in fes]
 
+    sliced = args.pipe_mode == "slice" and len(fes) > 1
+    h_parts = [h_frames[o:o + z] for o, z in zip(fe.offsets, fe.sizes)] if sliced else None
+
     def e2e_run(nsteps):
         done = [None] * nsteps
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(st)
         for f in fes:
             f.wait_event_all(start)
+        ahead = nset if sliced else nset * len(fes)      # steps the host may run ahead of the results
         for i in range(nsteps):
-            f = fes[i % len(fes)]
-            k = (i // len(fes)) % nset
-            if i >= nset * len(fes):
-                for ev in done[i - nset * len(fes)]:
+            if i >= ahead:
+                for ev in done[i - ahead]:
                     ev.synchronize()               # the host buffers of that step are free again
-            f.step_host(h_frames, ios[i % len(fes)][k])
-            done[i] = f.host_done_events()
-        for evs in done[-nset * len(fes):]:
+            if sliced:       # every pipeline takes its slice of the batch
+                k = i % nset
+                evs = []
+                for j, f in enumerate(fes):
+                    f.step_host(h_parts[j], ios[j][k])
+                    evs += f.host_done_events()
+                done[i] = evs
+            else:            # whole batches go to the pipelines in turn
+                f = fes[i % len(fes)]
+                k = (i // len(fes)) % nset
+                f.step_host(h_frames, ios[i % len(fes)][k])
+                done[i] = f.host_done_events()
+        for evs in done[-ahead:]:
             for ev in evs or ():
                 ev.wait_on(st)
         stop.record(st)
         stop.synchronize()
         return start, stop
 
-    e2e_run(2)
+    e2e_run(max(2, 2 * len(fes)))   # every pipeline has used both of its staging buffers / result sets (allocations, graph captures)
     barrier()
     f0, f1 = e2e_run(args.steps)
     barrier()
@@ -467,7 +482,7 @@ def main():
     # plvi_orb_extract_batch_async_from_line: the ORB handle reads the line handle's upload (one upload per batch); without
     # it each extractor call takes the image
     h2d = int(h_frames.numel()) * (2 if (fes[0].line is not None and not fes[0].share_upload) else 1)
-    d2h = int(sum(v.numel() * v.element_size() for v in ios[0][0].values()))
+    d2h = int(sum(v.numel() * v.element_size() for j in range(len(fes) if sliced else 1) for v in ios[j][0].values()))
 
     # ---- per-kernel profile of one extra step (events after every launch; not part of the timed numbers)
     fe.set_profile(True)

@@ -177,6 +177,11 @@ typedef struct plvi_line plvi_line;
 int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float lsd_scale, int nlevels,
                      float scale, int extractor, int max_width, int max_height, int max_batch,
                      int device, void* stream);
+/* plvi_line_create with the capacity of the band-run schedule (frames; see plvi_line_set_band_run_max) chosen at
+ * creation: its buffers (~10 MB per frame at 752x480) are only allocated for that many frames.  -1 = the default
+ * (min(384, max_batch), or the environment variable PLVI_LSD_BR_MAX). */
+int plvi_line_create_ex(plvi_line** out, int lsd_nfeatures, int lsd_refine, float lsd_scale, int nlevels, float scale,
+                        int extractor, int max_width, int max_height, int max_batch, int device, void* stream, int band_run_max);
 void plvi_line_destroy(plvi_line* h);
 /* rows per frame in keylines / desc / line_eq */
 int plvi_line_capacity(const plvi_line* h);
@@ -236,6 +241,13 @@ int plvi_line_extract_batch_device(plvi_line* h, const uint8_t* d_imgs, int n, i
  * 7 diagnostics of the small-batch (band-run) region growing: 40 ints = {serial fallback taken, fixed point reached,
  * -, bands re-run in round 1, 2, ...}; *count = rounds launched. */
 int plvi_line_set_debug(plvi_line* h, int on);
+/* Region growing has two exact schedules.  Band-run rounds (many bands per frame, warp per band, rounds to the fixed
+ * point): lowest latency for a small batch (one 752x480 frame: 5 ms), throughput-bound near 8 k frames/s.  Band
+ * speculation + serial commit: a latency floor of ~55 ms per batch whatever its size, but several batches in flight on
+ * different handles overlap well (8 x 512 frames: 15.6 k frames/s, one batch of 4096: 22.8 k frames/s).  Batches of up to
+ * max_frames frames take the band-run schedule (default: min(384, max_batch); 0 switches it off); returns the value
+ * in effect.  A caller that keeps many mid-size batches in flight sets a small value (frontend.py uses 32). */
+int plvi_line_set_band_run_max(plvi_line* h, int max_frames);
 int plvi_line_set_profile(plvi_line* h, int on);
 const char* plvi_line_profile(plvi_line* h);
 int plvi_line_read_lsd(plvi_line* h, int frame, int octave, int what, void* out, int cap, int* count);

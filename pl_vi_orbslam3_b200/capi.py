@@ -56,8 +56,10 @@ _SIGS = {
     "plvi_orb_set_profile": (ci, [vp, ci]),
     "plvi_orb_profile": (C.c_char_p, [vp]),
     "plvi_line_set_profile": (ci, [vp, ci]),
+    "plvi_line_set_band_run_max": (ci, [vp, ci]),
     "plvi_line_profile": (C.c_char_p, [vp]),
     "plvi_line_create": (ci, [C.POINTER(vp), ci, ci, cf, ci, cf, ci, ci, ci, ci, ci, vp]),
+    "plvi_line_create_ex": (ci, [C.POINTER(vp), ci, ci, cf, ci, cf, ci, ci, ci, ci, ci, vp, ci]),
     "plvi_line_destroy": (None, [vp]),
     "plvi_line_capacity": (ci, [vp]),
     "plvi_line_levels": (ci, [vp]),

@@ -81,6 +81,7 @@ struct LineBufs {
   int* brState;          // [brMax][brBandsPerFrame][8]  nrec[0], nrec[1], cur, dirty, hasPrev
   int* brFlags;          // [brMax][2][BR_FLAGS]  [0] fallback to the serial kernel, [1] converged, [2 + r] bands dirty in round r
   int brMax;             // frames the band-run buffers hold (0: off)
+  int brUse;             // batches of up to brUse (<= brMax) frames take the band-run path (plvi_line_set_band_run_max)
   int brRounds;          // rounds launched per batch
   LineRegion* regTab;    // [B][segTotal]
   int* regCount;         // [B][2]  (-1: segment table overflow)

@@ -2486,7 +2486,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   }
   if (fork) PLVI_CUDA_TRY(cudaEventRecord(aux.join, aux.stream));
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
-  const bool bandRun = b.brMax > 0 && n <= b.brMax && g.refine == 0;
+  const bool bandRun = b.brMax > 0 && n <= b.brUse && g.refine == 0;
   if (g.refine > 0) {
     // lsd_refine 1 / 2: refine() couples consecutive seeds through released pixels -- one serial warp per (frame, octave)
     k_lsd_grow_refine<<<dim3(g.noct, n), 32, growSmem, st>>>(g, b, g.refine, 1.0, 0.6);   // log_eps, density_th: src/LineExtractor.cc:62-63

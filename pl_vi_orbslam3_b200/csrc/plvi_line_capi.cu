@@ -15,7 +15,7 @@ struct plvi_line {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool ownStream = false;
-  int nfeat = 0, nlevels = 0, refine = 0;
+  int nfeat = 0, nlevels = 0, refine = 0, brMaxWanted = -1;
   float lsdScale = 0.8f, scale = 2.f;
   int maxW = 0, maxH = 0, maxBatch = 0;
   int curW = -1, curH = -1;
@@ -291,6 +291,12 @@ extern "C" {
 
 int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float lsd_scale, int nlevels, float scale,
                      int extractor, int max_width, int max_height, int max_batch, int device, void* stream) {
+  return plvi_line_create_ex(out, lsd_nfeatures, lsd_refine, lsd_scale, nlevels, scale, extractor, max_width, max_height, max_batch,
+                             device, stream, -1);
+}
+
+int plvi_line_create_ex(plvi_line** out, int lsd_nfeatures, int lsd_refine, float lsd_scale, int nlevels, float scale,
+                        int extractor, int max_width, int max_height, int max_batch, int device, void* stream, int band_run_max) {
   if (!out || lsd_nfeatures < 0 || max_batch < 1 || max_width < 1 || max_height < 1 || !(lsd_scale > 0.f)) {
     set_error("plvi_line_create: invalid argument");
     return PLVI_ERR_INVALID;
@@ -304,6 +310,7 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
   h->nfeat = lsd_nfeatures;
   h->lsdScale = lsd_scale;
   h->refine = lsd_refine;
+  h->brMaxWanted = band_run_max;
   h->nlevels = nlevels;
   h->scale = scale;
   h->maxW = max_width;
@@ -346,12 +353,13 @@ int plvi_line_create(plvi_line** out, int lsd_nfeatures, int lsd_refine, float l
     // B200 the band-run rounds beat band speculation + serial commit up to ~512 frames per batch (32 frames: 5.1x, 128:
     // 2.8x, 256: 1.7x, 512: 1.0x, profiles/r02_notes.md); about 10 MB of scratch per frame of that capacity.
     const char* ev = getenv("PLVI_LSD_BR_MAX");
-    const int brMax = std::min(ev ? std::max(0, atoi(ev)) : 384, max_batch);
+    const int brMax = std::min(h->brMaxWanted >= 0 ? h->brMaxWanted : (ev ? std::max(0, atoi(ev)) : 384), max_batch);
     const char* er = getenv("PLVI_LSD_BR_ROUNDS");
     // 28 rounds: of 3 x 512 (frame, octave) problems measured (640x480, 752x480, 1280x720) the slowest needed 16; rounds
     // after the fixed point only cost their launches, a problem that has not converged costs a full serial chain
     h->buf.brRounds = std::min(std::max(er ? atoi(er) : 28, 1), BR_FLAGS - 4);
     h->buf.brMax = brMax;
+    h->buf.brUse = brMax;
     if (brMax > 0) {
       const size_t S = brMax;
       A((void**)&h->buf.brIn, S * c.brBmTotal * sizeof(unsigned));
@@ -498,7 +506,8 @@ static int run_line_pipeline(plvi_line* h, const LinePtrs& p, int n, plvi_keylin
   if (h->prof.on || !h->graphs.on()) return record(&h->lastLaunches);
   std::vector<uint64_t> key = {(uint64_t)n, (uint64_t)h->curW, (uint64_t)h->curH, (uint64_t)(uintptr_t)p.img[0],
                                (uint64_t)p.ipitch[0], (uint64_t)p.ifs[0], (uint64_t)(uintptr_t)d_kl,
-                               (uint64_t)(uintptr_t)d_desc, (uint64_t)(uintptr_t)d_eq, (uint64_t)(uintptr_t)d_counts};
+                               (uint64_t)(uintptr_t)d_desc, (uint64_t)(uintptr_t)d_eq, (uint64_t)(uintptr_t)d_counts,
+                               (uint64_t)h->buf.brUse};
   return h->graphs.run(h->stream, key, &h->lastLaunches, record);
 }
 
@@ -596,6 +605,12 @@ int plvi_line_sync(plvi_line* h) {
 }
 
 void* plvi_line_results_event(plvi_line* h) { return h ? (void*)h->aout.last_done() : nullptr; }
+
+int plvi_line_set_band_run_max(plvi_line* h, int max_frames) {
+  if (!h || max_frames < 0) return PLVI_ERR_INVALID;
+  h->buf.brUse = std::min(max_frames, h->buf.brMax);
+  return h->buf.brUse;
+}
 
 int plvi_line_set_profile(plvi_line* h, int on) {
   if (!h) return PLVI_ERR_INVALID;

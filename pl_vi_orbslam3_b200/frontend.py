@@ -52,7 +52,7 @@ class FrontEnd:
     def __init__(self, batch, w=752, h=480, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
                  lsd_nfeatures=200, lsd_scale=0.8, line_levels=2, line_scale=2.0, device=0, stream=None,
                  with_lines=True, with_match=True, match_th=15.0, nnratio=0.9, overlap_lines=True, line_priority=0,
-                 out_sets=1, pairs=False, affine=None, init_window=100.0):
+                 out_sets=1, pairs=False, affine=None, init_window=100.0, band_run_max=None):
         import torch
         self.torch = torch
         self.B, self.w, self.h = batch, w, h
@@ -83,7 +83,8 @@ class FrontEnd:
         if with_lines:
             self.line = Lineextractor(lsd_nfeatures, 0, lsd_scale, line_levels, line_scale, 0, max_width=w,
                                       max_height=h, max_batch=batch, device=device,
-                                      stream=self.line_stream.cuda_stream)
+                                      stream=self.line_stream.cuda_stream,
+                                      band_run_max=-1 if band_run_max is None else int(band_run_max))
             self.line_outs = [self.line.alloc_device_outputs(batch, self.device) for _ in range(self.out_sets)]
             self.line_out = self.line_outs[0]
         # pairs=True: the batch holds C3 pairs (frame 2p, its warp 2p + 1) and every pair is matched in the
@@ -407,6 +408,8 @@ class PipelinedFrontEnd:
         else:
             self.sizes = [shard_range(batch, i, pipes)[1] - shard_range(batch, i, pipes)[0] for i in range(pipes)]
             self.offsets = [shard_range(batch, i, pipes)[0] for i in range(pipes)]
+        if pipes > 1 and "band_run_max" not in kw:
+            kw["band_run_max"] = 32      # several batches in flight: the speculation / commit schedule overlaps across them
         self.fes = [FrontEnd(sz, device=device, **kw) for sz in self.sizes]
         self._fork = torch.cuda.Event()
         self._joins = [torch.cuda.Event() for _ in self.fes]

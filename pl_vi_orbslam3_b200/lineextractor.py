@@ -13,11 +13,11 @@ from .capi import KEYLINE_DTYPE, check, lib, ptr
 
 class Lineextractor:
     def __init__(self, lsd_nfeatures, lsd_refine, lsd_scale, nlevels, scale, extractor=0,
-                 max_width=752, max_height=480, max_batch=1, device=0, stream=None):
+                 max_width=752, max_height=480, max_batch=1, device=0, stream=None, band_run_max=-1):
         self._h = C.c_void_p()
-        check(lib().plvi_line_create(C.byref(self._h), int(lsd_nfeatures), int(lsd_refine), float(lsd_scale),
-                                     int(nlevels), float(scale), int(extractor), int(max_width), int(max_height),
-                                     int(max_batch), int(device), ptr(stream) if stream else None))
+        check(lib().plvi_line_create_ex(C.byref(self._h), int(lsd_nfeatures), int(lsd_refine), float(lsd_scale),
+                                        int(nlevels), float(scale), int(extractor), int(max_width), int(max_height),
+                                        int(max_batch), int(device), ptr(stream) if stream else None, int(band_run_max)))
         self.nlevels_l = int(nlevels)
         self.capacity = check(lib().plvi_line_capacity(self._h))
         t = [np.empty(self.nlevels_l, np.float32) for _ in range(4)]
