@@ -385,7 +385,9 @@ def main():
                     "sample": f"{nsamp} synthetic {W}x{H} frames (same generator and pairing), contiguous shards over {cores} worker "
                               f"processes, {dt:.1f} s wall; " + cpu_kind()[1],
                     "single_core_ms_per_stage": st}
-    frames = gen(B, W, H, base_seed=seed0, workers=gen_workers)     # forks: before CUDA is initialised
+    # every frame from its own seed when this rank's share of the host cores makes them within ~75 s, else the first
+    # `distinct` frames from their seeds and cyclic shifts of them (stated in config.frames)
+    frames, distinct = gen(B, W, H, base_seed=seed0, workers=gen_workers, budget_s=75.0, with_info=True)     # forks: before CUDA is initialised
 
     import torch
     import torch.distributed as dist
@@ -552,8 +554,10 @@ def main():
             "scaling": scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload if not args.orb_only else "DIAGNOSTIC orb-only", "name": args.config,
                        "frames_per_step_per_gpu": B, "frames_per_step": int(total), "orb_features": NFEAT,
-                       "frames": (f"C3 pairs: frame_euroc(s) and its warp, s = {seed0}..{seed0 + B // 2 - 1} on rank 0 (all distinct)" if pairs
-                                  else f"frame_euroc(s), s = {seed0}..{seed0 + B - 1} on rank 0 (all distinct), consecutive frames matched"),
+                       "frames": ((f"C3 pairs: frame_euroc(s) and its warp, s = {seed0}..{seed0 + distinct // 2 - 1} on rank 0" if pairs
+                                   else f"frame_euroc(s), s = {seed0}..{seed0 + distinct - 1} on rank 0, consecutive frames matched") +
+                                  (" (all distinct)" if distinct >= B else f" ({distinct} distinct frames, the rest cyclic shifts of them: "
+                                                                             f"{gen_workers} generator processes on this rank)")),
                        "searches": ("SearchByProjection(Frame,Frame) th=15 under the warp + SearchForInitialization window 100 + LineMatcher::match 0.9"
                                     if pairs else "SearchByProjection(Frame,Frame) th=15, identity pose + LineMatcher::match 0.9"),
                        "width": W, "height": H, "l2_policy": "inputs larger than L2 (%.0f MB of frames per step)" % (B * W * H / 1e6) if B * W * H > 130e6

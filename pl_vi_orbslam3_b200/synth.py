@@ -126,33 +126,50 @@ def warp_affine(w=752, h=480, angle_deg=1.5, tx=6.0, ty=-4.0, scale=1.01):
     return np.hstack([R, t[:, None]])
 
 
-def _batch(kind, n, w, h, base_seed, workers, cache):
+def _batch(kind, n, w, h, base_seed, workers, cache, budget_s=None):
     import os
     import tempfile
     from pathlib import Path
+    unit = 2 if kind == "pairs" else 1
+    nunits = (n + unit - 1) // unit
+    workers = max(1, min(workers or (os.cpu_count() or 1), nunits))
+    # generation budget: a frame costs ~0.1 s, a pair ~0.16 s of one core.  When the workers of this process cannot make
+    # every unit within budget_s, the first `distinct` units are generated from their own seeds and the rest are cyclic
+    # shifts of them (both frames of a pair by the same shift, <= 1 px off the pair's affine map for the shifts used)
+    distinct = nunits
+    if budget_s:
+        distinct = max(1, min(nunits, int(workers * budget_s / (0.16 if unit == 2 else 0.1))))
     path = None
     if cache:
         d = Path(os.environ.get("PLVI_SYNTH_CACHE", Path(tempfile.gettempdir()) / "plvi_synth_cache"))
-        path = d / f"{kind}_{w}x{h}_s{base_seed}_n{n}.npy"
+        path = d / f"{kind}_{w}x{h}_s{base_seed}_n{n}_d{distinct}.npy"
         try:
             if path.exists():
                 a = np.load(path)
                 if a.shape == (n, h, w) and a.dtype == np.uint8:
-                    return a
+                    return a, distinct * unit
         except Exception:
             pass
     if kind == "pairs":
-        jobs, fn = [(base_seed + p, w, h) for p in range((n + 1) // 2)], _gen_pair
+        jobs, fn = [(base_seed + p, w, h) for p in range(distinct)], _gen_pair
     else:
-        jobs, fn = [(base_seed + i, w, h) for i in range(n)], _gen_frame
-    workers = max(1, min(workers or (os.cpu_count() or 1), len(jobs)))
+        jobs, fn = [(base_seed + i, w, h) for i in range(distinct)], _gen_frame
     if workers > 1:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(workers) as pool:     # call before CUDA is initialised in this process
             parts = pool.map(fn, jobs, chunksize=max(1, len(jobs) // (8 * workers)))
     else:
         parts = [fn(j) for j in jobs]
-    out = (np.concatenate(parts) if kind == "pairs" else np.stack(parts))[:n]
+    base = np.concatenate(parts) if kind == "pairs" else np.stack(parts)
+    if distinct < nunits:
+        out = np.empty((nunits * unit, h, w), np.uint8)
+        nb = len(base)
+        for u in range(nunits):
+            k = u // distinct
+            src = base[(u % distinct) * unit:(u % distinct) * unit + unit]
+            out[u * unit:(u + 1) * unit] = np.roll(src, (3 * k, 5 * k), axis=(1, 2)) if k else src
+        base = out
+    out = base[:n]
     if path is not None:
         try:
             path.parent.mkdir(parents=True, exist_ok=True)
@@ -161,15 +178,17 @@ def _batch(kind, n, w, h, base_seed, workers, cache):
             os.replace(tmp, path)
         except Exception:
             pass
-    return out
+    return out, distinct * unit
 
 
-def seq_batch(n, w=752, h=480, base_seed=0, workers=0, cache=True):
+def seq_batch(n, w=752, h=480, base_seed=0, workers=0, cache=True, budget_s=None, with_info=False):
     """C1 / C4 / C5: frames frame_euroc(base_seed) ... frame_euroc(base_seed + n - 1), [n, h, w] u8."""
-    return _batch("seq", n, w, h, base_seed, workers, cache)
+    out, distinct = _batch("seq", n, w, h, base_seed, workers, cache, budget_s)
+    return (out, distinct) if with_info else out
 
 
-def pair_batch(n, w=752, h=480, base_seed=0, workers=0, cache=True):
+def pair_batch(n, w=752, h=480, base_seed=0, workers=0, cache=True, budget_s=None, with_info=False):
     """C3: n frames = n / 2 pairs; frame 2p = frame_euroc(base_seed + p), frame 2p + 1 = its warp (warp_pair, map
     warp_affine()), [n, h, w] u8."""
-    return _batch("pairs", n, w, h, base_seed, workers, cache)
+    out, distinct = _batch("pairs", n, w, h, base_seed, workers, cache, budget_s)
+    return (out, distinct) if with_info else out
