@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(256) k_lsd_spec_init(const __grid_constant__ L
 }
 
 #define SPEC_SCAN_WORDS 8
-#define SPEC_RING 16
+#define SPEC_RING 32
 
 // One thread per (band, frame); the 32 lanes of a warp hold the same band of 32 consecutive
 // frames (similar content => similar amount of work).  Single flat loop: every iteration
@@ -543,6 +543,7 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
   // they were stored, and L1 (write-through, shared with 500+ other chains) never keeps them anyway
   __shared__ unsigned sring_all[GROW_WPB][SPEC_RING * 32];   // the last SPEC_RING pixels of each lane's region (BFS frontier)
   unsigned* sring = sring_all[threadIdx.x >> 5];
+  const unsigned sringAddr = (unsigned)__cvta_generic_to_shared(sring + (threadIdx.x & 31));   // this lane's column of the ring
   const int lane = threadIdx.x & 31;
   int row = r0, wi = 0;
   unsigned word = (r0 < r1) ? __ldcg(P + r0 * wpr) : 0u;
@@ -597,12 +598,22 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
     const bool needHi = sh >= 30 && wa + 1 < wpr;
     unsigned lo[3], hi[3];
     unsigned m9 = 0u;
+    // row pointers are formed once (and kept opaque, so that the compiler does not re-derive every address from the
+    // kernel parameters): the loads below take constant offsets from them
+    unsigned* Pw0 = P + ((ey - 1) * wpr + wa);   // word of column ex - 1 in row ey - 1
+    unsigned* Pw1 = Pw0 + wpr;
+    unsigned* Pw2 = Pw1 + wpr;
+    const float2* rq0 = rec + ((ey - 1) * W + xm);
+    const float2* rq1 = rq0 + W;
+    const float2* rq2 = rq1 + W;
+    asm volatile("" : "+l"(Pw0), "+l"(Pw1), "+l"(Pw2), "+l"(rq0), "+l"(rq1), "+l"(rq2));
 #pragma unroll
     for (int r = 0; r < 3; r++) {
       const int y = ey - 1 + r;
       const bool ok = y >= r0 && y < H;
-      lo[r] = ok ? __ldcg(P + y * wpr + wa) : 0u;
-      hi[r] = (ok && needHi) ? __ldcg(P + y * wpr + wa + 1) : 0u;
+      unsigned* const Pw = r == 0 ? Pw0 : (r == 1 ? Pw1 : Pw2);
+      lo[r] = ok ? __ldcg(Pw) : 0u;
+      hi[r] = (ok && needHi) ? __ldcg(Pw + 1) : 0u;
       const unsigned long long comb = ((unsigned long long)hi[r] << 32) | lo[r];
       const unsigned three = sh >= 0 ? ((unsigned)(comb >> sh) & 7u) : ((lo[r] << 1) & 7u);
       m9 |= three << (3 * r);
@@ -611,7 +622,8 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
 #pragma unroll
     for (int k = 0; k < 9; k++) {
       rk[k] = make_float2(0.f, 0.f);
-      if (k != 4 && ((m9 >> k) & 1u)) rk[k] = __ldg(rec + (ey + k / 3 - 1) * W + (ex + k % 3 - 1));
+      const float2* const rq = k < 3 ? rq0 : (k < 6 ? rq1 : rq2);
+      if (k != 4 && ((m9 >> k) & 1u)) rk[k] = __ldg(rq + k % 3);
     }
     if (isNew) {
       sang = sangNew;
@@ -620,26 +632,35 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
       fresh = true;
     }
     unsigned acc = 0u;
+    unsigned* lp = list + (base + size);          // next free slot of the pixel list
+    asm volatile("" : "+l"(lp));
+    float tLo = kLo * n2, tHi = kHi * n2;
 #pragma unroll
     for (int k = 0; k < 9; k++) {
-      if (k == 4 || !((m9 >> k) & 1u)) continue;
+      if (k == 4) continue;
+      // a neighbour that is not available has rk = (0, 0): dot = 0 fails the first test
       const float dot = __fmaf_rn(sumdx, rk[k].x, sumdy * rk[k].y);
       const float d2 = dot * dot;
-      if (!(dot > 0.f && d2 > kLo * n2)) continue;
-      if (!(d2 >= kHi * n2)) {
+      bool take = dot > 0.f && d2 > tLo;
+      if (take && !(d2 >= tHi)) {   // undecided band of the cheap test: the reference's own comparison (rare)
         const double regAngle = __dmul_rn((double)(fresh ? sang : fast_atan2_dev(sumdy, sumdx)), D2R);
-        const float la = __ldg(ang + (ey + k / 3 - 1) * W + (ex + k % 3 - 1));
-        if (!is_aligned_dev(__dmul_rn((double)la, D2R), regAngle, prec)) continue;
+        const float la = __ldg(ang + ((ey + k / 3 - 1) * W + (ex + k % 3 - 1)));
+        take = is_aligned_dev(__dmul_rn((double)la, D2R), regAngle, prec);
       }
-      acc |= 1u << k;
-      const unsigned q = (unsigned)(ex + k % 3 - 1) | ((unsigned)(ey + k / 3 - 1) << 16);
-      list[base + size] = q;
-      sring[(size & (SPEC_RING - 1)) * 32 + lane] = q;
-      size++;
-      fresh = false;
-      sumdx = __fadd_rn(sumdx, rk[k].x);
-      sumdy = __fadd_rn(sumdy, rk[k].y);
+      // the accept is straight-line code (two predicated stores, selects): no divergent branch around the common path
+      const unsigned q = p + (unsigned)((k / 3 - 1) * 65536 + (k % 3 - 1));
+      const int tk = take ? 1 : 0;
+      asm volatile("{ .reg .pred pt; setp.ne.s32 pt, %0, 0; @pt st.global.u32 [%1], %2; @pt st.shared.u32 [%3], %2; }"
+                   :: "r"(tk), "l"(lp), "r"(q), "r"(sringAddr + ((size & (SPEC_RING - 1)) << 7)) : "memory");
+      acc |= (unsigned)tk << k;
+      lp += tk;
+      size += tk;
+      fresh = fresh && !take;
+      const float nx = __fadd_rn(sumdx, rk[k].x), ny = __fadd_rn(sumdy, rk[k].y);
+      sumdx = take ? nx : sumdx;
+      sumdy = take ? ny : sumdy;
       n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
+      tLo = kLo * n2; tHi = kHi * n2;
     }
     if (acc) {
 #pragma unroll
@@ -647,9 +668,9 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
         const unsigned a3 = (acc >> (3 * r)) & 7u;
         if (a3) {
           const unsigned long long mk = sh >= 0 ? ((unsigned long long)a3 << sh) : (unsigned long long)(a3 >> 1);
-          const int y = ey - 1 + r;
-          __stcg(P + y * wpr + wa, lo[r] & ~(unsigned)mk);
-          if ((unsigned)(mk >> 32)) __stcg(P + y * wpr + wa + 1, hi[r] & ~(unsigned)(mk >> 32));
+          unsigned* const Pw = r == 0 ? Pw0 : (r == 1 ? Pw1 : Pw2);
+          __stcg(Pw, lo[r] & ~(unsigned)mk);
+          if ((unsigned)(mk >> 32)) __stcg(Pw + 1, hi[r] & ~(unsigned)(mk >> 32));
         }
       }
     }
@@ -715,7 +736,7 @@ template <int K> __device__ __forceinline__ void grow_clear_atomic(GrowBitmapT<K
   else atomicAnd(bm.gm + y * bm.wpr + (x >> 5), m);
 }
 
-__global__ void __launch_bounds__(32 * GROW_WPB, 6) k_lsd_commit(const __grid_constant__ LineGeom g, LineBufs b, int n,
+__global__ void __launch_bounds__(32 * GROW_WPB, 7) k_lsd_commit(const __grid_constant__ LineGeom g, LineBufs b, int n,
                                                               int smemWordsPerWarp) {
   // GROW_WPB independent warps per block (consecutive frames of one octave): single-warp blocks
   // would fill the SM's 32 block slots and keep the kernels of the other streams out
@@ -2457,7 +2478,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   }
   // The LBD pyramid + Sobel only depend on the input frame: they run on the auxiliary stream while
   // the latency-bound region growing occupies the main one (serially when profiling, for clean times).
-  const bool fork = aux.stream != nullptr && !prof->on;
+  const bool fork = aux.stream != nullptr && (!prof->on || StageProf::timeline());
   cudaStream_t ls = fork ? aux.stream : st;
   if (fork) {
     PLVI_CUDA_TRY(cudaEventRecord(aux.fork, st));

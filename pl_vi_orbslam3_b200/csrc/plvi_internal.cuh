@@ -127,7 +127,7 @@ struct StageProf {
   std::vector<cudaEvent_t> ev;
   std::vector<const char*> names;
   int n = 0;
-  void begin(cudaStream_t st) { n = 0; names.clear(); if (on) mark(nullptr, st); }
+  void begin(cudaStream_t st) { n = 0; names.clear(); if (on) { if (timeline()) origin(st); mark(nullptr, st); } }
   void mark(const char* name, cudaStream_t st) {
     if (!on) return;
     if ((int)ev.size() <= n) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
@@ -135,9 +135,26 @@ struct StageProf {
     if (name) names.push_back(name);
     n++;
   }
+  // PLVI_TIMELINE=1 (diagnostic, tools/timeline.py): the stages keep their streams (no serialisation by the caller) and
+  // report() gives "name=start,end;" in ms since one process-wide origin event instead of durations
+  static bool timeline() { static int t = -1; if (t < 0) { const char* e = getenv("PLVI_TIMELINE"); t = (e && e[0] == '1') ? 1 : 0; } return t == 1; }
+  static cudaEvent_t origin(cudaStream_t st) {
+    static cudaEvent_t o = nullptr;
+    if (!o) { cudaEventCreate(&o); cudaEventRecord(o, st); }
+    return o;
+  }
   // after the stream has been synchronised: "name=ms;name=ms;..." (same-named stages summed)
   std::string report() {
     std::string out;
+    if (timeline()) {
+      for (int i = 1; i < n; i++) {
+        float t0 = 0.f, t1 = 0.f;
+        if (cudaEventElapsedTime(&t0, origin(nullptr), ev[i - 1]) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&t1, origin(nullptr), ev[i]) != cudaSuccess) continue;
+        out += std::string(names[i - 1]) + "=" + std::to_string(t0) + "," + std::to_string(t1) + ";";
+      }
+      return out;
+    }
     std::vector<std::pair<std::string, float>> acc;
     for (int i = 1; i < n; i++) {
       float ms = 0.f;

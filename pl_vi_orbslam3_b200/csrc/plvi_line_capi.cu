@@ -125,9 +125,9 @@ int make_geom(const plvi_line* h, int w, int hh, LineGeom& g, std::vector<LineTa
   g.lsdScale = (double)h->lsdScale;
   g.prec = M_PI * 22.5 / 180;
   g.rho = 2.0 / sin(g.prec);
-  // fastAtan2 deviates from atan2 by <= 0.0092 deg (1.6e-4 rad); 2e-3 rad leaves a 10x margin
-  g.alignHi2 = (float)(cos(g.prec - 2e-3) * cos(g.prec - 2e-3));
-  g.alignLo2 = (float)(cos(g.prec + 2e-3) * cos(g.prec + 2e-3));
+  // fastAtan2 deviates from atan2 by <= 0.0092 deg (1.6e-4 rad); 5e-4 rad leaves a 3x margin (the exact test runs only inside that band)
+  g.alignHi2 = (float)(cos(g.prec - 5e-4) * cos(g.prec - 5e-4));
+  g.alignLo2 = (float)(cos(g.prec + 5e-4) * cos(g.prec + 5e-4));
   g.minLength = 0.025 * std::min(w, hh);
   // flsd (src/LSD/lsd.cpp:446-462): SCALE == 1 works on the image itself; else GaussianBlur(sigma = 0.6 / SCALE, ksize
   // 1 + 2 h) and resize by SCALE.  The range is (0, 1] by the reference's own yaml comment; h <= 8 <=> scale >= 0.279.
