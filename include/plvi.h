@@ -158,6 +158,10 @@ int plvi_orb_stereo_matches_host(plvi_orb* left, plvi_orb* right, const plvi_key
                                  float* depth, int* nstereo);
 /* Makes the handle's stream wait for a cudaEvent_t (e.g. plvi_line_stage_event) before the next batch. */
 int plvi_orb_wait_event(plvi_orb* h, void* cuda_event);
+/* As plvi_orb_wait_event, but the wait sits INSIDE the next batch's launch sequence, behind the image pyramid: the
+ * pyramid kernels (short, chained, one level from the previous) run at once, FAST and everything after it when the
+ * event has completed.  One-shot: applies to the next batch only. */
+int plvi_orb_wait_event_after_pyramid(plvi_orb* h, void* cuda_event);
 /* Per-kernel device time of the last batch: with profiling on, a CUDA event is recorded
  * on the handle's stream after every launch; plvi_orb_profile() synchronises and returns
  * "kernel=ms;kernel=ms;..." (valid until the next call). */

@@ -71,8 +71,10 @@ struct LineBufs {
   unsigned* specBm;      // [B][specBmTotal] private availability bitmaps of the speculation bands
   SpecRec* specRec;      // [B][specRecTotal]
   int* specCnt;          // [B][tasksPerFrame] speculative regions per band
+  int* bandRow;          // [B][tasksPerFrame + 2] first row of every band, octave o from taskOff + o (nbands + 1 entries): equal LOAD per band
   unsigned* phantom;     // [B][bmTotal]   pixels a discarded speculative region had consumed
   int useSpec;           // 0: serial k_lsd_grow only
+  int eqLoad;            // speculation bands of equal load (k_lsd_band_split): 1 by batch size, 2 always, 0 never (PLVI_LSD_EQLOAD)
   // band-run (small batches): per band the last input bitmap, the working / output bitmap, the initial phantom
   // bitmap of the next run; two generations of region records + pixel lists; per-band state; per-octave flags
   unsigned* brIn; unsigned* brWk; unsigned* brPh;   // [brMax][brBmTotal]

@@ -495,13 +495,76 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
 //                    angles as the serial algorithm, so it is the region the reference grows.
 //                    Everything else is grown serially as in k_lsd_grow.
 // ---------------------------------------------------------------------------------------
+// Band boundaries of one (frame, octave): the kernel time of k_lsd_spec is the LONGEST chain of the batch, and a chain
+// is as long as the number of available pixels it walks (each is a seed or is expanded once).  Bands of equal rows
+// put 2-3 times the mean load on the textured part of a frame; here the rows are cut so that every band holds the same
+// number of available pixels (any partition of the rows is exact: k_lsd_commit checks every region).
+__global__ void __launch_bounds__(256) k_lsd_band_split(const __grid_constant__ LineGeom g, LineBufs b) {
+  const int oct = blockIdx.x, f = blockIdx.y;
+  if (oct >= g.noct) return;
+  const LineOct& O = g.o[oct];
+  const int H = O.sh, wpr = O.wpr, nb = O.nbands;
+  __shared__ int cum[1025];
+  __shared__ int wsum[8];
+  const unsigned* __restrict__ bm = b.bitmap + (size_t)f * g.bmTotal + O.bmOff;
+  int* tab = b.bandRow + (size_t)f * (g.tasksPerFrame + 2) + O.taskOff + oct;
+  if (H > 1024 || !b.eqLoad) {   // taller than the scan below holds (or switched off): bands of equal rows
+    for (int k = threadIdx.x; k <= nb; k += 256) tab[k] = k == nb ? H : min(k * O.bandRows, H);
+    return;
+  }
+  // rows per thread (consecutive), seed rows are [0, H - 1)
+  const int rpt = (H + 255) / 256;
+  int loc[4];
+  int tot = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int y = threadIdx.x * rpt + k;
+    int c = 0;
+    if (k < rpt && y < H - 1)
+      for (int w = 0; w < wpr; w++) c += __popc(bm[y * wpr + w]);
+    loc[k] = c;
+    tot += c;
+  }
+  // block-wide exclusive scan of the per-thread totals
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = tot;
+  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < wid; w++) base += wsum[w];
+  int run = base + inc - tot;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int y = threadIdx.x * rpt + k;
+    if (k < rpt && y < H) cum[y] = run;    // available pixels in rows [0, y)
+    run += loc[k];
+  }
+  __syncthreads();
+  int total = 0;
+  for (int w = 0; w < 8; w++) total += wsum[w];
+  // band k starts at the first row y with cum[y] >= k * total / nb (monotone in k; empty bands are allowed)
+  for (int k = threadIdx.x; k <= nb; k += 256) {
+    int y;
+    if (k == 0) y = 0;
+    else if (k == nb) y = H;
+    else {
+      const long long target = (long long)k * total / nb;
+      int lo = 0, hi = H - 1;              // smallest y in [0, H - 1] with cum[y] >= target (cum[H - 1] = total of rows < H - 1)
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cum[mid] >= target) hi = mid; else lo = mid + 1; }
+      y = lo;
+    }
+    tab[k] = y;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_lsd_spec_init(const __grid_constant__ LineGeom g, LineBufs b) {
   const int t = blockIdx.y, f = blockIdx.z;
   const int oct = (g.noct > 1 && t >= g.o[1].taskOff) ? 1 : 0;
   const LineOct& O = g.o[oct];
   const int j = t - O.taskOff;
   if (j >= O.nbands) return;
-  const int r0 = j * O.bandRows;
+  const int r0 = b.bandRow[(size_t)f * (g.tasksPerFrame + 2) + t + oct];
   const int nw = (O.sh - r0) * O.wpr;
   const unsigned* __restrict__ src = b.bitmap + (size_t)f * g.bmTotal + O.bmOff + r0 * O.wpr;
   unsigned* __restrict__ dst = b.specBm + (size_t)f * g.specBmTotal + O.specBmOff + (size_t)j * O.wpr * O.sh + r0 * O.wpr;
@@ -527,7 +590,8 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
   const int j = t - O.taskOff;
   if (f >= n || j >= O.nbands) return;
   const int W = O.sw, H = O.sh, wpr = O.wpr;
-  const int r0 = j * O.bandRows, r1 = min(r0 + O.bandRows, H - 1);
+  const int* tab = b.bandRow + (size_t)f * (g.tasksPerFrame + 2) + t + oct;
+  const int r0 = tab[0], r1 = min(tab[1], H - 1);
   unsigned* P = b.specBm + (size_t)f * g.specBmTotal + O.specBmOff + (size_t)j * wpr * H;
   unsigned* list = b.reg + (size_t)f * g.regTotal + O.regOff + (size_t)W * H + (size_t)j * O.bandPxCap;
   uint4* recs = reinterpret_cast<uint4*>(b.specRec + (size_t)f * g.specRecTotal + O.specRecOff + (size_t)j * O.bandRecCap);
@@ -786,8 +850,10 @@ __global__ void __launch_bounds__(32 * GROW_WPB, 7) k_lsd_commit(const __grid_co
 
   for (int row = 0; row < H - 1; row++) {
     if (row == bandEnd) {
-      band++;
-      bandEnd = min((band + 1) * O.bandRows, H);
+      do {   // bands of equal load (k_lsd_band_split): a band without rows is skipped
+        band++;
+        bandEnd = b.bandRow[(size_t)f * (g.tasksPerFrame + 2) + O.taskOff + oct + band + 1];
+      } while (bandEnd <= row && band + 1 < O.nbands);
       bp = 0; runStart = 0;
       bcnt = b.specCnt[(size_t)f * g.tasksPerFrame + O.taskOff + band];
       brecs = reinterpret_cast<const uint4*>(b.specRec + (size_t)f * g.specRecTotal + O.specRecOff + (size_t)band * O.bandRecCap);
@@ -2471,7 +2537,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   }
   // From here on the main stream holds the latency-bound region growing (low issue-slot use): a caller may hold
   // other issue-bound work (the ORB pipeline) back until this point (plvi_line_stage_event).
-  if (aux.stage && !prof->on) {
+  if (aux.stage && (!prof->on || StageProf::timeline())) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
     PLVI_CUDA_TRY(cudaEventRecordWithFlags(aux.stage, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -2533,7 +2599,14 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     prof->mark("k_lsd_band_finish", st);
     nl += 3;
   } else if (b.useSpec) {
+    {  // equal-load bands shorten the longest chain while the batch is latency-bound (measured on B200: 512 frames +7 %,
+      // 1024 +2 %); from ~4096 frames on the kernel is bound by its memory instructions and equal rows are 1.5 % ahead
+      LineBufs bs = b;
+      bs.eqLoad = b.eqLoad == 1 ? (n <= 2048) : (b.eqLoad == 2);
+      k_lsd_band_split<<<dim3(g.noct, n), 256, 0, st>>>(g, bs);
+    }
     k_lsd_spec_init<<<dim3(8, g.tasksPerFrame, n), 256, 0, st>>>(g, b);
+    nl += 1;
     prof->mark("k_lsd_spec_init", st);
     k_lsd_spec<<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
     prof->mark("k_lsd_spec", st);

@@ -916,7 +916,7 @@ int orb_kernel_attrs(const OrbGeom& g, int* fastSmem, int* octSmem) {
 
 int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s, int n, int lap0,
                         int lap1, plvi_keypoint* d_kps, uint8_t* d_desc, int* d_counts,
-                        int* d_mono, int cap, cudaStream_t st, int* launches, StageProf* prof) {
+                        int* d_mono, int cap, cudaStream_t st, int* launches, StageProf* prof, cudaEvent_t waitAfterPyramid) {
   int nl = 0;
   StageProf nop;
   if (!prof) prof = &nop;
@@ -931,6 +931,12 @@ int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s,
     nl++;
   }
   prof->mark("k_resize", st);
+  if (waitAfterPyramid) {   // plvi_orb_wait_event_after_pyramid: the rest of the sequence follows the caller's event
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    PLVI_CUDA_TRY(cudaStreamWaitEvent(st, waitAfterPyramid, cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : cudaEventWaitDefault));
+    prof->mark("(wait)", st);
+  }
   // FAST tile geometry recomputed here must match capi's smem sizing
   {
     int tilePitch, maxH, listCap, maxSurv;

@@ -348,6 +348,7 @@ int plvi_line_create_ex(plvi_line** out, int lsd_nfeatures, int lsd_refine, floa
   A((void**)&h->buf.specBm, B * c.specBmTotal * sizeof(unsigned));
   A((void**)&h->buf.specRec, B * c.specRecTotal * sizeof(SpecRec));
   A((void**)&h->buf.specCnt, B * c.tasksPerFrame * sizeof(int));
+  A((void**)&h->buf.bandRow, B * (c.tasksPerFrame + 2) * sizeof(int));
   A((void**)&h->buf.phantom, B * c.bmTotal * sizeof(unsigned));
   {  // band-run buffers for batches of up to PLVI_LSD_BR_MAX frames (0 switches the path off).  Default 384: measured on
     // B200 the band-run rounds beat band speculation + serial commit up to ~512 frames per batch (32 frames: 5.1x, 128:
@@ -416,6 +417,8 @@ int plvi_line_create_ex(plvi_line** out, int lsd_nfeatures, int lsd_refine, floa
   {  // PLVI_LSD_SPEC=0 selects the serial region growing (A/B measurements)
     const char* ev = getenv("PLVI_LSD_SPEC");
     h->buf.useSpec = !(ev && ev[0] == '0');
+    const char* eq = getenv("PLVI_LSD_EQLOAD");
+    h->buf.eqLoad = eq ? (eq[0] == '0' ? 0 : 2) : 1;   // 1 (default): by batch size, 2 / 0: forced on / off
   }
   *out = h;
   return PLVI_OK;
@@ -432,7 +435,7 @@ void plvi_line_destroy(plvi_line* h) {
   if (h->aux.stage) cudaEventDestroy(h->aux.stage);
   cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
   cudaFree(h->buf.ang); cudaFree(h->buf.cs); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
-  cudaFree(h->buf.specBm); cudaFree(h->buf.specRec); cudaFree(h->buf.specCnt); cudaFree(h->buf.phantom);
+  cudaFree(h->buf.specBm); cudaFree(h->buf.specRec); cudaFree(h->buf.specCnt); cudaFree(h->buf.bandRow); cudaFree(h->buf.phantom);
   cudaFree(h->buf.brIn); cudaFree(h->buf.brWk); cudaFree(h->buf.brPh); cudaFree(h->buf.brRec); cudaFree(h->buf.brList);
   cudaFree(h->buf.brState); cudaFree(h->buf.brFlags);
   cudaFree(h->buf.reg); cudaFree(h->buf.regTab); cudaFree(h->buf.regCount); cudaFree(h->buf.segs);

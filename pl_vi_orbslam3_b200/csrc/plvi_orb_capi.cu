@@ -53,6 +53,7 @@ struct plvi_orb {
   AsyncOutput aout;
   int cap = 0;
   int lastN = 0, lastLaunches = 0;
+  cudaEvent_t waitAfterPyramid = nullptr;   // one-shot (plvi_orb_wait_event_after_pyramid)
   StageProf prof;
   GraphCache graphs;
   int* dStereoSad = nullptr;      // scratch of plvi_orb_stereo_matches
@@ -450,6 +451,11 @@ int plvi_orb_wait_event(plvi_orb* h, void* cuda_event) {
   PLVI_CUDA_TRY(cudaStreamWaitEvent(h->stream, (cudaEvent_t)cuda_event, 0));
   return PLVI_OK;
 }
+int plvi_orb_wait_event_after_pyramid(plvi_orb* h, void* cuda_event) {
+  if (!h) return PLVI_ERR_INVALID;
+  h->waitAfterPyramid = (cudaEvent_t)cuda_event;
+  return PLVI_OK;
+}
 int plvi_orb_graph_stats(const plvi_orb* h, int* captures) {
   if (!h) return PLVI_ERR_INVALID;
   if (captures) *captures = (int)h->graphs.captures;
@@ -486,15 +492,17 @@ int plvi_orb_level_sizes(const plvi_orb* h, int w, int hh, int* lw, int* lh) {
 // The per-batch launch sequence, replayed from a captured CUDA graph when possible (GraphCache).
 static int run_orb_pipeline(plvi_orb* h, const OrbPtrs& p, int n, int lap0, int lap1, plvi_keypoint* d_kps,
                             uint8_t* d_desc, int* d_counts, int* d_mono) {
+  const cudaEvent_t waitEv = h->waitAfterPyramid;
+  h->waitAfterPyramid = nullptr;
   auto record = [&](int* launches) {
     return launch_orb_pipeline(h->geom, p, h->scr, n, lap0, lap1, d_kps, d_desc, d_counts, d_mono, h->cap, h->stream,
-                               launches, &h->prof);
+                               launches, &h->prof, waitEv);
   };
   if (h->prof.on || !h->graphs.on()) return record(&h->lastLaunches);
   std::vector<uint64_t> key = {(uint64_t)n, (uint64_t)h->curW, (uint64_t)h->curH, (uint64_t)(uintptr_t)p.img[0],
                                (uint64_t)p.ipitch[0], (uint64_t)p.ifs[0], (uint64_t)(uint32_t)lap0, (uint64_t)(uint32_t)lap1,
                                (uint64_t)(uintptr_t)d_kps, (uint64_t)(uintptr_t)d_desc, (uint64_t)(uintptr_t)d_counts,
-                               (uint64_t)(uintptr_t)d_mono};
+                               (uint64_t)(uintptr_t)d_mono, (uint64_t)(uintptr_t)waitEv};
   return h->graphs.run(h->stream, key, &h->lastLaunches, record);
 }
 

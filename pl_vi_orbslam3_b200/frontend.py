@@ -58,7 +58,10 @@ class FrontEnd:
         self.B, self.w, self.h = batch, w, h
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
-        self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
+        # PLVI_ORB_PRIORITY < 0: the stream of the ORB kernels and the searches outranks the line stream, so their blocks
+        # take the block slots that the (long, latency-bound) region-growing kernels free
+        self.stream = stream if stream is not None else torch.cuda.Stream(
+            device=self.device, priority=int(os.environ.get("PLVI_ORB_PRIORITY", "0")))
         sp = self.stream.cuda_stream
         # points and lines are independent (the reference runs them on two threads, src/Frame.cc:558-561):
         # the line pipeline gets its own stream, forked from / joined into self.stream every step, so the
@@ -73,7 +76,10 @@ class FrontEnd:
         # out_sets > 1: the results of consecutive steps go to alternating output buffers, so the
         # device-to-host copy of step i can still run while step i+1 computes
         self.out_sets = max(1, int(out_sets))
-        self.skew = os.environ.get("PLVI_SKEW", "1") != "0"   # ORB kernels start when the line pipeline reaches region growing
+        # ORB kernels start when the line pipeline reaches region growing ("1", default: the whole ORB sequence waits;
+        # "2": the pyramid runs at once -- measured slower, its short chained kernels starve beside k_lsd_pre; "0": no coupling)
+        self.skew = os.environ.get("PLVI_SKEW", "1")
+        self.skew = 0 if self.skew == "0" else (1 if self.skew == "1" else 2)
         self.share_upload = os.environ.get("PLVI_SHARE_UPLOAD", "1") != "0"   # step_host: the frames are uploaded once for both extractors
         self._set = 0
         self.orb_outs = [self.orb.alloc_device_outputs(batch, self.device) for _ in range(self.out_sets)]
@@ -160,7 +166,7 @@ class FrontEnd:
             self.stream.wait_event(self._ev_join)
         elif forked and self.skew:
             # hold the (issue-bound) ORB kernels back until the line pipeline has reached region growing
-            check(lib().plvi_orb_wait_event(self.orb._h, lib().plvi_line_stage_event(self.line._h)))
+            self._orb_wait_stage()
         kps, desc, counts, mono = self.orb.extract_batch_device(d_frames, out=self.orb_out)
         nl += self.orb.last_launches
         # the point searches only need the ORB results: they run while the line pipeline (the longer one) is still busy;
@@ -176,6 +182,10 @@ class FrontEnd:
         self.launches = nl
         return nl
 
+
+    def _orb_wait_stage(self):
+        fn = lib().plvi_orb_wait_event_after_pyramid if self.skew == 2 else lib().plvi_orb_wait_event
+        check(fn(self.orb._h, lib().plvi_line_stage_event(self.line._h)))
 
     def _next_set(self):
         if self.out_sets > 1:   # next output buffer set
@@ -297,7 +307,7 @@ class FrontEnd:
             if self.line_stream is not self.stream:
                 self._ev_join.record(self.line_stream)
                 if self.skew:   # as in step(): the ORB kernels start when the line pipeline has reached region growing
-                    check(lib().plvi_orb_wait_event(self.orb._h, lib().plvi_line_stage_event(self.line._h)))
+                    self._orb_wait_stage()
         if self.line is not None and self.share_upload:
             # one upload per batch: the ORB handle reads the device copy the line handle just made
             check(lib().plvi_orb_extract_batch_async_from_line(self.orb._h, self.line._h, 0, 0, ptr(io["kps"]), ptr(io["desc"]),
