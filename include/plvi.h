@@ -156,6 +156,11 @@ int plvi_orb_stereo_matches(plvi_orb* left, plvi_orb* right, int n, const plvi_k
 int plvi_orb_stereo_matches_host(plvi_orb* left, plvi_orb* right, const plvi_keypoint* kps_l, const uint8_t* desc_l, int n_l,
                                  const plvi_keypoint* kps_r, const uint8_t* desc_r, int n_r, float mb, float mbf, float* u_right,
                                  float* depth, int* nstereo);
+/* Builds the image pyramid of a batch (ORBextractor::ComputePyramid, src/ORBextractor.cc:1152-1177) on the handle's
+ * stream, ahead of the extraction call: the next plvi_orb_extract_batch_device on the SAME images (pointer, n, size,
+ * strides) skips its pyramid stage.  Lets a caller place the pyramid's short chained kernels where nothing else
+ * competes for the SMs (before the line pipeline starts) and the rest of the sequence beside region growing. */
+int plvi_orb_pyramid_device(plvi_orb* h, const uint8_t* d_imgs, int n, int w, int h_, int stride, size_t frame_stride);
 /* Makes the handle's stream wait for a cudaEvent_t (e.g. plvi_line_stage_event) before the next batch. */
 int plvi_orb_wait_event(plvi_orb* h, void* cuda_event);
 /* As plvi_orb_wait_event, but the wait sits INSIDE the next batch's launch sequence, behind the image pyramid: the

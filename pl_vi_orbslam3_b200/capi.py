@@ -51,6 +51,7 @@ _SIGS = {
     "plvi_orb_last_launches": (ci, [vp]),
     "plvi_orb_graph_stats": (ci, [vp, vp]),
     "plvi_orb_wait_event": (ci, [vp, vp]),
+    "plvi_orb_pyramid_device": (ci, [vp, vp, ci, ci, ci, ci, sz]),
     "plvi_orb_wait_event_after_pyramid": (ci, [vp, vp]),
     "plvi_orb_stereo_matches_host": (ci, [vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp, vp]),
     "plvi_orb_stereo_matches": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp, ci, cf, cf, vp, vp, vp]),

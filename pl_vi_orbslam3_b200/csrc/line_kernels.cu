@@ -261,7 +261,11 @@ __device__ __forceinline__ bool is_aligned_dev(double a, double theta, double pr
   return n <= prec;
 }
 
-#define GROW_WPB 4    // independent warps per block in k_lsd_spec / k_lsd_commit
+#define GROW_WPB 4    // independent warps per block in k_lsd_spec
+#ifndef COMMIT_WPB
+#define COMMIT_WPB 4  // ... and in k_lsd_commit
+#endif
+#define COMMIT_BPS (28 / COMMIT_WPB)   // resident blocks per SM: 28 warps of 72 registers
 #define GROW_RQ 512   // shared ring holding the most recent region pixels (BFS frontier)
 #define GROW_K 32     // bitmap rows kept in shared memory (sliding window below the seed row)
 
@@ -508,7 +512,7 @@ __global__ void __launch_bounds__(256) k_lsd_band_split(const __grid_constant__ 
   __shared__ int wsum[8];
   const unsigned* __restrict__ bm = b.bitmap + (size_t)f * g.bmTotal + O.bmOff;
   int* tab = b.bandRow + (size_t)f * (g.tasksPerFrame + 2) + O.taskOff + oct;
-  if (H > 1024 || !b.eqLoad) {   // taller than the scan below holds (or switched off): bands of equal rows
+  if (H > 1024 || !b.eqLoad) {   // switched off (or taller than the scan below holds): bands of equal rows
     for (int k = threadIdx.x; k <= nb; k += 256) tab[k] = k == nb ? H : min(k * O.bandRows, H);
     return;
   }
@@ -582,6 +586,9 @@ __global__ void __launch_bounds__(256) k_lsd_spec_init(const __grid_constant__ L
 // frames (similar content => similar amount of work).  Single flat loop: every iteration
 // expands one queue entry of the lane's current region, so lanes with regions of different
 // sizes stay converged.  Same tests, in the same order, as k_lsd_grow.
+// EQLOAD: band rows from the table of k_lsd_band_split; else bands of equal rows (the first row is then a warp-uniform
+// value, which keeps a few comparisons per iteration on the uniform datapath: 3 ms per 4096 frames)
+template <bool EQLOAD>
 __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constant__ LineGeom g, LineBufs b, int n) {
   const int t = blockIdx.x;
   const int f = blockIdx.y * (32 * GROW_WPB) + threadIdx.x;
@@ -590,8 +597,11 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
   const int j = t - O.taskOff;
   if (f >= n || j >= O.nbands) return;
   const int W = O.sw, H = O.sh, wpr = O.wpr;
-  const int* tab = b.bandRow + (size_t)f * (g.tasksPerFrame + 2) + t + oct;
-  const int r0 = tab[0], r1 = min(tab[1], H - 1);
+  int r0 = j * O.bandRows, r1 = min(r0 + O.bandRows, H - 1);
+  if (EQLOAD) {
+    const int* tab = b.bandRow + (size_t)f * (g.tasksPerFrame + 2) + t + oct;
+    r0 = tab[0]; r1 = min(tab[1], H - 1);
+  }
   unsigned* P = b.specBm + (size_t)f * g.specBmTotal + O.specBmOff + (size_t)j * wpr * H;
   unsigned* list = b.reg + (size_t)f * g.regTotal + O.regOff + (size_t)W * H + (size_t)j * O.bandPxCap;
   uint4* recs = reinterpret_cast<uint4*>(b.specRec + (size_t)f * g.specRecTotal + O.specRecOff + (size_t)j * O.bandRecCap);
@@ -800,15 +810,15 @@ template <int K> __device__ __forceinline__ void grow_clear_atomic(GrowBitmapT<K
   else atomicAnd(bm.gm + y * bm.wpr + (x >> 5), m);
 }
 
-__global__ void __launch_bounds__(32 * GROW_WPB, 7) k_lsd_commit(const __grid_constant__ LineGeom g, LineBufs b, int n,
+__global__ void __launch_bounds__(32 * COMMIT_WPB, COMMIT_BPS) k_lsd_commit(const __grid_constant__ LineGeom g, LineBufs b, int n,
                                                               int smemWordsPerWarp) {
-  // GROW_WPB independent warps per block (consecutive frames of one octave): single-warp blocks
+  // COMMIT_WPB independent warps per block (consecutive frames of one octave): single-warp blocks
   // would fill the SM's 32 block slots and keep the kernels of the other streams out
   extern __shared__ unsigned smem_all[];
   unsigned* smem_u = smem_all + (threadIdx.x >> 5) * smemWordsPerWarp;
   // longest jobs first: all octave-0 blocks (four times the pixels) precede the octave-1 blocks in launch order
-  const int nblk = (n + GROW_WPB - 1) / GROW_WPB;
-  const int oct = (int)blockIdx.x / nblk, f = ((int)blockIdx.x - oct * nblk) * GROW_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int nblk = (n + COMMIT_WPB - 1) / COMMIT_WPB;
+  const int oct = (int)blockIdx.x / nblk, f = ((int)blockIdx.x - oct * nblk) * COMMIT_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (oct >= g.noct || f >= n) return;
   const LineOct& O = g.o[oct];
   const int W = O.sw, H = O.sh, wpr = O.wpr;
@@ -2599,19 +2609,19 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     prof->mark("k_lsd_band_finish", st);
     nl += 3;
   } else if (b.useSpec) {
-    {  // equal-load bands shorten the longest chain while the batch is latency-bound (measured on B200: 512 frames +7 %,
-      // 1024 +2 %); from ~4096 frames on the kernel is bound by its memory instructions and equal rows are 1.5 % ahead
-      LineBufs bs = b;
-      bs.eqLoad = b.eqLoad == 1 ? (n <= 2048) : (b.eqLoad == 2);
-      k_lsd_band_split<<<dim3(g.noct, n), 256, 0, st>>>(g, bs);
-    }
+    // equal-load bands shorten the longest chain while the batch is latency-bound (measured on B200: 512 frames +7 %,
+    // 1024 +2 %); from ~4096 frames on the kernel is bound by its memory instructions and equal rows are 1.5 % ahead
+    LineBufs bs = b;
+    bs.eqLoad = (b.eqLoad == 1 ? (n <= 2048) : (b.eqLoad == 2)) && g.o[0].sh <= 1024;
+    k_lsd_band_split<<<dim3(g.noct, n), 256, 0, st>>>(g, bs);
     k_lsd_spec_init<<<dim3(8, g.tasksPerFrame, n), 256, 0, st>>>(g, b);
     nl += 1;
     prof->mark("k_lsd_spec_init", st);
-    k_lsd_spec<<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
+    if (bs.eqLoad) k_lsd_spec<true><<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
+    else k_lsd_spec<false><<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
     prof->mark("k_lsd_spec", st);
     const size_t commitSmem = growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned);
-    k_lsd_commit<<<dim3(g.noct * ((n + GROW_WPB - 1) / GROW_WPB)), 32 * GROW_WPB, commitSmem * GROW_WPB, st>>>(
+    k_lsd_commit<<<dim3(g.noct * ((n + COMMIT_WPB - 1) / COMMIT_WPB)), 32 * COMMIT_WPB, commitSmem * COMMIT_WPB, st>>>(
         g, b, n, (int)(commitSmem / sizeof(unsigned)));
     prof->mark("k_lsd_commit", st);
     nl += 2;
@@ -2639,7 +2649,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
 
 int line_kernel_attrs(const LineGeom& g) {
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
-  const size_t commitSmem = (growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned)) * GROW_WPB;
+  const size_t commitSmem = (growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned)) * COMMIT_WPB;
   if (commitSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
   {
     size_t psm = 0;

@@ -868,7 +868,8 @@ void launch_resize_u8(const u8* src, int spitch, size_t sfs, int sw, int sh, u8*
   // staged variant: 16-byte aligned rows and a source window that fits the shared tile (scale factors up to 2)
   const bool aligned = ((uintptr_t)src & 15) == 0 && (spitch & 15) == 0 && (sfs & 15) == 0 && spitch >= ((sw + 15) & ~15);
   const long spanW = ((long)RS_TW * sw + dw - 1) / dw + 3 + 32, spanH = ((long)RS_TH * sh + dh - 1) / dh + 3;
-  if (aligned && spanW <= RS_SRC_W && spanH <= RS_SRC_H) {
+  static const bool direct = [] { const char* e = getenv("PLVI_RESIZE_DIRECT"); return e && e[0] == '1'; }();
+  if (!direct && aligned && spanW <= RS_SRC_W && spanH <= RS_SRC_H) {
     dim3 grd((dw + RS_TW - 1) / RS_TW, (dh + RS_TH - 1) / RS_TH, n);
     k_resize_tma<<<grd, 256, 0, st>>>(src, spitch, sfs, sw, sh, dst, dpitch, dfs, dw, dh, xtab, ytab);
     return;
@@ -916,21 +917,29 @@ int orb_kernel_attrs(const OrbGeom& g, int* fastSmem, int* octSmem) {
 
 int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s, int n, int lap0,
                         int lap1, plvi_keypoint* d_kps, uint8_t* d_desc, int* d_counts,
-                        int* d_mono, int cap, cudaStream_t st, int* launches, StageProf* prof, cudaEvent_t waitAfterPyramid) {
+                        int* d_mono, int cap, cudaStream_t st, int* launches, StageProf* prof, cudaEvent_t waitAfterPyramid, int stages) {
+  // stages: bit 0 = the pyramid, bit 1 = everything after it (plvi_orb_pyramid_device runs the pyramid ahead)
   int nl = 0;
   StageProf nop;
   if (!prof) prof = &nop;
   prof->begin(st);
-  PLVI_CUDA_TRY(cudaMemsetAsync(s.candCount, 0, sizeof(int) * (size_t)n * g.nlevels, st));
-  // pyramid (chained: level l from level l-1)
-  for (int l = 1; l < g.nlevels; l++) {
-    const OrbLevel& d = g.lv[l];
-    const OrbLevel& sl = g.lv[l - 1];
-    launch_resize_u8(p.img[l - 1], p.ipitch[l - 1], p.ifs[l - 1], sl.w, sl.h, const_cast<u8*>(p.img[l]), p.ipitch[l],
-                     p.ifs[l], d.w, d.h, s.rsTab + d.rsOff, s.rsTab + d.rsOff + d.w, n, st);
-    nl++;
+  if (stages & 1) {
+    // pyramid (chained: level l from level l-1)
+    for (int l = 1; l < g.nlevels; l++) {
+      const OrbLevel& d = g.lv[l];
+      const OrbLevel& sl = g.lv[l - 1];
+      launch_resize_u8(p.img[l - 1], p.ipitch[l - 1], p.ifs[l - 1], sl.w, sl.h, const_cast<u8*>(p.img[l]), p.ipitch[l],
+                       p.ifs[l], d.w, d.h, s.rsTab + d.rsOff, s.rsTab + d.rsOff + d.w, n, st);
+      nl++;
+    }
+    prof->mark("k_resize", st);
   }
-  prof->mark("k_resize", st);
+  if (!(stages & 2)) {
+    PLVI_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches = nl;
+    return PLVI_OK;
+  }
+  PLVI_CUDA_TRY(cudaMemsetAsync(s.candCount, 0, sizeof(int) * (size_t)n * g.nlevels, st));
   if (waitAfterPyramid) {   // plvi_orb_wait_event_after_pyramid: the rest of the sequence follows the caller's event
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);

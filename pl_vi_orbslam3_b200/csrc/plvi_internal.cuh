@@ -443,7 +443,7 @@ int launch_stereo(const OrbGeom& g, const OrbPtrs& L, const OrbPtrs& R, const fl
                   cudaStream_t st);
 int launch_orb_pipeline(const OrbGeom& g, const OrbPtrs& p, const OrbScratch& s, int n, int lap0,
                         int lap1, plvi_keypoint* d_kps, uint8_t* d_desc, int* d_counts,
-                        int* d_mono, int cap, cudaStream_t st, int* launches, StageProf* prof, cudaEvent_t waitAfterPyramid = nullptr);
+                        int* d_mono, int cap, cudaStream_t st, int* launches, StageProf* prof, cudaEvent_t waitAfterPyramid = nullptr, int stages = 3);
 int orb_kernel_attrs(const OrbGeom& g, int* fastSmem, int* octSmem);
 
 }  // namespace plvi

@@ -54,6 +54,8 @@ struct plvi_orb {
   int cap = 0;
   int lastN = 0, lastLaunches = 0;
   cudaEvent_t waitAfterPyramid = nullptr;   // one-shot (plvi_orb_wait_event_after_pyramid)
+  bool pyrValid = false;                    // plvi_orb_pyramid_device built the pyramid of pyrKey ahead of the extraction call
+  uint64_t pyrKey[6] = {0, 0, 0, 0, 0, 0};
   StageProf prof;
   GraphCache graphs;
   int* dStereoSad = nullptr;      // scratch of plvi_orb_stereo_matches
@@ -494,16 +496,38 @@ static int run_orb_pipeline(plvi_orb* h, const OrbPtrs& p, int n, int lap0, int 
                             uint8_t* d_desc, int* d_counts, int* d_mono) {
   const cudaEvent_t waitEv = h->waitAfterPyramid;
   h->waitAfterPyramid = nullptr;
+  // the pyramid of exactly these images was built ahead (plvi_orb_pyramid_device): skip that stage
+  const uint64_t pk[6] = {(uint64_t)(uintptr_t)p.img[0], (uint64_t)n, (uint64_t)h->curW, (uint64_t)h->curH, (uint64_t)p.ipitch[0], (uint64_t)p.ifs[0]};
+  const bool havePyr = h->pyrValid && std::equal(pk, pk + 6, h->pyrKey);
+  h->pyrValid = false;
+  const int stages = havePyr ? 2 : 3;
   auto record = [&](int* launches) {
     return launch_orb_pipeline(h->geom, p, h->scr, n, lap0, lap1, d_kps, d_desc, d_counts, d_mono, h->cap, h->stream,
-                               launches, &h->prof, waitEv);
+                               launches, &h->prof, waitEv, stages);
   };
   if (h->prof.on || !h->graphs.on()) return record(&h->lastLaunches);
   std::vector<uint64_t> key = {(uint64_t)n, (uint64_t)h->curW, (uint64_t)h->curH, (uint64_t)(uintptr_t)p.img[0],
                                (uint64_t)p.ipitch[0], (uint64_t)p.ifs[0], (uint64_t)(uint32_t)lap0, (uint64_t)(uint32_t)lap1,
                                (uint64_t)(uintptr_t)d_kps, (uint64_t)(uintptr_t)d_desc, (uint64_t)(uintptr_t)d_counts,
-                               (uint64_t)(uintptr_t)d_mono, (uint64_t)(uintptr_t)waitEv};
+                               (uint64_t)(uintptr_t)d_mono, (uint64_t)(uintptr_t)waitEv, (uint64_t)stages};
   return h->graphs.run(h->stream, key, &h->lastLaunches, record);
+}
+
+int plvi_orb_pyramid_device(plvi_orb* h, const uint8_t* d_imgs, int n, int w, int hh, int stride, size_t frame_stride) {
+  int rc = check_batch(h, d_imgs, n, w, hh, stride);
+  if (rc) return rc;
+  PLVI_CUDA_TRY(cudaSetDevice(h->device));
+  if ((rc = ensure_geom(h, w, hh))) return rc;
+  OrbPtrs p;
+  fill_ptrs(h, d_imgs, stride, frame_stride, p);
+  int nl = 0;
+  StageProf off;
+  rc = launch_orb_pipeline(h->geom, p, h->scr, n, 0, 0, nullptr, nullptr, nullptr, nullptr, h->cap, h->stream, &nl, &off, nullptr, 1);
+  if (rc) return rc;
+  const uint64_t pk[6] = {(uint64_t)(uintptr_t)p.img[0], (uint64_t)n, (uint64_t)h->curW, (uint64_t)h->curH, (uint64_t)p.ipitch[0], (uint64_t)p.ifs[0]};
+  std::copy(pk, pk + 6, h->pyrKey);
+  h->pyrValid = true;
+  return PLVI_OK;
 }
 
 int plvi_orb_extract_batch_device(plvi_orb* h, const uint8_t* d_imgs, int n, int w, int hh,

@@ -66,6 +66,8 @@ class FrontEnd:
         # points and lines are independent (the reference runs them on two threads, src/Frame.cc:558-561):
         # the line pipeline gets its own stream, forked from / joined into self.stream every step, so the
         # latency-bound LSD region growing overlaps the throughput-bound ORB kernels
+        if line_priority == 0:
+            line_priority = int(os.environ.get("PLVI_LINE_PRIORITY", "0"))
         self.line_stream = torch.cuda.Stream(device=self.device, priority=line_priority) if overlap_lines else self.stream
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
@@ -80,6 +82,7 @@ class FrontEnd:
         # "2": the pyramid runs at once -- measured slower, its short chained kernels starve beside k_lsd_pre; "0": no coupling)
         self.skew = os.environ.get("PLVI_SKEW", "1")
         self.skew = 0 if self.skew == "0" else (1 if self.skew == "1" else 2)
+        self.pyr_first = os.environ.get("PLVI_PYR_FIRST", "0") != "0"   # step(): ORB pyramid ahead of the line pipeline
         self.share_upload = os.environ.get("PLVI_SHARE_UPLOAD", "1") != "0"   # step_host: the frames are uploaded once for both extractors
         self._set = 0
         self.orb_outs = [self.orb.alloc_device_outputs(batch, self.device) for _ in range(self.out_sets)]
@@ -155,6 +158,11 @@ class FrontEnd:
         nl = 0
         self._next_set()
         forked = self.line is not None and self.line_stream is not self.stream
+        if forked and self.pyr_first and not serialize:
+            # the ORB pyramid (seven short chained kernels) before anything else is in flight: beside k_lsd_pre or the
+            # region growing its blocks wait for slots and the chain takes 5x as long
+            check(lib().plvi_orb_pyramid_device(self.orb._h, ptr(d_frames), n, d_frames.shape[2], d_frames.shape[1],
+                                                d_frames.stride(1), d_frames.stride(0)))
         if forked:
             self._ev_fork.record(self.stream)
             self.line_stream.wait_event(self._ev_fork)

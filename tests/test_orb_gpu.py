@@ -234,3 +234,38 @@ def test_cuda_graph_replay_is_used_and_identical(gpu):
     finally:
         e.close()
         le.close()
+
+
+def test_pyramid_ahead_and_wait_after_pyramid_give_the_same_result(ext):
+    """Scheduling hooks of the batched front end: plvi_orb_pyramid_device builds the pyramid ahead of the extraction call
+    (which then skips that stage), plvi_orb_wait_event_after_pyramid places an event wait behind the pyramid.  Neither
+    changes a bit of the result; a pyramid built for OTHER images is not reused."""
+    import torch
+    from pl_vi_orbslam3_b200.capi import check, lib, ptr
+    frames = np.stack([synth.frame_euroc(s) for s in (3, 4, 5, 6)])
+    d = torch.from_numpy(frames).cuda()
+    other = torch.from_numpy(np.stack([synth.frame_euroc(s) for s in (7, 8, 9, 10)])).cuda()
+    base = [t.clone() for t in ext.extract_batch_device(d)]
+    torch.cuda.synchronize()
+    n, h, w = d.shape
+    # pyramid ahead, same images
+    check(lib().plvi_orb_pyramid_device(ext._h, ptr(d), n, w, h, d.stride(1), d.stride(0)))
+    got = ext.extract_batch_device(d)
+    torch.cuda.synchronize()
+    for a, b in zip(base, got):
+        assert torch.equal(a.contiguous().view(torch.uint8), b.contiguous().view(torch.uint8))   # bytes: class_id -1 reads as NaN
+    # pyramid of other images: the extraction call rebuilds its own
+    check(lib().plvi_orb_pyramid_device(ext._h, ptr(other), n, w, h, other.stride(1), other.stride(0)))
+    got = ext.extract_batch_device(d)
+    torch.cuda.synchronize()
+    for a, b in zip(base, got):
+        assert torch.equal(a.contiguous().view(torch.uint8), b.contiguous().view(torch.uint8))   # bytes: class_id -1 reads as NaN
+    # event wait behind the pyramid (an event that has already completed)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    check(lib().plvi_orb_wait_event_after_pyramid(ext._h, ptr(ev.cuda_event)))
+    got = ext.extract_batch_device(d)
+    torch.cuda.synchronize()
+    for a, b in zip(base, got):
+        assert torch.equal(a.contiguous().view(torch.uint8), b.contiguous().view(torch.uint8))   # bytes: class_id -1 reads as NaN
