@@ -163,6 +163,10 @@ int plvi_orb_stereo_matches_host(plvi_orb* left, plvi_orb* right, const plvi_key
 int plvi_orb_pyramid_device(plvi_orb* h, const uint8_t* d_imgs, int n, int w, int h_, int stride, size_t frame_stride);
 /* Makes the handle's stream wait for a cudaEvent_t (e.g. plvi_line_stage_event) before the next batch. */
 int plvi_orb_wait_event(plvi_orb* h, void* cuda_event);
+/* Makes the handle's stream wait (one polling thread, 30 ms time limit) until a device counter has reached `target`:
+ * with plvi_line_stage_counter the ORB kernels start when the blocks of the line pipeline's region-growing kernel are
+ * resident (launched first, they otherwise queue behind the ORB kernels' blocks and the latency-bound chain starts late). */
+int plvi_orb_wait_counter(plvi_orb* h, const int* d_counter, int target);
 /* As plvi_orb_wait_event, but the wait sits INSIDE the next batch's launch sequence, behind the image pyramid: the
  * pyramid kernels (short, chained, one level from the previous) run at once, FAST and everything after it when the
  * event has completed.  One-shot: applies to the next batch only. */
@@ -204,6 +208,10 @@ int plvi_line_graph_stats(const plvi_line* h, int* captures);   /* see plvi_orb_
  * (plvi_orb_wait_event): the two issue-bound phases no longer share the SMs and the ORB kernels fill the slots region
  * growing leaves idle.  The reference runs both extractors as two host threads per frame (src/Frame.cc:558-561). */
 void* plvi_line_stage_event(plvi_line* h);
+/* Device counter of region-growing blocks that have started in the current batch (reset before the stage event is
+ * recorded) and the count at which all of the last batch's blocks that fit the GPU at once are resident.  Schedules
+ * without that kernel (small batches, lsd_refine > 0) set the counter to a large value. */
+const int* plvi_line_stage_counter(plvi_line* h, int* target);
 /* mvScaleFactor_l / mvInvScaleFactor_l / mvLevelSigma2_l / mvInvLevelSigma2_l
  * (src/LineExtractor.cc:86-101) */
 int plvi_line_scale_factors(const plvi_line* h, float* scale, float* inv_scale, float* sigma2,

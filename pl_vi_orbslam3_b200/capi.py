@@ -51,6 +51,7 @@ _SIGS = {
     "plvi_orb_last_launches": (ci, [vp]),
     "plvi_orb_graph_stats": (ci, [vp, vp]),
     "plvi_orb_wait_event": (ci, [vp, vp]),
+    "plvi_orb_wait_counter": (ci, [vp, vp, ci]),
     "plvi_orb_pyramid_device": (ci, [vp, vp, ci, ci, ci, ci, sz]),
     "plvi_orb_wait_event_after_pyramid": (ci, [vp, vp]),
     "plvi_orb_stereo_matches_host": (ci, [vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp, vp]),
@@ -69,6 +70,7 @@ _SIGS = {
     "plvi_line_last_launches": (ci, [vp]),
     "plvi_line_graph_stats": (ci, [vp, vp]),
     "plvi_line_stage_event": (vp, [vp]),
+    "plvi_line_stage_counter": (vp, [vp, vp]),
     "plvi_line_scale_factors": (ci, [vp, vp, vp, vp, vp]),
     "plvi_line_octave_sizes": (ci, [vp, ci, ci, vp, vp, vp, vp]),
     "plvi_line_extract_batch": (ci, [vp, vp, ci, ci, ci, ci, sz, vp, vp, vp, vp]),

@@ -71,6 +71,7 @@ struct LineBufs {
   unsigned* specBm;      // [B][specBmTotal] private availability bitmaps of the speculation bands
   SpecRec* specRec;      // [B][specRecTotal]
   int* specCnt;          // [B][tasksPerFrame] speculative regions per band
+  int* specStart;        // [1] blocks of k_lsd_spec that have started in the current batch (plvi_line_stage_counter)
   int* bandRow;          // [B][tasksPerFrame + 2] first row of every band, octave o from taskOff + o (nbands + 1 entries): equal LOAD per band
   unsigned* phantom;     // [B][bmTotal]   pixels a discarded speculative region had consumed
   int useSpec;           // 0: serial k_lsd_grow only

@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
   const int oct = (g.noct > 1 && t >= g.o[1].taskOff) ? 1 : 0;
   const LineOct& O = g.o[oct];
   const int j = t - O.taskOff;
+  if (threadIdx.x == 0) atomicAdd(b.specStart, 1);   // plvi_line_stage_counter: this block is resident
   if (f >= n || j >= O.nbands) return;
   const int W = O.sw, H = O.sh, wpr = O.wpr;
   int r0 = j * O.bandRows, r1 = min(r0 + O.bandRows, H - 1);
@@ -759,6 +760,7 @@ __global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constan
 template <int K> struct PhantomMapT {
   unsigned* sm;      // [K][wpr] shared window, slides with the availability window
   unsigned* gm;      // [H][wpr] global copy (rows below the window)
+  unsigned* rm = nullptr;   // [K] per window row: bit min(w, 31) set if word w of the row holds a phantom pixel (nullptr: not kept)
   bool any;          // warp-uniform: some phantom pixel exists
   // warp-uniform bounding box (grown by one pixel) of the phantom pixels marked for the CURRENT band: only a
   // discarded speculation of the same band can have hidden a pixel from a speculative region, and most regions lie
@@ -777,8 +779,10 @@ template <int K> struct PhantomMapT {
   }
   __device__ __forceinline__ void mark(const GrowBitmapT<K>& bm, int x, int y) {
     const unsigned bit = 1u << (x & 31);
-    if (y - bm.top < K) atomicOr(&sm[(y & (K - 1)) * bm.wpr + (x >> 5)], bit);
-    else atomicOr(gm + y * bm.wpr + (x >> 5), bit);
+    if (y - bm.top < K) {
+      atomicOr(&sm[(y & (K - 1)) * bm.wpr + (x >> 5)], bit);
+      if (rm) atomicOr(&rm[y & (K - 1)], 1u << min(x >> 5, 31));
+    } else atomicOr(gm + y * bm.wpr + (x >> 5), bit);
   }
   // any available phantom pixel in the 3x3 neighbourhood of (x, y)?  (y >= bm.top; rows above the window top hold
   // no available pixel).  Same instruction path for every lane: the three rows are read unconditionally (a row
@@ -786,6 +790,12 @@ template <int K> struct PhantomMapT {
   __device__ __forceinline__ bool near(const GrowBitmapT<K>& bm, int x, int y, int H) const {
     const int xm = x - 1;
     const int wa = max(xm, 0) >> 5;
+    // quick reject from the row masks while the three rows lie inside the window (a row above the window top reads the
+    // mask of a row further down: a superset, never a miss)
+    if (rm && y + 1 - bm.top < K) {
+      const unsigned wm = (1u << min(wa, 31)) | (1u << min((x + 1) >> 5, 31));
+      if (!((rm[(y - 1) & (K - 1)] | rm[y & (K - 1)] | rm[(y + 1) & (K - 1)]) & wm)) return false;
+    }
     const int sh = xm - (wa << 5);   // -1 .. 31
     const bool two = sh >= 30 && wa + 1 < bm.wpr;
     unsigned hit = 0u;
@@ -831,9 +841,11 @@ __global__ void __launch_bounds__(32 * COMMIT_WPB, COMMIT_BPS) k_lsd_commit(cons
   PhantomMap ph;
   ph.gm = b.phantom + (size_t)f * g.bmTotal + O.bmOff;
   ph.sm = bm.sm + GROW_K * wpr;
+  ph.rm = ph.sm + GROW_K * wpr;
   ph.any = false;
   ph.box_reset();
   for (int i = lane; i < min(GROW_K, H) * wpr; i += 32) { bm.sm[i] = __ldcg(bm.gm + i); ph.sm[i] = 0u; }
+  ph.rm[lane & (GROW_K - 1)] = 0u;
   __syncwarp();
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
   const float2* __restrict__ rec = b.cs + pbase;
@@ -875,11 +887,17 @@ __global__ void __launch_bounds__(32 * COMMIT_WPB, COMMIT_BPS) k_lsd_commit(cons
     // slide the shared windows: rows [top, row) are exhausted, rows up to row + GROW_K enter
     if (row > bm.top) {
       const int r0 = bm.top + GROW_K, r1 = min(row + GROW_K, H);
-      for (int r = r0; r < r1; r++)
+      for (int r = r0; r < r1; r++) {
+        unsigned rmask = 0u;
         for (int wv = lane; wv < wpr; wv += 32) {
           bm.sm[(r & (GROW_K - 1)) * wpr + wv] = __ldcg(bm.gm + r * wpr + wv);
-          ph.sm[(r & (GROW_K - 1)) * wpr + wv] = ph.any ? __ldcg(ph.gm + r * wpr + wv) : 0u;
+          const unsigned pw = ph.any ? __ldcg(ph.gm + r * wpr + wv) : 0u;
+          ph.sm[(r & (GROW_K - 1)) * wpr + wv] = pw;
+          if (pw) rmask |= 1u << min(wv, 31);
         }
+        rmask = __reduce_or_sync(0xffffffffu, rmask);
+        if (lane == 0) ph.rm[r & (GROW_K - 1)] = rmask;
+      }
       bm.top = row;
       __syncwarp();
     }
@@ -2547,6 +2565,11 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   }
   // From here on the main stream holds the latency-bound region growing (low issue-slot use): a caller may hold
   // other issue-bound work (the ORB pipeline) back until this point (plvi_line_stage_event).
+  // plvi_line_stage_counter: k_lsd_spec counts its blocks as they start; the other schedules let a waiter pass at once
+  {
+    const bool specPath = g.refine == 0 && !(b.brMax > 0 && n <= b.brUse) && b.useSpec;
+    PLVI_CUDA_TRY(cudaMemsetAsync(b.specStart, specPath ? 0 : 0x3f, sizeof(int), st));
+  }
   if (aux.stage && (!prof->on || StageProf::timeline())) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
@@ -2620,7 +2643,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     if (bs.eqLoad) k_lsd_spec<true><<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
     else k_lsd_spec<false><<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
     prof->mark("k_lsd_spec", st);
-    const size_t commitSmem = growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned);
+    const size_t commitSmem = growSmem + ((size_t)g.o[0].wpr + 1) * GROW_K * sizeof(unsigned);   // + phantom window and its row masks
     k_lsd_commit<<<dim3(g.noct * ((n + COMMIT_WPB - 1) / COMMIT_WPB)), 32 * COMMIT_WPB, commitSmem * COMMIT_WPB, st>>>(
         g, b, n, (int)(commitSmem / sizeof(unsigned)));
     prof->mark("k_lsd_commit", st);
@@ -2649,7 +2672,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
 
 int line_kernel_attrs(const LineGeom& g) {
   const size_t growSmem = ((size_t)g.o[0].wpr * GROW_K + GROW_RQ) * sizeof(unsigned);
-  const size_t commitSmem = (growSmem + (size_t)g.o[0].wpr * GROW_K * sizeof(unsigned)) * COMMIT_WPB;
+  const size_t commitSmem = (growSmem + ((size_t)g.o[0].wpr + 1) * GROW_K * sizeof(unsigned)) * COMMIT_WPB;
   if (commitSmem > 200 * 1024) { set_error("image too large for the LSD shared-memory bitmap"); return PLVI_ERR_CAPACITY; }
   {
     size_t psm = 0;

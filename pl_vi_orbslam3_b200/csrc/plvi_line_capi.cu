@@ -348,6 +348,7 @@ int plvi_line_create_ex(plvi_line** out, int lsd_nfeatures, int lsd_refine, floa
   A((void**)&h->buf.specBm, B * c.specBmTotal * sizeof(unsigned));
   A((void**)&h->buf.specRec, B * c.specRecTotal * sizeof(SpecRec));
   A((void**)&h->buf.specCnt, B * c.tasksPerFrame * sizeof(int));
+  A((void**)&h->buf.specStart, 64);
   A((void**)&h->buf.bandRow, B * (c.tasksPerFrame + 2) * sizeof(int));
   A((void**)&h->buf.phantom, B * c.bmTotal * sizeof(unsigned));
   {  // band-run buffers for batches of up to PLVI_LSD_BR_MAX frames (0 switches the path off).  Default 384: measured on
@@ -435,7 +436,7 @@ void plvi_line_destroy(plvi_line* h) {
   if (h->aux.stage) cudaEventDestroy(h->aux.stage);
   cudaFree(h->dImg[0]); cudaFree(h->dImg[1]);
   cudaFree(h->buf.ang); cudaFree(h->buf.cs); cudaFree(h->buf.seed); cudaFree(h->buf.mod); cudaFree(h->buf.bitmap);
-  cudaFree(h->buf.specBm); cudaFree(h->buf.specRec); cudaFree(h->buf.specCnt); cudaFree(h->buf.bandRow); cudaFree(h->buf.phantom);
+  cudaFree(h->buf.specBm); cudaFree(h->buf.specRec); cudaFree(h->buf.specCnt); cudaFree(h->buf.bandRow); cudaFree(h->buf.specStart); cudaFree(h->buf.phantom);
   cudaFree(h->buf.brIn); cudaFree(h->buf.brWk); cudaFree(h->buf.brPh); cudaFree(h->buf.brRec); cudaFree(h->buf.brList);
   cudaFree(h->buf.brState); cudaFree(h->buf.brFlags);
   cudaFree(h->buf.reg); cudaFree(h->buf.regTab); cudaFree(h->buf.regCount); cudaFree(h->buf.segs);
@@ -453,6 +454,18 @@ int plvi_line_capacity(const plvi_line* h) { return h ? h->capGeom.keepCap : PLV
 void* plvi_line_stream(const plvi_line* h) { return h ? (void*)h->stream : nullptr; }
 int plvi_line_last_launches(const plvi_line* h) { return h ? h->lastLaunches : PLVI_ERR_INVALID; }
 void* plvi_line_stage_event(plvi_line* h) { return h ? (void*)h->aux.stage : nullptr; }
+const int* plvi_line_stage_counter(plvi_line* h, int* target) {
+  if (!h) return nullptr;
+  if (target) {
+    // blocks of k_lsd_spec in the last batch, capped at what is resident at once beside a few other blocks (5 of the 6
+    // blocks of 128 threads per SM)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int blocks = h->geom.tasksPerFrame * ((h->lastN + 127) / 128);
+    *target = std::min(blocks, sms * 5);
+  }
+  return h->buf.specStart;
+}
 int plvi_line_graph_stats(const plvi_line* h, int* captures) {
   if (!h) return PLVI_ERR_INVALID;
   if (captures) *captures = (int)h->graphs.captures;

@@ -453,6 +453,24 @@ int plvi_orb_wait_event(plvi_orb* h, void* cuda_event) {
   PLVI_CUDA_TRY(cudaStreamWaitEvent(h->stream, (cudaEvent_t)cuda_event, 0));
   return PLVI_OK;
 }
+// one thread polls a device counter (another pipeline's progress) with a time limit: stream-ordered work behind it starts
+// when the counter has reached the target
+__global__ void k_wait_counter(const int* counter, int target, unsigned long long maxNs) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (*(volatile const int*)counter < target) {
+    __nanosleep(2000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > maxNs) break;
+  }
+}
+int plvi_orb_wait_counter(plvi_orb* h, const int* d_counter, int target) {
+  if (!h || !d_counter) return PLVI_ERR_INVALID;
+  PLVI_CUDA_TRY(cudaSetDevice(h->device));
+  k_wait_counter<<<1, 1, 0, h->stream>>>(d_counter, target, 30ull * 1000 * 1000);
+  PLVI_CUDA_TRY(cudaGetLastError());
+  return PLVI_OK;
+}
 int plvi_orb_wait_event_after_pyramid(plvi_orb* h, void* cuda_event) {
   if (!h) return PLVI_ERR_INVALID;
   h->waitAfterPyramid = (cudaEvent_t)cuda_event;

@@ -81,7 +81,7 @@ class FrontEnd:
         # ORB kernels start when the line pipeline reaches region growing ("1", default: the whole ORB sequence waits;
         # "2": the pyramid runs at once -- measured slower, its short chained kernels starve beside k_lsd_pre; "0": no coupling)
         self.skew = os.environ.get("PLVI_SKEW", "1")
-        self.skew = 0 if self.skew == "0" else (1 if self.skew == "1" else 2)
+        self.skew = int(self.skew) if self.skew in ("0", "1", "2", "3") else 1
         self.pyr_first = os.environ.get("PLVI_PYR_FIRST", "0") != "0"   # step(): ORB pyramid ahead of the line pipeline
         self.share_upload = os.environ.get("PLVI_SHARE_UPLOAD", "1") != "0"   # step_host: the frames are uploaded once for both extractors
         self._set = 0
@@ -194,6 +194,11 @@ class FrontEnd:
     def _orb_wait_stage(self):
         fn = lib().plvi_orb_wait_event_after_pyramid if self.skew == 2 else lib().plvi_orb_wait_event
         check(fn(self.orb._h, lib().plvi_line_stage_event(self.line._h)))
+        if self.skew == 3:   # ... and until the blocks of the region-growing kernel are resident
+            import ctypes as C
+            target = C.c_int(0)
+            ctr = lib().plvi_line_stage_counter(self.line._h, C.byref(target))
+            check(lib().plvi_orb_wait_counter(self.orb._h, C.c_void_p(ctr), target.value))
 
     def _next_set(self):
         if self.out_sets > 1:   # next output buffer set

@@ -60,16 +60,24 @@ def _check_pairs_against_oracle(out, A, B):
             assert rnl == nl and np.array_equal(rlm, lm12)
 
 
-@pytest.mark.parametrize("share", ["1", "0"])
+@pytest.mark.parametrize("share", ["1", "0", "sched"])
 def test_c3_pairs_device_path_and_host_buffer_path(gpu, share, monkeypatch):
     """share = 1: the frames are uploaded once (plvi_orb_extract_batch_async_from_line reads the line handle's copy);
-    0: each extractor call uploads them."""
+    0: each extractor call uploads them; sched: the scheduling hooks between the two pipelines (ORB pyramid ahead of
+    the line pipeline, ORB kernels behind the stage event AND the resident-block counter of the region-growing kernel,
+    band speculation instead of the small-batch schedule) -- results are the same bits."""
     import torch
+    kw = {}
+    if share == "sched":
+        share = "1"
+        monkeypatch.setenv("PLVI_SKEW", "3")
+        monkeypatch.setenv("PLVI_PYR_FIRST", "1")
+        kw["band_run_max"] = 0
     monkeypatch.setenv("PLVI_SHARE_UPLOAD", share)
     B = 6
     frames = synth.pair_batch(B, W, H, base_seed=40, workers=1, cache=False)
     A = synth.warp_affine(W, H).astype(np.float32).reshape(6)
-    fe = FrontEnd(B, w=W, h=H, pairs=True, affine=A, out_sets=2)
+    fe = FrontEnd(B, w=W, h=H, pairs=True, affine=A, out_sets=2, **kw)
     try:
         d = torch.from_numpy(frames).cuda()
         with torch.cuda.stream(fe.stream):

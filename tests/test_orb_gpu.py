@@ -245,7 +245,9 @@ def test_pyramid_ahead_and_wait_after_pyramid_give_the_same_result(ext):
     frames = np.stack([synth.frame_euroc(s) for s in (3, 4, 5, 6)])
     d = torch.from_numpy(frames).cuda()
     other = torch.from_numpy(np.stack([synth.frame_euroc(s) for s in (7, 8, 9, 10)])).cuda()
-    base = [t.clone() for t in ext.extract_batch_device(d)]
+    base = ext.extract_batch_device(d)
+    torch.cuda.synchronize()   # the handle has its own stream
+    base = [t.clone() for t in base]
     torch.cuda.synchronize()
     n, h, w = d.shape
     # pyramid ahead, same images
