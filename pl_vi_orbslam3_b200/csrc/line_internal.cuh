@@ -103,6 +103,9 @@ struct LineBufs {
 };
 
 #define BR_FLAGS 40
+// warps per block of k_lsd_spec: 640 blocks of 4 warps put 5 blocks on 48 of the 148 SMs and 4 on the others at 4096
+// frames; blocks of 2 warps spread evenly (54.2 -> 50.4 ms)
+#define SPEC_WPB 2
 
 struct LineAux { cudaStream_t stream; cudaEvent_t fork, join; cudaEvent_t stage; };   // stage: recorded when the streaming kernels are done and region growing starts   // side stream for the LBD pre-processing
 

@@ -261,7 +261,14 @@ __device__ __forceinline__ bool is_aligned_dev(double a, double theta, double pr
   return n <= prec;
 }
 
-#define GROW_WPB 4    // independent warps per block in k_lsd_spec
+#define GROW_WPB SPEC_WPB   // independent warps per block in k_lsd_spec (line_internal.cuh)
+#ifndef SPEC_MINB
+// resident blocks per SM the register allocation of k_lsd_spec allows for: 16 x 64 threads = 64 registers (20 bytes of
+// spills).  Alone the kernel is slower than with its natural 78 registers (56 vs 50 ms per 4096 frames), but a third of
+// the register file stays free for the ORB kernels that run beside it: the whole step gains 3 % (12: 23.5 k, 14: 23.1 k,
+// 16: 24.2 k, 18: 23.1 k, 20: 21.2 k frames/s)
+#define SPEC_MINB 16
+#endif
 #ifndef COMMIT_WPB
 #define COMMIT_WPB 4  // ... and in k_lsd_commit
 #endif
@@ -589,7 +596,7 @@ __global__ void __launch_bounds__(256) k_lsd_spec_init(const __grid_constant__ L
 // EQLOAD: band rows from the table of k_lsd_band_split; else bands of equal rows (the first row is then a warp-uniform
 // value, which keeps a few comparisons per iteration on the uniform datapath: 3 ms per 4096 frames)
 template <bool EQLOAD>
-__global__ void __launch_bounds__(32 * GROW_WPB) k_lsd_spec(const __grid_constant__ LineGeom g, LineBufs b, int n) {
+__global__ void __launch_bounds__(32 * GROW_WPB, SPEC_MINB) k_lsd_spec(const __grid_constant__ LineGeom g, LineBufs b, int n) {
   const int t = blockIdx.x;
   const int f = blockIdx.y * (32 * GROW_WPB) + threadIdx.x;
   const int oct = (g.noct > 1 && t >= g.o[1].taskOff) ? 1 : 0;

@@ -457,12 +457,12 @@ void* plvi_line_stage_event(plvi_line* h) { return h ? (void*)h->aux.stage : nul
 const int* plvi_line_stage_counter(plvi_line* h, int* target) {
   if (!h) return nullptr;
   if (target) {
-    // blocks of k_lsd_spec in the last batch, capped at what is resident at once beside a few other blocks (5 of the 6
-    // blocks of 128 threads per SM)
+    // blocks of k_lsd_spec in the last batch, capped at what is resident at once beside a few other blocks (20 of the
+    // 24 warps of 80 registers per SM)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const int blocks = h->geom.tasksPerFrame * ((h->lastN + 127) / 128);
-    *target = std::min(blocks, sms * 5);
+    const int blocks = h->geom.tasksPerFrame * ((h->lastN + 32 * SPEC_WPB - 1) / (32 * SPEC_WPB));
+    *target = std::min(blocks, sms * (20 / SPEC_WPB));
   }
   return h->buf.specStart;
 }
