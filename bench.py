@@ -97,7 +97,10 @@ def algo_bytes(w, h, cap, lw, lh, ow, oh, sw, sh, lines=200):
 
 
 GROW_NOTE = ("LSD region growing is a serial dependency chain per band (k_lsd_spec) / per frame and octave (k_lsd_commit): "
-             "bound by instruction latency along the chain, not by HBM; see DESIGN.md section 4 and profiles/")
+             "k_lsd_spec is bound by the latency of dependent L2 / DRAM round trips with 17 warps per SM (ncu at 4096 frames: issue "
+             "active 32 %, L1 / L2 / DRAM throughput 29 / 29 / 15 %, DRAM traffic 7.7x the algorithmic bytes because every 32-byte "
+             "sector of the neighbour records is fetched several times), k_lsd_commit half by instruction issue (64 %); neither by "
+             "HBM bandwidth; see DESIGN.md section 4 and profiles/r02b_notes.md")
 
 
 SCALE_FACTORS = np.cumprod(np.concatenate([[np.float32(1.0)], np.full(7, np.float32(1.2))]).astype(np.float32), dtype=np.float32)
@@ -290,7 +293,7 @@ class ClockSampler:
 
 def latest_profile(pattern):
     """The newest committed ncu-derived json under profiles/ matching rNN_<pattern> (highest round wins)."""
-    c = sorted((ROOT / "profiles").glob(f"r[0-9][0-9]_{pattern}"))
+    c = sorted((ROOT / "profiles").glob(f"r[0-9][0-9]*_{pattern}"))   # r02_x < r02b_x < r03_x
     return c[-1] if c else None
 
 

@@ -268,6 +268,7 @@ __device__ __forceinline__ bool is_aligned_dev(double a, double theta, double pr
 // the register file stays free for the ORB kernels that run beside it: the whole step gains 3 % (12: 23.5 k, 14: 23.1 k,
 // 16: 24.2 k, 18: 23.1 k, 20: 21.2 k frames/s)
 #define SPEC_MINB 16
+#define SPEC_MINB_SMALL 12   // 85 registers allowed: the natural allocation (78)
 #endif
 #ifndef COMMIT_WPB
 #define COMMIT_WPB 4  // ... and in k_lsd_commit
@@ -595,8 +596,8 @@ __global__ void __launch_bounds__(256) k_lsd_spec_init(const __grid_constant__ L
 // sizes stay converged.  Same tests, in the same order, as k_lsd_grow.
 // EQLOAD: band rows from the table of k_lsd_band_split; else bands of equal rows (the first row is then a warp-uniform
 // value, which keeps a few comparisons per iteration on the uniform datapath: 3 ms per 4096 frames)
-template <bool EQLOAD>
-__global__ void __launch_bounds__(32 * GROW_WPB, SPEC_MINB) k_lsd_spec(const __grid_constant__ LineGeom g, LineBufs b, int n) {
+template <bool EQLOAD, int MINB>
+__global__ void __launch_bounds__(32 * GROW_WPB, MINB) k_lsd_spec(const __grid_constant__ LineGeom g, LineBufs b, int n) {
   const int t = blockIdx.x;
   const int f = blockIdx.y * (32 * GROW_WPB) + threadIdx.x;
   const int oct = (g.noct > 1 && t >= g.o[1].taskOff) ? 1 : 0;
@@ -2647,8 +2648,14 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     k_lsd_spec_init<<<dim3(8, g.tasksPerFrame, n), 256, 0, st>>>(g, b);
     nl += 1;
     prof->mark("k_lsd_spec_init", st);
-    if (bs.eqLoad) k_lsd_spec<true><<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
-    else k_lsd_spec<false><<<dim3(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB)), 32 * GROW_WPB, 0, st>>>(g, b, n);
+    {
+      const dim3 sgrid(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB));
+      // large batches: the 64-register build (room for the ORB kernels beside it); smaller ones are bound by the length
+      // of the chain and take the natural allocation (512 frames: 29 vs 35 ms)
+      if (bs.eqLoad) k_lsd_spec<true, SPEC_MINB_SMALL><<<sgrid, 32 * GROW_WPB, 0, st>>>(g, b, n);
+      else if (n > 2048) k_lsd_spec<false, SPEC_MINB><<<sgrid, 32 * GROW_WPB, 0, st>>>(g, b, n);
+      else k_lsd_spec<false, SPEC_MINB_SMALL><<<sgrid, 32 * GROW_WPB, 0, st>>>(g, b, n);
+    }
     prof->mark("k_lsd_spec", st);
     const size_t commitSmem = growSmem + ((size_t)g.o[0].wpr + 1) * GROW_K * sizeof(unsigned);   // + phantom window and its row masks
     k_lsd_commit<<<dim3(g.noct * ((n + COMMIT_WPB - 1) / COMMIT_WPB)), 32 * COMMIT_WPB, commitSmem * COMMIT_WPB, st>>>(
