@@ -379,7 +379,8 @@ def main():
     if B < 2:
         pairs, affine = False, None
     if args.pipes <= 0:   # frames in flight ~ 4096 frames of 752x480 (device memory: ~25 MB per frame of capacity at that size)
-        args.pipes = 1 if B < 32 else max(1, min(8, int(4096 * 752 * 480 / (B * W * H))))
+        # (2048 frames of 752x480 and more: one pipeline -- two 2048-frame batches in flight measured 20.9 k against 21.6 k)
+        args.pipes = 1 if (B < 32 or B * W * H >= 2048 * 752 * 480) else max(1, min(8, int(4096 * 752 * 480 / (B * W * H))))
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu:
         nsamp = args.cpu_sample or min(32 * cores, 1024)
