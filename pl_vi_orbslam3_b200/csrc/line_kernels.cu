@@ -1501,11 +1501,35 @@ __device__ __forceinline__ double warp_max_d(double v) {
   return v;
 }
 
+// reductions inside groups of G consecutive lanes (xor butterfly: every lane of a group ends with the same value)
+template <int G> __device__ __forceinline__ double group_sum_d(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int G> __device__ __forceinline__ double group_min_d(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int G> __device__ __forceinline__ double group_max_d(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+#ifndef RECT_G
+#define RECT_G 8    // 32: 7.6 ms, 16: 5.35 ms, 8: 4.8 ms per 4096 frames
+#endif
+// G lanes per region (32 / G regions per warp at a time): most regions are a few dozen pixels, and the fixed part of a
+// region -- eight reductions, the square root, sincos, the divisions -- is paid per warp instruction, not per region.
+template <int G>
 __global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGeom g, LineBufs b, int bandRun) {
   const int oct = blockIdx.x, f = blockIdx.y, part = blockIdx.z, nparts = gridDim.z;
   if (oct >= g.noct) return;
   const LineOct& O = g.o[oct];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G, gbase = lane - sub, ngrp = 32 / G;
   const int nreg = b.regCount[f * 2 + oct];
   const size_t pbase = (size_t)f * g.pxTotal + O.pxOff;
   // band-run path: the region table indexes the frame's band lists, unless the octave fell back to the serial kernel
@@ -1516,11 +1540,16 @@ __global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGe
   const LineRegion* rtab = b.regTab + (size_t)f * g.segTotal + O.segOff;
   float4* segs = b.segs + (size_t)f * g.segTotal + O.segOff;
   const int W = O.sw;
-  for (int r = part * nw + wid; r < nreg; r += nparts * nw) {
-    const LineRegion R = rtab[r];
+  // all lanes of a warp make the same number of trips (the shuffles are warp-wide); a group without a region idles
+  for (int r0 = (part * nw + wid) * ngrp; r0 < nreg; r0 += nparts * nw * ngrp) {
+    const int r = r0 + grp;
+    const bool have = r < nreg;
+    LineRegion R;
+    R.start = 0; R.size = 0; R.angle = 0.0;
+    if (have) R = rtab[r];
     const unsigned* rp = reg + R.start;
     double x = 0, y = 0, sum = 0;
-    for (int i = lane; i < R.size; i += 32) {
+    for (int i = sub; i < R.size; i += G) {
       const unsigned p = rp[i];
       const int px = p & 0xffff, py = p >> 16;
       const double wgt = mod[py * W + px];
@@ -1528,14 +1557,14 @@ __global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGe
       y += (double)py * wgt;
       sum += wgt;
     }
-    x = warp_sum_d(x); y = warp_sum_d(y); sum = warp_sum_d(sum);
+    x = group_sum_d<G>(x); y = group_sum_d<G>(y); sum = group_sum_d<G>(sum);
     {   // x / sum and y / sum in one division sequence (odd lanes take y)
       const double q = ((lane & 1) ? y : x) / sum;
-      x = __shfl_sync(0xffffffffu, q, 0);
-      y = __shfl_sync(0xffffffffu, q, 1);
+      x = __shfl_sync(0xffffffffu, q, gbase);
+      y = __shfl_sync(0xffffffffu, q, gbase + 1);
     }
     double Ixx = 0, Iyy = 0, Ixy = 0;
-    for (int i = lane; i < R.size; i += 32) {
+    for (int i = sub; i < R.size; i += G) {
       const unsigned p = rp[i];
       const int px = p & 0xffff, py = p >> 16;
       const double wgt = mod[py * W + px];
@@ -1544,36 +1573,38 @@ __global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGe
       Iyy += dx * dx * wgt;
       Ixy -= dx * dy * wgt;
     }
-    Ixx = warp_sum_d(Ixx); Iyy = warp_sum_d(Iyy); Ixy = warp_sum_d(Ixy);
+    Ixx = group_sum_d<G>(Ixx); Iyy = group_sum_d<G>(Iyy); Ixy = group_sum_d<G>(Ixy);
     const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
     double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_dev((float)(lambda - Ixx), (float)Ixy)
                                            : (double)fast_atan2_dev((float)Ixy, (float)(lambda - Iyy));
     theta *= D2R;
-    {
+    if (have) {
       double diff = theta - R.angle;
       while (diff <= -PI_D) diff += 2 * PI_D;
       while (diff > PI_D) diff -= 2 * PI_D;
       if (fabs(diff) > g.prec) theta += PI_D;
+    } else {
+      theta = 0.0;   // (an idle group: keep the argument of sincos finite)
     }
     double dx, dy;
     sincos(theta, &dy, &dx);
     double lmin = 0, lmax = 0;
-    for (int i = lane; i < R.size; i += 32) {
+    for (int i = sub; i < R.size; i += G) {
       const unsigned p = rp[i];
       const double rdx = (double)(p & 0xffff) - x, rdy = (double)(p >> 16) - y;
       const double l = __dadd_rn(__dmul_rn(rdx, dx), __dmul_rn(rdy, dy));
       lmax = fmax(lmax, l);
       lmin = fmin(lmin, l);
     }
-    lmin = warp_min_d(lmin);
-    lmax = warp_max_d(lmax);
-    if (lane < 4) {   // lanes 0..3 finish x1, y1, x2, y2 (all inputs are warp-uniform): one division sequence instead of four
-      const double l = (lane & 2) ? lmax : lmin;
-      const double c = (lane & 1) ? y : x, d = (lane & 1) ? dy : dx;
+    lmin = group_min_d<G>(lmin);
+    lmax = group_max_d<G>(lmax);
+    if (have && sub < 4) {   // lanes 0..3 of the group finish x1, y1, x2, y2: one division sequence instead of four
+      const double l = (sub & 2) ? lmax : lmin;
+      const double c = (sub & 1) ? y : x, d = (sub & 1) ? dy : dx;
       double v = c + l * d;
       v += 0.5;
       if (g.lsdScale != 1.0) v /= g.lsdScale;
-      reinterpret_cast<float*>(segs + r)[lane] = (float)v;
+      reinterpret_cast<float*>(segs + r)[sub] = (float)v;
     }
   }
 }
@@ -2667,7 +2698,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     prof->mark("k_lsd_grow", st);
   }
   if (g.refine == 0) {
-    k_lsd_rect<<<dim3(g.noct, n, bandRun ? 8 : 2), 256, 0, st>>>(g, b, bandRun ? 1 : 0);
+    k_lsd_rect<RECT_G><<<dim3(g.noct, n, bandRun ? 8 : 2), 256, 0, st>>>(g, b, bandRun ? 1 : 0);
     prof->mark("k_lsd_rect", st);
   }
   k_line_assemble<512><<<n, 512, 0, st>>>(g, b, dKl, dCounts);
