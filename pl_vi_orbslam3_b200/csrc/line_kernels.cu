@@ -2470,20 +2470,22 @@ __global__ void __launch_bounds__(64, 16) k_lbd_rows(const __grid_constant__ Lin
   rows[4 * 64 + tid] = pO; rows[5 * 64 + tid] = nO; rows[6 * 64 + tid] = __fmul_rn(pO, pO); rows[7 * 64 + tid] = __fmul_rn(nO, nO);
 }
 
-// k_lbd_fold: one warp per line.  Lanes 0-7 fold the 63 rows of one statistic into the 9 bands
-// in row order, lane 0 forms / normalises the 72 floats, all lanes pack the 32 bytes.
+// k_lbd_fold: eight lanes per line (four lines per warp, 16 per block).  Each lane folds the 63 rows of one statistic
+// into the 9 bands in row order, the group's first lane forms / normalises the 72 floats (a serial chain in the
+// reference's order: with a whole warp per line 31 lanes idled through it), the eight lanes pack 4 bytes each.
+#define LBD_FOLD_LPB 16
 __global__ void __launch_bounds__(128) k_lbd_fold(const __grid_constant__ LineGeom g, LineBufs b,
                                                   const plvi_keyline* __restrict__ kls,
                                                   const int* __restrict__ counts, uint8_t* __restrict__ desc,
                                                   double* __restrict__ lineEq) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int li = blockIdx.x * 4 + wid, f = blockIdx.y;
+  const int lane = threadIdx.x & 7, wid = threadIdx.x >> 3;
+  const int li = blockIdx.x * LBD_FOLD_LPB + wid, f = blockIdx.y;
   if (li >= counts[f]) return;
-  __shared__ float sband[4][8][9];
-  __shared__ float sdes[4][72];
+  __shared__ float sband[LBD_FOLD_LPB][8][9];
+  __shared__ float sdes[LBD_FOLD_LPB][72];
   const float* rows = b.lbdRows + ((size_t)f * g.keepCap + li) * 512;
   float* des = sdes[wid];
-  if (lane < 8) {
+  {
     const int q = lane;
     const bool sq = (q == 2 || q == 3 || q == 6 || q == 7);
     float band[9];
@@ -2552,12 +2554,20 @@ __global__ void __launch_bounds__(128) k_lbd_fold(const __grid_constant__ LineGe
   }
   __syncwarp();
   {
-    const float* f1 = des + 8 * c_comb[lane][0];
-    const float* f2 = des + 8 * c_comb[lane][1];
-    unsigned r = 0;
+    unsigned word = 0u;
 #pragma unroll
-    for (int i = 0; i < 8; i++) r |= (unsigned)(f1[i] > f2[i]) << i;
-    desc[((size_t)f * g.keepCap + li) * 32 + lane] = (uint8_t)r;
+    for (int j = 0; j < 4; j++) {
+      const int byte = lane * 4 + j;
+      const float* f1 = des + 8 * c_comb[byte][0];
+      const float* f2 = des + 8 * c_comb[byte][1];
+      unsigned r = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) r |= (unsigned)(f1[i] > f2[i]) << i;
+      word |= r << (8 * j);
+    }
+    uint8_t* out = desc + ((size_t)f * g.keepCap + li) * 32 + lane * 4;
+    if ((reinterpret_cast<uintptr_t>(out) & 3u) == 0) *reinterpret_cast<unsigned*>(out) = word;
+    else { out[0] = (uint8_t)word; out[1] = (uint8_t)(word >> 8); out[2] = (uint8_t)(word >> 16); out[3] = (uint8_t)(word >> 24); }
   }
 }
 
@@ -2707,7 +2717,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
   if (fork) PLVI_CUDA_TRY(cudaStreamWaitEvent(st, aux.join, 0));
   k_lbd_rows<<<dim3(g.keepCap, n), 64, 0, st>>>(g, b, dKl, dCounts);
   prof->mark("k_lbd_rows", st);
-  k_lbd_fold<<<dim3((g.keepCap + 3) / 4, n), 128, 0, st>>>(g, b, dKl, dCounts, dDesc, dEq);
+  k_lbd_fold<<<dim3((g.keepCap + LBD_FOLD_LPB - 1) / LBD_FOLD_LPB, n), 128, 0, st>>>(g, b, dKl, dCounts, dDesc, dEq);
   prof->mark("k_lbd_fold", st);
   nl += 2;
   PLVI_CUDA_TRY(cudaGetLastError());
