@@ -540,8 +540,14 @@ def main():
         int_roof = None
         ij, pj = latest_profile("int_ops.json"), latest_profile("instr_peaks.json")
         if ij is not None and pj is not None and args.config == "c23":
-            ops, ipk = json.loads(ij.read_text()), json.loads(pj.read_text())["ginstr_per_s"]
-            int_roof = {"peak_ginstr_per_s": ipk["iadd3"], "peak_source": str(pj.relative_to(ROOT)), "ops_source": str(ij.relative_to(ROOT)), "kernels": {}}
+            # every committed capture, the newest one of a kernel wins (a later capture may hold only the kernels that changed)
+            ops = {"kernels": {}}
+            srcs = sorted((ROOT / "profiles").glob("r[0-9][0-9]*_int_ops.json"))
+            for sj in srcs:
+                ops["kernels"].update(json.loads(sj.read_text()).get("kernels", {}))
+            ipk = json.loads(pj.read_text())["ginstr_per_s"]
+            int_roof = {"peak_ginstr_per_s": ipk["iadd3"], "peak_source": str(pj.relative_to(ROOT)),
+                        "ops_source": ", ".join(str(sj.relative_to(ROOT)) for sj in srcs), "kernels": {}}
             for k, o in ops.get("kernels", {}).items():
                 ms_k = prof.get(k) or prof.get(k + "(+queries)")
                 if ms_k:

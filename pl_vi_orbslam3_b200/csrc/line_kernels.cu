@@ -273,7 +273,10 @@ __device__ __forceinline__ bool is_aligned_dev(double a, double theta, double pr
 #ifndef COMMIT_WPB
 #define COMMIT_WPB 4  // ... and in k_lsd_commit
 #endif
-#define COMMIT_BPS (28 / COMMIT_WPB)   // resident blocks per SM: 28 warps of 72 registers
+#ifndef COMMIT_WARPS
+#define COMMIT_WARPS 28
+#endif
+#define COMMIT_BPS (COMMIT_WARPS / COMMIT_WPB)   // resident blocks per SM: 28 warps of 72 registers
 #define GROW_RQ 512   // shared ring holding the most recent region pixels (BFS frontier)
 #define GROW_K 32     // bitmap rows kept in shared memory (sliding window below the seed row)
 
