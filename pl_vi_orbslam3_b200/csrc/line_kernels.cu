@@ -1141,35 +1141,55 @@ __global__ void __launch_bounds__(256) k_lsd_band_compose(const __grid_constant_
   int* st = b.brState + ((size_t)f * g.brBandsPerFrame + O.brBandOff) * BR_ST;
   unsigned acc = 0u;
   bool anyChange = false;
-  for (int j = 0; j < O.brBands; j++) {
-    if (row < j * O.brRows) break;
-    const size_t idx = base + (size_t)j * nwords;
-    const unsigned nin = I0 & ~acc;
-    if (round == 1) {
-      b.brIn[idx] = nin;
+  const int jmax = min(O.brBands, row / O.brRows + 1);   // the bands whose rows start at or above this row
+  if (round == 1) {
+    // nothing is known about what the bands consume yet
+    for (int j = 0; j < jmax; j++) {
+      const size_t idx = base + (size_t)j * nwords;
+      b.brIn[idx] = I0;
       b.brPh[idx] = 0u;
       if (i == 0 || row == j * O.brRows) {   // one thread per band is enough; several writing the same values is harmless
         st[j * BR_ST + 0] = 0; st[j * BR_ST + 1] = 0; st[j * BR_ST + 2] = 0; st[j * BR_ST + 3] = 1; st[j * BR_ST + 4] = 0; st[j * BR_ST + 6] = 0;
       }
-      anyChange = true;
-      continue;   // nothing is known about what the bands consume yet
     }
-    const unsigned old = b.brIn[idx];
-    if (nin != old) {
-      if (check) { flags[0] = 1; return; }
-      b.brPh[idx] = nin & ~old;      // available now, was not when the band last ran
-      b.brIn[idx] = nin;
-      st[j * BR_ST + 3] = 1;
-      anyChange = true;
-    } else if (!check) {
-      b.brPh[idx] = 0u;
+    anyChange = jmax > 0;
+  } else {
+    // the words of four bands are requested together: the chain through acc is ALU work only (one L2 round trip per
+    // four bands instead of one per band; the thread of the last row walks all 64 bands)
+    for (int j0 = 0; j0 < jmax; j0 += 4) {
+      unsigned oldv[4], wkv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const size_t idx = base + (size_t)min(j0 + u, jmax - 1) * nwords;
+        oldv[u] = __ldcg(b.brIn + idx);
+        wkv[u] = __ldcg(b.brWk + idx);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u;
+        if (j >= jmax) break;
+        const size_t idx = base + (size_t)j * nwords;
+        const unsigned nin = I0 & ~acc;
+        const unsigned old = oldv[u];
+        if (nin != old) {
+          if (check) { flags[0] = 1; return; }
+          b.brPh[idx] = nin & ~old;      // available now, was not when the band last ran
+          b.brIn[idx] = nin;
+          st[j * BR_ST + 3] = 1;
+          anyChange = true;
+        } else if (!check) {
+          b.brPh[idx] = 0u;
+        }
+        acc |= old & ~wkv[u];            // what band j's latest run took (from the input that run saw)
+      }
     }
-    acc |= old & ~b.brWk[idx];       // what band j's latest run took (from the input that run saw)
   }
   if (anyChange && !check) flags[2 + round] = 1;
 }
 
-template <int BR_K> __global__ void __launch_bounds__(32) k_lsd_band_run(const __grid_constant__ LineGeom g, LineBufs b) {
+// (the small-window instantiation runs with many frames in flight: it keeps the 72 registers = 28 warps per SM it had
+// before the prologue held eight words per lane in flight)
+template <int BR_K> __global__ void __launch_bounds__(32, BR_K == BR_K_BIG ? 1 : 28) k_lsd_band_run(const __grid_constant__ LineGeom g, LineBufs b) {
   extern __shared__ unsigned smem_u[];
   const int t = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
   const int oct = (g.noct > 1 && t >= g.o[1].brBandOff) ? 1 : 0;
@@ -1214,13 +1234,9 @@ template <int BR_K> __global__ void __launch_bounds__(32) k_lsd_band_run(const _
     const char* s1 = reinterpret_cast<const char*>(seedcs + (size_t)r1 * W);
     for (const char* q = s0 + lane * 128; q < s1; q += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
   }
-  // working copy of the input (rows above the band hold nothing by definition) + is there any initial phantom?
-  bool anyPh = false;
-  for (int i = r0 * wpr + lane; i < nwords; i += 32) {
-    Wk[i] = In[i];
-    anyPh |= Ph[i] != 0u;
-  }
-  __syncwarp();
+  // working copy of the input (rows above the band hold nothing by definition), the first BR_K rows of it and of the
+  // initial phantom map into the shared windows (a ring of BR_K rows: linear from the band's first row, wrapping once),
+  // and: is there any initial phantom?  Eight (four) independent words per lane are in flight; one pass over the input.
   unsigned* ring = smem_u;
   GrowBitmapT<BR_K> bm;
   bm.sm = smem_u + GROW_RQ;
@@ -1230,12 +1246,35 @@ template <int BR_K> __global__ void __launch_bounds__(32) k_lsd_band_run(const _
   PhantomMapT<BR_K> ph;
   ph.gm = Ph;
   ph.sm = bm.sm + BR_K * wpr;
-  ph.any = bcnt > 0 && __any_sync(0xffffffffu, anyPh);
-  for (int i = lane; i < (min(r0 + BR_K, H) - r0) * wpr; i += 32) {
-    const int r = r0 + i / wpr, wv = i - (r - r0) * wpr;
-    bm.sm[(r & (BR_K - 1)) * wpr + wv] = In[r * wpr + wv];
-    ph.sm[(r & (BR_K - 1)) * wpr + wv] = ph.any ? Ph[r * wpr + wv] : 0u;
+  bool anyPh = false;
+  {
+    const int first = r0 * wpr;
+    const int winWords = (min(r0 + BR_K, H) - r0) * wpr, ringWords = BR_K * wpr;
+    const int sbase = (r0 & (BR_K - 1)) * wpr - first;
+    constexpr int U = BR_K == BR_K_BIG ? 8 : 4;
+    for (int i0 = first + lane; i0 < nwords; i0 += 32 * U) {
+      unsigned v[U], q[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = i0 + 32 * u;
+        v[u] = i < nwords ? __ldcg(In + i) : 0u;
+        q[u] = (i < nwords && bcnt > 0) ? __ldcg(Ph + i) : 0u;   // a first run has no record a phantom could invalidate
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = i0 + 32 * u;
+        if (i < nwords) Wk[i] = v[u];
+        anyPh |= q[u] != 0u;
+        if (i - first < winWords) {
+          int sidx = sbase + i;
+          if (sidx >= ringWords) sidx -= ringWords;
+          bm.sm[sidx] = v[u];
+          ph.sm[sidx] = q[u];     // all zero when no phantom exists
+        }
+      }
+    }
   }
+  ph.any = bcnt > 0 && __any_sync(0xffffffffu, anyPh);
   __syncwarp();
   const double prec = g.prec;
   const float kHi = g.alignHi2, kLo = g.alignLo2;
@@ -1433,8 +1472,15 @@ template <int BR_K> __global__ void __launch_bounds__(32) k_lsd_band_run(const _
   }
   // output bitmap: the band's own rows are exhausted; rows of the shared window go back to global memory
   for (int i = r0 * wpr + lane; i < r1 * wpr; i += 32) Wk[i] = 0u;
-  for (int r = max(r1, bm.top); r < min(bm.top + BR_K, H); r++)
-    for (int wv = lane; wv < wpr; wv += 32) Wk[r * wpr + wv] = bm.sm[(r & (BR_K - 1)) * wpr + wv];
+  {
+    const int ra = max(r1, bm.top), rb = min(bm.top + BR_K, H);   // rb - ra <= BR_K: the ring wraps at most once
+    const int sbase = (ra & (BR_K - 1)) * wpr - ra * wpr, ringWords = BR_K * wpr;
+    for (int i = ra * wpr + lane; i < rb * wpr; i += 32) {
+      int sidx = sbase + i;
+      if (sidx >= ringWords) sidx -= ringWords;
+      Wk[i] = bm.sm[sidx];
+    }
+  }
   if (lane == 0) { st[nxt] = nnew; st[2] = nxt; st[3] = 0; st[4] = 1; st[5] = npx; st[6] += 1; st[7] = (int)(clock64() - tStart); }
 }
 
