@@ -209,7 +209,7 @@ __device__ __forceinline__ int fast_arc_score(const int (&d)[16]) {
 // detection column (c = 3) is word aligned and groups of 4 detection pixels are one 32-bit word.
 #define FAST_PAD 1
 
-__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
+__global__ void __launch_bounds__(256, 5) k_fast(const __grid_constant__ OrbGeom g,
                                               const __grid_constant__ OrbPtrs p,
                                               const FastTile* __restrict__ tiles,
                                               uint32_t* __restrict__ cand,
@@ -268,108 +268,130 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
 
   const int minTh = g.minTh, iniTh = g.iniTh;
   const int dw = rw - 6, dh = rh - 6;
-  // ---- pass A: 4 pixels per thread.  Any 9-arc of the 16-pixel ring covers two neighbouring compass
-  // pixels (ring 0/4/8/12), so a corner needs two neighbouring compass pixels that are both brighter
-  // than c + minTh or both darker than c - minTh.
-  {
-    const int dwords = (dw + 3) >> 2;
-    const uint32_t th4 = (uint32_t)minTh * 0x01010101u;
-    for (int dy = ty; dy < dh; dy += 4) {
-      if (tx >= dwords) continue;
-      const uint32_t* row = reinterpret_cast<const uint32_t*>(simg + (dy + 3) * tilePitch) + 1 + tx;
-      const uint32_t c = row[0], lft = row[-1], rgt = row[1];
-      const uint32_t up = row[-3 * (tilePitch >> 2)], dn = row[3 * (tilePitch >> 2)];
-      const uint32_t l3 = __funnelshift_r(lft, c, 8), r3 = __funnelshift_r(c, rgt, 24);   // columns -3 / +3
-      const uint32_t hi4 = __vaddus4(c, th4), lo4 = __vsubus4(c, th4);                    // saturated: never passed if clipped
-      const uint32_t bU = __vsetgtu4(up, hi4), bD = __vsetgtu4(dn, hi4), bL = __vsetgtu4(l3, hi4), bR = __vsetgtu4(r3, hi4);
-      const uint32_t kU = __vsetltu4(up, lo4), kD = __vsetltu4(dn, lo4), kL = __vsetltu4(l3, lo4), kR = __vsetltu4(r3, lo4);
-      const uint32_t cnt = ((bU | bD) & (bL | bR)) | ((kU | kD) & (kL | kR));             // 0x01 per candidate byte
-      if (!cnt) continue;
-      const int dx0 = tx * 4;
-      int npass = 0;
-      unsigned short loc[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if ((cnt >> (8 * k)) & 1u && dx0 + k < dw) loc[npass++] = (unsigned short)((dy << 8) | (dx0 + k));
-      if (npass) {
-        const int o = atomicAdd(&s_n1, npass);
-        for (int k = 0; k < npass; k++) list1[o + k] = loc[k];
-      }
-    }
-  }
-  __syncthreads();
-  // ---- pass B: exact segment test for the listed pixels; corners go to a second list
-  const int n1 = s_n1;
-  for (int i = tid; i < n1; i += 256) {
-    const unsigned short pos = list1[i];
-    const int dy = pos >> 8, dx = pos & 0xff;
-    const u8* q = simg + (dy + 3) * tilePitch + 3 + FAST_PAD + dx;
-    const int c = q[0];
-    const int hi = c + minTh, lo = c - minTh;
-    uint32_t mb = 0, md = 0;       // one bit per ring pixel: brighter than c+th / darker than c-th
-#define FAST_RING(OFF)                                              \
-    {                                                               \
-      const int v = q[OFF];                                         \
-      mb = __funnelshift_l((uint32_t)(hi - v), mb, 1);              \
-      md = __funnelshift_l((uint32_t)(v - lo), md, 1);              \
-    }
-    FAST_RING(3 * tilePitch) FAST_RING(3 * tilePitch + 1) FAST_RING(2 * tilePitch + 2) FAST_RING(tilePitch + 3)
-    FAST_RING(3) FAST_RING(-tilePitch + 3) FAST_RING(-2 * tilePitch + 2) FAST_RING(-3 * tilePitch + 1)
-    FAST_RING(-3 * tilePitch) FAST_RING(-3 * tilePitch - 1) FAST_RING(-2 * tilePitch - 2) FAST_RING(-tilePitch - 3)
-    FAST_RING(-3) FAST_RING(tilePitch - 3) FAST_RING(2 * tilePitch - 2) FAST_RING(3 * tilePitch - 1)
-#undef FAST_RING
-    mb |= mb << 16;
-    md |= md << 16;
-    mb &= mb >> 1; mb &= mb >> 2; mb &= mb >> 4; mb &= mb >> 1;
-    md &= md >> 1; md &= md >> 2; md &= md >> 4; md &= md >> 1;
-    if (((mb | md) & 0xffffu) == 0) continue;
-    list2[atomicAdd(&s_n2, 1)] = pos;
-  }
-  __syncthreads();
-  // ---- pass C: score of every corner (all lanes busy)
-  const int n2 = s_n2;
-  for (int i = tid; i < n2; i += 256) {
-    const int dy = list2[i] >> 8, dx = list2[i] & 0xff;
-    const u8* q = simg + (dy + 3) * tilePitch + 3 + FAST_PAD + dx;
-    const int c = q[0];
-    int d[16];
-    d[0] = c - q[3 * tilePitch];        d[1] = c - q[3 * tilePitch + 1];   d[2] = c - q[2 * tilePitch + 2];
-    d[3] = c - q[tilePitch + 3];        d[4] = c - q[3];                   d[5] = c - q[-tilePitch + 3];
-    d[6] = c - q[-2 * tilePitch + 2];   d[7] = c - q[-3 * tilePitch + 1];  d[8] = c - q[-3 * tilePitch];
-    d[9] = c - q[-3 * tilePitch - 1];   d[10] = c - q[-2 * tilePitch - 2]; d[11] = c - q[-tilePitch - 3];
-    d[12] = c - q[-3];                  d[13] = c - q[tilePitch - 3];      d[14] = c - q[2 * tilePitch - 2];
-    d[15] = c - q[3 * tilePitch - 1];
-    ssc[(dy + 3) * tilePitch + 3 + FAST_PAD + dx] = (u8)fast_arc_score(d);
-  }
-  __syncthreads();
-  // ---- pass D: 3x3 non-maximum suppression confined to the cell
   const int wCell = L.wCell;
-  for (int i = tid; i < n2; i += 256) {
-    const int dy = list2[i] >> 8, dx = list2[i] & 0xff;
-    const u8* r1 = ssc + (dy + 3) * tilePitch + 3 + FAST_PAD + dx;
-    const int s = r1[0];
-    const int cell = dx / wCell, xin = dx - cell * wCell;
-    // scores outside the detection area are 0 in the tile; only the cell's vertical borders need masking
-    const int mL = xin > 0 ? 0xff : 0, mR = (xin < wCell - 1) ? 0xff : 0;
-    const u8* r0 = r1 - tilePitch;
-    const u8* r2 = r1 + tilePitch;
-    const int m = max(max(max(r0[-1] & mL, r1[-1] & mL), max(r2[-1] & mL, r0[0])),
-                      max(max(r2[0], r0[1] & mR), max(r1[1] & mR, r2[1] & mR)));
-    if (m >= s) continue;
-    const int idx = atomicAdd(&s_nsurv, 1);
-    if (idx < survCap) surv[idx] = pack_xys(iniX + 3 + dx - kEdge, iniY + 3 + dy - kEdge, s);
-    if (s >= iniTh) s_cellFlag[cell] = 1;
+  const float invWCell = 1.f / (float)wCell;
+  // cell of detection column dx: (dx + 0.5) / wCell is at least 0.5 / wCell away from an integer, far beyond float rounding
+  auto cell_of = [&](int dx) { return __float2int_rz(((float)dx + 0.5f) * invWCell); };
+  // Two phases, as the reference does per cell (src/ORBextractor.cc:809-817): FAST at iniTh; the cells that are left
+  // without a corner run FAST again at minTh.  The score does not depend on the threshold and a corner's 3x3 NMS only
+  // loses to scores >= its own, so phase 0 is exactly cv::FAST(iniTh) + NMS, and phase 1 touches nothing but the
+  // pixels of the empty cells (scores of neighbouring cells are masked in pass D).  Most of the work -- segment tests of
+  // the pre-test's false positives, the arc scores -- is proportional to the corners at the threshold in use: on
+  // textured frames 9 of 10 cells are settled at iniTh with a third of the corners minTh would raise.
+  unsigned fb = 0u;   // phase 1: cells (bits) that run again at minTh
+  for (int phase = 0; phase < 2; phase++) {
+    const int th = phase == 0 ? iniTh : minTh;
+    if (phase == 1) {
+      for (int cidx = 0; cidx < t.ncells; cidx++) fb |= s_cellFlag[cidx] ? 0u : (1u << cidx);
+      if (fb == 0u || iniTh == minTh) break;
+      __syncthreads();   // every thread has read the flags and the list counters of phase 0
+      if (tid == 0) { s_n1 = 0; s_n2 = 0; }
+      __syncthreads();
+    }
+    // ---- pass A: 4 pixels per thread.  Any 9-arc of the 16-pixel ring covers two neighbouring compass
+    // pixels (ring 0/4/8/12), so a corner needs two neighbouring compass pixels that are both brighter
+    // than c + th or both darker than c - th.
+    {
+      const int dwords = (dw + 3) >> 2;
+      const uint32_t th4 = (uint32_t)th * 0x01010101u;
+      // pixels of this thread's word that count: inside the detection area and, in phase 1, inside an empty cell
+      // (the same for every row)
+      const int dx0 = tx * 4;
+      unsigned kmask = dw - dx0 >= 4 ? 0xfu : ((1u << max(dw - dx0, 0)) - 1u);
+      if (phase == 1) {
+        unsigned fm = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) fm |= ((fb >> cell_of(min(dx0 + k, dw - 1))) & 1u) << k;
+        kmask &= fm;
+      }
+      if (tx < dwords && kmask)
+        for (int dy = ty; dy < dh; dy += 4) {
+          const uint32_t* row = reinterpret_cast<const uint32_t*>(simg + (dy + 3) * tilePitch) + 1 + tx;
+          const uint32_t c = row[0], lft = row[-1], rgt = row[1];
+          const uint32_t up = row[-3 * (tilePitch >> 2)], dn = row[3 * (tilePitch >> 2)];
+          const uint32_t l3 = __funnelshift_r(lft, c, 8), r3 = __funnelshift_r(c, rgt, 24);   // columns -3 / +3
+          const uint32_t hi4 = __vaddus4(c, th4), lo4 = __vsubus4(c, th4);                    // saturated: never passed if clipped
+          const uint32_t bU = __vsetgtu4(up, hi4), bD = __vsetgtu4(dn, hi4), bL = __vsetgtu4(l3, hi4), bR = __vsetgtu4(r3, hi4);
+          const uint32_t kU = __vsetltu4(up, lo4), kD = __vsetltu4(dn, lo4), kL = __vsetltu4(l3, lo4), kR = __vsetltu4(r3, lo4);
+          const uint32_t cnt = ((bU | bD) & (bL | bR)) | ((kU | kD) & (kL | kR));             // 0x01 per candidate byte
+          // the four flag bytes gathered into a nibble: byte k (bit 8k) times 2^(21 - 7k) lands on bit 21 + k, and no
+          // two of the sixteen partial products share a bit
+          unsigned m = ((cnt * 0x00204081u) >> 21) & kmask;
+          if (!m) continue;
+          int o = atomicAdd(&s_n1, __popc(m));
+          const unsigned base = (unsigned)((dy << 8) | dx0);
+          do {
+            list1[o++] = (unsigned short)(base + (unsigned)(__ffs(m) - 1));
+            m &= m - 1u;
+          } while (m);
+        }
+    }
+    __syncthreads();
+    // ---- pass B: exact segment test for the listed pixels; corners go to a second list
+    const int n1 = s_n1;
+    for (int i = tid; i < n1; i += 256) {
+      const unsigned short pos = list1[i];
+      const int dy = pos >> 8, dx = pos & 0xff;
+      const u8* q = simg + (dy + 3) * tilePitch + 3 + FAST_PAD + dx;
+      const int c = q[0];
+      const int hi = c + th, lo = c - th;
+      uint32_t mb = 0, md = 0;       // one bit per ring pixel: brighter than c+th / darker than c-th
+#define FAST_RING(OFF)                                              \
+      {                                                             \
+        const int v = q[OFF];                                       \
+        mb = __funnelshift_l((uint32_t)(hi - v), mb, 1);            \
+        md = __funnelshift_l((uint32_t)(v - lo), md, 1);            \
+      }
+      FAST_RING(3 * tilePitch) FAST_RING(3 * tilePitch + 1) FAST_RING(2 * tilePitch + 2) FAST_RING(tilePitch + 3)
+      FAST_RING(3) FAST_RING(-tilePitch + 3) FAST_RING(-2 * tilePitch + 2) FAST_RING(-3 * tilePitch + 1)
+      FAST_RING(-3 * tilePitch) FAST_RING(-3 * tilePitch - 1) FAST_RING(-2 * tilePitch - 2) FAST_RING(-tilePitch - 3)
+      FAST_RING(-3) FAST_RING(tilePitch - 3) FAST_RING(2 * tilePitch - 2) FAST_RING(3 * tilePitch - 1)
+#undef FAST_RING
+      mb |= mb << 16;
+      md |= md << 16;
+      mb &= mb >> 1; mb &= mb >> 2; mb &= mb >> 4; mb &= mb >> 1;
+      md &= md >> 1; md &= md >> 2; md &= md >> 4; md &= md >> 1;
+      if (((mb | md) & 0xffffu) == 0) continue;
+      list2[atomicAdd(&s_n2, 1)] = pos;
+    }
+    __syncthreads();
+    // ---- pass C: score of every corner (all lanes busy)
+    const int n2 = s_n2;
+    for (int i = tid; i < n2; i += 256) {
+      const int dy = list2[i] >> 8, dx = list2[i] & 0xff;
+      const u8* q = simg + (dy + 3) * tilePitch + 3 + FAST_PAD + dx;
+      const int c = q[0];
+      int d[16];
+      d[0] = c - q[3 * tilePitch];        d[1] = c - q[3 * tilePitch + 1];   d[2] = c - q[2 * tilePitch + 2];
+      d[3] = c - q[tilePitch + 3];        d[4] = c - q[3];                   d[5] = c - q[-tilePitch + 3];
+      d[6] = c - q[-2 * tilePitch + 2];   d[7] = c - q[-3 * tilePitch + 1];  d[8] = c - q[-3 * tilePitch];
+      d[9] = c - q[-3 * tilePitch - 1];   d[10] = c - q[-2 * tilePitch - 2]; d[11] = c - q[-tilePitch - 3];
+      d[12] = c - q[-3];                  d[13] = c - q[tilePitch - 3];      d[14] = c - q[2 * tilePitch - 2];
+      d[15] = c - q[3 * tilePitch - 1];
+      ssc[(dy + 3) * tilePitch + 3 + FAST_PAD + dx] = (u8)fast_arc_score(d);
+    }
+    __syncthreads();
+    // ---- pass D: 3x3 non-maximum suppression confined to the cell; every survivor is kept (phase 0: its cell is
+    // settled; phase 1: its cell had no corner at iniTh)
+    for (int i = tid; i < n2; i += 256) {
+      const int dy = list2[i] >> 8, dx = list2[i] & 0xff;
+      const u8* r1 = ssc + (dy + 3) * tilePitch + 3 + FAST_PAD + dx;
+      const int sc = r1[0];
+      const int cell = cell_of(dx), xin = dx - cell * wCell;
+      // scores outside the detection area are 0 in the tile; only the cell's vertical borders need masking
+      const int mL = xin > 0 ? 0xff : 0, mR = (xin < wCell - 1) ? 0xff : 0;
+      const u8* r0 = r1 - tilePitch;
+      const u8* r2 = r1 + tilePitch;
+      const int m = max(max(max(r0[-1] & mL, r1[-1] & mL), max(r2[-1] & mL, r0[0])),
+                        max(max(r2[0], r0[1] & mR), max(r1[1] & mR, r2[1] & mR)));
+      if (m >= sc) continue;
+      const int idx = atomicAdd(&s_nkept, 1);
+      if (idx < survCap) kept[idx] = pack_xys(iniX + 3 + dx - kEdge, iniY + 3 + dy - kEdge, sc);
+      if (phase == 0) s_cellFlag[cell] = 1;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  const int ns = min(s_nsurv, survCap);
-  for (int i = tid; i < ns; i += 256) {
-    const uint32_t v = surv[i];
-    const int cell = (unpack_x(v) + kEdge - iniX - 3) / wCell;
-    const int th = s_cellFlag[cell] ? iniTh : minTh;
-    if (unpack_s(v) >= th) kept[atomicAdd(&s_nkept, 1)] = v;
-  }
-  __syncthreads();
-  const int nk = s_nkept;
+  const int nk = min(s_nkept, survCap);
   if (nk == 0) return;
   if (tid == 0) s_base = atomicAdd(&candCount[f * g.nlevels + t.level], nk);
   __syncthreads();
