@@ -806,18 +806,21 @@ __device__ __forceinline__ float dev_fast_atan2(float y, float x) {
 }
 
 #define OD_WARPS 4
-__global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(
+#ifndef OD_MINB
+#define OD_MINB 5   // 96 registers: 5.4 ms per 4096 frames (128 registers: slower step, 80 / 72 with spills: 5.7 / 6.2 ms)
+#endif
+__global__ void __launch_bounds__(OD_WARPS * 32, OD_MINB) k_orient_desc(
     const __grid_constant__ OrbGeom g, const __grid_constant__ OrbPtrs p,
     const uint32_t* __restrict__ lvlKp, const int* __restrict__ lvlCount,
     const int* __restrict__ slot, int kpPerCta, plvi_keypoint* __restrict__ kps,
     uint8_t* __restrict__ desc, int cap) {
   const int f = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // this lane's 8 pair tests
-  int px[16], py[16];
+  float px[16], py[16];   // kept as floats: the rotation below would convert them for every keypoint
 #pragma unroll
   for (int j = 0; j < 16; j++) {
-    px[j] = d_pattern[lane * 32 + j * 2];
-    py[j] = d_pattern[lane * 32 + j * 2 + 1];
+    px[j] = (float)d_pattern[lane * 32 + j * 2];
+    py[j] = (float)d_pattern[lane * 32 + j * 2 + 1];
   }
   const int sBeg = blockIdx.x * kpPerCta, sEnd = min(sBeg + kpPerCta, g.kpTotal);
   for (int s = sBeg + wid; s < sEnd; s += OD_WARPS) {
@@ -832,14 +835,18 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(
     int m10 = 0, m01 = 0;
     if (lane < 31) {
       const int au = abs(u);
-#pragma unroll 4
+      // fully unrolled: the row bounds become constants and the 31 loads of the patch column are in flight together
+      // (the kernel waited on them four at a time: half of its stall samples)
+      int vals[31];
+#pragma unroll
+      for (int v = -15; v <= 15; v++) vals[v + 15] = (au <= c_umax[v < 0 ? -v : v]) ? (int)__ldg(c0 + v * ipitch + u) : 0;
+      int colsum = 0;
+#pragma unroll
       for (int v = -15; v <= 15; v++) {
-        if (au <= c_umax[abs(v)]) {
-          const int val = __ldg(c0 + v * ipitch + u);
-          m10 += u * val;
-          m01 += v * val;
-        }
+        colsum += vals[v + 15];
+        m01 += v * vals[v + 15];
       }
+      m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -859,8 +866,8 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(
     int val = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const float x0 = (float)px[2 * j], y0 = (float)py[2 * j];
-      const float x1 = (float)px[2 * j + 1], y1 = (float)py[2 * j + 1];
+      const float x0 = px[2 * j], y0 = py[2 * j];
+      const float x1 = px[2 * j + 1], y1 = py[2 * j + 1];
       const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
       const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
       const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
