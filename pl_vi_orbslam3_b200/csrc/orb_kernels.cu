@@ -244,24 +244,29 @@ __global__ void __launch_bounds__(256, 5) k_fast(const __grid_constant__ OrbGeom
   const u8* gbase = p.img[t.level] + (size_t)f * p.ifs[t.level];
   const int nwords = (rw + FAST_PAD + 3) >> 2;
   const bool aligned4 = ((ipitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(gbase) & 3) == 0);
-  const int tx = tid & 63, ty = tid >> 6;
-  if (tx < nwords) {
-    const int gx = iniX + 4 * tx - FAST_PAD;          // global x of the word's first byte (>= 15)
-    for (int r = ty; r < rh; r += 4) {
-      const u8* grow = gbase + (size_t)(iniY + r) * ipitch;
-      uint32_t w;
-      if (aligned4) {
-        const int ax = gx & ~3, sh = (gx & 3) * 8;
-        const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(grow + ax));
-        const uint32_t hi = __ldg(reinterpret_cast<const uint32_t*>(grow + min(ax + 4, (L.w - 1) & ~3)));
-        w = __funnelshift_r(lo, hi, sh);
-      } else {
-        w = 0;
+  {
+    // 7 row groups x 36 word columns (a tile row is 32 .. 36 words): 9 of 10 threads load, where 64 columns x 4 rows
+    // left half of them idle
+    const int ty = (tid * 1821) >> 16, tx = tid - ty * 36;   // tid / 36, tid % 36 for tid < 256
+    if (ty < 7)
+      for (int wv = tx; wv < nwords; wv += 36) {
+        const int gx = iniX + 4 * wv - FAST_PAD;          // global x of the word's first byte (>= 15)
+        for (int r = ty; r < rh; r += 7) {
+          const u8* grow = gbase + (size_t)(iniY + r) * ipitch;
+          uint32_t w;
+          if (aligned4) {
+            const int ax = gx & ~3, sh = (gx & 3) * 8;
+            const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(grow + ax));
+            const uint32_t hi = __ldg(reinterpret_cast<const uint32_t*>(grow + min(ax + 4, (L.w - 1) & ~3)));
+            w = __funnelshift_r(lo, hi, sh);
+          } else {
+            w = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) w |= (uint32_t)__ldg(grow + min(gx + k, L.w - 1)) << (8 * k);
+            for (int k = 0; k < 4; k++) w |= (uint32_t)__ldg(grow + min(gx + k, L.w - 1)) << (8 * k);
+          }
+          reinterpret_cast<uint32_t*>(simg + r * tilePitch)[wv] = w;
+        }
       }
-      reinterpret_cast<uint32_t*>(simg + r * tilePitch)[tx] = w;
-    }
   }
   for (int i = tid; i < (tileRows * tilePitch) >> 2; i += 256) reinterpret_cast<uint32_t*>(ssc)[i] = 0;
   __syncthreads();
@@ -294,19 +299,21 @@ __global__ void __launch_bounds__(256, 5) k_fast(const __grid_constant__ OrbGeom
     {
       const int dwords = (dw + 3) >> 2;
       const uint32_t th4 = (uint32_t)th * 0x01010101u;
-      // pixels of this thread's word that count: inside the detection area and, in phase 1, inside an empty cell
-      // (the same for every row)
-      const int dx0 = tx * 4;
-      unsigned kmask = dw - dx0 >= 4 ? 0xfu : ((1u << max(dw - dx0, 0)) - 1u);
-      if (phase == 1) {
-        unsigned fm = 0u;
+      // warp = rows wid, wid + 8, ..., lane = word column (a detection row is 31 .. 33 words: the second trip is rare and
+      // short).  kmask: pixels of the word that count -- inside the detection area and, in phase 1, inside an empty cell
+      const int lane = tid & 31, wid = tid >> 5;
+      for (int wv = lane; wv < dwords; wv += 32) {
+        const int dx0 = wv * 4;
+        unsigned kmask = dw - dx0 >= 4 ? 0xfu : ((1u << max(dw - dx0, 0)) - 1u);
+        if (phase == 1) {
+          unsigned fm = 0u;
 #pragma unroll
-        for (int k = 0; k < 4; k++) fm |= ((fb >> cell_of(min(dx0 + k, dw - 1))) & 1u) << k;
-        kmask &= fm;
-      }
-      if (tx < dwords && kmask)
-        for (int dy = ty; dy < dh; dy += 4) {
-          const uint32_t* row = reinterpret_cast<const uint32_t*>(simg + (dy + 3) * tilePitch) + 1 + tx;
+          for (int k = 0; k < 4; k++) fm |= ((fb >> cell_of(min(dx0 + k, dw - 1))) & 1u) << k;
+          kmask &= fm;
+        }
+        if (!kmask) continue;
+        for (int dy = wid; dy < dh; dy += 8) {
+          const uint32_t* row = reinterpret_cast<const uint32_t*>(simg + (dy + 3) * tilePitch) + 1 + wv;
           const uint32_t c = row[0], lft = row[-1], rgt = row[1];
           const uint32_t up = row[-3 * (tilePitch >> 2)], dn = row[3 * (tilePitch >> 2)];
           const uint32_t l3 = __funnelshift_r(lft, c, 8), r3 = __funnelshift_r(c, rgt, 24);   // columns -3 / +3
@@ -325,6 +332,7 @@ __global__ void __launch_bounds__(256, 5) k_fast(const __grid_constant__ OrbGeom
             m &= m - 1u;
           } while (m);
         }
+      }
     }
     __syncthreads();
     // ---- pass B: exact segment test for the listed pixels; corners go to a second list
