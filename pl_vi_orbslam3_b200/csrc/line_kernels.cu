@@ -268,8 +268,8 @@ __device__ __forceinline__ bool is_aligned_dev(double a, double theta, double pr
 // the register file stays free for the ORB kernels that run beside it: the whole step gains 3 % (12: 23.5 k, 14: 23.1 k,
 // 16: 24.2 k, 18: 23.1 k, 20: 21.2 k frames/s)
 #define SPEC_MINB 16
-#define SPEC_MINB_SMALL 12   // 85 registers allowed: the natural allocation (78)
 #endif
+#define SPEC_MINB_SMALL 12   // 85 registers allowed: the natural allocation (78)
 #ifndef COMMIT_WPB
 #define COMMIT_WPB 4  // ... and in k_lsd_commit
 #endif
@@ -573,8 +573,10 @@ __global__ void __launch_bounds__(256) k_lsd_band_split(const __grid_constant__ 
   }
 }
 
+// one block per (band, frame): 20 blocks of ~15 words per thread instead of 160 of ~2 (the kernel was bound by the rate
+// at which blocks start, not by the 0.5 MB per frame it moves)
 __global__ void __launch_bounds__(256) k_lsd_spec_init(const __grid_constant__ LineGeom g, LineBufs b) {
-  const int t = blockIdx.y, f = blockIdx.z;
+  const int t = blockIdx.x, f = blockIdx.y;
   const int oct = (g.noct > 1 && t >= g.o[1].taskOff) ? 1 : 0;
   const LineOct& O = g.o[oct];
   const int j = t - O.taskOff;
@@ -583,10 +585,17 @@ __global__ void __launch_bounds__(256) k_lsd_spec_init(const __grid_constant__ L
   const int nw = (O.sh - r0) * O.wpr;
   const unsigned* __restrict__ src = b.bitmap + (size_t)f * g.bmTotal + O.bmOff + r0 * O.wpr;
   unsigned* __restrict__ dst = b.specBm + (size_t)f * g.specBmTotal + O.specBmOff + (size_t)j * O.wpr * O.sh + r0 * O.wpr;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < nw; i += gridDim.x * 256) dst[i] = src[i];
+  for (int i0 = threadIdx.x; i0 < nw; i0 += 256 * 4) {   // four independent words per thread in flight
+    unsigned v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = i0 + 256 * u < nw ? __ldg(src + i0 + 256 * u) : 0u;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + 256 * u < nw) dst[i0 + 256 * u] = v[u];
+  }
   if (j == 0) {   // the commit pass starts without phantom pixels
     unsigned* ph = b.phantom + (size_t)f * g.bmTotal + O.bmOff;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < nw; i += gridDim.x * 256) ph[i] = 0u;
+    for (int i = threadIdx.x; i < nw; i += 256) ph[i] = 0u;
   }
 }
 
@@ -2735,7 +2744,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     LineBufs bs = b;
     bs.eqLoad = (b.eqLoad == 1 ? (n <= 2048) : (b.eqLoad == 2)) && g.o[0].sh <= 1024;
     k_lsd_band_split<<<dim3(g.noct, n), 256, 0, st>>>(g, bs);
-    k_lsd_spec_init<<<dim3(8, g.tasksPerFrame, n), 256, 0, st>>>(g, b);
+    k_lsd_spec_init<<<dim3(g.tasksPerFrame, n), 256, 0, st>>>(g, b);
     nl += 1;
     prof->mark("k_lsd_spec_init", st);
     {

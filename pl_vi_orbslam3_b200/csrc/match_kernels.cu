@@ -90,9 +90,18 @@ struct SearchArgs {
 struct QRes {
   int best, bestDist, second, secondDist;  // indices or -1; dist INT_MAX when absent
 };
+// what the in-order commit needs besides the result, fetched by the evaluating warps (eight at a time) so that the
+// serial commit reads shared memory only: the query record and the candidates' key points were two dependent L2 round
+// trips per committed query
+struct QAux {
+  int flags;            // query flags (bit 0: skip)
+  float qangle;         // query angle
+  float bangle;         // angle of the best candidate's key point
+  int l1, l2;           // octaves of the best / second candidate (-1: none)
+};
 
 __device__ __forceinline__ bool eligible(const SearchArgs& a, int i2, int d, const uint8_t* blk,
-                                         const int* mdist) {
+                                         const unsigned short* mdist) {
   if (a.mode == 2) return !(mdist[i2] <= d);
   return !blk[i2];
 }
@@ -101,7 +110,7 @@ __device__ __forceinline__ bool eligible(const SearchArgs& a, int i2, int d, con
 __device__ QRes eval_query(const SearchArgs& a, const plvi_keypoint* __restrict__ keys,
                            const uint8_t* __restrict__ desc, const plvi_query& q,
                            const uint8_t* __restrict__ qd, const int* cellStart,
-                           const unsigned short* items, const uint8_t* blk, const int* mdist,
+                           const unsigned short* items, const uint8_t* blk, const unsigned short* mdist,
                            const float* __restrict__ uright, float qur) {
   const int lane = threadIdx.x & 31;
   QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
@@ -188,14 +197,18 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
   const uint8_t* qdesc = a.qdesc + (size_t)pair * a.qstride * 32;
   int* owner = a.matchTrain + (size_t)pair * a.tstride;   // train -> query (mvpMapPoints / vnMatches21)
   int* m12 = a.matchQuery + (size_t)pair * a.qstride;     // query -> train
-  int* mdist = a.matchedDist ? a.matchedDist + (size_t)pair * a.tstride : nullptr;
 
   int* cellStart = reinterpret_cast<int*>(smem);                 // [GRID_CELLS + 1]
   int* cursor = cellStart + GRID_CELLS + 1;                      // [GRID_CELLS]
   unsigned short* items = reinterpret_cast<unsigned short*>(cursor + GRID_CELLS);  // [tstride]
   uint8_t* blk = reinterpret_cast<uint8_t*>(items + a.tstride);  // [tstride]
   signed char* qbin = reinterpret_cast<signed char*>(blk + a.tstride);  // [qstride] rot bin of a commit
+  // initialisation mode: smallest distance a train feature has been claimed with (distances are <= 256; in shared
+  // memory because every candidate of every query tests it)
+  unsigned short* mdist = a.mode == 2 ? reinterpret_cast<unsigned short*>(smem + (((GRID_CELLS * 2 + 1) * sizeof(int) + (size_t)a.tstride * 3 + a.qstride + 1) & ~(size_t)1)) : nullptr;
+  unsigned short* sown = mdist ? mdist + a.tstride : nullptr;   // ... and the query that holds it (copy of owner[])
   __shared__ QRes res[SEARCH_WARPS];
+  __shared__ QAux aux[SEARCH_WARPS];
   __shared__ int hist[HISTO_LENGTH];
   __shared__ int s_nm, s_keep[3];
   __shared__ int wtmp[33];
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
     if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) atomicAdd(&cursor[px * GRID_ROWS + py], 1);
     owner[i] = -1;
     blk[i] = a.blocked ? a.blocked[(size_t)pair * a.tstride + i] : 0;
-    if (mdist) mdist[i] = 0x7fffffff;
+    if (mdist) { mdist[i] = 0x7fffu; sown[i] = 0xffffu; }
   }
   for (int i = tid; i < nq; i += NT) { m12[i] = -1; qbin[i] = -1; }
   __syncthreads();
@@ -272,16 +285,27 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
   for (int q0 = 0; q0 < nq; q0 += SEARCH_WARPS) {
     const int qi = q0 + wid;
     QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
-    if (qi < nq && !(q[qi].flags & 1))
-      r = a.mode == 3 ? eval_query_bow(desc, q[qi], qdesc + (size_t)qi * 32, a.items + (size_t)pair * a.istride, blk)
-                      : eval_query(a, keys, desc, q[qi], qdesc + (size_t)qi * 32, cellStart, items, blk, mdist, uright, qur ? qur[qi] : 0.f);
-    if (lane == 0) res[wid] = r;
+    QAux x = {1, 0.f, 0.f, -1, -1};
+    if (qi < nq) {
+      const plvi_query qv = q[qi];
+      x.flags = qv.flags;
+      x.qangle = qv.angle;
+      if (!(qv.flags & 1))
+        r = a.mode == 3 ? eval_query_bow(desc, qv, qdesc + (size_t)qi * 32, a.items + (size_t)pair * a.istride, blk)
+                        : eval_query(a, keys, desc, qv, qdesc + (size_t)qi * 32, cellStart, items, blk, mdist, uright, qur ? qur[qi] : 0.f);
+    }
+    if (lane == 0) {
+      if (r.best >= 0) { x.bangle = keys[r.best].angle; x.l1 = keys[r.best].octave; }
+      if (r.second >= 0) x.l2 = keys[r.second].octave;
+      res[wid] = r;
+      aux[wid] = x;
+    }
     __syncthreads();
     if (wid == 0) {
       for (int j = 0; j < SEARCH_WARPS && q0 + j < nq; j++) {
         const int qj = q0 + j;
-        const plvi_query qq = q[qj];
-        if (qq.flags & 1) continue;
+        QAux ax = aux[j];
+        if (ax.flags & 1) continue;
         QRes rr = res[j];
         // stale if an earlier commit of this chunk removed the best or the second best
         bool stale = false;
@@ -291,31 +315,36 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
         } else {
           stale = (rr.best >= 0 && blk[rr.best]) || (a.mode != 0 && rr.second >= 0 && blk[rr.second]);
         }
-        if (stale)
+        if (stale) {
+          const plvi_query qq = q[qj];
           rr = a.mode == 3 ? eval_query_bow(desc, qq, qdesc + (size_t)qj * 32, a.items + (size_t)pair * a.istride, blk)
                            : eval_query(a, keys, desc, qq, qdesc + (size_t)qj * 32, cellStart, items, blk, mdist, uright, qur ? qur[qj] : 0.f);
+          ax.l1 = ax.l2 = -1;
+          if (rr.best >= 0) { ax.bangle = keys[rr.best].angle; ax.l1 = keys[rr.best].octave; }
+          if (rr.second >= 0) ax.l2 = keys[rr.second].octave;
+        }
         if (lane == 0 && rr.best >= 0) {
           if (a.mode == 0) {
             if (rr.bestDist <= a.th) {
               owner[rr.best] = qj;
               m12[qj] = rr.best;
-              if (!(qq.flags & 2)) blk[rr.best] = 1;
+              if (!(ax.flags & 2)) blk[rr.best] = 1;
               s_nm++;
               if (a.checkOri) {
-                const int b = rot_bin(qq.angle, keys[rr.best].angle);
+                const int b = rot_bin(ax.qangle, ax.bangle);
                 qbin[qj] = (signed char)b;
                 hist[b]++;
               }
             }
           } else if (a.mode == 1) {
             if (rr.bestDist <= a.th) {
-              const int l1 = keys[rr.best].octave, l2 = rr.second >= 0 ? keys[rr.second].octave : -1;
+              const int l1 = ax.l1, l2 = rr.second >= 0 ? ax.l2 : -1;
               const int d2 = rr.second >= 0 ? rr.secondDist : 256;
               const bool reject = (l1 == l2) && ((float)rr.bestDist > __fmul_rn(a.nnratio, (float)d2));
               if (!reject && (l1 != l2 || (float)rr.bestDist <= __fmul_rn(a.nnratio, (float)d2))) {
                 owner[rr.best] = qj;
                 m12[qj] = rr.best;
-                if (!(qq.flags & 2)) blk[rr.best] = 1;
+                if (!(ax.flags & 2)) blk[rr.best] = 1;
                 s_nm++;
               }
             }
@@ -327,7 +356,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
               blk[rr.best] = 1;       // vpMapPointMatches[realIdxF] != NULL blocks, whatever the observations
               s_nm++;
               if (a.checkOri) {
-                const int b = rot_bin(qq.angle, keys[rr.best].angle);
+                const int b = rot_bin(ax.qangle, ax.bangle);
                 qbin[qj] = (signed char)b;
                 hist[b]++;
               }
@@ -335,13 +364,15 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
           } else {
             if (rr.bestDist <= a.th &&
                 (float)rr.bestDist < __fmul_rn((float)rr.secondDist, a.nnratio)) {
-              if (owner[rr.best] >= 0) { m12[owner[rr.best]] = -1; s_nm--; }
+              const int prev = sown[rr.best];   // the query that held this feature (0xffff: none)
+              if (prev != 0xffff) { m12[prev] = -1; s_nm--; }
               m12[qj] = rr.best;
               owner[rr.best] = qj;
+              sown[rr.best] = (unsigned short)qj;
               mdist[rr.best] = rr.bestDist;
               s_nm++;
               if (a.checkOri) {
-                const int b = rot_bin(qq.angle, keys[rr.best].angle);
+                const int b = rot_bin(ax.qangle, ax.bangle);
                 qbin[qj] = (signed char)b;
                 hist[b]++;
               }
@@ -1374,6 +1405,10 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
     set_error("plvi_search_by_projection: exceeds matcher capacity");
     return PLVI_ERR_CAPACITY;
   }
+  if (mode == 2 && query_stride > 65534) {   // the kernel keeps the claiming query of a feature as 16 bits
+    set_error("plvi_search_by_projection: initialisation mode takes at most 65534 queries per pair");
+    return PLVI_ERR_CAPACITY;
+  }
   PLVI_CUDA_TRY(cudaSetDevice(m->device));
   SearchArgs a;
   a.mode = mode;
@@ -1412,7 +1447,7 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
     a.tcount = m->dTCount; a.q = m->dQ; a.qdesc = m->dQDesc; a.qcount = m->dQCount;
     a.matchTrain = m->dMatchTrain; a.matchQuery = m->dMatchQuery; a.nmatches = m->dNMatches;
   }
-  const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + 16;
+  const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + 16 + (mode == 2 ? T * 4 : 0);   // init mode: claimed distances + owners
   if (smem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_search<<<npairs, SEARCH_WARPS * 32, smem, st>>>(a);
