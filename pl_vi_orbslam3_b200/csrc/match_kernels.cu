@@ -31,6 +31,7 @@ namespace plvi {
 #define GRID_CELLS (GRID_COLS * GRID_ROWS)
 #define HISTO_LENGTH 30
 #define SEARCH_WARPS 8
+#define SEARCH_CHUNK (2 * (SEARCH_WARPS - 1))   // queries per chunk of k_search: two per evaluating warp
 
 __device__ __forceinline__ int hamming256_regs(const uint32_t (&q)[8], const uint8_t* __restrict__ d) {
   const uint4 a = __ldg(reinterpret_cast<const uint4*>(d));
@@ -207,8 +208,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
   // memory because every candidate of every query tests it)
   unsigned short* mdist = a.mode == 2 ? reinterpret_cast<unsigned short*>(smem + (((GRID_CELLS * 2 + 1) * sizeof(int) + (size_t)a.tstride * 3 + a.qstride + 1) & ~(size_t)1)) : nullptr;
   unsigned short* sown = mdist ? mdist + a.tstride : nullptr;   // ... and the query that holds it (copy of owner[])
-  __shared__ QRes res[SEARCH_WARPS];
-  __shared__ QAux aux[SEARCH_WARPS];
+  __shared__ QRes res[2][SEARCH_CHUNK];
+  __shared__ QAux aux[2][SEARCH_CHUNK];
   __shared__ int hist[HISTO_LENGTH];
   __shared__ int s_nm, s_keep[3];
   __shared__ int wtmp[33];
@@ -281,11 +282,15 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
   }
   __syncthreads();
 
-  // ---- queries, W at a time
-  for (int q0 = 0; q0 < nq; q0 += SEARCH_WARPS) {
-    const int qi = q0 + wid;
-    QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
-    QAux x = {1, 0.f, 0.f, -1, -1};
+  // ---- queries.  Warps 1 .. 7 evaluate chunk c + 1 (SEARCH_CHUNK queries, two per warp) while warp 0 commits chunk c in
+  // order: one barrier per chunk, and the serial commit no longer waits for the evaluation.  An evaluation may be
+  // arbitrarily early: a feature, once blocked (or, in the initialisation mode, claimed with a distance), never becomes
+  // eligible again, so the set an evaluation saw is a superset of the eligible set at commit time whatever mixture of
+  // old and new flags it read, and its two smallest candidates are still the two smallest if both are still eligible --
+  // which is what the commit checks (re-evaluating otherwise).
+  auto evaluate = [&](int qi, QRes& r, QAux& x) {
+    r = QRes{-1, 0x7fffffff, -1, 0x7fffffff};
+    x = QAux{1, 0.f, 0.f, -1, -1};
     if (qi < nq) {
       const plvi_query qv = q[qi];
       x.flags = qv.flags;
@@ -294,19 +299,28 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
         r = a.mode == 3 ? eval_query_bow(desc, qv, qdesc + (size_t)qi * 32, a.items + (size_t)pair * a.istride, blk)
                         : eval_query(a, keys, desc, qv, qdesc + (size_t)qi * 32, cellStart, items, blk, mdist, uright, qur ? qur[qi] : 0.f);
     }
-    if (lane == 0) {
-      if (r.best >= 0) { x.bangle = keys[r.best].angle; x.l1 = keys[r.best].octave; }
-      if (r.second >= 0) x.l2 = keys[r.second].octave;
-      res[wid] = r;
-      aux[wid] = x;
+    if (r.best >= 0) { x.bangle = keys[r.best].angle; x.l1 = keys[r.best].octave; }
+    if (r.second >= 0) x.l2 = keys[r.second].octave;
+  };
+  const int nchunk = (nq + SEARCH_CHUNK - 1) / SEARCH_CHUNK;
+  for (int c = -1; c < nchunk; c++) {
+    if (wid > 0 && c + 1 < nchunk) {
+      const int base = (c + 1) * SEARCH_CHUNK, buf = (c + 1) & 1;
+#pragma unroll 1
+      for (int k = 0; k < SEARCH_CHUNK / (SEARCH_WARPS - 1); k++) {
+        const int slot = (wid - 1) + (SEARCH_WARPS - 1) * k;
+        QRes r; QAux x;
+        evaluate(base + slot, r, x);
+        if (lane == 0) { res[buf][slot] = r; aux[buf][slot] = x; }
+      }
     }
-    __syncthreads();
-    if (wid == 0) {
-      for (int j = 0; j < SEARCH_WARPS && q0 + j < nq; j++) {
+    if (wid == 0 && c >= 0) {
+      const int q0 = c * SEARCH_CHUNK, buf = c & 1;
+      for (int j = 0; j < SEARCH_CHUNK && q0 + j < nq; j++) {
         const int qj = q0 + j;
-        QAux ax = aux[j];
+        QAux ax = aux[buf][j];
         if (ax.flags & 1) continue;
-        QRes rr = res[j];
+        QRes rr = res[buf][j];
         // stale if an earlier commit of this chunk removed the best or the second best
         bool stale = false;
         if (a.mode == 2) {
