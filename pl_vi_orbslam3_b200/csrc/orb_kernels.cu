@@ -660,22 +660,36 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g
   const int ipitch = p.ipitch[t.level];
   const u8* src = p.img[t.level] + (size_t)f * p.ifs[t.level];
   const bool aligned4 = ((ipitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
-  for (int i = tid; i < (BLUR_TH + 6) * 34; i += 256) {
-    const int r = i / 34, wq = i - r * 34;
-    const int gy = reflect101(min(y0 + r - 3, L.h + 2), L.h);
-    const int gx = x0 - 4 + 4 * wq;
-    const u8* row = src + (size_t)gy * ipitch;
-    uint32_t w;
-    if (aligned4 && gx >= 0 && gx + 3 < L.w) {
-      w = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-    } else if (gx > L.w + 2 || y0 + r - 3 > L.h + 2) {
-      w = 0;   // beyond the reflected border: read by no output pixel
-    } else {
-      w = 0;
+  // Input tile: 7 row groups x 36 word columns (34 used): the column's place relative to the image border is decided
+  // once per thread, and a thread's six row loads are in flight together (one load per loop trip with a division and
+  // the border tests around it was 30 % of the kernel's instructions and most of its stalls).
+  {
+    const int ty = (tid * 1821) >> 16, wq = tid - ty * 36;   // tid / 36, tid % 36 for tid < 256
+    if (ty < 7 && wq < 34) {
+      const int gx = x0 - 4 + 4 * wq;
+      // 0: aligned word inside the row, 1: touches the border (bytes, reflected), 2: beyond the reflected border
+      const int cls = (aligned4 && gx >= 0 && gx + 3 < L.w) ? 0 : (gx > L.w + 2 ? 2 : 1);
+      uint32_t w[6];
 #pragma unroll
-      for (int k = 0; k < 4; k++) w |= (uint32_t)__ldg(row + reflect101(min(gx + k, L.w + 2), L.w)) << (8 * k);
+      for (int k = 0; k < 6; k++) {
+        const int r = ty + 7 * k, yy = y0 + r - 3;
+        w[k] = 0;   // beyond the reflected border: read by no output pixel
+        if (r < BLUR_TH + 6 && cls != 2 && yy <= L.h + 2) {
+          const u8* row = src + (size_t)reflect101(yy, L.h) * ipitch;
+          if (cls == 0) {
+            w[k] = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) w[k] |= (uint32_t)__ldg(row + reflect101(min(gx + kk, L.w + 2), L.w)) << (8 * kk);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const int r = ty + 7 * k;
+        if (r < BLUR_TH + 6) sin_[r * 36 + wq] = w[k];
+      }
     }
-    sin_[r * 36 + wq] = w;
   }
   __syncthreads();
   const uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
