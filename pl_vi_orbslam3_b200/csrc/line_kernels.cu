@@ -2677,11 +2677,19 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     const bool specPath = g.refine == 0 && !(b.brMax > 0 && n <= b.brUse) && b.useSpec;
     PLVI_CUDA_TRY(cudaMemsetAsync(b.specStart, specPath ? 0 : 0x3f, sizeof(int), st));
   }
-  if (aux.stage && (!prof->on || StageProf::timeline())) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cs);
-    PLVI_CUDA_TRY(cudaEventRecordWithFlags(aux.stage, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
-  }
+  // (on the speculation path the event is recorded behind k_lsd_spec_init: released right after k_lsd_pre, the ORB
+  // pyramid flooded the SMs and the two short set-up kernels of the speculation took 4.2 ms instead of 0.3 -- on the
+  // critical path of the step)
+  auto record_stage = [&]() -> int {
+    if (aux.stage && (!prof->on || StageProf::timeline())) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      PLVI_CUDA_TRY(cudaEventRecordWithFlags(aux.stage, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    }
+    return PLVI_OK;
+  };
+  const bool stageLate = g.refine == 0 && !(b.brMax > 0 && n <= b.brUse) && b.useSpec;
+  if (!stageLate) { const int rc = record_stage(); if (rc != PLVI_OK) return rc; }
   // The LBD pyramid + Sobel only depend on the input frame: they run on the auxiliary stream while
   // the latency-bound region growing occupies the main one (serially when profiling, for clean times).
   const bool fork = aux.stream != nullptr && (!prof->on || StageProf::timeline());
@@ -2747,6 +2755,7 @@ int launch_line_pipeline(const LineGeom& g, const LinePtrs& p, const LineBufs& b
     k_lsd_spec_init<<<dim3(g.tasksPerFrame, n), 256, 0, st>>>(g, b);
     nl += 1;
     prof->mark("k_lsd_spec_init", st);
+    { const int rc = record_stage(); if (rc != PLVI_OK) return rc; }
     {
       const dim3 sgrid(g.tasksPerFrame, (n + 32 * GROW_WPB - 1) / (32 * GROW_WPB));
       // large batches: the 64-register build (room for the ORB kernels beside it); smaller ones are bound by the length
