@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--distinct", type=int, default=128)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--host", action="store_true", help="steps through the host-buffer entry points (FrontEnd.step_host: pinned frames in, pinned results out)")
     args = ap.parse_args()
     from pl_vi_orbslam3_b200 import synth
     W, H = 752, 480
@@ -32,22 +33,35 @@ def main():
     from pl_vi_orbslam3_b200.frontend import FrontEnd
     fe = FrontEnd(args.batch, w=W, h=H, pairs=True, affine=affine, out_sets=2)
     st = fe.stream
+    h_frames = torch.from_numpy(frames).pin_memory() if args.host else None
+    ios = [fe.alloc_host_io() for _ in range(2)] if args.host else None
+
+    def one_step(i):
+        if args.host:
+            fe.step_host(h_frames, ios[i % 2])
+        else:
+            fe.step(d_frames)
+
     with torch.cuda.stream(st):
         d_frames = torch.from_numpy(frames).to(fe.device)
-        for _ in range(2):
-            fe.step(d_frames)
+        for i in range(2):
+            one_step(i)
     st.synchronize()
+    if args.host:
+        fe.sync_host()
     fe.set_profile(True)
     rows = []
     e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with torch.cuda.stream(st):
         e[0].record(st)
         for i in range(args.steps):
-            fe.step(d_frames)
+            one_step(i)
             e[i + 1].record(st)
             if i == args.steps - 1:
                 st.synchronize()
                 fe.line_stream.synchronize()
+                if args.host:
+                    fe.sync_host()
                 for tag, txt in (("orb", lib().plvi_orb_profile(fe.orb._h).decode()),
                                  ("line", lib().plvi_line_profile(fe.line._h).decode())):
                     for item in txt.split(";"):
