@@ -131,10 +131,78 @@ def _stress_images():
     return {"saw": saw, "stripes": stripes, "diag": diag, "mixed": mixed, "blobs": blobs}
 
 
-def test_lsd_speculation_stress(ext):
+@pytest.fixture(scope="module", params=["band_run", "spec", "serial"])
+def ext_sched(gpu, request):
+    """One extractor per region-growing schedule: band-run rounds (what a small batch takes by default), band
+    speculation + serial commit (what batches of more than 384 frames take: the bench path) and the serial kernel."""
+    import os
+    old = os.environ.get("PLVI_LSD_SPEC")
+    if request.param == "serial":
+        os.environ["PLVI_LSD_SPEC"] = "0"          # read when the handle is created
+    try:
+        e = Lineextractor(200, 0, 0.8, 2, 2.0, 0, max_width=752, max_height=480, max_batch=4,
+                          band_run_max=-1 if request.param == "band_run" else 0)
+    finally:
+        if old is None:
+            os.environ.pop("PLVI_LSD_SPEC", None)
+        else:
+            os.environ["PLVI_LSD_SPEC"] = old
+    yield e
+    e.close()
+
+
+def test_lsd_schedules_agree_on_a_batch(gpu):
+    """The three schedules of the region growing give the same raw segments, KeyLines and LBD bytes on a batch of 40
+    frames (synthetic frames, their warps, noise, a flat frame and the stress images): the band speculation + commit
+    path is the one the bench measures at 4096 frames per step, and batches this small would not reach it by default."""
+    import os
+    imgs = _stress_images()
+    rng = np.random.RandomState(5)
+    frames = [synth.frame_euroc(s) for s in range(24)] + [synth.warp_pair(s)[1] for s in range(9)]
+    frames += [imgs[n] for n in sorted(imgs)] + [rng.randint(0, 256, (480, 752)).astype(np.uint8), np.full((480, 752), 90, np.uint8)]
+    batch = np.stack(frames)
+    n = len(batch)
+    res = {}
+    for sched in ("band_run", "spec", "serial"):
+        old = os.environ.get("PLVI_LSD_SPEC")
+        if sched == "serial":
+            os.environ["PLVI_LSD_SPEC"] = "0"
+        try:
+            e = Lineextractor(200, 0, 0.8, 2, 2.0, 0, max_width=752, max_height=480, max_batch=n,
+                              band_run_max=-1 if sched == "band_run" else 0)
+        finally:
+            if old is None:
+                os.environ.pop("PLVI_LSD_SPEC", None)
+            else:
+                os.environ["PLVI_LSD_SPEC"] = old
+        try:
+            kl, desc, eq, counts = e.extract_batch(batch)
+            segs = [[e.read_lsd(i, o, "segments", 752, 480).copy() for o in (0, 1)] for i in range(n)]
+            res[sched] = (kl.copy(), desc.copy(), eq.copy(), counts.copy(), segs)
+        finally:
+            e.close()
+    ref = res["serial"]
+    for sched in ("band_run", "spec"):
+        got = res[sched]
+        assert np.array_equal(got[3], ref[3]), sched
+        for i in range(n):
+            c = ref[3][i]
+            for o in (0, 1):
+                assert np.array_equal(got[4][i][o], ref[4][i][o]), (sched, i, o)
+            assert np.array_equal(got[0][i, :c].view(np.uint8), ref[0][i, :c].view(np.uint8)), (sched, i)
+            assert np.array_equal(got[1][i, :c], ref[1][i, :c]), (sched, i)
+            assert np.array_equal(got[2][i, :c].view(np.uint8), ref[2][i, :c].view(np.uint8)), (sched, i)
+    # ... and the serial kernel against the oracle on a few of them
+    kl, desc, eq, counts, _ = ref
+    for i in (0, 13, 27, n - 2):
+        _check_lines(kl[i, :counts[i]], desc[i, :counts[i]], eq[i, :counts[i]], oracle.line_extract(batch[i]))
+
+
+def test_lsd_speculation_stress(ext_sched):
     """Raw LSD segments (the output of seed scan + region growing + rectangle fit) stay exact when
     speculative regions overflow their lists, collide across bands or are discarded in bulk; the
-    images run as one batch so the lanes of a warp follow very different paths."""
+    images run as one batch so the lanes of a warp follow very different paths.  Runs under each schedule."""
+    ext = ext_sched
     imgs = _stress_images()
     names = sorted(imgs)
     batch = np.stack([imgs[n] for n in names[:4]])
