@@ -419,12 +419,15 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
         int flushed = 0;     // ring entries [flushed, regSize) are not in global memory yet
         int i = 0, nb = 1;
         GrowBatch cur = grow_fetch(bm, ring, reg, regSize, 0, 1, e, ndx, ndy, W, H, rec);
+        bool curDirty = false;   // a pixel was accepted after cur's candidates were fetched
         while (nb > 0) {
           const int ni = i + nb, nnb = min(4, regSize - ni);
           GrowBatch nxt = grow_fetch(bm, ring, reg, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
-          // candidates fetched ahead may have been absorbed by the previous batch in the meantime
+          // candidates fetched ahead may have been absorbed by the previous batch in the meantime (only then is their
+          // availability tested again)
           unsigned pm = cur.mask;
-          if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cur.bw, cur.bbit));
+          if (pm && curDirty) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cur.bw, cur.bbit));
+          const int sizeBefore = regSize;
           float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
           while (pm) {
             // every pending candidate against the current region direction at once
@@ -467,9 +470,11 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const __grid_constant__ LineGeo
           if (nnb > 0) {
             cur = nxt;
             nb = nnb;
+            curDirty = regSize != sizeBefore;   // fetched before this batch's accepts
           } else {
             nb = min(4, regSize - i);
             if (nb > 0) cur = grow_fetch(bm, ring, reg, regSize, i, nb, e, ndx, ndy, W, H, rec);
+            curDirty = false;
           }
         }
         if (regSize >= O.minRegSize) {
@@ -1019,11 +1024,13 @@ __global__ void __launch_bounds__(32 * COMMIT_WPB, COMMIT_BPS) k_lsd_commit(cons
         int flushed = 0;
         int i = 0, nb = 1;
         GrowBatch cb = grow_fetch(bm, ring, reg, regSize, 0, 1, e, ndx, ndy, W, H, rec);
+        bool cbDirty = false;   // a pixel was accepted after cb's candidates were fetched (only then are they tested again)
         while (nb > 0) {
           const int ni = i + nb, nnb = min(4, regSize - ni);
           GrowBatch nxt = grow_fetch(bm, ring, reg, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
           unsigned pm = cb.mask;
-          if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cb.bw, cb.bbit));
+          if (pm && cbDirty) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cb.bw, cb.bbit));
+          const int sizeBefore = regSize;
           float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
           while (pm) {
             const float dot = __fmaf_rn(sumdx, cb.rec.x, sumdy * cb.rec.y);
@@ -1062,9 +1069,11 @@ __global__ void __launch_bounds__(32 * COMMIT_WPB, COMMIT_BPS) k_lsd_commit(cons
           if (nnb > 0) {
             cb = nxt;
             nb = nnb;
+            cbDirty = regSize != sizeBefore;   // fetched before this batch's accepts
           } else {
             nb = min(4, regSize - i);
             if (nb > 0) cb = grow_fetch(bm, ring, reg, regSize, i, nb, e, ndx, ndy, W, H, rec);
+            cbDirty = false;
           }
         }
         if (regSize >= O.minRegSize) {
@@ -1392,12 +1401,14 @@ template <int BR_K> __global__ void __launch_bounds__(32, BR_K == BR_K_BIG ? 1 :
         int flushed = 0;
         int i = 0, nb = 1;
         GrowBatch cb = grow_fetch(bm, ring, reg, regSize, 0, 1, e, ndx, ndy, W, H, rec);
+        bool cbDirty = false;   // a pixel was accepted after cb's candidates were fetched (only then are they tested again)
         while (nb > 0) {
           if (npx + regSize + 64 > pxCap) { overflow = true; break; }
           const int ni = i + nb, nnb = min(4, regSize - ni);
           GrowBatch nxtb = grow_fetch(bm, ring, reg, regSize, ni, nnb, e, ndx, ndy, W, H, rec);
           unsigned pm = cb.mask;
-          if (pm) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cb.bw, cb.bbit));
+          if (pm && cbDirty) pm = __ballot_sync(0xffffffffu, (pm & laneBit) && grow_bit(bm, cb.bw, cb.bbit));
+          const int sizeBefore = regSize;
           float n2 = __fmaf_rn(sumdx, sumdx, sumdy * sumdy);
           while (pm) {
             const float dot = __fmaf_rn(sumdx, cb.rec.x, sumdy * cb.rec.y);
@@ -1444,9 +1455,11 @@ template <int BR_K> __global__ void __launch_bounds__(32, BR_K == BR_K_BIG ? 1 :
           if (nnb > 0) {
             cb = nxtb;
             nb = nnb;
+            cbDirty = regSize != sizeBefore;   // fetched before this batch's accepts
           } else {
             nb = min(4, regSize - i);
             if (nb > 0) cb = grow_fetch(bm, ring, reg, regSize, i, nb, e, ndx, ndy, W, H, rec);
+            cbDirty = false;
           }
         }
         if (overflow) break;
