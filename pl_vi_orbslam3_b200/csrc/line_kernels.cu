@@ -1136,6 +1136,12 @@ __global__ void __launch_bounds__(32 * COMMIT_WPB, COMMIT_BPS) k_lsd_commit(cons
 // the warp an SM's shared memory to itself (a window that holds nearly every region keeps the availability tests off
 // the L2 round trip), 32 when many frames are in flight and resident warps per SM count more
 #define BR_K_BIG 256
+#ifndef BR_PREFETCH
+// L1 prefetches of the per-pixel records in k_lsd_band_run: 2 / 1 = the lower neighbours of every accepted pixel (both
+// sides / one line) + the band's rows in the prologue, 0 = the prologue only, -1 = none.  Measured on one frame (B200,
+// end of round 2): 4.35 / 4.34 / 4.23 / 4.19 ms -- the loads they spare cost less than the instructions they add
+#define BR_PREFETCH -1
+#endif
 #define BR_K_SMALL 32
 
 // thread = one bitmap word (row, w) of one (frame, octave); walks the bands that contain the row in band order
@@ -1237,6 +1243,7 @@ template <int BR_K> __global__ void __launch_bounds__(32, BR_K == BR_K_BIG ? 1 :
   const float2* __restrict__ rec = b.cs + pbase;
   const float* __restrict__ ang = b.ang + pbase;
   const float2* __restrict__ seedcs = b.seed + pbase;
+#if BR_PREFETCH >= 0
   {
     // The warp has an SM sub-partition (and most of its L1) to itself: pull the per-pixel records of the band's own
     // rows and of the rows right below into L1 while the bitmaps are copied, so that the dependent loads of the
@@ -1252,6 +1259,7 @@ template <int BR_K> __global__ void __launch_bounds__(32, BR_K == BR_K_BIG ? 1 :
     const char* s1 = reinterpret_cast<const char*>(seedcs + (size_t)r1 * W);
     for (const char* q = s0 + lane * 128; q < s1; q += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
   }
+#endif
   // working copy of the input (rows above the band hold nothing by definition), the first BR_K rows of it and of the
   // initial phantom map into the shared windows (a ring of BR_K rows: linear from the band's first row, wrapping once),
   // and: is there any initial phantom?  Eight (four) independent words per lane are in flight; one pass over the input.
@@ -1434,11 +1442,15 @@ template <int BR_K> __global__ void __launch_bounds__(32, BR_K == BR_K_BIG ? 1 :
               // this pixel is expanded a few queue entries from now: its lower neighbours' records are what that
               // expansion waits for (rows up to its own are in L1 already when it was reached from above)
               const int py = (qpk >> 16) + 1, px = qpk & 0xffff;
+#if BR_PREFETCH == 2
               if (py < H) {
                 const float2* pr = rec + py * W + px;
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(pr - 1));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 1));
               }
+#elif BR_PREFETCH == 1
+              if (py < H) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + py * W + px));
+#endif
             }
             regSize++;
             fresh = false;
