@@ -1676,8 +1676,8 @@ __global__ void __launch_bounds__(256) k_lsd_rect(const __grid_constant__ LineGe
       const unsigned p = rp[i];
       const double rdx = (double)(p & 0xffff) - x, rdy = (double)(p >> 16) - y;
       const double l = __dadd_rn(__dmul_rn(rdx, dx), __dmul_rn(rdy, dy));
-      lmax = fmax(lmax, l);
-      lmin = fmin(lmin, l);
+      lmax = l > lmax ? l : lmax;   // (l is never NaN: plain selects instead of the NaN-aware fmax / fmin sequences)
+      lmin = l < lmin ? l : lmin;
     }
     lmin = group_min_d<G>(lmin);
     lmax = group_max_d<G>(lmax);

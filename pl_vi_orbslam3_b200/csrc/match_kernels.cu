@@ -111,7 +111,7 @@ __device__ __forceinline__ bool eligible(const SearchArgs& a, int i2, int d, con
 __device__ QRes eval_query(const SearchArgs& a, const plvi_keypoint* __restrict__ keys,
                            const uint8_t* __restrict__ desc, const plvi_query& q,
                            const uint8_t* __restrict__ qd, const int* cellStart,
-                           const unsigned short* items, const uint8_t* blk, const unsigned short* mdist,
+                           const unsigned short* items, const uint8_t* ioct, const uint8_t* blk, const unsigned short* mdist,
                            const float* __restrict__ uright, float qur) {
   const int lane = threadIdx.x & 31;
   QRes r = {-1, 0x7fffffff, -1, 0x7fffffff};
@@ -134,12 +134,14 @@ __device__ QRes eval_query(const SearchArgs& a, const plvi_keypoint* __restrict_
     const int s = cellStart[cell], e = cellStart[cell + 1];
     for (int k = s; k < e; k++) {
       const int i2 = items[k];
-      const plvi_keypoint kp = keys[i2];
-      if (checkLevels) {
-        if (kp.octave < q.min_level) continue;
-        if (q.max_level >= 0 && kp.octave > q.max_level) continue;
+      if (checkLevels) {   // from the shared-memory copy of the octaves: most candidates of a wide window end here
+        const int oc = ioct[k];
+        if (oc < q.min_level) continue;
+        if (q.max_level >= 0 && oc > q.max_level) continue;
       }
-      if (!(fabsf(__fsub_rn(kp.x, x)) < rad && fabsf(__fsub_rn(kp.y, y)) < rad)) continue;
+      if (a.mode != 2 && blk[i2]) continue;   // (the initialisation mode decides by the distance: eligible())
+      const float kx = keys[i2].x, ky = keys[i2].y;
+      if (!(fabsf(__fsub_rn(kx, x)) < rad && fabsf(__fsub_rn(ky, y)) < rad)) continue;
       if (uright) {   // stereo observation: |ur - mvuRight[i2]| must stay inside the window (src/ORBmatcher.cc:91-96, 2041-2047)
         const float ur2 = __ldg(uright + i2);
         if (ur2 > 0.f && fabsf(__fsub_rn(qur, ur2)) > rad) continue;
@@ -206,7 +208,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
   signed char* qbin = reinterpret_cast<signed char*>(blk + a.tstride);  // [qstride] rot bin of a commit
   // initialisation mode: smallest distance a train feature has been claimed with (distances are <= 256; in shared
   // memory because every candidate of every query tests it)
-  unsigned short* mdist = a.mode == 2 ? reinterpret_cast<unsigned short*>(smem + (((GRID_CELLS * 2 + 1) * sizeof(int) + (size_t)a.tstride * 3 + a.qstride + 1) & ~(size_t)1)) : nullptr;
+  uint8_t* ioct = reinterpret_cast<uint8_t*>(qbin + a.qstride);          // [tstride] octave of items[k]: the level test of a candidate without its key point
+  unsigned short* mdist = a.mode == 2 ? reinterpret_cast<unsigned short*>(smem + (((GRID_CELLS * 2 + 1) * sizeof(int) + (size_t)a.tstride * 4 + a.qstride + 1) & ~(size_t)1)) : nullptr;
   unsigned short* sown = mdist ? mdist + a.tstride : nullptr;   // ... and the query that holds it (copy of owner[])
   __shared__ QRes res[2][SEARCH_CHUNK];
   __shared__ QAux aux[2][SEARCH_CHUNK];
@@ -281,6 +284,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
     }
   }
   __syncthreads();
+  for (int k = tid; k < cellStart[GRID_CELLS]; k += NT) ioct[k] = (uint8_t)min(max(keys[items[k]].octave, 0), 255);
+  __syncthreads();
 
   // ---- queries.  Warps 1 .. 7 evaluate chunk c + 1 (SEARCH_CHUNK queries, two per warp) while warp 0 commits chunk c in
   // order: one barrier per chunk, and the serial commit no longer waits for the evaluation.  An evaluation may be
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
       x.qangle = qv.angle;
       if (!(qv.flags & 1))
         r = a.mode == 3 ? eval_query_bow(desc, qv, qdesc + (size_t)qi * 32, a.items + (size_t)pair * a.istride, blk)
-                        : eval_query(a, keys, desc, qv, qdesc + (size_t)qi * 32, cellStart, items, blk, mdist, uright, qur ? qur[qi] : 0.f);
+                        : eval_query(a, keys, desc, qv, qdesc + (size_t)qi * 32, cellStart, items, ioct, blk, mdist, uright, qur ? qur[qi] : 0.f);
     }
     if (r.best >= 0) { x.bangle = keys[r.best].angle; x.l1 = keys[r.best].octave; }
     if (r.second >= 0) x.l2 = keys[r.second].octave;
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_search(const SearchArgs a
         if (stale) {
           const plvi_query qq = q[qj];
           rr = a.mode == 3 ? eval_query_bow(desc, qq, qdesc + (size_t)qj * 32, a.items + (size_t)pair * a.istride, blk)
-                           : eval_query(a, keys, desc, qq, qdesc + (size_t)qj * 32, cellStart, items, blk, mdist, uright, qur ? qur[qj] : 0.f);
+                           : eval_query(a, keys, desc, qq, qdesc + (size_t)qj * 32, cellStart, items, ioct, blk, mdist, uright, qur ? qur[qj] : 0.f);
           ax.l1 = ax.l2 = -1;
           if (rr.best >= 0) { ax.bangle = keys[rr.best].angle; ax.l1 = keys[rr.best].octave; }
           if (rr.second >= 0) ax.l2 = keys[rr.second].octave;
@@ -1461,7 +1466,7 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
     a.tcount = m->dTCount; a.q = m->dQ; a.qdesc = m->dQDesc; a.qcount = m->dQCount;
     a.matchTrain = m->dMatchTrain; a.matchQuery = m->dMatchQuery; a.nmatches = m->dNMatches;
   }
-  const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + 16 + (mode == 2 ? T * 4 : 0);   // init mode: claimed distances + owners
+  const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + T + 16 + (mode == 2 ? T * 4 : 0);   // + octaves of the items; init mode: claimed distances + owners
   if (smem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_search<<<npairs, SEARCH_WARPS * 32, smem, st>>>(a);
@@ -1527,7 +1532,7 @@ static int search_by_bow_impl(plvi_matcher* m, int npairs, const plvi_keypoint* 
     a.q = m->dQ; a.qdesc = m->dQDesc; a.qcount = m->dQCount;
     a.matchTrain = m->dMatchTrain; a.matchQuery = m->dMatchQuery; a.nmatches = m->dNMatches;
   }
-  const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + 16;
+  const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + T + 16;
   if (smem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_search<<<npairs, SEARCH_WARPS * 32, smem, st>>>(a);
