@@ -31,7 +31,10 @@ namespace plvi {
 #define GRID_CELLS (GRID_COLS * GRID_ROWS)
 #define HISTO_LENGTH 30
 #define SEARCH_WARPS 8
-#define SEARCH_CHUNK (2 * (SEARCH_WARPS - 1))   // queries per chunk of k_search: two per evaluating warp
+#ifndef SEARCH_PER_WARP
+#define SEARCH_PER_WARP 2
+#endif
+#define SEARCH_CHUNK (SEARCH_PER_WARP * (SEARCH_WARPS - 1))   // queries per chunk of k_search: two per evaluating warp (four: 1.80 vs 1.70 ms per 1024 frames)
 
 __device__ __forceinline__ int hamming256_regs(const uint32_t (&q)[8], const uint8_t* __restrict__ d) {
   const uint4 a = __ldg(reinterpret_cast<const uint4*>(d));
