@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(256) k_resize_tma(const u8* __restrict__ src, 
 // [ini, ini+cell+6) separately: scores exist only >= 3 px inside the ROI, so the
 // detection strips of the cells tile the level without overlap and the 3x3 NMS never
 // sees a score from a neighbouring cell.  A cell keeps its th=iniTh survivors, or, if
-// it has none, its th=minTh survivors (the score is threshold independent).
+// it has none, its th=minTh survivors: two phases over the tile, the second one confined to
+// the cells the first one left empty (the score is threshold independent).
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ int fast_arc_score(const int (&d)[16]) {
   // max over the 16 arcs of 9 contiguous ring pixels of min(d) and of min(-d)
@@ -231,12 +232,11 @@ __global__ void __launch_bounds__(256, 5) k_fast(const __grid_constant__ OrbGeom
   u8* ssc = smem + tileRows * tilePitch;             // scores, same shape
   unsigned short* list1 = reinterpret_cast<unsigned short*>(ssc + tileRows * tilePitch);  // [listCap] dy << 8 | dx
   unsigned short* list2 = list1 + listCap;                                               // [listCap] corners
-  uint32_t* surv = reinterpret_cast<uint32_t*>(list2 + listCap);                         // [survCap]
-  uint32_t* kept = surv + survCap;                                                       // [survCap]
-  __shared__ int s_n1, s_n2, s_nsurv, s_nkept, s_base;
+  uint32_t* kept = reinterpret_cast<uint32_t*>(list2 + listCap);                         // [survCap] NMS survivors of the cells' deciding phase
+  __shared__ int s_n1, s_n2, s_nkept, s_base;
   __shared__ int s_cellFlag[8];
   const int tid = threadIdx.x;
-  if (tid == 0) { s_n1 = 0; s_n2 = 0; s_nsurv = 0; s_nkept = 0; }
+  if (tid == 0) { s_n1 = 0; s_n2 = 0; s_nkept = 0; }
   if (tid < 8) s_cellFlag[tid] = 0;
 
   // ---- tile load: smem word k of a row holds ROI bytes 4k-1 .. 4k+2
@@ -957,7 +957,7 @@ static void fast_tile_dims(const OrbGeom& g, int* tilePitch, int* tileRows, int*
 int orb_kernel_attrs(const OrbGeom& g, int* fastSmem, int* octSmem) {
   int tp, tr, lc, sc;
   fast_tile_dims(g, &tp, &tr, &lc, &sc);
-  *fastSmem = 2 * tp * tr + 2 * lc * (int)sizeof(unsigned short) + 2 * sc * (int)sizeof(uint32_t);
+  *fastSmem = 2 * tp * tr + 2 * lc * (int)sizeof(unsigned short) + sc * (int)sizeof(uint32_t);
   *octSmem = (int)octree_smem_bytes(g.maxNodes);
   if (*octSmem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_octree<OCT_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, *octSmem));
