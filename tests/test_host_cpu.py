@@ -148,3 +148,17 @@ def test_cpp_shim_compiles_and_links(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     out = subprocess.run([str(exe), "tolerate-no-device"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_kernel_integer_identities():
+    """Integer identities the kernels lean on (csrc/orb_kernels.cu), checked exhaustively on the host.
+    * k_fast pass A gathers the four 0/1 flag bytes of a SWAR comparison into a nibble with one 32-bit multiplication:
+      byte k (bit 8k) times 2^(21 - 7k) lands on bit 21 + k and no two of the sixteen partial products share a bit.
+    * k_fast / k_blur7 map 256 threads onto 7 rows x 36 columns with tid * 1821 >> 16 = tid // 36."""
+    for m in range(16):
+        cnt = sum(((m >> k) & 1) << (8 * k) for k in range(4))
+        assert (((cnt * 0x00204081) & 0xFFFFFFFF) >> 21) & 0xF == m
+    bits = [8 * j + 21 - 7 * i for i in range(4) for j in range(4)]
+    assert len(set(bits)) == 16                      # no two partial products collide (so no carries either)
+    for tid in range(256):
+        assert (tid * 1821) >> 16 == tid // 36
