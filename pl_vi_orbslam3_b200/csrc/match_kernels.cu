@@ -1470,6 +1470,10 @@ int plvi_search_by_projection(plvi_matcher* m, int mode, int npairs, const plvi_
     a.matchTrain = m->dMatchTrain; a.matchQuery = m->dMatchQuery; a.nmatches = m->dNMatches;
   }
   const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + T + 16 + (mode == 2 ? T * 4 : 0);   // + octaves of the items; init mode: claimed distances + owners
+  if (smem > 227 * 1024) {   // items, flags, octaves (+ claimed distances / owners) of one pair live in shared memory
+    set_error("search: train / query strides too large for the shared-memory tables of one pair");
+    return PLVI_ERR_CAPACITY;
+  }
   if (smem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_search<<<npairs, SEARCH_WARPS * 32, smem, st>>>(a);
@@ -1536,6 +1540,10 @@ static int search_by_bow_impl(plvi_matcher* m, int npairs, const plvi_keypoint* 
     a.matchTrain = m->dMatchTrain; a.matchQuery = m->dMatchQuery; a.nmatches = m->dNMatches;
   }
   const size_t smem = (GRID_CELLS * 2 + 1) * sizeof(int) + T * 2 + T + Q + T + 16;
+  if (smem > 227 * 1024) {   // items, flags, octaves (+ claimed distances / owners) of one pair live in shared memory
+    set_error("search: train / query strides too large for the shared-memory tables of one pair");
+    return PLVI_ERR_CAPACITY;
+  }
   if (smem > 48 * 1024)
     PLVI_CUDA_TRY(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_search<<<npairs, SEARCH_WARPS * 32, smem, st>>>(a);
