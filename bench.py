@@ -100,7 +100,7 @@ GROW_NOTE = ("LSD region growing is a serial dependency chain per band (k_lsd_sp
              "k_lsd_spec is bound by the latency of dependent L2 / DRAM round trips with 17 warps per SM (ncu at 4096 frames: issue "
              "active 32 %, L1 / L2 / DRAM throughput 29 / 29 / 15 %, DRAM traffic 7.7x the algorithmic bytes because every 32-byte "
              "sector of the neighbour records is fetched several times), k_lsd_commit half by instruction issue (64 %); neither by "
-             "HBM bandwidth; see DESIGN.md section 4 and profiles/r02b_notes.md")
+             "HBM bandwidth; see DESIGN.md section 4 and profiles/r02b_notes.md, profiles/r02c_notes.md (the step is the sum of its kernels)")
 
 
 SCALE_FACTORS = np.cumprod(np.concatenate([[np.float32(1.0)], np.full(7, np.float32(1.2))]).astype(np.float32), dtype=np.float32)
